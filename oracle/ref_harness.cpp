@@ -1,0 +1,499 @@
+// TEST INFRASTRUCTURE — not part of the product.
+//
+// C-ABI harness around the UNMODIFIED reference implementation (nashaudio/klang,
+// klang.h v0.7.8 and examples/*.k).  oracle/build_ref.py compiles this file
+// against a build-time patched copy of /root/reference/klang.h (the one
+// mechanical g++ patch described in oracle/build_ref.py) into
+// oracle/_ref/libklang_ref.so.  Nothing here re-implements klang arithmetic: it
+// only instantiates reference objects, drives them through their public API
+// (set()/process()/start()/release()/Synth::process()/Effect::process()) and
+// copies samples out, so it is the ground truth the restatement in
+// oracle/klang_port.c and the CUDA path are checked against.
+//
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+// --impl reference legs may load the resulting library.
+//
+// Reference state is process-global (klang::fs, rand(), debug.buffer, the abs/sqr
+// Function objects — klang.h:1593-1604, 3063-3069, 3196), so this library is
+// single-threaded by contract; parallel CPU timing uses fork()ed processes.
+
+#include <klang.h>
+
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+// ---------------------------------------------------------------------------
+// The example programs, each inside its own namespace so that their global
+// `using namespace klang::{optimised,basic}` directives and struct names do
+// not collide.  klang.h is already included above (#pragma once).
+// ---------------------------------------------------------------------------
+namespace k_gain {
+#include "Gain/Gain.k"
+}
+namespace k_filter {
+#include "Subtractive/Filter.k"
+}
+namespace k_supersaw {
+#include "SuperSaw.k"
+}
+namespace k_pingpong {
+#include "PingPong.k"
+}
+namespace k_reverb {
+#include "Reverb.k"
+}
+namespace k_tb303 {
+#include "TB303_patched.k"   // one-token g++ disambiguation, see build_ref.py
+}
+namespace k_synthx {
+#include "SynTHX_patched.k"  // one-token g++ disambiguation, see build_ref.py
+}
+namespace k_delay_pingpong {
+#include "Delay/PingPong.k"
+}
+namespace k_delay_reverb {
+#include "Delay/Reverb.k"
+}
+
+// ---------------------------------------------------------------------------
+// Canonical C2 graph: examples/Subtractive/Filter.k's note with
+// `Square osc` replaced by `Saw osc`, ADSR times taken from four controls
+// (defaults 0.01, 0.1, 0.7, 0.25).  Written in the reference DSL so the
+// reference header evaluates it.
+// ---------------------------------------------------------------------------
+namespace k_subtractive {
+using namespace klang::optimised;
+
+struct Subtractive : Synth {
+	struct SubNote : public Note {
+		Saw osc;
+		ADSR adsr;
+		Envelope env;
+		LPF filter;
+
+		event on(Pitch pitch, Amplitude velocity) {
+			param f = pitch -> Frequency;
+			osc(f, 0);
+			adsr(controls[0], controls[1], controls[2], controls[3]);
+			env = { { 0, f * 2 }, { 0.25, f * 10 }, { 2, f * 5 } };
+			filter.reset();
+		}
+
+		event off(Amplitude velocity) {
+			adsr.release();
+		}
+
+		void process() {
+			filter.set(env++, 10);
+			osc >> filter >> out;
+
+			out *= adsr++;
+			if (adsr.finished())
+				stop();
+		}
+	};
+
+	Subtractive() {
+		controls = {
+			Dial("Attack", 0.0, 1.0, 0.01),
+			Dial("Decay", 0.0, 1.0, 0.1),
+			Dial("Sustain", 0.0, 1.0, 0.7),
+			Dial("Release", 0.0, 1.0, 0.25),
+		};
+	}
+};
+}
+
+using klang::Debug;
+
+extern "C" {
+
+// --------------------------------------------------------------------- globals
+void ref_set_fs(float fs) { klang::fs = klang::SampleRate(fs); }
+float ref_get_fs() { return klang::fs.f; }
+void ref_srand(unsigned seed) { srand(seed); }
+int ref_version() { return klang::version.major * 10000 + klang::version.minor * 100 + klang::version.build; }
+
+float ref_pitch_to_frequency(float pitch) {
+	klang::Pitch p(pitch);
+	klang::param f = p -> Frequency;
+	return f;
+}
+
+// ------------------------------------------------------------------ oscillators
+enum { OSC_FAST_SAW = 0, OSC_FAST_TRIANGLE, OSC_FAST_SQUARE, OSC_FAST_PULSE, OSC_FAST_SINE,
+       OSC_BASIC_SINE, OSC_BASIC_SAW, OSC_BASIC_TRIANGLE, OSC_BASIC_SQUARE, OSC_BASIC_PULSE,
+       OSC_WT_SINE, OSC_WT_SAW };
+
+extern "C++" {
+template<class OSC>
+static void run_osc(int nargs, float f, float phase, float duty, int n, float* out) {
+	OSC osc;
+	if (nargs == 1) osc(klang::param(f));
+	else if (nargs == 2) osc(klang::param(f), klang::param(phase));
+	else if constexpr (std::is_base_of_v<klang::Generators::Fast::Osm, OSC> || std::is_same_v<OSC, klang::Generators::Basic::Pulse>)
+		osc(klang::param(f), klang::param(phase), klang::param(duty));
+	for (int s = 0; s < n; s++) {
+		klang::signal y = osc;   // conversion ticks process() (klang.h:2214,2264)
+		out[s] = y;
+	}
+}
+} // extern "C++"
+
+// nargs = number of set() arguments: 1 set(f), 2 set(f,phase), 3 set(f,phase,duty)
+int ref_osc(int kind, int nargs, float f, float phase, float duty, int n, float* out) {
+	using namespace klang::Generators;
+	switch (kind) {
+	case OSC_FAST_SAW:       run_osc<Fast::Saw>(nargs, f, phase, duty, n, out); break;
+	case OSC_FAST_TRIANGLE:  run_osc<Fast::Triangle>(nargs, f, phase, duty, n, out); break;
+	case OSC_FAST_SQUARE:    run_osc<Fast::Square>(nargs, f, phase, duty, n, out); break;
+	case OSC_FAST_PULSE:     run_osc<Fast::Pulse>(nargs, f, phase, duty, n, out); break;
+	case OSC_FAST_SINE:      run_osc<Fast::Sine>(nargs, f, phase, duty, n, out); break;
+	case OSC_BASIC_SINE:     run_osc<Basic::Sine>(nargs, f, phase, duty, n, out); break;
+	case OSC_BASIC_SAW:      run_osc<Basic::Saw>(nargs, f, phase, duty, n, out); break;
+	case OSC_BASIC_TRIANGLE: run_osc<Basic::Triangle>(nargs, f, phase, duty, n, out); break;
+	case OSC_BASIC_SQUARE:   run_osc<Basic::Square>(nargs, f, phase, duty, n, out); break;
+	case OSC_BASIC_PULSE:    run_osc<Basic::Pulse>(nargs, f, phase, duty, n, out); break;
+	case OSC_WT_SINE:        run_osc<Wavetables::Sine>(nargs, f, phase, duty, n, out); break;
+	case OSC_WT_SAW:         run_osc<Wavetables::Saw>(nargs, f, phase, duty, n, out); break;
+	default: return -1;
+	}
+	return 0;
+}
+
+// Wavetable contents (2048 floats) as the reference builds them (klang.h:3645-3650, 5372-5379).
+int ref_wavetable(int kind, float* table) {
+	using namespace klang::Generators;
+	if (kind == OSC_WT_SINE) { Wavetables::Sine w; for (int i = 0; i < 2048; i++) table[i] = w[i]; return 0; }
+	if (kind == OSC_WT_SAW)  { Wavetables::Saw w;  for (int i = 0; i < 2048; i++) table[i] = w[i]; return 0; }
+	return -1;
+}
+
+// ---------------------------------------------------------------------- filters
+enum { FLT_BIQUAD_LPF = 0, FLT_BIQUAD_HPF, FLT_ONEPOLE_LPF, FLT_ONEPOLE_HPF,
+       FLT_BIQUAD_BPF, FLT_BIQUAD_BRF, FLT_BIQUAD_APF, FLT_BUTTERWORTH_LPF1, FLT_BUTTERWORTH_LPF2 };
+
+extern "C++" {
+template<class F>
+static void run_biquad(int nset, const float* f, const float* Q, int n, const float* in, float* out, float* coeffs) {
+	F flt;
+	for (int s = 0; s < n; s++) {
+		if (s < nset) {
+			if (Q) flt.set(klang::param(f[s]), klang::param(Q[s]));
+			else flt.set(klang::param(f[s]));
+		}
+		klang::signal x = in[s];
+		klang::signal y;
+		x >> flt >> y;
+		out[s] = y;
+	}
+	if (coeffs) { coeffs[0] = flt.b0; coeffs[1] = flt.b1; coeffs[2] = flt.b2; coeffs[3] = flt.a1; coeffs[4] = flt.a2; }
+}
+
+template<class F>
+static void run_onepole(int nset, const float* f, int n, const float* in, float* out, float* coeffs) {
+	F flt;
+	for (int s = 0; s < n; s++) {
+		if (s < nset) flt.set(klang::param(f[s]));
+		klang::signal x = in[s];
+		klang::signal y;
+		x >> flt >> y;
+		out[s] = y;
+	}
+	if (coeffs) { coeffs[0] = flt.b0; coeffs[1] = flt.b1; coeffs[2] = 0; coeffs[3] = flt.a1; coeffs[4] = 0; }
+}
+} // extern "C++"
+
+// nset: how many leading samples call set(f[s](,Q[s])) before processing (1 = static, n = per-sample).
+// Q == NULL → set(f) (default Q = 1/sqrt2 for biquads).
+int ref_filter(int kind, int nset, const float* f, const float* Q, int n, const float* in, float* out, float* coeffs) {
+	using namespace klang::Filters;
+	switch (kind) {
+	case FLT_BIQUAD_LPF: run_biquad<Biquad::LPF>(nset, f, Q, n, in, out, coeffs); break;
+	case FLT_BIQUAD_HPF: run_biquad<Biquad::HPF>(nset, f, Q, n, in, out, coeffs); break;
+	case FLT_BIQUAD_BPF: run_biquad<Biquad::BPF>(nset, f, Q, n, in, out, coeffs); break;
+	case FLT_BIQUAD_BRF: run_biquad<Biquad::BRF>(nset, f, Q, n, in, out, coeffs); break;
+	case FLT_BIQUAD_APF: run_biquad<Biquad::APF>(nset, f, Q, n, in, out, coeffs); break;
+	case FLT_BUTTERWORTH_LPF2: run_biquad<Butterworth::LPF<2>>(nset, f, Q, n, in, out, coeffs); break;
+	case FLT_ONEPOLE_LPF: run_onepole<OnePole::LPF>(nset, f, n, in, out, coeffs); break;
+	case FLT_ONEPOLE_HPF: run_onepole<OnePole::HPF>(nset, f, n, in, out, coeffs); break;
+	case FLT_BUTTERWORTH_LPF1: run_onepole<Butterworth::LPF<1>>(nset, f, n, in, out, coeffs); break;
+	default: return -1;
+	}
+	return 0;
+}
+
+// -------------------------------------------------------------------- envelopes
+// points: npts (x,y) pairs.  loop_start/loop_end = -1 for none.  release_at: sample index at which
+// release(release_time, release_level) is called (-1 never).  stage_out[s] = stage after sample s.
+int ref_envelope(int npts, const float* xy, int loop_start, int loop_end, int n, int release_at,
+                 float release_time, float release_level, float* out, int* stage_out) {
+	std::vector<klang::Envelope::Point> pts;
+	for (int p = 0; p < npts; p++) pts.push_back({ xy[2 * p], xy[2 * p + 1] });
+	klang::Envelope env;
+	env.set(pts);
+	if (loop_start >= 0) env.setLoop(loop_start, loop_end);
+	for (int s = 0; s < n; s++) {
+		if (s == release_at) env.release(release_time, release_level);
+		out[s] = env++;
+		if (stage_out) stage_out[s] = (int)env.getStage();
+	}
+	return 0;
+}
+
+int ref_envelope_at(int npts, const float* xy, int n, const float* t, float* out) {
+	std::vector<klang::Envelope::Point> pts;
+	for (int p = 0; p < npts; p++) pts.push_back({ xy[2 * p], xy[2 * p + 1] });
+	klang::Envelope env;
+	env.set(pts);
+	for (int s = 0; s < n; s++) out[s] = env.at(t[s]);
+	return 0;
+}
+
+int ref_adsr(float A, float D, float S, float R, int n, int release_at, float* out, int* stage_out) {
+	klang::ADSR adsr;
+	adsr(klang::param(A), klang::param(D), klang::param(S), klang::param(R));
+	for (int s = 0; s < n; s++) {
+		if (s == release_at) adsr.release();
+		out[s] = adsr++;
+		if (stage_out) stage_out[s] = (int)adsr.getStage();
+	}
+	return 0;
+}
+
+// ----------------------------------------------------------------------- delays
+// Mono Delay<1000>: per sample s: write in[s]; then out_i[s] = tap(int di[s]); out_f[s] = tap(float df[s]);
+// if set_at[s] >= 0: set(set_at[s]); out_p[s] = process() result (read head), only valid after first set.
+int ref_delay1000(int n, const float* in, const int* di, const float* df, const float* set_at,
+                  float* out_i, float* out_f, float* out_p) {
+	klang::Delay<1000>* d = new klang::Delay<1000>();
+	bool have_set = false;
+	for (int s = 0; s < n; s++) {
+		klang::signal x = in[s];
+		x >> *d;
+		out_i[s] = d->tap(di[s]);
+		out_f[s] = d->tap(df[s]);
+		if (set_at[s] >= 0.f) { d->set(klang::param(set_at[s])); have_set = true; }
+		if (have_set) { d->process(); out_p[s] = d->out; } else out_p[s] = 0.f;
+	}
+	delete d;
+	return 0;
+}
+
+// Stereo::Delay<1000>: per sample write (inl,inr); out = tap(float df[s]) (klang.h:4668-4681).
+int ref_stereo_delay1000(int n, const float* inl, const float* inr, const float* df, float* outl, float* outr) {
+	klang::Stereo::Delay<1000>* d = new klang::Stereo::Delay<1000>();
+	for (int s = 0; s < n; s++) {
+		klang::Stereo::signal x(inl[s], inr[s]);
+		x >> *d;
+		klang::Stereo::signal y = (*d)(df[s]);
+		outl[s] = y.l; outr[s] = y.r;
+	}
+	delete d;
+	return 0;
+}
+
+// Control::smooth / Control::set (klang.h:1715-1728)
+int ref_control_smooth(float lo, float hi, float initial, int n, const float* values, float* out) {
+	klang::Control c = klang::Dial("c", lo, hi, initial);
+	for (int s = 0; s < n; s++) {
+		c.set(values[s]);
+		out[s] = c.smooth();
+	}
+	return 0;
+}
+
+// ---------------------------------------------------------------------- effects
+enum { FX_GAIN = 0, FX_PINGPONG = 1, FX_REVERB = 2, FX_DELAY_PINGPONG = 3, FX_DELAY_REVERB = 4 };
+
+struct RefFx {
+	int graph;
+	klang::Effect* mono = nullptr;
+	klang::Stereo::Effect* stereo = nullptr;
+	klang::Controls* controls = nullptr;
+};
+
+void* ref_fx_create(int graph) {
+	RefFx* fx = new RefFx;
+	fx->graph = graph;
+	switch (graph) {
+	case FX_GAIN:     { auto* e = new k_gain::Gain();         fx->mono = e;   fx->controls = &e->controls; } break;
+	case FX_PINGPONG: { auto* e = new k_pingpong::PingPong(); fx->stereo = e; fx->controls = &e->controls; } break;
+	case FX_REVERB:   { auto* e = new k_reverb::Reverb();     fx->stereo = e; fx->controls = &e->controls; } break;
+	case FX_DELAY_PINGPONG: { auto* e = new k_delay_pingpong::PingPong(); fx->stereo = e; fx->controls = &e->controls; } break;
+	case FX_DELAY_REVERB:   { auto* e = new k_delay_reverb::Reverb();     fx->mono = e;   fx->controls = &e->controls; } break;
+	default: delete fx; return nullptr;
+	}
+	return fx;
+}
+
+void ref_fx_destroy(void* h) {
+	RefFx* fx = (RefFx*)h;
+	if (!fx) return;
+	delete fx->mono;
+	delete fx->stereo;
+	delete fx;
+}
+
+int ref_fx_channels(void* h) { return ((RefFx*)h)->stereo ? 2 : 1; }
+int ref_fx_num_controls(void* h) { return (int)((RefFx*)h)->controls->size(); }
+void ref_fx_set_control(void* h, int idx, float v) { (*((RefFx*)h)->controls)[idx].set(v); }
+float ref_fx_get_control(void* h, int idx) { return (*((RefFx*)h)->controls)[idx].value; }
+
+// In-place block processing through Effect::process(buffer) (klang.h:4208-4216, 4708-4716).
+int ref_fx_process(void* h, float* l, float* r, int n) {
+	RefFx* fx = (RefFx*)h;
+	if (n > 16384) return -1; // debug.buffer capacity (klang.h:3141)
+	Debug::Session session(nullptr, n, Debug::Buffer::Effect);
+	if (fx->mono) {
+		klang::buffer b(l, n);
+		fx->mono->process(b);
+	} else {
+		klang::buffer bl(l, n), br(r, n);
+		klang::Stereo::buffer b(bl, br);
+		fx->stereo->process(b);
+	}
+	return 0;
+}
+
+// ----------------------------------------------------------------------- synths
+enum { SY_SUBTRACTIVE = 0, SY_SUPERSAW = 1, SY_TB303 = 2, SY_SYNTHX = 3, SY_FILTER_K = 4 };
+
+struct RefSynth {
+	int graph;
+	int nvoices;
+	klang::Synth* mono = nullptr;
+	klang::Stereo::Synth* stereo = nullptr;
+	klang::Controls* controls = nullptr;
+	std::vector<float> scratch;
+};
+
+extern "C++" {
+template<class SYNTH, class NOTE>
+static SYNTH* make_synth(int nvoices) {
+	SYNTH* s = new SYNTH();
+	int have = (int)s->notes.count;
+	if (nvoices > have) s->notes.template add<NOTE>(nvoices - have);
+	return s;
+}
+} // extern "C++"
+
+void* ref_synth_create(int graph, int nvoices) {
+	if (nvoices < 1 || nvoices > 128) return nullptr;
+	RefSynth* s = new RefSynth;
+	s->graph = graph;
+	switch (graph) {
+	case SY_SUBTRACTIVE: { auto* p = make_synth<k_subtractive::Subtractive, k_subtractive::Subtractive::SubNote>(nvoices); s->mono = p; s->controls = &p->controls; } break;
+	case SY_SUPERSAW:    { auto* p = make_synth<k_supersaw::SuperSaw, k_supersaw::SuperSaw::MyNote>(nvoices); s->mono = p; s->controls = &p->controls; } break;
+	case SY_TB303:       { auto* p = make_synth<k_tb303::TB303, k_tb303::TB303::MyNote>(nvoices); s->mono = p; s->controls = &p->controls; } break;
+	case SY_FILTER_K:    { auto* p = make_synth<k_filter::Filter, k_filter::Filter::FilterNote>(nvoices); s->mono = p; s->controls = &p->controls; } break;
+	case SY_SYNTHX:      { auto* p = make_synth<k_synthx::SynTHX, k_synthx::SynTHX::MyNote>(nvoices); s->stereo = p; s->controls = &p->controls; } break;
+	default: delete s; return nullptr;
+	}
+	s->nvoices = s->mono ? (int)s->mono->notes.count : (int)s->stereo->notes.count;
+	return s;
+}
+
+void ref_synth_destroy(void* h) {
+	RefSynth* s = (RefSynth*)h;
+	if (!s) return;
+	delete s->mono;
+	delete s->stereo;
+	delete s;
+}
+
+int ref_synth_channels(void* h) { return ((RefSynth*)h)->stereo ? 2 : 1; }
+int ref_synth_num_voices(void* h) { return ((RefSynth*)h)->nvoices; }
+int ref_synth_num_controls(void* h) { return (int)((RefSynth*)h)->controls->size(); }
+void ref_synth_set_control(void* h, int idx, float v) { (*((RefSynth*)h)->controls)[idx].set(v); }
+float ref_synth_get_control(void* h, int idx) { return (*((RefSynth*)h)->controls)[idx].value; }
+
+// Synth::noteOn (klang.h:4423-4427); returns the voice index Notes::assign() picked.
+int ref_synth_note_on(void* h, int pitch, float velocity) {
+	RefSynth* s = (RefSynth*)h;
+	if (s->mono) {
+		s->mono->noteOn(pitch, velocity);
+		for (unsigned i = 0; i < s->mono->notes.count; i++)
+			if (s->mono->notes.noteStart[i] == s->mono->notes.noteOns - 1) return (int)i;
+	} else {
+		s->stereo->noteOn(pitch, velocity);
+		for (unsigned i = 0; i < s->stereo->notes.count; i++)
+			if (s->stereo->notes.noteStart[i] == s->stereo->notes.noteOns - 1) return (int)i;
+	}
+	return -1;
+}
+
+// Synth::noteOff (klang.h:4430-4434)
+void ref_synth_note_off(void* h, int pitch, float velocity) {
+	RefSynth* s = (RefSynth*)h;
+	if (s->mono) s->mono->noteOff(pitch, velocity); else s->stereo->noteOff(pitch, velocity);
+}
+
+// Direct voice control: NoteBase::start / release (klang.h:4257-4275)
+void ref_synth_voice_start(void* h, int voice, float pitch, float velocity) {
+	RefSynth* s = (RefSynth*)h;
+	if (s->mono) s->mono->notes[voice]->start(pitch, velocity); else s->stereo->notes[voice]->start(pitch, velocity);
+}
+void ref_synth_voice_release(void* h, int voice, float velocity) {
+	RefSynth* s = (RefSynth*)h;
+	if (s->mono) s->mono->notes[voice]->release(velocity); else s->stereo->notes[voice]->release(velocity);
+}
+// 0 Onset, 1 Sustain, 2 Release, 3 Off (klang.h:4284)
+int ref_synth_voice_stage(void* h, int voice) {
+	RefSynth* s = (RefSynth*)h;
+	return s->mono ? (int)s->mono->notes[voice]->stage : (int)s->stereo->notes[voice]->stage;
+}
+
+// The reference block driver itself: Synth::process(float*,int,float*) (klang.h:4440-4466) or
+// Stereo::Synth::process(float**,int,float*) (klang.h:4830-4858).  Buffers are cleared first
+// (stereo notes accumulate, klang.h:4731).
+int ref_synth_process(void* h, float* l, float* r, int n) {
+	RefSynth* s = (RefSynth*)h;
+	if (n > 16384) return -1;
+	Debug::Session session(nullptr, n, Debug::Buffer::Synth);
+	memset(l, 0, sizeof(float) * n);
+	if (s->mono) {
+		s->mono->klang::Synth::process(l, n, nullptr);
+	} else {
+		memset(r, 0, sizeof(float) * n);
+		float* bufs[2] = { l, r };
+		s->stereo->klang::Stereo::Synth::process(bufs, n, nullptr);
+	}
+	return 0;
+}
+
+// Per-voice rendering: every voice whose stage != Off is rendered ALONE through its public
+// Note::process(buffer) into a zeroed buffer (out[v][c][n], c < channels); finished voices are
+// stop()ped exactly like the Synth driver does (klang.h:4452-4455).  active[v] = 1 if rendered.
+// No synth-level post-fx is applied.
+int ref_synth_process_voices(void* h, float* out, int n, int* active) {
+	RefSynth* s = (RefSynth*)h;
+	if (n > 16384) return -1;
+	const int C = s->stereo ? 2 : 1;
+	for (int v = 0; v < s->nvoices; v++) {
+		float* o = out + (size_t)v * C * n;
+		memset(o, 0, sizeof(float) * C * n);
+		if (s->mono) {
+			klang::Note* note = s->mono->notes[v];
+			active[v] = note->stage != klang::Note::Off;
+			if (active[v]) {
+				Debug::Session session(nullptr, n, Debug::Buffer::Synth);
+				klang::buffer b(o, n);
+				if (!note->process(b)) note->stop();
+			}
+		} else {
+			klang::Stereo::Note* note = s->stereo->notes[v];
+			active[v] = note->stage != klang::Stereo::Note::Off;
+			if (active[v]) {
+				Debug::Session session(nullptr, n, Debug::Buffer::Synth);
+				klang::buffer bl(o, n), br(o + n, n);
+				klang::Stereo::buffer b(bl, br);
+				if (!note->process(b)) note->stop();
+			}
+		}
+	}
+	return 0;
+}
+
+} // extern "C"
