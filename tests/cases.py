@@ -1,0 +1,252 @@
+"""Shared parity cases.
+
+Every case is a function of an "engine": an object with the interface of oracle.bindings.Oracle
+(osc / filt / envelope / adsr / ... primitives, `Fx(graph)` and `Synth(graph, nvoices)` factories).
+The same cases are run
+
+  * by tests/gen_golden.py against the compiled reference (oracle.ref) to produce tests/golden/*.npz,
+  * by tests/test_oracle.py against the plain-C restatement (oracle.port) — bit-exact vs golden,
+  * by tests/test_gpu_parity.py against the CUDA path through the C ABI (klang_b200.Engine).
+
+Inputs are generated from fixed integer hashes (no dependence on numpy's RNG version).
+"""
+import numpy as np
+
+# graph / primitive ids — identical in oracle/bindings.py and include/klang_b200.h
+(OSC_FAST_SAW, OSC_FAST_TRIANGLE, OSC_FAST_SQUARE, OSC_FAST_PULSE, OSC_FAST_SINE,
+ OSC_BASIC_SINE, OSC_BASIC_SAW, OSC_BASIC_TRIANGLE, OSC_BASIC_SQUARE, OSC_BASIC_PULSE,
+ OSC_WT_SINE, OSC_WT_SAW) = range(12)
+(FLT_BIQUAD_LPF, FLT_BIQUAD_HPF, FLT_ONEPOLE_LPF, FLT_ONEPOLE_HPF,
+ FLT_BIQUAD_BPF, FLT_BIQUAD_BRF, FLT_BIQUAD_APF, FLT_BUTTERWORTH_LPF1, FLT_BUTTERWORTH_LPF2) = range(9)
+FX_GAIN, FX_PINGPONG, FX_REVERB, FX_DELAY_PINGPONG, FX_DELAY_REVERB = range(5)
+SY_SUBTRACTIVE, SY_SUPERSAW, SY_TB303, SY_SYNTHX, SY_FILTER_K = range(5)
+
+FX_NAMES = {FX_GAIN: "gain", FX_PINGPONG: "pingpong", FX_REVERB: "reverb",
+            FX_DELAY_PINGPONG: "delay_pingpong", FX_DELAY_REVERB: "delay_reverb"}
+SY_NAMES = {SY_SUBTRACTIVE: "subtractive", SY_SUPERSAW: "supersaw", SY_TB303: "tb303",
+            SY_SYNTHX: "synthx", SY_FILTER_K: "filter_k"}
+
+
+def noise(n, seed=1, lo=-1.0, hi=1.0):
+    """PCG-style hash noise, uniform [lo, hi) in float32 — reproducible without numpy.random."""
+    i = np.arange(n, dtype=np.uint64) + np.uint64((seed * 0x9E3779B97F4A7C15) % (1 << 64))
+    x = i * np.uint64(6364136223846793005) + np.uint64(1442695040888963407)
+    x ^= x >> np.uint64(33)
+    x = x * np.uint64(0xFF51AFD7ED558CCD)
+    x ^= x >> np.uint64(33)
+    u = (x >> np.uint64(40)).astype(np.float64) / float(1 << 24)
+    return (lo + (hi - lo) * u).astype(np.float32)
+
+
+def voice_pitch(v):
+    """pitch 36 + (7 v mod 61)."""
+    return 36 + (7 * v) % 61
+
+
+def voice_velocity(v):
+    """0.25 + 0.75 * ((v * 2654435761 mod 2^32) >> 16) / 65535."""
+    return 0.25 + 0.75 * (((v * 2654435761) % (1 << 32)) >> 16) / 65535.0
+
+
+# ----------------------------------------------------------------------------- primitives
+
+def primitive_cases(eng, fs):
+    """dict name -> float32/int32 array for every primitive on the hot path."""
+    eng.set_fs(fs)
+    out = {}
+    n = 256
+    for kind, name in ((OSC_FAST_SAW, "fast_saw"), (OSC_FAST_TRIANGLE, "fast_triangle"), (OSC_FAST_SQUARE, "fast_square"),
+                       (OSC_FAST_PULSE, "fast_pulse"), (OSC_FAST_SINE, "fast_sine"), (OSC_BASIC_SINE, "basic_sine"),
+                       (OSC_BASIC_SAW, "basic_saw"), (OSC_BASIC_TRIANGLE, "basic_triangle"), (OSC_BASIC_SQUARE, "basic_square"),
+                       (OSC_BASIC_PULSE, "basic_pulse"), (OSC_WT_SINE, "wt_sine"), (OSC_WT_SAW, "wt_saw")):
+        for f in (441.0, 55.0, 3520.5, 1000.0):
+            out[f"osc/{name}/f{f}"] = eng.osc(kind, n, f)
+        out[f"osc/{name}/f441_p1"] = eng.osc(kind, n, 441.0, 1.0)
+    for kind, name in ((OSC_FAST_SAW, "fast_saw"), (OSC_FAST_TRIANGLE, "fast_triangle"), (OSC_FAST_SQUARE, "fast_square"),
+                       (OSC_FAST_PULSE, "fast_pulse"), (OSC_BASIC_PULSE, "basic_pulse")):
+        for duty in (0.05, 0.5, 0.93):
+            out[f"osc/{name}/f441_p0_d{duty}"] = eng.osc(kind, n, 441.0, 0.0, duty)
+            out[f"osc/{name}/f2093_p2_d{duty}"] = eng.osc(kind, n, 2093.0, 2.0, duty)
+    out["wavetable/sine"] = eng.wavetable(OSC_WT_SINE)
+    out["wavetable/saw"] = eng.wavetable(OSC_WT_SAW)
+
+    x = noise(512, seed=7)
+    imp = np.zeros(64, np.float32)
+    imp[0] = 1
+    sweep = (200.0 + 6000.0 * (0.5 + 0.5 * np.sin(np.arange(512) * 0.01))).astype(np.float32)
+    for kind, name in ((FLT_BIQUAD_LPF, "biquad_lpf"), (FLT_BIQUAD_HPF, "biquad_hpf"), (FLT_BIQUAD_BPF, "biquad_bpf"),
+                       (FLT_BIQUAD_BRF, "biquad_brf"), (FLT_BUTTERWORTH_LPF2, "butterworth_lpf2")):
+        y, c = eng.filt(kind, imp, 1000.0)
+        out[f"filter/{name}/impulse"] = y
+        out[f"filter/{name}/coeffs"] = c
+        y, c = eng.filt(kind, x, 50.0, 1.0)
+        out[f"filter/{name}/noise_f50_q1"] = y
+        out[f"filter/{name}/coeffs_f50_q1"] = c
+        y, _ = eng.filt(kind, x, sweep, 10.0, per_sample=True)
+        out[f"filter/{name}/sweep_q10"] = y
+    y, c = eng.filt(FLT_BIQUAD_APF, x, 1000.0, 0.5)
+    out["filter/biquad_apf/noise"] = y
+    for kind, name in ((FLT_ONEPOLE_LPF, "onepole_lpf"), (FLT_ONEPOLE_HPF, "onepole_hpf"), (FLT_BUTTERWORTH_LPF1, "butterworth_lpf1")):
+        y, c = eng.filt(kind, imp, 1000.0)
+        out[f"filter/{name}/impulse"] = y
+        out[f"filter/{name}/coeffs"] = c
+        y, _ = eng.filt(kind, x, sweep, None, per_sample=True)
+        out[f"filter/{name}/sweep"] = y
+
+    y, st = eng.envelope([(0, 0), (0.001, 1), (0.003, 0.25), (0.005, 0.5)], 400)
+    out["envelope/4pt"] = y
+    out["envelope/4pt_stage"] = st
+    y, st = eng.envelope([(0, 100), (0.002, 1000), (0.004, 500)], 400, release_at=120, release_time=0.002, release_level=0.0)
+    out["envelope/3pt_release"] = y
+    out["envelope/3pt_release_stage"] = st
+    y, st = eng.envelope([(0, 0), (0.001, 1), (0.002, 0.5), (0.003, 0.8)], 600, loop=(1, 3))
+    out["envelope/loop13"] = y
+    out["envelope/at"] = eng.envelope_at([(0, 0.0625), (0.25, 0.125), (0.5, 0.25), (1.0, 1.0)],
+                                         np.linspace(-0.1, 1.2, 53).astype(np.float32))
+    y, st = eng.adsr(0.01, 0.1, 0.7, 0.25, 20000, release_at=6000)
+    out["adsr/a"] = y
+    out["adsr/a_stage"] = st
+    y, st = eng.adsr(0.0, 0.0, 1.0, 0.001, 600, release_at=100)
+    out["adsr/zero_attack"] = y
+    out["adsr/zero_attack_stage"] = st
+    y, st = eng.adsr(0.001, 0.25, 1.0, 0.5, 2000, release_at=20)   # release during attack
+    out["adsr/early_release"] = y
+
+    n = 1500
+    xin = (np.arange(n) + 1).astype(np.float32)
+    di = (np.arange(n) * 7 % 900).astype(np.int32)
+    df = (noise(n, seed=3, lo=0.0, hi=998.0)).astype(np.float32)
+    set_at = np.full(n, -1.0, np.float32)
+    set_at[10] = 4.0
+    set_at[700] = 333.25
+    set_at[1200] = 999.5
+    oi, of, op = eng.delay1000(xin, di, df, set_at)
+    out["delay/tap_int"], out["delay/tap_float"], out["delay/process"] = oi, of, op
+    ol, orr = eng.stereo_delay1000(noise(n, seed=4), noise(n, seed=5), df)
+    out["delay/stereo_l"], out["delay/stereo_r"] = ol, orr
+    vals = np.where(np.arange(2000) < 1000, 0.8, 0.1).astype(np.float32)
+    out["control/smooth"] = eng.control_smooth(0.0, 1.0, 0.5, vals)
+    out["pitch/frequency"] = np.array([eng.pitch_to_frequency(p) for p in range(128)], np.float32)
+    return out
+
+
+# -------------------------------------------------------------------------------- effects
+
+def fx_input(channels, n, seed, burst=None):
+    """PCG noise in [-0.5, 0.5); if `burst` only the first `burst` frames are non-zero."""
+    x = np.stack([noise(n, seed=seed * 2 + c, lo=-0.5, hi=0.5) for c in range(channels)])
+    if burst is not None:
+        x[:, burst:] = 0
+    return x
+
+
+FX_SCRIPTS = {
+    # name: (graph, total frames, block, [(block_index, control, value)], burst)
+    "gain": (FX_GAIN, 4096, 1024, [(2, 0, 0.25)], None),
+    "pingpong_default": (FX_PINGPONG, 6144, 1024, [], None),
+    # short delay so the feedback path and the moving read head are exercised, plus scratch LFO
+    "pingpong_short": (FX_PINGPONG, 8192, 1024, [(0, 1, 0.02), (0, 5, 0.02), (0, 0, 0.9), (0, 4, 0.3), (3, 2, 0.4), (3, 3, 0.579)], None),
+    "reverb_default": (FX_REVERB, 4096, 1024, [], 1024),
+    "reverb_hall": (FX_REVERB, 6144, 2048, [(0, 0, 1.0), (0, 2, 0.419), (0, 3, 0.329), (0, 7, 0.5), (0, 8, 0.5), (1, 6, 0.4)], None),
+    "delay_pingpong": (FX_DELAY_PINGPONG, 6144, 1024, [(0, 0, 0.01), (0, 1, 0.7), (0, 2, 0.02), (0, 3, 0.6)], None),
+    "delay_reverb": (FX_DELAY_REVERB, 8192, 4096, [(1, 1, 0.05)], None),
+}
+
+
+def run_fx_script(eng, name, fs, seed=1):
+    graph, total, block, events, burst = FX_SCRIPTS[name]
+    eng.set_fs(fs)
+    eng.srand(1)
+    fx = eng.Fx(graph)
+    x = fx_input(fx.channels, total, seed, burst)
+    if fx.channels == 1:
+        x = x[0]
+    ys = []
+    for b in range(total // block):
+        for (bi, c, v) in events:
+            if bi == b:
+                fx.set_control(c, v)
+        ys.append(fx.process(x[..., b * block:(b + 1) * block]))
+    fx.close()
+    return np.concatenate(ys, axis=-1)
+
+
+# --------------------------------------------------------------------------------- synths
+
+SYNTH_SCRIPTS = {
+    # name: (graph, nvoices, started voices, blocks, block size, release block base, [(block, control, value)])
+    "subtractive": (SY_SUBTRACTIVE, 32, 12, 8, 512, 2, []),
+    "subtractive_fast_release": (SY_SUBTRACTIVE, 32, 8, 6, 1024, 1, [(0, 0, 0.001), (0, 1, 0.01), (0, 3, 0.01)]),
+    "filter_k": (SY_FILTER_K, 32, 6, 5, 512, 2, []),
+    "supersaw": (SY_SUPERSAW, 32, 10, 6, 512, 2, []),
+    "supersaw_wide": (SY_SUPERSAW, 32, 6, 4, 512, 1, [(0, 1, 0.5), (0, 2, 1.0), (0, 0, 0.01)]),
+    "tb303": (SY_TB303, 32, 8, 6, 512, 2, []),
+    "tb303_square": (SY_TB303, 32, 6, 6, 512, 2, [(0, 3, 1.0), (0, 1, 0.9), (0, 4, 3.0), (2, 0, 0.4)]),
+    "synthx": (SY_SYNTHX, 32, 4, 4, 256, 1, [(0, 0, 0.01)]),
+}
+
+
+def run_synth_script(eng, name, fs, per_voice=True):
+    """Drive voices through start/release/process like Synth::process does (klang.h:4440-4466).
+
+    Returns dict with 'voices' [blocks][V, C, n] concatenated over time (per-voice streams, each voice
+    rendered alone — SURVEY Q6) or 'mix' (the Synth::process block output), plus 'stages'."""
+    graph, nvoices, started, blocks, n, rel0, events = SYNTH_SCRIPTS[name]
+    eng.set_fs(fs)
+    eng.srand(1)
+    sy = eng.Synth(graph, nvoices)
+    outs, stages = [], []
+    for b in range(blocks):
+        for (bi, c, v) in events:
+            if bi == b:
+                sy.set_control(c, v)
+        if b == 0:
+            for v in range(started):
+                sy.voice_start(v, voice_pitch(v), voice_velocity(v))
+        for v in range(started):
+            if b == rel0 + (v % 3):
+                sy.voice_release(v, 0.0)
+        if per_voice:
+            o, _ = sy.process_voices(n)
+            outs.append(o[:started])
+        else:
+            outs.append(sy.process(n))
+        stages.append([sy.voice_stage(v) for v in range(started)])
+    sy.close()
+    return {"out": np.concatenate(outs, axis=-1), "stages": np.array(stages, np.int32)}
+
+
+def run_synth_noteon_script(eng, graph, fs, nvoices=32, notes=40, blocks=4, n=256):
+    """Synth::noteOn / noteOff with voice stealing (Notes::assign, klang.h:4336-4372)."""
+    eng.set_fs(fs)
+    eng.srand(1)
+    sy = eng.Synth(graph, nvoices)
+    assigned, outs = [], []
+    k = 0
+    for b in range(blocks):
+        for _ in range(notes // blocks):
+            assigned.append(sy.note_on(voice_pitch(k), voice_velocity(k)))
+            k += 1
+        if b >= 1:
+            for j in range(5):
+                sy.note_off(voice_pitch(j + 5 * (b - 1)), 0.0)
+        outs.append(sy.process(n))
+    sy.close()
+    return {"out": np.concatenate(outs, axis=-1), "assigned": np.array(assigned, np.int32)}
+
+
+def all_graph_cases(eng, fs):
+    out = {}
+    for name in FX_SCRIPTS:
+        out[f"fx/{name}"] = run_fx_script(eng, name, fs)
+    for name in SYNTH_SCRIPTS:
+        r = run_synth_script(eng, name, fs, per_voice=True)
+        out[f"synth/{name}/voices"] = r["out"]
+        out[f"synth/{name}/stages"] = r["stages"]
+        r = run_synth_script(eng, name, fs, per_voice=False)
+        out[f"synth/{name}/mix"] = r["out"]
+    for graph in (SY_SUBTRACTIVE, SY_SYNTHX):
+        r = run_synth_noteon_script(eng, graph, fs)
+        out[f"synth/{SY_NAMES[graph]}/noteon_mix"] = r["out"]
+        out[f"synth/{SY_NAMES[graph]}/noteon_assigned"] = r["assigned"]
+    return out
