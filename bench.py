@@ -1,0 +1,407 @@
+#!/usr/bin/env python3
+"""klang-b200 benchmark (driver contract: python bench.py --gpus N --steps K --warmup W [--impl reference]).
+
+Headline workload (BASELINE.json configs[1]): Subtractive synth (Saw >> LPF(env) >> ADSR), 1024 voices = 8 Synth
+instances x 128 voices per GPU, fs = 48 kHz, 4096-sample blocks.  A step = one Synth::process pass over one block for
+every voice, preceded by that block's note events (1/16 of the voices are re-triggered each block so envelopes and
+filter coefficients keep moving — SURVEY §8d "steady-state variant").  metric = voice-samples/s.
+
+  value      events + process with the output left in HBM (KB_DEVICE_PTR), CUDA-event timed per step, L2 flushed
+             between steps (flush outside the per-step events).
+  e2e        the same through the public host-buffer call: events, state upload, kernels, output D2H into pinned memory.
+  roofline   dominant kernel (the voice kernel) bracketed by CUDA events inside the library (kb_*_bank_profile).
+  cpu_baseline / --impl reference: the compiled reference klang.h (oracle/_ref) — or the plain-C port when the reference
+             library is absent — on all host cores as fork()ed workers (the reference is not thread-safe).
+N > 1: one rank per GPU, every rank renders its own 1024 voices (weak scaling) and the per-rank bank mixes
+[channels][n] are reduced to rank 0 over NCCL each step (the polyphonic mix-down is the path's only exchange).
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FS = 48000.0
+BLOCK = 4096
+INSTANCES, VOICES = 8, 128           # 1024 voices per GPU
+RETRIGGER_GROUPS = 16
+
+
+def voice_pitch(v):
+    return 36 + (7 * v) % 61
+
+
+def voice_velocity(v):
+    return 0.25 + 0.75 * (((v * 2654435761) % (1 << 32)) >> 16) / 65535.0
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(p.get("sm_max_mhz", 1965.0))
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(prefix="kb_clocks_", suffix=".csv")
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+# ------------------------------------------------------------------------------------- reference (CPU) arm
+def _cpu_worker(args):
+    """One fork()ed worker: its share of the voices as one reference Synth, W+K steps of the steady-state schedule."""
+    kind, voice_ids, steps, warmup, block = args
+    import oracle
+    eng = oracle.ref if kind == "reference" else oracle.port
+    eng.set_fs(FS)
+    eng.srand(1)
+    sy = eng.Synth(oracle.SY_SUBTRACTIVE, max(1, len(voice_ids)))
+    for k, g in enumerate(voice_ids):
+        sy.voice_start(k, voice_pitch(g), voice_velocity(g))
+    t0 = 0.0
+    for s in range(warmup + steps):
+        if s == warmup:
+            t0 = time.perf_counter()
+        for k, g in enumerate(voice_ids):
+            if g % RETRIGGER_GROUPS == s % RETRIGGER_GROUPS:
+                sy.voice_start(k, voice_pitch(g), voice_velocity(g))
+        sy.process(block)
+    dt = time.perf_counter() - t0
+    sy.close()
+    return dt
+
+
+def cpu_reference_run(steps, warmup, total_voices=INSTANCES * VOICES, block=BLOCK, cores=None):
+    """Times the reference CPU implementation of the C2 step on all host cores. Returns (value, dict)."""
+    import oracle
+    kind = "reference" if oracle.ref.available() else "port"
+    (oracle.ref if kind == "reference" else oracle.port).lib()
+    cores = cores or len(os.sched_getaffinity(0))
+    cores = max(1, min(cores, total_voices))
+    shares = [list(range(w, total_voices, cores)) for w in range(cores)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        times = pool.map(_cpu_worker, [(kind, sh, steps, warmup, block) for sh in shares])
+    wall = max(times)
+    value = total_voices * block * steps / wall
+    info = {"value": value, "unit": "voice-samples/s", "cores": cores, "kind": kind,
+            "sample": f"{steps} steps x {total_voices} voices x {block} samples of the C2 schedule, {cores} fork()ed workers "
+                      f"({'oracle/_ref = compiled klang.h' if kind == 'reference' else 'oracle/klang_port.c'}, g++/gcc -O3/-O2 -ffp-contract=off), "
+                      f"wall = slowest worker {wall:.3f} s"}
+    return value, wall, info
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    steps, warmup = args.steps, args.warmup
+    value, wall, info = cpu_reference_run(steps, warmup)
+    line = {
+        "impl": "reference", "metric": "voice-samples/sec (48 kHz equiv) at 1024 voices", "value": value, "unit": "voice-samples/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": wall / steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(),
+        "realtime_voices_48k": value / 48000.0,
+        "cpu_baseline": info,
+        "e2e": {"value": value, "unit": "voice-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config():
+    return {"workload": "C2 Subtractive synth (Saw>>LPF(env,Q=10)>>ADSR), 8 Synth instances x 128 voices = 1024 voices per GPU, "
+                        "fs 48 kHz, block 4096, 1/16 of the voices re-triggered per block",
+            "instances": INSTANCES, "voices_per_instance": VOICES, "block": BLOCK, "fs": FS,
+            "l2": "flushed between timed steps (256 MiB write, outside the per-step events)"}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads (C1/C3/C4/C5 lines inside the JSON)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import klang_b200 as kb
+
+    if not torch.cuda.is_available() or kb.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device — klang_b200 has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stream = torch.cuda.current_stream()
+    hbm_peak, peak_src, sm_max = load_peaks()
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def flush_l2():
+        flush_buf.fill_(1)
+
+    # ---- C2 bank
+    kb.lib().kb_srand(1)
+    bank = kb.SynthBank(kb.SY_SUBTRACTIVE, INSTANCES, VOICES, FS, BLOCK, local_rank)
+    bank.set_stream(stream.cuda_stream)
+    total = INSTANCES * VOICES
+    gid0 = rank * total                                   # global voice ids of this rank
+    for g in range(total):
+        bank.voice_start(g % VOICES, voice_pitch(gid0 + g), voice_velocity(gid0 + g), g // VOICES)
+    flags = kb.BANK_MIX | kb.MIX_SUM if world > 1 else 0
+    out_dev = torch.empty(bank.out_shape(BLOCK, flags), dtype=torch.float32, device=dev)
+    out_host = torch.empty(bank.out_shape(BLOCK, flags), dtype=torch.float32).pin_memory()
+    step_counter = [0]
+
+    def events():
+        s = step_counter[0]
+        step_counter[0] += 1
+        n = 0
+        for g in range(s % RETRIGGER_GROUPS, total, RETRIGGER_GROUPS):
+            bank.voice_start(g % VOICES, voice_pitch(gid0 + g), voice_velocity(gid0 + g), g // VOICES)
+            n += 1
+        return n
+
+    def step_device():
+        events()
+        bank.process_into(out_dev, BLOCK, flags)
+        if dist is not None:
+            dist.reduce(out_dev, dst=0)
+
+    def step_e2e():
+        events()
+        if dist is None:
+            bank.process_into(out_host.numpy(), BLOCK, flags)       # host-buffer call: upload state, kernels, D2H, sync
+        else:
+            bank.process_into(out_dev, BLOCK, flags)
+            dist.reduce(out_dev, dst=0)
+            out_host.copy_(out_dev, non_blocking=True)
+            torch.cuda.synchronize()
+
+    def timed(step_fn, steps, warmup):
+        for _ in range(warmup):
+            step_fn()
+        barrier()
+        evs = []
+        t_wall0 = time.perf_counter()
+        for _ in range(steps):
+            flush_l2()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            step_fn()
+            b.record(stream)
+            evs.append((a, b))
+        barrier()
+        wall = time.perf_counter() - t_wall0
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), wall
+
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = bank.launches
+    ms_total, _ = timed(step_device, args.steps, args.warmup)
+    gpu_launches = (bank.launches - launches0) * args.steps // (args.steps + args.warmup)
+    clk = clocks.stop() if clocks else None
+    ms_per_step = ms_total / args.steps
+    value = world * total * BLOCK / (ms_per_step * 1e-3)
+
+    # ---- e2e through host buffers (host wall clock is part of it: events run on the host)
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * total * BLOCK * args.steps / float(t.item())
+    out_bytes = out_host.numel() * 4
+    e2e = {"value": e2e_value, "unit": "voice-samples/s",
+           "h2d_bytes_per_step": int(bank.state_bytes), "d2h_bytes_per_step": int(out_bytes + bank.state_bytes),
+           "note": "per step: host applies 64 note events (state fetch D2H + upload H2D), kernels, output D2H to pinned memory"}
+
+    # ---- dominant kernel, CUDA events inside the library
+    bank.profile(True)
+    for _ in range(args.steps):
+        flush_l2()
+        step_device()
+    k_ms, k_n = bank.profile_read()
+    bank.profile(False)
+    k_ms_avg = k_ms / max(1, k_n)
+    alg_bytes = total * BLOCK * 4.0 * 2 + INSTANCES * BLOCK * 4.0      # per-voice stream write + mix read, mix write
+    achieved = alg_bytes / (k_ms_avg * 1e-3) / 1e9
+    issue_peak = 148 * 128 * sm_max * 1e6                                # fp32 lanes x clock
+    roofline = {"bound": "hbm", "kernel": "kb_voice_kernel<SUBTRACTIVE>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "kernel_ms": k_ms_avg, "kernel_share_of_step": k_ms_avg / ms_per_step,
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "note": "C2 is bound by dependent-issue latency, not HBM (SURVEY H6): 8 B of stream traffic per voice-sample",
+                "voice_samples_per_s_kernel": total * BLOCK / (k_ms_avg * 1e-3),
+                "fp32_lane_cycles_per_voice_sample": issue_peak / (total * BLOCK / (k_ms_avg * 1e-3))}
+    bank.close()
+
+    line = {
+        "metric": "voice-samples/sec (48 kHz equiv) at 1024 voices", "value": value, "unit": "voice-samples/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(), "realtime_voices_48k": value / 48000.0,
+        "clocks": clk, "e2e": e2e, "gpu_launches": int(gpu_launches), "roofline": roofline,
+    }
+
+    if rank == 0 and not args.no_extras:
+        try:
+            line["other_workloads"] = extras(kb, torch, dev, stream, flush_l2, hbm_peak, peak_src, local_rank)
+        except Exception as e:   # secondary numbers never take the headline down
+            line["other_workloads"] = {"error": repr(e)}
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            _, _, info = cpu_reference_run(steps=4, warmup=1)
+            line["cpu_baseline"] = info
+        except Exception as e:
+            line["cpu_baseline"] = {"error": repr(e)}
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+def extras(kb, torch, dev, stream, flush_l2, hbm_peak, peak_src, device_index):
+    """Secondary BASELINE configs, short runs: C1 Gain, C3 SuperSaw, C4 PingPong / Reverb (HBM roofline), C5 share."""
+    import numpy as np
+    res = {}
+
+    def time_steps(fn, steps, warmup=3):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        tot = 0.0
+        for _ in range(steps):
+            flush_l2()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            fn()
+            b.record(stream)
+            torch.cuda.synchronize()
+            tot += a.elapsed_time(b)
+        return tot / steps
+
+    # C1: Gain, 1 channel x 4096 (launch-bound) and batched 64 Mi samples (HBM-bound)
+    for name, inst, n in (("c1_gain_1x4096", 1, 4096), ("c1_gain_batched_64x1Mi", 64, 1 << 20)):
+        fx = kb.FxBank(kb.FX_GAIN, inst, FS, n, device_index)
+        fx.set_stream(stream.cuda_stream)
+        io = torch.rand(inst, 1, n, device=dev) - 0.5
+        ms = time_steps(lambda: fx.process_inplace(io), 10)
+        gbs = inst * n * 8 / (ms * 1e-3) / 1e9
+        res[name] = {"samples_per_s": inst * n / (ms * 1e-3), "ms_per_step": ms,
+                     "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "peak_source": peak_src}}
+        fx.close()
+
+    # C4: delay-line effects, 64 stereo instances
+    for name, graph, n, steps in (("c4_pingpong_64", kb.FX_PINGPONG, 4096, 3), ("c4_reverb_64", kb.FX_REVERB, 1024, 2)):
+        fx = kb.FxBank(graph, 64, FS, n, device_index)
+        fx.set_stream(stream.cuda_stream)
+        io = torch.rand(64, 2, n, device=dev) - 0.5
+        fx.profile(True)
+        ms = time_steps(lambda: fx.process_inplace(io), steps, warmup=3)
+        k_ms, k_n = fx.profile_read()
+        bpf = fx.bytes_per_frame()
+        k_avg = k_ms / max(1, k_n)
+        gbs = 64 * n * bpf / (k_avg * 1e-3) / 1e9
+        res[name] = {"frames_per_s": 64 * n / (ms * 1e-3), "ms_per_step": ms, "block": n, "bytes_per_frame": bpf,
+                     "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                                  "kernel_ms": k_avg, "peak_source": peak_src}}
+        fx.close()
+
+    # C3 SuperSaw 8 x 32 voices; C5 per-GPU share: 4 x 128 TB303 + 4 x 128 SynTHX voices
+    for name, graph, inst, voices, n, steps in (("c3_supersaw_256", kb.SY_SUPERSAW, 8, 32, 4096, 5),
+                                                ("c5_tb303_512", kb.SY_TB303, 4, 128, 4096, 3),
+                                                ("c5_synthx_512", kb.SY_SYNTHX, 4, 128, 1024, 2)):
+        kb.lib().kb_srand(1)
+        sb = kb.SynthBank(graph, inst, voices, FS, n, device_index)
+        sb.set_stream(stream.cuda_stream)
+        for g in range(inst * voices):
+            sb.voice_start(g % voices, voice_pitch(g), voice_velocity(g), g // voices)
+        out = torch.empty(sb.out_shape(n), dtype=torch.float32, device=dev)
+        ms = time_steps(lambda: sb.process_into(out, n), steps, warmup=3)
+        res[name] = {"voice_samples_per_s": inst * voices * n / (ms * 1e-3), "ms_per_step": ms, "block": n}
+        sb.close()
+    return res
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,134 @@
+/* klang-b200 — C ABI of the B200-native klang hot path.
+ *
+ * The reference (nashaudio/klang v0.7.8) has no FFI boundary: its hot path is entered through the C++
+ * block drivers of klang.h.  Each entry point below names the reference interface it replaces
+ * (klang.h:line); INTEGRATION.md shows the binding a klang maintainer adds to route
+ * Effect::process / Synth::process through this library.
+ *
+ * A *bank* is many independent instances of one klang plugin (Effect or Synth) evaluated together by
+ * hand-written sm_100a kernels; voice / instance state lives in HBM between calls.  Conventions follow the
+ * reference: buffers are caller-owned planar float32, effects run in place, events (controls, notes) are
+ * block-granular and take effect at the next process call in call order, there are no exceptions.
+ * Every function that can fail returns 0 on success or a negative KB_E* code (the reference returns
+ * void); kb_last_error() describes the last failure on the calling thread.  One caller thread per bank.
+ * There is no CPU implementation behind these calls: without a CUDA device create() fails.
+ */
+#ifndef KLANG_B200_H
+#define KLANG_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KB_VERSION 100            /* library 0.1.0 */
+#define KB_KLANG_VERSION 708      /* restates klang v0.7.8 (klang.h:85) */
+
+/* error codes */
+#define KB_OK 0
+#define KB_EINVAL (-1)            /* bad argument (range, null, block > max_block) */
+#define KB_ECUDA (-2)             /* CUDA runtime error, see kb_last_error() */
+#define KB_ENODEV (-3)            /* no usable CUDA device */
+
+/* effect graphs (the user .k program each one reproduces) */
+#define KB_FX_GAIN 0              /* examples/Gain/Gain.k          mono   */
+#define KB_FX_PINGPONG 1          /* examples/PingPong.k           stereo */
+#define KB_FX_REVERB 2            /* examples/Reverb.k             stereo */
+#define KB_FX_DELAY_PINGPONG 3    /* examples/Delay/PingPong.k     stereo */
+#define KB_FX_DELAY_REVERB 4      /* examples/Delay/Reverb.k       mono   */
+
+/* synth graphs */
+#define KB_SY_SUBTRACTIVE 0       /* Saw >> LPF(env) >> ADSR: Filter.k with a Saw and ADSR controls mono */
+#define KB_SY_SUPERSAW 1          /* examples/SuperSaw.k           mono   */
+#define KB_SY_TB303 2             /* examples/TB303.k              mono   */
+#define KB_SY_SYNTHX 3            /* examples/SynTHX.k             stereo */
+#define KB_SY_FILTER_K 4          /* examples/Subtractive/Filter.k mono   */
+
+/* process flags */
+#define KB_DEVICE_PTR 1u          /* `io` / `out` is device memory on the bank's device; the call is asynchronous on the bank stream */
+#define KB_PER_VOICE 2u           /* synth: write every voice alone, out = [instances][voices][channels][n] (parity / debugging) */
+#define KB_MIX_SUM 4u             /* synth: mono synths sum their voices (Stereo::Note rule, klang.h:4731) instead of the reference's
+                                     overwrite (klang.h:4299) */
+#define KB_BANK_MIX 8u            /* synth: additionally sum all instances, out = [channels][n] (the multi-GPU mix-down input) */
+
+typedef struct kb_fx_bank kb_fx_bank;
+typedef struct kb_synth_bank kb_synth_bank;
+
+/* ------------------------------------------------------------------------------------------- library */
+int kb_version(void);
+int kb_device_count(void);                          /* 0 when no CUDA device / driver is usable */
+const char* kb_last_error(void);                    /* thread-local, never NULL */
+void kb_srand(unsigned seed);                       /* klang::random(seed) = srand()            klang.h:240 */
+float kb_pitch_to_frequency(float pitch);           /* Pitch::operator-> Frequency              klang.h:1568-1571 */
+
+/* ------------------------------------------------------------------------------------ effect banks */
+/* `instances` objects of the Effect / Stereo::Effect subclass `graph`, constructed with klang::fs = fs
+ * (klang.h:1593-1604).  max_block bounds `n` of process().  device = CUDA ordinal. */
+kb_fx_bank* kb_fx_bank_create(int graph, int instances, float fs, int max_block, int device);
+void kb_fx_bank_destroy(kb_fx_bank* bank);
+int kb_fx_bank_channels(const kb_fx_bank* bank);
+int kb_fx_bank_instances(const kb_fx_bank* bank);
+int kb_fx_bank_num_controls(const kb_fx_bank* bank);
+/* controls[idx].set(value) — clamps to the control's range                               klang.h:1725-1728, 4444-4447 */
+int kb_fx_bank_set_control(kb_fx_bank* bank, int instance, int idx, float value);
+/* params[c] = controls[c].value write-back (PingPong.k modifies a control per sample)    klang.h:4462-4465 */
+int kb_fx_bank_get_control(kb_fx_bank* bank, int instance, int idx, float* value);
+/* Effect::process(buffer) / Stereo::Effect::process(Stereo::buffer) for every instance, in place.
+ * io = [instances][channels][n] planar float32.                                          klang.h:4208-4216, 4708-4716 */
+int kb_fx_bank_process(kb_fx_bank* bank, float* io, int n, unsigned flags);
+int kb_fx_bank_sync(kb_fx_bank* bank);              /* join the bank stream (after KB_DEVICE_PTR calls) */
+int kb_fx_bank_set_stream(kb_fx_bank* bank, void* cuda_stream);   /* run on a caller-owned cudaStream_t (NULL = bank's own) */
+/* algorithmic (unique) HBM bytes one frame of one instance moves with the current controls */
+double kb_fx_bank_bytes_per_frame(kb_fx_bank* bank);
+long long kb_fx_bank_launches(const kb_fx_bank* bank);   /* kernels launched so far */
+long long kb_fx_bank_state_bytes(const kb_fx_bank* bank); /* bytes of instance state mirrored between host and device */
+/* Measurement: when enabled, every process() brackets its dominant kernel with CUDA events on the bank stream;
+ * read() joins the stream and returns the accumulated kernel milliseconds and launch count since enable. */
+int kb_fx_bank_profile(kb_fx_bank* bank, int enable);
+int kb_fx_bank_profile_read(kb_fx_bank* bank, double* kernel_ms, long long* kernel_launches);
+
+/* ------------------------------------------------------------------------------------- synth bank */
+/* `instances` Synth objects of `graph`, each with `voices` notes (notes.add<MyNote>(voices), <= 128, klang.h:4311). */
+kb_synth_bank* kb_synth_bank_create(int graph, int instances, int voices, float fs, int max_block, int device);
+void kb_synth_bank_destroy(kb_synth_bank* bank);
+int kb_synth_bank_channels(const kb_synth_bank* bank);
+int kb_synth_bank_instances(const kb_synth_bank* bank);
+int kb_synth_bank_voices(const kb_synth_bank* bank);
+int kb_synth_bank_num_controls(const kb_synth_bank* bank);
+int kb_synth_bank_set_control(kb_synth_bank* bank, int instance, int idx, float value);
+int kb_synth_bank_get_control(kb_synth_bank* bank, int instance, int idx, float* value);
+/* Synth::noteOn(pitch, velocity): Notes::assign() voice allocation / stealing, then Note::start().
+ * Returns the voice index (>= 0) or a negative error.                                    klang.h:4423-4427, 4336-4372 */
+int kb_synth_bank_note_on(kb_synth_bank* bank, int instance, int pitch, float velocity);
+/* Synth::noteOff(pitch, velocity): releases every sustaining note of that pitch           klang.h:4430-4434 */
+int kb_synth_bank_note_off(kb_synth_bank* bank, int instance, int pitch, float velocity);
+/* NoteBase::start / release / stage of one voice                                          klang.h:4257-4284 */
+int kb_synth_bank_voice_start(kb_synth_bank* bank, int instance, int voice, float pitch, float velocity);
+int kb_synth_bank_voice_release(kb_synth_bank* bank, int instance, int voice, float velocity);
+int kb_synth_bank_voice_stage(kb_synth_bank* bank, int instance, int voice);   /* 0 Onset 1 Sustain 2 Release 3 Off, <0 error */
+/* Synth::process(float*, int) / Stereo::Synth::process(float**, int) for every instance.
+ * out = [instances][channels][n] (see flags for the other layouts); out is overwritten.   klang.h:4440-4466, 4830-4858 */
+int kb_synth_bank_process(kb_synth_bank* bank, float* out, int n, unsigned flags);
+int kb_synth_bank_sync(kb_synth_bank* bank);
+int kb_synth_bank_set_stream(kb_synth_bank* bank, void* cuda_stream);
+long long kb_synth_bank_launches(const kb_synth_bank* bank);
+long long kb_synth_bank_state_bytes(const kb_synth_bank* bank);
+int kb_synth_bank_profile(kb_synth_bank* bank, int enable);
+int kb_synth_bank_profile_read(kb_synth_bank* bank, double* kernel_ms, long long* kernel_launches);
+
+/* ---------------------------------------------------------------------------- primitive operators */
+/* Single-object runs of the primitive operators ON THE DEVICE (one thread), for known-answer tests.
+ * kinds as in tests/cases.py.  Generators::Fast / Basic / Wavetables (klang.h:4893-5381). */
+int kb_prim_osc(int kind, int nargs, float f, float phase, float duty, float fs, int n, float* out);
+/* Filters::Biquad::{LPF,HPF}, OnePole::{LPF,HPF} (klang.h:5470-5683): set(f[s],Q[s]) before sample s < nset */
+int kb_prim_filter(int kind, int nset, const float* f, const float* Q, float fs, int n, const float* in, float* out, float* coeffs);
+/* Envelope / ADSR (klang.h:3723-4137) */
+int kb_prim_envelope(int npts, const float* xy, int loop_start, int loop_end, float fs, int n, int release_at,
+                     float release_time, float release_level, float* out, int* stage_out);
+int kb_prim_adsr(float A, float D, float S, float R, float fs, int n, int release_at, float* out, int* stage_out);
+/* libm agreement probe: out[i] = device sinf / cosf / tanhf of x[i] (fn 0 / 1 / 2) */
+int kb_prim_math(int fn, int n, const float* x, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

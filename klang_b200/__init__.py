@@ -1,0 +1,15 @@
+"""klang_b200 — B200-native implementation of klang's per-sample signal-flow path.
+
+Host-side mirror of the reference's plugin interface (`Effect` / `Synth` block drivers, klang.h:4203-4467,
+4703-4859) over the C-ABI library klang_b200/lib/libklang_b200.so (include/klang_b200.h).  Everything that
+processes samples runs in the library's sm_100a kernels; this package only marshals buffers.  Importing it
+never touches oracle/.
+"""
+from .api import (  # noqa: F401
+    Engine, FxBank, SynthBank, KlangB200Error, lib, lib_path, device_count,
+    FX_GAIN, FX_PINGPONG, FX_REVERB, FX_DELAY_PINGPONG, FX_DELAY_REVERB,
+    SY_SUBTRACTIVE, SY_SUPERSAW, SY_TB303, SY_SYNTHX, SY_FILTER_K,
+    DEVICE_PTR, PER_VOICE, MIX_SUM, BANK_MIX,
+)
+
+__version__ = "0.1.0"

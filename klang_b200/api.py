@@ -1,0 +1,351 @@
+"""ctypes binding of include/klang_b200.h plus thin bank objects.
+
+`Engine` exposes the same surface as the parity oracles (oracle/bindings.py: set_fs / srand / osc / filt /
+envelope / adsr / Fx / Synth) so the parity tests drive the CUDA path and the CPU oracles with the same
+script — but it shares no code with them and never falls back to them: if the library or a CUDA device is
+missing, calls raise KlangB200Error."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+lib_path = os.path.join(_HERE, "lib", "libklang_b200.so")
+
+FX_GAIN, FX_PINGPONG, FX_REVERB, FX_DELAY_PINGPONG, FX_DELAY_REVERB = range(5)
+SY_SUBTRACTIVE, SY_SUPERSAW, SY_TB303, SY_SYNTHX, SY_FILTER_K = range(5)
+DEVICE_PTR, PER_VOICE, MIX_SUM, BANK_MIX = 1, 2, 4, 8
+
+# every symbol include/klang_b200.h declares: (name, restype, argtypes)
+_vp, _i, _f, _u, _ll, _d = C.c_void_p, C.c_int, C.c_float, C.c_uint, C.c_longlong, C.c_double
+_fp, _ip = C.POINTER(C.c_float), C.POINTER(C.c_int)
+SYMBOLS = [
+    ("kb_version", _i, []), ("kb_device_count", _i, []), ("kb_last_error", C.c_char_p, []),
+    ("kb_srand", None, [_u]), ("kb_pitch_to_frequency", _f, [_f]),
+    ("kb_fx_bank_create", _vp, [_i, _i, _f, _i, _i]), ("kb_fx_bank_destroy", None, [_vp]),
+    ("kb_fx_bank_channels", _i, [_vp]), ("kb_fx_bank_instances", _i, [_vp]), ("kb_fx_bank_num_controls", _i, [_vp]),
+    ("kb_fx_bank_set_control", _i, [_vp, _i, _i, _f]), ("kb_fx_bank_get_control", _i, [_vp, _i, _i, _fp]),
+    ("kb_fx_bank_process", _i, [_vp, _vp, _i, _u]), ("kb_fx_bank_sync", _i, [_vp]), ("kb_fx_bank_set_stream", _i, [_vp, _vp]),
+    ("kb_fx_bank_bytes_per_frame", _d, [_vp]), ("kb_fx_bank_launches", _ll, [_vp]), ("kb_fx_bank_state_bytes", _ll, [_vp]),
+    ("kb_fx_bank_profile", _i, [_vp, _i]), ("kb_fx_bank_profile_read", _i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
+    ("kb_synth_bank_create", _vp, [_i, _i, _i, _f, _i, _i]), ("kb_synth_bank_destroy", None, [_vp]),
+    ("kb_synth_bank_channels", _i, [_vp]), ("kb_synth_bank_instances", _i, [_vp]), ("kb_synth_bank_voices", _i, [_vp]),
+    ("kb_synth_bank_num_controls", _i, [_vp]),
+    ("kb_synth_bank_set_control", _i, [_vp, _i, _i, _f]), ("kb_synth_bank_get_control", _i, [_vp, _i, _i, _fp]),
+    ("kb_synth_bank_note_on", _i, [_vp, _i, _i, _f]), ("kb_synth_bank_note_off", _i, [_vp, _i, _i, _f]),
+    ("kb_synth_bank_voice_start", _i, [_vp, _i, _i, _f, _f]), ("kb_synth_bank_voice_release", _i, [_vp, _i, _i, _f]),
+    ("kb_synth_bank_voice_stage", _i, [_vp, _i, _i]),
+    ("kb_synth_bank_process", _i, [_vp, _vp, _i, _u]), ("kb_synth_bank_sync", _i, [_vp]), ("kb_synth_bank_set_stream", _i, [_vp, _vp]),
+    ("kb_synth_bank_launches", _ll, [_vp]), ("kb_synth_bank_state_bytes", _ll, [_vp]),
+    ("kb_synth_bank_profile", _i, [_vp, _i]), ("kb_synth_bank_profile_read", _i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
+    ("kb_prim_osc", _i, [_i, _i, _f, _f, _f, _f, _i, _vp]),
+    ("kb_prim_filter", _i, [_i, _i, _vp, _vp, _f, _i, _vp, _vp, _vp]),
+    ("kb_prim_envelope", _i, [_i, _vp, _i, _i, _f, _i, _i, _f, _f, _vp, _vp]),
+    ("kb_prim_adsr", _i, [_f, _f, _f, _f, _f, _i, _i, _vp, _vp]),
+    ("kb_prim_math", _i, [_i, _i, _vp, _vp]),
+]
+
+
+class KlangB200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """The loaded C-ABI library (loads it on first use; raises if it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(lib_path):
+            raise KlangB200Error(f"{lib_path} is missing — run `python -m klang_b200.build` (needs nvcc); there is no CPU path")
+        L = C.CDLL(lib_path)
+        for name, res, args in SYMBOLS:
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def device_count():
+    return lib().kb_device_count()
+
+
+def _check(rc, what):
+    if rc < 0:
+        raise KlangB200Error(f"{what}: error {rc}: {lib().kb_last_error().decode()}")
+    return rc
+
+
+def _ptr(x):
+    """Device pointer of a torch CUDA tensor, or host pointer of a numpy array."""
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data, False
+    return x.data_ptr(), bool(x.is_cuda)
+
+
+class FxBank:
+    """`instances` objects of one klang Effect evaluated together (Effect::process(buffer), klang.h:4208-4216)."""
+
+    def __init__(self, graph, instances=1, fs=44100.0, max_block=16384, device=0):
+        self.h = lib().kb_fx_bank_create(graph, instances, float(fs), max_block, device)
+        if not self.h:
+            raise KlangB200Error("kb_fx_bank_create: " + lib().kb_last_error().decode())
+        self.graph, self.instances, self.max_block = graph, instances, max_block
+        self.channels = lib().kb_fx_bank_channels(self.h)
+        self.num_controls = lib().kb_fx_bank_num_controls(self.h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().kb_fx_bank_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def set_control(self, idx, value, instance=None):
+        for i in (range(self.instances) if instance is None else [instance]):
+            _check(lib().kb_fx_bank_set_control(self.h, i, idx, float(value)), "kb_fx_bank_set_control")
+
+    def get_control(self, idx, instance=0):
+        v = C.c_float()
+        _check(lib().kb_fx_bank_get_control(self.h, instance, idx, C.byref(v)), "kb_fx_bank_get_control")
+        return float(v.value)
+
+    def process_inplace(self, io, n=None):
+        """io: float32 [instances, channels, n], numpy (host) or torch CUDA tensor (asynchronous)."""
+        p, dev = _ptr(io)
+        n = io.shape[-1] if n is None else n
+        _check(lib().kb_fx_bank_process(self.h, p, n, DEVICE_PTR if dev else 0), "kb_fx_bank_process")
+        return io
+
+    def set_stream(self, cuda_stream):
+        _check(lib().kb_fx_bank_set_stream(self.h, cuda_stream), "kb_fx_bank_set_stream")
+
+    def sync(self):
+        _check(lib().kb_fx_bank_sync(self.h), "kb_fx_bank_sync")
+
+    def bytes_per_frame(self):
+        return lib().kb_fx_bank_bytes_per_frame(self.h)
+
+    @property
+    def state_bytes(self):
+        return lib().kb_fx_bank_state_bytes(self.h)
+
+    def profile(self, enable=True):
+        _check(lib().kb_fx_bank_profile(self.h, int(enable)), "kb_fx_bank_profile")
+
+    def profile_read(self):
+        """(accumulated milliseconds of the dominant kernel, launches) since profile(True)."""
+        ms, cnt = C.c_double(), C.c_longlong()
+        _check(lib().kb_fx_bank_profile_read(self.h, C.byref(ms), C.byref(cnt)), "kb_fx_bank_profile_read")
+        return ms.value, cnt.value
+
+    @property
+    def launches(self):
+        return lib().kb_fx_bank_launches(self.h)
+
+
+class SynthBank:
+    """`instances` klang Synth objects with `voices` notes each (Synth::process, klang.h:4440-4466 / 4830-4858)."""
+
+    def __init__(self, graph, instances=1, voices=32, fs=44100.0, max_block=16384, device=0):
+        self.h = lib().kb_synth_bank_create(graph, instances, voices, float(fs), max_block, device)
+        if not self.h:
+            raise KlangB200Error("kb_synth_bank_create: " + lib().kb_last_error().decode())
+        self.graph, self.instances, self.max_block = graph, instances, max_block
+        self.channels = lib().kb_synth_bank_channels(self.h)
+        self.voices = lib().kb_synth_bank_voices(self.h)
+        self.num_controls = lib().kb_synth_bank_num_controls(self.h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().kb_synth_bank_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def set_control(self, idx, value, instance=None):
+        for i in (range(self.instances) if instance is None else [instance]):
+            _check(lib().kb_synth_bank_set_control(self.h, i, idx, float(value)), "kb_synth_bank_set_control")
+
+    def get_control(self, idx, instance=0):
+        v = C.c_float()
+        _check(lib().kb_synth_bank_get_control(self.h, instance, idx, C.byref(v)), "kb_synth_bank_get_control")
+        return float(v.value)
+
+    def note_on(self, pitch, velocity, instance=0):
+        return _check(lib().kb_synth_bank_note_on(self.h, instance, int(pitch), float(velocity)), "kb_synth_bank_note_on")
+
+    def note_off(self, pitch, velocity=0.0, instance=0):
+        _check(lib().kb_synth_bank_note_off(self.h, instance, int(pitch), float(velocity)), "kb_synth_bank_note_off")
+
+    def voice_start(self, voice, pitch, velocity, instance=0):
+        _check(lib().kb_synth_bank_voice_start(self.h, instance, voice, float(pitch), float(velocity)), "kb_synth_bank_voice_start")
+
+    def voice_release(self, voice, velocity=0.0, instance=0):
+        _check(lib().kb_synth_bank_voice_release(self.h, instance, voice, float(velocity)), "kb_synth_bank_voice_release")
+
+    def voice_stage(self, voice, instance=0):
+        return _check(lib().kb_synth_bank_voice_stage(self.h, instance, voice), "kb_synth_bank_voice_stage")
+
+    def out_shape(self, n, flags=0):
+        if flags & PER_VOICE:
+            return (self.instances, self.voices, self.channels, n)
+        if flags & BANK_MIX:
+            return (self.channels, n)
+        return (self.instances, self.channels, n)
+
+    def process_into(self, out, n, flags=0):
+        """out: float32 buffer of out_shape(n, flags), numpy (host, synchronous) or torch CUDA tensor (asynchronous)."""
+        p, dev = _ptr(out)
+        _check(lib().kb_synth_bank_process(self.h, p, n, (flags | DEVICE_PTR) if dev else (flags & ~DEVICE_PTR)), "kb_synth_bank_process")
+        return out
+
+    def process_block(self, n, flags=0):
+        return self.process_into(np.empty(self.out_shape(n, flags), np.float32), n, flags)
+
+    def set_stream(self, cuda_stream):
+        _check(lib().kb_synth_bank_set_stream(self.h, cuda_stream), "kb_synth_bank_set_stream")
+
+    def sync(self):
+        _check(lib().kb_synth_bank_sync(self.h), "kb_synth_bank_sync")
+
+    @property
+    def state_bytes(self):
+        return lib().kb_synth_bank_state_bytes(self.h)
+
+    def profile(self, enable=True):
+        _check(lib().kb_synth_bank_profile(self.h, int(enable)), "kb_synth_bank_profile")
+
+    def profile_read(self):
+        ms, cnt = C.c_double(), C.c_longlong()
+        _check(lib().kb_synth_bank_profile_read(self.h, C.byref(ms), C.byref(cnt)), "kb_synth_bank_profile_read")
+        return ms.value, cnt.value
+
+    @property
+    def launches(self):
+        return lib().kb_synth_bank_launches(self.h)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Single-object views with the call surface of the reference objects (and of the parity oracles).
+
+class _Fx:
+    def __init__(self, eng, graph):
+        self.bank = FxBank(graph, 1, eng.fs, eng.max_block, eng.device)
+        self.channels, self.num_controls = self.bank.channels, self.bank.num_controls
+
+    def close(self):
+        self.bank.close()
+
+    def set_control(self, idx, v):
+        self.bank.set_control(idx, v, 0)
+
+    def get_control(self, idx):
+        return self.bank.get_control(idx, 0)
+
+    def process(self, x):
+        """x: float32 [channels, n] ([n] for mono effects). Returns a processed copy (the reference works in place)."""
+        y = np.array(x, np.float32, copy=True, order="C")
+        self.bank.process_inplace(y.reshape(1, self.channels, -1))
+        return y
+
+
+class _Synth:
+    def __init__(self, eng, graph, nvoices):
+        self.bank = SynthBank(graph, 1, nvoices, eng.fs, eng.max_block, eng.device)
+        self.channels, self.nvoices, self.num_controls = self.bank.channels, self.bank.voices, self.bank.num_controls
+
+    def close(self):
+        self.bank.close()
+
+    def set_control(self, idx, v):
+        self.bank.set_control(idx, v, 0)
+
+    def get_control(self, idx):
+        return self.bank.get_control(idx, 0)
+
+    def note_on(self, pitch, vel):
+        return self.bank.note_on(pitch, vel, 0)
+
+    def note_off(self, pitch, vel=0.0):
+        self.bank.note_off(pitch, vel, 0)
+
+    def voice_start(self, voice, pitch, vel):
+        self.bank.voice_start(voice, pitch, vel, 0)
+
+    def voice_release(self, voice, vel=0.0):
+        self.bank.voice_release(voice, vel, 0)
+
+    def voice_stage(self, voice):
+        return self.bank.voice_stage(voice, 0)
+
+    def process(self, n):
+        return self.bank.process_block(n)[0]
+
+    def process_voices(self, n):
+        stages = np.array([self.bank.voice_stage(v, 0) for v in range(self.nvoices)], np.int32)
+        out = self.bank.process_block(n, PER_VOICE)[0]
+        return out, (stages != 3).astype(np.int32)
+
+
+class Engine:
+    """The CUDA path behind the call surface the parity scripts use (tests/cases.py)."""
+
+    def __init__(self, fs=44100.0, device=0, max_block=16384):
+        self.fs, self.device, self.max_block = float(fs), device, max_block
+        lib()
+
+    def set_fs(self, fs):
+        self.fs = float(fs)   # klang::fs is per bank here: applies to banks created afterwards
+
+    def srand(self, seed):
+        lib().kb_srand(int(seed))
+
+    def pitch_to_frequency(self, p):
+        return float(lib().kb_pitch_to_frequency(float(p)))
+
+    def Fx(self, graph):
+        return _Fx(self, graph)
+
+    def Synth(self, graph, nvoices):
+        return _Synth(self, graph, nvoices)
+
+    # primitives on the device (one thread) -------------------------------------------------------------
+    def osc(self, kind, n, f, phase=None, duty=None):
+        out = np.zeros(n, np.float32)
+        nargs = 1 if phase is None else (2 if duty is None else 3)
+        _check(lib().kb_prim_osc(kind, nargs, float(f), float(phase or 0.0), float(duty or 0.0), self.fs, n, out.ctypes.data), "kb_prim_osc")
+        return out
+
+    def filt(self, kind, x, f, Q=None, per_sample=False):
+        x = np.ascontiguousarray(x, np.float32)
+        n = len(x)
+        nset = n if per_sample else 1
+        f = np.ascontiguousarray(np.broadcast_to(np.asarray(f, np.float32), (nset,)))
+        qp = None
+        if Q is not None:
+            Q = np.ascontiguousarray(np.broadcast_to(np.asarray(Q, np.float32), (nset,)))
+            qp = Q.ctypes.data
+        out, coeffs = np.zeros(n, np.float32), np.zeros(5, np.float32)
+        _check(lib().kb_prim_filter(kind, nset, f.ctypes.data, qp, self.fs, n, x.ctypes.data, out.ctypes.data, coeffs.ctypes.data), "kb_prim_filter")
+        return out, coeffs
+
+    def envelope(self, points, n, loop=None, release_at=-1, release_time=0.0, release_level=0.0):
+        xy = np.ascontiguousarray(np.asarray(points, np.float32).reshape(-1))
+        out, stage = np.zeros(n, np.float32), np.zeros(n, np.int32)
+        ls, le = loop if loop is not None else (-1, -1)
+        _check(lib().kb_prim_envelope(len(xy) // 2, xy.ctypes.data, ls, le, self.fs, n, release_at, release_time, release_level,
+                                      out.ctypes.data, stage.ctypes.data), "kb_prim_envelope")
+        return out, stage
+
+    def adsr(self, A, D, S, R, n, release_at=-1):
+        out, stage = np.zeros(n, np.float32), np.zeros(n, np.int32)
+        _check(lib().kb_prim_adsr(A, D, S, R, self.fs, n, release_at, out.ctypes.data, stage.ctypes.data), "kb_prim_adsr")
+        return out, stage
+
+    def math(self, fn, x):
+        x = np.ascontiguousarray(x, np.float32)
+        out = np.zeros_like(x)
+        _check(lib().kb_prim_math({"sinf": 0, "cosf": 1, "tanhf": 2}[fn], len(x), x.ctypes.data, out.ctypes.data), "kb_prim_math")
+        return out

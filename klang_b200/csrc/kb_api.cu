@@ -1,0 +1,586 @@
+// klang-b200 — C ABI (include/klang_b200.h) over the kernels of kb_kernels.cuh.
+//
+// Host side of a bank: a mirror of the POD state for the event-rate code (Note::on/off, Notes::assign,
+// Control::set, Effect::prepare), kept coherent with the device copy by two flags:
+//   host_stale  the device ran a block since the mirror was last fetched  -> fetch before the next event
+//   dirty       the mirror was modified by events                         -> upload before the next block
+// Blocks never touch the host mirror and never run on the host.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/klang_b200.h"
+#include "kb_kernels.cuh"
+
+static thread_local std::string g_err = "";
+static int kb_fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define KB_CUDA(call)                                                                              \
+	do {                                                                                           \
+		cudaError_t e_ = (call);                                                                   \
+		if (e_ != cudaSuccess) return kb_fail(KB_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+	} while (0)
+
+extern "C" int kb_version(void) { return KB_VERSION; }
+extern "C" const char* kb_last_error(void) { return g_err.c_str(); }
+extern "C" int kb_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
+extern "C" void kb_srand(unsigned seed) { srand(seed); }
+extern "C" float kb_pitch_to_frequency(float pitch) { return kb_pitch_to_frequency_host(pitch); }
+
+template <class T> static cudaError_t dev_alloc(T** p, size_t count) { return cudaMalloc((void**)p, count * sizeof(T) > 0 ? count * sizeof(T) : 1); }
+
+struct kb_bank_base {
+	int device = 0;
+	cudaStream_t stream = nullptr, own_stream = nullptr;
+	long long launches = 0;
+	KbFs fs;
+	int max_block = 0;
+	float* d_io = nullptr; size_t io_floats = 0;   // staging for host-pointer calls
+	bool host_stale = false, dirty = true;
+	// measurement: CUDA events around the dominant kernel of each process() call
+	bool profiling = false; std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events; size_t prof_used = 0;
+	void prof_begin() {
+		if (!profiling) return;
+		if (prof_used == prof_events.size()) { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); prof_events.push_back({ a, b }); }
+		cudaEventRecord(prof_events[prof_used].first, stream);
+	}
+	void prof_end() { if (profiling) cudaEventRecord(prof_events[prof_used++].second, stream); }
+	int prof_read(double* ms, long long* count) {
+		if (cudaStreamSynchronize(stream) != cudaSuccess) return KB_ECUDA;
+		double sum = 0;
+		for (size_t i = 0; i < prof_used; i++) { float t = 0; cudaEventElapsedTime(&t, prof_events[i].first, prof_events[i].second); sum += t; }
+		if (ms) *ms = sum;
+		if (count) *count = (long long)prof_used;
+		return KB_OK;
+	}
+	void prof_free() { for (auto& e : prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); } prof_events.clear(); prof_used = 0; }
+};
+
+// =============================================================================================== effects
+struct kb_fx_bank : kb_bank_base {
+	int graph = 0, instances = 0, channels = 0, ncontrols = 0;
+	size_t state_bytes = 0; long long ring_floats = 0;
+	std::vector<KbFxHdr> hdr; std::vector<unsigned char> state;
+	KbFxHdr* d_hdr = nullptr; unsigned char* d_state = nullptr; float* d_rings = nullptr;
+	bool device_writes_controls = false;
+	template <class T> T& st(int i) { return *reinterpret_cast<T*>(state.data() + (size_t)i * state_bytes); }
+};
+
+static int fx_fetch(kb_fx_bank* b) {
+	if (!b->host_stale) return KB_OK;
+	KB_CUDA(cudaSetDevice(b->device));
+	KB_CUDA(cudaMemcpyAsync(b->hdr.data(), b->d_hdr, b->hdr.size() * sizeof(KbFxHdr), cudaMemcpyDeviceToHost, b->stream));
+	KB_CUDA(cudaMemcpyAsync(b->state.data(), b->d_state, b->state.size(), cudaMemcpyDeviceToHost, b->stream));
+	KB_CUDA(cudaStreamSynchronize(b->stream));
+	b->host_stale = false;
+	return KB_OK;
+}
+static int fx_upload(kb_fx_bank* b) {
+	if (!b->dirty) return KB_OK;
+	KB_CUDA(cudaMemcpyAsync(b->d_hdr, b->hdr.data(), b->hdr.size() * sizeof(KbFxHdr), cudaMemcpyHostToDevice, b->stream));
+	KB_CUDA(cudaMemcpyAsync(b->d_state, b->state.data(), b->state.size(), cudaMemcpyHostToDevice, b->stream));
+	// the mirror may be modified again before the copy engine has read it
+	KB_CUDA(cudaStreamSynchronize(b->stream));
+	b->dirty = false;
+	return KB_OK;
+}
+
+extern "C" kb_fx_bank* kb_fx_bank_create(int graph, int instances, float fs, int max_block, int device) {
+	if (graph < 0 || graph >= KB_FX_COUNT || instances < 1 || max_block < 1 || !(fs > 0)) { kb_fail(KB_EINVAL, "kb_fx_bank_create: bad argument"); return nullptr; }
+	if (device < 0 || device >= kb_device_count()) { kb_fail(KB_ENODEV, "kb_fx_bank_create: no such CUDA device (klang-b200 has no CPU path)"); return nullptr; }
+	kb_fx_bank* b = new kb_fx_bank();
+	b->graph = graph; b->instances = instances; b->device = device; b->max_block = max_block; b->fs = kb_make_fs(fs);
+	switch (graph) {
+	case KB_FX_GAIN: b->channels = 1; b->ncontrols = 1; b->state_bytes = sizeof(KbGainFx); b->ring_floats = 0; break;
+	case KB_FX_PINGPONG: b->channels = 2; b->ncontrols = 6; b->state_bytes = sizeof(KbPingPong); b->ring_floats = KB_PINGPONG_RING_FLOATS; b->device_writes_controls = true; break;
+	case KB_FX_REVERB: b->channels = 2; b->ncontrols = 10; b->state_bytes = sizeof(KbReverb); b->ring_floats = KB_REVERB_RING_FLOATS; break;
+	case KB_FX_DELAY_PINGPONG: b->channels = 2; b->ncontrols = 4; b->state_bytes = sizeof(KbDPingPong); b->ring_floats = KB_PINGPONG_RING_FLOATS; break;
+	case KB_FX_DELAY_REVERB: b->channels = 1; b->ncontrols = 3; b->state_bytes = sizeof(KbDReverb); b->ring_floats = KB_PINGPONG_RING_FLOATS; break;
+	}
+	b->hdr.assign(instances, KbFxHdr());
+	memset(b->hdr.data(), 0, b->hdr.size() * sizeof(KbFxHdr));
+	b->state.assign((size_t)instances * b->state_bytes, 0);
+	for (int i = 0; i < instances; i++) {
+		const long long ring0 = (long long)i * b->ring_floats;
+		switch (graph) {
+		case KB_FX_GAIN: b->hdr[i].controls[0] = kb_dial(0.f, 1.f, 0.5f); break;                  // Gain.k:10
+		case KB_FX_PINGPONG: kb_pingpong_construct(b->hdr[i], b->st<KbPingPong>(i), ring0); break;
+		case KB_FX_REVERB: kb_reverb_construct(b->hdr[i], b->st<KbReverb>(i), ring0); break;
+		case KB_FX_DELAY_PINGPONG: kb_dpingpong_construct(b->hdr[i], b->st<KbDPingPong>(i), ring0); break;
+		case KB_FX_DELAY_REVERB: kb_dreverb_construct(b->hdr[i], b->st<KbDReverb>(i), ring0); break;
+		}
+	}
+	bool ok = cudaSetDevice(device) == cudaSuccess;
+	ok = ok && cudaStreamCreateWithFlags(&b->own_stream, cudaStreamNonBlocking) == cudaSuccess;
+	b->stream = b->own_stream;
+	ok = ok && dev_alloc(&b->d_hdr, instances) == cudaSuccess;
+	ok = ok && dev_alloc(&b->d_state, b->state.size()) == cudaSuccess;
+	ok = ok && dev_alloc(&b->d_rings, (size_t)instances * b->ring_floats) == cudaSuccess;
+	if (ok && b->ring_floats) ok = cudaMemsetAsync(b->d_rings, 0, (size_t)instances * b->ring_floats * sizeof(float), b->stream) == cudaSuccess;
+	b->io_floats = (size_t)instances * b->channels * max_block;
+	ok = ok && dev_alloc(&b->d_io, b->io_floats) == cudaSuccess;
+	if (!ok) { kb_fail(KB_ECUDA, std::string("kb_fx_bank_create: ") + cudaGetErrorString(cudaGetLastError())); kb_fx_bank_destroy(b); return nullptr; }
+	return b;
+}
+extern "C" void kb_fx_bank_destroy(kb_fx_bank* b) {
+	if (!b) return;
+	cudaSetDevice(b->device);
+	if (b->stream) cudaStreamSynchronize(b->stream);
+	cudaFree(b->d_hdr); cudaFree(b->d_state); cudaFree(b->d_rings); cudaFree(b->d_io);
+	b->prof_free();
+	if (b->own_stream) cudaStreamDestroy(b->own_stream);
+	delete b;
+}
+extern "C" int kb_fx_bank_channels(const kb_fx_bank* b) { return b ? b->channels : KB_EINVAL; }
+extern "C" int kb_fx_bank_instances(const kb_fx_bank* b) { return b ? b->instances : KB_EINVAL; }
+extern "C" int kb_fx_bank_num_controls(const kb_fx_bank* b) { return b ? b->ncontrols : KB_EINVAL; }
+extern "C" long long kb_fx_bank_launches(const kb_fx_bank* b) { return b ? b->launches : 0; }
+extern "C" long long kb_fx_bank_state_bytes(const kb_fx_bank* b) { return b ? (long long)(b->hdr.size() * sizeof(KbFxHdr) + b->state.size()) : 0; }
+extern "C" int kb_fx_bank_profile(kb_fx_bank* b, int enable) { if (!b) return kb_fail(KB_EINVAL, "null bank"); cudaSetDevice(b->device); cudaStreamSynchronize(b->stream); b->profiling = enable != 0; b->prof_used = 0; return KB_OK; }
+extern "C" int kb_fx_bank_profile_read(kb_fx_bank* b, double* ms, long long* count) { if (!b) return kb_fail(KB_EINVAL, "null bank"); cudaSetDevice(b->device); return b->prof_read(ms, count); }
+extern "C" int kb_fx_bank_sync(kb_fx_bank* b) { if (!b) return kb_fail(KB_EINVAL, "null bank"); KB_CUDA(cudaSetDevice(b->device)); KB_CUDA(cudaStreamSynchronize(b->stream)); return KB_OK; }
+extern "C" int kb_fx_bank_set_stream(kb_fx_bank* b, void* s) {
+	if (!b) return kb_fail(KB_EINVAL, "null bank");
+	KB_CUDA(cudaStreamSynchronize(b->stream));
+	b->stream = s ? (cudaStream_t)s : b->own_stream;
+	return KB_OK;
+}
+extern "C" int kb_fx_bank_set_control(kb_fx_bank* b, int inst, int idx, float v) {
+	if (!b || inst < 0 || inst >= b->instances || idx < 0 || idx >= b->ncontrols) return kb_fail(KB_EINVAL, "kb_fx_bank_set_control: bad argument");
+	// the upload replaces the whole blob, so the mirror must be current before it is modified
+	int rc = fx_fetch(b); if (rc) return rc;
+	kb_control_set(b->hdr[inst].controls[idx], v);
+	b->dirty = true;
+	return KB_OK;
+}
+extern "C" int kb_fx_bank_get_control(kb_fx_bank* b, int inst, int idx, float* v) {
+	if (!b || !v || inst < 0 || inst >= b->instances || idx < 0 || idx >= b->ncontrols) return kb_fail(KB_EINVAL, "kb_fx_bank_get_control: bad argument");
+	if (b->device_writes_controls) { int rc = fx_fetch(b); if (rc) return rc; }
+	*v = b->hdr[inst].controls[idx].value;
+	return KB_OK;
+}
+extern "C" double kb_fx_bank_bytes_per_frame(kb_fx_bank* b) {
+	if (!b) return 0;
+	switch (b->graph) {
+	case KB_FX_GAIN: return 8;
+	case KB_FX_PINGPONG: return 48;                                // 16 io + 2 x (4 write + 12 read), SURVEY §8d
+	case KB_FX_REVERB: { fx_fetch(b); int taps = 10 + (int)(b->hdr[0].controls[6].value * (float)10.999); return 16 + 2 * (4 + taps * 8) + 16 * 20; }
+	case KB_FX_DELAY_PINGPONG: return 40;
+	case KB_FX_DELAY_REVERB: return 88;
+	}
+	return 0;
+}
+
+static int fx_prepare(kb_fx_bank* b) {
+	// Effect::prepare() of every instance (klang.h:4209), on the host mirror
+	if (b->graph == KB_FX_PINGPONG) {
+		// dcfilter.set(50,1) is idempotent: it only does work the first time (PingPong.k:36-40, klang.h:5588)
+		bool need = false;
+		for (int i = 0; i < b->instances && !need; i++) { const KbPingPong& p = b->st<KbPingPong>(i); need = p.dc[0].f != 50.f || p.dc[0].Q != 1.f; }
+		if (need) {
+			int rc = fx_fetch(b); if (rc) return rc;
+			for (int i = 0; i < b->instances; i++) kb_pingpong_prepare(b->fs, b->st<KbPingPong>(i));
+			b->dirty = true;
+		}
+	} else if (b->graph == KB_FX_REVERB) {
+		bool changed = false;
+		for (int i = 0; i < b->instances && !changed; i++)
+			for (int c = 0; c < 10; c++) if (b->hdr[i].controls[c].value != b->hdr[i].cached[c]) changed = true;
+		if (changed) {
+			int rc = fx_fetch(b); if (rc) return rc;
+			for (int i = 0; i < b->instances; i++) kb_reverb_prepare(b->fs, b->hdr[i], b->st<KbReverb>(i));
+			b->dirty = true;
+		}
+	} else if (b->graph == KB_FX_DELAY_REVERB) {
+		// filter.set(controls[2]) (Delay/Reverb.k:59-61)
+		bool need = false;
+		for (int i = 0; i < b->instances && !need; i++) { const KbDReverb& p = b->st<KbDReverb>(i); need = p.filter.f != b->hdr[i].controls[2].value || p.filter.Q != KB_ROOT2_INV_F; }
+		if (need) {
+			int rc = fx_fetch(b); if (rc) return rc;
+			for (int i = 0; i < b->instances; i++) kb_biquad_set_f(b->fs, b->st<KbDReverb>(i).filter, b->hdr[i].controls[2].value);
+			b->dirty = true;
+		}
+	}
+	return KB_OK;
+}
+
+extern "C" int kb_fx_bank_process(kb_fx_bank* b, float* io, int n, unsigned flags) {
+	if (!b || !io || n < 0 || n > b->max_block) return kb_fail(KB_EINVAL, "kb_fx_bank_process: bad argument (n > max_block?)");
+	if (n == 0) return KB_OK;
+	KB_CUDA(cudaSetDevice(b->device));
+	int rc = fx_prepare(b); if (rc) return rc;
+	rc = fx_upload(b); if (rc) return rc;
+	const size_t floats = (size_t)b->instances * b->channels * n;
+	float* d = io;
+	if (!(flags & KB_DEVICE_PTR)) { d = b->d_io; KB_CUDA(cudaMemcpyAsync(d, io, floats * sizeof(float), cudaMemcpyHostToDevice, b->stream)); }
+	b->prof_begin();
+	switch (b->graph) {
+	case KB_FX_GAIN: {
+		dim3 grid((unsigned)std::max(1, std::min((n / 4 + 255) / 256, 148 * 8 / std::min(b->instances, 148 * 8) + 1)), b->instances);
+		kb_gain_kernel<<<grid, 256, 0, b->stream>>>(b->d_hdr, d, n);
+		break; }
+	case KB_FX_PINGPONG: kb_fx_seq_kernel<KB_FX_PINGPONG, KbPingPong><<<(b->instances + 31) / 32, 32, 0, b->stream>>>(b->d_hdr, (KbPingPong*)b->d_state, b->d_rings, d, n, 2, b->instances, b->fs); break;
+	case KB_FX_REVERB: kb_fx_seq_kernel<KB_FX_REVERB, KbReverb><<<(b->instances + 31) / 32, 32, 0, b->stream>>>(b->d_hdr, (KbReverb*)b->d_state, b->d_rings, d, n, 2, b->instances, b->fs); break;
+	case KB_FX_DELAY_PINGPONG: kb_fx_seq_kernel<KB_FX_DELAY_PINGPONG, KbDPingPong><<<(b->instances + 31) / 32, 32, 0, b->stream>>>(b->d_hdr, (KbDPingPong*)b->d_state, b->d_rings, d, n, 2, b->instances, b->fs); break;
+	case KB_FX_DELAY_REVERB: kb_fx_seq_kernel<KB_FX_DELAY_REVERB, KbDReverb><<<(b->instances + 31) / 32, 32, 0, b->stream>>>(b->d_hdr, (KbDReverb*)b->d_state, b->d_rings, d, n, 1, b->instances, b->fs); break;
+	}
+	b->prof_end();
+	b->launches++;
+	KB_CUDA(cudaGetLastError());
+	if (b->graph != KB_FX_GAIN) b->host_stale = true;
+	if (!(flags & KB_DEVICE_PTR)) {
+		KB_CUDA(cudaMemcpyAsync(io, d, floats * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
+		KB_CUDA(cudaStreamSynchronize(b->stream));
+	}
+	return KB_OK;
+}
+
+// ================================================================================================ synths
+struct kb_synth_bank : kb_bank_base {
+	int graph = 0, instances = 0, voices = 0, channels = 1, ncontrols = 0;
+	size_t voice_bytes = 0;
+	std::vector<KbControl> controls;              // [instances][KB_MAX_CONTROLS], host-owned
+	std::vector<KbVoiceHdr> hdr; std::vector<unsigned char> vstate;
+	std::vector<unsigned> noteOns, noteStart;     // Notes::noteOns / noteStart  klang.h:4333-4334
+	std::vector<KbSynthBlock> blk; bool blk_dirty = true;
+	KbVoiceHdr* d_hdr = nullptr; unsigned char* d_vstate = nullptr; KbSynthBlock* d_blk = nullptr;
+	float *d_scratch = nullptr, *d_out = nullptr, *d_adsr = nullptr, *d_mix = nullptr;
+	int total() const { return instances * voices; }
+	template <class T> T& vs(int v) { return *reinterpret_cast<T*>(vstate.data() + (size_t)v * voice_bytes); }
+	KbControl* ctl(int inst) { return controls.data() + (size_t)inst * KB_MAX_CONTROLS; }
+};
+
+static int sy_fetch(kb_synth_bank* b) {
+	if (!b->host_stale) return KB_OK;
+	KB_CUDA(cudaSetDevice(b->device));
+	KB_CUDA(cudaMemcpyAsync(b->hdr.data(), b->d_hdr, b->hdr.size() * sizeof(KbVoiceHdr), cudaMemcpyDeviceToHost, b->stream));
+	KB_CUDA(cudaMemcpyAsync(b->vstate.data(), b->d_vstate, b->vstate.size(), cudaMemcpyDeviceToHost, b->stream));
+	KB_CUDA(cudaStreamSynchronize(b->stream));
+	b->host_stale = false;
+	return KB_OK;
+}
+static int sy_upload(kb_synth_bank* b) {
+	if (b->dirty) {
+		KB_CUDA(cudaMemcpyAsync(b->d_hdr, b->hdr.data(), b->hdr.size() * sizeof(KbVoiceHdr), cudaMemcpyHostToDevice, b->stream));
+		KB_CUDA(cudaMemcpyAsync(b->d_vstate, b->vstate.data(), b->vstate.size(), cudaMemcpyHostToDevice, b->stream));
+	}
+	if (b->blk_dirty) {
+		for (int i = 0; i < b->instances; i++) {
+			KbSynthBlock& k = b->blk[i];
+			memset(&k, 0, sizeof(k));
+			if (b->graph == KB_SY_TB303) k.tb = kb_tb_block(b->fs, b->ctl(i));
+			if (b->graph == KB_SY_SYNTHX) { k.sx_tr_at = kb_sx_tr_at(b->ctl(i)[2].value); k.sx_dt_at = kb_sx_dt_at(b->ctl(i)[1].value); }
+		}
+		KB_CUDA(cudaMemcpyAsync(b->d_blk, b->blk.data(), b->blk.size() * sizeof(KbSynthBlock), cudaMemcpyHostToDevice, b->stream));
+	}
+	if (b->dirty || b->blk_dirty) KB_CUDA(cudaStreamSynchronize(b->stream));
+	b->dirty = false; b->blk_dirty = false;
+	return KB_OK;
+}
+
+extern "C" kb_synth_bank* kb_synth_bank_create(int graph, int instances, int voices, float fs, int max_block, int device) {
+	if (graph < 0 || graph >= KB_SY_COUNT || instances < 1 || voices < 1 || voices > KB_MAX_VOICES || max_block < 1 || !(fs > 0)) {
+		kb_fail(KB_EINVAL, "kb_synth_bank_create: bad argument"); return nullptr;
+	}
+	if (device < 0 || device >= kb_device_count()) { kb_fail(KB_ENODEV, "kb_synth_bank_create: no such CUDA device (klang-b200 has no CPU path)"); return nullptr; }
+	kb_synth_bank* b = new kb_synth_bank();
+	b->graph = graph; b->instances = instances; b->device = device; b->max_block = max_block; b->fs = kb_make_fs(fs);
+	// the example synths allocate at least 32 notes (Filter.k:39, SuperSaw.k:52, TB303.k:128, SynTHX.k:198)
+	if (graph != KB_SY_SUBTRACTIVE && voices < 32) voices = 32;
+	b->voices = voices;
+	b->controls.assign((size_t)instances * KB_MAX_CONTROLS, KbControl{ 0, 0, 0, 0 });
+	switch (graph) {
+	case KB_SY_SUBTRACTIVE: b->ncontrols = 4; b->voice_bytes = sizeof(KbSubVoice); break;
+	case KB_SY_FILTER_K: b->ncontrols = 0; b->voice_bytes = sizeof(KbSubVoice); break;
+	case KB_SY_SUPERSAW: b->ncontrols = 3; b->voice_bytes = sizeof(KbSsawVoice); break;
+	case KB_SY_TB303: b->ncontrols = 5; b->voice_bytes = sizeof(KbTbVoice); break;
+	case KB_SY_SYNTHX: b->ncontrols = 5; b->voice_bytes = sizeof(KbSxVoice); b->channels = 2; break;
+	}
+	for (int i = 0; i < instances; i++) {
+		KbControl* c = b->ctl(i);
+		switch (graph) {
+		case KB_SY_SUBTRACTIVE: c[0] = kb_dial(0.f, 1.f, 0.01f); c[1] = kb_dial(0.f, 1.f, 0.1f); c[2] = kb_dial(0.f, 1.f, 0.7f); c[3] = kb_dial(0.f, 1.f, 0.25f); break;
+		case KB_SY_SUPERSAW: c[0] = kb_dial(0.001f, 1.f, 0.001f); c[1] = kb_dial(0.f, 1.f, 0.05f); c[2] = kb_dial(0.f, 1.f, 0.6f); break;   // SuperSaw.k:38-43
+		case KB_SY_TB303: c[0] = kb_dial(0.f, 1.f, 1.f); c[1] = kb_dial(0.f, 1.f, 0.5f); c[2] = kb_dial(0.1f, 1.f, 0.5f);                     // TB303.k:118-126
+		                  c[3] = kb_dial(0.f, 1.f, 0.f); c[4] = kb_dial(0.01f, 10.f, 1.f); break;
+		case KB_SY_SYNTHX: c[0] = kb_dial(0.f, 5.f, 0.5f); c[1] = kb_dial(0.f, 1.f, 0.5f); c[2] = kb_dial(0.f, 1.f, 0.6f);                   // SynTHX.k:186-194
+		                   c[3] = kb_dial(0.f, 1.f, 1.f); c[4] = kb_dial(0.f, 1.f, 0.f); break;
+		}
+	}
+	const int total = b->total();
+	b->hdr.assign(total, KbVoiceHdr{ KB_NOTE_OFF, 0.f, 0.f, 0 });
+	b->vstate.assign((size_t)total * b->voice_bytes, 0);
+	b->noteOns.assign(instances, 0u); b->noteStart.assign(total, 0u);
+	b->blk.assign(instances, KbSynthBlock());
+	for (int v = 0; v < total; v++) {
+		switch (graph) {
+		case KB_SY_SUBTRACTIVE: case KB_SY_FILTER_K: kb_sub_construct(b->fs, graph, b->vs<KbSubVoice>(v)); break;
+		case KB_SY_SUPERSAW: kb_ssaw_construct(b->fs, b->vs<KbSsawVoice>(v)); break;
+		case KB_SY_TB303: kb_tb_construct(b->fs, b->vs<KbTbVoice>(v)); break;
+		case KB_SY_SYNTHX: kb_sx_construct(b->fs, b->vs<KbSxVoice>(v)); break;
+		}
+	}
+	bool ok = cudaSetDevice(device) == cudaSuccess;
+	ok = ok && cudaStreamCreateWithFlags(&b->own_stream, cudaStreamNonBlocking) == cudaSuccess;
+	b->stream = b->own_stream;
+	ok = ok && dev_alloc(&b->d_hdr, total) == cudaSuccess;
+	ok = ok && dev_alloc(&b->d_vstate, b->vstate.size()) == cudaSuccess;
+	ok = ok && dev_alloc(&b->d_blk, instances) == cudaSuccess;
+	ok = ok && dev_alloc(&b->d_scratch, (size_t)total * b->channels * max_block) == cudaSuccess;
+	ok = ok && dev_alloc(&b->d_out, (size_t)instances * b->channels * max_block) == cudaSuccess;
+	ok = ok && dev_alloc(&b->d_mix, (size_t)b->channels * max_block) == cudaSuccess;
+	if (graph == KB_SY_SYNTHX) ok = ok && dev_alloc(&b->d_adsr, (size_t)total * max_block) == cudaSuccess;
+	if (!ok) { kb_fail(KB_ECUDA, std::string("kb_synth_bank_create: ") + cudaGetErrorString(cudaGetLastError())); kb_synth_bank_destroy(b); return nullptr; }
+	return b;
+}
+extern "C" void kb_synth_bank_destroy(kb_synth_bank* b) {
+	if (!b) return;
+	cudaSetDevice(b->device);
+	if (b->stream) cudaStreamSynchronize(b->stream);
+	b->prof_free();
+	cudaFree(b->d_hdr); cudaFree(b->d_vstate); cudaFree(b->d_blk); cudaFree(b->d_scratch); cudaFree(b->d_out); cudaFree(b->d_adsr); cudaFree(b->d_mix);
+	if (b->own_stream) cudaStreamDestroy(b->own_stream);
+	delete b;
+}
+extern "C" int kb_synth_bank_channels(const kb_synth_bank* b) { return b ? b->channels : KB_EINVAL; }
+extern "C" int kb_synth_bank_instances(const kb_synth_bank* b) { return b ? b->instances : KB_EINVAL; }
+extern "C" int kb_synth_bank_voices(const kb_synth_bank* b) { return b ? b->voices : KB_EINVAL; }
+extern "C" int kb_synth_bank_num_controls(const kb_synth_bank* b) { return b ? b->ncontrols : KB_EINVAL; }
+extern "C" long long kb_synth_bank_launches(const kb_synth_bank* b) { return b ? b->launches : 0; }
+extern "C" long long kb_synth_bank_state_bytes(const kb_synth_bank* b) { return b ? (long long)(b->hdr.size() * sizeof(KbVoiceHdr) + b->vstate.size()) : 0; }
+extern "C" int kb_synth_bank_profile(kb_synth_bank* b, int enable) { if (!b) return kb_fail(KB_EINVAL, "null bank"); cudaSetDevice(b->device); cudaStreamSynchronize(b->stream); b->profiling = enable != 0; b->prof_used = 0; return KB_OK; }
+extern "C" int kb_synth_bank_profile_read(kb_synth_bank* b, double* ms, long long* count) { if (!b) return kb_fail(KB_EINVAL, "null bank"); cudaSetDevice(b->device); return b->prof_read(ms, count); }
+extern "C" int kb_synth_bank_sync(kb_synth_bank* b) { if (!b) return kb_fail(KB_EINVAL, "null bank"); KB_CUDA(cudaSetDevice(b->device)); KB_CUDA(cudaStreamSynchronize(b->stream)); return KB_OK; }
+extern "C" int kb_synth_bank_set_stream(kb_synth_bank* b, void* s) {
+	if (!b) return kb_fail(KB_EINVAL, "null bank");
+	KB_CUDA(cudaStreamSynchronize(b->stream));
+	b->stream = s ? (cudaStream_t)s : b->own_stream;
+	return KB_OK;
+}
+extern "C" int kb_synth_bank_set_control(kb_synth_bank* b, int inst, int idx, float v) {
+	if (!b || inst < 0 || inst >= b->instances || idx < 0 || idx >= b->ncontrols) return kb_fail(KB_EINVAL, "kb_synth_bank_set_control: bad argument");
+	kb_control_set(b->ctl(inst)[idx], v);
+	b->blk_dirty = true;
+	return KB_OK;
+}
+extern "C" int kb_synth_bank_get_control(kb_synth_bank* b, int inst, int idx, float* v) {
+	if (!b || !v || inst < 0 || inst >= b->instances || idx < 0 || idx >= b->ncontrols) return kb_fail(KB_EINVAL, "kb_synth_bank_get_control: bad argument");
+	*v = b->ctl(inst)[idx].value;
+	return KB_OK;
+}
+
+// NoteBase::start: stage = Onset; on(pitch, velocity); stage = Sustain           klang.h:4257-4263
+static void sy_start(kb_synth_bank* b, int inst, int voice, float pitch, float velocity) {
+	const int v = inst * b->voices + voice;
+	KbVoiceHdr& h = b->hdr[v];
+	h.pitch = pitch; h.velocity = velocity;
+	const KbControl* c = b->ctl(inst);
+	switch (b->graph) {
+	case KB_SY_SUBTRACTIVE: case KB_SY_FILTER_K: kb_sub_on(b->fs, b->graph, c, b->vs<KbSubVoice>(v), pitch); break;
+	case KB_SY_SUPERSAW: kb_ssaw_on(b->fs, c, b->vs<KbSsawVoice>(v), pitch); break;
+	case KB_SY_TB303: kb_tb_on(b->fs, c, b->vs<KbTbVoice>(v), pitch); break;
+	case KB_SY_SYNTHX: kb_sx_on(b->fs, c, b->vs<KbSxVoice>(v), pitch); break;
+	}
+	h.stage = KB_NOTE_SUSTAIN;
+	b->dirty = true;
+}
+// NoteBase::release: Off stays Off; otherwise stage = Release; off(velocity)     klang.h:4265-4275
+static void sy_release(kb_synth_bank* b, int inst, int voice) {
+	const int v = inst * b->voices + voice;
+	KbVoiceHdr& h = b->hdr[v];
+	if (h.stage == KB_NOTE_OFF || h.stage == KB_NOTE_RELEASE) return;
+	h.stage = KB_NOTE_RELEASE;
+	switch (b->graph) {
+	case KB_SY_SUBTRACTIVE: case KB_SY_FILTER_K: kb_adsr_release(b->fs, b->vs<KbSubVoice>(v).adsr); break;   // Filter.k:25-27
+	case KB_SY_SUPERSAW: kb_adsr_release(b->fs, b->vs<KbSsawVoice>(v).adsr); break;                          // SuperSaw.k:21-23
+	case KB_SY_TB303: kb_adsr_release(b->fs, b->vs<KbTbVoice>(v).adsr); break;                               // TB303.k:99-101
+	case KB_SY_SYNTHX: kb_adsr_release(b->fs, b->vs<KbSxVoice>(v).adsr); break;                              // SynTHX.k:163-165
+	}
+	b->dirty = true;
+}
+// Notes::assign: first Off voice, else the oldest Released, else the oldest      klang.h:4336-4372
+static int sy_assign(kb_synth_bank* b, int inst) {
+	const KbVoiceHdr* h = b->hdr.data() + (size_t)inst * b->voices;
+	unsigned* start = b->noteStart.data() + (size_t)inst * b->voices;
+	unsigned& ons = b->noteOns[inst];
+	for (int i = 0; i < b->voices; i++) if (h[i].stage == KB_NOTE_OFF) { start[i] = ons++; return i; }
+	int oldest = -1; unsigned oldest_start = 0;
+	for (int i = 0; i < b->voices; i++)
+		if (h[i].stage == KB_NOTE_RELEASE && (oldest == -1 || start[i] < oldest_start)) { oldest = i; oldest_start = start[i]; }
+	if (oldest != -1) { start[oldest] = ons++; return oldest; }
+	for (int i = 0; i < b->voices; i++) if (oldest == -1 || start[i] < oldest_start) { oldest = i; oldest_start = start[i]; }
+	start[oldest] = ons++;
+	return oldest;
+}
+extern "C" int kb_synth_bank_note_on(kb_synth_bank* b, int inst, int pitch, float velocity) {
+	if (!b || inst < 0 || inst >= b->instances) return kb_fail(KB_EINVAL, "kb_synth_bank_note_on: bad argument");
+	int rc = sy_fetch(b); if (rc) return rc;
+	const int n = sy_assign(b, inst);
+	sy_start(b, inst, n, (float)pitch, velocity);
+	return n;
+}
+extern "C" int kb_synth_bank_note_off(kb_synth_bank* b, int inst, int pitch, float velocity) {
+	(void)velocity;
+	if (!b || inst < 0 || inst >= b->instances) return kb_fail(KB_EINVAL, "kb_synth_bank_note_off: bad argument");
+	int rc = sy_fetch(b); if (rc) return rc;
+	for (int n = 0; n < b->voices; n++) {
+		const KbVoiceHdr& h = b->hdr[(size_t)inst * b->voices + n];
+		if (h.pitch == pitch && h.stage == KB_NOTE_SUSTAIN) sy_release(b, inst, n);
+	}
+	return KB_OK;
+}
+extern "C" int kb_synth_bank_voice_start(kb_synth_bank* b, int inst, int voice, float pitch, float velocity) {
+	if (!b || inst < 0 || inst >= b->instances || voice < 0 || voice >= b->voices) return kb_fail(KB_EINVAL, "kb_synth_bank_voice_start: bad argument");
+	int rc = sy_fetch(b); if (rc) return rc;
+	sy_start(b, inst, voice, pitch, velocity);
+	return KB_OK;
+}
+extern "C" int kb_synth_bank_voice_release(kb_synth_bank* b, int inst, int voice, float velocity) {
+	(void)velocity;
+	if (!b || inst < 0 || inst >= b->instances || voice < 0 || voice >= b->voices) return kb_fail(KB_EINVAL, "kb_synth_bank_voice_release: bad argument");
+	int rc = sy_fetch(b); if (rc) return rc;
+	sy_release(b, inst, voice);
+	return KB_OK;
+}
+extern "C" int kb_synth_bank_voice_stage(kb_synth_bank* b, int inst, int voice) {
+	if (!b || inst < 0 || inst >= b->instances || voice < 0 || voice >= b->voices) return kb_fail(KB_EINVAL, "kb_synth_bank_voice_stage: bad argument");
+	int rc = sy_fetch(b); if (rc) return rc;
+	return b->hdr[(size_t)inst * b->voices + voice].stage;
+}
+
+extern "C" int kb_synth_bank_process(kb_synth_bank* b, float* out, int n, unsigned flags) {
+	if (!b || !out || n < 0 || n > b->max_block) return kb_fail(KB_EINVAL, "kb_synth_bank_process: bad argument (n > max_block?)");
+	if (n == 0) return KB_OK;
+	KB_CUDA(cudaSetDevice(b->device));
+	int rc = sy_upload(b); if (rc) return rc;
+	const int total = b->total(), C = b->channels;
+	const bool per_voice = flags & KB_PER_VOICE, dev = flags & KB_DEVICE_PTR, bank_mix = (flags & KB_BANK_MIX) && !per_voice;
+	const size_t out_floats = per_voice ? (size_t)total * C * n : bank_mix ? (size_t)C * n : (size_t)b->instances * C * n;
+	cudaStream_t st = b->stream;
+	float* d_voice_dst = (per_voice && dev) ? out : b->d_scratch;
+	float* d_inst_dst = (!per_voice && !bank_mix && dev) ? out : b->d_out;
+	if (b->graph == KB_SY_SYNTHX) {
+		const int pthreads = total * 132;
+		kb_sx_prepare_kernel<<<(pthreads + 127) / 128, 128, 0, st>>>((KbSxVoice*)b->d_vstate, b->d_hdr, b->d_blk, b->voices, total, b->fs);
+		kb_sx_adsr_kernel<<<(total + 31) / 32, 32, 0, st>>>((KbSxVoice*)b->d_vstate, b->d_hdr, b->d_adsr, n, total, b->fs);
+		dim3 grid((n + 127) / 128, b->instances);
+		b->prof_begin();
+		kb_sx_render_kernel<<<grid, 128, 0, st>>>((const KbSxVoice*)b->d_vstate, b->d_hdr, b->d_adsr, per_voice ? d_voice_dst : d_inst_dst, n, b->voices, per_voice ? 1 : 0);
+		b->prof_end();
+		kb_sx_advance_kernel<<<(pthreads + 127) / 128, 128, 0, st>>>((KbSxVoice*)b->d_vstate, b->d_hdr, n, total);
+		b->launches += 4;
+	} else {
+		const int blocks = (total + 127) / 128;
+		b->prof_begin();
+		switch (b->graph) {
+		case KB_SY_SUBTRACTIVE: case KB_SY_FILTER_K:
+			kb_voice_kernel<KB_SY_SUBTRACTIVE, KbSubVoice><<<blocks, 128, 0, st>>>((KbSubVoice*)b->d_vstate, b->d_hdr, b->d_blk, d_voice_dst, n, b->voices, total, b->fs); break;
+		case KB_SY_SUPERSAW:
+			kb_voice_kernel<KB_SY_SUPERSAW, KbSsawVoice><<<blocks, 128, 0, st>>>((KbSsawVoice*)b->d_vstate, b->d_hdr, b->d_blk, d_voice_dst, n, b->voices, total, b->fs); break;
+		case KB_SY_TB303:
+			kb_voice_kernel<KB_SY_TB303, KbTbVoice><<<blocks, 128, 0, st>>>((KbTbVoice*)b->d_vstate, b->d_hdr, b->d_blk, d_voice_dst, n, b->voices, total, b->fs); break;
+		}
+		b->prof_end();
+		b->launches++;
+		if (!per_voice) {
+			dim3 grid((n + 255) / 256, b->instances);
+			kb_mix_kernel<<<grid, 256, 0, st>>>(b->d_scratch, b->d_hdr, d_inst_dst, n, b->voices, (flags & KB_MIX_SUM) ? 1 : 0);
+			b->launches++;
+		}
+	}
+	float* d_result = per_voice ? d_voice_dst : d_inst_dst;
+	if (bank_mix) {
+		d_result = dev ? out : b->d_mix;
+		kb_bank_mix_kernel<<<(C * n + 255) / 256, 256, 0, st>>>(b->d_out, d_result, C * n, b->instances);
+		b->launches++;
+	}
+	KB_CUDA(cudaGetLastError());
+	b->host_stale = true;
+	if (!dev) {
+		KB_CUDA(cudaMemcpyAsync(out, d_result, out_floats * sizeof(float), cudaMemcpyDeviceToHost, st));
+		KB_CUDA(cudaStreamSynchronize(st));
+	}
+	return KB_OK;
+}
+
+// ============================================================================================ primitives
+struct DevBuf {
+	void* p = nullptr;
+	DevBuf(size_t bytes, const void* src = nullptr) { if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) p = nullptr; else if (src) cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice); }
+	~DevBuf() { cudaFree(p); }
+	template <class T> T* as() { return (T*)p; }
+};
+static int prim_finish(const char* what) {
+	cudaError_t e = cudaDeviceSynchronize();
+	if (e == cudaSuccess) e = cudaGetLastError();
+	if (e != cudaSuccess) return kb_fail(KB_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+	return KB_OK;
+}
+extern "C" int kb_prim_osc(int kind, int nargs, float f, float phase, float duty, float fs, int n, float* out) {
+	if (kb_device_count() < 1) return kb_fail(KB_ENODEV, "no CUDA device");
+	if (!out || n < 0 || !(kind <= 5 || kind == 10 || kind == 11)) return kb_fail(KB_EINVAL, "kb_prim_osc: unsupported kind");
+	const KbFs F = kb_make_fs(fs);
+	std::vector<float> table(2048, 0.f);
+	if (kind >= 10) {   // Wavetable::operator=(Oscillator) fills the table with a Basic osc at fs/size Hz on the host (klang.h:3645-3650)
+		KbBasicOsc o; kb_bosc_init(o); kb_bosc_set_f(F, o, F.f / 2048);
+		for (int s = 0; s < 2048; s++) {
+			table[s] = (kind == 10) ? ::sinf(o.position + o.offset) : (o.position * KB_PI_INV_F - 1.f);
+			kb_bosc_advance(o);
+		}
+	}
+	DevBuf dout(sizeof(float) * n), dtab(sizeof(float) * 2048, table.data());
+	kb_prim_osc_kernel<<<1, 32>>>(kind, nargs, f, phase, duty, F, n, dout.as<float>(), dtab.as<float>());
+	int rc = prim_finish("kb_prim_osc"); if (rc) return rc;
+	cudaMemcpy(out, dout.p, sizeof(float) * n, cudaMemcpyDeviceToHost);
+	return KB_OK;
+}
+extern "C" int kb_prim_filter(int kind, int nset, const float* f, const float* Q, float fs, int n, const float* in, float* out, float* coeffs) {
+	if (kb_device_count() < 1) return kb_fail(KB_ENODEV, "no CUDA device");
+	if (kind < 0 || kind > 3 || !f || !in || !out || !coeffs || nset < 0 || nset > n || (kind >= 2 && nset > 1)) return kb_fail(KB_EINVAL, "kb_prim_filter: unsupported");
+	const KbFs F = kb_make_fs(fs);
+	KbOnePole op; kb_onepole_construct(op, kind == 2 ? KB_OP_LPF : KB_OP_HPF);
+	if (kind >= 2 && nset == 1) kb_onepole_set(F, op, f[0]);
+	DevBuf df(sizeof(float) * (nset ? nset : 1), f), dq(sizeof(float) * (nset ? nset : 1), Q), din(sizeof(float) * n, in), dout(sizeof(float) * n), dc(sizeof(float) * 5);
+	kb_prim_filter_kernel<<<1, 32>>>(kind, nset, df.as<float>(), Q ? dq.as<float>() : nullptr, F, n, din.as<float>(), dout.as<float>(), dc.as<float>(), op);
+	int rc = prim_finish("kb_prim_filter"); if (rc) return rc;
+	cudaMemcpy(out, dout.p, sizeof(float) * n, cudaMemcpyDeviceToHost);
+	cudaMemcpy(coeffs, dc.p, sizeof(float) * 5, cudaMemcpyDeviceToHost);
+	return KB_OK;
+}
+static int prim_env(KbEnv e, const KbFs& F, int n, int release_at, float rt, float rl, int adsr, float* out, int* stage_out) {
+	DevBuf dout(sizeof(float) * n), dst(sizeof(int) * n);
+	kb_prim_env_kernel<<<1, 32>>>(e, F, n, release_at, rt, rl, adsr, dout.as<float>(), dst.as<int>());
+	int rc = prim_finish("kb_prim_envelope"); if (rc) return rc;
+	cudaMemcpy(out, dout.p, sizeof(float) * n, cudaMemcpyDeviceToHost);
+	if (stage_out) cudaMemcpy(stage_out, dst.p, sizeof(int) * n, cudaMemcpyDeviceToHost);
+	return KB_OK;
+}
+extern "C" int kb_prim_envelope(int npts, const float* xy, int loop_start, int loop_end, float fs, int n, int release_at,
+                                float release_time, float release_level, float* out, int* stage_out) {
+	if (kb_device_count() < 1) return kb_fail(KB_ENODEV, "no CUDA device");
+	if (npts < 0 || npts > KB_ENV_MAXPTS || !xy || !out) return kb_fail(KB_EINVAL, "kb_prim_envelope: bad argument");
+	const KbFs F = kb_make_fs(fs);
+	KbEnv e; kb_env_construct(F, e); kb_env_set_points(F, e, npts, xy);
+	if (loop_start >= 0) kb_env_set_loop(e, loop_start, loop_end);
+	return prim_env(e, F, n, release_at, release_time, release_level, 0, out, stage_out);
+}
+extern "C" int kb_prim_adsr(float A, float D, float S, float R, float fs, int n, int release_at, float* out, int* stage_out) {
+	if (kb_device_count() < 1) return kb_fail(KB_ENODEV, "no CUDA device");
+	if (!out) return kb_fail(KB_EINVAL, "kb_prim_adsr: bad argument");
+	const KbFs F = kb_make_fs(fs);
+	KbEnv e; kb_adsr_construct(F, e); kb_adsr_set(F, e, A, D, S, R);
+	return prim_env(e, F, n, release_at, 0.f, 0.f, 1, out, stage_out);
+}
+extern "C" int kb_prim_math(int fn, int n, const float* x, float* out) {
+	if (kb_device_count() < 1) return kb_fail(KB_ENODEV, "no CUDA device");
+	if (fn < 0 || fn > 2 || !x || !out || n < 0) return kb_fail(KB_EINVAL, "kb_prim_math: bad argument");
+	DevBuf dx(sizeof(float) * n, x), dout(sizeof(float) * n);
+	kb_prim_math_kernel<<<148, 256>>>(fn, n, dx.as<float>(), dout.as<float>());
+	int rc = prim_finish("kb_prim_math"); if (rc) return rc;
+	cudaMemcpy(out, dout.p, sizeof(float) * n, cudaMemcpyDeviceToHost);
+	return KB_OK;
+}

