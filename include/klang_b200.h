@@ -48,6 +48,7 @@ extern "C" {
 #define KB_PER_VOICE 2u           /* synth: write every voice alone, out = [instances][voices][channels][n] (parity / debugging) */
 #define KB_MIX_SUM 4u             /* synth: mono synths sum their voices (Stereo::Note rule, klang.h:4731) instead of the reference's
                                      overwrite (klang.h:4299) */
+#define KB_LANE_PER_VOICE 16u     /* synth: use the plain lane-per-voice schedule instead of the tiled one (A/B measurement; same results) */
 #define KB_BANK_MIX 8u            /* synth: additionally sum all instances, out = [channels][n] (the multi-GPU mix-down input) */
 
 typedef struct kb_fx_bank kb_fx_bank;

@@ -9,7 +9,7 @@ from .api import (  # noqa: F401
     Engine, FxBank, SynthBank, KlangB200Error, lib, lib_path, device_count,
     FX_GAIN, FX_PINGPONG, FX_REVERB, FX_DELAY_PINGPONG, FX_DELAY_REVERB,
     SY_SUBTRACTIVE, SY_SUPERSAW, SY_TB303, SY_SYNTHX, SY_FILTER_K,
-    DEVICE_PTR, PER_VOICE, MIX_SUM, BANK_MIX,
+    DEVICE_PTR, PER_VOICE, MIX_SUM, BANK_MIX, LANE_PER_VOICE,
 )
 
 __version__ = "0.1.0"

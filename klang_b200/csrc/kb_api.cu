@@ -16,6 +16,7 @@
 
 #include "../../include/klang_b200.h"
 #include "kb_kernels.cuh"
+#include "kb_tiled.cuh"
 
 static thread_local std::string g_err = "";
 static int kb_fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -325,6 +326,10 @@ extern "C" kb_synth_bank* kb_synth_bank_create(int graph, int instances, int voi
 		}
 	}
 	bool ok = cudaSetDevice(device) == cudaSuccess;
+	// the pipelined kernels stage ~75 KB of hand-over buffers per CTA in shared memory
+	ok = ok && cudaFuncSetAttribute(kb_sub_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KbSubSmem)) == cudaSuccess;
+	ok = ok && cudaFuncSetAttribute(kb_ssaw_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KbSsawSmem)) == cudaSuccess;
+	ok = ok && cudaFuncSetAttribute(kb_tb_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KbTbSmem)) == cudaSuccess;
 	ok = ok && cudaStreamCreateWithFlags(&b->own_stream, cudaStreamNonBlocking) == cudaSuccess;
 	b->stream = b->own_stream;
 	ok = ok && dev_alloc(&b->d_hdr, total) == cudaSuccess;
@@ -474,15 +479,27 @@ extern "C" int kb_synth_bank_process(kb_synth_bank* b, float* out, int n, unsign
 		kb_sx_advance_kernel<<<(pthreads + 127) / 128, 128, 0, st>>>((KbSxVoice*)b->d_vstate, b->d_hdr, n, total);
 		b->launches += 4;
 	} else {
-		const int blocks = (total + 127) / 128;
 		b->prof_begin();
-		switch (b->graph) {
-		case KB_SY_SUBTRACTIVE: case KB_SY_FILTER_K:
-			kb_voice_kernel<KB_SY_SUBTRACTIVE, KbSubVoice><<<blocks, 128, 0, st>>>((KbSubVoice*)b->d_vstate, b->d_hdr, b->d_blk, d_voice_dst, n, b->voices, total, b->fs); break;
-		case KB_SY_SUPERSAW:
-			kb_voice_kernel<KB_SY_SUPERSAW, KbSsawVoice><<<blocks, 128, 0, st>>>((KbSsawVoice*)b->d_vstate, b->d_hdr, b->d_blk, d_voice_dst, n, b->voices, total, b->fs); break;
-		case KB_SY_TB303:
-			kb_voice_kernel<KB_SY_TB303, KbTbVoice><<<blocks, 128, 0, st>>>((KbTbVoice*)b->d_vstate, b->d_hdr, b->d_blk, d_voice_dst, n, b->voices, total, b->fs); break;
+		if (flags & KB_LANE_PER_VOICE) {
+			const int blocks = (total + 127) / 128;
+			switch (b->graph) {
+			case KB_SY_SUBTRACTIVE: case KB_SY_FILTER_K:
+				kb_voice_kernel<KB_SY_SUBTRACTIVE, KbSubVoice><<<blocks, 128, 0, st>>>((KbSubVoice*)b->d_vstate, b->d_hdr, b->d_blk, d_voice_dst, n, b->voices, total, b->fs); break;
+			case KB_SY_SUPERSAW:
+				kb_voice_kernel<KB_SY_SUPERSAW, KbSsawVoice><<<blocks, 128, 0, st>>>((KbSsawVoice*)b->d_vstate, b->d_hdr, b->d_blk, d_voice_dst, n, b->voices, total, b->fs); break;
+			case KB_SY_TB303:
+				kb_voice_kernel<KB_SY_TB303, KbTbVoice><<<blocks, 128, 0, st>>>((KbTbVoice*)b->d_vstate, b->d_hdr, b->d_blk, d_voice_dst, n, b->voices, total, b->fs); break;
+			}
+		} else {
+			const int blocks = (total + KB_TILE_G - 1) / KB_TILE_G;
+			switch (b->graph) {
+			case KB_SY_SUBTRACTIVE: case KB_SY_FILTER_K:
+				kb_sub_tiled_kernel<<<blocks, KB_TILE_THREADS, sizeof(KbSubSmem), st>>>((KbSubVoice*)b->d_vstate, b->d_hdr, d_voice_dst, n, total, b->fs); break;
+			case KB_SY_SUPERSAW:
+				kb_ssaw_tiled_kernel<<<blocks, KB_TILE_THREADS, sizeof(KbSsawSmem), st>>>((KbSsawVoice*)b->d_vstate, b->d_hdr, d_voice_dst, n, total, b->fs); break;
+			case KB_SY_TB303:
+				kb_tb_tiled_kernel<<<blocks, KB_TILE_THREADS, sizeof(KbTbSmem), st>>>((KbTbVoice*)b->d_vstate, b->d_hdr, b->d_blk, d_voice_dst, n, b->voices, total, b->fs); break;
+			}
 		}
 		b->prof_end();
 		b->launches++;

@@ -70,9 +70,102 @@ KB_D float kb_sincosf_impl(float y, int cosine) {
 	}
 	return cosine ? (float)cos(x) : (float)sin(x);
 }
+// sinf and cosf of the same argument with one shared reduction (each result identical to the separate calls)
+KB_D void kb_sincosf(float y, float& sn, float& cs) {
+	double x = (double)y;
+	if (kb_abstop12(y) < 0x3f4) {
+		const double x2 = x * x;
+		if (kb_abstop12(y) < 0x398) { sn = y; cs = 1.0f; return; }
+		sn = kb_sincos_poly(x, x2, 0, false);
+		cs = kb_sincos_poly(x, x2, 1, false);
+	} else if (kb_abstop12(y) < 0x42f) {
+		const double hpi_inv = 0x1.45F306DC9C883p+23, hpi = 0x1.921FB54442D18p0;
+		const double r = x * hpi_inv;
+		const int n = ((int32_t)r + 0x800000) >> 24;
+		x = KB_MADD(-(double)n, hpi, x);
+		const double s = ((n & 3) == 1 || (n & 3) == 2) ? -1.0 : 1.0;
+		const double xs = x * s, x2 = x * x;
+		sn = kb_sincos_poly(xs, x2, n, (n & 2) != 0);
+		cs = kb_sincos_poly(xs, x2, n ^ 1, (n & 2) != 0);
+	} else { sn = (float)sin(x); cs = (float)cos(x); }
+}
 KB_D float kb_sinf(float y) { return kb_sincosf_impl(y, 0); }
 KB_D float kb_cosf(float y) { return kb_sincosf_impl(y, 1); }
 
-// tanhf: used only on output paths (TB303 soft clip, SynTHX post-fx), where a last-bit difference
-// stays a last-bit difference.  Evaluated in double and rounded once.
-KB_D float kb_tanhf(float x) { return (float)tanh((double)x); }
+// tanhf (TB303 soft clip, SynTHX post-fx): glibc 2.39 still ships the FDLIBM float routines
+// (sysdeps/ieee754/flt-32/s_tanhf.c on top of s_expm1f.c, no FMA variant), restated here operation by operation in
+// fp32; bit-identical to the host libm for every finite float (exhaustive check on the build host).
+KB_D float kb_expm1f(float x) {
+	const float one = 1.0f, huge = 1.0e+30f, tiny = 1.0e-30f, o_threshold = 8.8721679688e+01f,
+	            ln2_hi = 6.9313812256e-01f, ln2_lo = 9.0580006145e-06f, invln2 = 1.4426950216e+00f,
+	            Q1 = -3.3333335072e-02f, Q2 = 1.5873016091e-03f, Q3 = -7.9365076090e-05f, Q4 = 4.0082177293e-06f, Q5 = -2.0109921195e-07f;
+	float y, hi, lo, c = 0.f, t, e, hxs, hfx, r1;
+	int k;
+	uint32_t hx = __float_as_uint(x);
+	const uint32_t xsb = hx & 0x80000000u;
+	hx &= 0x7fffffffu;
+	if (hx >= 0x4195b844u) {                  /* |x| >= 27 ln2 */
+		if (hx >= 0x42b17218u) {
+			if (hx > 0x7f800000u) return x + x;
+			if (hx == 0x7f800000u) return (xsb == 0) ? x : -1.0f;
+			if (x > o_threshold) return huge * huge;
+		}
+		if (xsb != 0) return tiny - one;
+	}
+	if (hx > 0x3eb17218u) {                   /* |x| > 0.5 ln2 */
+		if (hx < 0x3F851592u) {               /* |x| < 1.5 ln2 */
+			if (xsb == 0) { hi = x - ln2_hi; lo = ln2_lo; k = 1; }
+			else { hi = x + ln2_hi; lo = -ln2_lo; k = -1; }
+		} else {
+			k = (int)(invln2 * x + ((xsb == 0) ? 0.5f : -0.5f));
+			t = (float)k;
+			hi = x - t * ln2_hi;
+			lo = t * ln2_lo;
+		}
+		x = hi - lo;
+		c = (hi - x) - lo;
+	} else if (hx < 0x33000000u) {            /* |x| < 2^-25 */
+		t = huge + x;
+		return x - (t - (huge + x));
+	} else k = 0;
+	hfx = 0.5f * x;
+	hxs = x * hfx;
+	r1 = one + hxs * (Q1 + hxs * (Q2 + hxs * (Q3 + hxs * (Q4 + hxs * Q5))));
+	t = 3.0f - r1 * hfx;
+	e = hxs * ((r1 - t) / (6.0f - x * t));
+	if (k == 0) return x - (x * e - hxs);
+	e = (x * (e - c) - c);
+	e -= hxs;
+	if (k == -1) return 0.5f * (x - e) - 0.5f;
+	if (k == 1) { if (x < -0.25f) return -2.0f * (e - (x + 0.5f)); else return one + 2.0f * (x - e); }
+	if (k <= -2 || k > 56) {
+		y = one - (e - x);
+		y = __uint_as_float(__float_as_uint(y) + ((uint32_t)k << 23));
+		return y - one;
+	}
+	if (k < 23) {
+		t = __uint_as_float(0x3f800000u - (0x1000000u >> k));
+		y = t - (e - x);
+		y = __uint_as_float(__float_as_uint(y) + ((uint32_t)k << 23));
+	} else {
+		t = __uint_as_float((uint32_t)(0x7f - k) << 23);
+		y = x - (e + t);
+		y += one;
+		y = __uint_as_float(__float_as_uint(y) + ((uint32_t)k << 23));
+	}
+	return y;
+}
+KB_D float kb_tanhf(float x) {
+	const float one = 1.0f, tiny = 1.0e-30f;
+	float t, z;
+	const int jx = (int)__float_as_uint(x);
+	const int ix = jx & 0x7fffffff;
+	if (ix >= 0x7f800000) return (jx >= 0) ? one / x + one : one / x - one;
+	if (ix < 0x41b00000) {                    /* |x| < 22 */
+		if (ix == 0) return x;
+		if (ix < 0x24000000) return x * (one + x);
+		if (ix >= 0x3f800000) { t = kb_expm1f(2.0f * fabsf(x)); z = one - 2.0f / (t + 2.0f); }
+		else { t = kb_expm1f(-2.0f * fabsf(x)); z = -t / (t + 2.0f); }
+	} else z = one - tiny;
+	return (jx >= 0) ? z : -z;
+}

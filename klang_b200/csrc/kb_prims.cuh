@@ -308,6 +308,59 @@ KB_HD float kb_env_tick(const KbFs& fs, KbEnv& e) {
 	}
 	return e.out;
 }
+// The same Envelope::process over a register-resident scalar state with the breakpoints held elsewhere (shared
+// memory): the breakpoint arrays are only touched when a ramp segment ends, so the per-sample path is a handful of
+// register operations.  Bit-identical to kb_env_tick.
+struct KbEnvR { float r_out, r_target, r_rate, time, timeInc, out; int r_active, stage, point, loop_start, loop_end, npoints; };
+KB_HD void kb_envr_load(KbEnvR& r, const KbEnv& e) {
+	r.r_out = e.r_out; r.r_target = e.r_target; r.r_rate = e.r_rate; r.time = e.time; r.timeInc = e.timeInc; r.out = e.out;
+	r.r_active = e.r_active; r.stage = e.stage; r.point = e.point; r.loop_start = e.loop_start; r.loop_end = e.loop_end; r.npoints = e.npoints;
+}
+KB_HD void kb_envr_store(const KbEnvR& r, KbEnv& e) {
+	e.r_out = r.r_out; e.r_target = r.r_target; e.r_rate = r.r_rate; e.time = r.time; e.out = r.out;
+	e.r_active = r.r_active; e.stage = r.stage; e.point = r.point;
+}
+KB_HD void kbr_set_value(KbEnvR& e, float v) { e.r_out = v; e.r_target = v; e.r_active = 0; }
+KB_HD void kbr_set_target(const KbFs& fs, KbEnvR& e, float x, float y, float time) {
+	e.time = time;
+	e.r_target = y; e.r_active = (e.r_out != y);
+	e.r_rate = fabsf(y - e.r_out) / ((x - time) * fs.f);
+}
+KB_HD float kb_envr_tick(const KbFs& fs, KbEnvR& e, const float* px, const float* py) {
+	const float output = e.r_out;
+	if (e.r_active) {
+		if (e.r_target > e.r_out) {
+			e.r_out += e.r_rate;
+			if (e.r_out >= e.r_target) { e.r_out = e.r_target; e.r_active = 0; }
+		} else {
+			e.r_out -= e.r_rate;
+			if (e.r_out <= e.r_target) { e.r_out = e.r_target; e.r_active = 0; }
+		}
+	}
+	e.out = output;
+	if (e.stage == KB_ENV_SUSTAIN) {
+		e.time += e.timeInc;
+		if (!e.r_active) {
+			const bool loop_active = e.loop_start != -1 && e.loop_end != -1;
+			if (loop_active && (e.point + 1) >= e.loop_end) {
+				e.point = e.loop_start;
+				kbr_set_value(e, py[e.point]);
+				if (e.loop_start != e.loop_end) kbr_set_target(fs, e, px[e.point + 1], py[e.point + 1], px[e.point]);
+			} else if ((e.point + 1) < e.npoints) {
+				if (e.time >= px[e.point + 1]) {
+					e.point++;
+					kbr_set_value(e, py[e.point]);
+					if ((e.point + 1) < e.npoints) kbr_set_target(fs, e, px[e.point + 1], py[e.point + 1], px[e.point]);
+				}
+			} else {
+				e.stage = KB_ENV_OFF;
+			}
+		}
+	} else if (e.stage == KB_ENV_RELEASE) {
+		if (!e.r_active) e.stage = KB_ENV_OFF;
+	}
+	return output;
+}
 // Envelope::at                                                              klang.h:3929-3942
 KB_HD float kb_env_at(const float* px, const float* py, int npoints, float time) {
 	if (npoints == 0) return 0;

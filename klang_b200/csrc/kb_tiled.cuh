@@ -1,0 +1,350 @@
+// klang-b200 — pipelined synth-voice kernels.
+//
+// A voice is a few short recurrences (envelope ramps, the filter) wrapped around work that is a pure function of
+// the sample index (band-limited oscillators on an integer phase ramp, filter coefficients = f(cutoff)).  With
+// only ~1000 voices a lane-per-voice loop leaves the chip idle and is bound by the dependent-issue latency of
+// the whole per-sample expression.  Here a CTA owns G voices, the block is cut into tiles of T samples,
+// and four stages work on four consecutive tiles at once, in lock step (one __syncthreads per tick):
+//   A  recurrences that feed others   warp 0, lane = envelope   tile k     (Envelope::process, klang.h:4018-4051)
+//   B  time-parallel work             warps 2.., thread=(v,t)   tile k-1   (OSM samples, Biquad::set / TB303 coefficients)
+//   C  the filter recurrence          warp 1, lane = voice      tile k-2   (only the 2- / 5-state update is serial)
+//   D  output                         warps 2.., thread=(v,t)   tile k-3   (soft clip, *= adsr, coalesced stores)
+// so a tick costs max(A, B+D, C) instead of their sum, and the serial stages hide behind the parallel one.
+// Arithmetic per sample is the reference's, operation for operation (bit-exact vs the oracle); only the order in
+// which independent samples are computed changes.  Shared rows are padded to T+1 floats so that the lane=voice
+// stages (stride T+1) and the thread=(voice,t) stages (stride 1) are both bank-conflict free; stage hand-over
+// buffers are double (A->B, B->C, C->D) or triple (A->C) buffered.
+#pragma once
+#include "kb_graphs.cuh"
+
+#define KB_TILE_G 8        // voices per CTA
+#define KB_TILE_T 128      // samples per tile
+#define KB_TILE_THREADS 512
+
+struct KbTileRows { float r[KB_TILE_G][KB_TILE_T + 1]; };
+
+struct KbTileCommon {
+	float px[2 * KB_TILE_G][KB_ENV_MAXPTS], py[2 * KB_TILE_G][KB_ENV_MAXPTS];   // envelope breakpoints of the A lanes
+	int active[KB_TILE_G];
+};
+
+// prologue shared by the kernels: active flags, and the envelope lanes (warp 0: lanes 0..G-1 first envelope,
+// lanes G..2G-1 the ADSR) load their scalar state into registers and their breakpoints into shared memory
+template <class VOICE>
+KB_D void kb_tile_prologue(KbTileCommon& c, VOICE* voices, KbVoiceHdr* hdr, int v0, int total) {
+	if (threadIdx.x < KB_TILE_G) {
+		const int v = v0 + threadIdx.x;
+		const int act = (v < total && hdr[v].stage != KB_NOTE_OFF) ? 1 : 0;
+		c.active[threadIdx.x] = act;
+		if (v < total) hdr[v].active = act;
+	}
+	__syncthreads();
+}
+KB_D void kb_tile_load_env(KbTileCommon& c, int slot, const KbEnv& src, KbEnvR& e) {
+	kb_envr_load(e, src);
+	for (int p = 0; p < KB_ENV_MAXPTS; p++) { c.px[slot][p] = src.px[p]; c.py[slot][p] = src.py[p]; }
+}
+
+// ----------------------------------------------------------------------------------- Subtractive / Filter.k
+// Filter.k:29-36.  A: env (cutoff) and adsr.  B: Biquad::Filter::set(cutoff, 10) + LPF::init (klang.h:5584-5600,
+// 5658-5665) and the oscillator sample.  C: Filter::process (klang.h:5605-5612) and `out *= adsr`.  D: stores.
+// Biquad::set is a pure function of (f, Q) and is re-evaluated for every sample; the reference's "unchanged (f,Q)"
+// early-out returns the same coefficients (Q is the constant 10, so the first set after reset() always computes).
+struct KbSubSmem {
+	KbTileCommon c;
+	KbTileRows cut[2], amp[3], b0[2], b1[2], a1[2], a2[2], x[2], out[2];
+	KbOsm osc[KB_TILE_G];
+};
+__global__ void __launch_bounds__(KB_TILE_THREADS) kb_sub_tiled_kernel(KbSubVoice* __restrict__ voices, KbVoiceHdr* __restrict__ hdr,
+                                                                        float* __restrict__ dst, int n, int total, KbFs fs) {
+	constexpr int G = KB_TILE_G, T = KB_TILE_T;
+	extern __shared__ __align__(16) unsigned char kb_smem[];
+	KbSubSmem& S = *reinterpret_cast<KbSubSmem*>(kb_smem);
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int v0 = blockIdx.x * G;
+	kb_tile_prologue(S.c, voices, hdr, v0, total);
+
+	const int role_voice = lane & (G - 1);
+	const bool is_env = warp == 0 && lane < 2 * G && S.c.active[role_voice];
+	const bool is_flt = warp == 1 && lane < G && S.c.active[role_voice];
+	KbEnvR env;
+	float z0 = 0.f, z1 = 0.f, lb0 = 1.f, lb1 = 0.f, la1 = 0.f, la2 = 0.f;
+	if (is_env) kb_tile_load_env(S.c, lane, (lane < G) ? voices[v0 + role_voice].env : voices[v0 + role_voice].adsr, env);
+	if (is_flt) { const KbBiquad& b = voices[v0 + role_voice].filter; z0 = b.z0; z1 = b.z1; lb0 = b.b0; lb1 = b.b1; la1 = b.a1; la2 = b.a2; }
+	if (warp == 2 && lane < G && S.c.active[lane]) S.osc[lane] = voices[v0 + lane].osc;
+	__syncthreads();
+
+	const int ntiles = (n + T - 1) / T;
+	const int wtid = tid - 64, wthreads = KB_TILE_THREADS - 64;      // the B/D worker threads
+	for (int k = 0; k < ntiles + 3; k++) {
+		if (warp == 0) {                                                 // ---- A, tile k
+			if (is_env && k < ntiles) {
+				const int steps = min(T, n - k * T);
+				float* row = (lane < G) ? S.cut[k & 1].r[role_voice] : S.amp[k % 3].r[role_voice];
+				const float* px = S.c.px[lane]; const float* py = S.c.py[lane];
+				for (int t = 0; t < steps; t++) row[t] = kb_envr_tick(fs, env, px, py);
+			}
+		} else if (warp == 1) {                                          // ---- C, tile k-2
+			const int c = k - 2;
+			if (is_flt && c >= 0 && c < ntiles) {
+				const int steps = min(T, n - c * T), v = role_voice;
+				const float *pb0 = S.b0[c & 1].r[v], *pb1 = S.b1[c & 1].r[v], *pa1 = S.a1[c & 1].r[v], *pa2 = S.a2[c & 1].r[v];
+				const float *px = S.x[c & 1].r[v], *pamp = S.amp[c % 3].r[v];
+				float* po = S.out[c & 1].r[v];
+				#pragma unroll 4
+				for (int t = 0; t < steps; t++) {
+					lb0 = pb0[t]; lb1 = pb1[t]; la1 = pa1[t]; la2 = pa2[t];
+					const float in = px[t];
+					const float y = lb0 * in + z0;
+					z0 = lb1 * in - la1 * y + z1;
+					z1 = lb0 * in - la2 * y;
+					po[t] = y * pamp[t];                                     // out *= adsr++   Filter.k:33
+				}
+			}
+		} else {
+			const int b = k - 1, d = k - 3;
+			if (b >= 0 && b < ntiles) {                                      // ---- B, tile k-1
+				const int steps = min(T, n - b * T);
+				for (int item = wtid; item < G * T; item += wthreads) {
+					const int v = item / T, t = item % T;
+					if (t < steps && S.c.active[v]) {
+						const float f = S.cut[b & 1].r[v][t];
+						const float w = f * fs.w;
+						float sin0, cos0;
+						kb_sincosf(w, sin0, cos0);
+						const float a = sin0 / (2.f * 10.f);
+						const float inv = kb_const_inv(1.f + a);
+						S.a1[b & 1].r[v][t] = inv * (-2.f * cos0);
+						S.a2[b & 1].r[v][t] = inv * (1.f - a);
+						S.b0[b & 1].r[v][t] = inv * (1.f - cos0) * 0.5f;
+						S.b1[b & 1].r[v][t] = inv * (1.f - cos0);
+						S.x[b & 1].r[v][t] = kb_osm_at(S.osc[v], (uint32_t)(b * T + t));
+					}
+				}
+			}
+			if (d >= 0 && d < ntiles) {                                      // ---- D, tile k-3
+				const int steps = min(T, n - d * T);
+				for (int item = wtid; item < G * T; item += wthreads) {
+					const int v = item / T, t = item % T;
+					if (t < steps && v0 + v < total) dst[(size_t)(v0 + v) * n + d * T + t] = S.c.active[v] ? S.out[d & 1].r[v][t] : 0.f;
+				}
+			}
+		}
+		__syncthreads();
+	}
+
+	// write the state back
+	if (is_env) {
+		if (lane < G) { kb_envr_store(env, voices[v0 + role_voice].env); voices[v0 + role_voice].filter.f = env.out; voices[v0 + role_voice].filter.Q = 10.f; }
+		else {
+			kb_envr_store(env, voices[v0 + role_voice].adsr);
+			if (env.stage == KB_ENV_OFF) hdr[v0 + role_voice].stage = KB_NOTE_OFF;   // if (adsr.finished()) stop()   Filter.k:34-35
+		}
+	}
+	if (is_flt) {
+		KbBiquad& b = voices[v0 + role_voice].filter;
+		b.z0 = z0; b.z1 = z1; b.b0 = lb0; b.b2 = lb0; b.b1 = lb1; b.a1 = la1; b.a2 = la2;
+	}
+	if (warp == 2 && lane < G && S.c.active[lane]) {
+		KbOsm o = S.osc[lane];
+		kb_osm_advance(o, (uint32_t)n);
+		voices[v0 + lane].osc.offset = o.offset;
+		voices[v0 + lane].osc.state = o.state;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ SuperSaw
+// SuperSaw.k:25-33: seven detuned saws summed (each `/ 7`, in index order) times the ADSR.  A: adsr (tile k).
+// B+D fused (tile k-1): thread = (voice, t) evaluates the seven oscillators in closed form, scales and stores.
+struct KbSsawSmem {
+	KbTileCommon c;
+	KbTileRows amp[2];
+	KbOsm osc[KB_TILE_G][7];
+};
+__global__ void __launch_bounds__(KB_TILE_THREADS) kb_ssaw_tiled_kernel(KbSsawVoice* __restrict__ voices, KbVoiceHdr* __restrict__ hdr,
+                                                                         float* __restrict__ dst, int n, int total, KbFs fs) {
+	constexpr int G = KB_TILE_G, T = KB_TILE_T;
+	extern __shared__ __align__(16) unsigned char kb_smem[];
+	KbSsawSmem& S = *reinterpret_cast<KbSsawSmem*>(kb_smem);
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int v0 = blockIdx.x * G;
+	kb_tile_prologue(S.c, voices, hdr, v0, total);
+	const bool is_env = warp == 0 && lane < G && S.c.active[lane];
+	KbEnvR env;
+	if (is_env) kb_tile_load_env(S.c, lane, voices[v0 + lane].adsr, env);
+	if (tid >= 32 && tid < 32 + G * 7 && S.c.active[(tid - 32) / 7]) S.osc[(tid - 32) / 7][(tid - 32) % 7] = voices[v0 + (tid - 32) / 7].osc[(tid - 32) % 7];
+	__syncthreads();
+	const int ntiles = (n + T - 1) / T;
+	const int wtid = tid - 32, wthreads = KB_TILE_THREADS - 32;
+	for (int k = 0; k < ntiles + 1; k++) {
+		if (warp == 0) {
+			if (is_env && k < ntiles) {
+				const int steps = min(T, n - k * T);
+				float* row = S.amp[k & 1].r[lane];
+				const float* px = S.c.px[lane]; const float* py = S.c.py[lane];
+				for (int t = 0; t < steps; t++) row[t] = kb_envr_tick(fs, env, px, py);
+			}
+		} else {
+			const int b = k - 1;
+			if (b >= 0) {
+				const int steps = min(T, n - b * T);
+				for (int item = wtid; item < G * T; item += wthreads) {
+					const int v = item / T, t = item % T;
+					if (t < steps && v0 + v < total) {
+						float out = 0.f;
+						if (S.c.active[v]) {
+							#pragma unroll
+							for (int j = 0; j < 7; j++) out += kb_osm_at(S.osc[v][j], (uint32_t)(b * T + t)) / 7;
+							out *= S.amp[b & 1].r[v][t];
+						}
+						dst[(size_t)(v0 + v) * n + b * T + t] = out;
+					}
+				}
+			}
+		}
+		__syncthreads();
+	}
+	if (is_env) {
+		kb_envr_store(env, voices[v0 + lane].adsr);
+		if (env.stage == KB_ENV_OFF) hdr[v0 + lane].stage = KB_NOTE_OFF;
+	}
+	if (tid >= 32 && tid < 32 + G * 7 && S.c.active[(tid - 32) / 7]) {
+		KbOsm o = S.osc[(tid - 32) / 7][(tid - 32) % 7];
+		kb_osm_advance(o, (uint32_t)n);
+		voices[v0 + (tid - 32) / 7].osc[(tid - 32) % 7].offset = o.offset;
+		voices[v0 + (tid - 32) / 7].osc[(tid - 32) % 7].state = o.state;
+	}
+}
+
+// --------------------------------------------------------------------------------------------------- TB303
+// TB303.k:103-113.  A: filter envelope and ADSR.  B: oscillator sample and Filter::set coefficients b0, k, g
+// (TB303.k:37-55; polynomials of the cutoff, no transcendental: r and the feedback one-pole are control-rate
+// constants from the host, KbTbBlock).  C: the ladder recurrence with its one-pole feedback (TB303.k:70-79), which
+// parks g*z[3] per sample.  D: the soft clip (tanhf, double divide), `* adsr`, stores.
+// Filter::set only recomputes when (cutoff, resonance, drive) change; its outputs are pure functions of those three, so
+// B evaluates them for every sample and C adopts them exactly when the reference's comparison says "changed".
+struct KbTbSmem {
+	KbTileCommon c;
+	KbTileRows e[2], amp[4], b0[2], kk[2], g[2], x[2], cut[2], y[2];
+	KbOsm osc[KB_TILE_G];
+	KbTbBlock blk[KB_TILE_G];
+	float vf[KB_TILE_G], last_out[KB_TILE_G];
+};
+__global__ void __launch_bounds__(KB_TILE_THREADS) kb_tb_tiled_kernel(KbTbVoice* __restrict__ voices, KbVoiceHdr* __restrict__ hdr,
+                                                                       const KbSynthBlock* __restrict__ blk, float* __restrict__ dst,
+                                                                       int n, int voices_per_inst, int total, KbFs fs) {
+	constexpr int G = KB_TILE_G, T = KB_TILE_T;
+	extern __shared__ __align__(16) unsigned char kb_smem[];
+	KbTbSmem& S = *reinterpret_cast<KbTbSmem*>(kb_smem);
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int v0 = blockIdx.x * G;
+	kb_tile_prologue(S.c, voices, hdr, v0, total);
+	if (warp == 2 && lane < G && v0 + lane < total) {
+		S.blk[lane] = blk[(v0 + lane) / voices_per_inst].tb;
+		if (S.c.active[lane]) {
+			S.osc[lane] = S.blk[lane].is_square ? voices[v0 + lane].square : voices[v0 + lane].saw;
+			S.vf[lane] = voices[v0 + lane].f;
+			S.last_out[lane] = voices[v0 + lane].filter.out;
+		}
+	}
+	const int role_voice = lane & (G - 1);
+	const bool is_env = warp == 0 && lane < 2 * G && S.c.active[role_voice];
+	const bool is_flt = warp == 1 && lane < G && S.c.active[role_voice];
+	KbEnvR env;
+	if (is_env) kb_tile_load_env(S.c, lane, (lane < G) ? voices[v0 + role_voice].env : voices[v0 + role_voice].adsr, env);
+	KbTbFilter F;
+	if (is_flt) F = voices[v0 + role_voice].filter;
+	__syncthreads();
+	const int ntiles = (n + T - 1) / T;
+	const int wtid = tid - 64, wthreads = KB_TILE_THREADS - 64;
+	for (int k = 0; k < ntiles + 3; k++) {
+		if (warp == 0) {                                                 // ---- A, tile k
+			if (is_env && k < ntiles) {
+				const int steps = min(T, n - k * T);
+				float* row = (lane < G) ? S.e[k & 1].r[role_voice] : S.amp[k & 3].r[role_voice];
+				const float* px = S.c.px[lane]; const float* py = S.c.py[lane];
+				for (int t = 0; t < steps; t++) row[t] = kb_envr_tick(fs, env, px, py);
+			}
+		} else if (warp == 1) {                                          // ---- C, tile k-2
+			const int c = k - 2;
+			if (is_flt && c >= 0 && c < ntiles) {
+				const int steps = min(T, n - c * T), v = role_voice;
+				const KbTbBlock B = S.blk[v];
+				for (int t = 0; t < steps; t++) {
+					const float cutoff = S.cut[c & 1].r[v][t];
+					if (F.cutoff != cutoff || F.resonance != B.resonance || F.drive != B.drive) {
+						F.cutoff = cutoff; F.resonance = B.resonance; F.drive = B.drive; F.r = B.r;
+						F.b0 = S.b0[c & 1].r[v][t]; F.k = S.kk[c & 1].r[v][t]; F.g = S.g[c & 1].r[v][t];
+					}
+					if (F.feedback.f != B.hpf_f) { F.feedback.f = B.hpf_f; F.feedback.b0 = B.hpf_b0; F.feedback.b1 = B.hpf_b1; F.feedback.a1 = B.hpf_a1; }   // setHPF  TB303.k:33-35
+					F.in = S.x[c & 1].r[v][t];
+					const float y0 = kb_onepole_tick(F.feedback, F.k * F.z[3]) * 0.9f * F.resonance;
+					const float shaped = (y0 > KB_ROOT2_F) ? KB_ROOT2_F : (y0 < -0.5) ? -0.5f : y0;
+					F.in -= shaped;
+					F.z[0] += 2.f * F.b0 * (F.in - F.z[0] + F.z[1]);
+					F.z[1] += F.b0 * (F.z[0] - 2.f * F.z[1] + F.z[2]);
+					F.z[2] += F.b0 * (F.z[1] - 2.f * F.z[2] + F.z[3]);
+					F.z[3] += F.b0 * (F.z[2] - 2.f * F.z[3]);
+					S.y[c & 1].r[v][t] = F.g * F.z[3];
+				}
+			}
+		} else {
+			const int b = k - 1, d = k - 3;
+			if (b >= 0 && b < ntiles) {                                      // ---- B, tile k-1
+				const int steps = min(T, n - b * T);
+				for (int item = wtid; item < G * T; item += wthreads) {
+					const int v = item / T, t = item % T;
+					if (t < steps && S.c.active[v]) {
+						const KbTbBlock& B = S.blk[v];
+						const float e = S.e[b & 1].r[v][t];
+						float cutoff = (S.vf[v] + B.c0sq_nyq) * (e * e);                 // TB303.k:106
+						if (cutoff > fs.nyquist) cutoff = fs.nyquist;
+						const float fx = cutoff * fs.inv * KB_ROOT2_INV_F;
+						S.b0[b & 1].r[v][t] = (0.00045522346f + 6.1922189f * fx) / (1.f + 12.358354f * fx + 4.4156345f * (fx * fx));
+						float kq = fx*(fx*(fx*(fx*(fx*(fx+7198.6997f)-5837.7917f)-476.47308f)+614.95611f)+213.87126f)+16.998792f;
+						float g = kq * 0.058823529411764705882352941176471f;
+						g = (g - 1.f) * B.r + 1.f;
+						g = (g * (1.f + B.r));
+						kq = kq * B.r;
+						S.kk[b & 1].r[v][t] = kq; S.g[b & 1].r[v][t] = g;
+						S.cut[b & 1].r[v][t] = cutoff;
+						const float osc = kb_osm_at(S.osc[v], (uint32_t)(b * T + t));
+						S.x[b & 1].r[v][t] = B.is_square ? osc * 0.5f : osc;
+					}
+				}
+			}
+			if (d >= 0 && d < ntiles) {                                      // ---- D, tile k-3
+				const int steps = min(T, n - d * T);
+				for (int item = wtid; item < G * T; item += wthreads) {
+					const int v = item / T, t = item % T;
+					if (t < steps && v0 + v < total) {
+						float out = 0.f;
+						if (S.c.active[v]) {
+							const float x = S.y[d & 1].r[v][t];
+							const float hard = (x > 1.f) ? 1.f : (x < -1.f) ? -1.f : x;
+							const float clipped = (float)((double)kb_tanhf(hard * S.blk[v].drive) / S.blk[v].clip_den);   // TB303.k:66-68
+							if (d * T + t == n - 1) S.last_out[v] = clipped;                                              // Filter::out after the block
+							out = clipped * S.amp[d & 3].r[v][t];
+						}
+						dst[(size_t)(v0 + v) * n + d * T + t] = out;
+					}
+				}
+			}
+		}
+		__syncthreads();
+	}
+	if (is_env) {
+		if (lane < G) kb_envr_store(env, voices[v0 + role_voice].env);
+		else {
+			kb_envr_store(env, voices[v0 + role_voice].adsr);
+			if (env.stage == KB_ENV_OFF) hdr[v0 + role_voice].stage = KB_NOTE_OFF;
+		}
+	}
+	if (is_flt) { F.out = S.last_out[role_voice]; voices[v0 + role_voice].filter = F; }
+	if (warp == 2 && lane < G && S.c.active[lane]) {
+		KbOsm o = S.osc[lane];
+		kb_osm_advance(o, (uint32_t)n);
+		KbOsm& dsto = S.blk[lane].is_square ? voices[v0 + lane].square : voices[v0 + lane].saw;
+		dsto.offset = o.offset; dsto.state = o.state;
+	}
+}
