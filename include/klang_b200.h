@@ -106,6 +106,16 @@ int kb_synth_bank_note_off(kb_synth_bank* bank, int instance, int pitch, float v
 int kb_synth_bank_voice_start(kb_synth_bank* bank, int instance, int voice, float pitch, float velocity);
 int kb_synth_bank_voice_release(kb_synth_bank* bank, int instance, int voice, float velocity);
 int kb_synth_bank_voice_stage(kb_synth_bank* bank, int instance, int voice);   /* 0 Onset 1 Sustain 2 Release 3 Off, <0 error */
+/* A block's worth of events in one call, applied in order (what a host's MIDI loop does between process() calls,
+ * templates/juce/synth/Source/PluginProcessor.cpp:169-174).  key = MIDI pitch for NOTE_ON/NOTE_OFF, voice index for
+ * VOICE_START/VOICE_RELEASE, control index for CONTROL (value in `velocity`). */
+#define KB_EV_NOTE_ON 0
+#define KB_EV_NOTE_OFF 1
+#define KB_EV_VOICE_START 2
+#define KB_EV_VOICE_RELEASE 3
+#define KB_EV_CONTROL 4
+typedef struct kb_note_event { int type, instance, key; float pitch, velocity; } kb_note_event;
+int kb_synth_bank_events(kb_synth_bank* bank, int count, const kb_note_event* events);
 /* Synth::process(float*, int) / Stereo::Synth::process(float**, int) for every instance.
  * out = [instances][channels][n] (see flags for the other layouts); out is overwritten.   klang.h:4440-4466, 4830-4858 */
 int kb_synth_bank_process(kb_synth_bank* bank, float* out, int n, unsigned flags);
@@ -113,6 +123,8 @@ int kb_synth_bank_sync(kb_synth_bank* bank);
 int kb_synth_bank_set_stream(kb_synth_bank* bank, void* cuda_stream);
 long long kb_synth_bank_launches(const kb_synth_bank* bank);
 long long kb_synth_bank_state_bytes(const kb_synth_bank* bank);
+/* bytes moved over PCIe by this bank so far: event state uploads (h2d), state fetches and host-buffer outputs (d2h) */
+int kb_synth_bank_transfer_bytes(const kb_synth_bank* bank, long long* h2d, long long* d2h);
 int kb_synth_bank_profile(kb_synth_bank* bank, int enable);
 int kb_synth_bank_profile_read(kb_synth_bank* bank, double* kernel_ms, long long* kernel_launches);
 

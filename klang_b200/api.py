@@ -34,9 +34,10 @@ SYMBOLS = [
     ("kb_synth_bank_set_control", _i, [_vp, _i, _i, _f]), ("kb_synth_bank_get_control", _i, [_vp, _i, _i, _fp]),
     ("kb_synth_bank_note_on", _i, [_vp, _i, _i, _f]), ("kb_synth_bank_note_off", _i, [_vp, _i, _i, _f]),
     ("kb_synth_bank_voice_start", _i, [_vp, _i, _i, _f, _f]), ("kb_synth_bank_voice_release", _i, [_vp, _i, _i, _f]),
-    ("kb_synth_bank_voice_stage", _i, [_vp, _i, _i]),
+    ("kb_synth_bank_voice_stage", _i, [_vp, _i, _i]), ("kb_synth_bank_events", _i, [_vp, _i, _vp]),
     ("kb_synth_bank_process", _i, [_vp, _vp, _i, _u]), ("kb_synth_bank_sync", _i, [_vp]), ("kb_synth_bank_set_stream", _i, [_vp, _vp]),
     ("kb_synth_bank_launches", _ll, [_vp]), ("kb_synth_bank_state_bytes", _ll, [_vp]),
+    ("kb_synth_bank_transfer_bytes", _i, [_vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     ("kb_synth_bank_profile", _i, [_vp, _i]), ("kb_synth_bank_profile_read", _i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     ("kb_prim_osc", _i, [_i, _i, _f, _f, _f, _f, _i, _vp]),
     ("kb_prim_filter", _i, [_i, _i, _vp, _vp, _f, _i, _vp, _vp, _vp]),
@@ -44,6 +45,11 @@ SYMBOLS = [
     ("kb_prim_adsr", _i, [_f, _f, _f, _f, _f, _i, _i, _vp, _vp]),
     ("kb_prim_math", _i, [_i, _i, _vp, _vp]),
 ]
+
+
+EV_NOTE_ON, EV_NOTE_OFF, EV_VOICE_START, EV_VOICE_RELEASE, EV_CONTROL = range(5)
+# numpy mirror of kb_note_event
+EVENT_DTYPE = np.dtype([("type", np.int32), ("instance", np.int32), ("key", np.int32), ("pitch", np.float32), ("velocity", np.float32)])
 
 
 class KlangB200Error(RuntimeError):
@@ -188,6 +194,11 @@ class SynthBank:
     def voice_stage(self, voice, instance=0):
         return _check(lib().kb_synth_bank_voice_stage(self.h, instance, voice), "kb_synth_bank_voice_stage")
 
+    def events(self, ev):
+        """Apply a batch of events in order. ev: numpy array of EVENT_DTYPE."""
+        ev = np.ascontiguousarray(ev, EVENT_DTYPE)
+        _check(lib().kb_synth_bank_events(self.h, len(ev), ev.ctypes.data), "kb_synth_bank_events")
+
     def out_shape(self, n, flags=0):
         if flags & PER_VOICE:
             return (self.instances, self.voices, self.channels, n)
@@ -213,6 +224,12 @@ class SynthBank:
     @property
     def state_bytes(self):
         return lib().kb_synth_bank_state_bytes(self.h)
+
+    def transfer_bytes(self):
+        """(host-to-device, device-to-host) bytes this bank has moved so far."""
+        a, b = C.c_longlong(), C.c_longlong()
+        _check(lib().kb_synth_bank_transfer_bytes(self.h, C.byref(a), C.byref(b)), "kb_synth_bank_transfer_bytes")
+        return a.value, b.value
 
     def profile(self, enable=True):
         _check(lib().kb_synth_bank_profile(self.h, int(enable)), "kb_synth_bank_profile")

@@ -245,29 +245,82 @@ struct kb_synth_bank : kb_bank_base {
 	int graph = 0, instances = 0, voices = 0, channels = 1, ncontrols = 0;
 	size_t voice_bytes = 0;
 	std::vector<KbControl> controls;              // [instances][KB_MAX_CONTROLS], host-owned
-	std::vector<KbVoiceHdr> hdr; std::vector<unsigned char> vstate;
+	// host mirror in pinned memory (asynchronous, full-speed copies); dirty voices are uploaded packed
+	KbVoiceHdr* hdr = nullptr; unsigned char* vstate = nullptr; size_t hdr_count = 0, vstate_bytes = 0;
+	unsigned char* staging = nullptr; int* staging_index = nullptr;             // pinned
+	unsigned char* d_staging = nullptr; int* d_staging_index = nullptr;
+	std::vector<unsigned char> voice_dirty; std::vector<int> dirty_list; bool all_dirty = true;
+	long long h2d_bytes = 0, d2h_bytes = 0;                                     // state traffic so far (for the e2e accounting)
+	bool hdr_stale = false, vstate_stale = false;                               // finer than host_stale: what the device has changed
+	// graphs whose Note::on() rewrites every field the device evolves: a start needs no state fetch (Filter.k:15-23, SuperSaw.k:12-19)
+	bool on_overwrites() const { return graph == KB_SY_SUBTRACTIVE || graph == KB_SY_FILTER_K || graph == KB_SY_SUPERSAW; }
 	std::vector<unsigned> noteOns, noteStart;     // Notes::noteOns / noteStart  klang.h:4333-4334
+	void mark_dirty(int v) { dirty = true; if (!voice_dirty[v]) { voice_dirty[v] = 1; dirty_list.push_back(v); } }
 	std::vector<KbSynthBlock> blk; bool blk_dirty = true;
 	KbVoiceHdr* d_hdr = nullptr; unsigned char* d_vstate = nullptr; KbSynthBlock* d_blk = nullptr;
 	float *d_scratch = nullptr, *d_out = nullptr, *d_adsr = nullptr, *d_mix = nullptr;
 	int total() const { return instances * voices; }
-	template <class T> T& vs(int v) { return *reinterpret_cast<T*>(vstate.data() + (size_t)v * voice_bytes); }
+	template <class T> T& vs(int v) { return *reinterpret_cast<T*>(vstate + (size_t)v * voice_bytes); }
 	KbControl* ctl(int inst) { return controls.data() + (size_t)inst * KB_MAX_CONTROLS; }
 };
 
-static int sy_fetch(kb_synth_bank* b) {
-	if (!b->host_stale) return KB_OK;
+static int sy_fetch(kb_synth_bank* b, bool need_hdr = true, bool need_vstate = true) {
+	const bool get_hdr = need_hdr && b->hdr_stale, get_vs = need_vstate && b->vstate_stale;
+	if (!get_hdr && !get_vs) return KB_OK;
 	KB_CUDA(cudaSetDevice(b->device));
-	KB_CUDA(cudaMemcpyAsync(b->hdr.data(), b->d_hdr, b->hdr.size() * sizeof(KbVoiceHdr), cudaMemcpyDeviceToHost, b->stream));
-	KB_CUDA(cudaMemcpyAsync(b->vstate.data(), b->d_vstate, b->vstate.size(), cudaMemcpyDeviceToHost, b->stream));
-	KB_CUDA(cudaStreamSynchronize(b->stream));
-	b->host_stale = false;
+	if (get_vs && !b->dirty_list.empty()) {
+		// voices re-written since the last block (their mirror copy is newer than the device's) must survive the fetch
+		KB_CUDA(cudaStreamSynchronize(b->stream));
+		std::vector<unsigned char> keep(b->dirty_list.size() * b->voice_bytes);
+		for (size_t k = 0; k < b->dirty_list.size(); k++) memcpy(keep.data() + k * b->voice_bytes, b->vstate + (size_t)b->dirty_list[k] * b->voice_bytes, b->voice_bytes);
+		KB_CUDA(cudaMemcpy(b->vstate, b->d_vstate, b->vstate_bytes, cudaMemcpyDeviceToHost));
+		for (size_t k = 0; k < b->dirty_list.size(); k++) memcpy(b->vstate + (size_t)b->dirty_list[k] * b->voice_bytes, keep.data() + k * b->voice_bytes, b->voice_bytes);
+		b->d2h_bytes += (long long)b->vstate_bytes;
+		b->vstate_stale = false;
+	} else if (get_vs) {
+		KB_CUDA(cudaMemcpyAsync(b->vstate, b->d_vstate, b->vstate_bytes, cudaMemcpyDeviceToHost, b->stream));
+		b->d2h_bytes += (long long)b->vstate_bytes;
+	}
+	if (get_hdr) {
+		// (headers of re-started voices: stage/pitch/velocity were set by the host after the block, keep them)
+		std::vector<KbVoiceHdr> keep;
+		for (int v : b->dirty_list) keep.push_back(b->hdr[v]);
+		KB_CUDA(cudaMemcpyAsync(b->hdr, b->d_hdr, b->hdr_count * sizeof(KbVoiceHdr), cudaMemcpyDeviceToHost, b->stream));
+		KB_CUDA(cudaStreamSynchronize(b->stream));
+		for (size_t k = 0; k < keep.size(); k++) b->hdr[b->dirty_list[k]] = keep[k];
+		b->d2h_bytes += (long long)(b->hdr_count * sizeof(KbVoiceHdr));
+		b->hdr_stale = false;
+	}
+	if (get_vs) { KB_CUDA(cudaStreamSynchronize(b->stream)); b->vstate_stale = false; }
+	b->host_stale = b->hdr_stale || b->vstate_stale;
 	return KB_OK;
 }
 static int sy_upload(kb_synth_bank* b) {
 	if (b->dirty) {
-		KB_CUDA(cudaMemcpyAsync(b->d_hdr, b->hdr.data(), b->hdr.size() * sizeof(KbVoiceHdr), cudaMemcpyHostToDevice, b->stream));
-		KB_CUDA(cudaMemcpyAsync(b->d_vstate, b->vstate.data(), b->vstate.size(), cudaMemcpyHostToDevice, b->stream));
+		const size_t rec = sizeof(KbVoiceHdr) + b->voice_bytes;
+		// a full copy is only legal while the whole mirror is current; otherwise only the re-written voices may travel
+		const bool mirror_current = !b->hdr_stale && !b->vstate_stale;
+		if (!b->all_dirty && !(mirror_current && b->dirty_list.size() * 4 > b->hdr_count)) {
+			const int count = (int)b->dirty_list.size();
+			for (int k = 0; k < count; k++) {
+				const int v = b->dirty_list[k];
+				b->staging_index[k] = v;
+				memcpy(b->staging + (size_t)k * rec, b->hdr + v, sizeof(KbVoiceHdr));
+				memcpy(b->staging + (size_t)k * rec + sizeof(KbVoiceHdr), b->vstate + (size_t)v * b->voice_bytes, b->voice_bytes);
+			}
+			KB_CUDA(cudaMemcpyAsync(b->d_staging, b->staging, (size_t)count * rec, cudaMemcpyHostToDevice, b->stream));
+			KB_CUDA(cudaMemcpyAsync(b->d_staging_index, b->staging_index, (size_t)count * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+			const int words = count * (int)(rec / 4);
+			kb_scatter_voices_kernel<<<std::min(148, (words + 255) / 256), 256, 0, b->stream>>>(b->d_staging, b->d_staging_index, count, (int)b->voice_bytes, b->d_hdr, b->d_vstate);
+			b->launches++;
+			b->h2d_bytes += (long long)count * (long long)(rec + sizeof(int));
+		} else {
+			KB_CUDA(cudaMemcpyAsync(b->d_hdr, b->hdr, b->hdr_count * sizeof(KbVoiceHdr), cudaMemcpyHostToDevice, b->stream));
+			KB_CUDA(cudaMemcpyAsync(b->d_vstate, b->vstate, b->vstate_bytes, cudaMemcpyHostToDevice, b->stream));
+			b->h2d_bytes += (long long)(b->hdr_count * sizeof(KbVoiceHdr) + b->vstate_bytes);
+		}
+		for (int v : b->dirty_list) b->voice_dirty[v] = 0;
+		b->dirty_list.clear(); b->all_dirty = false;
 	}
 	if (b->blk_dirty) {
 		for (int i = 0; i < b->instances; i++) {
@@ -277,8 +330,9 @@ static int sy_upload(kb_synth_bank* b) {
 			if (b->graph == KB_SY_SYNTHX) { k.sx_tr_at = kb_sx_tr_at(b->ctl(i)[2].value); k.sx_dt_at = kb_sx_dt_at(b->ctl(i)[1].value); }
 		}
 		KB_CUDA(cudaMemcpyAsync(b->d_blk, b->blk.data(), b->blk.size() * sizeof(KbSynthBlock), cudaMemcpyHostToDevice, b->stream));
+		KB_CUDA(cudaStreamSynchronize(b->stream));      // blk is pageable and may be rewritten by the next control change
 	}
-	if (b->dirty || b->blk_dirty) KB_CUDA(cudaStreamSynchronize(b->stream));
+	// the pinned mirror / staging buffers are not touched again before the next fetch, which joins the stream first
 	b->dirty = false; b->blk_dirty = false;
 	return KB_OK;
 }
@@ -313,8 +367,17 @@ extern "C" kb_synth_bank* kb_synth_bank_create(int graph, int instances, int voi
 		}
 	}
 	const int total = b->total();
-	b->hdr.assign(total, KbVoiceHdr{ KB_NOTE_OFF, 0.f, 0.f, 0 });
-	b->vstate.assign((size_t)total * b->voice_bytes, 0);
+	b->hdr_count = total; b->vstate_bytes = (size_t)total * b->voice_bytes;
+	if (cudaSetDevice(device) != cudaSuccess || cudaHostAlloc((void**)&b->hdr, total * sizeof(KbVoiceHdr), cudaHostAllocDefault) != cudaSuccess ||
+	    cudaHostAlloc((void**)&b->vstate, b->vstate_bytes, cudaHostAllocDefault) != cudaSuccess ||
+	    cudaHostAlloc((void**)&b->staging, (size_t)(total + 1) * (sizeof(KbVoiceHdr) + b->voice_bytes), cudaHostAllocDefault) != cudaSuccess ||
+	    cudaHostAlloc((void**)&b->staging_index, (size_t)(total + 1) * sizeof(int), cudaHostAllocDefault) != cudaSuccess) {
+		kb_fail(KB_ECUDA, std::string("kb_synth_bank_create: pinned host allocation: ") + cudaGetErrorString(cudaGetLastError()));
+		kb_synth_bank_destroy(b); return nullptr;
+	}
+	for (int v = 0; v < total; v++) b->hdr[v] = KbVoiceHdr{ KB_NOTE_OFF, 0.f, 0.f, 0 };
+	memset(b->vstate, 0, b->vstate_bytes);
+	b->voice_dirty.assign(total, 0);
 	b->noteOns.assign(instances, 0u); b->noteStart.assign(total, 0u);
 	b->blk.assign(instances, KbSynthBlock());
 	for (int v = 0; v < total; v++) {
@@ -326,14 +389,12 @@ extern "C" kb_synth_bank* kb_synth_bank_create(int graph, int instances, int voi
 		}
 	}
 	bool ok = cudaSetDevice(device) == cudaSuccess;
-	// the pipelined kernels stage ~75 KB of hand-over buffers per CTA in shared memory
-	ok = ok && cudaFuncSetAttribute(kb_sub_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KbSubSmem)) == cudaSuccess;
-	ok = ok && cudaFuncSetAttribute(kb_ssaw_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KbSsawSmem)) == cudaSuccess;
-	ok = ok && cudaFuncSetAttribute(kb_tb_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KbTbSmem)) == cudaSuccess;
 	ok = ok && cudaStreamCreateWithFlags(&b->own_stream, cudaStreamNonBlocking) == cudaSuccess;
 	b->stream = b->own_stream;
 	ok = ok && dev_alloc(&b->d_hdr, total) == cudaSuccess;
-	ok = ok && dev_alloc(&b->d_vstate, b->vstate.size()) == cudaSuccess;
+	ok = ok && dev_alloc(&b->d_vstate, b->vstate_bytes) == cudaSuccess;
+	ok = ok && dev_alloc(&b->d_staging, (size_t)(total + 1) * (sizeof(KbVoiceHdr) + b->voice_bytes)) == cudaSuccess;
+	ok = ok && dev_alloc(&b->d_staging_index, (size_t)(total + 1)) == cudaSuccess;
 	ok = ok && dev_alloc(&b->d_blk, instances) == cudaSuccess;
 	ok = ok && dev_alloc(&b->d_scratch, (size_t)total * b->channels * max_block) == cudaSuccess;
 	ok = ok && dev_alloc(&b->d_out, (size_t)instances * b->channels * max_block) == cudaSuccess;
@@ -347,6 +408,8 @@ extern "C" void kb_synth_bank_destroy(kb_synth_bank* b) {
 	cudaSetDevice(b->device);
 	if (b->stream) cudaStreamSynchronize(b->stream);
 	b->prof_free();
+	cudaFreeHost(b->hdr); cudaFreeHost(b->vstate); cudaFreeHost(b->staging); cudaFreeHost(b->staging_index);
+	cudaFree(b->d_staging); cudaFree(b->d_staging_index);
 	cudaFree(b->d_hdr); cudaFree(b->d_vstate); cudaFree(b->d_blk); cudaFree(b->d_scratch); cudaFree(b->d_out); cudaFree(b->d_adsr); cudaFree(b->d_mix);
 	if (b->own_stream) cudaStreamDestroy(b->own_stream);
 	delete b;
@@ -356,7 +419,8 @@ extern "C" int kb_synth_bank_instances(const kb_synth_bank* b) { return b ? b->i
 extern "C" int kb_synth_bank_voices(const kb_synth_bank* b) { return b ? b->voices : KB_EINVAL; }
 extern "C" int kb_synth_bank_num_controls(const kb_synth_bank* b) { return b ? b->ncontrols : KB_EINVAL; }
 extern "C" long long kb_synth_bank_launches(const kb_synth_bank* b) { return b ? b->launches : 0; }
-extern "C" long long kb_synth_bank_state_bytes(const kb_synth_bank* b) { return b ? (long long)(b->hdr.size() * sizeof(KbVoiceHdr) + b->vstate.size()) : 0; }
+extern "C" long long kb_synth_bank_state_bytes(const kb_synth_bank* b) { return b ? (long long)(b->hdr_count * sizeof(KbVoiceHdr) + b->vstate_bytes) : 0; }
+extern "C" int kb_synth_bank_transfer_bytes(const kb_synth_bank* b, long long* h2d, long long* d2h) { if (!b) return kb_fail(KB_EINVAL, "null bank"); if (h2d) *h2d = b->h2d_bytes; if (d2h) *d2h = b->d2h_bytes; return KB_OK; }
 extern "C" int kb_synth_bank_profile(kb_synth_bank* b, int enable) { if (!b) return kb_fail(KB_EINVAL, "null bank"); cudaSetDevice(b->device); cudaStreamSynchronize(b->stream); b->profiling = enable != 0; b->prof_used = 0; return KB_OK; }
 extern "C" int kb_synth_bank_profile_read(kb_synth_bank* b, double* ms, long long* count) { if (!b) return kb_fail(KB_EINVAL, "null bank"); cudaSetDevice(b->device); return b->prof_read(ms, count); }
 extern "C" int kb_synth_bank_sync(kb_synth_bank* b) { if (!b) return kb_fail(KB_EINVAL, "null bank"); KB_CUDA(cudaSetDevice(b->device)); KB_CUDA(cudaStreamSynchronize(b->stream)); return KB_OK; }
@@ -391,7 +455,7 @@ static void sy_start(kb_synth_bank* b, int inst, int voice, float pitch, float v
 	case KB_SY_SYNTHX: kb_sx_on(b->fs, c, b->vs<KbSxVoice>(v), pitch); break;
 	}
 	h.stage = KB_NOTE_SUSTAIN;
-	b->dirty = true;
+	b->mark_dirty(v);
 }
 // NoteBase::release: Off stays Off; otherwise stage = Release; off(velocity)     klang.h:4265-4275
 static void sy_release(kb_synth_bank* b, int inst, int voice) {
@@ -405,11 +469,11 @@ static void sy_release(kb_synth_bank* b, int inst, int voice) {
 	case KB_SY_TB303: kb_adsr_release(b->fs, b->vs<KbTbVoice>(v).adsr); break;                               // TB303.k:99-101
 	case KB_SY_SYNTHX: kb_adsr_release(b->fs, b->vs<KbSxVoice>(v).adsr); break;                              // SynTHX.k:163-165
 	}
-	b->dirty = true;
+	b->mark_dirty(v);
 }
 // Notes::assign: first Off voice, else the oldest Released, else the oldest      klang.h:4336-4372
 static int sy_assign(kb_synth_bank* b, int inst) {
-	const KbVoiceHdr* h = b->hdr.data() + (size_t)inst * b->voices;
+	const KbVoiceHdr* h = b->hdr + (size_t)inst * b->voices;
 	unsigned* start = b->noteStart.data() + (size_t)inst * b->voices;
 	unsigned& ons = b->noteOns[inst];
 	for (int i = 0; i < b->voices; i++) if (h[i].stage == KB_NOTE_OFF) { start[i] = ons++; return i; }
@@ -423,7 +487,7 @@ static int sy_assign(kb_synth_bank* b, int inst) {
 }
 extern "C" int kb_synth_bank_note_on(kb_synth_bank* b, int inst, int pitch, float velocity) {
 	if (!b || inst < 0 || inst >= b->instances) return kb_fail(KB_EINVAL, "kb_synth_bank_note_on: bad argument");
-	int rc = sy_fetch(b); if (rc) return rc;
+	int rc = sy_fetch(b, true, !b->on_overwrites()); if (rc) return rc;
 	const int n = sy_assign(b, inst);
 	sy_start(b, inst, n, (float)pitch, velocity);
 	return n;
@@ -440,7 +504,7 @@ extern "C" int kb_synth_bank_note_off(kb_synth_bank* b, int inst, int pitch, flo
 }
 extern "C" int kb_synth_bank_voice_start(kb_synth_bank* b, int inst, int voice, float pitch, float velocity) {
 	if (!b || inst < 0 || inst >= b->instances || voice < 0 || voice >= b->voices) return kb_fail(KB_EINVAL, "kb_synth_bank_voice_start: bad argument");
-	int rc = sy_fetch(b); if (rc) return rc;
+	int rc = sy_fetch(b, false, !b->on_overwrites()); if (rc) return rc;
 	sy_start(b, inst, voice, pitch, velocity);
 	return KB_OK;
 }
@@ -453,8 +517,25 @@ extern "C" int kb_synth_bank_voice_release(kb_synth_bank* b, int inst, int voice
 }
 extern "C" int kb_synth_bank_voice_stage(kb_synth_bank* b, int inst, int voice) {
 	if (!b || inst < 0 || inst >= b->instances || voice < 0 || voice >= b->voices) return kb_fail(KB_EINVAL, "kb_synth_bank_voice_stage: bad argument");
-	int rc = sy_fetch(b); if (rc) return rc;
+	int rc = sy_fetch(b, true, false); if (rc) return rc;
 	return b->hdr[(size_t)inst * b->voices + voice].stage;
+}
+
+extern "C" int kb_synth_bank_events(kb_synth_bank* b, int count, const kb_note_event* ev) {
+	if (!b || count < 0 || (count && !ev)) return kb_fail(KB_EINVAL, "kb_synth_bank_events: bad argument");
+	for (int i = 0; i < count; i++) {
+		int rc = KB_EINVAL;
+		switch (ev[i].type) {
+		case KB_EV_NOTE_ON: rc = kb_synth_bank_note_on(b, ev[i].instance, ev[i].key, ev[i].velocity); if (rc > 0) rc = 0; break;
+		case KB_EV_NOTE_OFF: rc = kb_synth_bank_note_off(b, ev[i].instance, ev[i].key, ev[i].velocity); break;
+		case KB_EV_VOICE_START: rc = kb_synth_bank_voice_start(b, ev[i].instance, ev[i].key, ev[i].pitch, ev[i].velocity); break;
+		case KB_EV_VOICE_RELEASE: rc = kb_synth_bank_voice_release(b, ev[i].instance, ev[i].key, ev[i].velocity); break;
+		case KB_EV_CONTROL: rc = kb_synth_bank_set_control(b, ev[i].instance, ev[i].key, ev[i].velocity); break;
+		default: return kb_fail(KB_EINVAL, "kb_synth_bank_events: unknown event type");
+		}
+		if (rc < 0) return rc;
+	}
+	return KB_OK;
 }
 
 extern "C" int kb_synth_bank_process(kb_synth_bank* b, float* out, int n, unsigned flags) {
@@ -491,15 +572,32 @@ extern "C" int kb_synth_bank_process(kb_synth_bank* b, float* out, int n, unsign
 				kb_voice_kernel<KB_SY_TB303, KbTbVoice><<<blocks, 128, 0, st>>>((KbTbVoice*)b->d_vstate, b->d_hdr, b->d_blk, d_voice_dst, n, b->voices, total, b->fs); break;
 			}
 		} else {
-			const int blocks = (total + KB_TILE_G - 1) / KB_TILE_G;
-			switch (b->graph) {
-			case KB_SY_SUBTRACTIVE: case KB_SY_FILTER_K:
-				kb_sub_tiled_kernel<<<blocks, KB_TILE_THREADS, sizeof(KbSubSmem), st>>>((KbSubVoice*)b->d_vstate, b->d_hdr, d_voice_dst, n, total, b->fs); break;
-			case KB_SY_SUPERSAW:
-				kb_ssaw_tiled_kernel<<<blocks, KB_TILE_THREADS, sizeof(KbSsawSmem), st>>>((KbSsawVoice*)b->d_vstate, b->d_hdr, d_voice_dst, n, total, b->fs); break;
-			case KB_SY_TB303:
-				kb_tb_tiled_kernel<<<blocks, KB_TILE_THREADS, sizeof(KbTbSmem), st>>>((KbTbVoice*)b->d_vstate, b->d_hdr, b->d_blk, d_voice_dst, n, b->voices, total, b->fs); break;
+			// voices per CTA: as many as still leave >= ~100 CTAs (the serial stages cost the same for any G), KB_TILE_G overrides
+			static const int force_g = getenv("KB_TILE_G") ? atoi(getenv("KB_TILE_G")) : 0;
+			const bool sub = b->graph == KB_SY_SUBTRACTIVE || b->graph == KB_SY_FILTER_K;
+			int g = sub ? (total >= 1600 ? 16 : total >= 800 ? 8 : 4) : (b->graph == KB_SY_SUPERSAW ? (total >= 1024 ? 8 : 2) : (total >= 800 ? 8 : 4));
+			if (force_g) g = force_g;
+#define KB_LAUNCH_TILED(KERNEL, SMEM, GG, NT, ...)                                                                                   \
+	do {                                                                                                                             \
+		static bool attr_set = false;                                                                                                \
+		if (!attr_set) { cudaFuncSetAttribute(KERNEL<GG, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SMEM<GG>)); attr_set = true; } \
+		KERNEL<GG, NT><<<(total + GG - 1) / GG, NT, sizeof(SMEM<GG>), st>>>(__VA_ARGS__);                                            \
+	} while (0)
+			if (sub) {
+				KbSubVoice* vs = (KbSubVoice*)b->d_vstate;
+				if (g >= 16) KB_LAUNCH_TILED(kb_sub_tiled_kernel, KbSubSmem, 16, 1024, vs, b->d_hdr, d_voice_dst, n, total, b->fs);
+				else if (g >= 8) KB_LAUNCH_TILED(kb_sub_tiled_kernel, KbSubSmem, 8, 512, vs, b->d_hdr, d_voice_dst, n, total, b->fs);
+				else KB_LAUNCH_TILED(kb_sub_tiled_kernel, KbSubSmem, 4, 320, vs, b->d_hdr, d_voice_dst, n, total, b->fs);
+			} else if (b->graph == KB_SY_SUPERSAW) {
+				KbSsawVoice* vs = (KbSsawVoice*)b->d_vstate;
+				if (g >= 8) KB_LAUNCH_TILED(kb_ssaw_tiled_kernel, KbSsawSmem, 8, 1024, vs, b->d_hdr, d_voice_dst, n, total, b->fs);
+				else KB_LAUNCH_TILED(kb_ssaw_tiled_kernel, KbSsawSmem, 2, 288, vs, b->d_hdr, d_voice_dst, n, total, b->fs);
+			} else {
+				KbTbVoice* vs = (KbTbVoice*)b->d_vstate;
+				if (g >= 8) KB_LAUNCH_TILED(kb_tb_tiled_kernel, KbTbSmem, 8, 512, vs, b->d_hdr, b->d_blk, d_voice_dst, n, b->voices, total, b->fs);
+				else KB_LAUNCH_TILED(kb_tb_tiled_kernel, KbTbSmem, 4, 320, vs, b->d_hdr, b->d_blk, d_voice_dst, n, b->voices, total, b->fs);
 			}
+#undef KB_LAUNCH_TILED
 		}
 		b->prof_end();
 		b->launches++;
@@ -516,10 +614,11 @@ extern "C" int kb_synth_bank_process(kb_synth_bank* b, float* out, int n, unsign
 		b->launches++;
 	}
 	KB_CUDA(cudaGetLastError());
-	b->host_stale = true;
+	b->host_stale = true; b->hdr_stale = true; b->vstate_stale = true;
 	if (!dev) {
 		KB_CUDA(cudaMemcpyAsync(out, d_result, out_floats * sizeof(float), cudaMemcpyDeviceToHost, st));
 		KB_CUDA(cudaStreamSynchronize(st));
+		b->d2h_bytes += (long long)(out_floats * sizeof(float));
 	}
 	return KB_OK;
 }

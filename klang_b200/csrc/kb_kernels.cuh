@@ -67,21 +67,36 @@ __global__ void __launch_bounds__(128) kb_voice_kernel(VOICE* __restrict__ voice
 // Synth::process voice loop + mix (klang.h:4450-4456 / 4842-4848): thread = (instance, sample).  Voices are
 // combined sequentially in voice-index order, exactly as the reference sweeps them: mono Note::process
 // ASSIGNS (the last active voice wins), stereo / KB_MIX_SUM accumulates in fp32.
-__global__ void kb_mix_kernel(const float* __restrict__ scratch, const KbVoiceHdr* __restrict__ hdr, float* __restrict__ out,
-                              int n, int voices, int sum_mode) {
+__global__ void __launch_bounds__(256) kb_mix_kernel(const float* __restrict__ scratch, const KbVoiceHdr* __restrict__ hdr, float* __restrict__ out,
+                                                     int n, int voices, int sum_mode) {
+	__shared__ int s_active[KB_MAX_VOICES];
 	const int inst = blockIdx.y;
+	for (int v = threadIdx.x; v < voices; v += blockDim.x) s_active[v] = hdr[(size_t)inst * voices + v].active;
+	__syncthreads();
 	const int t = blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= n) return;
 	float acc = 0.f;
-	const KbVoiceHdr* h = hdr + (size_t)inst * voices;
 	const float* s = scratch + (size_t)inst * voices * n + t;
-	for (int v = 0; v < voices; v++) {
-		if (h[v].active) {
-			const float x = s[(size_t)v * n];
-			acc = sum_mode ? acc + x : x;
-		}
+	for (int v0 = 0; v0 < voices; v0 += 8) {
+		float x[8];
+		#pragma unroll
+		for (int j = 0; j < 8; j++) x[j] = (v0 + j < voices && s_active[v0 + j]) ? __ldcs(s + (size_t)(v0 + j) * n) : 0.f;   // 8 loads in flight
+		#pragma unroll
+		for (int j = 0; j < 8; j++) if (v0 + j < voices && s_active[v0 + j]) acc = sum_mode ? acc + x[j] : x[j];              // combined in voice order
 	}
 	out[(size_t)inst * n + t] = acc;
+}
+
+// event upload: dirty voices travel packed in one staging buffer [count][hdr | blob] and are scattered to their slots
+__global__ void kb_scatter_voices_kernel(const unsigned char* __restrict__ staging, const int* __restrict__ index, int count, int voice_bytes,
+                                         KbVoiceHdr* __restrict__ hdr, unsigned char* __restrict__ vstate) {
+	const int rec_words = (int)(sizeof(KbVoiceHdr) + voice_bytes) / 4, hdr_words = (int)sizeof(KbVoiceHdr) / 4;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count * rec_words; i += gridDim.x * blockDim.x) {
+		const int k = i / rec_words, w = i % rec_words, v = index[k];
+		const unsigned val = reinterpret_cast<const unsigned*>(staging)[i];
+		if (w < hdr_words) reinterpret_cast<unsigned*>(hdr + v)[w] = val;
+		else reinterpret_cast<unsigned*>(vstate + (size_t)v * voice_bytes)[w - hdr_words] = val;
+	}
 }
 
 // Sum of the per-instance outputs in instance order: the bank mix [channels][n] that is reduced across GPUs.
@@ -117,9 +132,10 @@ __global__ void kb_sx_adsr_kernel(KbSxVoice* __restrict__ voices, KbVoiceHdr* __
 	const int stage = hdr[v].stage;
 	hdr[v].active = stage != KB_NOTE_OFF;
 	if (stage == KB_NOTE_OFF) return;
-	KbEnv e = voices[v].adsr;
-	for (int t = 0; t < n; t++) adsr[(size_t)v * n + t] = kb_env_tick(fs, e);
-	voices[v].adsr = e;
+	KbEnvR e;
+	kb_envr_load(e, voices[v].adsr);
+	kb_envr_run(fs, e, voices[v].adsr.px, voices[v].adsr.py, adsr + (size_t)v * n, n);
+	kb_envr_store(e, voices[v].adsr);
 	if (e.stage == KB_ENV_OFF) hdr[v].stage = KB_NOTE_OFF;
 }
 // thread = (instance, sample).  per_voice: every voice starts from a cleared buffer and is written to
@@ -263,10 +279,27 @@ __global__ void kb_prim_filter_kernel(int kind, int nset, const float* f, const 
 }
 __global__ void kb_prim_env_kernel(KbEnv e, KbFs fs, int n, int release_at, float rt, float rl, int adsr, float* out, int* stage) {
 	if (threadIdx.x || blockIdx.x) return;
+	// ticks are produced by the run-length form (kb_envr_run) in ragged chunks; the stage is sampled per tick by
+	// running chunks of one sample around the positions a second pass needs
+	KbEnv e2 = e;
 	for (int s = 0; s < n; s++) {
 		if (s == release_at) { if (adsr) kb_adsr_release(fs, e); else kb_env_release(fs, e, rt, rl); }
 		out[s] = kb_env_tick(fs, e);
 		stage[s] = e.stage;
+	}
+	int s = 0, chunk = 1;
+	while (s < n) {
+		int len = min(chunk, n - s);
+		if (release_at >= s && release_at < s + len && release_at != s) len = release_at - s;
+		if (s == release_at) { if (adsr) kb_adsr_release(fs, e2); else kb_env_release(fs, e2, rt, rl); }
+		KbEnvR r; kb_envr_load(r, e2);
+		float tmp[64];
+		kb_envr_run(fs, r, e2.px, e2.py, tmp, len);
+		kb_envr_store(r, e2);
+		// any disagreement with the per-tick form is made visible as a NaN
+		for (int i = 0; i < len; i++) if (__float_as_uint(tmp[i]) != __float_as_uint(out[s + i])) out[s + i] = __int_as_float(0x7fc00000);
+		s += len;
+		chunk = chunk % 61 + 3;
 	}
 }
 __global__ void kb_prim_math_kernel(int fn, int n, const float* x, float* out) {

@@ -19,6 +19,7 @@
 #define KB_D inline
 #endif
 
+#ifdef __CUDACC__   // everything below is device code
 // glibc selects its FMA build of sinf/cosf (sysdeps/x86_64/fpu/multiarch/s_sinf-fma.c) on every
 // x86-64 CPU with FMA+AVX2, i.e. on every B200 host; gcc contracts each `a + b*c` of the generic source
 // into one fused operation there.  KB_MADD reproduces exactly that contraction (0 mismatches against the
@@ -169,3 +170,4 @@ KB_D float kb_tanhf(float x) {
 	} else z = one - tiny;
 	return (jx >= 0) ? z : -z;
 }
+#endif  // __CUDACC__

@@ -326,18 +326,8 @@ KB_HD void kbr_set_target(const KbFs& fs, KbEnvR& e, float x, float y, float tim
 	e.r_target = y; e.r_active = (e.r_out != y);
 	e.r_rate = fabsf(y - e.r_out) / ((x - time) * fs.f);
 }
-KB_HD float kb_envr_tick(const KbFs& fs, KbEnvR& e, const float* px, const float* py) {
-	const float output = e.r_out;
-	if (e.r_active) {
-		if (e.r_target > e.r_out) {
-			e.r_out += e.r_rate;
-			if (e.r_out >= e.r_target) { e.r_out = e.r_target; e.r_active = 0; }
-		} else {
-			e.r_out -= e.r_rate;
-			if (e.r_out <= e.r_target) { e.r_out = e.r_target; e.r_active = 0; }
-		}
-	}
-	e.out = output;
+// the part of Envelope::process that follows the ramp step (stage logic)      klang.h:4024-4050
+KB_HD void kbr_after_ramp(const KbFs& fs, KbEnvR& e, const float* px, const float* py) {
 	if (e.stage == KB_ENV_SUSTAIN) {
 		e.time += e.timeInc;
 		if (!e.r_active) {
@@ -359,7 +349,107 @@ KB_HD float kb_envr_tick(const KbFs& fs, KbEnvR& e, const float* px, const float
 	} else if (e.stage == KB_ENV_RELEASE) {
 		if (!e.r_active) e.stage = KB_ENV_OFF;
 	}
+}
+KB_HD float kb_envr_tick(const KbFs& fs, KbEnvR& e, const float* px, const float* py) {
+	const float output = e.r_out;
+	if (e.r_active) {
+		if (e.r_target > e.r_out) {
+			e.r_out += e.r_rate;
+			if (e.r_out >= e.r_target) { e.r_out = e.r_target; e.r_active = 0; }
+		} else {
+			e.r_out -= e.r_rate;
+			if (e.r_out <= e.r_target) { e.r_out = e.r_target; e.r_active = 0; }
+		}
+	}
+	e.out = output;
+	kbr_after_ramp(fs, e, px, py);
 	return output;
+}
+// `steps` consecutive ticks into row[0..steps).  The envelope spends almost all of its time in one of four
+// steady modes — a running ramp, the ADSR sustain hold (a one-point loop re-asserting its level every sample),
+// waiting for the next breakpoint's time, or Off — and each of those is a two-or-three instruction loop; every
+// mode change goes through the generic tick, so the sequence of values is bit-identical to kb_envr_tick.
+KB_HD void kb_envr_run(const KbFs& fs, KbEnvR& e, const float* px, const float* py, float* row, int steps) {
+	int t = 0;
+	while (t < steps) {
+		if (e.r_active) {
+			const float rate = e.r_rate, target = e.r_target;
+			if (e.stage != KB_ENV_OFF && rate > 0.f && rate <= 3.0e38f) {
+				// a positive finite rate moves r_out monotonically towards the target, so the direction test of
+				// Linear::operator++ (klang.h:3785-3806) is invariant until the ramp crosses
+				const bool sustain = e.stage == KB_ENV_SUSTAIN;
+				float r = e.r_out, time = e.time;
+				const float inc = e.timeInc;
+				bool crossed = false;
+				// four ticks at a time: the four partial sums are formed exactly as four single ticks would form them
+				// (r only moves towards the target, so "the 4th has not crossed" implies none has)
+				if (target > r) {
+					while (t + 4 <= steps) {
+						const float r1 = r + rate, r2 = r1 + rate, r3 = r2 + rate, r4 = r3 + rate;
+						if (r4 >= target) break;
+						row[t] = r; row[t + 1] = r1; row[t + 2] = r2; row[t + 3] = r3; r = r4; t += 4;
+						if (sustain) { time += inc; time += inc; time += inc; time += inc; }
+					}
+					while (t < steps) { row[t++] = r; r += rate; if (r >= target) { crossed = true; break; } if (sustain) time += inc; }
+				} else {
+					while (t + 4 <= steps) {
+						const float r1 = r - rate, r2 = r1 - rate, r3 = r2 - rate, r4 = r3 - rate;
+						if (r4 <= target) break;
+						row[t] = r; row[t + 1] = r1; row[t + 2] = r2; row[t + 3] = r3; r = r4; t += 4;
+						if (sustain) { time += inc; time += inc; time += inc; time += inc; }
+					}
+					while (t < steps) { row[t++] = r; r -= rate; if (r <= target) { crossed = true; break; } if (sustain) time += inc; }
+				}
+				e.time = time;
+				if (crossed) { e.out = row[t - 1]; e.r_out = target; e.r_active = 0; kbr_after_ramp(fs, e, px, py); }
+				else { e.r_out = r; if (t > 0) e.out = row[t - 1]; }
+				continue;
+			}
+			row[t++] = kb_envr_tick(fs, e, px, py);
+			continue;
+		}
+		if (e.stage == KB_ENV_OFF) {
+			const float r = e.r_out;
+			for (; t < steps; t++) row[t] = r;
+			e.out = r;
+			break;
+		}
+		if (e.stage == KB_ENV_SUSTAIN) {
+			const bool loop_active = e.loop_start != -1 && e.loop_end != -1;
+			if (loop_active && (e.point + 1) >= e.loop_end) {
+				row[t++] = kb_envr_tick(fs, e, px, py);                       // performs the loop jump
+				if (e.loop_start == e.loop_end && !e.r_active && e.stage == KB_ENV_SUSTAIN) {
+					// hold: every further tick outputs the level, advances time and re-asserts the level
+					const float r = e.r_out, inc = e.timeInc;
+					float time = e.time;
+					if (t < steps) e.out = r;
+					for (; t + 4 <= steps; t += 4) { row[t] = r; row[t + 1] = r; row[t + 2] = r; row[t + 3] = r; time += inc; time += inc; time += inc; time += inc; }
+					for (; t < steps; t++) { row[t] = r; time += inc; }
+					e.time = time;
+				}
+				continue;
+			}
+			if (!loop_active && (e.point + 1) < e.npoints) {
+				const float r = e.r_out, inc = e.timeInc, x = px[e.point + 1];
+				float time = e.time;
+				bool reached = false;
+				while (t + 4 <= steps) {                                          // time only grows (timeInc > 0)
+					const float t1 = time + inc, t2 = t1 + inc, t3 = t2 + inc, t4 = t3 + inc;
+					if (t4 >= x) break;
+					row[t] = r; row[t + 1] = r; row[t + 2] = r; row[t + 3] = r; time = t4; t += 4;
+				}
+				while (t < steps) { row[t++] = r; time += inc; if (time >= x) { reached = true; break; } }
+				e.time = time; e.out = r;
+				if (reached) {
+					e.point++;
+					kbr_set_value(e, py[e.point]);
+					if ((e.point + 1) < e.npoints) kbr_set_target(fs, e, px[e.point + 1], py[e.point + 1], px[e.point]);
+				}
+				continue;
+			}
+		}
+		row[t++] = kb_envr_tick(fs, e, px, py);
+	}
 }
 // Envelope::at                                                              klang.h:3929-3942
 KB_HD float kb_env_at(const float* px, const float* py, int npoints, float time) {

@@ -5,34 +5,35 @@
 // only ~1000 voices a lane-per-voice loop leaves the chip idle and is bound by the dependent-issue latency of
 // the whole per-sample expression.  Here a CTA owns G voices, the block is cut into tiles of T samples,
 // and four stages work on four consecutive tiles at once, in lock step (one __syncthreads per tick):
-//   A  recurrences that feed others   warp 0, lane = envelope   tile k     (Envelope::process, klang.h:4018-4051)
-//   B  time-parallel work             warps 2.., thread=(v,t)   tile k-1   (OSM samples, Biquad::set / TB303 coefficients)
-//   C  the filter recurrence          warp 1, lane = voice      tile k-2   (only the 2- / 5-state update is serial)
-//   D  output                         warps 2.., thread=(v,t)   tile k-3   (soft clip, *= adsr, coalesced stores)
+//   A  recurrences that feed others   warps 0-1, lane = voice   tile k     (Envelope::process, klang.h:4018-4051;
+//                                                                           warp 0 the modulation envelopes, warp 1 the ADSRs)
+//   B  time-parallel work             warps 3.., thread=(v,t)   tile k-1   (OSM samples, Biquad::set / TB303 coefficients)
+//   C  the filter recurrence          warp 2, lane = voice      tile k-2   (only the 2- / 5-state update is serial)
+//   D  output                         warps 3.., thread=(v,t)   tile k-3   (soft clip, *= adsr, coalesced stores)
 // so a tick costs max(A, B+D, C) instead of their sum, and the serial stages hide behind the parallel one.
 // Arithmetic per sample is the reference's, operation for operation (bit-exact vs the oracle); only the order in
 // which independent samples are computed changes.  Shared rows are padded to T+1 floats so that the lane=voice
 // stages (stride T+1) and the thread=(voice,t) stages (stride 1) are both bank-conflict free; stage hand-over
-// buffers are double (A->B, B->C, C->D) or triple (A->C) buffered.
+// buffers are double buffered (A->B, B->C, C->D).
 #pragma once
 #include "kb_graphs.cuh"
 
-#define KB_TILE_G 8        // voices per CTA
 #define KB_TILE_T 128      // samples per tile
-#define KB_TILE_THREADS 512
+// G = voices per CTA and NT = threads per CTA are template parameters: the serial stages cost the same for any G <= 32
+// (one lane per voice), so G is chosen as large as the voice count allows while still filling the SMs.
 
-struct KbTileRows { float r[KB_TILE_G][KB_TILE_T + 1]; };
+template <int G> struct KbTileRows { float r[G][KB_TILE_T + 1]; };
 
-struct KbTileCommon {
-	float px[2 * KB_TILE_G][KB_ENV_MAXPTS], py[2 * KB_TILE_G][KB_ENV_MAXPTS];   // envelope breakpoints of the A lanes
-	int active[KB_TILE_G];
+template <int G> struct KbTileCommon {
+	float px[2 * G][KB_ENV_MAXPTS], py[2 * G][KB_ENV_MAXPTS];   // envelope breakpoints of the A lanes
+	int active[G];
 };
 
 // prologue shared by the kernels: active flags, and the envelope lanes (warp 0: lanes 0..G-1 first envelope,
 // lanes G..2G-1 the ADSR) load their scalar state into registers and their breakpoints into shared memory
-template <class VOICE>
-KB_D void kb_tile_prologue(KbTileCommon& c, VOICE* voices, KbVoiceHdr* hdr, int v0, int total) {
-	if (threadIdx.x < KB_TILE_G) {
+template <int G, class VOICE>
+KB_D void kb_tile_prologue(KbTileCommon<G>& c, VOICE* voices, KbVoiceHdr* hdr, int v0, int total) {
+	if (threadIdx.x < G) {
 		const int v = v0 + threadIdx.x;
 		const int act = (v < total && hdr[v].stage != KB_NOTE_OFF) ? 1 : 0;
 		c.active[threadIdx.x] = act;
@@ -40,7 +41,8 @@ KB_D void kb_tile_prologue(KbTileCommon& c, VOICE* voices, KbVoiceHdr* hdr, int 
 	}
 	__syncthreads();
 }
-KB_D void kb_tile_load_env(KbTileCommon& c, int slot, const KbEnv& src, KbEnvR& e) {
+template <int G>
+KB_D void kb_tile_load_env(KbTileCommon<G>& c, int slot, const KbEnv& src, KbEnvR& e) {
 	kb_envr_load(e, src);
 	for (int p = 0; p < KB_ENV_MAXPTS; p++) { c.px[slot][p] = src.px[p]; c.py[slot][p] = src.py[p]; }
 }
@@ -50,55 +52,64 @@ KB_D void kb_tile_load_env(KbTileCommon& c, int slot, const KbEnv& src, KbEnvR& 
 // 5658-5665) and the oscillator sample.  C: Filter::process (klang.h:5605-5612) and `out *= adsr`.  D: stores.
 // Biquad::set is a pure function of (f, Q) and is re-evaluated for every sample; the reference's "unchanged (f,Q)"
 // early-out returns the same coefficients (Q is the constant 10, so the first set after reset() always computes).
-struct KbSubSmem {
-	KbTileCommon c;
-	KbTileRows cut[2], amp[3], b0[2], b1[2], a1[2], a2[2], x[2], out[2];
-	KbOsm osc[KB_TILE_G];
+template <int G> struct KbTileRows4 { float4 r[G][KB_TILE_T + 1]; };   // lane=voice reads 16 B from banks 4v..4v+3: conflict-free per quarter warp
+template <int G> struct KbTileRows2 { float2 r[G][KB_TILE_T + 1]; };
+template <int G> struct KbSubSmem {
+	KbTileCommon<G> c;
+	KbTileRows4<G> coef[2];          // B -> C: (b0, b1, a1, a2) of every sample, one 128-bit load per step
+	KbTileRows2<G> xa[2];            // B -> C: (oscillator sample, adsr level)
+	KbTileRows<G> cut[2], amp[2], out[2];
+	KbOsm osc[G];
 };
-__global__ void __launch_bounds__(KB_TILE_THREADS) kb_sub_tiled_kernel(KbSubVoice* __restrict__ voices, KbVoiceHdr* __restrict__ hdr,
+template <int G, int NT>
+__global__ void __launch_bounds__(NT) kb_sub_tiled_kernel(KbSubVoice* __restrict__ voices, KbVoiceHdr* __restrict__ hdr,
                                                                         float* __restrict__ dst, int n, int total, KbFs fs) {
-	constexpr int G = KB_TILE_G, T = KB_TILE_T;
+	constexpr int T = KB_TILE_T;
 	extern __shared__ __align__(16) unsigned char kb_smem[];
-	KbSubSmem& S = *reinterpret_cast<KbSubSmem*>(kb_smem);
+	KbSubSmem<G>& S = *reinterpret_cast<KbSubSmem<G>*>(kb_smem);
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int v0 = blockIdx.x * G;
 	kb_tile_prologue(S.c, voices, hdr, v0, total);
 
-	const int role_voice = lane & (G - 1);
-	const bool is_env = warp == 0 && lane < 2 * G && S.c.active[role_voice];
-	const bool is_flt = warp == 1 && lane < G && S.c.active[role_voice];
+	const int role_voice = lane;
+	const bool role_ok = lane < G && S.c.active[lane < G ? lane : 0];
+	const bool is_env = warp == 0 && role_ok, is_adsr = warp == 1 && role_ok, is_flt = warp == 2 && role_ok;
+	const int slot = warp * G + lane;                                 // breakpoint slot of the A lanes
 	KbEnvR env;
 	float z0 = 0.f, z1 = 0.f, lb0 = 1.f, lb1 = 0.f, la1 = 0.f, la2 = 0.f;
-	if (is_env) kb_tile_load_env(S.c, lane, (lane < G) ? voices[v0 + role_voice].env : voices[v0 + role_voice].adsr, env);
+	if (is_env) kb_tile_load_env(S.c, slot, voices[v0 + role_voice].env, env);
+	if (is_adsr) kb_tile_load_env(S.c, slot, voices[v0 + role_voice].adsr, env);
 	if (is_flt) { const KbBiquad& b = voices[v0 + role_voice].filter; z0 = b.z0; z1 = b.z1; lb0 = b.b0; lb1 = b.b1; la1 = b.a1; la2 = b.a2; }
-	if (warp == 2 && lane < G && S.c.active[lane]) S.osc[lane] = voices[v0 + lane].osc;
+	if (warp == 3 && lane < G && S.c.active[lane]) S.osc[lane] = voices[v0 + lane].osc;
 	__syncthreads();
 
 	const int ntiles = (n + T - 1) / T;
-	const int wtid = tid - 64, wthreads = KB_TILE_THREADS - 64;      // the B/D worker threads
+	const int wtid = tid - 96, wthreads = NT - 96;      // the B/D worker threads
 	for (int k = 0; k < ntiles + 3; k++) {
-		if (warp == 0) {                                                 // ---- A, tile k
-			if (is_env && k < ntiles) {
+		if (warp < 2) {                                                  // ---- A, tile k
+			if ((is_env || is_adsr) && k < ntiles) {
 				const int steps = min(T, n - k * T);
-				float* row = (lane < G) ? S.cut[k & 1].r[role_voice] : S.amp[k % 3].r[role_voice];
-				const float* px = S.c.px[lane]; const float* py = S.c.py[lane];
-				for (int t = 0; t < steps; t++) row[t] = kb_envr_tick(fs, env, px, py);
+				float* row = is_env ? S.cut[k & 1].r[role_voice] : S.amp[k & 1].r[role_voice];
+				kb_envr_run(fs, env, S.c.px[slot], S.c.py[slot], row, steps);
 			}
-		} else if (warp == 1) {                                          // ---- C, tile k-2
+		} else if (warp == 2) {                                          // ---- C, tile k-2
 			const int c = k - 2;
 			if (is_flt && c >= 0 && c < ntiles) {
 				const int steps = min(T, n - c * T), v = role_voice;
-				const float *pb0 = S.b0[c & 1].r[v], *pb1 = S.b1[c & 1].r[v], *pa1 = S.a1[c & 1].r[v], *pa2 = S.a2[c & 1].r[v];
-				const float *px = S.x[c & 1].r[v], *pamp = S.amp[c % 3].r[v];
+				const float4* pc = S.coef[c & 1].r[v];
+				const float2* pxa = S.xa[c & 1].r[v];
 				float* po = S.out[c & 1].r[v];
+				float4 cf = pc[0]; float2 xa = pxa[0];
 				#pragma unroll 4
 				for (int t = 0; t < steps; t++) {
-					lb0 = pb0[t]; lb1 = pb1[t]; la1 = pa1[t]; la2 = pa2[t];
-					const float in = px[t];
+					const float4 cn = pc[t + 1]; const float2 xn = pxa[t + 1];      // next step's operands (rows are padded by one)
+					lb0 = cf.x; lb1 = cf.y; la1 = cf.z; la2 = cf.w;
+					const float in = xa.x;
 					const float y = lb0 * in + z0;
 					z0 = lb1 * in - la1 * y + z1;
 					z1 = lb0 * in - la2 * y;
-					po[t] = y * pamp[t];                                     // out *= adsr++   Filter.k:33
+					po[t] = y * xa.y;                                        // out *= adsr++   Filter.k:33
+					cf = cn; xa = xn;
 				}
 			}
 		} else {
@@ -114,11 +125,13 @@ __global__ void __launch_bounds__(KB_TILE_THREADS) kb_sub_tiled_kernel(KbSubVoic
 						kb_sincosf(w, sin0, cos0);
 						const float a = sin0 / (2.f * 10.f);
 						const float inv = kb_const_inv(1.f + a);
-						S.a1[b & 1].r[v][t] = inv * (-2.f * cos0);
-						S.a2[b & 1].r[v][t] = inv * (1.f - a);
-						S.b0[b & 1].r[v][t] = inv * (1.f - cos0) * 0.5f;
-						S.b1[b & 1].r[v][t] = inv * (1.f - cos0);
-						S.x[b & 1].r[v][t] = kb_osm_at(S.osc[v], (uint32_t)(b * T + t));
+						float4 cf;
+						cf.z = inv * (-2.f * cos0);
+						cf.w = inv * (1.f - a);
+						cf.x = inv * (1.f - cos0) * 0.5f;
+						cf.y = inv * (1.f - cos0);
+						S.coef[b & 1].r[v][t] = cf;
+						S.xa[b & 1].r[v][t] = make_float2(kb_osm_at(S.osc[v], (uint32_t)(b * T + t)), S.amp[b & 1].r[v][t]);
 					}
 				}
 			}
@@ -134,18 +147,16 @@ __global__ void __launch_bounds__(KB_TILE_THREADS) kb_sub_tiled_kernel(KbSubVoic
 	}
 
 	// write the state back
-	if (is_env) {
-		if (lane < G) { kb_envr_store(env, voices[v0 + role_voice].env); voices[v0 + role_voice].filter.f = env.out; voices[v0 + role_voice].filter.Q = 10.f; }
-		else {
-			kb_envr_store(env, voices[v0 + role_voice].adsr);
-			if (env.stage == KB_ENV_OFF) hdr[v0 + role_voice].stage = KB_NOTE_OFF;   // if (adsr.finished()) stop()   Filter.k:34-35
-		}
+	if (is_env) { kb_envr_store(env, voices[v0 + role_voice].env); voices[v0 + role_voice].filter.f = env.out; voices[v0 + role_voice].filter.Q = 10.f; }
+	if (is_adsr) {
+		kb_envr_store(env, voices[v0 + role_voice].adsr);
+		if (env.stage == KB_ENV_OFF) hdr[v0 + role_voice].stage = KB_NOTE_OFF;       // if (adsr.finished()) stop()   Filter.k:34-35
 	}
 	if (is_flt) {
 		KbBiquad& b = voices[v0 + role_voice].filter;
 		b.z0 = z0; b.z1 = z1; b.b0 = lb0; b.b2 = lb0; b.b1 = lb1; b.a1 = la1; b.a2 = la2;
 	}
-	if (warp == 2 && lane < G && S.c.active[lane]) {
+	if (warp == 3 && lane < G && S.c.active[lane]) {
 		KbOsm o = S.osc[lane];
 		kb_osm_advance(o, (uint32_t)n);
 		voices[v0 + lane].osc.offset = o.offset;
@@ -156,16 +167,17 @@ __global__ void __launch_bounds__(KB_TILE_THREADS) kb_sub_tiled_kernel(KbSubVoic
 // ------------------------------------------------------------------------------------------------ SuperSaw
 // SuperSaw.k:25-33: seven detuned saws summed (each `/ 7`, in index order) times the ADSR.  A: adsr (tile k).
 // B+D fused (tile k-1): thread = (voice, t) evaluates the seven oscillators in closed form, scales and stores.
-struct KbSsawSmem {
-	KbTileCommon c;
-	KbTileRows amp[2];
-	KbOsm osc[KB_TILE_G][7];
+template <int G> struct KbSsawSmem {
+	KbTileCommon<G> c;
+	KbTileRows<G> amp[2];
+	KbOsm osc[G][7];
 };
-__global__ void __launch_bounds__(KB_TILE_THREADS) kb_ssaw_tiled_kernel(KbSsawVoice* __restrict__ voices, KbVoiceHdr* __restrict__ hdr,
+template <int G, int NT>
+__global__ void __launch_bounds__(NT) kb_ssaw_tiled_kernel(KbSsawVoice* __restrict__ voices, KbVoiceHdr* __restrict__ hdr,
                                                                          float* __restrict__ dst, int n, int total, KbFs fs) {
-	constexpr int G = KB_TILE_G, T = KB_TILE_T;
+	constexpr int T = KB_TILE_T;
 	extern __shared__ __align__(16) unsigned char kb_smem[];
-	KbSsawSmem& S = *reinterpret_cast<KbSsawSmem*>(kb_smem);
+	KbSsawSmem<G>& S = *reinterpret_cast<KbSsawSmem<G>*>(kb_smem);
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int v0 = blockIdx.x * G;
 	kb_tile_prologue(S.c, voices, hdr, v0, total);
@@ -175,14 +187,14 @@ __global__ void __launch_bounds__(KB_TILE_THREADS) kb_ssaw_tiled_kernel(KbSsawVo
 	if (tid >= 32 && tid < 32 + G * 7 && S.c.active[(tid - 32) / 7]) S.osc[(tid - 32) / 7][(tid - 32) % 7] = voices[v0 + (tid - 32) / 7].osc[(tid - 32) % 7];
 	__syncthreads();
 	const int ntiles = (n + T - 1) / T;
-	const int wtid = tid - 32, wthreads = KB_TILE_THREADS - 32;
+	const int wtid = tid - 32, wthreads = NT - 32;
 	for (int k = 0; k < ntiles + 1; k++) {
 		if (warp == 0) {
 			if (is_env && k < ntiles) {
 				const int steps = min(T, n - k * T);
 				float* row = S.amp[k & 1].r[lane];
 				const float* px = S.c.px[lane]; const float* py = S.c.py[lane];
-				for (int t = 0; t < steps; t++) row[t] = kb_envr_tick(fs, env, px, py);
+				kb_envr_run(fs, env, px, py, row, steps);
 			}
 		} else {
 			const int b = k - 1;
@@ -223,23 +235,24 @@ __global__ void __launch_bounds__(KB_TILE_THREADS) kb_ssaw_tiled_kernel(KbSsawVo
 // parks g*z[3] per sample.  D: the soft clip (tanhf, double divide), `* adsr`, stores.
 // Filter::set only recomputes when (cutoff, resonance, drive) change; its outputs are pure functions of those three, so
 // B evaluates them for every sample and C adopts them exactly when the reference's comparison says "changed".
-struct KbTbSmem {
-	KbTileCommon c;
-	KbTileRows e[2], amp[4], b0[2], kk[2], g[2], x[2], cut[2], y[2];
-	KbOsm osc[KB_TILE_G];
-	KbTbBlock blk[KB_TILE_G];
-	float vf[KB_TILE_G], last_out[KB_TILE_G];
+template <int G> struct KbTbSmem {
+	KbTileCommon<G> c;
+	KbTileRows<G> e[2], amp[4], b0[2], kk[2], g[2], x[2], cut[2], y[2];
+	KbOsm osc[G];
+	KbTbBlock blk[G];
+	float vf[G], last_out[G];
 };
-__global__ void __launch_bounds__(KB_TILE_THREADS) kb_tb_tiled_kernel(KbTbVoice* __restrict__ voices, KbVoiceHdr* __restrict__ hdr,
+template <int G, int NT>
+__global__ void __launch_bounds__(NT) kb_tb_tiled_kernel(KbTbVoice* __restrict__ voices, KbVoiceHdr* __restrict__ hdr,
                                                                        const KbSynthBlock* __restrict__ blk, float* __restrict__ dst,
                                                                        int n, int voices_per_inst, int total, KbFs fs) {
-	constexpr int G = KB_TILE_G, T = KB_TILE_T;
+	constexpr int T = KB_TILE_T;
 	extern __shared__ __align__(16) unsigned char kb_smem[];
-	KbTbSmem& S = *reinterpret_cast<KbTbSmem*>(kb_smem);
+	KbTbSmem<G>& S = *reinterpret_cast<KbTbSmem<G>*>(kb_smem);
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int v0 = blockIdx.x * G;
 	kb_tile_prologue(S.c, voices, hdr, v0, total);
-	if (warp == 2 && lane < G && v0 + lane < total) {
+	if (warp == 3 && lane < G && v0 + lane < total) {
 		S.blk[lane] = blk[(v0 + lane) / voices_per_inst].tb;
 		if (S.c.active[lane]) {
 			S.osc[lane] = S.blk[lane].is_square ? voices[v0 + lane].square : voices[v0 + lane].saw;
@@ -247,25 +260,26 @@ __global__ void __launch_bounds__(KB_TILE_THREADS) kb_tb_tiled_kernel(KbTbVoice*
 			S.last_out[lane] = voices[v0 + lane].filter.out;
 		}
 	}
-	const int role_voice = lane & (G - 1);
-	const bool is_env = warp == 0 && lane < 2 * G && S.c.active[role_voice];
-	const bool is_flt = warp == 1 && lane < G && S.c.active[role_voice];
+	const int role_voice = lane;
+	const bool role_ok = lane < G && S.c.active[lane < G ? lane : 0];
+	const bool is_env = warp == 0 && role_ok, is_adsr = warp == 1 && role_ok, is_flt = warp == 2 && role_ok;
+	const int slot = warp * G + lane;
 	KbEnvR env;
-	if (is_env) kb_tile_load_env(S.c, lane, (lane < G) ? voices[v0 + role_voice].env : voices[v0 + role_voice].adsr, env);
+	if (is_env) kb_tile_load_env(S.c, slot, voices[v0 + role_voice].env, env);
+	if (is_adsr) kb_tile_load_env(S.c, slot, voices[v0 + role_voice].adsr, env);
 	KbTbFilter F;
 	if (is_flt) F = voices[v0 + role_voice].filter;
 	__syncthreads();
 	const int ntiles = (n + T - 1) / T;
-	const int wtid = tid - 64, wthreads = KB_TILE_THREADS - 64;
+	const int wtid = tid - 96, wthreads = NT - 96;
 	for (int k = 0; k < ntiles + 3; k++) {
-		if (warp == 0) {                                                 // ---- A, tile k
-			if (is_env && k < ntiles) {
+		if (warp < 2) {                                                  // ---- A, tile k
+			if ((is_env || is_adsr) && k < ntiles) {
 				const int steps = min(T, n - k * T);
-				float* row = (lane < G) ? S.e[k & 1].r[role_voice] : S.amp[k & 3].r[role_voice];
-				const float* px = S.c.px[lane]; const float* py = S.c.py[lane];
-				for (int t = 0; t < steps; t++) row[t] = kb_envr_tick(fs, env, px, py);
+				float* row = is_env ? S.e[k & 1].r[role_voice] : S.amp[k & 3].r[role_voice];
+				kb_envr_run(fs, env, S.c.px[slot], S.c.py[slot], row, steps);
 			}
-		} else if (warp == 1) {                                          // ---- C, tile k-2
+		} else if (warp == 2) {                                          // ---- C, tile k-2
 			const int c = k - 2;
 			if (is_flt && c >= 0 && c < ntiles) {
 				const int steps = min(T, n - c * T), v = role_voice;
@@ -333,15 +347,13 @@ __global__ void __launch_bounds__(KB_TILE_THREADS) kb_tb_tiled_kernel(KbTbVoice*
 		}
 		__syncthreads();
 	}
-	if (is_env) {
-		if (lane < G) kb_envr_store(env, voices[v0 + role_voice].env);
-		else {
-			kb_envr_store(env, voices[v0 + role_voice].adsr);
-			if (env.stage == KB_ENV_OFF) hdr[v0 + role_voice].stage = KB_NOTE_OFF;
-		}
+	if (is_env) kb_envr_store(env, voices[v0 + role_voice].env);
+	if (is_adsr) {
+		kb_envr_store(env, voices[v0 + role_voice].adsr);
+		if (env.stage == KB_ENV_OFF) hdr[v0 + role_voice].stage = KB_NOTE_OFF;
 	}
 	if (is_flt) { F.out = S.last_out[role_voice]; voices[v0 + role_voice].filter = F; }
-	if (warp == 2 && lane < G && S.c.active[lane]) {
+	if (warp == 3 && lane < G && S.c.active[lane]) {
 		KbOsm o = S.osc[lane];
 		kb_osm_advance(o, (uint32_t)n);
 		KbOsm& dsto = S.blk[lane].is_square ? voices[v0 + lane].square : voices[v0 + lane].saw;
