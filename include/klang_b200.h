@@ -49,6 +49,7 @@ extern "C" {
 #define KB_MIX_SUM 4u             /* synth: mono synths sum their voices (Stereo::Note rule, klang.h:4731) instead of the reference's
                                      overwrite (klang.h:4299) */
 #define KB_LANE_PER_VOICE 16u     /* synth: use the plain lane-per-voice schedule instead of the tiled one (A/B measurement; same results) */
+#define KB_FX_SEQUENTIAL 32u       /* effects: use only the frame-sequential schedule (A/B measurement; same results) */
 #define KB_BANK_MIX 8u            /* synth: additionally sum all instances, out = [channels][n] (the multi-GPU mix-down input) */
 
 typedef struct kb_fx_bank kb_fx_bank;
@@ -81,6 +82,9 @@ int kb_fx_bank_set_stream(kb_fx_bank* bank, void* cuda_stream);   /* run on a ca
 /* algorithmic (unique) HBM bytes one frame of one instance moves with the current controls */
 double kb_fx_bank_bytes_per_frame(kb_fx_bank* bank);
 long long kb_fx_bank_launches(const kb_fx_bank* bank);   /* kernels launched so far */
+/* how many instances the last process() ran on the chunk-parallel schedule (the others ran frame-sequentially because
+ * their control smoothers were still moving or their delays were shorter than a useful chunk); joins the stream */
+int kb_fx_bank_parallel_instances(kb_fx_bank* bank);
 long long kb_fx_bank_state_bytes(const kb_fx_bank* bank); /* bytes of instance state mirrored between host and device */
 /* Measurement: when enabled, every process() brackets its dominant kernel with CUDA events on the bank stream;
  * read() joins the stream and returns the accumulated kernel milliseconds and launch count since enable. */

@@ -14,7 +14,7 @@ lib_path = os.path.join(_HERE, "lib", "libklang_b200.so")
 
 FX_GAIN, FX_PINGPONG, FX_REVERB, FX_DELAY_PINGPONG, FX_DELAY_REVERB = range(5)
 SY_SUBTRACTIVE, SY_SUPERSAW, SY_TB303, SY_SYNTHX, SY_FILTER_K = range(5)
-DEVICE_PTR, PER_VOICE, MIX_SUM, BANK_MIX, LANE_PER_VOICE = 1, 2, 4, 8, 16
+DEVICE_PTR, PER_VOICE, MIX_SUM, BANK_MIX, LANE_PER_VOICE, FX_SEQUENTIAL = 1, 2, 4, 8, 16, 32
 
 # every symbol include/klang_b200.h declares: (name, restype, argtypes)
 _vp, _i, _f, _u, _ll, _d = C.c_void_p, C.c_int, C.c_float, C.c_uint, C.c_longlong, C.c_double
@@ -26,7 +26,7 @@ SYMBOLS = [
     ("kb_fx_bank_channels", _i, [_vp]), ("kb_fx_bank_instances", _i, [_vp]), ("kb_fx_bank_num_controls", _i, [_vp]),
     ("kb_fx_bank_set_control", _i, [_vp, _i, _i, _f]), ("kb_fx_bank_get_control", _i, [_vp, _i, _i, _fp]),
     ("kb_fx_bank_process", _i, [_vp, _vp, _i, _u]), ("kb_fx_bank_sync", _i, [_vp]), ("kb_fx_bank_set_stream", _i, [_vp, _vp]),
-    ("kb_fx_bank_bytes_per_frame", _d, [_vp]), ("kb_fx_bank_launches", _ll, [_vp]), ("kb_fx_bank_state_bytes", _ll, [_vp]),
+    ("kb_fx_bank_bytes_per_frame", _d, [_vp]), ("kb_fx_bank_launches", _ll, [_vp]), ("kb_fx_bank_state_bytes", _ll, [_vp]), ("kb_fx_bank_parallel_instances", _i, [_vp]),
     ("kb_fx_bank_profile", _i, [_vp, _i]), ("kb_fx_bank_profile_read", _i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     ("kb_synth_bank_create", _vp, [_i, _i, _i, _f, _i, _i]), ("kb_synth_bank_destroy", None, [_vp]),
     ("kb_synth_bank_channels", _i, [_vp]), ("kb_synth_bank_instances", _i, [_vp]), ("kb_synth_bank_voices", _i, [_vp]),
@@ -117,11 +117,11 @@ class FxBank:
         _check(lib().kb_fx_bank_get_control(self.h, instance, idx, C.byref(v)), "kb_fx_bank_get_control")
         return float(v.value)
 
-    def process_inplace(self, io, n=None):
+    def process_inplace(self, io, n=None, flags=0):
         """io: float32 [instances, channels, n], numpy (host) or torch CUDA tensor (asynchronous)."""
         p, dev = _ptr(io)
         n = io.shape[-1] if n is None else n
-        _check(lib().kb_fx_bank_process(self.h, p, n, DEVICE_PTR if dev else 0), "kb_fx_bank_process")
+        _check(lib().kb_fx_bank_process(self.h, p, n, (flags | DEVICE_PTR) if dev else (flags & ~DEVICE_PTR)), "kb_fx_bank_process")
         return io
 
     def set_stream(self, cuda_stream):
@@ -132,6 +132,10 @@ class FxBank:
 
     def bytes_per_frame(self):
         return lib().kb_fx_bank_bytes_per_frame(self.h)
+
+    def parallel_instances(self):
+        """Instances the last process() ran on the chunk-parallel schedule."""
+        return _check(lib().kb_fx_bank_parallel_instances(self.h), "kb_fx_bank_parallel_instances")
 
     @property
     def state_bytes(self):

@@ -66,7 +66,7 @@ struct kb_fx_bank : kb_bank_base {
 	int graph = 0, instances = 0, channels = 0, ncontrols = 0;
 	size_t state_bytes = 0; long long ring_floats = 0;
 	std::vector<KbFxHdr> hdr; std::vector<unsigned char> state;
-	KbFxHdr* d_hdr = nullptr; unsigned char* d_state = nullptr; float* d_rings = nullptr;
+	KbFxHdr* d_hdr = nullptr; unsigned char* d_state = nullptr; float* d_rings = nullptr; KbFxPlan* d_plan = nullptr;
 	bool device_writes_controls = false;
 	template <class T> T& st(int i) { return *reinterpret_cast<T*>(state.data() + (size_t)i * state_bytes); }
 };
@@ -121,6 +121,9 @@ extern "C" kb_fx_bank* kb_fx_bank_create(int graph, int instances, float fs, int
 	ok = ok && dev_alloc(&b->d_hdr, instances) == cudaSuccess;
 	ok = ok && dev_alloc(&b->d_state, b->state.size()) == cudaSuccess;
 	ok = ok && dev_alloc(&b->d_rings, (size_t)instances * b->ring_floats) == cudaSuccess;
+	ok = ok && dev_alloc(&b->d_plan, instances) == cudaSuccess;
+	ok = ok && cudaMemsetAsync(b->d_plan, 0, instances * sizeof(KbFxPlan), b->stream) == cudaSuccess;
+	ok = ok && cudaFuncSetAttribute(kb_reverb_par_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KbRvSmem)) == cudaSuccess;
 	if (ok && b->ring_floats) ok = cudaMemsetAsync(b->d_rings, 0, (size_t)instances * b->ring_floats * sizeof(float), b->stream) == cudaSuccess;
 	b->io_floats = (size_t)instances * b->channels * max_block;
 	ok = ok && dev_alloc(&b->d_io, b->io_floats) == cudaSuccess;
@@ -131,7 +134,7 @@ extern "C" void kb_fx_bank_destroy(kb_fx_bank* b) {
 	if (!b) return;
 	cudaSetDevice(b->device);
 	if (b->stream) cudaStreamSynchronize(b->stream);
-	cudaFree(b->d_hdr); cudaFree(b->d_state); cudaFree(b->d_rings); cudaFree(b->d_io);
+	cudaFree(b->d_hdr); cudaFree(b->d_state); cudaFree(b->d_rings); cudaFree(b->d_io); cudaFree(b->d_plan);
 	b->prof_free();
 	if (b->own_stream) cudaStreamDestroy(b->own_stream);
 	delete b;
@@ -140,6 +143,18 @@ extern "C" int kb_fx_bank_channels(const kb_fx_bank* b) { return b ? b->channels
 extern "C" int kb_fx_bank_instances(const kb_fx_bank* b) { return b ? b->instances : KB_EINVAL; }
 extern "C" int kb_fx_bank_num_controls(const kb_fx_bank* b) { return b ? b->ncontrols : KB_EINVAL; }
 extern "C" long long kb_fx_bank_launches(const kb_fx_bank* b) { return b ? b->launches : 0; }
+extern "C" int kb_fx_bank_parallel_instances(kb_fx_bank* b) {
+	if (!b) return kb_fail(KB_EINVAL, "null bank");
+	if (b->graph == KB_FX_GAIN) return b->instances;
+	if (b->graph == KB_FX_DELAY_REVERB) return 0;
+	std::vector<KbFxPlan> plan(b->instances);
+	KB_CUDA(cudaSetDevice(b->device));
+	KB_CUDA(cudaStreamSynchronize(b->stream));
+	KB_CUDA(cudaMemcpy(plan.data(), b->d_plan, plan.size() * sizeof(KbFxPlan), cudaMemcpyDeviceToHost));
+	int count = 0;
+	for (const KbFxPlan& p : plan) count += p.mode == KB_PLAN_PARALLEL;
+	return count;
+}
 extern "C" long long kb_fx_bank_state_bytes(const kb_fx_bank* b) { return b ? (long long)(b->hdr.size() * sizeof(KbFxHdr) + b->state.size()) : 0; }
 extern "C" int kb_fx_bank_profile(kb_fx_bank* b, int enable) { if (!b) return kb_fail(KB_EINVAL, "null bank"); cudaSetDevice(b->device); cudaStreamSynchronize(b->stream); b->profiling = enable != 0; b->prof_used = 0; return KB_OK; }
 extern "C" int kb_fx_bank_profile_read(kb_fx_bank* b, double* ms, long long* count) { if (!b) return kb_fail(KB_EINVAL, "null bank"); cudaSetDevice(b->device); return b->prof_read(ms, count); }
@@ -219,15 +234,61 @@ extern "C" int kb_fx_bank_process(kb_fx_bank* b, float* io, int n, unsigned flag
 	float* d = io;
 	if (!(flags & KB_DEVICE_PTR)) { d = b->d_io; KB_CUDA(cudaMemcpyAsync(d, io, floats * sizeof(float), cudaMemcpyHostToDevice, b->stream)); }
 	b->prof_begin();
+	const int ib = (b->instances + 31) / 32;
+	const bool seq_only = flags & KB_FX_SEQUENTIAL;
 	switch (b->graph) {
 	case KB_FX_GAIN: {
 		dim3 grid((unsigned)std::max(1, std::min((n / 4 + 255) / 256, 148 * 8 / std::min(b->instances, 148 * 8) + 1)), b->instances);
 		kb_gain_kernel<<<grid, 256, 0, b->stream>>>(b->d_hdr, d, n);
 		break; }
-	case KB_FX_PINGPONG: kb_fx_seq_kernel<KB_FX_PINGPONG, KbPingPong><<<(b->instances + 31) / 32, 32, 0, b->stream>>>(b->d_hdr, (KbPingPong*)b->d_state, b->d_rings, d, n, 2, b->instances, b->fs); break;
-	case KB_FX_REVERB: kb_fx_seq_kernel<KB_FX_REVERB, KbReverb><<<(b->instances + 31) / 32, 32, 0, b->stream>>>(b->d_hdr, (KbReverb*)b->d_state, b->d_rings, d, n, 2, b->instances, b->fs); break;
-	case KB_FX_DELAY_PINGPONG: kb_fx_seq_kernel<KB_FX_DELAY_PINGPONG, KbDPingPong><<<(b->instances + 31) / 32, 32, 0, b->stream>>>(b->d_hdr, (KbDPingPong*)b->d_state, b->d_rings, d, n, 2, b->instances, b->fs); break;
-	case KB_FX_DELAY_REVERB: kb_fx_seq_kernel<KB_FX_DELAY_REVERB, KbDReverb><<<(b->instances + 31) / 32, 32, 0, b->stream>>>(b->d_hdr, (KbDReverb*)b->d_state, b->d_rings, d, n, 1, b->instances, b->fs); break;
+	case KB_FX_PINGPONG: {
+		KbPingPong* st = (KbPingPong*)b->d_state;
+		// sub-blocks of at most 8192 frames (the staged block lives in shared memory); every sub-block is planned on the device
+		for (int o = 0; o < n; o += 8192) {
+			const int len = std::min(8192, n - o);
+			if (!seq_only) {
+				kb_pingpong_plan_kernel<<<ib, 32, 0, b->stream>>>(b->d_hdr, st, b->d_plan, b->instances, len, b->fs);
+				kb_pingpong_par_kernel<1024><<<b->instances * 2, 1024, len * sizeof(float), b->stream>>>(b->d_hdr, st, b->d_plan, b->d_rings, d + o, len, n, b->fs);
+				kb_pingpong_finish_kernel<<<ib, 32, 0, b->stream>>>(st, b->d_plan, b->instances, len);
+				b->launches += 3;
+			}
+			kb_fx_seq_kernel<KB_FX_PINGPONG, KbPingPong><<<ib, 32, 0, b->stream>>>(b->d_hdr, st, b->d_rings, d + o, len, n, 2, b->instances, b->fs, seq_only ? nullptr : b->d_plan);
+			if (o + 8192 < n) b->launches++;
+		}
+		break; }
+	case KB_FX_REVERB: {
+		KbReverb* st = (KbReverb*)b->d_state;
+		if (!seq_only) {
+			kb_reverb_plan_kernel<<<ib, 32, 0, b->stream>>>(st, b->d_plan, b->instances);
+			kb_reverb_par_kernel<<<b->instances, 256, sizeof(KbRvSmem), b->stream>>>(b->d_hdr, st, b->d_plan, b->d_rings, d, n, n);
+			b->launches += 2;
+		}
+		kb_fx_seq_kernel<KB_FX_REVERB, KbReverb><<<ib, 32, 0, b->stream>>>(b->d_hdr, st, b->d_rings, d, n, n, 2, b->instances, b->fs, seq_only ? nullptr : b->d_plan);
+		break; }
+	case KB_FX_DELAY_PINGPONG: {
+		KbDPingPong* st = (KbDPingPong*)b->d_state;
+		// sub-blocks no longer than the shorter delay so that a sub-block's reads precede its writes
+		int sub = n;
+		if (!seq_only) {
+			float dmin = 1e30f;
+			for (int i = 0; i < b->instances; i++) dmin = std::min(dmin, std::min(b->hdr[i].controls[0].value, b->hdr[i].controls[1].value) * b->fs.f);
+			sub = std::max(1, std::min(n, (int)dmin - 2));
+			if (sub < 64) sub = n;                                  // too short to be worth it: the plan falls back to the sequential kernel
+		}
+		for (int o = 0; o < n; o += sub) {
+			const int len = std::min(sub, n - o);
+			if (!seq_only) {
+				kb_dpingpong_plan_kernel<<<ib, 32, 0, b->stream>>>(b->d_hdr, st, b->d_plan, b->instances, len, b->fs);
+				dim3 grid((len + 255) / 256, b->instances);
+				kb_dpingpong_par_kernel<<<grid, 256, 0, b->stream>>>(b->d_hdr, st, b->d_plan, b->d_rings, d + o, len, n, b->fs);
+				kb_dpingpong_finish_kernel<<<ib, 32, 0, b->stream>>>(st, b->d_plan, b->instances, len);
+				b->launches += 3;
+			}
+			kb_fx_seq_kernel<KB_FX_DELAY_PINGPONG, KbDPingPong><<<ib, 32, 0, b->stream>>>(b->d_hdr, st, b->d_rings, d + o, len, n, 2, b->instances, b->fs, seq_only ? nullptr : b->d_plan);
+			if (o + sub < n) b->launches++;
+		}
+		break; }
+	case KB_FX_DELAY_REVERB: kb_fx_seq_kernel<KB_FX_DELAY_REVERB, KbDReverb><<<ib, 32, 0, b->stream>>>(b->d_hdr, (KbDReverb*)b->d_state, b->d_rings, d, n, n, 1, b->instances, b->fs, nullptr); break;
 	}
 	b->prof_end();
 	b->launches++;

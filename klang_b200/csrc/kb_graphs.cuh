@@ -315,10 +315,9 @@ KB_D float kb_tb_tick(const KbFs& fs, const KbTbBlock& B, KbTbVoice& n, int& not
 // Gain.k:15-18
 KB_D float kb_gain_frame(const KbFxHdr& h, float in) { return in * h.controls[0].value; }
 
-// PingPong.k:42-71
-KB_D void kb_pingpong_frame(const KbFs& fs, KbFxHdr& h, KbPingPong& p, float* rings, float inl, float inr, float& ol, float& orr) {
+// PingPong.k:42-59: the control half of the frame (smoothers, LFO, delay hand-over)
+KB_D void kb_pingpong_control(const KbFs& fs, KbFxHdr& h, KbPingPong& p, float& gain, float& delay, float& dry) {
 	KbControl* c = h.controls;
-	float* ringl = rings + p.left.ring; float* ringr = rings + p.right.ring;
 	const float rate = (c[3].value * c[3].value) * 100.f;                     // :44
 	const float new_delay = kb_control_smooth(c[5]);                          // :45
 	if (fabsf(p.delay - new_delay) > 0.001) {                                 // :46 (double compare)
@@ -329,11 +328,17 @@ KB_D void kb_pingpong_frame(const KbFs& fs, KbFxHdr& h, KbPingPong& p, float* ri
 		p.delay = c[5].value;
 		kb_bosc_set_f(fs, p.lfo, rate);
 	}
-	const float gain = c[0].value;                                            // :55
-	const float delay = kb_control_smooth(c[1]);                              // :56
+	gain = c[0].value;                                                        // :55
+	delay = kb_control_smooth(c[1]);                                          // :56
 	const float vibrato = (c[2].value * c[2].value) * rate * KB_ROOT2_F;      // :57
-	const float dry = c[4].value;                                             // :58
+	dry = c[4].value;                                                         // :58
 	kb_control_set(c[1], c[1].value + kb_bosc_sine_tick(p.lfo) * vibrato * (float)0.00005);   // :59
+}
+// PingPong.k:42-71
+KB_D void kb_pingpong_frame(const KbFs& fs, KbFxHdr& h, KbPingPong& p, float* rings, float inl, float inr, float& ol, float& orr) {
+	float* ringl = rings + p.left.ring; float* ringr = rings + p.right.ring;
+	float gain, delay, dry;
+	kb_pingpong_control(fs, h, p, gain, delay, dry);
 	kb_delay_set(p.left, delay * fs.f);                                       // :63
 	kb_delay_set(p.right, 0.5f * delay * fs.f);                               // :64
 	const float rr = kb_delay_tick(p.right, ringr);                           // :66 (Q13: two read ticks per line per frame)

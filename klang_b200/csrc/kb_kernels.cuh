@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include "kb_graphs.cuh"
+#include "kb_fx_parallel.cuh"
 
 // per-instance, per-block constants computed by the host at control rate (see kb_graphs.cuh)
 struct KbSynthBlock { KbTbBlock tb; float sx_tr_at, sx_dt_at; };
@@ -209,13 +210,14 @@ __global__ void kb_gain_kernel(const KbFxHdr* __restrict__ hdr, float* __restric
 // the feedback delays allow.
 template <int GRAPH, class STATE>
 __global__ void kb_fx_seq_kernel(KbFxHdr* __restrict__ hdrs, STATE* __restrict__ states, float* __restrict__ rings,
-                                 float* __restrict__ io, int n, int channels, int instances, KbFs fs) {
+                                 float* __restrict__ io, int n, int stride, int channels, int instances, KbFs fs, const KbFxPlan* __restrict__ plan) {
 	const int inst = blockIdx.x * blockDim.x + threadIdx.x;
 	if (inst >= instances) return;
+	if (plan && plan[inst].mode == KB_PLAN_PARALLEL) return;          // taken by the chunk-parallel kernel
 	KbFxHdr h = hdrs[inst];
 	STATE s = states[inst];
-	float* l = io + (size_t)inst * channels * n;
-	float* r = l + n;
+	float* l = io + (size_t)inst * channels * stride;
+	float* r = l + stride;
 	for (int i = 0; i < n; i++) {
 		if constexpr (GRAPH == KB_FX_PINGPONG) { float ol, orr; kb_pingpong_frame(fs, h, s, rings, l[i], r[i], ol, orr); l[i] = ol; r[i] = orr; }
 		if constexpr (GRAPH == KB_FX_REVERB) { float ol, orr; kb_reverb_frame(h, s, rings, l[i], r[i], ol, orr); l[i] = ol; r[i] = orr; }

@@ -346,3 +346,56 @@ def test_tiled_schedule_equals_lane_per_voice_schedule(eng, graph, inst, voices)
     assert_parity(a[0], b[0], f"tiled vs lane-per-voice graph {graph}", exact=True)
     assert np.array_equal(a[1], b[1])
     assert np.abs(a[0]).max() > 0.01
+
+
+@pytest.mark.parametrize("graph,blocks,n", [(cases.FX_PINGPONG, 30, 2048), (cases.FX_REVERB, 12, 1000), (cases.FX_DELAY_PINGPONG, 10, 3000)])
+def test_chunk_parallel_effects_match_oracle_and_sequential_schedule(eng, graph, blocks, n):
+    """The chunk-parallel effect kernels (engaged once control smoothers settle / delays allow) are bit-identical to the
+    oracle and to the frame-sequential schedule, including the hand-over between the two schedules, ragged block lengths
+    and a control change in the middle (which sends PingPong back to the sequential schedule while its smoothers move)."""
+    fs, inst = 48000, 4
+    oracle.port.set_fs(fs)
+    lens = [n] * blocks
+    lens[3] = 517
+    lens[5] = 1
+    total = sum(lens)
+    x = np.stack([cases.fx_input(2, total, seed=20 + i) for i in range(inst)])
+    change_at = blocks // 2
+
+    def controls_for(b, set_control):
+        if b == 0 and graph == cases.FX_PINGPONG:
+            set_control(0, 0.8)
+        if b == change_at:
+            if graph == cases.FX_PINGPONG:
+                set_control(1, 0.3)       # new delay target: smoothers move again
+                set_control(5, 0.3)
+            elif graph == cases.FX_REVERB:
+                set_control(6, 0.5)       # room size: early taps and all 16 delay times are re-drawn
+                set_control(2, 0.4)
+            else:
+                set_control(1, 0.31)
+
+    want = np.empty_like(x)
+    for i in range(inst):
+        fx = oracle.port.Fx(graph)
+        o = 0
+        for b, ln in enumerate(lens):
+            controls_for(b, fx.set_control)
+            want[i, :, o:o + ln] = fx.process(x[i, :, o:o + ln])
+            o += ln
+        fx.close()
+    for flags in (0, kb.FX_SEQUENTIAL):
+        bank = kb.FxBank(graph, inst, fs, max(lens))
+        got = np.empty_like(x)
+        o, engaged = 0, 0
+        for b, ln in enumerate(lens):
+            controls_for(b, bank.set_control)
+            blk = np.ascontiguousarray(x[:, :, o:o + ln])
+            bank.process_inplace(blk, flags=flags)
+            got[:, :, o:o + ln] = blk
+            engaged += bank.parallel_instances() if flags == 0 else 0
+            o += ln
+        bank.close()
+        assert_parity(got, want, f"fx graph {graph} flags {flags}", exact=True)
+        if flags == 0:
+            assert engaged > inst * blocks // 4, f"chunk-parallel schedule engaged on only {engaged} instance-blocks"
