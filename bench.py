@@ -140,6 +140,45 @@ def cpu_reference_run(steps, warmup, total_voices=INSTANCES * VOICES, block=BLOC
     return value, wall, info
 
 
+def _cpu_extra_worker(args):
+    kind, what, graph, units, n, blocks = args
+    import numpy as np
+    import oracle
+    eng = oracle.ref if kind == "reference" else oracle.port
+    eng.set_fs(FS)
+    eng.srand(1)
+    if what == "fx":
+        objs = [eng.Fx(graph) for _ in range(units)]
+        x = (np.random.default_rng(1).random((objs[0].channels, n), dtype=np.float32) - 0.5)
+        x = x[0] if objs[0].channels == 1 else x
+        for o in objs:
+            o.process(x)
+        t0 = time.perf_counter()
+        for _ in range(blocks):
+            for o in objs:
+                o.process(x)
+        return time.perf_counter() - t0
+    sy = eng.Synth(graph, max(1, units))
+    for k in range(units):
+        sy.voice_start(k, voice_pitch(k), voice_velocity(k))
+    sy.process(n)
+    t0 = time.perf_counter()
+    for _ in range(blocks):
+        sy.process(n)
+    return time.perf_counter() - t0
+
+
+def cpu_extra(what, graph, units_per_core, n, blocks):
+    """Reference CPU throughput (units x samples per second over all cores) for a secondary workload."""
+    import oracle
+    kind = "reference" if oracle.ref.available() else "port"
+    cores = len(os.sched_getaffinity(0))
+    with mp.get_context("fork").Pool(cores) as pool:
+        times = pool.map(_cpu_extra_worker, [(kind, what, graph, units_per_core, n, blocks)] * cores)
+    return {"value": cores * units_per_core * n * blocks / max(times), "cores": cores, "kind": kind,
+            "sample": f"{cores} workers x {units_per_core} {'instances' if what == 'fx' else 'voices'} x {blocks} blocks of {n}"}
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
@@ -215,8 +254,11 @@ def main():
     kb.lib().kb_srand(1)
     bank = kb.SynthBank(kb.SY_SUBTRACTIVE, INSTANCES, VOICES, FS, BLOCK, local_rank)
     bank.set_stream(stream.cuda_stream)
+    from klang_b200 import sharding
     total = INSTANCES * VOICES
-    gid0 = rank * total                                   # global voice ids of this rank
+    lo, hi = sharding.shard_instances(INSTANCES * world, rank, world)   # weak scaling: 8 Synth instances per rank
+    assert hi - lo == INSTANCES
+    gid0 = lo * VOICES                                    # global voice ids of this rank
     for g in range(total):
         bank.voice_start(g % VOICES, voice_pitch(gid0 + g), voice_velocity(gid0 + g), g // VOICES)
     flags = kb.BANK_MIX | kb.MIX_SUM if world > 1 else 0
@@ -245,8 +287,7 @@ def main():
     def step_device():
         events()
         bank.process_into(out_dev, BLOCK, flags)
-        if dist is not None:
-            dist.reduce(out_dev, dst=0)
+        sharding.reduce_mix(out_dev, dst=0)
 
     def step_e2e():
         events()
@@ -254,7 +295,7 @@ def main():
             bank.process_into(out_host.numpy(), BLOCK, flags)       # host-buffer call: upload state, kernels, D2H, sync
         else:
             bank.process_into(out_dev, BLOCK, flags)
-            dist.reduce(out_dev, dst=0)
+            sharding.reduce_mix(out_dev, dst=0)
             out_host.copy_(out_dev, non_blocking=True)
             torch.cuda.synchronize()
 
@@ -328,8 +369,14 @@ def main():
     alg_bytes = total * BLOCK * 4.0 * 2 + INSTANCES * BLOCK * 4.0      # per-voice stream write + mix read, mix write
     achieved = alg_bytes / (k_ms_avg * 1e-3) / 1e9
     issue_peak = 148 * 128 * sm_max * 1e6                                # fp32 lanes x clock
+    traffic = None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get("kb_sub_tiled_kernel")
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": "kb_sub_tiled_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "kernel_ms": k_ms_avg, "kernel_share_of_step": k_ms_avg / ms_per_step,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "note": "C2 is bound by dependent-issue latency, not HBM (SURVEY H6): 8 B of stream traffic per voice-sample",
@@ -348,7 +395,7 @@ def main():
 
     if rank == 0 and not args.no_extras:
         try:
-            line["other_workloads"] = extras(kb, torch, dev, stream, flush_l2, hbm_peak, peak_src, local_rank)
+            line["other_workloads"] = extras(kb, torch, dev, stream, flush_l2, hbm_peak, peak_src, local_rank, with_cpu=(world == 1 and not args.no_cpu))
         except Exception as e:   # secondary numbers never take the headline down
             line["other_workloads"] = {"error": repr(e)}
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -364,9 +411,9 @@ def main():
         print(json.dumps(line), flush=True)
 
 
-def extras(kb, torch, dev, stream, flush_l2, hbm_peak, peak_src, device_index):
-    """Secondary BASELINE configs, short runs: C1 Gain, C3 SuperSaw, C4 PingPong / Reverb (HBM roofline), C5 share."""
-    import numpy as np
+def extras(kb, torch, dev, stream, flush_l2, hbm_peak, peak_src, device_index, with_cpu=True):
+    """Secondary BASELINE configs, short runs: C1 Gain, C3 SuperSaw, C4 PingPong / Reverb / Delay-PingPong, C5 share."""
+    import oracle
     res = {}
 
     def time_steps(fn, steps, warmup=3):
@@ -384,32 +431,42 @@ def extras(kb, torch, dev, stream, flush_l2, hbm_peak, peak_src, device_index):
             tot += a.elapsed_time(b)
         return tot / steps
 
+    def roof(gbs):
+        return {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "peak_source": peak_src}
+
     # C1: Gain, 1 channel x 4096 (launch-bound) and batched 64 Mi samples (HBM-bound)
     for name, inst, n in (("c1_gain_1x4096", 1, 4096), ("c1_gain_batched_64x1Mi", 64, 1 << 20)):
         fx = kb.FxBank(kb.FX_GAIN, inst, FS, n, device_index)
         fx.set_stream(stream.cuda_stream)
         io = torch.rand(inst, 1, n, device=dev) - 0.5
         ms = time_steps(lambda: fx.process_inplace(io), 10)
-        gbs = inst * n * 8 / (ms * 1e-3) / 1e9
-        res[name] = {"samples_per_s": inst * n / (ms * 1e-3), "ms_per_step": ms,
-                     "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "peak_source": peak_src}}
+        res[name] = {"samples_per_s": inst * n / (ms * 1e-3), "ms_per_step": ms, "roofline": roof(inst * n * 8 / (ms * 1e-3) / 1e9)}
         fx.close()
+    if with_cpu:
+        res["c1_gain_1x4096"]["cpu_reference"] = cpu_extra("fx", oracle.FX_GAIN, 1, 4096, 2000)
 
-    # C4: delay-line effects, 64 stereo instances
-    for name, graph, n, steps in (("c4_pingpong_64", kb.FX_PINGPONG, 4096, 3), ("c4_reverb_64", kb.FX_REVERB, 1024, 2)):
+    # C4: delay-line effects, 64 stereo instances; chunk-parallel schedule vs the frame-sequential one (same results)
+    for name, graph, n, steps in (("c4_pingpong_64", kb.FX_PINGPONG, 4096, 5), ("c4_reverb_64", kb.FX_REVERB, 4096, 3),
+                                  ("c4_delay_pingpong_64", kb.FX_DELAY_PINGPONG, 8192, 5)):
         fx = kb.FxBank(graph, 64, FS, n, device_index)
         fx.set_stream(stream.cuda_stream)
         io = torch.rand(64, 2, n, device=dev) - 0.5
-        fx.profile(True)
-        ms = time_steps(lambda: fx.process_inplace(io), steps, warmup=3)
-        k_ms, k_n = fx.profile_read()
+        for _ in range(40000 // n + 2):                     # PingPong.k: let the control smoothers reach their fixed point
+            fx.process_inplace(io)
+        ms = time_steps(lambda: fx.process_inplace(io.uniform_(-0.5, 0.5)), steps, warmup=1)
+        fill = time_steps(lambda: io.uniform_(-0.5, 0.5), steps, warmup=1)
+        ms -= fill
+        par = fx.parallel_instances()
         bpf = fx.bytes_per_frame()
-        k_avg = k_ms / max(1, k_n)
-        gbs = 64 * n * bpf / (k_avg * 1e-3) / 1e9
+        ms_seq = time_steps(lambda: fx.process_inplace(io, flags=kb.FX_SEQUENTIAL), 1, warmup=0) if n <= 4096 else None
         res[name] = {"frames_per_s": 64 * n / (ms * 1e-3), "ms_per_step": ms, "block": n, "bytes_per_frame": bpf,
-                     "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                                  "kernel_ms": k_avg, "peak_source": peak_src}}
+                     "instances_on_parallel_schedule": par, "ms_per_step_sequential_schedule": ms_seq,
+                     "roofline": roof(64 * n * bpf / (ms * 1e-3) / 1e9)}
         fx.close()
+    if with_cpu:
+        res["c4_pingpong_64"]["cpu_reference"] = cpu_extra("fx", oracle.FX_PINGPONG, 1, 4096, 40)
+        res["c4_reverb_64"]["cpu_reference"] = cpu_extra("fx", oracle.FX_REVERB, 1, 4096, 8)
+        res["c4_delay_pingpong_64"]["cpu_reference"] = cpu_extra("fx", oracle.FX_DELAY_PINGPONG, 1, 4096, 40)
 
     # C3 SuperSaw 8 x 32 voices; C5 per-GPU share: 4 x 128 TB303 + 4 x 128 SynTHX voices
     for name, graph, inst, voices, n, steps in (("c3_supersaw_256", kb.SY_SUPERSAW, 8, 32, 4096, 5),
@@ -419,11 +476,15 @@ def extras(kb, torch, dev, stream, flush_l2, hbm_peak, peak_src, device_index):
         sb = kb.SynthBank(graph, inst, voices, FS, n, device_index)
         sb.set_stream(stream.cuda_stream)
         for g in range(inst * voices):
-            sb.voice_start(g % voices, voice_pitch(g), voice_velocity(g), g // voices)
+            sb.voice_start(g % voices, 36 + (5 * g) % 36, voice_velocity(g), g // voices)
         out = torch.empty(sb.out_shape(n), dtype=torch.float32, device=dev)
         ms = time_steps(lambda: sb.process_into(out, n), steps, warmup=3)
         res[name] = {"voice_samples_per_s": inst * voices * n / (ms * 1e-3), "ms_per_step": ms, "block": n}
         sb.close()
+    if with_cpu:
+        res["c3_supersaw_256"]["cpu_reference"] = cpu_extra("synth", oracle.SY_SUPERSAW, 16, 4096, 8)
+        res["c5_tb303_512"]["cpu_reference"] = cpu_extra("synth", oracle.SY_TB303, 16, 4096, 4)
+        res["c5_synthx_512"]["cpu_reference"] = cpu_extra("synth", oracle.SY_SYNTHX, 4, 1024, 2)
     return res
 
 

@@ -188,8 +188,10 @@ __global__ void kb_pingpong_finish_kernel(KbPingPong* __restrict__ states, const
 struct KbRvSmem {
 	float rd[16][2 * KB_RV_LMAX + 4];        // ring read windows (2L+1 used)
 	float yv[16][2 * KB_RV_LMAX + 4];        // filter outputs * gain, per tick
-	float xin[2][KB_RV_LMAX], xf[2][KB_RV_LMAX], r1[2][KB_RV_LMAX], r2[2][KB_RV_LMAX], r3[2][KB_RV_LMAX];
-	float carry[2][2][16];                     // FilteredDelay::in carried between frames and chunks: [stage parity][old/new][line]
+	float xin[2][2][KB_RV_LMAX];             // io block, double buffered: the early cascade runs one chunk ahead
+	float xf[2][2][KB_RV_LMAX];              // early LPF->HPF output, double buffered
+	float r1[2][KB_RV_LMAX], r2[2][KB_RV_LMAX], r3[2][KB_RV_LMAX];
+	float carry[2][16];                      // FilteredDelay::in carried between frames and chunks: [old/new][line]
 	float times[KB_RV_MAXREFL], gl[KB_RV_MAXREFL], gr[KB_RV_MAXREFL];
 };
 KB_D KbRvFDelay& kb_rv_line(KbReverb& rv, int line) { return (line < 8 ? rv.mid[line >> 2] : rv.late[(line - 8) >> 2]).d[line & 3]; }
@@ -220,20 +222,20 @@ __global__ void __launch_bounds__(256) kb_reverb_par_kernel(const KbFxHdr* __res
 	const int inst = blockIdx.x;
 	const KbFxPlan pl = plan[inst];
 	if (pl.mode != KB_PLAN_PARALLEL) return;
-	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, NT = blockDim.x;
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	constexpr int NT = 256;
 	KbReverb& rv = states[inst];
 	const KbControl* c = hdrs[inst].controls;
 	const float dry = c[0].value, wet = c[4].value, cE = c[1].value, cM = c[2].value, cL = c[3].value;
 	float* Lio = io + (size_t)inst * 2 * stride; float* Rio = Lio + stride;
 	const int count = rv.count;
 	if (tid < KB_RV_MAXREFL) { S.times[tid] = rv.times[tid]; S.gl[tid] = rv.gl[tid]; S.gr[tid] = rv.gr[tid]; }
-	if (tid < 16) { S.carry[0][0][tid] = kb_rv_line(rv, tid).in; S.carry[0][1][tid] = kb_rv_line(rv, tid).in; }
+	if (tid < 16) { S.carry[0][tid] = kb_rv_line(rv, tid).in; S.carry[1][tid] = S.carry[0][tid]; }
 	int cpar = 0;                                    // which copy of the carries is current
 
 	// per-role register state
 	float z0 = 0.f, z1 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, a1 = 0.f, a2 = 0.f, gain = 0.f, frac = 0.f;      // warp 0: line filter
-	float e_z[4] = { 0, 0, 0, 0 }, e_lp[5], e_hp[5];                                                       // warp 1: early cascade
-	int rpos = 0, wpos = 0, lsize = 1; long long lring = 0;
+	float e_z[4] = { 0, 0, 0, 0 }, e_lp[5] = { 0, 0, 0, 0, 0 }, e_hp[5] = { 0, 0, 0, 0, 0 };                // warp 1: early cascade
 	if (tid < 16) {
 		const KbRvFDelay& d = kb_rv_line(rv, tid);
 		z0 = d.filter.z0; z1 = d.filter.z1; b0 = d.filter.b0; b1 = d.filter.b1; b2 = d.filter.b2; a1 = d.filter.a1; a2 = d.filter.a2;
@@ -245,27 +247,58 @@ __global__ void __launch_bounds__(256) kb_reverb_par_kernel(const KbFxHdr* __res
 		e_lp[0] = lp.b0; e_lp[1] = lp.b1; e_lp[2] = lp.b2; e_lp[3] = lp.a1; e_lp[4] = lp.a2;
 		e_hp[0] = hp.b0; e_hp[1] = hp.b1; e_hp[2] = hp.b2; e_hp[3] = hp.a1; e_hp[4] = hp.a2;
 	}
-	// every thread keeps the ring geometry of line (tid & 15) for the cooperative loads / stores
-	{
-		const KbDelay& d = kb_rv_line(rv, tid & 15).delay;
-		rpos = d.last_position; wpos = d.position; lsize = d.SIZE; lring = d.ring;
-	}
+	// every thread keeps the ring geometry of line (tid & 15) for the cooperative window loads, and of the line it
+	// writes in S3/S4 (side, q) is looked up there
+	const KbDelay& myd = kb_rv_line(rv, tid & 15).delay;
+	int rpos = myd.last_position; const int lsize = myd.SIZE; const long long lring = myd.ring;
 	const int esize = rv.dl.SIZE;
 	int epos = rv.dl.position;                       // Stereo::Delay: both channels share the write position
 	float* ringel = rings + rv.dl.ring; float* ringer = rings + rv.dr.ring;
-	__syncthreads();
 
-	for (int g0 = 0; g0 < n; g0 += pl.chunk) {
+	// in >> lpf >> hpf for one chunk (Reverb.k:87), lane = channel
+	auto early_cascade = [&](int buf, int L) {
+		for (int t = 0; t < L; t++) {
+			const float x = S.xin[buf][lane][t];
+			const float y = e_lp[0] * x + e_z[0];
+			e_z[0] = e_lp[1] * x - e_lp[3] * y + e_z[1];
+			e_z[1] = e_lp[2] * x - e_lp[4] * y;
+			const float w = e_hp[0] * y + e_z[2];
+			e_z[2] = e_hp[1] * y - e_hp[3] * w + e_z[3];
+			e_z[3] = e_hp[2] * y - e_hp[4] * w;
+			S.xf[buf][lane][t] = w;
+		}
+	};
+	// prologue: chunk 0's input and early cascade
+	{
+		const int L0 = min(pl.chunk, n);
+		for (int i = tid; i < 2 * L0; i += NT) { const int ch = i / L0, t = i % L0; S.xin[0][ch][t] = (ch ? Rio : Lio)[t]; }
+		__syncthreads();
+		if (warp == 1 && lane < 2) early_cascade(0, L0);
+		__syncthreads();
+	}
+
+	int buf = 0;
+	for (int g0 = 0; g0 < n; g0 += pl.chunk, buf ^= 1) {
 		const int L = min(pl.chunk, n - g0);
-		// ---- S0: io block and ring read windows
-		for (int i = tid; i < 2 * L; i += NT) { const int ch = i / L, t = i % L; S.xin[ch][t] = (ch ? Rio : Lio)[g0 + t]; }
-		for (int i = tid; i < 16 * (2 * L + 1); i += NT) {
-			const int line = i & 15, k = i >> 4;                  // (tid & 15) == line because NT is a multiple of 16
-			int idx = rpos + k; if (idx >= lsize) idx -= lsize;
-			S.rd[line][k] = rings[lring + idx];
+		const int gn = g0 + L, Ln = min(pl.chunk, n - gn);        // next chunk
+		// ---- P0: ring read windows (8 loads in flight per thread) and the next chunk's io block
+		{
+			const int total = 16 * (2 * L + 1);
+			for (int i0 = tid; i0 < total; i0 += 8 * NT) {
+				float v[8];
+				#pragma unroll
+				for (int j = 0; j < 8; j++) {
+					const int i = i0 + j * NT;
+					if (i < total) { int idx = rpos + (i >> 4); if (idx >= lsize) idx -= lsize; v[j] = rings[lring + idx]; }
+				}
+				#pragma unroll
+				for (int j = 0; j < 8; j++) { const int i = i0 + j * NT; if (i < total) S.rd[i & 15][i >> 4] = v[j]; }
+			}
+			if (Ln > 0) for (int i = tid; i < 2 * Ln; i += NT) { const int ch = i / Ln, t = i % Ln; S.xin[buf ^ 1][ch][t] = (ch ? Rio : Lio)[gn + t]; }
 		}
 		__syncthreads();
-		// ---- S1: filter chains (serial, lane = chain)  ||  S2: early taps of the PREVIOUS samples are not needed: taps read older data
+		// ---- P1: warp 0 = the 16 line filters over their 2L ticks; warp 1 = early cascade of the NEXT chunk;
+		//          warps 2..7 = early ring write and taps of this chunk (taps read samples older than the chunk)
 		if (warp == 0) {
 			if (lane < 16) {
 				const float* rd = S.rd[lane]; float* yv = S.yv[lane];
@@ -282,37 +315,32 @@ __global__ void __launch_bounds__(256) kb_reverb_par_kernel(const KbFxHdr* __res
 				}
 			}
 		} else if (warp == 1) {
-			if (lane < 2) {
-				for (int t = 0; t < L; t++) {                            // in >> lpf >> hpf  Reverb.k:87
-					const float x = S.xin[lane][t];
-					const float y = e_lp[0] * x + e_z[0];
-					e_z[0] = e_lp[1] * x - e_lp[3] * y + e_z[1];
-					e_z[1] = e_lp[2] * x - e_lp[4] * y;
-					const float w = e_hp[0] * y + e_z[2];
-					e_z[2] = e_hp[1] * y - e_hp[3] * w + e_z[3];
-					e_z[3] = e_hp[2] * y - e_hp[4] * w;
-					S.xf[lane][t] = w;
+			if (lane < 2 && Ln > 0) early_cascade(buf ^ 1, Ln);
+		} else {
+			const int wt = tid - 64, WN = NT - 64;
+			for (int i = wt; i < 2 * L; i += WN) { const int ch = i / L, t = i % L; int idx = epos + t; if (idx >= esize) idx -= esize; (ch ? ringer : ringel)[idx] = S.xf[buf][ch][t]; }
+			for (int i = wt; i < 2 * L; i += WN) {
+				const int ch = i / L, t = i % L;
+				const float* ring = ch ? ringer : ringel; const float* gg = ch ? S.gr : S.gl;
+				int pos = epos + t + 1; if (pos >= esize) pos -= esize;      // position after this frame's write
+				float acc = 0.f;
+				for (int d0 = 0; d0 < count; d0 += 4) {                      // Stereo::Delay::tap(float)  klang.h:4668-4681
+					float va[4], vb[4], fr[4];
+					#pragma unroll
+					for (int j = 0; j < 4; j++) if (d0 + j < count) {
+						float read = (float)(pos - 1) - S.times[d0 + j]; if (read < 0.f) read += esize;
+						const float fl = floorf(read); fr[j] = read - fl;
+						const int ii = (int)read, jj = (ii == esize - 1) ? 0 : ii + 1;
+						va[j] = ring[ii]; vb[j] = ring[jj];
+					}
+					#pragma unroll
+					for (int j = 0; j < 4; j++) if (d0 + j < count) acc += (va[j] * (1.f - fr[j]) + vb[j] * fr[j]) * gg[d0 + j];   // r1 += tap * gain  Reverb.k:89-90
 				}
+				S.r1[ch][t] = acc;
 			}
 		}
 		__syncthreads();
-		// ---- S2: early ring write, then the taps (the reads of frame t address samples older than the chunk)
-		for (int i = tid; i < 2 * L; i += NT) { const int ch = i / L, t = i % L; int idx = epos + t; if (idx >= esize) idx -= esize; (ch ? ringer : ringel)[idx] = S.xf[ch][t]; }
-		for (int i = tid; i < 2 * L; i += NT) {
-			const int ch = i / L, t = i % L;
-			const float* ring = ch ? ringer : ringel; const float* gg = ch ? S.gr : S.gl;
-			int pos = epos + t + 1; if (pos >= esize) pos -= esize;      // position after this frame's write
-			float acc = 0.f;
-			for (int d = 0; d < count; d++) {                            // Stereo::Delay::tap(float)  klang.h:4668-4681
-				float read = (float)(pos - 1) - S.times[d]; if (read < 0.f) read += esize;
-				const float fl = floorf(read), fr = read - fl;
-				const int ii = (int)read, jj = (ii == esize - 1) ? 0 : ii + 1;
-				acc += (ring[ii] * (1.f - fr) + ring[jj] * fr) * gg[d];    // r1 += tap * gain  Reverb.k:89-90
-			}
-			S.r1[ch][t] = acc;
-		}
-		__syncthreads();
-		// ---- S3 / S4: FDN matrix, ring writes, outputs (mid then late, late's input is mid's output)
+		// ---- P2: FDN matrix, ring writes, outputs (mid then late, late's input is mid's output)
 		for (int stage = 0; stage < 2; stage++) {
 			for (int i = tid; i < 2 * L; i += NT) {
 				const int side = i / L, t = i % L, base = stage * 8 + side * 4;
@@ -333,40 +361,38 @@ __global__ void __launch_bounds__(256) kb_reverb_par_kernel(const KbFxHdr* __res
 				for (int q = 0; q < 4; q++) {
 					const KbDelay& dq = kb_rv_line(rv, base + q).delay;
 					float* ring = rings + dq.ring;
-					const int w0 = dq.position + 2 * (g0 + t) - 2 * g0;      // positions are advanced after every chunk
-					int wa = w0 + 1; if (wa >= dq.SIZE) wa -= dq.SIZE; if (wa >= dq.SIZE) wa -= dq.SIZE;
+					const int w0 = dq.position + 2 * t;                       // positions are advanced after every chunk
+					int wa = w0 + 1; if (wa >= dq.SIZE) wa -= dq.SIZE;
 					ring[wa] = fb[q];                                        // second tick of this frame writes fb
-					if (t + 1 < L) { int wb = w0 + 2; if (wb >= dq.SIZE) wb -= dq.SIZE; if (wb >= dq.SIZE) wb -= dq.SIZE; ring[wb] = fb[q]; }   // = first tick of the next frame
-					else S.carry[0][cpar ^ 1][base + q] = fb[q];
-					if (t == 0) { int wc = w0; if (wc >= dq.SIZE) wc -= dq.SIZE; ring[wc] = S.carry[0][cpar][base + q]; }
+					if (t + 1 < L) { int wb = w0 + 2; if (wb >= dq.SIZE) wb -= dq.SIZE; ring[wb] = fb[q]; }   // = first tick of the next frame
+					else S.carry[cpar ^ 1][base + q] = fb[q];
+					if (t == 0) { int wc = w0; if (wc >= dq.SIZE) wc -= dq.SIZE; ring[wc] = S.carry[cpar][base + q]; }
 				}
 			}
 			__syncthreads();
 		}
-		// ---- S5: output
 		for (int t = tid; t < L; t += NT) {
 			const float refl_l = (S.r1[0][t] * cE + S.r2[0][t] * cM) + S.r3[0][t] * cL;
 			const float refl_r = (S.r1[1][t] * cE + S.r2[1][t] * cM) + S.r3[1][t] * cL;
-			Lio[g0 + t] = S.xin[0][t] * dry + refl_l * wet;                   // Reverb.k:272 (Q7: the right wet gain is 0)
-			Rio[g0 + t] = S.xin[1][t] * dry + refl_r * 0.f;
+			Lio[g0 + t] = S.xin[buf][0][t] * dry + refl_l * wet;              // Reverb.k:272 (Q7: the right wet gain is 0)
+			Rio[g0 + t] = S.xin[buf][1][t] * dry + refl_r * 0.f;
 		}
-		__syncthreads();
 		// advance the ring geometry
 		if (tid < 16) {
 			KbDelay& d = kb_rv_line(rv, tid).delay;
 			d.position = (d.position + 2 * L) % d.SIZE;
 			d.last_position = (d.last_position + 2 * L) % d.SIZE;
 		}
-		rpos = (rpos + 2 * L) % lsize; wpos = (wpos + 2 * L) % lsize;
-		cpar ^= 1;
+		rpos = (rpos + 2 * L) % lsize;
 		epos = (epos + L) % esize;
+		cpar ^= 1;
 		__syncthreads();
 	}
 	// state back
 	if (tid < 16) {
 		KbRvFDelay& d = kb_rv_line(rv, tid);
 		d.filter.z0 = z0; d.filter.z1 = z1;
-		d.in = S.carry[0][cpar][tid];
+		d.in = S.carry[cpar][tid];
 	}
 	if (warp == 1 && lane < 2) {
 		rv.lpf[lane].z0 = e_z[0]; rv.lpf[lane].z1 = e_z[1]; rv.hpf[lane].z0 = e_z[2]; rv.hpf[lane].z1 = e_z[3];
