@@ -248,7 +248,7 @@ extern "C" int kb_fx_bank_process(kb_fx_bank* b, float* io, int n, unsigned flag
 			const int len = std::min(8192, n - o);
 			if (!seq_only) {
 				kb_pingpong_plan_kernel<<<ib, 32, 0, b->stream>>>(b->d_hdr, st, b->d_plan, b->instances, len, b->fs);
-				kb_pingpong_par_kernel<1024><<<b->instances * 2, 1024, len * sizeof(float), b->stream>>>(b->d_hdr, st, b->d_plan, b->d_rings, d + o, len, n, b->fs);
+				kb_pingpong_par_kernel<1024><<<b->instances * 2, 1024, (((size_t)len + 7) / 8 * 8 + 8) * sizeof(float), b->stream>>>(b->d_hdr, st, b->d_plan, b->d_rings, d + o, len, n, b->fs);
 				kb_pingpong_finish_kernel<<<ib, 32, 0, b->stream>>>(st, b->d_plan, b->instances, len);
 				b->launches += 3;
 			}
@@ -260,7 +260,7 @@ extern "C" int kb_fx_bank_process(kb_fx_bank* b, float* io, int n, unsigned flag
 		KbReverb* st = (KbReverb*)b->d_state;
 		if (!seq_only) {
 			kb_reverb_plan_kernel<<<ib, 32, 0, b->stream>>>(st, b->d_plan, b->instances);
-			kb_reverb_par_kernel<<<b->instances, 256, sizeof(KbRvSmem), b->stream>>>(b->d_hdr, st, b->d_plan, b->d_rings, d, n, n);
+			kb_reverb_par_kernel<<<b->instances * 2, 256, sizeof(KbRvSmem), b->stream>>>(b->d_hdr, st, b->d_plan, b->d_rings, d, n, n);
 			b->launches += 2;
 		}
 		kb_fx_seq_kernel<KB_FX_REVERB, KbReverb><<<ib, 32, 0, b->stream>>>(b->d_hdr, st, b->d_rings, d, n, n, 2, b->instances, b->fs, seq_only ? nullptr : b->d_plan);

@@ -102,7 +102,7 @@ __global__ void kb_pingpong_plan_kernel(const KbFxHdr* __restrict__ hdrs, const 
 template <int NT>
 __global__ void __launch_bounds__(NT) kb_pingpong_par_kernel(const KbFxHdr* __restrict__ hdrs, KbPingPong* __restrict__ states, const KbFxPlan* __restrict__ plan,
                                                              float* __restrict__ rings, float* __restrict__ io, int n, int stride, KbFs fs) {
-	extern __shared__ float kb_pp_smem[];          // n floats
+	extern __shared__ __align__(16) float kb_pp_smem[];          // n floats, padded to a multiple of 8 plus 8
 	const int inst = blockIdx.x >> 1, side = blockIdx.x & 1;
 	const KbFxPlan pl = plan[inst];
 	if (pl.mode != KB_PLAN_PARALLEL) return;
@@ -152,8 +152,24 @@ __global__ void __launch_bounds__(NT) kb_pingpong_par_kernel(const KbFxHdr* __re
 		KbBiquad b = p.dc[side];
 		float z0 = b.z0, z1 = b.z1;
 		const float b0 = b.b0, b1 = b.b1, b2 = b.b2, a1 = b.a1, a2 = b.a2;
-		#pragma unroll 4
-		for (int f = 0; f < n; f++) {
+		// groups of 8 samples: two 128-bit loads ahead of the 8 dependent updates, two 128-bit stores behind them
+		float4* v4 = reinterpret_cast<float4*>(kb_pp_smem);
+		int f = 0;
+		float4 xa = v4[0], xb = v4[1];                                        // (the buffer is padded to a multiple of 8 + 8)
+		for (; f + 8 <= n; f += 8) {
+			const float4 na = v4[(f >> 2) + 2], nb = v4[(f >> 2) + 3];
+			float x[8] = { xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w }, y[8];
+			#pragma unroll
+			for (int j = 0; j < 8; j++) {
+				y[j] = b0 * x[j] + z0;
+				z0 = b1 * x[j] - a1 * y[j] + z1;
+				z1 = b2 * x[j] - a2 * y[j];
+			}
+			v4[f >> 2] = make_float4(y[0], y[1], y[2], y[3]);
+			v4[(f >> 2) + 1] = make_float4(y[4], y[5], y[6], y[7]);
+			xa = na; xb = nb;
+		}
+		for (; f < n; f++) {
 			const float in = kb_pp_smem[f];
 			const float y = b0 * in + z0;
 			z0 = b1 * in - a1 * y + z1;
@@ -185,16 +201,19 @@ __global__ void kb_pingpong_finish_kernel(KbPingPong* __restrict__ states, const
 //   S3  thread = (side, frame): mid FDN matrix, ring writes, mid output;  S4: the same for late
 //   S5  thread = frame: output mix and store
 #define KB_RV_LMAX 160
+// one CTA per (instance, side): the left and right halves of Reverb.k never exchange samples (Reverb.k:212-231), so each
+// CTA owns one input channel, one early ring and the 8 feedback lines mid[side], late[side]
 struct KbRvSmem {
-	float rd[16][2 * KB_RV_LMAX + 4];        // ring read windows (2L+1 used)
-	float yv[16][2 * KB_RV_LMAX + 4];        // filter outputs * gain, per tick
-	float xin[2][2][KB_RV_LMAX];             // io block, double buffered: the early cascade runs one chunk ahead
-	float xf[2][2][KB_RV_LMAX];              // early LPF->HPF output, double buffered
-	float r1[2][KB_RV_LMAX], r2[2][KB_RV_LMAX], r3[2][KB_RV_LMAX];
-	float carry[2][16];                      // FilteredDelay::in carried between frames and chunks: [old/new][line]
-	float times[KB_RV_MAXREFL], gl[KB_RV_MAXREFL], gr[KB_RV_MAXREFL];
+	float rd[8][2 * KB_RV_LMAX + 4];         // ring read windows (2L+1 used); local line j: 0..3 mid, 4..7 late
+	float yv[8][2 * KB_RV_LMAX + 4];         // filter outputs * gain, per tick
+	float xin[2][KB_RV_LMAX];                // io block, double buffered: the early cascade runs one chunk ahead
+	float xf[2][KB_RV_LMAX];                 // early LPF->HPF output, double buffered
+	float r1[KB_RV_LMAX], r2[KB_RV_LMAX], r3[KB_RV_LMAX];
+	float carry[2][8];                       // FilteredDelay::in carried between frames and chunks: [old/new][line]
+	float times[KB_RV_MAXREFL], gg[KB_RV_MAXREFL];
 };
 KB_D KbRvFDelay& kb_rv_line(KbReverb& rv, int line) { return (line < 8 ? rv.mid[line >> 2] : rv.late[(line - 8) >> 2]).d[line & 3]; }
+KB_D KbRvFDelay& kb_rv_side_line(KbReverb& rv, int side, int j) { return (j < 4 ? rv.mid[side] : rv.late[side]).d[j & 3]; }
 
 __global__ void kb_reverb_plan_kernel(const KbReverb* __restrict__ states, KbFxPlan* __restrict__ plan, int instances) {
 	const int inst = blockIdx.x * blockDim.x + threadIdx.x;
@@ -219,61 +238,62 @@ __global__ void __launch_bounds__(256) kb_reverb_par_kernel(const KbFxHdr* __res
                                                             float* __restrict__ rings, float* __restrict__ io, int n, int stride) {
 	extern __shared__ __align__(16) unsigned char kb_rv_smem_raw[];
 	KbRvSmem& S = *reinterpret_cast<KbRvSmem*>(kb_rv_smem_raw);
-	const int inst = blockIdx.x;
+	const int inst = blockIdx.x >> 1, side = blockIdx.x & 1;
 	const KbFxPlan pl = plan[inst];
 	if (pl.mode != KB_PLAN_PARALLEL) return;
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	constexpr int NT = 256;
 	KbReverb& rv = states[inst];
 	const KbControl* c = hdrs[inst].controls;
-	const float dry = c[0].value, wet = c[4].value, cE = c[1].value, cM = c[2].value, cL = c[3].value;
-	float* Lio = io + (size_t)inst * 2 * stride; float* Rio = Lio + stride;
+	const float dry = c[0].value, wet = side == 0 ? c[4].value : 0.f;        // Reverb.k:272 (Q7): the right wet gain is the literal 0
+	const float cE = c[1].value, cM = c[2].value, cL = c[3].value;
+	float* X = io + ((size_t)inst * 2 + side) * stride;
 	const int count = rv.count;
-	if (tid < KB_RV_MAXREFL) { S.times[tid] = rv.times[tid]; S.gl[tid] = rv.gl[tid]; S.gr[tid] = rv.gr[tid]; }
-	if (tid < 16) { S.carry[0][tid] = kb_rv_line(rv, tid).in; S.carry[1][tid] = S.carry[0][tid]; }
+	if (tid < KB_RV_MAXREFL) { S.times[tid] = rv.times[tid]; S.gg[tid] = side ? rv.gr[tid] : rv.gl[tid]; }
+	if (tid < 8) { S.carry[0][tid] = kb_rv_side_line(rv, side, tid).in; S.carry[1][tid] = S.carry[0][tid]; }
 	int cpar = 0;                                    // which copy of the carries is current
 
 	// per-role register state
-	float z0 = 0.f, z1 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, a1 = 0.f, a2 = 0.f, gain = 0.f, frac = 0.f;      // warp 0: line filter
-	float e_z[4] = { 0, 0, 0, 0 }, e_lp[5] = { 0, 0, 0, 0, 0 }, e_hp[5] = { 0, 0, 0, 0, 0 };                // warp 1: early cascade
-	if (tid < 16) {
-		const KbRvFDelay& d = kb_rv_line(rv, tid);
+	float z0 = 0.f, z1 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, a1 = 0.f, a2 = 0.f, gain = 0.f, frac = 0.f;      // warp 0, lanes 0..7: line filter
+	float e_z[4] = { 0, 0, 0, 0 }, e_lp[5] = { 0, 0, 0, 0, 0 }, e_hp[5] = { 0, 0, 0, 0, 0 };                // warp 1, lane 0: early cascade
+	if (tid < 8) {
+		const KbRvFDelay& d = kb_rv_side_line(rv, side, tid);
 		z0 = d.filter.z0; z1 = d.filter.z1; b0 = d.filter.b0; b1 = d.filter.b1; b2 = d.filter.b2; a1 = d.filter.a1; a2 = d.filter.a2;
 		gain = d.gain; frac = d.delay.last_fraction;
 	}
-	if (warp == 1 && lane < 2) {
-		const KbBiquad& lp = rv.lpf[lane]; const KbBiquad& hp = rv.hpf[lane];
+	if (tid == 32) {
+		const KbBiquad& lp = rv.lpf[side]; const KbBiquad& hp = rv.hpf[side];
 		e_z[0] = lp.z0; e_z[1] = lp.z1; e_z[2] = hp.z0; e_z[3] = hp.z1;
 		e_lp[0] = lp.b0; e_lp[1] = lp.b1; e_lp[2] = lp.b2; e_lp[3] = lp.a1; e_lp[4] = lp.a2;
 		e_hp[0] = hp.b0; e_hp[1] = hp.b1; e_hp[2] = hp.b2; e_hp[3] = hp.a1; e_hp[4] = hp.a2;
 	}
-	// every thread keeps the ring geometry of line (tid & 15) for the cooperative window loads, and of the line it
-	// writes in S3/S4 (side, q) is looked up there
-	const KbDelay& myd = kb_rv_line(rv, tid & 15).delay;
+	// every thread keeps the ring geometry of local line (tid & 7) for the cooperative window loads
+	const KbDelay& myd = kb_rv_side_line(rv, side, tid & 7).delay;
 	int rpos = myd.last_position; const int lsize = myd.SIZE; const long long lring = myd.ring;
-	const int esize = rv.dl.SIZE;
-	int epos = rv.dl.position;                       // Stereo::Delay: both channels share the write position
-	float* ringel = rings + rv.dl.ring; float* ringer = rings + rv.dr.ring;
+	KbDelay& ed = side ? rv.dr : rv.dl;
+	const int esize = ed.SIZE;
+	int epos = ed.position;
+	float* ringe = rings + ed.ring;
 
-	// in >> lpf >> hpf for one chunk (Reverb.k:87), lane = channel
+	// in >> lpf >> hpf for one chunk (Reverb.k:87)
 	auto early_cascade = [&](int buf, int L) {
 		for (int t = 0; t < L; t++) {
-			const float x = S.xin[buf][lane][t];
+			const float x = S.xin[buf][t];
 			const float y = e_lp[0] * x + e_z[0];
 			e_z[0] = e_lp[1] * x - e_lp[3] * y + e_z[1];
 			e_z[1] = e_lp[2] * x - e_lp[4] * y;
 			const float w = e_hp[0] * y + e_z[2];
 			e_z[2] = e_hp[1] * y - e_hp[3] * w + e_z[3];
 			e_z[3] = e_hp[2] * y - e_hp[4] * w;
-			S.xf[buf][lane][t] = w;
+			S.xf[buf][t] = w;
 		}
 	};
 	// prologue: chunk 0's input and early cascade
 	{
 		const int L0 = min(pl.chunk, n);
-		for (int i = tid; i < 2 * L0; i += NT) { const int ch = i / L0, t = i % L0; S.xin[0][ch][t] = (ch ? Rio : Lio)[t]; }
+		for (int t = tid; t < L0; t += NT) S.xin[0][t] = X[t];
 		__syncthreads();
-		if (warp == 1 && lane < 2) early_cascade(0, L0);
+		if (tid == 32) early_cascade(0, L0);
 		__syncthreads();
 	}
 
@@ -281,26 +301,26 @@ __global__ void __launch_bounds__(256) kb_reverb_par_kernel(const KbFxHdr* __res
 	for (int g0 = 0; g0 < n; g0 += pl.chunk, buf ^= 1) {
 		const int L = min(pl.chunk, n - g0);
 		const int gn = g0 + L, Ln = min(pl.chunk, n - gn);        // next chunk
-		// ---- P0: ring read windows (8 loads in flight per thread) and the next chunk's io block
+		// ---- P0: ring read windows (up to 8 loads in flight per thread) and the next chunk's io block
 		{
-			const int total = 16 * (2 * L + 1);
+			const int total = 8 * (2 * L + 1);
 			for (int i0 = tid; i0 < total; i0 += 8 * NT) {
 				float v[8];
 				#pragma unroll
 				for (int j = 0; j < 8; j++) {
 					const int i = i0 + j * NT;
-					if (i < total) { int idx = rpos + (i >> 4); if (idx >= lsize) idx -= lsize; v[j] = rings[lring + idx]; }
+					if (i < total) { int idx = rpos + (i >> 3); if (idx >= lsize) idx -= lsize; v[j] = rings[lring + idx]; }
 				}
 				#pragma unroll
-				for (int j = 0; j < 8; j++) { const int i = i0 + j * NT; if (i < total) S.rd[i & 15][i >> 4] = v[j]; }
+				for (int j = 0; j < 8; j++) { const int i = i0 + j * NT; if (i < total) S.rd[i & 7][i >> 3] = v[j]; }
 			}
-			if (Ln > 0) for (int i = tid; i < 2 * Ln; i += NT) { const int ch = i / Ln, t = i % Ln; S.xin[buf ^ 1][ch][t] = (ch ? Rio : Lio)[gn + t]; }
+			if (Ln > 0) for (int t = tid; t < Ln; t += NT) S.xin[buf ^ 1][t] = X[gn + t];
 		}
 		__syncthreads();
-		// ---- P1: warp 0 = the 16 line filters over their 2L ticks; warp 1 = early cascade of the NEXT chunk;
+		// ---- P1: warp 0 = the 8 line filters over their 2L ticks; warp 1 = early cascade of the NEXT chunk;
 		//          warps 2..7 = early ring write and taps of this chunk (taps read samples older than the chunk)
 		if (warp == 0) {
-			if (lane < 16) {
+			if (lane < 8) {
 				const float* rd = S.rd[lane]; float* yv = S.yv[lane];
 				float xa = rd[0];
 				#pragma unroll 4
@@ -315,13 +335,11 @@ __global__ void __launch_bounds__(256) kb_reverb_par_kernel(const KbFxHdr* __res
 				}
 			}
 		} else if (warp == 1) {
-			if (lane < 2 && Ln > 0) early_cascade(buf ^ 1, Ln);
+			if (lane == 0 && Ln > 0) early_cascade(buf ^ 1, Ln);
 		} else {
 			const int wt = tid - 64, WN = NT - 64;
-			for (int i = wt; i < 2 * L; i += WN) { const int ch = i / L, t = i % L; int idx = epos + t; if (idx >= esize) idx -= esize; (ch ? ringer : ringel)[idx] = S.xf[buf][ch][t]; }
-			for (int i = wt; i < 2 * L; i += WN) {
-				const int ch = i / L, t = i % L;
-				const float* ring = ch ? ringer : ringel; const float* gg = ch ? S.gr : S.gl;
+			for (int t = wt; t < L; t += WN) { int idx = epos + t; if (idx >= esize) idx -= esize; ringe[idx] = S.xf[buf][t]; }
+			for (int t = wt; t < L; t += WN) {
 				int pos = epos + t + 1; if (pos >= esize) pos -= esize;      // position after this frame's write
 				float acc = 0.f;
 				for (int d0 = 0; d0 < count; d0 += 4) {                      // Stereo::Delay::tap(float)  klang.h:4668-4681
@@ -331,20 +349,20 @@ __global__ void __launch_bounds__(256) kb_reverb_par_kernel(const KbFxHdr* __res
 						float read = (float)(pos - 1) - S.times[d0 + j]; if (read < 0.f) read += esize;
 						const float fl = floorf(read); fr[j] = read - fl;
 						const int ii = (int)read, jj = (ii == esize - 1) ? 0 : ii + 1;
-						va[j] = ring[ii]; vb[j] = ring[jj];
+						va[j] = ringe[ii]; vb[j] = ringe[jj];
 					}
 					#pragma unroll
-					for (int j = 0; j < 4; j++) if (d0 + j < count) acc += (va[j] * (1.f - fr[j]) + vb[j] * fr[j]) * gg[d0 + j];   // r1 += tap * gain  Reverb.k:89-90
+					for (int j = 0; j < 4; j++) if (d0 + j < count) acc += (va[j] * (1.f - fr[j]) + vb[j] * fr[j]) * S.gg[d0 + j];   // r1 += tap * gain  Reverb.k:89-90
 				}
-				S.r1[ch][t] = acc;
+				S.r1[t] = acc;
 			}
 		}
 		__syncthreads();
 		// ---- P2: FDN matrix, ring writes, outputs (mid then late, late's input is mid's output)
 		for (int stage = 0; stage < 2; stage++) {
-			for (int i = tid; i < 2 * L; i += NT) {
-				const int side = i / L, t = i % L, base = stage * 8 + side * 4;
-				const float in = stage == 0 ? S.r1[side][t] : S.r2[side][t];
+			for (int t = tid; t < L; t += NT) {
+				const int base = stage * 4;
+				const float in = stage == 0 ? S.r1[t] : S.r2[t];
 				const float d0 = S.yv[base][2 * t], d1 = S.yv[base + 1][2 * t], d2 = S.yv[base + 2][2 * t], d3 = S.yv[base + 3][2 * t];
 				// feedback * delays + in, row by row with the literal 0 / +-1 products (Reverb.k:158-163, klang.h:1446-1470)
 				float fb[4];
@@ -356,10 +374,10 @@ __global__ void __launch_bounds__(256) kb_reverb_par_kernel(const KbFxHdr* __res
 				sum = sum + S.yv[base + 1][2 * t + 1];
 				sum = sum + S.yv[base + 2][2 * t + 1];
 				sum = sum + S.yv[base + 3][2 * t + 1];
-				(stage == 0 ? S.r2 : S.r3)[side][t] = sum;
+				(stage == 0 ? S.r2 : S.r3)[t] = sum;
 				#pragma unroll
 				for (int q = 0; q < 4; q++) {
-					const KbDelay& dq = kb_rv_line(rv, base + q).delay;
+					const KbDelay& dq = kb_rv_side_line(rv, side, base + q).delay;
 					float* ring = rings + dq.ring;
 					const int w0 = dq.position + 2 * t;                       // positions are advanced after every chunk
 					int wa = w0 + 1; if (wa >= dq.SIZE) wa -= dq.SIZE;
@@ -372,14 +390,12 @@ __global__ void __launch_bounds__(256) kb_reverb_par_kernel(const KbFxHdr* __res
 			__syncthreads();
 		}
 		for (int t = tid; t < L; t += NT) {
-			const float refl_l = (S.r1[0][t] * cE + S.r2[0][t] * cM) + S.r3[0][t] * cL;
-			const float refl_r = (S.r1[1][t] * cE + S.r2[1][t] * cM) + S.r3[1][t] * cL;
-			Lio[g0 + t] = S.xin[buf][0][t] * dry + refl_l * wet;              // Reverb.k:272 (Q7: the right wet gain is 0)
-			Rio[g0 + t] = S.xin[buf][1][t] * dry + refl_r * 0.f;
+			const float refl = (S.r1[t] * cE + S.r2[t] * cM) + S.r3[t] * cL;
+			X[g0 + t] = S.xin[buf][t] * dry + refl * wet;                     // Reverb.k:272
 		}
 		// advance the ring geometry
-		if (tid < 16) {
-			KbDelay& d = kb_rv_line(rv, tid).delay;
+		if (tid < 8) {
+			KbDelay& d = kb_rv_side_line(rv, side, tid).delay;
 			d.position = (d.position + 2 * L) % d.SIZE;
 			d.last_position = (d.last_position + 2 * L) % d.SIZE;
 		}
@@ -389,13 +405,11 @@ __global__ void __launch_bounds__(256) kb_reverb_par_kernel(const KbFxHdr* __res
 		__syncthreads();
 	}
 	// state back
-	if (tid < 16) {
-		KbRvFDelay& d = kb_rv_line(rv, tid);
+	if (tid < 8) {
+		KbRvFDelay& d = kb_rv_side_line(rv, side, tid);
 		d.filter.z0 = z0; d.filter.z1 = z1;
 		d.in = S.carry[cpar][tid];
 	}
-	if (warp == 1 && lane < 2) {
-		rv.lpf[lane].z0 = e_z[0]; rv.lpf[lane].z1 = e_z[1]; rv.hpf[lane].z0 = e_z[2]; rv.hpf[lane].z1 = e_z[3];
-	}
-	if (tid == 0) { rv.dl.position = epos; rv.dr.position = epos; }
+	if (tid == 32) { rv.lpf[side].z0 = e_z[0]; rv.lpf[side].z1 = e_z[1]; rv.hpf[side].z0 = e_z[2]; rv.hpf[side].z1 = e_z[3]; }
+	if (tid == 0) ed.position = epos;
 }
