@@ -614,9 +614,9 @@ extern "C" int kb_synth_bank_process(kb_synth_bank* b, float* out, int n, unsign
 		const int pthreads = total * 132;
 		kb_sx_prepare_kernel<<<(pthreads + 127) / 128, 128, 0, st>>>((KbSxVoice*)b->d_vstate, b->d_hdr, b->d_blk, b->voices, total, b->fs);
 		kb_sx_adsr_kernel<<<(total + 31) / 32, 32, 0, st>>>((KbSxVoice*)b->d_vstate, b->d_hdr, b->d_adsr, n, total, b->fs);
-		dim3 grid((n + 127) / 128, b->instances);
+		dim3 grid((n + 31) / 32, b->instances);
 		b->prof_begin();
-		kb_sx_render_kernel<<<grid, 128, 0, st>>>((const KbSxVoice*)b->d_vstate, b->d_hdr, b->d_adsr, per_voice ? d_voice_dst : d_inst_dst, n, b->voices, per_voice ? 1 : 0);
+		kb_sx_render_kernel<<<grid, 32 * (KB_SX_PRODUCERS + 1), 0, st>>>((const KbSxVoice*)b->d_vstate, b->d_hdr, b->d_adsr, per_voice ? d_voice_dst : d_inst_dst, n, b->voices, per_voice ? 1 : 0);
 		b->prof_end();
 		kb_sx_advance_kernel<<<(pthreads + 127) / 128, 128, 0, st>>>((KbSxVoice*)b->d_vstate, b->d_hdr, n, total);
 		b->launches += 4;

@@ -139,40 +139,104 @@ __global__ void kb_sx_adsr_kernel(KbSxVoice* __restrict__ voices, KbVoiceHdr* __
 	kb_envr_store(e, voices[v].adsr);
 	if (e.stage == KB_ENV_OFF) hdr[v].stage = KB_NOTE_OFF;
 }
-// thread = (instance, sample).  per_voice: every voice starts from a cleared buffer and is written to
-// dst[voice][2][n]; otherwise the instance buffer is carried from voice to voice (each voice's `buffer *= adsr`
-// also scales what earlier voices left there, exactly as Stereo::Synth::process hands the same buffer to every
-// note, klang.h:4842-4848) and the synth-level tanh post-fx (SynTHX.k:201-206) is applied at the end.
-__global__ void kb_sx_render_kernel(const KbSxVoice* __restrict__ voices, const KbVoiceHdr* __restrict__ hdr, const float* __restrict__ adsr,
-                                    float* __restrict__ dst, int n, int voices_per_inst, int per_voice) {
-	const int inst = blockIdx.y;
-	const int t = blockIdx.x * blockDim.x + threadIdx.x;
-	if (t >= n) return;
+// Render.  One CTA = (instance, 32 consecutive samples): the running buffer values of those samples live in the registers
+// of ONE consumer warp (lane = sample), which performs the reference's additions strictly in order; KB_SX_PRODUCERS other
+// warps evaluate the oscillators (closed form, lane = sample, one partial per warp at a time) one round ahead into a
+// double-buffered shared tile.  The fp32 sum therefore has exactly the reference's association, while the ~60
+// instructions per partial-sample run in parallel on all warps.
+// per_voice: every voice starts from a cleared buffer and is written to dst[voice][2][n]; otherwise the instance buffer
+// is carried from voice to voice (each voice's `buffer *= adsr` also scales what earlier voices left there, exactly as
+// Stereo::Synth::process hands the same buffer to every note, klang.h:4842-4848) and the synth-level tanh post-fx
+// (SynTHX.k:201-206) is applied at the end.
+#define KB_SX_PRODUCERS 12
+#define KB_SX_ROUND 24                      // partial slots per round = two Additive notes (2 x 4 harmonics x 3 partials)
+#define KB_SX_ROUNDS_PER_VOICE 6            // 11 notes = 5 full rounds + one half round
+__global__ void __launch_bounds__(32 * (KB_SX_PRODUCERS + 1)) kb_sx_render_kernel(const KbSxVoice* __restrict__ voices, const KbVoiceHdr* __restrict__ hdr,
+                                                                                const float* __restrict__ adsr, float* __restrict__ dst, int n,
+                                                                                int voices_per_inst, int per_voice) {
+	constexpr int NT = 32 * (KB_SX_PRODUCERS + 1);
+	constexpr int VW = (int)(sizeof(KbSxAdditive) * 11 / 4);       // words of a voice's 11 Additive notes (the ADSR follows them)
+	constexpr int VPT = (VW + NT - 1) / NT;                          // words per thread when a voice is staged
+	__shared__ float s_val[2][KB_SX_ROUND][32];
+	__shared__ int s_flag[2][KB_SX_ROUND];            // bit 0: slot is ticked this block, bit 1: routed to the right channel
+	__shared__ int s_vlist[KB_MAX_VOICES], s_nact;
+	__shared__ __align__(16) unsigned s_voice[2][VW];  // oscillator state of the current and the next voice
+	const int inst = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int t = blockIdx.x * 32 + lane;
+	if (threadIdx.x == 0) {
+		int c = 0;
+		for (int vi = 0; vi < voices_per_inst; vi++) if (hdr[inst * voices_per_inst + vi].active) s_vlist[c++] = inst * voices_per_inst + vi;
+		s_nact = c;
+	}
+	__syncthreads();
+	const int nact = s_nact, rounds = nact * KB_SX_ROUNDS_PER_VOICE;
 	float l = 0.f, r = 0.f;
-	for (int vi = 0; vi < voices_per_inst; vi++) {
-		const int v = inst * voices_per_inst + vi;
-		if (per_voice) { l = 0.f; r = 0.f; }
-		if (hdr[v].active) {
-			const KbSxVoice& V = voices[v];
-			for (int k = 0; k < 11; k++) {
-				const KbSxAdditive& A = V.notes[k];
-				const int partials = (A.frequency < 440.f) ? 2 : 3;
-				for (int p = 0; p < 4; p++)
-					for (int q = 0; q < partials; q++) {
-						const KbSxPartial& P = A.partial[p][q];
-						const float x = kb_osm_at(P.osc, (uint32_t)t) * 0.25f;
-						if (P.right) r += x; else l += x;
-					}
-			}
-			const float a = adsr[(size_t)v * n + t];
-			l *= a; r *= a;
-		}
-		if (per_voice) {
-			dst[((size_t)v * 2 + 0) * n + t] = l;
-			dst[((size_t)v * 2 + 1) * n + t] = r;
+	if (per_voice && warp == 0) {      // voices that are Off this block: cleared streams
+		for (int vi = 0; vi < voices_per_inst; vi++) {
+			const int v = inst * voices_per_inst + vi;
+			if (!hdr[v].active && t < n) { dst[((size_t)v * 2 + 0) * n + t] = 0.f; dst[((size_t)v * 2 + 1) * n + t] = 0.f; }
 		}
 	}
-	if (!per_voice) {
+	if (nact > 0) {
+		const unsigned* src = reinterpret_cast<const unsigned*>(&voices[s_vlist[0]]);
+		for (int w = threadIdx.x; w < VW; w += NT) s_voice[0][w] = src[w];
+	}
+	__syncthreads();
+	unsigned pre[VPT];                                 // the next voice travels through registers during the current one
+	for (int i = 0; i <= rounds; i++) {
+		const int vj = i / KB_SX_ROUNDS_PER_VOICE, rv = i % KB_SX_ROUNDS_PER_VOICE;
+		if (i < rounds && rv == 0 && vj + 1 < nact) {
+			const unsigned* src = reinterpret_cast<const unsigned*>(&voices[s_vlist[vj + 1]]);
+			#pragma unroll
+			for (int q = 0; q < VPT; q++) { const int w = threadIdx.x + q * NT; if (w < VW) pre[q] = src[w]; }
+		}
+		if (warp > 0 && i < rounds) {
+			// ---- producers: round i = voice i / 6, notes 2*(i % 6) and 2*(i % 6) + 1; this warp takes slots (warp-1) and (warp-1)+12
+			const KbSxAdditive* notes = reinterpret_cast<const KbSxAdditive*>(s_voice[vj & 1]);
+			#pragma unroll
+			for (int h = 0; h < 2; h++) {
+				const int slot = (warp - 1) + h * KB_SX_PRODUCERS;      // 0..23: note (slot / 12), harmonic ((slot % 12) / 3), partial (slot % 3)
+				const int k = 2 * rv + slot / 12;
+				int flag = 0;
+				float x = 0.f;
+				if (k < 11) {
+					const KbSxAdditive& A = notes[k];
+					const int q = slot % 3;
+					if (q < ((A.frequency < 440.f) ? 2 : 3)) {            // Additive::process picks partials<2> or <3>  SynTHX.k:124-127
+						const KbSxPartial& P = A.partial[(slot % 12) / 3][q];
+						x = kb_osm_at(P.osc, (uint32_t)t) * 0.25f;        // partial * 0.25f  SynTHX.k:113-118
+						flag = 1 | (P.right ? 2 : 0);
+					}
+				}
+				s_val[i & 1][slot][lane] = x;
+				if (lane == 0) s_flag[i & 1][slot] = flag;
+			}
+		} else if (warp == 0 && i > 0) {
+			// ---- consumer: round i-1, additions in the reference's order (note, harmonic, partial)
+			const int j = i - 1, b = j & 1;
+			#pragma unroll
+			for (int slot = 0; slot < KB_SX_ROUND; slot++) {
+				const int f = s_flag[b][slot];
+				const float x = s_val[b][slot][lane];
+				if (f & 1) { if (f & 2) r += x; else l += x; }
+			}
+			if (j % KB_SX_ROUNDS_PER_VOICE == KB_SX_ROUNDS_PER_VOICE - 1) {          // the voice is complete: buffer *= adsr++  SynTHX.k:176-178
+				const int v = s_vlist[j / KB_SX_ROUNDS_PER_VOICE];
+				const float a = t < n ? adsr[(size_t)v * n + t] : 0.f;
+				l *= a; r *= a;
+				if (per_voice) {
+					if (t < n) { dst[((size_t)v * 2 + 0) * n + t] = l; dst[((size_t)v * 2 + 1) * n + t] = r; }
+					l = 0.f; r = 0.f;
+				}
+			}
+		}
+		if (i < rounds && rv == KB_SX_ROUNDS_PER_VOICE - 1 && vj + 1 < nact) {
+			#pragma unroll
+			for (int q = 0; q < VPT; q++) { const int w = threadIdx.x + q * NT; if (w < VW) s_voice[(vj + 1) & 1][w] = pre[q]; }
+		}
+		__syncthreads();
+	}
+	if (!per_voice && warp == 0 && t < n) {
 		const float gain = 0.5f, _tanh = 0.761594155956f;
 		dst[((size_t)inst * 2 + 0) * n + t] = kb_tanhf(l * gain) * _tanh;
 		dst[((size_t)inst * 2 + 1) * n + t] = kb_tanhf(r * gain) * _tanh;

@@ -69,3 +69,36 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "import oracle" not in text and "from oracle" not in text and "klang_port" not in text, f
+
+
+def test_cpp_shim_compiles_links_and_fails_loudly_without_a_device(library, tmp_path):
+    """include/klang_b200.hpp (the C++ block-driver shim of INTEGRATION.md) builds against the library."""
+    import subprocess
+    src = tmp_path / "shim.cpp"
+    src.write_text('''
+#include <cstdio>
+#include <klang_b200.hpp>
+int main() {
+    std::vector<float> block(2 * 256, 0.25f);
+    try {
+        klang_b200::Effect fx(KB_FX_PINGPONG, 48000.f, 256);
+        klang_b200::Synth sy(KB_SY_SUBTRACTIVE, 48000.f, 256, 32);
+        fx.setControl(0, 0.7f);
+        if (!fx.process(block.data(), 256)) return 3;
+        sy.noteOn(60, 0.8f);
+        if (!sy.process(block.data(), 256)) return 4;
+        std::printf("ran on device %g\\n", block[0]);
+        return 0;
+    } catch (const klang_b200::Error& e) {
+        std::printf("no device: %s\\n", e.what());
+        return kb_device_count() == 0 ? 0 : 5;
+    }
+}
+''')
+    exe = tmp_path / "shim"
+    libdir = os.path.join(ROOT, "klang_b200", "lib")
+    subprocess.check_call(["g++", "-std=c++17", str(src), "-I", os.path.join(ROOT, "include"), "-L", libdir, "-lklang_b200",
+                           "-Wl,-rpath," + libdir, "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert ("no device" in out.stdout) == (kb.device_count() == 0)
