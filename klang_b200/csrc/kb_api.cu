@@ -66,7 +66,7 @@ struct kb_fx_bank : kb_bank_base {
 	int graph = 0, instances = 0, channels = 0, ncontrols = 0;
 	size_t state_bytes = 0; long long ring_floats = 0;
 	std::vector<KbFxHdr> hdr; std::vector<unsigned char> state;
-	KbFxHdr* d_hdr = nullptr; unsigned char* d_state = nullptr; float* d_rings = nullptr; KbFxPlan* d_plan = nullptr;
+	KbFxHdr* d_hdr = nullptr; unsigned char* d_state = nullptr; float* d_rings = nullptr; KbFxPlan* d_plan = nullptr; void* d_sync = nullptr; int epoch = 0; std::vector<KbFxPlan> plan_cache;
 	bool device_writes_controls = false;
 	template <class T> T& st(int i) { return *reinterpret_cast<T*>(state.data() + (size_t)i * state_bytes); }
 };
@@ -122,6 +122,8 @@ extern "C" kb_fx_bank* kb_fx_bank_create(int graph, int instances, float fs, int
 	ok = ok && dev_alloc(&b->d_state, b->state.size()) == cudaSuccess;
 	ok = ok && dev_alloc(&b->d_rings, (size_t)instances * b->ring_floats) == cudaSuccess;
 	ok = ok && dev_alloc(&b->d_plan, instances) == cudaSuccess;
+	ok = ok && cudaMalloc(&b->d_sync, sizeof(KbDppSync) + sizeof(int) * (size_t)instances * KB_DPP_MAXCHUNKS) == cudaSuccess;
+	ok = ok && cudaMemsetAsync(b->d_sync, 0, sizeof(KbDppSync) + sizeof(int) * (size_t)instances * KB_DPP_MAXCHUNKS, b->stream) == cudaSuccess;
 	ok = ok && cudaMemsetAsync(b->d_plan, 0, instances * sizeof(KbFxPlan), b->stream) == cudaSuccess;
 	ok = ok && cudaFuncSetAttribute(kb_reverb_par_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KbRvSmem)) == cudaSuccess;
 	if (ok && b->ring_floats) ok = cudaMemsetAsync(b->d_rings, 0, (size_t)instances * b->ring_floats * sizeof(float), b->stream) == cudaSuccess;
@@ -134,7 +136,7 @@ extern "C" void kb_fx_bank_destroy(kb_fx_bank* b) {
 	if (!b) return;
 	cudaSetDevice(b->device);
 	if (b->stream) cudaStreamSynchronize(b->stream);
-	cudaFree(b->d_hdr); cudaFree(b->d_state); cudaFree(b->d_rings); cudaFree(b->d_io); cudaFree(b->d_plan);
+	cudaFree(b->d_hdr); cudaFree(b->d_state); cudaFree(b->d_rings); cudaFree(b->d_io); cudaFree(b->d_plan); cudaFree(b->d_sync);
 	b->prof_free();
 	if (b->own_stream) cudaStreamDestroy(b->own_stream);
 	delete b;
@@ -267,25 +269,42 @@ extern "C" int kb_fx_bank_process(kb_fx_bank* b, float* io, int n, unsigned flag
 		break; }
 	case KB_FX_DELAY_PINGPONG: {
 		KbDPingPong* st = (KbDPingPong*)b->d_state;
-		// sub-blocks no longer than the shorter delay so that a sub-block's reads precede its writes
-		int sub = n;
+		// the plan of this graph depends on host-owned controls only: made on the host, uploaded when it changes
+		static const int cf = getenv("KB_DPP_CHUNK") ? atoi(getenv("KB_DPP_CHUNK")) : 1024;
+		bool all_parallel = !seq_only;
 		if (!seq_only) {
-			float dmin = 1e30f;
-			for (int i = 0; i < b->instances; i++) dmin = std::min(dmin, std::min(b->hdr[i].controls[0].value, b->hdr[i].controls[1].value) * b->fs.f);
-			sub = std::max(1, std::min(n, (int)dmin - 2));
-			if (sub < 64) sub = n;                                  // too short to be worth it: the plan falls back to the sequential kernel
-		}
-		for (int o = 0; o < n; o += sub) {
-			const int len = std::min(sub, n - o);
-			if (!seq_only) {
-				kb_dpingpong_plan_kernel<<<ib, 32, 0, b->stream>>>(b->d_hdr, st, b->d_plan, b->instances, len, b->fs);
-				dim3 grid((len + 255) / 256, b->instances);
-				kb_dpingpong_par_kernel<<<grid, 256, 0, b->stream>>>(b->d_hdr, st, b->d_plan, b->d_rings, d + o, len, n, b->fs);
-				kb_dpingpong_finish_kernel<<<ib, 32, 0, b->stream>>>(st, b->d_plan, b->instances, len);
-				b->launches += 3;
+			std::vector<KbFxPlan> plan(b->instances);
+			for (int i = 0; i < b->instances; i++) {
+				const float tl = b->hdr[i].controls[0].value * b->fs.f, tr = b->hdr[i].controls[1].value * b->fs.f;
+				KbFxPlan& p = plan[i];
+				p.chunk = (int)std::min(tl, tr) - 2;
+				p.mode = (p.chunk >= cf + 2 && tl < 192000.f && tr < 192000.f) ? KB_PLAN_PARALLEL : KB_PLAN_SEQUENTIAL;
+				p.gain = p.delay = p.dry = 0.f;
+				all_parallel = all_parallel && p.mode == KB_PLAN_PARALLEL;
 			}
-			kb_fx_seq_kernel<KB_FX_DELAY_PINGPONG, KbDPingPong><<<ib, 32, 0, b->stream>>>(b->d_hdr, st, b->d_rings, d + o, len, n, 2, b->instances, b->fs, seq_only ? nullptr : b->d_plan);
-			if (o + sub < n) b->launches++;
+			if (b->plan_cache.size() != plan.size() || memcmp(b->plan_cache.data(), plan.data(), plan.size() * sizeof(KbFxPlan)) != 0) {
+				KB_CUDA(cudaMemcpyAsync(b->d_plan, plan.data(), plan.size() * sizeof(KbFxPlan), cudaMemcpyHostToDevice, b->stream));
+				KB_CUDA(cudaStreamSynchronize(b->stream));
+				b->plan_cache = plan;
+			}
+		}
+		// streaming launches of at most 131072 frames (a longer launch could overwrite ring samples an earlier chunk still has to read)
+		for (int o = 0; o < n; o += 131072) {
+			const int len = std::min(131072, n - o);
+			if (!seq_only) {
+				// one launch: CTAs = chunks x instances, ordered by an in-kernel ticket, per-instance look-back on the delays
+				KbDppSync* sync = (KbDppSync*)b->d_sync;
+				const int chunks = (len + cf - 1) / cf;
+				++b->epoch;
+				if (cf == 512) kb_dpingpong_stream_kernel<512><<<chunks * b->instances, 256, 0, b->stream>>>(b->d_hdr, st, b->d_plan, b->d_rings, d + o, len, n, b->instances, b->fs, sync, b->epoch);
+				else if (cf == 2048) kb_dpingpong_stream_kernel<2048><<<chunks * b->instances, 256, 0, b->stream>>>(b->d_hdr, st, b->d_plan, b->d_rings, d + o, len, n, b->instances, b->fs, sync, b->epoch);
+				else kb_dpingpong_stream_kernel<1024><<<chunks * b->instances, 256, 0, b->stream>>>(b->d_hdr, st, b->d_plan, b->d_rings, d + o, len, n, b->instances, b->fs, sync, b->epoch);
+				b->launches++;
+			}
+			if (!all_parallel) {
+				kb_fx_seq_kernel<KB_FX_DELAY_PINGPONG, KbDPingPong><<<ib, 32, 0, b->stream>>>(b->d_hdr, st, b->d_rings, d + o, len, n, 2, b->instances, b->fs, seq_only ? nullptr : b->d_plan);
+				if (o + 131072 < n || !seq_only) b->launches++;
+			}
 		}
 		break; }
 	case KB_FX_DELAY_REVERB: kb_fx_seq_kernel<KB_FX_DELAY_REVERB, KbDReverb><<<ib, 32, 0, b->stream>>>(b->d_hdr, (KbDReverb*)b->d_state, b->d_rings, d, n, n, 1, b->instances, b->fs, nullptr); break;

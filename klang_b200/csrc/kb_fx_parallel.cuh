@@ -21,54 +21,86 @@ struct KbFxPlan { int mode; int chunk; float gain, delay, dry; };
 KB_D int kb_wrap(int i, int size) { return i >= size ? i - size : i; }
 
 // ===================================================================================== Delay/PingPong.k
-// Delay/PingPong.k:24-34: two cross-coupled delay lines, no filter: every frame of a chunk is independent.
-__global__ void kb_dpingpong_plan_kernel(const KbFxHdr* __restrict__ hdrs, const KbDPingPong* __restrict__ states, KbFxPlan* __restrict__ plan,
-                                         int instances, int n, KbFs fs) {
-	const int inst = blockIdx.x * blockDim.x + threadIdx.x;
-	if (inst >= instances) return;
-	const KbControl* c = hdrs[inst].controls;
-	const float tl = c[0].value * fs.f, tr = c[1].value * fs.f;
-	// frame f reads ring index >= (P + f - 1) - delay - 0 and <= that + 1; the chunk's first write is at P
-	const float dmin = fminf(tl, tr);
-	KbFxPlan p;
-	p.chunk = (int)dmin - 2;
-	p.mode = (p.chunk >= n && tl < (float)states[inst].l.SIZE && tr < (float)states[inst].r.SIZE) ? KB_PLAN_PARALLEL : KB_PLAN_SEQUENTIAL;
-	p.gain = p.delay = p.dry = 0.f;
-	plan[inst] = p;
+// Delay/PingPong.k:24-34: two cross-coupled delay lines, no filter: every frame is independent of every frame closer than
+// the shorter delay.
+// ONE launch for any block length.  A CTA takes a ticket (atomic counter: lower tickets are guaranteed to
+// be running or finished), which names an (instance, 1024-frame chunk) in chunk-major order; it waits for the (at most
+// four) chunks of its own instance that contain the ring samples it reads — a per-(instance, chunk) flag carrying the
+// launch epoch — processes its chunk (thread = frame, every access 128-byte coalesced), fences and raises its own flag.
+// Ring samples written by other CTAs of the same launch are read through L2 (ld.global.cg).  The dependency distance is
+// the delay itself (12000 / 24000 frames at the default controls), so ~11 chunks per instance are in flight and the
+// stream never drains between chunks.
+#define KB_DPP_MINCHUNK 1024
+#define KB_DPP_MAXCHUNKS 512               // a launch covers at most 131072 frames of >= 256-frame chunks
+struct KbDppSync { unsigned ticket; unsigned finished; int flag[1]; /* [instances][KB_DPP_MAXCHUNKS] follows */ };
+// wait until the chunks holding frames [g_lo, g_hi] of this launch have been published
+KB_D void kb_dpp_wait(volatile int* flags, int g_lo, int g_hi, int epoch, int chunk_frames) {
+	if (g_hi < 0) return;
+	const int c_lo = max(g_lo, 0) / chunk_frames, c_hi = g_hi / chunk_frames;
+	for (int c = c_lo; c <= c_hi; c++) while (flags[c] != epoch) { }
 }
-// thread = frame; grid = (ceil(n / blockDim), instances)
-__global__ void __launch_bounds__(256) kb_dpingpong_par_kernel(const KbFxHdr* __restrict__ hdrs, KbDPingPong* __restrict__ states, const KbFxPlan* __restrict__ plan,
-                                                               float* __restrict__ rings, float* __restrict__ io, int n, int stride, KbFs fs) {
-	const int inst = blockIdx.y;
-	if (plan[inst].mode != KB_PLAN_PARALLEL) return;
-	const int f = blockIdx.x * blockDim.x + threadIdx.x;
-	if (f >= n) return;
+template <int CHUNK>
+__global__ void __launch_bounds__(256) kb_dpingpong_stream_kernel(const KbFxHdr* __restrict__ hdrs, const KbDPingPong* __restrict__ states,
+                                                                  const KbFxPlan* __restrict__ plan, float* __restrict__ rings, float* __restrict__ io,
+                                                                  int n, int stride, int instances, KbFs fs, KbDppSync* __restrict__ sync, int epoch) {
+	// (the last CTA to finish resets the ticket counter and advances the write positions: nothing else is launched)
+	__shared__ unsigned s_ticket;
+	if (threadIdx.x == 0) s_ticket = atomicAdd(&sync->ticket, 1u);
+	__syncthreads();
+	const int chunk = (int)(s_ticket / (unsigned)instances), inst = (int)(s_ticket % (unsigned)instances);
+	const KbFxPlan pl = plan[inst];
+	const int f0 = chunk * CHUNK, len = min(CHUNK, n - f0);
 	const KbControl* c = hdrs[inst].controls;
+	if (pl.mode == KB_PLAN_PARALLEL) {
+	const float tl = c[0].value * fs.f, tr = c[1].value * fs.f, gl = c[1].value, gr = c[3].value;
+	volatile int* flags = sync->flag + (size_t)inst * KB_DPP_MAXCHUNKS;
+	if (threadIdx.x == 0) {
+		// frame f reads ring samples written in frames f-1-t-1 .. f-t+1 (t = tl for the left line, tr for the right line)
+		kb_dpp_wait(flags, f0 - (int)tl - 3, f0 + len - 1 - (int)tl + 1, epoch, CHUNK);
+		kb_dpp_wait(flags, f0 - (int)tr - 3, f0 + len - 1 - (int)tr + 1, epoch, CHUNK);
+	}
+	__syncthreads();
 	const KbDPingPong& p = states[inst];
 	float* ringl = rings + p.l.ring; float* ringr = rings + p.r.ring;
 	float* L = io + (size_t)inst * 2 * stride; float* R = L + stride;
-	const int SIZE = p.l.SIZE;
-	const float tl = c[0].value * fs.f, tr = c[1].value * fs.f;
-	const int posl = (int)(((long long)p.l.position + f) % SIZE), posr = (int)(((long long)p.r.position + f) % p.r.SIZE);
-	// Delay::tap(float)  klang.h:3412-3427 on the write position of this frame
-	float read = (float)(posl - 1) - tl; if (read < 0.f) read += SIZE;
-	int i = (int)read; float frac = read - i; int j = (i + 1) % SIZE;
-	const float a = ringl[i], b = ringl[j];
-	const float fl = (a + frac * (b - a)) * c[1].value;
-	read = (float)(posr - 1) - tr; if (read < 0.f) read += p.r.SIZE;
-	i = (int)read; frac = read - i; j = (i + 1) % p.r.SIZE;
-	const float a2 = ringr[i], b2 = ringr[j];
-	const float fr = (a2 + frac * (b2 - a2)) * c[3].value;
-	const float ol = L[f] + fr, orr = R[f] + fl;
-	ringl[posl] = ol; ringr[posr] = orr;
-	L[f] = ol; R[f] = orr;
-}
-__global__ void kb_dpingpong_finish_kernel(KbDPingPong* __restrict__ states, const KbFxPlan* __restrict__ plan, int instances, int n) {
-	const int inst = blockIdx.x * blockDim.x + threadIdx.x;
-	if (inst >= instances || plan[inst].mode != KB_PLAN_PARALLEL) return;
-	KbDPingPong& p = states[inst];
-	p.l.position = (int)(((long long)p.l.position + n) % p.l.SIZE);
-	p.r.position = (int)(((long long)p.r.position + n) % p.r.SIZE);
+	const int SIZE = p.l.SIZE, SIZER = p.r.SIZE;
+	const int pl0 = (int)(((long long)__ldcg(&p.l.position) + f0) % SIZE), pr0 = (int)(((long long)__ldcg(&p.r.position) + f0) % SIZER);
+	#pragma unroll
+	for (int u = 0; u < CHUNK / 256; u++) {
+		const int k = u * 256 + threadIdx.x, f = f0 + k;
+		if (k < len) {
+			int posl = pl0 + k; if (posl >= SIZE) posl -= SIZE;
+			int posr = pr0 + k; if (posr >= SIZER) posr -= SIZER;
+			float read = (float)(posl - 1) - tl; if (read < 0.f) read += SIZE;                 // Delay::tap(float)  klang.h:3412-3427
+			int i = (int)read; float frac = read - i; int j = i + 1; if (j == SIZE) j = 0;
+			const float a = __ldcg(ringl + i), b = __ldcg(ringl + j);
+			const float fl = (a + frac * (b - a)) * gl;
+			read = (float)(posr - 1) - tr; if (read < 0.f) read += SIZER;
+			i = (int)read; frac = read - i; j = i + 1; if (j == SIZER) j = 0;
+			const float a2 = __ldcg(ringr + i), b2 = __ldcg(ringr + j);
+			const float fr = (a2 + frac * (b2 - a2)) * gr;
+			const float ol = L[f] + fr, orr = R[f] + fl;                                        // Delay/PingPong.k:30-31
+			ringl[posl] = ol; ringr[posr] = orr;                                                // delay << out  :33
+			L[f] = ol; R[f] = orr;
+		}
+	}
+	__threadfence();
+	__syncthreads();
+	if (threadIdx.x == 0) flags[chunk] = epoch;
+	}
+	// epilogue of the launch: the CTA that finishes last advances every parallel instance's write heads
+	__shared__ bool s_last;
+	if (threadIdx.x == 0) { __threadfence(); s_last = atomicAdd(&sync->finished, 1u) == gridDim.x - 1; }
+	__syncthreads();
+	if (s_last) {
+		for (int i = threadIdx.x; i < instances; i += blockDim.x)
+			if (plan[i].mode == KB_PLAN_PARALLEL) {
+				KbDPingPong& q = const_cast<KbDPingPong&>(states[i]);
+				q.l.position = (int)(((long long)q.l.position + n) % q.l.SIZE);
+				q.r.position = (int)(((long long)q.r.position + n) % q.r.SIZE);
+			}
+		if (threadIdx.x == 0) { sync->ticket = 0u; sync->finished = 0u; }
+	}
 }
 
 // ============================================================================================ PingPong.k
