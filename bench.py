@@ -447,10 +447,10 @@ def extras(kb, torch, dev, stream, flush_l2, hbm_peak, peak_src, device_index, w
 
     # C4: delay-line effects, 64 stereo instances; chunk-parallel schedule vs the frame-sequential one (same results)
     for name, graph, n, steps in (("c4_pingpong_64", kb.FX_PINGPONG, 4096, 5), ("c4_reverb_64", kb.FX_REVERB, 4096, 3),
-                                  ("c4_delay_pingpong_64", kb.FX_DELAY_PINGPONG, 8192, 5)):
+                                  ("c4_delay_pingpong_64", kb.FX_DELAY_PINGPONG, 65536, 5), ("c4_delay_reverb_64", kb.FX_DELAY_REVERB, 4096, 5)):
         fx = kb.FxBank(graph, 64, FS, n, device_index)
         fx.set_stream(stream.cuda_stream)
-        io = torch.rand(64, 2, n, device=dev) - 0.5
+        io = torch.rand(64, fx.channels, n, device=dev) - 0.5
         for _ in range(40000 // n + 2):                     # PingPong.k: let the control smoothers reach their fixed point
             fx.process_inplace(io)
         ms = time_steps(lambda: fx.process_inplace(io.uniform_(-0.5, 0.5)), steps, warmup=1)
@@ -467,6 +467,7 @@ def extras(kb, torch, dev, stream, flush_l2, hbm_peak, peak_src, device_index, w
         res["c4_pingpong_64"]["cpu_reference"] = cpu_extra("fx", oracle.FX_PINGPONG, 1, 4096, 40)
         res["c4_reverb_64"]["cpu_reference"] = cpu_extra("fx", oracle.FX_REVERB, 1, 4096, 8)
         res["c4_delay_pingpong_64"]["cpu_reference"] = cpu_extra("fx", oracle.FX_DELAY_PINGPONG, 1, 4096, 40)
+        res["c4_delay_reverb_64"]["cpu_reference"] = cpu_extra("fx", oracle.FX_DELAY_REVERB, 1, 4096, 40)
 
     # C3 SuperSaw 8 x 32 voices; C5 per-GPU share: 4 x 128 TB303 + 4 x 128 SynTHX voices
     for name, graph, inst, voices, n, steps in (("c3_supersaw_256", kb.SY_SUPERSAW, 8, 32, 4096, 5),

@@ -148,7 +148,6 @@ extern "C" long long kb_fx_bank_launches(const kb_fx_bank* b) { return b ? b->la
 extern "C" int kb_fx_bank_parallel_instances(kb_fx_bank* b) {
 	if (!b) return kb_fail(KB_EINVAL, "null bank");
 	if (b->graph == KB_FX_GAIN) return b->instances;
-	if (b->graph == KB_FX_DELAY_REVERB) return 0;
 	std::vector<KbFxPlan> plan(b->instances);
 	KB_CUDA(cudaSetDevice(b->device));
 	KB_CUDA(cudaStreamSynchronize(b->stream));
@@ -307,7 +306,15 @@ extern "C" int kb_fx_bank_process(kb_fx_bank* b, float* io, int n, unsigned flag
 			}
 		}
 		break; }
-	case KB_FX_DELAY_REVERB: kb_fx_seq_kernel<KB_FX_DELAY_REVERB, KbDReverb><<<ib, 32, 0, b->stream>>>(b->d_hdr, (KbDReverb*)b->d_state, b->d_rings, d, n, n, 1, b->instances, b->fs, nullptr); break;
+	case KB_FX_DELAY_REVERB: {
+		KbDReverb* st = (KbDReverb*)b->d_state;
+		if (!seq_only) {
+			kb_dreverb_plan_kernel<<<ib, 32, 0, b->stream>>>(b->d_hdr, st, b->d_plan, b->instances, b->fs);
+			kb_dreverb_par_kernel<<<b->instances, 512, 0, b->stream>>>(b->d_hdr, st, b->d_plan, b->d_rings, d, n, n, b->fs);
+			b->launches += 2;
+		}
+		kb_fx_seq_kernel<KB_FX_DELAY_REVERB, KbDReverb><<<ib, 32, 0, b->stream>>>(b->d_hdr, st, b->d_rings, d, n, n, 1, b->instances, b->fs, seq_only ? nullptr : b->d_plan);
+		break; }
 	}
 	b->prof_end();
 	b->launches++;

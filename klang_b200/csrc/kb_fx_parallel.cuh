@@ -20,6 +20,35 @@ struct KbFxPlan { int mode; int chunk; float gain, delay, dry; };
 
 KB_D int kb_wrap(int i, int size) { return i >= size ? i - size : i; }
 
+// Biquad::Filter::process (klang.h:5605-5612) over a block staged in shared memory, in place and strictly in order, by ONE
+// thread: groups of 8 samples, two 128-bit loads issued ahead of the 8 dependent updates and two 128-bit stores behind
+// them, so the only latency left on the chain is the recurrence itself.  `buf` is 16-byte aligned and padded by 8 floats.
+KB_D void kb_biquad_block_smem(float* buf, int n, float b0, float b1, float b2, float a1, float a2, float& z0, float& z1) {
+	float4* v4 = reinterpret_cast<float4*>(buf);
+	int f = 0;
+	float4 xa = v4[0], xb = v4[1];
+	for (; f + 8 <= n; f += 8) {
+		const float4 na = v4[(f >> 2) + 2], nb = v4[(f >> 2) + 3];
+		float x[8] = { xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w }, y[8];
+		#pragma unroll
+		for (int j = 0; j < 8; j++) {
+			y[j] = b0 * x[j] + z0;
+			z0 = b1 * x[j] - a1 * y[j] + z1;
+			z1 = b2 * x[j] - a2 * y[j];
+		}
+		v4[f >> 2] = make_float4(y[0], y[1], y[2], y[3]);
+		v4[(f >> 2) + 1] = make_float4(y[4], y[5], y[6], y[7]);
+		xa = na; xb = nb;
+	}
+	for (; f < n; f++) {
+		const float in = buf[f];
+		const float y = b0 * in + z0;
+		z0 = b1 * in - a1 * y + z1;
+		z1 = b2 * in - a2 * y;
+		buf[f] = y;
+	}
+}
+
 // ===================================================================================== Delay/PingPong.k
 // Delay/PingPong.k:24-34: two cross-coupled delay lines, no filter: every frame is independent of every frame closer than
 // the shorter delay.
@@ -184,30 +213,7 @@ __global__ void __launch_bounds__(NT) kb_pingpong_par_kernel(const KbFxHdr* __re
 		KbBiquad b = p.dc[side];
 		float z0 = b.z0, z1 = b.z1;
 		const float b0 = b.b0, b1 = b.b1, b2 = b.b2, a1 = b.a1, a2 = b.a2;
-		// groups of 8 samples: two 128-bit loads ahead of the 8 dependent updates, two 128-bit stores behind them
-		float4* v4 = reinterpret_cast<float4*>(kb_pp_smem);
-		int f = 0;
-		float4 xa = v4[0], xb = v4[1];                                        // (the buffer is padded to a multiple of 8 + 8)
-		for (; f + 8 <= n; f += 8) {
-			const float4 na = v4[(f >> 2) + 2], nb = v4[(f >> 2) + 3];
-			float x[8] = { xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w }, y[8];
-			#pragma unroll
-			for (int j = 0; j < 8; j++) {
-				y[j] = b0 * x[j] + z0;
-				z0 = b1 * x[j] - a1 * y[j] + z1;
-				z1 = b2 * x[j] - a2 * y[j];
-			}
-			v4[f >> 2] = make_float4(y[0], y[1], y[2], y[3]);
-			v4[(f >> 2) + 1] = make_float4(y[4], y[5], y[6], y[7]);
-			xa = na; xb = nb;
-		}
-		for (; f < n; f++) {
-			const float in = kb_pp_smem[f];
-			const float y = b0 * in + z0;
-			z0 = b1 * in - a1 * y + z1;
-			z1 = b2 * in - a2 * y;
-			kb_pp_smem[f] = y;
-		}
+		kb_biquad_block_smem(kb_pp_smem, n, b0, b1, b2, a1, a2, z0, z1);
 		p.dc[side].z0 = z0; p.dc[side].z1 = z1;
 	}
 	__syncthreads();
@@ -444,4 +450,77 @@ __global__ void __launch_bounds__(256) kb_reverb_par_kernel(const KbFxHdr* __res
 	}
 	if (tid == 32) { rv.lpf[side].z0 = e_z[0]; rv.lpf[side].z1 = e_z[1]; rv.hpf[side].z0 = e_z[2]; rv.hpf[side].z1 = e_z[3]; }
 	if (tid == 0) ed.position = epos;
+}
+
+// ======================================================================================== Delay/Reverb.k
+// Delay/Reverb.k:59-78: an 8-tap FIR over the input (feedforward line, taps 2-17 ms), plus a feedback loop
+// out = mix + LPF(gain * feedback(time)), feedback << out.  The FIR only reads the input, so it is parallel over the whole
+// block; the loop is chunked by its delay (4800 frames at the default controls) and its LPF runs as one serial lane.
+#define KB_DRV_LMAX 4096
+__global__ void kb_dreverb_plan_kernel(const KbFxHdr* __restrict__ hdrs, const KbDReverb* __restrict__ states, KbFxPlan* __restrict__ plan, int instances, KbFs fs) {
+	const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+	if (inst >= instances) return;
+	const float t = hdrs[inst].controls[1].value * fs.f;                     // feedback(time * fs)  Delay/Reverb.k:72
+	KbFxPlan p;
+	p.chunk = min(KB_DRV_LMAX, (int)t - 2);
+	// the shortest FIR tap (2.078 ms) must not reach past the ring and the loop delay must fit the ring
+	p.mode = (p.chunk >= 64 && t < (float)states[inst].feedback.SIZE) ? KB_PLAN_PARALLEL : KB_PLAN_SEQUENTIAL;
+	p.gain = p.delay = p.dry = 0.f;
+	plan[inst] = p;
+}
+__global__ void __launch_bounds__(512) kb_dreverb_par_kernel(const KbFxHdr* __restrict__ hdrs, KbDReverb* __restrict__ states, const KbFxPlan* __restrict__ plan,
+                                                             float* __restrict__ rings, float* __restrict__ io, int n, int stride, KbFs fs) {
+	__shared__ __align__(16) float s_mix[KB_DRV_LMAX + 8], s_late[KB_DRV_LMAX + 8];
+	const int inst = blockIdx.x;
+	const KbFxPlan pl = plan[inst];
+	if (pl.mode != KB_PLAN_PARALLEL) return;
+	constexpr int NT = 512;
+	const int tid = threadIdx.x;
+	KbDReverb& p = states[inst];
+	const KbControl* c = hdrs[inst].controls;
+	float* ff = rings + p.feedforward.ring; float* fb = rings + p.feedback.ring;
+	float* X = io + (size_t)inst * stride;
+	const int FS = p.feedforward.SIZE, BS = p.feedback.SIZE;
+	const float times[8] = { (float)2.078, (float)5.154, (float)5.947, (float)7.544, (float)8.878, (float)10.422, (float)13.938, (float)17.140 };
+	const float gains[8] = { (float).609, (float).262, (float)-.360, (float)-.470, (float).290, (float)-.423, (float).100, (float).200 };
+	const float lgain = c[0].value, ltime = c[1].value * fs.f;
+	int fpos = p.feedforward.position, bpos = p.feedback.position;
+	float z0 = p.filter.z0, z1 = p.filter.z1;
+	const float b0 = p.filter.b0, b1 = p.filter.b1, b2 = p.filter.b2, a1 = p.filter.a1, a2 = p.filter.a2;
+	for (int g0 = 0; g0 < n; g0 += pl.chunk) {
+		const int L = min(pl.chunk, n - g0);
+		// in >> feedforward  (:64)
+		for (int t = tid; t < L; t += NT) { int idx = fpos + t; if (idx >= FS) idx -= FS; ff[idx] = X[g0 + t]; }
+		__syncthreads();
+		for (int t = tid; t < L; t += NT) {
+			int pos = fpos + t + 1; if (pos >= FS) pos -= FS;                        // write head after this frame's input
+			float mix = X[g0 + t];                                                   // signal mix = in  (:65)
+			#pragma unroll
+			for (int d = 0; d < 8; d++) {                                            // mix += feedforward(times[d] * fs / 1000) * gains[d]  (:66-67)
+				float read = (float)(pos - 1) - times[d] * fs.f / 1000; if (read < 0.f) read += FS;
+				const int i = (int)read; const float frac = read - i; const int j = (i + 1) % FS;
+				const float a = ff[i], b = ff[j];
+				mix += (a + frac * (b - a)) * gains[d];
+			}
+			s_mix[t] = mix;
+			int bp = bpos + t; if (bp >= BS) bp -= BS;                               // feedback write head before this frame's write
+			float read = (float)(bp - 1) - ltime; if (read < 0.f) read += BS;
+			const int i = (int)read; const float frac = read - i; const int j = (i + 1) % BS;
+			const float a = fb[i], b = fb[j];
+			s_late[t] = lgain * (a + frac * (b - a));                                // gain * feedback(time * fs)  (:72)
+		}
+		__syncthreads();
+		if (tid == 0) kb_biquad_block_smem(s_late, L, b0, b1, b2, a1, a2, z0, z1);          // >> filter  (:72), Biquad::LPF, in order
+		__syncthreads();
+		for (int t = tid; t < L; t += NT) {
+			const float out = s_mix[t] + s_late[t];                                  // (early() + late()) >> out  (:77)
+			int bp = bpos + t; if (bp >= BS) bp -= BS;
+			fb[bp] = out;                                                            // out >> feedback
+			X[g0 + t] = out;
+			if (g0 + t == n - 1) p.out = out;
+		}
+		fpos = (fpos + L) % FS; bpos = (bpos + L) % BS;
+		__syncthreads();
+	}
+	if (tid == 0) { p.feedforward.position = fpos; p.feedback.position = bpos; p.filter.z0 = z0; p.filter.z1 = z1; }
 }

@@ -348,7 +348,8 @@ def test_tiled_schedule_equals_lane_per_voice_schedule(eng, graph, inst, voices)
     assert np.abs(a[0]).max() > 0.01
 
 
-@pytest.mark.parametrize("graph,blocks,n", [(cases.FX_PINGPONG, 30, 2048), (cases.FX_REVERB, 12, 1000), (cases.FX_DELAY_PINGPONG, 10, 3000)])
+@pytest.mark.parametrize("graph,blocks,n", [(cases.FX_PINGPONG, 30, 2048), (cases.FX_REVERB, 12, 1000), (cases.FX_DELAY_PINGPONG, 10, 3000),
+                                            (cases.FX_DELAY_REVERB, 8, 5000)])
 def test_chunk_parallel_effects_match_oracle_and_sequential_schedule(eng, graph, blocks, n):
     """The chunk-parallel effect kernels (engaged once control smoothers settle / delays allow) are bit-identical to the
     oracle and to the frame-sequential schedule, including the hand-over between the two schedules, ragged block lengths
@@ -359,7 +360,8 @@ def test_chunk_parallel_effects_match_oracle_and_sequential_schedule(eng, graph,
     lens[3] = 517
     lens[5] = 1
     total = sum(lens)
-    x = np.stack([cases.fx_input(2, total, seed=20 + i) for i in range(inst)])
+    mono = graph == cases.FX_DELAY_REVERB
+    x = np.stack([cases.fx_input(1 if mono else 2, total, seed=20 + i) for i in range(inst)])
     change_at = blocks // 2
 
     def controls_for(b, set_control):
@@ -372,6 +374,9 @@ def test_chunk_parallel_effects_match_oracle_and_sequential_schedule(eng, graph,
             elif graph == cases.FX_REVERB:
                 set_control(6, 0.5)       # room size: early taps and all 16 delay times are re-drawn
                 set_control(2, 0.4)
+            elif graph == cases.FX_DELAY_REVERB:
+                set_control(1, 0.07)      # loop delay
+                set_control(2, 900.0)     # damping cutoff: prepare() recomputes the LPF
             else:
                 set_control(1, 0.31)
 
@@ -381,7 +386,7 @@ def test_chunk_parallel_effects_match_oracle_and_sequential_schedule(eng, graph,
         o = 0
         for b, ln in enumerate(lens):
             controls_for(b, fx.set_control)
-            want[i, :, o:o + ln] = fx.process(x[i, :, o:o + ln])
+            want[i, :, o:o + ln] = fx.process(x[i, 0, o:o + ln] if mono else x[i, :, o:o + ln])
             o += ln
         fx.close()
     for flags in (0, kb.FX_SEQUENTIAL):

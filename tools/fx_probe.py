@@ -5,7 +5,7 @@ import torch
 import klang_b200 as kb
 
 name = sys.argv[1] if len(sys.argv) > 1 else "reverb"
-graph = {"pingpong": kb.FX_PINGPONG, "reverb": kb.FX_REVERB, "dpingpong": kb.FX_DELAY_PINGPONG, "gain": kb.FX_GAIN}[name]
+graph = {"pingpong": kb.FX_PINGPONG, "reverb": kb.FX_REVERB, "dpingpong": kb.FX_DELAY_PINGPONG, "gain": kb.FX_GAIN, "dreverb": kb.FX_DELAY_REVERB}[name]
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 inst = int(sys.argv[3]) if len(sys.argv) > 3 else 64
 flags = kb.FX_SEQUENTIAL if "--seq" in sys.argv else 0

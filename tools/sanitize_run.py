@@ -1,0 +1,27 @@
+"""Small end-to-end run of every kernel family for compute-sanitizer (memcheck / racecheck): short blocks, few voices."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import klang_b200 as kb
+
+fs = 48000.0
+for graph, inst, voices, n in ((kb.SY_SUBTRACTIVE, 2, 16, 300), (kb.SY_SUPERSAW, 2, 32, 300), (kb.SY_TB303, 1, 32, 300), (kb.SY_SYNTHX, 1, 32, 70), (kb.SY_FILTER_K, 1, 32, 129)):
+    b = kb.SynthBank(graph, inst, voices, fs, n)
+    for g in range(0, inst * b.voices, 2):
+        b.voice_start(g % b.voices, 40 + g % 30, 0.7, g // b.voices)
+    for k in range(3):
+        if k == 1:
+            b.voice_release(0, 0.0, 0)
+        b.process_block(n)
+        b.process_block(n // 2, kb.PER_VOICE)
+        b.process_block(n, kb.BANK_MIX | kb.MIX_SUM)
+    b.process_block(n, kb.LANE_PER_VOICE)
+    b.close()
+for graph, n, blocks in ((kb.FX_GAIN, 1001, 2), (kb.FX_PINGPONG, 2048, 24), (kb.FX_REVERB, 700, 3), (kb.FX_DELAY_PINGPONG, 3000, 3), (kb.FX_DELAY_REVERB, 500, 2)):
+    fx = kb.FxBank(graph, 3, fs, n)
+    x = (np.random.default_rng(1).random((3, fx.channels, n), dtype=np.float32) - 0.5)
+    for k in range(blocks):
+        fx.process_inplace(x.copy())
+    print(graph, "parallel instances", fx.parallel_instances())
+    fx.close()
+print("sanitize run done")
