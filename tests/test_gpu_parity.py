@@ -404,3 +404,106 @@ def test_chunk_parallel_effects_match_oracle_and_sequential_schedule(eng, graph,
         assert_parity(got, want, f"fx graph {graph} flags {flags}", exact=True)
         if flags == 0:
             assert engaged > inst * blocks // 4, f"chunk-parallel schedule engaged on only {engaged} instance-blocks"
+
+
+# ------------------------------------------------------------------------- BASELINE-size properties, C3 / C4 / C5
+def test_c4_64_instances_are_replicas_of_one_instance(eng):
+    """C4 shape: 64 stereo instances fed the same input and controls produce 64 identical streams, equal to a
+    single-instance bank (instances never interact), on the chunk-parallel schedule, for every delay-line graph."""
+    fs, n, blocks = 48000, 4096, 3
+    for graph in (kb.FX_REVERB, kb.FX_DELAY_PINGPONG, kb.FX_DELAY_REVERB, kb.FX_PINGPONG):
+        ch = 1 if graph == kb.FX_DELAY_REVERB else 2
+        x = cases.fx_input(ch, n * blocks, seed=5)
+        one = kb.FxBank(graph, 1, fs, n)
+        many = kb.FxBank(graph, 64, fs, n)
+        for b in range(blocks):
+            blk1 = np.ascontiguousarray(x[None, :, b * n:(b + 1) * n])
+            blk64 = np.ascontiguousarray(np.broadcast_to(blk1, (64, ch, n)))
+            one.process_inplace(blk1)
+            many.process_inplace(blk64)
+            assert np.array_equal(blk64.view(np.uint32), np.broadcast_to(blk1, (64, ch, n)).view(np.uint32)), f"graph {graph} block {b}"
+        one.close()
+        many.close()
+
+
+def test_c3_c5_bank_mix_equals_sum_of_instance_outputs(eng):
+    """KB_BANK_MIX (the multi-GPU reduce input) is the instance-order fp32 sum of the per-instance Synth::process outputs,
+    at the C3 (8 x 32 SuperSaw) and C5 per-GPU (4 x 128 TB303, 4 x 128 SynTHX) sizes."""
+    for graph, inst, voices, n in ((kb.SY_SUPERSAW, 8, 32, 2048), (kb.SY_TB303, 4, 128, 1024), (kb.SY_SYNTHX, 4, 128, 256)):
+        outs = {}
+        for flags in (kb.MIX_SUM, kb.MIX_SUM | kb.BANK_MIX):
+            kb.lib().kb_srand(1)
+            bank = kb.SynthBank(graph, inst, voices, 48000, n)
+            for g in range(inst * voices):
+                bank.voice_start(g % voices, 36 + (5 * g) % 36, cases.voice_velocity(g), g // voices)
+            bank.process_block(n, flags)
+            outs[flags] = bank.process_block(n, flags)
+            bank.close()
+        per_inst, mix = outs[kb.MIX_SUM], outs[kb.MIX_SUM | kb.BANK_MIX]
+        acc = np.zeros_like(mix)
+        for i in range(inst):
+            acc = acc + per_inst[i]
+        assert_parity(mix, acc, f"bank mix graph {graph}", exact=True)
+        assert np.isfinite(mix).all() and np.abs(mix).max() > 1e-3
+
+
+def test_batched_events_equal_single_calls(eng):
+    """kb_synth_bank_events applies a block's events in order exactly like the individual calls (incl. rand() draws)."""
+    n, voices = 512, 32
+    ev = np.zeros(24, kb.EVENT_DTYPE)
+    for k in range(16):
+        ev[k] = (kb.EV_NOTE_ON, k % 2, 48 + k, 0.0, 0.5 + 0.03 * k)
+    for k in range(16, 20):
+        ev[k] = (kb.EV_NOTE_OFF, k % 2, 48 + (k - 16), 0.0, 0.0)
+    ev[20] = (kb.EV_CONTROL, 0, 2, 0.0, 0.9)
+    ev[21] = (kb.EV_VOICE_START, 1, 7, 61.5, 0.8)
+    ev[22] = (kb.EV_VOICE_RELEASE, 1, 7, 0.0, 0.0)
+    ev[23] = (kb.EV_NOTE_ON, 0, 72, 0.0, 1.0)
+    outs = []
+    for batched in (True, False):
+        kb.lib().kb_srand(7)
+        bank = kb.SynthBank(kb.SY_SUPERSAW, 2, voices, 48000, n)
+        res = []
+        for b in range(3):
+            if batched:
+                bank.events(ev if b == 0 else ev[16:20])
+            else:
+                for e in (ev if b == 0 else ev[16:20]):
+                    t, i, key, pitch, vel = int(e["type"]), int(e["instance"]), int(e["key"]), float(e["pitch"]), float(e["velocity"])
+                    if t == kb.EV_NOTE_ON:
+                        bank.note_on(key, vel, i)
+                    elif t == kb.EV_NOTE_OFF:
+                        bank.note_off(key, vel, i)
+                    elif t == kb.EV_CONTROL:
+                        bank.set_control(key, vel, i)
+                    elif t == kb.EV_VOICE_START:
+                        bank.voice_start(key, pitch, vel, i)
+                    else:
+                        bank.voice_release(key, vel, i)
+            res.append(bank.process_block(n, kb.PER_VOICE))
+        bank.close()
+        outs.append(np.concatenate(res, axis=-1))
+    assert_parity(outs[0], outs[1], "batched events", exact=True)
+    assert np.abs(outs[0]).max() > 0.01
+
+
+def test_device_pointer_calls_match_host_pointer_calls(eng):
+    """KB_DEVICE_PTR (asynchronous, caller-owned device buffers and stream) returns the same bits as the host-buffer call."""
+    torch = pytest.importorskip("torch")
+    n = 1024
+    x = cases.fx_input(2, n, seed=9)[None]
+    host = kb.FxBank(kb.FX_REVERB, 1, 48000, n)
+    a = np.ascontiguousarray(x)
+    host.process_inplace(a)
+    host.close()
+    dev = kb.FxBank(kb.FX_REVERB, 1, 48000, n)
+    s = torch.cuda.Stream()
+    dev.set_stream(s.cuda_stream)
+    with torch.cuda.stream(s):
+        t = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+        s.synchronize()
+        dev.process_inplace(t)
+        dev.sync()
+    b = t.cpu().numpy()
+    dev.close()
+    assert_parity(b, a, "device pointer fx", exact=True)
