@@ -136,7 +136,8 @@ int kb_synth_bank_profile_read(kb_synth_bank* bank, double* kernel_ms, long long
 /* Single-object runs of the primitive operators ON THE DEVICE (one thread), for known-answer tests.
  * kinds as in tests/cases.py.  Generators::Fast / Basic / Wavetables (klang.h:4893-5381). */
 int kb_prim_osc(int kind, int nargs, float f, float phase, float duty, float fs, int n, float* out);
-/* Filters::Biquad::{LPF,HPF}, OnePole::{LPF,HPF} (klang.h:5470-5683): set(f[s],Q[s]) before sample s < nset */
+/* Filters::Biquad::{LPF,HPF,BPF,BRF,APF}, OnePole::{LPF,HPF}, Butterworth::LPF<1>,<2> (klang.h:5470-5812; kinds as in
+ * tests/cases.py FLT_*): set(f[s],Q[s]) before sample s < nset (one-pole kinds: nset <= 1, coefficients from the host libm) */
 int kb_prim_filter(int kind, int nset, const float* f, const float* Q, float fs, int n, const float* in, float* out, float* coeffs);
 /* Envelope / ADSR (klang.h:3723-4137) */
 int kb_prim_envelope(int npts, const float* xy, int loop_start, int loop_end, float fs, int n, int release_at,

@@ -743,10 +743,11 @@ extern "C" int kb_prim_osc(int kind, int nargs, float f, float phase, float duty
 }
 extern "C" int kb_prim_filter(int kind, int nset, const float* f, const float* Q, float fs, int n, const float* in, float* out, float* coeffs) {
 	if (kb_device_count() < 1) return kb_fail(KB_ENODEV, "no CUDA device");
-	if (kind < 0 || kind > 3 || !f || !in || !out || !coeffs || nset < 0 || nset > n || (kind >= 2 && nset > 1)) return kb_fail(KB_EINVAL, "kb_prim_filter: unsupported");
+	const bool onepole = kind == 2 || kind == 3 || kind == 7;
+	if (kind < 0 || kind > 8 || !f || !in || !out || !coeffs || nset < 0 || nset > n || (onepole && nset > 1)) return kb_fail(KB_EINVAL, "kb_prim_filter: unsupported");
 	const KbFs F = kb_make_fs(fs);
-	KbOnePole op; kb_onepole_construct(op, kind == 2 ? KB_OP_LPF : KB_OP_HPF);
-	if (kind >= 2 && nset == 1) kb_onepole_set(F, op, f[0]);
+	KbOnePole op; kb_onepole_construct(op, kind == 2 ? KB_OP_LPF : kind == 3 ? KB_OP_HPF : KB_OP_BW1);
+	if (onepole && nset == 1) kb_onepole_set(F, op, f[0]);
 	DevBuf df(sizeof(float) * (nset ? nset : 1), f), dq(sizeof(float) * (nset ? nset : 1), Q), din(sizeof(float) * n, in), dout(sizeof(float) * n), dc(sizeof(float) * 5);
 	kb_prim_filter_kernel<<<1, 32>>>(kind, nset, df.as<float>(), Q ? dq.as<float>() : nullptr, F, n, din.as<float>(), dout.as<float>(), dc.as<float>(), op);
 	int rc = prim_finish("kb_prim_filter"); if (rc) return rc;

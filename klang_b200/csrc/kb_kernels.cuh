@@ -328,13 +328,19 @@ __global__ void kb_prim_osc_kernel(int kind, int nargs, float f, float phase, fl
 		}
 	}
 }
+// kinds (tests/cases.py): 0 Biquad::LPF 1 Biquad::HPF 2 OnePole::LPF 3 OnePole::HPF 4 Biquad::BPF 5 Biquad::BRF 6 Biquad::APF
+// 7 Butterworth::LPF<1> 8 Butterworth::LPF<2>; one-pole coefficients (expf / tanf) come from the host
 __global__ void kb_prim_filter_kernel(int kind, int nset, const float* f, const float* Q, KbFs fs, int n, const float* in, float* out, float* coeffs,
                                       KbOnePole op) {
 	if (threadIdx.x || blockIdx.x) return;
-	if (kind <= 1) {
-		KbBiquad b; kb_biquad_construct(b, kind == 0 ? KB_BQ_LPF : KB_BQ_HPF);
+	const int bq = kind == 0 ? KB_BQ_LPF : kind == 1 ? KB_BQ_HPF : kind == 4 ? KB_BQ_BPF : kind == 5 ? KB_BQ_BRF : kind == 6 ? KB_BQ_APF : kind == 8 ? KB_BQ_BW2 : -1;
+	if (bq >= 0) {
+		KbBiquad b; kb_biquad_construct(b, bq);
 		for (int s = 0; s < n; s++) {
-			if (s < nset) { if (Q) kb_biquad_set(fs, b, f[s], Q[s]); else kb_biquad_set_f(fs, b, f[s]); }
+			if (s < nset) {
+				if (Q) { if (bq == KB_BQ_APF) kb_apf_set(fs, b, f[s], Q[s]); else kb_biquad_set(fs, b, f[s], Q[s]); }
+				else kb_biquad_set_f(fs, b, f[s]);
+			}
 			out[s] = kb_biquad_tick(b, in[s]);
 		}
 		coeffs[0] = b.b0; coeffs[1] = b.b1; coeffs[2] = b.b2; coeffs[3] = b.a1; coeffs[4] = b.a2;

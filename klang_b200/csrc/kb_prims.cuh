@@ -206,7 +206,22 @@ KB_HD void kb_biquad_set(const KbFs& fs, KbBiquad& b, float f, float Q) {
 		kb_biquad_init(b);
 	}
 }
-KB_HD void kb_biquad_set_f(const KbFs& fs, KbBiquad& b, float f) { kb_biquad_set(fs, b, f, KB_ROOT2_INV_F); }   // klang.h:5575
+// APF::set(f, r) + APF::init                                                klang.h:5752-5772
+KB_HD void kb_apf_set(const KbFs& fs, KbBiquad& b, float f, float r) {
+	if (b.f != f || b.a != r) {
+		b.f = f; b.a = r;
+		const float w = f * fs.w;
+		b.cos0 = KB_COSF(w); b.sin0 = KB_SINF(w);
+		const float omega = 2.0f * KB_PI_F * f / fs.f;
+		const float c0 = KB_COSF(omega);
+		b.b0 = b.a2 = b.a * b.a;
+		b.b1 = b.a1 = (-2.f * b.a * c0);
+		b.b2 = 1.f;
+	}
+}
+KB_HD void kb_biquad_set_f(const KbFs& fs, KbBiquad& b, float f) {                                               // klang.h:5575
+	if (b.type == KB_BQ_APF) kb_apf_set(fs, b, f, 1.f); else kb_biquad_set(fs, b, f, KB_ROOT2_INV_F);
+}
 // Filter::process                                                           klang.h:5605-5612
 KB_HD float kb_biquad_tick(KbBiquad& b, float in) {
 	const float z0 = b.z0, z1 = b.z1;
@@ -216,13 +231,19 @@ KB_HD float kb_biquad_tick(KbBiquad& b, float in) {
 	return y;
 }
 
-enum { KB_OP_LPF = 0, KB_OP_HPF };
+enum { KB_OP_LPF = 0, KB_OP_HPF, KB_OP_BW1 };
 KB_HD void kb_onepole_construct(KbOnePole& p, int type) { memset(&p, 0, sizeof(p)); p.type = type; p.b0 = 1.f; }
 KB_HD void kb_onepole_reset(KbOnePole& p) { p.a1 = 0; p.b0 = 1; p.b1 = 0; p.f = 0; p.z = 0; }   // klang.h:5482-5488
 // OnePole::LPF::init / HPF::init — control-rate only (expf from the host libm)    klang.h:5508-5512, 5535-5541
 inline void kb_onepole_set(const KbFs& fs, KbOnePole& p, float f) {
 	if (p.f != f) {
 		p.f = f;
+		if (p.type == KB_OP_BW1) {                                             // Butterworth::LPF<1>::init  klang.h:5786-5793
+			const float c = 1.f / ::tanf(KB_PI_F * f * fs.inv);
+			const float inv = kb_const_inv(1.f + c);
+			p.b0 = inv; p.a1 = (1.f - c) * inv;
+			return;
+		}
 		const float e = ::expf(-f * fs.w);
 		if (p.type == KB_OP_LPF) { p.b0 = 1 - e; p.a1 = e; }
 		else { p.b0 = 0.5f * (1.f + e); p.b1 = -p.b0; p.a1 = e; }
@@ -230,7 +251,8 @@ inline void kb_onepole_set(const KbFs& fs, KbOnePole& p, float f) {
 }
 KB_HD float kb_onepole_tick(KbOnePole& p, float in) {
 	if (p.type == KB_OP_LPF) p.out = p.b0 * in + p.a1 * p.out + KB_DENORMALISE;                            // klang.h:5515-5517
-	else { p.out = p.b0 * in + p.b1 * p.z + p.a1 * p.out + KB_DENORMALISE; p.z = in; }                     // klang.h:5499-5502
+	else if (p.type == KB_OP_HPF) { p.out = p.b0 * in + p.b1 * p.z + p.a1 * p.out + KB_DENORMALISE; p.z = in; }   // klang.h:5499-5502
+	else { p.out = p.b0 * (in + p.z) - p.a1 * p.out; p.z = in; }                                           // Butterworth::LPF<1>  klang.h:5795-5798
 	return p.out;
 }
 

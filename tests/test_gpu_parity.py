@@ -116,10 +116,20 @@ def test_primitives_match_reference_golden(eng, golden, fs):
         assert_parity(y, g[f"filter/{name}/noise_f50_q1"], name + " noise", exact=True)
         y, _ = eng.filt(kind, x, sweep, 10.0, per_sample=True)        # device cosf/sinf every sample
         assert_parity(y, g[f"filter/{name}/sweep_q10"], name + " sweep", exact=True)
-    for kind, name in ((2, "onepole_lpf"), (3, "onepole_hpf")):
+    for kind, name in ((2, "onepole_lpf"), (3, "onepole_hpf"), (7, "butterworth_lpf1")):
         y, c = eng.filt(kind, imp, 1000.0)
         assert_parity(y, g[f"filter/{name}/impulse"], name + " impulse", exact=True)
         assert_parity(c, g[f"filter/{name}/coeffs"], name + " coeffs", exact=True)
+    for kind, name in ((4, "biquad_bpf"), (5, "biquad_brf"), (8, "butterworth_lpf2")):      # SURVEY §8f-3 primitives
+        y, c = eng.filt(kind, imp, 1000.0)
+        assert_parity(y, g[f"filter/{name}/impulse"], name + " impulse", exact=True)
+        assert_parity(c, g[f"filter/{name}/coeffs"], name + " coeffs", exact=True)
+        y, _ = eng.filt(kind, x, 50.0, 1.0)
+        assert_parity(y, g[f"filter/{name}/noise_f50_q1"], name + " noise", exact=True)
+        y, _ = eng.filt(kind, x, sweep, 10.0, per_sample=True)
+        assert_parity(y, g[f"filter/{name}/sweep_q10"], name + " sweep", exact=True)
+    y, _ = eng.filt(6, x, 1000.0, 0.5)
+    assert_parity(y, g["filter/biquad_apf/noise"], "biquad_apf noise", exact=True)
     y, st = eng.envelope([(0, 0), (0.001, 1), (0.003, 0.25), (0.005, 0.5)], 400)
     assert_parity(y, g["envelope/4pt"], "envelope/4pt", exact=True)
     assert_parity(st, g["envelope/4pt_stage"], "envelope/4pt_stage")

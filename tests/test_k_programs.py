@@ -1,0 +1,83 @@
+"""The reference's example `.k` programs, UNMODIFIED, against this repo's own klang.h (include/compat/klang.h):
+
+  * CPU: they compile and link (tools/build_k_host.py reads them where they lie under /root/reference/examples), and the
+    resulting host program refuses to run without a CUDA device;
+  * GPU (-m gpu): the prebuilt host program (tests/_k_bin/k_host, travels with the snapshot) drives each program's block
+    driver on the B200 — controls moved through the `.k` object's own table, MIDI through noteOn/noteOff — and the output
+    is bit-identical to the oracle run with the same script."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import cases
+import oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+K_HOST = os.path.join(ROOT, "tests", "_k_bin", "k_host")
+HAVE_REFERENCE = os.path.isfile("/root/reference/examples/PingPong.k")
+PROGRAMS = ["gain", "pingpong", "delay_pingpong", "delay_reverb", "supersaw", "filter_k", "tb303"]
+
+
+@pytest.mark.skipif(not HAVE_REFERENCE, reason="reference examples not present")
+def test_reference_k_programs_compile_unmodified_against_compat_header(tmp_path):
+    import klang_b200 as kb
+    from klang_b200 import build
+    build.build(verbose=False)
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import build_k_host
+    exe = build_k_host.build(verbose=False)
+    out = subprocess.run([exe, "pingpong", "48000", "64", "1", str(tmp_path / "o.f32")], capture_output=True, text=True)
+    if kb.device_count() == 0:
+        assert out.returncode == 3 and "no CPU path" in out.stderr      # fails loudly: nothing is computed on the host
+    else:
+        assert out.returncode == 0, out.stderr
+
+
+def _expected(prog, fs, n, blocks):
+    oracle.port.set_fs(fs)
+    oracle.port.srand(1)
+    if prog in ("gain", "pingpong", "delay_pingpong", "delay_reverb"):
+        graph = {"gain": oracle.FX_GAIN, "pingpong": oracle.FX_PINGPONG, "delay_pingpong": oracle.FX_DELAY_PINGPONG, "delay_reverb": oracle.FX_DELAY_REVERB}[prog]
+        fx = oracle.port.Fx(graph)
+        x = cases.fx_input(fx.channels, n * blocks, seed=1)
+        outs = []
+        for b in range(blocks):
+            if b == 1:
+                fx.set_control(0, 0.3)
+            blk = x[:, b * n:(b + 1) * n]
+            outs.append(np.atleast_2d(fx.process(blk[0] if fx.channels == 1 else blk)))
+        fx.close()
+        return np.stack(outs)                         # [blocks, channels, n]
+    graph = {"supersaw": oracle.SY_SUPERSAW, "filter_k": oracle.SY_FILTER_K, "tb303": oracle.SY_TB303}[prog]
+    sy = oracle.port.Synth(graph, 32)
+    outs = []
+    for b in range(blocks):
+        if b == 0:
+            for k in range(6):
+                sy.note_on(48 + 5 * k, np.float32(0.5) + np.float32(0.08) * np.float32(k))
+        if b == 2:
+            sy.note_off(48)
+            sy.note_off(58)
+            sy.note_on(77, 0.9)
+        outs.append(sy.process(n))
+    sy.close()
+    return np.stack(outs)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prog", PROGRAMS)
+def test_reference_k_programs_run_on_the_device_bit_exact(prog, tmp_path):
+    if not os.path.isfile(K_HOST):
+        pytest.skip("tests/_k_bin/k_host was not built (needs /root/reference at build time)")
+    fs, n, blocks = 48000, 512, 4
+    out = tmp_path / "o.f32"
+    r = subprocess.run([K_HOST, prog, str(fs), str(n), str(blocks), str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    want = _expected(prog, fs, n, blocks)
+    got = np.fromfile(out, np.float32).reshape(want.shape)
+    same = (got.view(np.uint32) == want.view(np.uint32)) | (np.isnan(got) & np.isnan(want))
+    assert same.all(), f"{prog}: {(~same).sum()} of {same.size} samples differ, first at {tuple(np.argwhere(~same)[0])}"
+    assert np.abs(want).max() > 1e-3

@@ -1,0 +1,100 @@
+// Host program: the reference's example `.k` programs, UNMODIFIED, compiled against include/compat/klang.h and run on the
+// B200 through libklang_b200.so.  Built by tools/build_k_host.py from the sources where they lie under
+// /root/reference/examples into tests/_k_bin/ (git-ignored build artefact, like oracle/_ref); used by
+// tests/test_k_programs.py.  Usage: k_host <program> <fs> <block> <blocks> <out.f32>
+#include <klang.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+namespace k_gain {
+#include "Gain/Gain.k"
+}
+namespace k_pingpong {
+#include "PingPong.k"
+}
+namespace k_delay_pingpong {
+#include "Delay/PingPong.k"
+}
+namespace k_delay_reverb {
+#include "Delay/Reverb.k"
+}
+namespace k_supersaw {
+#include "SuperSaw.k"
+}
+namespace k_filter {
+#include "Subtractive/Filter.k"
+}
+namespace k_tb303 {
+#include "TB303.k"
+}
+
+KLANG_B200_EFFECT(k_gain::Gain, KB_FX_GAIN)
+KLANG_B200_EFFECT(k_pingpong::PingPong, KB_FX_PINGPONG)
+KLANG_B200_EFFECT(k_delay_pingpong::PingPong, KB_FX_DELAY_PINGPONG)
+KLANG_B200_EFFECT(k_delay_reverb::Reverb, KB_FX_DELAY_REVERB)
+KLANG_B200_SYNTH(k_supersaw::SuperSaw, KB_SY_SUPERSAW)
+KLANG_B200_SYNTH(k_filter::Filter, KB_SY_FILTER_K)
+KLANG_B200_SYNTH(k_tb303::TB303, KB_SY_TB303)
+
+// the deterministic input of tests/cases.py::noise
+static float noise(uint64_t n, uint64_t seed, double lo, double hi) {
+	uint64_t x = (n + seed * 0x9E3779B97F4A7C15ull) * 6364136223846793005ull + 1442695040888963407ull;
+	x ^= x >> 33; x *= 0xFF51AFD7ED558CCDull; x ^= x >> 33;
+	return (float)(lo + (hi - lo) * ((double)(x >> 40) / 16777216.0));
+}
+
+template <class PLUGIN> static int run_effect(float fs, int n, int blocks, FILE* out) {
+	klang::b200::EffectHost<PLUGIN> host(fs, n);
+	const int C = host.channels();
+	std::vector<float> buf((size_t)C * n);
+	for (int b = 0; b < blocks; b++) {
+		if (b == 1) host.plugin.controls[0].set(0.3f);            // the host moves a control between blocks, through the .k object
+		for (int c = 0; c < C; c++) for (int t = 0; t < n; t++) buf[(size_t)c * n + t] = noise((uint64_t)b * n + t, 2 + c, -0.5, 0.5);
+		if (!host.process(buf.data(), n)) return 2;
+		fwrite(buf.data(), sizeof(float), buf.size(), out);
+	}
+	return 0;
+}
+template <class PLUGIN> static int run_synth(float fs, int n, int blocks, FILE* out) {
+	klang::b200::SynthHost<PLUGIN> host(fs, n);
+	kb_srand(1);
+	const int C = host.channels();
+	std::vector<float> buf((size_t)C * n);
+	for (int b = 0; b < blocks; b++) {
+		if (b == 0) for (int k = 0; k < 6; k++) host.noteOn(48 + 5 * k, 0.5f + 0.08f * k);
+		if (b == 2) { host.noteOff(48); host.noteOff(58); host.noteOn(77, 0.9f); }
+		if (!host.process(buf.data(), n)) return 2;
+		fwrite(buf.data(), sizeof(float), buf.size(), out);
+	}
+	return 0;
+}
+
+int main(int argc, char** argv) {
+	if (argc < 6) { fprintf(stderr, "usage: k_host <program> <fs> <block> <blocks> <out.f32>\n"); return 64; }
+	const std::string prog = argv[1];
+	const float fs = (float)atof(argv[2]);
+	const int n = atoi(argv[3]), blocks = atoi(argv[4]);
+	FILE* out = fopen(argv[5], "wb");
+	if (!out) return 65;
+	int rc = 66;
+	try {
+		if (prog == "gain") rc = run_effect<k_gain::Gain>(fs, n, blocks, out);
+		else if (prog == "pingpong") rc = run_effect<k_pingpong::PingPong>(fs, n, blocks, out);
+		else if (prog == "delay_pingpong") rc = run_effect<k_delay_pingpong::PingPong>(fs, n, blocks, out);
+		else if (prog == "delay_reverb") rc = run_effect<k_delay_reverb::Reverb>(fs, n, blocks, out);
+		else if (prog == "supersaw") rc = run_synth<k_supersaw::SuperSaw>(fs, n, blocks, out);
+		else if (prog == "filter_k") rc = run_synth<k_filter::Filter>(fs, n, blocks, out);
+		else if (prog == "tb303") rc = run_synth<k_tb303::TB303>(fs, n, blocks, out);
+	} catch (const klang::b200::Error& e) {
+		fprintf(stderr, "k_host: %s\n", e.what());
+		rc = kb_device_count() == 0 ? 3 : 4;          // 3 = no CUDA device (expected off the GPU box)
+	} catch (const std::exception& e) {
+		fprintf(stderr, "k_host: %s\n", e.what());
+		rc = 5;
+	}
+	fclose(out);
+	return rc;
+}
