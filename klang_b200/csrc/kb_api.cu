@@ -487,6 +487,7 @@ extern "C" kb_synth_bank* kb_synth_bank_create(int graph, int instances, int voi
 	ok = ok && dev_alloc(&b->d_out, (size_t)instances * b->channels * max_block) == cudaSuccess;
 	ok = ok && dev_alloc(&b->d_mix, (size_t)b->channels * max_block) == cudaSuccess;
 	if (graph == KB_SY_SYNTHX) ok = ok && dev_alloc(&b->d_adsr, (size_t)total * max_block) == cudaSuccess;
+	if (graph == KB_SY_SYNTHX) ok = ok && cudaFuncSetAttribute(kb_sx_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KbSxSmem)) == cudaSuccess;
 	if (!ok) { kb_fail(KB_ECUDA, std::string("kb_synth_bank_create: ") + cudaGetErrorString(cudaGetLastError())); kb_synth_bank_destroy(b); return nullptr; }
 	return b;
 }
@@ -642,7 +643,7 @@ extern "C" int kb_synth_bank_process(kb_synth_bank* b, float* out, int n, unsign
 		kb_sx_adsr_kernel<<<(total + 31) / 32, 32, 0, st>>>((KbSxVoice*)b->d_vstate, b->d_hdr, b->d_adsr, n, total, b->fs);
 		dim3 grid((n + 31) / 32, b->instances);
 		b->prof_begin();
-		kb_sx_render_kernel<<<grid, 32 * (KB_SX_PRODUCERS + 1), 0, st>>>((const KbSxVoice*)b->d_vstate, b->d_hdr, b->d_adsr, per_voice ? d_voice_dst : d_inst_dst, n, b->voices, per_voice ? 1 : 0);
+		kb_sx_render_kernel<<<grid, 32 * (KB_SX_PRODUCERS * KB_SX_WARPS_PER_PAIR + 1), sizeof(KbSxSmem), st>>>((const KbSxVoice*)b->d_vstate, b->d_hdr, b->d_adsr, per_voice ? d_voice_dst : d_inst_dst, n, b->voices, per_voice ? 1 : 0);
 		b->prof_end();
 		kb_sx_advance_kernel<<<(pthreads + 127) / 128, 128, 0, st>>>((KbSxVoice*)b->d_vstate, b->d_hdr, n, total);
 		b->launches += 4;

@@ -140,36 +140,40 @@ __global__ void kb_sx_adsr_kernel(KbSxVoice* __restrict__ voices, KbVoiceHdr* __
 	if (e.stage == KB_ENV_OFF) hdr[v].stage = KB_NOTE_OFF;
 }
 // Render.  One CTA = (instance, 32 consecutive samples): the running buffer values of those samples live in the registers
-// of ONE consumer warp (lane = sample), which performs the reference's additions strictly in order; KB_SX_PRODUCERS other
-// warps evaluate the oscillators (closed form, lane = sample, one partial per warp at a time) one round ahead into a
-// double-buffered shared tile.  The fp32 sum therefore has exactly the reference's association, while the ~60
-// instructions per partial-sample run in parallel on all warps.
+// of ONE consumer warp (lane = sample), which performs the reference's additions strictly in order; 24 producer warps —
+// two per partial [harmonic][partial] pair, splitting the 11 Additive notes — evaluate the oscillators of the NEXT voice
+// (closed form, lane = sample) into a double-buffered shared tile while the consumer adds the current one.  One round =
+// one voice = 132 partial slots, one __syncthreads.  The fp32 sum therefore has exactly the reference's association, while
+// the oscillator evaluation runs in parallel on all warps.
 // per_voice: every voice starts from a cleared buffer and is written to dst[voice][2][n]; otherwise the instance buffer
 // is carried from voice to voice (each voice's `buffer *= adsr` also scales what earlier voices left there, exactly as
 // Stereo::Synth::process hands the same buffer to every note, klang.h:4842-4848) and the synth-level tanh post-fx
 // (SynTHX.k:201-206) is applied at the end.
-#define KB_SX_PRODUCERS 12
-#define KB_SX_ROUND 24                      // partial slots per round = two Additive notes (2 x 4 harmonics x 3 partials)
-#define KB_SX_ROUNDS_PER_VOICE 6            // 11 notes = 5 full rounds + one half round
-__global__ void __launch_bounds__(32 * (KB_SX_PRODUCERS + 1)) kb_sx_render_kernel(const KbSxVoice* __restrict__ voices, const KbVoiceHdr* __restrict__ hdr,
+#define KB_SX_PRODUCERS 12                  // (harmonic, partial) pairs of an Additive note
+#define KB_SX_WARPS_PER_PAIR 2              // producer warps sharing one pair: they split the 11 notes
+struct KbSxSmem {
+	float val[2][11][KB_SX_PRODUCERS][32];
+	int flag[2][11][KB_SX_PRODUCERS];          // bit 0: slot is ticked this block, bit 1: routed to the right channel
+	unsigned voice[2][sizeof(KbSxAdditive) * 11 / 4];   // oscillator state of the current and the next voice
+	int vlist[KB_MAX_VOICES], nact;
+};
+__global__ void __launch_bounds__(32 * (KB_SX_PRODUCERS * KB_SX_WARPS_PER_PAIR + 1)) kb_sx_render_kernel(const KbSxVoice* __restrict__ voices, const KbVoiceHdr* __restrict__ hdr,
                                                                                 const float* __restrict__ adsr, float* __restrict__ dst, int n,
                                                                                 int voices_per_inst, int per_voice) {
-	constexpr int NT = 32 * (KB_SX_PRODUCERS + 1);
+	constexpr int NT = 32 * (KB_SX_PRODUCERS * KB_SX_WARPS_PER_PAIR + 1);
 	constexpr int VW = (int)(sizeof(KbSxAdditive) * 11 / 4);       // words of a voice's 11 Additive notes (the ADSR follows them)
 	constexpr int VPT = (VW + NT - 1) / NT;                          // words per thread when a voice is staged
-	__shared__ float s_val[2][KB_SX_ROUND][32];
-	__shared__ int s_flag[2][KB_SX_ROUND];            // bit 0: slot is ticked this block, bit 1: routed to the right channel
-	__shared__ int s_vlist[KB_MAX_VOICES], s_nact;
-	__shared__ __align__(16) unsigned s_voice[2][VW];  // oscillator state of the current and the next voice
+	extern __shared__ __align__(16) unsigned char kb_sx_smem_raw[];
+	KbSxSmem& S = *reinterpret_cast<KbSxSmem*>(kb_sx_smem_raw);
 	const int inst = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int t = blockIdx.x * 32 + lane;
 	if (threadIdx.x == 0) {
 		int c = 0;
-		for (int vi = 0; vi < voices_per_inst; vi++) if (hdr[inst * voices_per_inst + vi].active) s_vlist[c++] = inst * voices_per_inst + vi;
-		s_nact = c;
+		for (int vi = 0; vi < voices_per_inst; vi++) if (hdr[inst * voices_per_inst + vi].active) S.vlist[c++] = inst * voices_per_inst + vi;
+		S.nact = c;
 	}
 	__syncthreads();
-	const int nact = s_nact, rounds = nact * KB_SX_ROUNDS_PER_VOICE;
+	const int nact = S.nact;
 	float l = 0.f, r = 0.f;
 	if (per_voice && warp == 0) {      // voices that are Off this block: cleared streams
 		for (int vi = 0; vi < voices_per_inst; vi++) {
@@ -178,61 +182,59 @@ __global__ void __launch_bounds__(32 * (KB_SX_PRODUCERS + 1)) kb_sx_render_kerne
 		}
 	}
 	if (nact > 0) {
-		const unsigned* src = reinterpret_cast<const unsigned*>(&voices[s_vlist[0]]);
-		for (int w = threadIdx.x; w < VW; w += NT) s_voice[0][w] = src[w];
+		const unsigned* src = reinterpret_cast<const unsigned*>(&voices[S.vlist[0]]);
+		for (int w = threadIdx.x; w < VW; w += NT) S.voice[0][w] = src[w];
 	}
 	__syncthreads();
 	unsigned pre[VPT];                                 // the next voice travels through registers during the current one
-	for (int i = 0; i <= rounds; i++) {
-		const int vj = i / KB_SX_ROUNDS_PER_VOICE, rv = i % KB_SX_ROUNDS_PER_VOICE;
-		if (i < rounds && rv == 0 && vj + 1 < nact) {
-			const unsigned* src = reinterpret_cast<const unsigned*>(&voices[s_vlist[vj + 1]]);
+	for (int j = 0; j <= nact; j++) {
+		if (j + 1 < nact) {
+			const unsigned* src = reinterpret_cast<const unsigned*>(&voices[S.vlist[j + 1]]);
 			#pragma unroll
 			for (int q = 0; q < VPT; q++) { const int w = threadIdx.x + q * NT; if (w < VW) pre[q] = src[w]; }
 		}
-		if (warp > 0 && i < rounds) {
-			// ---- producers: round i = voice i / 6, notes 2*(i % 6) and 2*(i % 6) + 1; this warp takes slots (warp-1) and (warp-1)+12
-			const KbSxAdditive* notes = reinterpret_cast<const KbSxAdditive*>(s_voice[vj & 1]);
-			#pragma unroll
-			for (int h = 0; h < 2; h++) {
-				const int slot = (warp - 1) + h * KB_SX_PRODUCERS;      // 0..23: note (slot / 12), harmonic ((slot % 12) / 3), partial (slot % 3)
-				const int k = 2 * rv + slot / 12;
+		if (warp > 0 && j < nact) {
+			// ---- producers: voice j; this warp's partial of each of the 11 notes
+			const KbSxAdditive* notes = reinterpret_cast<const KbSxAdditive*>(S.voice[j & 1]);
+			const int w = (warp - 1) % KB_SX_PRODUCERS, p = w / 3, q = w % 3;
+			for (int k = (warp - 1) / KB_SX_PRODUCERS; k < 11; k += KB_SX_WARPS_PER_PAIR) {
+				const KbSxAdditive& A = notes[k];
 				int flag = 0;
 				float x = 0.f;
-				if (k < 11) {
-					const KbSxAdditive& A = notes[k];
-					const int q = slot % 3;
-					if (q < ((A.frequency < 440.f) ? 2 : 3)) {            // Additive::process picks partials<2> or <3>  SynTHX.k:124-127
-						const KbSxPartial& P = A.partial[(slot % 12) / 3][q];
-						x = kb_osm_at(P.osc, (uint32_t)t) * 0.25f;        // partial * 0.25f  SynTHX.k:113-118
-						flag = 1 | (P.right ? 2 : 0);
-					}
+				if (q < ((A.frequency < 440.f) ? 2 : 3)) {                // Additive::process picks partials<2> or <3>  SynTHX.k:124-127
+					const KbSxPartial& P = A.partial[p][q];
+					x = kb_osm_at(P.osc, (uint32_t)t) * 0.25f;            // partial * 0.25f  SynTHX.k:113-118
+					flag = 1 | (P.right ? 2 : 0);
 				}
-				s_val[i & 1][slot][lane] = x;
-				if (lane == 0) s_flag[i & 1][slot] = flag;
+				S.val[j & 1][k][w][lane] = x;
+				if (lane == 0) S.flag[j & 1][k][w] = flag;
 			}
-		} else if (warp == 0 && i > 0) {
-			// ---- consumer: round i-1, additions in the reference's order (note, harmonic, partial)
-			const int j = i - 1, b = j & 1;
+		} else if (warp == 0 && j > 0) {
+			// ---- consumer: voice j-1, additions in the reference's order (note, harmonic, partial)
+			const int b = (j - 1) & 1;
+			const int v = S.vlist[j - 1];
+			const float a = t < n ? adsr[(size_t)v * n + t] : 0.f;          // (issued before the additions: off the critical path)
 			#pragma unroll
-			for (int slot = 0; slot < KB_SX_ROUND; slot++) {
-				const int f = s_flag[b][slot];
-				const float x = s_val[b][slot][lane];
-				if (f & 1) { if (f & 2) r += x; else l += x; }
-			}
-			if (j % KB_SX_ROUNDS_PER_VOICE == KB_SX_ROUNDS_PER_VOICE - 1) {          // the voice is complete: buffer *= adsr++  SynTHX.k:176-178
-				const int v = s_vlist[j / KB_SX_ROUNDS_PER_VOICE];
-				const float a = t < n ? adsr[(size_t)v * n + t] : 0.f;
-				l *= a; r *= a;
-				if (per_voice) {
-					if (t < n) { dst[((size_t)v * 2 + 0) * n + t] = l; dst[((size_t)v * 2 + 1) * n + t] = r; }
-					l = 0.f; r = 0.f;
+			for (int k = 0; k < 11; k++) {
+				#pragma unroll
+				for (int w = 0; w < KB_SX_PRODUCERS; w++) {
+					// branch-free: the addition happens exactly when the reference performs it (a skipped slot must not add 0.0)
+					const int f = S.flag[b][k][w];
+					const float x = S.val[b][k][w][lane];
+					const float nl = l + x, nr = r + x;
+					l = (f == 1) ? nl : l;
+					r = (f == 3) ? nr : r;
 				}
+			}
+			l *= a; r *= a;                                               // the voice is complete: buffer *= adsr++  SynTHX.k:176-178
+			if (per_voice) {
+				if (t < n) { dst[((size_t)v * 2 + 0) * n + t] = l; dst[((size_t)v * 2 + 1) * n + t] = r; }
+				l = 0.f; r = 0.f;
 			}
 		}
-		if (i < rounds && rv == KB_SX_ROUNDS_PER_VOICE - 1 && vj + 1 < nact) {
+		if (j + 1 < nact) {
 			#pragma unroll
-			for (int q = 0; q < VPT; q++) { const int w = threadIdx.x + q * NT; if (w < VW) s_voice[(vj + 1) & 1][w] = pre[q]; }
+			for (int q = 0; q < VPT; q++) { const int w = threadIdx.x + q * NT; if (w < VW) S.voice[(j + 1) & 1][w] = pre[q]; }
 		}
 		__syncthreads();
 	}

@@ -135,6 +135,12 @@ KB_HD float kb_osm_tick(KbOsm& o) {
 KB_HD float kb_osm_at(const KbOsm& o, uint32_t i) {
 	const uint32_t inc = (uint32_t)o.increment;
 	const uint32_t off = o.offset + i * inc;
+	if (o.waveform == 0 && o.duty == 0u && (o.state & 1) == 0) {
+		// plain Saw (duty 0): `offset < duty` is never true, so the state machine only ever sees Down (0) and, on the
+		// tick where the phase wraps, DownUpDown (4) — the same two expressions the generic path would select
+		const float p = kb_phase_float(off + inc) - o.col;
+		return (off < inc) ? -o.rcpf * (1.f + o.c2 * o.omf * (p + p + o.omf)) + 1.f : o.c2 * (p + p - o.f) + 1.f;
+	}
 	const int prev = (i == 0) ? (o.state & 1) : ((off - inc) < o.duty ? 1 : 0);
 	const int st = (prev << 1) | (off < o.duty ? 1 : 0);
 	const int tr = st | (off < inc ? 4 : 0);
