@@ -179,7 +179,7 @@ def cpu_extra(what, graph, units_per_core, n, blocks):
             "sample": f"{cores} workers x {units_per_core} {'instances' if what == 'fx' else 'voices'} x {blocks} blocks of {n}"}
 
 
-def run_reference_arm(args, rank, world):
+def run_reference_arm(args, rank, world, emit):
     if rank != 0:
         return
     steps, warmup = args.steps, args.warmup
@@ -194,7 +194,7 @@ def run_reference_arm(args, rank, world):
         "e2e": {"value": value, "unit": "voice-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config():
@@ -218,9 +218,16 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: everything native libraries print there (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
 
     if args.impl == "reference":
-        run_reference_arm(args, rank, world)
+        run_reference_arm(args, rank, world, emit)
         return
 
     import numpy as np
@@ -366,7 +373,7 @@ def main():
         bank.profile(False)
         lane_ms = l_ms / max(1, l_n)
     k_ms_avg = k_ms / max(1, k_n)
-    alg_bytes = total * BLOCK * 4.0 * 2 + INSTANCES * BLOCK * 4.0      # per-voice stream write + mix read, mix write
+    alg_bytes = total * BLOCK * 4.0      # 4 B per voice-sample (the per-voice stream this kernel writes)
     achieved = alg_bytes / (k_ms_avg * 1e-3) / 1e9
     issue_peak = 148 * 128 * sm_max * 1e6                                # fp32 lanes x clock
     traffic = None
@@ -379,7 +386,7 @@ def main():
                 "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "kernel_ms": k_ms_avg, "kernel_share_of_step": k_ms_avg / ms_per_step,
                 "algorithmic_bytes_per_launch": alg_bytes,
-                "note": "C2 is bound by dependent-issue latency, not HBM (SURVEY H6): 8 B of stream traffic per voice-sample",
+                "note": "C2 is bound by the dependent-issue latency of its fp32 recurrences, not HBM (SURVEY H6, DESIGN.md 4.1): 4 B of stream traffic per voice-sample",
                 "voice_samples_per_s_kernel": total * BLOCK / (k_ms_avg * 1e-3),
                 "fp32_lane_cycles_per_voice_sample": issue_peak / (total * BLOCK / (k_ms_avg * 1e-3)),
                 "lane_per_voice_kernel_ms": lane_ms}
@@ -408,7 +415,7 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
 
 
 def extras(kb, torch, dev, stream, flush_l2, hbm_peak, peak_src, device_index, with_cpu=True):

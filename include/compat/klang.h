@@ -96,6 +96,7 @@ struct Control {
 	float min = 0.f, max = 1.f, initial = 0.f, value = 0.f;
 	signal smoothed;
 	std::vector<std::string> options;
+	struct Size { int x, y, w, h; } size = { 0, 0, 0, 0 };
 	Control() {}
 	operator float() const { return value; }
 	void set(float x) { value = x < min ? min : (max < x ? max : x); }
@@ -119,7 +120,6 @@ struct Group {
 	std::string name; std::vector<Control> items;
 	template <class... C> Group(const char* n, const C&... c) : name(n) { items = { static_cast<const Control&>(c)... }; }
 };
-struct Size { int x, y, w, h; };
 struct Controls {
 	std::vector<Control> items;
 	Controls& operator=(std::initializer_list<Control> list) { items.assign(list.begin(), list.end()); return *this; }
@@ -211,6 +211,56 @@ namespace Generators {
 	namespace Basic { struct Sine : Oscillator {}; struct Saw : Oscillator {}; struct Triangle : Oscillator {}; struct Square : Oscillator {}; struct Pulse : Oscillator {}; struct Noise : Generator {}; }
 }
 
+// fixed-capacity array with a live count (Reverb.k: `times.count = ...`)
+template <class T, int CAPACITY> struct Array {
+	T items[CAPACITY]; unsigned count = 0;
+	T& operator[](int i) { return items[i]; }
+	const T& operator[](int i) const { return items[i]; }
+	void add(const T& x) { if (count < (unsigned)CAPACITY) items[count++] = x; }
+	unsigned size() const { return count; }
+};
+
+// N-channel sample and the 4x4 feedback matrix of Reverb.k's FDN
+template <int N> struct signals {
+	signal value[N];
+	signals() {}
+	template <class... A> signals(A&&... a) : value{ signal(static_cast<A&&>(a))... } {}
+	signal& operator[](int i) { return value[i]; }
+	const signal& operator[](int i) const { return value[i]; }
+};
+template <int N> inline signals<N> operator+(const signals<N>& a, float b) { signals<N> r; for (int i = 0; i < N; i++) r.value[i] = a.value[i] + b; return r; }
+struct Matrix {
+	float v[4][4];
+	template <class... A> constexpr Matrix(A... a) : v{ { 0 } } { const float f[] = { (float)a... }; for (int i = 0; i < (int)sizeof...(A) && i < 16; i++) v[i / 4][i % 4] = f[i]; }
+};
+inline signals<4> operator>>(const signals<4>& in, const Matrix& m) {
+	signals<4> out;
+	for (int r = 0; r < 4; r++) { float acc = 0.f; for (int c = 0; c < 4; c++) acc += m.v[r][c] * in.value[c]; out.value[r] = acc; }
+	return out;
+}
+
+// sample cursors over caller-owned memory (what Note::process(buffer) receives)
+struct buffer {
+	float* samples = nullptr; int size = 0; float* ptr = nullptr;
+	buffer() {}
+	buffer(float* data, int n) : samples(data), size(n), ptr(data) {}
+	void rewind() { ptr = samples; }
+	bool finished() const { return ptr >= samples + size; }
+	signal& operator++(int) { return *reinterpret_cast<signal*>(ptr++); }
+	buffer& operator+=(float x) { *ptr += x; return *this; }
+	buffer& operator=(float x) { *ptr = x; return *this; }
+	operator float() const { return *ptr; }
+};
+
+namespace Mono {
+	typedef klang::signal signal;
+	typedef klang::buffer buffer;
+	typedef klang::Generator Generator;
+	typedef klang::Modifier Modifier;
+	typedef klang::Oscillator Oscillator;
+}
+namespace mono = Mono;
+
 // ------------------------------------------------------------------------------------------ plugin shells
 struct Plugin { Controls controls; Presets presets; virtual ~Plugin() {} };
 
@@ -248,27 +298,79 @@ namespace Stereo {
 		klang::signal l, r;
 		frame() {}
 		frame(klang::signal l_, klang::signal r_) : l(l_), r(r_) {}
+		frame& operator=(float v) { l = v; r = v; return *this; }
+		frame& operator+=(const frame& x) { l += x.l; r += x.r; return *this; }
 		frame& operator<<(const frame& x) { l = x.l; r = x.r; return *this; }
 	};
 	typedef frame signal;
 	inline frame operator*(const frame& a, const frame& b) { return frame(a.l * b.l, a.r * b.r); }
 	inline frame operator*(const frame& a, float b) { return frame(a.l * b, a.r * b); }
+	inline frame operator*(float a, const frame& b) { return frame(a * b.l, a * b.r); }
 	inline frame operator+(const frame& a, const frame& b) { return frame(a.l + b.l, a.r + b.r); }
 	inline frame& operator>>(const frame& a, frame& dst) { dst = a; return dst; }
+
+	struct Generator {
+		frame out;
+		virtual ~Generator() {}
+		virtual void process() {}
+		operator frame() { process(); return out; }
+	};
+	struct Modifier : Generator {
+		frame in;
+		virtual void set(param) {}
+		virtual void set(param, param) {}
+		virtual void set(param, param, param) {}
+		virtual void set(param, param, param, param) {}
+	};
+	inline Modifier& operator>>(const frame& x, Modifier& m) { m.in = x; return m; }
+	inline frame operator*(Modifier& m, float g) { return (frame)m * g; }
+	struct Oscillator : Generator {
+		param frequency = 1000.f;
+		virtual void set(param) {}
+		virtual void set(param, param) {}
+		virtual void set(param, param, param) {}
+	};
+	// N parallel copies of a mono modifier, one per channel (Reverb.k: Stereo::Bank<LPF>)
+	template <class T> struct Bank : Modifier {
+		T items[2];
+		void set(param f) override { items[0].set(f); items[1].set(f); }
+		void set(param f, param q) override { items[0].set(f, q); items[1].set(f, q); }
+	};
+	struct buffer {
+		klang::buffer left, right;
+		buffer() {}
+		buffer(float* l, float* r, int n) : left(l, n), right(r, n) {}
+		void rewind() { left.rewind(); right.rewind(); }
+		bool finished() const { return left.finished(); }
+		klang::buffer& channel(int c) { return c ? right : left; }
+		// `buffer++ *= env` (SynTHX.k:178) scales the frame the cursor just left, in place
+		struct Cursor {
+			float* l; float* r;
+			Cursor& operator*=(float g) { *l *= g; *r *= g; return *this; }
+			Cursor& operator=(const frame& x) { *l = x.l; *r = x.r; return *this; }
+			Cursor& operator+=(const frame& x) { *l += x.l; *r += x.r; return *this; }
+			operator frame() const { return frame(*l, *r); }
+		};
+		Cursor operator++(int) { Cursor c{ left.ptr, right.ptr }; left.ptr++; right.ptr++; return c; }
+		buffer& operator+=(const frame& x) { *left.ptr += x.l; *right.ptr += x.r; return *this; }
+	};
 
 	template <int SIZE> struct Delay {
 		klang::Delay<SIZE> l, r;
 		frame operator()(const frame& delay) const { (void)delay; return frame(); }
+		frame operator()(float delay) const { (void)delay; return frame(); }
 		Delay& operator<<(const frame& x) { l.in = x.l; r.in = x.r; return *this; }
 	};
 	template <int SIZE> inline Delay<SIZE>& operator>>(const frame& x, Delay<SIZE>& d) { return d << x; }
+	template <int SIZE> inline Delay<SIZE>& operator>>(Modifier& m, Delay<SIZE>& d) { return d << (frame)m; }
+	inline Modifier& operator>>(Modifier& a, Modifier& b) { b.in = (frame)a; return b; }
 
 	struct Effect : klang::Plugin {
 		frame in, out;
 		virtual void prepare() {}
 		virtual void process() {}
 	};
-	struct Note : klang::NoteBase { frame out; };
+	struct Note : klang::NoteBase { frame out; virtual bool process(buffer) { return !finished(); } using klang::NoteBase::process; };
 	struct Synth : Effect {
 		klang::Notes notes;
 		Synth() { notes.owner = &controls; }

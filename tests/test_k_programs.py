@@ -18,7 +18,7 @@ import oracle
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 K_HOST = os.path.join(ROOT, "tests", "_k_bin", "k_host")
 HAVE_REFERENCE = os.path.isfile("/root/reference/examples/PingPong.k")
-PROGRAMS = ["gain", "pingpong", "delay_pingpong", "delay_reverb", "supersaw", "filter_k", "tb303"]
+PROGRAMS = ["gain", "pingpong", "delay_pingpong", "delay_reverb", "reverb", "supersaw", "filter_k", "tb303", "synthx"]
 
 
 @pytest.mark.skipif(not HAVE_REFERENCE, reason="reference examples not present")
@@ -39,8 +39,9 @@ def test_reference_k_programs_compile_unmodified_against_compat_header(tmp_path)
 def _expected(prog, fs, n, blocks):
     oracle.port.set_fs(fs)
     oracle.port.srand(1)
-    if prog in ("gain", "pingpong", "delay_pingpong", "delay_reverb"):
-        graph = {"gain": oracle.FX_GAIN, "pingpong": oracle.FX_PINGPONG, "delay_pingpong": oracle.FX_DELAY_PINGPONG, "delay_reverb": oracle.FX_DELAY_REVERB}[prog]
+    if prog in ("gain", "pingpong", "delay_pingpong", "delay_reverb", "reverb"):
+        graph = {"gain": oracle.FX_GAIN, "pingpong": oracle.FX_PINGPONG, "delay_pingpong": oracle.FX_DELAY_PINGPONG, "delay_reverb": oracle.FX_DELAY_REVERB,
+                 "reverb": oracle.FX_REVERB}[prog]
         fx = oracle.port.Fx(graph)
         x = cases.fx_input(fx.channels, n * blocks, seed=1)
         outs = []
@@ -51,7 +52,7 @@ def _expected(prog, fs, n, blocks):
             outs.append(np.atleast_2d(fx.process(blk[0] if fx.channels == 1 else blk)))
         fx.close()
         return np.stack(outs)                         # [blocks, channels, n]
-    graph = {"supersaw": oracle.SY_SUPERSAW, "filter_k": oracle.SY_FILTER_K, "tb303": oracle.SY_TB303}[prog]
+    graph = {"supersaw": oracle.SY_SUPERSAW, "filter_k": oracle.SY_FILTER_K, "tb303": oracle.SY_TB303, "synthx": oracle.SY_SYNTHX}[prog]
     sy = oracle.port.Synth(graph, 32)
     outs = []
     for b in range(blocks):

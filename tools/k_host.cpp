@@ -30,6 +30,12 @@ namespace k_filter {
 namespace k_tb303 {
 #include "TB303.k"
 }
+namespace k_reverb {
+#include "Reverb.k"
+}
+namespace k_synthx {
+#include "SynTHX.k"
+}
 
 KLANG_B200_EFFECT(k_gain::Gain, KB_FX_GAIN)
 KLANG_B200_EFFECT(k_pingpong::PingPong, KB_FX_PINGPONG)
@@ -38,6 +44,8 @@ KLANG_B200_EFFECT(k_delay_reverb::Reverb, KB_FX_DELAY_REVERB)
 KLANG_B200_SYNTH(k_supersaw::SuperSaw, KB_SY_SUPERSAW)
 KLANG_B200_SYNTH(k_filter::Filter, KB_SY_FILTER_K)
 KLANG_B200_SYNTH(k_tb303::TB303, KB_SY_TB303)
+KLANG_B200_EFFECT(k_reverb::Reverb, KB_FX_REVERB)
+KLANG_B200_SYNTH(k_synthx::SynTHX, KB_SY_SYNTHX)
 
 // the deterministic input of tests/cases.py::noise
 static float noise(uint64_t n, uint64_t seed, double lo, double hi) {
@@ -88,6 +96,8 @@ int main(int argc, char** argv) {
 		else if (prog == "supersaw") rc = run_synth<k_supersaw::SuperSaw>(fs, n, blocks, out);
 		else if (prog == "filter_k") rc = run_synth<k_filter::Filter>(fs, n, blocks, out);
 		else if (prog == "tb303") rc = run_synth<k_tb303::TB303>(fs, n, blocks, out);
+		else if (prog == "reverb") rc = run_effect<k_reverb::Reverb>(fs, n, blocks, out);
+		else if (prog == "synthx") rc = run_synth<k_synthx::SynTHX>(fs, n, blocks, out);
 	} catch (const klang::b200::Error& e) {
 		fprintf(stderr, "k_host: %s\n", e.what());
 		rc = kb_device_count() == 0 ? 3 : 4;          // 3 = no CUDA device (expected off the GPU box)
