@@ -78,12 +78,19 @@ __global__ void __launch_bounds__(256) kb_mix_kernel(const float* __restrict__ s
 	if (t >= n) return;
 	float acc = 0.f;
 	const float* s = scratch + (size_t)inst * voices * n + t;
+	if (!sum_mode) {
+		// mono Note::process assigns (klang.h:4299): the block is whatever the last active voice wrote
+		int last = -1;
+		for (int v = voices - 1; v >= 0 && last < 0; v--) if (s_active[v]) last = v;
+		out[(size_t)inst * n + t] = last >= 0 ? __ldcs(s + (size_t)last * n) : 0.f;
+		return;
+	}
 	for (int v0 = 0; v0 < voices; v0 += 8) {
 		float x[8];
 		#pragma unroll
 		for (int j = 0; j < 8; j++) x[j] = (v0 + j < voices && s_active[v0 + j]) ? __ldcs(s + (size_t)(v0 + j) * n) : 0.f;   // 8 loads in flight
 		#pragma unroll
-		for (int j = 0; j < 8; j++) if (v0 + j < voices && s_active[v0 + j]) acc = sum_mode ? acc + x[j] : x[j];              // combined in voice order
+		for (int j = 0; j < 8; j++) if (v0 + j < voices && s_active[v0 + j]) acc = acc + x[j];                                // summed in voice order
 	}
 	out[(size_t)inst * n + t] = acc;
 }
