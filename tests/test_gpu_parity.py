@@ -517,3 +517,35 @@ def test_device_pointer_calls_match_host_pointer_calls(eng):
     b = t.cpu().numpy()
     dev.close()
     assert_parity(b, a, "device pointer fx", exact=True)
+
+
+def test_odd_bank_shapes_vs_live_oracle(eng):
+    """Instance / voice counts that are not multiples of the kernels' voices-per-CTA, and a block that is not a multiple
+    of the 128-sample tile."""
+    _drive_bank_vs_oracle(cases.SY_SUBTRACTIVE, 5, 33, 5, 333, 48000, exact=True)
+    _drive_bank_vs_oracle(cases.SY_TB303, 3, 37, 5, 200, 44100, exact=True)
+    _drive_bank_vs_oracle(cases.SY_SUPERSAW, 3, 35, 4, 130, 48000, exact=True)
+
+
+def test_pingpong_long_blocks_span_sub_blocks(eng):
+    """A 20000-frame process call is served as 8192-frame sub-blocks (the staged block lives in shared memory); the result
+    equals the oracle fed the same frames in its own block sizes."""
+    fs, inst = 48000, 2
+    oracle.port.set_fs(fs)
+    total = 60000
+    x = np.stack([cases.fx_input(2, total, seed=40 + i) for i in range(inst)])
+    want = np.empty_like(x)
+    for i in range(inst):
+        fx = oracle.port.Fx(cases.FX_PINGPONG)
+        for o in range(0, total, 10000):
+            want[i, :, o:o + 10000] = fx.process(x[i, :, o:o + 10000])
+        fx.close()
+    bank = kb.FxBank(cases.FX_PINGPONG, inst, fs, 20000)
+    got = np.empty_like(x)
+    for o in range(0, total, 20000):
+        blk = np.ascontiguousarray(x[:, :, o:o + 20000])
+        bank.process_inplace(blk)
+        got[:, :, o:o + 20000] = blk
+    assert bank.parallel_instances() == inst          # the last sub-block ran on the chunk-parallel schedule
+    bank.close()
+    assert_parity(got, want, "pingpong long blocks", exact=True)
