@@ -213,6 +213,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads (C1/C3/C4/C5 lines inside the JSON)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
+                    help="c2 = headline (Subtractive, 1024 voices/GPU); c5 = TB303.k + SynTHX.k mixed bank, 1024 voices/GPU, NCCL mix-down")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -236,6 +238,9 @@ def main():
 
     if not torch.cuda.is_available() or kb.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device — klang_b200 has no CPU path (use --impl reference for the CPU baseline)")
+    if args.workload == "c5":
+        run_c5(args, rank, world, local_rank, emit)
+        return
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
@@ -411,6 +416,115 @@ def main():
             line["cpu_baseline"] = info
         except Exception as e:
             line["cpu_baseline"] = {"error": repr(e)}
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        emit(line)
+
+
+def run_c5(args, rank, world, local_rank, emit):
+    """BASELINE config C5: TB303.k + SynTHX.k mixed bank, 8192 voices over 8 GPUs = per GPU 4 x 128 TB303 voices (mono)
+    + 4 x 128 SynTHX voices (stereo), block 4096; every rank mixes its instances into one stereo bus (KB_BANK_MIX, mono
+    voices to both channels) and the buses are sum-reduced to rank 0 over NCCL each block."""
+    import numpy as np
+    import torch
+    import klang_b200 as kb
+    from klang_b200 import sharding
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    hbm_peak, peak_src, _ = load_peaks()
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    inst, voices, n = 4, 128, BLOCK
+    kb.lib().kb_srand(1 + rank)
+    tb = kb.SynthBank(kb.SY_TB303, inst, voices, FS, n, local_rank)
+    sx = kb.SynthBank(kb.SY_SYNTHX, inst, voices, FS, n, local_rank)
+    for b in (tb, sx):
+        b.set_stream(stream.cuda_stream)
+    gid0 = rank * 2 * inst * voices
+    for g in range(inst * voices):
+        tb.voice_start(g % voices, 36 + (5 * (gid0 + g)) % 36, voice_velocity(gid0 + g), g // voices)
+        sx.voice_start(g % voices, 36 + (7 * (gid0 + g)) % 30, voice_velocity(gid0 + g), g // voices)
+    tb_mix = torch.empty(1, n, dtype=torch.float32, device=dev)
+    bus = torch.empty(2, n, dtype=torch.float32, device=dev)
+    bus_host = torch.empty(2, n, dtype=torch.float32).pin_memory()
+
+    def step(e2e=False):
+        tb.process_into(tb_mix, n, kb.BANK_MIX | kb.MIX_SUM)
+        sx.process_into(bus, n, kb.BANK_MIX)
+        bus.add_(tb_mix)                                   # mono voices feed both channels (SURVEY 8e)
+        sharding.reduce_mix(bus, dst=0)
+        if e2e:
+            bus_host.copy_(bus, non_blocking=True)
+            torch.cuda.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    evs = []
+    for _ in range(args.steps):
+        flush_buf.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        step()
+        b.record(stream)
+        evs.append((a, b))
+    barrier()
+    clk = clocks.stop() if clocks else None
+    t = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    total = 2 * inst * voices
+    value = world * total * n / (ms_per_step * 1e-3)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step(e2e=True)
+    barrier()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * total * n * args.steps / float(te.item())
+    sx.profile(True)
+    tb.profile(True)
+    for _ in range(5):
+        step()
+    sx_ms, sx_n = sx.profile_read()
+    tb_ms, tb_n = tb.profile_read()
+    launches = (tb.launches + sx.launches) // (max(3, args.warmup) + 2 * args.steps + 5)
+    k_ms = sx_ms / max(1, sx_n)
+    alg = inst * voices * n * 8.0                         # SynTHX per-voice streams are never materialised: 8 B per voice-sample of ADSR + bus traffic
+    line = {
+        "metric": "voice-samples/sec (48 kHz equiv) at 1024 voices", "value": value, "unit": "voice-samples/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C5 TB303.k + SynTHX.k mixed bank: per GPU 4 x 128 TB303 voices + 4 x 128 SynTHX voices, fs 48 kHz, block 4096, "
+                               "stereo bus sum-reduced to rank 0 over NCCL", "block": n, "fs": FS,
+                   "l2": "flushed between timed steps (256 MiB write, outside the per-step events)"},
+        "realtime_voices_48k": value / 48000.0, "clocks": clk,
+        "e2e": {"value": e2e_value, "unit": "voice-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 2 * n * 4,
+                "note": "no events in this schedule (all voices held); per step the reduced stereo bus is copied to pinned host memory"},
+        "gpu_launches": int(launches) + 1,
+        "roofline": {"bound": "hbm", "kernel": "kb_sx_render_kernel", "achieved": alg / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": alg / (k_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src, "kernel_ms": k_ms,
+                     "kernel_share_of_step": k_ms / ms_per_step, "tb303_kernel_ms": tb_ms / max(1, tb_n),
+                     "note": "bound by the ordered fp32 accumulation chain per output sample (DESIGN.md 4.2), not HBM"},
+    }
+    tb.close()
+    sx.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
