@@ -53,47 +53,91 @@ def load_peaks():
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region.  In-process NVML (nvidia_ml_py) polled by a thread every
+    5 ms, plus explicit sample() calls the timed loop makes right after queueing a step (the GPU is busy then, and the
+    per-step CUDA events do not see host time).  Falls back to one `nvidia-smi --query-gpu` per sample() without NVML."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.path = tempfile.mktemp(prefix="kb_clocks_", suffix=".csv")
-        self.proc = None
+        import threading
+        self.gpu_index = gpu_index
+        self.sm, self.reasons, self.mx = [], set(), None
+        self.nvml = self.handle = None
+        self.lock = threading.Lock()
+        self.running = False
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = gpu_index
+            if visible:
+                try:
+                    idx = int(visible.split(",")[gpu_index])
+                except Exception:
+                    idx = gpu_index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
         except Exception:
-            self.proc = None
+            self.nvml = None
+        self.thread = None
 
-    def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.proc is None:
-            return out
-        self.proc.terminate()
+    def start(self):
+        import threading
+        self.running = True
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+        return self
+
+    def _poll(self):
+        while self.running:
+            self.sample()
+            time.sleep(0.005)
+
+    def sample(self):
+        if self.nvml is not None:
+            try:
+                n = self.nvml
+                mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                names = (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40), ("sw_power_cap", 0x4))
+                with self.lock:
+                    self.sm.append(mhz)
+                    for name, bit in names:
+                        if mask & bit:
+                            self.reasons.add(name)
+                return
+            except Exception:
+                pass
         try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        try:
-            for line in open(self.path):
+            out = subprocess.run(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=10).stdout
+            for line in out.splitlines():
                 f = [x.strip() for x in line.split(",")]
                 if len(f) < 9:
                     continue
-                try:
-                    sm.append(float(f[1]))
-                    mx.append(float(f[2]))
-                except ValueError:
-                    continue
-                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
-            os.unlink(self.path)
+                with self.lock:
+                    self.sm.append(float(f[1]))
+                    self.mx = max(self.mx or 0.0, float(f[2]))
+                    for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                        if val.lower().startswith("active"):
+                            self.reasons.add(name)
         except Exception:
             pass
-        if sm:
-            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
-        return out
+
+    def stop(self):
+        self.running = False
+        if self.thread is not None:
+            self.thread.join(timeout=1.0)
+        with self.lock:
+            if not self.sm:
+                return {"sm_mhz": None, "sm_max_mhz": self.mx, "reasons": [], "samples": 0}
+            return {"sm_mhz": statistics.median(self.sm), "sm_min_mhz": min(self.sm), "sm_max_mhz": self.mx, "reasons": sorted(self.reasons),
+                    "samples": len(self.sm), "how": "NVML polled every 5 ms plus once per queued step inside the timed region" if self.nvml is not None
+                    else "nvidia-smi --query-gpu once per queued step inside the timed region"}
 
 
 # ------------------------------------------------------------------------------------- reference (CPU) arm
@@ -311,19 +355,23 @@ def main():
             out_host.copy_(out_dev, non_blocking=True)
             torch.cuda.synchronize()
 
-    def timed(step_fn, steps, warmup):
+    def timed(step_fn, steps, warmup, clocks=None):
         for _ in range(warmup):
             step_fn()
         barrier()
+        if clocks:
+            clocks.start()
         evs = []
         t_wall0 = time.perf_counter()
-        for _ in range(steps):
+        for i in range(steps):
             flush_l2()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(stream)
             step_fn()
             b.record(stream)
             evs.append((a, b))
+            if clocks and (clocks.nvml is not None or i % max(1, steps // 4) == 0):
+                clocks.sample()                      # the step just queued is running: host time is outside the CUDA events
         barrier()
         wall = time.perf_counter() - t_wall0
         ms = sum(a.elapsed_time(b) for a, b in evs)
@@ -334,7 +382,7 @@ def main():
 
     clocks = ClockSampler(local_rank) if rank == 0 else None
     launches0 = bank.launches
-    ms_total, _ = timed(step_device, args.steps, args.warmup)
+    ms_total, _ = timed(step_device, args.steps, args.warmup, clocks)
     gpu_launches = (bank.launches - launches0) * args.steps // (args.steps + args.warmup)
     clk = clocks.stop() if clocks else None
     ms_per_step = ms_total / args.steps
@@ -412,7 +460,7 @@ def main():
             line["other_workloads"] = {"error": repr(e)}
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
-            _, _, info = cpu_reference_run(steps=4, warmup=1)
+            _, _, info = cpu_reference_run(steps=200, warmup=2)      # ~1 s wall on every host core: 10-30 s of CPU work
             line["cpu_baseline"] = info
         except Exception as e:
             line["cpu_baseline"] = {"error": repr(e)}
@@ -472,15 +520,17 @@ def run_c5(args, rank, world, local_rank, emit):
     for _ in range(max(3, args.warmup)):
         step()
     barrier()
-    clocks = ClockSampler(local_rank) if rank == 0 else None
+    clocks = ClockSampler(local_rank).start() if rank == 0 else None
     evs = []
-    for _ in range(args.steps):
+    for i in range(args.steps):
         flush_buf.fill_(1)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
         step()
         b.record(stream)
         evs.append((a, b))
+        if clocks and (clocks.nvml is not None or i % max(1, args.steps // 4) == 0):
+            clocks.sample()
     barrier()
     clk = clocks.stop() if clocks else None
     t = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], dtype=torch.float64, device=dev)

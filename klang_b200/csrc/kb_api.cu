@@ -126,6 +126,7 @@ extern "C" kb_fx_bank* kb_fx_bank_create(int graph, int instances, float fs, int
 	ok = ok && cudaMemsetAsync(b->d_sync, 0, sizeof(KbDppSync) + sizeof(int) * (size_t)instances * KB_DPP_MAXCHUNKS, b->stream) == cudaSuccess;
 	ok = ok && cudaMemsetAsync(b->d_plan, 0, instances * sizeof(KbFxPlan), b->stream) == cudaSuccess;
 	ok = ok && cudaFuncSetAttribute(kb_reverb_par_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KbRvSmem)) == cudaSuccess;
+	ok = ok && cudaFuncSetAttribute(kb_reverb_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KbRv2Smem)) == cudaSuccess;
 	if (ok && b->ring_floats) ok = cudaMemsetAsync(b->d_rings, 0, (size_t)instances * b->ring_floats * sizeof(float), b->stream) == cudaSuccess;
 	b->io_floats = (size_t)instances * b->channels * max_block;
 	ok = ok && dev_alloc(&b->d_io, b->io_floats) == cudaSuccess;
@@ -259,12 +260,24 @@ extern "C" int kb_fx_bank_process(kb_fx_bank* b, float* io, int n, unsigned flag
 		break; }
 	case KB_FX_REVERB: {
 		KbReverb* st = (KbReverb*)b->d_state;
-		if (!seq_only) {
-			kb_reverb_plan_kernel<<<ib, 32, 0, b->stream>>>(st, b->d_plan, b->instances);
-			kb_reverb_par_kernel<<<b->instances * 2, 256, sizeof(KbRvSmem), b->stream>>>(b->d_hdr, st, b->d_plan, b->d_rings, d, n, n);
-			b->launches += 2;
+		// KB_RV_SCHEDULE=1 selects the unpipelined chunk kernel (A/B measurement; same results)
+		static const int rv_schedule = getenv("KB_RV_SCHEDULE") ? atoi(getenv("KB_RV_SCHEDULE")) : 2;
+		const int sub = 1 << 20;                       // sub-blocks keep the kernels' tick counters in 32 bits
+		for (int o = 0; o < n; o += sub) {
+			const int len = std::min(sub, n - o);
+			if (!seq_only) {
+				if (rv_schedule == 1) {
+					kb_reverb_plan_kernel<<<ib, 32, 0, b->stream>>>(st, b->d_plan, b->instances);
+					kb_reverb_par_kernel<<<b->instances * 2, 256, sizeof(KbRvSmem), b->stream>>>(b->d_hdr, st, b->d_plan, b->d_rings, d + o, len, n);
+				} else {
+					kb_reverb_plan2_kernel<<<ib, 32, 0, b->stream>>>(st, b->d_plan, b->instances);
+					kb_reverb_pipe_kernel<<<b->instances * 2, 256, sizeof(KbRv2Smem), b->stream>>>(b->d_hdr, st, b->d_plan, b->d_rings, d + o, len, n);
+				}
+				b->launches += 2;
+			}
+			kb_fx_seq_kernel<KB_FX_REVERB, KbReverb><<<ib, 32, 0, b->stream>>>(b->d_hdr, st, b->d_rings, d + o, len, n, 2, b->instances, b->fs, seq_only ? nullptr : b->d_plan);
+			if (o + sub < n) b->launches++;
 		}
-		kb_fx_seq_kernel<KB_FX_REVERB, KbReverb><<<ib, 32, 0, b->stream>>>(b->d_hdr, st, b->d_rings, d, n, n, 2, b->instances, b->fs, seq_only ? nullptr : b->d_plan);
 		break; }
 	case KB_FX_DELAY_PINGPONG: {
 		KbDPingPong* st = (KbDPingPong*)b->d_state;
@@ -673,9 +686,24 @@ extern "C" int kb_synth_bank_process(kb_synth_bank* b, float* out, int n, unsign
 	} while (0)
 			if (sub) {
 				KbSubVoice* vs = (KbSubVoice*)b->d_vstate;
-				if (g >= 16) KB_LAUNCH_TILED(kb_sub_tiled_kernel, KbSubSmem, 16, 1024, vs, b->d_hdr, d_voice_dst, n, total, b->fs);
-				else if (g >= 8) KB_LAUNCH_TILED(kb_sub_tiled_kernel, KbSubSmem, 8, 512, vs, b->d_hdr, d_voice_dst, n, total, b->fs);
-				else KB_LAUNCH_TILED(kb_sub_tiled_kernel, KbSubSmem, 4, 320, vs, b->d_hdr, d_voice_dst, n, total, b->fs);
+				// KB_TILE_LAYOUT: 0 = serial roles spread over the sub-partitions, 1 = serial roles alone on sub-partition 0 (kb_tiled.cuh);
+				// KB_TILE_NT: threads per CTA of the layout-1 kernels (512 / 768 / 1024)
+				static const int layout = getenv("KB_TILE_LAYOUT") ? atoi(getenv("KB_TILE_LAYOUT")) : 1;
+				static const int force_nt = getenv("KB_TILE_NT") ? atoi(getenv("KB_TILE_NT")) : 0;
+#define KB_LAUNCH_SUB(GG, NT, LAY)                                                                                                    \
+	do {                                                                                                                             \
+		static bool attr_set = false;                                                                                                \
+		if (!attr_set) { cudaFuncSetAttribute(kb_sub_tiled_kernel<GG, NT, LAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KbSubSmem<GG>)); attr_set = true; } \
+		kb_sub_tiled_kernel<GG, NT, LAY><<<(total + GG - 1) / GG, NT, sizeof(KbSubSmem<GG>), st>>>(vs, b->d_hdr, d_voice_dst, n, total, b->fs); \
+	} while (0)
+				if (layout == 0 || g < 7) {
+					if (g >= 16) KB_LAUNCH_SUB(16, 1024, 0);
+					else if (g >= 8) KB_LAUNCH_SUB(8, 512, 0);
+					else KB_LAUNCH_SUB(4, 320, 0);
+				} else if (g >= 16) KB_LAUNCH_SUB(16, 1024, 1);
+				else if (g == 7) { if (force_nt == 512) KB_LAUNCH_SUB(7, 512, 1); else if (force_nt == 1024) KB_LAUNCH_SUB(7, 1024, 1); else KB_LAUNCH_SUB(7, 768, 1); }
+				else { if (force_nt == 512) KB_LAUNCH_SUB(8, 512, 1); else if (force_nt == 1024) KB_LAUNCH_SUB(8, 1024, 1); else KB_LAUNCH_SUB(8, 768, 1); }
+#undef KB_LAUNCH_SUB
 			} else if (b->graph == KB_SY_SUPERSAW) {
 				KbSsawVoice* vs = (KbSsawVoice*)b->d_vstate;
 				if (g >= 8) KB_LAUNCH_TILED(kb_ssaw_tiled_kernel, KbSsawSmem, 8, 1024, vs, b->d_hdr, d_voice_dst, n, total, b->fs);

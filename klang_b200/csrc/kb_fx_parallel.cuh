@@ -452,6 +452,272 @@ __global__ void __launch_bounds__(256) kb_reverb_par_kernel(const KbFxHdr* __res
 	if (tid == 0) ed.position = epos;
 }
 
+// ------------------------------------------------------------------------------ Reverb.k, pipelined schedule (default)
+// Same arithmetic as kb_reverb_par_kernel, but the per-chunk phases no longer wait for each other.  The chunk is a
+// QUARTER of the shortest read-to-write distance (lag >= 4*Lc + 2 ring samples; ~75 frames at 48 kHz), so the ring window
+// of chunk k+2 is complete once chunk k has been written, and the CTA runs as a four-role software pipeline with ONE
+// __syncthreads per chunk.  In iteration k:
+//   warp 0, lanes 0..7   F(k+1)  the 8 line filters (Biquad TDF-II, in order) over pre-interpolated inputs: 9 issue slots
+//                                per tick around the 16-cycle recurrence — the role that bounds the kernel
+//   warp 1, lane 0       E(k+2)  early LPF -> HPF cascade
+//   warps 2..4 (A)       W(k)    FDN matrix, ring writes, mid -> late, output mix;  then  L(k+2): ring windows of chunk
+//                                k+2 -> Delay::process interpolation -> shared memory
+//   warps 5..7 (B)       T(k+1)  early ring write and the 20 early taps;  io block of chunk k+3 -> shared memory
+#define KB_RV2_LMAX 80
+#define KB_RV2_ROW 180                       // floats per (line, chunk) row: 2*LMAX ticks + read-ahead, 8 lanes on distinct banks
+struct KbRv2Smem {
+	float x[2][8][KB_RV2_ROW];               // filter inputs per tick (Delay::process output), double buffered
+	float y[2][8][KB_RV2_ROW];               // filter outputs per tick
+	float xin[4][KB_RV2_LMAX];               // io block, chunks k .. k+3
+	float xf[2][KB_RV2_LMAX];                // early LPF -> HPF output
+	float r1[2][KB_RV2_LMAX], r2[KB_RV2_LMAX], r3[KB_RV2_LMAX];
+	float carry[2][8];                       // FilteredDelay::in carried between frames and chunks: [old/new][line]
+	float times[KB_RV_MAXREFL], gg[KB_RV_MAXREFL];
+	long long lring[8]; int lsize[8], rpos0[8], wpos0[8]; float frac[8], gain[8];
+};
+__global__ void kb_reverb_plan2_kernel(const KbReverb* __restrict__ states, KbFxPlan* __restrict__ plan, int instances) {
+	const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+	if (inst >= instances) return;
+	KbReverb& rv = const_cast<KbReverb&>(states[inst]);
+	int chunk = KB_RV2_LMAX;
+	for (int line = 0; line < 16; line++) {
+		const KbDelay& d = kb_rv_line(rv, line).delay;
+		int lag = d.position - d.last_position; if (lag <= 0) lag += d.SIZE;    // write head minus read head, in ring samples
+		chunk = min(chunk, (lag - 2) / 4);                                      // two ticks per frame, window of chunk k+2 closed by chunk k
+	}
+	float tmin = 1e30f;
+	for (int r = 0; r < rv.count; r++) tmin = fminf(tmin, rv.times[r]);
+	chunk = min(chunk, (int)tmin - 3);
+	KbFxPlan p;
+	p.chunk = chunk; p.mode = chunk >= 8 ? KB_PLAN_PARALLEL : KB_PLAN_SEQUENTIAL;
+	p.gain = p.delay = p.dry = 0.f;
+	plan[inst] = p;
+}
+// Biquad::Filter::process (klang.h:5605-5612) from one shared-memory row into another, strictly in order, by ONE thread
+KB_D void kb_rv2_filter_row(const float* xr, float* yr, int ticks, float b0, float b1, float b2, float a1, float a2, float& z0, float& z1) {
+	const float4* x4 = reinterpret_cast<const float4*>(xr);
+	float4* y4 = reinterpret_cast<float4*>(yr);
+	int f = 0;
+	float4 xa = x4[0], xb = x4[1];
+	for (; f + 8 <= ticks; f += 8) {
+		const float4 na = x4[(f >> 2) + 2], nb = x4[(f >> 2) + 3];
+		float x[8] = { xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w }, y[8];
+		#pragma unroll
+		for (int j = 0; j < 8; j++) {
+			y[j] = b0 * x[j] + z0;
+			z0 = b1 * x[j] - a1 * y[j] + z1;
+			z1 = b2 * x[j] - a2 * y[j];
+		}
+		y4[f >> 2] = make_float4(y[0], y[1], y[2], y[3]);
+		y4[(f >> 2) + 1] = make_float4(y[4], y[5], y[6], y[7]);
+		xa = na; xb = nb;
+	}
+	for (; f < ticks; f++) {
+		const float in = xr[f];
+		const float y = b0 * in + z0;
+		z0 = b1 * in - a1 * y + z1;
+		z1 = b2 * in - a2 * y;
+		yr[f] = y;
+	}
+}
+KB_D void kb_bar_group(int id, int threads) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(threads) : "memory"); }
+
+__global__ void __launch_bounds__(256) kb_reverb_pipe_kernel(const KbFxHdr* __restrict__ hdrs, KbReverb* __restrict__ states, const KbFxPlan* __restrict__ plan,
+                                                             float* __restrict__ rings, float* __restrict__ io, int n, int stride) {
+	extern __shared__ __align__(16) unsigned char kb_rv_smem_raw[];
+	KbRv2Smem& S = *reinterpret_cast<KbRv2Smem*>(kb_rv_smem_raw);
+	const int inst = blockIdx.x >> 1, side = blockIdx.x & 1;
+	const KbFxPlan pl = plan[inst];
+	if (pl.mode != KB_PLAN_PARALLEL) return;
+	const int tid = threadIdx.x, warp = tid >> 5;
+	constexpr int GA = 96, GB = 96;                  // threads of group A (warps 2..4) and group B (warps 5..7)
+	const int ta = tid - 64, tb = tid - 160;
+	KbReverb& rv = states[inst];
+	const KbControl* c = hdrs[inst].controls;
+	const float dry = c[0].value, wet = side == 0 ? c[4].value : 0.f;        // Reverb.k:272 (Q7): the right wet gain is the literal 0
+	const float cE = c[1].value, cM = c[2].value, cL = c[3].value;
+	float* X = io + ((size_t)inst * 2 + side) * stride;
+	const int count = rv.count;
+	const int Lc = pl.chunk, K = (n + Lc - 1) / Lc;
+	if (tid < KB_RV_MAXREFL) { S.times[tid] = rv.times[tid]; S.gg[tid] = side ? rv.gr[tid] : rv.gl[tid]; }
+	if (tid < 8) {
+		const KbRvFDelay& d = kb_rv_side_line(rv, side, tid);
+		S.carry[0][tid] = d.in; S.carry[1][tid] = d.in;
+		S.lring[tid] = d.delay.ring; S.lsize[tid] = d.delay.SIZE; S.rpos0[tid] = d.delay.last_position; S.wpos0[tid] = d.delay.position;
+		S.frac[tid] = d.delay.last_fraction; S.gain[tid] = d.gain;
+	}
+	// per-role register state
+	float z0 = 0.f, z1 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, a1 = 0.f, a2 = 0.f;                              // warp 0, lanes 0..7: line filter
+	float e_z[4] = { 0, 0, 0, 0 }, e_lp[5] = { 0, 0, 0, 0, 0 }, e_hp[5] = { 0, 0, 0, 0, 0 };                // warp 1, lane 0: early cascade
+	if (tid < 8) {
+		const KbBiquad& f = kb_rv_side_line(rv, side, tid).filter;
+		z0 = f.z0; z1 = f.z1; b0 = f.b0; b1 = f.b1; b2 = f.b2; a1 = f.a1; a2 = f.a2;
+	}
+	if (tid == 32) {
+		const KbBiquad& lp = rv.lpf[side]; const KbBiquad& hp = rv.hpf[side];
+		e_z[0] = lp.z0; e_z[1] = lp.z1; e_z[2] = hp.z0; e_z[3] = hp.z1;
+		e_lp[0] = lp.b0; e_lp[1] = lp.b1; e_lp[2] = lp.b2; e_lp[3] = lp.a1; e_lp[4] = lp.a2;
+		e_hp[0] = hp.b0; e_hp[1] = hp.b1; e_hp[2] = hp.b2; e_hp[3] = hp.a1; e_hp[4] = hp.a2;
+	}
+	KbDelay& ed = side ? rv.dr : rv.dl;
+	const int esize = ed.SIZE, epos0 = ed.position;
+	float* ringe = rings + ed.ring;
+	__syncthreads();
+
+	auto chunk_len = [&](int k) { return min(Lc, n - k * Lc); };
+	// E(k): in >> lpf >> hpf over one chunk (Reverb.k:87), one lane
+	auto early_cascade = [&](int k) {
+		const int L = chunk_len(k);
+		const float* xi = S.xin[k & 3]; float* xo = S.xf[k & 1];
+		#pragma unroll 4
+		for (int t = 0; t < L; t++) {
+			const float x = xi[t];
+			const float y = e_lp[0] * x + e_z[0];
+			e_z[0] = e_lp[1] * x - e_lp[3] * y + e_z[1];
+			e_z[1] = e_lp[2] * x - e_lp[4] * y;
+			const float w = e_hp[0] * y + e_z[2];
+			e_z[2] = e_hp[1] * y - e_hp[3] * w + e_z[3];
+			e_z[3] = e_hp[2] * y - e_hp[4] * w;
+			xo[t] = w;
+		}
+	};
+	// F(k): lane = line, the 2L ticks of chunk k in order
+	auto filters = [&](int k) {
+		kb_rv2_filter_row(S.x[k & 1][tid], S.y[k & 1][tid], 2 * chunk_len(k), b0, b1, b2, a1, a2, z0, z1);
+	};
+	// L(k): ring read windows of chunk k, interpolated (Delay::process, klang.h:3461-3473) -> S.x; group-A thread = tick
+	auto load_windows = [&](int k) {
+		const int ticks = 2 * chunk_len(k);
+		const unsigned t0 = 2u * (unsigned)k * (unsigned)Lc;                     // (n < 2^29: checked by the caller)
+		for (int tk = ta; tk < ticks; tk += GA) {
+			float va[8], vb[8];
+			#pragma unroll
+			for (int j = 0; j < 8; j++) {
+				const int size = S.lsize[j];
+				int i0 = (int)(((unsigned)S.rpos0[j] + t0 + (unsigned)tk) % (unsigned)size);
+				int i1 = i0 + 1; if (i1 >= size) i1 -= size;
+				const float* ring = rings + S.lring[j];
+				va[j] = ring[i0]; vb[j] = ring[i1];
+			}
+			#pragma unroll
+			for (int j = 0; j < 8; j++) S.x[k & 1][j][tk] = va[j] + S.frac[j] * (vb[j] - va[j]);
+		}
+	};
+	// W(k): FDN matrix, ring writes and outputs of one LateReflections stage; group-A thread = frame
+	auto fdn_stage = [&](int k, int stage, int cpar) {
+		const int L = chunk_len(k);
+		const unsigned t0 = 2u * (unsigned)k * (unsigned)Lc;
+		const int t = ta;
+		if (t < L) {
+			const int base = stage * 4;
+			const float in = stage == 0 ? S.r1[k & 1][t] : S.r2[t];
+			float dv[4], sv[4];
+			#pragma unroll
+			for (int q = 0; q < 4; q++) {
+				const float2 yy = *reinterpret_cast<const float2*>(&S.y[k & 1][base + q][2 * t]);
+				dv[q] = yy.x * S.gain[base + q];                             // FilteredDelay::process  Reverb.k:130-132
+				sv[q] = yy.y * S.gain[base + q];
+			}
+			const float d0 = dv[0], d1 = dv[1], d2 = dv[2], d3 = dv[3];
+			// feedback * delays + in, row by row with the literal 0 / +-1 products (Reverb.k:158-163, klang.h:1446-1470)
+			float fb[4];
+			fb[0] = (0.f * d0 + 1.f * d1 + 1.f * d2 + -1.f * d3) + in;
+			fb[1] = (-1.f * d0 + 0.f * d1 + -1.f * d2 + 1.f * d3) + in;
+			fb[2] = (-1.f * d0 + 1.f * d1 + 0.f * d2 + -1.f * d3) + in;
+			fb[3] = (1.f * d0 + -1.f * d1 + 1.f * d2 + 0.f * d3) + in;
+			float sum = sv[0];
+			sum = sum + sv[1];
+			sum = sum + sv[2];
+			sum = sum + sv[3];
+			(stage == 0 ? S.r2 : S.r3)[t] = sum;
+			#pragma unroll
+			for (int q = 0; q < 4; q++) {
+				const int size = S.lsize[base + q];
+				float* ring = rings + S.lring[base + q];
+				const int w0 = (int)(((unsigned)S.wpos0[base + q] + t0 + 2u * (unsigned)t) % (unsigned)size);
+				int wa = w0 + 1; if (wa >= size) wa -= size;
+				ring[wa] = fb[q];                                            // second tick of this frame writes fb
+				if (t + 1 < L) { int wb = w0 + 2; if (wb >= size) wb -= size; ring[wb] = fb[q]; }   // = first tick of the next frame
+				else S.carry[cpar ^ 1][base + q] = fb[q];
+				if (t == 0) ring[w0] = S.carry[cpar][base + q];
+			}
+		}
+	};
+	// T(k): early ring write and taps of chunk k; group-B thread = frame
+	auto early_taps = [&](int k) {
+		const int L = chunk_len(k);
+		const int t = tb;
+		if (t < L) {
+			const int idx = (int)(((unsigned)epos0 + (unsigned)(k * Lc + t)) % (unsigned)esize);
+			ringe[idx] = S.xf[k & 1][t];
+			// (taps never reach into this chunk: Lc <= shortest tap - 3, so no barrier between the write and the reads)
+			int pos = idx + 1; if (pos >= esize) pos -= esize;                // position after this frame's write
+			float acc = 0.f;
+			for (int d0 = 0; d0 < count; d0 += 10) {                 // Stereo::Delay::tap(float)  klang.h:4668-4681
+				float va[10], vb[10], fr[10];
+				#pragma unroll
+				for (int j = 0; j < 10; j++) if (d0 + j < count) {
+					float read = (float)(pos - 1) - S.times[d0 + j]; if (read < 0.f) read += esize;
+					const float fl = floorf(read); fr[j] = read - fl;
+					const int ii = (int)read, jj = (ii == esize - 1) ? 0 : ii + 1;
+					va[j] = ringe[ii]; vb[j] = ringe[jj];
+				}
+				#pragma unroll
+				for (int j = 0; j < 10; j++) if (d0 + j < count) acc += (va[j] * (1.f - fr[j]) + vb[j] * fr[j]) * S.gg[d0 + j];   // r1 += tap * gain  Reverb.k:89-90
+			}
+			S.r1[k & 1][t] = acc;
+		}
+	};
+	auto load_io = [&](int k, int t, int step) {
+		const int L = chunk_len(k);
+		for (; t < L; t += step) S.xin[k & 3][t] = X[k * Lc + t];
+	};
+
+	// ---- prologue: windows of chunks 0 and 1 (both closed before the block), io of chunks 0..2; F(0), E(0), E(1); T(0)
+	if (warp >= 2 && warp < 5) { load_windows(0); if (K > 1) load_windows(1); }
+	else if (warp >= 5) { for (int k = 0; k < 3 && k < K; k++) load_io(k, tb, GB); }
+	__syncthreads();
+	if (warp == 0) { if (tid < 8) filters(0); }
+	else if (tid == 32) { early_cascade(0); if (K > 1) early_cascade(1); }
+	__syncthreads();
+	if (warp >= 5) early_taps(0);
+	__syncthreads();
+
+	int cpar = 0;
+	for (int k = 0; k < K; k++, cpar ^= 1) {
+		if (warp == 0) {
+			if (tid < 8 && k + 1 < K) filters(k + 1);
+		} else if (warp == 1) {
+			if (tid == 32 && k + 2 < K) early_cascade(k + 2);
+		} else if (warp < 5) {
+			fdn_stage(k, 0, cpar);
+			kb_bar_group(1, GA);
+			fdn_stage(k, 1, cpar);
+			kb_bar_group(1, GA);
+			const int L = chunk_len(k);
+			if (ta < L) {
+				const float refl = (S.r1[k & 1][ta] * cE + S.r2[ta] * cM) + S.r3[ta] * cL;
+				X[k * Lc + ta] = S.xin[k & 3][ta] * dry + refl * wet;           // Reverb.k:272
+			}
+			if (k + 2 < K) load_windows(k + 2);
+		} else {
+			if (k + 1 < K) early_taps(k + 1);
+			if (k + 3 < K) load_io(k + 3, tb, GB);
+		}
+		__syncthreads();
+	}
+	// state back
+	if (tid < 8) {
+		KbRvFDelay& d = kb_rv_side_line(rv, side, tid);
+		d.filter.z0 = z0; d.filter.z1 = z1;
+		d.in = S.carry[cpar][tid];
+		d.delay.position = (int)(((long long)d.delay.position + 2LL * n) % d.delay.SIZE);
+		d.delay.last_position = (int)(((long long)d.delay.last_position + 2LL * n) % d.delay.SIZE);
+	}
+	if (tid == 32) { rv.lpf[side].z0 = e_z[0]; rv.lpf[side].z1 = e_z[1]; rv.hpf[side].z0 = e_z[2]; rv.hpf[side].z1 = e_z[3]; }
+	if (tid == 0) ed.position = (int)(((long long)epos0 + n) % esize);
+}
+
 // ======================================================================================== Delay/Reverb.k
 // Delay/Reverb.k:59-78: an 8-tap FIR over the input (feedforward line, taps 2-17 ms), plus a feedback loop
 // out = mix + LPF(gain * feedback(time)), feedback << out.  The FIR only reads the input, so it is parallel over the whole

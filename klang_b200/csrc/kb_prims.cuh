@@ -176,7 +176,15 @@ enum { KB_BQ_LPF = 0, KB_BQ_HPF, KB_BQ_BPF, KB_BQ_BRF, KB_BQ_APF, KB_BQ_BW2 };
 KB_HD void kb_biquad_construct(KbBiquad& b, int type) { memset(&b, 0, sizeof(b)); b.type = type; b.b0 = 1.f; b.cos0 = 1.f; }
 KB_HD void kb_biquad_reset(KbBiquad& b) { b.f = 0; b.Q = 0; b.b0 = 1; b.a1 = b.a2 = b.b1 = b.b2 = 0; b.a = 0; b.z0 = b.z1 = 0; }   // klang.h:5565-5572
 // constant{x}.inv = float(1.0 / double(x))                                  klang.h:96-98
-KB_HD float kb_const_inv(float x) { const double v = (double)x; return v == 0.0 ? 0.0f : (float)(1.0 / v); }
+KB_HD float kb_const_inv(float x) {
+#ifdef __CUDA_ARCH__
+	// (float)(1.0 / (double)x) equals the correctly rounded fp32 reciprocal: rounding the quotient of 24-bit operands through a
+	// 53-bit intermediate is innocuous (53 >= 2*24 + 2; 0 mismatches over the 2^24 floats of [0.5, 2) on the host)
+	const float ax = fabsf(x);
+	if (ax >= 1e-30f && ax <= 1e30f) return __frcp_rn(x);
+#endif
+	const double v = (double)x; return v == 0.0 ? 0.0f : (float)(1.0 / v);
+}
 // LPF::init 5658-5665, HPF::init 5675-5682, BPF 5720-5729, BRF 5734-5739, Butterworth::LPF<2> 5803-5810
 KB_HD void kb_biquad_init(KbBiquad& b) {
 	const float inv = kb_const_inv(1.f + b.a);

@@ -61,7 +61,13 @@ template <int G> struct KbSubSmem {
 	KbTileRows<G> cut[2], amp[2], out[2];
 	KbOsm osc[G];
 };
-template <int G, int NT>
+// LAYOUT 0: the serial roles are warps 0, 1, 2 (one per SM sub-partition, each sharing its issue slots with worker warps).
+// LAYOUT 1: the serial roles are warps 0, 4, 8 — all on sub-partition 0 (warp id mod 4), whose other warps stay idle, so
+//           the dependent chains never lose an issue slot to the throughput-bound B/D warps on sub-partitions 1..3.
+template <int LAYOUT> KB_D int kb_tile_role(int warp) { return LAYOUT == 0 ? (warp < 3 ? warp : -1) : ((warp & 3) == 0 && warp < 12 ? warp >> 2 : -1); }
+template <int LAYOUT> KB_D bool kb_tile_is_worker(int warp) { return LAYOUT == 0 ? warp >= 3 : (warp & 3) != 0; }
+template <int LAYOUT> KB_D int kb_tile_worker_tid(int warp, int lane) { return LAYOUT == 0 ? (warp - 3) * 32 + lane : ((warp >> 2) * 3 + (warp & 3) - 1) * 32 + lane; }
+template <int G, int NT, int LAYOUT = 0>
 __global__ void __launch_bounds__(NT) kb_sub_tiled_kernel(KbSubVoice* __restrict__ voices, KbVoiceHdr* __restrict__ hdr,
                                                                         float* __restrict__ dst, int n, int total, KbFs fs) {
 	constexpr int T = KB_TILE_T;
@@ -73,26 +79,30 @@ __global__ void __launch_bounds__(NT) kb_sub_tiled_kernel(KbSubVoice* __restrict
 
 	const int role_voice = lane;
 	const bool role_ok = lane < G && S.c.active[lane < G ? lane : 0];
-	const bool is_env = warp == 0 && role_ok, is_adsr = warp == 1 && role_ok, is_flt = warp == 2 && role_ok;
-	const int slot = warp * G + lane;                                 // breakpoint slot of the A lanes
+	const int role = kb_tile_role<LAYOUT>(warp);                      // 0 = A (cutoff envelope), 1 = A (ADSR), 2 = C (filter), -1 = worker / idle
+	const bool worker = kb_tile_is_worker<LAYOUT>(warp);
+	const bool first_worker = worker && kb_tile_worker_tid<LAYOUT>(warp, lane) < 32;
+	const bool is_env = role == 0 && role_ok, is_adsr = role == 1 && role_ok, is_flt = role == 2 && role_ok;
+	const int slot = (role < 0 ? 0 : role) * G + lane;                // breakpoint slot of the A lanes
 	KbEnvR env;
 	float z0 = 0.f, z1 = 0.f, lb0 = 1.f, lb1 = 0.f, la1 = 0.f, la2 = 0.f;
 	if (is_env) kb_tile_load_env(S.c, slot, voices[v0 + role_voice].env, env);
 	if (is_adsr) kb_tile_load_env(S.c, slot, voices[v0 + role_voice].adsr, env);
 	if (is_flt) { const KbBiquad& b = voices[v0 + role_voice].filter; z0 = b.z0; z1 = b.z1; lb0 = b.b0; lb1 = b.b1; la1 = b.a1; la2 = b.a2; }
-	if (warp == 3 && lane < G && S.c.active[lane]) S.osc[lane] = voices[v0 + lane].osc;
+	if (first_worker && lane < G && S.c.active[lane]) S.osc[lane] = voices[v0 + lane].osc;
 	__syncthreads();
 
 	const int ntiles = (n + T - 1) / T;
-	const int wtid = tid - 96, wthreads = NT - 96;      // the B/D worker threads
+	const int wtid = kb_tile_worker_tid<LAYOUT>(warp, lane);         // the B/D worker threads
+	constexpr int wthreads = LAYOUT == 0 ? NT - 96 : NT / 128 * 96;
 	for (int k = 0; k < ntiles + 3; k++) {
-		if (warp < 2) {                                                  // ---- A, tile k
+		if (role == 0 || role == 1) {                                    // ---- A, tile k
 			if ((is_env || is_adsr) && k < ntiles) {
 				const int steps = min(T, n - k * T);
 				float* row = is_env ? S.cut[k & 1].r[role_voice] : S.amp[k & 1].r[role_voice];
 				kb_envr_run(fs, env, S.c.px[slot], S.c.py[slot], row, steps);
 			}
-		} else if (warp == 2) {                                          // ---- C, tile k-2
+		} else if (role == 2) {                                          // ---- C, tile k-2
 			const int c = k - 2;
 			if (is_flt && c >= 0 && c < ntiles) {
 				const int steps = min(T, n - c * T), v = role_voice;
@@ -112,7 +122,7 @@ __global__ void __launch_bounds__(NT) kb_sub_tiled_kernel(KbSubVoice* __restrict
 					cf = cn; xa = xn;
 				}
 			}
-		} else {
+		} else if (worker) {
 			const int b = k - 1, d = k - 3;
 			if (b >= 0 && b < ntiles) {                                      // ---- B, tile k-1
 				const int steps = min(T, n - b * T);
@@ -156,7 +166,7 @@ __global__ void __launch_bounds__(NT) kb_sub_tiled_kernel(KbSubVoice* __restrict
 		KbBiquad& b = voices[v0 + role_voice].filter;
 		b.z0 = z0; b.z1 = z1; b.b0 = lb0; b.b2 = lb0; b.b1 = lb1; b.a1 = la1; b.a2 = la2;
 	}
-	if (warp == 3 && lane < G && S.c.active[lane]) {
+	if (first_worker && lane < G && S.c.active[lane]) {
 		KbOsm o = S.osc[lane];
 		kb_osm_advance(o, (uint32_t)n);
 		voices[v0 + lane].osc.offset = o.offset;

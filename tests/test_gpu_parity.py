@@ -416,6 +416,45 @@ def test_chunk_parallel_effects_match_oracle_and_sequential_schedule(eng, graph,
             assert engaged > inst * blocks // 4, f"chunk-parallel schedule engaged on only {engaged} instance-blocks"
 
 
+@pytest.mark.parametrize("fs", [44100, 48000, 96000])
+def test_reverb_pipeline_chunk_boundaries(eng, fs):
+    """Reverb.k on the pipelined chunk schedule with every bus audible (direct, early, mid, late all non-zero), block
+    lengths straddling 1, 2, 3 and many pipeline chunks (prologue-only, one-iteration and steady-state paths), bit-exact
+    against the live oracle; KB_FX_SEQUENTIAL blocks are interleaved so the two schedules hand the state to each other."""
+    oracle.port.set_fs(fs)
+    inst = 3
+    lens = [1, 2, 7, 8, 9, 60, 69, 70, 74, 75, 76, 80, 81, 138, 139, 149, 150, 151, 160, 161, 225, 226, 240, 241, 1023, 4096, 333, 5000]
+    total = sum(lens)
+    x = np.stack([cases.fx_input(2, total, seed=40 + i) for i in range(inst)])
+    settings = {0: 0.3, 1: 0.9, 2: 0.4, 3: 0.5, 4: 0.8}
+    want = np.empty_like(x)
+    for i in range(inst):
+        fx = oracle.port.Fx(cases.FX_REVERB)
+        for c, v in settings.items():
+            fx.set_control(c, v)
+        o = 0
+        for ln in lens:
+            want[i, :, o:o + ln] = fx.process(x[i, :, o:o + ln])
+            o += ln
+        fx.close()
+    bank = kb.FxBank(kb.FX_REVERB, inst, fs, max(lens))
+    for c, v in settings.items():
+        bank.set_control(c, v)
+    got = np.empty_like(x)
+    o, engaged = 0, 0
+    for b, ln in enumerate(lens):
+        blk = np.ascontiguousarray(x[:, :, o:o + ln])
+        seq = (b % 5 == 3)
+        bank.process_inplace(blk, flags=kb.FX_SEQUENTIAL if seq else 0)
+        engaged += 0 if seq else bank.parallel_instances()
+        got[:, :, o:o + ln] = blk
+        o += ln
+    bank.close()
+    assert_parity(got, want, f"reverb pipeline fs {fs}", exact=True)
+    assert np.abs(want[:, 0]).max() > 0.01
+    assert engaged >= inst * (len(lens) - len(lens) // 5 - 1)
+
+
 # ------------------------------------------------------------------------- BASELINE-size properties, C3 / C4 / C5
 def test_c4_64_instances_are_replicas_of_one_instance(eng):
     """C4 shape: 64 stereo instances fed the same input and controls produce 64 identical streams, equal to a

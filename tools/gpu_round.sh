@@ -1,0 +1,31 @@
+#!/bin/bash
+# One gpurun call: GPU tests, schedule A/B probes, bench (both arms), launch list and ncu captures -> gpurun_out/$TAG/
+TAG=${1:-r1b}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+export PYTHONUNBUFFERED=1
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/smi.txt 2>&1
+echo "== tests"; timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -15 | tee $OUT/pytest_gpu.txt
+echo "== probes"
+{
+for cfg in "0 512 8" "1 512 8" "1 768 8" "1 1024 8" "1 768 7"; do
+  set -- $cfg
+  echo "layout $1 nt $2 g $3"; KB_TILE_LAYOUT=$1 KB_TILE_NT=$2 KB_TILE_G=$3 timeout 120 python tools/c2_probe.py sub
+done
+for sch in 1 2; do echo "reverb schedule $sch"; KB_RV_SCHEDULE=$sch timeout 120 python tools/fx_probe.py reverb 4096; done
+KB_RV_SCHEDULE=2 timeout 120 python tools/fx_probe.py reverb 16384
+timeout 120 python tools/fx_probe.py pingpong 4096
+timeout 120 python tools/fx_probe.py dreverb 4096
+for cf in 1024 2048; do echo "dpp chunk $cf"; KB_DPP_CHUNK=$cf timeout 120 python tools/fx_probe.py dpingpong 65536; done
+} 2>&1 | grep -v "^$" | tee $OUT/probes.txt
+echo "== bench"
+timeout 600 python bench.py --impl reference --steps 20 --warmup 3 > $OUT/bench_reference.json 2> $OUT/bench_reference.err
+timeout 900 python bench.py --steps 20 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err
+tail -c 600 $OUT/bench.json
+echo "== ncu launches"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $OUT/launches.csv python bench.py --steps 3 --warmup 3 --no-cpu > $OUT/ncu_launch_run.log 2>&1
+echo "== ncu full"
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:kb_reverb_pipe -s 3 -c 1 -o $OUT/prof_reverb_pipe -f python tools/fx_probe.py reverb 4096 > $OUT/ncu_rv.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:kb_dpingpong_stream -s 3 -c 1 -o $OUT/prof_dpp -f python tools/fx_probe.py dpingpong 65536 > $OUT/ncu_dpp.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:kb_sub_tiled -s 3 -c 1 -o $OUT/prof_sub -f python bench.py --steps 2 --warmup 3 --no-extras --no-cpu > $OUT/ncu_sub.log 2>&1
+ls -la $OUT
