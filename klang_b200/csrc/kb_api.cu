@@ -271,7 +271,7 @@ extern "C" int kb_fx_bank_process(kb_fx_bank* b, float* io, int n, unsigned flag
 					kb_reverb_par_kernel<<<b->instances * 2, 256, sizeof(KbRvSmem), b->stream>>>(b->d_hdr, st, b->d_plan, b->d_rings, d + o, len, n);
 				} else {
 					kb_reverb_plan2_kernel<<<ib, 32, 0, b->stream>>>(st, b->d_plan, b->instances);
-					kb_reverb_pipe_kernel<<<b->instances * 2, 256, sizeof(KbRv2Smem), b->stream>>>(b->d_hdr, st, b->d_plan, b->d_rings, d + o, len, n);
+					kb_reverb_pipe_kernel<<<b->instances * 2, KB_RV2_NT, sizeof(KbRv2Smem), b->stream>>>(b->d_hdr, st, b->d_plan, b->d_rings, d + o, len, n);
 				}
 				b->launches += 2;
 			}

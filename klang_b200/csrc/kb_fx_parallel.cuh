@@ -455,25 +455,35 @@ __global__ void __launch_bounds__(256) kb_reverb_par_kernel(const KbFxHdr* __res
 // ------------------------------------------------------------------------------ Reverb.k, pipelined schedule (default)
 // Same arithmetic as kb_reverb_par_kernel, but the per-chunk phases no longer wait for each other.  The chunk is a
 // QUARTER of the shortest read-to-write distance (lag >= 4*Lc + 2 ring samples; ~75 frames at 48 kHz), so the ring window
-// of chunk k+2 is complete once chunk k has been written, and the CTA runs as a four-role software pipeline with ONE
-// __syncthreads per chunk.  In iteration k:
+// of chunk k+2 is complete once chunk k has been written, and the CTA (512 threads) runs as a four-role software pipeline
+// with ONE __syncthreads per chunk.  In iteration k:
 //   warp 0, lanes 0..7   F(k+1)  the 8 line filters (Biquad TDF-II, in order) over pre-interpolated inputs: 9 issue slots
-//                                per tick around the 16-cycle recurrence — the role that bounds the kernel
-//   warp 1, lane 0       E(k+2)  early LPF -> HPF cascade
-//   warps 2..4 (A)       W(k)    FDN matrix, ring writes, mid -> late, output mix;  then  L(k+2): ring windows of chunk
-//                                k+2 -> Delay::process interpolation -> shared memory
-//   warps 5..7 (B)       T(k+1)  early ring write and the 20 early taps;  io block of chunk k+3 -> shared memory
+//                                per tick around the 16-cycle recurrence — the role that bounds the kernel.  It has SM
+//                                sub-partition 0 to itself (warps 4, 8, 12 stay idle)
+//   warp 1, lanes 0..1   E       early cascade, the two biquads on two lanes one chunk apart: LPF(k+3), HPF(k+2)
+//   group A (6 warps)    W(k)    FDN matrix, ring writes, mid -> late, output mix, thread = (frame, line);  then L(k+2):
+//                                ring windows of chunk k+2 -> Delay::process interpolation -> shared memory, 24 threads
+//                                per line with a running read position (no modulo)
+//   group B (5 warps)    T(k+1)  early ring write, the 20 early taps as thread = (frame, tap) products, then an in-order
+//                                sum per frame;  io block of chunk k+4 -> shared memory
 #define KB_RV2_LMAX 80
 #define KB_RV2_ROW 180                       // floats per (line, chunk) row: 2*LMAX ticks + read-ahead, 8 lanes on distinct banks
+#define KB_RV2_EROW (KB_RV2_LMAX + 16)       // early rows: LMAX frames + read-ahead of the row filter
+#define KB_RV2_NT 512
+#define KB_RV2_GA 192                        // threads of group A
+#define KB_RV2_GB 160                        // threads of group B
 struct KbRv2Smem {
 	float x[2][8][KB_RV2_ROW];               // filter inputs per tick (Delay::process output), double buffered
 	float y[2][8][KB_RV2_ROW];               // filter outputs per tick
-	float xin[4][KB_RV2_LMAX];               // io block, chunks k .. k+3
-	float xf[2][KB_RV2_LMAX];                // early LPF -> HPF output
+	float xin[8][KB_RV2_EROW];               // io block, chunks k .. k+4
+	float ylp[2][KB_RV2_EROW];               // early LPF output
+	float xf[2][KB_RV2_EROW];                // early LPF -> HPF output
+	float tp[KB_RV_MAXREFL][KB_RV2_LMAX];    // early tap products of one chunk: [tap][frame]
 	float r1[2][KB_RV2_LMAX], r2[KB_RV2_LMAX], r3[KB_RV2_LMAX];
 	float carry[2][8];                       // FilteredDelay::in carried between frames and chunks: [old/new][line]
 	float times[KB_RV_MAXREFL], gg[KB_RV_MAXREFL];
 	long long lring[8]; int lsize[8], rpos0[8], wpos0[8]; float frac[8], gain[8];
+	float M[4][4];
 };
 __global__ void kb_reverb_plan2_kernel(const KbReverb* __restrict__ states, KbFxPlan* __restrict__ plan, int instances) {
 	const int inst = blockIdx.x * blockDim.x + threadIdx.x;
@@ -522,16 +532,20 @@ KB_D void kb_rv2_filter_row(const float* xr, float* yr, int ticks, float b0, flo
 }
 KB_D void kb_bar_group(int id, int threads) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(threads) : "memory"); }
 
-__global__ void __launch_bounds__(256) kb_reverb_pipe_kernel(const KbFxHdr* __restrict__ hdrs, KbReverb* __restrict__ states, const KbFxPlan* __restrict__ plan,
-                                                             float* __restrict__ rings, float* __restrict__ io, int n, int stride) {
+__global__ void __launch_bounds__(KB_RV2_NT) kb_reverb_pipe_kernel(const KbFxHdr* __restrict__ hdrs, KbReverb* __restrict__ states, const KbFxPlan* __restrict__ plan,
+                                                                   float* __restrict__ rings, float* __restrict__ io, int n, int stride) {
 	extern __shared__ __align__(16) unsigned char kb_rv_smem_raw[];
 	KbRv2Smem& S = *reinterpret_cast<KbRv2Smem*>(kb_rv_smem_raw);
 	const int inst = blockIdx.x >> 1, side = blockIdx.x & 1;
 	const KbFxPlan pl = plan[inst];
 	if (pl.mode != KB_PLAN_PARALLEL) return;
-	const int tid = threadIdx.x, warp = tid >> 5;
-	constexpr int GA = 96, GB = 96;                  // threads of group A (warps 2..4) and group B (warps 5..7)
-	const int ta = tid - 64, tb = tid - 160;
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	constexpr int GA = KB_RV2_GA, GB = KB_RV2_GB;
+	// roles: warp 0 = F, warp 1 = E, warps 4/8/12 idle (they share sub-partition 0 with F), A = warps 2,3,5,6,7,9, B = warps 10,11,13,14,15
+	const int slot = warp - 2 - (warp > 4) - (warp > 8) - (warp > 12);      // 0..10 over the 11 worker warps
+	const bool idle = warp == 4 || warp == 8 || warp == 12;
+	const bool inA = warp >= 2 && !idle && slot < 6, inB = warp >= 2 && !idle && slot >= 6;
+	const int ta = slot * 32 + lane, tb = (slot - 6) * 32 + lane;
 	KbReverb& rv = states[inst];
 	const KbControl* c = hdrs[inst].controls;
 	const float dry = c[0].value, wet = side == 0 ? c[4].value : 0.f;        // Reverb.k:272 (Q7): the right wet gain is the literal 0
@@ -546,18 +560,19 @@ __global__ void __launch_bounds__(256) kb_reverb_pipe_kernel(const KbFxHdr* __re
 		S.lring[tid] = d.delay.ring; S.lsize[tid] = d.delay.SIZE; S.rpos0[tid] = d.delay.last_position; S.wpos0[tid] = d.delay.position;
 		S.frac[tid] = d.delay.last_fraction; S.gain[tid] = d.gain;
 	}
+	if (tid >= 32 && tid < 48) {
+		const float M[16] = { 0, 1, 1, -1,  -1, 0, -1, 1,  -1, 1, 0, -1,  1, -1, 1, 0 };      // Reverb.k:158-161
+		S.M[(tid - 32) >> 2][(tid - 32) & 3] = M[tid - 32];
+	}
 	// per-role register state
-	float z0 = 0.f, z1 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, a1 = 0.f, a2 = 0.f;                              // warp 0, lanes 0..7: line filter
-	float e_z[4] = { 0, 0, 0, 0 }, e_lp[5] = { 0, 0, 0, 0, 0 }, e_hp[5] = { 0, 0, 0, 0, 0 };                // warp 1, lane 0: early cascade
+	float z0 = 0.f, z1 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, a1 = 0.f, a2 = 0.f;      // warp 0 lanes 0..7: line filter; warp 1 lane 0: early LPF, lane 1: early HPF
 	if (tid < 8) {
 		const KbBiquad& f = kb_rv_side_line(rv, side, tid).filter;
 		z0 = f.z0; z1 = f.z1; b0 = f.b0; b1 = f.b1; b2 = f.b2; a1 = f.a1; a2 = f.a2;
 	}
-	if (tid == 32) {
-		const KbBiquad& lp = rv.lpf[side]; const KbBiquad& hp = rv.hpf[side];
-		e_z[0] = lp.z0; e_z[1] = lp.z1; e_z[2] = hp.z0; e_z[3] = hp.z1;
-		e_lp[0] = lp.b0; e_lp[1] = lp.b1; e_lp[2] = lp.b2; e_lp[3] = lp.a1; e_lp[4] = lp.a2;
-		e_hp[0] = hp.b0; e_hp[1] = hp.b1; e_hp[2] = hp.b2; e_hp[3] = hp.a1; e_hp[4] = hp.a2;
+	if (tid == 32 || tid == 33) {
+		const KbBiquad& f = tid == 32 ? rv.lpf[side] : rv.hpf[side];
+		z0 = f.z0; z1 = f.z1; b0 = f.b0; b1 = f.b1; b2 = f.b2; a1 = f.a1; a2 = f.a2;
 	}
 	KbDelay& ed = side ? rv.dr : rv.dl;
 	const int esize = ed.SIZE, epos0 = ed.position;
@@ -565,122 +580,125 @@ __global__ void __launch_bounds__(256) kb_reverb_pipe_kernel(const KbFxHdr* __re
 	__syncthreads();
 
 	auto chunk_len = [&](int k) { return min(Lc, n - k * Lc); };
-	// E(k): in >> lpf >> hpf over one chunk (Reverb.k:87), one lane
-	auto early_cascade = [&](int k) {
-		const int L = chunk_len(k);
-		const float* xi = S.xin[k & 3]; float* xo = S.xf[k & 1];
-		#pragma unroll 4
-		for (int t = 0; t < L; t++) {
-			const float x = xi[t];
-			const float y = e_lp[0] * x + e_z[0];
-			e_z[0] = e_lp[1] * x - e_lp[3] * y + e_z[1];
-			e_z[1] = e_lp[2] * x - e_lp[4] * y;
-			const float w = e_hp[0] * y + e_z[2];
-			e_z[2] = e_hp[1] * y - e_hp[3] * w + e_z[3];
-			e_z[3] = e_hp[2] * y - e_hp[4] * w;
-			xo[t] = w;
+	// E step s: lane 0 runs the LPF over chunk s, lane 1 the HPF over chunk s-1 (in >> lpf >> hpf, Reverb.k:87)
+	auto early_cascade = [&](int s) {
+		const int k = s - lane;
+		if (lane < 2 && k >= 0 && k < K) {
+			const float* xi = lane == 0 ? S.xin[k & 7] : S.ylp[k & 1];
+			float* xo = lane == 0 ? S.ylp[k & 1] : S.xf[k & 1];
+			kb_rv2_filter_row(xi, xo, chunk_len(k), b0, b1, b2, a1, a2, z0, z1);
 		}
+		__syncwarp();                                           // lane 1 reads in a later step what lane 0 wrote in this one
 	};
 	// F(k): lane = line, the 2L ticks of chunk k in order
 	auto filters = [&](int k) {
 		kb_rv2_filter_row(S.x[k & 1][tid], S.y[k & 1][tid], 2 * chunk_len(k), b0, b1, b2, a1, a2, z0, z1);
 	};
-	// L(k): ring read windows of chunk k, interpolated (Delay::process, klang.h:3461-3473) -> S.x; group-A thread = tick
+	// L(k): ring read windows of chunk k, interpolated (Delay::process, klang.h:3461-3473) -> S.x; 24 group-A threads per line.
+	// Called for k = 0, 1, 2, ... in order: the read position of the line runs along in a register.
+	const int l_line = ta / 24, l_sub = ta % 24;
+	int l_size = 1, l_rbase = 0; float l_frac = 0.f; const float* l_ring = rings;
+	if (inA) { l_size = S.lsize[l_line]; l_rbase = S.rpos0[l_line]; l_frac = S.frac[l_line]; l_ring = rings + S.lring[l_line]; }
 	auto load_windows = [&](int k) {
 		const int ticks = 2 * chunk_len(k);
-		const unsigned t0 = 2u * (unsigned)k * (unsigned)Lc;                     // (n < 2^29: checked by the caller)
-		for (int tk = ta; tk < ticks; tk += GA) {
-			float va[8], vb[8];
+		float* xrow = S.x[k & 1][l_line];
+		for (int tk0 = l_sub; tk0 < ticks; tk0 += 96) {
+			float va[4], vb[4];
 			#pragma unroll
-			for (int j = 0; j < 8; j++) {
-				const int size = S.lsize[j];
-				int i0 = (int)(((unsigned)S.rpos0[j] + t0 + (unsigned)tk) % (unsigned)size);
-				int i1 = i0 + 1; if (i1 >= size) i1 -= size;
-				const float* ring = rings + S.lring[j];
-				va[j] = ring[i0]; vb[j] = ring[i1];
+			for (int j = 0; j < 4; j++) {
+				const int tk = tk0 + 24 * j;
+				if (tk < ticks) {
+					int i0 = l_rbase + tk; if (i0 >= l_size) i0 -= l_size;
+					int i1 = i0 + 1; if (i1 >= l_size) i1 -= l_size;
+					va[j] = l_ring[i0]; vb[j] = l_ring[i1];
+				}
 			}
 			#pragma unroll
-			for (int j = 0; j < 8; j++) S.x[k & 1][j][tk] = va[j] + S.frac[j] * (vb[j] - va[j]);
+			for (int j = 0; j < 4; j++) { const int tk = tk0 + 24 * j; if (tk < ticks) xrow[tk] = va[j] + l_frac * (vb[j] - va[j]); }
 		}
+		l_rbase += ticks; if (l_rbase >= l_size) l_rbase -= l_size;
 	};
-	// W(k): FDN matrix, ring writes and outputs of one LateReflections stage; group-A thread = frame
+	// W(k): FDN matrix, ring writes and outputs of one LateReflections stage; group-A thread = (line q, frame t)
 	auto fdn_stage = [&](int k, int stage, int cpar) {
 		const int L = chunk_len(k);
-		const unsigned t0 = 2u * (unsigned)k * (unsigned)Lc;
-		const int t = ta;
-		if (t < L) {
-			const int base = stage * 4;
+		const unsigned t0 = 2u * (unsigned)k * (unsigned)Lc;                   // (n <= 2^20: the caller splits longer blocks)
+		const int base = stage * 4;
+		for (int item = ta; item < 4 * L; item += GA) {
+			const int q = item / L, t = item - q * L;
 			const float in = stage == 0 ? S.r1[k & 1][t] : S.r2[t];
 			float dv[4], sv[4];
 			#pragma unroll
-			for (int q = 0; q < 4; q++) {
-				const float2 yy = *reinterpret_cast<const float2*>(&S.y[k & 1][base + q][2 * t]);
-				dv[q] = yy.x * S.gain[base + q];                             // FilteredDelay::process  Reverb.k:130-132
-				sv[q] = yy.y * S.gain[base + q];
+			for (int j = 0; j < 4; j++) {
+				const float2 yy = *reinterpret_cast<const float2*>(&S.y[k & 1][base + j][2 * t]);
+				dv[j] = yy.x * S.gain[base + j];                             // FilteredDelay::process  Reverb.k:130-132
+				sv[j] = yy.y * S.gain[base + j];
 			}
-			const float d0 = dv[0], d1 = dv[1], d2 = dv[2], d3 = dv[3];
-			// feedback * delays + in, row by row with the literal 0 / +-1 products (Reverb.k:158-163, klang.h:1446-1470)
-			float fb[4];
-			fb[0] = (0.f * d0 + 1.f * d1 + 1.f * d2 + -1.f * d3) + in;
-			fb[1] = (-1.f * d0 + 0.f * d1 + -1.f * d2 + 1.f * d3) + in;
-			fb[2] = (-1.f * d0 + 1.f * d1 + 0.f * d2 + -1.f * d3) + in;
-			fb[3] = (1.f * d0 + -1.f * d1 + 1.f * d2 + 0.f * d3) + in;
-			float sum = sv[0];
-			sum = sum + sv[1];
-			sum = sum + sv[2];
-			sum = sum + sv[3];
-			(stage == 0 ? S.r2 : S.r3)[t] = sum;
-			#pragma unroll
-			for (int q = 0; q < 4; q++) {
-				const int size = S.lsize[base + q];
-				float* ring = rings + S.lring[base + q];
-				const int w0 = (int)(((unsigned)S.wpos0[base + q] + t0 + 2u * (unsigned)t) % (unsigned)size);
-				int wa = w0 + 1; if (wa >= size) wa -= size;
-				ring[wa] = fb[q];                                            // second tick of this frame writes fb
-				if (t + 1 < L) { int wb = w0 + 2; if (wb >= size) wb -= size; ring[wb] = fb[q]; }   // = first tick of the next frame
-				else S.carry[cpar ^ 1][base + q] = fb[q];
-				if (t == 0) ring[w0] = S.carry[cpar][base + q];
+			// feedback * delays + in, row q with its literal 0 / +-1 products (Reverb.k:158-163, klang.h:1446-1470)
+			const float fb = (S.M[q][0] * dv[0] + S.M[q][1] * dv[1] + S.M[q][2] * dv[2] + S.M[q][3] * dv[3]) + in;
+			if (q == 0) {
+				float sum = sv[0];
+				sum = sum + sv[1];
+				sum = sum + sv[2];
+				sum = sum + sv[3];
+				(stage == 0 ? S.r2 : S.r3)[t] = sum;
 			}
+			const int size = S.lsize[base + q];
+			float* ring = rings + S.lring[base + q];
+			const int w0 = (int)(((unsigned)S.wpos0[base + q] + t0 + 2u * (unsigned)t) % (unsigned)size);
+			int wa = w0 + 1; if (wa >= size) wa -= size;
+			ring[wa] = fb;                                                   // second tick of this frame writes fb
+			if (t + 1 < L) { int wb = w0 + 2; if (wb >= size) wb -= size; ring[wb] = fb; }   // = first tick of the next frame
+			else S.carry[cpar ^ 1][base + q] = fb;
+			if (t == 0) ring[w0] = S.carry[cpar][base + q];
 		}
 	};
-	// T(k): early ring write and taps of chunk k; group-B thread = frame
+	// T(k): early ring write, tap products thread = (tap, frame), then the in-order sum per frame; group B
 	auto early_taps = [&](int k) {
 		const int L = chunk_len(k);
-		const int t = tb;
-		if (t < L) {
-			const int idx = (int)(((unsigned)epos0 + (unsigned)(k * Lc + t)) % (unsigned)esize);
-			ringe[idx] = S.xf[k & 1][t];
-			// (taps never reach into this chunk: Lc <= shortest tap - 3, so no barrier between the write and the reads)
-			int pos = idx + 1; if (pos >= esize) pos -= esize;                // position after this frame's write
-			float acc = 0.f;
-			for (int d0 = 0; d0 < count; d0 += 10) {                 // Stereo::Delay::tap(float)  klang.h:4668-4681
-				float va[10], vb[10], fr[10];
-				#pragma unroll
-				for (int j = 0; j < 10; j++) if (d0 + j < count) {
-					float read = (float)(pos - 1) - S.times[d0 + j]; if (read < 0.f) read += esize;
+		const int ebase = (int)(((unsigned)epos0 + (unsigned)(k * Lc)) % (unsigned)esize);
+		if (tb < L) { int idx = ebase + tb; if (idx >= esize) idx -= esize; ringe[idx] = S.xf[k & 1][tb]; }
+		// (taps never reach into this chunk: Lc <= shortest tap - 3, so no barrier between the write and the reads)
+		const int items = count * L;
+		for (int item0 = tb; item0 < items; item0 += 4 * GB) {
+			float va[4], vb[4], fr[4];
+			#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				const int item = item0 + j * GB;
+				if (item < items) {
+					const int d = item / L, t = item - d * L;
+					int pos = ebase + t + 1; if (pos >= esize) pos -= esize;          // position after this frame's write
+					float read = (float)(pos - 1) - S.times[d]; if (read < 0.f) read += esize;   // Stereo::Delay::tap(float)  klang.h:4668-4681
 					const float fl = floorf(read); fr[j] = read - fl;
 					const int ii = (int)read, jj = (ii == esize - 1) ? 0 : ii + 1;
 					va[j] = ringe[ii]; vb[j] = ringe[jj];
 				}
-				#pragma unroll
-				for (int j = 0; j < 10; j++) if (d0 + j < count) acc += (va[j] * (1.f - fr[j]) + vb[j] * fr[j]) * S.gg[d0 + j];   // r1 += tap * gain  Reverb.k:89-90
 			}
-			S.r1[k & 1][t] = acc;
+			#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				const int item = item0 + j * GB;
+				if (item < items) { const int d = item / L, t = item - d * L; S.tp[d][t] = (va[j] * (1.f - fr[j]) + vb[j] * fr[j]) * S.gg[d]; }
+			}
+		}
+		kb_bar_group(2, GB);
+		if (tb < L) {
+			float acc = 0.f;
+			for (int d = 0; d < count; d++) acc += S.tp[d][tb];                       // r1 += tap * gain, in tap order  Reverb.k:89-90
+			S.r1[k & 1][tb] = acc;
 		}
 	};
 	auto load_io = [&](int k, int t, int step) {
 		const int L = chunk_len(k);
-		for (; t < L; t += step) S.xin[k & 3][t] = X[k * Lc + t];
+		for (; t < L; t += step) S.xin[k & 7][t] = X[k * Lc + t];
 	};
 
-	// ---- prologue: windows of chunks 0 and 1 (both closed before the block), io of chunks 0..2; F(0), E(0), E(1); T(0)
-	if (warp >= 2 && warp < 5) { load_windows(0); if (K > 1) load_windows(1); }
-	else if (warp >= 5) { for (int k = 0; k < 3 && k < K; k++) load_io(k, tb, GB); }
+	// ---- prologue: windows of chunks 0 and 1 (both closed before the block), io of chunks 0..3; F(0); LPF(0..2), HPF(0..1); T(0)
+	if (inA) { load_windows(0); if (K > 1) load_windows(1); }
+	else if (inB) { for (int k = 0; k < 4 && k < K; k++) load_io(k, tb, GB); }
 	__syncthreads();
 	if (warp == 0) { if (tid < 8) filters(0); }
-	else if (tid == 32) { early_cascade(0); if (K > 1) early_cascade(1); }
+	else if (warp == 1) { early_cascade(0); early_cascade(1); early_cascade(2); }
 	__syncthreads();
-	if (warp >= 5) early_taps(0);
+	if (inB) early_taps(0);
 	__syncthreads();
 
 	int cpar = 0;
@@ -688,8 +706,8 @@ __global__ void __launch_bounds__(256) kb_reverb_pipe_kernel(const KbFxHdr* __re
 		if (warp == 0) {
 			if (tid < 8 && k + 1 < K) filters(k + 1);
 		} else if (warp == 1) {
-			if (tid == 32 && k + 2 < K) early_cascade(k + 2);
-		} else if (warp < 5) {
+			early_cascade(k + 3);                               // lane 0: LPF(k+3), lane 1: HPF(k+2)
+		} else if (inA) {
 			fdn_stage(k, 0, cpar);
 			kb_bar_group(1, GA);
 			fdn_stage(k, 1, cpar);
@@ -697,12 +715,12 @@ __global__ void __launch_bounds__(256) kb_reverb_pipe_kernel(const KbFxHdr* __re
 			const int L = chunk_len(k);
 			if (ta < L) {
 				const float refl = (S.r1[k & 1][ta] * cE + S.r2[ta] * cM) + S.r3[ta] * cL;
-				X[k * Lc + ta] = S.xin[k & 3][ta] * dry + refl * wet;           // Reverb.k:272
+				X[k * Lc + ta] = S.xin[k & 7][ta] * dry + refl * wet;           // Reverb.k:272
 			}
 			if (k + 2 < K) load_windows(k + 2);
-		} else {
+		} else if (inB) {
 			if (k + 1 < K) early_taps(k + 1);
-			if (k + 3 < K) load_io(k + 3, tb, GB);
+			if (k + 4 < K) load_io(k + 4, tb, GB);
 		}
 		__syncthreads();
 	}
@@ -714,7 +732,8 @@ __global__ void __launch_bounds__(256) kb_reverb_pipe_kernel(const KbFxHdr* __re
 		d.delay.position = (int)(((long long)d.delay.position + 2LL * n) % d.delay.SIZE);
 		d.delay.last_position = (int)(((long long)d.delay.last_position + 2LL * n) % d.delay.SIZE);
 	}
-	if (tid == 32) { rv.lpf[side].z0 = e_z[0]; rv.lpf[side].z1 = e_z[1]; rv.hpf[side].z0 = e_z[2]; rv.hpf[side].z1 = e_z[3]; }
+	if (tid == 32) { rv.lpf[side].z0 = z0; rv.lpf[side].z1 = z1; }
+	if (tid == 33) { rv.hpf[side].z0 = z0; rv.hpf[side].z1 = z1; }
 	if (tid == 0) ed.position = (int)(((long long)epos0 + n) % esize);
 }
 

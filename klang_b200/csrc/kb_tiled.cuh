@@ -109,17 +109,36 @@ __global__ void __launch_bounds__(NT) kb_sub_tiled_kernel(KbSubVoice* __restrict
 				const float4* pc = S.coef[c & 1].r[v];
 				const float2* pxa = S.xa[c & 1].r[v];
 				float* po = S.out[c & 1].r[v];
-				float4 cf = pc[0]; float2 xa = pxa[0];
-				#pragma unroll 4
-				for (int t = 0; t < steps; t++) {
-					const float4 cn = pc[t + 1]; const float2 xn = pxa[t + 1];      // next step's operands (rows are padded by one)
-					lb0 = cf.x; lb1 = cf.y; la1 = cf.z; la2 = cf.w;
-					const float in = xa.x;
+				// groups of 4 steps; the operands of the NEXT group are loaded before the current group's dependent updates, so no
+				// shared-memory latency sits on the recurrence (reads past `steps` stay inside the shared-memory struct and are unused)
+				float4 cf[4]; float2 xa[4];
+				#pragma unroll
+				for (int j = 0; j < 4; j++) { cf[j] = pc[j]; xa[j] = pxa[j]; }
+				int t = 0;
+				for (; t + 4 <= steps; t += 4) {
+					float4 cn[4]; float2 xn[4];
+					#pragma unroll
+					for (int j = 0; j < 4; j++) { cn[j] = pc[t + 4 + j]; xn[j] = pxa[t + 4 + j]; }
+					#pragma unroll
+					for (int j = 0; j < 4; j++) {
+						lb0 = cf[j].x; lb1 = cf[j].y; la1 = cf[j].z; la2 = cf[j].w;
+						const float in = xa[j].x;
+						const float y = lb0 * in + z0;
+						z0 = lb1 * in - la1 * y + z1;
+						z1 = lb0 * in - la2 * y;
+						po[t + j] = y * xa[j].y;                             // out *= adsr++   Filter.k:33
+					}
+					#pragma unroll
+					for (int j = 0; j < 4; j++) { cf[j] = cn[j]; xa[j] = xn[j]; }
+				}
+				#pragma unroll
+				for (int j = 0; j < 3; j++) if (t + j < steps) {
+					lb0 = cf[j].x; lb1 = cf[j].y; la1 = cf[j].z; la2 = cf[j].w;
+					const float in = xa[j].x;
 					const float y = lb0 * in + z0;
 					z0 = lb1 * in - la1 * y + z1;
 					z1 = lb0 * in - la2 * y;
-					po[t] = y * xa.y;                                        // out *= adsr++   Filter.k:33
-					cf = cn; xa = xn;
+					po[t + j] = y * xa[j].y;
 				}
 			}
 		} else if (worker) {
