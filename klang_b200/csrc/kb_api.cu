@@ -697,8 +697,10 @@ extern "C" int kb_synth_bank_process(kb_synth_bank* b, float* out, int n, unsign
 		kb_sub_tiled_kernel<GG, NT, LAY><<<(total + GG - 1) / GG, NT, sizeof(KbSubSmem<GG>), st>>>(vs, b->d_hdr, d_voice_dst, n, total, b->fs); \
 	} while (0)
 				if (layout == 0 || g < 7) {
+					// worker threads = NT - 96: 512 (NT 608) and 448 (G 7, NT 544) cover a G x 128 tile in exactly two rounds
 					if (g >= 16) KB_LAUNCH_SUB(16, 1024, 0);
-					else if (g >= 8) KB_LAUNCH_SUB(8, 512, 0);
+					else if (g >= 8) { if (force_nt == 608) KB_LAUNCH_SUB(8, 608, 0); else KB_LAUNCH_SUB(8, 512, 0); }
+					else if (g == 7) KB_LAUNCH_SUB(7, 544, 0);
 					else KB_LAUNCH_SUB(4, 320, 0);
 				} else if (g >= 16) KB_LAUNCH_SUB(16, 1024, 1);
 				else if (g == 7) { if (force_nt == 512) KB_LAUNCH_SUB(7, 512, 1); else if (force_nt == 1024) KB_LAUNCH_SUB(7, 1024, 1); else KB_LAUNCH_SUB(7, 768, 1); }

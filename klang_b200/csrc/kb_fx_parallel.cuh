@@ -618,13 +618,21 @@ __global__ void __launch_bounds__(KB_RV2_NT) kb_reverb_pipe_kernel(const KbFxHdr
 		}
 		l_rbase += ticks; if (l_rbase >= l_size) l_rbase -= l_size;
 	};
-	// W(k): FDN matrix, ring writes and outputs of one LateReflections stage; group-A thread = (line q, frame t)
+	// W(k): FDN matrix, ring writes and outputs of one LateReflections stage.  Group-A thread = (line pair, frame): thread
+	// (qh, t) owns lines qh and qh + 2 of both stages, with their write positions running along in registers (no modulo);
+	// called for k = 0, 1, 2, ... in order.
+	const int w_qh = ta >= 96 ? 1 : 0, w_t = ta - 96 * w_qh;
+	int w_pos[2][2] = { { 0, 0 }, { 0, 0 } };
+	if (inA) {
+		#pragma unroll
+		for (int st = 0; st < 2; st++)
+			#pragma unroll
+			for (int i = 0; i < 2; i++) w_pos[st][i] = S.wpos0[st * 4 + w_qh + 2 * i];
+	}
 	auto fdn_stage = [&](int k, int stage, int cpar) {
 		const int L = chunk_len(k);
-		const unsigned t0 = 2u * (unsigned)k * (unsigned)Lc;                   // (n <= 2^20: the caller splits longer blocks)
-		const int base = stage * 4;
-		for (int item = ta; item < 4 * L; item += GA) {
-			const int q = item / L, t = item - q * L;
+		const int base = stage * 4, t = w_t;
+		if (t < L) {
 			const float in = stage == 0 ? S.r1[k & 1][t] : S.r2[t];
 			float dv[4], sv[4];
 			#pragma unroll
@@ -633,50 +641,65 @@ __global__ void __launch_bounds__(KB_RV2_NT) kb_reverb_pipe_kernel(const KbFxHdr
 				dv[j] = yy.x * S.gain[base + j];                             // FilteredDelay::process  Reverb.k:130-132
 				sv[j] = yy.y * S.gain[base + j];
 			}
-			// feedback * delays + in, row q with its literal 0 / +-1 products (Reverb.k:158-163, klang.h:1446-1470)
-			const float fb = (S.M[q][0] * dv[0] + S.M[q][1] * dv[1] + S.M[q][2] * dv[2] + S.M[q][3] * dv[3]) + in;
-			if (q == 0) {
+			if (w_qh == 0) {
 				float sum = sv[0];
 				sum = sum + sv[1];
 				sum = sum + sv[2];
 				sum = sum + sv[3];
 				(stage == 0 ? S.r2 : S.r3)[t] = sum;
 			}
-			const int size = S.lsize[base + q];
-			float* ring = rings + S.lring[base + q];
-			const int w0 = (int)(((unsigned)S.wpos0[base + q] + t0 + 2u * (unsigned)t) % (unsigned)size);
-			int wa = w0 + 1; if (wa >= size) wa -= size;
-			ring[wa] = fb;                                                   // second tick of this frame writes fb
-			if (t + 1 < L) { int wb = w0 + 2; if (wb >= size) wb -= size; ring[wb] = fb; }   // = first tick of the next frame
-			else S.carry[cpar ^ 1][base + q] = fb;
-			if (t == 0) ring[w0] = S.carry[cpar][base + q];
+			#pragma unroll
+			for (int i = 0; i < 2; i++) {
+				const int q = w_qh + 2 * i;
+				// feedback * delays + in, row q with its literal 0 / +-1 products (Reverb.k:158-163, klang.h:1446-1470)
+				const float fb = (S.M[q][0] * dv[0] + S.M[q][1] * dv[1] + S.M[q][2] * dv[2] + S.M[q][3] * dv[3]) + in;
+				const int size = S.lsize[base + q];
+				float* ring = rings + S.lring[base + q];
+				int w0 = (stage == 0 ? w_pos[0][i] : w_pos[1][i]) + 2 * t; if (w0 >= size) w0 -= size;
+				int wa = w0 + 1; if (wa >= size) wa -= size;
+				ring[wa] = fb;                                               // second tick of this frame writes fb
+				if (t + 1 < L) { int wb = w0 + 2; if (wb >= size) wb -= size; ring[wb] = fb; }   // = first tick of the next frame
+				else S.carry[cpar ^ 1][base + q] = fb;
+				if (t == 0) ring[w0] = S.carry[cpar][base + q];
+			}
+		}
+		#pragma unroll
+		for (int i = 0; i < 2; i++) {
+			const int size = S.lsize[base + w_qh + 2 * i];
+			int& wp = stage == 0 ? w_pos[0][i] : w_pos[1][i];
+			wp += 2 * L; if (wp >= size) wp -= size;
 		}
 	};
-	// T(k): early ring write, tap products thread = (tap, frame), then the in-order sum per frame; group B
+	// T(k): early ring write, tap products thread = (tap parity, frame) with five taps in flight, then the in-order sum per
+	// frame; group B (2 x 80 threads)
+	const int e_dg = tb >= KB_RV2_LMAX ? 1 : 0, e_t = tb - KB_RV2_LMAX * e_dg;
 	auto early_taps = [&](int k) {
 		const int L = chunk_len(k);
 		const int ebase = (int)(((unsigned)epos0 + (unsigned)(k * Lc)) % (unsigned)esize);
-		if (tb < L) { int idx = ebase + tb; if (idx >= esize) idx -= esize; ringe[idx] = S.xf[k & 1][tb]; }
-		// (taps never reach into this chunk: Lc <= shortest tap - 3, so no barrier between the write and the reads)
-		const int items = count * L;
-		for (int item0 = tb; item0 < items; item0 += 4 * GB) {
-			float va[4], vb[4], fr[4];
-			#pragma unroll
-			for (int j = 0; j < 4; j++) {
-				const int item = item0 + j * GB;
-				if (item < items) {
-					const int d = item / L, t = item - d * L;
-					int pos = ebase + t + 1; if (pos >= esize) pos -= esize;          // position after this frame's write
-					float read = (float)(pos - 1) - S.times[d]; if (read < 0.f) read += esize;   // Stereo::Delay::tap(float)  klang.h:4668-4681
-					const float fl = floorf(read); fr[j] = read - fl;
-					const int ii = (int)read, jj = (ii == esize - 1) ? 0 : ii + 1;
-					va[j] = ringe[ii]; vb[j] = ringe[jj];
+		const int t = e_t;
+		if (t < L) {
+			int idx = ebase + t; if (idx >= esize) idx -= esize;
+			if (e_dg == 0) ringe[idx] = S.xf[k & 1][t];
+			// (taps never reach into this chunk: Lc <= shortest tap - 3, so no barrier between the write and the reads)
+			int pos = idx + 1; if (pos >= esize) pos -= esize;                    // position after this frame's write
+			const float posf = (float)(pos - 1);
+			for (int d0 = e_dg; d0 < count; d0 += 10) {                           // taps d0, d0+2, .., d0+8
+				float va[5], vb[5], fr[5];
+				#pragma unroll
+				for (int j = 0; j < 5; j++) {
+					const int d = d0 + 2 * j;
+					if (d < count) {
+						float read = posf - S.times[d]; if (read < 0.f) read += esize;       // Stereo::Delay::tap(float)  klang.h:4668-4681
+						const float fl = floorf(read); fr[j] = read - fl;
+						const int ii = (int)read, jj = (ii == esize - 1) ? 0 : ii + 1;
+						va[j] = ringe[ii]; vb[j] = ringe[jj];
+					}
 				}
-			}
-			#pragma unroll
-			for (int j = 0; j < 4; j++) {
-				const int item = item0 + j * GB;
-				if (item < items) { const int d = item / L, t = item - d * L; S.tp[d][t] = (va[j] * (1.f - fr[j]) + vb[j] * fr[j]) * S.gg[d]; }
+				#pragma unroll
+				for (int j = 0; j < 5; j++) {
+					const int d = d0 + 2 * j;
+					if (d < count) S.tp[d][t] = (va[j] * (1.f - fr[j]) + vb[j] * fr[j]) * S.gg[d];
+				}
 			}
 		}
 		kb_bar_group(2, GB);

@@ -401,87 +401,55 @@ KB_HD float kb_envr_tick(const KbFs& fs, KbEnvR& e, const float* px, const float
 	kbr_after_ramp(fs, e, px, py);
 	return output;
 }
-// `steps` consecutive ticks into row[0..steps).  The envelope spends almost all of its time in one of four
-// steady modes — a running ramp, the ADSR sustain hold (a one-point loop re-asserting its level every sample),
-// waiting for the next breakpoint's time, or Off — and each of those is a two-or-three instruction loop; every
-// mode change goes through the generic tick, so the sequence of values is bit-identical to kb_envr_tick.
+// `steps` consecutive ticks into row[0..steps).  The envelope spends almost all of its time in one of four steady modes —
+// a running ramp (up or down), the ADSR sustain hold (a one-point loop re-asserting its level every sample), waiting for
+// the next breakpoint's time, or Off.  All four are the SAME four-ticks-per-iteration loop with per-lane constants
+// (signed rate or -0, time increment or -0, and the exit test), so the lanes of a warp — voices in different envelope
+// phases — run it together instead of one mode after the other.  x + (-0) == x bit for bit, which is how a mode
+// switches an update off.  Every mode change (ramp crossing, breakpoint reached, loop jump, release end) and every tail
+// shorter than four ticks goes through the generic tick, so the sequence of values is bit-identical to kb_envr_tick.
+KB_HD uint32_t kb_fbits(float f) {
+#ifdef __CUDA_ARCH__
+	return __float_as_uint(f);
+#else
+	uint32_t u; memcpy(&u, &f, 4); return u;
+#endif
+}
 KB_HD void kb_envr_run(const KbFs& fs, KbEnvR& e, const float* px, const float* py, float* row, int steps) {
 	int t = 0;
 	while (t < steps) {
-		if (e.r_active) {
-			const float rate = e.r_rate, target = e.r_target;
-			if (e.stage != KB_ENV_OFF && rate > 0.f && rate <= 3.0e38f) {
-				// a positive finite rate moves r_out monotonically towards the target, so the direction test of
-				// Linear::operator++ (klang.h:3785-3806) is invariant until the ramp crosses
-				const bool sustain = e.stage == KB_ENV_SUSTAIN;
-				float r = e.r_out, time = e.time;
-				const float inc = e.timeInc;
-				bool crossed = false;
-				// four ticks at a time: the four partial sums are formed exactly as four single ticks would form them
-				// (r only moves towards the target, so "the 4th has not crossed" implies none has)
-				if (target > r) {
-					while (t + 4 <= steps) {
-						const float r1 = r + rate, r2 = r1 + rate, r3 = r2 + rate, r4 = r3 + rate;
-						if (r4 >= target) break;
-						row[t] = r; row[t + 1] = r1; row[t + 2] = r2; row[t + 3] = r3; r = r4; t += 4;
-						if (sustain) { time += inc; time += inc; time += inc; time += inc; }
-					}
-					while (t < steps) { row[t++] = r; r += rate; if (r >= target) { crossed = true; break; } if (sustain) time += inc; }
-				} else {
-					while (t + 4 <= steps) {
-						const float r1 = r - rate, r2 = r1 - rate, r3 = r2 - rate, r4 = r3 - rate;
-						if (r4 <= target) break;
-						row[t] = r; row[t + 1] = r1; row[t + 2] = r2; row[t + 3] = r3; r = r4; t += 4;
-						if (sustain) { time += inc; time += inc; time += inc; time += inc; }
-					}
-					while (t < steps) { row[t++] = r; r -= rate; if (r <= target) { crossed = true; break; } if (sustain) time += inc; }
-				}
-				e.time = time;
-				if (crossed) { e.out = row[t - 1]; e.r_out = target; e.r_active = 0; kbr_after_ramp(fs, e, px, py); }
-				else { e.r_out = r; if (t > 0) e.out = row[t - 1]; }
-				continue;
+		if (t + 4 <= steps) {
+			const bool act = e.r_active != 0, sus = e.stage == KB_ENV_SUSTAIN;
+			const bool at_loop_end = e.loop_start != -1 && e.loop_end != -1 && (e.point + 1) >= e.loop_end;
+			// ramp: a positive finite rate moves r_out monotonically towards the target, so the direction test of
+			// Linear::operator++ (klang.h:3785-3806) is invariant until the ramp crosses
+			const bool is_ramp = act && e.stage != KB_ENV_OFF && e.r_rate > 0.f && e.r_rate <= 3.0e38f;
+			const bool is_off = !act && e.stage == KB_ENV_OFF;
+			const bool is_wait = !act && sus && !at_loop_end && (e.point + 1) < e.npoints;       // klang.h:4036-4043
+			bool is_hold = false;                                                                // klang.h:4029-4035 at its fixed point
+			if (!act && sus && at_loop_end && e.loop_start == e.loop_end && e.point == e.loop_start) {
+				const uint32_t lvl = kb_fbits(py[e.loop_start]);
+				is_hold = lvl == kb_fbits(e.r_out) && lvl == kb_fbits(e.r_target);
 			}
-			row[t++] = kb_envr_tick(fs, e, px, py);
-			continue;
-		}
-		if (e.stage == KB_ENV_OFF) {
-			const float r = e.r_out;
-			for (; t < steps; t++) row[t] = r;
-			e.out = r;
-			break;
-		}
-		if (e.stage == KB_ENV_SUSTAIN) {
-			const bool loop_active = e.loop_start != -1 && e.loop_end != -1;
-			if (loop_active && (e.point + 1) >= e.loop_end) {
-				row[t++] = kb_envr_tick(fs, e, px, py);                       // performs the loop jump
-				if (e.loop_start == e.loop_end && !e.r_active && e.stage == KB_ENV_SUSTAIN) {
-					// hold: every further tick outputs the level, advances time and re-asserts the level
-					const float r = e.r_out, inc = e.timeInc;
-					float time = e.time;
-					if (t < steps) e.out = r;
-					for (; t + 4 <= steps; t += 4) { row[t] = r; row[t + 1] = r; row[t + 2] = r; row[t + 3] = r; time += inc; time += inc; time += inc; time += inc; }
-					for (; t < steps; t++) { row[t] = r; time += inc; }
-					e.time = time;
-				}
-				continue;
-			}
-			if (!loop_active && (e.point + 1) < e.npoints) {
-				const float r = e.r_out, inc = e.timeInc, x = px[e.point + 1];
-				float time = e.time;
-				bool reached = false;
-				while (t + 4 <= steps) {                                          // time only grows (timeInc > 0)
-					const float t1 = time + inc, t2 = t1 + inc, t3 = t2 + inc, t4 = t3 + inc;
-					if (t4 >= x) break;
-					row[t] = r; row[t + 1] = r; row[t + 2] = r; row[t + 3] = r; time = t4; t += 4;
-				}
-				while (t < steps) { row[t++] = r; time += inc; if (time >= x) { reached = true; break; } }
-				e.time = time; e.out = r;
-				if (reached) {
-					e.point++;
-					kbr_set_value(e, py[e.point]);
-					if ((e.point + 1) < e.npoints) kbr_set_target(fs, e, px[e.point + 1], py[e.point + 1], px[e.point]);
-				}
-				continue;
+			if (is_ramp || is_off || is_wait || is_hold) {
+				const bool up = e.r_target > e.r_out;
+				const float srate = is_ramp ? (up ? e.r_rate : -e.r_rate) : -0.f;
+				const float tinc = sus ? e.timeInc : -0.f;
+				const float target = e.r_target;
+				const float x = is_wait ? px[e.point + 1] : 0.f;
+				float r = e.r_out, time = e.time, last = e.out;
+				do {
+					// the partial sums are formed exactly as four single ticks would form them; r and time only move one way,
+					// so "the 4th has not crossed / arrived" implies none has
+					const float r1 = r + srate, r2 = r1 + srate, r3 = r2 + srate, r4 = r3 + srate;
+					const float t1 = time + tinc, t2 = t1 + tinc, t3 = t2 + tinc, t4 = t3 + tinc;
+					const bool leave = is_ramp ? (up ? r4 >= target : r4 <= target) : (is_wait && t4 >= x);
+					if (leave) break;
+					row[t] = r; row[t + 1] = r1; row[t + 2] = r2; row[t + 3] = r3;
+					last = r3; r = r4; time = t4; t += 4;
+				} while (t + 4 <= steps);
+				e.r_out = r; e.time = time; e.out = last;
+				if (t >= steps) break;
 			}
 		}
 		row[t++] = kb_envr_tick(fs, e, px, py);

@@ -14,14 +14,14 @@ static uint32_t bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 
 int main() {
 	long long checked = 0, bad = 0;
-	for (int trial = 0; trial < 3000; trial++) {
+	for (int trial = 0; trial < 6000; trial++) {
 		const KbFs fs = kb_make_fs(trial & 1 ? 48000.f : 44100.f);
 		KbEnv a;
 		if (trial % 3 == 0) { kb_adsr_construct(fs, a); kb_adsr_set(fs, a, frand(0, 0.02f), frand(0, 0.02f), frand(0, 1), frand(0, 0.02f)); }
 		else {
 			kb_env_construct(fs, a);
 			int np = 1 + rnd() % 6; float xy[32]; float x = 0;
-			for (int p = 0; p < np; p++) { xy[2 * p] = x; xy[2 * p + 1] = frand(-2, 2000); x += (rnd() % 5 == 0) ? 0.f : frand(0.0001f, 0.01f); }
+			for (int p = 0; p < np; p++) { xy[2 * p] = x; xy[2 * p + 1] = (rnd() % 8 == 0) ? ((rnd() & 1) ? -0.f : 0.f) : frand(-2, 2000); x += (rnd() % 5 == 0) ? 0.f : frand(0.0001f, (rnd() % 4 == 0) ? 0.05f : 0.01f); }
 			kb_env_set_points(fs, a, np, xy);
 			if (rnd() % 3 == 0) { int s = rnd() % np, t = s + rnd() % (np - s); kb_env_set_loop(a, s, t); }
 		}
