@@ -435,16 +435,20 @@ KB_HD void kb_envr_run(const KbFs& fs, KbEnvR& e, const float* px, const float* 
 				const bool up = e.r_target > e.r_out;
 				const float srate = is_ramp ? (up ? e.r_rate : -e.r_rate) : -0.f;
 				const float tinc = sus ? e.timeInc : -0.f;
-				const float target = e.r_target;
-				const float x = is_wait ? px[e.point + 1] : 0.f;
+				// the exit test as three comparisons against per-lane constants (no branches between the modes): a rising ramp stays
+				// while r4 < target, a falling one while r4 > target, a wait while t4 < x; everything else compares against +-inf.
+				// A NaN or infinite r4 / t4 merely sends the lane through the generic tick.
+				const float inf = kb_bits(0x7f800000u);
+				const float r_hi = (is_ramp && up) ? e.r_target : inf, r_lo = (is_ramp && !up) ? e.r_target : -inf;
+				const float t_hi = is_wait ? px[e.point + 1] : inf;
 				float r = e.r_out, time = e.time, last = e.out;
 				do {
 					// the partial sums are formed exactly as four single ticks would form them; r and time only move one way,
 					// so "the 4th has not crossed / arrived" implies none has
 					const float r1 = r + srate, r2 = r1 + srate, r3 = r2 + srate, r4 = r3 + srate;
 					const float t1 = time + tinc, t2 = t1 + tinc, t3 = t2 + tinc, t4 = t3 + tinc;
-					const bool leave = is_ramp ? (up ? r4 >= target : r4 <= target) : (is_wait && t4 >= x);
-					if (leave) break;
+					const bool stay = (r4 < r_hi) & (r4 > r_lo) & (t4 < t_hi);
+					if (!stay) break;
 					row[t] = r; row[t + 1] = r1; row[t + 2] = r2; row[t + 3] = r3;
 					last = r3; r = r4; time = t4; t += 4;
 				} while (t + 4 <= steps);
