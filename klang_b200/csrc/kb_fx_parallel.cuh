@@ -602,20 +602,18 @@ __global__ void __launch_bounds__(KB_RV2_NT) kb_reverb_pipe_kernel(const KbFxHdr
 	auto load_windows = [&](int k) {
 		const int ticks = 2 * chunk_len(k);
 		float* xrow = S.x[k & 1][l_line];
-		for (int tk0 = l_sub; tk0 < ticks; tk0 += 96) {
-			float va[4], vb[4];
-			#pragma unroll
-			for (int j = 0; j < 4; j++) {
-				const int tk = tk0 + 24 * j;
-				if (tk < ticks) {
-					int i0 = l_rbase + tk; if (i0 >= l_size) i0 -= l_size;
-					int i1 = i0 + 1; if (i1 >= l_size) i1 -= l_size;
-					va[j] = l_ring[i0]; vb[j] = l_ring[i1];
-				}
+		float va[7], vb[7];                                      // 2 * LMAX / 24 threads per line: at most 7 ticks per thread, all in flight
+		#pragma unroll
+		for (int j = 0; j < 7; j++) {
+			const int tk = l_sub + 24 * j;
+			if (tk < ticks) {
+				int i0 = l_rbase + tk; if (i0 >= l_size) i0 -= l_size;
+				int i1 = i0 + 1; if (i1 >= l_size) i1 -= l_size;
+				va[j] = l_ring[i0]; vb[j] = l_ring[i1];
 			}
-			#pragma unroll
-			for (int j = 0; j < 4; j++) { const int tk = tk0 + 24 * j; if (tk < ticks) xrow[tk] = va[j] + l_frac * (vb[j] - va[j]); }
 		}
+		#pragma unroll
+		for (int j = 0; j < 7; j++) { const int tk = l_sub + 24 * j; if (tk < ticks) xrow[tk] = va[j] + l_frac * (vb[j] - va[j]); }
 		l_rbase += ticks; if (l_rbase >= l_size) l_rbase -= l_size;
 	};
 	// W(k): FDN matrix, ring writes and outputs of one LateReflections stage.  Group-A thread = (line pair, frame): thread
@@ -683,29 +681,31 @@ __global__ void __launch_bounds__(KB_RV2_NT) kb_reverb_pipe_kernel(const KbFxHdr
 			// (taps never reach into this chunk: Lc <= shortest tap - 3, so no barrier between the write and the reads)
 			int pos = idx + 1; if (pos >= esize) pos -= esize;                    // position after this frame's write
 			const float posf = (float)(pos - 1);
-			for (int d0 = e_dg; d0 < count; d0 += 10) {                           // taps d0, d0+2, .., d0+8
-				float va[5], vb[5], fr[5];
-				#pragma unroll
-				for (int j = 0; j < 5; j++) {
-					const int d = d0 + 2 * j;
-					if (d < count) {
-						float read = posf - S.times[d]; if (read < 0.f) read += esize;       // Stereo::Delay::tap(float)  klang.h:4668-4681
-						const float fl = floorf(read); fr[j] = read - fl;
-						const int ii = (int)read, jj = (ii == esize - 1) ? 0 : ii + 1;
-						va[j] = ringe[ii]; vb[j] = ringe[jj];
-					}
+			float va[10], vb[10], fr[10];                                         // this thread's taps e_dg, e_dg+2, .., e_dg+18: all in flight
+			#pragma unroll
+			for (int j = 0; j < 10; j++) {
+				const int d = e_dg + 2 * j;
+				if (d < count) {
+					float read = posf - S.times[d]; if (read < 0.f) read += esize;           // Stereo::Delay::tap(float)  klang.h:4668-4681
+					const float fl = floorf(read); fr[j] = read - fl;
+					const int ii = (int)read, jj = (ii == esize - 1) ? 0 : ii + 1;
+					va[j] = ringe[ii]; vb[j] = ringe[jj];
 				}
-				#pragma unroll
-				for (int j = 0; j < 5; j++) {
-					const int d = d0 + 2 * j;
-					if (d < count) S.tp[d][t] = (va[j] * (1.f - fr[j]) + vb[j] * fr[j]) * S.gg[d];
-				}
+			}
+			#pragma unroll
+			for (int j = 0; j < 10; j++) {
+				const int d = e_dg + 2 * j;
+				if (d < count) S.tp[d][t] = (va[j] * (1.f - fr[j]) + vb[j] * fr[j]) * S.gg[d];
 			}
 		}
 		kb_bar_group(2, GB);
 		if (tb < L) {
+			float p[KB_RV_MAXREFL];
+			#pragma unroll
+			for (int d = 0; d < KB_RV_MAXREFL; d++) p[d] = d < count ? S.tp[d][tb] : 0.f;
 			float acc = 0.f;
-			for (int d = 0; d < count; d++) acc += S.tp[d][tb];                       // r1 += tap * gain, in tap order  Reverb.k:89-90
+			#pragma unroll
+			for (int d = 0; d < KB_RV_MAXREFL; d++) if (d < count) acc += p[d];          // r1 += tap * gain, in tap order  Reverb.k:89-90
 			S.r1[k & 1][tb] = acc;
 		}
 	};
@@ -742,8 +742,12 @@ __global__ void __launch_bounds__(KB_RV2_NT) kb_reverb_pipe_kernel(const KbFxHdr
 			}
 			if (k + 2 < K) load_windows(k + 2);
 		} else if (inB) {
+			// the io block of chunk k+4 travels through a register around the taps, so its latency is off this group's path
+			float xpre = 0.f;
+			const bool pre = k + 4 < K && tb < chunk_len(k + 4);
+			if (pre) xpre = X[(k + 4) * Lc + tb];
 			if (k + 1 < K) early_taps(k + 1);
-			if (k + 4 < K) load_io(k + 4, tb, GB);
+			if (pre) S.xin[(k + 4) & 7][tb] = xpre;
 		}
 		__syncthreads();
 	}
