@@ -454,23 +454,25 @@ __global__ void __launch_bounds__(256) kb_reverb_par_kernel(const KbFxHdr* __res
 
 // ------------------------------------------------------------------------------ Reverb.k, pipelined schedule (default)
 // Same arithmetic as kb_reverb_par_kernel, but the per-chunk phases no longer wait for each other.  The chunk is a
-// QUARTER of the shortest read-to-write distance (lag >= 4*Lc + 2 ring samples; ~75 frames at 48 kHz), so the ring window
-// of chunk k+2 is complete once chunk k has been written, and the CTA (512 threads) runs as a four-role software pipeline
-// with ONE __syncthreads per chunk.  In iteration k:
+// SIXTH of the shortest read-to-write distance (lag >= 6*Lc + 2 ring samples; ~50 frames at 48 kHz), so the ring window
+// of chunk k+2 is complete once chunk k-1 has been written, and the CTA (640 threads) runs as a five-role software
+// pipeline with ONE __syncthreads per chunk.  In iteration k, concurrently:
 //   warp 0, lanes 0..7   F(k+1)  the 8 line filters (Biquad TDF-II, in order) over pre-interpolated inputs: 9 issue slots
-//                                per tick around the 16-cycle recurrence — the role that bounds the kernel.  It has SM
-//                                sub-partition 0 to itself (warps 4, 8, 12 stay idle)
+//                                per tick around the 16-cycle recurrence — the role that bounds the kernel (20.4 cycles per
+//                                tick measured alone, tools/micro/serial_floor.cu).  It has SM sub-partition 0 to itself
+//                                (warps 4, 8, 12, 16 stay idle)
 //   warp 1, lanes 0..1   E       early cascade, the two biquads on two lanes one chunk apart: LPF(k+3), HPF(k+2)
-//   group A (6 warps)    W(k)    FDN matrix, ring writes, mid -> late, output mix, thread = (frame, line);  then L(k+2):
-//                                ring windows of chunk k+2 -> Delay::process interpolation -> shared memory, 24 threads
+//   group A1 (6 warps)   W(k)    FDN matrix, ring writes, mid -> late, output mix, thread = (line pair, frame)
+//   group A2 (3 warps)   L(k+2)  ring windows of chunk k+2 -> Delay::process interpolation -> shared memory, 12 threads
 //                                per line with a running read position (no modulo)
-//   group B (5 warps)    T(k+1)  early ring write, the 20 early taps as thread = (frame, tap) products, then an in-order
-//                                sum per frame;  io block of chunk k+4 -> shared memory
+//   group B (5 warps)    T(k+1)  early ring write, the 20 early taps as thread = (tap parity, frame) products, then an
+//                                in-order sum per frame;  io block of chunk k+4 -> shared memory
 #define KB_RV2_LMAX 80
 #define KB_RV2_ROW 180                       // floats per (line, chunk) row: 2*LMAX ticks + read-ahead, 8 lanes on distinct banks
 #define KB_RV2_EROW (KB_RV2_LMAX + 16)       // early rows: LMAX frames + read-ahead of the row filter
-#define KB_RV2_NT 512
-#define KB_RV2_GA 192                        // threads of group A
+#define KB_RV2_NT 640
+#define KB_RV2_GA 192                        // threads of group A1
+#define KB_RV2_GL 96                         // threads of group A2
 #define KB_RV2_GB 160                        // threads of group B
 struct KbRv2Smem {
 	float x[2][8][KB_RV2_ROW];               // filter inputs per tick (Delay::process output), double buffered
@@ -493,7 +495,7 @@ __global__ void kb_reverb_plan2_kernel(const KbReverb* __restrict__ states, KbFx
 	for (int line = 0; line < 16; line++) {
 		const KbDelay& d = kb_rv_line(rv, line).delay;
 		int lag = d.position - d.last_position; if (lag <= 0) lag += d.SIZE;    // write head minus read head, in ring samples
-		chunk = min(chunk, (lag - 2) / 4);                                      // two ticks per frame, window of chunk k+2 closed by chunk k
+		chunk = min(chunk, (lag - 2) / 6);                                      // two ticks per frame, window of chunk k+2 closed by chunk k-1
 	}
 	float tmin = 1e30f;
 	for (int r = 0; r < rv.count; r++) tmin = fminf(tmin, rv.times[r]);
@@ -540,12 +542,14 @@ __global__ void __launch_bounds__(KB_RV2_NT) kb_reverb_pipe_kernel(const KbFxHdr
 	const KbFxPlan pl = plan[inst];
 	if (pl.mode != KB_PLAN_PARALLEL) return;
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	constexpr int GA = KB_RV2_GA, GB = KB_RV2_GB;
-	// roles: warp 0 = F, warp 1 = E, warps 4/8/12 idle (they share sub-partition 0 with F), A = warps 2,3,5,6,7,9, B = warps 10,11,13,14,15
-	const int slot = warp - 2 - (warp > 4) - (warp > 8) - (warp > 12);      // 0..10 over the 11 worker warps
-	const bool idle = warp == 4 || warp == 8 || warp == 12;
-	const bool inA = warp >= 2 && !idle && slot < 6, inB = warp >= 2 && !idle && slot >= 6;
-	const int ta = slot * 32 + lane, tb = (slot - 6) * 32 + lane;
+	constexpr int GA = KB_RV2_GA, GL = KB_RV2_GL, GB = KB_RV2_GB;
+	// roles: warp 0 = F, warp 1 = E, warps 4/8/12/16 idle (they share sub-partition 0 with F); the 14 other warps in order:
+	// slots 0..5 = A1 (W), 6..8 = A2 (L), 9..13 = B (T)
+	const int slot = warp - 2 - (warp > 4) - (warp > 8) - (warp > 12) - (warp > 16);
+	const bool idle = (warp & 3) == 0 && warp >= 4;
+	const bool worker = warp >= 2 && !idle;
+	const bool inA = worker && slot < 6, inL = worker && slot >= 6 && slot < 9, inB = worker && slot >= 9;
+	const int ta = slot * 32 + lane, tl = (slot - 6) * 32 + lane, tb = (slot - 9) * 32 + lane;
 	KbReverb& rv = states[inst];
 	const KbControl* c = hdrs[inst].controls;
 	const float dry = c[0].value, wet = side == 0 ? c[4].value : 0.f;        // Reverb.k:272 (Q7): the right wet gain is the literal 0
@@ -594,26 +598,28 @@ __global__ void __launch_bounds__(KB_RV2_NT) kb_reverb_pipe_kernel(const KbFxHdr
 	auto filters = [&](int k) {
 		kb_rv2_filter_row(S.x[k & 1][tid], S.y[k & 1][tid], 2 * chunk_len(k), b0, b1, b2, a1, a2, z0, z1);
 	};
-	// L(k): ring read windows of chunk k, interpolated (Delay::process, klang.h:3461-3473) -> S.x; 24 group-A threads per line.
+	// L(k): ring read windows of chunk k, interpolated (Delay::process, klang.h:3461-3473) -> S.x; 12 group-A2 threads per line.
 	// Called for k = 0, 1, 2, ... in order: the read position of the line runs along in a register.
-	const int l_line = ta / 24, l_sub = ta % 24;
+	const int l_line = tl / 12, l_sub = tl % 12;
 	int l_size = 1, l_rbase = 0; float l_frac = 0.f; const float* l_ring = rings;
-	if (inA) { l_size = S.lsize[l_line]; l_rbase = S.rpos0[l_line]; l_frac = S.frac[l_line]; l_ring = rings + S.lring[l_line]; }
+	if (inL) { l_size = S.lsize[l_line]; l_rbase = S.rpos0[l_line]; l_frac = S.frac[l_line]; l_ring = rings + S.lring[l_line]; }
 	auto load_windows = [&](int k) {
 		const int ticks = 2 * chunk_len(k);
 		float* xrow = S.x[k & 1][l_line];
-		float va[7], vb[7];                                      // 2 * LMAX / 24 threads per line: at most 7 ticks per thread, all in flight
-		#pragma unroll
-		for (int j = 0; j < 7; j++) {
-			const int tk = l_sub + 24 * j;
-			if (tk < ticks) {
-				int i0 = l_rbase + tk; if (i0 >= l_size) i0 -= l_size;
-				int i1 = i0 + 1; if (i1 >= l_size) i1 -= l_size;
-				va[j] = l_ring[i0]; vb[j] = l_ring[i1];
+		for (int tk0 = l_sub; tk0 < ticks; tk0 += 12 * 7) {      // seven ticks (14 loads) in flight per thread
+			float va[7], vb[7];
+			#pragma unroll
+			for (int j = 0; j < 7; j++) {
+				const int tk = tk0 + 12 * j;
+				if (tk < ticks) {
+					int i0 = l_rbase + tk; if (i0 >= l_size) i0 -= l_size;
+					int i1 = i0 + 1; if (i1 >= l_size) i1 -= l_size;
+					va[j] = l_ring[i0]; vb[j] = l_ring[i1];
+				}
 			}
+			#pragma unroll
+			for (int j = 0; j < 7; j++) { const int tk = tk0 + 12 * j; if (tk < ticks) xrow[tk] = va[j] + l_frac * (vb[j] - va[j]); }
 		}
-		#pragma unroll
-		for (int j = 0; j < 7; j++) { const int tk = l_sub + 24 * j; if (tk < ticks) xrow[tk] = va[j] + l_frac * (vb[j] - va[j]); }
 		l_rbase += ticks; if (l_rbase >= l_size) l_rbase -= l_size;
 	};
 	// W(k): FDN matrix, ring writes and outputs of one LateReflections stage.  Group-A thread = (line pair, frame): thread
@@ -681,21 +687,23 @@ __global__ void __launch_bounds__(KB_RV2_NT) kb_reverb_pipe_kernel(const KbFxHdr
 			// (taps never reach into this chunk: Lc <= shortest tap - 3, so no barrier between the write and the reads)
 			int pos = idx + 1; if (pos >= esize) pos -= esize;                    // position after this frame's write
 			const float posf = (float)(pos - 1);
-			float va[10], vb[10], fr[10];                                         // this thread's taps e_dg, e_dg+2, .., e_dg+18: all in flight
-			#pragma unroll
-			for (int j = 0; j < 10; j++) {
-				const int d = e_dg + 2 * j;
-				if (d < count) {
-					float read = posf - S.times[d]; if (read < 0.f) read += esize;           // Stereo::Delay::tap(float)  klang.h:4668-4681
-					const float fl = floorf(read); fr[j] = read - fl;
-					const int ii = (int)read, jj = (ii == esize - 1) ? 0 : ii + 1;
-					va[j] = ringe[ii]; vb[j] = ringe[jj];
+			for (int d0 = e_dg; d0 < count; d0 += 10) {                           // taps d0, d0+2, .., d0+8 in flight
+				float va[5], vb[5], fr[5];
+				#pragma unroll
+				for (int j = 0; j < 5; j++) {
+					const int d = d0 + 2 * j;
+					if (d < count) {
+						float read = posf - S.times[d]; if (read < 0.f) read += esize;       // Stereo::Delay::tap(float)  klang.h:4668-4681
+						const float fl = floorf(read); fr[j] = read - fl;
+						const int ii = (int)read, jj = (ii == esize - 1) ? 0 : ii + 1;
+						va[j] = ringe[ii]; vb[j] = ringe[jj];
+					}
 				}
-			}
-			#pragma unroll
-			for (int j = 0; j < 10; j++) {
-				const int d = e_dg + 2 * j;
-				if (d < count) S.tp[d][t] = (va[j] * (1.f - fr[j]) + vb[j] * fr[j]) * S.gg[d];
+				#pragma unroll
+				for (int j = 0; j < 5; j++) {
+					const int d = d0 + 2 * j;
+					if (d < count) S.tp[d][t] = (va[j] * (1.f - fr[j]) + vb[j] * fr[j]) * S.gg[d];
+				}
 			}
 		}
 		kb_bar_group(2, GB);
@@ -715,7 +723,7 @@ __global__ void __launch_bounds__(KB_RV2_NT) kb_reverb_pipe_kernel(const KbFxHdr
 	};
 
 	// ---- prologue: windows of chunks 0 and 1 (both closed before the block), io of chunks 0..3; F(0); LPF(0..2), HPF(0..1); T(0)
-	if (inA) { load_windows(0); if (K > 1) load_windows(1); }
+	if (inL) { load_windows(0); if (K > 1) load_windows(1); }
 	else if (inB) { for (int k = 0; k < 4 && k < K; k++) load_io(k, tb, GB); }
 	__syncthreads();
 	if (warp == 0) { if (tid < 8) filters(0); }
@@ -740,7 +748,8 @@ __global__ void __launch_bounds__(KB_RV2_NT) kb_reverb_pipe_kernel(const KbFxHdr
 				const float refl = (S.r1[k & 1][ta] * cE + S.r2[ta] * cM) + S.r3[ta] * cL;
 				X[k * Lc + ta] = S.xin[k & 7][ta] * dry + refl * wet;           // Reverb.k:272
 			}
-			if (k + 2 < K) load_windows(k + 2);
+		} else if (inL) {
+			if (k + 2 < K) load_windows(k + 2);                 // complete since W(k-1): lag >= 6 Lc + 2
 		} else if (inB) {
 			// the io block of chunk k+4 travels through a register around the taps, so its latency is off this group's path
 			float xpre = 0.f;
