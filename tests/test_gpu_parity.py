@@ -423,7 +423,7 @@ def test_reverb_pipeline_chunk_boundaries(eng, fs):
     against the live oracle; KB_FX_SEQUENTIAL blocks are interleaved so the two schedules hand the state to each other."""
     oracle.port.set_fs(fs)
     inst = 3
-    lens = [1, 2, 7, 8, 9, 45, 46, 47, 49, 50, 51, 60, 69, 70, 74, 75, 76, 80, 81, 91, 92, 93, 99, 100, 101, 138, 139, 149, 150, 151, 160, 161, 225, 226,
+    lens = [1, 2, 7, 8, 9, 43, 44, 45, 46, 47, 48, 49, 50, 51, 87, 88, 89, 95, 96, 97, 143, 144, 145, 60, 69, 70, 74, 75, 76, 80, 81, 91, 92, 93, 99, 100, 101, 138, 139, 149, 150, 151, 160, 161, 225, 226,
             240, 241, 1023, 4096, 333, 5000]
     total = sum(lens)
     x = np.stack([cases.fx_input(2, total, seed=40 + i) for i in range(inst)])
