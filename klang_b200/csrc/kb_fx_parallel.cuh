@@ -455,25 +455,25 @@ __global__ void __launch_bounds__(256) kb_reverb_par_kernel(const KbFxHdr* __res
 // ------------------------------------------------------------------------------ Reverb.k, pipelined schedule (default)
 // Same arithmetic as kb_reverb_par_kernel, but the per-chunk phases no longer wait for each other.  The chunk is a
 // SIXTH of the shortest read-to-write distance (lag >= 6*Lc + 2 ring samples; ~50 frames at 48 kHz), so the ring window
-// of chunk k+2 is complete once chunk k-1 has been written, and the CTA (640 threads) runs as a five-role software
+// of chunk k+2 is complete once chunk k-1 has been written, and the CTA (512 threads) runs as a five-role software
 // pipeline with ONE __syncthreads per chunk.  In iteration k, concurrently:
 //   warp 0, lanes 0..7   F(k+1)  the 8 line filters (Biquad TDF-II, in order) over pre-interpolated inputs: 9 issue slots
 //                                per tick around the 16-cycle recurrence — the role that bounds the kernel (20.4 cycles per
 //                                tick measured alone, tools/micro/serial_floor.cu).  It has SM sub-partition 0 to itself
-//                                (warps 4, 8, 12, 16 stay idle)
+//                                (warps 4, 8, 12 stay idle)
 //   warp 1, lanes 0..1   E       early cascade, the two biquads on two lanes one chunk apart: LPF(k+3), HPF(k+2)
-//   group A1 (6 warps)   W(k)    FDN matrix, ring writes, mid -> late, output mix, thread = (line pair, frame)
+//   group A1 (4 warps)   W(k)    FDN matrix, ring writes, mid -> late, output mix, thread = (line pair, frame)
 //   group A2 (3 warps)   L(k+2)  ring windows of chunk k+2 -> Delay::process interpolation -> shared memory, 12 threads
 //                                per line with a running read position (no modulo)
-//   group B (5 warps)    T(k+1)  early ring write, the 20 early taps as thread = (tap parity, frame) products, then an
+//   group B (4 warps)    T(k+1)  early ring write, the 20 early taps as thread = (tap parity, frame) products, then an
 //                                in-order sum per frame;  io block of chunk k+4 -> shared memory
-#define KB_RV2_LMAX 80
-#define KB_RV2_ROW 180                       // floats per (line, chunk) row: 2*LMAX ticks + read-ahead, 8 lanes on distinct banks
+#define KB_RV2_LMAX 64
+#define KB_RV2_ROW 148                       // floats per (line, chunk) row: 2*LMAX ticks + read-ahead, 8 lanes on distinct banks
 #define KB_RV2_EROW (KB_RV2_LMAX + 16)       // early rows: LMAX frames + read-ahead of the row filter
-#define KB_RV2_NT 640
-#define KB_RV2_GA 192                        // threads of group A1
+#define KB_RV2_NT 512
+#define KB_RV2_GA 128                        // threads of group A1
 #define KB_RV2_GL 96                         // threads of group A2
-#define KB_RV2_GB 160                        // threads of group B
+#define KB_RV2_GB 128                        // threads of group B
 struct KbRv2Smem {
 	float x[2][8][KB_RV2_ROW];               // filter inputs per tick (Delay::process output), double buffered
 	float y[2][8][KB_RV2_ROW];               // filter outputs per tick
@@ -534,6 +534,9 @@ KB_D void kb_rv2_filter_row(const float* xr, float* yr, int ticks, float b0, flo
 	}
 }
 KB_D void kb_bar_group(int id, int threads) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(threads) : "memory"); }
+// pins a per-thread role index in a register: without it ptxas re-derives the index from threadIdx at every use inside the
+// unrolled role bodies (measured: a quarter of all executed instructions)
+KB_D int kb_pin(int x) { asm volatile("" : "+r"(x)); return x; }
 
 __global__ void __launch_bounds__(KB_RV2_NT) kb_reverb_pipe_kernel(const KbFxHdr* __restrict__ hdrs, KbReverb* __restrict__ states, const KbFxPlan* __restrict__ plan,
                                                                    float* __restrict__ rings, float* __restrict__ io, int n, int stride) {
@@ -544,13 +547,14 @@ __global__ void __launch_bounds__(KB_RV2_NT) kb_reverb_pipe_kernel(const KbFxHdr
 	if (pl.mode != KB_PLAN_PARALLEL) return;
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	constexpr int GA = KB_RV2_GA, GL = KB_RV2_GL, GB = KB_RV2_GB;
-	// roles: warp 0 = F, warp 1 = E, warps 4/8/12/16 idle (they share sub-partition 0 with F); the 14 other warps in order:
-	// slots 0..5 = A1 (W), 6..8 = A2 (L), 9..13 = B (T)
-	const int slot = warp - 2 - (warp > 4) - (warp > 8) - (warp > 12) - (warp > 16);
+	// roles: warp 0 = F, warp 1 = E, warps 4/8/12 idle (they share sub-partition 0 with F); the 11 other warps in order:
+	// slots 0..3 = A1 (W), 4..6 = A2 (L), 7..10 = B (T)
+	const int slot = kb_pin(warp - 2 - (warp > 4) - (warp > 8) - (warp > 12));
 	const bool idle = (warp & 3) == 0 && warp >= 4;
 	const bool worker = warp >= 2 && !idle;
-	const bool inA = worker && slot < 6, inL = worker && slot >= 6 && slot < 9, inB = worker && slot >= 9;
-	const int ta = slot * 32 + lane, tl = (slot - 6) * 32 + lane, tb = (slot - 9) * 32 + lane;
+	const int group = kb_pin(!worker ? 0 : slot < 4 ? 1 : slot < 7 ? 2 : 3);
+	const bool inA = group == 1, inL = group == 2, inB = group == 3;
+	const int ta = kb_pin(slot * 32 + lane), tl = kb_pin((slot - 4) * 32 + lane), tb = kb_pin((slot - 7) * 32 + lane);
 	KbReverb& rv = states[inst];
 	const KbControl* c = hdrs[inst].controls;
 	const float dry = c[0].value, wet = side == 0 ? c[4].value : 0.f;        // Reverb.k:272 (Q7): the right wet gain is the literal 0
@@ -601,7 +605,7 @@ __global__ void __launch_bounds__(KB_RV2_NT) kb_reverb_pipe_kernel(const KbFxHdr
 	};
 	// L(k): ring read windows of chunk k, interpolated (Delay::process, klang.h:3461-3473) -> S.x; 12 group-A2 threads per line.
 	// Called for k = 0, 1, 2, ... in order: the read position of the line runs along in a register.
-	const int l_line = tl / 12, l_sub = tl % 12;
+	const int l_line = kb_pin(tl / 12), l_sub = kb_pin(tl % 12);
 	int l_size = 1, l_rbase = 0; float l_frac = 0.f; const float* l_ring = rings;
 	if (inL) { l_size = S.lsize[l_line]; l_rbase = S.rpos0[l_line]; l_frac = S.frac[l_line]; l_ring = rings + S.lring[l_line]; }
 	auto load_windows = [&](int k) {
@@ -626,7 +630,7 @@ __global__ void __launch_bounds__(KB_RV2_NT) kb_reverb_pipe_kernel(const KbFxHdr
 	// W(k): FDN matrix, ring writes and outputs of one LateReflections stage.  Group-A thread = (line pair, frame): thread
 	// (qh, t) owns lines qh and qh + 2 of both stages, with their write positions running along in registers (no modulo);
 	// called for k = 0, 1, 2, ... in order.
-	const int w_qh = ta >= 96 ? 1 : 0, w_t = ta - 96 * w_qh;
+	const int w_qh = kb_pin(ta >= KB_RV2_LMAX ? 1 : 0), w_t = kb_pin(ta - KB_RV2_LMAX * (ta >= KB_RV2_LMAX ? 1 : 0));
 	int w_pos[2][2] = { { 0, 0 }, { 0, 0 } };
 	if (inA) {
 		#pragma unroll
@@ -675,10 +679,10 @@ __global__ void __launch_bounds__(KB_RV2_NT) kb_reverb_pipe_kernel(const KbFxHdr
 			wp += 2 * L; if (wp >= size) wp -= size;
 		}
 	};
-	// T(k): early ring write, tap products thread = (tap parity, frame), then the in-order sum per frame; group B (2 x 80
+	// T(k): early ring write, tap products thread = (tap parity, frame), then the in-order sum per frame; group B (2 x 64
 	// threads).  The tap samples of a chunk are LOADED one iteration before they are used (taps_issue(k+2) follows
 	// taps_finish(k+1)), so the L1 / L2 latency of the 20 gathers sits behind the chunk barrier, not on this group's path.
-	const int e_dg = tb >= KB_RV2_LMAX ? 1 : 0, e_t = tb - KB_RV2_LMAX * e_dg;
+	const int e_dg = kb_pin(tb >= KB_RV2_LMAX ? 1 : 0), e_t = kb_pin(tb - KB_RV2_LMAX * (tb >= KB_RV2_LMAX ? 1 : 0));
 	float e_va[10], e_vb[10], e_fr[10];                                           // this thread's taps e_dg, e_dg+2, .., e_dg+18
 	auto taps_issue = [&](int k) {
 		const int L = chunk_len(k);
