@@ -462,18 +462,21 @@ __global__ void __launch_bounds__(256) kb_reverb_par_kernel(const KbFxHdr* __res
 //                                tick measured alone, tools/micro/serial_floor.cu).  It has SM sub-partition 0 to itself
 //                                (warps 4, 8, 12 stay idle)
 //   warp 1, lanes 0..1   E       early cascade, the two biquads on two lanes one chunk apart: LPF(k+3), HPF(k+2)
-//   group A1 (4 warps)   W(k)    FDN matrix, ring writes, mid -> late, output mix, thread = (line pair, frame)
+//   group A1 (2 warps)   W(k)    FDN matrix, ring writes, mid -> late, output mix, thread = frame
 //   group A2 (3 warps)   L(k+2)  ring windows of chunk k+2 -> Delay::process interpolation -> shared memory, 12 threads
 //                                per line with a running read position (no modulo)
-//   group B (4 warps)    T(k+1)  early ring write, the 20 early taps as thread = (tap parity, frame) products, then an
+//   group B (6 warps)    T(k+1)  early ring write, the 20 early taps as thread = (tap mod 3, frame) products, then an
 //                                in-order sum per frame;  io block of chunk k+4 -> shared memory
 #define KB_RV2_LMAX 64
 #define KB_RV2_ROW 148                       // floats per (line, chunk) row: 2*LMAX ticks + read-ahead, 8 lanes on distinct banks
 #define KB_RV2_EROW (KB_RV2_LMAX + 16)       // early rows: LMAX frames + read-ahead of the row filter
 #define KB_RV2_NT 512
-#define KB_RV2_GA 128                        // threads of group A1
+#define KB_RV2_WS 1                          // W: frames are split over WS thread groups, each owning 4 / WS lines
+#define KB_RV2_TS 3                          // T: taps are split over TS thread groups
+#define KB_RV2_TN ((KB_RV_MAXREFL + KB_RV2_TS - 1) / KB_RV2_TS)   // taps per thread
+#define KB_RV2_GA (KB_RV2_WS * KB_RV2_LMAX)  // threads of group A1
 #define KB_RV2_GL 96                         // threads of group A2
-#define KB_RV2_GB 128                        // threads of group B
+#define KB_RV2_GB (KB_RV2_TS * KB_RV2_LMAX)  // threads of group B
 struct KbRv2Smem {
 	float x[2][8][KB_RV2_ROW];               // filter inputs per tick (Delay::process output), double buffered
 	float y[2][8][KB_RV2_ROW];               // filter outputs per tick
@@ -548,13 +551,13 @@ __global__ void __launch_bounds__(KB_RV2_NT) kb_reverb_pipe_kernel(const KbFxHdr
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	constexpr int GA = KB_RV2_GA, GL = KB_RV2_GL, GB = KB_RV2_GB;
 	// roles: warp 0 = F, warp 1 = E, warps 4/8/12 idle (they share sub-partition 0 with F); the 11 other warps in order:
-	// slots 0..3 = A1 (W), 4..6 = A2 (L), 7..10 = B (T)
+	// slots 0..1 = A1 (W), 2..4 = A2 (L), 5..10 = B (T)
 	const int slot = kb_pin(warp - 2 - (warp > 4) - (warp > 8) - (warp > 12));
 	const bool idle = (warp & 3) == 0 && warp >= 4;
 	const bool worker = warp >= 2 && !idle;
-	const int group = kb_pin(!worker ? 0 : slot < 4 ? 1 : slot < 7 ? 2 : 3);
+	const int group = kb_pin(!worker ? 0 : slot < GA / 32 ? 1 : slot < (GA + GL) / 32 ? 2 : 3);
 	const bool inA = group == 1, inL = group == 2, inB = group == 3;
-	const int ta = kb_pin(slot * 32 + lane), tl = kb_pin((slot - 4) * 32 + lane), tb = kb_pin((slot - 7) * 32 + lane);
+	const int ta = kb_pin(slot * 32 + lane), tl = kb_pin((slot - GA / 32) * 32 + lane), tb = kb_pin((slot - (GA + GL) / 32) * 32 + lane);
 	KbReverb& rv = states[inst];
 	const KbControl* c = hdrs[inst].controls;
 	const float dry = c[0].value, wet = side == 0 ? c[4].value : 0.f;        // Reverb.k:272 (Q7): the right wet gain is the literal 0
@@ -627,17 +630,16 @@ __global__ void __launch_bounds__(KB_RV2_NT) kb_reverb_pipe_kernel(const KbFxHdr
 		}
 		l_rbase += ticks; if (l_rbase >= l_size) l_rbase -= l_size;
 	};
-	// W(k): FDN matrix, ring writes and outputs of one LateReflections stage.  Group-A thread = (line pair, frame): thread
-	// (qh, t) owns lines qh and qh + 2 of both stages, with their write positions running along in registers (no modulo);
+	// W(k): FDN matrix, ring writes and outputs of one LateReflections stage.  Group-A1 thread = (line subset, frame): thread
+	// (qh, t) owns lines qh, qh + WS, .. of both stages, with their write positions running along in registers (no modulo);
 	// called for k = 0, 1, 2, ... in order.
-	const int w_qh = kb_pin(ta >= KB_RV2_LMAX ? 1 : 0), w_t = kb_pin(ta - KB_RV2_LMAX * (ta >= KB_RV2_LMAX ? 1 : 0));
-	int w_pos[2][2] = { { 0, 0 }, { 0, 0 } };
-	if (inA) {
+	constexpr int WS = KB_RV2_WS, WL = 4 / KB_RV2_WS;
+	const int w_qh = kb_pin(ta / KB_RV2_LMAX), w_t = kb_pin(ta % KB_RV2_LMAX);
+	int w_pos[2][WL];
+	#pragma unroll
+	for (int st = 0; st < 2; st++)
 		#pragma unroll
-		for (int st = 0; st < 2; st++)
-			#pragma unroll
-			for (int i = 0; i < 2; i++) w_pos[st][i] = S.wpos0[st * 4 + w_qh + 2 * i];
-	}
+		for (int i = 0; i < WL; i++) w_pos[st][i] = inA ? S.wpos0[st * 4 + w_qh + WS * i] : 0;
 	auto fdn_stage = [&](int k, int stage, int cpar) {
 		const int L = chunk_len(k);
 		const int base = stage * 4, t = w_t;
@@ -658,8 +660,8 @@ __global__ void __launch_bounds__(KB_RV2_NT) kb_reverb_pipe_kernel(const KbFxHdr
 				(stage == 0 ? S.r2 : S.r3)[t] = sum;
 			}
 			#pragma unroll
-			for (int i = 0; i < 2; i++) {
-				const int q = w_qh + 2 * i;
+			for (int i = 0; i < WL; i++) {
+				const int q = w_qh + WS * i;
 				// feedback * delays + in, row q with its literal 0 / +-1 products (Reverb.k:158-163, klang.h:1446-1470)
 				const float fb = (S.M[q][0] * dv[0] + S.M[q][1] * dv[1] + S.M[q][2] * dv[2] + S.M[q][3] * dv[3]) + in;
 				const int size = S.lsize[base + q];
@@ -673,17 +675,18 @@ __global__ void __launch_bounds__(KB_RV2_NT) kb_reverb_pipe_kernel(const KbFxHdr
 			}
 		}
 		#pragma unroll
-		for (int i = 0; i < 2; i++) {
-			const int size = S.lsize[base + w_qh + 2 * i];
+		for (int i = 0; i < WL; i++) {
+			const int size = S.lsize[base + w_qh + WS * i];
 			int& wp = stage == 0 ? w_pos[0][i] : w_pos[1][i];
 			wp += 2 * L; if (wp >= size) wp -= size;
 		}
 	};
-	// T(k): early ring write, tap products thread = (tap parity, frame), then the in-order sum per frame; group B (2 x 64
+	// T(k): early ring write, tap products thread = (tap mod TS, frame), then the in-order sum per frame; group B (TS x 64
 	// threads).  The tap samples of a chunk are LOADED one iteration before they are used (taps_issue(k+2) follows
 	// taps_finish(k+1)), so the L1 / L2 latency of the 20 gathers sits behind the chunk barrier, not on this group's path.
-	const int e_dg = kb_pin(tb >= KB_RV2_LMAX ? 1 : 0), e_t = kb_pin(tb - KB_RV2_LMAX * (tb >= KB_RV2_LMAX ? 1 : 0));
-	float e_va[10], e_vb[10], e_fr[10];                                           // this thread's taps e_dg, e_dg+2, .., e_dg+18
+	constexpr int TS = KB_RV2_TS, TN = KB_RV2_TN;
+	const int e_dg = kb_pin(tb / KB_RV2_LMAX), e_t = kb_pin(tb % KB_RV2_LMAX);
+	float e_va[TN], e_vb[TN], e_fr[TN];                                           // this thread's taps e_dg, e_dg + TS, ..
 	auto taps_issue = [&](int k) {
 		const int L = chunk_len(k);
 		const int ebase = (int)(((unsigned)epos0 + (unsigned)(k * Lc)) % (unsigned)esize);
@@ -693,8 +696,8 @@ __global__ void __launch_bounds__(KB_RV2_NT) kb_reverb_pipe_kernel(const KbFxHdr
 			const float posf = (float)(pos - 1);
 			// (taps never reach into chunks k-2 .. k: Lc <= (shortest tap - 3) / 3, so the early ring writes of those chunks do not matter)
 			#pragma unroll
-			for (int j = 0; j < 10; j++) {
-				const int d = e_dg + 2 * j;
+			for (int j = 0; j < TN; j++) {
+				const int d = e_dg + TS * j;
 				if (d < count) {
 					float read = posf - S.times[d]; if (read < 0.f) read += esize;           // Stereo::Delay::tap(float)  klang.h:4668-4681
 					const float fl = floorf(read); e_fr[j] = read - fl;
@@ -710,8 +713,8 @@ __global__ void __launch_bounds__(KB_RV2_NT) kb_reverb_pipe_kernel(const KbFxHdr
 		if (e_t < L) {
 			if (e_dg == 0) { int idx = ebase + e_t; if (idx >= esize) idx -= esize; ringe[idx] = S.xf[k & 1][e_t]; }
 			#pragma unroll
-			for (int j = 0; j < 10; j++) {
-				const int d = e_dg + 2 * j;
+			for (int j = 0; j < TN; j++) {
+				const int d = e_dg + TS * j;
 				if (d < count) S.tp[d][e_t] = (e_va[j] * (1.f - e_fr[j]) + e_vb[j] * e_fr[j]) * S.gg[d];
 			}
 		}
