@@ -467,15 +467,15 @@ __global__ void __launch_bounds__(256) kb_reverb_par_kernel(const KbFxHdr* __res
 //                                per line with a running read position (no modulo)
 //   group B (6 warps)    T(k+1)  early ring write, the 20 early taps as thread = (tap mod 3, frame) products, then an
 //                                in-order sum per frame;  io block of chunk k+4 -> shared memory
-#define KB_RV2_LMAX 64
-#define KB_RV2_ROW 148                       // floats per (line, chunk) row: 2*LMAX ticks + read-ahead, 8 lanes on distinct banks
+#define KB_RV2_LMAX 48
+#define KB_RV2_ROW 116                       // floats per (line, chunk) row: 2*LMAX ticks + read-ahead, 8 lanes on distinct banks
 #define KB_RV2_EROW (KB_RV2_LMAX + 16)       // early rows: LMAX frames + read-ahead of the row filter
-#define KB_RV2_NT 512
-#define KB_RV2_WS 1                          // W: frames are split over WS thread groups, each owning 4 / WS lines
-#define KB_RV2_TS 3                          // T: taps are split over TS thread groups
+#define KB_RV2_NT 608
+#define KB_RV2_WS 2                          // W: frames are split over WS thread groups, each owning 4 / WS lines
+#define KB_RV2_TS 4                          // T: taps are split over TS thread groups
 #define KB_RV2_TN ((KB_RV_MAXREFL + KB_RV2_TS - 1) / KB_RV2_TS)   // taps per thread
 #define KB_RV2_GA (KB_RV2_WS * KB_RV2_LMAX)  // threads of group A1
-#define KB_RV2_GL 96                         // threads of group A2
+#define KB_RV2_GL 128                        // threads of group A2: 16 per line
 #define KB_RV2_GB (KB_RV2_TS * KB_RV2_LMAX)  // threads of group B
 struct KbRv2Smem {
 	float x[2][8][KB_RV2_ROW];               // filter inputs per tick (Delay::process output), double buffered
@@ -552,7 +552,7 @@ __global__ void __launch_bounds__(KB_RV2_NT) kb_reverb_pipe_kernel(const KbFxHdr
 	constexpr int GA = KB_RV2_GA, GL = KB_RV2_GL, GB = KB_RV2_GB;
 	// roles: warp 0 = F, warp 1 = E, warps 4/8/12 idle (they share sub-partition 0 with F); the 11 other warps in order:
 	// slots 0..1 = A1 (W), 2..4 = A2 (L), 5..10 = B (T)
-	const int slot = kb_pin(warp - 2 - (warp > 4) - (warp > 8) - (warp > 12));
+	const int slot = kb_pin(warp - 2 - (warp > 4) - (warp > 8) - (warp > 12) - (warp > 16));
 	const bool idle = (warp & 3) == 0 && warp >= 4;
 	const bool worker = warp >= 2 && !idle;
 	const int group = kb_pin(!worker ? 0 : slot < GA / 32 ? 1 : slot < (GA + GL) / 32 ? 2 : 3);
@@ -608,17 +608,17 @@ __global__ void __launch_bounds__(KB_RV2_NT) kb_reverb_pipe_kernel(const KbFxHdr
 	};
 	// L(k): ring read windows of chunk k, interpolated (Delay::process, klang.h:3461-3473) -> S.x; 12 group-A2 threads per line.
 	// Called for k = 0, 1, 2, ... in order: the read position of the line runs along in a register.
-	const int l_line = kb_pin(tl / 12), l_sub = kb_pin(tl % 12);
+	const int l_line = kb_pin(tl / 16), l_sub = kb_pin(tl % 16);
 	int l_size = 1, l_rbase = 0; float l_frac = 0.f; const float* l_ring = rings;
 	if (inL) { l_size = S.lsize[l_line]; l_rbase = S.rpos0[l_line]; l_frac = S.frac[l_line]; l_ring = rings + S.lring[l_line]; }
 	auto load_windows = [&](int k) {
 		const int ticks = 2 * chunk_len(k);
 		float* xrow = S.x[k & 1][l_line];
-		for (int tk0 = l_sub; tk0 < ticks; tk0 += 12 * 7) {      // seven ticks (14 loads) in flight per thread
-			float va[7], vb[7];
+		for (int tk0 = l_sub; tk0 < ticks; tk0 += 16 * 6) {      // 2 * LMAX / 16 = six ticks (12 loads) in flight per thread: one batch
+			float va[6], vb[6];
 			#pragma unroll
-			for (int j = 0; j < 7; j++) {
-				const int tk = tk0 + 12 * j;
+			for (int j = 0; j < 6; j++) {
+				const int tk = tk0 + 16 * j;
 				if (tk < ticks) {
 					int i0 = l_rbase + tk; if (i0 >= l_size) i0 -= l_size;
 					int i1 = i0 + 1; if (i1 >= l_size) i1 -= l_size;
@@ -626,7 +626,7 @@ __global__ void __launch_bounds__(KB_RV2_NT) kb_reverb_pipe_kernel(const KbFxHdr
 				}
 			}
 			#pragma unroll
-			for (int j = 0; j < 7; j++) { const int tk = tk0 + 12 * j; if (tk < ticks) xrow[tk] = va[j] + l_frac * (vb[j] - va[j]); }
+			for (int j = 0; j < 6; j++) { const int tk = tk0 + 16 * j; if (tk < ticks) xrow[tk] = va[j] + l_frac * (vb[j] - va[j]); }
 		}
 		l_rbase += ticks; if (l_rbase >= l_size) l_rbase -= l_size;
 	};
