@@ -541,6 +541,9 @@ KB_D void kb_bar_group(int id, int threads) { asm volatile("bar.sync %0, %1;" ::
 // unrolled role bodies (measured: a quarter of all executed instructions)
 KB_D int kb_pin(int x) { asm volatile("" : "+r"(x)); return x; }
 
+// diagnostics (KB_RV_TRACE=1): CTA 0 records when each role reaches the chunk barrier and prints the table when it is done
+__device__ int kb_rv_trace_on = 0;
+#define KB_RV_TRACE_MAX 96
 __global__ void __launch_bounds__(KB_RV2_NT) kb_reverb_pipe_kernel(const KbFxHdr* __restrict__ hdrs, KbReverb* __restrict__ states, const KbFxPlan* __restrict__ plan,
                                                                    float* __restrict__ rings, float* __restrict__ io, int n, int stride) {
 	extern __shared__ __align__(16) unsigned char kb_rv_smem_raw[];
@@ -687,37 +690,39 @@ __global__ void __launch_bounds__(KB_RV2_NT) kb_reverb_pipe_kernel(const KbFxHdr
 	constexpr int TS = KB_RV2_TS, TN = KB_RV2_TN;
 	const int e_dg = kb_pin(tb / KB_RV2_LMAX), e_t = kb_pin(tb % KB_RV2_LMAX);
 	float e_va[TN], e_vb[TN], e_fr[TN];                                           // this thread's taps e_dg, e_dg + TS, ..
+	float e_time[TN], e_gain[TN];                                                 // their times and gains, and how many exist
+	#pragma unroll
+	for (int j = 0; j < TN; j++) { const int d = min(e_dg + TS * j, KB_RV_MAXREFL - 1); e_time[j] = inB ? S.times[d] : 0.f; e_gain[j] = inB ? S.gg[d] : 0.f; }
+	const int e_n = kb_pin(inB ? max(0, (count - e_dg + TS - 1) / TS) : 0);
+	int e_issue_base = epos0, e_finish_base = epos0;                              // early write position of the chunk each lambda sees next (called for k = 0, 1, 2, ..)
 	auto taps_issue = [&](int k) {
 		const int L = chunk_len(k);
-		const int ebase = (int)(((unsigned)epos0 + (unsigned)(k * Lc)) % (unsigned)esize);
 		if (e_t < L) {
-			int idx = ebase + e_t; if (idx >= esize) idx -= esize;
+			int idx = e_issue_base + e_t; if (idx >= esize) idx -= esize;
 			int pos = idx + 1; if (pos >= esize) pos -= esize;                    // position after this frame's write
 			const float posf = (float)(pos - 1);
 			// (taps never reach into chunks k-2 .. k: Lc <= (shortest tap - 3) / 3, so the early ring writes of those chunks do not matter)
 			#pragma unroll
 			for (int j = 0; j < TN; j++) {
-				const int d = e_dg + TS * j;
-				if (d < count) {
-					float read = posf - S.times[d]; if (read < 0.f) read += esize;           // Stereo::Delay::tap(float)  klang.h:4668-4681
+				if (j < e_n) {
+					float read = posf - e_time[j]; if (read < 0.f) read += esize;            // Stereo::Delay::tap(float)  klang.h:4668-4681
 					const float fl = floorf(read); e_fr[j] = read - fl;
 					const int ii = (int)read, jj = (ii == esize - 1) ? 0 : ii + 1;
 					e_va[j] = ringe[ii]; e_vb[j] = ringe[jj];
 				}
 			}
 		}
+		e_issue_base += L; if (e_issue_base >= esize) e_issue_base -= esize;
 	};
 	auto taps_finish = [&](int k) {
 		const int L = chunk_len(k);
-		const int ebase = (int)(((unsigned)epos0 + (unsigned)(k * Lc)) % (unsigned)esize);
 		if (e_t < L) {
-			if (e_dg == 0) { int idx = ebase + e_t; if (idx >= esize) idx -= esize; ringe[idx] = S.xf[k & 1][e_t]; }
+			if (e_dg == 0) { int idx = e_finish_base + e_t; if (idx >= esize) idx -= esize; ringe[idx] = S.xf[k & 1][e_t]; }
 			#pragma unroll
-			for (int j = 0; j < TN; j++) {
-				const int d = e_dg + TS * j;
-				if (d < count) S.tp[d][e_t] = (e_va[j] * (1.f - e_fr[j]) + e_vb[j] * e_fr[j]) * S.gg[d];
-			}
+			for (int j = 0; j < TN; j++)
+				if (j < e_n) S.tp[e_dg + TS * j][e_t] = (e_va[j] * (1.f - e_fr[j]) + e_vb[j] * e_fr[j]) * e_gain[j];
 		}
+		e_finish_base += L; if (e_finish_base >= esize) e_finish_base -= esize;
 		kb_bar_group(2, GB);
 		if (tb < L) {
 			float p[KB_RV_MAXREFL];
@@ -744,6 +749,9 @@ __global__ void __launch_bounds__(KB_RV2_NT) kb_reverb_pipe_kernel(const KbFxHdr
 	if (inB) { taps_issue(0); taps_finish(0); if (K > 1) taps_issue(1); }
 	__syncthreads();
 
+	__shared__ int s_trace[6][KB_RV_TRACE_MAX];
+	const bool trace = kb_rv_trace_on != 0 && blockIdx.x == 0;
+	const long long t_start = clock64();
 	int cpar = 0;
 	for (int k = 0; k < K; k++, cpar ^= 1) {
 		if (warp == 0) {
@@ -771,7 +779,20 @@ __global__ void __launch_bounds__(KB_RV2_NT) kb_reverb_pipe_kernel(const KbFxHdr
 			if (k + 2 < K) taps_issue(k + 2);
 			if (pre) S.xin[(k + 4) & 7][tb] = xpre;
 		}
+		if (trace && lane == 0 && k < KB_RV_TRACE_MAX) {
+			const int role = warp == 0 ? 0 : warp == 1 ? 1 : (inA && ta < 32) ? 2 : (inL && tl < 32) ? 3 : (inB && tb < 32) ? 4 : -1;
+			if (role >= 0) s_trace[role][k] = (int)(clock64() - t_start);
+		}
 		__syncthreads();
+		if (trace && tid == 0 && k < KB_RV_TRACE_MAX) s_trace[5][k] = (int)(clock64() - t_start);
+	}
+	if (trace) {
+		__syncthreads();
+		if (tid == 0) {
+			printf("reverb pipe trace (CTA 0): Lc %d, K %d; cycles since start when F / E / W / L / T reached the chunk barrier, and when it opened\n", Lc, K);
+			for (int k = 0; k < K && k < KB_RV_TRACE_MAX; k++)
+				printf("  k %3d  F %7d  E %7d  W %7d  L %7d  T %7d  open %7d\n", k, s_trace[0][k], s_trace[1][k], s_trace[2][k], s_trace[3][k], s_trace[4][k], s_trace[5][k]);
+		}
 	}
 	// state back
 	if (tid < 8) {
