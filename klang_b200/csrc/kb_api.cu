@@ -270,8 +270,6 @@ extern "C" int kb_fx_bank_process(kb_fx_bank* b, float* io, int n, unsigned flag
 					kb_reverb_plan_kernel<<<ib, 32, 0, b->stream>>>(st, b->d_plan, b->instances);
 					kb_reverb_par_kernel<<<b->instances * 2, 256, sizeof(KbRvSmem), b->stream>>>(b->d_hdr, st, b->d_plan, b->d_rings, d + o, len, n);
 				} else {
-					static const int rv_trace = getenv("KB_RV_TRACE") ? atoi(getenv("KB_RV_TRACE")) : 0;
-					if (rv_trace) { static bool set = false; if (!set) { cudaMemcpyToSymbol(kb_rv_trace_on, &rv_trace, sizeof(int)); set = true; } }
 					kb_reverb_plan2_kernel<<<ib, 32, 0, b->stream>>>(st, b->d_plan, b->instances);
 					kb_reverb_pipe_kernel<<<b->instances * 2, KB_RV2_NT, sizeof(KbRv2Smem), b->stream>>>(b->d_hdr, st, b->d_plan, b->d_rings, d + o, len, n);
 				}

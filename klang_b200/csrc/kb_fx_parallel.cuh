@@ -454,29 +454,24 @@ __global__ void __launch_bounds__(256) kb_reverb_par_kernel(const KbFxHdr* __res
 
 // ------------------------------------------------------------------------------ Reverb.k, pipelined schedule (default)
 // Same arithmetic as kb_reverb_par_kernel, but the per-chunk phases no longer wait for each other.  The chunk is a
-// SIXTH of the shortest read-to-write distance (lag >= 6*Lc + 2 ring samples; ~50 frames at 48 kHz), so the ring window
-// of chunk k+2 is complete once chunk k-1 has been written, and the CTA (512 threads) runs as a five-role software
-// pipeline with ONE __syncthreads per chunk.  In iteration k, concurrently:
+// QUARTER of the shortest read-to-write distance (lag >= 4*Lc + 2 ring samples; ~75 frames at 48 kHz), so the ring window
+// of chunk k+2 is complete once chunk k has been written, and the CTA (512 threads) runs as a four-role software pipeline
+// with ONE __syncthreads per chunk.  In iteration k:
 //   warp 0, lanes 0..7   F(k+1)  the 8 line filters (Biquad TDF-II, in order) over pre-interpolated inputs: 9 issue slots
-//                                per tick around the 16-cycle recurrence — the role that bounds the kernel (20.4 cycles per
-//                                tick measured alone, tools/micro/serial_floor.cu).  It has SM sub-partition 0 to itself
-//                                (warps 4, 8, 12 stay idle)
+//                                per tick around the 16-cycle recurrence — the role that bounds the kernel.  It has SM
+//                                sub-partition 0 to itself (warps 4, 8, 12 stay idle)
 //   warp 1, lanes 0..1   E       early cascade, the two biquads on two lanes one chunk apart: LPF(k+3), HPF(k+2)
-//   group A1 (2 warps)   W(k)    FDN matrix, ring writes, mid -> late, output mix, thread = frame
-//   group A2 (3 warps)   L(k+2)  ring windows of chunk k+2 -> Delay::process interpolation -> shared memory, 12 threads
+//   group A (6 warps)    W(k)    FDN matrix, ring writes, mid -> late, output mix, thread = (frame, line);  then L(k+2):
+//                                ring windows of chunk k+2 -> Delay::process interpolation -> shared memory, 24 threads
 //                                per line with a running read position (no modulo)
-//   group B (6 warps)    T(k+1)  early ring write, the 20 early taps as thread = (tap mod 3, frame) products, then an
-//                                in-order sum per frame;  io block of chunk k+4 -> shared memory
-#define KB_RV2_LMAX 48
-#define KB_RV2_ROW 116                       // floats per (line, chunk) row: 2*LMAX ticks + read-ahead, 8 lanes on distinct banks
+//   group B (5 warps)    T(k+1)  early ring write, the 20 early taps as thread = (frame, tap) products, then an in-order
+//                                sum per frame;  io block of chunk k+4 -> shared memory
+#define KB_RV2_LMAX 80
+#define KB_RV2_ROW 180                       // floats per (line, chunk) row: 2*LMAX ticks + read-ahead, 8 lanes on distinct banks
 #define KB_RV2_EROW (KB_RV2_LMAX + 16)       // early rows: LMAX frames + read-ahead of the row filter
-#define KB_RV2_NT 608
-#define KB_RV2_WS 2                          // W: frames are split over WS thread groups, each owning 4 / WS lines
-#define KB_RV2_TS 4                          // T: taps are split over TS thread groups
-#define KB_RV2_TN ((KB_RV_MAXREFL + KB_RV2_TS - 1) / KB_RV2_TS)   // taps per thread
-#define KB_RV2_GA (KB_RV2_WS * KB_RV2_LMAX)  // threads of group A1
-#define KB_RV2_GL 128                        // threads of group A2: 16 per line
-#define KB_RV2_GB (KB_RV2_TS * KB_RV2_LMAX)  // threads of group B
+#define KB_RV2_NT 512
+#define KB_RV2_GA 192                        // threads of group A
+#define KB_RV2_GB 160                        // threads of group B
 struct KbRv2Smem {
 	float x[2][8][KB_RV2_ROW];               // filter inputs per tick (Delay::process output), double buffered
 	float y[2][8][KB_RV2_ROW];               // filter outputs per tick
@@ -498,12 +493,11 @@ __global__ void kb_reverb_plan2_kernel(const KbReverb* __restrict__ states, KbFx
 	for (int line = 0; line < 16; line++) {
 		const KbDelay& d = kb_rv_line(rv, line).delay;
 		int lag = d.position - d.last_position; if (lag <= 0) lag += d.SIZE;    // write head minus read head, in ring samples
-		chunk = min(chunk, (lag - 2) / 6);                                      // two ticks per frame, window of chunk k+2 closed by chunk k-1
+		chunk = min(chunk, (lag - 2) / 4);                                      // two ticks per frame, window of chunk k+2 closed by chunk k
 	}
 	float tmin = 1e30f;
 	for (int r = 0; r < rv.count; r++) tmin = fminf(tmin, rv.times[r]);
-	chunk = min(chunk, ((int)tmin - 3) / 3);                                    // the early taps of chunk k+2 are gathered while chunk k is written
-	chunk &= ~3;                                                                // 2 * chunk ticks = whole groups of 8 for the row filter
+	chunk = min(chunk, (int)tmin - 3);
 	KbFxPlan p;
 	p.chunk = chunk; p.mode = chunk >= 8 ? KB_PLAN_PARALLEL : KB_PLAN_SEQUENTIAL;
 	p.gain = p.delay = p.dry = 0.f;
@@ -537,13 +531,7 @@ KB_D void kb_rv2_filter_row(const float* xr, float* yr, int ticks, float b0, flo
 	}
 }
 KB_D void kb_bar_group(int id, int threads) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(threads) : "memory"); }
-// pins a per-thread role index in a register: without it ptxas re-derives the index from threadIdx at every use inside the
-// unrolled role bodies (measured: a quarter of all executed instructions)
-KB_D int kb_pin(int x) { asm volatile("" : "+r"(x)); return x; }
 
-// diagnostics (KB_RV_TRACE=1): CTA 0 records when each role reaches the chunk barrier and prints the table when it is done
-__device__ int kb_rv_trace_on = 0;
-#define KB_RV_TRACE_MAX 96
 __global__ void __launch_bounds__(KB_RV2_NT) kb_reverb_pipe_kernel(const KbFxHdr* __restrict__ hdrs, KbReverb* __restrict__ states, const KbFxPlan* __restrict__ plan,
                                                                    float* __restrict__ rings, float* __restrict__ io, int n, int stride) {
 	extern __shared__ __align__(16) unsigned char kb_rv_smem_raw[];
@@ -552,15 +540,12 @@ __global__ void __launch_bounds__(KB_RV2_NT) kb_reverb_pipe_kernel(const KbFxHdr
 	const KbFxPlan pl = plan[inst];
 	if (pl.mode != KB_PLAN_PARALLEL) return;
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	constexpr int GA = KB_RV2_GA, GL = KB_RV2_GL, GB = KB_RV2_GB;
-	// roles: warp 0 = F, warp 1 = E, warps 4/8/12 idle (they share sub-partition 0 with F); the 11 other warps in order:
-	// slots 0..1 = A1 (W), 2..4 = A2 (L), 5..10 = B (T)
-	const int slot = kb_pin(warp - 2 - (warp > 4) - (warp > 8) - (warp > 12) - (warp > 16));
-	const bool idle = (warp & 3) == 0 && warp >= 4;
-	const bool worker = warp >= 2 && !idle;
-	const int group = kb_pin(!worker ? 0 : slot < GA / 32 ? 1 : slot < (GA + GL) / 32 ? 2 : 3);
-	const bool inA = group == 1, inL = group == 2, inB = group == 3;
-	const int ta = kb_pin(slot * 32 + lane), tl = kb_pin((slot - GA / 32) * 32 + lane), tb = kb_pin((slot - (GA + GL) / 32) * 32 + lane);
+	constexpr int GA = KB_RV2_GA, GB = KB_RV2_GB;
+	// roles: warp 0 = F, warp 1 = E, warps 4/8/12 idle (they share sub-partition 0 with F), A = warps 2,3,5,6,7,9, B = warps 10,11,13,14,15
+	const int slot = warp - 2 - (warp > 4) - (warp > 8) - (warp > 12);      // 0..10 over the 11 worker warps
+	const bool idle = warp == 4 || warp == 8 || warp == 12;
+	const bool inA = warp >= 2 && !idle && slot < 6, inB = warp >= 2 && !idle && slot >= 6;
+	const int ta = slot * 32 + lane, tb = (slot - 6) * 32 + lane;
 	KbReverb& rv = states[inst];
 	const KbControl* c = hdrs[inst].controls;
 	const float dry = c[0].value, wet = side == 0 ? c[4].value : 0.f;        // Reverb.k:272 (Q7): the right wet gain is the literal 0
@@ -609,19 +594,19 @@ __global__ void __launch_bounds__(KB_RV2_NT) kb_reverb_pipe_kernel(const KbFxHdr
 	auto filters = [&](int k) {
 		kb_rv2_filter_row(S.x[k & 1][tid], S.y[k & 1][tid], 2 * chunk_len(k), b0, b1, b2, a1, a2, z0, z1);
 	};
-	// L(k): ring read windows of chunk k, interpolated (Delay::process, klang.h:3461-3473) -> S.x; 12 group-A2 threads per line.
+	// L(k): ring read windows of chunk k, interpolated (Delay::process, klang.h:3461-3473) -> S.x; 24 group-A threads per line.
 	// Called for k = 0, 1, 2, ... in order: the read position of the line runs along in a register.
-	const int l_line = kb_pin(tl / 16), l_sub = kb_pin(tl % 16);
+	const int l_line = ta / 24, l_sub = ta % 24;
 	int l_size = 1, l_rbase = 0; float l_frac = 0.f; const float* l_ring = rings;
-	if (inL) { l_size = S.lsize[l_line]; l_rbase = S.rpos0[l_line]; l_frac = S.frac[l_line]; l_ring = rings + S.lring[l_line]; }
+	if (inA) { l_size = S.lsize[l_line]; l_rbase = S.rpos0[l_line]; l_frac = S.frac[l_line]; l_ring = rings + S.lring[l_line]; }
 	auto load_windows = [&](int k) {
 		const int ticks = 2 * chunk_len(k);
 		float* xrow = S.x[k & 1][l_line];
-		for (int tk0 = l_sub; tk0 < ticks; tk0 += 16 * 6) {      // 2 * LMAX / 16 = six ticks (12 loads) in flight per thread: one batch
-			float va[6], vb[6];
+		for (int tk0 = l_sub; tk0 < ticks; tk0 += 96) {
+			float va[4], vb[4];
 			#pragma unroll
-			for (int j = 0; j < 6; j++) {
-				const int tk = tk0 + 16 * j;
+			for (int j = 0; j < 4; j++) {
+				const int tk = tk0 + 24 * j;
 				if (tk < ticks) {
 					int i0 = l_rbase + tk; if (i0 >= l_size) i0 -= l_size;
 					int i1 = i0 + 1; if (i1 >= l_size) i1 -= l_size;
@@ -629,20 +614,21 @@ __global__ void __launch_bounds__(KB_RV2_NT) kb_reverb_pipe_kernel(const KbFxHdr
 				}
 			}
 			#pragma unroll
-			for (int j = 0; j < 6; j++) { const int tk = tk0 + 16 * j; if (tk < ticks) xrow[tk] = va[j] + l_frac * (vb[j] - va[j]); }
+			for (int j = 0; j < 4; j++) { const int tk = tk0 + 24 * j; if (tk < ticks) xrow[tk] = va[j] + l_frac * (vb[j] - va[j]); }
 		}
 		l_rbase += ticks; if (l_rbase >= l_size) l_rbase -= l_size;
 	};
-	// W(k): FDN matrix, ring writes and outputs of one LateReflections stage.  Group-A1 thread = (line subset, frame): thread
-	// (qh, t) owns lines qh, qh + WS, .. of both stages, with their write positions running along in registers (no modulo);
+	// W(k): FDN matrix, ring writes and outputs of one LateReflections stage.  Group-A thread = (line pair, frame): thread
+	// (qh, t) owns lines qh and qh + 2 of both stages, with their write positions running along in registers (no modulo);
 	// called for k = 0, 1, 2, ... in order.
-	constexpr int WS = KB_RV2_WS, WL = 4 / KB_RV2_WS;
-	const int w_qh = kb_pin(ta / KB_RV2_LMAX), w_t = kb_pin(ta % KB_RV2_LMAX);
-	int w_pos[2][WL];
-	#pragma unroll
-	for (int st = 0; st < 2; st++)
+	const int w_qh = ta >= 96 ? 1 : 0, w_t = ta - 96 * w_qh;
+	int w_pos[2][2] = { { 0, 0 }, { 0, 0 } };
+	if (inA) {
 		#pragma unroll
-		for (int i = 0; i < WL; i++) w_pos[st][i] = inA ? S.wpos0[st * 4 + w_qh + WS * i] : 0;
+		for (int st = 0; st < 2; st++)
+			#pragma unroll
+			for (int i = 0; i < 2; i++) w_pos[st][i] = S.wpos0[st * 4 + w_qh + 2 * i];
+	}
 	auto fdn_stage = [&](int k, int stage, int cpar) {
 		const int L = chunk_len(k);
 		const int base = stage * 4, t = w_t;
@@ -663,8 +649,8 @@ __global__ void __launch_bounds__(KB_RV2_NT) kb_reverb_pipe_kernel(const KbFxHdr
 				(stage == 0 ? S.r2 : S.r3)[t] = sum;
 			}
 			#pragma unroll
-			for (int i = 0; i < WL; i++) {
-				const int q = w_qh + WS * i;
+			for (int i = 0; i < 2; i++) {
+				const int q = w_qh + 2 * i;
 				// feedback * delays + in, row q with its literal 0 / +-1 products (Reverb.k:158-163, klang.h:1446-1470)
 				const float fb = (S.M[q][0] * dv[0] + S.M[q][1] * dv[1] + S.M[q][2] * dv[2] + S.M[q][3] * dv[3]) + in;
 				const int size = S.lsize[base + q];
@@ -678,59 +664,48 @@ __global__ void __launch_bounds__(KB_RV2_NT) kb_reverb_pipe_kernel(const KbFxHdr
 			}
 		}
 		#pragma unroll
-		for (int i = 0; i < WL; i++) {
-			const int size = S.lsize[base + w_qh + WS * i];
+		for (int i = 0; i < 2; i++) {
+			const int size = S.lsize[base + w_qh + 2 * i];
 			int& wp = stage == 0 ? w_pos[0][i] : w_pos[1][i];
 			wp += 2 * L; if (wp >= size) wp -= size;
 		}
 	};
-	// T(k): early ring write, tap products thread = (tap mod TS, frame), then the in-order sum per frame; group B (TS x 64
-	// threads).  The tap samples of a chunk are LOADED one iteration before they are used (taps_issue(k+2) follows
-	// taps_finish(k+1)), so the L1 / L2 latency of the 20 gathers sits behind the chunk barrier, not on this group's path.
-	constexpr int TS = KB_RV2_TS, TN = KB_RV2_TN;
-	const int e_dg = kb_pin(tb / KB_RV2_LMAX), e_t = kb_pin(tb % KB_RV2_LMAX);
-	float e_va[TN], e_vb[TN], e_fr[TN];                                           // this thread's taps e_dg, e_dg + TS, ..
-	float e_time[TN], e_gain[TN];                                                 // their times and gains, and how many exist
-	#pragma unroll
-	for (int j = 0; j < TN; j++) { const int d = min(e_dg + TS * j, KB_RV_MAXREFL - 1); e_time[j] = inB ? S.times[d] : 0.f; e_gain[j] = inB ? S.gg[d] : 0.f; }
-	const int e_n = kb_pin(inB ? max(0, (count - e_dg + TS - 1) / TS) : 0);
-	int e_issue_base = epos0, e_finish_base = epos0;                              // early write position of the chunk each lambda sees next (called for k = 0, 1, 2, ..)
-	auto taps_issue = [&](int k) {
+	// T(k): early ring write, tap products thread = (tap parity, frame) with five taps in flight, then the in-order sum per
+	// frame; group B (2 x 80 threads)
+	const int e_dg = tb >= KB_RV2_LMAX ? 1 : 0, e_t = tb - KB_RV2_LMAX * e_dg;
+	auto early_taps = [&](int k) {
 		const int L = chunk_len(k);
-		if (e_t < L) {
-			int idx = e_issue_base + e_t; if (idx >= esize) idx -= esize;
+		const int ebase = (int)(((unsigned)epos0 + (unsigned)(k * Lc)) % (unsigned)esize);
+		const int t = e_t;
+		if (t < L) {
+			int idx = ebase + t; if (idx >= esize) idx -= esize;
+			if (e_dg == 0) ringe[idx] = S.xf[k & 1][t];
+			// (taps never reach into this chunk: Lc <= shortest tap - 3, so no barrier between the write and the reads)
 			int pos = idx + 1; if (pos >= esize) pos -= esize;                    // position after this frame's write
 			const float posf = (float)(pos - 1);
-			// (taps never reach into chunks k-2 .. k: Lc <= (shortest tap - 3) / 3, so the early ring writes of those chunks do not matter)
-			#pragma unroll
-			for (int j = 0; j < TN; j++) {
-				if (j < e_n) {
-					float read = posf - e_time[j]; if (read < 0.f) read += esize;            // Stereo::Delay::tap(float)  klang.h:4668-4681
-					const float fl = floorf(read); e_fr[j] = read - fl;
-					const int ii = (int)read, jj = (ii == esize - 1) ? 0 : ii + 1;
-					e_va[j] = ringe[ii]; e_vb[j] = ringe[jj];
+			for (int d0 = e_dg; d0 < count; d0 += 10) {                           // taps d0, d0+2, .., d0+8
+				float va[5], vb[5], fr[5];
+				#pragma unroll
+				for (int j = 0; j < 5; j++) {
+					const int d = d0 + 2 * j;
+					if (d < count) {
+						float read = posf - S.times[d]; if (read < 0.f) read += esize;       // Stereo::Delay::tap(float)  klang.h:4668-4681
+						const float fl = floorf(read); fr[j] = read - fl;
+						const int ii = (int)read, jj = (ii == esize - 1) ? 0 : ii + 1;
+						va[j] = ringe[ii]; vb[j] = ringe[jj];
+					}
+				}
+				#pragma unroll
+				for (int j = 0; j < 5; j++) {
+					const int d = d0 + 2 * j;
+					if (d < count) S.tp[d][t] = (va[j] * (1.f - fr[j]) + vb[j] * fr[j]) * S.gg[d];
 				}
 			}
 		}
-		e_issue_base += L; if (e_issue_base >= esize) e_issue_base -= esize;
-	};
-	auto taps_finish = [&](int k) {
-		const int L = chunk_len(k);
-		if (e_t < L) {
-			if (e_dg == 0) { int idx = e_finish_base + e_t; if (idx >= esize) idx -= esize; ringe[idx] = S.xf[k & 1][e_t]; }
-			#pragma unroll
-			for (int j = 0; j < TN; j++)
-				if (j < e_n) S.tp[e_dg + TS * j][e_t] = (e_va[j] * (1.f - e_fr[j]) + e_vb[j] * e_fr[j]) * e_gain[j];
-		}
-		e_finish_base += L; if (e_finish_base >= esize) e_finish_base -= esize;
 		kb_bar_group(2, GB);
 		if (tb < L) {
-			float p[KB_RV_MAXREFL];
-			#pragma unroll
-			for (int d = 0; d < KB_RV_MAXREFL; d++) p[d] = d < count ? S.tp[d][tb] : 0.f;
 			float acc = 0.f;
-			#pragma unroll
-			for (int d = 0; d < KB_RV_MAXREFL; d++) if (d < count) acc += p[d];          // r1 += tap * gain, in tap order  Reverb.k:89-90
+			for (int d = 0; d < count; d++) acc += S.tp[d][tb];                       // r1 += tap * gain, in tap order  Reverb.k:89-90
 			S.r1[k & 1][tb] = acc;
 		}
 	};
@@ -740,18 +715,15 @@ __global__ void __launch_bounds__(KB_RV2_NT) kb_reverb_pipe_kernel(const KbFxHdr
 	};
 
 	// ---- prologue: windows of chunks 0 and 1 (both closed before the block), io of chunks 0..3; F(0); LPF(0..2), HPF(0..1); T(0)
-	if (inL) { load_windows(0); if (K > 1) load_windows(1); }
+	if (inA) { load_windows(0); if (K > 1) load_windows(1); }
 	else if (inB) { for (int k = 0; k < 4 && k < K; k++) load_io(k, tb, GB); }
 	__syncthreads();
 	if (warp == 0) { if (tid < 8) filters(0); }
 	else if (warp == 1) { early_cascade(0); early_cascade(1); early_cascade(2); }
 	__syncthreads();
-	if (inB) { taps_issue(0); taps_finish(0); if (K > 1) taps_issue(1); }
+	if (inB) early_taps(0);
 	__syncthreads();
 
-	__shared__ int s_trace[6][KB_RV_TRACE_MAX];
-	const bool trace = kb_rv_trace_on != 0 && blockIdx.x == 0;
-	const long long t_start = clock64();
 	int cpar = 0;
 	for (int k = 0; k < K; k++, cpar ^= 1) {
 		if (warp == 0) {
@@ -768,31 +740,12 @@ __global__ void __launch_bounds__(KB_RV2_NT) kb_reverb_pipe_kernel(const KbFxHdr
 				const float refl = (S.r1[k & 1][ta] * cE + S.r2[ta] * cM) + S.r3[ta] * cL;
 				X[k * Lc + ta] = S.xin[k & 7][ta] * dry + refl * wet;           // Reverb.k:272
 			}
-		} else if (inL) {
-			if (k + 2 < K) load_windows(k + 2);                 // complete since W(k-1): lag >= 6 Lc + 2
+			if (k + 2 < K) load_windows(k + 2);
 		} else if (inB) {
-			// the io block of chunk k+4 travels through a register around the taps, so its latency is off this group's path
-			float xpre = 0.f;
-			const bool pre = k + 4 < K && tb < chunk_len(k + 4);
-			if (pre) xpre = X[(k + 4) * Lc + tb];
-			if (k + 1 < K) taps_finish(k + 1);
-			if (k + 2 < K) taps_issue(k + 2);
-			if (pre) S.xin[(k + 4) & 7][tb] = xpre;
-		}
-		if (trace && lane == 0 && k < KB_RV_TRACE_MAX) {
-			const int role = warp == 0 ? 0 : warp == 1 ? 1 : (inA && ta < 32) ? 2 : (inL && tl < 32) ? 3 : (inB && tb < 32) ? 4 : -1;
-			if (role >= 0) s_trace[role][k] = (int)(clock64() - t_start);
+			if (k + 1 < K) early_taps(k + 1);
+			if (k + 4 < K) load_io(k + 4, tb, GB);
 		}
 		__syncthreads();
-		if (trace && tid == 0 && k < KB_RV_TRACE_MAX) s_trace[5][k] = (int)(clock64() - t_start);
-	}
-	if (trace) {
-		__syncthreads();
-		if (tid == 0) {
-			printf("reverb pipe trace (CTA 0): Lc %d, K %d; cycles since start when F / E / W / L / T reached the chunk barrier, and when it opened\n", Lc, K);
-			for (int k = 0; k < K && k < KB_RV_TRACE_MAX; k++)
-				printf("  k %3d  F %7d  E %7d  W %7d  L %7d  T %7d  open %7d\n", k, s_trace[0][k], s_trace[1][k], s_trace[2][k], s_trace[3][k], s_trace[4][k], s_trace[5][k]);
-		}
 	}
 	// state back
 	if (tid < 8) {
