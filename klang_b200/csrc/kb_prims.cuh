@@ -442,16 +442,28 @@ KB_HD void kb_envr_run(const KbFs& fs, KbEnvR& e, const float* px, const float* 
 				const float r_hi = (is_ramp && up) ? e.r_target : inf, r_lo = (is_ramp && !up) ? e.r_target : -inf;
 				const float t_hi = is_wait ? px[e.point + 1] : inf;
 				float r = e.r_out, time = e.time, last = e.out;
-				do {
-					// the partial sums are formed exactly as four single ticks would form them; r and time only move one way,
-					// so "the 4th has not crossed / arrived" implies none has
+				// the partial sums are formed exactly as single ticks would form them; r and time only move one way, so "the last
+				// of the group has not crossed / arrived" implies none has.  Groups of 16 first (the exit test and its branch cost
+				// as much as a dozen dependent adds), then groups of 4 up to the mode change.
+				while (t + 16 <= steps) {
+					float rr[17], tt = time;
+					rr[0] = r;
+					#pragma unroll
+					for (int j = 0; j < 16; j++) { rr[j + 1] = rr[j] + srate; tt = tt + tinc; }
+					const bool stay = (rr[16] < r_hi) & (rr[16] > r_lo) & (tt < t_hi);
+					if (!stay) break;
+					#pragma unroll
+					for (int j = 0; j < 16; j++) row[t + j] = rr[j];
+					last = rr[15]; r = rr[16]; time = tt; t += 16;
+				}
+				while (t + 4 <= steps) {
 					const float r1 = r + srate, r2 = r1 + srate, r3 = r2 + srate, r4 = r3 + srate;
 					const float t1 = time + tinc, t2 = t1 + tinc, t3 = t2 + tinc, t4 = t3 + tinc;
 					const bool stay = (r4 < r_hi) & (r4 > r_lo) & (t4 < t_hi);
 					if (!stay) break;
 					row[t] = r; row[t + 1] = r1; row[t + 2] = r2; row[t + 3] = r3;
 					last = r3; r = r4; time = t4; t += 4;
-				} while (t + 4 <= steps);
+				}
 				e.r_out = r; e.time = time; e.out = last;
 				if (t >= steps) break;
 			}

@@ -56,9 +56,9 @@ template <int G> struct KbTileRows4 { float4 r[G][KB_TILE_T + 1]; };   // lane=v
 template <int G> struct KbTileRows2 { float2 r[G][KB_TILE_T + 1]; };
 template <int G> struct KbSubSmem {
 	KbTileCommon<G> c;
-	KbTileRows4<G> coef[2];          // B -> C: (b0, b1, a1, a2) of every sample, one 128-bit load per step
-	KbTileRows2<G> xa[2];            // B -> C: (oscillator sample, adsr level)
-	KbTileRows<G> cut[2], amp[2], out[2];
+	KbTileRows4<G> coef[2];          // B -> C: (b0*in, b1*in, a1, a2) of every sample: one 128-bit load per step is all C reads
+	KbTileRows<G> cut[2], amp[4], out[2];   // A -> B cutoff; A -> D adsr level (three ticks later); C -> D filter output
+	float4 lastc[G];                 // (b0, b1, a1, a2) of the block's last sample, for the state write-back
 	KbOsm osc[G];
 };
 // LAYOUT 0: the serial roles are warps 0, 1, 2 (one per SM sub-partition, each sharing its issue slots with worker warps).
@@ -68,7 +68,7 @@ template <int LAYOUT> KB_D int kb_tile_role(int warp) { return LAYOUT == 0 ? (wa
 template <int LAYOUT> KB_D bool kb_tile_is_worker(int warp) { return LAYOUT == 0 ? warp >= 3 : (warp & 3) != 0; }
 template <int LAYOUT> KB_D int kb_tile_worker_tid(int warp, int lane) { return LAYOUT == 0 ? (warp - 3) * 32 + lane : ((warp >> 2) * 3 + (warp & 3) - 1) * 32 + lane; }
 template <int G, int NT, int LAYOUT = 0>
-__global__ void __launch_bounds__(NT) kb_sub_tiled_kernel(KbSubVoice* __restrict__ voices, KbVoiceHdr* __restrict__ hdr,
+__global__ void __launch_bounds__(NT, 1) kb_sub_tiled_kernel(KbSubVoice* __restrict__ voices, KbVoiceHdr* __restrict__ hdr,
                                                                         float* __restrict__ dst, int n, int total, KbFs fs) {
 	constexpr int T = KB_TILE_T;
 	extern __shared__ __align__(16) unsigned char kb_smem[];
@@ -85,10 +85,10 @@ __global__ void __launch_bounds__(NT) kb_sub_tiled_kernel(KbSubVoice* __restrict
 	const bool is_env = role == 0 && role_ok, is_adsr = role == 1 && role_ok, is_flt = role == 2 && role_ok;
 	const int slot = (role < 0 ? 0 : role) * G + lane;                // breakpoint slot of the A lanes
 	KbEnvR env;
-	float z0 = 0.f, z1 = 0.f, lb0 = 1.f, lb1 = 0.f, la1 = 0.f, la2 = 0.f;
+	float z0 = 0.f, z1 = 0.f;
 	if (is_env) kb_tile_load_env(S.c, slot, voices[v0 + role_voice].env, env);
 	if (is_adsr) kb_tile_load_env(S.c, slot, voices[v0 + role_voice].adsr, env);
-	if (is_flt) { const KbBiquad& b = voices[v0 + role_voice].filter; z0 = b.z0; z1 = b.z1; lb0 = b.b0; lb1 = b.b1; la1 = b.a1; la2 = b.a2; }
+	if (is_flt) { const KbBiquad& b = voices[v0 + role_voice].filter; z0 = b.z0; z1 = b.z1; }
 	if (first_worker && lane < G && S.c.active[lane]) S.osc[lane] = voices[v0 + lane].osc;
 	__syncthreads();
 
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(NT) kb_sub_tiled_kernel(KbSubVoice* __restrict
 		if (role == 0 || role == 1) {                                    // ---- A, tile k
 			if ((is_env || is_adsr) && k < ntiles) {
 				const int steps = min(T, n - k * T);
-				float* row = is_env ? S.cut[k & 1].r[role_voice] : S.amp[k & 1].r[role_voice];
+				float* row = is_env ? S.cut[k & 1].r[role_voice] : S.amp[k & 3].r[role_voice];
 				kb_envr_run(fs, env, S.c.px[slot], S.c.py[slot], row, steps);
 			}
 		} else if (role == 2) {                                          // ---- C, tile k-2
@@ -107,38 +107,35 @@ __global__ void __launch_bounds__(NT) kb_sub_tiled_kernel(KbSubVoice* __restrict
 			if (is_flt && c >= 0 && c < ntiles) {
 				const int steps = min(T, n - c * T), v = role_voice;
 				const float4* pc = S.coef[c & 1].r[v];
-				const float2* pxa = S.xa[c & 1].r[v];
 				float* po = S.out[c & 1].r[v];
-				// groups of 4 steps; the operands of the NEXT group are loaded before the current group's dependent updates, so no
-				// shared-memory latency sits on the recurrence (reads past `steps` stay inside the shared-memory struct and are unused)
-				float4 cf[4]; float2 xa[4];
+				// Filter::process (klang.h:5605-5612) with the input products b0*in, b1*in (b2 = b0) formed by B: per step one 128-bit
+				// load, the four dependent operations of the recurrence, two independent ones and a store.  Groups of 4 steps; the
+				// operands of the NEXT group are loaded before the current group's updates, so no shared-memory latency sits on
+				// the recurrence (reads past `steps` stay inside the shared-memory struct and are unused)
+				float4 cf[4];
 				#pragma unroll
-				for (int j = 0; j < 4; j++) { cf[j] = pc[j]; xa[j] = pxa[j]; }
+				for (int j = 0; j < 4; j++) cf[j] = pc[j];
 				int t = 0;
 				for (; t + 4 <= steps; t += 4) {
-					float4 cn[4]; float2 xn[4];
+					float4 cn[4];
 					#pragma unroll
-					for (int j = 0; j < 4; j++) { cn[j] = pc[t + 4 + j]; xn[j] = pxa[t + 4 + j]; }
+					for (int j = 0; j < 4; j++) cn[j] = pc[t + 4 + j];
 					#pragma unroll
 					for (int j = 0; j < 4; j++) {
-						lb0 = cf[j].x; lb1 = cf[j].y; la1 = cf[j].z; la2 = cf[j].w;
-						const float in = xa[j].x;
-						const float y = lb0 * in + z0;
-						z0 = lb1 * in - la1 * y + z1;
-						z1 = lb0 * in - la2 * y;
-						po[t + j] = y * xa[j].y;                             // out *= adsr++   Filter.k:33
+						const float y = cf[j].x + z0;                        // y = b0*in + z0
+						z0 = cf[j].y - cf[j].z * y + z1;                     // z0 = b1*in - a1*y + z1
+						z1 = cf[j].x - cf[j].w * y;                          // z1 = b2*in - a2*y   (LPF: b2 == b0)
+						po[t + j] = y;
 					}
 					#pragma unroll
-					for (int j = 0; j < 4; j++) { cf[j] = cn[j]; xa[j] = xn[j]; }
+					for (int j = 0; j < 4; j++) cf[j] = cn[j];
 				}
 				#pragma unroll
 				for (int j = 0; j < 3; j++) if (t + j < steps) {
-					lb0 = cf[j].x; lb1 = cf[j].y; la1 = cf[j].z; la2 = cf[j].w;
-					const float in = xa[j].x;
-					const float y = lb0 * in + z0;
-					z0 = lb1 * in - la1 * y + z1;
-					z1 = lb0 * in - la2 * y;
-					po[t + j] = y * xa[j].y;
+					const float y = cf[j].x + z0;
+					z0 = cf[j].y - cf[j].z * y + z1;
+					z1 = cf[j].x - cf[j].w * y;
+					po[t + j] = y;
 				}
 			}
 		} else if (worker) {
@@ -159,8 +156,10 @@ __global__ void __launch_bounds__(NT) kb_sub_tiled_kernel(KbSubVoice* __restrict
 						cf.w = inv * (1.f - a);
 						cf.x = inv * (1.f - cos0) * 0.5f;
 						cf.y = inv * (1.f - cos0);
+						if (b * T + t == n - 1) S.lastc[v] = cf;
+						const float in = kb_osm_at(S.osc[v], (uint32_t)(b * T + t));
+						cf.x = cf.x * in; cf.y = cf.y * in;                  // the input products of Filter::process
 						S.coef[b & 1].r[v][t] = cf;
-						S.xa[b & 1].r[v][t] = make_float2(kb_osm_at(S.osc[v], (uint32_t)(b * T + t)), S.amp[b & 1].r[v][t]);
 					}
 				}
 			}
@@ -168,7 +167,8 @@ __global__ void __launch_bounds__(NT) kb_sub_tiled_kernel(KbSubVoice* __restrict
 				const int steps = min(T, n - d * T);
 				for (int item = wtid; item < G * T; item += wthreads) {
 					const int v = item / T, t = item % T;
-					if (t < steps && v0 + v < total) dst[(size_t)(v0 + v) * n + d * T + t] = S.c.active[v] ? S.out[d & 1].r[v][t] : 0.f;
+					if (t < steps && v0 + v < total)                             // out *= adsr++   Filter.k:33
+						dst[(size_t)(v0 + v) * n + d * T + t] = S.c.active[v] ? S.out[d & 1].r[v][t] * S.amp[d & 3].r[v][t] : 0.f;
 				}
 			}
 		}
@@ -183,7 +183,8 @@ __global__ void __launch_bounds__(NT) kb_sub_tiled_kernel(KbSubVoice* __restrict
 	}
 	if (is_flt) {
 		KbBiquad& b = voices[v0 + role_voice].filter;
-		b.z0 = z0; b.z1 = z1; b.b0 = lb0; b.b2 = lb0; b.b1 = lb1; b.a1 = la1; b.a2 = la2;
+		const float4 lc = S.lastc[role_voice];
+		b.z0 = z0; b.z1 = z1; b.b0 = lc.x; b.b2 = lc.x; b.b1 = lc.y; b.a1 = lc.z; b.a2 = lc.w;
 	}
 	if (first_worker && lane < G && S.c.active[lane]) {
 		KbOsm o = S.osc[lane];
@@ -202,7 +203,7 @@ template <int G> struct KbSsawSmem {
 	KbOsm osc[G][7];
 };
 template <int G, int NT>
-__global__ void __launch_bounds__(NT) kb_ssaw_tiled_kernel(KbSsawVoice* __restrict__ voices, KbVoiceHdr* __restrict__ hdr,
+__global__ void __launch_bounds__(NT, 1) kb_ssaw_tiled_kernel(KbSsawVoice* __restrict__ voices, KbVoiceHdr* __restrict__ hdr,
                                                                          float* __restrict__ dst, int n, int total, KbFs fs) {
 	constexpr int T = KB_TILE_T;
 	extern __shared__ __align__(16) unsigned char kb_smem[];
@@ -272,7 +273,7 @@ template <int G> struct KbTbSmem {
 	float vf[G], last_out[G];
 };
 template <int G, int NT>
-__global__ void __launch_bounds__(NT) kb_tb_tiled_kernel(KbTbVoice* __restrict__ voices, KbVoiceHdr* __restrict__ hdr,
+__global__ void __launch_bounds__(NT, 1) kb_tb_tiled_kernel(KbTbVoice* __restrict__ voices, KbVoiceHdr* __restrict__ hdr,
                                                                        const KbSynthBlock* __restrict__ blk, float* __restrict__ dst,
                                                                        int n, int voices_per_inst, int total, KbFs fs) {
 	constexpr int T = KB_TILE_T;

@@ -1,0 +1,25 @@
+#!/bin/bash
+TAG=${1:-r1m}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+export PYTHONUNBUFFERED=1
+echo "== micro"; timeout 60 tools/micro/serial_floor 2>&1 | tee $OUT/micro.txt
+echo "== tests"; timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -15 | tee $OUT/pytest_gpu.txt
+echo "== probes"
+{
+for cfg in "0 512 8" "0 544 7" "1 768 8" "1 768 7"; do
+  set -- $cfg
+  echo "layout $1 nt $2 g $3"
+  KB_TILE_LAYOUT=$1 KB_TILE_NT=$2 KB_TILE_G=$3 timeout 120 python tools/c2_probe.py sub
+  KB_TILE_LAYOUT=$1 KB_TILE_NT=$2 KB_TILE_G=$3 timeout 300 python bench.py --steps 20 --warmup 3 --no-extras --no-cpu | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); r=d['roofline']
+print('  bench: value %.3e e2e %.3e ms_per_step %.4f kernel_ms %.4f' % (d['value'], d['e2e']['value'], d['ms_per_step'], r['kernel_ms']))"
+done
+timeout 120 python tools/c2_probe.py tb
+timeout 120 python tools/c2_probe.py ssaw
+timeout 120 python tools/fx_probe.py reverb 4096
+} 2>&1 | grep -v "^$" | tee $OUT/probes.txt
+echo "== ncu full"
+KB_TILE_LAYOUT=0 KB_TILE_G=7 timeout 300 ncu --set full --clock-control none --import-source on -k regex:kb_sub_tiled -s 3 -c 1 -o $OUT/prof_sub_g7 -f python bench.py --steps 2 --warmup 3 --no-extras --no-cpu > $OUT/ncu_sub.log 2>&1
+ls -la $OUT
