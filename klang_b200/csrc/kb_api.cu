@@ -702,7 +702,8 @@ extern "C" int kb_synth_bank_process(kb_synth_bank* b, float* out, int n, unsign
 					else if (g >= 8) { if (force_nt == 608) KB_LAUNCH_SUB(8, 608, 0); else KB_LAUNCH_SUB(8, 512, 0); }
 					else if (g == 7) KB_LAUNCH_SUB(7, 544, 0);
 					else KB_LAUNCH_SUB(4, 320, 0);
-				} else if (g >= 16) KB_LAUNCH_SUB(16, 1024, 1);
+				} else if (layout == 2 && g < 16) KB_LAUNCH_SUB(8, 768, 2);
+				else if (g >= 16) KB_LAUNCH_SUB(16, 1024, 1);
 				else if (g == 7) { if (force_nt == 512) KB_LAUNCH_SUB(7, 512, 1); else if (force_nt == 1024) KB_LAUNCH_SUB(7, 1024, 1); else KB_LAUNCH_SUB(7, 768, 1); }
 				else { if (force_nt == 512) KB_LAUNCH_SUB(8, 512, 1); else if (force_nt == 1024) KB_LAUNCH_SUB(8, 1024, 1); else KB_LAUNCH_SUB(8, 768, 1); }
 #undef KB_LAUNCH_SUB
