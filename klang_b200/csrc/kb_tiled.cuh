@@ -65,13 +65,14 @@ template <int G> struct KbSubSmem {
 // LAYOUT 1: the serial roles are warps 0, 4, 8 — all on sub-partition 0 (warp id mod 4), whose other warps stay idle.
 // LAYOUT 2 (NT = 768): the filter recurrence (C, warp 0) has sub-partition 0 to itself (warps 4, 8, .. idle): its 16-cycle
 //           dependent chain is what bounds the kernel and every issue slot it loses to another warp stretches it (measured:
-//           20 cycles per sample alone, 40 when sharing).  The two envelope warps (1 and 5) share sub-partition 1 with four
+//           20 cycles per sample alone, 40 when sharing).  Warp 1 runs BOTH envelopes (cutoff envelope on lanes 0..G-1, ADSR on
+//           lanes G..2G-1: the run loop is one instruction stream for every envelope mode) and shares sub-partition 1 with four
 //           worker warps; sub-partitions 2 and 3 hold six worker warps each: 16 worker warps = 512 threads = exactly two
 //           rounds over an 8-voice x 128-sample tile.
 template <int LAYOUT> KB_D int kb_tile_role(int warp) {
 	if (LAYOUT == 0) return warp < 3 ? warp : -1;
 	if (LAYOUT == 1) return ((warp & 3) == 0 && warp < 12) ? warp >> 2 : -1;
-	return warp == 0 ? 2 : warp == 1 ? 0 : warp == 5 ? 1 : -1;
+	return warp == 0 ? 2 : warp == 1 ? 0 : -1;                              // (one warp runs both envelopes: lanes 0..G-1 and G..2G-1)
 }
 template <int LAYOUT> KB_D bool kb_tile_is_worker(int warp) {
 	if (LAYOUT == 0) return warp >= 3;
@@ -94,13 +95,15 @@ __global__ void __launch_bounds__(NT, 1) kb_sub_tiled_kernel(KbSubVoice* __restr
 	const int v0 = blockIdx.x * G;
 	kb_tile_prologue(S.c, voices, hdr, v0, total);
 
-	const int role_voice = lane;
-	const bool role_ok = lane < G && S.c.active[lane < G ? lane : 0];
 	const int role = kb_tile_role<LAYOUT>(warp);                      // 0 = A (cutoff envelope), 1 = A (ADSR), 2 = C (filter), -1 = worker / idle
+	constexpr bool MERGED_A = LAYOUT == 2 && 2 * G <= 32;             // role 0 runs both envelopes of a voice on lanes v and G + v
+	const int a_sub = (MERGED_A && role == 0 && lane >= G) ? 1 : 0;
+	const int role_voice = lane - a_sub * G;
+	const bool role_ok = role_voice < G && S.c.active[role_voice < G ? role_voice : 0];
 	const bool worker = kb_tile_is_worker<LAYOUT>(warp);
 	const bool first_worker = worker && kb_tile_worker_tid<LAYOUT>(warp, lane) < 32;
-	const bool is_env = role == 0 && role_ok, is_adsr = role == 1 && role_ok, is_flt = role == 2 && role_ok;
-	const int slot = (role < 0 ? 0 : role) * G + lane;                // breakpoint slot of the A lanes
+	const bool is_env = role == 0 && a_sub == 0 && role_ok, is_adsr = (role == 1 || a_sub == 1) && role_ok, is_flt = role == 2 && role_ok;
+	const int slot = (is_adsr ? G : 0) + role_voice;                  // breakpoint slot of the A lanes
 	KbEnvR env;
 	float z0 = 0.f, z1 = 0.f;
 	if (is_env) kb_tile_load_env(S.c, slot, voices[v0 + role_voice].env, env);
@@ -130,14 +133,14 @@ __global__ void __launch_bounds__(NT, 1) kb_sub_tiled_kernel(KbSubVoice* __restr
 				// load, the four dependent operations of the recurrence, two independent ones and a store.  Groups of 4 steps; the
 				// operands of the NEXT group are loaded before the current group's updates, so no shared-memory latency sits on
 				// the recurrence (reads past `steps` stay inside the shared-memory struct and are unused)
-				float4 cf[4];
+				float4 cf[4], c1[4];                                 // operands of the current group and of the next one
 				#pragma unroll
-				for (int j = 0; j < 4; j++) cf[j] = pc[j];
+				for (int j = 0; j < 4; j++) { cf[j] = pc[j]; c1[j] = pc[4 + j]; }
 				int t = 0;
 				for (; t + 4 <= steps; t += 4) {
-					float4 cn[4];
+					float4 c2[4];                                        // two groups ahead: ~130 cycles of cover for the shared-memory latency
 					#pragma unroll
-					for (int j = 0; j < 4; j++) cn[j] = pc[t + 4 + j];
+					for (int j = 0; j < 4; j++) c2[j] = pc[t + 8 + j];
 					#pragma unroll
 					for (int j = 0; j < 4; j++) {
 						const float y = cf[j].x + z0;                        // y = b0*in + z0
@@ -146,7 +149,7 @@ __global__ void __launch_bounds__(NT, 1) kb_sub_tiled_kernel(KbSubVoice* __restr
 						po[t + j] = y;
 					}
 					#pragma unroll
-					for (int j = 0; j < 4; j++) cf[j] = cn[j];
+					for (int j = 0; j < 4; j++) { cf[j] = c1[j]; c1[j] = c2[j]; }
 				}
 				#pragma unroll
 				for (int j = 0; j < 3; j++) if (t + j < steps) {
