@@ -133,14 +133,14 @@ __global__ void __launch_bounds__(NT, 1) kb_sub_tiled_kernel(KbSubVoice* __restr
 				// load, the four dependent operations of the recurrence, two independent ones and a store.  Groups of 4 steps; the
 				// operands of the NEXT group are loaded before the current group's updates, so no shared-memory latency sits on
 				// the recurrence (reads past `steps` stay inside the shared-memory struct and are unused)
-				float4 cf[4], c1[4];                                 // operands of the current group and of the next one
+				float4 cf[4];
 				#pragma unroll
-				for (int j = 0; j < 4; j++) { cf[j] = pc[j]; c1[j] = pc[4 + j]; }
+				for (int j = 0; j < 4; j++) cf[j] = pc[j];
 				int t = 0;
 				for (; t + 4 <= steps; t += 4) {
-					float4 c2[4];                                        // two groups ahead: ~130 cycles of cover for the shared-memory latency
+					float4 cn[4];
 					#pragma unroll
-					for (int j = 0; j < 4; j++) c2[j] = pc[t + 8 + j];
+					for (int j = 0; j < 4; j++) cn[j] = pc[t + 4 + j];
 					#pragma unroll
 					for (int j = 0; j < 4; j++) {
 						const float y = cf[j].x + z0;                        // y = b0*in + z0
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(NT, 1) kb_sub_tiled_kernel(KbSubVoice* __restr
 						po[t + j] = y;
 					}
 					#pragma unroll
-					for (int j = 0; j < 4; j++) { cf[j] = c1[j]; c1[j] = c2[j]; }
+					for (int j = 0; j < 4; j++) cf[j] = cn[j];
 				}
 				#pragma unroll
 				for (int j = 0; j < 3; j++) if (t + j < steps) {
