@@ -686,26 +686,20 @@ extern "C" int kb_synth_bank_process(kb_synth_bank* b, float* out, int n, unsign
 	} while (0)
 			if (sub) {
 				KbSubVoice* vs = (KbSubVoice*)b->d_vstate;
-				// KB_TILE_LAYOUT: 0 = serial roles spread over the sub-partitions, 1 = serial roles alone on sub-partition 0 (kb_tiled.cuh);
-				// KB_TILE_NT: threads per CTA of the layout-1 kernels (512 / 768 / 1024)
-				static const int layout = getenv("KB_TILE_LAYOUT") ? atoi(getenv("KB_TILE_LAYOUT")) : 1;
-				static const int force_nt = getenv("KB_TILE_NT") ? atoi(getenv("KB_TILE_NT")) : 0;
+				// KB_TILE_LAYOUT (A/B measurement, same results): 2 = default for 800..1599 voices, the filter warp alone on its SM
+				// sub-partition and both envelopes in one warp (kb_tiled.cuh); 0 = serial roles spread over the sub-partitions
+				static const int layout = getenv("KB_TILE_LAYOUT") ? atoi(getenv("KB_TILE_LAYOUT")) : 2;
 #define KB_LAUNCH_SUB(GG, NT, LAY)                                                                                                    \
 	do {                                                                                                                             \
 		static bool attr_set = false;                                                                                                \
 		if (!attr_set) { cudaFuncSetAttribute(kb_sub_tiled_kernel<GG, NT, LAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KbSubSmem<GG>)); attr_set = true; } \
 		kb_sub_tiled_kernel<GG, NT, LAY><<<(total + GG - 1) / GG, NT, sizeof(KbSubSmem<GG>), st>>>(vs, b->d_hdr, d_voice_dst, n, total, b->fs); \
 	} while (0)
-				if (layout == 0 || g < 7) {
-					// worker threads = NT - 96: 512 (NT 608) and 448 (G 7, NT 544) cover a G x 128 tile in exactly two rounds
-					if (g >= 16) KB_LAUNCH_SUB(16, 1024, 0);
-					else if (g >= 8) { if (force_nt == 608) KB_LAUNCH_SUB(8, 608, 0); else KB_LAUNCH_SUB(8, 512, 0); }
-					else if (g == 7) KB_LAUNCH_SUB(7, 544, 0);
-					else KB_LAUNCH_SUB(4, 320, 0);
-				} else if (layout == 2 && g < 16) KB_LAUNCH_SUB(8, 768, 2);
-				else if (g >= 16) KB_LAUNCH_SUB(16, 1024, 1);
-				else if (g == 7) { if (force_nt == 512) KB_LAUNCH_SUB(7, 512, 1); else if (force_nt == 1024) KB_LAUNCH_SUB(7, 1024, 1); else KB_LAUNCH_SUB(7, 768, 1); }
-				else { if (force_nt == 512) KB_LAUNCH_SUB(8, 512, 1); else if (force_nt == 1024) KB_LAUNCH_SUB(8, 1024, 1); else KB_LAUNCH_SUB(8, 768, 1); }
+				if (g >= 16) KB_LAUNCH_SUB(16, 1024, 0);
+				else if (g >= 7 && layout == 2) KB_LAUNCH_SUB(8, 768, 2);
+				else if (g >= 8) KB_LAUNCH_SUB(8, 512, 0);
+				else if (g == 7) KB_LAUNCH_SUB(7, 544, 0);               // 448 worker threads cover a 7 x 128 tile in exactly two rounds
+				else KB_LAUNCH_SUB(4, 320, 0);
 #undef KB_LAUNCH_SUB
 			} else if (b->graph == KB_SY_SUPERSAW) {
 				KbSsawVoice* vs = (KbSsawVoice*)b->d_vstate;

@@ -62,26 +62,22 @@ template <int G> struct KbSubSmem {
 	KbOsm osc[G];
 };
 // LAYOUT 0: the serial roles are warps 0, 1, 2 (one per SM sub-partition, each sharing its issue slots with worker warps).
-// LAYOUT 1: the serial roles are warps 0, 4, 8 — all on sub-partition 0 (warp id mod 4), whose other warps stay idle.
-// LAYOUT 2 (NT = 768): the filter recurrence (C, warp 0) has sub-partition 0 to itself (warps 4, 8, .. idle): its 16-cycle
-//           dependent chain is what bounds the kernel and every issue slot it loses to another warp stretches it (measured:
-//           20 cycles per sample alone, 40 when sharing).  Warp 1 runs BOTH envelopes (cutoff envelope on lanes 0..G-1, ADSR on
-//           lanes G..2G-1: the run loop is one instruction stream for every envelope mode) and shares sub-partition 1 with four
-//           worker warps; sub-partitions 2 and 3 hold six worker warps each: 16 worker warps = 512 threads = exactly two
-//           rounds over an 8-voice x 128-sample tile.
+// LAYOUT 2 (NT = 768): the filter recurrence (C, warp 0) has sub-partition 0 (warp id mod 4) to itself — warps 4, 8, .. stay
+//           idle: its 16-cycle dependent chain is what bounds the kernel and every issue slot it loses to another warp
+//           stretches it (measured: ~20 cycles per sample alone, ~40 when sharing).  Warp 1 runs BOTH envelopes (cutoff
+//           envelope on lanes 0..G-1, ADSR on lanes G..2G-1: the run loop is one instruction stream for every envelope mode)
+//           and shares sub-partition 1 with four worker warps; sub-partitions 2 and 3 hold six worker warps each: 16 worker
+//           warps = 512 threads = exactly two rounds over an 8-voice x 128-sample tile.
 template <int LAYOUT> KB_D int kb_tile_role(int warp) {
 	if (LAYOUT == 0) return warp < 3 ? warp : -1;
-	if (LAYOUT == 1) return ((warp & 3) == 0 && warp < 12) ? warp >> 2 : -1;
-	return warp == 0 ? 2 : warp == 1 ? 0 : -1;                              // (one warp runs both envelopes: lanes 0..G-1 and G..2G-1)
+	return warp == 0 ? 2 : warp == 1 ? 0 : -1;
 }
 template <int LAYOUT> KB_D bool kb_tile_is_worker(int warp) {
 	if (LAYOUT == 0) return warp >= 3;
-	if (LAYOUT == 1) return (warp & 3) != 0;
 	return (warp & 3) >= 2 || ((warp & 3) == 1 && warp >= 9);
 }
 template <int LAYOUT> KB_D int kb_tile_worker_tid(int warp, int lane) {
 	if (LAYOUT == 0) return (warp - 3) * 32 + lane;
-	if (LAYOUT == 1) return ((warp >> 2) * 3 + (warp & 3) - 1) * 32 + lane;
 	const int sp = warp & 3, row = warp >> 2;
 	return (sp == 1 ? row - 2 : sp == 2 ? 4 + row : 10 + row) * 32 + lane;
 }
@@ -114,7 +110,7 @@ __global__ void __launch_bounds__(NT, 1) kb_sub_tiled_kernel(KbSubVoice* __restr
 
 	const int ntiles = (n + T - 1) / T;
 	const int wtid = kb_tile_worker_tid<LAYOUT>(warp, lane);         // the B/D worker threads
-	constexpr int wthreads = LAYOUT == 0 ? NT - 96 : LAYOUT == 1 ? NT / 128 * 96 : 512;
+	constexpr int wthreads = LAYOUT == 0 ? NT - 96 : 512;
 	static_assert(LAYOUT != 2 || NT == 768, "layout 2 is laid out for 24 warps");
 	for (int k = 0; k < ntiles + 3; k++) {
 		if (role == 0 || role == 1) {                                    // ---- A, tile k
