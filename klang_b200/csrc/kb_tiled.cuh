@@ -76,11 +76,13 @@ template <int LAYOUT> KB_D bool kb_tile_is_worker(int warp) {
 	if (LAYOUT == 0) return warp >= 3;
 	return (warp & 3) >= 2 || ((warp & 3) == 1 && warp >= 9);
 }
-template <int LAYOUT> KB_D int kb_tile_worker_tid(int warp, int lane) {
+template <int LAYOUT, int NT> KB_D int kb_tile_worker_tid(int warp, int lane) {
 	if (LAYOUT == 0) return (warp - 3) * 32 + lane;
+	constexpr int R = NT / 128;                                       // warps per sub-partition
 	const int sp = warp & 3, row = warp >> 2;
-	return (sp == 1 ? row - 2 : sp == 2 ? 4 + row : 10 + row) * 32 + lane;
+	return (sp == 1 ? row - 2 : sp == 2 ? (R - 2) + row : (2 * R - 2) + row) * 32 + lane;
 }
+template <int LAYOUT, int NT> constexpr int kb_tile_worker_threads_v = LAYOUT == 0 ? NT - 96 : (3 * (NT / 128) - 2) * 32;
 template <int G, int NT, int LAYOUT = 0>
 __global__ void __launch_bounds__(NT, 1) kb_sub_tiled_kernel(KbSubVoice* __restrict__ voices, KbVoiceHdr* __restrict__ hdr,
                                                                         float* __restrict__ dst, int n, int total, KbFs fs) {
@@ -97,7 +99,7 @@ __global__ void __launch_bounds__(NT, 1) kb_sub_tiled_kernel(KbSubVoice* __restr
 	const int role_voice = lane - a_sub * G;
 	const bool role_ok = role_voice < G && S.c.active[role_voice < G ? role_voice : 0];
 	const bool worker = kb_tile_is_worker<LAYOUT>(warp);
-	const bool first_worker = worker && kb_tile_worker_tid<LAYOUT>(warp, lane) < 32;
+	const bool first_worker = worker && kb_tile_worker_tid<LAYOUT, NT>(warp, lane) < 32;
 	const bool is_env = role == 0 && a_sub == 0 && role_ok, is_adsr = (role == 1 || a_sub == 1) && role_ok, is_flt = role == 2 && role_ok;
 	const int slot = (is_adsr ? G : 0) + role_voice;                  // breakpoint slot of the A lanes
 	KbEnvR env;
@@ -109,9 +111,9 @@ __global__ void __launch_bounds__(NT, 1) kb_sub_tiled_kernel(KbSubVoice* __restr
 	__syncthreads();
 
 	const int ntiles = (n + T - 1) / T;
-	const int wtid = kb_tile_worker_tid<LAYOUT>(warp, lane);         // the B/D worker threads
-	constexpr int wthreads = LAYOUT == 0 ? NT - 96 : 512;
-	static_assert(LAYOUT != 2 || NT == 768, "layout 2 is laid out for 24 warps");
+	const int wtid = kb_tile_worker_tid<LAYOUT, NT>(warp, lane);         // the B/D worker threads
+	constexpr int wthreads = kb_tile_worker_threads_v<LAYOUT, NT>;
+	static_assert(LAYOUT != 2 || NT % 128 == 0, "layout 2 needs whole rows of four warps");
 	for (int k = 0; k < ntiles + 3; k++) {
 		if (role == 0 || role == 1) {                                    // ---- A, tile k
 			if ((is_env || is_adsr) && k < ntiles) {
@@ -289,7 +291,7 @@ template <int G> struct KbTbSmem {
 	KbTbBlock blk[G];
 	float vf[G], last_out[G];
 };
-template <int G, int NT>
+template <int G, int NT, int LAYOUT = 0>
 __global__ void __launch_bounds__(NT, 1) kb_tb_tiled_kernel(KbTbVoice* __restrict__ voices, KbVoiceHdr* __restrict__ hdr,
                                                                        const KbSynthBlock* __restrict__ blk, float* __restrict__ dst,
                                                                        int n, int voices_per_inst, int total, KbFs fs) {
@@ -299,7 +301,11 @@ __global__ void __launch_bounds__(NT, 1) kb_tb_tiled_kernel(KbTbVoice* __restric
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int v0 = blockIdx.x * G;
 	kb_tile_prologue(S.c, voices, hdr, v0, total);
-	if (warp == 3 && lane < G && v0 + lane < total) {
+	const int role = kb_tile_role<LAYOUT>(warp);                      // 0 = A (filter envelope), 1 = A (ADSR), 2 = C (ladder), -1 = worker / idle
+	constexpr bool MERGED_A = LAYOUT == 2 && 2 * G <= 32;             // role 0 runs both envelopes of a voice on lanes v and G + v
+	const bool worker = kb_tile_is_worker<LAYOUT>(warp);
+	const bool first_worker = worker && kb_tile_worker_tid<LAYOUT, NT>(warp, lane) < 32;
+	if (first_worker && lane < G && v0 + lane < total) {
 		S.blk[lane] = blk[(v0 + lane) / voices_per_inst].tb;
 		if (S.c.active[lane]) {
 			S.osc[lane] = S.blk[lane].is_square ? voices[v0 + lane].square : voices[v0 + lane].saw;
@@ -307,10 +313,11 @@ __global__ void __launch_bounds__(NT, 1) kb_tb_tiled_kernel(KbTbVoice* __restric
 			S.last_out[lane] = voices[v0 + lane].filter.out;
 		}
 	}
-	const int role_voice = lane;
-	const bool role_ok = lane < G && S.c.active[lane < G ? lane : 0];
-	const bool is_env = warp == 0 && role_ok, is_adsr = warp == 1 && role_ok, is_flt = warp == 2 && role_ok;
-	const int slot = warp * G + lane;
+	const int a_sub = (MERGED_A && role == 0 && lane >= G) ? 1 : 0;
+	const int role_voice = lane - a_sub * G;
+	const bool role_ok = role_voice < G && S.c.active[role_voice < G ? role_voice : 0];
+	const bool is_env = role == 0 && a_sub == 0 && role_ok, is_adsr = (role == 1 || a_sub == 1) && role_ok, is_flt = role == 2 && role_ok;
+	const int slot = (is_adsr ? G : 0) + role_voice;
 	KbEnvR env;
 	if (is_env) kb_tile_load_env(S.c, slot, voices[v0 + role_voice].env, env);
 	if (is_adsr) kb_tile_load_env(S.c, slot, voices[v0 + role_voice].adsr, env);
@@ -318,27 +325,34 @@ __global__ void __launch_bounds__(NT, 1) kb_tb_tiled_kernel(KbTbVoice* __restric
 	if (is_flt) F = voices[v0 + role_voice].filter;
 	__syncthreads();
 	const int ntiles = (n + T - 1) / T;
-	const int wtid = tid - 96, wthreads = NT - 96;
+	const int wtid = kb_tile_worker_tid<LAYOUT, NT>(warp, lane);
+	constexpr int wthreads = kb_tile_worker_threads_v<LAYOUT, NT>;
+	static_assert(LAYOUT != 2 || NT % 128 == 0, "layout 2 needs whole rows of four warps");
 	for (int k = 0; k < ntiles + 3; k++) {
-		if (warp < 2) {                                                  // ---- A, tile k
+		if (role == 0 || role == 1) {                                    // ---- A, tile k
 			if ((is_env || is_adsr) && k < ntiles) {
 				const int steps = min(T, n - k * T);
 				float* row = is_env ? S.e[k & 1].r[role_voice] : S.amp[k & 3].r[role_voice];
 				kb_envr_run(fs, env, S.c.px[slot], S.c.py[slot], row, steps);
 			}
-		} else if (warp == 2) {                                          // ---- C, tile k-2
+		} else if (role == 2) {                                          // ---- C, tile k-2
 			const int c = k - 2;
 			if (is_flt && c >= 0 && c < ntiles) {
 				const int steps = min(T, n - c * T), v = role_voice;
 				const KbTbBlock B = S.blk[v];
+				const float* pcut = S.cut[c & 1].r[v]; const float* pb0 = S.b0[c & 1].r[v]; const float* pkk = S.kk[c & 1].r[v];
+				const float* pg = S.g[c & 1].r[v]; const float* px_ = S.x[c & 1].r[v];
+				// the operands of the NEXT sample are loaded before this sample's dependent chain (rows are padded by one)
+				float n_cut = pcut[0], n_b0 = pb0[0], n_kk = pkk[0], n_g = pg[0], n_x = px_[0];
 				for (int t = 0; t < steps; t++) {
-					const float cutoff = S.cut[c & 1].r[v][t];
+					const float cutoff = n_cut, o_b0 = n_b0, o_kk = n_kk, o_g = n_g, o_x = n_x;
+					n_cut = pcut[t + 1]; n_b0 = pb0[t + 1]; n_kk = pkk[t + 1]; n_g = pg[t + 1]; n_x = px_[t + 1];
 					if (F.cutoff != cutoff || F.resonance != B.resonance || F.drive != B.drive) {
 						F.cutoff = cutoff; F.resonance = B.resonance; F.drive = B.drive; F.r = B.r;
-						F.b0 = S.b0[c & 1].r[v][t]; F.k = S.kk[c & 1].r[v][t]; F.g = S.g[c & 1].r[v][t];
+						F.b0 = o_b0; F.k = o_kk; F.g = o_g;
 					}
 					if (F.feedback.f != B.hpf_f) { F.feedback.f = B.hpf_f; F.feedback.b0 = B.hpf_b0; F.feedback.b1 = B.hpf_b1; F.feedback.a1 = B.hpf_a1; }   // setHPF  TB303.k:33-35
-					F.in = S.x[c & 1].r[v][t];
+					F.in = o_x;
 					const float y0 = kb_onepole_tick(F.feedback, F.k * F.z[3]) * 0.9f * F.resonance;
 					const float shaped = (y0 > KB_ROOT2_F) ? KB_ROOT2_F : (y0 < -0.5) ? -0.5f : y0;
 					F.in -= shaped;
@@ -349,7 +363,7 @@ __global__ void __launch_bounds__(NT, 1) kb_tb_tiled_kernel(KbTbVoice* __restric
 					S.y[c & 1].r[v][t] = F.g * F.z[3];
 				}
 			}
-		} else {
+		} else if (worker) {
 			const int b = k - 1, d = k - 3;
 			if (b >= 0 && b < ntiles) {                                      // ---- B, tile k-1
 				const int steps = min(T, n - b * T);
@@ -400,7 +414,7 @@ __global__ void __launch_bounds__(NT, 1) kb_tb_tiled_kernel(KbTbVoice* __restric
 		if (env.stage == KB_ENV_OFF) hdr[v0 + role_voice].stage = KB_NOTE_OFF;
 	}
 	if (is_flt) { F.out = S.last_out[role_voice]; voices[v0 + role_voice].filter = F; }
-	if (warp == 3 && lane < G && S.c.active[lane]) {
+	if (first_worker && lane < G && S.c.active[lane]) {
 		KbOsm o = S.osc[lane];
 		kb_osm_advance(o, (uint32_t)n);
 		KbOsm& dsto = S.blk[lane].is_square ? voices[v0 + lane].square : voices[v0 + lane].saw;
