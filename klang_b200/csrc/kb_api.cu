@@ -66,7 +66,7 @@ struct kb_fx_bank : kb_bank_base {
 	int graph = 0, instances = 0, channels = 0, ncontrols = 0;
 	size_t state_bytes = 0; long long ring_floats = 0;
 	std::vector<KbFxHdr> hdr; std::vector<unsigned char> state;
-	KbFxHdr* d_hdr = nullptr; unsigned char* d_state = nullptr; float* d_rings = nullptr; KbFxPlan* d_plan = nullptr; void* d_sync = nullptr; int epoch = 0, dpp_protocol = -1; std::vector<KbFxPlan> plan_cache;
+	KbFxHdr* d_hdr = nullptr; unsigned char* d_state = nullptr; float* d_rings = nullptr; KbFxPlan* d_plan = nullptr; void* d_sync = nullptr; int epoch = 0; std::vector<KbFxPlan> plan_cache;
 	bool device_writes_controls = false;
 	template <class T> T& st(int i) { return *reinterpret_cast<T*>(state.data() + (size_t)i * state_bytes); }
 };
@@ -308,16 +308,9 @@ extern "C" int kb_fx_bank_process(kb_fx_bank* b, float* io, int n, unsigned flag
 				KbDppSync* sync = (KbDppSync*)b->d_sync;
 				const int chunks = (len + cf - 1) / cf;
 				++b->epoch;
-				// KB_DPP_SYNC=0 selects the CTA-level flag protocol (A/B measurement; same results)
-				static const int perwarp = getenv("KB_DPP_SYNC") ? atoi(getenv("KB_DPP_SYNC")) : 1;
-				if (perwarp != b->dpp_protocol) {   // the two protocols leave different values in the flag array: clear it when switching
-					KB_CUDA(cudaMemsetAsync(sync->flag, 0, sizeof(int) * (size_t)b->instances * KB_DPP_MAXCHUNKS, b->stream));
-					b->dpp_protocol = perwarp;
-				}
-#define KB_LAUNCH_DPP(CF, PW) kb_dpingpong_stream_kernel<CF, PW><<<chunks * b->instances, 256, 0, b->stream>>>(b->d_hdr, st, b->d_plan, b->d_rings, d + o, len, n, b->instances, b->fs, sync, b->epoch)
-				if (perwarp) { if (cf == 512) KB_LAUNCH_DPP(512, true); else if (cf == 2048) KB_LAUNCH_DPP(2048, true); else KB_LAUNCH_DPP(1024, true); }
-				else { if (cf == 512) KB_LAUNCH_DPP(512, false); else if (cf == 2048) KB_LAUNCH_DPP(2048, false); else KB_LAUNCH_DPP(1024, false); }
-#undef KB_LAUNCH_DPP
+				if (cf == 512) kb_dpingpong_stream_kernel<512><<<chunks * b->instances, 256, 0, b->stream>>>(b->d_hdr, st, b->d_plan, b->d_rings, d + o, len, n, b->instances, b->fs, sync, b->epoch);
+				else if (cf == 2048) kb_dpingpong_stream_kernel<2048><<<chunks * b->instances, 256, 0, b->stream>>>(b->d_hdr, st, b->d_plan, b->d_rings, d + o, len, n, b->instances, b->fs, sync, b->epoch);
+				else kb_dpingpong_stream_kernel<1024><<<chunks * b->instances, 256, 0, b->stream>>>(b->d_hdr, st, b->d_plan, b->d_rings, d + o, len, n, b->instances, b->fs, sync, b->epoch);
 				b->launches++;
 			}
 			if (!all_parallel) {
@@ -714,15 +707,9 @@ extern "C" int kb_synth_bank_process(kb_synth_bank* b, float* out, int n, unsign
 				else KB_LAUNCH_TILED(kb_ssaw_tiled_kernel, KbSsawSmem, 2, 288, vs, b->d_hdr, d_voice_dst, n, total, b->fs);
 			} else {
 				KbTbVoice* vs = (KbTbVoice*)b->d_vstate;
-				// the ladder recurrence (one lane per voice, ~100 dependent cycles per sample) bounds this kernel for any G: layout 2 gives
-				// it an SM sub-partition of its own (KB_TILE_LAYOUT=0: the shared layout, A/B measurement)
-				static const int tb_layout = getenv("KB_TILE_LAYOUT") ? atoi(getenv("KB_TILE_LAYOUT")) : 2;
-				if (tb_layout == 2) {
-					static bool attr_set = false;
-					if (!attr_set) { cudaFuncSetAttribute(kb_tb_tiled_kernel<8, 640, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KbTbSmem<8>)); attr_set = true; }
-					kb_tb_tiled_kernel<8, 640, 2><<<(total + 7) / 8, 640, sizeof(KbTbSmem<8>), st>>>(vs, b->d_hdr, b->d_blk, d_voice_dst, n, b->voices, total, b->fs);
-				}
-				else if (g >= 8) KB_LAUNCH_TILED(kb_tb_tiled_kernel, KbTbSmem, 8, 512, vs, b->d_hdr, b->d_blk, d_voice_dst, n, b->voices, total, b->fs);
+				// (the ladder recurrence, one lane per voice and ~100 dependent cycles per sample, bounds this kernel for any G; giving it a
+				// sub-partition of its own — layout 2 of the Subtractive kernel — measured no faster here)
+				if (g >= 8) KB_LAUNCH_TILED(kb_tb_tiled_kernel, KbTbSmem, 8, 512, vs, b->d_hdr, b->d_blk, d_voice_dst, n, b->voices, total, b->fs);
 				else KB_LAUNCH_TILED(kb_tb_tiled_kernel, KbTbSmem, 4, 320, vs, b->d_hdr, b->d_blk, d_voice_dst, n, b->voices, total, b->fs);
 			}
 #undef KB_LAUNCH_TILED

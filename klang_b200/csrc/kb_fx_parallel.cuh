@@ -68,12 +68,7 @@ KB_D void kb_dpp_wait(volatile int* flags, int g_lo, int g_hi, int epoch, int ch
 	const int c_lo = max(g_lo, 0) / chunk_frames, c_hi = g_hi / chunk_frames;
 	for (int c = c_lo; c <= c_hi; c++) while (flags[c] != epoch) { }
 }
-// PERWARP = false: thread 0 waits for the flags, the CTA processes its chunk between two __syncthreads and thread 0 publishes
-//                  the launch epoch.
-// PERWARP = true:  no CTA barrier on the dependency path: every warp waits for its own dependencies (lane 0 polls), processes
-//                  its quarter of the frames and adds 1 to the chunk's counter; a chunk is complete at 8 (= warps per CTA);
-//                  the last CTA of the launch clears the counters.
-template <int CHUNK, bool PERWARP>
+template <int CHUNK>
 __global__ void __launch_bounds__(256) kb_dpingpong_stream_kernel(const KbFxHdr* __restrict__ hdrs, const KbDPingPong* __restrict__ states,
                                                                   const KbFxPlan* __restrict__ plan, float* __restrict__ rings, float* __restrict__ io,
                                                                   int n, int stride, int instances, KbFs fs, KbDppSync* __restrict__ sync, int epoch) {
@@ -88,14 +83,12 @@ __global__ void __launch_bounds__(256) kb_dpingpong_stream_kernel(const KbFxHdr*
 	if (pl.mode == KB_PLAN_PARALLEL) {
 	const float tl = c[0].value * fs.f, tr = c[1].value * fs.f, gl = c[1].value, gr = c[3].value;
 	volatile int* flags = sync->flag + (size_t)inst * KB_DPP_MAXCHUNKS;
-	const int done = PERWARP ? 8 : epoch;
-	if (PERWARP ? (threadIdx.x & 31) == 0 : threadIdx.x == 0) {
+	if (threadIdx.x == 0) {
 		// frame f reads ring samples written in frames f-1-t-1 .. f-t+1 (t = tl for the left line, tr for the right line)
-		kb_dpp_wait(flags, f0 - (int)tl - 3, f0 + len - 1 - (int)tl + 1, done, CHUNK);
-		kb_dpp_wait(flags, f0 - (int)tr - 3, f0 + len - 1 - (int)tr + 1, done, CHUNK);
-		__threadfence();
+		kb_dpp_wait(flags, f0 - (int)tl - 3, f0 + len - 1 - (int)tl + 1, epoch, CHUNK);
+		kb_dpp_wait(flags, f0 - (int)tr - 3, f0 + len - 1 - (int)tr + 1, epoch, CHUNK);
 	}
-	if (PERWARP) __syncwarp(); else __syncthreads();
+	__syncthreads();
 	const KbDPingPong& p = states[inst];
 	float* ringl = rings + p.l.ring; float* ringr = rings + p.r.ring;
 	float* L = io + (size_t)inst * 2 * stride; float* R = L + stride;
@@ -121,12 +114,11 @@ __global__ void __launch_bounds__(256) kb_dpingpong_stream_kernel(const KbFxHdr*
 		}
 	}
 	__threadfence();
-	if (PERWARP) { __syncwarp(); if ((threadIdx.x & 31) == 0) atomicAdd(const_cast<int*>(flags) + chunk, 1); }
-	else { __syncthreads(); if (threadIdx.x == 0) flags[chunk] = epoch; }
+	__syncthreads();
+	if (threadIdx.x == 0) flags[chunk] = epoch;
 	}
 	// epilogue of the launch: the CTA that finishes last advances every parallel instance's write heads
 	__shared__ bool s_last;
-	__syncthreads();
 	if (threadIdx.x == 0) { __threadfence(); s_last = atomicAdd(&sync->finished, 1u) == gridDim.x - 1; }
 	__syncthreads();
 	if (s_last) {
@@ -136,10 +128,6 @@ __global__ void __launch_bounds__(256) kb_dpingpong_stream_kernel(const KbFxHdr*
 				q.l.position = (int)(((long long)q.l.position + n) % q.l.SIZE);
 				q.r.position = (int)(((long long)q.r.position + n) % q.r.SIZE);
 			}
-		if (PERWARP) {
-			const int chunks = (n + CHUNK - 1) / CHUNK;
-			for (int i = threadIdx.x; i < instances * chunks; i += blockDim.x) sync->flag[(size_t)(i / chunks) * KB_DPP_MAXCHUNKS + (i % chunks)] = 0;
-		}
 		if (threadIdx.x == 0) { sync->ticket = 0u; sync->finished = 0u; }
 	}
 }
