@@ -241,6 +241,18 @@ def run_reference_arm(args, rank, world, emit):
     emit(line)
 
 
+def make_mixdown(sharding, dist, local_rank, max_floats):
+    """N > 1: the peer-memory mix-down (kb_mixdown_*), or NCCL when KB_MIXDOWN=nccl / the peer mapping is unavailable."""
+    if dist is None:
+        return None, "none (one GPU)"
+    if os.environ.get("KB_MIXDOWN", "peer") == "nccl":
+        return None, "ncclReduce of the [channels][n] mix per block (KB_MIXDOWN=nccl)"
+    try:
+        return sharding.PeerMixdown(local_rank, max_floats), "NVLink peer memory: bank-mix kernels store into rank 0's arena, rank 0 sums in rank order (kb_mixdown_*)"
+    except Exception as e:
+        return None, f"ncclReduce of the [channels][n] mix per block (peer mapping unavailable: {e})"
+
+
 def workload_config():
     return {"workload": "C2 Subtractive synth (Saw>>LPF(env,Q=10)>>ADSR), 8 Synth instances x 128 voices = 1024 voices per GPU, "
                         "fs 48 kHz, block 4096, 1/16 of the voices re-triggered per block",
@@ -340,18 +352,30 @@ def main():
         bank.events(batches[s % RETRIGGER_GROUPS])
         return len(batches[s % RETRIGGER_GROUPS])
 
+    mixdown, mix_kind = make_mixdown(sharding, dist, local_rank, out_dev.numel())
+
+    def mix_down():
+        """one process() of this rank's bank and the cross-GPU mix-down into out_dev on rank 0"""
+        if mixdown is not None:
+            # the bank-mix kernel stores straight into rank 0's arena over NVLink; rank 0 sums the slots in rank order
+            bank.process_into_device_ptr(mixdown.acquire(stream.cuda_stream), BLOCK, flags)
+            mixdown.publish(stream.cuda_stream)
+            if rank == 0:
+                mixdown.collect(out_dev, out_dev.numel(), stream.cuda_stream)
+        else:
+            bank.process_into(out_dev, BLOCK, flags)
+            sharding.reduce_mix(out_dev, dst=0)
+
     def step_device():
         events()
-        bank.process_into(out_dev, BLOCK, flags)
-        sharding.reduce_mix(out_dev, dst=0)
+        mix_down()
 
     def step_e2e():
         events()
         if dist is None:
             bank.process_into(out_host.numpy(), BLOCK, flags)       # host-buffer call: upload state, kernels, D2H, sync
         else:
-            bank.process_into(out_dev, BLOCK, flags)
-            sharding.reduce_mix(out_dev, dst=0)
+            mix_down()
             out_host.copy_(out_dev, non_blocking=True)
             torch.cuda.synchronize()
 
@@ -449,9 +473,13 @@ def main():
         "metric": "voice-samples/sec (48 kHz equiv) at 1024 voices", "value": value, "unit": "voice-samples/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(), "realtime_voices_48k": value / 48000.0,
-        "clocks": clk, "e2e": e2e, "gpu_launches": int(gpu_launches), "roofline": roofline,
+        "config": dict(workload_config(), mixdown=mix_kind), "realtime_voices_48k": value / 48000.0,
+        "clocks": clk, "e2e": e2e, "gpu_launches": int(gpu_launches) + (3 if mixdown is not None else 0), "roofline": roofline,
     }
+    if mixdown is not None:
+        torch.cuda.synchronize()
+        dist.barrier()
+        mixdown.close()
 
     if rank == 0 and not args.no_extras:
         try:
@@ -503,13 +531,21 @@ def run_c5(args, rank, world, local_rank, emit):
     bus = torch.empty(2, n, dtype=torch.float32, device=dev)
     bus_host = torch.empty(2, n, dtype=torch.float32).pin_memory()
 
+    mixdown, mix_kind = make_mixdown(sharding, dist, local_rank, 2 * n)
+    bus_out = torch.empty(2, n, dtype=torch.float32, device=dev) if mixdown is not None else bus
+
     def step(e2e=False):
         tb.process_into(tb_mix, n, kb.BANK_MIX | kb.MIX_SUM)
         sx.process_into(bus, n, kb.BANK_MIX)
         bus.add_(tb_mix)                                   # mono voices feed both channels
-        sharding.reduce_mix(bus, dst=0)
+        if mixdown is not None:
+            mixdown.put(bus, 2 * n, stream.cuda_stream)    # this rank's stereo bus into rank 0's arena over NVLink
+            if rank == 0:
+                mixdown.collect(bus_out, 2 * n, stream.cuda_stream)
+        else:
+            sharding.reduce_mix(bus, dst=0)
         if e2e:
-            bus_host.copy_(bus, non_blocking=True)
+            bus_host.copy_(bus_out, non_blocking=True)
             torch.cuda.synchronize()
 
     def barrier():
@@ -562,7 +598,7 @@ def run_c5(args, rank, world, local_rank, emit):
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "C5 TB303.k + SynTHX.k mixed bank: per GPU 4 x 128 TB303 voices + 4 x 128 SynTHX voices, fs 48 kHz, block 4096, "
-                               "stereo bus sum-reduced to rank 0 over NCCL", "block": n, "fs": FS,
+                               "stereo bus summed on rank 0", "mixdown": mix_kind, "block": n, "fs": FS,
                    "l2": "flushed between timed steps (256 MiB write, outside the per-step events)"},
         "realtime_voices_48k": value / 48000.0, "clocks": clk,
         "e2e": {"value": e2e_value, "unit": "voice-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 2 * n * 4,
@@ -575,6 +611,10 @@ def run_c5(args, rank, world, local_rank, emit):
     }
     tb.close()
     sx.close()
+    if mixdown is not None:
+        torch.cuda.synchronize()
+        dist.barrier()
+        mixdown.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

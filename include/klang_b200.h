@@ -132,6 +132,33 @@ int kb_synth_bank_transfer_bytes(const kb_synth_bank* bank, long long* h2d, long
 int kb_synth_bank_profile(kb_synth_bank* bank, int enable);
 int kb_synth_bank_profile_read(kb_synth_bank* bank, double* kernel_ms, long long* kernel_launches);
 
+/* --------------------------------------------------------------------- multi-GPU mix-down (one node) */
+/* The polyphonic mix-down of a bank sharded over the GPUs of one box (the path's only exchange; it replaces
+ * nothing in klang.h, which runs one Synth per host thread and sums on the host, klang.h:4842-4848).  One process per
+ * GPU.  Rank 0 owns an arena of [2][world][max_floats] slots; every other rank maps it over NVLink (CUDA IPC) and passes
+ * its slot as the `out` of kb_synth_bank_process(KB_DEVICE_PTR | KB_BANK_MIX): the bank-mix kernel itself stores the
+ * rank's [channels][n] mix into rank 0's memory (no staging copy, no collective library on the data path).
+ * publish() then raises the rank's flag; collect() on rank 0 waits for the flags of the step and sums the slots in RANK
+ * ORDER (deterministic fp32).  Slots are double buffered by step parity; acquire() holds a rank that is two steps ahead.
+ * Per step and rank: p = acquire(); process(out = p); publish(); rank 0 additionally: collect(dst). */
+typedef struct kb_mixdown kb_mixdown;
+#define KB_IPC_HANDLE_BYTES 64
+kb_mixdown* kb_mixdown_create(int device, int world, int rank, int max_floats);
+void kb_mixdown_destroy(kb_mixdown* m);
+/* rank 0: the CUDA IPC handle of the arena (KB_IPC_HANDLE_BYTES bytes), to be sent to the other ranks by any means */
+int kb_mixdown_export(kb_mixdown* m, void* handle);
+/* ranks > 0: map rank 0's arena */
+int kb_mixdown_import(kb_mixdown* m, const void* handle);
+/* device pointer of this rank's slot for the next step (peer memory on ranks > 0); on `cuda_stream` the slot is first
+ * waited free (rank 0 has consumed the step before the previous one).  NULL on error. */
+float* kb_mixdown_acquire(kb_mixdown* m, void* cuda_stream);
+/* after the kernels that filled the slot, on the same stream: make it visible to rank 0 and raise this rank's flag */
+int kb_mixdown_publish(kb_mixdown* m, void* cuda_stream);
+/* acquire + copy `count` floats of device memory into the slot + publish, for mixes that were finished locally */
+int kb_mixdown_put(kb_mixdown* m, const float* src, int count, void* cuda_stream);
+/* rank 0: dst[i] = slot[0][i] + slot[1][i] + ... (rank order) for i < count, once every rank has published this step */
+int kb_mixdown_collect(kb_mixdown* m, float* dst, int count, void* cuda_stream);
+
 /* ---------------------------------------------------------------------------- primitive operators */
 /* Single-object runs of the primitive operators ON THE DEVICE (one thread), for known-answer tests.
  * kinds as in tests/cases.py.  Generators::Fast / Basic / Wavetables (klang.h:4893-5381). */

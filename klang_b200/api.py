@@ -39,6 +39,10 @@ SYMBOLS = [
     ("kb_synth_bank_launches", _ll, [_vp]), ("kb_synth_bank_state_bytes", _ll, [_vp]),
     ("kb_synth_bank_transfer_bytes", _i, [_vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     ("kb_synth_bank_profile", _i, [_vp, _i]), ("kb_synth_bank_profile_read", _i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
+    ("kb_mixdown_create", _vp, [_i, _i, _i, _i]), ("kb_mixdown_destroy", None, [_vp]),
+    ("kb_mixdown_export", _i, [_vp, _vp]), ("kb_mixdown_import", _i, [_vp, _vp]),
+    ("kb_mixdown_acquire", _vp, [_vp, _vp]), ("kb_mixdown_publish", _i, [_vp, _vp]), ("kb_mixdown_put", _i, [_vp, _vp, _i, _vp]),
+    ("kb_mixdown_collect", _i, [_vp, _vp, _i, _vp]),
     ("kb_prim_osc", _i, [_i, _i, _f, _f, _f, _f, _i, _vp]),
     ("kb_prim_filter", _i, [_i, _i, _vp, _vp, _f, _i, _vp, _vp, _vp]),
     ("kb_prim_envelope", _i, [_i, _vp, _i, _i, _f, _i, _i, _f, _f, _vp, _vp]),
@@ -215,6 +219,10 @@ class SynthBank:
         p, dev = _ptr(out)
         _check(lib().kb_synth_bank_process(self.h, p, n, (flags | DEVICE_PTR) if dev else (flags & ~DEVICE_PTR)), "kb_synth_bank_process")
         return out
+
+    def process_into_device_ptr(self, ptr, n, flags=0):
+        """out = a raw device pointer (e.g. a peer-mapped slot of sharding.PeerMixdown); asynchronous on the bank stream."""
+        _check(lib().kb_synth_bank_process(self.h, ptr, n, flags | DEVICE_PTR), "kb_synth_bank_process")
 
     def process_block(self, n, flags=0):
         return self.process_into(np.empty(self.out_shape(n, flags), np.float32), n, flags)

@@ -738,6 +738,107 @@ extern "C" int kb_synth_bank_process(kb_synth_bank* b, float* out, int n, unsign
 	return KB_OK;
 }
 
+// ==================================================================================== multi-GPU mix-down
+// (include/klang_b200.h: kb_mixdown_*)  Arena on rank 0: float slots[2][world][max_floats]; then unsigned flags[world] (the
+// last step each rank has published) and unsigned consumed (the last step rank 0 has summed).  All waits are device-side
+// spins on system-scope volatile words, reached over NVLink by the peers.
+struct kb_mixdown {
+	int device = 0, world = 1, rank = 0, max_floats = 0;
+	unsigned step = 0;                  // steps acquired so far on this rank
+	unsigned char* arena = nullptr;     // rank 0: own allocation; others: the IPC mapping
+	bool mapped = false;
+	size_t slot_bytes() const { return (size_t)max_floats * sizeof(float); }
+	float* slot(unsigned step_, int r) const { return (float*)(arena + ((size_t)(step_ & 1u) * world + r) * slot_bytes()); }
+	volatile unsigned* flags() const { return (volatile unsigned*)(arena + 2 * (size_t)world * slot_bytes()); }
+	volatile unsigned* consumed() const { return flags() + world; }
+	size_t arena_bytes() const { return 2 * (size_t)world * slot_bytes() + sizeof(unsigned) * ((size_t)world + 1); }
+};
+__global__ void kb_mixdown_wait_free_kernel(volatile unsigned* consumed, unsigned need) {
+	while ((int)(*consumed - need) < 0) __nanosleep(200);
+}
+__global__ void kb_mixdown_publish_kernel(volatile unsigned* flag, unsigned step) {
+	__threadfence_system();
+	*flag = step;
+}
+__global__ void __launch_bounds__(1024) kb_mixdown_collect_kernel(const float* __restrict__ slots, size_t slot_floats, volatile unsigned* flags, volatile unsigned* consumed,
+                                                                 unsigned step, int world, float* __restrict__ dst, int count) {
+	if ((int)threadIdx.x < world) while ((int)(flags[threadIdx.x] - step) < 0) __nanosleep(100);
+	__syncthreads();
+	__threadfence_system();
+	for (int i = threadIdx.x; i < count; i += blockDim.x) {
+		float acc = __ldcv(slots + i);                                    // (peer-written memory: never from a stale cache line)
+		for (int r = 1; r < world; r++) acc += __ldcv(slots + (size_t)r * slot_floats + i);
+		dst[i] = acc;
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) { __threadfence_system(); *consumed = step; }
+}
+extern "C" kb_mixdown* kb_mixdown_create(int device, int world, int rank, int max_floats) {
+	if (world < 1 || world > 1024 || rank < 0 || rank >= world || max_floats < 1) { kb_fail(KB_EINVAL, "kb_mixdown_create: bad argument"); return nullptr; }
+	if (kb_device_count() < 1) { kb_fail(KB_ENODEV, "kb_mixdown_create: no CUDA device"); return nullptr; }
+	if (cudaSetDevice(device) != cudaSuccess) { kb_fail(KB_ECUDA, "kb_mixdown_create: cudaSetDevice failed"); return nullptr; }
+	kb_mixdown* m = new kb_mixdown();
+	m->device = device; m->world = world; m->rank = rank; m->max_floats = max_floats;
+	if (rank == 0) {
+		if (cudaMalloc(&m->arena, m->arena_bytes()) != cudaSuccess || cudaMemset(m->arena, 0, m->arena_bytes()) != cudaSuccess) {
+			kb_fail(KB_ECUDA, "kb_mixdown_create: arena allocation failed"); delete m; return nullptr;
+		}
+	}
+	return m;
+}
+extern "C" void kb_mixdown_destroy(kb_mixdown* m) {
+	if (!m) return;
+	cudaSetDevice(m->device);
+	cudaDeviceSynchronize();
+	if (m->arena) { if (m->mapped) cudaIpcCloseMemHandle(m->arena); else cudaFree(m->arena); }
+	delete m;
+}
+extern "C" int kb_mixdown_export(kb_mixdown* m, void* handle) {
+	if (!m || !handle || m->rank != 0) return kb_fail(KB_EINVAL, "kb_mixdown_export: rank 0 only");
+	static_assert(sizeof(cudaIpcMemHandle_t) == KB_IPC_HANDLE_BYTES, "IPC handle size");
+	KB_CUDA(cudaSetDevice(m->device));
+	KB_CUDA(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)handle, m->arena));
+	return KB_OK;
+}
+extern "C" int kb_mixdown_import(kb_mixdown* m, const void* handle) {
+	if (!m || !handle || m->rank == 0 || m->arena) return kb_fail(KB_EINVAL, "kb_mixdown_import: ranks > 0, once");
+	KB_CUDA(cudaSetDevice(m->device));
+	cudaIpcMemHandle_t h; memcpy(&h, handle, sizeof(h));
+	void* p = nullptr;
+	KB_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+	m->arena = (unsigned char*)p; m->mapped = true;
+	return KB_OK;
+}
+extern "C" float* kb_mixdown_acquire(kb_mixdown* m, void* stream) {
+	if (!m || !m->arena) { kb_fail(KB_EINVAL, "kb_mixdown_acquire: arena not mapped"); return nullptr; }
+	if (cudaSetDevice(m->device) != cudaSuccess) { kb_fail(KB_ECUDA, "kb_mixdown_acquire: cudaSetDevice failed"); return nullptr; }
+	const unsigned step = ++m->step;
+	// the slot of this parity was last used by step - 2: rank 0 must have summed that step
+	if (step > 2) kb_mixdown_wait_free_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(m->consumed(), step - 2);
+	return m->slot(step, m->rank);
+}
+extern "C" int kb_mixdown_publish(kb_mixdown* m, void* stream) {
+	if (!m || !m->arena || m->step == 0) return kb_fail(KB_EINVAL, "kb_mixdown_publish: nothing acquired");
+	KB_CUDA(cudaSetDevice(m->device));
+	kb_mixdown_publish_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(m->flags() + m->rank, m->step);
+	KB_CUDA(cudaGetLastError());
+	return KB_OK;
+}
+extern "C" int kb_mixdown_put(kb_mixdown* m, const float* src, int count, void* stream) {
+	if (!m || !src || count < 0 || count > m->max_floats) return kb_fail(KB_EINVAL, "kb_mixdown_put: bad argument");
+	float* slot = kb_mixdown_acquire(m, stream);
+	if (!slot) return KB_EINVAL;
+	KB_CUDA(cudaMemcpyAsync(slot, src, (size_t)count * sizeof(float), cudaMemcpyDefault, (cudaStream_t)stream));
+	return kb_mixdown_publish(m, stream);
+}
+extern "C" int kb_mixdown_collect(kb_mixdown* m, float* dst, int count, void* stream) {
+	if (!m || !dst || m->rank != 0 || count < 0 || count > m->max_floats || m->step == 0) return kb_fail(KB_EINVAL, "kb_mixdown_collect: bad argument (rank 0 only, count <= max_floats)");
+	KB_CUDA(cudaSetDevice(m->device));
+	kb_mixdown_collect_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(m->slot(m->step, 0), (size_t)m->max_floats, m->flags(), m->consumed(), m->step, m->world, dst, count);
+	KB_CUDA(cudaGetLastError());
+	return KB_OK;
+}
+
 // ============================================================================================ primitives
 struct DevBuf {
 	void* p = nullptr;

@@ -24,3 +24,61 @@ def reduce_mix(mix, dst=0, group=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.reduce(mix, dst=dst, op=dist.ReduceOp.SUM, group=group)
     return mix
+
+
+class PeerMixdown:
+    """The mix-down over NVLink peer memory (include/klang_b200.h: kb_mixdown_*): every rank's bank-mix kernel stores its
+    [channels][n] mix straight into rank 0's arena; rank 0 sums the slots in rank order.  One process per GPU of one node;
+    the 64-byte CUDA IPC handle of the arena travels once, at construction, through torch.distributed.
+
+    per step:   ptr = mix.acquire(stream); bank.process_into_device_ptr(ptr, n, BANK_MIX | ...); mix.publish(stream)
+                rank 0 only: mix.collect(dst_tensor, count, stream)
+    """
+
+    def __init__(self, device_index, max_floats, group=None):
+        import ctypes as C
+        import torch.distributed as dist
+        from . import api
+        self._api = api
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        L = api.lib()
+        self.h = L.kb_mixdown_create(device_index, self.world, self.rank, int(max_floats))
+        if not self.h:
+            raise api.KlangB200Error("kb_mixdown_create: " + L.kb_last_error().decode())
+        box = [None]
+        if self.rank == 0:
+            buf = C.create_string_buffer(64)
+            api._check(L.kb_mixdown_export(self.h, buf), "kb_mixdown_export")
+            box[0] = bytes(buf.raw)
+        dist.broadcast_object_list(box, src=0, group=group)
+        ok = 1
+        if self.rank != 0:
+            rc = L.kb_mixdown_import(self.h, C.create_string_buffer(box[0], 64))
+            ok = 1 if rc >= 0 else 0
+            self.error = None if ok else L.kb_last_error().decode()
+        flags = [None] * self.world
+        dist.all_gather_object(flags, ok, group=group)          # every rank learns whether the peer mapping exists everywhere
+        if not all(flags):
+            self.close()
+            raise api.KlangB200Error("kb_mixdown_import failed on a rank (CUDA IPC / peer access unavailable)")
+
+    def acquire(self, cuda_stream):
+        p = self._api.lib().kb_mixdown_acquire(self.h, cuda_stream)
+        if not p:
+            raise self._api.KlangB200Error("kb_mixdown_acquire: " + self._api.lib().kb_last_error().decode())
+        return p
+
+    def publish(self, cuda_stream):
+        self._api._check(self._api.lib().kb_mixdown_publish(self.h, cuda_stream), "kb_mixdown_publish")
+
+    def put(self, src, count, cuda_stream):
+        """acquire + device copy of a finished local mix (torch CUDA tensor) into the slot + publish."""
+        self._api._check(self._api.lib().kb_mixdown_put(self.h, src.data_ptr(), int(count), cuda_stream), "kb_mixdown_put")
+
+    def collect(self, dst, count, cuda_stream):
+        self._api._check(self._api.lib().kb_mixdown_collect(self.h, dst.data_ptr(), int(count), cuda_stream), "kb_mixdown_collect")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._api.lib().kb_mixdown_destroy(self.h)
+            self.h = None

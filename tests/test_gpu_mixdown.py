@@ -1,0 +1,105 @@
+"""GPU tests of the multi-GPU mix-down (kb_mixdown_*): the single-rank round trip on one device, and — when the
+box has two devices — two processes whose bank mixes meet in rank 0's arena over peer memory, compared bit for bit with the
+rank-order fp32 sum of the same banks rendered on one device."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+import klang_b200 as kb
+
+pytestmark = pytest.mark.gpu
+
+
+def _bank(device, first_voice, fs, n, inst=2, voices=32):
+    b = kb.SynthBank(kb.SY_SUBTRACTIVE, inst, voices, fs, n, device)
+    for g in range(inst * voices):
+        b.voice_start(g % voices, 40 + (first_voice + g) % 40, 0.5 + 0.4 * ((first_voice + g) % 3) / 2.0, g // voices)
+    return b
+
+
+def test_mixdown_single_rank_round_trip():
+    import torch
+    if kb.device_count() < 1:
+        pytest.skip("needs a CUDA device")
+    L = kb.lib()
+    n, fs = 1024, 48000.0
+    h = L.kb_mixdown_create(0, 1, 0, n)
+    assert h, L.kb_last_error()
+    stream = torch.cuda.current_stream().cuda_stream
+    # (a) put / collect of arbitrary data, more steps than the two slot parities
+    x = torch.rand(5, n, device="cuda")
+    out = torch.empty(n, device="cuda")
+    for k in range(5):
+        assert L.kb_mixdown_put(h, x[k].data_ptr(), n, stream) == 0
+        assert L.kb_mixdown_collect(h, out.data_ptr(), n, stream) == 0
+        torch.cuda.synchronize()
+        assert torch.equal(out, x[k])
+    # (b) the bank-mix kernel writing the slot itself (KB_DEVICE_PTR | KB_BANK_MIX with the slot as `out`)
+    a, b = _bank(0, 0, fs, n), _bank(0, 0, fs, n)
+    want = torch.empty(1, n, device="cuda")
+    for blk in range(3):
+        a.process_into(want, n, kb.BANK_MIX | kb.MIX_SUM)
+        b.set_stream(stream)
+        p = L.kb_mixdown_acquire(h, stream)
+        assert p
+        b.process_into_device_ptr(p, n, kb.BANK_MIX | kb.MIX_SUM)
+        assert L.kb_mixdown_publish(h, stream) == 0
+        assert L.kb_mixdown_collect(h, out.data_ptr(), n, stream) == 0
+        a.sync()
+        torch.cuda.synchronize()
+        assert torch.equal(out, want[0]) and float(out.abs().max()) > 1e-3
+    a.close(); b.close()
+    L.kb_mixdown_destroy(h)
+    # (c) bad arguments
+    assert not L.kb_mixdown_create(0, 2, 2, n)
+    assert b"bad argument" in L.kb_last_error()
+
+
+def _worker(rank, world, port, n, fs, out_path):
+    import torch
+    import torch.distributed as dist
+    from klang_b200 import sharding
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    stream = torch.cuda.current_stream().cuda_stream
+    mix = sharding.PeerMixdown(rank, n)
+    bank = _bank(rank, rank * 64, fs, n)
+    bank.set_stream(stream)
+    got = torch.empty(4, n, device="cuda")
+    for blk in range(4):
+        bank.process_into_device_ptr(mix.acquire(stream), n, kb.BANK_MIX | kb.MIX_SUM)
+        mix.publish(stream)
+        if rank == 0:
+            mix.collect(got[blk], n, stream)
+    torch.cuda.synchronize()
+    dist.barrier()
+    if rank == 0:
+        np.save(out_path, got.cpu().numpy())
+    mix.close()
+    bank.close()
+    dist.destroy_process_group()
+
+
+def test_mixdown_two_gpus_equals_rank_order_sum(tmp_path):
+    import torch
+    import torch.multiprocessing as mp
+    if kb.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    n, fs = 2048, 48000.0
+    out_path = str(tmp_path / "mix.npy")
+    mp.spawn(_worker, args=(2, port, n, fs, out_path), nprocs=2, join=True)
+    got = np.load(out_path)
+    banks = [_bank(0, r * 64, fs, n) for r in range(2)]
+    for blk in range(4):
+        parts = [b.process_block(n, kb.BANK_MIX | kb.MIX_SUM)[0] for b in banks]
+        want = parts[0] + parts[1]                                   # rank order, fp32
+        assert np.array_equal(got[blk].view(np.uint32), want.view(np.uint32)), f"block {blk}"
+        assert np.abs(want).max() > 1e-3
+    for b in banks:
+        b.close()
