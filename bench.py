@@ -54,8 +54,10 @@ def load_peaks():
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
     """SM clock and throttle reasons DURING the timed region.  In-process NVML (nvidia_ml_py) polled by a thread every
-    5 ms, plus explicit sample() calls the timed loop makes right after queueing a step (the GPU is busy then, and the
-    per-step CUDA events do not see host time).  Falls back to one `nvidia-smi --query-gpu` per sample() without NVML."""
+    millisecond (the calls release the GIL, the timed loop is not held up), plus one explicit sample() right after the last
+    timed step has been queued, while the GPU is still working through the region.  No NVML call sits between two timed
+    steps: with N > 1 a rank that is late to queue a step would be waited for by the others inside their timed intervals.
+    Falls back to one `nvidia-smi --query-gpu` per sample() without NVML."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -94,7 +96,7 @@ class ClockSampler:
     def _poll(self):
         while self.running:
             self.sample()
-            time.sleep(0.005)
+            time.sleep(0.001)
 
     def sample(self):
         if self.nvml is not None:
@@ -136,8 +138,8 @@ class ClockSampler:
             if not self.sm:
                 return {"sm_mhz": None, "sm_max_mhz": self.mx, "reasons": [], "samples": 0}
             return {"sm_mhz": statistics.median(self.sm), "sm_min_mhz": min(self.sm), "sm_max_mhz": self.mx, "reasons": sorted(self.reasons),
-                    "samples": len(self.sm), "how": "NVML polled every 5 ms plus once per queued step inside the timed region" if self.nvml is not None
-                    else "nvidia-smi --query-gpu once per queued step inside the timed region"}
+                    "samples": len(self.sm), "how": "NVML polled every ms during the timed region plus once after the last step was queued" if self.nvml is not None
+                    else "nvidia-smi --query-gpu once after the last timed step was queued"}
 
 
 # ------------------------------------------------------------------------------------- reference (CPU) arm
@@ -394,8 +396,8 @@ def main():
             step_fn()
             b.record(stream)
             evs.append((a, b))
-            if clocks and (clocks.nvml is not None or i % max(1, steps // 4) == 0):
-                clocks.sample()                      # the step just queued is running: host time is outside the CUDA events
+        if clocks:
+            clocks.sample()                          # everything is queued, the GPU is still inside the timed region
         barrier()
         wall = time.perf_counter() - t_wall0
         ms = sum(a.elapsed_time(b) for a, b in evs)
@@ -565,8 +567,8 @@ def run_c5(args, rank, world, local_rank, emit):
         step()
         b.record(stream)
         evs.append((a, b))
-        if clocks and (clocks.nvml is not None or i % max(1, args.steps // 4) == 0):
-            clocks.sample()
+    if clocks:
+        clocks.sample()
     barrier()
     clk = clocks.stop() if clocks else None
     t = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], dtype=torch.float64, device=dev)

@@ -27,7 +27,9 @@ def test_mixdown_single_rank_round_trip():
     n, fs = 1024, 48000.0
     h = L.kb_mixdown_create(0, 1, 0, n)
     assert h, L.kb_last_error()
-    stream = torch.cuda.current_stream().cuda_stream
+    ts = torch.cuda.Stream()            # (a NULL stream handle means "the bank's own stream" in the ABI: use a real one)
+    torch.cuda.set_stream(ts)
+    stream = ts.cuda_stream
     # (a) put / collect of arbitrary data, more steps than the two slot parities
     x = torch.rand(5, n, device="cuda")
     out = torch.empty(n, device="cuda")
@@ -64,7 +66,9 @@ def _worker(rank, world, port, n, fs, out_path):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    stream = torch.cuda.current_stream().cuda_stream
+    ts = torch.cuda.Stream()
+    torch.cuda.set_stream(ts)
+    stream = ts.cuda_stream
     mix = sharding.PeerMixdown(rank, n)
     bank = _bank(rank, rank * 64, fs, n)
     bank.set_stream(stream)
