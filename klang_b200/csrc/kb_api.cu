@@ -756,6 +756,9 @@ struct kb_mixdown {
 __global__ void kb_mixdown_wait_free_kernel(volatile unsigned* consumed, unsigned need) {
 	while ((int)(*consumed - need) < 0) __nanosleep(200);
 }
+__global__ void kb_mixdown_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, int count) {
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
 __global__ void kb_mixdown_publish_kernel(volatile unsigned* flag, unsigned step) {
 	__threadfence_system();
 	*flag = step;
@@ -828,7 +831,8 @@ extern "C" int kb_mixdown_put(kb_mixdown* m, const float* src, int count, void* 
 	if (!m || !src || count < 0 || count > m->max_floats) return kb_fail(KB_EINVAL, "kb_mixdown_put: bad argument");
 	float* slot = kb_mixdown_acquire(m, stream);
 	if (!slot) return KB_EINVAL;
-	KB_CUDA(cudaMemcpyAsync(slot, src, (size_t)count * sizeof(float), cudaMemcpyDefault, (cudaStream_t)stream));
+	// a kernel storing through the peer mapping (cudaMemcpyAsync into IPC-mapped memory measured ~100 us per call)
+	if (count > 0) kb_mixdown_copy_kernel<<<(count + 1023) / 1024, 256, 0, (cudaStream_t)stream>>>(src, slot, count);
 	return kb_mixdown_publish(m, stream);
 }
 extern "C" int kb_mixdown_collect(kb_mixdown* m, float* dst, int count, void* stream) {
