@@ -244,11 +244,12 @@ def run_reference_arm(args, rank, world, emit):
 
 
 def make_mixdown(sharding, dist, local_rank, max_floats):
-    """N > 1: the peer-memory mix-down (kb_mixdown_*), or NCCL when KB_MIXDOWN=nccl / the peer mapping is unavailable."""
+    """N > 1: one ncclReduce of the [channels][n] mix per block (default: measured equal or faster at 2 and 8 GPUs,
+    profiles/r01_bench_n*.json), or with KB_MIXDOWN=peer the mix-down through NVLink peer memory (kb_mixdown_*)."""
     if dist is None:
         return None, "none (one GPU)"
-    if os.environ.get("KB_MIXDOWN", "peer") == "nccl":
-        return None, "ncclReduce of the [channels][n] mix per block (KB_MIXDOWN=nccl)"
+    if os.environ.get("KB_MIXDOWN", "nccl") != "peer":
+        return None, "ncclReduce of the [channels][n] mix per block (KB_MIXDOWN=peer selects the peer-memory mix-down)"
     try:
         return sharding.PeerMixdown(local_rank, max_floats), "NVLink peer memory: bank-mix kernels store into rank 0's arena, rank 0 sums in rank order (kb_mixdown_*)"
     except Exception as e:

@@ -17,7 +17,7 @@ except Exception as e:
 PY
   tail -3 $OUT/$name.err
 }
-run bench_n$N 29511 --no-extras
+KB_MIXDOWN=peer run bench_n$N 29511 --no-extras
 KB_MIXDOWN=nccl run bench_n${N}_nccl 29512 --no-extras
-run bench_c5_n$N 29513 --workload c5
+KB_MIXDOWN=peer run bench_c5_n$N 29513 --workload c5
 KB_MIXDOWN=nccl run bench_c5_n${N}_nccl 29514 --workload c5
