@@ -249,7 +249,7 @@ def make_mixdown(sharding, dist, local_rank, max_floats):
     if dist is None:
         return None, "none (one GPU)"
     if os.environ.get("KB_MIXDOWN", "nccl") != "peer":
-        return None, "ncclReduce of the [channels][n] mix per block (KB_MIXDOWN=peer selects the peer-memory mix-down)"
+        return None, "ncclReduce of the [channels][n] mix per block, overlapped with the next block's kernels (KB_MIXDOWN=peer selects the peer-memory mix-down)"
     try:
         return sharding.PeerMixdown(local_rank, max_floats), "NVLink peer memory: bank-mix kernels store into rank 0's arena, rank 0 sums in rank order (kb_mixdown_*)"
     except Exception as e:
@@ -365,9 +365,27 @@ def main():
             mixdown.publish(stream.cuda_stream)
             if rank == 0:
                 mixdown.collect(out_dev, out_dev.numel(), stream.cuda_stream)
-        else:
+        elif dist is None:
             bank.process_into(out_dev, BLOCK, flags)
-            sharding.reduce_mix(out_dev, dst=0)
+        else:
+            # the reduce of block k runs on NCCL's stream beside the voice kernels of block k+1 (two mix buffers); it is
+            # joined after the next block's kernels have been queued, and the last one by drain() inside the timed region
+            buf = mix_bufs[pipe["k"] & 1]
+            pipe["k"] += 1
+            bank.process_into(buf, BLOCK, flags)
+            if pipe["work"] is not None:
+                pipe["work"].wait()
+            pipe["work"] = dist.reduce(buf, dst=0, op=dist.ReduceOp.SUM, async_op=True)
+            pipe["last"] = buf
+
+    def drain():
+        """join the reduce still in flight (the timed loops call it before their closing event / barrier)"""
+        if pipe["work"] is not None:
+            pipe["work"].wait()
+            pipe["work"] = None
+
+    pipe = {"k": 0, "work": None, "last": out_dev}
+    mix_bufs = [out_dev, torch.empty_like(out_dev)]
 
     def step_device():
         events()
@@ -379,12 +397,14 @@ def main():
             bank.process_into(out_host.numpy(), BLOCK, flags)       # host-buffer call: upload state, kernels, D2H, sync
         else:
             mix_down()
-            out_host.copy_(out_dev, non_blocking=True)
+            drain()                                              # e2e: every block's reduced mix is read back before the next block
+            out_host.copy_(pipe["last"] if mixdown is None else out_dev, non_blocking=True)
             torch.cuda.synchronize()
 
     def timed(step_fn, steps, warmup, clocks=None):
         for _ in range(warmup):
             step_fn()
+        drain()
         barrier()
         if clocks:
             clocks.start()
@@ -395,6 +415,12 @@ def main():
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(stream)
             step_fn()
+            b.record(stream)
+            evs.append((a, b))
+        if dist is not None and mixdown is None:     # the last block's reduce, still in flight, belongs to the timed region
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            drain()
             b.record(stream)
             evs.append((a, b))
         if clocks:
@@ -441,6 +467,7 @@ def main():
     for _ in range(args.steps):
         flush_l2()
         step_device()
+    drain()
     k_ms, k_n = bank.profile_read()
     bank.profile(False)
     # A/B: the plain lane-per-voice schedule of the same arithmetic (same results, see tests)
