@@ -5,7 +5,7 @@ import numpy as np
 import klang_b200 as kb
 
 fs = 48000.0
-for graph, inst, voices, n in ((kb.SY_SUBTRACTIVE, 2, 16, 300), (kb.SY_SUPERSAW, 2, 32, 300), (kb.SY_TB303, 1, 32, 300), (kb.SY_SYNTHX, 1, 32, 70), (kb.SY_FILTER_K, 1, 32, 129)):
+for graph, inst, voices, n in ((kb.SY_SUBTRACTIVE, 2, 16, 300), (kb.SY_SUBTRACTIVE, 8, 100, 260), (kb.SY_SUPERSAW, 2, 32, 300), (kb.SY_TB303, 1, 32, 300), (kb.SY_SYNTHX, 1, 32, 70), (kb.SY_FILTER_K, 1, 32, 129)):
     b = kb.SynthBank(graph, inst, voices, fs, n)
     for g in range(0, inst * b.voices, 2):
         b.voice_start(g % b.voices, 40 + g % 30, 0.7, g // b.voices)
@@ -24,4 +24,17 @@ for graph, n, blocks in ((kb.FX_GAIN, 1001, 2), (kb.FX_PINGPONG, 2048, 24), (kb.
         fx.process_inplace(x.copy())
     print(graph, "parallel instances", fx.parallel_instances())
     fx.close()
+# the mix-down protocol on one rank (put / acquire + publish / collect over more steps than slot parities)
+import ctypes as C
+import torch
+L = kb.lib()
+h = L.kb_mixdown_create(0, 1, 0, 512)
+ts = torch.cuda.Stream(); torch.cuda.set_stream(ts)
+src = torch.rand(512, device="cuda"); dst = torch.empty(512, device="cuda")
+for k in range(5):
+    L.kb_mixdown_put(h, src.data_ptr(), 512, ts.cuda_stream)
+    L.kb_mixdown_collect(h, dst.data_ptr(), 512, ts.cuda_stream)
+torch.cuda.synchronize()
+assert torch.equal(src, dst)
+L.kb_mixdown_destroy(h)
 print("sanitize run done")
