@@ -704,7 +704,7 @@ extern "C" int kb_synth_bank_process(kb_synth_bank* b, float* out, int n, unsign
 			} else if (b->graph == KB_SY_SUPERSAW) {
 				KbSsawVoice* vs = (KbSsawVoice*)b->d_vstate;
 				if (g >= 8) KB_LAUNCH_TILED(kb_ssaw_tiled_kernel, KbSsawSmem, 8, 1024, vs, b->d_hdr, d_voice_dst, n, total, b->fs);
-				else KB_LAUNCH_TILED(kb_ssaw_tiled_kernel, KbSsawSmem, 2, 288, vs, b->d_hdr, d_voice_dst, n, total, b->fs);
+				else KB_LAUNCH_TILED(kb_ssaw_tiled_kernel, KbSsawSmem, 2, 1024, vs, b->d_hdr, d_voice_dst, n, total, b->fs);   // 992 workers: 7 x 2 x 128 items in two rounds
 			} else {
 				KbTbVoice* vs = (KbTbVoice*)b->d_vstate;
 				// (the ladder recurrence, one lane per voice and ~100 dependent cycles per sample, bounds this kernel for any G; giving it a

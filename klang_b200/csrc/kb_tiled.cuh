@@ -214,11 +214,17 @@ __global__ void __launch_bounds__(NT, 1) kb_sub_tiled_kernel(KbSubVoice* __restr
 }
 
 // ------------------------------------------------------------------------------------------------ SuperSaw
-// SuperSaw.k:25-33: seven detuned saws summed (each `/ 7`, in index order) times the ADSR.  A: adsr (tile k).
-// B+D fused (tile k-1): thread = (voice, t) evaluates the seven oscillators in closed form, scales and stores.
+// SuperSaw.k:25-33: seven detuned saws summed (each `/ 7`, in index order) times the ADSR.
+//   A (tile k)    warp 0, lane = voice: the ADSR
+//   B (tile k-1)  thread = (oscillator, voice, t): one closed-form oscillator sample `/ 7` into shared memory — seven times
+//                 the parallelism of a thread per (voice, t), which matters because 256 voices x 128 samples fill only a
+//                 quarter of the chip's lanes
+//   D (tile k-2)  thread = (voice, t): the seven parts added in oscillator order (the reference's `out +=` order), `* adsr`,
+//                 coalesced store
 template <int G> struct KbSsawSmem {
 	KbTileCommon<G> c;
-	KbTileRows<G> amp[2];
+	KbTileRows<G> amp[4];            // A -> D, two ticks later
+	KbTileRows<G> part[2][7];        // B -> D: osc[j] / 7 per (voice, t)
 	KbOsm osc[G][7];
 };
 template <int G, int NT>
@@ -237,28 +243,33 @@ __global__ void __launch_bounds__(NT, 1) kb_ssaw_tiled_kernel(KbSsawVoice* __res
 	__syncthreads();
 	const int ntiles = (n + T - 1) / T;
 	const int wtid = tid - 32, wthreads = NT - 32;
-	for (int k = 0; k < ntiles + 1; k++) {
-		if (warp == 0) {
+	for (int k = 0; k < ntiles + 2; k++) {
+		if (warp == 0) {                                                     // ---- A, tile k
 			if (is_env && k < ntiles) {
 				const int steps = min(T, n - k * T);
-				float* row = S.amp[k & 1].r[lane];
-				const float* px = S.c.px[lane]; const float* py = S.c.py[lane];
-				kb_envr_run(fs, env, px, py, row, steps);
+				kb_envr_run(fs, env, S.c.px[lane], S.c.py[lane], S.amp[k & 3].r[lane], steps);
 			}
 		} else {
-			const int b = k - 1;
-			if (b >= 0) {
+			const int b = k - 1, d = k - 2;
+			if (b >= 0 && b < ntiles) {                                      // ---- B, tile k-1
 				const int steps = min(T, n - b * T);
+				for (int item = wtid; item < 7 * G * T; item += wthreads) {
+					const int j = item / (G * T), v = (item / T) % G, t = item % T;
+					if (t < steps && S.c.active[v]) S.part[b & 1][j].r[v][t] = kb_osm_at(S.osc[v][j], (uint32_t)(b * T + t)) / 7;
+				}
+			}
+			if (d >= 0 && d < ntiles) {                                      // ---- D, tile k-2
+				const int steps = min(T, n - d * T);
 				for (int item = wtid; item < G * T; item += wthreads) {
 					const int v = item / T, t = item % T;
 					if (t < steps && v0 + v < total) {
 						float out = 0.f;
 						if (S.c.active[v]) {
 							#pragma unroll
-							for (int j = 0; j < 7; j++) out += kb_osm_at(S.osc[v][j], (uint32_t)(b * T + t)) / 7;
-							out *= S.amp[b & 1].r[v][t];
+							for (int j = 0; j < 7; j++) out += S.part[d & 1][j].r[v][t];   // out += osc[j] / 7, j = 0..6  SuperSaw.k:29-31
+							out *= S.amp[d & 3].r[v][t];
 						}
-						dst[(size_t)(v0 + v) * n + b * T + t] = out;
+						dst[(size_t)(v0 + v) * n + d * T + t] = out;
 					}
 				}
 			}
