@@ -443,8 +443,19 @@ KB_HD void kb_envr_run(const KbFs& fs, KbEnvR& e, const float* px, const float* 
 				const float t_hi = is_wait ? px[e.point + 1] : inf;
 				float r = e.r_out, time = e.time, last = e.out;
 				// the partial sums are formed exactly as single ticks would form them; r and time only move one way, so "the last
-				// of the group has not crossed / arrived" implies none has.  Groups of 16 first (the exit test and its branch cost
-				// as much as a dozen dependent adds), then groups of 4 up to the mode change.
+				// of the group has not crossed / arrived" implies none has.  Groups of 32 first (the exit test and its branch cost
+				// as much as a dozen dependent adds), then groups of 16 and of 4 up to the mode change.
+				while (t + 32 <= steps) {
+					float rr[33], tt = time;
+					rr[0] = r;
+					#pragma unroll
+					for (int j = 0; j < 32; j++) { rr[j + 1] = rr[j] + srate; tt = tt + tinc; }
+					const bool stay = (rr[32] < r_hi) & (rr[32] > r_lo) & (tt < t_hi);
+					if (!stay) break;
+					#pragma unroll
+					for (int j = 0; j < 32; j++) row[t + j] = rr[j];
+					last = rr[31]; r = rr[32]; time = tt; t += 32;
+				}
 				while (t + 16 <= steps) {
 					float rr[17], tt = time;
 					rr[0] = r;

@@ -52,12 +52,14 @@ KB_D void kb_tile_load_env(KbTileCommon<G>& c, int slot, const KbEnv& src, KbEnv
 // 5658-5665) and the oscillator sample.  C: Filter::process (klang.h:5605-5612) and `out *= adsr`.  D: stores.
 // Biquad::set is a pure function of (f, Q) and is re-evaluated for every sample; the reference's "unchanged (f,Q)"
 // early-out returns the same coefficients (Q is the constant 10, so the first set after reset() always computes).
+template <int G> struct alignas(16) KbTileRowsA { float r[G][KB_TILE_T + 4]; };     // row stride 132 floats: lane=voice 128-bit stores hit banks 4v..4v+3
 template <int G> struct KbTileRows4 { float4 r[G][KB_TILE_T + 1]; };   // lane=voice reads 16 B from banks 4v..4v+3: conflict-free per quarter warp
 template <int G> struct KbTileRows2 { float2 r[G][KB_TILE_T + 1]; };
 template <int G> struct KbSubSmem {
 	KbTileCommon<G> c;
 	KbTileRows4<G> coef[2];          // B -> C: (b0*in, b1*in, a1, a2) of every sample: one 128-bit load per step is all C reads
-	KbTileRows<G> cut[2], amp[4], out[2];   // A -> B cutoff; A -> D adsr level (three ticks later); C -> D filter output
+	KbTileRows<G> cut[2], amp[4];    // A -> B cutoff; A -> D adsr level (three ticks later)
+	KbTileRowsA<G> out[2];           // C -> D filter output (16-byte aligned rows: C stores four samples at a time)
 	float4 lastc[G];                 // (b0, b1, a1, a2) of the block's last sample, for the state write-back
 	KbOsm osc[G];
 };
@@ -131,30 +133,35 @@ __global__ void __launch_bounds__(NT, 1) kb_sub_tiled_kernel(KbSubVoice* __restr
 				// load, the four dependent operations of the recurrence, two independent ones and a store.  Groups of 4 steps; the
 				// operands of the NEXT group are loaded before the current group's updates, so no shared-memory latency sits on
 				// the recurrence (reads past `steps` stay inside the shared-memory struct and are unused)
-				float4 cf[4];
-				#pragma unroll
-				for (int j = 0; j < 4; j++) cf[j] = pc[j];
-				int t = 0;
-				for (; t + 4 <= steps; t += 4) {
-					float4 cn[4];
-					#pragma unroll
-					for (int j = 0; j < 4; j++) cn[j] = pc[t + 4 + j];
+				// two register sets used alternately (no copies): while set A is consumed set B is loaded, and vice versa
+				auto group = [&](const float4 (&cf)[4], int t) {
+					float y[4];
 					#pragma unroll
 					for (int j = 0; j < 4; j++) {
-						const float y = cf[j].x + z0;                        // y = b0*in + z0
-						z0 = cf[j].y - cf[j].z * y + z1;                     // z0 = b1*in - a1*y + z1
-						z1 = cf[j].x - cf[j].w * y;                          // z1 = b2*in - a2*y   (LPF: b2 == b0)
-						po[t + j] = y;
+						y[j] = cf[j].x + z0;                                 // y = b0*in + z0
+						z0 = cf[j].y - cf[j].z * y[j] + z1;                  // z0 = b1*in - a1*y + z1
+						z1 = cf[j].x - cf[j].w * y[j];                       // z1 = b2*in - a2*y   (LPF: b2 == b0)
 					}
-					#pragma unroll
-					for (int j = 0; j < 4; j++) cf[j] = cn[j];
-				}
+					*reinterpret_cast<float4*>(po + t) = make_float4(y[0], y[1], y[2], y[3]);
+				};
+				float4 ca[4], cb[4];
 				#pragma unroll
-				for (int j = 0; j < 3; j++) if (t + j < steps) {
-					const float y = cf[j].x + z0;
-					z0 = cf[j].y - cf[j].z * y + z1;
-					z1 = cf[j].x - cf[j].w * y;
-					po[t + j] = y;
+				for (int j = 0; j < 4; j++) ca[j] = pc[j];
+				int t = 0;
+				for (; t + 8 <= steps; t += 8) {
+					#pragma unroll
+					for (int j = 0; j < 4; j++) cb[j] = pc[t + 4 + j];
+					group(ca, t);
+					#pragma unroll
+					for (int j = 0; j < 4; j++) ca[j] = pc[t + 8 + j];
+					group(cb, t + 4);
+				}
+				for (; t < steps; t++) {                                 // ragged tail (only the last tile of a block)
+					const float4 c1 = pc[t];
+					const float y = c1.x + z0;
+					z0 = c1.y - c1.z * y + z1;
+					z1 = c1.x - c1.w * y;
+					po[t] = y;
 				}
 			}
 		} else if (worker) {
