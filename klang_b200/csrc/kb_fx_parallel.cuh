@@ -497,7 +497,7 @@ __global__ void kb_reverb_plan2_kernel(const KbReverb* __restrict__ states, KbFx
 	}
 	float tmin = 1e30f;
 	for (int r = 0; r < rv.count; r++) tmin = fminf(tmin, rv.times[r]);
-	chunk = min(chunk, ((int)tmin - 3) / 3);                                    // the early taps of chunk k+2 are gathered while chunk k is written
+	chunk = min(chunk, (int)tmin - 3);
 	KbFxPlan p;
 	p.chunk = chunk; p.mode = chunk >= 8 ? KB_PLAN_PARALLEL : KB_PLAN_SEQUENTIAL;
 	p.gain = p.delay = p.dry = 0.f;
@@ -670,42 +670,37 @@ __global__ void __launch_bounds__(KB_RV2_NT) kb_reverb_pipe_kernel(const KbFxHdr
 			wp += 2 * L; if (wp >= size) wp -= size;
 		}
 	};
-	// T(k): early ring write, tap products thread = (tap parity, frame), then the in-order sum per frame; group B (2 x 80
-	// threads).  The tap samples of a chunk are LOADED one iteration before they are used (taps_issue(k+2) follows
-	// taps_finish(k+1) and the values wait in registers), so the L1 / L2 latency of the gathers sits behind the chunk barrier
-	// instead of on this group's path; the taps' times and gains live in registers as well.
+	// T(k): early ring write, tap products thread = (tap parity, frame) with five taps in flight, then the in-order sum per
+	// frame; group B (2 x 80 threads)
 	const int e_dg = tb >= KB_RV2_LMAX ? 1 : 0, e_t = tb - KB_RV2_LMAX * e_dg;
-	float e_va[10], e_vb[10], e_fr[10], e_time[10], e_gain[10];                   // this thread's taps e_dg, e_dg + 2, .., e_dg + 18
-	#pragma unroll
-	for (int j = 0; j < 10; j++) { const int d = min(e_dg + 2 * j, KB_RV_MAXREFL - 1); e_time[j] = S.times[d]; e_gain[j] = S.gg[d]; }
-	const int e_n = max(0, (count - e_dg + 1) / 2);                                // how many of them exist
-	auto taps_issue = [&](int k) {
+	auto early_taps = [&](int k) {
 		const int L = chunk_len(k);
 		const int ebase = (int)(((unsigned)epos0 + (unsigned)(k * Lc)) % (unsigned)esize);
-		if (e_t < L) {
-			int idx = ebase + e_t; if (idx >= esize) idx -= esize;
+		const int t = e_t;
+		if (t < L) {
+			int idx = ebase + t; if (idx >= esize) idx -= esize;
+			if (e_dg == 0) ringe[idx] = S.xf[k & 1][t];
+			// (taps never reach into this chunk: Lc <= shortest tap - 3, so no barrier between the write and the reads)
 			int pos = idx + 1; if (pos >= esize) pos -= esize;                    // position after this frame's write
 			const float posf = (float)(pos - 1);
-			// (the taps of chunk k never reach into chunks k-2 .. k: Lc <= (shortest tap - 3) / 3, kb_reverb_plan2_kernel)
-			#pragma unroll
-			for (int j = 0; j < 10; j++) {
-				if (j < e_n) {
-					float read = posf - e_time[j]; if (read < 0.f) read += esize;            // Stereo::Delay::tap(float)  klang.h:4668-4681
-					const float fl = floorf(read); e_fr[j] = read - fl;
-					const int ii = (int)read, jj = (ii == esize - 1) ? 0 : ii + 1;
-					e_va[j] = ringe[ii]; e_vb[j] = ringe[jj];
+			for (int d0 = e_dg; d0 < count; d0 += 10) {                           // taps d0, d0+2, .., d0+8
+				float va[5], vb[5], fr[5];
+				#pragma unroll
+				for (int j = 0; j < 5; j++) {
+					const int d = d0 + 2 * j;
+					if (d < count) {
+						float read = posf - S.times[d]; if (read < 0.f) read += esize;       // Stereo::Delay::tap(float)  klang.h:4668-4681
+						const float fl = floorf(read); fr[j] = read - fl;
+						const int ii = (int)read, jj = (ii == esize - 1) ? 0 : ii + 1;
+						va[j] = ringe[ii]; vb[j] = ringe[jj];
+					}
+				}
+				#pragma unroll
+				for (int j = 0; j < 5; j++) {
+					const int d = d0 + 2 * j;
+					if (d < count) S.tp[d][t] = (va[j] * (1.f - fr[j]) + vb[j] * fr[j]) * S.gg[d];
 				}
 			}
-		}
-	};
-	auto taps_finish = [&](int k) {
-		const int L = chunk_len(k);
-		const int ebase = (int)(((unsigned)epos0 + (unsigned)(k * Lc)) % (unsigned)esize);
-		if (e_t < L) {
-			if (e_dg == 0) { int idx = ebase + e_t; if (idx >= esize) idx -= esize; ringe[idx] = S.xf[k & 1][e_t]; }
-			#pragma unroll
-			for (int j = 0; j < 10; j++)
-				if (j < e_n) S.tp[e_dg + 2 * j][e_t] = (e_va[j] * (1.f - e_fr[j]) + e_vb[j] * e_fr[j]) * e_gain[j];
 		}
 		kb_bar_group(2, GB);
 		if (tb < L) {
@@ -726,7 +721,7 @@ __global__ void __launch_bounds__(KB_RV2_NT) kb_reverb_pipe_kernel(const KbFxHdr
 	if (warp == 0) { if (tid < 8) filters(0); }
 	else if (warp == 1) { early_cascade(0); early_cascade(1); early_cascade(2); }
 	__syncthreads();
-	if (inB) { taps_issue(0); taps_finish(0); if (K > 1) taps_issue(1); }
+	if (inB) early_taps(0);
 	__syncthreads();
 
 	int cpar = 0;
@@ -747,8 +742,7 @@ __global__ void __launch_bounds__(KB_RV2_NT) kb_reverb_pipe_kernel(const KbFxHdr
 			}
 			if (k + 2 < K) load_windows(k + 2);
 		} else if (inB) {
-			if (k + 1 < K) taps_finish(k + 1);
-			if (k + 2 < K) taps_issue(k + 2);
+			if (k + 1 < K) early_taps(k + 1);
 			if (k + 4 < K) load_io(k + 4, tb, GB);
 		}
 		__syncthreads();
