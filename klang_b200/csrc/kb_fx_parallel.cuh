@@ -83,17 +83,25 @@ __global__ void __launch_bounds__(256) kb_dpingpong_stream_kernel(const KbFxHdr*
 	if (pl.mode == KB_PLAN_PARALLEL) {
 	const float tl = c[0].value * fs.f, tr = c[1].value * fs.f, gl = c[1].value, gr = c[3].value;
 	volatile int* flags = sync->flag + (size_t)inst * KB_DPP_MAXCHUNKS;
-	if (threadIdx.x == 0) {
-		// frame f reads ring samples written in frames f-1-t-1 .. f-t+1 (t = tl for the left line, tr for the right line)
-		kb_dpp_wait(flags, f0 - (int)tl - 3, f0 + len - 1 - (int)tl + 1, epoch, CHUNK);
-		kb_dpp_wait(flags, f0 - (int)tr - 3, f0 + len - 1 - (int)tr + 1, epoch, CHUNK);
-	}
-	__syncthreads();
 	const KbDPingPong& p = states[inst];
 	float* ringl = rings + p.l.ring; float* ringr = rings + p.r.ring;
 	float* L = io + (size_t)inst * 2 * stride; float* R = L + stride;
 	const int SIZE = p.l.SIZE, SIZER = p.r.SIZE;
 	const int pl0 = (int)(((long long)__ldcg(&p.l.position) + f0) % SIZE), pr0 = (int)(((long long)__ldcg(&p.r.position) + f0) % SIZER);
+	// the io block does not depend on other chunks: its loads are in flight while thread 0 waits for the ring dependencies
+	float inl[CHUNK / 256], inr[CHUNK / 256];
+	#pragma unroll
+	for (int u = 0; u < CHUNK / 256; u++) {
+		const int k = u * 256 + threadIdx.x;
+		if (k < len) { inl[u] = L[f0 + k]; inr[u] = R[f0 + k]; }
+	}
+	if (threadIdx.x == 0) {
+		// frame f reads ring samples written in frames f-1-t-1 .. f-t+1 (t = tl for the left line, tr for the right line)
+		kb_dpp_wait(flags, f0 - (int)tl - 3, f0 + len - 1 - (int)tl + 1, epoch, CHUNK);
+		kb_dpp_wait(flags, f0 - (int)tr - 3, f0 + len - 1 - (int)tr + 1, epoch, CHUNK);
+		__threadfence();
+	}
+	__syncthreads();
 	#pragma unroll
 	for (int u = 0; u < CHUNK / 256; u++) {
 		const int k = u * 256 + threadIdx.x, f = f0 + k;
@@ -108,14 +116,15 @@ __global__ void __launch_bounds__(256) kb_dpingpong_stream_kernel(const KbFxHdr*
 			i = (int)read; frac = read - i; j = i + 1; if (j == SIZER) j = 0;
 			const float a2 = __ldcg(ringr + i), b2 = __ldcg(ringr + j);
 			const float fr = (a2 + frac * (b2 - a2)) * gr;
-			const float ol = L[f] + fr, orr = R[f] + fl;                                        // Delay/PingPong.k:30-31
+			const float ol = inl[u] + fr, orr = inr[u] + fl;                                    // Delay/PingPong.k:30-31
 			ringl[posl] = ol; ringr[posr] = orr;                                                // delay << out  :33
 			L[f] = ol; R[f] = orr;
 		}
 	}
-	__threadfence();
+	// publish: the CTA barrier orders every thread's ring stores before thread 0, whose device-scope fence (cumulative) orders
+	// them before the flag
 	__syncthreads();
-	if (threadIdx.x == 0) flags[chunk] = epoch;
+	if (threadIdx.x == 0) { __threadfence(); flags[chunk] = epoch; }
 	}
 	// epilogue of the launch: the CTA that finishes last advances every parallel instance's write heads
 	__shared__ bool s_last;
