@@ -858,7 +858,7 @@ static int prim_finish(const char* what) {
 }
 extern "C" int kb_prim_osc(int kind, int nargs, float f, float phase, float duty, float fs, int n, float* out) {
 	if (kb_device_count() < 1) return kb_fail(KB_ENODEV, "no CUDA device");
-	if (!out || n < 0 || !(kind <= 5 || kind == 10 || kind == 11)) return kb_fail(KB_EINVAL, "kb_prim_osc: unsupported kind");
+	if (!out || n < 0 || kind < 0 || !(kind <= 9 || kind == 10 || kind == 11)) return kb_fail(KB_EINVAL, "kb_prim_osc: unsupported kind");
 	const KbFs F = kb_make_fs(fs);
 	std::vector<float> table(2048, 0.f);
 	if (kind >= 10) {   // Wavetable::operator=(Oscillator) fills the table with a Basic osc at fs/size Hz on the host (klang.h:3645-3650)

@@ -327,6 +327,11 @@ __global__ void kb_prim_osc_kernel(int kind, int nargs, float f, float phase, fl
 		KbBasicOsc o; kb_bosc_init(o);
 		if (nargs == 1) kb_bosc_set_f(fs, o, f); else kb_bosc_set_fp(fs, o, f, phase);
 		for (int s = 0; s < n; s++) out[s] = kb_bosc_sine_tick(o);
+	} else if (kind >= 6 && kind <= 9) {   // Basic::Saw / Triangle / Square / Pulse (Pulse::set(f, phase, duty), klang.h:4935-4938)
+		KbBasicOsc o; kb_bosc_init(o);
+		if (nargs == 1) kb_bosc_set_f(fs, o, f); else if (nargs == 2) kb_bosc_set_fp(fs, o, f, phase);
+		else if (kind == 9) { kb_bosc_set_fp(fs, o, f, phase); o.duty = duty; }
+		for (int s = 0; s < n; s++) out[s] = kb_bosc_shape_tick(o, kind - 5);
 	} else if (kind == 10 || kind == 11) {   // Wavetable::process + buffer::operator[](float)  klang.h:3672-3675, 2070-2078
 		float increment = f * (2048 / fs.f), position = (nargs >= 2) ? phase * 2048.f : 0.f;
 		for (int s = 0; s < n; s++) {

@@ -170,6 +170,19 @@ KB_HD float kb_bosc_sine_tick(KbBasicOsc& o) {            // Basic::Sine::proces
 	kb_bosc_advance(o);
 	return out;
 }
+// Basic::{Saw,Triangle,Square,Pulse}::process (aliased shapes; abs == fabsf, Q4)     klang.h:4907-4944
+enum { KB_BOSC_SAW = 1, KB_BOSC_TRIANGLE, KB_BOSC_SQUARE, KB_BOSC_PULSE };
+KB_HD float kb_bosc_shape_tick(KbBasicOsc& o, int shape) {
+	float out;
+	switch (shape) {
+	case KB_BOSC_SAW: out = o.position * KB_PI_INV_F - 1.f; break;
+	case KB_BOSC_TRIANGLE: out = fabsf(2.f * o.position * KB_PI_INV_F - 2) - 1.f; break;
+	case KB_BOSC_SQUARE: out = o.position > KB_PI_F ? 1.f : -1.f; break;
+	default: out = o.position > (o.duty * KB_PI_F) ? 1.f : -1.f; break;
+	}
+	kb_bosc_advance(o);
+	return out;
+}
 
 // ------------------------------------------------------------ Filters (klang.h:5383-5813)
 enum { KB_BQ_LPF = 0, KB_BQ_HPF, KB_BQ_BPF, KB_BQ_BRF, KB_BQ_APF, KB_BQ_BW2 };

@@ -93,14 +93,15 @@ def test_primitives_match_reference_golden(eng, golden, fs):
     eng.set_fs(fs)
     g = golden[fs]
     n = 256
-    kinds = {"fast_saw": 0, "fast_triangle": 1, "fast_square": 2, "fast_pulse": 3, "fast_sine": 4, "basic_sine": 5, "wt_sine": 10, "wt_saw": 11}
+    kinds = {"fast_saw": 0, "fast_triangle": 1, "fast_square": 2, "fast_pulse": 3, "fast_sine": 4, "basic_sine": 5,
+             "basic_saw": 6, "basic_triangle": 7, "basic_square": 8, "basic_pulse": 9, "wt_sine": 10, "wt_saw": 11}
     checked = 0
     for name, kind in kinds.items():
         for f in (441.0, 55.0, 3520.5, 1000.0):
             assert_parity(eng.osc(kind, n, f), g[f"osc/{name}/f{f}"], f"osc/{name}/f{f}", exact=True)
         assert_parity(eng.osc(kind, n, 441.0, 1.0), g[f"osc/{name}/f441_p1"], f"osc/{name}/f441_p1", exact=True)
         checked += 5
-        if kind <= 3:
+        if kind <= 3 or kind == 9:
             for duty in (0.05, 0.5, 0.93):
                 assert_parity(eng.osc(kind, n, 441.0, 0.0, duty), g[f"osc/{name}/f441_p0_d{duty}"], f"osc/{name}/d{duty}", exact=True)
                 assert_parity(eng.osc(kind, n, 2093.0, 2.0, duty), g[f"osc/{name}/f2093_p2_d{duty}"], f"osc/{name}/p2 d{duty}", exact=True)
