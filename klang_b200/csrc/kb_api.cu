@@ -876,13 +876,26 @@ extern "C" int kb_prim_osc(int kind, int nargs, float f, float phase, float duty
 }
 extern "C" int kb_prim_filter(int kind, int nset, const float* f, const float* Q, float fs, int n, const float* in, float* out, float* coeffs) {
 	if (kb_device_count() < 1) return kb_fail(KB_ENODEV, "no CUDA device");
-	const bool onepole = kind == 2 || kind == 3 || kind == 7;
-	if (kind < 0 || kind > 8 || !f || !in || !out || !coeffs || nset < 0 || nset > n || (onepole && nset > 1)) return kb_fail(KB_EINVAL, "kb_prim_filter: unsupported");
+	const bool onepole = kind == 2 || kind == 3 || kind == 7, host_set = kind >= 12;     // kinds whose set() runs on the host (libm)
+	if (kind < 0 || kind > 14 || !f || !in || !out || !coeffs || nset < 0 || nset > n || ((onepole || host_set) && nset > 1) || (kind >= 11 && !Q))
+		return kb_fail(KB_EINVAL, "kb_prim_filter: unsupported");
 	const KbFs F = kb_make_fs(fs);
+	float4 hc = make_float4(0.f, 0.f, 0.05f, 0.f);
+	if (kind == 12 && nset == 1) {               // Modal::set(f, decay)  klang.h:5832-5845 (exp / cos of floats: expf / cosf)
+		const float w = f[0] * F.w;
+		const float d = kb_clampf(::expf(-KB_PI_F / (Q[0] * F.f)), 1e-6f, 0.9999f);
+		hc.x = 2.f * d * kb_clampf(::cosf(w), -0.9999f, 0.9999f);
+		hc.y = -d * d;
+	} else if (kind == 13 || kind == 14) {       // Follower() { set(0.01f, 0.1f); } then AR::set(attack, release)  klang.h:5871-5878, 5882-5885
+		float attack = 0.01f, release = 0.1f;
+		if (nset == 1) { attack = f[0]; release = Q[0]; }
+		hc.x = 1.f - (attack == 0.f ? 0.f : ::expf(-1.0f / (F.f * attack)));
+		hc.y = 1.f - (release == 0.f ? 0.f : ::expf(-1.0f / (F.f * release)));
+	}
 	KbOnePole op; kb_onepole_construct(op, kind == 2 ? KB_OP_LPF : kind == 3 ? KB_OP_HPF : KB_OP_BW1);
 	if (onepole && nset == 1) kb_onepole_set(F, op, f[0]);
 	DevBuf df(sizeof(float) * (nset ? nset : 1), f), dq(sizeof(float) * (nset ? nset : 1), Q), din(sizeof(float) * n, in), dout(sizeof(float) * n), dc(sizeof(float) * 5);
-	kb_prim_filter_kernel<<<1, 32>>>(kind, nset, df.as<float>(), Q ? dq.as<float>() : nullptr, F, n, din.as<float>(), dout.as<float>(), dc.as<float>(), op);
+	kb_prim_filter_kernel<<<1, 32>>>(kind, nset, df.as<float>(), Q ? dq.as<float>() : nullptr, F, n, din.as<float>(), dout.as<float>(), dc.as<float>(), op, hc);
 	int rc = prim_finish("kb_prim_filter"); if (rc) return rc;
 	cudaMemcpy(out, dout.p, sizeof(float) * n, cudaMemcpyDeviceToHost);
 	cudaMemcpy(coeffs, dc.p, sizeof(float) * 5, cudaMemcpyDeviceToHost);

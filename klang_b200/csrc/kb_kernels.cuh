@@ -343,10 +343,49 @@ __global__ void kb_prim_osc_kernel(int kind, int nargs, float f, float phase, fl
 	}
 }
 // kinds (tests/cases.py): 0 Biquad::LPF 1 Biquad::HPF 2 OnePole::LPF 3 OnePole::HPF 4 Biquad::BPF 5 Biquad::BRF 6 Biquad::APF
-// 7 Butterworth::LPF<1> 8 Butterworth::LPF<2>; one-pole coefficients (expf / tanf) come from the host
+// 7 Butterworth::LPF<1> 8 Butterworth::LPF<2> 9 DCF 10 IIR<1> 11 IIR<2>; one-pole coefficients (expf / tanf) come from the host
+// 12 Modifiers::Modal, 13 / 14 Envelope::Follower peak / rms: coefficients hc from the host libm (set() is event-rate code)
 __global__ void kb_prim_filter_kernel(int kind, int nset, const float* f, const float* Q, KbFs fs, int n, const float* in, float* out, float* coeffs,
-                                      KbOnePole op) {
+                                      KbOnePole op, float4 hc) {
 	if (threadIdx.x || blockIdx.x) return;
+	if (kind == 12) {   // Modal::input + process  klang.h:5847-5856: in *= gain; out = in + a1*y1 + a2*y2
+		const float a1 = hc.x, a2 = hc.y, gain = hc.z;
+		float y1 = 0.f, y2 = 0.f;
+		for (int s = 0; s < n; s++) {
+			const float x = in[s] * gain;
+			const float o = x + a1 * y1 + a2 * y2;
+			y2 = y1; y1 = o;
+			out[s] = o;
+		}
+		coeffs[0] = a1; coeffs[1] = a2; coeffs[2] = gain; coeffs[3] = y1; coeffs[4] = y2;
+		return;
+	}
+	if (kind == 13 || kind == 14) {   // Follower::peak / rms over AR::process  klang.h:5866-5896 (abs, sqrt == fabsf, sqrtf: Q4)
+		const float A = hc.x, R = hc.y;
+		float ar = 0.f;
+		for (int s = 0; s < n; s++) {
+			const float x = kind == 13 ? fabsf(in[s]) : in[s] * in[s];
+			const float smoothing = x > ar ? A : R;
+			ar = ar + smoothing * (x - ar);
+			out[s] = kind == 13 ? ar : sqrtf(ar);
+		}
+		coeffs[0] = A; coeffs[1] = R; coeffs[2] = ar; coeffs[3] = 0.f; coeffs[4] = 0.f;
+		return;
+	}
+	if (kind >= 9) {   // 9 Filters::DCF (f = r), 10 IIR<1> (f = coefficient), 11 IIR<2> (f = a1, Q = a2)   klang.h:5387-5446
+		float r = 0.995f, z = 0.f, a = 1.f, b = 0.f, a2[2] = { 0.f, 0.f }, y2[2] = { 0.f, 0.f }, o = 0.f;
+		for (int s = 0; s < n; s++) {
+			if (s < nset) { if (kind == 9) r = f[s]; else if (kind == 10) { a = f[s]; b = 1.f - a; } else { a2[0] = f[s]; a2[1] = Q[s]; } }
+			const float x = in[s];
+			if (kind == 9) { o = x - z + r * o; z = x; }                       // DCF::process
+			else if (kind == 10) o = x * a + o * b;                           // IIR<1>::process
+			else { o = x; o -= a2[0] * y2[0]; o -= a2[1] * y2[1]; y2[1] = y2[0]; y2[0] = o; }   // IIR<2>::process
+			out[s] = o;
+		}
+		coeffs[0] = kind == 9 ? r : kind == 10 ? a : a2[0]; coeffs[1] = kind == 9 ? z : kind == 10 ? b : a2[1];
+		coeffs[2] = kind == 11 ? y2[0] : 0.f; coeffs[3] = kind == 11 ? y2[1] : 0.f; coeffs[4] = 0.f;
+		return;
+	}
 	const int bq = kind == 0 ? KB_BQ_LPF : kind == 1 ? KB_BQ_HPF : kind == 4 ? KB_BQ_BPF : kind == 5 ? KB_BQ_BRF : kind == 6 ? KB_BQ_APF : kind == 8 ? KB_BQ_BW2 : -1;
 	if (bq >= 0) {
 		KbBiquad b; kb_biquad_construct(b, bq);

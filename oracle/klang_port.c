@@ -585,11 +585,79 @@ int kp_wavetable(int kind, float* table) {
 }
 
 enum { FLT_BIQUAD_LPF = 0, FLT_BIQUAD_HPF, FLT_ONEPOLE_LPF, FLT_ONEPOLE_HPF,
-       FLT_BIQUAD_BPF, FLT_BIQUAD_BRF, FLT_BIQUAD_APF, FLT_BUTTERWORTH_LPF1, FLT_BUTTERWORTH_LPF2 };
+       FLT_BIQUAD_BPF, FLT_BIQUAD_BRF, FLT_BIQUAD_APF, FLT_BUTTERWORTH_LPF1, FLT_BUTTERWORTH_LPF2,
+       FLT_DCF, FLT_IIR1, FLT_IIR2, FLT_MODAL, FLT_FOLLOWER_PEAK, FLT_FOLLOWER_RMS };
 
 int kp_filter(int kind, int nset, const float* f, const float* Q, int n, const float* in, float* out, float* coeffs) {
 	kp_ensure_fs();
 	int bq = -1, op = -1;
+	if (kind == FLT_DCF) {                       /* Filters::DCF  klang.h:5387-5398: out = in - z + r*out; z = in */
+		float r = 0.995f, z = 0.f, o = 0.f;
+		for (int s = 0; s < n; s++) { if (s < nset) r = f[s]; o = in[s] - z + r * o; z = in[s]; out[s] = o; }
+		if (coeffs) { coeffs[0] = r; coeffs[1] = z; coeffs[2] = coeffs[3] = coeffs[4] = 0; }
+		return 0;
+	}
+	if (kind == FLT_IIR1) {                      /* Filters::IIR<1>  klang.h:5433-5446: out = in*a + out*b */
+		float a = 1.f, b = 0.f, o = 0.f;
+		for (int s = 0; s < n; s++) { if (s < nset) { a = f[s]; b = 1.f - a; } o = in[s] * a + o * b; out[s] = o; }
+		if (coeffs) { coeffs[0] = a; coeffs[1] = b; coeffs[2] = coeffs[3] = coeffs[4] = 0; }
+		return 0;
+	}
+	if (kind == FLT_IIR2) {                      /* Filters::IIR<2>  klang.h:5401-5430 */
+		if (!Q) return -1;
+		float a[2] = { 0.f, 0.f }, y[2] = { 0.f, 0.f };
+		for (int s = 0; s < n; s++) {
+			if (s < nset) { a[0] = f[s]; a[1] = Q[s]; }
+			float o = in[s];
+			o -= a[0] * y[0];
+			o -= a[1] * y[1];
+			y[1] = y[0]; y[0] = o;
+			out[s] = o;
+		}
+		if (coeffs) { coeffs[0] = a[0]; coeffs[1] = a[1]; coeffs[2] = y[0]; coeffs[3] = y[1]; coeffs[4] = 0; }
+		return 0;
+	}
+	if (kind == FLT_MODAL) {                     /* Modifiers::Modal  klang.h:5817-5857 */
+		if (!Q) return -1;
+		float a1 = 0.f, a2 = 0.f, y1 = 0.f, y2 = 0.f, gain = 0.05f;
+		for (int s = 0; s < n; s++) {
+			if (s < nset) {                      /* set(f, decay): exp / cos bind to expf / cosf (float arguments) */
+				gain = 0.05f;
+				const float w = f[s] * kp_fs.w;
+				float d = expf(-KP_PI_F / (Q[s] * kp_fs.f));
+				d = d < 1e-6f ? 1e-6f : (0.9999f < d ? 0.9999f : d);
+				float c = cosf(w);
+				c = c < -0.9999f ? -0.9999f : (0.9999f < c ? 0.9999f : c);
+				a1 = 2.f * d * c;
+				a2 = -d * d;
+				y2 = 0.f; y1 = 0.f;
+			}
+			const float x = in[s] * gain;        /* input(): in *= gain */
+			const float o = x + a1 * y1 + a2 * y2;
+			y2 = y1; y1 = o;
+			out[s] = o;
+		}
+		if (coeffs) { coeffs[0] = a1; coeffs[1] = a2; coeffs[2] = gain; coeffs[3] = y1; coeffs[4] = y2; }
+		return 0;
+	}
+	if (kind == FLT_FOLLOWER_PEAK || kind == FLT_FOLLOWER_RMS) {   /* Envelope::Follower + AR  klang.h:5862-5896 */
+		if (!Q) return -1;
+		float attack = 0.01f, release = 0.1f;    /* Follower() { set(0.01f, 0.1f); } */
+		float A = 1.f - expf(-1.0f / (kp_fs.f * attack)), R = 1.f - expf(-1.0f / (kp_fs.f * release)), ar = 0.f;
+		for (int s = 0; s < n; s++) {
+			if (s < nset && (attack != f[s] || release != Q[s])) {
+				attack = f[s]; release = Q[s];
+				A = 1.f - (attack == 0.f ? 0.f : expf(-1.0f / (kp_fs.f * attack)));
+				R = 1.f - (release == 0.f ? 0.f : expf(-1.0f / (kp_fs.f * release)));
+			}
+			const float x = kind == FLT_FOLLOWER_PEAK ? fabsf(in[s]) : in[s] * in[s];
+			const float smoothing = x > ar ? A : R;
+			ar = ar + smoothing * (x - ar);
+			out[s] = kind == FLT_FOLLOWER_PEAK ? ar : sqrtf(ar);
+		}
+		if (coeffs) { coeffs[0] = A; coeffs[1] = R; coeffs[2] = ar; coeffs[3] = coeffs[4] = 0; }
+		return 0;
+	}
 	switch (kind) {
 	case FLT_BIQUAD_LPF: bq = KP_BQ_LPF; break;
 	case FLT_BIQUAD_HPF: bq = KP_BQ_HPF; break;

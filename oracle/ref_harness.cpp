@@ -172,7 +172,8 @@ int ref_wavetable(int kind, float* table) {
 
 // ---------------------------------------------------------------------- filters
 enum { FLT_BIQUAD_LPF = 0, FLT_BIQUAD_HPF, FLT_ONEPOLE_LPF, FLT_ONEPOLE_HPF,
-       FLT_BIQUAD_BPF, FLT_BIQUAD_BRF, FLT_BIQUAD_APF, FLT_BUTTERWORTH_LPF1, FLT_BUTTERWORTH_LPF2 };
+       FLT_BIQUAD_BPF, FLT_BIQUAD_BRF, FLT_BIQUAD_APF, FLT_BUTTERWORTH_LPF1, FLT_BUTTERWORTH_LPF2,
+       FLT_DCF, FLT_IIR1, FLT_IIR2, FLT_MODAL, FLT_FOLLOWER_PEAK, FLT_FOLLOWER_RMS };
 
 extern "C++" {
 template<class F>
@@ -203,6 +204,17 @@ static void run_onepole(int nset, const float* f, int n, const float* in, float*
 	}
 	if (coeffs) { coeffs[0] = flt.b0; coeffs[1] = flt.b1; coeffs[2] = 0; coeffs[3] = flt.a1; coeffs[4] = 0; }
 }
+// Filters::DCF (f = r), IIR<1> (f = coefficient), IIR<2> (f = a1, Q = a2)   klang.h:5387-5464
+template<class F, class SET>
+static void run_simple(int nset, int n, const float* in, float* out, F& flt, SET set) {
+	for (int s = 0; s < n; s++) {
+		if (s < nset) set(s);
+		klang::signal x = in[s];
+		klang::signal y;
+		x >> flt >> y;
+		out[s] = y;
+	}
+}
 } // extern "C++"
 
 // nset: how many leading samples call set(f[s](,Q[s])) before processing (1 = static, n = per-sample).
@@ -219,6 +231,15 @@ int ref_filter(int kind, int nset, const float* f, const float* Q, int n, const 
 	case FLT_ONEPOLE_LPF: run_onepole<OnePole::LPF>(nset, f, n, in, out, coeffs); break;
 	case FLT_ONEPOLE_HPF: run_onepole<OnePole::HPF>(nset, f, n, in, out, coeffs); break;
 	case FLT_BUTTERWORTH_LPF1: run_onepole<Butterworth::LPF<1>>(nset, f, n, in, out, coeffs); break;
+	case FLT_DCF: { DCF flt; run_simple(nset, n, in, out, flt, [&](int s) { flt.set(f[s]); }); if (coeffs) { coeffs[0] = flt.r; coeffs[1] = flt.z; coeffs[2] = coeffs[3] = coeffs[4] = 0; } break; }
+	case FLT_IIR1: { IIR<1> flt; run_simple(nset, n, in, out, flt, [&](int s) { flt.set(klang::param(f[s])); }); if (coeffs) { coeffs[0] = flt.a; coeffs[1] = flt.b; coeffs[2] = coeffs[3] = coeffs[4] = 0; } break; }
+	case FLT_IIR2: { if (!Q) return -1; IIR<2> flt; run_simple(nset, n, in, out, flt, [&](int s) { flt.set(f[s], Q[s]); }); if (coeffs) { coeffs[0] = flt.a[0]; coeffs[1] = flt.a[1]; coeffs[2] = flt.y[0]; coeffs[3] = flt.y[1]; coeffs[4] = 0; } break; }
+	// Modifiers::Modal (f, Q = decay seconds)  klang.h:5817-5857;  Envelope::Follower peak / rms (f = attack, Q = release)  5862-5896
+	case FLT_MODAL: { if (!Q) return -1; klang::Modifiers::Modal flt; run_simple(nset, n, in, out, flt, [&](int s) { flt.set(klang::param(f[s]), klang::param(Q[s])); });
+		if (coeffs) { coeffs[0] = flt.a1; coeffs[1] = flt.a2; coeffs[2] = flt.gain; coeffs[3] = flt.y1; coeffs[4] = flt.y2; } break; }
+	case FLT_FOLLOWER_PEAK: case FLT_FOLLOWER_RMS: { if (!Q) return -1; klang::Envelope::Follower flt; flt = (kind == FLT_FOLLOWER_RMS) ? klang::RMS : klang::Peak;
+		run_simple(nset, n, in, out, flt, [&](int s) { flt.set(klang::param(f[s]), klang::param(Q[s])); });
+		if (coeffs) { coeffs[0] = flt.ar.A; coeffs[1] = flt.ar.R; coeffs[2] = flt.ar.out; coeffs[3] = coeffs[4] = 0; } break; }
 	default: return -1;
 	}
 	return 0;

@@ -17,7 +17,8 @@ import numpy as np
  OSC_BASIC_SINE, OSC_BASIC_SAW, OSC_BASIC_TRIANGLE, OSC_BASIC_SQUARE, OSC_BASIC_PULSE,
  OSC_WT_SINE, OSC_WT_SAW) = range(12)
 (FLT_BIQUAD_LPF, FLT_BIQUAD_HPF, FLT_ONEPOLE_LPF, FLT_ONEPOLE_HPF,
- FLT_BIQUAD_BPF, FLT_BIQUAD_BRF, FLT_BIQUAD_APF, FLT_BUTTERWORTH_LPF1, FLT_BUTTERWORTH_LPF2) = range(9)
+ FLT_BIQUAD_BPF, FLT_BIQUAD_BRF, FLT_BIQUAD_APF, FLT_BUTTERWORTH_LPF1, FLT_BUTTERWORTH_LPF2,
+ FLT_DCF, FLT_IIR1, FLT_IIR2, FLT_MODAL, FLT_FOLLOWER_PEAK, FLT_FOLLOWER_RMS) = range(15)
 FX_GAIN, FX_PINGPONG, FX_REVERB, FX_DELAY_PINGPONG, FX_DELAY_REVERB = range(5)
 SY_SUBTRACTIVE, SY_SUPERSAW, SY_TB303, SY_SYNTHX, SY_FILTER_K = range(5)
 
@@ -92,6 +93,25 @@ def primitive_cases(eng, fs):
         out[f"filter/{name}/coeffs"] = c
         y, _ = eng.filt(kind, x, sweep, None, per_sample=True)
         out[f"filter/{name}/sweep"] = y
+
+    # Filters::DCF / IIR<1> / IIR<2> (klang.h:5387-5464): f = r / coefficient / a1, Q = a2
+    for kind, name, f, Q in ((FLT_DCF, "dcf", 0.995, None), (FLT_DCF, "dcf_r09", 0.9, None), (FLT_IIR1, "iir1", 0.25, None),
+                             (FLT_IIR2, "iir2", -1.6, 0.8)):
+        y, c = eng.filt(kind, x, f, Q)
+        out[f"filter/{name}/noise"] = y
+        out[f"filter/{name}/coeffs"] = c
+        y, c = eng.filt(kind, imp, f, Q)
+        out[f"filter/{name}/impulse"] = y
+
+    # Modifiers::Modal (f, decay) and Envelope::Follower peak / rms (attack, release)   klang.h:5817-5896
+    for kind, name, f, Q in ((FLT_MODAL, "modal", 440.0, 0.25), (FLT_MODAL, "modal_hi", 7040.0, 0.01),
+                             (FLT_FOLLOWER_PEAK, "follower_peak", 0.01, 0.1), (FLT_FOLLOWER_RMS, "follower_rms", 0.002, 0.05),
+                             (FLT_FOLLOWER_PEAK, "follower_peak_instant", 0.0, 0.02)):
+        y, c = eng.filt(kind, x, f, Q)
+        out[f"filter/{name}/noise"] = y
+        out[f"filter/{name}/coeffs"] = c
+        y, c = eng.filt(kind, imp, f, Q)
+        out[f"filter/{name}/impulse"] = y
 
     y, st = eng.envelope([(0, 0), (0.001, 1), (0.003, 0.25), (0.005, 0.5)], 400)
     out["envelope/4pt"] = y

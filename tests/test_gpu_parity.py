@@ -131,6 +131,14 @@ def test_primitives_match_reference_golden(eng, golden, fs):
         assert_parity(y, g[f"filter/{name}/sweep_q10"], name + " sweep", exact=True)
     y, _ = eng.filt(6, x, 1000.0, 0.5)
     assert_parity(y, g["filter/biquad_apf/noise"], "biquad_apf noise", exact=True)
+    for kind, name, f, Q in ((9, "dcf", 0.995, None), (9, "dcf_r09", 0.9, None), (10, "iir1", 0.25, None), (11, "iir2", -1.6, 0.8),   # klang.h:5387-5446
+                             (12, "modal", 440.0, 0.25), (12, "modal_hi", 7040.0, 0.01), (13, "follower_peak", 0.01, 0.1),       # klang.h:5817-5896
+                             (14, "follower_rms", 0.002, 0.05), (13, "follower_peak_instant", 0.0, 0.02)):
+        y, c = eng.filt(kind, x, f, Q)
+        assert_parity(y, g[f"filter/{name}/noise"], name + " noise", exact=True)
+        assert_parity(c, g[f"filter/{name}/coeffs"], name + " coeffs", exact=True)
+        y, _ = eng.filt(kind, imp, f, Q)
+        assert_parity(y, g[f"filter/{name}/impulse"], name + " impulse", exact=True)
     y, st = eng.envelope([(0, 0), (0.001, 1), (0.003, 0.25), (0.005, 0.5)], 400)
     assert_parity(y, g["envelope/4pt"], "envelope/4pt", exact=True)
     assert_parity(st, g["envelope/4pt_stage"], "envelope/4pt_stage")
