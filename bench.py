@@ -496,7 +496,12 @@ def main():
                 "note": "C2 is bound by the dependent-issue latency of its fp32 recurrences, not HBM (SURVEY H6, DESIGN.md 4.1): 4 B of stream traffic per voice-sample",
                 "voice_samples_per_s_kernel": total * BLOCK / (k_ms_avg * 1e-3),
                 "fp32_lane_cycles_per_voice_sample": issue_peak / (total * BLOCK / (k_ms_avg * 1e-3)),
-                "lane_per_voice_kernel_ms": lane_ms}
+                "lane_per_voice_kernel_ms": lane_ms,
+                # what actually bounds this kernel: one fp32 recurrence per voice that parity forbids re-ordering.  Floor = the
+                # TDF-II biquad chain measured alone on one warp of this chip (tools/micro/serial_floor.cu, profiles/r01_probes.txt)
+                "latency_bound": {"floor_cycles_per_sample": 16.9, "achieved_cycles_per_sample": k_ms_avg * 1e-3 * sm_max * 1e6 / BLOCK,
+                                  "frac": 16.9 / (k_ms_avg * 1e-3 * sm_max * 1e6 / BLOCK), "clock_mhz": sm_max,
+                                  "note": "every voice's filter chain advances one sample per tick of its CTA; 128 CTAs tick in parallel"}}
     bank.close()
 
     line = {
