@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(NT, 1) kb_tb_tiled_kernel(KbTbVoice* __restric
 					if (F.feedback.f != B.hpf_f) { F.feedback.f = B.hpf_f; F.feedback.b0 = B.hpf_b0; F.feedback.b1 = B.hpf_b1; F.feedback.a1 = B.hpf_a1; }   // setHPF  TB303.k:33-35
 					F.in = o_x;
 					const float y0 = kb_onepole_tick(F.feedback, F.k * F.z[3]) * 0.9f * F.resonance;
-					const float shaped = (y0 > KB_ROOT2_F) ? KB_ROOT2_F : (y0 < -0.5) ? -0.5f : y0;
+					const float shaped = (y0 > KB_ROOT2_F) ? KB_ROOT2_F : (y0 < -0.5f) ? -0.5f : y0;   // (float)y0 < -0.5 (double literal) == y0 < -0.5f: -0.5 is exact
 					F.in -= shaped;
 					F.z[0] += 2.f * F.b0 * (F.in - F.z[0] + F.z[1]);
 					F.z[1] += F.b0 * (F.z[0] - 2.f * F.z[1] + F.z[2]);
