@@ -14,3 +14,32 @@ def test_run_length_envelope_and_closed_form_oscillator():
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert " 0 mismatches" in out.stdout
+
+
+def test_bench_reference_arm_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) prints ONE JSON line with the contract's keys;
+    it needs no GPU: the compiled reference (or the C port) on the host cores."""
+    import json
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "voice-samples/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["steps"] == 1 and d["config"]["block"] == 4096 and d["config"]["voices_per_instance"] == 128
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "voice-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_clock_sampler_without_nvml_reports_nothing():
+    """The bench's clock sampler never raises and reports `sm_mhz: None` when neither NVML nor nvidia-smi can see a GPU."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("kb_bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    s = bench.ClockSampler(0).start()
+    s.sample()
+    r = s.stop()
+    assert "sm_mhz" in r and "reasons" in r
