@@ -574,6 +574,9 @@ def test_odd_bank_shapes_vs_live_oracle(eng):
     _drive_bank_vs_oracle(cases.SY_SUBTRACTIVE, 5, 33, 5, 333, 48000, exact=True)
     _drive_bank_vs_oracle(cases.SY_TB303, 3, 37, 5, 200, 44100, exact=True)
     _drive_bank_vs_oracle(cases.SY_SUPERSAW, 3, 35, 4, 130, 48000, exact=True)
+    # the 8-voice layout-2 Subtractive kernel with a partial last CTA (819 voices) and the 16-voice kernel (1625 voices)
+    _drive_bank_vs_oracle(cases.SY_SUBTRACTIVE, 7, 117, 3, 333, 48000, exact=True)
+    _drive_bank_vs_oracle(cases.SY_SUBTRACTIVE, 13, 125, 2, 200, 44100, exact=True)
 
 
 def test_pingpong_long_blocks_span_sub_blocks(eng):
