@@ -391,10 +391,22 @@ def main():
         events()
         mix_down()
 
+    host_bufs = [out_host, torch.empty_like(out_host).pin_memory()]
+    host_done = [torch.cuda.Event(), torch.cuda.Event()]
+    e2e_k = [0]
+
     def step_e2e():
         events()
         if dist is None:
-            bank.process_into(out_host.numpy(), BLOCK, flags)       # host-buffer call: upload state, kernels, D2H, sync
+            # host-buffer call with KB_ASYNC_HOST: state upload, kernels and the D2H copy into pinned memory are queued; the host
+            # prepares the next block's events meanwhile and joins a buffer only before reusing it (two buffers, as a streaming
+            # host would).  Every block's result still crosses PCIe inside the timed region.
+            i = e2e_k[0] & 1
+            if e2e_k[0] >= 2:
+                host_done[i].synchronize()
+            bank.process_into(host_bufs[i].numpy(), BLOCK, flags | kb.ASYNC_HOST)
+            host_done[i].record(stream)
+            e2e_k[0] += 1
         else:
             mix_down()
             drain()                                              # e2e: every block's reduced mix is read back before the next block
@@ -459,8 +471,9 @@ def main():
     out_bytes = out_host.numel() * 4 if dist is not None else 0      # (N=1: the library's host-buffer call counts its own D2H)
     e2e = {"value": e2e_value, "unit": "voice-samples/s",
            "h2d_bytes_per_step": int((h2d1 - h2d0) / args.steps), "d2h_bytes_per_step": int((d2h1 - d2h0) / args.steps + out_bytes),
-           "note": "per step: the host applies 64 note events on its state mirror (state fetch D2H, packed dirty-voice upload H2D), "
-                   "kernels, output D2H into pinned memory; bytes counted by the library"}
+           "note": "per step: the host applies 64 note events on its state mirror (packed dirty-voice upload H2D), kernels, output D2H "
+                   "into pinned memory (KB_ASYNC_HOST, two host buffers: block k+1's events are prepared while block k renders; "
+                   "every buffer is joined before reuse and at the end of the timed region); bytes counted by the library"}
 
     # ---- dominant kernel, CUDA events inside the library
     bank.profile(True)

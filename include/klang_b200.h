@@ -51,6 +51,9 @@ extern "C" {
 #define KB_LANE_PER_VOICE 16u     /* synth: use the plain lane-per-voice schedule instead of the tiled one (A/B measurement; same results) */
 #define KB_FX_SEQUENTIAL 32u       /* effects: use only the frame-sequential schedule (A/B measurement; same results) */
 #define KB_BANK_MIX 8u            /* synth: additionally sum all instances, out = [channels][n] (the multi-GPU mix-down input) */
+#define KB_ASYNC_HOST 64u         /* host-pointer call: return once the work and the device-to-host copy are queued on the bank stream;
+                                     `io` / `out` must be page-locked and is valid after kb_*_bank_sync (or an event the caller
+                                     records on its stream).  Lets a host prepare block k+1's events while block k renders. */
 
 typedef struct kb_fx_bank kb_fx_bank;
 typedef struct kb_synth_bank kb_synth_bank;

@@ -14,7 +14,7 @@ lib_path = os.path.join(_HERE, "lib", "libklang_b200.so")
 
 FX_GAIN, FX_PINGPONG, FX_REVERB, FX_DELAY_PINGPONG, FX_DELAY_REVERB = range(5)
 SY_SUBTRACTIVE, SY_SUPERSAW, SY_TB303, SY_SYNTHX, SY_FILTER_K = range(5)
-DEVICE_PTR, PER_VOICE, MIX_SUM, BANK_MIX, LANE_PER_VOICE, FX_SEQUENTIAL = 1, 2, 4, 8, 16, 32
+DEVICE_PTR, PER_VOICE, MIX_SUM, BANK_MIX, LANE_PER_VOICE, FX_SEQUENTIAL, ASYNC_HOST = 1, 2, 4, 8, 16, 32, 64
 
 # every symbol include/klang_b200.h declares: (name, restype, argtypes)
 _vp, _i, _f, _u, _ll, _d = C.c_void_p, C.c_int, C.c_float, C.c_uint, C.c_longlong, C.c_double

@@ -335,7 +335,7 @@ extern "C" int kb_fx_bank_process(kb_fx_bank* b, float* io, int n, unsigned flag
 	if (b->graph != KB_FX_GAIN) b->host_stale = true;
 	if (!(flags & KB_DEVICE_PTR)) {
 		KB_CUDA(cudaMemcpyAsync(io, d, floats * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
-		KB_CUDA(cudaStreamSynchronize(b->stream));
+		if (!(flags & KB_ASYNC_HOST)) KB_CUDA(cudaStreamSynchronize(b->stream));
 	}
 	return KB_OK;
 }
@@ -347,7 +347,12 @@ struct kb_synth_bank : kb_bank_base {
 	std::vector<KbControl> controls;              // [instances][KB_MAX_CONTROLS], host-owned
 	// host mirror in pinned memory (asynchronous, full-speed copies); dirty voices are uploaded packed
 	KbVoiceHdr* hdr = nullptr; unsigned char* vstate = nullptr; size_t hdr_count = 0, vstate_bytes = 0;
-	unsigned char* staging = nullptr; int* staging_index = nullptr;             // pinned
+	// pinned upload staging: a ring of KB_NSTAGE slots, each guarded by an event recorded after its H2D copies, so a caller
+	// that runs ahead of the device (KB_DEVICE_PTR calls are asynchronous) never rewrites a slot whose copy is still queued
+	static constexpr int KB_NSTAGE = 4;
+	unsigned char* staging = nullptr; int* staging_index = nullptr;             // pinned, KB_NSTAGE slots each
+	cudaEvent_t stage_done[KB_NSTAGE] = {}; bool stage_used[KB_NSTAGE] = {}; int stage_next = 0;
+	size_t stage_bytes = 0, stage_ints = 0;
 	unsigned char* d_staging = nullptr; int* d_staging_index = nullptr;
 	std::vector<unsigned char> voice_dirty; std::vector<int> dirty_list; bool all_dirty = true;
 	long long h2d_bytes = 0, d2h_bytes = 0;                                     // state traffic so far (for the e2e accounting)
@@ -402,14 +407,20 @@ static int sy_upload(kb_synth_bank* b) {
 		const bool mirror_current = !b->hdr_stale && !b->vstate_stale;
 		if (!b->all_dirty && !(mirror_current && b->dirty_list.size() * 4 > b->hdr_count)) {
 			const int count = (int)b->dirty_list.size();
+			const int slot = b->stage_next; b->stage_next = (slot + 1) % kb_synth_bank::KB_NSTAGE;
+			if (b->stage_used[slot]) KB_CUDA(cudaEventSynchronize(b->stage_done[slot]));    // its previous copies have left the host buffer
+			unsigned char* stage = b->staging + (size_t)slot * b->stage_bytes;
+			int* stage_index = b->staging_index + (size_t)slot * b->stage_ints;
 			for (int k = 0; k < count; k++) {
 				const int v = b->dirty_list[k];
-				b->staging_index[k] = v;
-				memcpy(b->staging + (size_t)k * rec, b->hdr + v, sizeof(KbVoiceHdr));
-				memcpy(b->staging + (size_t)k * rec + sizeof(KbVoiceHdr), b->vstate + (size_t)v * b->voice_bytes, b->voice_bytes);
+				stage_index[k] = v;
+				memcpy(stage + (size_t)k * rec, b->hdr + v, sizeof(KbVoiceHdr));
+				memcpy(stage + (size_t)k * rec + sizeof(KbVoiceHdr), b->vstate + (size_t)v * b->voice_bytes, b->voice_bytes);
 			}
-			KB_CUDA(cudaMemcpyAsync(b->d_staging, b->staging, (size_t)count * rec, cudaMemcpyHostToDevice, b->stream));
-			KB_CUDA(cudaMemcpyAsync(b->d_staging_index, b->staging_index, (size_t)count * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+			KB_CUDA(cudaMemcpyAsync(b->d_staging, stage, (size_t)count * rec, cudaMemcpyHostToDevice, b->stream));
+			KB_CUDA(cudaMemcpyAsync(b->d_staging_index, stage_index, (size_t)count * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+			KB_CUDA(cudaEventRecord(b->stage_done[slot], b->stream));
+			b->stage_used[slot] = true;
 			const int words = count * (int)(rec / 4);
 			kb_scatter_voices_kernel<<<std::min(148, (words + 255) / 256), 256, 0, b->stream>>>(b->d_staging, b->d_staging_index, count, (int)b->voice_bytes, b->d_hdr, b->d_vstate);
 			b->launches++;
@@ -417,6 +428,7 @@ static int sy_upload(kb_synth_bank* b) {
 		} else {
 			KB_CUDA(cudaMemcpyAsync(b->d_hdr, b->hdr, b->hdr_count * sizeof(KbVoiceHdr), cudaMemcpyHostToDevice, b->stream));
 			KB_CUDA(cudaMemcpyAsync(b->d_vstate, b->vstate, b->vstate_bytes, cudaMemcpyHostToDevice, b->stream));
+			KB_CUDA(cudaStreamSynchronize(b->stream));      // the source is the live mirror, which the next event rewrites (rare path: first upload / most voices dirty)
 			b->h2d_bytes += (long long)(b->hdr_count * sizeof(KbVoiceHdr) + b->vstate_bytes);
 		}
 		for (int v : b->dirty_list) b->voice_dirty[v] = 0;
@@ -432,7 +444,6 @@ static int sy_upload(kb_synth_bank* b) {
 		KB_CUDA(cudaMemcpyAsync(b->d_blk, b->blk.data(), b->blk.size() * sizeof(KbSynthBlock), cudaMemcpyHostToDevice, b->stream));
 		KB_CUDA(cudaStreamSynchronize(b->stream));      // blk is pageable and may be rewritten by the next control change
 	}
-	// the pinned mirror / staging buffers are not touched again before the next fetch, which joins the stream first
 	b->dirty = false; b->blk_dirty = false;
 	return KB_OK;
 }
@@ -470,11 +481,14 @@ extern "C" kb_synth_bank* kb_synth_bank_create(int graph, int instances, int voi
 	b->hdr_count = total; b->vstate_bytes = (size_t)total * b->voice_bytes;
 	if (cudaSetDevice(device) != cudaSuccess || cudaHostAlloc((void**)&b->hdr, total * sizeof(KbVoiceHdr), cudaHostAllocDefault) != cudaSuccess ||
 	    cudaHostAlloc((void**)&b->vstate, b->vstate_bytes, cudaHostAllocDefault) != cudaSuccess ||
-	    cudaHostAlloc((void**)&b->staging, (size_t)(total + 1) * (sizeof(KbVoiceHdr) + b->voice_bytes), cudaHostAllocDefault) != cudaSuccess ||
-	    cudaHostAlloc((void**)&b->staging_index, (size_t)(total + 1) * sizeof(int), cudaHostAllocDefault) != cudaSuccess) {
+	    cudaHostAlloc((void**)&b->staging, kb_synth_bank::KB_NSTAGE * (size_t)(total + 1) * (sizeof(KbVoiceHdr) + b->voice_bytes), cudaHostAllocDefault) != cudaSuccess ||
+	    cudaHostAlloc((void**)&b->staging_index, kb_synth_bank::KB_NSTAGE * (size_t)(total + 1) * sizeof(int), cudaHostAllocDefault) != cudaSuccess) {
 		kb_fail(KB_ECUDA, std::string("kb_synth_bank_create: pinned host allocation: ") + cudaGetErrorString(cudaGetLastError()));
 		kb_synth_bank_destroy(b); return nullptr;
 	}
+	b->stage_bytes = (size_t)(total + 1) * (sizeof(KbVoiceHdr) + b->voice_bytes); b->stage_ints = (size_t)total + 1;
+	for (int k = 0; k < kb_synth_bank::KB_NSTAGE; k++)
+		if (cudaEventCreateWithFlags(&b->stage_done[k], cudaEventDisableTiming) != cudaSuccess) { kb_fail(KB_ECUDA, "kb_synth_bank_create: event"); kb_synth_bank_destroy(b); return nullptr; }
 	for (int v = 0; v < total; v++) b->hdr[v] = KbVoiceHdr{ KB_NOTE_OFF, 0.f, 0.f, 0 };
 	memset(b->vstate, 0, b->vstate_bytes);
 	b->voice_dirty.assign(total, 0);
@@ -509,6 +523,7 @@ extern "C" void kb_synth_bank_destroy(kb_synth_bank* b) {
 	cudaSetDevice(b->device);
 	if (b->stream) cudaStreamSynchronize(b->stream);
 	b->prof_free();
+	for (int k = 0; k < kb_synth_bank::KB_NSTAGE; k++) if (b->stage_done[k]) cudaEventDestroy(b->stage_done[k]);
 	cudaFreeHost(b->hdr); cudaFreeHost(b->vstate); cudaFreeHost(b->staging); cudaFreeHost(b->staging_index);
 	cudaFree(b->d_staging); cudaFree(b->d_staging_index);
 	cudaFree(b->d_hdr); cudaFree(b->d_vstate); cudaFree(b->d_blk); cudaFree(b->d_scratch); cudaFree(b->d_out); cudaFree(b->d_adsr); cudaFree(b->d_mix);
@@ -732,7 +747,7 @@ extern "C" int kb_synth_bank_process(kb_synth_bank* b, float* out, int n, unsign
 	b->host_stale = true; b->hdr_stale = true; b->vstate_stale = true;
 	if (!dev) {
 		KB_CUDA(cudaMemcpyAsync(out, d_result, out_floats * sizeof(float), cudaMemcpyDeviceToHost, st));
-		KB_CUDA(cudaStreamSynchronize(st));
+		if (!(flags & KB_ASYNC_HOST)) KB_CUDA(cudaStreamSynchronize(st));
 		b->d2h_bytes += (long long)(out_floats * sizeof(float));
 	}
 	return KB_OK;

@@ -601,3 +601,61 @@ def test_pingpong_long_blocks_span_sub_blocks(eng):
     assert bank.parallel_instances() == inst          # the last sub-block ran on the chunk-parallel schedule
     bank.close()
     assert_parity(got, want, "pingpong long blocks", exact=True)
+
+
+def test_async_calls_with_events_every_block_match_synchronous_calls(eng):
+    """A caller that runs AHEAD of the device — note events before every block, device-pointer outputs that are never joined,
+    and page-locked host outputs with KB_ASYNC_HOST — gets the same bits as block-by-block synchronous calls: the packed
+    event uploads go through a ring of pinned staging slots, so a queued copy is never overwritten by the next block's events."""
+    torch = pytest.importorskip("torch")
+    fs, n, inst, voices, blocks = 48000, 2048, 8, 128, 24
+    total = inst * voices
+
+    def schedule(b, bank):
+        ev = np.zeros(len(range(b % 16, total, 16)), kb.EVENT_DTYPE)
+        ids = np.arange(b % 16, total, 16)
+        ev["type"] = kb.EV_VOICE_START
+        ev["instance"], ev["key"] = ids // voices, ids % voices
+        ev["pitch"] = [cases.voice_pitch(int(g) + b) for g in ids]
+        ev["velocity"] = [cases.voice_velocity(int(g)) for g in ids]
+        bank.events(ev)
+
+    def make():
+        kb.lib().kb_srand(1)
+        bank = kb.SynthBank(kb.SY_SUBTRACTIVE, inst, voices, fs, n)
+        for g in range(total):
+            bank.voice_start(g % voices, cases.voice_pitch(g), cases.voice_velocity(g), g // voices)
+        return bank
+
+    ref = make()
+    want = []
+    for b in range(blocks):
+        schedule(b, ref)
+        want.append(ref.process_block(n, kb.MIX_SUM))
+    ref.close()
+
+    ts = torch.cuda.Stream()
+    torch.cuda.set_stream(ts)
+    # (a) device-pointer outputs, nothing joined until the end
+    bank = make()
+    bank.set_stream(ts.cuda_stream)
+    outs = [torch.empty(bank.out_shape(n), dtype=torch.float32, device="cuda") for _ in range(blocks)]
+    for b in range(blocks):
+        schedule(b, bank)
+        bank.process_into(outs[b], n, kb.MIX_SUM)
+    torch.cuda.synchronize()
+    for b in range(blocks):
+        assert np.array_equal(outs[b].cpu().numpy().view(np.uint32), want[b].view(np.uint32)), f"device-pointer block {b}"
+    bank.close()
+    # (b) page-locked host outputs with KB_ASYNC_HOST
+    bank = make()
+    bank.set_stream(ts.cuda_stream)
+    houts = [torch.empty(bank.out_shape(n), dtype=torch.float32).pin_memory() for _ in range(blocks)]
+    for b in range(blocks):
+        schedule(b, bank)
+        bank.process_into(houts[b].numpy(), n, kb.MIX_SUM | kb.ASYNC_HOST)
+    bank.sync()
+    for b in range(blocks):
+        assert np.array_equal(houts[b].numpy().view(np.uint32), want[b].view(np.uint32)), f"async host block {b}"
+    bank.close()
+    assert np.abs(want[-1]).max() > 0.01
