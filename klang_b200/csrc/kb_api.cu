@@ -350,10 +350,10 @@ struct kb_synth_bank : kb_bank_base {
 	// pinned upload staging: a ring of KB_NSTAGE slots, each guarded by an event recorded after its H2D copies, so a caller
 	// that runs ahead of the device (KB_DEVICE_PTR calls are asynchronous) never rewrites a slot whose copy is still queued
 	static constexpr int KB_NSTAGE = 4;
-	unsigned char* staging = nullptr; int* staging_index = nullptr;             // pinned, KB_NSTAGE slots each
+	unsigned char* staging = nullptr;                                           // pinned, KB_NSTAGE slots
 	cudaEvent_t stage_done[KB_NSTAGE] = {}; bool stage_used[KB_NSTAGE] = {}; int stage_next = 0;
-	size_t stage_bytes = 0, stage_ints = 0;
-	unsigned char* d_staging = nullptr; int* d_staging_index = nullptr;
+	size_t stage_bytes = 0;
+	unsigned char* d_staging = nullptr;
 	std::vector<unsigned char> voice_dirty; std::vector<int> dirty_list; bool all_dirty = true;
 	long long h2d_bytes = 0, d2h_bytes = 0;                                     // state traffic so far (for the e2e accounting)
 	bool hdr_stale = false, vstate_stale = false;                               // finer than host_stale: what the device has changed
@@ -409,20 +409,21 @@ static int sy_upload(kb_synth_bank* b) {
 			const int count = (int)b->dirty_list.size();
 			const int slot = b->stage_next; b->stage_next = (slot + 1) % kb_synth_bank::KB_NSTAGE;
 			if (b->stage_used[slot]) KB_CUDA(cudaEventSynchronize(b->stage_done[slot]));    // its previous copies have left the host buffer
+			// one slot = [voice index list, padded to 16 bytes][packed records]: ONE host-to-device copy per block
 			unsigned char* stage = b->staging + (size_t)slot * b->stage_bytes;
-			int* stage_index = b->staging_index + (size_t)slot * b->stage_ints;
+			const size_t rec_off = ((size_t)count * sizeof(int) + 15) & ~(size_t)15;
+			int* stage_index = (int*)stage;
 			for (int k = 0; k < count; k++) {
 				const int v = b->dirty_list[k];
 				stage_index[k] = v;
-				memcpy(stage + (size_t)k * rec, b->hdr + v, sizeof(KbVoiceHdr));
-				memcpy(stage + (size_t)k * rec + sizeof(KbVoiceHdr), b->vstate + (size_t)v * b->voice_bytes, b->voice_bytes);
+				memcpy(stage + rec_off + (size_t)k * rec, b->hdr + v, sizeof(KbVoiceHdr));
+				memcpy(stage + rec_off + (size_t)k * rec + sizeof(KbVoiceHdr), b->vstate + (size_t)v * b->voice_bytes, b->voice_bytes);
 			}
-			KB_CUDA(cudaMemcpyAsync(b->d_staging, stage, (size_t)count * rec, cudaMemcpyHostToDevice, b->stream));
-			KB_CUDA(cudaMemcpyAsync(b->d_staging_index, stage_index, (size_t)count * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+			KB_CUDA(cudaMemcpyAsync(b->d_staging, stage, rec_off + (size_t)count * rec, cudaMemcpyHostToDevice, b->stream));
 			KB_CUDA(cudaEventRecord(b->stage_done[slot], b->stream));
 			b->stage_used[slot] = true;
 			const int words = count * (int)(rec / 4);
-			kb_scatter_voices_kernel<<<std::min(148, (words + 255) / 256), 256, 0, b->stream>>>(b->d_staging, b->d_staging_index, count, (int)b->voice_bytes, b->d_hdr, b->d_vstate);
+			kb_scatter_voices_kernel<<<std::min(148, (words + 255) / 256), 256, 0, b->stream>>>(b->d_staging + rec_off, (const int*)b->d_staging, count, (int)b->voice_bytes, b->d_hdr, b->d_vstate);
 			b->launches++;
 			b->h2d_bytes += (long long)count * (long long)(rec + sizeof(int));
 		} else {
@@ -481,12 +482,11 @@ extern "C" kb_synth_bank* kb_synth_bank_create(int graph, int instances, int voi
 	b->hdr_count = total; b->vstate_bytes = (size_t)total * b->voice_bytes;
 	if (cudaSetDevice(device) != cudaSuccess || cudaHostAlloc((void**)&b->hdr, total * sizeof(KbVoiceHdr), cudaHostAllocDefault) != cudaSuccess ||
 	    cudaHostAlloc((void**)&b->vstate, b->vstate_bytes, cudaHostAllocDefault) != cudaSuccess ||
-	    cudaHostAlloc((void**)&b->staging, kb_synth_bank::KB_NSTAGE * (size_t)(total + 1) * (sizeof(KbVoiceHdr) + b->voice_bytes), cudaHostAllocDefault) != cudaSuccess ||
-	    cudaHostAlloc((void**)&b->staging_index, kb_synth_bank::KB_NSTAGE * (size_t)(total + 1) * sizeof(int), cudaHostAllocDefault) != cudaSuccess) {
+	    cudaHostAlloc((void**)&b->staging, kb_synth_bank::KB_NSTAGE * ((size_t)(total + 1) * (sizeof(KbVoiceHdr) + b->voice_bytes + sizeof(int)) + 16), cudaHostAllocDefault) != cudaSuccess) {
 		kb_fail(KB_ECUDA, std::string("kb_synth_bank_create: pinned host allocation: ") + cudaGetErrorString(cudaGetLastError()));
 		kb_synth_bank_destroy(b); return nullptr;
 	}
-	b->stage_bytes = (size_t)(total + 1) * (sizeof(KbVoiceHdr) + b->voice_bytes); b->stage_ints = (size_t)total + 1;
+	b->stage_bytes = (size_t)(total + 1) * (sizeof(KbVoiceHdr) + b->voice_bytes + sizeof(int)) + 16;
 	for (int k = 0; k < kb_synth_bank::KB_NSTAGE; k++)
 		if (cudaEventCreateWithFlags(&b->stage_done[k], cudaEventDisableTiming) != cudaSuccess) { kb_fail(KB_ECUDA, "kb_synth_bank_create: event"); kb_synth_bank_destroy(b); return nullptr; }
 	for (int v = 0; v < total; v++) b->hdr[v] = KbVoiceHdr{ KB_NOTE_OFF, 0.f, 0.f, 0 };
@@ -507,8 +507,7 @@ extern "C" kb_synth_bank* kb_synth_bank_create(int graph, int instances, int voi
 	b->stream = b->own_stream;
 	ok = ok && dev_alloc(&b->d_hdr, total) == cudaSuccess;
 	ok = ok && dev_alloc(&b->d_vstate, b->vstate_bytes) == cudaSuccess;
-	ok = ok && dev_alloc(&b->d_staging, (size_t)(total + 1) * (sizeof(KbVoiceHdr) + b->voice_bytes)) == cudaSuccess;
-	ok = ok && dev_alloc(&b->d_staging_index, (size_t)(total + 1)) == cudaSuccess;
+	ok = ok && dev_alloc(&b->d_staging, (size_t)(total + 1) * (sizeof(KbVoiceHdr) + b->voice_bytes + sizeof(int)) + 16) == cudaSuccess;
 	ok = ok && dev_alloc(&b->d_blk, instances) == cudaSuccess;
 	ok = ok && dev_alloc(&b->d_scratch, (size_t)total * b->channels * max_block) == cudaSuccess;
 	ok = ok && dev_alloc(&b->d_out, (size_t)instances * b->channels * max_block) == cudaSuccess;
@@ -524,8 +523,8 @@ extern "C" void kb_synth_bank_destroy(kb_synth_bank* b) {
 	if (b->stream) cudaStreamSynchronize(b->stream);
 	b->prof_free();
 	for (int k = 0; k < kb_synth_bank::KB_NSTAGE; k++) if (b->stage_done[k]) cudaEventDestroy(b->stage_done[k]);
-	cudaFreeHost(b->hdr); cudaFreeHost(b->vstate); cudaFreeHost(b->staging); cudaFreeHost(b->staging_index);
-	cudaFree(b->d_staging); cudaFree(b->d_staging_index);
+	cudaFreeHost(b->hdr); cudaFreeHost(b->vstate); cudaFreeHost(b->staging);
+	cudaFree(b->d_staging);
 	cudaFree(b->d_hdr); cudaFree(b->d_vstate); cudaFree(b->d_blk); cudaFree(b->d_scratch); cudaFree(b->d_out); cudaFree(b->d_adsr); cudaFree(b->d_mix);
 	if (b->own_stream) cudaStreamDestroy(b->own_stream);
 	delete b;
