@@ -54,8 +54,8 @@ def load_peaks():
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
     """SM clock and throttle reasons DURING the timed region.  In-process NVML (nvidia_ml_py) polled by a thread every
-    millisecond (the calls release the GIL, the timed loop is not held up), plus one explicit sample() right after the last
-    timed step has been queued, while the GPU is still working through the region.  No NVML call sits between two timed
+    10 ms (sparse on purpose: NVML queries can serialise with kernel launches in the driver), plus one explicit sample() right
+    after the last timed step has been queued, while the GPU is still working through the region.  No NVML call sits between two timed
     steps: with N > 1 a rank that is late to queue a step would be waited for by the others inside their timed intervals.
     Falls back to one `nvidia-smi --query-gpu` per sample() without NVML."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -96,7 +96,7 @@ class ClockSampler:
     def _poll(self):
         while self.running:
             self.sample()
-            time.sleep(0.001)
+            time.sleep(0.010)
 
     def sample(self):
         if self.nvml is not None:
@@ -138,7 +138,7 @@ class ClockSampler:
             if not self.sm:
                 return {"sm_mhz": None, "sm_max_mhz": self.mx, "reasons": [], "samples": 0}
             return {"sm_mhz": statistics.median(self.sm), "sm_min_mhz": min(self.sm), "sm_max_mhz": self.mx, "reasons": sorted(self.reasons),
-                    "samples": len(self.sm), "how": "NVML polled every ms during the timed region plus once after the last step was queued" if self.nvml is not None
+                    "samples": len(self.sm), "how": "NVML polled every 10 ms during the timed region plus once after the last step was queued" if self.nvml is not None
                     else "nvidia-smi --query-gpu once after the last timed step was queued"}
 
 
