@@ -467,8 +467,10 @@ __global__ void __launch_bounds__(256) kb_reverb_par_kernel(const KbFxHdr* __res
 // of chunk k+2 is complete once chunk k has been written, and the CTA (512 threads) runs as a four-role software pipeline
 // with ONE __syncthreads per chunk.  In iteration k:
 //   warp 0, lanes 0..7   F(k+1)  the 8 line filters (Biquad TDF-II, in order) over pre-interpolated inputs: 9 issue slots
-//                                per tick around the 16-cycle recurrence — the role that bounds the kernel.  It has SM
-//                                sub-partition 0 to itself (warps 4, 8, 12 stay idle)
+//                                per tick around the 16-cycle recurrence — the floor of the kernel (20.4 cycles per tick
+//                                measured alone, tools/micro/serial_floor.cu; 8192 ticks per 4096-frame block).  It has SM
+//                                sub-partition 0 to itself (warps 4, 8, 12 stay idle).  Today the tap group T is the
+//                                longest role of a chunk and the chunk period is 1.8x F's own work
 //   warp 1, lanes 0..1   E       early cascade, the two biquads on two lanes one chunk apart: LPF(k+3), HPF(k+2)
 //   group A (6 warps)    W(k)    FDN matrix, ring writes, mid -> late, output mix, thread = (frame, line);  then L(k+2):
 //                                ring windows of chunk k+2 -> Delay::process interpolation -> shared memory, 24 threads
