@@ -731,7 +731,8 @@ def extras(kb, torch, dev, stream, flush_l2, hbm_peak, peak_src, device_index, w
     # C3 SuperSaw 8 x 32 voices; C5 per-GPU share: 4 x 128 TB303 + 4 x 128 SynTHX voices
     for name, graph, inst, voices, n, steps in (("c3_supersaw_256", kb.SY_SUPERSAW, 8, 32, 4096, 5),
                                                 ("c5_tb303_512", kb.SY_TB303, 4, 128, 4096, 3),
-                                                ("c5_synthx_512", kb.SY_SYNTHX, 4, 128, 1024, 2)):
+                                                ("c5_synthx_512", kb.SY_SYNTHX, 4, 128, 1024, 2),
+                                                ("fm_k_1024", kb.SY_FM, 8, 128, 4096, 3)):      # examples/FM.k (lane-per-voice kernel)
         kb.lib().kb_srand(1)
         sb = kb.SynthBank(graph, inst, voices, FS, n, device_index)
         sb.set_stream(stream.cuda_stream)
@@ -745,6 +746,7 @@ def extras(kb, torch, dev, stream, flush_l2, hbm_peak, peak_src, device_index, w
         res["c3_supersaw_256"]["cpu_reference"] = cpu_extra("synth", oracle.SY_SUPERSAW, 16, 4096, 8)
         res["c5_tb303_512"]["cpu_reference"] = cpu_extra("synth", oracle.SY_TB303, 16, 4096, 4)
         res["c5_synthx_512"]["cpu_reference"] = cpu_extra("synth", oracle.SY_SYNTHX, 4, 1024, 2)
+        res["fm_k_1024"]["cpu_reference"] = cpu_extra("synth", oracle.SY_FM, 16, 4096, 8)
     return res
 
 

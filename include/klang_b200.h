@@ -42,6 +42,7 @@ extern "C" {
 #define KB_SY_TB303 2             /* examples/TB303.k              mono   */
 #define KB_SY_SYNTHX 3            /* examples/SynTHX.k             stereo */
 #define KB_SY_FILTER_K 4          /* examples/Subtractive/Filter.k mono   */
+#define KB_SY_FM 5                /* examples/FM.k (three Operator<Sine> in series) mono */
 
 /* process flags */
 #define KB_DEVICE_PTR 1u          /* `io` / `out` is device memory on the bank's device; the call is asynchronous on the bank stream */

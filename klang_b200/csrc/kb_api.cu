@@ -441,6 +441,7 @@ static int sy_upload(kb_synth_bank* b) {
 			memset(&k, 0, sizeof(k));
 			if (b->graph == KB_SY_TB303) k.tb = kb_tb_block(b->fs, b->ctl(i));
 			if (b->graph == KB_SY_SYNTHX) { k.sx_tr_at = kb_sx_tr_at(b->ctl(i)[2].value); k.sx_dt_at = kb_sx_dt_at(b->ctl(i)[1].value); }
+			if (b->graph == KB_SY_FM) { k.fm_i1 = b->ctl(i)[1].value; k.fm_i2 = b->ctl(i)[2].value; }
 		}
 		KB_CUDA(cudaMemcpyAsync(b->d_blk, b->blk.data(), b->blk.size() * sizeof(KbSynthBlock), cudaMemcpyHostToDevice, b->stream));
 		KB_CUDA(cudaStreamSynchronize(b->stream));      // blk is pageable and may be rewritten by the next control change
@@ -466,6 +467,7 @@ extern "C" kb_synth_bank* kb_synth_bank_create(int graph, int instances, int voi
 	case KB_SY_SUPERSAW: b->ncontrols = 3; b->voice_bytes = sizeof(KbSsawVoice); break;
 	case KB_SY_TB303: b->ncontrols = 5; b->voice_bytes = sizeof(KbTbVoice); break;
 	case KB_SY_SYNTHX: b->ncontrols = 5; b->voice_bytes = sizeof(KbSxVoice); b->channels = 2; break;
+	case KB_SY_FM: b->ncontrols = 4; b->voice_bytes = sizeof(KbFmVoice); break;
 	}
 	for (int i = 0; i < instances; i++) {
 		KbControl* c = b->ctl(i);
@@ -474,6 +476,7 @@ extern "C" kb_synth_bank* kb_synth_bank_create(int graph, int instances, int voi
 		case KB_SY_SUPERSAW: c[0] = kb_dial(0.001f, 1.f, 0.001f); c[1] = kb_dial(0.f, 1.f, 0.05f); c[2] = kb_dial(0.f, 1.f, 0.6f); break;   // SuperSaw.k:38-43
 		case KB_SY_TB303: c[0] = kb_dial(0.f, 1.f, 1.f); c[1] = kb_dial(0.f, 1.f, 0.5f); c[2] = kb_dial(0.1f, 1.f, 0.5f);                     // TB303.k:118-126
 		                  c[3] = kb_dial(0.f, 1.f, 0.f); c[4] = kb_dial(0.01f, 10.f, 1.f); break;
+		case KB_SY_FM: c[0] = kb_dial(0.001f, 10.f, 1.0f); c[1] = kb_dial(0.f, 10.f, 0.37f); c[2] = kb_dial(0.f, 10.f, 0.37f); c[3] = kb_dial(0.f, 1.f, 0.5f); break;   // FM.k:80-86
 		case KB_SY_SYNTHX: c[0] = kb_dial(0.f, 5.f, 0.5f); c[1] = kb_dial(0.f, 1.f, 0.5f); c[2] = kb_dial(0.f, 1.f, 0.6f);                   // SynTHX.k:186-194
 		                   c[3] = kb_dial(0.f, 1.f, 1.f); c[4] = kb_dial(0.f, 1.f, 0.f); break;
 		}
@@ -498,6 +501,7 @@ extern "C" kb_synth_bank* kb_synth_bank_create(int graph, int instances, int voi
 		switch (graph) {
 		case KB_SY_SUBTRACTIVE: case KB_SY_FILTER_K: kb_sub_construct(b->fs, graph, b->vs<KbSubVoice>(v)); break;
 		case KB_SY_SUPERSAW: kb_ssaw_construct(b->fs, b->vs<KbSsawVoice>(v)); break;
+		case KB_SY_FM: kb_fm_construct(b->fs, b->vs<KbFmVoice>(v)); break;
 		case KB_SY_TB303: kb_tb_construct(b->fs, b->vs<KbTbVoice>(v)); break;
 		case KB_SY_SYNTHX: kb_sx_construct(b->fs, b->vs<KbSxVoice>(v)); break;
 		}
@@ -566,6 +570,7 @@ static void sy_start(kb_synth_bank* b, int inst, int voice, float pitch, float v
 	switch (b->graph) {
 	case KB_SY_SUBTRACTIVE: case KB_SY_FILTER_K: kb_sub_on(b->fs, b->graph, c, b->vs<KbSubVoice>(v), pitch); break;
 	case KB_SY_SUPERSAW: kb_ssaw_on(b->fs, c, b->vs<KbSsawVoice>(v), pitch); break;
+	case KB_SY_FM: kb_fm_on(b->fs, c, b->vs<KbFmVoice>(v), pitch); break;
 	case KB_SY_TB303: kb_tb_on(b->fs, c, b->vs<KbTbVoice>(v), pitch); break;
 	case KB_SY_SYNTHX: kb_sx_on(b->fs, c, b->vs<KbSxVoice>(v), pitch); break;
 	}
@@ -581,6 +586,7 @@ static void sy_release(kb_synth_bank* b, int inst, int voice) {
 	switch (b->graph) {
 	case KB_SY_SUBTRACTIVE: case KB_SY_FILTER_K: kb_adsr_release(b->fs, b->vs<KbSubVoice>(v).adsr); break;   // Filter.k:25-27
 	case KB_SY_SUPERSAW: kb_adsr_release(b->fs, b->vs<KbSsawVoice>(v).adsr); break;                          // SuperSaw.k:21-23
+	case KB_SY_FM: kb_adsr_release(b->fs, b->vs<KbFmVoice>(v).adsr); break;                                  // FM.k:56-58
 	case KB_SY_TB303: kb_adsr_release(b->fs, b->vs<KbTbVoice>(v).adsr); break;                               // TB303.k:99-101
 	case KB_SY_SYNTHX: kb_adsr_release(b->fs, b->vs<KbSxVoice>(v).adsr); break;                              // SynTHX.k:163-165
 	}
@@ -676,7 +682,7 @@ extern "C" int kb_synth_bank_process(kb_synth_bank* b, float* out, int n, unsign
 		b->launches += 4;
 	} else {
 		b->prof_begin();
-		if (flags & KB_LANE_PER_VOICE) {
+		if ((flags & KB_LANE_PER_VOICE) || b->graph == KB_SY_FM) {   // (FM.k has no tiled kernel yet: one lane per voice)
 			const int blocks = (total + 127) / 128;
 			switch (b->graph) {
 			case KB_SY_SUBTRACTIVE: case KB_SY_FILTER_K:
@@ -685,6 +691,8 @@ extern "C" int kb_synth_bank_process(kb_synth_bank* b, float* out, int n, unsign
 				kb_voice_kernel<KB_SY_SUPERSAW, KbSsawVoice><<<blocks, 128, 0, st>>>((KbSsawVoice*)b->d_vstate, b->d_hdr, b->d_blk, d_voice_dst, n, b->voices, total, b->fs); break;
 			case KB_SY_TB303:
 				kb_voice_kernel<KB_SY_TB303, KbTbVoice><<<blocks, 128, 0, st>>>((KbTbVoice*)b->d_vstate, b->d_hdr, b->d_blk, d_voice_dst, n, b->voices, total, b->fs); break;
+			case KB_SY_FM:
+				kb_voice_kernel<KB_SY_FM, KbFmVoice><<<blocks, 128, 0, st>>>((KbFmVoice*)b->d_vstate, b->d_hdr, b->d_blk, d_voice_dst, n, b->voices, total, b->fs); break;
 			}
 		} else {
 			// voices per CTA: as many as still leave >= ~100 CTAs (the serial stages cost the same for any G), KB_TILE_G overrides

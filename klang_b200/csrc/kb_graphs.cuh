@@ -8,7 +8,7 @@
 #include "kb_prims.cuh"
 
 #include "../../include/klang_b200.h"   // graph ids KB_SY_* / KB_FX_*
-#define KB_SY_COUNT 5
+#define KB_SY_COUNT 6
 #define KB_FX_COUNT 5
 
 // =========================================================================================== HOST halves
@@ -66,6 +66,21 @@ inline void kb_ssaw_on(const KbFs& fs, const KbControl* c, KbSsawVoice& n, float
 		kb_osm_set_fpd(fs, n.osc[k], fk, 0.f, c[1].value);
 	}
 	kb_adsr_set(fs, n.adsr, c[0].value, 0.25f, 1.0f, 0.5f);                                 // SuperSaw.k:18
+}
+
+// ---- FM (examples/FM.k:27-74)
+inline void kb_fm_construct(const KbFs& fs, KbFmVoice& n) {
+	for (int k = 0; k < 3; k++) { kb_fsine_init(n.op[k].osc); kb_env_construct(fs, n.op[k].env); n.op[k].amp = 1.f; n.op[k].in = 0.f; }
+	kb_adsr_construct(fs, n.adsr);
+}
+inline void kb_fm_on(const KbFs& fs, const KbControl* c, KbFmVoice& n, float pitch) {
+	const float fc = kb_pitch_to_frequency_host(pitch);                                     // FM.k:42
+	const float fd = fc * c[0].value;                                                       // FM.k:43
+	const float e1[4] = { 0.f, 0.f, 3.f, 1.f }, e2[4] = { 0.f, 1.5f, 3.f, 0.5f };
+	kb_fsine_set_fp(fs, n.op[0].osc, fd, 0.f); kb_env_set_points(fs, n.op[0].env, 2, e1);   // FM.k:45-46
+	kb_fsine_set_fp(fs, n.op[1].osc, fd, 0.f); kb_env_set_points(fs, n.op[1].env, 2, e2);   // FM.k:48-49
+	kb_fsine_set_fp(fs, n.op[2].osc, fc, 0.f);                                              // FM.k:51
+	kb_adsr_set(fs, n.adsr, c[3].value, 0.1f, 1.f, 1.f);                                    // FM.k:53
 }
 
 // ---- TB303 (examples/TB303.k:8-114)
@@ -253,6 +268,27 @@ inline void kb_dreverb_construct(KbFxHdr& h, KbDReverb& p, long long ring0) {   
 	kb_delay_construct(p.feedforward, 192000, ring0); kb_delay_construct(p.feedback, 192000, ring0 + 192001);
 	kb_biquad_construct(p.filter, KB_BQ_LPF);
 	h.controls[0] = kb_dial(0.f, 0.5f, 0.4f); h.controls[1] = kb_dial(0.f, 0.4f, 0.1f); h.controls[2] = kb_dial(500.f, 5000.f, 1500.f);
+}
+
+// ---- FM.k per-sample half (host + device: tests/host/fm_check.cpp renders it with g++)
+// Operator::process (klang.h:4163-4167): OSCILLATOR::set(+in) -> Fast::Sine::set(relative): offset = phase * twoPi through
+// Fast::Phase::operator=(klang::Phase) (klang.h:5160-5162, 4993-4997, Q2); Sine::process; out *= env++ * amp
+KB_HD float kb_fm_op_tick(const KbFs& fs, KbFmOp& o) {
+	o.osc.offset = kb_phase_from_radians(o.in * KB_TWO_PI_F);
+	float out = kb_fsine_tick(o.osc);
+	out *= kb_env_tick(fs, o.env) * o.amp;
+	return out;
+}
+// FM.k:61-73: op1 * I1 >> op2 * I2 >> op3 >> out; out *= adsr++ * 0.1f
+KB_HD float kb_fm_tick(const KbFs& fs, float i1, float i2, KbFmVoice& n, int& note_stage) {
+	n.op[0].amp = i1;
+	n.op[1].amp = i2;
+	n.op[1].in = kb_fm_op_tick(fs, n.op[0]);
+	n.op[2].in = kb_fm_op_tick(fs, n.op[1]);
+	float out = kb_fm_op_tick(fs, n.op[2]);
+	out *= kb_env_tick(fs, n.adsr) * 0.1f;
+	if (n.adsr.stage == KB_ENV_OFF) note_stage = KB_NOTE_OFF;
+	return out;
 }
 
 // =========================================================================================== DEVICE halves

@@ -13,7 +13,7 @@
 #include "kb_fx_parallel.cuh"
 
 // per-instance, per-block constants computed by the host at control rate (see kb_graphs.cuh)
-struct KbSynthBlock { KbTbBlock tb; float sx_tr_at, sx_dt_at; };
+struct KbSynthBlock { KbTbBlock tb; float sx_tr_at, sx_dt_at; float fm_i1, fm_i2; /* FM.k:63-64: controls[1], controls[2] */ };
 
 // ============================================================================================ synth voices
 // One lane = one voice (Note::process(buffer), klang.h:4295-4303): the lane runs the block's n-step recurrence
@@ -39,9 +39,11 @@ __global__ void __launch_bounds__(128) kb_voice_kernel(VOICE* __restrict__ voice
 	}
 	VOICE s;
 	KbTbBlock tb;
+	float fm_i1 = 0.f, fm_i2 = 0.f;
 	if (active) {
 		s = voices[v];
 		if (GRAPH == KB_SY_TB303) tb = blk[v / voices_per_inst].tb;
+		if (GRAPH == KB_SY_FM) { fm_i1 = blk[v / voices_per_inst].fm_i1; fm_i2 = blk[v / voices_per_inst].fm_i2; }
 	}
 	for (int base = 0; base < n; base += 32) {
 		const int steps = min(32, n - base);
@@ -51,6 +53,7 @@ __global__ void __launch_bounds__(128) kb_voice_kernel(VOICE* __restrict__ voice
 				if constexpr (GRAPH == KB_SY_SUBTRACTIVE) y = kb_sub_tick(fs, s, stage);
 				if constexpr (GRAPH == KB_SY_SUPERSAW) y = kb_ssaw_tick(fs, s, stage);
 				if constexpr (GRAPH == KB_SY_TB303) y = kb_tb_tick(fs, tb, s, stage);
+				if constexpr (GRAPH == KB_SY_FM) y = kb_fm_tick(fs, fm_i1, fm_i2, s, stage);
 			}
 			tile[warp][lane][t] = y;
 		}

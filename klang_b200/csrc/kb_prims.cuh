@@ -157,6 +157,21 @@ KB_HD void kb_osm_advance(KbOsm& o, uint32_t n) {
 }
 
 // ------------------------------------------- Generic::Oscillator + Generators::Basic (klang.h:2849-2880, 4899-4944)
+// Generators::Fast::Sine (klang.h:5135-5172): uint32 phase, fastsinp (5117-5132), polysin (5093-5096); Q3: set(f) is a no-op
+// while f equals the cached frequency, which starts at 1000 with a zero increment (klang.h:2855)
+KB_HD void kb_fsine_init(KbFastSine& o) { o.frequency = 1000.f; o.increment = 0; o.position = 0u; o.offset = 0u; }
+KB_HD void kb_fsine_set_f(const KbFs& fs, KbFastSine& o, float f) { if (f != o.frequency) { o.frequency = f; o.increment = kb_increment_set(fs, f); } }
+KB_HD void kb_fsine_set_fp(const KbFs& fs, KbFastSine& o, float f, float phase) {
+	o.position = kb_phase_from_radians(phase); o.offset = kb_phase_from_radians(0.f); kb_fsine_set_f(fs, o, f);
+}
+KB_HD float kb_fsine_tick(KbFastSine& o) {
+	float x = (kb_bits(((o.position + o.offset) >> 9) | 0x3f800000) - 1.f) * KB_TWO_PI_F;             // fast_modp  klang.h:1424-1428
+	if (x > 3.f / 2.f * KB_PI_F) x -= KB_TWO_PI_F; else if (x > KB_PI_F / 2.f) x = KB_PI_F - x;
+	const float x2 = x * x;
+	const float out = (((-0.00018542f * x2 + 0.0083143f) * x2 - 0.16666f) * x2 + 1.0f) * x;
+	o.position += (uint32_t)o.increment;
+	return out;
+}
 KB_HD void kb_bosc_init(KbBasicOsc& o) { o.increment = 0.f; o.position = 0.f; o.frequency = 1000.f; o.offset = 0.f; o.duty = 0.5f; }
 KB_HD void kb_bosc_set_f(const KbFs& fs, KbBasicOsc& o, float f) { o.frequency = f; o.increment = f * 2.f * KB_PI_F / fs.f; }
 KB_HD void kb_bosc_set_fp(const KbFs& fs, KbBasicOsc& o, float f, float phase) { o.position = phase; kb_bosc_set_f(fs, o, f); }

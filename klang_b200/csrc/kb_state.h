@@ -68,6 +68,10 @@ struct KbSxPartial { KbOsm osc; float f0, range, seed; int right; };
 struct KbSxAdditive { KbSxPartial partial[4][3]; float frequency; };
 struct KbSxVoice { KbSxAdditive notes[11]; KbEnv adsr; };
 
+// examples/FM.k:27-74: three Operator<Fast::Sine> (klang.h:4140-4173) in series
+struct KbFmOp { KbFastSine osc; KbEnv env; float amp, in; };
+struct KbFmVoice { KbFmOp op[3]; KbEnv adsr; };
+
 // ------------------------------------------------------------------ effect instances (graphs)
 struct KbFxHdr { KbControl controls[KB_MAX_CONTROLS]; float cached[KB_MAX_CONTROLS]; };
 // examples/PingPong.k

@@ -49,6 +49,9 @@ namespace k_tb303 {
 namespace k_synthx {
 #include "SynTHX_patched.k"  // one-token g++ disambiguation, see build_ref.py
 }
+namespace k_fm {
+#include "FM.k"
+}
 namespace k_delay_pingpong {
 #include "Delay/PingPong.k"
 }
@@ -379,7 +382,7 @@ int ref_fx_process(void* h, float* l, float* r, int n) {
 }
 
 // ----------------------------------------------------------------------- synths
-enum { SY_SUBTRACTIVE = 0, SY_SUPERSAW = 1, SY_TB303 = 2, SY_SYNTHX = 3, SY_FILTER_K = 4 };
+enum { SY_SUBTRACTIVE = 0, SY_SUPERSAW = 1, SY_TB303 = 2, SY_SYNTHX = 3, SY_FILTER_K = 4, SY_FM = 5 };
 
 struct RefSynth {
 	int graph;
@@ -410,6 +413,7 @@ void* ref_synth_create(int graph, int nvoices) {
 	case SY_TB303:       { auto* p = make_synth<k_tb303::TB303, k_tb303::TB303::MyNote>(nvoices); s->mono = p; s->controls = &p->controls; } break;
 	case SY_FILTER_K:    { auto* p = make_synth<k_filter::Filter, k_filter::Filter::FilterNote>(nvoices); s->mono = p; s->controls = &p->controls; } break;
 	case SY_SYNTHX:      { auto* p = make_synth<k_synthx::SynTHX, k_synthx::SynTHX::MyNote>(nvoices); s->stereo = p; s->controls = &p->controls; } break;
+	case SY_FM:          { auto* p = make_synth<k_fm::FM, k_fm::FM::MyNote>(nvoices); s->mono = p; s->controls = &p->controls; } break;
 	default: delete s; return nullptr;
 	}
 	s->nvoices = s->mono ? (int)s->mono->notes.count : (int)s->stereo->notes.count;

@@ -20,12 +20,12 @@ import numpy as np
  FLT_BIQUAD_BPF, FLT_BIQUAD_BRF, FLT_BIQUAD_APF, FLT_BUTTERWORTH_LPF1, FLT_BUTTERWORTH_LPF2,
  FLT_DCF, FLT_IIR1, FLT_IIR2, FLT_MODAL, FLT_FOLLOWER_PEAK, FLT_FOLLOWER_RMS) = range(15)
 FX_GAIN, FX_PINGPONG, FX_REVERB, FX_DELAY_PINGPONG, FX_DELAY_REVERB = range(5)
-SY_SUBTRACTIVE, SY_SUPERSAW, SY_TB303, SY_SYNTHX, SY_FILTER_K = range(5)
+SY_SUBTRACTIVE, SY_SUPERSAW, SY_TB303, SY_SYNTHX, SY_FILTER_K, SY_FM = range(6)
 
 FX_NAMES = {FX_GAIN: "gain", FX_PINGPONG: "pingpong", FX_REVERB: "reverb",
             FX_DELAY_PINGPONG: "delay_pingpong", FX_DELAY_REVERB: "delay_reverb"}
 SY_NAMES = {SY_SUBTRACTIVE: "subtractive", SY_SUPERSAW: "supersaw", SY_TB303: "tb303",
-            SY_SYNTHX: "synthx", SY_FILTER_K: "filter_k"}
+            SY_SYNTHX: "synthx", SY_FILTER_K: "filter_k", SY_FM: "fm"}
 
 
 def noise(n, seed=1, lo=-1.0, hi=1.0):
@@ -203,6 +203,8 @@ SYNTH_SCRIPTS = {
     "tb303": (SY_TB303, 32, 8, 6, 512, 2, []),
     "tb303_square": (SY_TB303, 32, 6, 6, 512, 2, [(0, 3, 1.0), (0, 1, 0.9), (0, 4, 3.0), (2, 0, 0.4)]),
     "synthx": (SY_SYNTHX, 32, 4, 4, 256, 1, [(0, 0, 0.01)]),
+    "fm": (SY_FM, 32, 10, 6, 512, 2, [(0, 3, 0.01)]),
+    "fm_deep": (SY_FM, 32, 6, 5, 512, 1, [(0, 0, 2.5), (0, 1, 3.0), (0, 2, 7.5), (0, 3, 0.002), (2, 1, 0.5)]),
 }
 
 

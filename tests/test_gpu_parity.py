@@ -245,6 +245,11 @@ def test_tb303_bank_vs_live_oracle(eng):
     _drive_bank_vs_oracle(cases.SY_TB303, 2, 64, 6, 512, 48000, exact=True)
 
 
+def test_fm_bank_vs_live_oracle(eng):
+    """FM.k (three Operator<Sine> in series, SURVEY 8f widening): 4 x 64 voices against the live oracle, bit-exact."""
+    _drive_bank_vs_oracle(cases.SY_FM, 4, 64, 5, 300, 48000, exact=True)
+
+
 def test_synthx_bank_vs_live_oracle(eng):
     _drive_bank_vs_oracle(cases.SY_SYNTHX, 2, 32, 4, 300, 48000, exact=True)
 

@@ -43,3 +43,33 @@ def test_clock_sampler_without_nvml_reports_nothing():
     s.sample()
     r = s.stop()
     assert "sm_mhz" in r and "reasons" in r
+
+
+def test_fm_voice_product_functions_match_oracle_on_host():
+    """The product's FM.k voice (kb_fm_on / kb_fm_tick, the functions kb_voice_kernel<KB_SY_FM> runs per lane) compiled with
+    g++ equals the oracle port bit for bit over two scenarios (release included)."""
+    import sys
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import oracle
+    exe = os.path.join(tempfile.mkdtemp(prefix="kb_host_"), "fm_check")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-x", "c++",
+                           os.path.join(ROOT, "tests", "host", "fm_check.cpp"), "-o", exe])
+    got = np.frombuffer(subprocess.run([exe], capture_output=True).stdout, np.float32)
+
+    def port(fs, pitch, ctl, n, rel):
+        oracle.port.set_fs(fs)
+        oracle.port.srand(1)
+        sy = oracle.port.Synth(oracle.SY_FM, 32)
+        for i, v in enumerate(ctl):
+            sy.set_control(i, v)
+        sy.voice_start(0, pitch, 0.8)
+        a, _ = sy.process_voices(rel)
+        sy.voice_release(0, 0.0)
+        b, _ = sy.process_voices(n - rel)
+        sy.close()
+        return np.concatenate([a[0, 0], b[0, 0]])
+
+    want = np.concatenate([port(48000.0, 60, (1.0, 0.37, 0.37, 0.5), 3000, 1500), port(44100.0, 72, (2.5, 3.0, 7.5, 0.002), 2000, 700)])
+    assert len(got) == len(want) and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert np.abs(want).max() > 0.05
