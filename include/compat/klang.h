@@ -184,6 +184,30 @@ struct ADSR : Envelope {
 	void operator()(param a, param d, param s, param r) { set(a, d, s, r); }
 };
 
+// FM operator (klang.h:4140-4173): an oscillator with an input, an envelope and an amplitude; `a * i >> b` feeds b's input
+template <class OSCILLATOR> struct Operator : OSCILLATOR {
+	signal in; Envelope env; Amplitude amp = 1.f;
+	Operator& operator()(param f) { OSCILLATOR::set(f); return *this; }
+	Operator& operator()(param f, param phase) { OSCILLATOR::set(f, phase); return *this; }
+	Operator& operator=(std::initializer_list<Envelope::Point> p) { env = p; return *this; }
+	Operator& operator=(const Envelope& e) { env = e; return *this; }
+	Operator& operator*(signal a) { amp = a; return *this; }
+	Operator& operator>>(Operator& carrier) { carrier.in = float(*this); return carrier; }
+};
+
+// lookup table filled from a function or a list (klang.h Table; FM.k:18-22), and the debug graph a Note may draw into
+#define FUNCTION(type) (void(*)(type, type&))[](type x, type& y)
+template <class T, int SIZE> struct Table {
+	T v[SIZE];
+	Table(void (*fn)(T, T&)) { for (int i = 0; i < SIZE; i++) { v[i] = T(); fn((T)i, v[i]); } }
+	Table(T (*fn)(T)) { for (int i = 0; i < SIZE; i++) v[i] = fn((T)i); }
+	Table(std::initializer_list<T> l) { int i = 0; for (const T& x : l) if (i < SIZE) v[i++] = x; for (; i < SIZE; i++) v[i] = T(); }
+	T operator[](int i) const { return v[i]; }
+};
+struct Graph { void clear() {} template <class T> void add(const T&) {} };
+static Graph graph;
+typedef param Frequency;
+
 template <int SIZE> struct Delay : Modifier {
 	param time = 1.f;
 	using Modifier::set;

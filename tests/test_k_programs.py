@@ -18,7 +18,7 @@ import oracle
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 K_HOST = os.path.join(ROOT, "tests", "_k_bin", "k_host")
 HAVE_REFERENCE = os.path.isfile("/root/reference/examples/PingPong.k")
-PROGRAMS = ["gain", "pingpong", "delay_pingpong", "delay_reverb", "reverb", "supersaw", "filter_k", "tb303", "synthx"]
+PROGRAMS = ["gain", "pingpong", "delay_pingpong", "delay_reverb", "reverb", "supersaw", "filter_k", "tb303", "synthx", "fm"]
 
 
 @pytest.mark.skipif(not HAVE_REFERENCE, reason="reference examples not present")
@@ -52,7 +52,7 @@ def _expected(prog, fs, n, blocks):
             outs.append(np.atleast_2d(fx.process(blk[0] if fx.channels == 1 else blk)))
         fx.close()
         return np.stack(outs)                         # [blocks, channels, n]
-    graph = {"supersaw": oracle.SY_SUPERSAW, "filter_k": oracle.SY_FILTER_K, "tb303": oracle.SY_TB303, "synthx": oracle.SY_SYNTHX}[prog]
+    graph = {"supersaw": oracle.SY_SUPERSAW, "filter_k": oracle.SY_FILTER_K, "tb303": oracle.SY_TB303, "synthx": oracle.SY_SYNTHX, "fm": oracle.SY_FM}[prog]
     sy = oracle.port.Synth(graph, 32)
     outs = []
     for b in range(blocks):

@@ -36,6 +36,9 @@ namespace k_reverb {
 namespace k_synthx {
 #include "SynTHX.k"
 }
+namespace k_fm {
+#include "FM.k"
+}
 
 KLANG_B200_EFFECT(k_gain::Gain, KB_FX_GAIN)
 KLANG_B200_EFFECT(k_pingpong::PingPong, KB_FX_PINGPONG)
@@ -46,6 +49,7 @@ KLANG_B200_SYNTH(k_filter::Filter, KB_SY_FILTER_K)
 KLANG_B200_SYNTH(k_tb303::TB303, KB_SY_TB303)
 KLANG_B200_EFFECT(k_reverb::Reverb, KB_FX_REVERB)
 KLANG_B200_SYNTH(k_synthx::SynTHX, KB_SY_SYNTHX)
+KLANG_B200_SYNTH(k_fm::FM, KB_SY_FM)
 
 // the deterministic input of tests/cases.py::noise
 static float noise(uint64_t n, uint64_t seed, double lo, double hi) {
@@ -98,6 +102,7 @@ int main(int argc, char** argv) {
 		else if (prog == "tb303") rc = run_synth<k_tb303::TB303>(fs, n, blocks, out);
 		else if (prog == "reverb") rc = run_effect<k_reverb::Reverb>(fs, n, blocks, out);
 		else if (prog == "synthx") rc = run_synth<k_synthx::SynTHX>(fs, n, blocks, out);
+		else if (prog == "fm") rc = run_synth<k_fm::FM>(fs, n, blocks, out);
 	} catch (const klang::b200::Error& e) {
 		fprintf(stderr, "k_host: %s\n", e.what());
 		rc = kb_device_count() == 0 ? 3 : 4;          // 3 = no CUDA device (expected off the GPU box)
