@@ -477,6 +477,8 @@ public:
 	int voices() const { return kb_synth_bank_voices(bank_); }
 	int noteOn(int pitch, float velocity, int instance = 0) { sync(); return kb_synth_bank_note_on(bank_, instance, pitch, velocity); }
 	void noteOff(int pitch, float velocity = 0.f, int instance = 0) { sync(); kb_synth_bank_note_off(bank_, instance, pitch, velocity); }
+	// Synth::input(status, byte1, byte2): raw MIDI (templates/juce/synth/Source/klang.h:3921-3929)
+	void input(int status, int byte1, int byte2, int instance = 0) { sync(); kb_synth_bank_midi(bank_, instance, status, byte1, byte2); }
 	bool process(float* buffer, int length, unsigned flags = 0) { sync(); return kb_synth_bank_process(bank_, buffer, length, flags) == KB_OK; }
 	kb_synth_bank* bank() { return bank_; }
 private:

@@ -110,6 +110,10 @@ int kb_synth_bank_get_control(kb_synth_bank* bank, int instance, int idx, float*
 int kb_synth_bank_note_on(kb_synth_bank* bank, int instance, int pitch, float velocity);
 /* Synth::noteOff(pitch, velocity): releases every sustaining note of that pitch           klang.h:4430-4434 */
 int kb_synth_bank_note_off(kb_synth_bank* bank, int instance, int pitch, float velocity);
+/* Synth::input(status, byte1, byte2), the raw MIDI entry of the v0.7.2 template: 0x90 with velocity > 0 = noteOn(byte1, byte2 / 127.f),
+ * 0x80 or 0x90 with velocity 0 = noteOff, anything else = onMIDI() (a no-op for the bound graphs).  Returns 0 or a negative
+ * error.                                                                 templates/juce/synth/Source/klang.h:3921-3929 */
+int kb_synth_bank_midi(kb_synth_bank* bank, int instance, int status, int byte1, int byte2);
 /* NoteBase::start / release / stage of one voice                                          klang.h:4257-4284 */
 int kb_synth_bank_voice_start(kb_synth_bank* bank, int instance, int voice, float pitch, float velocity);
 int kb_synth_bank_voice_release(kb_synth_bank* bank, int instance, int voice, float velocity);

@@ -64,6 +64,8 @@ public:
 	// Synth::noteOn / noteOff                                                  klang.h:4423-4434
 	int noteOn(int pitch, float velocity, int instance = 0) { return kb_synth_bank_note_on(bank_, instance, pitch, velocity); }
 	void noteOff(int pitch, float velocity = 0.f, int instance = 0) { kb_synth_bank_note_off(bank_, instance, pitch, velocity); }
+	// Synth::input(status, byte1, byte2): raw MIDI                             templates/juce/synth/Source/klang.h:3921-3929
+	void input(int status, int byte1, int byte2, int instance = 0) { kb_synth_bank_midi(bank_, instance, status, byte1, byte2); }
 	// Synth::process(float* buffer, int length) / Stereo::Synth::process: the output block is overwritten,
 	// planar [instances][channels][length]                                     klang.h:4440-4466, 4830-4858
 	bool process(float* buffer, int length, unsigned flags = 0) noexcept { return kb_synth_bank_process(bank_, buffer, length, flags) == KB_OK; }

@@ -33,6 +33,7 @@ SYMBOLS = [
     ("kb_synth_bank_num_controls", _i, [_vp]),
     ("kb_synth_bank_set_control", _i, [_vp, _i, _i, _f]), ("kb_synth_bank_get_control", _i, [_vp, _i, _i, _fp]),
     ("kb_synth_bank_note_on", _i, [_vp, _i, _i, _f]), ("kb_synth_bank_note_off", _i, [_vp, _i, _i, _f]),
+    ("kb_synth_bank_midi", _i, [_vp, _i, _i, _i, _i]),
     ("kb_synth_bank_voice_start", _i, [_vp, _i, _i, _f, _f]), ("kb_synth_bank_voice_release", _i, [_vp, _i, _i, _f]),
     ("kb_synth_bank_voice_stage", _i, [_vp, _i, _i]), ("kb_synth_bank_events", _i, [_vp, _i, _vp]),
     ("kb_synth_bank_process", _i, [_vp, _vp, _i, _u]), ("kb_synth_bank_sync", _i, [_vp]), ("kb_synth_bank_set_stream", _i, [_vp, _vp]),
@@ -192,6 +193,10 @@ class SynthBank:
 
     def note_off(self, pitch, velocity=0.0, instance=0):
         _check(lib().kb_synth_bank_note_off(self.h, instance, int(pitch), float(velocity)), "kb_synth_bank_note_off")
+
+    def midi(self, status, byte1, byte2, instance=0):
+        """Synth::input(status, byte1, byte2) (templates/juce/synth/Source/klang.h:3921-3929)."""
+        _check(lib().kb_synth_bank_midi(self.h, instance, int(status), int(byte1), int(byte2)), "kb_synth_bank_midi")
 
     def voice_start(self, voice, pitch, velocity, instance=0):
         _check(lib().kb_synth_bank_voice_start(self.h, instance, voice, float(pitch), float(velocity)), "kb_synth_bank_voice_start")

@@ -642,6 +642,15 @@ extern "C" int kb_synth_bank_voice_stage(kb_synth_bank* b, int inst, int voice) 
 	return b->hdr[(size_t)inst * b->voices + voice].stage;
 }
 
+// Synth::input(status, byte1, byte2) of the v0.7.2 template (templates/juce/synth/Source/klang.h:3921-3929): the status byte is compared
+// whole (channel 1 only, as there); every other message goes to onMIDI(), which none of the bound graphs overrides.
+extern "C" int kb_synth_bank_midi(kb_synth_bank* b, int inst, int status, int byte1, int byte2) {
+	if (!b || inst < 0 || inst >= b->instances) return kb_fail(KB_EINVAL, "kb_synth_bank_midi: bad argument");
+	if (status == 0x90 && byte2 > 0) { const int rc = kb_synth_bank_note_on(b, inst, byte1, byte2 / 127.f); return rc > 0 ? KB_OK : rc; }
+	if (status == 0x80 || (status == 0x90 && byte2 == 0)) return kb_synth_bank_note_off(b, inst, byte1, byte2 / 127.f);
+	return KB_OK;
+}
+
 extern "C" int kb_synth_bank_events(kb_synth_bank* b, int count, const kb_note_event* ev) {
 	if (!b || count < 0 || (count && !ev)) return kb_fail(KB_EINVAL, "kb_synth_bank_events: bad argument");
 	for (int i = 0; i < count; i++) {
