@@ -691,7 +691,10 @@ extern "C" int kb_synth_bank_process(kb_synth_bank* b, float* out, int n, unsign
 		b->launches += 4;
 	} else {
 		b->prof_begin();
-		if ((flags & KB_LANE_PER_VOICE) || b->graph == KB_SY_FM) {   // (FM.k has no tiled kernel yet: one lane per voice)
+		// FM.k: the time-parallel kernel (kb_fm_tiled_kernel) is the default; KB_FM_TILED=0 keeps the lane-per-voice kernel for the whole
+		// process (A/B measurement, same results — tools/fm_tiled_probe.py)
+		static const bool fm_tiled = !getenv("KB_FM_TILED") || atoi(getenv("KB_FM_TILED")) != 0;
+		if ((flags & KB_LANE_PER_VOICE) || (b->graph == KB_SY_FM && !fm_tiled)) {
 			const int blocks = (total + 127) / 128;
 			switch (b->graph) {
 			case KB_SY_SUBTRACTIVE: case KB_SY_FILTER_K:
@@ -736,6 +739,8 @@ extern "C" int kb_synth_bank_process(kb_synth_bank* b, float* out, int n, unsign
 				KbSsawVoice* vs = (KbSsawVoice*)b->d_vstate;
 				if (g >= 8) KB_LAUNCH_TILED(kb_ssaw_tiled_kernel, KbSsawSmem, 8, 1024, vs, b->d_hdr, d_voice_dst, n, total, b->fs);
 				else KB_LAUNCH_TILED(kb_ssaw_tiled_kernel, KbSsawSmem, 2, 1024, vs, b->d_hdr, d_voice_dst, n, total, b->fs);   // 992 workers: 7 x 2 x 128 items in two rounds
+			} else if (b->graph == KB_SY_FM) {
+				KB_LAUNCH_TILED(kb_fm_tiled_kernel, KbFmSmem, 8, 544, (KbFmVoice*)b->d_vstate, b->d_hdr, b->d_blk, d_voice_dst, n, b->voices, total, b->fs);   // 512 workers: an 8 x 128 tile in two rounds
 			} else {
 				KbTbVoice* vs = (KbTbVoice*)b->d_vstate;
 				// (the ladder recurrence, one lane per voice and ~100 dependent cycles per sample, bounds this kernel for any G; giving it a

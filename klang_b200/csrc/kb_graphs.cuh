@@ -291,6 +291,34 @@ KB_HD float kb_fm_tick(const KbFs& fs, float i1, float i2, KbFmVoice& n, int& no
 	return out;
 }
 
+// The same sample as a pure function of the sample index: tick `t` of a block whose first tick finds the voice in state `n`.
+// The three operator phases are integer ramps and an operator's phase offset is the previous operator's output of the SAME
+// sample, so the only values carried from sample to sample are the four envelopes (e0..e2 the operators', ea the ADSR), which
+// the caller supplies for tick t.  kb_fm_block_end leaves the voice as `ticks` calls of kb_fm_tick would (envelopes aside).
+struct KbFmSample { float y0, y1, out; uint32_t off0, off1, off2; };
+KB_HD KbFmSample kb_fm_at(const KbFmVoice& n, uint32_t t, float i1, float i2, float e0, float e1, float e2, float ea) {
+	KbFmSample r;
+	r.off0 = kb_phase_from_radians(n.op[0].in * KB_TWO_PI_F);
+	r.y0 = kb_fsine_value(n.op[0].osc.position + t * (uint32_t)n.op[0].osc.increment + r.off0);
+	r.y0 *= e0 * i1;
+	r.off1 = kb_phase_from_radians(r.y0 * KB_TWO_PI_F);
+	r.y1 = kb_fsine_value(n.op[1].osc.position + t * (uint32_t)n.op[1].osc.increment + r.off1);
+	r.y1 *= e1 * i2;
+	r.off2 = kb_phase_from_radians(r.y1 * KB_TWO_PI_F);
+	float out = kb_fsine_value(n.op[2].osc.position + t * (uint32_t)n.op[2].osc.increment + r.off2);
+	out *= e2 * n.op[2].amp;
+	out *= ea * 0.1f;
+	r.out = out;
+	return r;
+}
+KB_HD void kb_fm_block_end(KbFmVoice& n, uint32_t ticks, float i1, float i2, const KbFmSample& last) {
+	if (ticks == 0) return;
+	n.op[0].amp = i1; n.op[1].amp = i2;
+	n.op[1].in = last.y0; n.op[2].in = last.y1;
+	n.op[0].osc.offset = last.off0; n.op[1].osc.offset = last.off1; n.op[2].osc.offset = last.off2;
+	for (int k = 0; k < 3; k++) n.op[k].osc.position += ticks * (uint32_t)n.op[k].osc.increment;
+}
+
 // =========================================================================================== DEVICE halves
 #ifdef __CUDACC__
 

@@ -164,11 +164,14 @@ KB_HD void kb_fsine_set_f(const KbFs& fs, KbFastSine& o, float f) { if (f != o.f
 KB_HD void kb_fsine_set_fp(const KbFs& fs, KbFastSine& o, float f, float phase) {
 	o.position = kb_phase_from_radians(phase); o.offset = kb_phase_from_radians(0.f); kb_fsine_set_f(fs, o, f);
 }
-KB_HD float kb_fsine_tick(KbFastSine& o) {
-	float x = (kb_bits(((o.position + o.offset) >> 9) | 0x3f800000) - 1.f) * KB_TWO_PI_F;             // fast_modp  klang.h:1424-1428
+KB_HD float kb_fsine_value(uint32_t phase) {                                                       // fastsinp(position + offset)
+	float x = (kb_bits((phase >> 9) | 0x3f800000) - 1.f) * KB_TWO_PI_F;                               // fast_modp  klang.h:1424-1428
 	if (x > 3.f / 2.f * KB_PI_F) x -= KB_TWO_PI_F; else if (x > KB_PI_F / 2.f) x = KB_PI_F - x;
 	const float x2 = x * x;
-	const float out = (((-0.00018542f * x2 + 0.0083143f) * x2 - 0.16666f) * x2 + 1.0f) * x;
+	return (((-0.00018542f * x2 + 0.0083143f) * x2 - 0.16666f) * x2 + 1.0f) * x;
+}
+KB_HD float kb_fsine_tick(KbFastSine& o) {
+	const float out = kb_fsine_value(o.position + o.offset);
 	o.position += (uint32_t)o.increment;
 	return out;
 }

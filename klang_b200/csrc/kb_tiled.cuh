@@ -295,6 +295,96 @@ __global__ void __launch_bounds__(NT, 1) kb_ssaw_tiled_kernel(KbSsawVoice* __res
 	}
 }
 
+// ------------------------------------------------------------------------------------------------------ FM
+// FM.k:61-73 (three Operator<Sine> in series, klang.h:4140-4173).  Nothing in the voice but its four envelopes is a recurrence:
+// the operator phases are integer ramps and each operator is phase-modulated by the previous operator's output of the SAME
+// sample (kb_fm_at, kb_graphs.cuh).
+//   A (tile k)    warp 0, lane = (envelope, voice): the three operator envelopes and the ADSR, run-length form
+//   D (tile k-1)  thread = (voice, t): the whole operator chain of one sample, coalesced store
+// The block-start voice state sits read-only in shared memory; kb_fm_block_end writes the oscillators back.
+// tests/host/fm_tiled_check.cpp proves this formulation (same functions, g++) bit-identical to the per-tick kb_fm_tick,
+// samples and state; tools/fm_tiled_probe.py compares the kernel with the lane-per-voice kernel on the device
+// (1024 voices x 4096 samples: 58 us against 2502 us).
+template <int G> struct KbFmSmem {
+	KbFmVoice voice[G];
+	KbTileRows<G> env[2][4];         // A -> D: [tile parity][op0, op1, op2, adsr]
+	KbFmSample last[G];              // the block's final sample (offsets and operator outputs the next block starts from)
+	float i1[G], i2[G];
+	int active[G];
+};
+template <int G, int NT>
+__global__ void __launch_bounds__(NT, 1) kb_fm_tiled_kernel(KbFmVoice* __restrict__ voices, KbVoiceHdr* __restrict__ hdr,
+                                                                       const KbSynthBlock* __restrict__ blk, float* __restrict__ dst,
+                                                                       int n, int voices_per_inst, int total, KbFs fs) {
+	static_assert(4 * G <= 32, "the four envelopes of every voice share warp 0");
+	constexpr int T = KB_TILE_T;
+	extern __shared__ __align__(16) unsigned char kb_smem[];
+	KbFmSmem<G>& S = *reinterpret_cast<KbFmSmem<G>*>(kb_smem);
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int v0 = blockIdx.x * G;
+	if (tid < G) {
+		const int v = v0 + tid;
+		const int act = (v < total && hdr[v].stage != KB_NOTE_OFF) ? 1 : 0;
+		S.active[tid] = act;
+		if (v < total) hdr[v].active = act;
+		if (act) {
+			S.voice[tid] = voices[v];
+			S.i1[tid] = blk[v / voices_per_inst].fm_i1;
+			S.i2[tid] = blk[v / voices_per_inst].fm_i2;
+		}
+	}
+	__syncthreads();
+	const int ev = lane % G, ee = lane / G;                               // A lanes: envelope ee (3 = ADSR) of voice ev
+	const bool is_env = warp == 0 && lane < 4 * G && S.active[ev];
+	const KbEnv* esrc = nullptr;
+	KbEnvR env;
+	if (is_env) {
+		esrc = ee < 3 ? &S.voice[ev].op[ee].env : &S.voice[ev].adsr;      // breakpoints stay in shared memory
+		kb_envr_load(env, *esrc);
+	}
+	const int ntiles = (n + T - 1) / T;
+	const int wtid = tid - 32, wthreads = NT - 32;
+	for (int k = 0; k < ntiles + 1; k++) {
+		if (warp == 0) {                                                     // ---- A, tile k
+			if (is_env && k < ntiles) {
+				const int steps = min(T, n - k * T);
+				kb_envr_run(fs, env, esrc->px, esrc->py, S.env[k & 1][ee].r[ev], steps);
+			}
+		} else {
+			const int d = k - 1;
+			if (d >= 0) {                                                    // ---- D, tile k-1
+				const int steps = min(T, n - d * T);
+				for (int item = wtid; item < G * T; item += wthreads) {
+					const int v = item / T, t = item % T;
+					if (t < steps && v0 + v < total) {
+						float out = 0.f;
+						if (S.active[v]) {
+							const KbFmSample s = kb_fm_at(S.voice[v], (uint32_t)(d * T + t), S.i1[v], S.i2[v], S.env[d & 1][0].r[v][t],
+							                              S.env[d & 1][1].r[v][t], S.env[d & 1][2].r[v][t], S.env[d & 1][3].r[v][t]);
+							out = s.out;
+							if (d * T + t == n - 1) S.last[v] = s;
+						}
+						dst[(size_t)(v0 + v) * n + d * T + t] = out;
+					}
+				}
+			}
+		}
+		__syncthreads();
+	}
+	if (is_env) {
+		KbEnv& e = ee < 3 ? voices[v0 + ev].op[ee].env : voices[v0 + ev].adsr;
+		kb_envr_store(env, e);
+		if (ee == 3 && env.stage == KB_ENV_OFF) hdr[v0 + ev].stage = KB_NOTE_OFF;    // FM.k:71-72 `if (adsr.finished()) stop()`
+	}
+	if (warp == 1 && lane < G && S.active[lane]) {
+		KbFmVoice m = S.voice[lane];
+		kb_fm_block_end(m, (uint32_t)n, S.i1[lane], S.i2[lane], S.last[lane]);
+		KbFmVoice& o = voices[v0 + lane];
+		#pragma unroll
+		for (int j = 0; j < 3; j++) { o.op[j].osc.position = m.op[j].osc.position; o.op[j].osc.offset = m.op[j].osc.offset; o.op[j].amp = m.op[j].amp; o.op[j].in = m.op[j].in; }
+	}
+}
+
 // --------------------------------------------------------------------------------------------------- TB303
 // TB303.k:103-113.  A: filter envelope and ADSR.  B: oscillator sample and Filter::set coefficients b0, k, g
 // (TB303.k:37-55; polynomials of the cutoff, no transcendental: r and the feedback one-pole are control-rate

@@ -73,3 +73,14 @@ def test_fm_voice_product_functions_match_oracle_on_host():
     want = np.concatenate([port(48000.0, 60, (1.0, 0.37, 0.37, 0.5), 3000, 1500), port(44100.0, 72, (2.5, 3.0, 7.5, 0.002), 2000, 700)])
     assert len(got) == len(want) and np.array_equal(got.view(np.uint32), want.view(np.uint32))
     assert np.abs(want).max() > 0.05
+
+
+def test_fm_time_parallel_form_equals_per_tick_form():
+    """kb_fm_at / kb_fm_block_end with kb_envr_run rows (what the opt-in kb_fm_tiled_kernel runs) equal kb_fm_tick bit for bit,
+    samples and the state left behind, over ragged blocks, mid-tile releases, notes running into Off and re-triggers."""
+    exe = os.path.join(tempfile.mkdtemp(prefix="kb_host_"), "fm_tiled_check")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-x", "c++",
+                           os.path.join(ROOT, "tests", "host", "fm_tiled_check.cpp"), "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert " 0 mismatches, 0 state mismatches" in out.stdout
