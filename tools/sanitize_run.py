@@ -5,7 +5,7 @@ import numpy as np
 import klang_b200 as kb
 
 fs = 48000.0
-for graph, inst, voices, n in ((kb.SY_SUBTRACTIVE, 2, 16, 300), (kb.SY_SUBTRACTIVE, 8, 100, 260), (kb.SY_SUPERSAW, 2, 32, 300), (kb.SY_TB303, 1, 32, 300), (kb.SY_SYNTHX, 1, 32, 70), (kb.SY_FILTER_K, 1, 32, 129)):
+for graph, inst, voices, n in ((kb.SY_SUBTRACTIVE, 2, 16, 300), (kb.SY_SUBTRACTIVE, 8, 100, 260), (kb.SY_SUPERSAW, 2, 32, 300), (kb.SY_TB303, 1, 32, 300), (kb.SY_SYNTHX, 1, 32, 70), (kb.SY_FILTER_K, 1, 32, 129), (kb.SY_FM, 2, 21, 300)):
     b = kb.SynthBank(graph, inst, voices, fs, n)
     for g in range(0, inst * b.voices, 2):
         b.voice_start(g % b.voices, 40 + g % 30, 0.7, g // b.voices)
