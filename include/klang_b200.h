@@ -169,7 +169,9 @@ int kb_mixdown_collect(kb_mixdown* m, float* dst, int count, void* cuda_stream);
 
 /* ---------------------------------------------------------------------------- primitive operators */
 /* Single-object runs of the primitive operators ON THE DEVICE (one thread), for known-answer tests.
- * kinds as in tests/cases.py.  Generators::Fast / Basic / Wavetables (klang.h:4893-5381). */
+ * kinds as in tests/cases.py.  Generators::Fast / Basic / Wavetables (klang.h:4893-5381).  Kinds 12 / 13 = Basic::Noise / Fast::Noise
+ * (klang.h:4947-4951, 5357-5366): the n ticks are the next n draws of the PROCESS's libc rand() stream, produced on the device,
+ * and the call leaves libc's rand() advanced by n draws exactly as the reference's loop would. */
 int kb_prim_osc(int kind, int nargs, float f, float phase, float duty, float fs, int n, float* out);
 /* Filters::Biquad::{LPF,HPF,BPF,BRF,APF}, OnePole::{LPF,HPF}, Butterworth::LPF<1>,<2>, DCF, IIR<1>, IIR<2>, Modifiers::Modal,
  * Envelope::Follower peak / rms (klang.h:5387-5896; kinds as in tests/cases.py FLT_*): set(f[s],Q[s]) before sample s < nset

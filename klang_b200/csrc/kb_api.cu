@@ -894,8 +894,19 @@ static int prim_finish(const char* what) {
 }
 extern "C" int kb_prim_osc(int kind, int nargs, float f, float phase, float duty, float fs, int n, float* out) {
 	if (kb_device_count() < 1) return kb_fail(KB_ENODEV, "no CUDA device");
-	if (!out || n < 0 || kind < 0 || !(kind <= 9 || kind == 10 || kind == 11)) return kb_fail(KB_EINVAL, "kb_prim_osc: unsupported kind");
+	if (!out || n < 0 || kind < 0 || kind > 13) return kb_fail(KB_EINVAL, "kb_prim_osc: unsupported kind");
 	const KbFs F = kb_make_fs(fs);
+	if (kind >= 12) {   // Basic::Noise / Fast::Noise: the device continues the process's libc rand() stream (kb_rand.h)
+		KbRand g;
+		if (!kb_rand_capture(g)) return kb_fail(KB_EINVAL, "kb_prim_osc: libc rand() is not running its default (TYPE_3) generator");
+		DevBuf dn(sizeof(float) * (n ? n : 1));
+		kb_prim_noise_kernel<<<1, 32>>>(kind == 13 ? 1 : 0, g, n, dn.as<float>());
+		int nrc = prim_finish("kb_prim_osc"); if (nrc) return nrc;
+		cudaMemcpy(out, dn.p, sizeof(float) * n, cudaMemcpyDeviceToHost);
+		kb_rand_jump(g, (unsigned long long)n);          // the draws the device consumed
+		kb_rand_commit(g);
+		return KB_OK;
+	}
 	std::vector<float> table(2048, 0.f);
 	if (kind >= 10) {   // Wavetable::operator=(Oscillator) fills the table with a Basic osc at fs/size Hz on the host (klang.h:3645-3650)
 		KbBasicOsc o; kb_bosc_init(o); kb_bosc_set_f(F, o, F.f / 2048);

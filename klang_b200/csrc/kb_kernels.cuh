@@ -305,6 +305,12 @@ __global__ void kb_fx_seq_kernel(KbFxHdr* __restrict__ hdrs, STATE* __restrict__
 }
 
 // ============================================================================================= primitives
+// Generators::Basic::Noise / Fast::Noise (klang.h:4947-4951, 5357-5366): n ticks = n draws of the libc stream whose captured state
+// arrives by value (kb_rand.h); the host advances its copy by the same n draws and hands it back to libc
+__global__ void kb_prim_noise_kernel(int fast, KbRand g, int n, float* out) {
+	if (threadIdx.x || blockIdx.x) return;
+	for (int s = 0; s < n; s++) { const uint32_t r = kb_rand_next(g); out[s] = fast ? kb_noise_fast(r) : kb_noise_basic(r); }
+}
 __global__ void kb_prim_osc_kernel(int kind, int nargs, float f, float phase, float duty, KbFs fs, int n, float* out, const float* table) {
 	if (threadIdx.x || blockIdx.x) return;
 	if (kind <= 3) {

@@ -13,6 +13,7 @@
 
 #include "kb_math.cuh"
 #include "kb_state.h"
+#include "kb_rand.h"
 
 #ifdef __CUDA_ARCH__
 #define KB_SINF(x) kb_sinf(x)

@@ -545,7 +545,7 @@ static void kp_sdelay_tap_f(const kp_delay* l, const kp_delay* r, float delay, f
 
 enum { OSC_FAST_SAW = 0, OSC_FAST_TRIANGLE, OSC_FAST_SQUARE, OSC_FAST_PULSE, OSC_FAST_SINE,
        OSC_BASIC_SINE, OSC_BASIC_SAW, OSC_BASIC_TRIANGLE, OSC_BASIC_SQUARE, OSC_BASIC_PULSE,
-       OSC_WT_SINE, OSC_WT_SAW };
+       OSC_WT_SINE, OSC_WT_SAW, OSC_BASIC_NOISE, OSC_FAST_NOISE };
 
 int kp_osc(int kind, int nargs, float f, float phase, float duty, int n, float* out) {
 	kp_ensure_fs();
@@ -570,6 +570,14 @@ int kp_osc(int kind, int nargs, float f, float phase, float duty, int n, float* 
 		if (nargs == 1) kp_wt_set_f(w, f); else if (nargs == 2) kp_wt_set_fp(w, f, phase);
 		for (int s = 0; s < n; s++) out[s] = kp_wt_tick(w);
 		free(w);
+	} else if (kind == OSC_BASIC_NOISE) {          /* Generators::Basic::Noise::process  klang.h:4947-4951: one libc rand() per tick */
+		for (int s = 0; s < n; s++) out[s] = rand() * 2.f / (const float)RAND_MAX - 1.f;
+	} else if (kind == OSC_FAST_NOISE) {           /* Generators::Fast::Noise::process   klang.h:5357-5366 */
+		for (int s = 0; s < n; s++) {
+			union { unsigned int i; float f; } u;
+			u.i = ((rand() & 0x7fffu) << 1) | 0x43800000u;
+			out[s] = u.f - 257.f;
+		}
 	} else return -1;
 	return 0;
 }

@@ -127,7 +127,7 @@ float ref_pitch_to_frequency(float pitch) {
 // ------------------------------------------------------------------ oscillators
 enum { OSC_FAST_SAW = 0, OSC_FAST_TRIANGLE, OSC_FAST_SQUARE, OSC_FAST_PULSE, OSC_FAST_SINE,
        OSC_BASIC_SINE, OSC_BASIC_SAW, OSC_BASIC_TRIANGLE, OSC_BASIC_SQUARE, OSC_BASIC_PULSE,
-       OSC_WT_SINE, OSC_WT_SAW };
+       OSC_WT_SINE, OSC_WT_SAW, OSC_BASIC_NOISE, OSC_FAST_NOISE };
 
 extern "C++" {
 template<class OSC>
@@ -160,6 +160,9 @@ int ref_osc(int kind, int nargs, float f, float phase, float duty, int n, float*
 	case OSC_BASIC_PULSE:    run_osc<Basic::Pulse>(nargs, f, phase, duty, n, out); break;
 	case OSC_WT_SINE:        run_osc<Wavetables::Sine>(nargs, f, phase, duty, n, out); break;
 	case OSC_WT_SAW:         run_osc<Wavetables::Saw>(nargs, f, phase, duty, n, out); break;
+	// Noise has no set(): each tick is one libc rand() of the process-wide stream (klang.h:4947-4951, 5357-5366)
+	case OSC_BASIC_NOISE:    { Basic::Noise o; for (int s = 0; s < n; s++) { klang::signal y = o; out[s] = y; } } break;
+	case OSC_FAST_NOISE:     { Fast::Noise o; for (int s = 0; s < n; s++) { klang::signal y = o; out[s] = y; } } break;
 	default: return -1;
 	}
 	return 0;

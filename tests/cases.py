@@ -15,7 +15,7 @@ import numpy as np
 # graph / primitive ids — identical in oracle/bindings.py and include/klang_b200.h
 (OSC_FAST_SAW, OSC_FAST_TRIANGLE, OSC_FAST_SQUARE, OSC_FAST_PULSE, OSC_FAST_SINE,
  OSC_BASIC_SINE, OSC_BASIC_SAW, OSC_BASIC_TRIANGLE, OSC_BASIC_SQUARE, OSC_BASIC_PULSE,
- OSC_WT_SINE, OSC_WT_SAW) = range(12)
+ OSC_WT_SINE, OSC_WT_SAW, OSC_BASIC_NOISE, OSC_FAST_NOISE) = range(14)
 (FLT_BIQUAD_LPF, FLT_BIQUAD_HPF, FLT_ONEPOLE_LPF, FLT_ONEPOLE_HPF,
  FLT_BIQUAD_BPF, FLT_BIQUAD_BRF, FLT_BIQUAD_APF, FLT_BUTTERWORTH_LPF1, FLT_BUTTERWORTH_LPF2,
  FLT_DCF, FLT_IIR1, FLT_IIR2, FLT_MODAL, FLT_FOLLOWER_PEAK, FLT_FOLLOWER_RMS) = range(15)
@@ -51,6 +51,20 @@ def voice_velocity(v):
 
 # ----------------------------------------------------------------------------- primitives
 
+def noise_cases(eng):
+    """Basic::Noise / Fast::Noise (klang.h:4947-4951, 5357-5366): one libc rand() per tick from the process-wide stream (SURVEY Q9) —
+    seeded runs, and runs that continue the stream where the previous call left it."""
+    out = {}
+    eng.srand(5)
+    out["osc/basic_noise/seed5"] = eng.osc(OSC_BASIC_NOISE, 256, 0.0)
+    out["osc/fast_noise/continued"] = eng.osc(OSC_FAST_NOISE, 256, 0.0)
+    eng.srand(272839)
+    out["osc/fast_noise/seed272839"] = eng.osc(OSC_FAST_NOISE, 1000, 0.0)
+    out["osc/basic_noise/continued"] = eng.osc(OSC_BASIC_NOISE, 777, 0.0)
+    return out
+
+
+
 def primitive_cases(eng, fs):
     """dict name -> float32/int32 array for every primitive on the hot path."""
     eng.set_fs(fs)
@@ -70,6 +84,7 @@ def primitive_cases(eng, fs):
             out[f"osc/{name}/f2093_p2_d{duty}"] = eng.osc(kind, n, 2093.0, 2.0, duty)
     out["wavetable/sine"] = eng.wavetable(OSC_WT_SINE)
     out["wavetable/saw"] = eng.wavetable(OSC_WT_SAW)
+    out.update(noise_cases(eng))
 
     x = noise(512, seed=7)
     imp = np.zeros(64, np.float32)

@@ -84,3 +84,14 @@ def test_fm_time_parallel_form_equals_per_tick_form():
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert " 0 mismatches, 0 state mismatches" in out.stdout
+
+
+def test_device_rand_restates_glibc_and_attaches_to_the_live_stream():
+    """klang_b200/csrc/kb_rand.h against this box's libc: srand()/rand() draw for draw over 12 seeds, jump-ahead == sequential stepping,
+    capture / commit read and advance the LIVE libc stream, and the two Noise maps equal the reference's expressions."""
+    exe = os.path.join(tempfile.mkdtemp(prefix="kb_host_"), "rand_check")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-x", "c++",
+                           os.path.join(ROOT, "tests", "host", "rand_check.cpp"), "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert " 0 mismatches, 0 jump mismatches, 0 live-stream mismatches, 0 noise mismatches" in out.stdout

@@ -1,0 +1,59 @@
+"""Device-side libc rand(): Basic::Noise / Fast::Noise ticks produced on the GPU continue the process-wide rand() stream bit for bit
+and hand it back advanced (klang_b200/csrc/kb_rand.h).  The generator, the jump-ahead and the libc hand-over are
+pinned on the CPU (tests/host/rand_check.cpp); this file checks the device kernel against the golden vectors of the compiled
+reference and the host/device interleaving against the live oracle.  (Sorted last: written after the round's last full GPU run.)"""
+import numpy as np
+import pytest
+
+import cases
+import klang_b200 as kb
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _exact(got, want, name):
+    assert got.shape == want.shape, name
+    same = got.view(np.uint32) == want.view(np.uint32)
+    assert same.all(), f"{name}: first mismatch at {int(np.argmin(same))}: got {got[np.argmin(same)]!r} want {want[np.argmin(same)]!r}"
+
+
+@pytest.mark.parametrize("fs", [44100, 48000])
+def test_device_noise_matches_reference_golden(golden, fs):
+    if kb.device_count() < 1:
+        pytest.fail("no CUDA device: the gpu tests must run on the B200 box")
+    eng = kb.Engine()
+    eng.set_fs(fs)
+    got = cases.noise_cases(eng)
+    assert len(got) == 4
+    for name, arr in got.items():
+        _exact(arr, golden[fs][name], name)
+        assert arr.min() < -0.9 and arr.max() > 0.9
+
+
+def test_host_draws_after_device_noise_continue_the_stream():
+    """srand(11); 300 noise ticks on the device; then a SuperSaw note-on, whose on() draws seven detune factors with libc rand() on the
+    host (SuperSaw.k:17): the voice must be the one the reference gets, i.e. libc was advanced by exactly the 300 device draws."""
+    fs, n = 48000.0, 128
+    oracle.port.set_fs(fs)
+    oracle.port.srand(11)
+    wn = oracle.port.osc(cases.OSC_BASIC_NOISE, 300, 0.0)
+    sy = oracle.port.Synth(cases.SY_SUPERSAW, 4)
+    sy.voice_start(0, 60, 0.8)
+    want = sy.process_voices(n)[0]
+    wn2 = oracle.port.osc(cases.OSC_FAST_NOISE, 50, 0.0)
+    sy.close()
+
+    eng = kb.Engine()
+    eng.set_fs(fs)
+    eng.srand(11)
+    gn = eng.osc(cases.OSC_BASIC_NOISE, 300, 0.0)
+    bank = kb.SynthBank(kb.SY_SUPERSAW, 1, 4, fs, n)
+    bank.voice_start(0, 60, 0.8, 0)
+    got = bank.process_block(n, kb.PER_VOICE)[0]
+    gn2 = eng.osc(cases.OSC_FAST_NOISE, 50, 0.0)
+    bank.close()
+    _exact(gn, wn, "noise before the note")
+    _exact(np.ascontiguousarray(got), np.ascontiguousarray(want), "SuperSaw voice after device noise")
+    _exact(gn2, wn2, "noise after the note")
+    assert np.abs(want).max() > 0.01
