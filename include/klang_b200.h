@@ -173,6 +173,11 @@ int kb_mixdown_collect(kb_mixdown* m, float* dst, int count, void* cuda_stream);
  * (klang.h:4947-4951, 5357-5366): the n ticks are the next n draws of the PROCESS's libc rand() stream, produced on the device,
  * and the call leaves libc's rand() advanced by n draws exactly as the reference's loop would. */
 int kb_prim_osc(int kind, int nargs, float f, float phase, float duty, float fs, int n, float* out);
+/* One Delay<1000> (klang.h:3381-3512), sample by sample: write in[s]; out_i = tap(int di[s]); out_f = tap(float df[s]);
+ * out_l = lagrange(df[s]) (klang.h:3429-3458); set(set_at[s]) when set_at[s] >= 0; out_p = process() once set() has placed a read
+ * head, else 0.  Delays must lie inside the line (0 <= di < 1000, 0 <= df < 999). */
+int kb_prim_delay(int n, const float* in, const int* di, const float* df, const float* set_at,
+                  float* out_i, float* out_f, float* out_p, float* out_l);
 /* Filters::Biquad::{LPF,HPF,BPF,BRF,APF}, OnePole::{LPF,HPF}, Butterworth::LPF<1>,<2>, DCF, IIR<1>, IIR<2>, Modifiers::Modal,
  * Envelope::Follower peak / rms (klang.h:5387-5896; kinds as in tests/cases.py FLT_*): set(f[s],Q[s]) before sample s < nset
  * (one-pole, Modal and Follower kinds: nset <= 1, coefficients from the host libm; DCF: f = r; IIR<1>: f = coefficient;

@@ -49,6 +49,7 @@ SYMBOLS = [
     ("kb_prim_envelope", _i, [_i, _vp, _i, _i, _f, _i, _i, _f, _f, _vp, _vp]),
     ("kb_prim_adsr", _i, [_f, _f, _f, _f, _f, _i, _i, _vp, _vp]),
     ("kb_prim_math", _i, [_i, _i, _vp, _vp]),
+    ("kb_prim_delay", _i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 ]
 
 
@@ -351,6 +352,24 @@ class Engine:
         nargs = 1 if phase is None else (2 if duty is None else 3)
         _check(lib().kb_prim_osc(kind, nargs, float(f), float(phase or 0.0), float(duty or 0.0), self.fs, n, out.ctypes.data), "kb_prim_osc")
         return out
+
+    def _delay_kat(self, x, di, df, set_at):
+        x, di = np.ascontiguousarray(x, np.float32), np.ascontiguousarray(di, np.int32)
+        df, set_at = np.ascontiguousarray(df, np.float32), np.ascontiguousarray(set_at, np.float32)
+        n = len(x)
+        oi, of, op, ol = (np.zeros(n, np.float32) for _ in range(4))
+        _check(lib().kb_prim_delay(n, x.ctypes.data, di.ctypes.data, df.ctypes.data, set_at.ctypes.data,
+                                   oi.ctypes.data, of.ctypes.data, op.ctypes.data, ol.ctypes.data), "kb_prim_delay")
+        return oi, of, op, ol
+
+    def delay1000(self, x, di, df, set_at):
+        """Delay<1000>: tap(int), tap(float), process() per sample (tests/cases.py)."""
+        return self._delay_kat(x, di, df, set_at)[:3]
+
+    def delay_lagrange(self, x, df):
+        """Delay<1000>::lagrange(df[s]) after writing x[s] (klang.h:3429-3458)."""
+        n = len(x)
+        return self._delay_kat(x, np.zeros(n, np.int32), df, np.full(n, -1.0, np.float32))[3]
 
     def filt(self, kind, x, f, Q=None, per_sample=False):
         x = np.ascontiguousarray(x, np.float32)

@@ -921,6 +921,22 @@ extern "C" int kb_prim_osc(int kind, int nargs, float f, float phase, float duty
 	cudaMemcpy(out, dout.p, sizeof(float) * n, cudaMemcpyDeviceToHost);
 	return KB_OK;
 }
+extern "C" int kb_prim_delay(int n, const float* in, const int* di, const float* df, const float* set_at,
+                             float* out_i, float* out_f, float* out_p, float* out_l) {
+	if (kb_device_count() < 1) return kb_fail(KB_ENODEV, "no CUDA device");
+	if (n < 0 || !in || !di || !df || !set_at || !out_i || !out_f || !out_p || !out_l) return kb_fail(KB_EINVAL, "kb_prim_delay: bad argument");
+	for (int s = 0; s < n; s++)
+		if (di[s] < 0 || di[s] >= 1000 || !(df[s] >= 0.f && df[s] < 999.f)) return kb_fail(KB_EINVAL, "kb_prim_delay: delay outside the 1000-sample line");
+	if (n == 0) return KB_OK;
+	const size_t B = sizeof(float) * n;
+	DevBuf din(B, in), ddi(sizeof(int) * n, di), ddf(B, df), dset(B, set_at), dring(sizeof(float) * 1001), oi(B), of(B), op(B), ol(B);
+	kb_prim_delay_kernel<<<1, 32>>>(n, din.as<float>(), ddi.as<int>(), ddf.as<float>(), dset.as<float>(), dring.as<float>(),
+	                                oi.as<float>(), of.as<float>(), op.as<float>(), ol.as<float>());
+	int rc = prim_finish("kb_prim_delay"); if (rc) return rc;
+	cudaMemcpy(out_i, oi.p, B, cudaMemcpyDeviceToHost); cudaMemcpy(out_f, of.p, B, cudaMemcpyDeviceToHost);
+	cudaMemcpy(out_p, op.p, B, cudaMemcpyDeviceToHost); cudaMemcpy(out_l, ol.p, B, cudaMemcpyDeviceToHost);
+	return KB_OK;
+}
 extern "C" int kb_prim_filter(int kind, int nset, const float* f, const float* Q, float fs, int n, const float* in, float* out, float* coeffs) {
 	if (kb_device_count() < 1) return kb_fail(KB_ENODEV, "no CUDA device");
 	const bool onepole = kind == 2 || kind == 3 || kind == 7, host_set = kind >= 12;     // kinds whose set() runs on the host (libm)

@@ -305,6 +305,11 @@ __global__ void kb_fx_seq_kernel(KbFxHdr* __restrict__ hdrs, STATE* __restrict__
 }
 
 // ============================================================================================= primitives
+__global__ void kb_prim_delay_kernel(int n, const float* in, const int* di, const float* df, const float* set_at, float* ring,
+                                     float* out_i, float* out_f, float* out_p, float* out_l) {
+	if (threadIdx.x || blockIdx.x) return;
+	kb_delay_kat(n, in, di, df, set_at, ring, out_i, out_f, out_p, out_l);
+}
 // Generators::Basic::Noise / Fast::Noise (klang.h:4947-4951, 5357-5366): n ticks = n draws of the libc stream whose captured state
 // arrives by value (kb_rand.h); the host advances its copy by the same n draws and hands it back to libc
 __global__ void kb_prim_noise_kernel(int fast, KbRand g, int n, float* out) {

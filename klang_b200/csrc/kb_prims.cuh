@@ -566,6 +566,40 @@ KB_D float kb_delay_tap_f(const KbDelay& d, const float* ring, float delay) {   
 	const int j = (i + 1) % d.SIZE;
 	return ring[i] + fraction * (ring[j] - ring[i]);
 }
+KB_D float kb_delay_tap_i(const KbDelay& d, const float* ring, int delay) {     // Delay::tap(int)  klang.h:3405-3410
+	int read = (d.position - 1) - delay;
+	if (read < 0) read += d.SIZE;
+	return ring[read];
+}
+KB_D float kb_delay_lagrange(const KbDelay& d, const float* ring, float delay) {   // Delay::lagrange (third order)  klang.h:3429-3458
+	float read = (float)(d.position - 1) - delay;
+	if (read < 0.f) read += d.SIZE;
+	const int i = (int)read;
+	const float x = read - i;
+	const float y0 = ring[(i - 1 + d.SIZE) % d.SIZE], y1 = ring[i], y2 = ring[(i + 1) % d.SIZE], y3 = ring[(i + 2) % d.SIZE];
+	const float c0 = (-x * (x - 1) * (x - 2)) / 6.0f;
+	const float c1 = ((x + 1) * (x - 1) * (x - 2)) / 2.0f;
+	const float c2 = (-x * (x + 1) * (x - 2)) / 2.0f;
+	const float c3 = (x * (x + 1) * (x - 1)) / 6.0f;
+	return c0 * y0 + c1 * y1 + c2 * y2 + c3 * y3;
+}
+// The Delay<1000> known-answer loop of tests/cases.py (one object, sample by sample): write in[s]; tap(int di[s]); tap(float df[s]);
+// lagrange(df[s]); set(set_at[s]) when >= 0; process() once a read head exists.  Host + device (tests/host/delay_check.cpp).
+KB_D float kb_delay_tick(KbDelay& d, const float* ring);
+KB_D void kb_delay_kat(int n, const float* in, const int* di, const float* df, const float* set_at, float* ring,
+                       float* out_i, float* out_f, float* out_p, float* out_l) {
+	KbDelay d; kb_delay_construct(d, 1000, 0);
+	for (int s = 0; s <= 1000; s++) ring[s] = 0.f;
+	bool have_set = false;
+	for (int s = 0; s < n; s++) {
+		kb_delay_write(d, ring, in[s]);
+		out_i[s] = kb_delay_tap_i(d, ring, di[s]);
+		out_f[s] = kb_delay_tap_f(d, ring, df[s]);
+		out_l[s] = kb_delay_lagrange(d, ring, df[s]);
+		if (set_at[s] >= 0.f) { kb_delay_set(d, set_at[s]); have_set = true; }
+		out_p[s] = have_set ? kb_delay_tick(d, ring) : 0.f;
+	}
+}
 KB_D float kb_delay_tick(KbDelay& d, const float* ring) {                    // Delay::process  klang.h:3461-3473
 	const int i = d.last_position;
 	const int j = (i + 1) % d.SIZE;

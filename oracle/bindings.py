@@ -62,6 +62,7 @@ class Oracle:
         sig("adsr", [f32, f32, f32, f32, i, i, _f32p, vp])
         sig("delay1000", [i, _f32p, _i32p, _f32p, _f32p, _f32p, _f32p, _f32p])
         sig("stereo_delay1000", [i, _f32p, _f32p, _f32p, _f32p, _f32p])
+        sig("delay1000_lagrange", [i, _f32p, _f32p, _f32p])
         sig("control_smooth", [f32, f32, f32, i, _f32p, _f32p])
         sig("fx_create", [i], vp)
         sig("fx_destroy", [vp], None)
@@ -154,6 +155,12 @@ class Oracle:
         self.fn("delay1000")(n, x, np.ascontiguousarray(di, np.int32), np.ascontiguousarray(df, np.float32),
                              np.ascontiguousarray(set_at, np.float32), oi, of, op)
         return oi, of, op
+
+    def delay_lagrange(self, x, df):
+        x = np.ascontiguousarray(x, np.float32)
+        out = np.zeros(len(x), np.float32)
+        self.fn("delay1000_lagrange")(len(x), x, np.ascontiguousarray(df, np.float32), out)
+        return out
 
     def stereo_delay1000(self, xl, xr, df):
         xl = np.ascontiguousarray(xl, np.float32)

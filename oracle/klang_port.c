@@ -513,6 +513,20 @@ static float kp_delay_tap_f(const kp_delay* d, float delay) {
 	const int j = (i + 1) % d->SIZE;
 	return d->buf[i] + fraction * (d->buf[j] - d->buf[i]);
 }
+/* Delay::lagrange  klang.h:3429-3458 */
+static float kp_delay_lagrange(const kp_delay* d, float delay) {
+	float read = (float)(d->position - 1) - delay;
+	if (read < 0.f) read += d->SIZE;
+	int i = (int)read;
+	float x = read - i;
+	int i0 = (i - 1 + d->SIZE) % d->SIZE, i1 = i, i2 = (i + 1) % d->SIZE, i3 = (i + 2) % d->SIZE;
+	float y0 = d->buf[i0], y1 = d->buf[i1], y2 = d->buf[i2], y3 = d->buf[i3];
+	float c0 = (-x * (x - 1) * (x - 2)) / 6.0f;
+	float c1 = ((x + 1) * (x - 1) * (x - 2)) / 2.0f;
+	float c2 = (-x * (x + 1) * (x - 2)) / 2.0f;
+	float c3 = (x * (x + 1) * (x - 1)) / 6.0f;
+	return c0 * y0 + c1 * y1 + c2 * y2 + c3 * y3;
+}
 /* Delay::set  klang.h:3480-3489 */
 static void kp_delay_set(kp_delay* d, float samples) {
 	d->time = samples < d->SIZE ? (float)samples : d->SIZE;
@@ -746,6 +760,13 @@ int kp_delay1000(int n, const float* in, const int* di, const float* df, const f
 		if (set_at[s] >= 0.f) { kp_delay_set(&d, set_at[s]); have_set = 1; }
 		out_p[s] = have_set ? kp_delay_tick(&d) : 0.f;
 	}
+	kp_delay_free(&d);
+	return 0;
+}
+
+int kp_delay1000_lagrange(int n, const float* in, const float* df, float* out) {
+	kp_delay d; kp_delay_construct(&d, 1000);
+	for (int s = 0; s < n; s++) { kp_delay_write(&d, in[s]); out[s] = kp_delay_lagrange(&d, df[s]); }
 	kp_delay_free(&d);
 	return 0;
 }

@@ -308,6 +308,18 @@ int ref_delay1000(int n, const float* in, const int* di, const float* df, const 
 	return 0;
 }
 
+// Delay<1000>::lagrange(df[s]) after writing in[s] (third-order interpolation, klang.h:3429-3458)
+int ref_delay1000_lagrange(int n, const float* in, const float* df, float* out) {
+	klang::Delay<1000>* d = new klang::Delay<1000>();
+	for (int s = 0; s < n; s++) {
+		klang::signal x = in[s];
+		x >> *d;
+		out[s] = d->lagrange(df[s]);
+	}
+	delete d;
+	return 0;
+}
+
 // Stereo::Delay<1000>: per sample write (inl,inr); out = tap(float df[s]) (klang.h:4668-4681).
 int ref_stereo_delay1000(int n, const float* inl, const float* inr, const float* df, float* outl, float* outr) {
 	klang::Stereo::Delay<1000>* d = new klang::Stereo::Delay<1000>();

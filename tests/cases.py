@@ -157,6 +157,7 @@ def primitive_cases(eng, fs):
     set_at[1200] = 999.5
     oi, of, op = eng.delay1000(xin, di, df, set_at)
     out["delay/tap_int"], out["delay/tap_float"], out["delay/process"] = oi, of, op
+    out["delay/lagrange"] = eng.delay_lagrange(noise(n, seed=6), df)      # Delay::lagrange, third order (klang.h:3429-3458)
     ol, orr = eng.stereo_delay1000(noise(n, seed=4), noise(n, seed=5), df)
     out["delay/stereo_l"], out["delay/stereo_r"] = ol, orr
     vals = np.where(np.arange(2000) < 1000, 0.8, 0.1).astype(np.float32)

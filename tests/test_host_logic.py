@@ -95,3 +95,42 @@ def test_device_rand_restates_glibc_and_attaches_to_the_live_stream():
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert " 0 mismatches, 0 jump mismatches, 0 live-stream mismatches, 0 noise mismatches" in out.stdout
+
+
+def test_delay_known_answer_loop_matches_reference_golden_on_host():
+    """kb_delay_kat (write / tap(int) / tap(float) / lagrange / set / process of one Delay<1000>, the loop kb_prim_delay_kernel runs)
+    compiled with g++ reproduces the compiled reference's golden vectors bit for bit, Delay::lagrange included."""
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cases
+    tmp = tempfile.mkdtemp(prefix="kb_host_")
+    exe = os.path.join(tmp, "delay_check")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-x", "c++",
+                           os.path.join(ROOT, "tests", "host", "delay_check.cpp"), "-o", exe])
+
+    class HostDelay:                         # the delay entries of the engine interface, backed by the host build of the product loop
+        def run(self, x, di, df, set_at):
+            n = len(x)
+            path = os.path.join(tmp, "in.bin")
+            with open(path, "wb") as f:
+                f.write(np.int32(n).tobytes())
+                for a, t in ((x, np.float32), (di, np.int32), (df, np.float32), (set_at, np.float32)):
+                    f.write(np.ascontiguousarray(a, t).tobytes())
+            out = subprocess.run([exe, path], capture_output=True)
+            assert out.returncode == 0
+            return np.frombuffer(out.stdout, np.float32).reshape(4, n)
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "klang_ref_fs48000.npz"))
+    n = 1500                                 # the inputs of cases.primitive_cases
+    xin = (np.arange(n) + 1).astype(np.float32)
+    di = (np.arange(n) * 7 % 900).astype(np.int32)
+    df = cases.noise(n, seed=3, lo=0.0, hi=998.0).astype(np.float32)
+    set_at = np.full(n, -1.0, np.float32)
+    set_at[10], set_at[700], set_at[1200] = 4.0, 333.25, 999.5
+    h = HostDelay()
+    oi, of, op, _ = h.run(xin, di, df, set_at)
+    lag = h.run(cases.noise(n, seed=6), np.zeros(n, np.int32), df, np.full(n, -1.0, np.float32))[3]
+    for got, key in ((oi, "delay/tap_int"), (of, "delay/tap_float"), (op, "delay/process"), (lag, "delay/lagrange")):
+        assert np.array_equal(got.view(np.uint32), g[key].view(np.uint32)), key
+    assert np.abs(lag).max() > 0.1

@@ -1,4 +1,4 @@
-"""Device-side libc rand(): Basic::Noise / Fast::Noise ticks produced on the GPU continue the process-wide rand() stream bit for bit
+"""Primitives added after the round's last full GPU run (sorted last).  Device-side libc rand(): Basic::Noise / Fast::Noise ticks produced on the GPU continue the process-wide rand() stream bit for bit
 and hand it back advanced (klang_b200/csrc/kb_rand.h).  The generator, the jump-ahead and the libc hand-over are
 pinned on the CPU (tests/host/rand_check.cpp); this file checks the device kernel against the golden vectors of the compiled
 reference and the host/device interleaving against the live oracle.  (Sorted last: written after the round's last full GPU run.)"""
@@ -57,3 +57,24 @@ def test_host_draws_after_device_noise_continue_the_stream():
     _exact(np.ascontiguousarray(got), np.ascontiguousarray(want), "SuperSaw voice after device noise")
     _exact(gn2, wn2, "noise after the note")
     assert np.abs(want).max() > 0.01
+
+
+@pytest.mark.parametrize("fs", [48000])
+def test_device_delay_primitive_matches_reference_golden(golden, fs):
+    """One Delay<1000> on the device, sample by sample (kb_prim_delay): tap(int), tap(float), set() + process() and the third-order
+    Delay::lagrange (klang.h:3405-3489) against the compiled reference's golden vectors, bit for bit.  (The effect graphs already
+    exercise write / tap / process; lagrange() is used by none of them.)"""
+    eng = kb.Engine()
+    eng.set_fs(fs)
+    g = golden[fs]
+    n = 1500
+    xin = (np.arange(n) + 1).astype(np.float32)
+    di = (np.arange(n) * 7 % 900).astype(np.int32)
+    df = cases.noise(n, seed=3, lo=0.0, hi=998.0).astype(np.float32)
+    set_at = np.full(n, -1.0, np.float32)
+    set_at[10], set_at[700], set_at[1200] = 4.0, 333.25, 999.5
+    oi, of, op = eng.delay1000(xin, di, df, set_at)
+    _exact(oi, g["delay/tap_int"], "delay/tap_int")
+    _exact(of, g["delay/tap_float"], "delay/tap_float")
+    _exact(op, g["delay/process"], "delay/process")
+    _exact(eng.delay_lagrange(cases.noise(n, seed=6), df), g["delay/lagrange"], "delay/lagrange")
