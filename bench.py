@@ -732,7 +732,7 @@ def extras(kb, torch, dev, stream, flush_l2, hbm_peak, peak_src, device_index, w
     for name, graph, inst, voices, n, steps in (("c3_supersaw_256", kb.SY_SUPERSAW, 8, 32, 4096, 5),
                                                 ("c5_tb303_512", kb.SY_TB303, 4, 128, 4096, 3),
                                                 ("c5_synthx_512", kb.SY_SYNTHX, 4, 128, 1024, 2),
-                                                ("fm_k_1024", kb.SY_FM, 8, 128, 4096, 3)):      # examples/FM.k (lane-per-voice kernel)
+                                                ("fm_k_1024", kb.SY_FM, 8, 128, 4096, 3)):      # examples/FM.k (time-parallel kernel)
         kb.lib().kb_srand(1)
         sb = kb.SynthBank(graph, inst, voices, FS, n, device_index)
         sb.set_stream(stream.cuda_stream)
@@ -741,6 +741,8 @@ def extras(kb, torch, dev, stream, flush_l2, hbm_peak, peak_src, device_index, w
         out = torch.empty(sb.out_shape(n), dtype=torch.float32, device=dev)
         ms = time_steps(lambda: sb.process_into(out, n), steps, warmup=3)
         res[name] = {"voice_samples_per_s": inst * voices * n / (ms * 1e-3), "ms_per_step": ms, "block": n}
+        if graph == kb.SY_FM:                              # A/B against the plain lane-per-voice schedule (same results)
+            res[name]["ms_per_step_lane_per_voice_schedule"] = time_steps(lambda: sb.process_into(out, n, kb.LANE_PER_VOICE), 1, warmup=1)
         sb.close()
     if with_cpu:
         res["c3_supersaw_256"]["cpu_reference"] = cpu_extra("synth", oracle.SY_SUPERSAW, 16, 4096, 8)
