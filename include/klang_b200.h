@@ -179,9 +179,10 @@ int kb_prim_osc(int kind, int nargs, float f, float phase, float duty, float fs,
 int kb_prim_delay(int n, const float* in, const int* di, const float* df, const float* set_at,
                   float* out_i, float* out_f, float* out_p, float* out_l);
 /* Filters::Biquad::{LPF,HPF,BPF,BRF,APF}, OnePole::{LPF,HPF}, Butterworth::LPF<1>,<2>, DCF, IIR<1>, IIR<2>, Modifiers::Modal,
- * Envelope::Follower peak / rms (klang.h:5387-5896; kinds as in tests/cases.py FLT_*): set(f[s],Q[s]) before sample s < nset
- * (one-pole, Modal and Follower kinds: nset <= 1, coefficients from the host libm; DCF: f = r; IIR<1>: f = coefficient;
- * IIR<2>: f = a1, Q = a2; Modal: f, Q = decay seconds; Follower: f = attack, Q = release seconds) */
+ * Envelope::Follower peak / rms, Follower::Window<64> mean / rms (klang.h:5387-5948; kinds as in tests/cases.py FLT_*):
+ * set(f[s],Q[s]) before sample s < nset (one-pole, Modal and Follower kinds: nset <= 1, coefficients from the host libm;
+ * DCF: f = r; IIR<1>: f = coefficient; IIR<2>: f = a1, Q = a2; Modal: f, Q = decay seconds; Follower / Window: f = attack,
+ * Q = release seconds) */
 int kb_prim_filter(int kind, int nset, const float* f, const float* Q, float fs, int n, const float* in, float* out, float* coeffs);
 /* Envelope / ADSR (klang.h:3723-4137) */
 int kb_prim_envelope(int npts, const float* xy, int loop_start, int loop_end, float fs, int n, int release_at,

@@ -940,7 +940,7 @@ extern "C" int kb_prim_delay(int n, const float* in, const int* di, const float*
 extern "C" int kb_prim_filter(int kind, int nset, const float* f, const float* Q, float fs, int n, const float* in, float* out, float* coeffs) {
 	if (kb_device_count() < 1) return kb_fail(KB_ENODEV, "no CUDA device");
 	const bool onepole = kind == 2 || kind == 3 || kind == 7, host_set = kind >= 12;     // kinds whose set() runs on the host (libm)
-	if (kind < 0 || kind > 14 || !f || !in || !out || !coeffs || nset < 0 || nset > n || ((onepole || host_set) && nset > 1) || (kind >= 11 && !Q))
+	if (kind < 0 || kind > 16 || !f || !in || !out || !coeffs || nset < 0 || nset > n || ((onepole || host_set) && nset > 1) || (kind >= 11 && !Q))
 		return kb_fail(KB_EINVAL, "kb_prim_filter: unsupported");
 	const KbFs F = kb_make_fs(fs);
 	float4 hc = make_float4(0.f, 0.f, 0.05f, 0.f);
@@ -949,7 +949,7 @@ extern "C" int kb_prim_filter(int kind, int nset, const float* f, const float* Q
 		const float d = kb_clampf(::expf(-KB_PI_F / (Q[0] * F.f)), 1e-6f, 0.9999f);
 		hc.x = 2.f * d * kb_clampf(::cosf(w), -0.9999f, 0.9999f);
 		hc.y = -d * d;
-	} else if (kind == 13 || kind == 14) {       // Follower() { set(0.01f, 0.1f); } then AR::set(attack, release)  klang.h:5871-5878, 5882-5885
+	} else if (kind >= 13 && kind <= 16) {       // Follower() / Window() { set(0.01f, 0.1f); } then AR::set(attack, release)  klang.h:5871-5878, 5882-5885, 5912-5918
 		float attack = 0.01f, release = 0.1f;
 		if (nset == 1) { attack = f[0]; release = Q[0]; }
 		hc.x = 1.f - (attack == 0.f ? 0.f : ::expf(-1.0f / (F.f * attack)));

@@ -358,7 +358,8 @@ __global__ void kb_prim_osc_kernel(int kind, int nargs, float f, float phase, fl
 }
 // kinds (tests/cases.py): 0 Biquad::LPF 1 Biquad::HPF 2 OnePole::LPF 3 OnePole::HPF 4 Biquad::BPF 5 Biquad::BRF 6 Biquad::APF
 // 7 Butterworth::LPF<1> 8 Butterworth::LPF<2> 9 DCF 10 IIR<1> 11 IIR<2>; one-pole coefficients (expf / tanf) come from the host
-// 12 Modifiers::Modal, 13 / 14 Envelope::Follower peak / rms: coefficients hc from the host libm (set() is event-rate code)
+// 12 Modifiers::Modal, 13 / 14 Envelope::Follower peak / rms, 15 / 16 Follower::Window<64> mean / rms: coefficients hc from the host
+// libm (set() is event-rate code)
 __global__ void kb_prim_filter_kernel(int kind, int nset, const float* f, const float* Q, KbFs fs, int n, const float* in, float* out, float* coeffs,
                                       KbOnePole op, float4 hc) {
 	if (threadIdx.x || blockIdx.x) return;
@@ -374,6 +375,7 @@ __global__ void kb_prim_filter_kernel(int kind, int nset, const float* f, const 
 		coeffs[0] = a1; coeffs[1] = a2; coeffs[2] = gain; coeffs[3] = y1; coeffs[4] = y2;
 		return;
 	}
+	if (kind == 15 || kind == 16) { kb_window_follower_run(kind == 16, hc.x, hc.y, n, in, out, coeffs); return; }   // Follower::Window<64> mean / rms
 	if (kind == 13 || kind == 14) {   // Follower::peak / rms over AR::process  klang.h:5866-5896 (abs, sqrt == fabsf, sqrtf: Q4)
 		const float A = hc.x, R = hc.y;
 		float ar = 0.f;

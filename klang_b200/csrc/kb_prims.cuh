@@ -542,6 +542,31 @@ KB_HD void kb_adsr_set(const KbFs& fs, KbEnv& e, float attack, float decay, floa
 KB_HD void kb_adsr_construct(const KbFs& fs, KbEnv& e) { kb_env_construct(fs, e); kb_adsr_set(fs, e, 0.5f, 0.5f, 1.f, 0.5f); }
 KB_HD void kb_adsr_release(const KbFs& fs, KbEnv& e) { kb_env_release(fs, e, e.R, 0.f); }
 
+// ------------------------------------------------------------ Envelope::Follower::Window<64> (klang.h:5904-5948)
+// mean (rms = 0) / rms over a 64-sample moving sum kept in a DOUBLE (klang.h:5909), `sum * window.inv` rounded to float, sqrt for
+// rms, then AR::process (klang.h:5881-5884) with the attack / release coefficients A, R from the host (AR::set is event-rate code).
+// Host + device: tests/host/window_check.cpp renders it with g++ against the golden vectors.
+KB_HD void kb_window_follower_run(int rms, float A, float R, int n, const float* in, float* out, float* coeffs) {
+	const float inv = (float)(1.0 / 64.0);
+	float buf[64];
+	for (int i = 0; i < 64; i++) buf[i] = 0.f;
+	int pos = 0;
+	double sum = 0;
+	float ar = 0.f;
+	for (int s = 0; s < n; s++) {
+		sum -= (double)buf[pos];
+		buf[pos] = rms ? in[s] * in[s] : fabsf(in[s]);
+		sum += (double)buf[pos];
+		if (++pos == 64) pos = 0;
+		float x = (float)(sum * inv);
+		if (rms) x = sqrtf(x);
+		const float smoothing = x > ar ? A : R;
+		ar = ar + smoothing * (x - ar);
+		out[s] = ar;
+	}
+	coeffs[0] = A; coeffs[1] = R; coeffs[2] = ar; coeffs[3] = (float)sum; coeffs[4] = 0.f;
+}
+
 // ------------------------------------------------------------ Delay (klang.h:3381-3512), ring in HBM
 KB_HD void kb_delay_construct(KbDelay& d, int size, long long ring) {
 	d.SIZE = size; d.time = 1; d.position = 0; d.last_position = 0; d.last_fraction = 0.f; d.out = 0.f; d.ring = ring;

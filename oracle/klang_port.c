@@ -608,7 +608,7 @@ int kp_wavetable(int kind, float* table) {
 
 enum { FLT_BIQUAD_LPF = 0, FLT_BIQUAD_HPF, FLT_ONEPOLE_LPF, FLT_ONEPOLE_HPF,
        FLT_BIQUAD_BPF, FLT_BIQUAD_BRF, FLT_BIQUAD_APF, FLT_BUTTERWORTH_LPF1, FLT_BUTTERWORTH_LPF2,
-       FLT_DCF, FLT_IIR1, FLT_IIR2, FLT_MODAL, FLT_FOLLOWER_PEAK, FLT_FOLLOWER_RMS };
+       FLT_DCF, FLT_IIR1, FLT_IIR2, FLT_MODAL, FLT_FOLLOWER_PEAK, FLT_FOLLOWER_RMS, FLT_WINDOW_MEAN, FLT_WINDOW_RMS };
 
 int kp_filter(int kind, int nset, const float* f, const float* Q, int n, const float* in, float* out, float* coeffs) {
 	kp_ensure_fs();
@@ -678,6 +678,34 @@ int kp_filter(int kind, int nset, const float* f, const float* Q, int n, const f
 			out[s] = kind == FLT_FOLLOWER_PEAK ? ar : sqrtf(ar);
 		}
 		if (coeffs) { coeffs[0] = A; coeffs[1] = R; coeffs[2] = ar; coeffs[3] = coeffs[4] = 0; }
+		return 0;
+	}
+	if (kind == FLT_WINDOW_MEAN || kind == FLT_WINDOW_RMS) {   /* Envelope::Follower::Window<64>  klang.h:5904-5948 */
+		if (!Q) return -1;
+		enum { WINDOW = 64 };
+		const float inv = (float)(1.0 / (double)WINDOW);         /* constant window = { WINDOW }; window.inv  klang.h:93-104 */
+		float buf[WINDOW] = { 0 };
+		int pos = 0;
+		double sum = 0;                                           /* 64-bit on purpose (klang.h:5909) */
+		float attack = 0.01f, release = 0.1f;                     /* Window() { set(0.01f, 0.1f); } */
+		float A = 1.f - expf(-1.0f / (kp_fs.f * attack)), R = 1.f - expf(-1.0f / (kp_fs.f * release)), ar = 0.f;
+		for (int s = 0; s < n; s++) {
+			if (s < nset && (attack != f[s] || release != Q[s])) {
+				attack = f[s]; release = Q[s];
+				A = 1.f - (attack == 0.f ? 0.f : expf(-1.0f / (kp_fs.f * attack)));
+				R = 1.f - (release == 0.f ? 0.f : expf(-1.0f / (kp_fs.f * release)));
+			}
+			sum -= (double)buf[pos];
+			buf[pos] = kind == FLT_WINDOW_MEAN ? fabsf(in[s]) : in[s] * in[s];
+			sum += (double)buf[pos];
+			if (++pos == WINDOW) pos = 0;
+			float x = (float)(sum * inv);
+			if (kind == FLT_WINDOW_RMS) x = sqrtf(x);
+			const float smoothing = x > ar ? A : R;
+			ar = ar + smoothing * (x - ar);
+			out[s] = ar;
+		}
+		if (coeffs) { coeffs[0] = A; coeffs[1] = R; coeffs[2] = ar; coeffs[3] = (float)sum; coeffs[4] = 0; }
 		return 0;
 	}
 	switch (kind) {

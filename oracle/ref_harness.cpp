@@ -179,7 +179,7 @@ int ref_wavetable(int kind, float* table) {
 // ---------------------------------------------------------------------- filters
 enum { FLT_BIQUAD_LPF = 0, FLT_BIQUAD_HPF, FLT_ONEPOLE_LPF, FLT_ONEPOLE_HPF,
        FLT_BIQUAD_BPF, FLT_BIQUAD_BRF, FLT_BIQUAD_APF, FLT_BUTTERWORTH_LPF1, FLT_BUTTERWORTH_LPF2,
-       FLT_DCF, FLT_IIR1, FLT_IIR2, FLT_MODAL, FLT_FOLLOWER_PEAK, FLT_FOLLOWER_RMS };
+       FLT_DCF, FLT_IIR1, FLT_IIR2, FLT_MODAL, FLT_FOLLOWER_PEAK, FLT_FOLLOWER_RMS, FLT_WINDOW_MEAN, FLT_WINDOW_RMS };
 
 extern "C++" {
 template<class F>
@@ -246,6 +246,10 @@ int ref_filter(int kind, int nset, const float* f, const float* Q, int n, const 
 	case FLT_FOLLOWER_PEAK: case FLT_FOLLOWER_RMS: { if (!Q) return -1; klang::Envelope::Follower flt; flt = (kind == FLT_FOLLOWER_RMS) ? klang::RMS : klang::Peak;
 		run_simple(nset, n, in, out, flt, [&](int s) { flt.set(klang::param(f[s]), klang::param(Q[s])); });
 		if (coeffs) { coeffs[0] = flt.ar.A; coeffs[1] = flt.ar.R; coeffs[2] = flt.ar.out; coeffs[3] = coeffs[4] = 0; } break; }
+	// Envelope::Follower::Window<64> (klang.h:5904-5948): 64-sample moving sum kept in a double, then the attack / release smoother
+	case FLT_WINDOW_MEAN: case FLT_WINDOW_RMS: { if (!Q) return -1; klang::Envelope::Follower::Window<64> flt; flt = (kind == FLT_WINDOW_RMS) ? klang::RMS : klang::Mean;
+		run_simple(nset, n, in, out, flt, [&](int s) { flt.set(klang::param(f[s]), klang::param(Q[s])); });
+		if (coeffs) { coeffs[0] = flt.ar.A; coeffs[1] = flt.ar.R; coeffs[2] = flt.ar.out; coeffs[3] = (float)flt.sum; coeffs[4] = 0; } break; }
 	default: return -1;
 	}
 	return 0;

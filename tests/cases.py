@@ -18,7 +18,7 @@ import numpy as np
  OSC_WT_SINE, OSC_WT_SAW, OSC_BASIC_NOISE, OSC_FAST_NOISE) = range(14)
 (FLT_BIQUAD_LPF, FLT_BIQUAD_HPF, FLT_ONEPOLE_LPF, FLT_ONEPOLE_HPF,
  FLT_BIQUAD_BPF, FLT_BIQUAD_BRF, FLT_BIQUAD_APF, FLT_BUTTERWORTH_LPF1, FLT_BUTTERWORTH_LPF2,
- FLT_DCF, FLT_IIR1, FLT_IIR2, FLT_MODAL, FLT_FOLLOWER_PEAK, FLT_FOLLOWER_RMS) = range(15)
+ FLT_DCF, FLT_IIR1, FLT_IIR2, FLT_MODAL, FLT_FOLLOWER_PEAK, FLT_FOLLOWER_RMS, FLT_WINDOW_MEAN, FLT_WINDOW_RMS) = range(17)
 FX_GAIN, FX_PINGPONG, FX_REVERB, FX_DELAY_PINGPONG, FX_DELAY_REVERB = range(5)
 SY_SUBTRACTIVE, SY_SUPERSAW, SY_TB303, SY_SYNTHX, SY_FILTER_K, SY_FM = range(6)
 
@@ -50,6 +50,19 @@ def voice_velocity(v):
 
 
 # ----------------------------------------------------------------------------- primitives
+
+def window_follower_cases(eng, x, imp):
+    """Envelope::Follower::Window<64> mean / rms (klang.h:5904-5948): moving sum over 64 samples kept in a double, then the AR smoother."""
+    out = {}
+    for kind, name, f, Q in ((FLT_WINDOW_MEAN, "window_mean", 0.01, 0.1), (FLT_WINDOW_RMS, "window_rms", 0.002, 0.05),
+                             (FLT_WINDOW_MEAN, "window_mean_instant", 0.0, 0.02)):
+        y, c = eng.filt(kind, x, f, Q)
+        out[f"filter/{name}/noise"] = y
+        out[f"filter/{name}/coeffs"] = c
+        y, c = eng.filt(kind, imp, f, Q)
+        out[f"filter/{name}/impulse"] = y
+    return out
+
 
 def noise_cases(eng):
     """Basic::Noise / Fast::Noise (klang.h:4947-4951, 5357-5366): one libc rand() per tick from the process-wide stream (SURVEY Q9) —
@@ -127,6 +140,8 @@ def primitive_cases(eng, fs):
         out[f"filter/{name}/coeffs"] = c
         y, c = eng.filt(kind, imp, f, Q)
         out[f"filter/{name}/impulse"] = y
+
+    out.update(window_follower_cases(eng, x, imp))
 
     y, st = eng.envelope([(0, 0), (0.001, 1), (0.003, 0.25), (0.005, 0.5)], 400)
     out["envelope/4pt"] = y

@@ -134,3 +134,33 @@ def test_delay_known_answer_loop_matches_reference_golden_on_host():
     for got, key in ((oi, "delay/tap_int"), (of, "delay/tap_float"), (op, "delay/process"), (lag, "delay/lagrange")):
         assert np.array_equal(got.view(np.uint32), g[key].view(np.uint32)), key
     assert np.abs(lag).max() > 0.1
+
+
+def test_window_follower_loop_matches_reference_golden_on_host():
+    """kb_window_follower_run (Envelope::Follower::Window<64> mean / rms, the loop kb_prim_filter_kernel runs for kinds 15 / 16)
+    compiled with g++ reproduces the compiled reference's golden vectors bit for bit (double moving sum included)."""
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cases
+    tmp = tempfile.mkdtemp(prefix="kb_host_")
+    exe = os.path.join(tmp, "window_check")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-x", "c++",
+                           os.path.join(ROOT, "tests", "host", "window_check.cpp"), "-o", exe])
+    x = cases.noise(512, seed=7)
+    imp = np.zeros(64, np.float32)
+    imp[0] = 1
+    for fs in (44100, 48000):
+        g = np.load(os.path.join(ROOT, "tests", "golden", f"klang_ref_fs{fs}.npz"))
+        for name, rms in (("window_mean", 0), ("window_rms", 1), ("window_mean_instant", 0)):
+            c = g[f"filter/{name}/coeffs"]
+            for sig, key in ((x, "noise"), (imp, "impulse")):
+                path = os.path.join(tmp, "in.bin")
+                with open(path, "wb") as f:
+                    f.write(np.int32(rms).tobytes() + c[0:1].tobytes() + c[1:2].tobytes() + np.int32(len(sig)).tobytes() + sig.tobytes())
+                out = subprocess.run([exe, path], capture_output=True)
+                assert out.returncode == 0
+                got = np.frombuffer(out.stdout, np.float32)
+                assert np.array_equal(got[:len(sig)].view(np.uint32), g[f"filter/{name}/{key}"].view(np.uint32)), (fs, name, key)
+                if key == "noise":
+                    assert np.array_equal(got[len(sig):].view(np.uint32), c.view(np.uint32)), (fs, name, "coeffs")

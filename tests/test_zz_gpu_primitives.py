@@ -78,3 +78,18 @@ def test_device_delay_primitive_matches_reference_golden(golden, fs):
     _exact(of, g["delay/tap_float"], "delay/tap_float")
     _exact(op, g["delay/process"], "delay/process")
     _exact(eng.delay_lagrange(cases.noise(n, seed=6), df), g["delay/lagrange"], "delay/lagrange")
+
+
+@pytest.mark.parametrize("fs", [44100, 48000])
+def test_device_window_follower_matches_reference_golden(golden, fs):
+    """Envelope::Follower::Window<64> mean / rms (klang.h:5904-5948; kb_prim_filter kinds 15 / 16): the moving sum is a double on the
+    device as in the reference; bit-exact against the compiled reference's golden vectors."""
+    eng = kb.Engine()
+    eng.set_fs(fs)
+    x = cases.noise(512, seed=7)
+    imp = np.zeros(64, np.float32)
+    imp[0] = 1
+    got = cases.window_follower_cases(eng, x, imp)
+    assert len(got) == 9
+    for name, arr in got.items():
+        _exact(np.asarray(arr, np.float32), golden[fs][name], name)
