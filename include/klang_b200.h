@@ -43,6 +43,9 @@ extern "C" {
 #define KB_SY_SYNTHX 3            /* examples/SynTHX.k             stereo */
 #define KB_SY_FILTER_K 4          /* examples/Subtractive/Filter.k mono   */
 #define KB_SY_FM 5                /* examples/FM.k (three Operator<Sine> in series) mono */
+#define KB_SY_BREAKPOINT 6        /* examples/Subtractive/Breakpoint.k (Sine x attack / decay envelope; noteOff cuts the note) mono */
+#define KB_SY_RAMP 7              /* examples/Subtractive/Ramp.k       (Sine x one ramp) mono */
+#define KB_SY_RELEASE 8           /* examples/Subtractive/Release.k    (Sine x looped envelope with release()) mono */
 
 /* process flags */
 #define KB_DEVICE_PTR 1u          /* `io` / `out` is device memory on the bank's device; the call is asynchronous on the bank stream */

@@ -468,6 +468,9 @@ extern "C" kb_synth_bank* kb_synth_bank_create(int graph, int instances, int voi
 	case KB_SY_TB303: b->ncontrols = 5; b->voice_bytes = sizeof(KbTbVoice); break;
 	case KB_SY_SYNTHX: b->ncontrols = 5; b->voice_bytes = sizeof(KbSxVoice); b->channels = 2; break;
 	case KB_SY_FM: b->ncontrols = 4; b->voice_bytes = sizeof(KbFmVoice); break;
+	case KB_SY_BREAKPOINT: b->ncontrols = 2; b->voice_bytes = sizeof(KbSenvVoice); break;
+	case KB_SY_RAMP: b->ncontrols = 1; b->voice_bytes = sizeof(KbSenvVoice); break;
+	case KB_SY_RELEASE: b->ncontrols = 4; b->voice_bytes = sizeof(KbSenvVoice); break;
 	}
 	for (int i = 0; i < instances; i++) {
 		KbControl* c = b->ctl(i);
@@ -477,6 +480,9 @@ extern "C" kb_synth_bank* kb_synth_bank_create(int graph, int instances, int voi
 		case KB_SY_TB303: c[0] = kb_dial(0.f, 1.f, 1.f); c[1] = kb_dial(0.f, 1.f, 0.5f); c[2] = kb_dial(0.1f, 1.f, 0.5f);                     // TB303.k:118-126
 		                  c[3] = kb_dial(0.f, 1.f, 0.f); c[4] = kb_dial(0.01f, 10.f, 1.f); break;
 		case KB_SY_FM: c[0] = kb_dial(0.001f, 10.f, 1.0f); c[1] = kb_dial(0.f, 10.f, 0.37f); c[2] = kb_dial(0.f, 10.f, 0.37f); c[3] = kb_dial(0.f, 1.f, 0.5f); break;   // FM.k:80-86
+		case KB_SY_BREAKPOINT: c[0] = kb_dial(0.05f, 1.0f, 0.05f); c[1] = kb_dial(0.1f, 1.0f, 0.1f); break;                                  // Breakpoint.k:25-28
+		case KB_SY_RAMP: c[0] = kb_dial(0.1f, 1.0f, 0.1f); break;                                                                            // Ramp.k:23-25
+		case KB_SY_RELEASE: c[0] = kb_dial(0.f, 1.f, 0.002f); c[1] = kb_dial(0.f, 1.f, 0.1f); c[2] = kb_dial(0.f, 1.f, 0.05f); c[3] = kb_dial(0.f, 1.f, 1.0f); break;   // Release.k:33-38
 		case KB_SY_SYNTHX: c[0] = kb_dial(0.f, 5.f, 0.5f); c[1] = kb_dial(0.f, 1.f, 0.5f); c[2] = kb_dial(0.f, 1.f, 0.6f);                   // SynTHX.k:186-194
 		                   c[3] = kb_dial(0.f, 1.f, 1.f); c[4] = kb_dial(0.f, 1.f, 0.f); break;
 		}
@@ -502,6 +508,7 @@ extern "C" kb_synth_bank* kb_synth_bank_create(int graph, int instances, int voi
 		case KB_SY_SUBTRACTIVE: case KB_SY_FILTER_K: kb_sub_construct(b->fs, graph, b->vs<KbSubVoice>(v)); break;
 		case KB_SY_SUPERSAW: kb_ssaw_construct(b->fs, b->vs<KbSsawVoice>(v)); break;
 		case KB_SY_FM: kb_fm_construct(b->fs, b->vs<KbFmVoice>(v)); break;
+		case KB_SY_BREAKPOINT: case KB_SY_RAMP: case KB_SY_RELEASE: kb_senv_construct(b->fs, graph, b->vs<KbSenvVoice>(v)); break;
 		case KB_SY_TB303: kb_tb_construct(b->fs, b->vs<KbTbVoice>(v)); break;
 		case KB_SY_SYNTHX: kb_sx_construct(b->fs, b->vs<KbSxVoice>(v)); break;
 		}
@@ -571,6 +578,7 @@ static void sy_start(kb_synth_bank* b, int inst, int voice, float pitch, float v
 	case KB_SY_SUBTRACTIVE: case KB_SY_FILTER_K: kb_sub_on(b->fs, b->graph, c, b->vs<KbSubVoice>(v), pitch); break;
 	case KB_SY_SUPERSAW: kb_ssaw_on(b->fs, c, b->vs<KbSsawVoice>(v), pitch); break;
 	case KB_SY_FM: kb_fm_on(b->fs, c, b->vs<KbFmVoice>(v), pitch); break;
+	case KB_SY_BREAKPOINT: case KB_SY_RAMP: case KB_SY_RELEASE: kb_senv_on(b->fs, b->graph, c, b->vs<KbSenvVoice>(v), pitch); break;
 	case KB_SY_TB303: kb_tb_on(b->fs, c, b->vs<KbTbVoice>(v), pitch); break;
 	case KB_SY_SYNTHX: kb_sx_on(b->fs, c, b->vs<KbSxVoice>(v), pitch); break;
 	}
@@ -587,6 +595,8 @@ static void sy_release(kb_synth_bank* b, int inst, int voice) {
 	case KB_SY_SUBTRACTIVE: case KB_SY_FILTER_K: kb_adsr_release(b->fs, b->vs<KbSubVoice>(v).adsr); break;   // Filter.k:25-27
 	case KB_SY_SUPERSAW: kb_adsr_release(b->fs, b->vs<KbSsawVoice>(v).adsr); break;                          // SuperSaw.k:21-23
 	case KB_SY_FM: kb_adsr_release(b->fs, b->vs<KbFmVoice>(v).adsr); break;                                  // FM.k:56-58
+	case KB_SY_RELEASE: kb_env_release(b->fs, b->vs<KbSenvVoice>(v).env, b->ctl(inst)[3].value, 0.f); break;  // Release.k:21-24
+	case KB_SY_BREAKPOINT: case KB_SY_RAMP: h.stage = KB_NOTE_OFF; break;                                    // NoteBase::off default: stage = Off  klang.h:4237
 	case KB_SY_TB303: kb_adsr_release(b->fs, b->vs<KbTbVoice>(v).adsr); break;                               // TB303.k:99-101
 	case KB_SY_SYNTHX: kb_adsr_release(b->fs, b->vs<KbSxVoice>(v).adsr); break;                              // SynTHX.k:163-165
 	}
@@ -694,7 +704,7 @@ extern "C" int kb_synth_bank_process(kb_synth_bank* b, float* out, int n, unsign
 		// FM.k: the time-parallel kernel (kb_fm_tiled_kernel) is the default; KB_FM_TILED=0 keeps the lane-per-voice kernel for the whole
 		// process (A/B measurement, same results — tools/fm_tiled_probe.py)
 		static const bool fm_tiled = !getenv("KB_FM_TILED") || atoi(getenv("KB_FM_TILED")) != 0;
-		if ((flags & KB_LANE_PER_VOICE) || (b->graph == KB_SY_FM && !fm_tiled)) {
+		if ((flags & KB_LANE_PER_VOICE) || (b->graph == KB_SY_FM && !fm_tiled) || b->graph >= KB_SY_BREAKPOINT) {   // (the Sine x envelope graphs: lane per voice)
 			const int blocks = (total + 127) / 128;
 			switch (b->graph) {
 			case KB_SY_SUBTRACTIVE: case KB_SY_FILTER_K:
@@ -705,6 +715,8 @@ extern "C" int kb_synth_bank_process(kb_synth_bank* b, float* out, int n, unsign
 				kb_voice_kernel<KB_SY_TB303, KbTbVoice><<<blocks, 128, 0, st>>>((KbTbVoice*)b->d_vstate, b->d_hdr, b->d_blk, d_voice_dst, n, b->voices, total, b->fs); break;
 			case KB_SY_FM:
 				kb_voice_kernel<KB_SY_FM, KbFmVoice><<<blocks, 128, 0, st>>>((KbFmVoice*)b->d_vstate, b->d_hdr, b->d_blk, d_voice_dst, n, b->voices, total, b->fs); break;
+			case KB_SY_BREAKPOINT: case KB_SY_RAMP: case KB_SY_RELEASE:
+				kb_voice_kernel<KB_SY_BREAKPOINT, KbSenvVoice><<<blocks, 128, 0, st>>>((KbSenvVoice*)b->d_vstate, b->d_hdr, b->d_blk, d_voice_dst, n, b->voices, total, b->fs); break;
 			}
 		} else {
 			// voices per CTA: as many as still leave >= ~100 CTAs (the serial stages cost the same for any G), KB_TILE_G overrides

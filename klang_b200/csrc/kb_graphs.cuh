@@ -8,7 +8,7 @@
 #include "kb_prims.cuh"
 
 #include "../../include/klang_b200.h"   // graph ids KB_SY_* / KB_FX_*
-#define KB_SY_COUNT 6
+#define KB_SY_COUNT 9
 #define KB_FX_COUNT 5
 
 // =========================================================================================== HOST halves
@@ -81,6 +81,28 @@ inline void kb_fm_on(const KbFs& fs, const KbControl* c, KbFmVoice& n, float pit
 	kb_fsine_set_fp(fs, n.op[1].osc, fd, 0.f); kb_env_set_points(fs, n.op[1].env, 2, e2);   // FM.k:48-49
 	kb_fsine_set_fp(fs, n.op[2].osc, fc, 0.f);                                              // FM.k:51
 	kb_adsr_set(fs, n.adsr, c[3].value, 0.1f, 1.f, 1.f);                                    // FM.k:53
+}
+
+// ---- Breakpoint.k / Ramp.k / Release.k (examples/Subtractive): `osc * env++ >> out` with a Fast::Sine and one Envelope
+inline void kb_senv_construct(const KbFs& fs, int graph, KbSenvVoice& n) {
+	kb_fsine_init(n.osc); kb_env_construct(fs, n.env);
+	n.stop_when_finished = graph == KB_SY_RELEASE;                                          // Release.k:28-29; the other two never stop()
+}
+inline void kb_senv_on(const KbFs& fs, int graph, const KbControl* c, KbSenvVoice& n, float pitch) {
+	kb_fsine_set_fp(fs, n.osc, kb_pitch_to_frequency_host(pitch), 0.f);                     // osc(pitch -> Frequency, 0)
+	if (graph == KB_SY_BREAKPOINT) {                                                        // Breakpoint.k:14-16 (decay reads controls[0] too)
+		const float attack = c[0].value, decay = c[0].value;
+		const float pts[6] = { 0.f, 0.f, attack, 1.f, attack + decay, 0.f };
+		kb_env_set_points(fs, n.env, 3, pts);
+	} else if (graph == KB_SY_RAMP) {                                                       // Ramp.k:14-15
+		const float pts[4] = { 0.f, 1.f, c[0].value, 0.f };
+		kb_env_set_points(fs, n.env, 2, pts);
+	} else {                                                                                // Release.k:14-18
+		const float A = c[0].value, D = c[1].value, S = c[2].value;
+		const float pts[6] = { 0.f, 0.f, A, 1.f, A + D, S };
+		kb_env_set_points(fs, n.env, 3, pts);
+		kb_env_set_loop(n.env, 2, 2);
+	}
 }
 
 // ---- TB303 (examples/TB303.k:8-114)
@@ -288,6 +310,14 @@ KB_HD float kb_fm_tick(const KbFs& fs, float i1, float i2, KbFmVoice& n, int& no
 	float out = kb_fm_op_tick(fs, n.op[2]);
 	out *= kb_env_tick(fs, n.adsr) * 0.1f;
 	if (n.adsr.stage == KB_ENV_OFF) note_stage = KB_NOTE_OFF;
+	return out;
+}
+
+// Breakpoint.k:20 / Ramp.k:19 / Release.k:27-29: osc * env++ >> out; Release.k stops the note when the envelope has finished
+KB_HD float kb_senv_tick(const KbFs& fs, KbSenvVoice& n, int& note_stage) {
+	const float o = kb_fsine_tick(n.osc);
+	const float out = o * kb_env_tick(fs, n.env);
+	if (n.stop_when_finished && n.env.stage == KB_ENV_OFF) note_stage = KB_NOTE_OFF;
 	return out;
 }
 

@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(128) kb_voice_kernel(VOICE* __restrict__ voice
 				if constexpr (GRAPH == KB_SY_SUPERSAW) y = kb_ssaw_tick(fs, s, stage);
 				if constexpr (GRAPH == KB_SY_TB303) y = kb_tb_tick(fs, tb, s, stage);
 				if constexpr (GRAPH == KB_SY_FM) y = kb_fm_tick(fs, fm_i1, fm_i2, s, stage);
+				if constexpr (GRAPH == KB_SY_BREAKPOINT) y = kb_senv_tick(fs, s, stage);         // Breakpoint.k, Ramp.k and Release.k share the voice
 			}
 			tile[warp][lane][t] = y;
 		}

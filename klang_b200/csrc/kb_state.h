@@ -72,6 +72,9 @@ struct KbSxVoice { KbSxAdditive notes[11]; KbEnv adsr; };
 struct KbFmOp { KbFastSine osc; KbEnv env; float amp, in; };
 struct KbFmVoice { KbFmOp op[3]; KbEnv adsr; };
 
+// examples/Subtractive/{Breakpoint,Ramp,Release}.k: a Fast::Sine times one breakpoint envelope
+struct KbSenvVoice { KbFastSine osc; KbEnv env; int stop_when_finished; };
+
 // ------------------------------------------------------------------ effect instances (graphs)
 struct KbFxHdr { KbControl controls[KB_MAX_CONTROLS]; float cached[KB_MAX_CONTROLS]; };
 // examples/PingPong.k

@@ -52,6 +52,15 @@ namespace k_synthx {
 namespace k_fm {
 #include "FM.k"
 }
+namespace k_breakpoint {
+#include "Subtractive/Breakpoint.k"
+}
+namespace k_ramp {
+#include "Subtractive/Ramp.k"
+}
+namespace k_release {
+#include "Subtractive/Release.k"
+}
 namespace k_delay_pingpong {
 #include "Delay/PingPong.k"
 }
@@ -401,7 +410,7 @@ int ref_fx_process(void* h, float* l, float* r, int n) {
 }
 
 // ----------------------------------------------------------------------- synths
-enum { SY_SUBTRACTIVE = 0, SY_SUPERSAW = 1, SY_TB303 = 2, SY_SYNTHX = 3, SY_FILTER_K = 4, SY_FM = 5 };
+enum { SY_SUBTRACTIVE = 0, SY_SUPERSAW = 1, SY_TB303 = 2, SY_SYNTHX = 3, SY_FILTER_K = 4, SY_FM = 5, SY_BREAKPOINT = 6, SY_RAMP = 7, SY_RELEASE = 8 };
 
 struct RefSynth {
 	int graph;
@@ -433,6 +442,9 @@ void* ref_synth_create(int graph, int nvoices) {
 	case SY_FILTER_K:    { auto* p = make_synth<k_filter::Filter, k_filter::Filter::FilterNote>(nvoices); s->mono = p; s->controls = &p->controls; } break;
 	case SY_SYNTHX:      { auto* p = make_synth<k_synthx::SynTHX, k_synthx::SynTHX::MyNote>(nvoices); s->stereo = p; s->controls = &p->controls; } break;
 	case SY_FM:          { auto* p = make_synth<k_fm::FM, k_fm::FM::MyNote>(nvoices); s->mono = p; s->controls = &p->controls; } break;
+	case SY_BREAKPOINT:  { auto* p = make_synth<k_breakpoint::Breakpoint, k_breakpoint::Breakpoint::BreakpointNote>(nvoices); s->mono = p; s->controls = &p->controls; } break;
+	case SY_RAMP:        { auto* p = make_synth<k_ramp::Ramp, k_ramp::Ramp::RampNote>(nvoices); s->mono = p; s->controls = &p->controls; } break;
+	case SY_RELEASE:     { auto* p = make_synth<k_release::Release, k_release::Release::ReleaseNote>(nvoices); s->mono = p; s->controls = &p->controls; } break;
 	default: delete s; return nullptr;
 	}
 	s->nvoices = s->mono ? (int)s->mono->notes.count : (int)s->stereo->notes.count;

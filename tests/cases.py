@@ -20,12 +20,13 @@ import numpy as np
  FLT_BIQUAD_BPF, FLT_BIQUAD_BRF, FLT_BIQUAD_APF, FLT_BUTTERWORTH_LPF1, FLT_BUTTERWORTH_LPF2,
  FLT_DCF, FLT_IIR1, FLT_IIR2, FLT_MODAL, FLT_FOLLOWER_PEAK, FLT_FOLLOWER_RMS, FLT_WINDOW_MEAN, FLT_WINDOW_RMS) = range(17)
 FX_GAIN, FX_PINGPONG, FX_REVERB, FX_DELAY_PINGPONG, FX_DELAY_REVERB = range(5)
-SY_SUBTRACTIVE, SY_SUPERSAW, SY_TB303, SY_SYNTHX, SY_FILTER_K, SY_FM = range(6)
+SY_SUBTRACTIVE, SY_SUPERSAW, SY_TB303, SY_SYNTHX, SY_FILTER_K, SY_FM, SY_BREAKPOINT, SY_RAMP, SY_RELEASE = range(9)
 
 FX_NAMES = {FX_GAIN: "gain", FX_PINGPONG: "pingpong", FX_REVERB: "reverb",
             FX_DELAY_PINGPONG: "delay_pingpong", FX_DELAY_REVERB: "delay_reverb"}
 SY_NAMES = {SY_SUBTRACTIVE: "subtractive", SY_SUPERSAW: "supersaw", SY_TB303: "tb303",
-            SY_SYNTHX: "synthx", SY_FILTER_K: "filter_k", SY_FM: "fm"}
+            SY_SYNTHX: "synthx", SY_FILTER_K: "filter_k", SY_FM: "fm", SY_BREAKPOINT: "breakpoint", SY_RAMP: "ramp",
+            SY_RELEASE: "release"}
 
 
 def noise(n, seed=1, lo=-1.0, hi=1.0):
@@ -239,12 +240,22 @@ SYNTH_SCRIPTS = {
 }
 
 
+# examples/Subtractive/{Breakpoint,Ramp,Release}.k (a Fast::Sine times one breakpoint envelope).  Kept apart from SYNTH_SCRIPTS:
+# their device tests live in tests/test_zz_gpu_primitives.py.
+SYNTH_SCRIPTS_LATE = {
+    "breakpoint": (SY_BREAKPOINT, 32, 8, 12, 512, 4, []),                  # noteOff cuts the note (NoteBase::off default, klang.h:4237)
+    "ramp": (SY_RAMP, 32, 6, 12, 512, 8, [(0, 0, 0.1)]),
+    "release": (SY_RELEASE, 32, 10, 10, 512, 2, [(0, 3, 0.03)]),
+    "release_slow_attack": (SY_RELEASE, 32, 5, 8, 512, 1, [(0, 0, 0.02), (0, 1, 0.01), (0, 2, 0.6), (0, 3, 0.01)]),
+}
+
+
 def run_synth_script(eng, name, fs, per_voice=True):
     """Drive voices through start/release/process like Synth::process does (klang.h:4440-4466).
 
     Returns dict with 'voices' [blocks][V, C, n] concatenated over time (per-voice streams, each voice
     rendered alone — SURVEY Q6) or 'mix' (the Synth::process block output), plus 'stages'."""
-    graph, nvoices, started, blocks, n, rel0, events = SYNTH_SCRIPTS[name]
+    graph, nvoices, started, blocks, n, rel0, events = (SYNTH_SCRIPTS.get(name) or SYNTH_SCRIPTS_LATE[name])
     eng.set_fs(fs)
     eng.srand(1)
     sy = eng.Synth(graph, nvoices)
@@ -292,7 +303,7 @@ def all_graph_cases(eng, fs):
     out = {}
     for name in FX_SCRIPTS:
         out[f"fx/{name}"] = run_fx_script(eng, name, fs)
-    for name in SYNTH_SCRIPTS:
+    for name in list(SYNTH_SCRIPTS) + list(SYNTH_SCRIPTS_LATE):
         r = run_synth_script(eng, name, fs, per_voice=True)
         out[f"synth/{name}/voices"] = r["out"]
         out[f"synth/{name}/stages"] = r["stages"]

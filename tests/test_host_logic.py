@@ -164,3 +164,38 @@ def test_window_follower_loop_matches_reference_golden_on_host():
                 assert np.array_equal(got[:len(sig)].view(np.uint32), g[f"filter/{name}/{key}"].view(np.uint32)), (fs, name, key)
                 if key == "noise":
                     assert np.array_equal(got[len(sig):].view(np.uint32), c.view(np.uint32)), (fs, name, "coeffs")
+
+
+def test_sine_envelope_voices_match_oracle_on_host():
+    """Breakpoint.k / Ramp.k / Release.k: the product's voice functions (kb_senv_on / kb_senv_tick) compiled with g++ equal the oracle
+    port bit for bit, the cut on noteOff (NoteBase::off default) and Release.k's release() included."""
+    import sys
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import oracle
+    exe = os.path.join(tempfile.mkdtemp(prefix="kb_host_"), "senv_check")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-x", "c++",
+                           os.path.join(ROOT, "tests", "host", "senv_check.cpp"), "-o", exe])
+    got = np.frombuffer(subprocess.run([exe], capture_output=True).stdout, np.float32)
+
+    def port(graph, fs, pitch, ctl, n, rel):
+        oracle.port.set_fs(fs)
+        oracle.port.srand(1)
+        sy = oracle.port.Synth(graph, 32)
+        for i, v in ctl:
+            sy.set_control(i, v)
+        sy.voice_start(0, pitch, 0.8)
+        if rel < 0:
+            out = sy.process_voices(n)[0][0, 0]
+        else:
+            a, _ = sy.process_voices(rel)
+            sy.voice_release(0, 0.0)
+            b, _ = sy.process_voices(n - rel)
+            out = np.concatenate([a[0, 0], b[0, 0]])
+        sy.close()
+        return out
+
+    want = np.concatenate([port(oracle.SY_BREAKPOINT, 48000.0, 60, (), 6000, 5500), port(oracle.SY_RAMP, 44100.0, 72, (), 6000, -1),
+                           port(oracle.SY_RELEASE, 48000.0, 45, ((1, 0.01), (2, 0.5), (3, 0.02)), 4000, 1500)])
+    assert len(got) == len(want) and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert np.abs(want[:6000]).max() > 0.5 and np.abs(want[12000:]).max() > 0.3

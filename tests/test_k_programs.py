@@ -52,7 +52,8 @@ def _expected(prog, fs, n, blocks):
             outs.append(np.atleast_2d(fx.process(blk[0] if fx.channels == 1 else blk)))
         fx.close()
         return np.stack(outs)                         # [blocks, channels, n]
-    graph = {"supersaw": oracle.SY_SUPERSAW, "filter_k": oracle.SY_FILTER_K, "tb303": oracle.SY_TB303, "synthx": oracle.SY_SYNTHX, "fm": oracle.SY_FM}[prog]
+    graph = {"supersaw": oracle.SY_SUPERSAW, "filter_k": oracle.SY_FILTER_K, "tb303": oracle.SY_TB303, "synthx": oracle.SY_SYNTHX, "fm": oracle.SY_FM,
+             "breakpoint": oracle.SY_BREAKPOINT, "ramp": oracle.SY_RAMP, "release": oracle.SY_RELEASE}[prog]
     sy = oracle.port.Synth(graph, 32)
     outs = []
     for b in range(blocks):
@@ -68,9 +69,7 @@ def _expected(prog, fs, n, blocks):
     return np.stack(outs)
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("prog", PROGRAMS)
-def test_reference_k_programs_run_on_the_device_bit_exact(prog, tmp_path):
+def run_k_program_on_device(prog, tmp_path):
     if not os.path.isfile(K_HOST):
         pytest.skip("tests/_k_bin/k_host was not built (needs /root/reference at build time)")
     fs, n, blocks = 48000, 512, 4
@@ -82,3 +81,9 @@ def test_reference_k_programs_run_on_the_device_bit_exact(prog, tmp_path):
     same = (got.view(np.uint32) == want.view(np.uint32)) | (np.isnan(got) & np.isnan(want))
     assert same.all(), f"{prog}: {(~same).sum()} of {same.size} samples differ, first at {tuple(np.argwhere(~same)[0])}"
     assert np.abs(want).max() > 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prog", PROGRAMS)
+def test_reference_k_programs_run_on_the_device_bit_exact(prog, tmp_path):
+    run_k_program_on_device(prog, tmp_path)

@@ -93,3 +93,24 @@ def test_device_window_follower_matches_reference_golden(golden, fs):
     assert len(got) == 9
     for name, arr in got.items():
         _exact(np.asarray(arr, np.float32), golden[fs][name], name)
+
+
+# ---- examples/Subtractive/{Breakpoint,Ramp,Release}.k: KB_SY_BREAKPOINT / KB_SY_RAMP / KB_SY_RELEASE (a Fast::Sine times one envelope) on the
+# lane-per-voice kernel; the voice functions are proven against the oracle with g++ (tests/host/senv_check.cpp)
+@pytest.mark.parametrize("fs", [44100, 48000])
+@pytest.mark.parametrize("name", list(cases.SYNTH_SCRIPTS_LATE))
+def test_sine_envelope_synths_match_reference_golden(golden, fs, name):
+    eng = kb.Engine()
+    r = cases.run_synth_script(eng, name, fs, per_voice=True)
+    _exact(np.ascontiguousarray(r["out"]), golden[fs][f"synth/{name}/voices"], f"synth/{name}/voices")
+    assert np.array_equal(r["stages"], golden[fs][f"synth/{name}/stages"]), f"synth/{name}/stages"
+    r = cases.run_synth_script(eng, name, fs, per_voice=False)
+    _exact(np.ascontiguousarray(r["out"]), golden[fs][f"synth/{name}/mix"], f"synth/{name}/mix")
+
+
+@pytest.mark.parametrize("prog", ["breakpoint", "ramp", "release"])
+def test_sine_envelope_k_programs_run_unmodified_on_the_device(prog, tmp_path):
+    """examples/Subtractive/{Breakpoint,Ramp,Release}.k compiled UNMODIFIED against include/compat/klang.h (tools/k_host.cpp) and run on
+    the device through the host program: bit-identical to the oracle run with the same MIDI script."""
+    from test_k_programs import run_k_program_on_device
+    run_k_program_on_device(prog, tmp_path)

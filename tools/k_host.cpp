@@ -39,6 +39,15 @@ namespace k_synthx {
 namespace k_fm {
 #include "FM.k"
 }
+namespace k_breakpoint {
+#include "Subtractive/Breakpoint.k"
+}
+namespace k_ramp {
+#include "Subtractive/Ramp.k"
+}
+namespace k_release {
+#include "Subtractive/Release.k"
+}
 
 KLANG_B200_EFFECT(k_gain::Gain, KB_FX_GAIN)
 KLANG_B200_EFFECT(k_pingpong::PingPong, KB_FX_PINGPONG)
@@ -50,6 +59,9 @@ KLANG_B200_SYNTH(k_tb303::TB303, KB_SY_TB303)
 KLANG_B200_EFFECT(k_reverb::Reverb, KB_FX_REVERB)
 KLANG_B200_SYNTH(k_synthx::SynTHX, KB_SY_SYNTHX)
 KLANG_B200_SYNTH(k_fm::FM, KB_SY_FM)
+KLANG_B200_SYNTH(k_breakpoint::Breakpoint, KB_SY_BREAKPOINT)
+KLANG_B200_SYNTH(k_ramp::Ramp, KB_SY_RAMP)
+KLANG_B200_SYNTH(k_release::Release, KB_SY_RELEASE)
 
 // the deterministic input of tests/cases.py::noise
 static float noise(uint64_t n, uint64_t seed, double lo, double hi) {
@@ -103,6 +115,9 @@ int main(int argc, char** argv) {
 		else if (prog == "reverb") rc = run_effect<k_reverb::Reverb>(fs, n, blocks, out);
 		else if (prog == "synthx") rc = run_synth<k_synthx::SynTHX>(fs, n, blocks, out);
 		else if (prog == "fm") rc = run_synth<k_fm::FM>(fs, n, blocks, out);
+		else if (prog == "breakpoint") rc = run_synth<k_breakpoint::Breakpoint>(fs, n, blocks, out);
+		else if (prog == "ramp") rc = run_synth<k_ramp::Ramp>(fs, n, blocks, out);
+		else if (prog == "release") rc = run_synth<k_release::Release>(fs, n, blocks, out);
 	} catch (const klang::b200::Error& e) {
 		fprintf(stderr, "k_host: %s\n", e.what());
 		rc = kb_device_count() == 0 ? 3 : 4;          // 3 = no CUDA device (expected off the GPU box)
