@@ -162,7 +162,7 @@ struct Oscillator : Generator {
 	void set(param f) { frequency = f; }
 	void set(param f, param p) { frequency = f; phase = p; }
 	void set(param f, param p, param d) { frequency = f; phase = p; duty = d; }
-	template <class... P> void operator()(P... p) { set(param(p)...); }
+	template <class... P> Oscillator& operator()(P... p) { set(param(p)...); return *this; }   // `lfo(rate) * depth`: set, then read (klang.h:2258-2260)
 	void reset() { phase = 0.f; }
 };
 

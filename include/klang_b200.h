@@ -35,6 +35,10 @@ extern "C" {
 #define KB_FX_REVERB 2            /* examples/Reverb.k             stereo */
 #define KB_FX_DELAY_PINGPONG 3    /* examples/Delay/PingPong.k     stereo */
 #define KB_FX_DELAY_REVERB 4      /* examples/Delay/Reverb.k       mono   */
+#define KB_FX_PAN 5               /* examples/Gain/Pan.k           stereo (elementwise) */
+#define KB_FX_RM 6                /* examples/Gain/RM.k            mono   (elementwise, Fast::Sine LFO) */
+#define KB_FX_TREMOLO 7           /* examples/Gain/Tremolo.k       mono   (elementwise, Fast::Sine LFO) */
+#define KB_FX_CLIPPING 8          /* examples/Distortion/Clipping.k mono  (elementwise) */
 
 /* synth graphs */
 #define KB_SY_SUBTRACTIVE 0       /* Saw >> LPF(env) >> ADSR: Filter.k with a Saw and ADSR controls mono */

@@ -101,6 +101,9 @@ extern "C" kb_fx_bank* kb_fx_bank_create(int graph, int instances, float fs, int
 	case KB_FX_REVERB: b->channels = 2; b->ncontrols = 10; b->state_bytes = sizeof(KbReverb); b->ring_floats = KB_REVERB_RING_FLOATS; break;
 	case KB_FX_DELAY_PINGPONG: b->channels = 2; b->ncontrols = 4; b->state_bytes = sizeof(KbDPingPong); b->ring_floats = KB_PINGPONG_RING_FLOATS; break;
 	case KB_FX_DELAY_REVERB: b->channels = 1; b->ncontrols = 3; b->state_bytes = sizeof(KbDReverb); b->ring_floats = KB_PINGPONG_RING_FLOATS; break;
+	case KB_FX_PAN: b->channels = 2; b->ncontrols = 1; b->state_bytes = sizeof(KbGainFx); b->ring_floats = 0; break;
+	case KB_FX_RM: case KB_FX_TREMOLO: b->channels = 1; b->ncontrols = 2; b->state_bytes = sizeof(KbLfoFx); b->ring_floats = 0; break;
+	case KB_FX_CLIPPING: b->channels = 1; b->ncontrols = 1; b->state_bytes = sizeof(KbGainFx); b->ring_floats = 0; break;
 	}
 	b->hdr.assign(instances, KbFxHdr());
 	memset(b->hdr.data(), 0, b->hdr.size() * sizeof(KbFxHdr));
@@ -113,6 +116,11 @@ extern "C" kb_fx_bank* kb_fx_bank_create(int graph, int instances, float fs, int
 		case KB_FX_REVERB: kb_reverb_construct(b->hdr[i], b->st<KbReverb>(i), ring0); break;
 		case KB_FX_DELAY_PINGPONG: kb_dpingpong_construct(b->hdr[i], b->st<KbDPingPong>(i), ring0); break;
 		case KB_FX_DELAY_REVERB: kb_dreverb_construct(b->hdr[i], b->st<KbDReverb>(i), ring0); break;
+		case KB_FX_PAN: b->hdr[i].controls[0] = kb_dial(0.f, 1.f, 0.5f); break;                                               // Pan.k:10
+		case KB_FX_RM: case KB_FX_TREMOLO:                                                                                    // RM.k:11-12, Tremolo.k:11-12
+			b->hdr[i].controls[0] = kb_dial(1.f, graph == KB_FX_RM ? 1000.f : 10.f, 6.f); b->hdr[i].controls[1] = kb_dial(0.f, 0.5f, 0.5f);
+			kb_fsine_init(b->st<KbLfoFx>(i).lfo); break;
+		case KB_FX_CLIPPING: b->hdr[i].controls[0] = kb_dial(1.f, 11.f, 1.f); break;                                          // Clipping.k:10
 		}
 	}
 	bool ok = cudaSetDevice(device) == cudaSuccess;
@@ -148,7 +156,7 @@ extern "C" int kb_fx_bank_num_controls(const kb_fx_bank* b) { return b ? b->ncon
 extern "C" long long kb_fx_bank_launches(const kb_fx_bank* b) { return b ? b->launches : 0; }
 extern "C" int kb_fx_bank_parallel_instances(kb_fx_bank* b) {
 	if (!b) return kb_fail(KB_EINVAL, "null bank");
-	if (b->graph == KB_FX_GAIN) return b->instances;
+	if (b->graph == KB_FX_GAIN || b->graph >= KB_FX_PAN) return b->instances;
 	std::vector<KbFxPlan> plan(b->instances);
 	KB_CUDA(cudaSetDevice(b->device));
 	KB_CUDA(cudaStreamSynchronize(b->stream));
@@ -189,6 +197,8 @@ extern "C" double kb_fx_bank_bytes_per_frame(kb_fx_bank* b) {
 	case KB_FX_REVERB: { fx_fetch(b); int taps = 10 + (int)(b->hdr[0].controls[6].value * (float)10.999); return 16 + 2 * (4 + taps * 8) + 16 * 20; }
 	case KB_FX_DELAY_PINGPONG: return 40;
 	case KB_FX_DELAY_REVERB: return 88;
+	case KB_FX_PAN: return 16;
+	case KB_FX_RM: case KB_FX_TREMOLO: case KB_FX_CLIPPING: return 8;
 	}
 	return 0;
 }
@@ -211,6 +221,16 @@ static int fx_prepare(kb_fx_bank* b) {
 		if (changed) {
 			int rc = fx_fetch(b); if (rc) return rc;
 			for (int i = 0; i < b->instances; i++) kb_reverb_prepare(b->fs, b->hdr[i], b->st<KbReverb>(i));
+			b->dirty = true;
+		}
+	} else if (b->graph == KB_FX_RM || b->graph == KB_FX_TREMOLO) {
+		// `lfo(rate)` = Fast::Sine::set(rate), a no-op while the rate equals the cached frequency (RM.k:21, Tremolo.k:26, klang.h:5143-5147, Q3).
+		// The device only ever advances the phase, so the mirror's frequency is current without a fetch.
+		bool need = false;
+		for (int i = 0; i < b->instances && !need; i++) need = b->st<KbLfoFx>(i).lfo.frequency != b->hdr[i].controls[0].value;
+		if (need) {
+			int rc = fx_fetch(b); if (rc) return rc;
+			for (int i = 0; i < b->instances; i++) kb_fsine_set_f(b->fs, b->st<KbLfoFx>(i).lfo, b->hdr[i].controls[0].value);
 			b->dirty = true;
 		}
 	} else if (b->graph == KB_FX_DELAY_REVERB) {
@@ -242,6 +262,13 @@ extern "C" int kb_fx_bank_process(kb_fx_bank* b, float* io, int n, unsigned flag
 	case KB_FX_GAIN: {
 		dim3 grid((unsigned)std::max(1, std::min((n / 4 + 255) / 256, 148 * 8 / std::min(b->instances, 148 * 8) + 1)), b->instances);
 		kb_gain_kernel<<<grid, 256, 0, b->stream>>>(b->d_hdr, d, n);
+		break; }
+	case KB_FX_PAN: case KB_FX_RM: case KB_FX_TREMOLO: case KB_FX_CLIPPING: {
+		const int rows = b->instances * b->channels;
+		const bool lfo = b->graph == KB_FX_RM || b->graph == KB_FX_TREMOLO;
+		dim3 grid((unsigned)std::max(1, std::min((n / 4 + 255) / 256, 148 * 8 / std::min(rows, 148 * 8) + 1)), rows);
+		kb_elementwise_kernel<<<grid, 256, 0, b->stream>>>(b->graph, b->channels, b->d_hdr, lfo ? (const KbLfoFx*)b->d_state : nullptr, d, n, n);
+		if (lfo) { kb_lfo_advance_kernel<<<ib, 32, 0, b->stream>>>((KbLfoFx*)b->d_state, b->instances, n); b->launches++; }
 		break; }
 	case KB_FX_PINGPONG: {
 		KbPingPong* st = (KbPingPong*)b->d_state;
@@ -332,7 +359,7 @@ extern "C" int kb_fx_bank_process(kb_fx_bank* b, float* io, int n, unsigned flag
 	b->prof_end();
 	b->launches++;
 	KB_CUDA(cudaGetLastError());
-	if (b->graph != KB_FX_GAIN) b->host_stale = true;
+	if (b->graph != KB_FX_GAIN && b->graph != KB_FX_PAN && b->graph != KB_FX_CLIPPING) b->host_stale = true;
 	if (!(flags & KB_DEVICE_PTR)) {
 		KB_CUDA(cudaMemcpyAsync(io, d, floats * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
 		if (!(flags & KB_ASYNC_HOST)) KB_CUDA(cudaStreamSynchronize(b->stream));

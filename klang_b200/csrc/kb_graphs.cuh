@@ -9,7 +9,7 @@
 
 #include "../../include/klang_b200.h"   // graph ids KB_SY_* / KB_FX_*
 #define KB_SY_COUNT 9
-#define KB_FX_COUNT 5
+#define KB_FX_COUNT 9
 
 // =========================================================================================== HOST halves
 
@@ -319,6 +319,22 @@ KB_HD float kb_senv_tick(const KbFs& fs, KbSenvVoice& n, int& note_stage) {
 	const float out = o * kb_env_tick(fs, n.env);
 	if (n.stop_when_finished && n.env.stage == KB_ENV_OFF) note_stage = KB_NOTE_OFF;
 	return out;
+}
+
+// ---- elementwise effects: Gain/Pan.k:16-21, Gain/RM.k:17-24, Gain/Tremolo.k:22-29, Distortion/Clipping.k:14-25.  Sample `t` of a block as a
+// pure function of the input sample: the LFO of RM.k / Tremolo.k is a Fast::Sine on an integer phase ramp, and `lfo(rate)` sets a
+// frequency that is constant over the block (controls move between blocks), so Sine::set runs once per block on the host.
+// c0, c1 = controls[0], controls[1]; channel = 0 left / mono, 1 right.
+KB_HD float kb_ew_sample(int graph, float c0, float c1, const KbFastSine& lfo, int channel, uint32_t t, float in) {
+	if (graph == KB_FX_PAN) return channel == 0 ? in * (1 - c0) : in * c0;
+	if (graph == KB_FX_CLIPPING) {
+		in *= c0;
+		if (in > 1) in = 1; else if (in < -1) in = -1;
+		return in;
+	}
+	const float s = kb_fsine_value(lfo.position + t * (uint32_t)lfo.increment + lfo.offset);
+	const float mod = graph == KB_FX_RM ? s : s * c1 + (1 - c1);
+	return in * mod;
 }
 
 // The same sample as a pure function of the sample index: tick `t` of a block whose first tick finds the voice in state `n`.

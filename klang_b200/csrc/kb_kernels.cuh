@@ -282,6 +282,32 @@ __global__ void kb_gain_kernel(const KbFxHdr* __restrict__ hdr, float* __restric
 	for (int i = (n4 << 2) + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = p[i] * gain;
 }
 
+// Pan.k / RM.k / Tremolo.k / Clipping.k: elementwise streaming kernel over planar rows [instance][channel][n], 16-byte vector loads and
+// stores like kb_gain_kernel; blockIdx.y = instance * channels + channel.  The LFO phase of sample t is closed-form (kb_ew_sample).
+__global__ void kb_elementwise_kernel(int graph, int channels, const KbFxHdr* __restrict__ hdr, const KbLfoFx* __restrict__ lfos,
+                                      float* __restrict__ io, int n, int stride) {
+	const int inst = blockIdx.y / channels, ch = blockIdx.y % channels;
+	const float c0 = hdr[inst].controls[0].value, c1 = hdr[inst].controls[1].value;
+	KbFastSine lfo = { 0.f, 0, 0u, 0u };
+	if (lfos) lfo = lfos[inst].lfo;
+	float* p = io + ((size_t)inst * channels + ch) * stride;
+	const int n4 = ((reinterpret_cast<uintptr_t>(p) & 15) == 0) ? (n >> 2) : 0;
+	float4* p4 = reinterpret_cast<float4*>(p);
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+		float4 x = p4[i];
+		const uint32_t t = (uint32_t)i << 2;
+		x.x = kb_ew_sample(graph, c0, c1, lfo, ch, t, x.x); x.y = kb_ew_sample(graph, c0, c1, lfo, ch, t + 1, x.y);
+		x.z = kb_ew_sample(graph, c0, c1, lfo, ch, t + 2, x.z); x.w = kb_ew_sample(graph, c0, c1, lfo, ch, t + 3, x.w);
+		p4[i] = x;
+	}
+	for (int i = (n4 << 2) + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = kb_ew_sample(graph, c0, c1, lfo, ch, (uint32_t)i, p[i]);
+}
+// after the block: the n ticks the LFO made (Fast::Sine::process, klang.h:5164-5170)
+__global__ void kb_lfo_advance_kernel(KbLfoFx* __restrict__ lfos, int instances, int n) {
+	const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+	if (inst < instances) lfos[inst].lfo.position += (uint32_t)n * (uint32_t)lfos[inst].lfo.increment;
+}
+
 // Delay-line effects, sequential form: one lane = one instance (Effect::process(buffer), klang.h:4208-4216 /
 // 4708-4716), rings in HBM.  Exact for any control setting; the time-parallel kernels below take over whenever
 // the feedback delays allow.

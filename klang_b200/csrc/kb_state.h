@@ -94,3 +94,5 @@ struct KbReverb {
 struct KbDPingPong { KbDelay l, r; };
 struct KbDReverb { KbDelay feedforward, feedback; KbBiquad filter; float out; };
 struct KbGainFx { int unused; };
+// examples/Gain/RM.k, Tremolo.k: the LFO (Pan.k and Clipping.k carry no state and use KbGainFx)
+struct KbLfoFx { KbFastSine lfo; };

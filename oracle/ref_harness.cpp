@@ -61,6 +61,18 @@ namespace k_ramp {
 namespace k_release {
 #include "Subtractive/Release.k"
 }
+namespace k_pan {
+#include "Gain/Pan.k"
+}
+namespace k_rm {
+#include "Gain/RM.k"
+}
+namespace k_tremolo {
+#include "Gain/Tremolo.k"
+}
+namespace k_clipping {
+#include "Distortion/Clipping.k"
+}
 namespace k_delay_pingpong {
 #include "Delay/PingPong.k"
 }
@@ -357,7 +369,7 @@ int ref_control_smooth(float lo, float hi, float initial, int n, const float* va
 }
 
 // ---------------------------------------------------------------------- effects
-enum { FX_GAIN = 0, FX_PINGPONG = 1, FX_REVERB = 2, FX_DELAY_PINGPONG = 3, FX_DELAY_REVERB = 4 };
+enum { FX_GAIN = 0, FX_PINGPONG = 1, FX_REVERB = 2, FX_DELAY_PINGPONG = 3, FX_DELAY_REVERB = 4, FX_PAN = 5, FX_RM = 6, FX_TREMOLO = 7, FX_CLIPPING = 8 };
 
 struct RefFx {
 	int graph;
@@ -375,6 +387,10 @@ void* ref_fx_create(int graph) {
 	case FX_REVERB:   { auto* e = new k_reverb::Reverb();     fx->stereo = e; fx->controls = &e->controls; } break;
 	case FX_DELAY_PINGPONG: { auto* e = new k_delay_pingpong::PingPong(); fx->stereo = e; fx->controls = &e->controls; } break;
 	case FX_DELAY_REVERB:   { auto* e = new k_delay_reverb::Reverb();     fx->mono = e;   fx->controls = &e->controls; } break;
+	case FX_PAN:      { auto* e = new k_pan::Pan();           fx->stereo = e; fx->controls = &e->controls; } break;
+	case FX_RM:       { auto* e = new k_rm::RM();             fx->mono = e;   fx->controls = &e->controls; } break;
+	case FX_TREMOLO:  { auto* e = new k_tremolo::Tremolo();   fx->mono = e;   fx->controls = &e->controls; } break;
+	case FX_CLIPPING: { auto* e = new k_clipping::Clipping(); fx->mono = e;   fx->controls = &e->controls; } break;
 	default: delete fx; return nullptr;
 	}
 	return fx;

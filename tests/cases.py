@@ -19,11 +19,12 @@ import numpy as np
 (FLT_BIQUAD_LPF, FLT_BIQUAD_HPF, FLT_ONEPOLE_LPF, FLT_ONEPOLE_HPF,
  FLT_BIQUAD_BPF, FLT_BIQUAD_BRF, FLT_BIQUAD_APF, FLT_BUTTERWORTH_LPF1, FLT_BUTTERWORTH_LPF2,
  FLT_DCF, FLT_IIR1, FLT_IIR2, FLT_MODAL, FLT_FOLLOWER_PEAK, FLT_FOLLOWER_RMS, FLT_WINDOW_MEAN, FLT_WINDOW_RMS) = range(17)
-FX_GAIN, FX_PINGPONG, FX_REVERB, FX_DELAY_PINGPONG, FX_DELAY_REVERB = range(5)
+FX_GAIN, FX_PINGPONG, FX_REVERB, FX_DELAY_PINGPONG, FX_DELAY_REVERB, FX_PAN, FX_RM, FX_TREMOLO, FX_CLIPPING = range(9)
 SY_SUBTRACTIVE, SY_SUPERSAW, SY_TB303, SY_SYNTHX, SY_FILTER_K, SY_FM, SY_BREAKPOINT, SY_RAMP, SY_RELEASE = range(9)
 
 FX_NAMES = {FX_GAIN: "gain", FX_PINGPONG: "pingpong", FX_REVERB: "reverb",
-            FX_DELAY_PINGPONG: "delay_pingpong", FX_DELAY_REVERB: "delay_reverb"}
+            FX_DELAY_PINGPONG: "delay_pingpong", FX_DELAY_REVERB: "delay_reverb", FX_PAN: "pan", FX_RM: "rm", FX_TREMOLO: "tremolo",
+            FX_CLIPPING: "clipping"}
 SY_NAMES = {SY_SUBTRACTIVE: "subtractive", SY_SUPERSAW: "supersaw", SY_TB303: "tb303",
             SY_SYNTHX: "synthx", SY_FILTER_K: "filter_k", SY_FM: "fm", SY_BREAKPOINT: "breakpoint", SY_RAMP: "ramp",
             SY_RELEASE: "release"}
@@ -205,8 +206,19 @@ FX_SCRIPTS = {
 }
 
 
+# examples/Gain/{Pan,RM,Tremolo}.k and Distortion/Clipping.k: elementwise effects (RM / Tremolo with a Fast::Sine LFO).  Kept apart from
+# FX_SCRIPTS: their device tests live in tests/test_zz_gpu_primitives.py.
+FX_SCRIPTS_LATE = {
+    "pan": (FX_PAN, 3000, 1000, [(1, 0, 0.2), (2, 0, 1.0)], None),
+    "rm": (FX_RM, 4096, 1024, [(2, 0, 440.0)], None),
+    "rm_at_cached_rate": (FX_RM, 3072, 1024, [(0, 0, 1000.0), (2, 0, 999.0)], None),      # set(1000) on a fresh Sine is a no-op: silent LFO (Q3)
+    "tremolo": (FX_TREMOLO, 4500, 1500, [(1, 1, 0.2), (2, 0, 10.0)], None),
+    "clipping": (FX_CLIPPING, 3072, 1024, [(1, 0, 3.0), (2, 0, 11.0)], None),
+}
+
+
 def run_fx_script(eng, name, fs, seed=1):
-    graph, total, block, events, burst = FX_SCRIPTS[name]
+    graph, total, block, events, burst = (FX_SCRIPTS.get(name) or FX_SCRIPTS_LATE[name])
     eng.set_fs(fs)
     eng.srand(1)
     fx = eng.Fx(graph)
@@ -301,7 +313,7 @@ def run_synth_noteon_script(eng, graph, fs, nvoices=32, notes=40, blocks=4, n=25
 
 def all_graph_cases(eng, fs):
     out = {}
-    for name in FX_SCRIPTS:
+    for name in list(FX_SCRIPTS) + list(FX_SCRIPTS_LATE):
         out[f"fx/{name}"] = run_fx_script(eng, name, fs)
     for name in list(SYNTH_SCRIPTS) + list(SYNTH_SCRIPTS_LATE):
         r = run_synth_script(eng, name, fs, per_voice=True)

@@ -199,3 +199,32 @@ def test_sine_envelope_voices_match_oracle_on_host():
                            port(oracle.SY_RELEASE, 48000.0, 45, ((1, 0.01), (2, 0.5), (3, 0.02)), 4000, 1500)])
     assert len(got) == len(want) and np.array_equal(got.view(np.uint32), want.view(np.uint32))
     assert np.abs(want[:6000]).max() > 0.5 and np.abs(want[12000:]).max() > 0.3
+
+
+def test_elementwise_effects_match_reference_golden_on_host():
+    """Pan.k / RM.k / Tremolo.k / Clipping.k: the product's per-sample function (kb_ew_sample, closed-form LFO phase) with the library's
+    per-block steps, compiled with g++, reproduces the compiled reference's golden vectors bit for bit — the silent LFO of a fresh
+    Sine set to its cached 1000 Hz (Q3) included."""
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cases
+    tmp = tempfile.mkdtemp(prefix="kb_host_")
+    exe = os.path.join(tmp, "ew_check")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-x", "c++",
+                           os.path.join(ROOT, "tests", "host", "ew_check.cpp"), "-o", exe])
+    for fs in (44100, 48000):
+        g = np.load(os.path.join(ROOT, "tests", "golden", f"klang_ref_fs{fs}.npz"))
+        for name, (graph, total, block, events, burst) in cases.FX_SCRIPTS_LATE.items():
+            channels = 2 if graph == cases.FX_PAN else 1
+            x = cases.fx_input(channels, total, 1, burst)
+            path = os.path.join(tmp, "in.f32")
+            np.ascontiguousarray(x, np.float32).tofile(path)
+            args = [exe, str(graph), str(fs), str(channels), str(total), str(block), path]
+            for (bi, c, v) in events:
+                args += [str(bi), str(c), repr(float(v))]
+            out = subprocess.run(args, capture_output=True)
+            assert out.returncode == 0, name
+            got = np.frombuffer(out.stdout, np.float32).reshape(channels, total)
+            want = g[f"fx/{name}"].reshape(channels, total)
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (fs, name)

@@ -39,9 +39,10 @@ def test_reference_k_programs_compile_unmodified_against_compat_header(tmp_path)
 def _expected(prog, fs, n, blocks):
     oracle.port.set_fs(fs)
     oracle.port.srand(1)
-    if prog in ("gain", "pingpong", "delay_pingpong", "delay_reverb", "reverb"):
-        graph = {"gain": oracle.FX_GAIN, "pingpong": oracle.FX_PINGPONG, "delay_pingpong": oracle.FX_DELAY_PINGPONG, "delay_reverb": oracle.FX_DELAY_REVERB,
-                 "reverb": oracle.FX_REVERB}[prog]
+    fx_graphs = {"gain": oracle.FX_GAIN, "pingpong": oracle.FX_PINGPONG, "delay_pingpong": oracle.FX_DELAY_PINGPONG, "delay_reverb": oracle.FX_DELAY_REVERB,
+                 "reverb": oracle.FX_REVERB, "pan": oracle.FX_PAN, "rm": oracle.FX_RM, "tremolo": oracle.FX_TREMOLO, "clipping": oracle.FX_CLIPPING}
+    if prog in fx_graphs:
+        graph = fx_graphs[prog]
         fx = oracle.port.Fx(graph)
         x = cases.fx_input(fx.channels, n * blocks, seed=1)
         outs = []

@@ -108,9 +108,51 @@ def test_sine_envelope_synths_match_reference_golden(golden, fs, name):
     _exact(np.ascontiguousarray(r["out"]), golden[fs][f"synth/{name}/mix"], f"synth/{name}/mix")
 
 
-@pytest.mark.parametrize("prog", ["breakpoint", "ramp", "release"])
-def test_sine_envelope_k_programs_run_unmodified_on_the_device(prog, tmp_path):
-    """examples/Subtractive/{Breakpoint,Ramp,Release}.k compiled UNMODIFIED against include/compat/klang.h (tools/k_host.cpp) and run on
-    the device through the host program: bit-identical to the oracle run with the same MIDI script."""
+@pytest.mark.parametrize("prog", ["breakpoint", "ramp", "release", "pan", "rm", "tremolo", "clipping"])
+def test_late_k_programs_run_unmodified_on_the_device(prog, tmp_path):
+    """examples/Subtractive/{Breakpoint,Ramp,Release}.k, Gain/{Pan,RM,Tremolo}.k and Distortion/Clipping.k compiled UNMODIFIED against
+    include/compat/klang.h (tools/k_host.cpp) and run on the device through the host program: bit-identical to the oracle run with
+    the same script."""
     from test_k_programs import run_k_program_on_device
     run_k_program_on_device(prog, tmp_path)
+
+
+# ---- examples/Gain/{Pan,RM,Tremolo}.k, Distortion/Clipping.k: KB_FX_PAN / RM / TREMOLO / CLIPPING on the elementwise streaming kernel
+# (kb_elementwise_kernel); the per-sample function and the per-block steps are proven with g++ against the golden vectors
+# (tests/host/ew_check.cpp)
+@pytest.mark.parametrize("fs", [44100, 48000])
+@pytest.mark.parametrize("name", list(cases.FX_SCRIPTS_LATE))
+def test_elementwise_effects_match_reference_golden(golden, fs, name):
+    eng = kb.Engine()
+    got = cases.run_fx_script(eng, name, fs)
+    _exact(np.ascontiguousarray(got), golden[fs][f"fx/{name}"], f"fx/{name}")
+
+
+@pytest.mark.parametrize("graph", [cases.FX_PAN, cases.FX_RM, cases.FX_TREMOLO, cases.FX_CLIPPING])
+def test_elementwise_effect_bank_vs_live_oracle(graph):
+    """Five instances with different controls, ragged blocks (1001 frames: rows that are not 16-byte aligned take the scalar path,
+    1024 the vector path), a control change between blocks: every instance equals its own oracle object."""
+    fs, inst = 48000.0, 5
+    oracle.port.set_fs(fs)
+    refs = [oracle.port.Fx(graph) for _ in range(inst)]
+    bank = kb.FxBank(graph, inst, fs, 1024)
+    ch = bank.channels
+    lo, hi = {cases.FX_PAN: (0.0, 1.0), cases.FX_RM: (1.0, 1000.0), cases.FX_TREMOLO: (1.0, 10.0), cases.FX_CLIPPING: (1.0, 11.0)}[graph]
+    for i in range(inst):
+        v = lo + (hi - lo) * (i + 0.5) / inst
+        refs[i].set_control(0, v)
+        bank.set_control(0, v, i)
+    for b, n in enumerate((1001, 1024, 7, 1024)):
+        if b == 2:
+            refs[3].set_control(0, hi)
+            bank.set_control(0, hi, 3)
+            if graph in (cases.FX_RM, cases.FX_TREMOLO):
+                refs[1].set_control(1, 0.1)
+                bank.set_control(1, 0.1, 1)
+        x = np.stack([cases.fx_input(ch, n, seed=10 * b + i) for i in range(inst)])          # [inst, ch, n]
+        want = np.stack([np.atleast_2d(refs[i].process(x[i][0] if ch == 1 else x[i])) for i in range(inst)])
+        got = bank.process_inplace(np.ascontiguousarray(x, np.float32).copy())
+        _exact(np.ascontiguousarray(got), np.ascontiguousarray(want, np.float32), f"graph {graph} block {b}")
+    bank.close()
+    for r in refs:
+        r.close()

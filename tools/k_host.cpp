@@ -39,6 +39,18 @@ namespace k_synthx {
 namespace k_fm {
 #include "FM.k"
 }
+namespace k_pan {
+#include "Gain/Pan.k"
+}
+namespace k_rm {
+#include "Gain/RM.k"
+}
+namespace k_tremolo {
+#include "Gain/Tremolo.k"
+}
+namespace k_clipping {
+#include "Distortion/Clipping.k"
+}
 namespace k_breakpoint {
 #include "Subtractive/Breakpoint.k"
 }
@@ -59,6 +71,10 @@ KLANG_B200_SYNTH(k_tb303::TB303, KB_SY_TB303)
 KLANG_B200_EFFECT(k_reverb::Reverb, KB_FX_REVERB)
 KLANG_B200_SYNTH(k_synthx::SynTHX, KB_SY_SYNTHX)
 KLANG_B200_SYNTH(k_fm::FM, KB_SY_FM)
+KLANG_B200_EFFECT(k_pan::Pan, KB_FX_PAN)
+KLANG_B200_EFFECT(k_rm::RM, KB_FX_RM)
+KLANG_B200_EFFECT(k_tremolo::Tremolo, KB_FX_TREMOLO)
+KLANG_B200_EFFECT(k_clipping::Clipping, KB_FX_CLIPPING)
 KLANG_B200_SYNTH(k_breakpoint::Breakpoint, KB_SY_BREAKPOINT)
 KLANG_B200_SYNTH(k_ramp::Ramp, KB_SY_RAMP)
 KLANG_B200_SYNTH(k_release::Release, KB_SY_RELEASE)
@@ -115,6 +131,10 @@ int main(int argc, char** argv) {
 		else if (prog == "reverb") rc = run_effect<k_reverb::Reverb>(fs, n, blocks, out);
 		else if (prog == "synthx") rc = run_synth<k_synthx::SynTHX>(fs, n, blocks, out);
 		else if (prog == "fm") rc = run_synth<k_fm::FM>(fs, n, blocks, out);
+		else if (prog == "pan") rc = run_effect<k_pan::Pan>(fs, n, blocks, out);
+		else if (prog == "rm") rc = run_effect<k_rm::RM>(fs, n, blocks, out);
+		else if (prog == "tremolo") rc = run_effect<k_tremolo::Tremolo>(fs, n, blocks, out);
+		else if (prog == "clipping") rc = run_effect<k_clipping::Clipping>(fs, n, blocks, out);
 		else if (prog == "breakpoint") rc = run_synth<k_breakpoint::Breakpoint>(fs, n, blocks, out);
 		else if (prog == "ramp") rc = run_synth<k_ramp::Ramp>(fs, n, blocks, out);
 		else if (prog == "release") rc = run_synth<k_release::Release>(fs, n, blocks, out);
