@@ -39,6 +39,8 @@ extern "C" {
 #define KB_FX_RM 6                /* examples/Gain/RM.k            mono   (elementwise, Fast::Sine LFO) */
 #define KB_FX_TREMOLO 7           /* examples/Gain/Tremolo.k       mono   (elementwise, Fast::Sine LFO) */
 #define KB_FX_CLIPPING 8          /* examples/Distortion/Clipping.k mono  (elementwise) */
+#define KB_FX_ECHO 9              /* examples/Delay/Echo.k         mono   (one Delay<192000>, feed-forward tap) */
+#define KB_FX_FEEDBACK 10         /* examples/Delay/Feedback.k     mono   (one Delay<192000> fed the output) */
 
 /* synth graphs */
 #define KB_SY_SUBTRACTIVE 0       /* Saw >> LPF(env) >> ADSR: Filter.k with a Saw and ADSR controls mono */

@@ -104,6 +104,7 @@ extern "C" kb_fx_bank* kb_fx_bank_create(int graph, int instances, float fs, int
 	case KB_FX_PAN: b->channels = 2; b->ncontrols = 1; b->state_bytes = sizeof(KbGainFx); b->ring_floats = 0; break;
 	case KB_FX_RM: case KB_FX_TREMOLO: b->channels = 1; b->ncontrols = 2; b->state_bytes = sizeof(KbLfoFx); b->ring_floats = 0; break;
 	case KB_FX_CLIPPING: b->channels = 1; b->ncontrols = 1; b->state_bytes = sizeof(KbGainFx); b->ring_floats = 0; break;
+	case KB_FX_ECHO: case KB_FX_FEEDBACK: b->channels = 1; b->ncontrols = 2; b->state_bytes = sizeof(KbOneDelayFx); b->ring_floats = KB_ONEDELAY_RING_FLOATS; break;
 	}
 	b->hdr.assign(instances, KbFxHdr());
 	memset(b->hdr.data(), 0, b->hdr.size() * sizeof(KbFxHdr));
@@ -121,6 +122,9 @@ extern "C" kb_fx_bank* kb_fx_bank_create(int graph, int instances, float fs, int
 			b->hdr[i].controls[0] = kb_dial(1.f, graph == KB_FX_RM ? 1000.f : 10.f, 6.f); b->hdr[i].controls[1] = kb_dial(0.f, 0.5f, 0.5f);
 			kb_fsine_init(b->st<KbLfoFx>(i).lfo); break;
 		case KB_FX_CLIPPING: b->hdr[i].controls[0] = kb_dial(1.f, 11.f, 1.f); break;                                          // Clipping.k:10
+		case KB_FX_ECHO: case KB_FX_FEEDBACK:                                                                                 // Echo.k:10-13, Feedback.k:10-13
+			b->hdr[i].controls[0] = kb_dial(0.f, 1.f, 0.5f); b->hdr[i].controls[1] = kb_dial(0.f, 1.f, 0.5f);
+			kb_delay_construct(b->st<KbOneDelayFx>(i).delay, 192000, ring0); break;
 		}
 	}
 	bool ok = cudaSetDevice(device) == cudaSuccess;
@@ -156,7 +160,8 @@ extern "C" int kb_fx_bank_num_controls(const kb_fx_bank* b) { return b ? b->ncon
 extern "C" long long kb_fx_bank_launches(const kb_fx_bank* b) { return b ? b->launches : 0; }
 extern "C" int kb_fx_bank_parallel_instances(kb_fx_bank* b) {
 	if (!b) return kb_fail(KB_EINVAL, "null bank");
-	if (b->graph == KB_FX_GAIN || b->graph >= KB_FX_PAN) return b->instances;
+	if (b->graph == KB_FX_GAIN || (b->graph >= KB_FX_PAN && b->graph <= KB_FX_CLIPPING)) return b->instances;
+	if (b->graph == KB_FX_ECHO || b->graph == KB_FX_FEEDBACK) return 0;              // frame-sequential schedule only, so far
 	std::vector<KbFxPlan> plan(b->instances);
 	KB_CUDA(cudaSetDevice(b->device));
 	KB_CUDA(cudaStreamSynchronize(b->stream));
@@ -199,6 +204,7 @@ extern "C" double kb_fx_bank_bytes_per_frame(kb_fx_bank* b) {
 	case KB_FX_DELAY_REVERB: return 88;
 	case KB_FX_PAN: return 16;
 	case KB_FX_RM: case KB_FX_TREMOLO: case KB_FX_CLIPPING: return 8;
+	case KB_FX_ECHO: case KB_FX_FEEDBACK: return 20;               // 8 io + 4 write + two adjacent floats read
 	}
 	return 0;
 }
@@ -270,6 +276,12 @@ extern "C" int kb_fx_bank_process(kb_fx_bank* b, float* io, int n, unsigned flag
 		kb_elementwise_kernel<<<grid, 256, 0, b->stream>>>(b->graph, b->channels, b->d_hdr, lfo ? (const KbLfoFx*)b->d_state : nullptr, d, n, n);
 		if (lfo) { kb_lfo_advance_kernel<<<ib, 32, 0, b->stream>>>((KbLfoFx*)b->d_state, b->instances, n); b->launches++; }
 		break; }
+	case KB_FX_ECHO:       // one lane per instance, frame by frame (a chunk-parallel schedule like Delay/PingPong.k's applies and is not built)
+		kb_fx_seq_kernel<KB_FX_ECHO, KbOneDelayFx><<<ib, 32, 0, b->stream>>>(b->d_hdr, (KbOneDelayFx*)b->d_state, b->d_rings, d, n, n, 1, b->instances, b->fs, nullptr);
+		break;
+	case KB_FX_FEEDBACK:
+		kb_fx_seq_kernel<KB_FX_FEEDBACK, KbOneDelayFx><<<ib, 32, 0, b->stream>>>(b->d_hdr, (KbOneDelayFx*)b->d_state, b->d_rings, d, n, n, 1, b->instances, b->fs, nullptr);
+		break;
 	case KB_FX_PINGPONG: {
 		KbPingPong* st = (KbPingPong*)b->d_state;
 		// sub-blocks of at most 8192 frames (the staged block lives in shared memory); every sub-block is planned on the device

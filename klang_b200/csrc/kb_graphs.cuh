@@ -9,7 +9,7 @@
 
 #include "../../include/klang_b200.h"   // graph ids KB_SY_* / KB_FX_*
 #define KB_SY_COUNT 9
-#define KB_FX_COUNT 9
+#define KB_FX_COUNT 11
 
 // =========================================================================================== HOST halves
 
@@ -290,6 +290,22 @@ inline void kb_dreverb_construct(KbFxHdr& h, KbDReverb& p, long long ring0) {   
 	kb_delay_construct(p.feedforward, 192000, ring0); kb_delay_construct(p.feedback, 192000, ring0 + 192001);
 	kb_biquad_construct(p.filter, KB_BQ_LPF);
 	h.controls[0] = kb_dial(0.f, 0.5f, 0.4f); h.controls[1] = kb_dial(0.f, 0.4f, 0.1f); h.controls[2] = kb_dial(500.f, 5000.f, 1500.f);
+}
+
+// ---- Delay/Echo.k:16-23 and Delay/Feedback.k:16-24: one frame (host + device: tests/host/onedelay_check.cpp renders them with g++)
+#define KB_ONEDELAY_RING_FLOATS 192008LL
+KB_D float kb_echo_frame(const KbFs& fs, const KbFxHdr& h, KbOneDelayFx& s, float* rings, float in) {
+	float* ring = rings + s.delay.ring;
+	const float time = h.controls[0].value * fs.f, gain = h.controls[1].value;
+	kb_delay_write(s.delay, ring, in);                                        // in >> delay
+	return in + kb_delay_tap_f(s.delay, ring, time) * gain;                  // in + delay(time) * gain >> out
+}
+KB_D float kb_feedback_frame(const KbFs& fs, const KbFxHdr& h, KbOneDelayFx& s, float* rings, float in) {
+	float* ring = rings + s.delay.ring;
+	const float time = h.controls[0].value * fs.f, gain = h.controls[1].value;
+	const float out = in + kb_delay_tap_f(s.delay, ring, time) * gain;       // in + delay(time) * gain >> out
+	kb_delay_write(s.delay, ring, out);                                       // delay << out
+	return out;
 }
 
 // ---- FM.k per-sample half (host + device: tests/host/fm_check.cpp renders it with g++)

@@ -96,3 +96,5 @@ struct KbDReverb { KbDelay feedforward, feedback; KbBiquad filter; float out; };
 struct KbGainFx { int unused; };
 // examples/Gain/RM.k, Tremolo.k: the LFO (Pan.k and Clipping.k carry no state and use KbGainFx)
 struct KbLfoFx { KbFastSine lfo; };
+// examples/Delay/Echo.k, Feedback.k: one Delay<192000>
+struct KbOneDelayFx { KbDelay delay; };

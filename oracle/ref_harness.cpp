@@ -73,6 +73,12 @@ namespace k_tremolo {
 namespace k_clipping {
 #include "Distortion/Clipping.k"
 }
+namespace k_echo {
+#include "Delay/Echo.k"
+}
+namespace k_feedback {
+#include "Delay/Feedback.k"
+}
 namespace k_delay_pingpong {
 #include "Delay/PingPong.k"
 }
@@ -369,7 +375,7 @@ int ref_control_smooth(float lo, float hi, float initial, int n, const float* va
 }
 
 // ---------------------------------------------------------------------- effects
-enum { FX_GAIN = 0, FX_PINGPONG = 1, FX_REVERB = 2, FX_DELAY_PINGPONG = 3, FX_DELAY_REVERB = 4, FX_PAN = 5, FX_RM = 6, FX_TREMOLO = 7, FX_CLIPPING = 8 };
+enum { FX_GAIN = 0, FX_PINGPONG = 1, FX_REVERB = 2, FX_DELAY_PINGPONG = 3, FX_DELAY_REVERB = 4, FX_PAN = 5, FX_RM = 6, FX_TREMOLO = 7, FX_CLIPPING = 8, FX_ECHO = 9, FX_FEEDBACK = 10 };
 
 struct RefFx {
 	int graph;
@@ -391,6 +397,8 @@ void* ref_fx_create(int graph) {
 	case FX_RM:       { auto* e = new k_rm::RM();             fx->mono = e;   fx->controls = &e->controls; } break;
 	case FX_TREMOLO:  { auto* e = new k_tremolo::Tremolo();   fx->mono = e;   fx->controls = &e->controls; } break;
 	case FX_CLIPPING: { auto* e = new k_clipping::Clipping(); fx->mono = e;   fx->controls = &e->controls; } break;
+	case FX_ECHO:     { auto* e = new k_echo::Echo();         fx->mono = e;   fx->controls = &e->controls; } break;
+	case FX_FEEDBACK: { auto* e = new k_feedback::Feedback(); fx->mono = e;   fx->controls = &e->controls; } break;
 	default: delete fx; return nullptr;
 	}
 	return fx;

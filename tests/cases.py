@@ -19,12 +19,12 @@ import numpy as np
 (FLT_BIQUAD_LPF, FLT_BIQUAD_HPF, FLT_ONEPOLE_LPF, FLT_ONEPOLE_HPF,
  FLT_BIQUAD_BPF, FLT_BIQUAD_BRF, FLT_BIQUAD_APF, FLT_BUTTERWORTH_LPF1, FLT_BUTTERWORTH_LPF2,
  FLT_DCF, FLT_IIR1, FLT_IIR2, FLT_MODAL, FLT_FOLLOWER_PEAK, FLT_FOLLOWER_RMS, FLT_WINDOW_MEAN, FLT_WINDOW_RMS) = range(17)
-FX_GAIN, FX_PINGPONG, FX_REVERB, FX_DELAY_PINGPONG, FX_DELAY_REVERB, FX_PAN, FX_RM, FX_TREMOLO, FX_CLIPPING = range(9)
+FX_GAIN, FX_PINGPONG, FX_REVERB, FX_DELAY_PINGPONG, FX_DELAY_REVERB, FX_PAN, FX_RM, FX_TREMOLO, FX_CLIPPING, FX_ECHO, FX_FEEDBACK = range(11)
 SY_SUBTRACTIVE, SY_SUPERSAW, SY_TB303, SY_SYNTHX, SY_FILTER_K, SY_FM, SY_BREAKPOINT, SY_RAMP, SY_RELEASE = range(9)
 
 FX_NAMES = {FX_GAIN: "gain", FX_PINGPONG: "pingpong", FX_REVERB: "reverb",
             FX_DELAY_PINGPONG: "delay_pingpong", FX_DELAY_REVERB: "delay_reverb", FX_PAN: "pan", FX_RM: "rm", FX_TREMOLO: "tremolo",
-            FX_CLIPPING: "clipping"}
+            FX_CLIPPING: "clipping", FX_ECHO: "echo", FX_FEEDBACK: "feedback"}
 SY_NAMES = {SY_SUBTRACTIVE: "subtractive", SY_SUPERSAW: "supersaw", SY_TB303: "tb303",
             SY_SYNTHX: "synthx", SY_FILTER_K: "filter_k", SY_FM: "fm", SY_BREAKPOINT: "breakpoint", SY_RAMP: "ramp",
             SY_RELEASE: "release"}
@@ -214,6 +214,11 @@ FX_SCRIPTS_LATE = {
     "rm_at_cached_rate": (FX_RM, 3072, 1024, [(0, 0, 1000.0), (2, 0, 999.0)], None),      # set(1000) on a fresh Sine is a no-op: silent LFO (Q3)
     "tremolo": (FX_TREMOLO, 4500, 1500, [(1, 1, 0.2), (2, 0, 10.0)], None),
     "clipping": (FX_CLIPPING, 3072, 1024, [(1, 0, 3.0), (2, 0, 11.0)], None),
+    # Delay/Echo.k (feed-forward tap) and Delay/Feedback.k (the line is fed the output): short delays so echoes land inside the run,
+    # a delay time that moves between blocks, and a fractional delay (0.0123 s x fs)
+    "echo": (FX_ECHO, 6144, 1024, [(0, 0, 0.01), (0, 1, 0.7), (3, 0, 0.0123)], 4096),
+    "feedback": (FX_FEEDBACK, 8192, 1024, [(0, 0, 0.005), (0, 1, 0.8), (4, 0, 0.0123), (6, 1, 0.3)], 1500),
+    "feedback_zero_delay": (FX_FEEDBACK, 2048, 1024, [(0, 0, 0.0), (0, 1, 0.5)], None),
 }
 
 

@@ -1,0 +1,36 @@
+// Host-side check (g++, no CUDA): the product's Delay/Echo.k and Delay/Feedback.k frame functions (kb_echo_frame / kb_feedback_frame of
+// klang_b200/csrc/kb_graphs.cuh, what kb_fx_seq_kernel runs per lane) over a host ring.
+// Usage: onedelay_check <graph> <fs> <total> <block> <input.f32> [<block> <ctl> <value>]...   Output to stdout; tests/test_host_logic.py
+// compares it with the golden vectors of the compiled reference.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cstdint>
+#include <vector>
+#include "../../klang_b200/csrc/kb_graphs.cuh"
+
+int main(int argc, char** argv) {
+	if (argc < 6) return 2;
+	const int graph = atoi(argv[1]);
+	const KbFs fs = kb_make_fs((float)atof(argv[2]));
+	const int total = atoi(argv[3]), block = atoi(argv[4]);
+	std::vector<float> io(total), ring(KB_ONEDELAY_RING_FLOATS, 0.f);
+	FILE* f = fopen(argv[5], "rb");
+	if (!f || fread(io.data(), 4, io.size(), f) != io.size()) return 2;
+	fclose(f);
+	KbFxHdr h;
+	memset(&h, 0, sizeof(h));
+	h.controls[0] = kb_dial(0.f, 1.f, 0.5f); h.controls[1] = kb_dial(0.f, 1.f, 0.5f);
+	KbOneDelayFx s;
+	kb_delay_construct(s.delay, 192000, 0);
+	for (int b = 0; b * block < total; b++) {
+		for (int a = 6; a + 2 < argc; a += 3) if (atoi(argv[a]) == b) kb_control_set(h.controls[atoi(argv[a + 1])], (float)atof(argv[a + 2]));
+		const int n = total - b * block < block ? total - b * block : block;
+		for (int t = 0; t < n; t++) {
+			float& x = io[(size_t)b * block + t];
+			x = graph == KB_FX_ECHO ? kb_echo_frame(fs, h, s, ring.data(), x) : kb_feedback_frame(fs, h, s, ring.data(), x);
+		}
+	}
+	fwrite(io.data(), 4, io.size(), stdout);
+	return 0;
+}

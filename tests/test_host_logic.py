@@ -216,6 +216,8 @@ def test_elementwise_effects_match_reference_golden_on_host():
     for fs in (44100, 48000):
         g = np.load(os.path.join(ROOT, "tests", "golden", f"klang_ref_fs{fs}.npz"))
         for name, (graph, total, block, events, burst) in cases.FX_SCRIPTS_LATE.items():
+            if graph in (cases.FX_ECHO, cases.FX_FEEDBACK):
+                continue                                  # test_one_delay_effects_match_reference_golden_on_host
             channels = 2 if graph == cases.FX_PAN else 1
             x = cases.fx_input(channels, total, 1, burst)
             path = os.path.join(tmp, "in.f32")
@@ -228,3 +230,33 @@ def test_elementwise_effects_match_reference_golden_on_host():
             got = np.frombuffer(out.stdout, np.float32).reshape(channels, total)
             want = g[f"fx/{name}"].reshape(channels, total)
             assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (fs, name)
+
+
+def test_one_delay_effects_match_reference_golden_on_host():
+    """Delay/Echo.k and Delay/Feedback.k: the product's frame functions (kb_echo_frame / kb_feedback_frame) compiled with g++ reproduce
+    the compiled reference's golden vectors bit for bit (moving and fractional delay times, zero delay)."""
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cases
+    tmp = tempfile.mkdtemp(prefix="kb_host_")
+    exe = os.path.join(tmp, "onedelay_check")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-x", "c++",
+                           os.path.join(ROOT, "tests", "host", "onedelay_check.cpp"), "-o", exe])
+    checked = 0
+    for fs in (44100, 48000):
+        g = np.load(os.path.join(ROOT, "tests", "golden", f"klang_ref_fs{fs}.npz"))
+        for name, (graph, total, block, events, burst) in cases.FX_SCRIPTS_LATE.items():
+            if graph not in (cases.FX_ECHO, cases.FX_FEEDBACK):
+                continue
+            path = os.path.join(tmp, "in.f32")
+            np.ascontiguousarray(cases.fx_input(1, total, 1, burst)[0], np.float32).tofile(path)
+            args = [exe, str(graph), str(fs), str(total), str(block), path]
+            for (bi, c, v) in events:
+                args += [str(bi), str(c), repr(float(v))]
+            out = subprocess.run(args, capture_output=True)
+            assert out.returncode == 0, name
+            got = np.frombuffer(out.stdout, np.float32)
+            assert np.array_equal(got.view(np.uint32), g[f"fx/{name}"].view(np.uint32)), (fs, name)
+            checked += 1
+    assert checked == 6

@@ -108,9 +108,9 @@ def test_sine_envelope_synths_match_reference_golden(golden, fs, name):
     _exact(np.ascontiguousarray(r["out"]), golden[fs][f"synth/{name}/mix"], f"synth/{name}/mix")
 
 
-@pytest.mark.parametrize("prog", ["breakpoint", "ramp", "release", "pan", "rm", "tremolo", "clipping"])
+@pytest.mark.parametrize("prog", ["breakpoint", "ramp", "release", "pan", "rm", "tremolo", "clipping", "echo", "feedback"])
 def test_late_k_programs_run_unmodified_on_the_device(prog, tmp_path):
-    """examples/Subtractive/{Breakpoint,Ramp,Release}.k, Gain/{Pan,RM,Tremolo}.k and Distortion/Clipping.k compiled UNMODIFIED against
+    """examples/Subtractive/{Breakpoint,Ramp,Release}.k, Gain/{Pan,RM,Tremolo}.k, Distortion/Clipping.k and Delay/{Echo,Feedback}.k compiled UNMODIFIED against
     include/compat/klang.h (tools/k_host.cpp) and run on the device through the host program: bit-identical to the oracle run with
     the same script."""
     from test_k_programs import run_k_program_on_device
@@ -119,25 +119,28 @@ def test_late_k_programs_run_unmodified_on_the_device(prog, tmp_path):
 
 # ---- examples/Gain/{Pan,RM,Tremolo}.k, Distortion/Clipping.k: KB_FX_PAN / RM / TREMOLO / CLIPPING on the elementwise streaming kernel
 # (kb_elementwise_kernel); the per-sample function and the per-block steps are proven with g++ against the golden vectors
-# (tests/host/ew_check.cpp)
+# (tests/host/ew_check.cpp).  examples/Delay/{Echo,Feedback}.k: KB_FX_ECHO / KB_FX_FEEDBACK on the frame-sequential kernel.
 @pytest.mark.parametrize("fs", [44100, 48000])
 @pytest.mark.parametrize("name", list(cases.FX_SCRIPTS_LATE))
-def test_elementwise_effects_match_reference_golden(golden, fs, name):
+def test_late_effects_match_reference_golden(golden, fs, name):
     eng = kb.Engine()
     got = cases.run_fx_script(eng, name, fs)
     _exact(np.ascontiguousarray(got), golden[fs][f"fx/{name}"], f"fx/{name}")
 
 
-@pytest.mark.parametrize("graph", [cases.FX_PAN, cases.FX_RM, cases.FX_TREMOLO, cases.FX_CLIPPING])
-def test_elementwise_effect_bank_vs_live_oracle(graph):
-    """Five instances with different controls, ragged blocks (1001 frames: rows that are not 16-byte aligned take the scalar path,
-    1024 the vector path), a control change between blocks: every instance equals its own oracle object."""
+@pytest.mark.parametrize("graph", [cases.FX_PAN, cases.FX_RM, cases.FX_TREMOLO, cases.FX_CLIPPING, cases.FX_ECHO, cases.FX_FEEDBACK])
+def test_late_effect_bank_vs_live_oracle(graph):
+    """Five instances with different controls, ragged blocks (1001 frames: rows that are not 16-byte aligned take the scalar path of
+    the streaming kernel, 1024 the vector path), a control change between blocks: every instance equals its own oracle object.
+    Echo.k / Feedback.k (KB_FX_ECHO / KB_FX_FEEDBACK, one Delay<192000> per instance in the HBM ring arena, frame-sequential kernel;
+    frame functions proven with g++, tests/host/onedelay_check.cpp): delay times of a few hundred frames so the echoes land."""
     fs, inst = 48000.0, 5
     oracle.port.set_fs(fs)
     refs = [oracle.port.Fx(graph) for _ in range(inst)]
     bank = kb.FxBank(graph, inst, fs, 1024)
     ch = bank.channels
-    lo, hi = {cases.FX_PAN: (0.0, 1.0), cases.FX_RM: (1.0, 1000.0), cases.FX_TREMOLO: (1.0, 10.0), cases.FX_CLIPPING: (1.0, 11.0)}[graph]
+    lo, hi = {cases.FX_PAN: (0.0, 1.0), cases.FX_RM: (1.0, 1000.0), cases.FX_TREMOLO: (1.0, 10.0), cases.FX_CLIPPING: (1.0, 11.0),
+              cases.FX_ECHO: (0.0, 0.02), cases.FX_FEEDBACK: (0.0, 0.02)}[graph]
     for i in range(inst):
         v = lo + (hi - lo) * (i + 0.5) / inst
         refs[i].set_control(0, v)
@@ -146,7 +149,7 @@ def test_elementwise_effect_bank_vs_live_oracle(graph):
         if b == 2:
             refs[3].set_control(0, hi)
             bank.set_control(0, hi, 3)
-            if graph in (cases.FX_RM, cases.FX_TREMOLO):
+            if graph in (cases.FX_RM, cases.FX_TREMOLO, cases.FX_ECHO, cases.FX_FEEDBACK):
                 refs[1].set_control(1, 0.1)
                 bank.set_control(1, 0.1, 1)
         x = np.stack([cases.fx_input(ch, n, seed=10 * b + i) for i in range(inst)])          # [inst, ch, n]

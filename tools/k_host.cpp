@@ -51,6 +51,12 @@ namespace k_tremolo {
 namespace k_clipping {
 #include "Distortion/Clipping.k"
 }
+namespace k_echo {
+#include "Delay/Echo.k"
+}
+namespace k_feedback {
+#include "Delay/Feedback.k"
+}
 namespace k_breakpoint {
 #include "Subtractive/Breakpoint.k"
 }
@@ -75,6 +81,8 @@ KLANG_B200_EFFECT(k_pan::Pan, KB_FX_PAN)
 KLANG_B200_EFFECT(k_rm::RM, KB_FX_RM)
 KLANG_B200_EFFECT(k_tremolo::Tremolo, KB_FX_TREMOLO)
 KLANG_B200_EFFECT(k_clipping::Clipping, KB_FX_CLIPPING)
+KLANG_B200_EFFECT(k_echo::Echo, KB_FX_ECHO)
+KLANG_B200_EFFECT(k_feedback::Feedback, KB_FX_FEEDBACK)
 KLANG_B200_SYNTH(k_breakpoint::Breakpoint, KB_SY_BREAKPOINT)
 KLANG_B200_SYNTH(k_ramp::Ramp, KB_SY_RAMP)
 KLANG_B200_SYNTH(k_release::Release, KB_SY_RELEASE)
@@ -135,6 +143,8 @@ int main(int argc, char** argv) {
 		else if (prog == "rm") rc = run_effect<k_rm::RM>(fs, n, blocks, out);
 		else if (prog == "tremolo") rc = run_effect<k_tremolo::Tremolo>(fs, n, blocks, out);
 		else if (prog == "clipping") rc = run_effect<k_clipping::Clipping>(fs, n, blocks, out);
+		else if (prog == "echo") rc = run_effect<k_echo::Echo>(fs, n, blocks, out);
+		else if (prog == "feedback") rc = run_effect<k_feedback::Feedback>(fs, n, blocks, out);
 		else if (prog == "breakpoint") rc = run_synth<k_breakpoint::Breakpoint>(fs, n, blocks, out);
 		else if (prog == "ramp") rc = run_synth<k_ramp::Ramp>(fs, n, blocks, out);
 		else if (prog == "release") rc = run_synth<k_release::Release>(fs, n, blocks, out);
