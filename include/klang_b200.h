@@ -52,6 +52,8 @@ extern "C" {
 #define KB_SY_BREAKPOINT 6        /* examples/Subtractive/Breakpoint.k (Sine x attack / decay envelope; noteOff cuts the note) mono */
 #define KB_SY_RAMP 7              /* examples/Subtractive/Ramp.k       (Sine x one ramp) mono */
 #define KB_SY_RELEASE 8           /* examples/Subtractive/Release.k    (Sine x looped envelope with release()) mono */
+#define KB_SY_ADDITIVE_SAW 9      /* examples/Additive/Saw.k    (32 Sine partials summed in order) mono */
+#define KB_SY_ADDITIVE_SQUARE 10  /* examples/Additive/Square.k (odd partials below Nyquist) mono */
 
 /* process flags */
 #define KB_DEVICE_PTR 1u          /* `io` / `out` is device memory on the bank's device; the call is asynchronous on the bank stream */

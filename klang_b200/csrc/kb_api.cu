@@ -510,6 +510,7 @@ extern "C" kb_synth_bank* kb_synth_bank_create(int graph, int instances, int voi
 	case KB_SY_BREAKPOINT: b->ncontrols = 2; b->voice_bytes = sizeof(KbSenvVoice); break;
 	case KB_SY_RAMP: b->ncontrols = 1; b->voice_bytes = sizeof(KbSenvVoice); break;
 	case KB_SY_RELEASE: b->ncontrols = 4; b->voice_bytes = sizeof(KbSenvVoice); break;
+	case KB_SY_ADDITIVE_SAW: case KB_SY_ADDITIVE_SQUARE: b->ncontrols = 0; b->voice_bytes = sizeof(KbAddVoice); break;
 	}
 	for (int i = 0; i < instances; i++) {
 		KbControl* c = b->ctl(i);
@@ -548,6 +549,7 @@ extern "C" kb_synth_bank* kb_synth_bank_create(int graph, int instances, int voi
 		case KB_SY_SUPERSAW: kb_ssaw_construct(b->fs, b->vs<KbSsawVoice>(v)); break;
 		case KB_SY_FM: kb_fm_construct(b->fs, b->vs<KbFmVoice>(v)); break;
 		case KB_SY_BREAKPOINT: case KB_SY_RAMP: case KB_SY_RELEASE: kb_senv_construct(b->fs, graph, b->vs<KbSenvVoice>(v)); break;
+		case KB_SY_ADDITIVE_SAW: case KB_SY_ADDITIVE_SQUARE: kb_add_construct(graph, b->vs<KbAddVoice>(v)); break;
 		case KB_SY_TB303: kb_tb_construct(b->fs, b->vs<KbTbVoice>(v)); break;
 		case KB_SY_SYNTHX: kb_sx_construct(b->fs, b->vs<KbSxVoice>(v)); break;
 		}
@@ -618,6 +620,7 @@ static void sy_start(kb_synth_bank* b, int inst, int voice, float pitch, float v
 	case KB_SY_SUPERSAW: kb_ssaw_on(b->fs, c, b->vs<KbSsawVoice>(v), pitch); break;
 	case KB_SY_FM: kb_fm_on(b->fs, c, b->vs<KbFmVoice>(v), pitch); break;
 	case KB_SY_BREAKPOINT: case KB_SY_RAMP: case KB_SY_RELEASE: kb_senv_on(b->fs, b->graph, c, b->vs<KbSenvVoice>(v), pitch); break;
+	case KB_SY_ADDITIVE_SAW: case KB_SY_ADDITIVE_SQUARE: kb_add_on(b->fs, b->vs<KbAddVoice>(v), pitch); break;
 	case KB_SY_TB303: kb_tb_on(b->fs, c, b->vs<KbTbVoice>(v), pitch); break;
 	case KB_SY_SYNTHX: kb_sx_on(b->fs, c, b->vs<KbSxVoice>(v), pitch); break;
 	}
@@ -635,7 +638,8 @@ static void sy_release(kb_synth_bank* b, int inst, int voice) {
 	case KB_SY_SUPERSAW: kb_adsr_release(b->fs, b->vs<KbSsawVoice>(v).adsr); break;                          // SuperSaw.k:21-23
 	case KB_SY_FM: kb_adsr_release(b->fs, b->vs<KbFmVoice>(v).adsr); break;                                  // FM.k:56-58
 	case KB_SY_RELEASE: kb_env_release(b->fs, b->vs<KbSenvVoice>(v).env, b->ctl(inst)[3].value, 0.f); break;  // Release.k:21-24
-	case KB_SY_BREAKPOINT: case KB_SY_RAMP: h.stage = KB_NOTE_OFF; break;                                    // NoteBase::off default: stage = Off  klang.h:4237
+	case KB_SY_BREAKPOINT: case KB_SY_RAMP: case KB_SY_ADDITIVE_SAW: case KB_SY_ADDITIVE_SQUARE:
+		h.stage = KB_NOTE_OFF; break;                                                                        // NoteBase::off default: stage = Off  klang.h:4237
 	case KB_SY_TB303: kb_adsr_release(b->fs, b->vs<KbTbVoice>(v).adsr); break;                               // TB303.k:99-101
 	case KB_SY_SYNTHX: kb_adsr_release(b->fs, b->vs<KbSxVoice>(v).adsr); break;                              // SynTHX.k:163-165
 	}
@@ -756,6 +760,16 @@ extern "C" int kb_synth_bank_process(kb_synth_bank* b, float* out, int n, unsign
 				kb_voice_kernel<KB_SY_FM, KbFmVoice><<<blocks, 128, 0, st>>>((KbFmVoice*)b->d_vstate, b->d_hdr, b->d_blk, d_voice_dst, n, b->voices, total, b->fs); break;
 			case KB_SY_BREAKPOINT: case KB_SY_RAMP: case KB_SY_RELEASE:
 				kb_voice_kernel<KB_SY_BREAKPOINT, KbSenvVoice><<<blocks, 128, 0, st>>>((KbSenvVoice*)b->d_vstate, b->d_hdr, b->d_blk, d_voice_dst, n, b->voices, total, b->fs); break;
+			case KB_SY_ADDITIVE_SAW: case KB_SY_ADDITIVE_SQUARE:
+				if (flags & KB_LANE_PER_VOICE) {
+					kb_voice_kernel<KB_SY_ADDITIVE_SAW, KbAddVoice><<<blocks, 128, 0, st>>>((KbAddVoice*)b->d_vstate, b->d_hdr, b->d_blk, d_voice_dst, n, b->voices, total, b->fs);
+				} else {                                   // time-parallel: thread = (voice, sample), then the phase advance
+					dim3 grid((unsigned)std::max(1, std::min((n + 255) / 256, 16)), total);
+					kb_additive_kernel<<<grid, 256, 0, st>>>((const KbAddVoice*)b->d_vstate, b->d_hdr, d_voice_dst, n, b->fs);
+					kb_additive_advance_kernel<<<(total * 32 + 127) / 128, 128, 0, st>>>((KbAddVoice*)b->d_vstate, b->d_hdr, total, n, b->fs);
+					b->launches++;
+				}
+				break;
 			}
 		} else {
 			// voices per CTA: as many as still leave >= ~100 CTAs (the serial stages cost the same for any G), KB_TILE_G overrides

@@ -8,7 +8,7 @@
 #include "kb_prims.cuh"
 
 #include "../../include/klang_b200.h"   // graph ids KB_SY_* / KB_FX_*
-#define KB_SY_COUNT 9
+#define KB_SY_COUNT 11
 #define KB_FX_COUNT 11
 
 // =========================================================================================== HOST halves
@@ -103,6 +103,16 @@ inline void kb_senv_on(const KbFs& fs, int graph, const KbControl* c, KbSenvVoic
 		kb_env_set_points(fs, n.env, 3, pts);
 		kb_env_set_loop(n.env, 2, 2);
 	}
+}
+
+// ---- Additive/Saw.k, Additive/Square.k: on() only sets the 32 frequencies, the partials keep their phase from note to note (Saw.k:7-10, 25-27)
+inline void kb_add_construct(int graph, KbAddVoice& n) {
+	for (int o = 0; o < 32; o++) kb_fsine_init(n.osc[o]);
+	n.square = graph == KB_SY_ADDITIVE_SQUARE;
+}
+inline void kb_add_on(const KbFs& fs, KbAddVoice& n, float pitch) {
+	const float f = kb_pitch_to_frequency_host(pitch);
+	for (int o = 0; o < 32; o++) kb_fsine_set_f(fs, n.osc[o], f * (o + 1));
 }
 
 // ---- TB303 (examples/TB303.k:8-114)
@@ -351,6 +361,26 @@ KB_HD float kb_ew_sample(int graph, float c0, float c1, const KbFastSine& lfo, i
 	const float s = kb_fsine_value(lfo.position + t * (uint32_t)lfo.increment + lfo.offset);
 	const float mod = graph == KB_FX_RM ? s : s * c1 + (1 - c1);
 	return in * mod;
+}
+
+// Additive/Saw.k:12-16, Square.k:12-19: out = 0; out += osc[o] / (o + 1) in partial order; Square.k ticks only the odd harmonics whose
+// frequency lies below Nyquist.  kb_add_tick is the per-tick form, kb_add_at sample `t` of a block as a pure function of the block-start
+// phases (no value is carried from sample to sample: the voice is 32 integer phase ramps); kb_add_block_end leaves the voice as
+// `ticks` calls of kb_add_tick would.
+KB_HD bool kb_add_partial_on(const KbFs& fs, const KbAddVoice& n, int o) { return !n.square || (((o + 1) % 2) && n.osc[o].frequency < fs.nyquist); }
+KB_HD float kb_add_tick(const KbFs& fs, KbAddVoice& n) {
+	float out = 0;
+	for (int o = 0; o < 32; o++) if (kb_add_partial_on(fs, n, o)) out += kb_fsine_tick(n.osc[o]) / (o + 1);
+	return out;
+}
+KB_HD float kb_add_at(const KbFs& fs, const KbAddVoice& n, uint32_t t) {
+	float out = 0;
+	for (int o = 0; o < 32; o++)
+		if (kb_add_partial_on(fs, n, o)) out += kb_fsine_value(n.osc[o].position + t * (uint32_t)n.osc[o].increment + n.osc[o].offset) / (o + 1);
+	return out;
+}
+KB_HD void kb_add_block_end(const KbFs& fs, KbAddVoice& n, uint32_t ticks) {
+	for (int o = 0; o < 32; o++) if (kb_add_partial_on(fs, n, o)) n.osc[o].position += ticks * (uint32_t)n.osc[o].increment;
 }
 
 // The same sample as a pure function of the sample index: tick `t` of a block whose first tick finds the voice in state `n`.

@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(128) kb_voice_kernel(VOICE* __restrict__ voice
 				if constexpr (GRAPH == KB_SY_TB303) y = kb_tb_tick(fs, tb, s, stage);
 				if constexpr (GRAPH == KB_SY_FM) y = kb_fm_tick(fs, fm_i1, fm_i2, s, stage);
 				if constexpr (GRAPH == KB_SY_BREAKPOINT) y = kb_senv_tick(fs, s, stage);         // Breakpoint.k, Ramp.k and Release.k share the voice
+				if constexpr (GRAPH == KB_SY_ADDITIVE_SAW) y = kb_add_tick(fs, s);               // Additive/Saw.k and Square.k share the voice
 			}
 			tile[warp][lane][t] = y;
 		}
@@ -67,6 +68,24 @@ __global__ void __launch_bounds__(128) kb_voice_kernel(VOICE* __restrict__ voice
 		voices[v] = s;
 		hdr[v].stage = stage;
 	}
+}
+
+// Additive/Saw.k, Square.k, time-parallel: nothing in the voice is a recurrence (32 integer phase ramps), so thread = (voice, sample)
+// evaluates the whole partial sum of one sample from the block-start state (kb_add_at) and a second kernel advances the phases.
+// blockIdx.y = voice; the voice state is staged in shared memory.
+__global__ void __launch_bounds__(256) kb_additive_kernel(const KbAddVoice* __restrict__ voices, KbVoiceHdr* __restrict__ hdr, float* __restrict__ dst, int n, KbFs fs) {
+	__shared__ KbAddVoice s;
+	const int v = blockIdx.y;
+	const bool active = hdr[v].stage != KB_NOTE_OFF;
+	if (threadIdx.x == 0 && blockIdx.x == 0) hdr[v].active = active ? 1 : 0;
+	if (active) for (int w = threadIdx.x; w < (int)(sizeof(KbAddVoice) / 4); w += blockDim.x) reinterpret_cast<unsigned*>(&s)[w] = reinterpret_cast<const unsigned*>(voices + v)[w];
+	__syncthreads();
+	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) dst[(size_t)v * n + t] = active ? kb_add_at(fs, s, (uint32_t)t) : 0.f;
+}
+__global__ void kb_additive_advance_kernel(KbAddVoice* __restrict__ voices, const KbVoiceHdr* __restrict__ hdr, int total, int n, KbFs fs) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x, v = i >> 5, o = i & 31;
+	if (v >= total || hdr[v].stage == KB_NOTE_OFF) return;
+	if (kb_add_partial_on(fs, voices[v], o)) voices[v].osc[o].position += (uint32_t)n * (uint32_t)voices[v].osc[o].increment;
 }
 
 // Synth::process voice loop + mix (klang.h:4450-4456 / 4842-4848): thread = (instance, sample).  Voices are

@@ -75,6 +75,9 @@ struct KbFmVoice { KbFmOp op[3]; KbEnv adsr; };
 // examples/Subtractive/{Breakpoint,Ramp,Release}.k: a Fast::Sine times one breakpoint envelope
 struct KbSenvVoice { KbFastSine osc; KbEnv env; int stop_when_finished; };
 
+// examples/Additive/{Saw,Square}.k: 32 Fast::Sine partials
+struct KbAddVoice { KbFastSine osc[32]; int square; };
+
 // ------------------------------------------------------------------ effect instances (graphs)
 struct KbFxHdr { KbControl controls[KB_MAX_CONTROLS]; float cached[KB_MAX_CONTROLS]; };
 // examples/PingPong.k

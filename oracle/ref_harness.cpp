@@ -73,6 +73,12 @@ namespace k_tremolo {
 namespace k_clipping {
 #include "Distortion/Clipping.k"
 }
+namespace k_add_saw {
+#include "Additive/Saw.k"
+}
+namespace k_add_square {
+#include "Additive/Square.k"
+}
 namespace k_echo {
 #include "Delay/Echo.k"
 }
@@ -434,7 +440,7 @@ int ref_fx_process(void* h, float* l, float* r, int n) {
 }
 
 // ----------------------------------------------------------------------- synths
-enum { SY_SUBTRACTIVE = 0, SY_SUPERSAW = 1, SY_TB303 = 2, SY_SYNTHX = 3, SY_FILTER_K = 4, SY_FM = 5, SY_BREAKPOINT = 6, SY_RAMP = 7, SY_RELEASE = 8 };
+enum { SY_SUBTRACTIVE = 0, SY_SUPERSAW = 1, SY_TB303 = 2, SY_SYNTHX = 3, SY_FILTER_K = 4, SY_FM = 5, SY_BREAKPOINT = 6, SY_RAMP = 7, SY_RELEASE = 8, SY_ADDITIVE_SAW = 9, SY_ADDITIVE_SQUARE = 10 };
 
 struct RefSynth {
 	int graph;
@@ -469,6 +475,8 @@ void* ref_synth_create(int graph, int nvoices) {
 	case SY_BREAKPOINT:  { auto* p = make_synth<k_breakpoint::Breakpoint, k_breakpoint::Breakpoint::BreakpointNote>(nvoices); s->mono = p; s->controls = &p->controls; } break;
 	case SY_RAMP:        { auto* p = make_synth<k_ramp::Ramp, k_ramp::Ramp::RampNote>(nvoices); s->mono = p; s->controls = &p->controls; } break;
 	case SY_RELEASE:     { auto* p = make_synth<k_release::Release, k_release::Release::ReleaseNote>(nvoices); s->mono = p; s->controls = &p->controls; } break;
+	case SY_ADDITIVE_SAW:    { auto* p = make_synth<k_add_saw::Saw, k_add_saw::Saw::SawNote>(nvoices); s->mono = p; s->controls = &p->controls; } break;
+	case SY_ADDITIVE_SQUARE: { auto* p = make_synth<k_add_square::Square, k_add_square::Square::SquareNote>(nvoices); s->mono = p; s->controls = &p->controls; } break;
 	default: delete s; return nullptr;
 	}
 	s->nvoices = s->mono ? (int)s->mono->notes.count : (int)s->stereo->notes.count;

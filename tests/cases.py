@@ -20,14 +20,14 @@ import numpy as np
  FLT_BIQUAD_BPF, FLT_BIQUAD_BRF, FLT_BIQUAD_APF, FLT_BUTTERWORTH_LPF1, FLT_BUTTERWORTH_LPF2,
  FLT_DCF, FLT_IIR1, FLT_IIR2, FLT_MODAL, FLT_FOLLOWER_PEAK, FLT_FOLLOWER_RMS, FLT_WINDOW_MEAN, FLT_WINDOW_RMS) = range(17)
 FX_GAIN, FX_PINGPONG, FX_REVERB, FX_DELAY_PINGPONG, FX_DELAY_REVERB, FX_PAN, FX_RM, FX_TREMOLO, FX_CLIPPING, FX_ECHO, FX_FEEDBACK = range(11)
-SY_SUBTRACTIVE, SY_SUPERSAW, SY_TB303, SY_SYNTHX, SY_FILTER_K, SY_FM, SY_BREAKPOINT, SY_RAMP, SY_RELEASE = range(9)
+SY_SUBTRACTIVE, SY_SUPERSAW, SY_TB303, SY_SYNTHX, SY_FILTER_K, SY_FM, SY_BREAKPOINT, SY_RAMP, SY_RELEASE, SY_ADDITIVE_SAW, SY_ADDITIVE_SQUARE = range(11)
 
 FX_NAMES = {FX_GAIN: "gain", FX_PINGPONG: "pingpong", FX_REVERB: "reverb",
             FX_DELAY_PINGPONG: "delay_pingpong", FX_DELAY_REVERB: "delay_reverb", FX_PAN: "pan", FX_RM: "rm", FX_TREMOLO: "tremolo",
             FX_CLIPPING: "clipping", FX_ECHO: "echo", FX_FEEDBACK: "feedback"}
 SY_NAMES = {SY_SUBTRACTIVE: "subtractive", SY_SUPERSAW: "supersaw", SY_TB303: "tb303",
             SY_SYNTHX: "synthx", SY_FILTER_K: "filter_k", SY_FM: "fm", SY_BREAKPOINT: "breakpoint", SY_RAMP: "ramp",
-            SY_RELEASE: "release"}
+            SY_RELEASE: "release", SY_ADDITIVE_SAW: "additive_saw", SY_ADDITIVE_SQUARE: "additive_square"}
 
 
 def noise(n, seed=1, lo=-1.0, hi=1.0):
@@ -264,6 +264,9 @@ SYNTH_SCRIPTS_LATE = {
     "ramp": (SY_RAMP, 32, 6, 12, 512, 8, [(0, 0, 0.1)]),
     "release": (SY_RELEASE, 32, 10, 10, 512, 2, [(0, 3, 0.03)]),
     "release_slow_attack": (SY_RELEASE, 32, 5, 8, 512, 1, [(0, 0, 0.02), (0, 1, 0.01), (0, 2, 0.6), (0, 3, 0.01)]),
+    # Additive/Saw.k, Additive/Square.k: 32 Fast::Sine partials summed in order (Square.k: odd harmonics below Nyquist only)
+    "additive_saw": (SY_ADDITIVE_SAW, 32, 10, 5, 512, 2, []),
+    "additive_square": (SY_ADDITIVE_SQUARE, 32, 10, 5, 512, 2, []),
 }
 
 

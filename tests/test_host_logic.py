@@ -260,3 +260,33 @@ def test_one_delay_effects_match_reference_golden_on_host():
             assert np.array_equal(got.view(np.uint32), g[f"fx/{name}"].view(np.uint32)), (fs, name)
             checked += 1
     assert checked == 6
+
+
+def test_additive_voices_match_oracle_and_time_parallel_form_on_host():
+    """Additive/Saw.k / Square.k: per-tick form == time-parallel form (samples and state, checked inside the program) == the oracle port,
+    bit for bit, across a re-trigger that keeps the partial phases and a pitch whose upper partials cross Nyquist."""
+    import sys
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import oracle
+    exe = os.path.join(tempfile.mkdtemp(prefix="kb_host_"), "add_check")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-x", "c++",
+                           os.path.join(ROOT, "tests", "host", "add_check.cpp"), "-o", exe])
+    out = subprocess.run([exe], capture_output=True)
+    assert out.returncode == 0, "per-tick and time-parallel forms differ"
+    got = np.frombuffer(out.stdout, np.float32)
+
+    def port(graph, fs):
+        oracle.port.set_fs(fs)
+        oracle.port.srand(1)
+        sy = oracle.port.Synth(graph, 32)
+        sy.voice_start(0, 57, 0.8)
+        a = sy.process_voices(830)[0][0, 0]
+        sy.voice_start(0, 88, 0.8)
+        b = sy.process_voices(2170)[0][0, 0]
+        sy.close()
+        return np.concatenate([a, b])
+
+    want = np.concatenate([port(oracle.SY_ADDITIVE_SAW, 48000.0), port(oracle.SY_ADDITIVE_SQUARE, 44100.0)])
+    assert len(got) == len(want) and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert np.abs(want).max() > 0.5

@@ -108,9 +108,9 @@ def test_sine_envelope_synths_match_reference_golden(golden, fs, name):
     _exact(np.ascontiguousarray(r["out"]), golden[fs][f"synth/{name}/mix"], f"synth/{name}/mix")
 
 
-@pytest.mark.parametrize("prog", ["breakpoint", "ramp", "release", "pan", "rm", "tremolo", "clipping", "echo", "feedback"])
+@pytest.mark.parametrize("prog", ["breakpoint", "ramp", "release", "pan", "rm", "tremolo", "clipping", "echo", "feedback", "additive_saw", "additive_square"])
 def test_late_k_programs_run_unmodified_on_the_device(prog, tmp_path):
-    """examples/Subtractive/{Breakpoint,Ramp,Release}.k, Gain/{Pan,RM,Tremolo}.k, Distortion/Clipping.k and Delay/{Echo,Feedback}.k compiled UNMODIFIED against
+    """examples/Subtractive/{Breakpoint,Ramp,Release}.k, Gain/{Pan,RM,Tremolo}.k, Distortion/Clipping.k, Delay/{Echo,Feedback}.k and Additive/{Saw,Square}.k compiled UNMODIFIED against
     include/compat/klang.h (tools/k_host.cpp) and run on the device through the host program: bit-identical to the oracle run with
     the same script."""
     from test_k_programs import run_k_program_on_device
@@ -159,3 +159,28 @@ def test_late_effect_bank_vs_live_oracle(graph):
     bank.close()
     for r in refs:
         r.close()
+
+
+@pytest.mark.parametrize("graph", [cases.SY_ADDITIVE_SAW, cases.SY_ADDITIVE_SQUARE])
+def test_additive_time_parallel_kernel_equals_lane_per_voice_kernel(graph):
+    """Additive/Saw.k / Square.k: kb_additive_kernel (thread = (voice, sample), the default) against the lane-per-voice kernel
+    (KB_LANE_PER_VOICE), bit for bit over ragged blocks with re-triggers (the partials keep their phase) and cut notes; 3 x 21 voices."""
+    inst, voices, fs = 3, 21, 48000.0
+    outs = []
+    for flag in (kb.LANE_PER_VOICE, 0):
+        bank = kb.SynthBank(graph, inst, voices, fs, 1024)
+        res = []
+        for b, n in enumerate((1024, 117, 1, 700, 1024)):
+            for g in range(inst * bank.voices):
+                if b == g % 3:
+                    bank.voice_start(g % bank.voices, 30 + (7 * g) % 70, 0.8, g // bank.voices)
+                if b == 2 + g % 2 and g % 4 == 0:
+                    bank.voice_release(g % bank.voices, 0.0, g // bank.voices)
+                if b == 3 and g % 5 == 0:
+                    bank.voice_start(g % bank.voices, 90 - g % 40, 0.5, g // bank.voices)
+            res.append(bank.process_block(n, kb.PER_VOICE | flag))
+        res.append(bank.process_block(512, kb.PER_VOICE | flag))
+        bank.close()
+        outs.append(np.concatenate(res, axis=-1))
+    _exact(np.ascontiguousarray(outs[1]), np.ascontiguousarray(outs[0]), f"additive graph {graph}")
+    assert np.abs(outs[0]).max() > 0.5

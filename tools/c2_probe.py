@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import klang_b200 as kb
 
-graph = {"sub": kb.SY_SUBTRACTIVE, "ssaw": kb.SY_SUPERSAW, "tb": kb.SY_TB303, "sx": kb.SY_SYNTHX, "fm": kb.SY_FM}[sys.argv[1] if len(sys.argv) > 1 else "sub"]
+graph = {"sub": kb.SY_SUBTRACTIVE, "ssaw": kb.SY_SUPERSAW, "tb": kb.SY_TB303, "sx": kb.SY_SYNTHX, "fm": kb.SY_FM, "add": kb.SY_ADDITIVE_SAW, "senv": kb.SY_RELEASE}[sys.argv[1] if len(sys.argv) > 1 else "sub"]
 inst, voices = (8, 128) if graph != kb.SY_SUPERSAW else (8, 32)
 if len(sys.argv) > 3:
     inst, voices = int(sys.argv[2]), int(sys.argv[3])

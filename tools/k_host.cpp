@@ -57,6 +57,12 @@ namespace k_echo {
 namespace k_feedback {
 #include "Delay/Feedback.k"
 }
+namespace k_add_saw {
+#include "Additive/Saw.k"
+}
+namespace k_add_square {
+#include "Additive/Square.k"
+}
 namespace k_breakpoint {
 #include "Subtractive/Breakpoint.k"
 }
@@ -83,6 +89,8 @@ KLANG_B200_EFFECT(k_tremolo::Tremolo, KB_FX_TREMOLO)
 KLANG_B200_EFFECT(k_clipping::Clipping, KB_FX_CLIPPING)
 KLANG_B200_EFFECT(k_echo::Echo, KB_FX_ECHO)
 KLANG_B200_EFFECT(k_feedback::Feedback, KB_FX_FEEDBACK)
+KLANG_B200_SYNTH(k_add_saw::Saw, KB_SY_ADDITIVE_SAW)
+KLANG_B200_SYNTH(k_add_square::Square, KB_SY_ADDITIVE_SQUARE)
 KLANG_B200_SYNTH(k_breakpoint::Breakpoint, KB_SY_BREAKPOINT)
 KLANG_B200_SYNTH(k_ramp::Ramp, KB_SY_RAMP)
 KLANG_B200_SYNTH(k_release::Release, KB_SY_RELEASE)
@@ -145,6 +153,8 @@ int main(int argc, char** argv) {
 		else if (prog == "clipping") rc = run_effect<k_clipping::Clipping>(fs, n, blocks, out);
 		else if (prog == "echo") rc = run_effect<k_echo::Echo>(fs, n, blocks, out);
 		else if (prog == "feedback") rc = run_effect<k_feedback::Feedback>(fs, n, blocks, out);
+		else if (prog == "additive_saw") rc = run_synth<k_add_saw::Saw>(fs, n, blocks, out);
+		else if (prog == "additive_square") rc = run_synth<k_add_square::Square>(fs, n, blocks, out);
 		else if (prog == "breakpoint") rc = run_synth<k_breakpoint::Breakpoint>(fs, n, blocks, out);
 		else if (prog == "ramp") rc = run_synth<k_ramp::Ramp>(fs, n, blocks, out);
 		else if (prog == "release") rc = run_synth<k_release::Release>(fs, n, blocks, out);
