@@ -54,6 +54,9 @@ extern "C" {
 #define KB_SY_RELEASE 8           /* examples/Subtractive/Release.k    (Sine x looped envelope with release()) mono */
 #define KB_SY_ADDITIVE_SAW 9      /* examples/Additive/Saw.k    (32 Sine partials summed in order) mono */
 #define KB_SY_ADDITIVE_SQUARE 10  /* examples/Additive/Square.k (odd partials below Nyquist) mono */
+#define KB_SY_AM 11               /* examples/Modulation/AM.k  (sine carrier x sine modulator, ADSR) mono */
+#define KB_SY_MOD_FM 12           /* examples/Modulation/FM.k  (carrier frequency set every sample from a sine modulator) mono */
+#define KB_SY_MOD_FM2 13          /* examples/Modulation/FM2.k (two modulators in series) mono */
 
 /* process flags */
 #define KB_DEVICE_PTR 1u          /* `io` / `out` is device memory on the bank's device; the call is asynchronous on the bank stream */

@@ -8,7 +8,7 @@
 #include "kb_prims.cuh"
 
 #include "../../include/klang_b200.h"   // graph ids KB_SY_* / KB_FX_*
-#define KB_SY_COUNT 11
+#define KB_SY_COUNT 14
 #define KB_FX_COUNT 11
 
 // =========================================================================================== HOST halves
@@ -113,6 +113,26 @@ inline void kb_add_construct(int graph, KbAddVoice& n) {
 inline void kb_add_on(const KbFs& fs, KbAddVoice& n, float pitch) {
 	const float f = kb_pitch_to_frequency_host(pitch);
 	for (int o = 0; o < 32; o++) kb_fsine_set_f(fs, n.osc[o], f * (o + 1));
+}
+
+// ---- Modulation/AM.k:12-15, Modulation/FM.k:13-18, Modulation/FM2.k:13-19
+KB_HD void kb_fsine_reset(KbFastSine& o) { o.position = 0u; o.offset = 0u; }   // Fast::Sine::reset (klang.h:5136-5140): set(frequency, 0) finds the frequency unchanged
+inline void kb_smod_construct(const KbFs& fs, int graph, KbSmodVoice& n) {
+	kb_fsine_init(n.carrier); kb_fsine_init(n.mod1); kb_fsine_init(n.mod2);
+	kb_adsr_construct(fs, n.adsr);
+	n.f0 = 0.f; n.graph = graph;
+}
+inline void kb_smod_on(const KbFs& fs, KbSmodVoice& n, float pitch) {
+	const float f = kb_pitch_to_frequency_host(pitch);
+	if (n.graph == KB_SY_AM) {                                 // the modulator keeps phase and frequency from the last note
+		kb_fsine_set_fp(fs, n.carrier, f, 0.f);
+		kb_adsr_set(fs, n.adsr, 0.f, .1f, 0.1f, 0.25f);
+	} else {
+		n.f0 = f;
+		kb_fsine_reset(n.carrier); kb_fsine_reset(n.mod1);
+		if (n.graph == KB_SY_MOD_FM2) kb_fsine_reset(n.mod2);
+		if (n.graph == KB_SY_MOD_FM) kb_adsr_set(fs, n.adsr, 0.001f, 0.f, 1.f, 0.25f); else kb_adsr_set(fs, n.adsr, 0.5f, 0.f, 1.f, 0.25f);
+	}
 }
 
 // ---- TB303 (examples/TB303.k:8-114)
@@ -361,6 +381,35 @@ KB_HD float kb_ew_sample(int graph, float c0, float c1, const KbFastSine& lfo, i
 	const float s = kb_fsine_value(lfo.position + t * (uint32_t)lfo.increment + lfo.offset);
 	const float mod = graph == KB_FX_RM ? s : s * c1 + (1 - c1);
 	return in * mod;
+}
+
+// Modulation/AM.k:22-30, FM.k:25-32, FM2.k:26-36: `modulator(rate)` / `carrier(f0 + mod)` = Fast::Sine::set(f) (recomputes the integer
+// increment whenever f differs from the cached frequency) followed by one tick; c0..c2 = controls[0..2]
+KB_HD float kb_smod_tick(const KbFs& fs, float c0, float c1, float c2, KbSmodVoice& n, int& note_stage) {
+	float out;
+	if (n.graph == KB_SY_AM) {
+		const float mod_rate = c0 * n.carrier.frequency, mod_depth = c1;
+		kb_fsine_set_f(fs, n.mod1, mod_rate);
+		const float mod = kb_fsine_tick(n.mod1) * mod_depth + (1 - mod_depth);
+		out = kb_fsine_tick(n.carrier) * mod;
+		out = out * kb_env_tick(fs, n.adsr);
+	} else if (n.graph == KB_SY_MOD_FM) {
+		const float mod_rate = c0 * n.f0, mod_depth = c1 * n.f0;
+		kb_fsine_set_f(fs, n.mod1, mod_rate);
+		const float mod = kb_fsine_tick(n.mod1) * mod_depth;
+		kb_fsine_set_f(fs, n.carrier, n.f0 + mod);
+		out = kb_fsine_tick(n.carrier) * kb_env_tick(fs, n.adsr);
+	} else {
+		const float mod_rate = c0 * n.f0, d1 = c1 * n.f0, d2 = c2 * n.f0;
+		kb_fsine_set_f(fs, n.mod1, mod_rate);
+		const float mod1 = kb_fsine_tick(n.mod1) * d1;
+		kb_fsine_set_f(fs, n.mod2, n.f0 + mod1);
+		const float mod2 = kb_fsine_tick(n.mod2) * d2;
+		kb_fsine_set_f(fs, n.carrier, n.f0 + mod2);
+		out = kb_fsine_tick(n.carrier) * kb_env_tick(fs, n.adsr);
+	}
+	if (n.adsr.stage == KB_ENV_OFF) note_stage = KB_NOTE_OFF;
+	return out;
 }
 
 // Additive/Saw.k:12-16, Square.k:12-19: out = 0; out += osc[o] / (o + 1) in partial order; Square.k ticks only the odd harmonics whose

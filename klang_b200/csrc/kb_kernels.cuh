@@ -13,7 +13,8 @@
 #include "kb_fx_parallel.cuh"
 
 // per-instance, per-block constants computed by the host at control rate (see kb_graphs.cuh)
-struct KbSynthBlock { KbTbBlock tb; float sx_tr_at, sx_dt_at; float fm_i1, fm_i2; /* FM.k:63-64: controls[1], controls[2] */ };
+struct KbSynthBlock { KbTbBlock tb; float sx_tr_at, sx_dt_at; float fm_i1, fm_i2; /* FM.k:63-64: controls[1], controls[2] */
+                      float c[3]; /* Modulation/{AM,FM,FM2}.k: controls[0..2] */ };
 
 // ============================================================================================ synth voices
 // One lane = one voice (Note::process(buffer), klang.h:4295-4303): the lane runs the block's n-step recurrence
@@ -39,11 +40,12 @@ __global__ void __launch_bounds__(128) kb_voice_kernel(VOICE* __restrict__ voice
 	}
 	VOICE s;
 	KbTbBlock tb;
-	float fm_i1 = 0.f, fm_i2 = 0.f;
+	float fm_i1 = 0.f, fm_i2 = 0.f, sm_c2 = 0.f;
 	if (active) {
 		s = voices[v];
 		if (GRAPH == KB_SY_TB303) tb = blk[v / voices_per_inst].tb;
 		if (GRAPH == KB_SY_FM) { fm_i1 = blk[v / voices_per_inst].fm_i1; fm_i2 = blk[v / voices_per_inst].fm_i2; }
+		if (GRAPH == KB_SY_AM) { fm_i1 = blk[v / voices_per_inst].c[0]; fm_i2 = blk[v / voices_per_inst].c[1]; sm_c2 = blk[v / voices_per_inst].c[2]; }
 	}
 	for (int base = 0; base < n; base += 32) {
 		const int steps = min(32, n - base);
@@ -56,6 +58,7 @@ __global__ void __launch_bounds__(128) kb_voice_kernel(VOICE* __restrict__ voice
 				if constexpr (GRAPH == KB_SY_FM) y = kb_fm_tick(fs, fm_i1, fm_i2, s, stage);
 				if constexpr (GRAPH == KB_SY_BREAKPOINT) y = kb_senv_tick(fs, s, stage);         // Breakpoint.k, Ramp.k and Release.k share the voice
 				if constexpr (GRAPH == KB_SY_ADDITIVE_SAW) y = kb_add_tick(fs, s);               // Additive/Saw.k and Square.k share the voice
+				if constexpr (GRAPH == KB_SY_AM) y = kb_smod_tick(fs, fm_i1, fm_i2, sm_c2, s, stage);   // Modulation/AM.k, FM.k and FM2.k share the voice
 			}
 			tile[warp][lane][t] = y;
 		}

@@ -78,6 +78,9 @@ struct KbSenvVoice { KbFastSine osc; KbEnv env; int stop_when_finished; };
 // examples/Additive/{Saw,Square}.k: 32 Fast::Sine partials
 struct KbAddVoice { KbFastSine osc[32]; int square; };
 
+// examples/Modulation/{AM,FM,FM2}.k: sine carrier, one or two sine modulators, ADSR
+struct KbSmodVoice { KbFastSine carrier, mod1, mod2; KbEnv adsr; float f0; int graph; };
+
 // ------------------------------------------------------------------ effect instances (graphs)
 struct KbFxHdr { KbControl controls[KB_MAX_CONTROLS]; float cached[KB_MAX_CONTROLS]; };
 // examples/PingPong.k

@@ -290,3 +290,36 @@ def test_additive_voices_match_oracle_and_time_parallel_form_on_host():
     want = np.concatenate([port(oracle.SY_ADDITIVE_SAW, 48000.0), port(oracle.SY_ADDITIVE_SQUARE, 44100.0)])
     assert len(got) == len(want) and np.array_equal(got.view(np.uint32), want.view(np.uint32))
     assert np.abs(want).max() > 0.5
+
+
+def test_sine_modulation_voices_match_oracle_on_host():
+    """Modulation/AM.k, FM.k, FM2.k: the product's voice functions (kb_smod_on / kb_smod_tick) compiled with g++ equal the oracle port bit
+    for bit — frequencies set every sample (negative ones included), release, and a second note on the same voice."""
+    import sys
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import oracle
+    exe = os.path.join(tempfile.mkdtemp(prefix="kb_host_"), "smod_check")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-x", "c++",
+                           os.path.join(ROOT, "tests", "host", "smod_check.cpp"), "-o", exe])
+    got = np.frombuffer(subprocess.run([exe], capture_output=True).stdout, np.float32)
+
+    def port(graph, fs, ctl):
+        oracle.port.set_fs(fs)
+        oracle.port.srand(1)
+        sy = oracle.port.Synth(graph, 32)
+        for i, v in enumerate(ctl):
+            sy.set_control(i, v)
+        sy.voice_start(0, 60, 0.8)
+        a = sy.process_voices(1500)[0][0, 0]
+        sy.voice_release(0, 0.0)
+        b = sy.process_voices(600)[0][0, 0]
+        sy.voice_start(0, 67, 0.8)
+        c = sy.process_voices(1900)[0][0, 0]
+        sy.close()
+        return np.concatenate([a, b, c])
+
+    want = np.concatenate([port(oracle.SY_AM, 48000.0, (2.2, 0.9)), port(oracle.SY_MOD_FM, 44100.0, (1.5, 7.0)),
+                           port(oracle.SY_MOD_FM2, 48000.0, (3.0, 10.0, 6.791))])
+    assert len(got) == len(want) and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert np.abs(want[:4000]).max() > 0.3 and np.abs(want[4000:8000]).max() > 0.3 and np.abs(want[8000:]).max() > 0.01

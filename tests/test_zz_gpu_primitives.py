@@ -96,7 +96,8 @@ def test_device_window_follower_matches_reference_golden(golden, fs):
 
 
 # ---- examples/Subtractive/{Breakpoint,Ramp,Release}.k: KB_SY_BREAKPOINT / KB_SY_RAMP / KB_SY_RELEASE (a Fast::Sine times one envelope) on the
-# lane-per-voice kernel; the voice functions are proven against the oracle with g++ (tests/host/senv_check.cpp)
+# lane-per-voice kernel; the voice functions are proven against the oracle with g++ (tests/host/senv_check.cpp).  Likewise Additive/{Saw,Square}.k
+# (tests/host/add_check.cpp) and Modulation/{AM,FM,FM2}.k (tests/host/smod_check.cpp): every script of cases.SYNTH_SCRIPTS_LATE.
 @pytest.mark.parametrize("fs", [44100, 48000])
 @pytest.mark.parametrize("name", list(cases.SYNTH_SCRIPTS_LATE))
 def test_sine_envelope_synths_match_reference_golden(golden, fs, name):
@@ -108,9 +109,9 @@ def test_sine_envelope_synths_match_reference_golden(golden, fs, name):
     _exact(np.ascontiguousarray(r["out"]), golden[fs][f"synth/{name}/mix"], f"synth/{name}/mix")
 
 
-@pytest.mark.parametrize("prog", ["breakpoint", "ramp", "release", "pan", "rm", "tremolo", "clipping", "echo", "feedback", "additive_saw", "additive_square"])
+@pytest.mark.parametrize("prog", ["breakpoint", "ramp", "release", "pan", "rm", "tremolo", "clipping", "echo", "feedback", "additive_saw", "additive_square", "am", "mod_fm", "mod_fm2"])
 def test_late_k_programs_run_unmodified_on_the_device(prog, tmp_path):
-    """examples/Subtractive/{Breakpoint,Ramp,Release}.k, Gain/{Pan,RM,Tremolo}.k, Distortion/Clipping.k, Delay/{Echo,Feedback}.k and Additive/{Saw,Square}.k compiled UNMODIFIED against
+    """examples/Subtractive/{Breakpoint,Ramp,Release}.k, Gain/{Pan,RM,Tremolo}.k, Distortion/Clipping.k, Delay/{Echo,Feedback}.k Additive/{Saw,Square}.k and Modulation/{AM,FM,FM2}.k compiled UNMODIFIED against
     include/compat/klang.h (tools/k_host.cpp) and run on the device through the host program: bit-identical to the oracle run with
     the same script."""
     from test_k_programs import run_k_program_on_device

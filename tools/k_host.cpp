@@ -63,6 +63,15 @@ namespace k_add_saw {
 namespace k_add_square {
 #include "Additive/Square.k"
 }
+namespace k_am {
+#include "Modulation/AM.k"
+}
+namespace k_mod_fm {
+#include "Modulation/FM.k"
+}
+namespace k_mod_fm2 {
+#include "Modulation/FM2.k"
+}
 namespace k_breakpoint {
 #include "Subtractive/Breakpoint.k"
 }
@@ -91,6 +100,9 @@ KLANG_B200_EFFECT(k_echo::Echo, KB_FX_ECHO)
 KLANG_B200_EFFECT(k_feedback::Feedback, KB_FX_FEEDBACK)
 KLANG_B200_SYNTH(k_add_saw::Saw, KB_SY_ADDITIVE_SAW)
 KLANG_B200_SYNTH(k_add_square::Square, KB_SY_ADDITIVE_SQUARE)
+KLANG_B200_SYNTH(k_am::AM, KB_SY_AM)
+KLANG_B200_SYNTH(k_mod_fm::FM, KB_SY_MOD_FM)
+KLANG_B200_SYNTH(k_mod_fm2::FM2, KB_SY_MOD_FM2)
 KLANG_B200_SYNTH(k_breakpoint::Breakpoint, KB_SY_BREAKPOINT)
 KLANG_B200_SYNTH(k_ramp::Ramp, KB_SY_RAMP)
 KLANG_B200_SYNTH(k_release::Release, KB_SY_RELEASE)
@@ -155,6 +167,9 @@ int main(int argc, char** argv) {
 		else if (prog == "feedback") rc = run_effect<k_feedback::Feedback>(fs, n, blocks, out);
 		else if (prog == "additive_saw") rc = run_synth<k_add_saw::Saw>(fs, n, blocks, out);
 		else if (prog == "additive_square") rc = run_synth<k_add_square::Square>(fs, n, blocks, out);
+		else if (prog == "am") rc = run_synth<k_am::AM>(fs, n, blocks, out);
+		else if (prog == "mod_fm") rc = run_synth<k_mod_fm::FM>(fs, n, blocks, out);
+		else if (prog == "mod_fm2") rc = run_synth<k_mod_fm2::FM2>(fs, n, blocks, out);
 		else if (prog == "breakpoint") rc = run_synth<k_breakpoint::Breakpoint>(fs, n, blocks, out);
 		else if (prog == "ramp") rc = run_synth<k_ramp::Ramp>(fs, n, blocks, out);
 		else if (prog == "release") rc = run_synth<k_release::Release>(fs, n, blocks, out);
