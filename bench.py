@@ -759,19 +759,21 @@ def extras(kb, torch, dev, stream, flush_l2, hbm_peak, peak_src, device_index, w
             streaming_line(name, graph, inst, 1 << 20)
         except Exception as e:
             res[name] = {"error": repr(e)}
-    # Additive/Saw.k (32 sine partials per voice, no recurrence at all): time-parallel kernel, with the lane-per-voice A/B
-    try:
-        sb = kb.SynthBank(kb.SY_ADDITIVE_SAW, 8, 128, FS, 4096, device_index)
-        sb.set_stream(stream.cuda_stream)
-        for g in range(1024):
-            sb.voice_start(g % 128, 36 + (5 * g) % 36, voice_velocity(g), g // 128)
-        out = torch.empty(sb.out_shape(4096), dtype=torch.float32, device=dev)
-        ms = time_steps(lambda: sb.process_into(out, 4096), 3, warmup=3)
-        res["additive_saw_k_1024"] = {"voice_samples_per_s": 1024 * 4096 / (ms * 1e-3), "ms_per_step": ms, "block": 4096,
-                                      "ms_per_step_lane_per_voice_schedule": time_steps(lambda: sb.process_into(out, 4096, kb.LANE_PER_VOICE), 1, warmup=1)}
-        sb.close()
-    except Exception as e:
-        res["additive_saw_k_1024"] = {"error": repr(e)}
+    # Additive/Saw.k (32 sine partials per voice, no recurrence at all), Subtractive/Release.k and Modulation/AM.k (one envelope x closed-form
+    # sines): time-parallel kernels, each with the lane-per-voice A/B
+    for name, graph in (("additive_saw_k_1024", kb.SY_ADDITIVE_SAW), ("release_k_1024", kb.SY_RELEASE), ("am_k_1024", kb.SY_AM)):
+        try:
+            sb = kb.SynthBank(graph, 8, 128, FS, 4096, device_index)
+            sb.set_stream(stream.cuda_stream)
+            for g in range(1024):
+                sb.voice_start(g % 128, 36 + (5 * g) % 36, voice_velocity(g), g // 128)
+            out = torch.empty(sb.out_shape(4096), dtype=torch.float32, device=dev)
+            ms = time_steps(lambda: sb.process_into(out, 4096), 3, warmup=3)
+            res[name] = {"voice_samples_per_s": 1024 * 4096 / (ms * 1e-3), "ms_per_step": ms, "block": 4096,
+                         "ms_per_step_lane_per_voice_schedule": time_steps(lambda: sb.process_into(out, 4096, kb.LANE_PER_VOICE), 1, warmup=1)}
+            sb.close()
+        except Exception as e:
+            res[name] = {"error": repr(e)}
     return res
 
 

@@ -482,6 +482,7 @@ static int sy_upload(kb_synth_bank* b) {
 			if (b->graph == KB_SY_SYNTHX) { k.sx_tr_at = kb_sx_tr_at(b->ctl(i)[2].value); k.sx_dt_at = kb_sx_dt_at(b->ctl(i)[1].value); }
 			if (b->graph == KB_SY_FM) { k.fm_i1 = b->ctl(i)[1].value; k.fm_i2 = b->ctl(i)[2].value; }
 			if (b->graph >= KB_SY_AM && b->graph <= KB_SY_MOD_FM2) for (int c = 0; c < 3; c++) k.c[c] = b->ctl(i)[c].value;
+			else k.c[0] = k.c[1] = k.c[2] = 0.f;
 		}
 		KB_CUDA(cudaMemcpyAsync(b->d_blk, b->blk.data(), b->blk.size() * sizeof(KbSynthBlock), cudaMemcpyHostToDevice, b->stream));
 		KB_CUDA(cudaStreamSynchronize(b->stream));      // blk is pageable and may be rewritten by the next control change
@@ -767,9 +768,22 @@ extern "C" int kb_synth_bank_process(kb_synth_bank* b, float* out, int n, unsign
 				kb_voice_kernel<KB_SY_TB303, KbTbVoice><<<blocks, 128, 0, st>>>((KbTbVoice*)b->d_vstate, b->d_hdr, b->d_blk, d_voice_dst, n, b->voices, total, b->fs); break;
 			case KB_SY_FM:
 				kb_voice_kernel<KB_SY_FM, KbFmVoice><<<blocks, 128, 0, st>>>((KbFmVoice*)b->d_vstate, b->d_hdr, b->d_blk, d_voice_dst, n, b->voices, total, b->fs); break;
-			case KB_SY_BREAKPOINT: case KB_SY_RAMP: case KB_SY_RELEASE:
-				kb_voice_kernel<KB_SY_BREAKPOINT, KbSenvVoice><<<blocks, 128, 0, st>>>((KbSenvVoice*)b->d_vstate, b->d_hdr, b->d_blk, d_voice_dst, n, b->voices, total, b->fs); break;
-			case KB_SY_AM: case KB_SY_MOD_FM: case KB_SY_MOD_FM2:
+#define KB_LAUNCH_ESINE(VOICE)                                                                                                       \
+	do {                                                                                                                             \
+		static bool attr_set = false;                                                                                                \
+		if (!attr_set) { cudaFuncSetAttribute(kb_esine_tiled_kernel<VOICE, 8, 544>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KbEsSmem<VOICE, 8>)); attr_set = true; } \
+		kb_esine_tiled_kernel<VOICE, 8, 544><<<(total + 7) / 8, 544, sizeof(KbEsSmem<VOICE, 8>), st>>>((VOICE*)b->d_vstate, b->d_hdr, b->d_blk, d_voice_dst, n, b->voices, total, b->fs); \
+	} while (0)
+			case KB_SY_BREAKPOINT: case KB_SY_RAMP: case KB_SY_RELEASE:      // time-parallel unless KB_LANE_PER_VOICE: one envelope lane per voice, thread per (voice, sample)
+				if (flags & KB_LANE_PER_VOICE) kb_voice_kernel<KB_SY_BREAKPOINT, KbSenvVoice><<<blocks, 128, 0, st>>>((KbSenvVoice*)b->d_vstate, b->d_hdr, b->d_blk, d_voice_dst, n, b->voices, total, b->fs);
+				else KB_LAUNCH_ESINE(KbSenvVoice);
+				break;
+			case KB_SY_AM:
+				if (flags & KB_LANE_PER_VOICE) kb_voice_kernel<KB_SY_AM, KbSmodVoice><<<blocks, 128, 0, st>>>((KbSmodVoice*)b->d_vstate, b->d_hdr, b->d_blk, d_voice_dst, n, b->voices, total, b->fs);
+				else KB_LAUNCH_ESINE(KbSmodVoice);
+				break;
+#undef KB_LAUNCH_ESINE
+			case KB_SY_MOD_FM: case KB_SY_MOD_FM2:
 				kb_voice_kernel<KB_SY_AM, KbSmodVoice><<<blocks, 128, 0, st>>>((KbSmodVoice*)b->d_vstate, b->d_hdr, b->d_blk, d_voice_dst, n, b->voices, total, b->fs); break;
 			case KB_SY_ADDITIVE_SAW: case KB_SY_ADDITIVE_SQUARE:
 				if (flags & KB_LANE_PER_VOICE) {

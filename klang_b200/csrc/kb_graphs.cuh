@@ -412,6 +412,34 @@ KB_HD float kb_smod_tick(const KbFs& fs, float c0, float c1, float c2, KbSmodVoi
 	return out;
 }
 
+// Time-parallel forms of the voices whose only recurrence is ONE envelope (Breakpoint.k / Ramp.k / Release.k, and Modulation/AM.k, whose
+// modulator frequency c0 * carrier.frequency is constant over a block): kb_es_begin = what the first tick of the block does to the
+// oscillator settings, kb_es_at = sample `t` from the block-start state and the envelope value e of that sample, kb_es_end = the
+// oscillators after `ticks` ticks.  Same contract as kb_fm_at; kb_esine_tiled_kernel (kb_tiled.cuh) runs them.
+KB_HD KbEnv& kb_es_env(KbSenvVoice& n) { return n.env; }
+KB_HD KbEnv& kb_es_env(KbSmodVoice& n) { return n.adsr; }
+KB_HD bool kb_es_stops(const KbSenvVoice& n) { return n.stop_when_finished != 0; }
+KB_HD bool kb_es_stops(const KbSmodVoice&) { return true; }
+KB_HD void kb_es_begin(const KbFs&, KbSenvVoice&, float) {}
+KB_HD void kb_es_begin(const KbFs& fs, KbSmodVoice& n, float c0) { kb_fsine_set_f(fs, n.mod1, c0 * n.carrier.frequency); }   // AM.k:23, 26
+KB_HD float kb_es_at(const KbSenvVoice& n, uint32_t t, float, float e) {
+	return kb_fsine_value(n.osc.position + t * (uint32_t)n.osc.increment + n.osc.offset) * e;
+}
+KB_HD float kb_es_at(const KbSmodVoice& n, uint32_t t, float c1, float e) {
+	const float mod = kb_fsine_value(n.mod1.position + t * (uint32_t)n.mod1.increment + n.mod1.offset) * c1 + (1 - c1);
+	float out = kb_fsine_value(n.carrier.position + t * (uint32_t)n.carrier.increment + n.carrier.offset) * mod;
+	out = out * e;
+	return out;
+}
+KB_HD void kb_es_end(KbSenvVoice& n, uint32_t ticks) { n.osc.position += ticks * (uint32_t)n.osc.increment; }
+KB_HD void kb_es_end(KbSmodVoice& n, uint32_t ticks) {
+	n.carrier.position += ticks * (uint32_t)n.carrier.increment;
+	n.mod1.position += ticks * (uint32_t)n.mod1.increment;
+}
+// the oscillator fields a block changes (the envelope is written back by its own lane)
+KB_HD void kb_es_writeback(KbSenvVoice& dst, const KbSenvVoice& m) { dst.osc = m.osc; }
+KB_HD void kb_es_writeback(KbSmodVoice& dst, const KbSmodVoice& m) { dst.carrier = m.carrier; dst.mod1 = m.mod1; }
+
 // Additive/Saw.k:12-16, Square.k:12-19: out = 0; out += osc[o] / (o + 1) in partial order; Square.k ticks only the odd harmonics whose
 // frequency lies below Nyquist.  kb_add_tick is the per-tick form, kb_add_at sample `t` of a block as a pure function of the block-start
 // phases (no value is carried from sample to sample: the voice is 32 integer phase ramps); kb_add_block_end leaves the voice as

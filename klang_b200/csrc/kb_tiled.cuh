@@ -385,6 +385,78 @@ __global__ void __launch_bounds__(NT, 1) kb_fm_tiled_kernel(KbFmVoice* __restric
 	}
 }
 
+// ------------------------------------------------------------------ one envelope x closed-form oscillators
+// Breakpoint.k / Ramp.k / Release.k (KbSenvVoice) and Modulation/AM.k (KbSmodVoice): the FM.k kernel with one envelope per voice.
+//   A (tile k)    warp 0, lane = voice: the envelope, run-length form
+//   D (tile k-1)  thread = (voice, t): kb_es_at, coalesced store
+// tests/host/esine_check.cpp proves the formulation (same functions, g++) bit-identical to the per-tick forms, samples and state.
+template <class VOICE, int G> struct KbEsSmem {
+	VOICE voice[G];                  // block-start state after kb_es_begin (read-only during the block)
+	KbTileRows<G> env[2];            // A -> D
+	float c1[G];
+	int active[G];
+};
+template <class VOICE, int G, int NT>
+__global__ void __launch_bounds__(NT, 1) kb_esine_tiled_kernel(VOICE* __restrict__ voices, KbVoiceHdr* __restrict__ hdr,
+                                                                          const KbSynthBlock* __restrict__ blk, float* __restrict__ dst,
+                                                                          int n, int voices_per_inst, int total, KbFs fs) {
+	static_assert(G <= 32, "one envelope lane per voice in warp 0");
+	constexpr int T = KB_TILE_T;
+	extern __shared__ __align__(16) unsigned char kb_smem[];
+	KbEsSmem<VOICE, G>& S = *reinterpret_cast<KbEsSmem<VOICE, G>*>(kb_smem);
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int v0 = blockIdx.x * G;
+	if (tid < G) {
+		const int v = v0 + tid;
+		const int act = (v < total && hdr[v].stage != KB_NOTE_OFF) ? 1 : 0;
+		S.active[tid] = act;
+		if (v < total) hdr[v].active = act;
+		if (act) {
+			S.voice[tid] = voices[v];
+			S.c1[tid] = blk[v / voices_per_inst].c[1];
+			kb_es_begin(fs, S.voice[tid], blk[v / voices_per_inst].c[0]);
+		}
+	}
+	__syncthreads();
+	const bool is_env = warp == 0 && lane < G && S.active[lane];
+	const KbEnv* esrc = nullptr;
+	KbEnvR env;
+	if (is_env) {
+		esrc = &kb_es_env(S.voice[lane]);                                 // breakpoints stay in shared memory
+		kb_envr_load(env, *esrc);
+	}
+	const int ntiles = (n + T - 1) / T;
+	const int wtid = tid - 32, wthreads = NT - 32;
+	for (int k = 0; k < ntiles + 1; k++) {
+		if (warp == 0) {                                                     // ---- A, tile k
+			if (is_env && k < ntiles) {
+				const int steps = min(T, n - k * T);
+				kb_envr_run(fs, env, esrc->px, esrc->py, S.env[k & 1].r[lane], steps);
+			}
+		} else {
+			const int d = k - 1;
+			if (d >= 0) {                                                    // ---- D, tile k-1
+				const int steps = min(T, n - d * T);
+				for (int item = wtid; item < G * T; item += wthreads) {
+					const int v = item / T, t = item % T;
+					if (t < steps && v0 + v < total)
+						dst[(size_t)(v0 + v) * n + d * T + t] = S.active[v] ? kb_es_at(S.voice[v], (uint32_t)(d * T + t), S.c1[v], S.env[d & 1].r[v][t]) : 0.f;
+				}
+			}
+		}
+		__syncthreads();
+	}
+	if (is_env) {
+		kb_envr_store(env, kb_es_env(voices[v0 + lane]));
+		if (kb_es_stops(S.voice[lane]) && env.stage == KB_ENV_OFF) hdr[v0 + lane].stage = KB_NOTE_OFF;
+	}
+	if (warp == 1 && lane < G && S.active[lane]) {
+		VOICE m = S.voice[lane];
+		kb_es_end(m, (uint32_t)n);
+		kb_es_writeback(voices[v0 + lane], m);
+	}
+}
+
 // --------------------------------------------------------------------------------------------------- TB303
 // TB303.k:103-113.  A: filter envelope and ADSR.  B: oscillator sample and Filter::set coefficients b0, k, g
 // (TB303.k:37-55; polynomials of the cutoff, no transcendental: r and the feedback one-pole are control-rate

@@ -323,3 +323,15 @@ def test_sine_modulation_voices_match_oracle_on_host():
                            port(oracle.SY_MOD_FM2, 48000.0, (3.0, 10.0, 6.791))])
     assert len(got) == len(want) and np.array_equal(got.view(np.uint32), want.view(np.uint32))
     assert np.abs(want[:4000]).max() > 0.3 and np.abs(want[4000:8000]).max() > 0.3 and np.abs(want[8000:]).max() > 0.01
+
+
+def test_one_envelope_time_parallel_form_equals_per_tick_form():
+    """kb_es_begin / kb_es_at / kb_es_end with kb_envr_run rows (what kb_esine_tiled_kernel runs for Breakpoint.k / Ramp.k / Release.k /
+    Modulation/AM.k) equal kb_senv_tick / kb_smod_tick bit for bit, samples and state, over ragged blocks, releases, notes running into
+    Off, re-triggers and control changes."""
+    exe = os.path.join(tempfile.mkdtemp(prefix="kb_host_"), "esine_check")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-x", "c++",
+                           os.path.join(ROOT, "tests", "host", "esine_check.cpp"), "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert " 0 mismatches, 0 state mismatches" in out.stdout

@@ -185,3 +185,39 @@ def test_additive_time_parallel_kernel_equals_lane_per_voice_kernel(graph):
         outs.append(np.concatenate(res, axis=-1))
     _exact(np.ascontiguousarray(outs[1]), np.ascontiguousarray(outs[0]), f"additive graph {graph}")
     assert np.abs(outs[0]).max() > 0.5
+
+
+@pytest.mark.parametrize("graph", [cases.SY_BREAKPOINT, cases.SY_RAMP, cases.SY_RELEASE, cases.SY_AM])
+def test_one_envelope_time_parallel_kernel_equals_lane_per_voice_kernel(graph):
+    """kb_esine_tiled_kernel (one envelope lane per voice + a thread per (voice, sample); the default for Breakpoint.k / Ramp.k /
+    Release.k / Modulation/AM.k) against the lane-per-voice kernel (KB_LANE_PER_VOICE): per-voice streams, the instance mix and the note
+    stages, bit for bit, over ragged blocks with releases, re-triggers and control changes; 3 x 21 voices (ragged last CTA)."""
+    inst, voices, fs = 3, 21, 48000.0
+    outs = []
+    for flag in (kb.LANE_PER_VOICE, 0):
+        bank = kb.SynthBank(graph, inst, voices, fs, 4096)
+        if graph == cases.SY_RELEASE:
+            bank.set_control(3, 0.02)
+        res = []
+        for b, n in enumerate((4096, 117, 1, 128, 129, 1000, 4096, 300)):
+            for g in range(inst * bank.voices):
+                i, v = g // bank.voices, g % bank.voices
+                if b == 0 and g % 2 == 0:
+                    bank.voice_start(v, 36 + (5 * g) % 40, 0.8, i)
+                if b == 2 and g % 4 == 0:
+                    bank.voice_release(v, 0.0, i)
+                if b == 5 and g % 6 == 1:
+                    bank.voice_start(v, 50 + g % 30, 0.7, i)
+            if b == 4:
+                bank.set_control(0, 0.3)
+                if bank.num_controls > 1:
+                    bank.set_control(1, 0.25)
+            res.append(bank.process_block(n, kb.PER_VOICE | flag))
+        stages = np.array([bank.voice_stage(v, i) for i in range(inst) for v in range(bank.voices)])
+        mix = bank.process_block(512, flag)
+        bank.close()
+        outs.append((np.concatenate(res, axis=-1), stages, mix))
+    _exact(np.ascontiguousarray(outs[1][0]), np.ascontiguousarray(outs[0][0]), f"graph {graph} voices")
+    assert np.array_equal(outs[0][1], outs[1][1]), f"graph {graph} stages"
+    _exact(np.ascontiguousarray(outs[1][2]), np.ascontiguousarray(outs[0][2]), f"graph {graph} mix")
+    assert np.abs(outs[0][0]).max() > 0.3
