@@ -759,6 +759,18 @@ def extras(kb, torch, dev, stream, flush_l2, hbm_peak, peak_src, device_index, w
             streaming_line(name, graph, inst, 1 << 20)
         except Exception as e:
             res[name] = {"error": repr(e)}
+    # Delay/Echo.k, 64 instances x 65536 frames: write sweep + read sweep (20 algorithmic bytes per frame)
+    try:
+        fx = kb.FxBank(kb.FX_ECHO, 64, FS, 65536, device_index)
+        fx.set_stream(stream.cuda_stream)
+        fx.set_control(0, 0.25)
+        io = torch.rand(64, 1, 65536, device=dev) - 0.5
+        ms = time_steps(lambda: fx.process_inplace(io), 5, warmup=2)
+        res["echo_k_64"] = {"frames_per_s": 64 * 65536 / (ms * 1e-3), "ms_per_step": ms, "block": 65536, "bytes_per_frame": 20,
+                            "roofline": roof(64 * 65536 * 20 / (ms * 1e-3) / 1e9)}
+        fx.close()
+    except Exception as e:
+        res["echo_k_64"] = {"error": repr(e)}
     # Additive/Saw.k (32 sine partials per voice, no recurrence at all), Subtractive/Release.k and Modulation/AM.k (one envelope x closed-form
     # sines): time-parallel kernels, each with the lane-per-voice A/B
     for name, graph in (("additive_saw_k_1024", kb.SY_ADDITIVE_SAW), ("release_k_1024", kb.SY_RELEASE), ("am_k_1024", kb.SY_AM)):

@@ -161,7 +161,8 @@ extern "C" long long kb_fx_bank_launches(const kb_fx_bank* b) { return b ? b->la
 extern "C" int kb_fx_bank_parallel_instances(kb_fx_bank* b) {
 	if (!b) return kb_fail(KB_EINVAL, "null bank");
 	if (b->graph == KB_FX_GAIN || (b->graph >= KB_FX_PAN && b->graph <= KB_FX_CLIPPING)) return b->instances;
-	if (b->graph == KB_FX_ECHO || b->graph == KB_FX_FEEDBACK) return 0;              // frame-sequential schedule only, so far
+	if (b->graph == KB_FX_ECHO) return b->instances;                                 // (blocks longer than SIZE - fs frames fall back to the sequential schedule)
+	if (b->graph == KB_FX_FEEDBACK) return 0;                                        // frame-sequential schedule only, so far
 	std::vector<KbFxPlan> plan(b->instances);
 	KB_CUDA(cudaSetDevice(b->device));
 	KB_CUDA(cudaStreamSynchronize(b->stream));
@@ -276,9 +277,20 @@ extern "C" int kb_fx_bank_process(kb_fx_bank* b, float* io, int n, unsigned flag
 		kb_elementwise_kernel<<<grid, 256, 0, b->stream>>>(b->graph, b->channels, b->d_hdr, lfo ? (const KbLfoFx*)b->d_state : nullptr, d, n, n);
 		if (lfo) { kb_lfo_advance_kernel<<<ib, 32, 0, b->stream>>>((KbLfoFx*)b->d_state, b->instances, n); b->launches++; }
 		break; }
-	case KB_FX_ECHO:       // one lane per instance, frame by frame (a chunk-parallel schedule like Delay/PingPong.k's applies and is not built)
-		kb_fx_seq_kernel<KB_FX_ECHO, KbOneDelayFx><<<ib, 32, 0, b->stream>>>(b->d_hdr, (KbOneDelayFx*)b->d_state, b->d_rings, d, n, n, 1, b->instances, b->fs, nullptr);
-		break;
+	case KB_FX_ECHO: {
+		bool echo_par = !seq_only;                             // (controls are host-authoritative for this graph: the mirror is current)
+		for (int i = 0; i < b->instances && echo_par; i++) echo_par = kb_echo_parallel_ok(b->fs, n, b->hdr[i].controls[0].value);
+		if (echo_par) {                                        // time-parallel: write sweep, read sweep, position advance (kb_graphs.cuh)
+			KbOneDelayFx* st = (KbOneDelayFx*)b->d_state;
+			dim3 grid((unsigned)std::max(1, std::min((n + 255) / 256, 148 * 8 / std::min(b->instances, 148 * 8) + 1)), b->instances);
+			kb_echo_write_kernel<<<grid, 256, 0, b->stream>>>(st, b->d_rings, d, n, n);
+			kb_echo_read_kernel<<<grid, 256, 0, b->stream>>>(b->d_hdr, st, b->d_rings, d, n, n, b->fs);
+			kb_onedelay_advance_kernel<<<ib, 32, 0, b->stream>>>(st, b->instances, n);
+			b->launches += 2;
+		} else {                                               // one lane per instance, frame by frame
+			kb_fx_seq_kernel<KB_FX_ECHO, KbOneDelayFx><<<ib, 32, 0, b->stream>>>(b->d_hdr, (KbOneDelayFx*)b->d_state, b->d_rings, d, n, n, 1, b->instances, b->fs, nullptr);
+		}
+		break; }
 	case KB_FX_FEEDBACK:
 		kb_fx_seq_kernel<KB_FX_FEEDBACK, KbOneDelayFx><<<ib, 32, 0, b->stream>>>(b->d_hdr, (KbOneDelayFx*)b->d_state, b->d_rings, d, n, n, 1, b->instances, b->fs, nullptr);
 		break;

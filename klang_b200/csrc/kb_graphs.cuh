@@ -338,6 +338,22 @@ KB_D float kb_feedback_frame(const KbFs& fs, const KbFxHdr& h, KbOneDelayFx& s, 
 	return out;
 }
 
+// Echo.k, time-parallel: the line is only ever fed the INPUT, so a block is two independent sweeps — write all n inputs into the ring, then
+// every output sample from its own tap.  Exact as long as no tap of the block reads a slot that a LATER sample of the same block
+// overwrites: n + delay + 2 < SIZE at the far end, and delay >= 1 at the near end (with a delay below one frame the interpolation's
+// second slot is the NEXT frame's — weight 0, but an exact zero times a different value can flip the sign of a zero).
+// kb_echo_parallel_ok checks both; frame t sees the line with position (p0 + t + 1) mod SIZE.
+KB_HD bool kb_echo_parallel_ok(const KbFs& fs, int n, float control0) {
+	const float delay = control0 * fs.f;
+	return delay >= 1.f && (double)n + (double)delay + 3.0 < 192000.0;
+}
+KB_D void kb_echo_write_at(const KbOneDelayFx& s, float* rings, int t, float in) { rings[s.delay.ring + (s.delay.position + t) % s.delay.SIZE] = in; }
+KB_D float kb_echo_read_at(const KbFs& fs, const KbFxHdr& h, const KbOneDelayFx& s, const float* rings, int t, float in) {
+	KbDelay d = s.delay;
+	d.position = (s.delay.position + t + 1) % s.delay.SIZE;
+	return in + kb_delay_tap_f(d, rings + s.delay.ring, h.controls[0].value * fs.f) * h.controls[1].value;
+}
+
 // ---- FM.k per-sample half (host + device: tests/host/fm_check.cpp renders it with g++)
 // Operator::process (klang.h:4163-4167): OSCILLATOR::set(+in) -> Fast::Sine::set(relative): offset = phase * twoPi through
 // Fast::Phase::operator=(klang::Phase) (klang.h:5160-5162, 4993-4997, Q2); Sine::process; out *= env++ * amp

@@ -330,6 +330,24 @@ __global__ void kb_lfo_advance_kernel(KbLfoFx* __restrict__ lfos, int instances,
 	if (inst < instances) lfos[inst].lfo.position += (uint32_t)n * (uint32_t)lfos[inst].lfo.increment;
 }
 
+// Echo.k, time-parallel (kb_echo_write_at / kb_echo_read_at): two streaming sweeps over the block and the position advance; blockIdx.y = instance
+__global__ void kb_echo_write_kernel(const KbOneDelayFx* __restrict__ st, float* __restrict__ rings, const float* __restrict__ io, int n, int stride) {
+	const KbOneDelayFx s = st[blockIdx.y];
+	const float* p = io + (size_t)blockIdx.y * stride;
+	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) kb_echo_write_at(s, rings, t, p[t]);
+}
+__global__ void kb_echo_read_kernel(const KbFxHdr* __restrict__ hdr, const KbOneDelayFx* __restrict__ st, const float* __restrict__ rings,
+                                    float* __restrict__ io, int n, int stride, KbFs fs) {
+	const KbOneDelayFx s = st[blockIdx.y];
+	const KbFxHdr& h = hdr[blockIdx.y];
+	float* p = io + (size_t)blockIdx.y * stride;
+	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) p[t] = kb_echo_read_at(fs, h, s, rings, t, p[t]);
+}
+__global__ void kb_onedelay_advance_kernel(KbOneDelayFx* __restrict__ st, int instances, int n) {
+	const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+	if (inst < instances) st[inst].delay.position = (st[inst].delay.position + n) % st[inst].delay.SIZE;
+}
+
 // Delay-line effects, sequential form: one lane = one instance (Effect::process(buffer), klang.h:4208-4216 /
 // 4708-4716), rings in HBM.  Exact for any control setting; the time-parallel kernels below take over whenever
 // the feedback delays allow.

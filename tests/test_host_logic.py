@@ -335,3 +335,15 @@ def test_one_envelope_time_parallel_form_equals_per_tick_form():
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert " 0 mismatches, 0 state mismatches" in out.stdout
+
+
+def test_echo_time_parallel_form_equals_frame_sequential_form():
+    """Echo.k: write sweep + read sweep + position advance (kb_echo_write_at / kb_echo_read_at, what the time-parallel kernels run) equal
+    the frame-sequential kb_echo_frame bit for bit — samples, ring contents, position — with the ring wrapping, moving / fractional
+    delays, and the sequential fallback for delays below one frame."""
+    exe = os.path.join(tempfile.mkdtemp(prefix="kb_host_"), "echo_par_check")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-x", "c++",
+                           os.path.join(ROOT, "tests", "host", "echo_par_check.cpp"), "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert " 0 block mismatches, 0 ring / position mismatches" in out.stdout

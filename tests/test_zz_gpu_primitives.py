@@ -221,3 +221,31 @@ def test_one_envelope_time_parallel_kernel_equals_lane_per_voice_kernel(graph):
     assert np.array_equal(outs[0][1], outs[1][1]), f"graph {graph} stages"
     _exact(np.ascontiguousarray(outs[1][2]), np.ascontiguousarray(outs[0][2]), f"graph {graph} mix")
     assert np.abs(outs[0][0]).max() > 0.3
+
+
+def test_echo_time_parallel_schedule_equals_sequential_schedule():
+    """Echo.k: the write-sweep / read-sweep kernels (default) against the frame-sequential kernel (KB_FX_SEQUENTIAL), bit for bit over
+    ragged blocks, a delay that moves between blocks, and a block with a zero delay (which the library runs sequentially either way);
+    4 instances with different delays."""
+    fs, inst = 48000.0, 4
+    outs = []
+    for flag in (kb.FX_SEQUENTIAL, 0):
+        bank = kb.FxBank(kb.FX_ECHO, inst, fs, 4096)
+        for i in range(inst):
+            bank.set_control(0, 0.001 + 0.004 * i, i)
+            bank.set_control(1, 0.3 + 0.2 * i, i)
+        res = []
+        for b, n in enumerate((4096, 1001, 1, 4096, 2048, 4096)):
+            if b == 3:
+                bank.set_control(0, 0.0123, 1)
+            if b == 4:
+                bank.set_control(0, 0.0, 2)
+            if b == 5:
+                bank.set_control(0, 0.02, 2)
+            x = np.stack([cases.fx_input(1, n, seed=20 * b + i) for i in range(inst)]).astype(np.float32)
+            res.append(bank.process_inplace(x.copy(), flags=flag))
+        par = bank.parallel_instances()
+        bank.close()
+        outs.append(np.concatenate(res, axis=-1))
+    _exact(np.ascontiguousarray(outs[1]), np.ascontiguousarray(outs[0]), "echo schedules")
+    assert par == inst and np.abs(outs[0]).max() > 0.4
