@@ -162,7 +162,11 @@ extern "C" int kb_fx_bank_parallel_instances(kb_fx_bank* b) {
 	if (!b) return kb_fail(KB_EINVAL, "null bank");
 	if (b->graph == KB_FX_GAIN || (b->graph >= KB_FX_PAN && b->graph <= KB_FX_CLIPPING)) return b->instances;
 	if (b->graph == KB_FX_ECHO) return b->instances;                                 // (blocks longer than SIZE - fs frames fall back to the sequential schedule)
-	if (b->graph == KB_FX_FEEDBACK) return 0;                                        // frame-sequential schedule only, so far
+	if (b->graph == KB_FX_FEEDBACK) {                                                // instances whose delay is long enough for a chunk (at this block size)
+		int count = 0;
+		for (int i = 0; i < b->instances; i++) count += kb_feedback_chunk(b->fs, b->max_block, b->hdr[i].controls[0].value) > 0;
+		return count;
+	}
 	std::vector<KbFxPlan> plan(b->instances);
 	KB_CUDA(cudaSetDevice(b->device));
 	KB_CUDA(cudaStreamSynchronize(b->stream));
@@ -291,8 +295,9 @@ extern "C" int kb_fx_bank_process(kb_fx_bank* b, float* io, int n, unsigned flag
 			kb_fx_seq_kernel<KB_FX_ECHO, KbOneDelayFx><<<ib, 32, 0, b->stream>>>(b->d_hdr, (KbOneDelayFx*)b->d_state, b->d_rings, d, n, n, 1, b->instances, b->fs, nullptr);
 		}
 		break; }
-	case KB_FX_FEEDBACK:
-		kb_fx_seq_kernel<KB_FX_FEEDBACK, KbOneDelayFx><<<ib, 32, 0, b->stream>>>(b->d_hdr, (KbOneDelayFx*)b->d_state, b->d_rings, d, n, n, 1, b->instances, b->fs, nullptr);
+	case KB_FX_FEEDBACK:   // chunk-parallel (chunks shorter than the delay, one CTA per instance) unless KB_FX_SEQUENTIAL
+		if (!seq_only) kb_feedback_par_kernel<<<b->instances, 1024, 0, b->stream>>>(b->d_hdr, (KbOneDelayFx*)b->d_state, b->d_rings, d, n, n, b->fs);
+		else kb_fx_seq_kernel<KB_FX_FEEDBACK, KbOneDelayFx><<<ib, 32, 0, b->stream>>>(b->d_hdr, (KbOneDelayFx*)b->d_state, b->d_rings, d, n, n, 1, b->instances, b->fs, nullptr);
 		break;
 	case KB_FX_PINGPONG: {
 		KbPingPong* st = (KbPingPong*)b->d_state;

@@ -354,6 +354,24 @@ KB_D float kb_echo_read_at(const KbFs& fs, const KbFxHdr& h, const KbOneDelayFx&
 	return in + kb_delay_tap_f(d, rings + s.delay.ring, h.controls[0].value * fs.f) * h.controls[1].value;
 }
 
+// Feedback.k, chunk-parallel: frame t reads the line `delay` frames back and the line is fed the OUTPUT, so frames closer together than the
+// delay do not see each other.  A block is cut into chunks of kb_feedback_chunk frames (<= floor(delay) - 1, so both interpolation
+// slots of every frame in a chunk were written before the chunk began); chunks run in order, the frames of a chunk in any order
+// (kb_feedback_at).  Chunk 0 = not parallelisable (delay below 3 frames, or the far end n + delay + 2 >= SIZE): frame-sequential.
+KB_HD int kb_feedback_chunk(const KbFs& fs, int n, float control0) {
+	const float delay = control0 * fs.f;
+	if (!(delay >= 3.f) || !((double)n + (double)delay + 3.0 < 192000.0)) return 0;
+	return (int)delay - 1;
+}
+KB_D float kb_feedback_at(const KbFs& fs, const KbFxHdr& h, const KbOneDelayFx& s, float* rings, int t, float in) {
+	float* ring = rings + s.delay.ring;
+	KbDelay d = s.delay;
+	d.position = (s.delay.position + t) % s.delay.SIZE;                       // the line as frame t finds it: t frames written since the block began
+	const float out = in + kb_delay_tap_f(d, ring, h.controls[0].value * fs.f) * h.controls[1].value;
+	ring[d.position] = out;                                                   // delay << out
+	return out;
+}
+
 // ---- FM.k per-sample half (host + device: tests/host/fm_check.cpp renders it with g++)
 // Operator::process (klang.h:4163-4167): OSCILLATOR::set(+in) -> Fast::Sine::set(relative): offset = phase * twoPi through
 // Fast::Phase::operator=(klang::Phase) (klang.h:5160-5162, 4993-4997, Q2); Sine::process; out *= env++ * amp

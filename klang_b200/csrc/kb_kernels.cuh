@@ -343,6 +343,26 @@ __global__ void kb_echo_read_kernel(const KbFxHdr* __restrict__ hdr, const KbOne
 	float* p = io + (size_t)blockIdx.y * stride;
 	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) p[t] = kb_echo_read_at(fs, h, s, rings, t, p[t]);
 }
+// Feedback.k, chunk-parallel (kb_feedback_chunk / kb_feedback_at): one CTA per instance walks the block chunk by chunk, one barrier per chunk;
+// instances whose delay is too short for a chunk (chunk 0) run frame by frame on thread 0.  The position advances at the end.
+__global__ void __launch_bounds__(1024) kb_feedback_par_kernel(const KbFxHdr* __restrict__ hdr, KbOneDelayFx* __restrict__ st, float* __restrict__ rings,
+                                                                float* __restrict__ io, int n, int stride, KbFs fs) {
+	const KbFxHdr& h = hdr[blockIdx.x];
+	const KbOneDelayFx s = st[blockIdx.x];
+	float* p = io + (size_t)blockIdx.x * stride;
+	const int chunk = kb_feedback_chunk(fs, n, h.controls[0].value);
+	if (chunk == 0) {
+		if (threadIdx.x == 0) for (int t = 0; t < n; t++) p[t] = kb_feedback_at(fs, h, s, rings, t, p[t]);
+	} else {
+		for (int c0 = 0; c0 < n; c0 += chunk) {
+			const int c1 = min(n, c0 + chunk);
+			for (int t = c0 + threadIdx.x; t < c1; t += blockDim.x) p[t] = kb_feedback_at(fs, h, s, rings, t, p[t]);
+			__syncthreads();                                                 // the chunk's ring writes are visible to the next chunk's taps
+		}
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) st[blockIdx.x].delay.position = (s.delay.position + n) % s.delay.SIZE;
+}
 __global__ void kb_onedelay_advance_kernel(KbOneDelayFx* __restrict__ st, int instances, int n) {
 	const int inst = blockIdx.x * blockDim.x + threadIdx.x;
 	if (inst < instances) st[inst].delay.position = (st[inst].delay.position + n) % st[inst].delay.SIZE;

@@ -347,3 +347,15 @@ def test_echo_time_parallel_form_equals_frame_sequential_form():
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert " 0 block mismatches, 0 ring / position mismatches" in out.stdout
+
+
+def test_feedback_chunk_parallel_form_equals_frame_sequential_form():
+    """Feedback.k: chunks shorter than the delay, frames of a chunk in any order (kb_feedback_chunk / kb_feedback_at, what
+    kb_feedback_par_kernel runs) equal the frame-sequential kb_feedback_frame bit for bit — samples, ring contents, position — down to
+    the 3-frame delay limit, with the frame-by-frame path below it."""
+    exe = os.path.join(tempfile.mkdtemp(prefix="kb_host_"), "feedback_par_check")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-x", "c++",
+                           os.path.join(ROOT, "tests", "host", "feedback_par_check.cpp"), "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert " 0 block mismatches, 0 ring / position mismatches" in out.stdout

@@ -249,3 +249,30 @@ def test_echo_time_parallel_schedule_equals_sequential_schedule():
         outs.append(np.concatenate(res, axis=-1))
     _exact(np.ascontiguousarray(outs[1]), np.ascontiguousarray(outs[0]), "echo schedules")
     assert par == inst and np.abs(outs[0]).max() > 0.4
+
+
+def test_feedback_chunk_parallel_schedule_equals_sequential_schedule():
+    """Feedback.k: kb_feedback_par_kernel (default: chunks shorter than the delay, one CTA per instance) against the frame-sequential kernel
+    (KB_FX_SEQUENTIAL), bit for bit over ragged blocks: delays of 3.5 frames to 20 ms, a delay that moves, a zero delay (frame by frame
+    inside the parallel kernel); 5 instances."""
+    fs, inst = 48000.0, 5
+    outs = []
+    for flag in (kb.FX_SEQUENTIAL, 0):
+        bank = kb.FxBank(kb.FX_FEEDBACK, inst, fs, 4096)
+        for i, d in enumerate((0.00008, 0.001, 0.005, 0.0123, 0.02)):
+            bank.set_control(0, d, i)
+            bank.set_control(1, 0.3 + 0.15 * i, i)
+        res = []
+        for b, n in enumerate((4096, 1001, 1, 4096, 2048, 4096)):
+            if b == 3:
+                bank.set_control(0, 0.0031, 1)
+            if b == 4:
+                bank.set_control(0, 0.0, 2)
+            if b == 5:
+                bank.set_control(0, 0.01, 2)
+            x = np.stack([cases.fx_input(1, n, seed=30 * b + i) for i in range(inst)]).astype(np.float32)
+            res.append(bank.process_inplace(x.copy(), flags=flag))
+        bank.close()
+        outs.append(np.concatenate(res, axis=-1))
+    _exact(np.ascontiguousarray(outs[1]), np.ascontiguousarray(outs[0]), "feedback schedules")
+    assert np.abs(outs[0]).max() > 0.4
