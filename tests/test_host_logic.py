@@ -359,3 +359,13 @@ def test_feedback_chunk_parallel_form_equals_frame_sequential_form():
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert " 0 block mismatches, 0 ring / position mismatches" in out.stdout
+
+
+def test_late_gpu_tests_execute_against_the_oracle_backed_stub():
+    """The GPU tests written after the round's last GPU run (tests/test_zz_gpu_primitives.py, the MIDI test) are executed here with the
+    klang_b200 names replaced by oracle-backed stand-ins (tests/dryrun_stub.py): every test body runs — shapes, keys, argument order,
+    golden lookups.  Says nothing about the CUDA path; it keeps typos out of tests whose first real run is on the GPU box."""
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "dryrun_stub.py")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-1000:]
+    assert " passed" in out.stdout and "failed" not in out.stdout
