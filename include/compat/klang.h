@@ -204,7 +204,13 @@ template <class T, int SIZE> struct Table {
 	Table(std::initializer_list<T> l) { int i = 0; for (const T& x : l) if (i < SIZE) v[i++] = x; for (; i < SIZE; i++) v[i] = T(); }
 	T operator[](int i) const { return v[i]; }
 };
-struct Graph { void clear() {} template <class T> void add(const T&) {} };
+struct Graph {                           // UI only: `f >> graph(x0, x1, y0, y1)` plots a function (klang.h:2536-2840); nothing is evaluated here
+	void clear() {}
+	template <class T> void add(const T&) {}
+	Graph& operator()(double, double) { return *this; }
+	Graph& operator()(double, double, double, double) { return *this; }
+};
+inline Graph& operator>>(float (*)(float), Graph& g) { return g; }
 static Graph graph;
 typedef param Frequency;
 

@@ -41,6 +41,8 @@ extern "C" {
 #define KB_FX_CLIPPING 8          /* examples/Distortion/Clipping.k mono  (elementwise) */
 #define KB_FX_ECHO 9              /* examples/Delay/Echo.k         mono   (one Delay<192000>, feed-forward tap) */
 #define KB_FX_FEEDBACK 10         /* examples/Delay/Feedback.k     mono   (one Delay<192000> fed the output) */
+#define KB_FX_FUNCTIONS 11        /* examples/Distortion/Functions.k mono (elementwise: hardclip(in * gain)) */
+#define KB_FX_MUTE 12             /* examples/Distortion/Mute.k    mono   (elementwise: a Toggle) */
 
 /* synth graphs */
 #define KB_SY_SUBTRACTIVE 0       /* Saw >> LPF(env) >> ADSR: Filter.k with a Saw and ADSR controls mono */

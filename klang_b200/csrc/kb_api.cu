@@ -103,7 +103,7 @@ extern "C" kb_fx_bank* kb_fx_bank_create(int graph, int instances, float fs, int
 	case KB_FX_DELAY_REVERB: b->channels = 1; b->ncontrols = 3; b->state_bytes = sizeof(KbDReverb); b->ring_floats = KB_PINGPONG_RING_FLOATS; break;
 	case KB_FX_PAN: b->channels = 2; b->ncontrols = 1; b->state_bytes = sizeof(KbGainFx); b->ring_floats = 0; break;
 	case KB_FX_RM: case KB_FX_TREMOLO: b->channels = 1; b->ncontrols = 2; b->state_bytes = sizeof(KbLfoFx); b->ring_floats = 0; break;
-	case KB_FX_CLIPPING: b->channels = 1; b->ncontrols = 1; b->state_bytes = sizeof(KbGainFx); b->ring_floats = 0; break;
+	case KB_FX_CLIPPING: case KB_FX_FUNCTIONS: case KB_FX_MUTE: b->channels = 1; b->ncontrols = 1; b->state_bytes = sizeof(KbGainFx); b->ring_floats = 0; break;
 	case KB_FX_ECHO: case KB_FX_FEEDBACK: b->channels = 1; b->ncontrols = 2; b->state_bytes = sizeof(KbOneDelayFx); b->ring_floats = KB_ONEDELAY_RING_FLOATS; break;
 	}
 	b->hdr.assign(instances, KbFxHdr());
@@ -122,6 +122,8 @@ extern "C" kb_fx_bank* kb_fx_bank_create(int graph, int instances, float fs, int
 			b->hdr[i].controls[0] = kb_dial(1.f, graph == KB_FX_RM ? 1000.f : 10.f, 6.f); b->hdr[i].controls[1] = kb_dial(0.f, 0.5f, 0.5f);
 			kb_fsine_init(b->st<KbLfoFx>(i).lfo); break;
 		case KB_FX_CLIPPING: b->hdr[i].controls[0] = kb_dial(1.f, 11.f, 1.f); break;                                          // Clipping.k:10
+		case KB_FX_FUNCTIONS: b->hdr[i].controls[0] = kb_dial(1.f, 25.f, 1.f); break;                                         // Functions.k:18
+		case KB_FX_MUTE: b->hdr[i].controls[0] = kb_dial(0.f, 1.f, 0.f); break;                                               // Toggle("Mute"), Mute.k:10
 		case KB_FX_ECHO: case KB_FX_FEEDBACK:                                                                                 // Echo.k:10-13, Feedback.k:10-13
 			b->hdr[i].controls[0] = kb_dial(0.f, 1.f, 0.5f); b->hdr[i].controls[1] = kb_dial(0.f, 1.f, 0.5f);
 			kb_delay_construct(b->st<KbOneDelayFx>(i).delay, 192000, ring0); break;
@@ -160,7 +162,7 @@ extern "C" int kb_fx_bank_num_controls(const kb_fx_bank* b) { return b ? b->ncon
 extern "C" long long kb_fx_bank_launches(const kb_fx_bank* b) { return b ? b->launches : 0; }
 extern "C" int kb_fx_bank_parallel_instances(kb_fx_bank* b) {
 	if (!b) return kb_fail(KB_EINVAL, "null bank");
-	if (b->graph == KB_FX_GAIN || (b->graph >= KB_FX_PAN && b->graph <= KB_FX_CLIPPING)) return b->instances;
+	if (b->graph == KB_FX_GAIN || (b->graph >= KB_FX_PAN && b->graph <= KB_FX_CLIPPING) || b->graph == KB_FX_FUNCTIONS || b->graph == KB_FX_MUTE) return b->instances;
 	if (b->graph == KB_FX_ECHO) return b->instances;                                 // (blocks longer than SIZE - fs frames fall back to the sequential schedule)
 	if (b->graph == KB_FX_FEEDBACK) {                                                // instances whose delay is long enough for a chunk (at this block size)
 		int count = 0;
@@ -208,7 +210,7 @@ extern "C" double kb_fx_bank_bytes_per_frame(kb_fx_bank* b) {
 	case KB_FX_DELAY_PINGPONG: return 40;
 	case KB_FX_DELAY_REVERB: return 88;
 	case KB_FX_PAN: return 16;
-	case KB_FX_RM: case KB_FX_TREMOLO: case KB_FX_CLIPPING: return 8;
+	case KB_FX_RM: case KB_FX_TREMOLO: case KB_FX_CLIPPING: case KB_FX_FUNCTIONS: case KB_FX_MUTE: return 8;
 	case KB_FX_ECHO: case KB_FX_FEEDBACK: return 20;               // 8 io + 4 write + two adjacent floats read
 	}
 	return 0;
@@ -274,7 +276,7 @@ extern "C" int kb_fx_bank_process(kb_fx_bank* b, float* io, int n, unsigned flag
 		dim3 grid((unsigned)std::max(1, std::min((n / 4 + 255) / 256, 148 * 8 / std::min(b->instances, 148 * 8) + 1)), b->instances);
 		kb_gain_kernel<<<grid, 256, 0, b->stream>>>(b->d_hdr, d, n);
 		break; }
-	case KB_FX_PAN: case KB_FX_RM: case KB_FX_TREMOLO: case KB_FX_CLIPPING: {
+	case KB_FX_PAN: case KB_FX_RM: case KB_FX_TREMOLO: case KB_FX_CLIPPING: case KB_FX_FUNCTIONS: case KB_FX_MUTE: {
 		const int rows = b->instances * b->channels;
 		const bool lfo = b->graph == KB_FX_RM || b->graph == KB_FX_TREMOLO;
 		dim3 grid((unsigned)std::max(1, std::min((n / 4 + 255) / 256, 148 * 8 / std::min(rows, 148 * 8) + 1)), rows);
@@ -388,7 +390,7 @@ extern "C" int kb_fx_bank_process(kb_fx_bank* b, float* io, int n, unsigned flag
 	b->prof_end();
 	b->launches++;
 	KB_CUDA(cudaGetLastError());
-	if (b->graph != KB_FX_GAIN && b->graph != KB_FX_PAN && b->graph != KB_FX_CLIPPING) b->host_stale = true;
+	if (b->graph != KB_FX_GAIN && b->graph != KB_FX_PAN && b->graph != KB_FX_CLIPPING && b->graph != KB_FX_FUNCTIONS && b->graph != KB_FX_MUTE) b->host_stale = true;
 	if (!(flags & KB_DEVICE_PTR)) {
 		KB_CUDA(cudaMemcpyAsync(io, d, floats * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
 		if (!(flags & KB_ASYNC_HOST)) KB_CUDA(cudaStreamSynchronize(b->stream));

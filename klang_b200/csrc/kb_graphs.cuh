@@ -9,7 +9,7 @@
 
 #include "../../include/klang_b200.h"   // graph ids KB_SY_* / KB_FX_*
 #define KB_SY_COUNT 14
-#define KB_FX_COUNT 11
+#define KB_FX_COUNT 13
 
 // =========================================================================================== HOST halves
 
@@ -401,13 +401,14 @@ KB_HD float kb_senv_tick(const KbFs& fs, KbSenvVoice& n, int& note_stage) {
 	return out;
 }
 
-// ---- elementwise effects: Gain/Pan.k:16-21, Gain/RM.k:17-24, Gain/Tremolo.k:22-29, Distortion/Clipping.k:14-25.  Sample `t` of a block as a
+// ---- elementwise effects: Gain/Pan.k:16-21, Gain/RM.k:17-24, Gain/Tremolo.k:22-29, Distortion/Clipping.k:14-25, Functions.k, Mute.k.  Sample `t` of a block as a
 // pure function of the input sample: the LFO of RM.k / Tremolo.k is a Fast::Sine on an integer phase ramp, and `lfo(rate)` sets a
 // frequency that is constant over the block (controls move between blocks), so Sine::set runs once per block on the host.
 // c0, c1 = controls[0], controls[1]; channel = 0 left / mono, 1 right.
 KB_HD float kb_ew_sample(int graph, float c0, float c1, const KbFastSine& lfo, int channel, uint32_t t, float in) {
 	if (graph == KB_FX_PAN) return channel == 0 ? in * (1 - c0) : in * c0;
-	if (graph == KB_FX_CLIPPING) {
+	if (graph == KB_FX_MUTE) return in * (c0 ? 0.f : 1.f);                    // Mute.k:20-31 (the product keeps the sign of a zero)
+	if (graph == KB_FX_CLIPPING || graph == KB_FX_FUNCTIONS) {               // Clipping.k:14-25; Functions.k:4-11, 25-29 hardclip(in * gain)
 		in *= c0;
 		if (in > 1) in = 1; else if (in < -1) in = -1;
 		return in;

@@ -88,6 +88,12 @@ namespace k_mod_fm {
 namespace k_mod_fm2 {
 #include "Modulation/FM2.k"
 }
+namespace k_functions {
+#include "Distortion/Functions.k"
+}
+namespace k_mute {
+#include "Distortion/Mute.k"
+}
 namespace k_echo {
 #include "Delay/Echo.k"
 }
@@ -390,7 +396,7 @@ int ref_control_smooth(float lo, float hi, float initial, int n, const float* va
 }
 
 // ---------------------------------------------------------------------- effects
-enum { FX_GAIN = 0, FX_PINGPONG = 1, FX_REVERB = 2, FX_DELAY_PINGPONG = 3, FX_DELAY_REVERB = 4, FX_PAN = 5, FX_RM = 6, FX_TREMOLO = 7, FX_CLIPPING = 8, FX_ECHO = 9, FX_FEEDBACK = 10 };
+enum { FX_GAIN = 0, FX_PINGPONG = 1, FX_REVERB = 2, FX_DELAY_PINGPONG = 3, FX_DELAY_REVERB = 4, FX_PAN = 5, FX_RM = 6, FX_TREMOLO = 7, FX_CLIPPING = 8, FX_ECHO = 9, FX_FEEDBACK = 10, FX_FUNCTIONS = 11, FX_MUTE = 12 };
 
 struct RefFx {
 	int graph;
@@ -414,6 +420,8 @@ void* ref_fx_create(int graph) {
 	case FX_CLIPPING: { auto* e = new k_clipping::Clipping(); fx->mono = e;   fx->controls = &e->controls; } break;
 	case FX_ECHO:     { auto* e = new k_echo::Echo();         fx->mono = e;   fx->controls = &e->controls; } break;
 	case FX_FEEDBACK: { auto* e = new k_feedback::Feedback(); fx->mono = e;   fx->controls = &e->controls; } break;
+	case FX_FUNCTIONS: { auto* e = new k_functions::Functions(); fx->mono = e; fx->controls = &e->controls; } break;
+	case FX_MUTE:     { auto* e = new k_mute::Mute();         fx->mono = e;   fx->controls = &e->controls; } break;
 	default: delete fx; return nullptr;
 	}
 	return fx;

@@ -22,6 +22,8 @@ int main(int argc, char** argv) {
 	KbControl c[2] = { kb_dial(0.f, 1.f, 0.5f), kb_dial(0.f, 0.5f, 0.5f) };                  // Pan.k:10
 	if (graph == KB_FX_RM || graph == KB_FX_TREMOLO) c[0] = kb_dial(1.f, graph == KB_FX_RM ? 1000.f : 10.f, 6.f);
 	if (graph == KB_FX_CLIPPING) c[0] = kb_dial(1.f, 11.f, 1.f);
+	if (graph == KB_FX_FUNCTIONS) c[0] = kb_dial(1.f, 25.f, 1.f);
+	if (graph == KB_FX_MUTE) c[0] = kb_dial(0.f, 1.f, 0.f);
 	KbFastSine lfo; kb_fsine_init(lfo);
 	for (int b = 0; b * block < total; b++) {
 		for (int a = 7; a + 2 < argc; a += 3) if (atoi(argv[a]) == b) kb_control_set(c[atoi(argv[a + 1])], (float)atof(argv[a + 2]));

@@ -72,6 +72,12 @@ namespace k_mod_fm {
 namespace k_mod_fm2 {
 #include "Modulation/FM2.k"
 }
+namespace k_functions {
+#include "Distortion/Functions.k"
+}
+namespace k_mute {
+#include "Distortion/Mute.k"
+}
 namespace k_breakpoint {
 #include "Subtractive/Breakpoint.k"
 }
@@ -103,6 +109,8 @@ KLANG_B200_SYNTH(k_add_square::Square, KB_SY_ADDITIVE_SQUARE)
 KLANG_B200_SYNTH(k_am::AM, KB_SY_AM)
 KLANG_B200_SYNTH(k_mod_fm::FM, KB_SY_MOD_FM)
 KLANG_B200_SYNTH(k_mod_fm2::FM2, KB_SY_MOD_FM2)
+KLANG_B200_EFFECT(k_functions::Functions, KB_FX_FUNCTIONS)
+KLANG_B200_EFFECT(k_mute::Mute, KB_FX_MUTE)
 KLANG_B200_SYNTH(k_breakpoint::Breakpoint, KB_SY_BREAKPOINT)
 KLANG_B200_SYNTH(k_ramp::Ramp, KB_SY_RAMP)
 KLANG_B200_SYNTH(k_release::Release, KB_SY_RELEASE)
@@ -170,6 +178,8 @@ int main(int argc, char** argv) {
 		else if (prog == "am") rc = run_synth<k_am::AM>(fs, n, blocks, out);
 		else if (prog == "mod_fm") rc = run_synth<k_mod_fm::FM>(fs, n, blocks, out);
 		else if (prog == "mod_fm2") rc = run_synth<k_mod_fm2::FM2>(fs, n, blocks, out);
+		else if (prog == "functions") rc = run_effect<k_functions::Functions>(fs, n, blocks, out);
+		else if (prog == "mute") rc = run_effect<k_mute::Mute>(fs, n, blocks, out);
 		else if (prog == "breakpoint") rc = run_synth<k_breakpoint::Breakpoint>(fs, n, blocks, out);
 		else if (prog == "ramp") rc = run_synth<k_ramp::Ramp>(fs, n, blocks, out);
 		else if (prog == "release") rc = run_synth<k_release::Release>(fs, n, blocks, out);
