@@ -59,6 +59,7 @@ extern "C" {
 #define KB_SY_AM 11               /* examples/Modulation/AM.k  (sine carrier x sine modulator, ADSR) mono */
 #define KB_SY_MOD_FM 12           /* examples/Modulation/FM.k  (carrier frequency set every sample from a sine modulator) mono */
 #define KB_SY_MOD_FM2 13          /* examples/Modulation/FM2.k (two modulators in series) mono */
+#define KB_SY_ADDITIVE_NYQUIST 14 /* examples/Additive/Nyquist.k (every partial below Nyquist) mono */
 
 /* process flags */
 #define KB_DEVICE_PTR 1u          /* `io` / `out` is device memory on the bank's device; the call is asynchronous on the bank stream */

@@ -500,7 +500,7 @@ static int sy_upload(kb_synth_bank* b) {
 			if (b->graph == KB_SY_TB303) k.tb = kb_tb_block(b->fs, b->ctl(i));
 			if (b->graph == KB_SY_SYNTHX) { k.sx_tr_at = kb_sx_tr_at(b->ctl(i)[2].value); k.sx_dt_at = kb_sx_dt_at(b->ctl(i)[1].value); }
 			if (b->graph == KB_SY_FM) { k.fm_i1 = b->ctl(i)[1].value; k.fm_i2 = b->ctl(i)[2].value; }
-			if (b->graph >= KB_SY_AM && b->graph <= KB_SY_MOD_FM2) for (int c = 0; c < 3; c++) k.c[c] = b->ctl(i)[c].value;
+			if (b->graph >= KB_SY_AM && b->graph <= KB_SY_MOD_FM2) for (int c = 0; c < 3; c++) k.c[c] = b->ctl(i)[c].value;   // (graph 14 has no controls)
 			else k.c[0] = k.c[1] = k.c[2] = 0.f;
 		}
 		KB_CUDA(cudaMemcpyAsync(b->d_blk, b->blk.data(), b->blk.size() * sizeof(KbSynthBlock), cudaMemcpyHostToDevice, b->stream));
@@ -531,7 +531,7 @@ extern "C" kb_synth_bank* kb_synth_bank_create(int graph, int instances, int voi
 	case KB_SY_BREAKPOINT: b->ncontrols = 2; b->voice_bytes = sizeof(KbSenvVoice); break;
 	case KB_SY_RAMP: b->ncontrols = 1; b->voice_bytes = sizeof(KbSenvVoice); break;
 	case KB_SY_RELEASE: b->ncontrols = 4; b->voice_bytes = sizeof(KbSenvVoice); break;
-	case KB_SY_ADDITIVE_SAW: case KB_SY_ADDITIVE_SQUARE: b->ncontrols = 0; b->voice_bytes = sizeof(KbAddVoice); break;
+	case KB_SY_ADDITIVE_SAW: case KB_SY_ADDITIVE_SQUARE: case KB_SY_ADDITIVE_NYQUIST: b->ncontrols = 0; b->voice_bytes = sizeof(KbAddVoice); break;
 	case KB_SY_AM: case KB_SY_MOD_FM: b->ncontrols = 2; b->voice_bytes = sizeof(KbSmodVoice); break;
 	case KB_SY_MOD_FM2: b->ncontrols = 3; b->voice_bytes = sizeof(KbSmodVoice); break;
 	}
@@ -575,7 +575,7 @@ extern "C" kb_synth_bank* kb_synth_bank_create(int graph, int instances, int voi
 		case KB_SY_SUPERSAW: kb_ssaw_construct(b->fs, b->vs<KbSsawVoice>(v)); break;
 		case KB_SY_FM: kb_fm_construct(b->fs, b->vs<KbFmVoice>(v)); break;
 		case KB_SY_BREAKPOINT: case KB_SY_RAMP: case KB_SY_RELEASE: kb_senv_construct(b->fs, graph, b->vs<KbSenvVoice>(v)); break;
-		case KB_SY_ADDITIVE_SAW: case KB_SY_ADDITIVE_SQUARE: kb_add_construct(graph, b->vs<KbAddVoice>(v)); break;
+		case KB_SY_ADDITIVE_SAW: case KB_SY_ADDITIVE_SQUARE: case KB_SY_ADDITIVE_NYQUIST: kb_add_construct(graph, b->vs<KbAddVoice>(v)); break;
 		case KB_SY_AM: case KB_SY_MOD_FM: case KB_SY_MOD_FM2: kb_smod_construct(b->fs, graph, b->vs<KbSmodVoice>(v)); break;
 		case KB_SY_TB303: kb_tb_construct(b->fs, b->vs<KbTbVoice>(v)); break;
 		case KB_SY_SYNTHX: kb_sx_construct(b->fs, b->vs<KbSxVoice>(v)); break;
@@ -647,7 +647,7 @@ static void sy_start(kb_synth_bank* b, int inst, int voice, float pitch, float v
 	case KB_SY_SUPERSAW: kb_ssaw_on(b->fs, c, b->vs<KbSsawVoice>(v), pitch); break;
 	case KB_SY_FM: kb_fm_on(b->fs, c, b->vs<KbFmVoice>(v), pitch); break;
 	case KB_SY_BREAKPOINT: case KB_SY_RAMP: case KB_SY_RELEASE: kb_senv_on(b->fs, b->graph, c, b->vs<KbSenvVoice>(v), pitch); break;
-	case KB_SY_ADDITIVE_SAW: case KB_SY_ADDITIVE_SQUARE: kb_add_on(b->fs, b->vs<KbAddVoice>(v), pitch); break;
+	case KB_SY_ADDITIVE_SAW: case KB_SY_ADDITIVE_SQUARE: case KB_SY_ADDITIVE_NYQUIST: kb_add_on(b->fs, b->vs<KbAddVoice>(v), pitch); break;
 	case KB_SY_AM: case KB_SY_MOD_FM: case KB_SY_MOD_FM2: kb_smod_on(b->fs, b->vs<KbSmodVoice>(v), pitch); break;
 	case KB_SY_TB303: kb_tb_on(b->fs, c, b->vs<KbTbVoice>(v), pitch); break;
 	case KB_SY_SYNTHX: kb_sx_on(b->fs, c, b->vs<KbSxVoice>(v), pitch); break;
@@ -667,7 +667,7 @@ static void sy_release(kb_synth_bank* b, int inst, int voice) {
 	case KB_SY_FM: kb_adsr_release(b->fs, b->vs<KbFmVoice>(v).adsr); break;                                  // FM.k:56-58
 	case KB_SY_RELEASE: kb_env_release(b->fs, b->vs<KbSenvVoice>(v).env, b->ctl(inst)[3].value, 0.f); break;  // Release.k:21-24
 	case KB_SY_AM: case KB_SY_MOD_FM: case KB_SY_MOD_FM2: kb_adsr_release(b->fs, b->vs<KbSmodVoice>(v).adsr); break;   // AM.k:17-19
-	case KB_SY_BREAKPOINT: case KB_SY_RAMP: case KB_SY_ADDITIVE_SAW: case KB_SY_ADDITIVE_SQUARE:
+	case KB_SY_BREAKPOINT: case KB_SY_RAMP: case KB_SY_ADDITIVE_SAW: case KB_SY_ADDITIVE_SQUARE: case KB_SY_ADDITIVE_NYQUIST:
 		h.stage = KB_NOTE_OFF; break;                                                                        // NoteBase::off default: stage = Off  klang.h:4237
 	case KB_SY_TB303: kb_adsr_release(b->fs, b->vs<KbTbVoice>(v).adsr); break;                               // TB303.k:99-101
 	case KB_SY_SYNTHX: kb_adsr_release(b->fs, b->vs<KbSxVoice>(v).adsr); break;                              // SynTHX.k:163-165
@@ -804,7 +804,7 @@ extern "C" int kb_synth_bank_process(kb_synth_bank* b, float* out, int n, unsign
 #undef KB_LAUNCH_ESINE
 			case KB_SY_MOD_FM: case KB_SY_MOD_FM2:
 				kb_voice_kernel<KB_SY_AM, KbSmodVoice><<<blocks, 128, 0, st>>>((KbSmodVoice*)b->d_vstate, b->d_hdr, b->d_blk, d_voice_dst, n, b->voices, total, b->fs); break;
-			case KB_SY_ADDITIVE_SAW: case KB_SY_ADDITIVE_SQUARE:
+			case KB_SY_ADDITIVE_SAW: case KB_SY_ADDITIVE_SQUARE: case KB_SY_ADDITIVE_NYQUIST:
 				if (flags & KB_LANE_PER_VOICE) {
 					kb_voice_kernel<KB_SY_ADDITIVE_SAW, KbAddVoice><<<blocks, 128, 0, st>>>((KbAddVoice*)b->d_vstate, b->d_hdr, b->d_blk, d_voice_dst, n, b->voices, total, b->fs);
 				} else {                                   // time-parallel: thread = (voice, sample), then the phase advance

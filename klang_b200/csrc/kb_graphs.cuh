@@ -8,7 +8,7 @@
 #include "kb_prims.cuh"
 
 #include "../../include/klang_b200.h"   // graph ids KB_SY_* / KB_FX_*
-#define KB_SY_COUNT 14
+#define KB_SY_COUNT 15
 #define KB_FX_COUNT 13
 
 // =========================================================================================== HOST halves
@@ -108,7 +108,7 @@ inline void kb_senv_on(const KbFs& fs, int graph, const KbControl* c, KbSenvVoic
 // ---- Additive/Saw.k, Additive/Square.k: on() only sets the 32 frequencies, the partials keep their phase from note to note (Saw.k:7-10, 25-27)
 inline void kb_add_construct(int graph, KbAddVoice& n) {
 	for (int o = 0; o < 32; o++) kb_fsine_init(n.osc[o]);
-	n.square = graph == KB_SY_ADDITIVE_SQUARE;
+	n.square = graph == KB_SY_ADDITIVE_SQUARE ? 1 : graph == KB_SY_ADDITIVE_NYQUIST ? 2 : 0;
 }
 inline void kb_add_on(const KbFs& fs, KbAddVoice& n, float pitch) {
 	const float f = kb_pitch_to_frequency_host(pitch);
@@ -479,7 +479,10 @@ KB_HD void kb_es_writeback(KbSmodVoice& dst, const KbSmodVoice& m) { dst.carrier
 // frequency lies below Nyquist.  kb_add_tick is the per-tick form, kb_add_at sample `t` of a block as a pure function of the block-start
 // phases (no value is carried from sample to sample: the voice is 32 integer phase ramps); kb_add_block_end leaves the voice as
 // `ticks` calls of kb_add_tick would.
-KB_HD bool kb_add_partial_on(const KbFs& fs, const KbAddVoice& n, int o) { return !n.square || (((o + 1) % 2) && n.osc[o].frequency < fs.nyquist); }
+KB_HD bool kb_add_partial_on(const KbFs& fs, const KbAddVoice& n, int o) {
+	if (n.square == 0) return true;
+	return (n.square == 2 || ((o + 1) % 2)) && n.osc[o].frequency < fs.nyquist;      // Square.k:15-17, Nyquist.k:14-16
+}
 KB_HD float kb_add_tick(const KbFs& fs, KbAddVoice& n) {
 	float out = 0;
 	for (int o = 0; o < 32; o++) if (kb_add_partial_on(fs, n, o)) out += kb_fsine_tick(n.osc[o]) / (o + 1);

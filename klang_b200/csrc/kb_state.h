@@ -76,7 +76,7 @@ struct KbFmVoice { KbFmOp op[3]; KbEnv adsr; };
 struct KbSenvVoice { KbFastSine osc; KbEnv env; int stop_when_finished; };
 
 // examples/Additive/{Saw,Square}.k: 32 Fast::Sine partials
-struct KbAddVoice { KbFastSine osc[32]; int square; };
+struct KbAddVoice { KbFastSine osc[32]; int square; /* 0 Saw.k: all partials, 1 Square.k: odd ones below Nyquist, 2 Nyquist.k: all below Nyquist */ };
 
 // examples/Modulation/{AM,FM,FM2}.k: sine carrier, one or two sine modulators, ADSR
 struct KbSmodVoice { KbFastSine carrier, mod1, mod2; KbEnv adsr; float f0; int graph; };

@@ -94,6 +94,9 @@ namespace k_functions {
 namespace k_mute {
 #include "Distortion/Mute.k"
 }
+namespace k_add_nyquist {
+#include "Additive/Nyquist.k"
+}
 namespace k_echo {
 #include "Delay/Echo.k"
 }
@@ -457,7 +460,7 @@ int ref_fx_process(void* h, float* l, float* r, int n) {
 }
 
 // ----------------------------------------------------------------------- synths
-enum { SY_SUBTRACTIVE = 0, SY_SUPERSAW = 1, SY_TB303 = 2, SY_SYNTHX = 3, SY_FILTER_K = 4, SY_FM = 5, SY_BREAKPOINT = 6, SY_RAMP = 7, SY_RELEASE = 8, SY_ADDITIVE_SAW = 9, SY_ADDITIVE_SQUARE = 10, SY_AM = 11, SY_MOD_FM = 12, SY_MOD_FM2 = 13 };
+enum { SY_SUBTRACTIVE = 0, SY_SUPERSAW = 1, SY_TB303 = 2, SY_SYNTHX = 3, SY_FILTER_K = 4, SY_FM = 5, SY_BREAKPOINT = 6, SY_RAMP = 7, SY_RELEASE = 8, SY_ADDITIVE_SAW = 9, SY_ADDITIVE_SQUARE = 10, SY_AM = 11, SY_MOD_FM = 12, SY_MOD_FM2 = 13, SY_ADDITIVE_NYQUIST = 14 };
 
 struct RefSynth {
 	int graph;
@@ -494,6 +497,7 @@ void* ref_synth_create(int graph, int nvoices) {
 	case SY_RELEASE:     { auto* p = make_synth<k_release::Release, k_release::Release::ReleaseNote>(nvoices); s->mono = p; s->controls = &p->controls; } break;
 	case SY_ADDITIVE_SAW:    { auto* p = make_synth<k_add_saw::Saw, k_add_saw::Saw::SawNote>(nvoices); s->mono = p; s->controls = &p->controls; } break;
 	case SY_ADDITIVE_SQUARE: { auto* p = make_synth<k_add_square::Square, k_add_square::Square::SquareNote>(nvoices); s->mono = p; s->controls = &p->controls; } break;
+	case SY_ADDITIVE_NYQUIST: { auto* p = make_synth<k_add_nyquist::Nyquist, k_add_nyquist::Nyquist::NyquistNote>(nvoices); s->mono = p; s->controls = &p->controls; } break;
 	case SY_AM:      { auto* p = make_synth<k_am::AM, k_am::AM::AMNote>(nvoices); s->mono = p; s->controls = &p->controls; } break;
 	case SY_MOD_FM:  { auto* p = make_synth<k_mod_fm::FM, k_mod_fm::FM::FMNote>(nvoices); s->mono = p; s->controls = &p->controls; } break;
 	case SY_MOD_FM2: { auto* p = make_synth<k_mod_fm2::FM2, k_mod_fm2::FM2::FM2Note>(nvoices); s->mono = p; s->controls = &p->controls; } break;

@@ -20,7 +20,7 @@ import numpy as np
  FLT_BIQUAD_BPF, FLT_BIQUAD_BRF, FLT_BIQUAD_APF, FLT_BUTTERWORTH_LPF1, FLT_BUTTERWORTH_LPF2,
  FLT_DCF, FLT_IIR1, FLT_IIR2, FLT_MODAL, FLT_FOLLOWER_PEAK, FLT_FOLLOWER_RMS, FLT_WINDOW_MEAN, FLT_WINDOW_RMS) = range(17)
 FX_GAIN, FX_PINGPONG, FX_REVERB, FX_DELAY_PINGPONG, FX_DELAY_REVERB, FX_PAN, FX_RM, FX_TREMOLO, FX_CLIPPING, FX_ECHO, FX_FEEDBACK, FX_FUNCTIONS, FX_MUTE = range(13)
-SY_SUBTRACTIVE, SY_SUPERSAW, SY_TB303, SY_SYNTHX, SY_FILTER_K, SY_FM, SY_BREAKPOINT, SY_RAMP, SY_RELEASE, SY_ADDITIVE_SAW, SY_ADDITIVE_SQUARE, SY_AM, SY_MOD_FM, SY_MOD_FM2 = range(14)
+SY_SUBTRACTIVE, SY_SUPERSAW, SY_TB303, SY_SYNTHX, SY_FILTER_K, SY_FM, SY_BREAKPOINT, SY_RAMP, SY_RELEASE, SY_ADDITIVE_SAW, SY_ADDITIVE_SQUARE, SY_AM, SY_MOD_FM, SY_MOD_FM2, SY_ADDITIVE_NYQUIST = range(15)
 
 FX_NAMES = {FX_GAIN: "gain", FX_PINGPONG: "pingpong", FX_REVERB: "reverb",
             FX_DELAY_PINGPONG: "delay_pingpong", FX_DELAY_REVERB: "delay_reverb", FX_PAN: "pan", FX_RM: "rm", FX_TREMOLO: "tremolo",
@@ -28,7 +28,7 @@ FX_NAMES = {FX_GAIN: "gain", FX_PINGPONG: "pingpong", FX_REVERB: "reverb",
 SY_NAMES = {SY_SUBTRACTIVE: "subtractive", SY_SUPERSAW: "supersaw", SY_TB303: "tb303",
             SY_SYNTHX: "synthx", SY_FILTER_K: "filter_k", SY_FM: "fm", SY_BREAKPOINT: "breakpoint", SY_RAMP: "ramp",
             SY_RELEASE: "release", SY_ADDITIVE_SAW: "additive_saw", SY_ADDITIVE_SQUARE: "additive_square",
-            SY_AM: "am", SY_MOD_FM: "mod_fm", SY_MOD_FM2: "mod_fm2"}
+            SY_AM: "am", SY_MOD_FM: "mod_fm", SY_MOD_FM2: "mod_fm2", SY_ADDITIVE_NYQUIST: "additive_nyquist"}
 
 
 def noise(n, seed=1, lo=-1.0, hi=1.0):
@@ -271,6 +271,7 @@ SYNTH_SCRIPTS_LATE = {
     # Additive/Saw.k, Additive/Square.k: 32 Fast::Sine partials summed in order (Square.k: odd harmonics below Nyquist only)
     "additive_saw": (SY_ADDITIVE_SAW, 32, 10, 5, 512, 2, []),
     "additive_square": (SY_ADDITIVE_SQUARE, 32, 10, 5, 512, 2, []),
+    "additive_nyquist": (SY_ADDITIVE_NYQUIST, 32, 10, 5, 512, 2, []),            # Nyquist.k: every partial below Nyquist
     # Modulation/AM.k, FM.k, FM2.k: sine carrier with one or two sine modulators whose frequency is set every sample
     "am": (SY_AM, 32, 8, 6, 512, 2, [(3, 0, 2.2), (3, 1, 0.9)]),
     "mod_fm": (SY_MOD_FM, 32, 8, 6, 512, 2, [(3, 0, 1.5), (3, 1, 7.0)]),

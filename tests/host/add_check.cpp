@@ -13,7 +13,7 @@
 int main() {
 	int bad = 0;
 	const int blocks[6] = { 700, 1, 129, 1000, 512, 658 };                        // 3000 samples; the second note starts after block 2
-	for (int graph : { KB_SY_ADDITIVE_SAW, KB_SY_ADDITIVE_SQUARE }) {
+	for (int graph : { KB_SY_ADDITIVE_SAW, KB_SY_ADDITIVE_SQUARE, KB_SY_ADDITIVE_NYQUIST }) {
 		const KbFs fs = kb_make_fs(graph == KB_SY_ADDITIVE_SAW ? 48000.f : 44100.f);
 		KbAddVoice a, b;
 		memset(&a, 0, sizeof(a)); memset(&b, 0, sizeof(b));

@@ -287,7 +287,7 @@ def test_additive_voices_match_oracle_and_time_parallel_form_on_host():
         sy.close()
         return np.concatenate([a, b])
 
-    want = np.concatenate([port(oracle.SY_ADDITIVE_SAW, 48000.0), port(oracle.SY_ADDITIVE_SQUARE, 44100.0)])
+    want = np.concatenate([port(oracle.SY_ADDITIVE_SAW, 48000.0), port(oracle.SY_ADDITIVE_SQUARE, 44100.0), port(oracle.SY_ADDITIVE_NYQUIST, 44100.0)])
     assert len(got) == len(want) and np.array_equal(got.view(np.uint32), want.view(np.uint32))
     assert np.abs(want).max() > 0.5
 

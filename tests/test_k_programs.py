@@ -56,7 +56,7 @@ def _expected(prog, fs, n, blocks):
         return np.stack(outs)                         # [blocks, channels, n]
     graph = {"supersaw": oracle.SY_SUPERSAW, "filter_k": oracle.SY_FILTER_K, "tb303": oracle.SY_TB303, "synthx": oracle.SY_SYNTHX, "fm": oracle.SY_FM,
              "breakpoint": oracle.SY_BREAKPOINT, "ramp": oracle.SY_RAMP, "release": oracle.SY_RELEASE,
-             "additive_saw": oracle.SY_ADDITIVE_SAW, "additive_square": oracle.SY_ADDITIVE_SQUARE,
+             "additive_saw": oracle.SY_ADDITIVE_SAW, "additive_square": oracle.SY_ADDITIVE_SQUARE, "additive_nyquist": oracle.SY_ADDITIVE_NYQUIST,
              "am": oracle.SY_AM, "mod_fm": oracle.SY_MOD_FM, "mod_fm2": oracle.SY_MOD_FM2}[prog]
     sy = oracle.port.Synth(graph, 32)
     outs = []

@@ -109,7 +109,7 @@ def test_sine_envelope_synths_match_reference_golden(golden, fs, name):
     _exact(np.ascontiguousarray(r["out"]), golden[fs][f"synth/{name}/mix"], f"synth/{name}/mix")
 
 
-@pytest.mark.parametrize("prog", ["breakpoint", "ramp", "release", "pan", "rm", "tremolo", "clipping", "echo", "feedback", "additive_saw", "additive_square", "am", "mod_fm", "mod_fm2", "functions", "mute"])
+@pytest.mark.parametrize("prog", ["breakpoint", "ramp", "release", "pan", "rm", "tremolo", "clipping", "echo", "feedback", "additive_saw", "additive_square", "am", "mod_fm", "mod_fm2", "functions", "mute", "additive_nyquist"])
 def test_late_k_programs_run_unmodified_on_the_device(prog, tmp_path):
     """examples/Subtractive/{Breakpoint,Ramp,Release}.k, Gain/{Pan,RM,Tremolo}.k, Distortion/Clipping.k, Delay/{Echo,Feedback}.k Additive/{Saw,Square}.k and Modulation/{AM,FM,FM2}.k, Distortion/{Functions,Mute}.k compiled UNMODIFIED against
     include/compat/klang.h (tools/k_host.cpp) and run on the device through the host program: bit-identical to the oracle run with
@@ -163,7 +163,7 @@ def test_late_effect_bank_vs_live_oracle(graph):
         r.close()
 
 
-@pytest.mark.parametrize("graph", [cases.SY_ADDITIVE_SAW, cases.SY_ADDITIVE_SQUARE])
+@pytest.mark.parametrize("graph", [cases.SY_ADDITIVE_SAW, cases.SY_ADDITIVE_SQUARE, cases.SY_ADDITIVE_NYQUIST])
 def test_additive_time_parallel_kernel_equals_lane_per_voice_kernel(graph):
     """Additive/Saw.k / Square.k: kb_additive_kernel (thread = (voice, sample), the default) against the lane-per-voice kernel
     (KB_LANE_PER_VOICE), bit for bit over ragged blocks with re-triggers (the partials keep their phase) and cut notes; 3 x 21 voices."""

@@ -78,6 +78,9 @@ namespace k_functions {
 namespace k_mute {
 #include "Distortion/Mute.k"
 }
+namespace k_add_nyquist {
+#include "Additive/Nyquist.k"
+}
 namespace k_breakpoint {
 #include "Subtractive/Breakpoint.k"
 }
@@ -111,6 +114,7 @@ KLANG_B200_SYNTH(k_mod_fm::FM, KB_SY_MOD_FM)
 KLANG_B200_SYNTH(k_mod_fm2::FM2, KB_SY_MOD_FM2)
 KLANG_B200_EFFECT(k_functions::Functions, KB_FX_FUNCTIONS)
 KLANG_B200_EFFECT(k_mute::Mute, KB_FX_MUTE)
+KLANG_B200_SYNTH(k_add_nyquist::Nyquist, KB_SY_ADDITIVE_NYQUIST)
 KLANG_B200_SYNTH(k_breakpoint::Breakpoint, KB_SY_BREAKPOINT)
 KLANG_B200_SYNTH(k_ramp::Ramp, KB_SY_RAMP)
 KLANG_B200_SYNTH(k_release::Release, KB_SY_RELEASE)
@@ -180,6 +184,7 @@ int main(int argc, char** argv) {
 		else if (prog == "mod_fm2") rc = run_synth<k_mod_fm2::FM2>(fs, n, blocks, out);
 		else if (prog == "functions") rc = run_effect<k_functions::Functions>(fs, n, blocks, out);
 		else if (prog == "mute") rc = run_effect<k_mute::Mute>(fs, n, blocks, out);
+		else if (prog == "additive_nyquist") rc = run_synth<k_add_nyquist::Nyquist>(fs, n, blocks, out);
 		else if (prog == "breakpoint") rc = run_synth<k_breakpoint::Breakpoint>(fs, n, blocks, out);
 		else if (prog == "ramp") rc = run_synth<k_ramp::Ramp>(fs, n, blocks, out);
 		else if (prog == "release") rc = run_synth<k_release::Release>(fs, n, blocks, out);
