@@ -72,6 +72,7 @@ static SampleRate fs;
 template <class T> inline T sqr(T x) { return x * x; }
 inline float sqr(const Control& c);
 template <class T> inline T cube(T x) { return x * x * x; }
+inline float cube(const Control& c);
 inline float random(float lo, float hi) { return rand() * ((hi - lo) / (float)RAND_MAX) + lo; }
 inline double random(double lo, double hi) { return rand() * ((hi - lo) / (double)RAND_MAX) + lo; }
 inline void random(unsigned seed) { srand(seed); }
@@ -107,6 +108,7 @@ protected:
 inline signal::signal(const Control& c) : value(c.value) {}
 inline param::param(const Control& c) : signal(c.value) {}
 inline float sqr(const Control& c) { return c.value * c.value; }
+inline float cube(const Control& c) { return c.value * c.value * c.value; }
 
 struct Dial : Control { Dial(const char* n, float lo = 0.f, float hi = 1.f, float init = 0.f) : Control(n, lo, hi, init) {} };
 struct Slider : Control { Slider(const char* n, float lo = 0.f, float hi = 1.f, float init = 0.f) : Control(n, lo, hi, init) {} };

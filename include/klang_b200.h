@@ -43,6 +43,7 @@ extern "C" {
 #define KB_FX_FEEDBACK 10         /* examples/Delay/Feedback.k     mono   (one Delay<192000> fed the output) */
 #define KB_FX_FUNCTIONS 11        /* examples/Distortion/Functions.k mono (elementwise: hardclip(in * gain)) */
 #define KB_FX_MUTE 12             /* examples/Distortion/Mute.k    mono   (elementwise: a Toggle) */
+#define KB_FX_IIR 13              /* examples/Filtering/IIR.k      mono   (one-pole smoother, coefficient cube(control)) */
 
 /* synth graphs */
 #define KB_SY_SUBTRACTIVE 0       /* Saw >> LPF(env) >> ADSR: Filter.k with a Saw and ADSR controls mono */

@@ -9,7 +9,7 @@
 
 #include "../../include/klang_b200.h"   // graph ids KB_SY_* / KB_FX_*
 #define KB_SY_COUNT 15
-#define KB_FX_COUNT 13
+#define KB_FX_COUNT 14
 
 // =========================================================================================== HOST halves
 
@@ -336,6 +336,14 @@ KB_D float kb_feedback_frame(const KbFs& fs, const KbFxHdr& h, KbOneDelayFx& s, 
 	const float out = in + kb_delay_tap_f(s.delay, ring, time) * gain;       // in + delay(time) * gain >> out
 	kb_delay_write(s.delay, ring, out);                                       // delay << out
 	return out;
+}
+
+// Filtering/IIR.k:14-26: f = cube(controls[0]); filtered = (1 - f) * last + f * dry; last = filtered   (a true fp32 recurrence: one lane)
+KB_HD float kb_iir_frame(const KbFxHdr& h, KbIirFx& s, float in) {
+	const float x = h.controls[0].value, f = x * x * x;
+	const float filtered = (1 - f) * s.last + f * in;
+	s.last = filtered;
+	return filtered;
 }
 
 // Echo.k, time-parallel: the line is only ever fed the INPUT, so a block is two independent sweeps — write all n inputs into the ring, then

@@ -104,3 +104,5 @@ struct KbGainFx { int unused; };
 struct KbLfoFx { KbFastSine lfo; };
 // examples/Delay/Echo.k, Feedback.k: one Delay<192000>
 struct KbOneDelayFx { KbDelay delay; };
+// examples/Filtering/IIR.k: the smoother's last output
+struct KbIirFx { float last; };

@@ -81,6 +81,9 @@ namespace k_mute {
 namespace k_add_nyquist {
 #include "Additive/Nyquist.k"
 }
+namespace k_iir {
+#include "Filtering/IIR.k"
+}
 namespace k_breakpoint {
 #include "Subtractive/Breakpoint.k"
 }
@@ -115,6 +118,7 @@ KLANG_B200_SYNTH(k_mod_fm2::FM2, KB_SY_MOD_FM2)
 KLANG_B200_EFFECT(k_functions::Functions, KB_FX_FUNCTIONS)
 KLANG_B200_EFFECT(k_mute::Mute, KB_FX_MUTE)
 KLANG_B200_SYNTH(k_add_nyquist::Nyquist, KB_SY_ADDITIVE_NYQUIST)
+KLANG_B200_EFFECT(k_iir::IIR, KB_FX_IIR)
 KLANG_B200_SYNTH(k_breakpoint::Breakpoint, KB_SY_BREAKPOINT)
 KLANG_B200_SYNTH(k_ramp::Ramp, KB_SY_RAMP)
 KLANG_B200_SYNTH(k_release::Release, KB_SY_RELEASE)
@@ -185,6 +189,7 @@ int main(int argc, char** argv) {
 		else if (prog == "functions") rc = run_effect<k_functions::Functions>(fs, n, blocks, out);
 		else if (prog == "mute") rc = run_effect<k_mute::Mute>(fs, n, blocks, out);
 		else if (prog == "additive_nyquist") rc = run_synth<k_add_nyquist::Nyquist>(fs, n, blocks, out);
+		else if (prog == "iir") rc = run_effect<k_iir::IIR>(fs, n, blocks, out);
 		else if (prog == "breakpoint") rc = run_synth<k_breakpoint::Breakpoint>(fs, n, blocks, out);
 		else if (prog == "ramp") rc = run_synth<k_ramp::Ramp>(fs, n, blocks, out);
 		else if (prog == "release") rc = run_synth<k_release::Release>(fs, n, blocks, out);
