@@ -151,7 +151,7 @@ struct Generator {
 struct Modifier : Generator {
 	signal in;
 	virtual void input() {}
-	template <class... P> void operator()(P... p) { set(param(p)...); }
+	template <class... P> Modifier& operator()(P... p) { set(param(p)...); return *this; }   // `in >> lpf(f, Q) >> out` (klang.h:2306-2308)
 	virtual void set(param) {}
 	virtual void set(param, param) {}
 	virtual void set(param, param, param) {}

@@ -44,6 +44,7 @@ extern "C" {
 #define KB_FX_FUNCTIONS 11        /* examples/Distortion/Functions.k mono (elementwise: hardclip(in * gain)) */
 #define KB_FX_MUTE 12             /* examples/Distortion/Mute.k    mono   (elementwise: a Toggle) */
 #define KB_FX_IIR 13              /* examples/Filtering/IIR.k      mono   (one-pole smoother, coefficient cube(control)) */
+#define KB_FX_WAHWAH 14           /* examples/Filtering/WahWah.k   mono   (Biquad::LPF, cutoff set every sample from a sine LFO) */
 
 /* synth graphs */
 #define KB_SY_SUBTRACTIVE 0       /* Saw >> LPF(env) >> ADSR: Filter.k with a Saw and ADSR controls mono */

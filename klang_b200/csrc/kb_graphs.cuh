@@ -9,7 +9,7 @@
 
 #include "../../include/klang_b200.h"   // graph ids KB_SY_* / KB_FX_*
 #define KB_SY_COUNT 15
-#define KB_FX_COUNT 14
+#define KB_FX_COUNT 15
 
 // =========================================================================================== HOST halves
 
@@ -344,6 +344,16 @@ KB_HD float kb_iir_frame(const KbFxHdr& h, KbIirFx& s, float in) {
 	const float filtered = (1 - f) * s.last + f * in;
 	s.last = filtered;
 	return filtered;
+}
+
+// Filtering/WahWah.k:18-27: mod = lfo(rate) * 0.5 + 0.5f; in >> lpf(sqr(mod) * f, Q) >> out.  Biquad::Filter::set runs every sample
+// (cosf / sinf of the moving cutoff, klang.h:5584-5600); the filter state is the serial chain: one lane per instance.
+KB_HD float kb_wahwah_frame(const KbFs& fs, const KbFxHdr& h, KbWahWahFx& s, float in) {
+	const float f = h.controls[0].value, Q = h.controls[1].value, rate = h.controls[2].value;
+	kb_fsine_set_f(fs, s.lfo, rate);
+	const float mod = kb_fsine_tick(s.lfo) * 0.5f + 0.5f;
+	kb_biquad_set(fs, s.lpf, (mod * mod) * f, Q);
+	return kb_biquad_tick(s.lpf, in);
 }
 
 // Echo.k, time-parallel: the line is only ever fed the INPUT, so a block is two independent sweeps — write all n inputs into the ring, then

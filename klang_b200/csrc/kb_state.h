@@ -106,3 +106,5 @@ struct KbLfoFx { KbFastSine lfo; };
 struct KbOneDelayFx { KbDelay delay; };
 // examples/Filtering/IIR.k: the smoother's last output
 struct KbIirFx { float last; };
+// examples/Filtering/WahWah.k: Biquad::LPF + Fast::Sine LFO
+struct KbWahWahFx { KbBiquad lpf; KbFastSine lfo; };

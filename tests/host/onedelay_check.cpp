@@ -23,13 +23,16 @@ int main(int argc, char** argv) {
 	h.controls[0] = kb_dial(0.f, 1.f, 0.5f); h.controls[1] = kb_dial(0.f, 1.f, 0.5f);
 	KbOneDelayFx s;
 	kb_delay_construct(s.delay, 192000, 0);
-	KbIirFx iir = { 0.f };                                                    // Filtering/IIR.k rides along: same block / event driver
+	KbIirFx iir = { 0.f };                                                    // Filtering/IIR.k and WahWah.k ride along: same block / event driver
+	KbWahWahFx wah;
+	kb_biquad_construct(wah.lpf, KB_BQ_LPF); kb_fsine_init(wah.lfo);
+	if (graph == KB_FX_WAHWAH) { h.controls[0] = kb_dial(10.f, 10000.f, 1000.f); h.controls[1] = kb_dial(0.1f, 10.f, 1.f); h.controls[2] = kb_dial(4.f, 10.f, 6.f); }
 	for (int b = 0; b * block < total; b++) {
 		for (int a = 6; a + 2 < argc; a += 3) if (atoi(argv[a]) == b) kb_control_set(h.controls[atoi(argv[a + 1])], (float)atof(argv[a + 2]));
 		const int n = total - b * block < block ? total - b * block : block;
 		for (int t = 0; t < n; t++) {
 			float& x = io[(size_t)b * block + t];
-			x = graph == KB_FX_IIR ? kb_iir_frame(h, iir, x) : graph == KB_FX_ECHO ? kb_echo_frame(fs, h, s, ring.data(), x) : kb_feedback_frame(fs, h, s, ring.data(), x);
+			x = graph == KB_FX_WAHWAH ? kb_wahwah_frame(fs, h, wah, x) : graph == KB_FX_IIR ? kb_iir_frame(h, iir, x) : graph == KB_FX_ECHO ? kb_echo_frame(fs, h, s, ring.data(), x) : kb_feedback_frame(fs, h, s, ring.data(), x);
 		}
 	}
 	fwrite(io.data(), 4, io.size(), stdout);

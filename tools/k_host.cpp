@@ -84,6 +84,9 @@ namespace k_add_nyquist {
 namespace k_iir {
 #include "Filtering/IIR.k"
 }
+namespace k_wahwah {
+#include "Filtering/WahWah.k"
+}
 namespace k_breakpoint {
 #include "Subtractive/Breakpoint.k"
 }
@@ -119,6 +122,7 @@ KLANG_B200_EFFECT(k_functions::Functions, KB_FX_FUNCTIONS)
 KLANG_B200_EFFECT(k_mute::Mute, KB_FX_MUTE)
 KLANG_B200_SYNTH(k_add_nyquist::Nyquist, KB_SY_ADDITIVE_NYQUIST)
 KLANG_B200_EFFECT(k_iir::IIR, KB_FX_IIR)
+KLANG_B200_EFFECT(k_wahwah::WahWah, KB_FX_WAHWAH)
 KLANG_B200_SYNTH(k_breakpoint::Breakpoint, KB_SY_BREAKPOINT)
 KLANG_B200_SYNTH(k_ramp::Ramp, KB_SY_RAMP)
 KLANG_B200_SYNTH(k_release::Release, KB_SY_RELEASE)
@@ -190,6 +194,7 @@ int main(int argc, char** argv) {
 		else if (prog == "mute") rc = run_effect<k_mute::Mute>(fs, n, blocks, out);
 		else if (prog == "additive_nyquist") rc = run_synth<k_add_nyquist::Nyquist>(fs, n, blocks, out);
 		else if (prog == "iir") rc = run_effect<k_iir::IIR>(fs, n, blocks, out);
+		else if (prog == "wahwah") rc = run_effect<k_wahwah::WahWah>(fs, n, blocks, out);
 		else if (prog == "breakpoint") rc = run_synth<k_breakpoint::Breakpoint>(fs, n, blocks, out);
 		else if (prog == "ramp") rc = run_synth<k_ramp::Ramp>(fs, n, blocks, out);
 		else if (prog == "release") rc = run_synth<k_release::Release>(fs, n, blocks, out);
