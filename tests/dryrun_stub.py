@@ -106,5 +106,4 @@ import pytest  # noqa: E402
 
 if __name__ == "__main__":
     # subprocess-based tests (k_host, probes) cannot be dry-run: deselect them
-    sys.exit(pytest.main([os.path.join(HERE, "test_zz_gpu_primitives.py"), os.path.join(HERE, "test_gpu_parity.py::test_midi_input_equals_note_on_off_calls"),
-                          "-q", "-x", "-p", "no:cacheprovider", "-k", "not k_programs"]))
+    sys.exit(pytest.main([os.path.join(HERE, "test_zz_gpu_primitives.py"), "-q", "-x", "-p", "no:cacheprovider", "-k", "not k_programs"]))

@@ -551,33 +551,6 @@ def test_batched_events_equal_single_calls(eng):
     assert np.abs(outs[0]).max() > 0.01
 
 
-def test_midi_input_equals_note_on_off_calls(eng):
-    """kb_synth_bank_midi is Synth::input(status, b1, b2) (templates/juce/synth/Source/klang.h:3921-3929): 0x90 with a velocity is
-    noteOn(b1, b2 / 127.f), 0x80 or 0x90 with velocity 0 is noteOff, other messages change nothing."""
-    n, voices = 384, 8
-    msgs = [[(0x90, 48 + 3 * k, 20 + 9 * k) for k in range(10)] + [(0xB0, 1, 64), (0xE0, 0, 64)],    # 10 notes into 8 voices: stealing
-            [(0x80, 72, 0), (0x90, 75, 0), (0x80, 60, 100), (0x91, 50, 100), (0xC0, 5, 0)],
-            [(0x90, 40, 127), (0x80, 40, 0)]]
-    outs = []
-    for raw in (True, False):
-        kb.lib().kb_srand(3)
-        bank = kb.SynthBank(kb.SY_SUPERSAW, 1, voices, 48000, n)
-        res = []
-        for block in msgs:
-            for st, b1, b2 in block:
-                if raw:
-                    bank.midi(st, b1, b2)
-                elif st == 0x90 and b2 > 0:
-                    bank.note_on(b1, float(np.float32(b2) / np.float32(127)))
-                elif st == 0x80 or (st == 0x90 and b2 == 0):
-                    bank.note_off(b1, float(np.float32(b2) / np.float32(127)))
-            res.append(bank.process_block(n, kb.PER_VOICE))
-        bank.close()
-        outs.append(np.concatenate(res, axis=-1))
-    assert_parity(outs[0], outs[1], "midi input", exact=True)
-    assert np.abs(outs[0]).max() > 0.01
-
-
 def test_device_pointer_calls_match_host_pointer_calls(eng):
     """KB_DEVICE_PTR (asynchronous, caller-owned device buffers and stream) returns the same bits as the host-buffer call."""
     torch = pytest.importorskip("torch")
