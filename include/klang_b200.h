@@ -45,6 +45,9 @@ extern "C" {
 #define KB_FX_MUTE 12             /* examples/Distortion/Mute.k    mono   (elementwise: a Toggle) */
 #define KB_FX_IIR 13              /* examples/Filtering/IIR.k      mono   (one-pole smoother, coefficient cube(control)) */
 #define KB_FX_WAHWAH 14           /* examples/Filtering/WahWah.k   mono   (Biquad::LPF, cutoff set every sample from a sine LFO) */
+#define KB_FX_FLANGER 15          /* examples/Modulation/Flanger.k  mono  (delay tapped at a triangle-LFO time, plus the input) */
+#define KB_FX_MODDELAY 16         /* examples/Modulation/ModDelay.k mono  (delay tapped at a sine-LFO time, smoothed depth control) */
+#define KB_FX_MOD_CHORUS 17       /* examples/Modulation/Chorus.k   mono  (one delay, three sine-LFO taps) */
 
 /* synth graphs */
 #define KB_SY_SUBTRACTIVE 0       /* Saw >> LPF(env) >> ADSR: Filter.k with a Saw and ADSR controls mono */

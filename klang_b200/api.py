@@ -12,7 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 lib_path = os.path.join(_HERE, "lib", "libklang_b200.so")
 
-FX_GAIN, FX_PINGPONG, FX_REVERB, FX_DELAY_PINGPONG, FX_DELAY_REVERB, FX_PAN, FX_RM, FX_TREMOLO, FX_CLIPPING, FX_ECHO, FX_FEEDBACK, FX_FUNCTIONS, FX_MUTE, FX_IIR, FX_WAHWAH = range(15)
+FX_GAIN, FX_PINGPONG, FX_REVERB, FX_DELAY_PINGPONG, FX_DELAY_REVERB, FX_PAN, FX_RM, FX_TREMOLO, FX_CLIPPING, FX_ECHO, FX_FEEDBACK, FX_FUNCTIONS, FX_MUTE, FX_IIR, FX_WAHWAH, FX_FLANGER, FX_MODDELAY, FX_MOD_CHORUS = range(18)
 SY_SUBTRACTIVE, SY_SUPERSAW, SY_TB303, SY_SYNTHX, SY_FILTER_K, SY_FM, SY_BREAKPOINT, SY_RAMP, SY_RELEASE, SY_ADDITIVE_SAW, SY_ADDITIVE_SQUARE, SY_AM, SY_MOD_FM, SY_MOD_FM2, SY_ADDITIVE_NYQUIST = range(15)
 DEVICE_PTR, PER_VOICE, MIX_SUM, BANK_MIX, LANE_PER_VOICE, FX_SEQUENTIAL, ASYNC_HOST = 1, 2, 4, 8, 16, 32, 64
 

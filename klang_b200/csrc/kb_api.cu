@@ -107,6 +107,7 @@ extern "C" kb_fx_bank* kb_fx_bank_create(int graph, int instances, float fs, int
 	case KB_FX_ECHO: case KB_FX_FEEDBACK: b->channels = 1; b->ncontrols = 2; b->state_bytes = sizeof(KbOneDelayFx); b->ring_floats = KB_ONEDELAY_RING_FLOATS; break;
 	case KB_FX_IIR: b->channels = 1; b->ncontrols = 1; b->state_bytes = sizeof(KbIirFx); b->ring_floats = 0; break;
 	case KB_FX_WAHWAH: b->channels = 1; b->ncontrols = 3; b->state_bytes = sizeof(KbWahWahFx); b->ring_floats = 0; break;
+	case KB_FX_FLANGER: case KB_FX_MODDELAY: case KB_FX_MOD_CHORUS: b->channels = 1; b->ncontrols = 2; b->state_bytes = sizeof(KbModDelayFx); b->ring_floats = KB_ONEDELAY_RING_FLOATS; break;
 	}
 	b->hdr.assign(instances, KbFxHdr());
 	memset(b->hdr.data(), 0, b->hdr.size() * sizeof(KbFxHdr));
@@ -127,6 +128,15 @@ extern "C" kb_fx_bank* kb_fx_bank_create(int graph, int instances, float fs, int
 		case KB_FX_FUNCTIONS: b->hdr[i].controls[0] = kb_dial(1.f, 25.f, 1.f); break;                                         // Functions.k:18
 		case KB_FX_MUTE: b->hdr[i].controls[0] = kb_dial(0.f, 1.f, 0.f); break;                                               // Toggle("Mute"), Mute.k:10
 		case KB_FX_IIR: b->hdr[i].controls[0] = kb_dial(0.f, 1.f, 0.5f); b->st<KbIirFx>(i).last = 0.f; break;                  // IIR.k:5, 10
+		case KB_FX_FLANGER: case KB_FX_MODDELAY: case KB_FX_MOD_CHORUS: {                                                     // Flanger.k:11-14, ModDelay.k:11-14, Chorus.k:11-14
+			KbModDelayFx& m = b->st<KbModDelayFx>(i);
+			kb_delay_construct(m.delay, 192000, ring0);
+			for (int k = 0; k < 3; k++) kb_fsine_init(m.lfo[k]);
+			kb_osm_construct(m.tri, 0, 1.0f);                                                                                 // Fast::Triangle (saw waveform, duty 1)
+			if (graph == KB_FX_FLANGER) { b->hdr[i].controls[0] = kb_dial(0.1f, 1.0f, 0.75f); b->hdr[i].controls[1] = kb_dial(0.1f, 5.0f, 1.5f); }
+			else if (graph == KB_FX_MODDELAY) { b->hdr[i].controls[0] = kb_dial(1.f, 10.f, 6.f); b->hdr[i].controls[1] = kb_dial(0.f, 1.f, 0.2f); }
+			else { b->hdr[i].controls[0] = kb_dial(1.f, 10.f, 6.f); b->hdr[i].controls[1] = kb_dial(0.f, 1.f, 0.1f); }
+			break; }
 		case KB_FX_WAHWAH:                                                                                                    // WahWah.k:10-14
 			b->hdr[i].controls[0] = kb_dial(10.f, 10000.f, 1000.f); b->hdr[i].controls[1] = kb_dial(0.1f, 10.f, 1.f); b->hdr[i].controls[2] = kb_dial(4.f, 10.f, 6.f);
 			kb_biquad_construct(b->st<KbWahWahFx>(i).lpf, KB_BQ_LPF); kb_fsine_init(b->st<KbWahWahFx>(i).lfo); break;
@@ -170,6 +180,7 @@ extern "C" int kb_fx_bank_parallel_instances(kb_fx_bank* b) {
 	if (!b) return kb_fail(KB_EINVAL, "null bank");
 	if (b->graph == KB_FX_GAIN || (b->graph >= KB_FX_PAN && b->graph <= KB_FX_CLIPPING) || b->graph == KB_FX_FUNCTIONS || b->graph == KB_FX_MUTE) return b->instances;
 	if (b->graph == KB_FX_IIR || b->graph == KB_FX_WAHWAH) return 0;                 // a recurrence: one lane per instance
+	if (b->graph >= KB_FX_FLANGER && b->graph <= KB_FX_MOD_CHORUS) return 0;         // frame-sequential schedule only, so far
 	if (b->graph == KB_FX_ECHO) return b->instances;                                 // (blocks longer than SIZE - fs frames fall back to the sequential schedule)
 	if (b->graph == KB_FX_FEEDBACK) {                                                // instances whose delay is long enough for a chunk (at this block size)
 		int count = 0;
@@ -219,6 +230,8 @@ extern "C" double kb_fx_bank_bytes_per_frame(kb_fx_bank* b) {
 	case KB_FX_PAN: return 16;
 	case KB_FX_RM: case KB_FX_TREMOLO: case KB_FX_CLIPPING: case KB_FX_FUNCTIONS: case KB_FX_MUTE: return 8;
 	case KB_FX_IIR: case KB_FX_WAHWAH: return 8;
+	case KB_FX_FLANGER: case KB_FX_MODDELAY: return 20;
+	case KB_FX_MOD_CHORUS: return 36;                               // 8 io + 4 write + 3 taps x 8
 	case KB_FX_ECHO: case KB_FX_FEEDBACK: return 20;               // 8 io + 4 write + two adjacent floats read
 	}
 	return 0;
@@ -307,6 +320,15 @@ extern "C" int kb_fx_bank_process(kb_fx_bank* b, float* io, int n, unsigned flag
 		break; }
 	case KB_FX_IIR:        // one lane per instance (the smoother is a serial fp32 chain)
 		kb_fx_seq_kernel<KB_FX_IIR, KbIirFx><<<ib, 32, 0, b->stream>>>(b->d_hdr, (KbIirFx*)b->d_state, b->d_rings, d, n, n, 1, b->instances, b->fs, nullptr);
+		break;
+	case KB_FX_FLANGER:    // one lane per instance, frame by frame (feed-forward taps: Echo.k's two sweeps apply, not built)
+		kb_fx_seq_kernel<KB_FX_FLANGER, KbModDelayFx><<<ib, 32, 0, b->stream>>>(b->d_hdr, (KbModDelayFx*)b->d_state, b->d_rings, d, n, n, 1, b->instances, b->fs, nullptr);
+		break;
+	case KB_FX_MODDELAY:
+		kb_fx_seq_kernel<KB_FX_MODDELAY, KbModDelayFx><<<ib, 32, 0, b->stream>>>(b->d_hdr, (KbModDelayFx*)b->d_state, b->d_rings, d, n, n, 1, b->instances, b->fs, nullptr);
+		break;
+	case KB_FX_MOD_CHORUS:
+		kb_fx_seq_kernel<KB_FX_MOD_CHORUS, KbModDelayFx><<<ib, 32, 0, b->stream>>>(b->d_hdr, (KbModDelayFx*)b->d_state, b->d_rings, d, n, n, 1, b->instances, b->fs, nullptr);
 		break;
 	case KB_FX_WAHWAH:     // one lane per instance (the biquad state is a serial fp32 chain; the coefficients could come from parallel workers as in C2)
 		kb_fx_seq_kernel<KB_FX_WAHWAH, KbWahWahFx><<<ib, 32, 0, b->stream>>>(b->d_hdr, (KbWahWahFx*)b->d_state, b->d_rings, d, n, n, 1, b->instances, b->fs, nullptr);

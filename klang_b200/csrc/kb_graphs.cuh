@@ -9,7 +9,7 @@
 
 #include "../../include/klang_b200.h"   // graph ids KB_SY_* / KB_FX_*
 #define KB_SY_COUNT 15
-#define KB_FX_COUNT 15
+#define KB_FX_COUNT 18
 
 // =========================================================================================== HOST halves
 
@@ -354,6 +354,38 @@ KB_HD float kb_wahwah_frame(const KbFs& fs, const KbFxHdr& h, KbWahWahFx& s, flo
 	const float mod = kb_fsine_tick(s.lfo) * 0.5f + 0.5f;
 	kb_biquad_set(fs, s.lpf, (mod * mod) * f, Q);
 	return kb_biquad_tick(s.lpf, in);
+}
+
+// Modulation/Flanger.k:17-24, ModDelay.k:18-26, Chorus.k:17-28: the input is written to the line, which is tapped at LFO-modulated times
+// (feed-forward: the two-sweep schedule of Echo.k applies; frame-sequential for now).  ModDelay.k smooths its depth control per
+// sample (Control::smooth, klang.h:1715-1716), which lives in the header's control block.
+KB_D float kb_moddelay_frame(int graph, const KbFs& fs, KbFxHdr& h, KbModDelayFx& s, float* rings, float in) {
+	float* ring = rings + s.delay.ring;
+	if (graph == KB_FX_FLANGER) {
+		const float rate = h.controls[0].value, depth = h.controls[1].value / 1000.f;
+		kb_osm_set_f(fs, s.tri, rate);
+		const float mod = kb_osm_tick(s.tri) * depth + depth;
+		kb_delay_write(s.delay, ring, in);
+		return in + kb_delay_tap_f(s.delay, ring, mod * fs.f);
+	}
+	if (graph == KB_FX_MODDELAY) {
+		const float rate = h.controls[0].value;
+		const float sm = kb_control_smooth(h.controls[1]);
+		const float depth = (sm * sm * sm) / 10.f;
+		kb_fsine_set_f(fs, s.lfo[0], rate);
+		const float mod = kb_fsine_tick(s.lfo[0]) * depth + depth;
+		kb_delay_write(s.delay, ring, in);
+		return kb_delay_tap_f(s.delay, ring, mod * fs.f);
+	}
+	const float rates[3] = { 2.5f, 3.f, 3.5f }, depths[3] = { 0.45f, 0.5f, 0.55f };
+	kb_delay_write(s.delay, ring, in);
+	float acc = in;
+	for (int k = 0; k < 3; k++) {
+		kb_fsine_set_f(fs, s.lfo[k], rates[k]);
+		const float t = (kb_fsine_tick(s.lfo[k]) * depths[k] + depths[k]) * fs.f / 1000.f;
+		acc = acc + kb_delay_tap_f(s.delay, ring, t);
+	}
+	return 0.5f * acc;
 }
 
 // Echo.k, time-parallel: the line is only ever fed the INPUT, so a block is two independent sweeps — write all n inputs into the ring, then

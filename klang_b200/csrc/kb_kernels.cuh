@@ -389,6 +389,7 @@ __global__ void kb_fx_seq_kernel(KbFxHdr* __restrict__ hdrs, STATE* __restrict__
 		if constexpr (GRAPH == KB_FX_ECHO) { l[i] = kb_echo_frame(fs, h, s, rings, l[i]); }
 		if constexpr (GRAPH == KB_FX_IIR) { l[i] = kb_iir_frame(h, s, l[i]); }
 		if constexpr (GRAPH == KB_FX_WAHWAH) { l[i] = kb_wahwah_frame(fs, h, s, l[i]); }
+		if constexpr (GRAPH == KB_FX_FLANGER || GRAPH == KB_FX_MODDELAY || GRAPH == KB_FX_MOD_CHORUS) { l[i] = kb_moddelay_frame(GRAPH, fs, h, s, rings, l[i]); }
 		if constexpr (GRAPH == KB_FX_FEEDBACK) { l[i] = kb_feedback_frame(fs, h, s, rings, l[i]); }
 	}
 	hdrs[inst] = h;

@@ -108,3 +108,5 @@ struct KbOneDelayFx { KbDelay delay; };
 struct KbIirFx { float last; };
 // examples/Filtering/WahWah.k: Biquad::LPF + Fast::Sine LFO
 struct KbWahWahFx { KbBiquad lpf; KbFastSine lfo; };
+// examples/Modulation/{Flanger,ModDelay,Chorus}.k: one Delay<192000>, sine LFOs / a triangle LFO
+struct KbModDelayFx { KbDelay delay; KbFastSine lfo[3]; KbOsm tri; };

@@ -103,6 +103,15 @@ namespace k_iir {
 namespace k_wahwah {
 #include "Filtering/WahWah.k"
 }
+namespace k_flanger {
+#include "Modulation/Flanger.k"
+}
+namespace k_moddelay {
+#include "Modulation/ModDelay.k"
+}
+namespace k_mod_chorus {
+#include "Modulation/Chorus.k"
+}
 namespace k_echo {
 #include "Delay/Echo.k"
 }
@@ -405,7 +414,7 @@ int ref_control_smooth(float lo, float hi, float initial, int n, const float* va
 }
 
 // ---------------------------------------------------------------------- effects
-enum { FX_GAIN = 0, FX_PINGPONG = 1, FX_REVERB = 2, FX_DELAY_PINGPONG = 3, FX_DELAY_REVERB = 4, FX_PAN = 5, FX_RM = 6, FX_TREMOLO = 7, FX_CLIPPING = 8, FX_ECHO = 9, FX_FEEDBACK = 10, FX_FUNCTIONS = 11, FX_MUTE = 12, FX_IIR = 13, FX_WAHWAH = 14 };
+enum { FX_GAIN = 0, FX_PINGPONG = 1, FX_REVERB = 2, FX_DELAY_PINGPONG = 3, FX_DELAY_REVERB = 4, FX_PAN = 5, FX_RM = 6, FX_TREMOLO = 7, FX_CLIPPING = 8, FX_ECHO = 9, FX_FEEDBACK = 10, FX_FUNCTIONS = 11, FX_MUTE = 12, FX_IIR = 13, FX_WAHWAH = 14, FX_FLANGER = 15, FX_MODDELAY = 16, FX_MOD_CHORUS = 17 };
 
 struct RefFx {
 	int graph;
@@ -433,6 +442,9 @@ void* ref_fx_create(int graph) {
 	case FX_MUTE:     { auto* e = new k_mute::Mute();         fx->mono = e;   fx->controls = &e->controls; } break;
 	case FX_IIR:      { auto* e = new k_iir::IIR();           fx->mono = e;   fx->controls = &e->controls; } break;
 	case FX_WAHWAH:   { auto* e = new k_wahwah::WahWah();     fx->mono = e;   fx->controls = &e->controls; } break;
+	case FX_FLANGER:  { auto* e = new k_flanger::Flanger();   fx->mono = e;   fx->controls = &e->controls; } break;
+	case FX_MODDELAY: { auto* e = new k_moddelay::ModDelay(); fx->mono = e;   fx->controls = &e->controls; } break;
+	case FX_MOD_CHORUS: { auto* e = new k_mod_chorus::Chorus(); fx->mono = e; fx->controls = &e->controls; } break;
 	default: delete fx; return nullptr;
 	}
 	return fx;

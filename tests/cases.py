@@ -19,12 +19,13 @@ import numpy as np
 (FLT_BIQUAD_LPF, FLT_BIQUAD_HPF, FLT_ONEPOLE_LPF, FLT_ONEPOLE_HPF,
  FLT_BIQUAD_BPF, FLT_BIQUAD_BRF, FLT_BIQUAD_APF, FLT_BUTTERWORTH_LPF1, FLT_BUTTERWORTH_LPF2,
  FLT_DCF, FLT_IIR1, FLT_IIR2, FLT_MODAL, FLT_FOLLOWER_PEAK, FLT_FOLLOWER_RMS, FLT_WINDOW_MEAN, FLT_WINDOW_RMS) = range(17)
-FX_GAIN, FX_PINGPONG, FX_REVERB, FX_DELAY_PINGPONG, FX_DELAY_REVERB, FX_PAN, FX_RM, FX_TREMOLO, FX_CLIPPING, FX_ECHO, FX_FEEDBACK, FX_FUNCTIONS, FX_MUTE, FX_IIR, FX_WAHWAH = range(15)
+FX_GAIN, FX_PINGPONG, FX_REVERB, FX_DELAY_PINGPONG, FX_DELAY_REVERB, FX_PAN, FX_RM, FX_TREMOLO, FX_CLIPPING, FX_ECHO, FX_FEEDBACK, FX_FUNCTIONS, FX_MUTE, FX_IIR, FX_WAHWAH, FX_FLANGER, FX_MODDELAY, FX_MOD_CHORUS = range(18)
 SY_SUBTRACTIVE, SY_SUPERSAW, SY_TB303, SY_SYNTHX, SY_FILTER_K, SY_FM, SY_BREAKPOINT, SY_RAMP, SY_RELEASE, SY_ADDITIVE_SAW, SY_ADDITIVE_SQUARE, SY_AM, SY_MOD_FM, SY_MOD_FM2, SY_ADDITIVE_NYQUIST = range(15)
 
 FX_NAMES = {FX_GAIN: "gain", FX_PINGPONG: "pingpong", FX_REVERB: "reverb",
             FX_DELAY_PINGPONG: "delay_pingpong", FX_DELAY_REVERB: "delay_reverb", FX_PAN: "pan", FX_RM: "rm", FX_TREMOLO: "tremolo",
-            FX_CLIPPING: "clipping", FX_ECHO: "echo", FX_FEEDBACK: "feedback", FX_FUNCTIONS: "functions", FX_MUTE: "mute", FX_IIR: "iir", FX_WAHWAH: "wahwah"}
+            FX_CLIPPING: "clipping", FX_ECHO: "echo", FX_FEEDBACK: "feedback", FX_FUNCTIONS: "functions", FX_MUTE: "mute", FX_IIR: "iir", FX_WAHWAH: "wahwah", FX_FLANGER: "flanger",
+            FX_MODDELAY: "moddelay", FX_MOD_CHORUS: "mod_chorus"}
 SY_NAMES = {SY_SUBTRACTIVE: "subtractive", SY_SUPERSAW: "supersaw", SY_TB303: "tb303",
             SY_SYNTHX: "synthx", SY_FILTER_K: "filter_k", SY_FM: "fm", SY_BREAKPOINT: "breakpoint", SY_RAMP: "ramp",
             SY_RELEASE: "release", SY_ADDITIVE_SAW: "additive_saw", SY_ADDITIVE_SQUARE: "additive_square",
@@ -227,6 +228,11 @@ FX_SCRIPTS_LATE = {
     "iir": (FX_IIR, 4096, 1024, [(1, 0, 0.2), (2, 0, 0.9), (3, 0, 0.0)], 3000),
     # Filtering/WahWah.k: Biquad::LPF whose cutoff is set every sample from a squared sine LFO (cosf / sinf per sample)
     "wahwah": (FX_WAHWAH, 6144, 1024, [(2, 0, 4000.0), (2, 1, 8.0), (4, 2, 10.0)], None),
+    # Modulation/Flanger.k (triangle LFO), ModDelay.k (sine LFO, smoothed depth control), Chorus.k (three sine LFOs): one delay line tapped
+    # at a delay that moves every sample
+    "flanger": (FX_FLANGER, 8192, 1024, [(3, 0, 1.0), (3, 1, 5.0)], None),
+    "moddelay": (FX_MODDELAY, 8192, 1024, [(2, 1, 1.0), (5, 0, 10.0)], None),
+    "mod_chorus": (FX_MOD_CHORUS, 8192, 1024, [], None),
 }
 
 

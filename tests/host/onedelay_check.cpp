@@ -24,6 +24,13 @@ int main(int argc, char** argv) {
 	KbOneDelayFx s;
 	kb_delay_construct(s.delay, 192000, 0);
 	KbIirFx iir = { 0.f };                                                    // Filtering/IIR.k and WahWah.k ride along: same block / event driver
+	KbModDelayFx md;
+	kb_delay_construct(md.delay, 192000, 0);
+	for (int k = 0; k < 3; k++) kb_fsine_init(md.lfo[k]);
+	kb_osm_construct(md.tri, 0, 1.0f);
+	if (graph == KB_FX_FLANGER) { h.controls[0] = kb_dial(0.1f, 1.0f, 0.75f); h.controls[1] = kb_dial(0.1f, 5.0f, 1.5f); }
+	if (graph == KB_FX_MODDELAY) { h.controls[0] = kb_dial(1.f, 10.f, 6.f); h.controls[1] = kb_dial(0.f, 1.f, 0.2f); }
+	if (graph == KB_FX_MOD_CHORUS) { h.controls[0] = kb_dial(1.f, 10.f, 6.f); h.controls[1] = kb_dial(0.f, 1.f, 0.1f); }
 	KbWahWahFx wah;
 	kb_biquad_construct(wah.lpf, KB_BQ_LPF); kb_fsine_init(wah.lfo);
 	if (graph == KB_FX_WAHWAH) { h.controls[0] = kb_dial(10.f, 10000.f, 1000.f); h.controls[1] = kb_dial(0.1f, 10.f, 1.f); h.controls[2] = kb_dial(4.f, 10.f, 6.f); }
@@ -32,7 +39,7 @@ int main(int argc, char** argv) {
 		const int n = total - b * block < block ? total - b * block : block;
 		for (int t = 0; t < n; t++) {
 			float& x = io[(size_t)b * block + t];
-			x = graph == KB_FX_WAHWAH ? kb_wahwah_frame(fs, h, wah, x) : graph == KB_FX_IIR ? kb_iir_frame(h, iir, x) : graph == KB_FX_ECHO ? kb_echo_frame(fs, h, s, ring.data(), x) : kb_feedback_frame(fs, h, s, ring.data(), x);
+			x = (graph >= KB_FX_FLANGER && graph <= KB_FX_MOD_CHORUS) ? kb_moddelay_frame(graph, fs, h, md, ring.data(), x) : graph == KB_FX_WAHWAH ? kb_wahwah_frame(fs, h, wah, x) : graph == KB_FX_IIR ? kb_iir_frame(h, iir, x) : graph == KB_FX_ECHO ? kb_echo_frame(fs, h, s, ring.data(), x) : kb_feedback_frame(fs, h, s, ring.data(), x);
 		}
 	}
 	fwrite(io.data(), 4, io.size(), stdout);

@@ -216,7 +216,7 @@ def test_elementwise_effects_match_reference_golden_on_host():
     for fs in (44100, 48000):
         g = np.load(os.path.join(ROOT, "tests", "golden", f"klang_ref_fs{fs}.npz"))
         for name, (graph, total, block, events, burst) in cases.FX_SCRIPTS_LATE.items():
-            if graph in (cases.FX_ECHO, cases.FX_FEEDBACK, cases.FX_IIR, cases.FX_WAHWAH):
+            if graph in (cases.FX_ECHO, cases.FX_FEEDBACK, cases.FX_IIR, cases.FX_WAHWAH, cases.FX_FLANGER, cases.FX_MODDELAY, cases.FX_MOD_CHORUS):
                 continue                                  # test_one_delay_effects_match_reference_golden_on_host
             channels = 2 if graph == cases.FX_PAN else 1
             x = cases.fx_input(channels, total, 1, burst)
@@ -247,7 +247,7 @@ def test_one_delay_effects_match_reference_golden_on_host():
     for fs in (44100, 48000):
         g = np.load(os.path.join(ROOT, "tests", "golden", f"klang_ref_fs{fs}.npz"))
         for name, (graph, total, block, events, burst) in cases.FX_SCRIPTS_LATE.items():
-            if graph not in (cases.FX_ECHO, cases.FX_FEEDBACK, cases.FX_IIR, cases.FX_WAHWAH):
+            if graph not in (cases.FX_ECHO, cases.FX_FEEDBACK, cases.FX_IIR, cases.FX_WAHWAH, cases.FX_FLANGER, cases.FX_MODDELAY, cases.FX_MOD_CHORUS):
                 continue
             path = os.path.join(tmp, "in.f32")
             np.ascontiguousarray(cases.fx_input(1, total, 1, burst)[0], np.float32).tofile(path)
@@ -259,7 +259,7 @@ def test_one_delay_effects_match_reference_golden_on_host():
             got = np.frombuffer(out.stdout, np.float32)
             assert np.array_equal(got.view(np.uint32), g[f"fx/{name}"].view(np.uint32)), (fs, name)
             checked += 1
-    assert checked == 10                                  # echo, feedback, feedback_zero_delay, iir, wahwah at both rates
+    assert checked == 16                                  # echo, feedback, feedback_zero_delay, iir, wahwah, flanger, moddelay, mod_chorus at both rates
 
 
 def test_additive_voices_match_oracle_and_time_parallel_form_on_host():

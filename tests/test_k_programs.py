@@ -42,7 +42,7 @@ def _expected(prog, fs, n, blocks):
     fx_graphs = {"gain": oracle.FX_GAIN, "pingpong": oracle.FX_PINGPONG, "delay_pingpong": oracle.FX_DELAY_PINGPONG, "delay_reverb": oracle.FX_DELAY_REVERB,
                  "reverb": oracle.FX_REVERB, "pan": oracle.FX_PAN, "rm": oracle.FX_RM, "tremolo": oracle.FX_TREMOLO, "clipping": oracle.FX_CLIPPING,
                  "echo": oracle.FX_ECHO, "feedback": oracle.FX_FEEDBACK, "functions": oracle.FX_FUNCTIONS, "mute": oracle.FX_MUTE,
-                 "iir": oracle.FX_IIR, "wahwah": oracle.FX_WAHWAH}
+                 "iir": oracle.FX_IIR, "wahwah": oracle.FX_WAHWAH, "flanger": oracle.FX_FLANGER, "moddelay": oracle.FX_MODDELAY, "mod_chorus": oracle.FX_MOD_CHORUS}
     if prog in fx_graphs:
         graph = fx_graphs[prog]
         fx = oracle.port.Fx(graph)

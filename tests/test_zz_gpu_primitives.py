@@ -109,7 +109,8 @@ def test_sine_envelope_synths_match_reference_golden(golden, fs, name):
     _exact(np.ascontiguousarray(r["out"]), golden[fs][f"synth/{name}/mix"], f"synth/{name}/mix")
 
 
-@pytest.mark.parametrize("prog", ["breakpoint", "ramp", "release", "pan", "rm", "tremolo", "clipping", "echo", "feedback", "additive_saw", "additive_square", "am", "mod_fm", "mod_fm2", "functions", "mute", "additive_nyquist", "iir", "wahwah"])
+@pytest.mark.parametrize("prog", ["breakpoint", "ramp", "release", "pan", "rm", "tremolo", "clipping", "echo", "feedback", "additive_saw", "additive_square", "am", "mod_fm", "mod_fm2", "functions", "mute", "additive_nyquist", "iir", "wahwah", "flanger", "moddelay",
+                                  "mod_chorus"])
 def test_late_k_programs_run_unmodified_on_the_device(prog, tmp_path):
     """examples/Subtractive/{Breakpoint,Ramp,Release}.k, Gain/{Pan,RM,Tremolo}.k, Distortion/Clipping.k, Delay/{Echo,Feedback}.k Additive/{Saw,Square}.k and Modulation/{AM,FM,FM2}.k, Distortion/{Functions,Mute}.k compiled UNMODIFIED against
     include/compat/klang.h (tools/k_host.cpp) and run on the device through the host program: bit-identical to the oracle run with
@@ -130,7 +131,7 @@ def test_late_effects_match_reference_golden(golden, fs, name):
 
 
 @pytest.mark.parametrize("graph", [cases.FX_PAN, cases.FX_RM, cases.FX_TREMOLO, cases.FX_CLIPPING, cases.FX_ECHO, cases.FX_FEEDBACK, cases.FX_FUNCTIONS,
-                                   cases.FX_MUTE, cases.FX_IIR, cases.FX_WAHWAH])
+                                   cases.FX_MUTE, cases.FX_IIR, cases.FX_WAHWAH, cases.FX_FLANGER, cases.FX_MODDELAY, cases.FX_MOD_CHORUS])
 def test_late_effect_bank_vs_live_oracle(graph):
     """Five instances with different controls, ragged blocks (1001 frames: rows that are not 16-byte aligned take the scalar path of
     the streaming kernel, 1024 the vector path), a control change between blocks: every instance equals its own oracle object.
@@ -143,7 +144,8 @@ def test_late_effect_bank_vs_live_oracle(graph):
     ch = bank.channels
     lo, hi = {cases.FX_PAN: (0.0, 1.0), cases.FX_RM: (1.0, 1000.0), cases.FX_TREMOLO: (1.0, 10.0), cases.FX_CLIPPING: (1.0, 11.0),
               cases.FX_ECHO: (0.0, 0.02), cases.FX_FEEDBACK: (0.0, 0.02), cases.FX_FUNCTIONS: (1.0, 25.0), cases.FX_MUTE: (0.0, 1.0),
-              cases.FX_IIR: (0.0, 1.0), cases.FX_WAHWAH: (10.0, 10000.0)}[graph]
+              cases.FX_IIR: (0.0, 1.0), cases.FX_WAHWAH: (10.0, 10000.0), cases.FX_FLANGER: (0.1, 1.0), cases.FX_MODDELAY: (1.0, 10.0),
+              cases.FX_MOD_CHORUS: (1.0, 10.0)}[graph]
     for i in range(inst):
         v = lo + (hi - lo) * (i + 0.5) / inst
         refs[i].set_control(0, v)

@@ -87,6 +87,15 @@ namespace k_iir {
 namespace k_wahwah {
 #include "Filtering/WahWah.k"
 }
+namespace k_flanger {
+#include "Modulation/Flanger.k"
+}
+namespace k_moddelay {
+#include "Modulation/ModDelay.k"
+}
+namespace k_mod_chorus {
+#include "Modulation/Chorus.k"
+}
 namespace k_breakpoint {
 #include "Subtractive/Breakpoint.k"
 }
@@ -123,6 +132,9 @@ KLANG_B200_EFFECT(k_mute::Mute, KB_FX_MUTE)
 KLANG_B200_SYNTH(k_add_nyquist::Nyquist, KB_SY_ADDITIVE_NYQUIST)
 KLANG_B200_EFFECT(k_iir::IIR, KB_FX_IIR)
 KLANG_B200_EFFECT(k_wahwah::WahWah, KB_FX_WAHWAH)
+KLANG_B200_EFFECT(k_flanger::Flanger, KB_FX_FLANGER)
+KLANG_B200_EFFECT(k_moddelay::ModDelay, KB_FX_MODDELAY)
+KLANG_B200_EFFECT(k_mod_chorus::Chorus, KB_FX_MOD_CHORUS)
 KLANG_B200_SYNTH(k_breakpoint::Breakpoint, KB_SY_BREAKPOINT)
 KLANG_B200_SYNTH(k_ramp::Ramp, KB_SY_RAMP)
 KLANG_B200_SYNTH(k_release::Release, KB_SY_RELEASE)
@@ -195,6 +207,9 @@ int main(int argc, char** argv) {
 		else if (prog == "additive_nyquist") rc = run_synth<k_add_nyquist::Nyquist>(fs, n, blocks, out);
 		else if (prog == "iir") rc = run_effect<k_iir::IIR>(fs, n, blocks, out);
 		else if (prog == "wahwah") rc = run_effect<k_wahwah::WahWah>(fs, n, blocks, out);
+		else if (prog == "flanger") rc = run_effect<k_flanger::Flanger>(fs, n, blocks, out);
+		else if (prog == "moddelay") rc = run_effect<k_moddelay::ModDelay>(fs, n, blocks, out);
+		else if (prog == "mod_chorus") rc = run_effect<k_mod_chorus::Chorus>(fs, n, blocks, out);
 		else if (prog == "breakpoint") rc = run_synth<k_breakpoint::Breakpoint>(fs, n, blocks, out);
 		else if (prog == "ramp") rc = run_synth<k_ramp::Ramp>(fs, n, blocks, out);
 		else if (prog == "release") rc = run_synth<k_release::Release>(fs, n, blocks, out);
