@@ -771,6 +771,18 @@ def extras(kb, torch, dev, stream, flush_l2, hbm_peak, peak_src, device_index, w
         fx.close()
     except Exception as e:
         res["echo_k_64"] = {"error": repr(e)}
+    # Modulation/Flanger.k, 64 instances x 65536 frames: write sweep with stash + read sweep (24 algorithmic bytes per frame)
+    try:
+        fx = kb.FxBank(kb.FX_FLANGER, 64, FS, 65536, device_index)
+        fx.set_stream(stream.cuda_stream)
+        io = torch.rand(64, 1, 65536, device=dev) - 0.5
+        ms = time_steps(lambda: fx.process_inplace(io.uniform_(-0.5, 0.5)), 5, warmup=2)
+        ms -= time_steps(lambda: io.uniform_(-0.5, 0.5), 5, warmup=1)
+        res["flanger_k_64"] = {"frames_per_s": 64 * 65536 / (ms * 1e-3), "ms_per_step": ms, "block": 65536, "bytes_per_frame": 24,
+                               "roofline": roof(64 * 65536 * 24 / (ms * 1e-3) / 1e9)}
+        fx.close()
+    except Exception as e:
+        res["flanger_k_64"] = {"error": repr(e)}
     # Additive/Saw.k (32 sine partials per voice, no recurrence at all), Subtractive/Release.k and Modulation/AM.k (one envelope x closed-form
     # sines): time-parallel kernels, each with the lane-per-voice A/B
     for name, graph in (("additive_saw_k_1024", kb.SY_ADDITIVE_SAW), ("release_k_1024", kb.SY_RELEASE), ("am_k_1024", kb.SY_AM)):

@@ -41,6 +41,7 @@ struct kb_bank_base {
 	KbFs fs;
 	int max_block = 0;
 	float* d_io = nullptr; size_t io_floats = 0;   // staging for host-pointer calls
+	float* d_old = nullptr;                        // Flanger.k / Chorus.k: what the block's write sweep overwrote, [instances][max_block]
 	bool host_stale = false, dirty = true;
 	// measurement: CUDA events around the dominant kernel of each process() call
 	bool profiling = false; std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events; size_t prof_used = 0;
@@ -160,6 +161,7 @@ extern "C" kb_fx_bank* kb_fx_bank_create(int graph, int instances, float fs, int
 	if (ok && b->ring_floats) ok = cudaMemsetAsync(b->d_rings, 0, (size_t)instances * b->ring_floats * sizeof(float), b->stream) == cudaSuccess;
 	b->io_floats = (size_t)instances * b->channels * max_block;
 	ok = ok && dev_alloc(&b->d_io, b->io_floats) == cudaSuccess;
+	if (graph == KB_FX_FLANGER || graph == KB_FX_MOD_CHORUS) ok = ok && dev_alloc(&b->d_old, (size_t)instances * max_block) == cudaSuccess;
 	if (!ok) { kb_fail(KB_ECUDA, std::string("kb_fx_bank_create: ") + cudaGetErrorString(cudaGetLastError())); kb_fx_bank_destroy(b); return nullptr; }
 	return b;
 }
@@ -167,7 +169,7 @@ extern "C" void kb_fx_bank_destroy(kb_fx_bank* b) {
 	if (!b) return;
 	cudaSetDevice(b->device);
 	if (b->stream) cudaStreamSynchronize(b->stream);
-	cudaFree(b->d_hdr); cudaFree(b->d_state); cudaFree(b->d_rings); cudaFree(b->d_io); cudaFree(b->d_plan); cudaFree(b->d_sync);
+	cudaFree(b->d_hdr); cudaFree(b->d_state); cudaFree(b->d_rings); cudaFree(b->d_io); cudaFree(b->d_old); cudaFree(b->d_plan); cudaFree(b->d_sync);
 	b->prof_free();
 	if (b->own_stream) cudaStreamDestroy(b->own_stream);
 	delete b;
@@ -180,7 +182,8 @@ extern "C" int kb_fx_bank_parallel_instances(kb_fx_bank* b) {
 	if (!b) return kb_fail(KB_EINVAL, "null bank");
 	if (b->graph == KB_FX_GAIN || (b->graph >= KB_FX_PAN && b->graph <= KB_FX_CLIPPING) || b->graph == KB_FX_FUNCTIONS || b->graph == KB_FX_MUTE) return b->instances;
 	if (b->graph == KB_FX_IIR || b->graph == KB_FX_WAHWAH) return 0;                 // a recurrence: one lane per instance
-	if (b->graph >= KB_FX_FLANGER && b->graph <= KB_FX_MOD_CHORUS) return 0;         // frame-sequential schedule only, so far
+	if (b->graph == KB_FX_FLANGER || b->graph == KB_FX_MOD_CHORUS) return b->instances;
+	if (b->graph == KB_FX_MODDELAY) return 0;                                        // its depth control is smoothed per sample: frame by frame
 	if (b->graph == KB_FX_ECHO) return b->instances;                                 // (blocks longer than SIZE - fs frames fall back to the sequential schedule)
 	if (b->graph == KB_FX_FEEDBACK) {                                                // instances whose delay is long enough for a chunk (at this block size)
 		int count = 0;
@@ -321,14 +324,23 @@ extern "C" int kb_fx_bank_process(kb_fx_bank* b, float* io, int n, unsigned flag
 	case KB_FX_IIR:        // one lane per instance (the smoother is a serial fp32 chain)
 		kb_fx_seq_kernel<KB_FX_IIR, KbIirFx><<<ib, 32, 0, b->stream>>>(b->d_hdr, (KbIirFx*)b->d_state, b->d_rings, d, n, n, 1, b->instances, b->fs, nullptr);
 		break;
-	case KB_FX_FLANGER:    // one lane per instance, frame by frame (feed-forward taps: Echo.k's two sweeps apply, not built)
-		kb_fx_seq_kernel<KB_FX_FLANGER, KbModDelayFx><<<ib, 32, 0, b->stream>>>(b->d_hdr, (KbModDelayFx*)b->d_state, b->d_rings, d, n, n, 1, b->instances, b->fs, nullptr);
+	case KB_FX_FLANGER: case KB_FX_MOD_CHORUS:
+		if (!seq_only && n < 192000) {                         // time-parallel: write sweep with stash, read sweep (kb_modline_*, kb_graphs.cuh)
+			KbModDelayFx* st = (KbModDelayFx*)b->d_state;
+			dim3 grid((unsigned)std::max(1, std::min((n + 255) / 256, 148 * 8 / std::min(b->instances, 148 * 8) + 1)), b->instances);
+			kb_modline_begin_kernel<<<ib, 32, 0, b->stream>>>(b->graph, b->d_hdr, st, b->instances, b->fs);
+			kb_modline_write_kernel<<<grid, 256, 0, b->stream>>>(st, b->d_rings, b->d_old, d, n, n);
+			kb_modline_read_kernel<<<grid, 256, 0, b->stream>>>(b->graph, b->d_hdr, st, b->d_rings, b->d_old, d, n, n, b->fs);
+			kb_modline_end_kernel<<<ib, 32, 0, b->stream>>>(b->graph, st, b->instances, n);
+			b->launches += 3;
+		} else if (b->graph == KB_FX_FLANGER) {                // one lane per instance, frame by frame
+			kb_fx_seq_kernel<KB_FX_FLANGER, KbModDelayFx><<<ib, 32, 0, b->stream>>>(b->d_hdr, (KbModDelayFx*)b->d_state, b->d_rings, d, n, n, 1, b->instances, b->fs, nullptr);
+		} else {
+			kb_fx_seq_kernel<KB_FX_MOD_CHORUS, KbModDelayFx><<<ib, 32, 0, b->stream>>>(b->d_hdr, (KbModDelayFx*)b->d_state, b->d_rings, d, n, n, 1, b->instances, b->fs, nullptr);
+		}
 		break;
 	case KB_FX_MODDELAY:
 		kb_fx_seq_kernel<KB_FX_MODDELAY, KbModDelayFx><<<ib, 32, 0, b->stream>>>(b->d_hdr, (KbModDelayFx*)b->d_state, b->d_rings, d, n, n, 1, b->instances, b->fs, nullptr);
-		break;
-	case KB_FX_MOD_CHORUS:
-		kb_fx_seq_kernel<KB_FX_MOD_CHORUS, KbModDelayFx><<<ib, 32, 0, b->stream>>>(b->d_hdr, (KbModDelayFx*)b->d_state, b->d_rings, d, n, n, 1, b->instances, b->fs, nullptr);
 		break;
 	case KB_FX_WAHWAH:     // one lane per instance (the biquad state is a serial fp32 chain; the coefficients could come from parallel workers as in C2)
 		kb_fx_seq_kernel<KB_FX_WAHWAH, KbWahWahFx><<<ib, 32, 0, b->stream>>>(b->d_hdr, (KbWahWahFx*)b->d_state, b->d_rings, d, n, n, 1, b->instances, b->fs, nullptr);

@@ -388,6 +388,58 @@ KB_D float kb_moddelay_frame(int graph, const KbFs& fs, KbFxHdr& h, KbModDelayFx
 	return 0.5f * acc;
 }
 
+// Flanger.k / Modulation/Chorus.k, time-parallel (feed-forward taps, LFOs in closed form): a write sweep that also STASHES the value each
+// slot held before (old[t] = what frame t overwrote), then a read sweep in which frame t sees every slot as the frame-sequential run
+// would: a slot that a LATER frame of this block overwrote is read from the stash, every other slot from the ring.  Exact for any
+// delay (a zero delay included: its interpolation partner is the next frame's slot) as long as n < SIZE.
+KB_D float kb_line_slot(const float* ring, const float* old, int p0, int n, int SIZE, int t, int k) {
+	if (k < SIZE) {                                                           // (slot SIZE is the guard float: never written)
+		int writer = k - p0;                                                  // the frame of this block that writes slot k, if < n
+		if (writer < 0) writer += SIZE;
+		if (writer > t && writer < n) return old[writer];
+	}
+	return ring[k];
+}
+KB_D float kb_line_tap_f(const float* ring, const float* old, int p0, int n, int SIZE, int t, float delay) {     // Delay::tap(float) as frame t finds the line
+	const int position = (p0 + t + 1) % SIZE;
+	float read = (float)(position - 1) - delay;
+	if (read < 0.f) read += SIZE;
+	const int i = (int)read;
+	const float fraction = read - i;
+	const int j = (i + 1) % SIZE;
+	const float a = kb_line_slot(ring, old, p0, n, SIZE, t, i), b = kb_line_slot(ring, old, p0, n, SIZE, t, j);
+	return a + fraction * (b - a);
+}
+KB_HD void kb_modline_begin(int graph, const KbFs& fs, const KbFxHdr& h, KbModDelayFx& s) {      // what the block's first frame does to the LFO settings
+	if (graph == KB_FX_FLANGER) kb_osm_set_f(fs, s.tri, h.controls[0].value);
+	else { const float rates[3] = { 2.5f, 3.f, 3.5f }; for (int k = 0; k < 3; k++) kb_fsine_set_f(fs, s.lfo[k], rates[k]); }
+}
+KB_D void kb_modline_write_at(const KbDelay& d, float* rings, float* old, int t, float in) {
+	float* slot = rings + d.ring + (d.position + t) % d.SIZE;
+	old[t] = *slot;
+	*slot = in;
+}
+KB_D float kb_modline_read_at(int graph, const KbFs& fs, const KbFxHdr& h, const KbModDelayFx& s, const float* rings, const float* old, int n, int t, float in) {
+	const float* ring = rings + s.delay.ring;
+	if (graph == KB_FX_FLANGER) {
+		const float depth = h.controls[1].value / 1000.f;
+		const float mod = kb_osm_at(s.tri, (uint32_t)t) * depth + depth;
+		return in + kb_line_tap_f(ring, old, s.delay.position, n, s.delay.SIZE, t, mod * fs.f);
+	}
+	const float depths[3] = { 0.45f, 0.5f, 0.55f };
+	float acc = in;
+	for (int k = 0; k < 3; k++) {
+		const float sine = kb_fsine_value(s.lfo[k].position + (uint32_t)t * (uint32_t)s.lfo[k].increment + s.lfo[k].offset);
+		acc = acc + kb_line_tap_f(ring, old, s.delay.position, n, s.delay.SIZE, t, (sine * depths[k] + depths[k]) * fs.f / 1000.f);
+	}
+	return 0.5f * acc;
+}
+KB_HD void kb_modline_end(int graph, KbModDelayFx& s, int n) {
+	if (graph == KB_FX_FLANGER) kb_osm_advance(s.tri, (uint32_t)n);
+	else for (int k = 0; k < 3; k++) s.lfo[k].position += (uint32_t)n * (uint32_t)s.lfo[k].increment;
+	s.delay.position = (s.delay.position + n) % s.delay.SIZE;
+}
+
 // Echo.k, time-parallel: the line is only ever fed the INPUT, so a block is two independent sweeps — write all n inputs into the ring, then
 // every output sample from its own tap.  Exact as long as no tap of the block reads a slot that a LATER sample of the same block
 // overwrites: n + delay + 2 < SIZE at the far end, and delay >= 1 at the near end (with a delay below one frame the interpolation's

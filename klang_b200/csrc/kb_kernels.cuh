@@ -343,6 +343,33 @@ __global__ void kb_echo_read_kernel(const KbFxHdr* __restrict__ hdr, const KbOne
 	float* p = io + (size_t)blockIdx.y * stride;
 	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) p[t] = kb_echo_read_at(fs, h, s, rings, t, p[t]);
 }
+// Flanger.k / Modulation/Chorus.k, time-parallel (kb_modline_*): LFO settings of the block's first frame, write sweep with stash, read sweep,
+// LFO / position advance.  blockIdx.y = instance; `old` is [instances][stride] scratch.
+__global__ void kb_modline_begin_kernel(int graph, const KbFxHdr* __restrict__ hdr, KbModDelayFx* __restrict__ st, int instances, KbFs fs) {
+	const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+	if (inst < instances) kb_modline_begin(graph, fs, hdr[inst], st[inst]);
+}
+__global__ void kb_modline_write_kernel(const KbModDelayFx* __restrict__ st, float* __restrict__ rings, float* __restrict__ old, const float* __restrict__ io, int n, int stride) {
+	const KbDelay d = st[blockIdx.y].delay;
+	const float* p = io + (size_t)blockIdx.y * stride;
+	float* o = old + (size_t)blockIdx.y * stride;
+	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) kb_modline_write_at(d, rings, o, t, p[t]);
+}
+__global__ void kb_modline_read_kernel(int graph, const KbFxHdr* __restrict__ hdr, const KbModDelayFx* __restrict__ st, const float* __restrict__ rings,
+                                       const float* __restrict__ old, float* __restrict__ io, int n, int stride, KbFs fs) {
+	__shared__ KbModDelayFx s;
+	__shared__ KbFxHdr h;
+	for (int w = threadIdx.x; w < (int)(sizeof(KbModDelayFx) / 4); w += blockDim.x) reinterpret_cast<unsigned*>(&s)[w] = reinterpret_cast<const unsigned*>(st + blockIdx.y)[w];
+	for (int w = threadIdx.x; w < (int)(sizeof(KbFxHdr) / 4); w += blockDim.x) reinterpret_cast<unsigned*>(&h)[w] = reinterpret_cast<const unsigned*>(hdr + blockIdx.y)[w];
+	__syncthreads();
+	float* p = io + (size_t)blockIdx.y * stride;
+	const float* o = old + (size_t)blockIdx.y * stride;
+	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) p[t] = kb_modline_read_at(graph, fs, h, s, rings, o, n, t, p[t]);
+}
+__global__ void kb_modline_end_kernel(int graph, KbModDelayFx* __restrict__ st, int instances, int n) {
+	const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+	if (inst < instances) kb_modline_end(graph, st[inst], n);
+}
 // Feedback.k, chunk-parallel (kb_feedback_chunk / kb_feedback_at): one CTA per instance walks the block chunk by chunk, one barrier per chunk;
 // instances whose delay is too short for a chunk (chunk 0) run frame by frame on thread 0.  The position advances at the end.
 __global__ void __launch_bounds__(1024) kb_feedback_par_kernel(const KbFxHdr* __restrict__ hdr, KbOneDelayFx* __restrict__ st, float* __restrict__ rings,

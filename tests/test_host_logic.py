@@ -369,3 +369,15 @@ def test_late_gpu_tests_execute_against_the_oracle_backed_stub():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "dryrun_stub.py")], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-1000:]
     assert " passed" in out.stdout and "failed" not in out.stdout
+
+
+def test_modulated_line_time_parallel_form_equals_frame_sequential_form():
+    """Flanger.k / Modulation/Chorus.k: begin + write sweep with stash + read sweep (closed-form LFOs, stash-aware taps) + end — what the
+    kb_modline_* kernels run — equal the frame-sequential kb_moddelay_frame bit for bit (samples, ring, state), zero-delay frames and
+    negative-zero inputs included."""
+    exe = os.path.join(tempfile.mkdtemp(prefix="kb_host_"), "modline_check")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-x", "c++",
+                           os.path.join(ROOT, "tests", "host", "modline_check.cpp"), "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert " 0 block mismatches, 0 state / ring mismatches" in out.stdout

@@ -307,3 +307,28 @@ def test_midi_input_equals_note_on_off_calls():
         outs.append(np.concatenate(res, axis=-1))
     _exact(np.ascontiguousarray(outs[0]), np.ascontiguousarray(outs[1]), "midi input")
     assert np.abs(outs[0]).max() > 0.01
+
+
+@pytest.mark.parametrize("graph", [cases.FX_FLANGER, cases.FX_MOD_CHORUS])
+def test_modulated_line_time_parallel_schedule_equals_sequential_schedule(graph):
+    """Flanger.k / Modulation/Chorus.k: the kb_modline_* kernels (default: write sweep with stash, read sweep with closed-form LFOs) against
+    the frame-sequential kernel (KB_FX_SEQUENTIAL), bit for bit over ragged blocks with control changes; 4 instances."""
+    fs, inst = 48000.0, 4
+    outs = []
+    for flag in (kb.FX_SEQUENTIAL, 0):
+        bank = kb.FxBank(graph, inst, fs, 4096)
+        if graph == cases.FX_FLANGER:
+            for i in range(inst):
+                bank.set_control(0, 0.2 + 0.25 * i, i)
+                bank.set_control(1, 0.1 + 1.5 * i, i)
+        res = []
+        for b, n in enumerate((4096, 1001, 1, 4096, 2048, 4096)):
+            if b == 3 and graph == cases.FX_FLANGER:
+                bank.set_control(0, 1.0, 1)
+                bank.set_control(1, 5.0, 2)
+            x = np.stack([cases.fx_input(1, n, seed=40 * b + i) for i in range(inst)]).astype(np.float32)
+            res.append(bank.process_inplace(x.copy(), flags=flag))
+        bank.close()
+        outs.append(np.concatenate(res, axis=-1))
+    _exact(np.ascontiguousarray(outs[1]), np.ascontiguousarray(outs[0]), f"graph {graph} schedules")
+    assert np.abs(outs[0]).max() > 0.4
