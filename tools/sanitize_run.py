@@ -6,7 +6,7 @@ import klang_b200 as kb
 
 fs = 48000.0
 for graph, inst, voices, n in ((kb.SY_SUBTRACTIVE, 2, 16, 300), (kb.SY_SUBTRACTIVE, 8, 100, 260), (kb.SY_SUPERSAW, 2, 32, 300), (kb.SY_TB303, 1, 32, 300), (kb.SY_SYNTHX, 1, 32, 70), (kb.SY_FILTER_K, 1, 32, 129), (kb.SY_FM, 2, 21, 300),
-                                (kb.SY_RELEASE, 2, 21, 300), (kb.SY_AM, 2, 21, 300), (kb.SY_MOD_FM2, 1, 32, 200), (kb.SY_ADDITIVE_SQUARE, 2, 21, 300)):
+                                (kb.SY_RELEASE, 2, 21, 300), (kb.SY_AM, 2, 21, 300), (kb.SY_MOD_FM2, 1, 32, 200), (kb.SY_ADDITIVE_SQUARE, 2, 21, 300), (kb.SY_BREAKPOINT, 1, 32, 130)):
     b = kb.SynthBank(graph, inst, voices, fs, n)
     for g in range(0, inst * b.voices, 2):
         b.voice_start(g % b.voices, 40 + g % 30, 0.7, g // b.voices)
@@ -19,7 +19,8 @@ for graph, inst, voices, n in ((kb.SY_SUBTRACTIVE, 2, 16, 300), (kb.SY_SUBTRACTI
     b.process_block(n, kb.LANE_PER_VOICE)
     b.close()
 for graph, n, blocks in ((kb.FX_GAIN, 1001, 2), (kb.FX_PINGPONG, 2048, 24), (kb.FX_REVERB, 700, 3), (kb.FX_DELAY_PINGPONG, 3000, 3), (kb.FX_DELAY_REVERB, 500, 2),
-                         (kb.FX_PAN, 1001, 2), (kb.FX_TREMOLO, 1024, 2), (kb.FX_CLIPPING, 7, 2), (kb.FX_ECHO, 3000, 3), (kb.FX_FEEDBACK, 3000, 3)):
+                         (kb.FX_PAN, 1001, 2), (kb.FX_TREMOLO, 1024, 2), (kb.FX_CLIPPING, 7, 2), (kb.FX_ECHO, 3000, 3), (kb.FX_FEEDBACK, 3000, 3),
+                         (kb.FX_FLANGER, 3000, 3), (kb.FX_MOD_CHORUS, 3000, 3), (kb.FX_MODDELAY, 500, 2), (kb.FX_WAHWAH, 500, 2), (kb.FX_IIR, 500, 2), (kb.FX_MUTE, 9, 2)):
     fx = kb.FxBank(graph, 3, fs, n)
     if graph in (kb.FX_ECHO, kb.FX_FEEDBACK):
         fx.set_control(0, 0.004)                      # a 192-frame delay: several chunks per block
