@@ -162,6 +162,7 @@ extern "C" kb_fx_bank* kb_fx_bank_create(int graph, int instances, float fs, int
 	b->io_floats = (size_t)instances * b->channels * max_block;
 	ok = ok && dev_alloc(&b->d_io, b->io_floats) == cudaSuccess;
 	if (graph == KB_FX_FLANGER || graph == KB_FX_MOD_CHORUS) ok = ok && dev_alloc(&b->d_old, (size_t)instances * max_block) == cudaSuccess;
+	if (graph == KB_FX_MODDELAY) ok = ok && dev_alloc(&b->d_old, 2 * (size_t)instances * max_block) == cudaSuccess;      // stash + the per-frame depth rows
 	if (!ok) { kb_fail(KB_ECUDA, std::string("kb_fx_bank_create: ") + cudaGetErrorString(cudaGetLastError())); kb_fx_bank_destroy(b); return nullptr; }
 	return b;
 }
@@ -182,8 +183,7 @@ extern "C" int kb_fx_bank_parallel_instances(kb_fx_bank* b) {
 	if (!b) return kb_fail(KB_EINVAL, "null bank");
 	if (b->graph == KB_FX_GAIN || (b->graph >= KB_FX_PAN && b->graph <= KB_FX_CLIPPING) || b->graph == KB_FX_FUNCTIONS || b->graph == KB_FX_MUTE) return b->instances;
 	if (b->graph == KB_FX_IIR || b->graph == KB_FX_WAHWAH) return 0;                 // a recurrence: one lane per instance
-	if (b->graph == KB_FX_FLANGER || b->graph == KB_FX_MOD_CHORUS) return b->instances;
-	if (b->graph == KB_FX_MODDELAY) return 0;                                        // its depth control is smoothed per sample: frame by frame
+	if (b->graph >= KB_FX_FLANGER && b->graph <= KB_FX_MOD_CHORUS) return b->instances;
 	if (b->graph == KB_FX_ECHO) return b->instances;                                 // (blocks longer than SIZE - fs frames fall back to the sequential schedule)
 	if (b->graph == KB_FX_FEEDBACK) {                                                // instances whose delay is long enough for a chunk (at this block size)
 		int count = 0;
@@ -324,23 +324,23 @@ extern "C" int kb_fx_bank_process(kb_fx_bank* b, float* io, int n, unsigned flag
 	case KB_FX_IIR:        // one lane per instance (the smoother is a serial fp32 chain)
 		kb_fx_seq_kernel<KB_FX_IIR, KbIirFx><<<ib, 32, 0, b->stream>>>(b->d_hdr, (KbIirFx*)b->d_state, b->d_rings, d, n, n, 1, b->instances, b->fs, nullptr);
 		break;
-	case KB_FX_FLANGER: case KB_FX_MOD_CHORUS:
+	case KB_FX_FLANGER: case KB_FX_MOD_CHORUS: case KB_FX_MODDELAY:
 		if (!seq_only && n < 192000) {                         // time-parallel: write sweep with stash, read sweep (kb_modline_*, kb_graphs.cuh)
 			KbModDelayFx* st = (KbModDelayFx*)b->d_state;
 			dim3 grid((unsigned)std::max(1, std::min((n + 255) / 256, 148 * 8 / std::min(b->instances, 148 * 8) + 1)), b->instances);
-			kb_modline_begin_kernel<<<ib, 32, 0, b->stream>>>(b->graph, b->d_hdr, st, b->instances, b->fs);
+			float* depth = b->graph == KB_FX_MODDELAY ? b->d_old + (size_t)b->instances * b->max_block : nullptr;   // ModDelay.k: serial smoother pre-pass
+			kb_modline_begin_kernel<<<ib, 32, 0, b->stream>>>(b->graph, b->d_hdr, st, b->instances, b->fs, depth, n, n);
 			kb_modline_write_kernel<<<grid, 256, 0, b->stream>>>(st, b->d_rings, b->d_old, d, n, n);
-			kb_modline_read_kernel<<<grid, 256, 0, b->stream>>>(b->graph, b->d_hdr, st, b->d_rings, b->d_old, d, n, n, b->fs);
+			kb_modline_read_kernel<<<grid, 256, 0, b->stream>>>(b->graph, b->d_hdr, st, b->d_rings, b->d_old, depth, d, n, n, b->fs);
 			kb_modline_end_kernel<<<ib, 32, 0, b->stream>>>(b->graph, st, b->instances, n);
 			b->launches += 3;
-		} else if (b->graph == KB_FX_FLANGER) {                // one lane per instance, frame by frame
+		} else if (b->graph == KB_FX_MODDELAY) {               // one lane per instance, frame by frame
+			kb_fx_seq_kernel<KB_FX_MODDELAY, KbModDelayFx><<<ib, 32, 0, b->stream>>>(b->d_hdr, (KbModDelayFx*)b->d_state, b->d_rings, d, n, n, 1, b->instances, b->fs, nullptr);
+		} else if (b->graph == KB_FX_FLANGER) {
 			kb_fx_seq_kernel<KB_FX_FLANGER, KbModDelayFx><<<ib, 32, 0, b->stream>>>(b->d_hdr, (KbModDelayFx*)b->d_state, b->d_rings, d, n, n, 1, b->instances, b->fs, nullptr);
 		} else {
 			kb_fx_seq_kernel<KB_FX_MOD_CHORUS, KbModDelayFx><<<ib, 32, 0, b->stream>>>(b->d_hdr, (KbModDelayFx*)b->d_state, b->d_rings, d, n, n, 1, b->instances, b->fs, nullptr);
 		}
-		break;
-	case KB_FX_MODDELAY:
-		kb_fx_seq_kernel<KB_FX_MODDELAY, KbModDelayFx><<<ib, 32, 0, b->stream>>>(b->d_hdr, (KbModDelayFx*)b->d_state, b->d_rings, d, n, n, 1, b->instances, b->fs, nullptr);
 		break;
 	case KB_FX_WAHWAH:     // one lane per instance (the biquad state is a serial fp32 chain; the coefficients could come from parallel workers as in C2)
 		kb_fx_seq_kernel<KB_FX_WAHWAH, KbWahWahFx><<<ib, 32, 0, b->stream>>>(b->d_hdr, (KbWahWahFx*)b->d_state, b->d_rings, d, n, n, 1, b->instances, b->fs, nullptr);

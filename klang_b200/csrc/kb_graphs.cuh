@@ -410,17 +410,29 @@ KB_D float kb_line_tap_f(const float* ring, const float* old, int p0, int n, int
 	const float a = kb_line_slot(ring, old, p0, n, SIZE, t, i), b = kb_line_slot(ring, old, p0, n, SIZE, t, j);
 	return a + fraction * (b - a);
 }
-KB_HD void kb_modline_begin(int graph, const KbFs& fs, const KbFxHdr& h, KbModDelayFx& s) {      // what the block's first frame does to the LFO settings
+// ModDelay.k joins them with one serial pre-pass: its depth is cube(controls[1].smooth()) / 10 (ModDelay.k:20), and Control::smooth is a
+// one-pole recurrence per sample — kb_modline_begin runs it for the block's n frames on one lane and leaves the depth of every frame
+// in `depth`; everything else is the same two sweeps.
+KB_HD void kb_modline_begin(int graph, const KbFs& fs, KbFxHdr& h, KbModDelayFx& s, float* depth, int n) {   // what the block's first frame does to the LFO settings
 	if (graph == KB_FX_FLANGER) kb_osm_set_f(fs, s.tri, h.controls[0].value);
-	else { const float rates[3] = { 2.5f, 3.f, 3.5f }; for (int k = 0; k < 3; k++) kb_fsine_set_f(fs, s.lfo[k], rates[k]); }
+	else if (graph == KB_FX_MODDELAY) {
+		kb_fsine_set_f(fs, s.lfo[0], h.controls[0].value);
+		for (int t = 0; t < n; t++) { const float sm = kb_control_smooth(h.controls[1]); depth[t] = (sm * sm * sm) / 10.f; }
+	} else { const float rates[3] = { 2.5f, 3.f, 3.5f }; for (int k = 0; k < 3; k++) kb_fsine_set_f(fs, s.lfo[k], rates[k]); }
 }
 KB_D void kb_modline_write_at(const KbDelay& d, float* rings, float* old, int t, float in) {
 	float* slot = rings + d.ring + (d.position + t) % d.SIZE;
 	old[t] = *slot;
 	*slot = in;
 }
-KB_D float kb_modline_read_at(int graph, const KbFs& fs, const KbFxHdr& h, const KbModDelayFx& s, const float* rings, const float* old, int n, int t, float in) {
+KB_D float kb_modline_read_at(int graph, const KbFs& fs, const KbFxHdr& h, const KbModDelayFx& s, const float* rings, const float* old, const float* depth_row,
+                              int n, int t, float in) {
 	const float* ring = rings + s.delay.ring;
+	if (graph == KB_FX_MODDELAY) {
+		const float depth = depth_row[t];
+		const float mod = kb_fsine_value(s.lfo[0].position + (uint32_t)t * (uint32_t)s.lfo[0].increment + s.lfo[0].offset) * depth + depth;
+		return kb_line_tap_f(ring, old, s.delay.position, n, s.delay.SIZE, t, mod * fs.f);
+	}
 	if (graph == KB_FX_FLANGER) {
 		const float depth = h.controls[1].value / 1000.f;
 		const float mod = kb_osm_at(s.tri, (uint32_t)t) * depth + depth;
@@ -436,7 +448,7 @@ KB_D float kb_modline_read_at(int graph, const KbFs& fs, const KbFxHdr& h, const
 }
 KB_HD void kb_modline_end(int graph, KbModDelayFx& s, int n) {
 	if (graph == KB_FX_FLANGER) kb_osm_advance(s.tri, (uint32_t)n);
-	else for (int k = 0; k < 3; k++) s.lfo[k].position += (uint32_t)n * (uint32_t)s.lfo[k].increment;
+	else for (int k = 0; k < (graph == KB_FX_MODDELAY ? 1 : 3); k++) s.lfo[k].position += (uint32_t)n * (uint32_t)s.lfo[k].increment;
 	s.delay.position = (s.delay.position + n) % s.delay.SIZE;
 }
 

@@ -345,9 +345,9 @@ __global__ void kb_echo_read_kernel(const KbFxHdr* __restrict__ hdr, const KbOne
 }
 // Flanger.k / Modulation/Chorus.k, time-parallel (kb_modline_*): LFO settings of the block's first frame, write sweep with stash, read sweep,
 // LFO / position advance.  blockIdx.y = instance; `old` is [instances][stride] scratch.
-__global__ void kb_modline_begin_kernel(int graph, const KbFxHdr* __restrict__ hdr, KbModDelayFx* __restrict__ st, int instances, KbFs fs) {
+__global__ void kb_modline_begin_kernel(int graph, KbFxHdr* __restrict__ hdr, KbModDelayFx* __restrict__ st, int instances, KbFs fs, float* __restrict__ depth, int n, int stride) {
 	const int inst = blockIdx.x * blockDim.x + threadIdx.x;
-	if (inst < instances) kb_modline_begin(graph, fs, hdr[inst], st[inst]);
+	if (inst < instances) kb_modline_begin(graph, fs, hdr[inst], st[inst], depth ? depth + (size_t)inst * stride : nullptr, n);
 }
 __global__ void kb_modline_write_kernel(const KbModDelayFx* __restrict__ st, float* __restrict__ rings, float* __restrict__ old, const float* __restrict__ io, int n, int stride) {
 	const KbDelay d = st[blockIdx.y].delay;
@@ -356,7 +356,7 @@ __global__ void kb_modline_write_kernel(const KbModDelayFx* __restrict__ st, flo
 	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) kb_modline_write_at(d, rings, o, t, p[t]);
 }
 __global__ void kb_modline_read_kernel(int graph, const KbFxHdr* __restrict__ hdr, const KbModDelayFx* __restrict__ st, const float* __restrict__ rings,
-                                       const float* __restrict__ old, float* __restrict__ io, int n, int stride, KbFs fs) {
+                                       const float* __restrict__ old, const float* __restrict__ depth, float* __restrict__ io, int n, int stride, KbFs fs) {
 	__shared__ KbModDelayFx s;
 	__shared__ KbFxHdr h;
 	for (int w = threadIdx.x; w < (int)(sizeof(KbModDelayFx) / 4); w += blockDim.x) reinterpret_cast<unsigned*>(&s)[w] = reinterpret_cast<const unsigned*>(st + blockIdx.y)[w];
@@ -364,7 +364,8 @@ __global__ void kb_modline_read_kernel(int graph, const KbFxHdr* __restrict__ hd
 	__syncthreads();
 	float* p = io + (size_t)blockIdx.y * stride;
 	const float* o = old + (size_t)blockIdx.y * stride;
-	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) p[t] = kb_modline_read_at(graph, fs, h, s, rings, o, n, t, p[t]);
+	const float* dr = depth ? depth + (size_t)blockIdx.y * stride : nullptr;
+	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) p[t] = kb_modline_read_at(graph, fs, h, s, rings, o, dr, n, t, p[t]);
 }
 __global__ void kb_modline_end_kernel(int graph, KbModDelayFx* __restrict__ st, int instances, int n) {
 	const int inst = blockIdx.x * blockDim.x + threadIdx.x;

@@ -309,9 +309,9 @@ def test_midi_input_equals_note_on_off_calls():
     assert np.abs(outs[0]).max() > 0.01
 
 
-@pytest.mark.parametrize("graph", [cases.FX_FLANGER, cases.FX_MOD_CHORUS])
+@pytest.mark.parametrize("graph", [cases.FX_FLANGER, cases.FX_MOD_CHORUS, cases.FX_MODDELAY])
 def test_modulated_line_time_parallel_schedule_equals_sequential_schedule(graph):
-    """Flanger.k / Modulation/Chorus.k: the kb_modline_* kernels (default: write sweep with stash, read sweep with closed-form LFOs) against
+    """Flanger.k / Modulation/Chorus.k / ModDelay.k (its control smoother as a serial pre-pass): the kb_modline_* kernels (default: write sweep with stash, read sweep with closed-form LFOs) against
     the frame-sequential kernel (KB_FX_SEQUENTIAL), bit for bit over ragged blocks with control changes; 4 instances."""
     fs, inst = 48000.0, 4
     outs = []
@@ -326,6 +326,9 @@ def test_modulated_line_time_parallel_schedule_equals_sequential_schedule(graph)
             if b == 3 and graph == cases.FX_FLANGER:
                 bank.set_control(0, 1.0, 1)
                 bank.set_control(1, 5.0, 2)
+            if b in (1, 3) and graph == cases.FX_MODDELAY:
+                bank.set_control(1, 1.0 if b == 1 else 0.0, 1)
+                bank.set_control(0, 10.0, 2)
             x = np.stack([cases.fx_input(1, n, seed=40 * b + i) for i in range(inst)]).astype(np.float32)
             res.append(bank.process_inplace(x.copy(), flags=flag))
         bank.close()
