@@ -166,8 +166,9 @@ def _cpu_worker(args):
     return dt
 
 
-def cpu_reference_run(steps, warmup, total_voices=INSTANCES * VOICES, block=BLOCK, cores=None):
-    """Times the reference CPU implementation of the C2 step on all host cores. Returns (value, dict)."""
+def cpu_reference_run(steps, warmup, total_voices=INSTANCES * VOICES, block=BLOCK, cores=None, passes=5, one_thread=True):
+    """Times the reference CPU implementation of the C2 step on all host cores: best of `passes` runs of the whole (warmup + steps) schedule
+    (best of 5; wall = slowest fork()ed worker), plus a 1-thread figure on a 1/16 share of the voices.  Returns (value, wall, dict)."""
     import oracle
     kind = "reference" if oracle.ref.available() else "port"
     (oracle.ref if kind == "reference" else oracle.port).lib()
@@ -175,15 +176,34 @@ def cpu_reference_run(steps, warmup, total_voices=INSTANCES * VOICES, block=BLOC
     cores = max(1, min(cores, total_voices))
     shares = [list(range(w, total_voices, cores)) for w in range(cores)]
     ctx = mp.get_context("fork")
+    walls = []
     with ctx.Pool(cores) as pool:
-        times = pool.map(_cpu_worker, [(kind, sh, steps, warmup, block) for sh in shares])
-    wall = max(times)
+        for _ in range(max(1, passes)):
+            walls.append(max(pool.map(_cpu_worker, [(kind, sh, steps, warmup, block) for sh in shares])))
+    wall = min(walls)
     value = total_voices * block * steps / wall
     info = {"value": value, "unit": "voice-samples/s", "cores": cores, "kind": kind,
-            "sample": f"{steps} steps x {total_voices} voices x {block} samples of the C2 schedule, {cores} fork()ed workers "
+            "sample": f"best of {len(walls)} passes of {steps} steps x {total_voices} voices x {block} samples of the C2 schedule, {cores} fork()ed workers "
                       f"({'oracle/_ref = compiled klang.h' if kind == 'reference' else 'oracle/klang_port.c'}, g++/gcc -O3/-O2 -ffp-contract=off), "
-                      f"wall = slowest worker {wall:.3f} s"}
+                      f"wall = slowest worker, best pass {wall:.3f} s (passes: {', '.join('%.3f' % w for w in walls)})",
+            "cpu_model": _cpu_model()}
+    if one_thread:
+        share = list(range(0, total_voices, 16))                   # 64 voices on one thread, same schedule
+        with ctx.Pool(1) as pool:
+            t1 = min(pool.map(_cpu_worker, [(kind, share, max(2, steps // 4), 1, block)])[0] for _ in range(2))
+        info["one_thread_value"] = len(share) * block * max(2, steps // 4) / t1
     return value, wall, info
+
+
+def _cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
 
 
 def _cpu_extra_worker(args):
@@ -244,14 +264,16 @@ def run_reference_arm(args, rank, world, emit):
 
 
 def make_mixdown(sharding, dist, local_rank, max_floats):
-    """N > 1: one ncclReduce of the [channels][n] mix per block (default: measured equal or faster at 2 and 8 GPUs,
-    profiles/r01_bench_n*.json), or with KB_MIXDOWN=peer the mix-down through NVLink peer memory (kb_mixdown_*)."""
+    """N > 1: the mix-down of the per-rank bank mixes.  Default = the fused peer-memory step (kb_synth_bank_process_mixdown: the bank-mix
+    kernel stores into rank 0's arena over NVLink and rank 0's next kernel sums the previous block in rank order — no extra launches, no
+    collective library on the data path); KB_MIXDOWN=nccl selects one ncclReduce per block beside the next block's kernels."""
     if dist is None:
         return None, "none (one GPU)"
-    if os.environ.get("KB_MIXDOWN", "nccl") != "peer":
-        return None, "ncclReduce of the [channels][n] mix per block, overlapped with the next block's kernels (KB_MIXDOWN=peer selects the peer-memory mix-down)"
+    if os.environ.get("KB_MIXDOWN", "peer") == "nccl":
+        return None, "ncclReduce of the [channels][n] mix per block, overlapped with the next block's kernels (KB_MIXDOWN=nccl)"
     try:
-        return sharding.PeerMixdown(local_rank, max_floats), "NVLink peer memory: bank-mix kernels store into rank 0's arena, rank 0 sums in rank order (kb_mixdown_*)"
+        return sharding.PeerMixdown(local_rank, max_floats), ("NVLink peer memory, fused: every rank's bank-mix kernel stores its [channels][n] mix into rank 0's arena and raises a flag; "
+                                                              "rank 0's next bank-mix kernel sums the previous block in rank order (kb_synth_bank_process_mixdown)")
     except Exception as e:
         return None, f"ncclReduce of the [channels][n] mix per block (peer mapping unavailable: {e})"
 
@@ -270,10 +292,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads (C1/C3/C4/C5 lines inside the JSON)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads (C1/C3/C4/C5 numbers inside the JSON)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
-                    help="c2 = headline (Subtractive, 1024 voices/GPU); c5 = TB303.k + SynTHX.k mixed bank, 1024 voices/GPU, NCCL mix-down")
+                    help="c2 = headline (Subtractive, 1024 voices/GPU; carries the C4 / C5 numbers inside `roofline`); c5 = only TB303.k + SynTHX.k")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -297,9 +319,6 @@ def main():
 
     if not torch.cuda.is_available() or kb.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device — klang_b200 has no CPU path (use --impl reference for the CPU baseline)")
-    if args.workload == "c5":
-        run_c5(args, rank, world, local_rank, emit)
-        return
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
@@ -321,6 +340,17 @@ def main():
     def flush_l2():
         flush_buf.fill_(1)
 
+    ctx = {"args": args, "rank": rank, "world": world, "local_rank": local_rank, "dist": dist, "dev": dev, "stream": stream,
+           "flush_l2": flush_l2, "barrier": barrier, "hbm_peak": hbm_peak, "peak_src": peak_src, "sm_max": sm_max}
+    if args.workload == "c5":
+        line = c5_measure(kb, torch, ctx, args.steps, max(3, args.warmup), full_line=True)
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        if rank == 0:
+            emit(line)
+        return
+
     # ---- C2 bank
     kb.lib().kb_srand(1)
     bank = kb.SynthBank(kb.SY_SUBTRACTIVE, INSTANCES, VOICES, FS, BLOCK, local_rank)
@@ -332,7 +362,9 @@ def main():
     gid0 = lo * VOICES                                    # global voice ids of this rank
     for g in range(total):
         bank.voice_start(g % VOICES, voice_pitch(gid0 + g), voice_velocity(gid0 + g), g // VOICES)
-    flags = kb.BANK_MIX | kb.MIX_SUM if world > 1 else 0
+    # the SAME work at every world size: all voices rendered, summed per instance in voice order (the Stereo::Note rule, klang.h:4731,
+    # SURVEY Q6 / 8e) and over the bank's instances into one [1][n] mix; N > 1 adds only the exchange of that mix
+    flags = kb.BANK_MIX | kb.MIX_SUM
     out_dev = torch.empty(bank.out_shape(BLOCK, flags), dtype=torch.float32, device=dev)
     out_host = torch.empty(bank.out_shape(BLOCK, flags), dtype=torch.float32).pin_memory()
     step_counter = [0]
@@ -349,54 +381,47 @@ def main():
         ev["velocity"] = [voice_velocity(gid0 + g) for g in ids]
         batches.append(ev)
 
-    def events():
+    def next_events():
         s = step_counter[0]
         step_counter[0] += 1
-        bank.events(batches[s % RETRIGGER_GROUPS])
-        return len(batches[s % RETRIGGER_GROUPS])
+        return batches[s % RETRIGGER_GROUPS]
 
     mixdown, mix_kind = make_mixdown(sharding, dist, local_rank, out_dev.numel())
+    pipe = {"k": 0, "work": None, "last": out_dev}
+    mix_bufs = [out_dev, torch.empty_like(out_dev)]
 
-    def mix_down():
-        """one process() of this rank's bank and the cross-GPU mix-down into out_dev on rank 0"""
-        if mixdown is not None:
-            # the bank-mix kernel stores straight into rank 0's arena over NVLink; rank 0 sums the slots in rank order
-            bank.process_into_device_ptr(mixdown.acquire(stream.cuda_stream), BLOCK, flags)
-            mixdown.publish(stream.cuda_stream)
-            if rank == 0:
-                mixdown.collect(out_dev, out_dev.numel(), stream.cuda_stream)
-        elif dist is None:
-            bank.process_into(out_dev, BLOCK, flags)
+    def step_device():
+        """the block's note events, one process() of this rank's bank and (N > 1) the cross-GPU mix-down towards out_dev on rank 0"""
+        if dist is None:
+            bank.step_into(next_events(), out_dev, BLOCK, flags)           # kb_synth_bank_step: events + process in one call
+        elif mixdown is not None:
+            bank.events(next_events())
+            bank.process_mixdown(mixdown, out_dev if rank == 0 else None, BLOCK, kb.MIX_SUM)
         else:
             # the reduce of block k runs on NCCL's stream beside the voice kernels of block k+1 (two mix buffers); it is
             # joined after the next block's kernels have been queued, and the last one by drain() inside the timed region
             buf = mix_bufs[pipe["k"] & 1]
             pipe["k"] += 1
-            bank.process_into(buf, BLOCK, flags)
+            bank.step_into(next_events(), buf, BLOCK, flags)
             if pipe["work"] is not None:
                 pipe["work"].wait()
             pipe["work"] = dist.reduce(buf, dst=0, op=dist.ReduceOp.SUM, async_op=True)
             pipe["last"] = buf
 
     def drain():
-        """join the reduce still in flight (the timed loops call it before their closing event / barrier)"""
-        if pipe["work"] is not None:
+        """join the exchange still in flight (the timed loops call it before their closing event / barrier)"""
+        if mixdown is not None:
+            if rank == 0:
+                mixdown.collect(out_dev, out_dev.numel(), stream.cuda_stream)
+        elif pipe["work"] is not None:
             pipe["work"].wait()
             pipe["work"] = None
-
-    pipe = {"k": 0, "work": None, "last": out_dev}
-    mix_bufs = [out_dev, torch.empty_like(out_dev)]
-
-    def step_device():
-        events()
-        mix_down()
 
     host_bufs = [out_host, torch.empty_like(out_host).pin_memory()]
     host_done = [torch.cuda.Event(), torch.cuda.Event()]
     e2e_k = [0]
 
     def step_e2e():
-        events()
         if dist is None:
             # host-buffer call with KB_ASYNC_HOST: state upload, kernels and the D2H copy into pinned memory are queued; the host
             # prepares the next block's events meanwhile and joins a buffer only before reusing it (two buffers, as a streaming
@@ -404,13 +429,14 @@ def main():
             i = e2e_k[0] & 1
             if e2e_k[0] >= 2:
                 host_done[i].synchronize()
-            bank.process_into(host_bufs[i].numpy(), BLOCK, flags | kb.ASYNC_HOST)
+            bank.step_into(next_events(), host_bufs[i].numpy(), BLOCK, flags | kb.ASYNC_HOST)
             host_done[i].record(stream)
             e2e_k[0] += 1
         else:
-            mix_down()
+            step_device()
             drain()                                              # e2e: every block's reduced mix is read back before the next block
-            out_host.copy_(pipe["last"] if mixdown is None else out_dev, non_blocking=True)
+            if rank == 0:
+                out_host.copy_(pipe["last"] if mixdown is None else out_dev, non_blocking=True)
             torch.cuda.synchronize()
 
     def timed(step_fn, steps, warmup, clocks=None):
@@ -421,6 +447,7 @@ def main():
         if clocks:
             clocks.start()
         evs = []
+        launches0 = bank.launches
         t_wall0 = time.perf_counter()
         for i in range(steps):
             flush_l2()
@@ -429,12 +456,13 @@ def main():
             step_fn()
             b.record(stream)
             evs.append((a, b))
-        if dist is not None and mixdown is None:     # the last block's reduce, still in flight, belongs to the timed region
+        if dist is not None:                          # the last block's exchange, still in flight, belongs to the timed region
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(stream)
             drain()
             b.record(stream)
             evs.append((a, b))
+        launches = bank.launches - launches0 + (1 if (mixdown is not None and rank == 0) else 0)
         if clocks:
             clocks.sample()                          # everything is queued, the GPU is still inside the timed region
         barrier()
@@ -443,12 +471,11 @@ def main():
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         if dist is not None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), wall
+        return float(t.item()), wall, launches
 
     clocks = ClockSampler(local_rank) if rank == 0 else None
-    launches0 = bank.launches
-    ms_total, _ = timed(step_device, args.steps, args.warmup, clocks)
-    gpu_launches = (bank.launches - launches0) * args.steps // (args.steps + args.warmup)
+    ms_total, _, launches = timed(step_device, args.steps, args.warmup, clocks)
+    gpu_launches = launches / args.steps                 # this library's kernels per step (the L2 flush fill between steps is torch's)
     clk = clocks.stop() if clocks else None
     ms_per_step = ms_total / args.steps
     value = world * total * BLOCK / (ms_per_step * 1e-3)
@@ -472,8 +499,9 @@ def main():
     e2e = {"value": e2e_value, "unit": "voice-samples/s",
            "h2d_bytes_per_step": int((h2d1 - h2d0) / args.steps), "d2h_bytes_per_step": int((d2h1 - d2h0) / args.steps + out_bytes),
            "note": "per step: the host applies 64 note events on its state mirror (packed dirty-voice upload H2D), kernels, output D2H "
-                   "into pinned memory (KB_ASYNC_HOST, two host buffers: block k+1's events are prepared while block k renders; "
-                   "every buffer is joined before reuse and at the end of the timed region); bytes counted by the library"}
+                   "into pinned memory (N=1: KB_ASYNC_HOST, two host buffers, block k+1's events are prepared while block k renders; "
+                   "every buffer is joined before reuse and at the end of the timed region; N>1: the reduced mix is joined and read back every block); "
+                   "bytes counted by the library"}
 
     # ---- dominant kernel, CUDA events inside the library
     bank.profile(True)
@@ -494,49 +522,71 @@ def main():
         lane_ms = l_ms / max(1, l_n)
     k_ms_avg = k_ms / max(1, k_n)
     alg_bytes = total * BLOCK * 4.0      # 4 B per voice-sample (the per-voice stream this kernel writes)
-    achieved = alg_bytes / (k_ms_avg * 1e-3) / 1e9
-    issue_peak = 148 * 128 * sm_max * 1e6                                # fp32 lanes x clock
+    hbm_achieved = alg_bytes / (k_ms_avg * 1e-3) / 1e9
     traffic = None
     try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             traffic = json.load(f).get("kb_sub_tiled_kernel")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "kb_sub_tiled_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+    # What bounds this kernel: one fp32 recurrence per voice (the TDF-II biquad, klang.h:5605-5612) that parity forbids re-ordering:
+    # 4 dependent fp32 operations per sample.  Its floor was measured alone on one warp of this chip (tools/micro/serial_floor.cu,
+    # profiles/r01_probes.txt): 16.9 cycles per sample.  Every voice's chain advances one sample per tick of its CTA and all CTAs tick in
+    # parallel, so the floor of a block is BLOCK x 16.9 cycles whatever the voice count (up to one wave of CTAs).
+    floor_cycles = 16.9
+    kernel_vs = total * BLOCK / (k_ms_avg * 1e-3)
+    floor_vs = total * sm_max * 1e6 / floor_cycles
+    roofline = {"bound": "latency", "kernel": "kb_sub_tiled_kernel", "achieved": kernel_vs, "peak": floor_vs, "unit": "voice-samples/s",
+                "frac": kernel_vs / floor_vs, "traffic": traffic,
+                "peak_source": f"serial-chain floor: {floor_cycles} cycles per sample of the TDF-II biquad recurrence (measured alone, profiles/r01_probes.txt) at the {sm_max:.0f} MHz of MEASURED_PEAKS.json, x {total} voices in flight",
+                "latency_frac": kernel_vs / floor_vs,
+                "achieved_cycles_per_sample": k_ms_avg * 1e-3 * sm_max * 1e6 / BLOCK, "floor_cycles_per_sample": floor_cycles,
                 "kernel_ms": k_ms_avg, "kernel_share_of_step": k_ms_avg / ms_per_step,
-                "algorithmic_bytes_per_launch": alg_bytes,
-                "note": "C2 is bound by the dependent-issue latency of its fp32 recurrences, not HBM (SURVEY H6, DESIGN.md 4.1): 4 B of stream traffic per voice-sample",
-                "voice_samples_per_s_kernel": total * BLOCK / (k_ms_avg * 1e-3),
-                "fp32_lane_cycles_per_voice_sample": issue_peak / (total * BLOCK / (k_ms_avg * 1e-3)),
-                "lane_per_voice_kernel_ms": lane_ms,
-                # what actually bounds this kernel: one fp32 recurrence per voice that parity forbids re-ordering.  Floor = the
-                # TDF-II biquad chain measured alone on one warp of this chip (tools/micro/serial_floor.cu, profiles/r01_probes.txt)
-                "latency_bound": {"floor_cycles_per_sample": 16.9, "achieved_cycles_per_sample": k_ms_avg * 1e-3 * sm_max * 1e6 / BLOCK,
-                                  "frac": 16.9 / (k_ms_avg * 1e-3 * sm_max * 1e6 / BLOCK), "clock_mhz": sm_max,
-                                  "note": "every voice's filter chain advances one sample per tick of its CTA; 128 CTAs tick in parallel"}}
+                "hbm": {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak, "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": alg_bytes,
+                        "note": "4 B per voice-sample = the per-voice stream the kernel writes (SURVEY 8d, parity-dump figure); the streams stay in L2 "
+                                "(traffic = DRAM bytes of one launch from the ncu capture), so the HBM fraction of C2 is a few % by nature (SURVEY H6)"},
+                "lane_per_voice_kernel_ms": lane_ms}
     bank.close()
 
     line = {
         "metric": "voice-samples/sec (48 kHz equiv) at 1024 voices", "value": value, "unit": "voice-samples/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(workload_config(), mixdown=mix_kind), "realtime_voices_48k": value / 48000.0,
-        "clocks": clk, "e2e": e2e, "gpu_launches": int(gpu_launches) + (3 if mixdown is not None else 0), "roofline": roofline,
+        "config": workload_config(), "mixdown": mix_kind, "realtime_voices_48k": value / 48000.0,
+        "clocks": clk, "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline,
     }
     if mixdown is not None:
         torch.cuda.synchronize()
         dist.barrier()
         mixdown.close()
 
+    # ---- BASELINE configs C4 (one GPU: effect instances are replicas) and C5 (all ranks), inside keys the driver keeps
+    if not args.no_extras:
+        try:
+            c5 = c5_measure(kb, torch, ctx, steps=5, warmup=3, full_line=False)
+            if rank == 0:
+                roofline["c5"] = c5
+        except Exception as e:
+            roofline["c5"] = {"error": repr(e)}
     if rank == 0 and not args.no_extras:
         try:
-            line["other_workloads"] = extras(kb, torch, dev, stream, flush_l2, hbm_peak, peak_src, local_rank, with_cpu=(world == 1 and not args.no_cpu))
+            other = extras(kb, torch, dev, stream, flush_l2, hbm_peak, peak_src, local_rank, with_cpu=(world == 1 and not args.no_cpu))
+            line["other_workloads"] = other
+            for key, name in (("c4_reverb_64", "c4_reverb"), ("c4_reverb_64_tolerance", "c4_reverb_tolerance"), ("c4_pingpong_64", "c4_pingpong"),
+                              ("c4_delay_pingpong_64", "c4_delay_pingpong"), ("c4_delay_pingpong_64_x65536", "c4_delay_pingpong_65536"), ("c4_delay_reverb_64", "c4_delay_reverb")):
+                w = other.get(key)
+                if isinstance(w, dict) and "roofline" in w:
+                    roofline[name + "_frac"] = w["roofline"]["frac"]
+                    roofline[name + "_ms"] = w["ms_per_step"]
+            roofline["c4_note"] = ("C4 = 64 stereo instances x 4096-frame blocks, distinct input per step, L2 flushed before every timed step; frac = algorithmic bytes per frame "
+                                   "(SURVEY 8d: Reverb.k 664, PingPong.k 48, Delay/PingPong.k 40, Delay/Reverb.k 88) x frames / time / measured copy peak; "
+                                   "*_tolerance = the 1e-5-tolerance schedule (KB_FX_TOLERANCE), everything else bit-exact")
         except Exception as e:   # secondary numbers never take the headline down
             line["other_workloads"] = {"error": repr(e)}
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
-            _, _, info = cpu_reference_run(steps=200, warmup=2)      # ~1 s wall on every host core: 10-30 s of CPU work
+            _, _, info = cpu_reference_run(steps=100, warmup=2, passes=3)      # ~0.5 s wall per pass on every host core: 10-30 s of CPU work
             line["cpu_baseline"] = info
         except Exception as e:
             line["cpu_baseline"] = {"error": repr(e)}
@@ -547,140 +597,144 @@ def main():
         emit(line)
 
 
-def run_c5(args, rank, world, local_rank, emit):
+def c5_measure(kb, torch, ctx, steps, warmup, full_line):
     """BASELINE config C5: TB303.k + SynTHX.k mixed bank, 8192 voices over 8 GPUs = per GPU 4 x 128 TB303 voices (mono)
-    + 4 x 128 SynTHX voices (stereo), block 4096; every rank mixes its instances into one stereo bus (KB_BANK_MIX, mono
-    voices to both channels) and the buses are sum-reduced to rank 0 over NCCL each block."""
-    import numpy as np
-    import torch
-    import klang_b200 as kb
+    + 4 x 128 SynTHX voices (stereo), block 4096; the two banks render on two streams, every rank mixes its instances into one stereo
+    bus (KB_BANK_MIX, mono voices to both channels) and the buses are summed on rank 0."""
     from klang_b200 import sharding
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
-    stream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(stream)
-    hbm_peak, peak_src, _ = load_peaks()
-    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    rank, world, local_rank, dist, dev, stream = ctx["rank"], ctx["world"], ctx["local_rank"], ctx["dist"], ctx["dev"], ctx["stream"]
+    hbm_peak, peak_src = ctx["hbm_peak"], ctx["peak_src"]
     inst, voices, n = 4, 128, BLOCK
     kb.lib().kb_srand(1 + rank)
     tb = kb.SynthBank(kb.SY_TB303, inst, voices, FS, n, local_rank)
     sx = kb.SynthBank(kb.SY_SYNTHX, inst, voices, FS, n, local_rank)
-    for b in (tb, sx):
-        b.set_stream(stream.cuda_stream)
+    side = torch.cuda.Stream(device=dev)                   # TB303 renders beside SynTHX: neither fills the chip alone
+    tb.set_stream(side.cuda_stream)
+    sx.set_stream(stream.cuda_stream)
     gid0 = rank * 2 * inst * voices
     for g in range(inst * voices):
         tb.voice_start(g % voices, 36 + (5 * (gid0 + g)) % 36, voice_velocity(gid0 + g), g // voices)
         sx.voice_start(g % voices, 36 + (7 * (gid0 + g)) % 30, voice_velocity(gid0 + g), g // voices)
     tb_mix = torch.empty(1, n, dtype=torch.float32, device=dev)
     bus = torch.empty(2, n, dtype=torch.float32, device=dev)
+    bus_out = torch.empty(2, n, dtype=torch.float32, device=dev)
     bus_host = torch.empty(2, n, dtype=torch.float32).pin_memory()
-
     mixdown, mix_kind = make_mixdown(sharding, dist, local_rank, 2 * n)
-    bus_out = torch.empty(2, n, dtype=torch.float32, device=dev) if mixdown is not None else bus
+    fork, join = torch.cuda.Event(), torch.cuda.Event()
+
+    def drain():
+        if mixdown is not None and rank == 0:
+            mixdown.collect(bus_out, 2 * n, stream.cuda_stream)
 
     def step(e2e=False):
-        tb.process_into(tb_mix, n, kb.BANK_MIX | kb.MIX_SUM)
-        sx.process_into(bus, n, kb.BANK_MIX)
+        fork.record(stream)
+        side.wait_event(fork)
+        tb.process_into(tb_mix, n, kb.BANK_MIX | kb.MIX_SUM)       # side stream
+        join.record(side)
+        sx.process_into(bus, n, kb.BANK_MIX)                       # main stream
+        stream.wait_event(join)
         bus.add_(tb_mix)                                   # mono voices feed both channels (SURVEY 8e)
         if mixdown is not None:
-            mixdown.put(bus, 2 * n, stream.cuda_stream)    # this rank's stereo bus into rank 0's arena over NVLink
-            if rank == 0:
-                mixdown.collect(bus_out, 2 * n, stream.cuda_stream)
-        else:
+            mixdown.step(bus, 2 * n, bus_out if rank == 0 else None, stream.cuda_stream)   # fused: store into rank 0's arena + flag; rank 0 sums the previous block
+        elif dist is not None:
             sharding.reduce_mix(bus, dst=0)
         if e2e:
-            bus_host.copy_(bus_out, non_blocking=True)
+            drain()
+            if rank == 0:
+                bus_host.copy_(bus_out if mixdown is not None else bus, non_blocking=True)
             torch.cuda.synchronize()
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(3, args.warmup)):
+    for _ in range(warmup):
         step()
-    barrier()
-    clocks = ClockSampler(local_rank).start() if rank == 0 else None
+    drain()
+    ctx["barrier"]()
+    clocks = ClockSampler(local_rank).start() if (rank == 0 and full_line) else None
     evs = []
-    for i in range(args.steps):
-        flush_buf.fill_(1)
+    for i in range(steps):
+        ctx["flush_l2"]()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
         step()
         b.record(stream)
         evs.append((a, b))
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    drain()
+    b.record(stream)
+    evs.append((a, b))
     if clocks:
         clocks.sample()
-    barrier()
+    ctx["barrier"]()
     clk = clocks.stop() if clocks else None
     t = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_per_step = float(t.item()) / args.steps
+    ms_per_step = float(t.item()) / steps
     total = 2 * inst * voices
     value = world * total * n / (ms_per_step * 1e-3)
-    barrier()
+    ctx["barrier"]()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step(e2e=True)
-    barrier()
+    ctx["barrier"]()
     te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * total * n * args.steps / float(te.item())
+    e2e_value = world * total * n * steps / float(te.item())
     sx.profile(True)
     tb.profile(True)
+    l0 = tb.launches + sx.launches
     for _ in range(5):
         step()
+    drain()
     sx_ms, sx_n = sx.profile_read()
     tb_ms, tb_n = tb.profile_read()
-    launches = (tb.launches + sx.launches) // (max(3, args.warmup) + 2 * args.steps + 5)
+    launches = (tb.launches + sx.launches - l0) / 5 + (1 if mixdown is not None else 0)
     k_ms = sx_ms / max(1, sx_n)
-    alg = inst * voices * n * 8.0                         # SynTHX per-voice streams are never materialised: 8 B per voice-sample of ADSR + bus traffic
-    line = {
-        "metric": "voice-samples/sec (48 kHz equiv) at 1024 voices", "value": value, "unit": "voice-samples/s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C5 TB303.k + SynTHX.k mixed bank: per GPU 4 x 128 TB303 voices + 4 x 128 SynTHX voices, fs 48 kHz, block 4096, "
-                               "stereo bus summed on rank 0", "mixdown": mix_kind, "block": n, "fs": FS,
-                   "l2": "flushed between timed steps (256 MiB write, outside the per-step events)"},
-        "realtime_voices_48k": value / 48000.0, "clocks": clk,
-        "e2e": {"value": e2e_value, "unit": "voice-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 2 * n * 4,
-                "note": "no events in this schedule (all voices held); per step the reduced stereo bus is copied to pinned host memory"},
-        "gpu_launches": int(launches) + 1,
-        "roofline": {"bound": "hbm", "kernel": "kb_sx_render_kernel", "achieved": alg / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": alg / (k_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src, "kernel_ms": k_ms,
-                     "kernel_share_of_step": k_ms / ms_per_step, "tb303_kernel_ms": tb_ms / max(1, tb_n),
-                     "note": "bound by the ordered fp32 accumulation chain per output sample (DESIGN.md 4.2), not HBM"},
-    }
     tb.close()
     sx.close()
     if mixdown is not None:
         torch.cuda.synchronize()
         dist.barrier()
         mixdown.close()
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
-    if rank == 0:
-        emit(line)
+    workload = ("C5 TB303.k + SynTHX.k mixed bank: per GPU 4 x 128 TB303 voices + 4 x 128 SynTHX voices, fs 48 kHz, block 4096, the two banks on two streams, "
+                "stereo bus summed on rank 0")
+    if not full_line:
+        return {"workload": workload, "value": value, "unit": "voice-samples/s", "n_gpus": world, "voices_total": world * total, "ms_per_step": ms_per_step,
+                "e2e_value": e2e_value, "steps": steps, "synthx_kernel_ms": k_ms, "tb303_kernel_ms": tb_ms / max(1, tb_n), "mixdown": mix_kind, "gpu_launches": launches}
+    alg = inst * voices * n * 8.0                         # SynTHX per-voice streams are never materialised: 8 B per voice-sample of ADSR + bus traffic
+    return {
+        "metric": "voice-samples/sec (48 kHz equiv) at 1024 voices", "value": value, "unit": "voice-samples/s", "n_gpus": world,
+        "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload, "block": n, "fs": FS, "l2": "flushed between timed steps (256 MiB write, outside the per-step events)"},
+        "mixdown": mix_kind, "realtime_voices_48k": value / 48000.0, "clocks": clk,
+        "e2e": {"value": e2e_value, "unit": "voice-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 2 * n * 4,
+                "note": "no events in this schedule (all voices held); per step the reduced stereo bus is copied to pinned host memory"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": "kb_sx_render_kernel", "achieved": alg / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": alg / (k_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src, "kernel_ms": k_ms,
+                     "kernel_share_of_step": k_ms / ms_per_step, "tb303_kernel_ms": tb_ms / max(1, tb_n),
+                     "note": "bound by the ordered fp32 accumulation chain per output sample (DESIGN.md 4.2), not HBM"},
+    }
 
 
 def extras(kb, torch, dev, stream, flush_l2, hbm_peak, peak_src, device_index, with_cpu=True):
-    """Secondary BASELINE configs, short runs: C1 Gain, C3 SuperSaw, C4 PingPong / Reverb / Delay-PingPong, C5 share."""
+    """Secondary BASELINE configs, short runs: C1 Gain, C3 SuperSaw, C4 PingPong / Reverb / Delay-PingPong / Delay-Reverb, streaming effects."""
     import oracle
     res = {}
 
-    def time_steps(fn, steps, warmup=3):
+    def time_steps(fn, steps, warmup=3, pre=None):
+        """CUDA-event time of fn() per step; `pre` (untimed) runs before the L2 flush of every step, so what it writes is not L2-resident"""
         for _ in range(warmup):
+            if pre:
+                pre()
             fn()
         torch.cuda.synchronize()
         tot = 0.0
         for _ in range(steps):
+            if pre:
+                pre()
             flush_l2()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(stream)
@@ -707,24 +761,39 @@ def extras(kb, torch, dev, stream, flush_l2, hbm_peak, peak_src, device_index, w
     if with_cpu:
         res["c1_gain_1x4096"]["cpu_reference"] = cpu_extra("fx", oracle.FX_GAIN, 1, 4096, 2000)
 
-    # C4: delay-line effects, 64 stereo instances; chunk-parallel schedule vs the frame-sequential one (same results)
-    for name, graph, n, steps in (("c4_pingpong_64", kb.FX_PINGPONG, 4096, 5), ("c4_reverb_64", kb.FX_REVERB, 4096, 3),
-                                  ("c4_delay_pingpong_64", kb.FX_DELAY_PINGPONG, 65536, 5), ("c4_delay_reverb_64", kb.FX_DELAY_REVERB, 4096, 5)):
+    # C4: delay-line effects, 64 stereo instances x 4096-frame blocks (the BASELINE shape); every timed step gets fresh input copied from a
+    # master buffer BEFORE the L2 flush (effects work in place), so neither io nor rings are L2-warm from the previous step's input
+    def c4_line(name, graph, n, steps, flags=0, settle=True):
         fx = kb.FxBank(graph, 64, FS, n, device_index)
         fx.set_stream(stream.cuda_stream)
-        io = torch.rand(64, fx.channels, n, device=dev) - 0.5
-        for _ in range(40000 // n + 2):                     # PingPong.k: let the control smoothers reach their fixed point
-            fx.process_inplace(io)
-        ms = time_steps(lambda: fx.process_inplace(io.uniform_(-0.5, 0.5)), steps, warmup=1)
-        fill = time_steps(lambda: io.uniform_(-0.5, 0.5), steps, warmup=1)
-        ms -= fill
+        master = torch.rand(4, 64, fx.channels, n, device=dev) - 0.5
+        io = torch.empty(64, fx.channels, n, device=dev)
+        k = [0]
+
+        def refill():
+            io.copy_(master[k[0] & 3])
+            k[0] += 1
+
+        if settle:
+            for _ in range(40000 // n + 2):                     # PingPong.k: let the control smoothers reach their fixed point
+                refill()
+                fx.process_inplace(io, flags=flags)
+        ms = time_steps(lambda: fx.process_inplace(io, flags=flags), steps, warmup=2, pre=refill)
         par = fx.parallel_instances()
         bpf = fx.bytes_per_frame()
-        ms_seq = time_steps(lambda: fx.process_inplace(io, flags=kb.FX_SEQUENTIAL), 1, warmup=0) if n <= 4096 else None
         res[name] = {"frames_per_s": 64 * n / (ms * 1e-3), "ms_per_step": ms, "block": n, "bytes_per_frame": bpf,
-                     "instances_on_parallel_schedule": par, "ms_per_step_sequential_schedule": ms_seq,
-                     "roofline": roof(64 * n * bpf / (ms * 1e-3) / 1e9)}
+                     "instances_on_parallel_schedule": par, "roofline": roof(64 * n * bpf / (ms * 1e-3) / 1e9)}
+        if n <= 4096 and flags == 0:
+            res[name]["ms_per_step_sequential_schedule"] = time_steps(lambda: fx.process_inplace(io, flags=kb.FX_SEQUENTIAL), 1, warmup=0, pre=refill)
         fx.close()
+
+    c4_line("c4_reverb_64", kb.FX_REVERB, 4096, 5)
+    if hasattr(kb, "FX_TOLERANCE"):
+        c4_line("c4_reverb_64_tolerance", kb.FX_REVERB, 4096, 5, flags=kb.FX_TOLERANCE)
+    c4_line("c4_pingpong_64", kb.FX_PINGPONG, 4096, 5)
+    c4_line("c4_delay_pingpong_64", kb.FX_DELAY_PINGPONG, 4096, 5)
+    c4_line("c4_delay_pingpong_64_x65536", kb.FX_DELAY_PINGPONG, 65536, 5)
+    c4_line("c4_delay_reverb_64", kb.FX_DELAY_REVERB, 4096, 5)
     if with_cpu:
         res["c4_pingpong_64"]["cpu_reference"] = cpu_extra("fx", oracle.FX_PINGPONG, 1, 4096, 40)
         res["c4_reverb_64"]["cpu_reference"] = cpu_extra("fx", oracle.FX_REVERB, 1, 4096, 8)
@@ -752,37 +821,27 @@ def extras(kb, torch, dev, stream, flush_l2, hbm_peak, peak_src, device_index, w
         res["c5_tb303_512"]["cpu_reference"] = cpu_extra("synth", oracle.SY_TB303, 16, 4096, 4)
         res["c5_synthx_512"]["cpu_reference"] = cpu_extra("synth", oracle.SY_SYNTHX, 4, 1024, 2)
         res["fm_k_1024"]["cpu_reference"] = cpu_extra("synth", oracle.SY_FM, 16, 4096, 8)
-    # the other elementwise effects on the streaming schedule (Tremolo.k with its closed-form LFO, Pan.k stereo); last and on their own:
-    # these kernels had no device run when the round's GPU budget ended
+    # the other elementwise effects on the streaming schedule (Tremolo.k with its closed-form LFO, Pan.k stereo)
     for name, graph, inst in (("tremolo_k_batched_64x1Mi", kb.FX_TREMOLO, 64), ("pan_k_batched_32x1Mi", kb.FX_PAN, 32)):
         try:
             streaming_line(name, graph, inst, 1 << 20)
         except Exception as e:
             res[name] = {"error": repr(e)}
-    # Delay/Echo.k, 64 instances x 65536 frames: write sweep + read sweep (20 algorithmic bytes per frame)
-    try:
-        fx = kb.FxBank(kb.FX_ECHO, 64, FS, 65536, device_index)
-        fx.set_stream(stream.cuda_stream)
-        fx.set_control(0, 0.25)
-        io = torch.rand(64, 1, 65536, device=dev) - 0.5
-        ms = time_steps(lambda: fx.process_inplace(io), 5, warmup=2)
-        res["echo_k_64"] = {"frames_per_s": 64 * 65536 / (ms * 1e-3), "ms_per_step": ms, "block": 65536, "bytes_per_frame": 20,
-                            "roofline": roof(64 * 65536 * 20 / (ms * 1e-3) / 1e9)}
-        fx.close()
-    except Exception as e:
-        res["echo_k_64"] = {"error": repr(e)}
-    # Modulation/Flanger.k, 64 instances x 65536 frames: write sweep with stash + read sweep (24 algorithmic bytes per frame)
-    try:
-        fx = kb.FxBank(kb.FX_FLANGER, 64, FS, 65536, device_index)
-        fx.set_stream(stream.cuda_stream)
-        io = torch.rand(64, 1, 65536, device=dev) - 0.5
-        ms = time_steps(lambda: fx.process_inplace(io.uniform_(-0.5, 0.5)), 5, warmup=2)
-        ms -= time_steps(lambda: io.uniform_(-0.5, 0.5), 5, warmup=1)
-        res["flanger_k_64"] = {"frames_per_s": 64 * 65536 / (ms * 1e-3), "ms_per_step": ms, "block": 65536, "bytes_per_frame": 24,
-                               "roofline": roof(64 * 65536 * 24 / (ms * 1e-3) / 1e9)}
-        fx.close()
-    except Exception as e:
-        res["flanger_k_64"] = {"error": repr(e)}
+    # Delay/Echo.k and Modulation/Flanger.k, 64 instances x 65536 frames (20 / 24 algorithmic bytes per frame)
+    for name, graph, bpf in (("echo_k_64", kb.FX_ECHO, 20), ("flanger_k_64", kb.FX_FLANGER, 24)):
+        try:
+            fx = kb.FxBank(graph, 64, FS, 65536, device_index)
+            fx.set_stream(stream.cuda_stream)
+            if graph == kb.FX_ECHO:
+                fx.set_control(0, 0.25)
+            master = torch.rand(64, 1, 65536, device=dev) - 0.5
+            io = torch.empty_like(master)
+            ms = time_steps(lambda: fx.process_inplace(io), 5, warmup=2, pre=lambda: io.copy_(master))
+            res[name] = {"frames_per_s": 64 * 65536 / (ms * 1e-3), "ms_per_step": ms, "block": 65536, "bytes_per_frame": bpf,
+                         "roofline": roof(64 * 65536 * bpf / (ms * 1e-3) / 1e9)}
+            fx.close()
+        except Exception as e:
+            res[name] = {"error": repr(e)}
     # Additive/Saw.k (32 sine partials per voice, no recurrence at all), Subtractive/Release.k and Modulation/AM.k (one envelope x closed-form
     # sines): time-parallel kernels, each with the lane-per-voice A/B
     for name, graph in (("additive_saw_k_1024", kb.SY_ADDITIVE_SAW), ("release_k_1024", kb.SY_RELEASE), ("am_k_1024", kb.SY_AM)):

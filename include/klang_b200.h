@@ -150,6 +150,8 @@ int kb_synth_bank_voice_stage(kb_synth_bank* bank, int instance, int voice);   /
 #define KB_EV_CONTROL 4
 typedef struct kb_note_event { int type, instance, key; float pitch, velocity; } kb_note_event;
 int kb_synth_bank_events(kb_synth_bank* bank, int count, const kb_note_event* events);
+/* kb_synth_bank_events followed by kb_synth_bank_process in one call (a host's audio callback: MIDI loop, then the block) */
+int kb_synth_bank_step(kb_synth_bank* bank, int count, const kb_note_event* events, float* out, int n, unsigned flags);
 /* Synth::process(float*, int) / Stereo::Synth::process(float**, int) for every instance.
  * out = [instances][channels][n] (see flags for the other layouts); out is overwritten.   klang.h:4440-4466, 4830-4858 */
 int kb_synth_bank_process(kb_synth_bank* bank, float* out, int n, unsigned flags);
@@ -188,6 +190,14 @@ int kb_mixdown_publish(kb_mixdown* m, void* cuda_stream);
 int kb_mixdown_put(kb_mixdown* m, const float* src, int count, void* cuda_stream);
 /* rank 0: dst[i] = slot[0][i] + slot[1][i] + ... (rank order) for i < count, once every rank has published this step */
 int kb_mixdown_collect(kb_mixdown* m, float* dst, int count, void* cuda_stream);
+/* The fused form — ONE kernel per block and rank, no acquire / publish / collect launches: the kernel waits for the slot of the step to be
+ * free, stores `count` floats of `src` (device memory) into it, raises the rank's flag, and on rank 0 additionally sums the slots of the
+ * PREVIOUS step in rank order into out_prev (device memory, rank 0 only; ignored elsewhere).  The exchange of block k thus runs beside the
+ * kernels of block k + 1; kb_mixdown_collect() after the last block returns the last sum.  Do not mix with acquire / publish in one step. */
+int kb_mixdown_step(kb_mixdown* m, const float* src, int count, float* out_prev, void* cuda_stream);
+/* kb_synth_bank_process(KB_BANK_MIX) whose bank-mix kernel IS that fused step: the in-order sum of the bank's instances goes straight into
+ * rank 0's arena over NVLink (Synth voices / instances shard across GPUs; this is the path's only exchange). */
+int kb_synth_bank_process_mixdown(kb_synth_bank* bank, kb_mixdown* m, float* out_prev, int n, unsigned flags);
 
 /* ---------------------------------------------------------------------------- primitive operators */
 /* Single-object runs of the primitive operators ON THE DEVICE (one thread), for known-answer tests.
@@ -210,6 +220,15 @@ int kb_prim_filter(int kind, int nset, const float* f, const float* Q, float fs,
 int kb_prim_envelope(int npts, const float* xy, int loop_start, int loop_end, float fs, int n, int release_at,
                      float release_time, float release_level, float* out, int* stage_out);
 int kb_prim_adsr(float A, float D, float S, float R, float fs, int n, int release_at, float* out, int* stage_out);
+/* Wavetables::Sine / Saw (kind 10 / 11, klang.h:5372-5379): the 2048-entry table as the device oscillators read it (filled by the
+ * constructor code of Wavetable::operator=(Oscillator), klang.h:3645-3650, on the host; resident in HBM) */
+int kb_prim_wavetable(int kind, float fs, float* out2048);
+/* One Stereo::Delay<1000> (klang.h:4647-4700), sample by sample: write {inl[s], inr[s]}; {outl, outr}[s] = tap(float df[s]) */
+int kb_prim_stereo_delay(int n, const float* inl, const float* inr, const float* df, float* outl, float* outr);
+/* Control::set(values[s]) then Control::smooth() per sample on a Dial(lo, hi, initial)       klang.h:1715-1728, 1796-1799 */
+int kb_prim_control_smooth(float lo, float hi, float initial, int n, const float* values, float* out);
+/* Envelope::at(t[s]) on the breakpoints xy = {x0, y0, x1, y1, ...}                              klang.h:3929-3942 */
+int kb_prim_envelope_at(int npts, const float* xy, int n, const float* t, float* out);
 /* libm agreement probe: out[i] = device sinf / cosf / tanhf of x[i] (fn 0 / 1 / 2) */
 int kb_prim_math(int fn, int n, const float* x, float* out);
 

@@ -44,12 +44,16 @@ SYMBOLS = [
     ("kb_mixdown_export", _i, [_vp, _vp]), ("kb_mixdown_import", _i, [_vp, _vp]),
     ("kb_mixdown_acquire", _vp, [_vp, _vp]), ("kb_mixdown_publish", _i, [_vp, _vp]), ("kb_mixdown_put", _i, [_vp, _vp, _i, _vp]),
     ("kb_mixdown_collect", _i, [_vp, _vp, _i, _vp]),
+    ("kb_mixdown_step", _i, [_vp, _vp, _i, _vp, _vp]), ("kb_synth_bank_process_mixdown", _i, [_vp, _vp, _vp, _i, _u]),
+    ("kb_synth_bank_step", _i, [_vp, _i, _vp, _vp, _i, _u]),
     ("kb_prim_osc", _i, [_i, _i, _f, _f, _f, _f, _i, _vp]),
     ("kb_prim_filter", _i, [_i, _i, _vp, _vp, _f, _i, _vp, _vp, _vp]),
     ("kb_prim_envelope", _i, [_i, _vp, _i, _i, _f, _i, _i, _f, _f, _vp, _vp]),
     ("kb_prim_adsr", _i, [_f, _f, _f, _f, _f, _i, _i, _vp, _vp]),
     ("kb_prim_math", _i, [_i, _i, _vp, _vp]),
     ("kb_prim_delay", _i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    ("kb_prim_wavetable", _i, [_i, _f, _vp]), ("kb_prim_stereo_delay", _i, [_i, _vp, _vp, _vp, _vp, _vp]),
+    ("kb_prim_control_smooth", _i, [_f, _f, _f, _i, _vp, _vp]), ("kb_prim_envelope_at", _i, [_i, _vp, _i, _vp, _vp]),
 ]
 
 
@@ -89,10 +93,25 @@ def _check(rc, what):
     return rc
 
 
-def _ptr(x):
-    """Device pointer of a torch CUDA tensor, or host pointer of a numpy array."""
+def _ptr(x, numel=None, what="buffer", device=None):
+    """Device pointer of a torch CUDA tensor, or host pointer of a numpy array.  The C ABI takes raw pointers and reads / writes
+    `numel` float32 elements behind them, so dtype, contiguity, size (and the device of a CUDA tensor) are checked here."""
     if isinstance(x, np.ndarray):
+        if x.dtype != np.float32 or not x.flags["C_CONTIGUOUS"]:
+            raise KlangB200Error(f"{what}: need a C-contiguous float32 array, got dtype {x.dtype}, contiguous={x.flags['C_CONTIGUOUS']}")
+        if not x.flags["WRITEABLE"]:
+            raise KlangB200Error(f"{what}: array is read-only (the call writes into it)")
+        if numel is not None and x.size < numel:
+            raise KlangB200Error(f"{what}: {x.size} elements, the call needs {numel}")
         return x.ctypes.data, False
+    if not hasattr(x, "data_ptr"):
+        raise KlangB200Error(f"{what}: expected a numpy array or a torch tensor, got {type(x).__name__}")
+    if str(x.dtype) != "torch.float32" or not x.is_contiguous():
+        raise KlangB200Error(f"{what}: need a contiguous float32 tensor, got {x.dtype}, contiguous={x.is_contiguous()}")
+    if numel is not None and x.numel() < numel:
+        raise KlangB200Error(f"{what}: {x.numel()} elements, the call needs {numel}")
+    if x.is_cuda and device is not None and x.device.index != device:
+        raise KlangB200Error(f"{what}: tensor lives on cuda:{x.device.index}, the bank on cuda:{device}")
     return x.data_ptr(), bool(x.is_cuda)
 
 
@@ -103,7 +122,7 @@ class FxBank:
         self.h = lib().kb_fx_bank_create(graph, instances, float(fs), max_block, device)
         if not self.h:
             raise KlangB200Error("kb_fx_bank_create: " + lib().kb_last_error().decode())
-        self.graph, self.instances, self.max_block = graph, instances, max_block
+        self.graph, self.instances, self.max_block, self.device = graph, instances, max_block, device
         self.channels = lib().kb_fx_bank_channels(self.h)
         self.num_controls = lib().kb_fx_bank_num_controls(self.h)
 
@@ -125,8 +144,10 @@ class FxBank:
 
     def process_inplace(self, io, n=None, flags=0):
         """io: float32 [instances, channels, n], numpy (host) or torch CUDA tensor (asynchronous)."""
-        p, dev = _ptr(io)
         n = io.shape[-1] if n is None else n
+        if n < 0:
+            raise KlangB200Error("kb_fx_bank_process: negative block length")
+        p, dev = _ptr(io, self.instances * self.channels * n, "kb_fx_bank_process io [instances, channels, n]", self.device)
         _check(lib().kb_fx_bank_process(self.h, p, n, (flags | DEVICE_PTR) if dev else (flags & ~DEVICE_PTR)), "kb_fx_bank_process")
         return io
 
@@ -168,7 +189,7 @@ class SynthBank:
         self.h = lib().kb_synth_bank_create(graph, instances, voices, float(fs), max_block, device)
         if not self.h:
             raise KlangB200Error("kb_synth_bank_create: " + lib().kb_last_error().decode())
-        self.graph, self.instances, self.max_block = graph, instances, max_block
+        self.graph, self.instances, self.max_block, self.device = graph, instances, max_block, device
         self.channels = lib().kb_synth_bank_channels(self.h)
         self.voices = lib().kb_synth_bank_voices(self.h)
         self.num_controls = lib().kb_synth_bank_num_controls(self.h)
@@ -222,9 +243,28 @@ class SynthBank:
 
     def process_into(self, out, n, flags=0):
         """out: float32 buffer of out_shape(n, flags), numpy (host, synchronous) or torch CUDA tensor (asynchronous)."""
-        p, dev = _ptr(out)
+        if n < 0:
+            raise KlangB200Error("kb_synth_bank_process: negative block length")
+        p, dev = _ptr(out, int(np.prod(self.out_shape(n, flags))), "kb_synth_bank_process out", self.device)
         _check(lib().kb_synth_bank_process(self.h, p, n, (flags | DEVICE_PTR) if dev else (flags & ~DEVICE_PTR)), "kb_synth_bank_process")
         return out
+
+    def step_into(self, ev, out, n, flags=0):
+        """events(ev) then process_into(out, n, flags) in one call into the library (kb_synth_bank_step)."""
+        ev = np.ascontiguousarray(ev, EVENT_DTYPE)
+        p, dev = _ptr(out, int(np.prod(self.out_shape(n, flags))), "kb_synth_bank_step out", self.device)
+        _check(lib().kb_synth_bank_step(self.h, len(ev), ev.ctypes.data, p, n, (flags | DEVICE_PTR) if dev else (flags & ~DEVICE_PTR)), "kb_synth_bank_step")
+        return out
+
+    def process_mixdown(self, mixdown, out_prev, n, flags=0):
+        """process(KB_BANK_MIX) whose bank-mix kernel stores into rank 0's arena (sharding.PeerMixdown); on rank 0 `out_prev` (a torch CUDA
+        tensor [channels, n]) receives the rank-order sum of the PREVIOUS block."""
+        p = 0
+        if out_prev is not None:
+            p, dev = _ptr(out_prev, self.channels * n, "kb_synth_bank_process_mixdown out_prev", self.device)
+            if not dev:
+                raise KlangB200Error("kb_synth_bank_process_mixdown: out_prev must be device memory")
+        _check(lib().kb_synth_bank_process_mixdown(self.h, mixdown.h, p, n, flags), "kb_synth_bank_process_mixdown")
 
     def process_into_device_ptr(self, ptr, n, flags=0):
         """out = a raw device pointer (e.g. a peer-mapped slot of sharding.PeerMixdown); asynchronous on the bank stream."""
@@ -370,6 +410,32 @@ class Engine:
         """Delay<1000>::lagrange(df[s]) after writing x[s] (klang.h:3429-3458)."""
         n = len(x)
         return self._delay_kat(x, np.zeros(n, np.int32), df, np.full(n, -1.0, np.float32))[3]
+
+    def wavetable(self, kind):
+        """Wavetables::Sine / Saw (kinds 10 / 11): the 2048-entry table as the device reads it."""
+        out = np.zeros(2048, np.float32)
+        _check(lib().kb_prim_wavetable(kind, self.fs, out.ctypes.data), "kb_prim_wavetable")
+        return out
+
+    def stereo_delay1000(self, xl, xr, df):
+        """Stereo::Delay<1000>: write {xl[s], xr[s]}, then tap(float df[s]) (klang.h:4668-4681)."""
+        xl, xr, df = (np.ascontiguousarray(a, np.float32) for a in (xl, xr, df))
+        ol, orr = np.zeros(len(xl), np.float32), np.zeros(len(xl), np.float32)
+        _check(lib().kb_prim_stereo_delay(len(xl), xl.ctypes.data, xr.ctypes.data, df.ctypes.data, ol.ctypes.data, orr.ctypes.data), "kb_prim_stereo_delay")
+        return ol, orr
+
+    def control_smooth(self, lo, hi, initial, values):
+        values = np.ascontiguousarray(values, np.float32)
+        out = np.zeros(len(values), np.float32)
+        _check(lib().kb_prim_control_smooth(float(lo), float(hi), float(initial), len(values), values.ctypes.data, out.ctypes.data), "kb_prim_control_smooth")
+        return out
+
+    def envelope_at(self, points, t):
+        xy = np.ascontiguousarray(np.asarray(points, np.float32).reshape(-1))
+        t = np.ascontiguousarray(t, np.float32)
+        out = np.zeros(len(t), np.float32)
+        _check(lib().kb_prim_envelope_at(len(xy) // 2, xy.ctypes.data, len(t), t.ctypes.data, out.ctypes.data), "kb_prim_envelope_at")
+        return out
 
     def filt(self, kind, x, f, Q=None, per_sample=False):
         x = np.ascontiguousarray(x, np.float32)

@@ -93,6 +93,8 @@ static int fx_upload(kb_fx_bank* b) {
 
 extern "C" kb_fx_bank* kb_fx_bank_create(int graph, int instances, float fs, int max_block, int device) {
 	if (graph < 0 || graph >= KB_FX_COUNT || instances < 1 || max_block < 1 || !(fs > 0)) { kb_fail(KB_EINVAL, "kb_fx_bank_create: bad argument"); return nullptr; }
+	// (several kernels carry the row index instance * channels + channel in gridDim.y, which is limited to 65535)
+	if (instances > 32767) { kb_fail(KB_EINVAL, "kb_fx_bank_create: at most 32767 instances per bank (create several banks)"); return nullptr; }
 	if (device < 0 || device >= kb_device_count()) { kb_fail(KB_ENODEV, "kb_fx_bank_create: no such CUDA device (klang-b200 has no CPU path)"); return nullptr; }
 	kb_fx_bank* b = new kb_fx_bank();
 	b->graph = graph; b->instances = instances; b->device = device; b->max_block = max_block; b->fs = kb_make_fs(fs);
@@ -396,7 +398,10 @@ extern "C" int kb_fx_bank_process(kb_fx_bank* b, float* io, int n, unsigned flag
 				const float tl = b->hdr[i].controls[0].value * b->fs.f, tr = b->hdr[i].controls[1].value * b->fs.f;
 				KbFxPlan& p = plan[i];
 				p.chunk = (int)std::min(tl, tr) - 2;
-				p.mode = (p.chunk >= cf + 2 && tl < 192000.f && tr < 192000.f) ? KB_PLAN_PARALLEL : KB_PLAN_SEQUENTIAL;
+				// far-end guard: a frame of this launch must never overwrite a ring slot an EARLIER frame of the launch still has to read
+				// (frame f reads slots written SIZE - t - 2 .. SIZE - t frames later once the launch is longer than SIZE - t)
+				const float span = (float)std::min(n, 131072) + std::max(tl, tr) + 4.f;
+				p.mode = (p.chunk >= cf + 2 && tl < 192000.f && tr < 192000.f && span < 192000.f) ? KB_PLAN_PARALLEL : KB_PLAN_SEQUENTIAL;
 				p.gain = p.delay = p.dry = 0.f;
 				all_parallel = all_parallel && p.mode == KB_PLAN_PARALLEL;
 			}
@@ -561,6 +566,10 @@ static int sy_upload(kb_synth_bank* b) {
 extern "C" kb_synth_bank* kb_synth_bank_create(int graph, int instances, int voices, float fs, int max_block, int device) {
 	if (graph < 0 || graph >= KB_SY_COUNT || instances < 1 || voices < 1 || voices > KB_MAX_VOICES || max_block < 1 || !(fs > 0)) {
 		kb_fail(KB_EINVAL, "kb_synth_bank_create: bad argument"); return nullptr;
+	}
+	// (kernels carry the instance index — the additive graphs the voice index — in gridDim.y, which is limited to 65535)
+	if (instances > 65535 || ((graph == KB_SY_ADDITIVE_SAW || graph == KB_SY_ADDITIVE_SQUARE || graph == KB_SY_ADDITIVE_NYQUIST) && (long long)instances * std::max(voices, 32) > 65535)) {
+		kb_fail(KB_EINVAL, "kb_synth_bank_create: at most 65535 instances (additive graphs: 65535 voices) per bank (create several banks)"); return nullptr;
 	}
 	if (device < 0 || device >= kb_device_count()) { kb_fail(KB_ENODEV, "kb_synth_bank_create: no such CUDA device (klang-b200 has no CPU path)"); return nullptr; }
 	kb_synth_bank* b = new kb_synth_bank();
@@ -798,8 +807,19 @@ extern "C" int kb_synth_bank_events(kb_synth_bank* b, int count, const kb_note_e
 	return KB_OK;
 }
 
+struct kb_mixdown;
+static int mixdown_step(kb_mixdown* m, const float* src, int rows, size_t row_stride, int count, float* out_prev, cudaStream_t stream);
+static int sy_process(kb_synth_bank* b, float* out, int n, unsigned flags, kb_mixdown* mixdown, float* out_prev);
 extern "C" int kb_synth_bank_process(kb_synth_bank* b, float* out, int n, unsigned flags) {
 	if (!b || !out || n < 0 || n > b->max_block) return kb_fail(KB_EINVAL, "kb_synth_bank_process: bad argument (n > max_block?)");
+	return sy_process(b, out, n, flags, nullptr, nullptr);
+}
+// events of the block, then the block: what a host's audio callback does (templates/juce/synth/Source/PluginProcessor.cpp:169-177), one call
+extern "C" int kb_synth_bank_step(kb_synth_bank* b, int count, const kb_note_event* events, float* out, int n, unsigned flags) {
+	int rc = kb_synth_bank_events(b, count, events); if (rc) return rc;
+	return kb_synth_bank_process(b, out, n, flags);
+}
+static int sy_process(kb_synth_bank* b, float* out, int n, unsigned flags, kb_mixdown* mixdown, float* out_prev) {
 	if (n == 0) return KB_OK;
 	KB_CUDA(cudaSetDevice(b->device));
 	int rc = sy_upload(b); if (rc) return rc;
@@ -916,6 +936,13 @@ extern "C" int kb_synth_bank_process(kb_synth_bank* b, float* out, int n, unsign
 		}
 	}
 	float* d_result = per_voice ? d_voice_dst : d_inst_dst;
+	if (bank_mix && mixdown) {
+		// the bank mix goes straight into rank 0's arena (kb_mixdown_step_kernel); nothing is returned through `out`
+		rc = mixdown_step(mixdown, b->d_out, b->instances, (size_t)C * n, C * n, out_prev, st); if (rc) return rc;
+		b->launches++;
+		b->host_stale = true; b->hdr_stale = true; b->vstate_stale = true;
+		return KB_OK;
+	}
 	if (bank_mix) {
 		d_result = dev ? out : b->d_mix;
 		kb_bank_mix_kernel<<<(C * n + 255) / 256, 256, 0, st>>>(b->d_out, d_result, C * n, b->instances);
@@ -938,7 +965,9 @@ extern "C" int kb_synth_bank_process(kb_synth_bank* b, float* out, int n, unsign
 struct kb_mixdown {
 	int device = 0, world = 1, rank = 0, max_floats = 0;
 	unsigned step = 0;                  // steps acquired so far on this rank
+	unsigned collected = 0;             // rank 0: the last step whose slots have been summed
 	unsigned char* arena = nullptr;     // rank 0: own allocation; others: the IPC mapping
+	unsigned* d_tickets = nullptr;      // local device memory: two CTA tickets of the fused step kernel (publish, collect)
 	bool mapped = false;
 	size_t slot_bytes() const { return (size_t)max_floats * sizeof(float); }
 	float* slot(unsigned step_, int r) const { return (float*)(arena + ((size_t)(step_ & 1u) * world + r) * slot_bytes()); }
@@ -987,6 +1016,7 @@ extern "C" void kb_mixdown_destroy(kb_mixdown* m) {
 	cudaSetDevice(m->device);
 	cudaDeviceSynchronize();
 	if (m->arena) { if (m->mapped) cudaIpcCloseMemHandle(m->arena); else cudaFree(m->arena); }
+	cudaFree(m->d_tickets);
 	delete m;
 }
 extern "C" int kb_mixdown_export(kb_mixdown* m, void* handle) {
@@ -1032,8 +1062,74 @@ extern "C" int kb_mixdown_collect(kb_mixdown* m, float* dst, int count, void* st
 	if (!m || !dst || m->rank != 0 || count < 0 || count > m->max_floats || m->step == 0) return kb_fail(KB_EINVAL, "kb_mixdown_collect: bad argument (rank 0 only, count <= max_floats)");
 	KB_CUDA(cudaSetDevice(m->device));
 	kb_mixdown_collect_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(m->slot(m->step, 0), (size_t)m->max_floats, m->flags(), m->consumed(), m->step, m->world, dst, count);
+	m->collected = m->step;
 	KB_CUDA(cudaGetLastError());
 	return KB_OK;
+}
+
+// The fused step (kb_mixdown_step / kb_synth_bank_process_mixdown): ONE kernel per block and rank, no separate wait / publish / collect
+// launches and no collective library on the data path.
+//   (a) thread 0 of every CTA waits until rank 0 has consumed the step that last used this slot parity (back-pressure; ranks > 0 poll
+//       the word over NVLink only when they run two blocks ahead);
+//   (b) the rank's contribution — the in-order fp32 sum of `rows` rows of `src` (the per-instance Synth outputs: the bank mix,
+//       klang.h:4842-4848 applied across instances) — is stored into the rank's slot, peer memory on ranks > 0;
+//   (c) the last CTA to finish raises the rank's flag behind a system-scope fence;
+//   (d) on rank 0 the same kernel then sums the slots of the PREVIOUS step in rank order into out_prev and marks that step consumed:
+//       the exchange of block k overlaps the voice kernels of block k + 1, and a late rank never stalls the others' current block.
+__global__ void __launch_bounds__(256) kb_mixdown_step_kernel(const float* __restrict__ src, int rows, size_t row_stride, int count, float* __restrict__ slot,
+                                                              volatile unsigned* flags, volatile unsigned* consumed, unsigned* tickets, unsigned step, int rank, int world,
+                                                              const float* prev_slots, size_t slot_floats, float* __restrict__ out_prev, int do_prev) {
+	__shared__ bool s_last;
+	if (threadIdx.x == 0 && step > 2) while ((int)(*consumed - (step - 2)) < 0) __nanosleep(200);
+	__syncthreads();
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+		float acc = src[i];
+		for (int k = 1; k < rows; k++) acc += src[(size_t)k * row_stride + i];
+		slot[i] = acc;
+	}
+	__threadfence_system();
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		s_last = atomicAdd(&tickets[0], 1u) == gridDim.x - 1;
+		if (s_last) { tickets[0] = 0u; __threadfence_system(); flags[rank] = step; }
+	}
+	if (!do_prev) return;
+	for (int r = threadIdx.x; r < world; r += blockDim.x) while ((int)(flags[r] - (step - 1)) < 0) __nanosleep(100);
+	__syncthreads();
+	__threadfence_system();
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+		float acc = __ldcv(prev_slots + i);                                // (peer-written memory: never from a stale cache line)
+		for (int r = 1; r < world; r++) acc += __ldcv(prev_slots + (size_t)r * slot_floats + i);
+		out_prev[i] = acc;
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		__threadfence_system();
+		if (atomicAdd(&tickets[1], 1u) == gridDim.x - 1) { tickets[1] = 0u; __threadfence_system(); *consumed = step - 1; }
+	}
+}
+static int mixdown_step(kb_mixdown* m, const float* src, int rows, size_t row_stride, int count, float* out_prev, cudaStream_t stream) {
+	if (!m->d_tickets) { KB_CUDA(cudaMalloc(&m->d_tickets, 2 * sizeof(unsigned))); KB_CUDA(cudaMemset(m->d_tickets, 0, 2 * sizeof(unsigned))); }
+	const unsigned step = ++m->step;
+	const int do_prev = (m->rank == 0 && step > 1 && m->collected < step - 1 && out_prev) ? 1 : 0;
+	kb_mixdown_step_kernel<<<std::max(1, std::min(32, (count + 255) / 256)), 256, 0, stream>>>(src, rows, row_stride, count, m->slot(step, m->rank), m->flags(), m->consumed(), m->d_tickets,
+	                                                                                          step, m->rank, m->world, m->slot(step - 1, 0), (size_t)m->max_floats, out_prev, do_prev);
+	if (do_prev) m->collected = step - 1;
+	KB_CUDA(cudaGetLastError());
+	return KB_OK;
+}
+extern "C" int kb_synth_bank_process_mixdown(kb_synth_bank* b, kb_mixdown* m, float* out_prev, int n, unsigned flags) {
+	if (!b || !m || !m->arena || n < 1 || n > b->max_block || b->channels * n > m->max_floats || (flags & KB_PER_VOICE))
+		return kb_fail(KB_EINVAL, "kb_synth_bank_process_mixdown: bad argument (arena mapped? channels * n <= max_floats?)");
+	if (m->rank == 0 && m->step > m->collected + 1) return kb_fail(KB_EINVAL, "kb_synth_bank_process_mixdown: rank 0 must pass out_prev on every step (or collect) so the slots are consumed");
+	if (m->device != b->device) return kb_fail(KB_EINVAL, "kb_synth_bank_process_mixdown: bank and mix-down live on different devices");
+	return sy_process(b, (float*)b->d_mix, n, flags | KB_BANK_MIX | KB_DEVICE_PTR, m, out_prev);
+}
+extern "C" int kb_mixdown_step(kb_mixdown* m, const float* src, int count, float* out_prev, void* stream) {
+	if (!m || !m->arena || !src || count < 1 || count > m->max_floats) return kb_fail(KB_EINVAL, "kb_mixdown_step: bad argument (arena mapped? count <= max_floats?)");
+	if (m->rank == 0 && m->step > m->collected + 1) return kb_fail(KB_EINVAL, "kb_mixdown_step: rank 0 must pass out_prev on every step (or collect) so the slots are consumed");
+	KB_CUDA(cudaSetDevice(m->device));
+	return mixdown_step(m, src, 1, 0, count, out_prev, (cudaStream_t)stream);
 }
 
 // ============================================================================================ primitives
@@ -1047,6 +1143,57 @@ static int prim_finish(const char* what) {
 	cudaError_t e = cudaDeviceSynchronize();
 	if (e == cudaSuccess) e = cudaGetLastError();
 	if (e != cudaSuccess) return kb_fail(KB_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+	return KB_OK;
+}
+// Wavetable::operator=(Oscillator) fills the table with a Basic osc at fs/size Hz on the host (klang.h:3645-3650); kind 10 Sine, 11 Saw
+static void prim_fill_wavetable(int kind, const KbFs& F, float* table) {
+	KbBasicOsc o; kb_bosc_init(o); kb_bosc_set_f(F, o, F.f / 2048);
+	for (int s = 0; s < 2048; s++) {
+		table[s] = (kind == 10) ? ::sinf(o.position + o.offset) : (o.position * KB_PI_INV_F - 1.f);
+		kb_bosc_advance(o);
+	}
+}
+extern "C" int kb_prim_wavetable(int kind, float fs, float* out) {
+	if (kb_device_count() < 1) return kb_fail(KB_ENODEV, "no CUDA device");
+	if ((kind != 10 && kind != 11) || !out || !(fs > 0)) return kb_fail(KB_EINVAL, "kb_prim_wavetable: kind 10 (Wavetables::Sine) or 11 (Wavetables::Saw)");
+	std::vector<float> table(2048);
+	prim_fill_wavetable(kind, kb_make_fs(fs), table.data());
+	DevBuf dtab(sizeof(float) * 2048, table.data()), dout(sizeof(float) * 2048);
+	kb_prim_wavetable_kernel<<<8, 256>>>(dtab.as<float>(), dout.as<float>());
+	int rc = prim_finish("kb_prim_wavetable"); if (rc) return rc;
+	cudaMemcpy(out, dout.p, sizeof(float) * 2048, cudaMemcpyDeviceToHost);
+	return KB_OK;
+}
+extern "C" int kb_prim_stereo_delay(int n, const float* inl, const float* inr, const float* df, float* outl, float* outr) {
+	if (kb_device_count() < 1) return kb_fail(KB_ENODEV, "no CUDA device");
+	if (n < 0 || !inl || !inr || !df || !outl || !outr) return kb_fail(KB_EINVAL, "kb_prim_stereo_delay: bad argument");
+	for (int s = 0; s < n; s++) if (!(df[s] >= 0.f && df[s] < 999.f)) return kb_fail(KB_EINVAL, "kb_prim_stereo_delay: delay outside the 1000-sample line");
+	if (n == 0) return KB_OK;
+	const size_t B = sizeof(float) * n;
+	DevBuf dl(B, inl), dr(B, inr), ddf(B, df), rl(sizeof(float) * 1001), rr(sizeof(float) * 1001), ol(B), orr(B);
+	kb_prim_stereo_delay_kernel<<<1, 32>>>(n, dl.as<float>(), dr.as<float>(), ddf.as<float>(), rl.as<float>(), rr.as<float>(), ol.as<float>(), orr.as<float>());
+	int rc = prim_finish("kb_prim_stereo_delay"); if (rc) return rc;
+	cudaMemcpy(outl, ol.p, B, cudaMemcpyDeviceToHost); cudaMemcpy(outr, orr.p, B, cudaMemcpyDeviceToHost);
+	return KB_OK;
+}
+extern "C" int kb_prim_control_smooth(float lo, float hi, float initial, int n, const float* values, float* out) {
+	if (kb_device_count() < 1) return kb_fail(KB_ENODEV, "no CUDA device");
+	if (n < 0 || !values || !out) return kb_fail(KB_EINVAL, "kb_prim_control_smooth: bad argument");
+	if (n == 0) return KB_OK;
+	DevBuf dv(sizeof(float) * n, values), dout(sizeof(float) * n);
+	kb_prim_control_smooth_kernel<<<1, 32>>>(lo, hi, initial, n, dv.as<float>(), dout.as<float>());
+	int rc = prim_finish("kb_prim_control_smooth"); if (rc) return rc;
+	cudaMemcpy(out, dout.p, sizeof(float) * n, cudaMemcpyDeviceToHost);
+	return KB_OK;
+}
+extern "C" int kb_prim_envelope_at(int npts, const float* xy, int n, const float* t, float* out) {
+	if (kb_device_count() < 1) return kb_fail(KB_ENODEV, "no CUDA device");
+	if (npts < 0 || npts > KB_ENV_MAXPTS || !xy || n < 0 || !t || !out) return kb_fail(KB_EINVAL, "kb_prim_envelope_at: bad argument");
+	if (n == 0) return KB_OK;
+	DevBuf dxy(sizeof(float) * 2 * (npts ? npts : 1), xy), dt(sizeof(float) * n, t), dout(sizeof(float) * n);
+	kb_prim_envelope_at_kernel<<<std::min(148, (n + 127) / 128), 128>>>(npts, dxy.as<float>(), n, dt.as<float>(), dout.as<float>());
+	int rc = prim_finish("kb_prim_envelope_at"); if (rc) return rc;
+	cudaMemcpy(out, dout.p, sizeof(float) * n, cudaMemcpyDeviceToHost);
 	return KB_OK;
 }
 extern "C" int kb_prim_osc(int kind, int nargs, float f, float phase, float duty, float fs, int n, float* out) {
@@ -1065,13 +1212,7 @@ extern "C" int kb_prim_osc(int kind, int nargs, float f, float phase, float duty
 		return KB_OK;
 	}
 	std::vector<float> table(2048, 0.f);
-	if (kind >= 10) {   // Wavetable::operator=(Oscillator) fills the table with a Basic osc at fs/size Hz on the host (klang.h:3645-3650)
-		KbBasicOsc o; kb_bosc_init(o); kb_bosc_set_f(F, o, F.f / 2048);
-		for (int s = 0; s < 2048; s++) {
-			table[s] = (kind == 10) ? ::sinf(o.position + o.offset) : (o.position * KB_PI_INV_F - 1.f);
-			kb_bosc_advance(o);
-		}
-	}
+	if (kind >= 10) prim_fill_wavetable(kind, F, table.data());
 	DevBuf dout(sizeof(float) * n), dtab(sizeof(float) * 2048, table.data());
 	kb_prim_osc_kernel<<<1, 32>>>(kind, nargs, f, phase, duty, F, n, dout.as<float>(), dtab.as<float>());
 	int rc = prim_finish("kb_prim_osc"); if (rc) return rc;
@@ -1097,7 +1238,7 @@ extern "C" int kb_prim_delay(int n, const float* in, const int* di, const float*
 extern "C" int kb_prim_filter(int kind, int nset, const float* f, const float* Q, float fs, int n, const float* in, float* out, float* coeffs) {
 	if (kb_device_count() < 1) return kb_fail(KB_ENODEV, "no CUDA device");
 	const bool onepole = kind == 2 || kind == 3 || kind == 7, host_set = kind >= 12;     // kinds whose set() runs on the host (libm)
-	if (kind < 0 || kind > 16 || !f || !in || !out || !coeffs || nset < 0 || nset > n || ((onepole || host_set) && nset > 1) || (kind >= 11 && !Q))
+	if (kind < 0 || kind > 16 || !f || !in || !out || !coeffs || nset < 0 || nset > n || (host_set && nset > 1) || (kind >= 11 && !Q))
 		return kb_fail(KB_EINVAL, "kb_prim_filter: unsupported");
 	const KbFs F = kb_make_fs(fs);
 	float4 hc = make_float4(0.f, 0.f, 0.05f, 0.f);
@@ -1114,8 +1255,14 @@ extern "C" int kb_prim_filter(int kind, int nset, const float* f, const float* Q
 	}
 	KbOnePole op; kb_onepole_construct(op, kind == 2 ? KB_OP_LPF : kind == 3 ? KB_OP_HPF : KB_OP_BW1);
 	if (onepole && nset == 1) kb_onepole_set(F, op, f[0]);
+	std::vector<float> op_sets;                   // set() every sample: OnePole / Butterworth<1> coefficients are host libm code (klang.h:5508-5512, 5786-5793)
+	if (onepole && nset > 1) {
+		KbOnePole h = op;
+		for (int s = 0; s < nset; s++) { kb_onepole_set(F, h, f[s]); op_sets.push_back(h.b0); op_sets.push_back(h.b1); op_sets.push_back(h.a1); }
+	}
+	DevBuf dsets(sizeof(float) * (op_sets.empty() ? 1 : op_sets.size()), op_sets.empty() ? nullptr : op_sets.data());
 	DevBuf df(sizeof(float) * (nset ? nset : 1), f), dq(sizeof(float) * (nset ? nset : 1), Q), din(sizeof(float) * n, in), dout(sizeof(float) * n), dc(sizeof(float) * 5);
-	kb_prim_filter_kernel<<<1, 32>>>(kind, nset, df.as<float>(), Q ? dq.as<float>() : nullptr, F, n, din.as<float>(), dout.as<float>(), dc.as<float>(), op, hc);
+	kb_prim_filter_kernel<<<1, 32>>>(kind, nset, df.as<float>(), Q ? dq.as<float>() : nullptr, F, n, din.as<float>(), dout.as<float>(), dc.as<float>(), op, hc, op_sets.empty() ? nullptr : dsets.as<float>());
 	int rc = prim_finish("kb_prim_filter"); if (rc) return rc;
 	cudaMemcpy(out, dout.p, sizeof(float) * n, cudaMemcpyDeviceToHost);
 	cudaMemcpy(coeffs, dc.p, sizeof(float) * 5, cudaMemcpyDeviceToHost);

@@ -162,7 +162,8 @@ __global__ void kb_pingpong_plan_kernel(const KbFxHdr* __restrict__ hdrs, const 
 	for (int c = 0; c < 6; c++) fixed = fixed && kb_same_bits(h.controls[c].value, h0.controls[c].value) && kb_same_bits(h.controls[c].smoothed, h0.controls[c].smoothed);
 	const float dl = pl.delay * fs.f, dr = 0.5f * pl.delay * fs.f;
 	pl.chunk = (int)fminf(dl, dr) - 4;
-	pl.mode = (fixed && pl.chunk >= n && dl < (float)p0.left.SIZE) ? KB_PLAN_PARALLEL : KB_PLAN_SEQUENTIAL;
+	// far-end guard: the block's later frames must not overwrite ring slots its earlier frames still read (n + delay + 4 < SIZE)
+	pl.mode = (fixed && pl.chunk >= n && (float)n + dl + 4.f < (float)p0.left.SIZE) ? KB_PLAN_PARALLEL : KB_PLAN_SEQUENTIAL;
 	plan[inst] = pl;
 }
 // one CTA per (instance, side): side 0 produces out.l and the left ring, side 1 out.r and the right ring (PingPong.k:66 / :67).
@@ -783,7 +784,8 @@ __global__ void kb_dreverb_plan_kernel(const KbFxHdr* __restrict__ hdrs, const K
 	KbFxPlan p;
 	p.chunk = min(KB_DRV_LMAX, (int)t - 2);
 	// the shortest FIR tap (2.078 ms) must not reach past the ring and the loop delay must fit the ring
-	p.mode = (p.chunk >= 64 && t < (float)states[inst].feedback.SIZE) ? KB_PLAN_PARALLEL : KB_PLAN_SEQUENTIAL;
+	// (far end: a chunk's later frames must not overwrite loop-ring slots its earlier frames still read)
+	p.mode = (p.chunk >= 64 && t + (float)(KB_DRV_LMAX + 4) < (float)states[inst].feedback.SIZE) ? KB_PLAN_PARALLEL : KB_PLAN_SEQUENTIAL;
 	p.gain = p.delay = p.dry = 0.f;
 	plan[inst] = p;
 }

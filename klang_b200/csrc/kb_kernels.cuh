@@ -481,7 +481,7 @@ __global__ void kb_prim_osc_kernel(int kind, int nargs, float f, float phase, fl
 // 12 Modifiers::Modal, 13 / 14 Envelope::Follower peak / rms, 15 / 16 Follower::Window<64> mean / rms: coefficients hc from the host
 // libm (set() is event-rate code)
 __global__ void kb_prim_filter_kernel(int kind, int nset, const float* f, const float* Q, KbFs fs, int n, const float* in, float* out, float* coeffs,
-                                      KbOnePole op, float4 hc) {
+                                      KbOnePole op, float4 hc, const float* __restrict__ op_sets = nullptr) {
 	if (threadIdx.x || blockIdx.x) return;
 	if (kind == 12) {   // Modal::input + process  klang.h:5847-5856: in *= gain; out = in + a1*y1 + a2*y2
 		const float a1 = hc.x, a2 = hc.y, gain = hc.z;
@@ -534,7 +534,11 @@ __global__ void kb_prim_filter_kernel(int kind, int nset, const float* f, const 
 		}
 		coeffs[0] = b.b0; coeffs[1] = b.b1; coeffs[2] = b.b2; coeffs[3] = b.a1; coeffs[4] = b.a2;
 	} else {
-		for (int s = 0; s < n; s++) out[s] = kb_onepole_tick(op, in[s]);
+		// per-sample set(): the coefficient triples (b0, b1, a1) of every set() come from the host libm (expf / tanf), one per sample
+		for (int s = 0; s < n; s++) {
+			if (op_sets && s < nset) { op.b0 = op_sets[3 * s]; op.b1 = op_sets[3 * s + 1]; op.a1 = op_sets[3 * s + 2]; }
+			out[s] = kb_onepole_tick(op, in[s]);
+		}
 		coeffs[0] = op.b0; coeffs[1] = op.b1; coeffs[2] = 0; coeffs[3] = op.a1; coeffs[4] = 0;
 	}
 }
@@ -566,4 +570,34 @@ __global__ void kb_prim_env_kernel(KbEnv e, KbFs fs, int n, int release_at, floa
 __global__ void kb_prim_math_kernel(int fn, int n, const float* x, float* out) {
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
 		out[i] = fn == 0 ? kb_sinf(x[i]) : fn == 1 ? kb_cosf(x[i]) : kb_tanhf(x[i]);
+}
+
+// Stereo::Delay<1000> (klang.h:4647-4700), sample by sample: `x >> delay` writes both lines at the same position (Bank<Delay,2>,
+// klang.h:2901-2926), then tap(float df[s]) reads both channels at the LEFT line's position with the (1 - f) / f form.
+__global__ void kb_prim_stereo_delay_kernel(int n, const float* inl, const float* inr, const float* df, float* ringl, float* ringr, float* outl, float* outr) {
+	if (threadIdx.x || blockIdx.x) return;
+	KbDelay l, r; kb_delay_construct(l, 1000, 0); kb_delay_construct(r, 1000, 0);
+	for (int s = 0; s <= 1000; s++) { ringl[s] = 0.f; ringr[s] = 0.f; }
+	for (int s = 0; s < n; s++) {
+		kb_delay_write(l, ringl, inl[s]); kb_delay_write(r, ringr, inr[s]);
+		kb_sdelay_tap_f(l, ringl, ringr, df[s], outl[s], outr[s]);
+	}
+}
+// Control::set then Control::smooth per sample (klang.h:1715-1728), from a Dial(lo, hi, initial) (klang.h:1796-1799: smoothed starts at 0)
+__global__ void kb_prim_control_smooth_kernel(float lo, float hi, float initial, int n, const float* values, float* out) {
+	if (threadIdx.x || blockIdx.x) return;
+	KbControl c = { lo, hi, initial, 0.f };
+	for (int s = 0; s < n; s++) { kb_control_set(c, values[s]); out[s] = kb_control_smooth(c); }
+}
+// Envelope::at(t) (klang.h:3929-3942): static breakpoint lookup, thread = query
+__global__ void kb_prim_envelope_at_kernel(int npts, const float* xy, int n, const float* t, float* out) {
+	__shared__ float px[KB_ENV_MAXPTS], py[KB_ENV_MAXPTS];
+	if (threadIdx.x < npts) { px[threadIdx.x] = xy[2 * threadIdx.x]; py[threadIdx.x] = xy[2 * threadIdx.x + 1]; }
+	__syncthreads();
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = kb_env_at(px, py, npts, t[i]);
+}
+// Wavetable (klang.h:3627-3676): the 2048-entry table the device oscillators of kb_prim_osc_kernel read, entry by entry (buffer::operator[](int),
+// klang.h:2060-2068) — the table is filled on the host (Wavetable::operator=(Oscillator) is constructor code) and lives in HBM
+__global__ void kb_prim_wavetable_kernel(const float* table, float* out) {
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2048; i += gridDim.x * blockDim.x) out[i] = table[i];
 }

@@ -75,6 +75,11 @@ class PeerMixdown:
         """acquire + device copy of a finished local mix (torch CUDA tensor) into the slot + publish."""
         self._api._check(self._api.lib().kb_mixdown_put(self.h, src.data_ptr(), int(count), cuda_stream), "kb_mixdown_put")
 
+    def step(self, src, count, out_prev, cuda_stream):
+        """The fused form (kb_mixdown_step): one kernel stores `src` into this rank's slot and raises its flag; on rank 0 it also sums the
+        PREVIOUS step's slots into `out_prev`."""
+        self._api._check(self._api.lib().kb_mixdown_step(self.h, src.data_ptr(), int(count), out_prev.data_ptr() if out_prev is not None else 0, cuda_stream), "kb_mixdown_step")
+
     def collect(self, dst, count, cuda_stream):
         self._api._check(self._api.lib().kb_mixdown_collect(self.h, dst.data_ptr(), int(count), cuda_stream), "kb_mixdown_collect")
 

@@ -64,6 +64,20 @@ class SynthBank:
         elif st == 0x80 or (st == 0x90 and b2 == 0):
             self.note_off(b1, 0.0, instance)
 
+    def events(self, ev):
+        for e in ev:
+            t, i, key = int(e["type"]), int(e["instance"]), int(e["key"])
+            if t == real.EV_NOTE_ON:
+                self.note_on(key, float(e["velocity"]), i)
+            elif t == real.EV_NOTE_OFF:
+                self.note_off(key, float(e["velocity"]), i)
+            elif t == real.EV_VOICE_START:
+                self.voice_start(key, float(e["pitch"]), float(e["velocity"]), i)
+            elif t == real.EV_VOICE_RELEASE:
+                self.voice_release(key, float(e["velocity"]), i)
+            else:
+                self.set_control(key, float(e["velocity"]), i)
+
     def process_block(self, n, flags=0):
         if flags & real.PER_VOICE:
             return np.stack([s.process_voices(n)[0] for s in self.s])
@@ -98,7 +112,7 @@ class FxBank:
             f.close()
 
 
-stub.Engine, stub.SynthBank, stub.FxBank = Engine, SynthBank, FxBank
+stub.Engine, stub.SynthBank, stub.FxBank, stub.KlangB200Error = Engine, SynthBank, FxBank, real.KlangB200Error
 stub.lib = real.lib
 sys.modules["klang_b200"] = stub
 
@@ -106,4 +120,6 @@ import pytest  # noqa: E402
 
 if __name__ == "__main__":
     # subprocess-based tests (k_host, probes) cannot be dry-run: deselect them
-    sys.exit(pytest.main([os.path.join(HERE, "test_zz_gpu_primitives.py"), "-q", "-x", "-p", "no:cacheprovider", "-k", "not k_programs"]))
+    # (the far-end and validation tests of test_gpu_baseline_shapes.py assert on the schedule the CUDA library picked / on its argument checks)
+    sys.exit(pytest.main([os.path.join(HERE, "test_zz_gpu_primitives.py"), os.path.join(HERE, "test_gpu_baseline_shapes.py"), "-q", "-x", "-p", "no:cacheprovider",
+                          "-k", "not k_programs and not far_end and not validation"]))

@@ -1,0 +1,297 @@
+"""GPU parity at the BASELINE.json shapes, against the REFERENCE itself where it is present.
+
+tests/test_gpu_parity.py compares small shapes with the C port; the tests here close the holes the round-1 review named:
+
+  * every key of the golden files (recorded from the compiled klang.h) is produced on the device — `set(got) == set(golden)`;
+  * C4 at its real shape: 64 stereo instances x 4096-frame blocks with a different input per instance, for all four delay-line
+    graphs, against the oracle run live on the same inputs (the chunk-parallel kernels must be the ones engaged);
+  * C5 at its per-GPU shape: SynTHX.k 4 x 128 voices (the ordered sum chains across all 128 voices of an instance) and TB303.k
+    4 x 128 voices;
+  * C2 exactly as bench.py runs it: 8 x 128 voices, 4096-sample blocks, 1/16 of the voices re-triggered through
+    kb_synth_bank_events before every block, for 17 blocks;
+  * the far-end ring wrap at fs = 192 kHz with delays close to the line length.
+
+The checker is oracle.ref (oracle/_ref/libklang_ref.so = /root/reference/klang.h compiled by oracle/build_ref.py; it travels to the
+GPU box as a built file) and falls back to the C port only where that library is absent.  Everything is asserted bit-exact."""
+import numpy as np
+import pytest
+
+import cases
+import klang_b200 as kb
+import oracle
+from test_gpu_parity import assert_parity
+
+pytestmark = pytest.mark.gpu
+
+
+def checker():
+    return oracle.ref if oracle.ref.available() else oracle.port
+
+
+@pytest.fixture(scope="module")
+def eng():
+    if kb.device_count() < 1:
+        pytest.fail("no CUDA device: the gpu tests must run on the B200 box")
+    return kb.Engine()
+
+
+# ----------------------------------------------------------------------------------------- golden key coverage
+@pytest.mark.parametrize("fs", [44100, 48000])
+def test_every_golden_key_is_produced_on_the_device(eng, golden, fs):
+    """tests/cases.py run end to end on the CUDA path: the device produces EVERY entry the golden files hold (wavetable dumps,
+    Stereo::Delay taps, Control::smooth, Envelope::at and the per-sample one-pole sets included), bit for bit."""
+    got = cases.primitive_cases(eng, fs)
+    got.update(cases.all_graph_cases(eng, fs))
+    g = golden[fs]
+    assert set(got) == set(g), f"missing on the device: {sorted(set(g) - set(got))}; not in golden: {sorted(set(got) - set(g))}"
+    for k in sorted(g):
+        assert_parity(got[k], g[k], k, exact=True)
+
+
+# --------------------------------------------------------------------------------------------------- C4, full shape
+@pytest.mark.parametrize("graph,warm_blocks", [(kb.FX_REVERB, 0), (kb.FX_PINGPONG, 10), (kb.FX_DELAY_PINGPONG, 0), (kb.FX_DELAY_REVERB, 0)])
+def test_c4_64_instances_x_4096_frames_vs_oracle(eng, graph, warm_blocks):
+    """BASELINE C4: 64 stereo instances, 4096-frame blocks, instance i fed PCG noise of seed 100 + i.  PingPong.k first runs
+    10 blocks so its control smoothers reach their fixed point and the chunk-parallel kernel takes over; then >= 4 blocks are compared
+    with the oracle fed the same frames, bit-exact, and every instance must have been on the parallel schedule."""
+    fs, n, inst = 48000, 4096, 64
+    blocks = warm_blocks + 5
+    chk = checker()
+    chk.set_fs(fs)
+    chk.srand(1)
+    ch = 1 if graph == kb.FX_DELAY_REVERB else 2
+    x = np.stack([cases.fx_input(ch, n * blocks, seed=100 + i) for i in range(inst)])
+    want = np.empty_like(x)
+    for i in range(inst):
+        fx = chk.Fx(graph)
+        for b in range(blocks):
+            seg = x[i, :, b * n:(b + 1) * n]
+            want[i, :, b * n:(b + 1) * n] = fx.process(seg[0] if ch == 1 else seg)
+        fx.close()
+    kb.lib().kb_srand(1)
+    bank = kb.FxBank(graph, inst, fs, n)
+    got = np.empty_like(x)
+    engaged = []
+    for b in range(blocks):
+        blk = np.ascontiguousarray(x[:, :, b * n:(b + 1) * n])
+        bank.process_inplace(blk)
+        got[:, :, b * n:(b + 1) * n] = blk
+        engaged.append(bank.parallel_instances())
+    bank.close()
+    assert_parity(got, want, f"C4 graph {graph}", exact=True)
+    assert np.abs(want).max() > 0.01
+    assert engaged[-4:] == [inst] * 4, f"chunk-parallel schedule engaged on {engaged} instances per block"
+
+
+def test_c4_reverb_all_buses_64_instances_vs_oracle(eng):
+    """Reverb.k at the C4 shape with every bus audible (the default patch only sends the early reflections to the output) and a
+    different room per instance, so the 16 feedback lines, their damping filters and the mid -> late chain all reach the output."""
+    fs, n, inst, blocks = 48000, 4096, 64, 4
+    chk = checker()
+    chk.set_fs(fs)
+    x = np.stack([cases.fx_input(2, n * blocks, seed=300 + i) for i in range(inst)])
+
+    def settings(i):
+        return {0: 0.3, 1: 0.9, 2: 0.4 + 0.005 * i, 3: 0.5, 4: 0.8, 6: 0.25 + 0.01 * i, 7: 0.6 + 0.006 * i}
+
+    want = np.empty_like(x)
+    for i in range(inst):
+        fx = chk.Fx(kb.FX_REVERB)
+        for c, v in settings(i).items():
+            fx.set_control(c, v)
+        for b in range(blocks):
+            want[i, :, b * n:(b + 1) * n] = fx.process(x[i, :, b * n:(b + 1) * n])
+        fx.close()
+    bank = kb.FxBank(kb.FX_REVERB, inst, fs, n)
+    for i in range(inst):
+        for c, v in settings(i).items():
+            bank.set_control(c, v, i)
+    got = np.empty_like(x)
+    for b in range(blocks):
+        blk = np.ascontiguousarray(x[:, :, b * n:(b + 1) * n])
+        bank.process_inplace(blk)
+        got[:, :, b * n:(b + 1) * n] = blk
+    par = bank.parallel_instances()
+    bank.close()
+    assert_parity(got, want, "C4 Reverb.k, all buses", exact=True)
+    assert par == inst
+
+
+# --------------------------------------------------------------------------------------------------- C5, per-GPU shape
+def _bank_vs_checker(graph, instances, voices, blocks, n, fs, mix):
+    """The same seeded note stream into `instances` oracle synths and one CUDA bank: per-voice streams (mix False) or the
+    Synth::process block output of every instance (mix True)."""
+    chk = checker()
+    chk.set_fs(fs)
+    chk.srand(1)
+    refs = [chk.Synth(graph, voices) for _ in range(instances)]
+    want = []
+    for b in range(blocks):
+        for i, sy in enumerate(refs):
+            for v in range(voices):
+                g = i * voices + v
+                if b == (g % 2):
+                    sy.voice_start(v, 36 + (5 * g) % 36, cases.voice_velocity(g))
+                if b == 2 + (g % 3):
+                    sy.voice_release(v)
+        want.append(np.stack([sy.process(n) if mix else sy.process_voices(n)[0] for sy in refs]))
+    want = np.concatenate(want, axis=-1)
+    for sy in refs:
+        sy.close()
+    kb.lib().kb_srand(1)
+    bank = kb.SynthBank(graph, instances, voices, fs, n)
+    got = []
+    for b in range(blocks):
+        for i in range(instances):
+            for v in range(voices):
+                g = i * voices + v
+                if b == (g % 2):
+                    bank.voice_start(v, 36 + (5 * g) % 36, cases.voice_velocity(g), i)
+                if b == 2 + (g % 3):
+                    bank.voice_release(v, 0.0, i)
+        got.append(bank.process_block(n, 0 if mix else kb.PER_VOICE))
+    bank.close()
+    got = np.concatenate(got, axis=-1)
+    assert np.nanmax(np.abs(want)) > 1e-3
+    return assert_parity(got, want, f"graph {graph} {instances} x {voices} voices ({'mix' if mix else 'voices'})", exact=True)
+
+
+def test_c5_synthx_4x128_voices_vs_oracle(eng):
+    """SynTHX.k at the C5 per-GPU shape: every instance's ordered fp32 sum chains across all of its 128 voices
+    (SynTHX.k:109-122, 176-178, klang.h:4842-4848), then the synth-level tanh."""
+    _bank_vs_checker(cases.SY_SYNTHX, 4, 128, 4, 192, 48000, mix=True)
+
+
+def test_c5_tb303_4x128_voices_vs_oracle(eng):
+    _bank_vs_checker(cases.SY_TB303, 4, 128, 5, 512, 48000, mix=False)
+    _bank_vs_checker(cases.SY_TB303, 4, 128, 3, 512, 48000, mix=True)
+
+
+def test_c3_supersaw_8x32_voices_vs_oracle(eng):
+    _bank_vs_checker(cases.SY_SUPERSAW, 8, 32, 5, 4096, 48000, mix=False)
+
+
+# --------------------------------------------------------------------------------------------- C2, the bench schedule
+@pytest.mark.parametrize("per_voice", [True, False])
+def test_c2_bench_schedule_vs_oracle(eng, per_voice):
+    """bench.py's headline step, literally: 8 Synth instances x 128 voices, fs 48 kHz, 4096-sample blocks, all voices started, then before
+    every block the voices of retrigger group (block mod 16) are re-started through ONE kb_synth_bank_events call (64 events), for 17
+    blocks so every group fires at least once and group 0 twice.  Compared with 8 reference Synths driven by the same calls: per-voice
+    streams (per_voice) and the Synth::process output (mono: the last active voice overwrites, klang.h:4299)."""
+    fs, n, inst, voices, blocks, groups = 48000, 4096, 8, 128, 17, 16
+    total = inst * voices
+    chk = checker()
+    chk.set_fs(fs)
+    chk.srand(1)
+    refs = [chk.Synth(cases.SY_SUBTRACTIVE, voices) for _ in range(inst)]
+    for g in range(total):
+        refs[g // voices].voice_start(g % voices, cases.voice_pitch(g), cases.voice_velocity(g))
+    kb.lib().kb_srand(1)
+    bank = kb.SynthBank(kb.SY_SUBTRACTIVE, inst, voices, fs, n)
+    for g in range(total):
+        bank.voice_start(g % voices, cases.voice_pitch(g), cases.voice_velocity(g), g // voices)
+    batches = []
+    for grp in range(groups):
+        ids = np.arange(grp, total, groups)
+        ev = np.zeros(len(ids), kb.EVENT_DTYPE)
+        ev["type"] = kb.EV_VOICE_START
+        ev["instance"], ev["key"] = ids // voices, ids % voices
+        ev["pitch"] = [cases.voice_pitch(int(g)) for g in ids]
+        ev["velocity"] = [cases.voice_velocity(int(g)) for g in ids]
+        batches.append(ev)
+    for b in range(blocks):
+        for e in batches[b % groups]:
+            refs[int(e["instance"])].voice_start(int(e["key"]), float(e["pitch"]), float(e["velocity"]))
+        bank.events(batches[b % groups])
+        if per_voice:
+            want = np.stack([sy.process_voices(n)[0] for sy in refs])
+            got = bank.process_block(n, kb.PER_VOICE)
+        else:
+            want = np.stack([sy.process(n) for sy in refs])
+            got = bank.process_block(n)
+        assert_parity(got, want, f"C2 bench schedule, block {b}", exact=True)
+        assert np.abs(want).max() > 0.01
+    for sy in refs:
+        sy.close()
+    bank.close()
+
+
+# ------------------------------------------------------------------------------------------ far-end ring wrap
+def test_delay_pingpong_far_end_wrap_at_192k(eng):
+    """Delay/PingPong.k at fs = 192 kHz with delay controls near 1.0: t = 191040 frames passes `t < SIZE`, but a launch longer than
+    SIZE - t frames would overwrite ring slots its own earlier frames still read.  Such instances must run frame-sequentially; the
+    rings wrap during the run (213k frames), every block is compared with the oracle."""
+    fs, n, blocks, inst = 192000, 16384, 13, 3
+    chk = checker()
+    chk.set_fs(fs)
+    ctl = [{0: 0.995, 1: 0.99}, {0: 0.93, 1: 0.999}, {0: 0.25, 1: 0.5}]        # the last instance stays on the parallel schedule
+    x = np.stack([cases.fx_input(2, n * blocks, seed=500 + i) for i in range(inst)])
+    want = np.empty_like(x)
+    for i in range(inst):
+        fx = chk.Fx(kb.FX_DELAY_PINGPONG)
+        for c, v in ctl[i].items():
+            fx.set_control(c, v)
+        for b in range(blocks):
+            want[i, :, b * n:(b + 1) * n] = fx.process(x[i, :, b * n:(b + 1) * n])
+        fx.close()
+    bank = kb.FxBank(kb.FX_DELAY_PINGPONG, inst, fs, n)
+    for i in range(inst):
+        for c, v in ctl[i].items():
+            bank.set_control(c, v, i)
+    got = np.empty_like(x)
+    for b in range(blocks):
+        blk = np.ascontiguousarray(x[:, :, b * n:(b + 1) * n])
+        bank.process_inplace(blk)
+        got[:, :, b * n:(b + 1) * n] = blk
+    par = bank.parallel_instances()
+    bank.close()
+    assert_parity(got, want, "Delay/PingPong.k far end", exact=True)
+    assert par == 1, f"{par} instances on the parallel schedule (expected only the short-delay one)"
+    chk.set_fs(48000)
+
+
+def test_pingpong_far_end_wrap_at_192k(eng):
+    """PingPong.k at fs = 192 kHz with the delay control at 0.99 (190080 frames): once the smoothers settle the plan kernel would accept the
+    instance (`delay < SIZE`), but an 8192-frame sub-block then overwrites slots its own earlier frames read.  Must stay sequential."""
+    fs, n, blocks, inst = 192000, 8192, 34, 2
+    chk = checker()
+    chk.set_fs(fs)
+    x = np.stack([cases.fx_input(2, n * blocks, seed=520 + i) for i in range(inst)])
+    want = np.empty_like(x)
+    for i in range(inst):
+        fx = chk.Fx(kb.FX_PINGPONG)
+        fx.set_control(1, 0.99)
+        fx.set_control(5, 0.99)
+        fx.set_control(0, 0.7)
+        for b in range(blocks):
+            want[i, :, b * n:(b + 1) * n] = fx.process(x[i, :, b * n:(b + 1) * n])
+        fx.close()
+    bank = kb.FxBank(kb.FX_PINGPONG, inst, fs, n)
+    for c, v in ((1, 0.99), (5, 0.99), (0, 0.7)):
+        bank.set_control(c, v)
+    got = np.empty_like(x)
+    for b in range(blocks):
+        blk = np.ascontiguousarray(x[:, :, b * n:(b + 1) * n])
+        bank.process_inplace(blk)
+        got[:, :, b * n:(b + 1) * n] = blk
+    par = bank.parallel_instances()
+    bank.close()
+    assert_parity(got, want, "PingPong.k far end", exact=True)
+    assert par == 0
+    chk.set_fs(48000)
+
+
+def test_buffer_validation_rejects_wrong_dtype_and_size(eng):
+    """klang_b200.api checks dtype, contiguity and size before a raw pointer crosses the C ABI."""
+    bank = kb.FxBank(kb.FX_GAIN, 2, 48000, 256)
+    with pytest.raises(kb.KlangB200Error):
+        bank.process_inplace(np.zeros((2, 1, 256), np.float64))
+    with pytest.raises(kb.KlangB200Error):
+        bank.process_inplace(np.zeros((2, 1, 512), np.float32)[:, :, ::2])
+    with pytest.raises(kb.KlangB200Error):
+        bank.process_inplace(np.zeros((1, 1, 256), np.float32), n=256)
+    bank.close()
+    sb = kb.SynthBank(kb.SY_SUBTRACTIVE, 1, 32, 48000, 256)
+    with pytest.raises(kb.KlangB200Error):
+        sb.process_into(np.zeros((1, 1, 100), np.float32), 256)
+    sb.close()

@@ -59,6 +59,48 @@ def test_mixdown_single_rank_round_trip():
     assert b"bad argument" in L.kb_last_error()
 
 
+def test_mixdown_fused_step_single_rank():
+    """kb_mixdown_step / kb_synth_bank_process_mixdown on one rank: every step's sum arrives one step later through out_prev, the last
+    one through collect(); more steps than slot parities, so the in-kernel back-pressure and the consumed counter are exercised."""
+    import torch
+    if kb.device_count() < 1:
+        pytest.skip("needs a CUDA device")
+    L = kb.lib()
+    n, fs = 1024, 48000.0
+    h = L.kb_mixdown_create(0, 1, 0, n)
+    assert h, L.kb_last_error()
+    ts = torch.cuda.Stream()
+    torch.cuda.set_stream(ts)
+    stream = ts.cuda_stream
+    x = torch.rand(7, n, device="cuda")
+    prev = torch.zeros(7, n, device="cuda")
+    torch.cuda.synchronize()
+    for k in range(7):
+        assert L.kb_mixdown_step(h, x[k].data_ptr(), n, prev[k].data_ptr(), stream) == 0, L.kb_last_error()
+    last = torch.empty(n, device="cuda")
+    assert L.kb_mixdown_collect(h, last.data_ptr(), n, stream) == 0
+    torch.cuda.synchronize()
+    for k in range(1, 7):
+        assert torch.equal(prev[k], x[k - 1]), f"step {k}"
+    assert torch.equal(last, x[6])
+    # a bank whose bank-mix kernel is the fused step, against the plain KB_BANK_MIX call
+    a, b = _bank(0, 0, fs, n), _bank(0, 0, fs, n)
+    b.set_stream(stream)
+    want = torch.empty(4, 1, n, device="cuda")
+    got = torch.zeros(5, 1, n, device="cuda")
+    for blk in range(4):
+        a.process_into(want[blk], n, kb.BANK_MIX | kb.MIX_SUM)
+        assert L.kb_synth_bank_process_mixdown(b.h, h, got[blk].data_ptr(), n, kb.MIX_SUM) == 0, L.kb_last_error()
+    assert L.kb_mixdown_collect(h, got[4].data_ptr(), n, stream) == 0
+    a.sync()
+    torch.cuda.synchronize()
+    assert float(got[0].abs().max()) == 0.0                    # (the step before the bank's first block was already collected above)
+    for blk in range(4):
+        assert torch.equal(got[blk + 1], want[blk]) and float(want[blk].abs().max()) > 1e-3, f"block {blk}"
+    a.close(); b.close()
+    L.kb_mixdown_destroy(h)
+
+
 def _worker(rank, world, port, n, fs, out_path):
     import torch
     import torch.distributed as dist
@@ -78,10 +120,17 @@ def _worker(rank, world, port, n, fs, out_path):
         mix.publish(stream)
         if rank == 0:
             mix.collect(got[blk], n, stream)
+    # the same four blocks again through the fused step (one kernel per block: store + flag, rank 0 sums the previous block)
+    fused = torch.zeros(5, 1, n, device="cuda")
+    for blk in range(4):
+        bank.process_mixdown(mix, fused[blk] if rank == 0 else None, n, kb.MIX_SUM)
+    if rank == 0:
+        mix.collect(fused[4], n, stream)
     torch.cuda.synchronize()
     dist.barrier()
     if rank == 0:
         np.save(out_path, got.cpu().numpy())
+        np.save(out_path + ".fused.npy", fused[1:, 0].cpu().numpy())
     mix.close()
     bank.close()
     dist.destroy_process_group()
@@ -98,9 +147,9 @@ def test_mixdown_two_gpus_equals_rank_order_sum(tmp_path):
     n, fs = 2048, 48000.0
     out_path = str(tmp_path / "mix.npy")
     mp.spawn(_worker, args=(2, port, n, fs, out_path), nprocs=2, join=True)
-    got = np.load(out_path)
+    got = np.concatenate([np.load(out_path), np.load(out_path + ".fused.npy")])
     banks = [_bank(0, r * 64, fs, n) for r in range(2)]
-    for blk in range(4):
+    for blk in range(8):
         parts = [b.process_block(n, kb.BANK_MIX | kb.MIX_SUM)[0] for b in banks]
         want = parts[0] + parts[1]                                   # rank order, fp32
         assert np.array_equal(got[blk].view(np.uint32), want.view(np.uint32)), f"block {blk}"
