@@ -73,6 +73,9 @@ extern "C" {
                                      overwrite (klang.h:4299) */
 #define KB_LANE_PER_VOICE 16u     /* synth: use the plain lane-per-voice schedule instead of the tiled one (A/B measurement; same results) */
 #define KB_FX_SEQUENTIAL 32u       /* effects: use only the frame-sequential schedule (A/B measurement; same results) */
+#define KB_FX_TOLERANCE 128u      /* effects: allow schedules that RE-ASSOCIATE fp32 recurrences (parallel scans over IIR filters) where the result provably
+                                     stays within the parity bar 1e-5 |r| + 1e-6 peak of the reference (BASELINE north_star).  Default off: every
+                                     schedule is bit-identical to the reference.  Today: the 16 damping low-passes of Reverb.k (kb_reverb3.cuh) */
 #define KB_BANK_MIX 8u            /* synth: additionally sum all instances, out = [channels][n] (the multi-GPU mix-down input) */
 #define KB_ASYNC_HOST 64u         /* host-pointer call: return once the work and the device-to-host copy are queued on the bank stream;
                                      `io` / `out` must be page-locked and is valid after kb_*_bank_sync (or an event the caller
@@ -111,6 +114,8 @@ long long kb_fx_bank_launches(const kb_fx_bank* bank);   /* kernels launched so 
 /* how many instances the last process() ran on the chunk-parallel schedule (the others ran frame-sequentially because
  * their control smoothers were still moving or their delays were shorter than a useful chunk); joins the stream */
 int kb_fx_bank_parallel_instances(kb_fx_bank* bank);
+/* how many instances the last process(KB_FX_TOLERANCE) ran on a re-associating schedule (0 when the flag was not given) */
+int kb_fx_bank_tolerance_instances(kb_fx_bank* bank);
 long long kb_fx_bank_state_bytes(const kb_fx_bank* bank); /* bytes of instance state mirrored between host and device */
 /* Measurement: when enabled, every process() brackets its dominant kernel with CUDA events on the bank stream;
  * read() joins the stream and returns the accumulated kernel milliseconds and launch count since enable. */

@@ -14,7 +14,7 @@ lib_path = os.path.join(_HERE, "lib", "libklang_b200.so")
 
 FX_GAIN, FX_PINGPONG, FX_REVERB, FX_DELAY_PINGPONG, FX_DELAY_REVERB, FX_PAN, FX_RM, FX_TREMOLO, FX_CLIPPING, FX_ECHO, FX_FEEDBACK, FX_FUNCTIONS, FX_MUTE, FX_IIR, FX_WAHWAH, FX_FLANGER, FX_MODDELAY, FX_MOD_CHORUS = range(18)
 SY_SUBTRACTIVE, SY_SUPERSAW, SY_TB303, SY_SYNTHX, SY_FILTER_K, SY_FM, SY_BREAKPOINT, SY_RAMP, SY_RELEASE, SY_ADDITIVE_SAW, SY_ADDITIVE_SQUARE, SY_AM, SY_MOD_FM, SY_MOD_FM2, SY_ADDITIVE_NYQUIST = range(15)
-DEVICE_PTR, PER_VOICE, MIX_SUM, BANK_MIX, LANE_PER_VOICE, FX_SEQUENTIAL, ASYNC_HOST = 1, 2, 4, 8, 16, 32, 64
+DEVICE_PTR, PER_VOICE, MIX_SUM, BANK_MIX, LANE_PER_VOICE, FX_SEQUENTIAL, ASYNC_HOST, FX_TOLERANCE = 1, 2, 4, 8, 16, 32, 64, 128
 
 # every symbol include/klang_b200.h declares: (name, restype, argtypes)
 _vp, _i, _f, _u, _ll, _d = C.c_void_p, C.c_int, C.c_float, C.c_uint, C.c_longlong, C.c_double
@@ -26,7 +26,7 @@ SYMBOLS = [
     ("kb_fx_bank_channels", _i, [_vp]), ("kb_fx_bank_instances", _i, [_vp]), ("kb_fx_bank_num_controls", _i, [_vp]),
     ("kb_fx_bank_set_control", _i, [_vp, _i, _i, _f]), ("kb_fx_bank_get_control", _i, [_vp, _i, _i, _fp]),
     ("kb_fx_bank_process", _i, [_vp, _vp, _i, _u]), ("kb_fx_bank_sync", _i, [_vp]), ("kb_fx_bank_set_stream", _i, [_vp, _vp]),
-    ("kb_fx_bank_bytes_per_frame", _d, [_vp]), ("kb_fx_bank_launches", _ll, [_vp]), ("kb_fx_bank_state_bytes", _ll, [_vp]), ("kb_fx_bank_parallel_instances", _i, [_vp]),
+    ("kb_fx_bank_bytes_per_frame", _d, [_vp]), ("kb_fx_bank_launches", _ll, [_vp]), ("kb_fx_bank_state_bytes", _ll, [_vp]), ("kb_fx_bank_parallel_instances", _i, [_vp]), ("kb_fx_bank_tolerance_instances", _i, [_vp]),
     ("kb_fx_bank_profile", _i, [_vp, _i]), ("kb_fx_bank_profile_read", _i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     ("kb_synth_bank_create", _vp, [_i, _i, _i, _f, _i, _i]), ("kb_synth_bank_destroy", None, [_vp]),
     ("kb_synth_bank_channels", _i, [_vp]), ("kb_synth_bank_instances", _i, [_vp]), ("kb_synth_bank_voices", _i, [_vp]),
@@ -163,6 +163,10 @@ class FxBank:
     def parallel_instances(self):
         """Instances the last process() ran on the chunk-parallel schedule."""
         return _check(lib().kb_fx_bank_parallel_instances(self.h), "kb_fx_bank_parallel_instances")
+
+    def tolerance_instances(self):
+        """Instances the last process(FX_TOLERANCE) ran on a re-associating (1e-5-tolerance) schedule."""
+        return _check(lib().kb_fx_bank_tolerance_instances(self.h), "kb_fx_bank_tolerance_instances")
 
     @property
     def state_bytes(self):

@@ -17,6 +17,7 @@
 #include "../../include/klang_b200.h"
 #include "kb_kernels.cuh"
 #include "kb_tiled.cuh"
+#include "kb_reverb3.cuh"
 
 static thread_local std::string g_err = "";
 static int kb_fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -69,6 +70,7 @@ struct kb_fx_bank : kb_bank_base {
 	std::vector<KbFxHdr> hdr; std::vector<unsigned char> state;
 	KbFxHdr* d_hdr = nullptr; unsigned char* d_state = nullptr; float* d_rings = nullptr; KbFxPlan* d_plan = nullptr; void* d_sync = nullptr; int epoch = 0; std::vector<KbFxPlan> plan_cache;
 	bool device_writes_controls = false;
+	unsigned last_flags = 0; int last_schedule = 0;             // flags / Reverb.k schedule of the last process() call
 	template <class T> T& st(int i) { return *reinterpret_cast<T*>(state.data() + (size_t)i * state_bytes); }
 };
 
@@ -160,6 +162,8 @@ extern "C" kb_fx_bank* kb_fx_bank_create(int graph, int instances, float fs, int
 	ok = ok && cudaMemsetAsync(b->d_plan, 0, instances * sizeof(KbFxPlan), b->stream) == cudaSuccess;
 	ok = ok && cudaFuncSetAttribute(kb_reverb_par_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KbRvSmem)) == cudaSuccess;
 	ok = ok && cudaFuncSetAttribute(kb_reverb_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KbRv2Smem)) == cudaSuccess;
+	ok = ok && cudaFuncSetAttribute(kb_reverb3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KbRv3Smem)) == cudaSuccess;
+	ok = ok && cudaFuncSetAttribute(kb_reverb3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KbRv3Smem)) == cudaSuccess;
 	if (ok && b->ring_floats) ok = cudaMemsetAsync(b->d_rings, 0, (size_t)instances * b->ring_floats * sizeof(float), b->stream) == cudaSuccess;
 	b->io_floats = (size_t)instances * b->channels * max_block;
 	ok = ok && dev_alloc(&b->d_io, b->io_floats) == cudaSuccess;
@@ -197,8 +201,19 @@ extern "C" int kb_fx_bank_parallel_instances(kb_fx_bank* b) {
 	KB_CUDA(cudaStreamSynchronize(b->stream));
 	KB_CUDA(cudaMemcpy(plan.data(), b->d_plan, plan.size() * sizeof(KbFxPlan), cudaMemcpyDeviceToHost));
 	int count = 0;
-	for (const KbFxPlan& p : plan) count += p.mode == KB_PLAN_PARALLEL;
+	for (const KbFxPlan& p : plan) count += (p.mode & KB_PLAN_PARALLEL) != 0;
 	return count;
+}
+extern "C" int kb_fx_bank_tolerance_instances(kb_fx_bank* b) {
+	if (!b) return kb_fail(KB_EINVAL, "null bank");
+	if (b->graph != KB_FX_REVERB || !(b->last_flags & KB_FX_TOLERANCE) || (b->last_flags & KB_FX_SEQUENTIAL)) return 0;
+	std::vector<KbFxPlan> plan(b->instances);
+	KB_CUDA(cudaSetDevice(b->device));
+	KB_CUDA(cudaStreamSynchronize(b->stream));
+	KB_CUDA(cudaMemcpy(plan.data(), b->d_plan, plan.size() * sizeof(KbFxPlan), cudaMemcpyDeviceToHost));
+	int count = 0;
+	for (const KbFxPlan& p : plan) count += (p.mode & KB_PLAN_PARALLEL) && (p.mode & KB_PLAN_SCAN_OK);
+	return b->last_schedule == 3 ? count : 0;
 }
 extern "C" long long kb_fx_bank_state_bytes(const kb_fx_bank* b) { return b ? (long long)(b->hdr.size() * sizeof(KbFxHdr) + b->state.size()) : 0; }
 extern "C" int kb_fx_bank_profile(kb_fx_bank* b, int enable) { if (!b) return kb_fail(KB_EINVAL, "null bank"); cudaSetDevice(b->device); cudaStreamSynchronize(b->stream); b->profiling = enable != 0; b->prof_used = 0; return KB_OK; }
@@ -295,6 +310,7 @@ extern "C" int kb_fx_bank_process(kb_fx_bank* b, float* io, int n, unsigned flag
 	float* d = io;
 	if (!(flags & KB_DEVICE_PTR)) { d = b->d_io; KB_CUDA(cudaMemcpyAsync(d, io, floats * sizeof(float), cudaMemcpyHostToDevice, b->stream)); }
 	b->prof_begin();
+	b->last_flags = flags;
 	const int ib = (b->instances + 31) / 32;
 	const bool seq_only = flags & KB_FX_SEQUENTIAL;
 	switch (b->graph) {
@@ -368,13 +384,23 @@ extern "C" int kb_fx_bank_process(kb_fx_bank* b, float* io, int n, unsigned flag
 		break; }
 	case KB_FX_REVERB: {
 		KbReverb* st = (KbReverb*)b->d_state;
-		// KB_RV_SCHEDULE=1 selects the unpipelined chunk kernel (A/B measurement; same results)
-		static const int rv_schedule = getenv("KB_RV_SCHEDULE") ? atoi(getenv("KB_RV_SCHEDULE")) : 2;
+		// KB_RV_SCHEDULE (A/B measurement; same results): 3 = default, decoupled roles around bulk-async staging (kb_reverb3.cuh);
+		// 2 = the round-1 software pipeline (one CTA barrier per chunk); 1 = the unpipelined chunk kernel
+		static const int rv_env = getenv("KB_RV_SCHEDULE") ? atoi(getenv("KB_RV_SCHEDULE")) : 3;
+		// the bulk copies of schedule 3 need 16-byte aligned io rows
+		const int rv_schedule = (rv_env == 3 && ((reinterpret_cast<uintptr_t>(d) & 15) != 0 || (n & 3) != 0)) ? 2 : rv_env;
+		b->last_schedule = rv_schedule;
 		const int sub = 1 << 20;                       // sub-blocks keep the kernels' tick counters in 32 bits
 		for (int o = 0; o < n; o += sub) {
 			const int len = std::min(sub, n - o);
 			if (!seq_only) {
-				if (rv_schedule == 1) {
+				if (rv_schedule == 3) {
+					kb_reverb_plan3_kernel<<<ib, 32, 0, b->stream>>>(st, b->d_plan, b->instances);
+					const int tol = (flags & KB_FX_TOLERANCE) ? 1 : 0;
+					// KB_FX_TOLERANCE: instances whose line filters the scan admits run on the tolerance kernel, the others on the exact one
+					if (tol) { kb_reverb3_kernel<1><<<b->instances * 2, KB_RV3_NT_TOL, sizeof(KbRv3Smem), b->stream>>>(b->d_hdr, st, b->d_plan, b->d_rings, d + o, len, n, 0); b->launches++; }
+					kb_reverb3_kernel<0><<<b->instances * 2, KB_RV3_NT, sizeof(KbRv3Smem), b->stream>>>(b->d_hdr, st, b->d_plan, b->d_rings, d + o, len, n, tol);
+				} else if (rv_schedule == 1) {
 					kb_reverb_plan_kernel<<<ib, 32, 0, b->stream>>>(st, b->d_plan, b->instances);
 					kb_reverb_par_kernel<<<b->instances * 2, 256, sizeof(KbRvSmem), b->stream>>>(b->d_hdr, st, b->d_plan, b->d_rings, d + o, len, n);
 				} else {

@@ -245,19 +245,20 @@ inline void kb_pingpong_prepare(const KbFs& fs, KbPingPong& p) {                
 inline void kb_reverb_construct(KbFxHdr& h, KbReverb& rv, long long ring0) {               // Reverb.k:12, 99-111, 119-123
 	memset(&rv, 0, sizeof(rv));
 	long long r = ring0;
-	kb_delay_construct(rv.dl, 21600, r); r += 21601;
-	kb_delay_construct(rv.dr, 21600, r); r += 21601;
+	// (every ring starts on a 16-byte boundary and is padded to a multiple of 4 floats: the ring windows travel as 1-D bulk copies)
+	kb_delay_construct(rv.dl, 21600, r); r += 21604;
+	kb_delay_construct(rv.dr, 21600, r); r += 21604;
 	for (int c = 0; c < 2; c++) { kb_biquad_construct(rv.lpf[c], KB_BQ_LPF); kb_biquad_construct(rv.hpf[c], KB_BQ_HPF); }
 	for (int k = 0; k < 2; k++) for (int i = 0; i < 4; i++) {
-		kb_delay_construct(rv.mid[k].d[i].delay, 192000, r); r += 192001; kb_biquad_construct(rv.mid[k].d[i].filter, KB_BQ_LPF);
-		kb_delay_construct(rv.late[k].d[i].delay, 192000, r); r += 192001; kb_biquad_construct(rv.late[k].d[i].filter, KB_BQ_LPF);
+		kb_delay_construct(rv.mid[k].d[i].delay, 192000, r); r += 192004; kb_biquad_construct(rv.mid[k].d[i].filter, KB_BQ_LPF);
+		kb_delay_construct(rv.late[k].d[i].delay, 192000, r); r += 192004; kb_biquad_construct(rv.late[k].d[i].filter, KB_BQ_LPF);
 	}
 	h.controls[0] = kb_dial(0.f, 1.f, 0.f); h.controls[1] = kb_dial(0.f, 1.f, 1.f); h.controls[2] = kb_dial(0.f, 1.f, 0.f);
 	h.controls[3] = kb_dial(0.f, 1.f, 0.f); h.controls[4] = kb_dial(0.f, 1.f, 1.f); h.controls[5] = kb_dial(0.f, 100.f, 10.f);
 	h.controls[6] = kb_dial(0.f, 1.f, 1.f); h.controls[7] = kb_dial(0.01f, 1.f, 1.f); h.controls[8] = kb_dial(0.01f, 1.f, 1.f);
 	h.controls[9] = kb_dial(0.f, 0.2f, 0.f);
 }
-#define KB_REVERB_RING_FLOATS (2LL * 21601 + 16LL * 192001)
+#define KB_REVERB_RING_FLOATS (2LL * 21604 + 16LL * 192004)
 #define KB_PINGPONG_RING_FLOATS (2LL * 192001)
 // EarlyReflections::update                                                   Reverb.k:23-52
 inline void kb_rv_early_update(const KbFs& fs, KbReverb& rv) {
@@ -738,6 +739,8 @@ KB_D void kb_pingpong_frame(const KbFs& fs, KbFxHdr& h, KbPingPong& p, float* ri
 	orr = kb_biquad_tick(p.dc[1], outr);                                      // :70
 }
 
+#endif  // __CUDACC__
+// (Reverb.k's frame uses no device-only math: also compiled by g++ for tests/host/reverb_scan_check.cpp)
 // FilteredDelay::process  Reverb.k:130-132
 KB_D float kb_rv_fdelay_tick(KbRvFDelay& d, float* rings) {
 	float* ring = rings + d.delay.ring;
@@ -787,6 +790,7 @@ KB_D void kb_reverb_frame(KbFxHdr& h, KbReverb& rv, float* rings, float inl, flo
 	ol = inl * dry + refl_l * wet;                 // Reverb.k:272: `(in >> reflections) * wet` is signals<2>{wet, 0} (Q7)
 	orr = inr * dry + refl_r * 0.f;
 }
+#ifdef __CUDACC__
 // Delay/PingPong.k:24-34
 KB_D void kb_dpingpong_frame(const KbFs& fs, KbFxHdr& h, KbDPingPong& p, float* rings, float inl, float inr, float& ol, float& orr) {
 	const KbControl* c = h.controls;

@@ -404,7 +404,7 @@ __global__ void kb_fx_seq_kernel(KbFxHdr* __restrict__ hdrs, STATE* __restrict__
                                  float* __restrict__ io, int n, int stride, int channels, int instances, KbFs fs, const KbFxPlan* __restrict__ plan) {
 	const int inst = blockIdx.x * blockDim.x + threadIdx.x;
 	if (inst >= instances) return;
-	if (plan && plan[inst].mode == KB_PLAN_PARALLEL) return;          // taken by the chunk-parallel kernel
+	if (plan && (plan[inst].mode & KB_PLAN_PARALLEL)) return;         // taken by the chunk-parallel kernel
 	KbFxHdr h = hdrs[inst];
 	STATE s = states[inst];
 	float* l = io + (size_t)inst * channels * stride;

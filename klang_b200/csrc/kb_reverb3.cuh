@@ -1,0 +1,474 @@
+// klang-b200 — Reverb.k (examples/Reverb.k:9-279), third schedule: decoupled warp roles around bulk-async (TMA) staging.
+//
+// Same arithmetic as kb_reverb_par_kernel / kb_reverb_pipe_kernel (kb_fx_parallel.cuh) and as the frame-sequential kb_reverb_frame: one
+// CTA per (instance, side), time cut into chunks of at most a QUARTER of the shortest read-to-write distance of the 8 feedback lines, so
+// the ring window of chunk k is complete once chunk k-2 has been written.  What changes is how the roles meet:
+//
+//   * no CTA-wide barrier per chunk.  Every role runs its own loop over the chunks and hands over through progress counters in shared
+//     memory (release / acquire fences around a volatile word) and, for data that arrives by bulk copy, mbarriers with a transaction
+//     count.  The slow role (the filter lane: ~17 cycles per tick, 2 ticks per frame) never waits for the latency of the fast ones.
+//   * no per-thread global loads on the hot path.  The ring windows of the 8 lines (contiguous modulo one wrap) and the io block arrive
+//     by 1-D cp.async.bulk (SASS UBLKCP) into shared memory, completing on an mbarrier (SYNCS); the early-reflection ring of the side
+//     (Stereo::Delay<21600>, 86.4 KB) is RESIDENT in shared memory for the whole launch, so the 20 taps per frame are shared-memory
+//     gathers.  The LSU the filter warp shares with the other warps of its SM carries stores only.
+//   * the filter lane receives PRE-MULTIPLIED operands (b0 x, b1 x, b2 x) from worker warps, so its own instruction stream is the bare
+//     recurrence  y = p0 + z0;  z0 = (p1 - a1 y) + z1;  z1 = p2 - a2 y  — 6 operations per tick, 4 of them on the dependent chain
+//     (the same roundings as Biquad::Filter::process, klang.h:5605-5612: every product and sum is rounded on its own).
+//
+// KB_FX_TOLERANCE (opt-in, include/klang_b200.h) replaces the serial filter lane by a warp-per-line parallel scan (kb_rv3_scan_chunk): each
+// lane runs 5 consecutive ticks, the lane-end states are combined by a Kogge-Stone scan over powers of the 2x2 state-transition matrix,
+// each lane re-runs its ticks from its true start state.  That RE-ASSOCIATES the fp32 recurrence, so results are no longer bit-identical:
+// the plan admits an instance only when the rounding-noise gain of its line filters keeps the output within the parity bar
+// 1e-5 |r| + 1e-6 peak of the reference (profiles/r02_reverb_tolerance.txt; the early LPF -> HPF cascade, whose 100 Hz high-pass
+// amplifies rounding noise 40x above that bar, stays serial and exact in both modes).
+#pragma once
+#include "kb_fx_parallel.cuh"
+#include "kb_scan.cuh"
+
+#define KB_RV3_LMAX 80                        // frames per chunk (a multiple of 4: io chunks are 16-byte bulk copies)
+#define KB_RV3_WROW 168                       // raw window row: 2 LMAX ticks + 1 + up to 3 floats of alignment slack, rounded to 16 bytes
+#define KB_RV3_XROW 161                       // float4 per operand row (odd: the 8 lanes of the filter warp hit distinct banks)
+#define KB_RV3_YROW 164                       // floats per output row (164 = 4 mod 32: conflict-free 128-bit stores from 8 lanes)
+#define KB_RV3_EROW (KB_RV3_LMAX + 16)        // early rows: LMAX frames + the read-ahead of the row filter
+#define KB_RV3_DI 8                           // io chunks in flight
+#define KB_RV3_DE 4                           // early-cascade output chunks in flight
+#define KB_RV3_ESIZE 21600                    // Stereo::Delay<21600>  Reverb.k:11
+#define KB_RV3_NT 512                         // threads, exact mode (16 warps)
+#define KB_RV3_NT_TOL 640                     // threads, tolerance mode (20 warps)
+
+struct KbRv3Smem {
+	float er[KB_RV3_ESIZE];                   // the early ring of this side, resident for the launch
+	float4 xq[2][8][KB_RV3_XROW];             // exact mode: filter operands per tick (b0 x, b1 x, b2 x, -), double buffered
+	float win[2][8][KB_RV3_WROW];             // raw ring windows (bulk copies), double buffered
+	float y[2][8][KB_RV3_YROW];               // filter outputs per tick, double buffered
+	float xin[KB_RV3_DI][KB_RV3_EROW];        // io chunks (bulk copies)
+	float ylp[2][KB_RV3_EROW];                // early LPF output
+	float xf[KB_RV3_DE][KB_RV3_EROW];         // early LPF -> HPF output
+	float r1[2][KB_RV3_LMAX];                 // early reflections per frame (taps summed in order)
+	float carry[2][8];                        // FilteredDelay::in carried between frames and chunks: [old/new][line]
+	float times[KB_RV_MAXREFL], gg[KB_RV_MAXREFL];
+	long long lring[8]; int lsize[8], rpos0[8], wpos0[8], woff[2][8];
+	float frac[8], gain[8], b0[8], b1[8], b2[8], a1[8], a2[8];
+	unsigned long long bar_win[2], bar_xin[KB_RV3_DI], bar_er;      // mbarriers: bulk-copy completion
+	int p_done, f_done, w_done, t_done, e_done;                     // chunks completed per role
+	int f_cnt[2];                                                   // tolerance mode: line-chunks completed, per chunk parity (8 per chunk)
+};
+
+// ---- hand-over primitives
+KB_D void kb_wait_ge(const int* counter, int target) {               // acquire: spin on a shared-memory word, then fence
+	const volatile int* c = counter;
+	while (*c < target) __nanosleep(20);
+	__threadfence_block();
+}
+KB_D void kb_signal(int* counter, int value) {                       // release: ONE thread, after the role's own barrier
+	__threadfence_block();
+	*(volatile int*)counter = value;
+}
+KB_D unsigned kb_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+KB_D void kb_mbar_init(unsigned long long* bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(kb_smem_u32(bar)), "r"(count) : "memory"); }
+KB_D void kb_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(kb_smem_u32(bar)), "r"(bytes) : "memory");
+}
+KB_D void kb_mbar_wait(unsigned long long* bar, unsigned parity) {
+	asm volatile(
+		"{\n\t.reg .pred p;\n\t"
+		"KB_MBAR_WAIT_%=:\n\t"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+		"@p bra KB_MBAR_DONE_%=;\n\t"
+		"bra KB_MBAR_WAIT_%=;\n\t"
+		"KB_MBAR_DONE_%=:\n\t}"
+		:: "r"(kb_smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared, completing `bytes` on the mbarrier.  Addresses and size are multiples of 16 bytes.
+KB_D void kb_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             :: "r"(kb_smem_u32(dst)), "l"(src), "r"(bytes), "r"(kb_smem_u32(bar)) : "memory");
+}
+KB_D void kb_fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// ---- plan: chunk length (a multiple of 4 frames), or the sequential schedule; mode bit 1 set = the scan is admissible for every line
+enum { KB_PLAN_SCAN_OK = 2 };
+__global__ void kb_reverb_plan3_kernel(const KbReverb* __restrict__ states, KbFxPlan* __restrict__ plan, int instances) {
+	const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+	if (inst >= instances) return;
+	KbReverb& rv = const_cast<KbReverb&>(states[inst]);
+	int chunk = KB_RV3_LMAX;
+	bool scan_ok = true;
+	for (int line = 0; line < 16; line++) {
+		const KbRvFDelay& fd = kb_rv_line(rv, line);
+		const KbDelay& d = fd.delay;
+		int lag = d.position - d.last_position; if (lag <= 0) lag += d.SIZE;    // write head minus read head, in ring samples
+		chunk = min(chunk, (lag - 2) / 4);                                      // two ticks per frame, window of chunk k closed by chunk k-2
+		scan_ok = scan_ok && kb_rv3_scan_admissible(fd.filter);
+	}
+	float tmin = 1e30f;
+	for (int r = 0; r < rv.count; r++) tmin = fminf(tmin, rv.times[r]);
+	chunk = min(chunk, (int)tmin - 3);
+	chunk &= ~3;
+	KbFxPlan p;
+	p.chunk = chunk;
+	p.mode = (chunk >= 8 && rv.dl.SIZE == KB_RV3_ESIZE && rv.dr.SIZE == KB_RV3_ESIZE) ? (KB_PLAN_PARALLEL | (scan_ok ? KB_PLAN_SCAN_OK : 0)) : KB_PLAN_SEQUENTIAL;
+	p.gain = p.delay = p.dry = 0.f;
+	plan[inst] = p;
+}
+
+// Biquad::Filter::process (klang.h:5605-5612) over pre-multiplied operands, strictly in order, by ONE thread: per tick
+//   y = b0 x + z0;  z0' = b1 x - a1 y + z1;  z1' = b2 x - a2 y        with q = (b0 x, b1 x, b2 x)
+KB_D void kb_rv3_filter_row(const float4* __restrict__ q, float* __restrict__ yr, int ticks, float a1, float a2, float& z0, float& z1) {
+	float4* y4 = reinterpret_cast<float4*>(yr);
+	int f = 0;
+	float4 p0 = q[0], p1 = q[1], p2 = q[2], p3 = q[3];
+	for (; f + 4 <= ticks; f += 4) {
+		float4 n0 = p0, n1 = p1, n2 = p2, n3 = p3;
+		if (f + 8 <= ticks) { n0 = q[f + 4]; n1 = q[f + 5]; n2 = q[f + 6]; n3 = q[f + 7]; }
+		else if (f + 4 < ticks) { n0 = q[f + 4]; n1 = q[f + 5]; }          // (ticks is even: a tail of two)
+		float4 o;
+		o.x = p0.x + z0; z0 = (p0.y - a1 * o.x) + z1; z1 = p0.z - a2 * o.x;
+		o.y = p1.x + z0; z0 = (p1.y - a1 * o.y) + z1; z1 = p1.z - a2 * o.y;
+		o.z = p2.x + z0; z0 = (p2.y - a1 * o.z) + z1; z1 = p2.z - a2 * o.z;
+		o.w = p3.x + z0; z0 = (p3.y - a1 * o.w) + z1; z1 = p3.z - a2 * o.w;
+		y4[f >> 2] = o;
+		p0 = n0; p1 = n1; p2 = n2; p3 = n3;
+	}
+	for (; f < ticks; f++) {
+		const float4 p = q[f];
+		const float y = p.x + z0;
+		z0 = (p.y - a1 * y) + z1;
+		z1 = p.z - a2 * y;
+		yr[f] = y;
+	}
+}
+
+#ifdef __CUDACC__
+// One line, one chunk, by one full warp.  w = the raw ring window (w[0] = the read head's sample), frac = Delay::process interpolation weight
+// (klang.h:3461-3473), yr = output row.  (z0, z1) = the line's filter state, identical in all lanes on entry and on exit.
+KB_D void kb_rv3_scan_chunk(const KbRv3ScanCoef& c, const float* __restrict__ w, float frac, int ticks, float* __restrict__ yr, float& z0, float& z1, int lane) {
+	const int t0 = lane * KB_RV3_SCAN_P;
+	const int cnt = max(0, min(KB_RV3_SCAN_P, ticks - t0));
+	float x[KB_RV3_SCAN_P];
+	{
+		float wa = cnt > 0 ? w[t0] : 0.f;
+		#pragma unroll
+		for (int j = 0; j < KB_RV3_SCAN_P; j++) {
+			const float wb = j < cnt ? w[t0 + j + 1] : 0.f;
+			x[j] = wa + frac * (wb - wa);
+			wa = wb;
+		}
+	}
+	float e0 = lane == 0 ? z0 : 0.f, e1 = lane == 0 ? z1 : 0.f;
+	kb_rv3_scan_run(c, x, cnt, e0, e1, nullptr);
+	#pragma unroll
+	for (int j = 0; j < 5; j++) {
+		const float u0 = __shfl_up_sync(0xffffffffu, e0, 1 << j), u1 = __shfl_up_sync(0xffffffffu, e1, 1 << j);
+		if (lane >= (1 << j)) {
+			e0 = kb_fma(c.T[j][0], u0, kb_fma(c.T[j][1], u1, e0));
+			e1 = kb_fma(c.T[j][2], u0, kb_fma(c.T[j][3], u1, e1));
+		}
+	}
+	// true start state of this lane = true end state of the lane before it (lanes past the last tick are never used)
+	float s0 = __shfl_up_sync(0xffffffffu, e0, 1), s1 = __shfl_up_sync(0xffffffffu, e1, 1);
+	if (lane == 0) { s0 = z0; s1 = z1; }
+	float yv[KB_RV3_SCAN_P];
+	kb_rv3_scan_run(c, x, cnt, s0, s1, yv);
+	#pragma unroll
+	for (int j = 0; j < KB_RV3_SCAN_P; j++) if (j < cnt) yr[t0 + j] = yv[j];
+	const int last = (ticks - 1) / KB_RV3_SCAN_P;                    // the lane that holds the chunk's last tick ends in the chunk's end state
+	z0 = __shfl_sync(0xffffffffu, s0, last); z1 = __shfl_sync(0xffffffffu, s1, last);
+}
+
+// role of a warp.  Exact mode (16 warps): the filter warp F is ALONE on SM sub-partition 0 (warps 4, 8, 12 exit at once).
+// Tolerance mode (20 warps): the early cascade E — now the longest serial chain — is alone on sub-partition 1 (warps 5, 9, 13, 17 exit).
+enum { KB_RV3_IDLE = 0, KB_RV3_F, KB_RV3_E, KB_RV3_M, KB_RV3_P, KB_RV3_T, KB_RV3_W, KB_RV3_S };
+template <int MODE> KB_D void kb_rv3_role(int warp, int& role, int& slot) {
+	if (MODE == 0) {
+		//                       0         1         2         3         4            5         6         7
+		const int r[16] = { KB_RV3_F, KB_RV3_E, KB_RV3_M, KB_RV3_P, KB_RV3_IDLE, KB_RV3_T, KB_RV3_P, KB_RV3_P,
+		                    KB_RV3_IDLE, KB_RV3_T, KB_RV3_W, KB_RV3_W, KB_RV3_IDLE, KB_RV3_T, KB_RV3_W, KB_RV3_IDLE };
+		const int q[16] = { 0, 0, 0, 0, 0, 0, 1, 2,  0, 1, 0, 1, 0, 2, 2, 0 };       // index of the warp inside its role
+		role = r[warp & 15]; slot = q[warp & 15];
+	} else {
+		const int r[20] = { KB_RV3_S, KB_RV3_E, KB_RV3_M, KB_RV3_S, KB_RV3_S, KB_RV3_IDLE, KB_RV3_S, KB_RV3_S,
+		                    KB_RV3_S, KB_RV3_IDLE, KB_RV3_S, KB_RV3_S, KB_RV3_T, KB_RV3_IDLE, KB_RV3_T, KB_RV3_T,
+		                    KB_RV3_W, KB_RV3_IDLE, KB_RV3_W, KB_RV3_W };
+		const int q[20] = { 0, 0, 0, 1, 2, 0, 3, 4,  5, 0, 6, 7, 0, 0, 1, 2,  0, 0, 1, 2 };
+		role = r[warp % 20]; slot = q[warp % 20];
+	}
+}
+
+// skip_scan_ok (exact kernel only): this launch leaves the instances the scan admits to the tolerance kernel launched beside it
+template <int MODE>
+__global__ void __launch_bounds__(MODE == 0 ? KB_RV3_NT : KB_RV3_NT_TOL) kb_reverb3_kernel(const KbFxHdr* __restrict__ hdrs, KbReverb* __restrict__ states, const KbFxPlan* __restrict__ plan,
+                                                                                           float* __restrict__ rings, float* __restrict__ io, int n, int stride, int skip_scan_ok) {
+	extern __shared__ __align__(128) unsigned char kb_rv3_smem_raw[];
+	KbRv3Smem& S = *reinterpret_cast<KbRv3Smem*>(kb_rv3_smem_raw);
+	const int inst = blockIdx.x >> 1, side = blockIdx.x & 1;
+	const KbFxPlan pl = plan[inst];
+	if (!(pl.mode & KB_PLAN_PARALLEL)) return;
+	if (MODE == 1 && !(pl.mode & KB_PLAN_SCAN_OK)) return;          // (the host launches the exact kernel for those)
+	if (MODE == 0 && (pl.mode & KB_PLAN_SCAN_OK) && skip_scan_ok) return;
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	int role, rslot;
+	kb_rv3_role<MODE>(warp, role, rslot);
+	KbReverb& rv = states[inst];
+	const KbControl* c = hdrs[inst].controls;
+	float* X = io + ((size_t)inst * 2 + side) * stride;
+	const int Lc = pl.chunk, K = (n + Lc - 1) / Lc;
+	KbDelay& ed = side ? rv.dr : rv.dl;
+	const int epos0 = ed.position;
+	float* ringe = rings + ed.ring;
+	auto chunk_len = [&](int k) { return min(Lc, n - k * Lc); };
+
+	// ---- prologue: per-line geometry and coefficients, mbarriers, counters
+	if (tid < KB_RV_MAXREFL) { S.times[tid] = rv.times[tid]; S.gg[tid] = side ? rv.gr[tid] : rv.gl[tid]; }
+	if (tid < 8) {
+		const KbRvFDelay& d = kb_rv_side_line(rv, side, tid);
+		S.carry[0][tid] = d.in; S.carry[1][tid] = d.in;
+		S.lring[tid] = d.delay.ring; S.lsize[tid] = d.delay.SIZE; S.rpos0[tid] = d.delay.last_position; S.wpos0[tid] = d.delay.position;
+		S.frac[tid] = d.delay.last_fraction; S.gain[tid] = d.gain;
+		S.b0[tid] = d.filter.b0; S.b1[tid] = d.filter.b1; S.b2[tid] = d.filter.b2; S.a1[tid] = d.filter.a1; S.a2[tid] = d.filter.a2;
+	}
+	if (tid == 32) {
+		kb_mbar_init(&S.bar_win[0], 1); kb_mbar_init(&S.bar_win[1], 1); kb_mbar_init(&S.bar_er, 1);
+		for (int i = 0; i < KB_RV3_DI; i++) kb_mbar_init(&S.bar_xin[i], 1);
+		S.p_done = S.f_done = S.w_done = S.t_done = S.e_done = 0; S.f_cnt[0] = S.f_cnt[1] = 0;
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	if (role == KB_RV3_IDLE) return;
+
+	if (role == KB_RV3_M) {
+		// ================================================================ M: the bulk-copy issuer (one thread)
+		if (lane != 0) return;
+		int rp[8];
+		#pragma unroll
+		for (int l = 0; l < 8; l++) rp[l] = S.rpos0[l];
+		// windows of chunk k: the floats [rp, rp + ticks] of every line, fetched as the enclosing 16-byte aligned span (two copies at the wrap)
+		auto issue_win = [&](int k) {
+			const int ticks = 2 * chunk_len(k), sl = k & 1;
+			unsigned bytes = 0;
+			int a0[8], n4[8];
+			#pragma unroll
+			for (int l = 0; l < 8; l++) {
+				a0[l] = rp[l] & ~3;
+				n4[l] = ((rp[l] + ticks + 1 + 3) & ~3) - a0[l];
+				S.woff[sl][l] = rp[l] & 3;
+				bytes += 4u * (unsigned)n4[l];
+			}
+			kb_fence_proxy_async();                                  // ring samples written by this CTA's W role (generic proxy) are read by the async proxy
+			kb_mbar_expect_tx(&S.bar_win[sl], bytes);
+			#pragma unroll
+			for (int l = 0; l < 8; l++) {
+				const float* ring = rings + S.lring[l];
+				const int size = S.lsize[l];
+				if (a0[l] + n4[l] <= size) kb_bulk_g2s(&S.win[sl][l][0], ring + a0[l], 4u * n4[l], &S.bar_win[sl]);
+				else {
+					const int first = size - a0[l];
+					kb_bulk_g2s(&S.win[sl][l][0], ring + a0[l], 4u * first, &S.bar_win[sl]);
+					kb_bulk_g2s(&S.win[sl][l][first], ring, 4u * (n4[l] - first), &S.bar_win[sl]);
+				}
+				rp[l] += ticks; if (rp[l] >= size) rp[l] -= size;
+			}
+		};
+		auto issue_xin = [&](int k) {
+			const int L = chunk_len(k), sl = k % KB_RV3_DI;
+			const unsigned bytes = 4u * (unsigned)((L + 3) & ~3);        // (a ragged tail reads up to 3 floats past n, inside the row: stride % 4 == 0)
+			kb_mbar_expect_tx(&S.bar_xin[sl], bytes);
+			kb_bulk_g2s(&S.xin[sl][0], X + (size_t)k * Lc, bytes, &S.bar_xin[sl]);
+		};
+		// the early ring, whole (four copies), then the first windows and io chunks
+		kb_mbar_expect_tx(&S.bar_er, 4u * KB_RV3_ESIZE);
+		for (int q = 0; q < 4; q++) kb_bulk_g2s(&S.er[q * (KB_RV3_ESIZE / 4)], ringe + q * (KB_RV3_ESIZE / 4), KB_RV3_ESIZE, &S.bar_er);
+		for (int k = 0; k < KB_RV3_DI && k < K; k++) issue_xin(k);
+		issue_win(0);
+		if (K > 1) issue_win(1);
+		for (int k = 2; k < K; k++) {
+			kb_wait_ge(&S.w_done, k - 1);                            // chunks 0 .. k-2 written: window k is complete, slot k & 1 and io slot (k - 2) % DI are free
+			issue_win(k);
+			if (k + KB_RV3_DI - 2 < K) issue_xin(k + KB_RV3_DI - 2);
+		}
+		return;
+	}
+
+	if (role == KB_RV3_E) {
+		// ================================================================ E: early cascade in >> lpf >> hpf (Reverb.k:87), lane 0 = LPF(chunk s), lane 1 = HPF(chunk s - 1)
+		float z0 = 0.f, z1 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, a1 = 0.f, a2 = 0.f;
+		if (lane < 2) {
+			const KbBiquad& f = lane == 0 ? rv.lpf[side] : rv.hpf[side];
+			z0 = f.z0; z1 = f.z1; b0 = f.b0; b1 = f.b1; b2 = f.b2; a1 = f.a1; a2 = f.a2;
+		}
+		for (int s = 0; s <= K; s++) {
+			if (s < K) kb_mbar_wait(&S.bar_xin[s % KB_RV3_DI], (unsigned)(s / KB_RV3_DI) & 1u);
+			if (s >= 1) kb_wait_ge(&S.t_done, s - KB_RV3_DE);        // xf slot (s - 1) % DE was last read by T(s - 1 - DE)
+			const int k = s - lane;
+			if (lane < 2 && k >= 0 && k < K) {
+				const float* xi = lane == 0 ? S.xin[k % KB_RV3_DI] : S.ylp[k & 1];
+				float* xo = lane == 0 ? S.ylp[k & 1] : S.xf[k % KB_RV3_DE];
+				kb_rv2_filter_row(xi, xo, chunk_len(k), b0, b1, b2, a1, a2, z0, z1);
+			}
+			__syncwarp();
+			if (lane == 0) kb_signal(&S.e_done, s + 1);
+		}
+		if (lane == 0) { rv.lpf[side].z0 = z0; rv.lpf[side].z1 = z1; }
+		if (lane == 1) { rv.hpf[side].z0 = z0; rv.hpf[side].z1 = z1; }
+		return;
+	}
+
+	if (role == KB_RV3_T) {
+		// ================================================================ T: early ring write and the taps (Reverb.k:86-92), thread = frame
+		const int tt = rslot * 32 + lane;
+		const int count = rv.count;
+		kb_mbar_wait(&S.bar_er, 0u);
+		int ebase = epos0;
+		for (int k = 0; k < K; k++) {
+			const int L = chunk_len(k);
+			kb_wait_ge(&S.e_done, k + 2);                            // xf(k) complete
+			kb_wait_ge(&S.w_done, k - 1);                            // r1 slot k & 1 was read by W(k - 2)
+			if (tt < L) {
+				int idx = ebase + tt; if (idx >= KB_RV3_ESIZE) idx -= KB_RV3_ESIZE;
+				const float v = S.xf[k % KB_RV3_DE][tt];
+				S.er[idx] = v; ringe[idx] = v;
+				// (taps never reach into this chunk: Lc <= shortest tap - 3; older samples were published by the barrier of their chunk)
+				int pos = idx + 1; if (pos >= KB_RV3_ESIZE) pos -= KB_RV3_ESIZE;      // position after this frame's write
+				const float posf = (float)(pos - 1);
+				float acc = 0.f;
+				for (int d0 = 0; d0 < count; d0 += 4) {
+					float va[4], vb[4], fr[4];
+					#pragma unroll
+					for (int j = 0; j < 4; j++) if (d0 + j < count) {
+						float read = posf - S.times[d0 + j]; if (read < 0.f) read += KB_RV3_ESIZE;      // Stereo::Delay::tap(float)  klang.h:4668-4681
+						const float fl = floorf(read); fr[j] = read - fl;
+						const int ii = (int)read, jj = (ii == KB_RV3_ESIZE - 1) ? 0 : ii + 1;
+						va[j] = S.er[ii]; vb[j] = S.er[jj];
+					}
+					#pragma unroll
+					for (int j = 0; j < 4; j++) if (d0 + j < count) acc += (va[j] * (1.f - fr[j]) + vb[j] * fr[j]) * S.gg[d0 + j];   // out += delay(times[d]) * gains[d]  Reverb.k:89-90
+				}
+				S.r1[k & 1][tt] = acc;
+			}
+			ebase += L; if (ebase >= KB_RV3_ESIZE) ebase -= KB_RV3_ESIZE;
+			kb_bar_group(2, 96);
+			if (tt == 0) kb_signal(&S.t_done, k + 1);
+		}
+		if (tt == 0) ed.position = (int)(((long long)epos0 + n) % KB_RV3_ESIZE);
+		return;
+	}
+
+	if (role == KB_RV3_P) {
+		// ================================================================ P (exact mode): ring windows -> Delay::process interpolation -> pre-multiplied operands
+		const int pt = rslot * 32 + lane;
+		for (int k = 0; k < K; k++) {
+			const int ticks = 2 * chunk_len(k), sl = k & 1;
+			kb_mbar_wait(&S.bar_win[sl], (unsigned)(k >> 1) & 1u);
+			#pragma unroll 2
+			for (int l = 0; l < 8; l++) {
+				const float* w = &S.win[sl][l][S.woff[sl][l]];
+				const float fr = S.frac[l], b0 = S.b0[l], b1 = S.b1[l], b2 = S.b2[l];
+				for (int tk = pt; tk < ticks; tk += 96) {
+					const float xa = w[tk], xb = w[tk + 1];
+					const float x = xa + fr * (xb - xa);                 // Delay::process  klang.h:3461-3473
+					S.xq[sl][l][tk] = make_float4(b0 * x, b1 * x, b2 * x, 0.f);
+				}
+			}
+			kb_bar_group(1, 96);
+			if (pt == 0) kb_signal(&S.p_done, k + 1);
+		}
+		return;
+	}
+
+	if (role == KB_RV3_F) {
+		// ================================================================ F (exact mode): the 8 line filters, lane = line, strictly in order
+		float z0 = 0.f, z1 = 0.f, a1 = 0.f, a2 = 0.f;
+		if (lane < 8) { const KbBiquad& f = kb_rv_side_line(rv, side, lane).filter; z0 = f.z0; z1 = f.z1; a1 = f.a1; a2 = f.a2; }
+		for (int k = 0; k < K; k++) {
+			kb_wait_ge(&S.p_done, k + 1);
+			if (lane < 8) kb_rv3_filter_row(S.xq[k & 1][lane], S.y[k & 1][lane], 2 * chunk_len(k), a1, a2, z0, z1);
+			__syncwarp();
+			if (lane == 0) kb_signal(&S.f_done, k + 1);
+		}
+		if (lane < 8) { KbBiquad& f = kb_rv_side_line(rv, side, lane).filter; f.z0 = z0; f.z1 = z1; }
+		return;
+	}
+
+	if (role == KB_RV3_S) {
+		// ================================================================ S (tolerance mode): one warp per line, parallel scan over the chunk's ticks
+		const int l = rslot;
+		KbRv3ScanCoef sc;
+		kb_rv3_scan_coef(kb_rv_side_line(rv, side, l).filter, sc);
+		float z0 = kb_rv_side_line(rv, side, l).filter.z0, z1 = kb_rv_side_line(rv, side, l).filter.z1;
+		const float fr = S.frac[l];
+		for (int k = 0; k < K; k++) {
+			const int sl = k & 1;
+			kb_mbar_wait(&S.bar_win[sl], (unsigned)(k >> 1) & 1u);
+			kb_rv3_scan_chunk(sc, &S.win[sl][l][S.woff[sl][l]], fr, 2 * chunk_len(k), S.y[sl][l], z0, z1, lane);
+			__syncwarp();
+			if (lane == 0) { __threadfence_block(); atomicAdd(&S.f_cnt[sl], 1); }       // chunk k is complete when its parity's count reaches 8 (k / 2 + 1)
+		}
+		if (lane == 0) { KbBiquad& f = kb_rv_side_line(rv, side, l).filter; f.z0 = z0; f.z1 = z1; }
+		return;
+	}
+
+	// ==================================================================== W: FDN matrix, ring writes, mid -> late, output mix (Reverb.k:152-169, 212-231, 272), thread = frame
+	{
+		const int t = rslot * 32 + lane;
+		const float dry = c[0].value, wet = side == 0 ? c[4].value : 0.f;        // Reverb.k:272 (Q7): the right wet gain is the literal 0
+		const float cE = c[1].value, cM = c[2].value, cL = c[3].value;
+		const float M[4][4] = { { 0, 1, 1, -1 }, { -1, 0, -1, 1 }, { -1, 1, 0, -1 }, { 1, -1, 1, 0 } };      // Reverb.k:158-161
+		int wp[8];
+		#pragma unroll
+		for (int l = 0; l < 8; l++) wp[l] = S.wpos0[l];
+		int cpar = 0;
+		for (int k = 0; k < K; k++, cpar ^= 1) {
+			const int L = chunk_len(k), sl = k & 1;
+			if (MODE == 1) kb_wait_ge(&S.f_cnt[sl], 8 * ((k >> 1) + 1)); else kb_wait_ge(&S.f_done, k + 1);
+			kb_wait_ge(&S.t_done, k + 1);
+			if (t < L) {
+				const float r1 = S.r1[sl][t];
+				float in = r1, r2 = 0.f, r3 = 0.f;
+				#pragma unroll
+				for (int stage = 0; stage < 2; stage++) {
+					const int base = stage * 4;
+					float dv[4], sv[4];
+					#pragma unroll
+					for (int j = 0; j < 4; j++) {
+						const float2 yy = *reinterpret_cast<const float2*>(&S.y[sl][base + j][2 * t]);
+						dv[j] = yy.x * S.gain[base + j];                         // FilteredDelay::process  Reverb.k:130-132
+						sv[j] = yy.y * S.gain[base + j];
+					}
+					float sum = sv[0];
+					sum = sum + sv[1];
+					sum = sum + sv[2];
+					sum = sum + sv[3];
+					#pragma unroll
+					for (int q = 0; q < 4; q++) {
+						// feedback * delays + in, row q with its literal 0 / +-1 products (Reverb.k:158-163, klang.h:1446-1470)
+						const float fb = (M[q][0] * dv[0] + M[q][1] * dv[1] + M[q][2] * dv[2] + M[q][3] * dv[3]) + in;
+						const int size = S.lsize[base + q];
+						float* ring = rings + S.lring[base + q];
+						int w0 = wp[base + q] + 2 * t; if (w0 >= size) w0 -= size;
+						int wa = w0 + 1; if (wa >= size) wa -= size;
+						ring[wa] = fb;                                           // second tick of this frame writes fb
+						if (t + 1 < L) { int wb = w0 + 2; if (wb >= size) wb -= size; ring[wb] = fb; }   // = first tick of the next frame
+						else S.carry[cpar ^ 1][base + q] = fb;
+						if (t == 0) ring[w0] = S.carry[cpar][base + q];
+					}
+					if (stage == 0) { r2 = sum; in = sum; } else r3 = sum;
+				}
+				const float refl = (r1 * cE + r2 * cM) + r3 * cL;
+				X[(size_t)k * Lc + t] = S.xin[k % KB_RV3_DI][t] * dry + refl * wet;      // Reverb.k:272
+			}
+			#pragma unroll
+			for (int l = 0; l < 8; l++) { wp[l] += 2 * L; if (wp[l] >= S.lsize[l]) wp[l] -= S.lsize[l]; }
+			__threadfence();                                         // the ring writes must have reached L2 before the bulk copy of a later window reads them
+			kb_fence_proxy_async();
+			kb_bar_group(3, 96);
+			if (t == 0) kb_signal(&S.w_done, k + 1);
+		}
+		if (t < 8) {
+			KbRvFDelay& d = kb_rv_side_line(rv, side, t);
+			d.in = S.carry[cpar][t];
+			d.delay.position = (int)(((long long)d.delay.position + 2LL * n) % d.delay.SIZE);
+			d.delay.last_position = (int)(((long long)d.delay.last_position + 2LL * n) % d.delay.SIZE);
+		}
+	}
+}
+#endif  // __CUDACC__

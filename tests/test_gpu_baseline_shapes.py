@@ -117,6 +117,60 @@ def test_c4_reverb_all_buses_64_instances_vs_oracle(eng):
     assert par == inst
 
 
+# ------------------------------------------------------------------------------------- C4 Reverb.k, tolerance mode
+BAR_RTOL, BAR_ATOL_PEAK = 1e-5, 1e-6
+
+
+def bar_fraction(got, want):
+    """max |g - r| / (1e-5 |r| + 1e-6 peak(r)): <= 1 is inside the parity bar of BASELINE.json's north_star"""
+    peak = float(np.abs(want).max())
+    return float((np.abs(got.astype(np.float64) - want.astype(np.float64)) / (BAR_RTOL * np.abs(want.astype(np.float64)) + BAR_ATOL_PEAK * peak)).max())
+
+
+@pytest.mark.parametrize("name,ctl,admitted", [
+    ("all buses, damping 10 kHz", {0: 0.3, 1: 0.9, 2: 0.4, 3: 0.5, 4: 0.8}, True),
+    ("mid + late only, damping 10 kHz", {0: 0.0, 1: 0.0, 2: 1.0, 3: 1.0, 4: 1.0}, True),
+    ("mid + late only, damping 4 kHz", {0: 0.0, 1: 0.0, 2: 1.0, 3: 1.0, 4: 1.0, 6: 0.3, 7: 0.4}, True),
+    ("Large Hall preset (late lines at 2.5 kHz: not admitted)", {0: 1.0, 1: 0.0, 2: 0.419, 3: 0.329, 4: 1.0, 7: 0.5, 8: 0.5, 9: 0.1}, False),
+])
+def test_c4_reverb_tolerance_mode_stays_inside_the_parity_bar(eng, name, ctl, admitted):
+    """KB_FX_TOLERANCE: Reverb.k's 16 damping low-passes run as a parallel scan (re-associated fp32).  At the C4 shape (64 instances x
+    4096-frame blocks, distinct inputs, 8 blocks so the FDN tails recirculate) the output must stay inside 1e-5 |r| + 1e-6 peak of the
+    REFERENCE; instances whose filters the plan does not admit must run the exact schedule and stay bit-identical."""
+    fs, n, inst, blocks = 48000, 4096, 64, 8
+    chk = checker()
+    chk.set_fs(fs)
+    x = np.stack([cases.fx_input(2, n * blocks, seed=700 + i) for i in range(inst)])
+    want = np.empty_like(x)
+    for i in range(inst):
+        fx = chk.Fx(kb.FX_REVERB)
+        for c, v in ctl.items():
+            fx.set_control(c, v)
+        for b in range(blocks):
+            want[i, :, b * n:(b + 1) * n] = fx.process(x[i, :, b * n:(b + 1) * n])
+        fx.close()
+    bank = kb.FxBank(kb.FX_REVERB, inst, fs, n)
+    for c, v in ctl.items():
+        bank.set_control(c, v)
+    got = np.empty_like(x)
+    for b in range(blocks):
+        blk = np.ascontiguousarray(x[:, :, b * n:(b + 1) * n])
+        bank.process_inplace(blk, flags=kb.FX_TOLERANCE)
+        got[:, :, b * n:(b + 1) * n] = blk
+    tol_inst, par = bank.tolerance_instances(), bank.parallel_instances()
+    bank.close()
+    assert par == inst
+    if admitted:
+        assert tol_inst == inst
+        worst = max(bar_fraction(got[i, :, b * n:(b + 1) * n], want[i, :, b * n:(b + 1) * n]) for i in range(inst) for b in range(blocks))
+        print(f"Reverb.k tolerance mode, {name}: worst block at {worst:.4f} of the parity bar")
+        assert worst <= 1.0, f"{name}: {worst:.3f} x the parity bar"
+        assert_parity(got[:, 1], want[:, 1], name + " right channel (dry only, Q7)", exact=True)
+    else:
+        assert tol_inst == 0
+        assert_parity(got, want, name, exact=True)
+
+
 # --------------------------------------------------------------------------------------------------- C5, per-GPU shape
 def _bank_vs_checker(graph, instances, voices, blocks, n, fs, mix):
     """The same seeded note stream into `instances` oracle synths and one CUDA bank: per-voice streams (mix False) or the
