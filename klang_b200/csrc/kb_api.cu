@@ -18,6 +18,7 @@
 #include "kb_kernels.cuh"
 #include "kb_tiled.cuh"
 #include "kb_reverb3.cuh"
+#include "kb_pingpong3.cuh"
 
 static thread_local std::string g_err = "";
 static int kb_fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -370,7 +371,15 @@ extern "C" int kb_fx_bank_process(kb_fx_bank* b, float* io, int n, unsigned flag
 	case KB_FX_PINGPONG: {
 		KbPingPong* st = (KbPingPong*)b->d_state;
 		// sub-blocks of at most 8192 frames (the staged block lives in shared memory); every sub-block is planned on the device
-		for (int o = 0; o < n; o += 8192) {
+		// KB_PP_SCHEDULE (A/B measurement; same results): 3 = default, ONE fused launch per sub-block (kb_pingpong3.cuh: in-kernel plan, producers eight
+		// chunks ahead of the filter lanes, sequential fallback inside); 2 = the round-1 plan / network / filter / finish launches
+		static const int pp_schedule = getenv("KB_PP_SCHEDULE") ? atoi(getenv("KB_PP_SCHEDULE")) : 3;
+		for (int o = 0; o < n && pp_schedule == 3 && !seq_only; o += 8192) {
+			const int len = std::min(8192, n - o);
+			kb_pingpong3_kernel<<<b->instances, KB_PP3_NT, 0, b->stream>>>(b->d_hdr, st, b->d_plan, b->d_rings, d + o, len, n, b->fs);
+			if (o + 8192 < n) b->launches++;
+		}
+		for (int o = 0; o < n && (pp_schedule != 3 || seq_only); o += 8192) {
 			const int len = std::min(8192, n - o);
 			if (!seq_only) {
 				kb_pingpong_plan_kernel<<<ib, 32, 0, b->stream>>>(b->d_hdr, st, b->d_plan, b->instances, len, b->fs);
@@ -400,6 +409,9 @@ extern "C" int kb_fx_bank_process(kb_fx_bank* b, float* io, int n, unsigned flag
 					// KB_FX_TOLERANCE: instances whose line filters the scan admits run on the tolerance kernel, the others on the exact one
 					if (tol) { kb_reverb3_kernel<1><<<b->instances * 2, KB_RV3_NT_TOL, sizeof(KbRv3Smem), b->stream>>>(b->d_hdr, st, b->d_plan, b->d_rings, d + o, len, n, 0); b->launches++; }
 					kb_reverb3_kernel<0><<<b->instances * 2, KB_RV3_NT, sizeof(KbRv3Smem), b->stream>>>(b->d_hdr, st, b->d_plan, b->d_rings, d + o, len, n, tol);
+					// instances whose live delay spans do not fit in shared memory (fs = 192 kHz) keep the round-1 pipeline (its CTAs exit at once otherwise)
+					kb_reverb_pipe_kernel<<<b->instances * 2, KB_RV2_NT, sizeof(KbRv2Smem), b->stream>>>(b->d_hdr, st, b->d_plan, b->d_rings, d + o, len, n);
+					b->launches++;
 				} else if (rv_schedule == 1) {
 					kb_reverb_plan_kernel<<<ib, 32, 0, b->stream>>>(st, b->d_plan, b->instances);
 					kb_reverb_par_kernel<<<b->instances * 2, 256, sizeof(KbRvSmem), b->stream>>>(b->d_hdr, st, b->d_plan, b->d_rings, d + o, len, n);

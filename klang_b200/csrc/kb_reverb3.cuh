@@ -1,19 +1,21 @@
-// klang-b200 — Reverb.k (examples/Reverb.k:9-279), third schedule: decoupled warp roles around bulk-async (TMA) staging.
+// klang-b200 — Reverb.k (examples/Reverb.k:9-279), third schedule: decoupled warp roles, delay lines RESIDENT in shared memory.
 //
 // Same arithmetic as kb_reverb_par_kernel / kb_reverb_pipe_kernel (kb_fx_parallel.cuh) and as the frame-sequential kb_reverb_frame: one
 // CTA per (instance, side), time cut into chunks of at most a QUARTER of the shortest read-to-write distance of the 8 feedback lines, so
-// the ring window of chunk k is complete once chunk k-2 has been written.  What changes is how the roles meet:
+// the ring window of chunk k is complete once chunk k-2 has been written.  What changes is where the data lives and how the roles meet:
 //
+//   * the LIVE SPAN of every delay line — the samples between its read head and its write head, 7 .. 34 ms each, ~30 KB for the 8 lines
+//     of a side at 48 kHz — and the whole early-reflection ring of the side (Stereo::Delay<21600>, 86.4 KB) are resident in shared memory
+//     for the launch: they arrive once by 1-D cp.async.bulk (SASS UBLKCP) completing on an mbarrier (SYNCS), as do the io chunks.  In
+//     the steady state a chunk touches HBM only for its io (one bulk copy in, coalesced stores out) and for the write-through of the
+//     ring samples it produces (stores nobody in this launch reads back): no load sits between two chunks of the feedback loop, and the
+//     LSU the filter warp shares with the rest of its SM carries stores only.  (Round 1 gathered every window and every tap from L2.)
 //   * no CTA-wide barrier per chunk.  Every role runs its own loop over the chunks and hands over through progress counters in shared
-//     memory (release / acquire fences around a volatile word) and, for data that arrives by bulk copy, mbarriers with a transaction
-//     count.  The slow role (the filter lane: ~17 cycles per tick, 2 ticks per frame) never waits for the latency of the fast ones.
-//   * no per-thread global loads on the hot path.  The ring windows of the 8 lines (contiguous modulo one wrap) and the io block arrive
-//     by 1-D cp.async.bulk (SASS UBLKCP) into shared memory, completing on an mbarrier (SYNCS); the early-reflection ring of the side
-//     (Stereo::Delay<21600>, 86.4 KB) is RESIDENT in shared memory for the whole launch, so the 20 taps per frame are shared-memory
-//     gathers.  The LSU the filter warp shares with the other warps of its SM carries stores only.
+//     memory (release / acquire fences around a volatile word).  The slow role never waits for the latency of the fast ones.
 //   * the filter lane receives PRE-MULTIPLIED operands (b0 x, b1 x, b2 x) from worker warps, so its own instruction stream is the bare
 //     recurrence  y = p0 + z0;  z0 = (p1 - a1 y) + z1;  z1 = p2 - a2 y  — 6 operations per tick, 4 of them on the dependent chain
 //     (the same roundings as Biquad::Filter::process, klang.h:5605-5612: every product and sum is rounded on its own).
+//   An instance whose live spans do not fit (fs = 192 kHz) keeps the round-1 pipeline (kb_reverb_pipe_kernel), chosen per instance by the plan.
 //
 // KB_FX_TOLERANCE (opt-in, include/klang_b200.h) replaces the serial filter lane by a warp-per-line parallel scan (kb_rv3_scan_chunk): each
 // lane runs 5 consecutive ticks, the lane-end states are combined by a Kogge-Stone scan over powers of the 2x2 state-transition matrix,
@@ -26,30 +28,32 @@
 #include "kb_scan.cuh"
 
 #define KB_RV3_LMAX 80                        // frames per chunk (a multiple of 4: io chunks are 16-byte bulk copies)
-#define KB_RV3_WROW 168                       // raw window row: 2 LMAX ticks + 1 + up to 3 floats of alignment slack, rounded to 16 bytes
 #define KB_RV3_XROW 161                       // float4 per operand row (odd: the 8 lanes of the filter warp hit distinct banks)
 #define KB_RV3_YROW 164                       // floats per output row (164 = 4 mod 32: conflict-free 128-bit stores from 8 lanes)
 #define KB_RV3_EROW (KB_RV3_LMAX + 16)        // early rows: LMAX frames + the read-ahead of the row filter
 #define KB_RV3_DI 8                           // io chunks in flight
 #define KB_RV3_DE 4                           // early-cascade output chunks in flight
+#define KB_RV3_DR 4                           // early-reflection rows (r1) in flight
 #define KB_RV3_ESIZE 21600                    // Stereo::Delay<21600>  Reverb.k:11
+#define KB_RV3_LRCAP 20480                    // floats of shared memory for the live spans of the 8 lines of a side
 #define KB_RV3_NT 512                         // threads, exact mode (16 warps)
 #define KB_RV3_NT_TOL 640                     // threads, tolerance mode (20 warps)
 
 struct KbRv3Smem {
 	float er[KB_RV3_ESIZE];                   // the early ring of this side, resident for the launch
+	float lr[KB_RV3_LRCAP];                   // the live spans of the 8 feedback lines: line l = a ring of lcap[l] floats at lbase[l]
 	float4 xq[2][8][KB_RV3_XROW];             // exact mode: filter operands per tick (b0 x, b1 x, b2 x, -), double buffered
-	float win[2][8][KB_RV3_WROW];             // raw ring windows (bulk copies), double buffered
 	float y[2][8][KB_RV3_YROW];               // filter outputs per tick, double buffered
 	float xin[KB_RV3_DI][KB_RV3_EROW];        // io chunks (bulk copies)
 	float ylp[2][KB_RV3_EROW];                // early LPF output
 	float xf[KB_RV3_DE][KB_RV3_EROW];         // early LPF -> HPF output
-	float r1[2][KB_RV3_LMAX];                 // early reflections per frame (taps summed in order)
+	float r1[KB_RV3_DR][KB_RV3_LMAX];         // early reflections per frame (taps summed in order)
 	float carry[2][8];                        // FilteredDelay::in carried between frames and chunks: [old/new][line]
 	float times[KB_RV_MAXREFL], gg[KB_RV_MAXREFL];
-	long long lring[8]; int lsize[8], rpos0[8], wpos0[8], woff[2][8];
+	long long lring[8]; int lsize[8], rpos0[8], wpos0[8];
+	int lbase[8], lcap[8], lro[8], lwo[8];    // shared-memory ring of line l: base, capacity, offsets of the read / write head at block start
 	float frac[8], gain[8], b0[8], b1[8], b2[8], a1[8], a2[8];
-	unsigned long long bar_win[2], bar_xin[KB_RV3_DI], bar_er;      // mbarriers: bulk-copy completion
+	unsigned long long bar_xin[KB_RV3_DI], bar_res;                 // mbarriers: bulk-copy completion (io chunks; the resident rings)
 	int p_done, f_done, w_done, t_done, e_done;                     // chunks completed per role
 	int f_cnt[2];                                                   // tolerance mode: line-chunks completed, per chunk parity (8 per chunk)
 };
@@ -86,13 +90,16 @@ KB_D void kb_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long 
 }
 KB_D void kb_fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-// ---- plan: chunk length (a multiple of 4 frames), or the sequential schedule; mode bit 1 set = the scan is admissible for every line
-enum { KB_PLAN_SCAN_OK = 2 };
+// ---- plan: chunk length (a multiple of 4 frames) and the schedule.  mode bits: KB_PLAN_PARALLEL; KB_PLAN_SCAN_OK = the scan is admissible
+// for every line; KB_PLAN_RESIDENT = the live spans of both sides fit in shared memory (this file's kernel; otherwise kb_reverb_pipe_kernel)
+enum { KB_PLAN_SCAN_OK = 2, KB_PLAN_RESIDENT = 4 };
+// shared-memory ring of one line: holds the global ring indices a0 = (read head & ~3) .. write head + one chunk, i.e. lag + 2 LMAX + slack floats
+KB_HD int kb_rv3_line_cap(int lag) { return (lag + 2 * KB_RV3_LMAX + 8 + 3) & ~3; }
 __global__ void kb_reverb_plan3_kernel(const KbReverb* __restrict__ states, KbFxPlan* __restrict__ plan, int instances) {
 	const int inst = blockIdx.x * blockDim.x + threadIdx.x;
 	if (inst >= instances) return;
 	KbReverb& rv = const_cast<KbReverb&>(states[inst]);
-	int chunk = KB_RV3_LMAX;
+	int chunk = KB_RV3_LMAX, need[2] = { 0, 0 };
 	bool scan_ok = true;
 	for (int line = 0; line < 16; line++) {
 		const KbRvFDelay& fd = kb_rv_line(rv, line);
@@ -100,6 +107,7 @@ __global__ void kb_reverb_plan3_kernel(const KbReverb* __restrict__ states, KbFx
 		int lag = d.position - d.last_position; if (lag <= 0) lag += d.SIZE;    // write head minus read head, in ring samples
 		chunk = min(chunk, (lag - 2) / 4);                                      // two ticks per frame, window of chunk k closed by chunk k-2
 		scan_ok = scan_ok && kb_rv3_scan_admissible(fd.filter);
+		need[(line >> 2) & 1] += kb_rv3_line_cap(lag);                          // lines 0-3, 8-11 belong to side 0 (mid[0], late[0]); 4-7, 12-15 to side 1
 	}
 	float tmin = 1e30f;
 	for (int r = 0; r < rv.count; r++) tmin = fminf(tmin, rv.times[r]);
@@ -107,7 +115,8 @@ __global__ void kb_reverb_plan3_kernel(const KbReverb* __restrict__ states, KbFx
 	chunk &= ~3;
 	KbFxPlan p;
 	p.chunk = chunk;
-	p.mode = (chunk >= 8 && rv.dl.SIZE == KB_RV3_ESIZE && rv.dr.SIZE == KB_RV3_ESIZE) ? (KB_PLAN_PARALLEL | (scan_ok ? KB_PLAN_SCAN_OK : 0)) : KB_PLAN_SEQUENTIAL;
+	const bool resident = need[0] <= KB_RV3_LRCAP && need[1] <= KB_RV3_LRCAP && rv.dl.SIZE == KB_RV3_ESIZE && rv.dr.SIZE == KB_RV3_ESIZE;
+	p.mode = chunk >= 8 ? (KB_PLAN_PARALLEL | (resident ? KB_PLAN_RESIDENT | (scan_ok ? KB_PLAN_SCAN_OK : 0) : 0)) : KB_PLAN_SEQUENTIAL;
 	p.gain = p.delay = p.dry = 0.f;
 	plan[inst] = p;
 }
@@ -121,7 +130,6 @@ KB_D void kb_rv3_filter_row(const float4* __restrict__ q, float* __restrict__ yr
 	for (; f + 4 <= ticks; f += 4) {
 		float4 n0 = p0, n1 = p1, n2 = p2, n3 = p3;
 		if (f + 8 <= ticks) { n0 = q[f + 4]; n1 = q[f + 5]; n2 = q[f + 6]; n3 = q[f + 7]; }
-		else if (f + 4 < ticks) { n0 = q[f + 4]; n1 = q[f + 5]; }          // (ticks is even: a tail of two)
 		float4 o;
 		o.x = p0.x + z0; z0 = (p0.y - a1 * o.x) + z1; z1 = p0.z - a2 * o.x;
 		o.y = p1.x + z0; z0 = (p1.y - a1 * o.y) + z1; z1 = p1.z - a2 * o.y;
@@ -140,17 +148,20 @@ KB_D void kb_rv3_filter_row(const float4* __restrict__ q, float* __restrict__ yr
 }
 
 #ifdef __CUDACC__
-// One line, one chunk, by one full warp.  w = the raw ring window (w[0] = the read head's sample), frac = Delay::process interpolation weight
-// (klang.h:3461-3473), yr = output row.  (z0, z1) = the line's filter state, identical in all lanes on entry and on exit.
-KB_D void kb_rv3_scan_chunk(const KbRv3ScanCoef& c, const float* __restrict__ w, float frac, int ticks, float* __restrict__ yr, float& z0, float& z1, int lane) {
+// Tolerance mode: one line, one chunk, by one full warp (kb_scan.cuh).  ring / cap / rb = the line's shared-memory ring, its capacity and the
+// index of the read head's sample; frac = Delay::process interpolation weight (klang.h:3461-3473); yr = output row.  (z0, z1) = the line's
+// filter state, identical in all lanes on entry and on exit.
+KB_D void kb_rv3_scan_chunk(const KbRv3ScanCoef& c, const float* __restrict__ ring, int cap, int rb, float frac, int ticks, float* __restrict__ yr, float& z0, float& z1, int lane) {
 	const int t0 = lane * KB_RV3_SCAN_P;
 	const int cnt = max(0, min(KB_RV3_SCAN_P, ticks - t0));
 	float x[KB_RV3_SCAN_P];
 	{
-		float wa = cnt > 0 ? w[t0] : 0.f;
+		int i = rb + t0; if (i >= cap) i -= cap;
+		float wa = cnt > 0 ? ring[i] : 0.f;
 		#pragma unroll
 		for (int j = 0; j < KB_RV3_SCAN_P; j++) {
-			const float wb = j < cnt ? w[t0 + j + 1] : 0.f;
+			if (++i >= cap) i -= cap;
+			const float wb = j < cnt ? ring[i] : 0.f;
 			x[j] = wa + frac * (wb - wa);
 			wa = wb;
 		}
@@ -203,8 +214,8 @@ __global__ void __launch_bounds__(MODE == 0 ? KB_RV3_NT : KB_RV3_NT_TOL) kb_reve
 	KbRv3Smem& S = *reinterpret_cast<KbRv3Smem*>(kb_rv3_smem_raw);
 	const int inst = blockIdx.x >> 1, side = blockIdx.x & 1;
 	const KbFxPlan pl = plan[inst];
-	if (!(pl.mode & KB_PLAN_PARALLEL)) return;
-	if (MODE == 1 && !(pl.mode & KB_PLAN_SCAN_OK)) return;          // (the host launches the exact kernel for those)
+	if (!(pl.mode & KB_PLAN_PARALLEL) || !(pl.mode & KB_PLAN_RESIDENT)) return;
+	if (MODE == 1 && !(pl.mode & KB_PLAN_SCAN_OK)) return;          // (the exact kernel launched beside this one takes those)
 	if (MODE == 0 && (pl.mode & KB_PLAN_SCAN_OK) && skip_scan_ok) return;
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	int role, rslot;
@@ -228,7 +239,18 @@ __global__ void __launch_bounds__(MODE == 0 ? KB_RV3_NT : KB_RV3_NT_TOL) kb_reve
 		S.b0[tid] = d.filter.b0; S.b1[tid] = d.filter.b1; S.b2[tid] = d.filter.b2; S.a1[tid] = d.filter.a1; S.a2[tid] = d.filter.a2;
 	}
 	if (tid == 32) {
-		kb_mbar_init(&S.bar_win[0], 1); kb_mbar_init(&S.bar_win[1], 1); kb_mbar_init(&S.bar_er, 1);
+		// the shared-memory rings: line l holds the global ring indices from a0 = read head & ~3 on; offset o (from a0) lives at lbase + o mod lcap
+		int base = 0;
+		for (int l = 0; l < 8; l++) {
+			const KbDelay& d = kb_rv_side_line(rv, side, l).delay;
+			int lag = d.position - d.last_position; if (lag <= 0) lag += d.SIZE;
+			const int a0 = d.last_position & ~3;
+			S.lbase[l] = base; S.lcap[l] = kb_rv3_line_cap(lag);
+			S.lro[l] = d.last_position - a0;                                    // 0 .. 3
+			S.lwo[l] = S.lro[l] + lag;
+			base += S.lcap[l];
+		}
+		kb_mbar_init(&S.bar_res, 1);
 		for (int i = 0; i < KB_RV3_DI; i++) kb_mbar_init(&S.bar_xin[i], 1);
 		S.p_done = S.f_done = S.w_done = S.t_done = S.e_done = 0; S.f_cnt[0] = S.f_cnt[1] = 0;
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -239,52 +261,32 @@ __global__ void __launch_bounds__(MODE == 0 ? KB_RV3_NT : KB_RV3_NT_TOL) kb_reve
 	if (role == KB_RV3_M) {
 		// ================================================================ M: the bulk-copy issuer (one thread)
 		if (lane != 0) return;
-		int rp[8];
-		#pragma unroll
-		for (int l = 0; l < 8; l++) rp[l] = S.rpos0[l];
-		// windows of chunk k: the floats [rp, rp + ticks] of every line, fetched as the enclosing 16-byte aligned span (two copies at the wrap)
-		auto issue_win = [&](int k) {
-			const int ticks = 2 * chunk_len(k), sl = k & 1;
-			unsigned bytes = 0;
-			int a0[8], n4[8];
-			#pragma unroll
-			for (int l = 0; l < 8; l++) {
-				a0[l] = rp[l] & ~3;
-				n4[l] = ((rp[l] + ticks + 1 + 3) & ~3) - a0[l];
-				S.woff[sl][l] = rp[l] & 3;
-				bytes += 4u * (unsigned)n4[l];
+		// resident data, once: the early ring (whole) and the live span of every line, as 16-byte aligned spans (two copies where the global ring wraps)
+		unsigned bytes = 4u * KB_RV3_ESIZE;
+		for (int l = 0; l < 8; l++) bytes += 4u * (unsigned)((S.lwo[l] + 3) & ~3);
+		kb_mbar_expect_tx(&S.bar_res, bytes);
+		for (int q = 0; q < 4; q++) kb_bulk_g2s(&S.er[q * (KB_RV3_ESIZE / 4)], ringe + q * (KB_RV3_ESIZE / 4), KB_RV3_ESIZE, &S.bar_res);
+		for (int l = 0; l < 8; l++) {
+			const float* ring = rings + S.lring[l];
+			const int size = S.lsize[l], a0 = S.rpos0[l] & ~3, n4 = (S.lwo[l] + 3) & ~3;
+			float* dst = &S.lr[S.lbase[l]];
+			if (a0 + n4 <= size) kb_bulk_g2s(dst, ring + a0, 4u * n4, &S.bar_res);
+			else {
+				const int first = size - a0;
+				kb_bulk_g2s(dst, ring + a0, 4u * first, &S.bar_res);
+				kb_bulk_g2s(dst + first, ring, 4u * (n4 - first), &S.bar_res);
 			}
-			kb_fence_proxy_async();                                  // ring samples written by this CTA's W role (generic proxy) are read by the async proxy
-			kb_mbar_expect_tx(&S.bar_win[sl], bytes);
-			#pragma unroll
-			for (int l = 0; l < 8; l++) {
-				const float* ring = rings + S.lring[l];
-				const int size = S.lsize[l];
-				if (a0[l] + n4[l] <= size) kb_bulk_g2s(&S.win[sl][l][0], ring + a0[l], 4u * n4[l], &S.bar_win[sl]);
-				else {
-					const int first = size - a0[l];
-					kb_bulk_g2s(&S.win[sl][l][0], ring + a0[l], 4u * first, &S.bar_win[sl]);
-					kb_bulk_g2s(&S.win[sl][l][first], ring, 4u * (n4[l] - first), &S.bar_win[sl]);
-				}
-				rp[l] += ticks; if (rp[l] >= size) rp[l] -= size;
-			}
-		};
+		}
 		auto issue_xin = [&](int k) {
 			const int L = chunk_len(k), sl = k % KB_RV3_DI;
-			const unsigned bytes = 4u * (unsigned)((L + 3) & ~3);        // (a ragged tail reads up to 3 floats past n, inside the row: stride % 4 == 0)
-			kb_mbar_expect_tx(&S.bar_xin[sl], bytes);
-			kb_bulk_g2s(&S.xin[sl][0], X + (size_t)k * Lc, bytes, &S.bar_xin[sl]);
+			const unsigned b = 4u * (unsigned)((L + 3) & ~3);            // (a ragged tail reads up to 3 floats past n, inside the row: stride % 4 == 0)
+			kb_mbar_expect_tx(&S.bar_xin[sl], b);
+			kb_bulk_g2s(&S.xin[sl][0], X + (size_t)k * Lc, b, &S.bar_xin[sl]);
 		};
-		// the early ring, whole (four copies), then the first windows and io chunks
-		kb_mbar_expect_tx(&S.bar_er, 4u * KB_RV3_ESIZE);
-		for (int q = 0; q < 4; q++) kb_bulk_g2s(&S.er[q * (KB_RV3_ESIZE / 4)], ringe + q * (KB_RV3_ESIZE / 4), KB_RV3_ESIZE, &S.bar_er);
 		for (int k = 0; k < KB_RV3_DI && k < K; k++) issue_xin(k);
-		issue_win(0);
-		if (K > 1) issue_win(1);
-		for (int k = 2; k < K; k++) {
-			kb_wait_ge(&S.w_done, k - 1);                            // chunks 0 .. k-2 written: window k is complete, slot k & 1 and io slot (k - 2) % DI are free
-			issue_win(k);
-			if (k + KB_RV3_DI - 2 < K) issue_xin(k + KB_RV3_DI - 2);
+		for (int k = KB_RV3_DI; k < K; k++) {
+			kb_wait_ge(&S.w_done, k - KB_RV3_DI + 1);                // W (the last reader of an io chunk) is done with chunk k - DI: its slot is free
+			issue_xin(k);
 		}
 		return;
 	}
@@ -317,12 +319,12 @@ __global__ void __launch_bounds__(MODE == 0 ? KB_RV3_NT : KB_RV3_NT_TOL) kb_reve
 		// ================================================================ T: early ring write and the taps (Reverb.k:86-92), thread = frame
 		const int tt = rslot * 32 + lane;
 		const int count = rv.count;
-		kb_mbar_wait(&S.bar_er, 0u);
+		kb_mbar_wait(&S.bar_res, 0u);
 		int ebase = epos0;
 		for (int k = 0; k < K; k++) {
 			const int L = chunk_len(k);
 			kb_wait_ge(&S.e_done, k + 2);                            // xf(k) complete
-			kb_wait_ge(&S.w_done, k - 1);                            // r1 slot k & 1 was read by W(k - 2)
+			kb_wait_ge(&S.w_done, k - KB_RV3_DR + 1);                // r1 slot k % DR was read by W(k - DR)
 			if (tt < L) {
 				int idx = ebase + tt; if (idx >= KB_RV3_ESIZE) idx -= KB_RV3_ESIZE;
 				const float v = S.xf[k % KB_RV3_DE][tt];
@@ -343,7 +345,7 @@ __global__ void __launch_bounds__(MODE == 0 ? KB_RV3_NT : KB_RV3_NT_TOL) kb_reve
 					#pragma unroll
 					for (int j = 0; j < 4; j++) if (d0 + j < count) acc += (va[j] * (1.f - fr[j]) + vb[j] * fr[j]) * S.gg[d0 + j];   // out += delay(times[d]) * gains[d]  Reverb.k:89-90
 				}
-				S.r1[k & 1][tt] = acc;
+				S.r1[k % KB_RV3_DR][tt] = acc;
 			}
 			ebase += L; if (ebase >= KB_RV3_ESIZE) ebase -= KB_RV3_ESIZE;
 			kb_bar_group(2, 96);
@@ -356,18 +358,26 @@ __global__ void __launch_bounds__(MODE == 0 ? KB_RV3_NT : KB_RV3_NT_TOL) kb_reve
 	if (role == KB_RV3_P) {
 		// ================================================================ P (exact mode): ring windows -> Delay::process interpolation -> pre-multiplied operands
 		const int pt = rslot * 32 + lane;
+		kb_mbar_wait(&S.bar_res, 0u);
+		int rb[8];                                                   // index of the read head's sample in each line's shared-memory ring
+		#pragma unroll
+		for (int l = 0; l < 8; l++) rb[l] = S.lro[l];
 		for (int k = 0; k < K; k++) {
 			const int ticks = 2 * chunk_len(k), sl = k & 1;
-			kb_mbar_wait(&S.bar_win[sl], (unsigned)(k >> 1) & 1u);
-			#pragma unroll 2
+			kb_wait_ge(&S.w_done, k - 1);                            // chunks 0 .. k-2 written: the windows of chunk k are complete, xq slot k & 1 is free
+			#pragma unroll
 			for (int l = 0; l < 8; l++) {
-				const float* w = &S.win[sl][l][S.woff[sl][l]];
+				const float* ring = &S.lr[S.lbase[l]];
+				const int cap = S.lcap[l];
 				const float fr = S.frac[l], b0 = S.b0[l], b1 = S.b1[l], b2 = S.b2[l];
 				for (int tk = pt; tk < ticks; tk += 96) {
-					const float xa = w[tk], xb = w[tk + 1];
+					int i = rb[l] + tk; if (i >= cap) i -= cap;
+					int j = i + 1; if (j >= cap) j -= cap;
+					const float xa = ring[i], xb = ring[j];
 					const float x = xa + fr * (xb - xa);                 // Delay::process  klang.h:3461-3473
 					S.xq[sl][l][tk] = make_float4(b0 * x, b1 * x, b2 * x, 0.f);
 				}
+				rb[l] += ticks; if (rb[l] >= cap) rb[l] -= cap;
 			}
 			kb_bar_group(1, 96);
 			if (pt == 0) kb_signal(&S.p_done, k + 1);
@@ -396,10 +406,15 @@ __global__ void __launch_bounds__(MODE == 0 ? KB_RV3_NT : KB_RV3_NT_TOL) kb_reve
 		kb_rv3_scan_coef(kb_rv_side_line(rv, side, l).filter, sc);
 		float z0 = kb_rv_side_line(rv, side, l).filter.z0, z1 = kb_rv_side_line(rv, side, l).filter.z1;
 		const float fr = S.frac[l];
+		const float* ring = &S.lr[S.lbase[l]];
+		const int cap = S.lcap[l];
+		int rb = S.lro[l];
+		kb_mbar_wait(&S.bar_res, 0u);
 		for (int k = 0; k < K; k++) {
-			const int sl = k & 1;
-			kb_mbar_wait(&S.bar_win[sl], (unsigned)(k >> 1) & 1u);
-			kb_rv3_scan_chunk(sc, &S.win[sl][l][S.woff[sl][l]], fr, 2 * chunk_len(k), S.y[sl][l], z0, z1, lane);
+			const int sl = k & 1, ticks = 2 * chunk_len(k);
+			kb_wait_ge(&S.w_done, k - 1);                            // the window of chunk k is complete, y slot k & 1 is free
+			kb_rv3_scan_chunk(sc, ring, cap, rb, fr, ticks, S.y[sl][l], z0, z1, lane);
+			rb += ticks; if (rb >= cap) rb -= cap;
 			__syncwarp();
 			if (lane == 0) { __threadfence_block(); atomicAdd(&S.f_cnt[sl], 1); }       // chunk k is complete when its parity's count reaches 8 (k / 2 + 1)
 		}
@@ -413,16 +428,17 @@ __global__ void __launch_bounds__(MODE == 0 ? KB_RV3_NT : KB_RV3_NT_TOL) kb_reve
 		const float dry = c[0].value, wet = side == 0 ? c[4].value : 0.f;        // Reverb.k:272 (Q7): the right wet gain is the literal 0
 		const float cE = c[1].value, cM = c[2].value, cL = c[3].value;
 		const float M[4][4] = { { 0, 1, 1, -1 }, { -1, 0, -1, 1 }, { -1, 1, 0, -1 }, { 1, -1, 1, 0 } };      // Reverb.k:158-161
-		int wp[8];
+		int wp[8], ws[8];                                            // write head of each line: in its global ring, in its shared-memory ring
 		#pragma unroll
-		for (int l = 0; l < 8; l++) wp[l] = S.wpos0[l];
+		for (int l = 0; l < 8; l++) { wp[l] = S.wpos0[l]; ws[l] = S.lwo[l]; if (ws[l] >= S.lcap[l]) ws[l] -= S.lcap[l]; }
+		kb_mbar_wait(&S.bar_res, 0u);                                // (the resident spans must have landed before this role writes behind them)
 		int cpar = 0;
 		for (int k = 0; k < K; k++, cpar ^= 1) {
 			const int L = chunk_len(k), sl = k & 1;
 			if (MODE == 1) kb_wait_ge(&S.f_cnt[sl], 8 * ((k >> 1) + 1)); else kb_wait_ge(&S.f_done, k + 1);
 			kb_wait_ge(&S.t_done, k + 1);
 			if (t < L) {
-				const float r1 = S.r1[sl][t];
+				const float r1 = S.r1[k % KB_RV3_DR][t];
 				float in = r1, r2 = 0.f, r3 = 0.f;
 				#pragma unroll
 				for (int stage = 0; stage < 2; stage++) {
@@ -442,14 +458,20 @@ __global__ void __launch_bounds__(MODE == 0 ? KB_RV3_NT : KB_RV3_NT_TOL) kb_reve
 					for (int q = 0; q < 4; q++) {
 						// feedback * delays + in, row q with its literal 0 / +-1 products (Reverb.k:158-163, klang.h:1446-1470)
 						const float fb = (M[q][0] * dv[0] + M[q][1] * dv[1] + M[q][2] * dv[2] + M[q][3] * dv[3]) + in;
-						const int size = S.lsize[base + q];
+						const int size = S.lsize[base + q], cap = S.lcap[base + q];
 						float* ring = rings + S.lring[base + q];
+						float* sring = &S.lr[S.lbase[base + q]];
 						int w0 = wp[base + q] + 2 * t; if (w0 >= size) w0 -= size;
+						int s0 = ws[base + q] + 2 * t; if (s0 >= cap) s0 -= cap;
 						int wa = w0 + 1; if (wa >= size) wa -= size;
-						ring[wa] = fb;                                           // second tick of this frame writes fb
-						if (t + 1 < L) { int wb = w0 + 2; if (wb >= size) wb -= size; ring[wb] = fb; }   // = first tick of the next frame
-						else S.carry[cpar ^ 1][base + q] = fb;
-						if (t == 0) ring[w0] = S.carry[cpar][base + q];
+						int sa = s0 + 1; if (sa >= cap) sa -= cap;
+						ring[wa] = fb; sring[sa] = fb;                           // second tick of this frame writes fb
+						if (t + 1 < L) {                                         // = first tick of the next frame
+							int wb = w0 + 2; if (wb >= size) wb -= size;
+							int sb = s0 + 2; if (sb >= cap) sb -= cap;
+							ring[wb] = fb; sring[sb] = fb;
+						} else S.carry[cpar ^ 1][base + q] = fb;
+						if (t == 0) { const float cv = S.carry[cpar][base + q]; ring[w0] = cv; sring[s0] = cv; }
 					}
 					if (stage == 0) { r2 = sum; in = sum; } else r3 = sum;
 				}
@@ -457,9 +479,10 @@ __global__ void __launch_bounds__(MODE == 0 ? KB_RV3_NT : KB_RV3_NT_TOL) kb_reve
 				X[(size_t)k * Lc + t] = S.xin[k % KB_RV3_DI][t] * dry + refl * wet;      // Reverb.k:272
 			}
 			#pragma unroll
-			for (int l = 0; l < 8; l++) { wp[l] += 2 * L; if (wp[l] >= S.lsize[l]) wp[l] -= S.lsize[l]; }
-			__threadfence();                                         // the ring writes must have reached L2 before the bulk copy of a later window reads them
-			kb_fence_proxy_async();
+			for (int l = 0; l < 8; l++) {
+				wp[l] += 2 * L; if (wp[l] >= S.lsize[l]) wp[l] -= S.lsize[l];
+				ws[l] += 2 * L; if (ws[l] >= S.lcap[l]) ws[l] -= S.lcap[l];
+			}
 			kb_bar_group(3, 96);
 			if (t == 0) kb_signal(&S.w_done, k + 1);
 		}

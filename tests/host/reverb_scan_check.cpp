@@ -189,7 +189,7 @@ int main(int argc, char** argv) {
 		{ "mid + late only, damping 5 kHz / 5 kHz",   { 0.0f, 0.0f, 1.0f, 1.0f, 1.0f, 10.f, 0.6f, 0.5f, 1.0f, 0.f } },
 		{ "mid + late only, damping 4 kHz / 4 kHz",   { 0.0f, 0.0f, 1.0f, 1.0f, 1.0f, 10.f, 0.3f, 0.4f, 1.0f, 0.f } },
 	};
-	FILE* dump = argc > 1 ? fopen(argv[1], "wb") : nullptr;                  // A of case 1, for the comparison with the compiled reference
+	FILE* dump = argc > 1 ? fopen(argv[1], "wb") : nullptr;                  // input and A of case 1 (first 8 blocks: [l, r, out l, out r] x 4096), for the comparison with the compiled reference
 	for (size_t ci = 0; ci < sizeof(cases) / sizeof(cases[0]); ci++) {
 		KbFxHdr hA; KbReverb A;
 		memset(&hA, 0, sizeof(hA));
@@ -212,7 +212,7 @@ int main(int argc, char** argv) {
 			reverb_chunked(hC, C, rc.data(), lc.data(), rrc.data(), n, true);
 			exact_same = exact_same && memcmp(la.data(), lb.data(), n * 4) == 0 && memcmp(rra.data(), rrb.data(), n * 4) == 0;
 			worst = std::max(worst, std::max(bar_excess(lc, la), bar_excess(rrc, rra)));
-			if (dump && ci == 1) { fwrite(la.data(), 4, n, dump); fwrite(rra.data(), 4, n, dump); }
+			if (dump && ci == 1 && blk < 8) { fwrite(l.data(), 4, n, dump); fwrite(r.data(), 4, n, dump); fwrite(la.data(), 4, n, dump); fwrite(rra.data(), 4, n, dump); }
 		}
 		exact_same = exact_same && memcmp(ra.data(), rb.data(), ra.size() * 4) == 0;
 		printf("%-46s %8d %22s %22.4f%s\n", cases[ci].name, chunk, exact_same ? "bit-identical" : "DIFFERENT", worst, admitted ? "" : "   (not admitted: lines run the sequential filter)");

@@ -381,3 +381,30 @@ def test_modulated_line_time_parallel_form_equals_frame_sequential_form():
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert " 0 block mismatches, 0 state / ring mismatches" in out.stdout
+
+
+def test_reverb_tolerance_scan_stays_inside_the_parity_bar_on_host(tmp_path):
+    """tests/host/reverb_scan_check.cpp: the arithmetic of the KB_FX_TOLERANCE filter scan (kb_scan.cuh), run lane by lane with g++, keeps
+    Reverb.k inside 1e-5 |r| + 1e-6 peak for every configuration the plan admits, and the chunked read-ahead evaluation with the sequential
+    filter is bit-identical to the frame-by-frame one.  The frame-by-frame output it dumps is compared with the compiled reference (or the
+    port) fed the same input, bit for bit: the yardstick of the check is the reference's own result."""
+    import numpy as np
+    import oracle
+    exe = str(tmp_path / "reverb_scan_check")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-x", "c++",
+                           os.path.join(ROOT, "tests", "host", "reverb_scan_check.cpp"), "-o", exe])
+    dump = str(tmp_path / "a.bin")
+    out = subprocess.run([exe, dump], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "DIFFERENT" not in out.stdout and out.stdout.strip().endswith("ok")
+    d = np.fromfile(dump, np.float32).reshape(8, 4, 4096)             # per block: in l, in r, out l, out r
+    chk = oracle.ref if oracle.ref.available() else oracle.port
+    chk.set_fs(48000)
+    fx = chk.Fx(oracle.FX_REVERB)
+    for c, v in enumerate((0.3, 0.9, 0.4, 0.5, 0.8)):
+        fx.set_control(c, v)
+    for b in range(8):
+        want = fx.process(np.ascontiguousarray(d[b, :2]))
+        assert np.array_equal(want.view(np.uint32), d[b, 2:].view(np.uint32)), f"block {b}: the host check's exact path differs from the reference"
+    fx.close()
+    chk.set_fs(44100)
