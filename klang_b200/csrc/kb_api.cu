@@ -404,11 +404,27 @@ extern "C" int kb_fx_bank_process(kb_fx_bank* b, float* io, int n, unsigned flag
 			const int len = std::min(sub, n - o);
 			if (!seq_only) {
 				if (rv_schedule == 3) {
-					kb_reverb_plan3_kernel<<<ib, 32, 0, b->stream>>>(st, b->d_plan, b->instances);
+					// (the plan of every instance is made inside the kernel by its own CTAs and left in d_plan for the kernels launched behind it)
 					const int tol = (flags & KB_FX_TOLERANCE) ? 1 : 0;
 					// KB_FX_TOLERANCE: instances whose line filters the scan admits run on the tolerance kernel, the others on the exact one
-					if (tol) { kb_reverb3_kernel<1><<<b->instances * 2, KB_RV3_NT_TOL, sizeof(KbRv3Smem), b->stream>>>(b->d_hdr, st, b->d_plan, b->d_rings, d + o, len, n, 0); b->launches++; }
-					kb_reverb3_kernel<0><<<b->instances * 2, KB_RV3_NT, sizeof(KbRv3Smem), b->stream>>>(b->d_hdr, st, b->d_plan, b->d_rings, d + o, len, n, tol);
+					// KB_RV3_TRACE=<file> (measurement aid): per-role, per-chunk clock64() stamps of CTA 0 of every launch, last launch wins
+					static const char* trace_path = getenv("KB_RV3_TRACE");
+					static long long* d_trace = nullptr;
+					const size_t trace_n = (size_t)KB_RV3_TRACE_ROLES * KB_RV3_TRACE_CHUNKS * 2;
+					if (trace_path && !d_trace) { KB_CUDA(cudaMalloc(&d_trace, trace_n * sizeof(long long))); }
+					if (d_trace) KB_CUDA(cudaMemsetAsync(d_trace, 0, trace_n * sizeof(long long), b->stream));
+					if (tol) { kb_reverb3_kernel<1><<<b->instances * 2, KB_RV3_NT_TOL, sizeof(KbRv3Smem), b->stream>>>(b->d_hdr, st, b->d_plan, b->d_rings, d + o, len, n, 0, d_trace); b->launches++; }
+					kb_reverb3_kernel<0><<<b->instances * 2, KB_RV3_NT, sizeof(KbRv3Smem), b->stream>>>(b->d_hdr, st, b->d_plan, b->d_rings, d + o, len, n, tol, tol ? nullptr : d_trace);
+					if (d_trace) {
+						std::vector<long long> tr(trace_n);
+						KB_CUDA(cudaMemcpyAsync(tr.data(), d_trace, trace_n * sizeof(long long), cudaMemcpyDeviceToHost, b->stream));
+						KB_CUDA(cudaStreamSynchronize(b->stream));
+						if (FILE* f = fopen(trace_path, "w")) {
+							for (int r = 0; r < KB_RV3_TRACE_ROLES; r++) for (int k = 0; k < KB_RV3_TRACE_CHUNKS; k++)
+								if (tr[((size_t)r * KB_RV3_TRACE_CHUNKS + k) * 2]) fprintf(f, "%d %d %lld %lld\n", r, k, tr[((size_t)r * KB_RV3_TRACE_CHUNKS + k) * 2], tr[((size_t)r * KB_RV3_TRACE_CHUNKS + k) * 2 + 1]);
+							fclose(f);
+						}
+					}
 					// instances whose live delay spans do not fit in shared memory (fs = 192 kHz) keep the round-1 pipeline (its CTAs exit at once otherwise)
 					kb_reverb_pipe_kernel<<<b->instances * 2, KB_RV2_NT, sizeof(KbRv2Smem), b->stream>>>(b->d_hdr, st, b->d_plan, b->d_rings, d + o, len, n);
 					b->launches++;

@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(KB_PP3_NT) kb_pingpong3_kernel(KbFxHdr* __rest
 				p.right.last_position = (ir2) % SIZE; p.right.last_fraction = fr; p.right.time = dr;
 			}
 		}
-		if (c >= KB_PP3_NSLOT) { kb_wait_ge(&S.f_done, c - KB_PP3_NSLOT + 1); store_chunk(c - KB_PP3_NSLOT); }     // the slot's previous chunk is filtered: store it, the slot is free
+		if (c >= KB_PP3_NSLOT) { kb_wait_ge_group(&S.f_done, c - KB_PP3_NSLOT + 1, warp == 1, 2, 128); store_chunk(c - KB_PP3_NSLOT); }     // the slot's previous chunk is filtered: store it, the slot is free
 		if (t < len) {
 			const float rtick = ra + fr * (rb - ra);                                // right's first read tick          PingPong.k:66
 			ringl[posl] = inl + rtick * gain;                                        // left write
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(KB_PP3_NT) kb_pingpong3_kernel(KbFxHdr* __rest
 		kb_bar_group(1, 128);
 		if (t == 0) kb_signal(&S.p_done, c + 1);
 	}
-	for (int c = max(0, K - KB_PP3_NSLOT); c < K; c++) { kb_wait_ge(&S.f_done, c + 1); store_chunk(c); }
+	for (int c = max(0, K - KB_PP3_NSLOT); c < K; c++) { kb_wait_ge_group(&S.f_done, c + 1, warp == 1, 2, 128); store_chunk(c); }
 	if (t == 0) {
 		p.left.position = (int)(((long long)pl0 + n) % SIZE);
 		p.right.position = (int)(((long long)pr0 + n) % SIZE);

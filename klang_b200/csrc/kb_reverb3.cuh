@@ -36,9 +36,10 @@
 #define KB_RV3_DR 4                           // early-reflection rows (r1) in flight
 #define KB_RV3_ESIZE 21600                    // Stereo::Delay<21600>  Reverb.k:11
 #define KB_RV3_LRCAP 20480                    // floats of shared memory for the live spans of the 8 lines of a side
-#define KB_RV3_NT 512                         // threads, exact mode (16 warps)
-#define KB_RV3_NT_TOL 640                     // threads, tolerance mode (20 warps)
+#define KB_RV3_NT 640                         // threads, exact mode (20 warps)
+#define KB_RV3_NT_TOL 768                     // threads, tolerance mode (24 warps)
 
+struct KbRv3LinePlan { int lag, cap, scan_ok; };
 struct KbRv3Smem {
 	float er[KB_RV3_ESIZE];                   // the early ring of this side, resident for the launch
 	float lr[KB_RV3_LRCAP];                   // the live spans of the 8 feedback lines: line l = a ring of lcap[l] floats at lbase[l]
@@ -56,17 +57,28 @@ struct KbRv3Smem {
 	unsigned long long bar_xin[KB_RV3_DI], bar_res;                 // mbarriers: bulk-copy completion (io chunks; the resident rings)
 	int p_done, f_done, w_done, t_done, e_done;                     // chunks completed per role
 	int f_cnt[2];                                                   // tolerance mode: line-chunks completed, per chunk parity (8 per chunk)
+	KbRv3LinePlan pline[16]; KbFxPlan plan;                         // the plan of this instance, made by the CTA itself
 };
 
-// ---- hand-over primitives
-KB_D void kb_wait_ge(const int* counter, int target) {               // acquire: spin on a shared-memory word, then fence
-	const volatile int* c = counter;
-	while (*c < target) __nanosleep(20);
-	__threadfence_block();
+// ---- hand-over primitives: a progress counter in shared memory, written with st.release.cta by ONE thread of the producing role (after the
+// role's own barrier, which orders the other threads' writes before it) and polled with ld.acquire.cta.  No sequentially-consistent fence
+// (__threadfence_block() is MEMBAR.SC.CTA, which also waits for the thread's outstanding global stores: ~1000 cycles per hand-over here).
+KB_D int kb_ld_acquire(const int* p) {
+	int v;
+	asm volatile("ld.acquire.cta.shared.b32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+	return v;
 }
-KB_D void kb_signal(int* counter, int value) {                       // release: ONE thread, after the role's own barrier
-	__threadfence_block();
-	*(volatile int*)counter = value;
+KB_D void kb_wait_ge(const int* counter, int target) {
+	while (kb_ld_acquire(counter) < target) __nanosleep(48);
+}
+KB_D void kb_signal(int* counter, int value) {
+	asm volatile("st.release.cta.shared.b32 [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(counter)), "r"(value) : "memory");
+}
+KB_D void kb_bar_group(int id, int threads);
+// a multi-warp role waits: its first warp polls, the others sleep at the role's named barrier (no issue slots, no shared-memory polling)
+KB_D void kb_wait_ge_group(const int* counter, int target, bool first_warp, int bar_id, int threads) {
+	if (first_warp) kb_wait_ge(counter, target);
+	asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "r"(threads) : "memory");
 }
 KB_D unsigned kb_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 KB_D void kb_mbar_init(unsigned long long* bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(kb_smem_u32(bar)), "r"(count) : "memory"); }
@@ -95,54 +107,73 @@ KB_D void kb_fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory
 enum { KB_PLAN_SCAN_OK = 2, KB_PLAN_RESIDENT = 4 };
 // shared-memory ring of one line: holds the global ring indices a0 = (read head & ~3) .. write head + one chunk, i.e. lag + 2 LMAX + slack floats
 KB_HD int kb_rv3_line_cap(int lag) { return (lag + 2 * KB_RV3_LMAX + 8 + 3) & ~3; }
-__global__ void kb_reverb_plan3_kernel(const KbReverb* __restrict__ states, KbFxPlan* __restrict__ plan, int instances) {
-	const int inst = blockIdx.x * blockDim.x + threadIdx.x;
-	if (inst >= instances) return;
-	KbReverb& rv = const_cast<KbReverb&>(states[inst]);
+// one line's contribution (any thread), and the combination (one thread)
+KB_D KbRv3LinePlan kb_rv3_plan_line(const KbRvFDelay& fd) {
+	const KbDelay& d = fd.delay;
+	KbRv3LinePlan r;
+	r.lag = d.position - d.last_position; if (r.lag <= 0) r.lag += d.SIZE;      // write head minus read head, in ring samples
+	r.cap = kb_rv3_line_cap(r.lag);
+	r.scan_ok = kb_rv3_scan_admissible(fd.filter) ? 1 : 0;
+	return r;
+}
+KB_D KbFxPlan kb_rv3_plan_combine(const KbRv3LinePlan* lines, const float* times, int count, int esize_l, int esize_r) {
 	int chunk = KB_RV3_LMAX, need[2] = { 0, 0 };
 	bool scan_ok = true;
 	for (int line = 0; line < 16; line++) {
-		const KbRvFDelay& fd = kb_rv_line(rv, line);
-		const KbDelay& d = fd.delay;
-		int lag = d.position - d.last_position; if (lag <= 0) lag += d.SIZE;    // write head minus read head, in ring samples
-		chunk = min(chunk, (lag - 2) / 4);                                      // two ticks per frame, window of chunk k closed by chunk k-2
-		scan_ok = scan_ok && kb_rv3_scan_admissible(fd.filter);
-		need[(line >> 2) & 1] += kb_rv3_line_cap(lag);                          // lines 0-3, 8-11 belong to side 0 (mid[0], late[0]); 4-7, 12-15 to side 1
+		chunk = min(chunk, (lines[line].lag - 2) / 4);                          // two ticks per frame, window of chunk k closed by chunk k-2
+		scan_ok = scan_ok && lines[line].scan_ok;
+		need[(line >> 2) & 1] += lines[line].cap;                               // lines 0-3, 8-11 belong to side 0 (mid[0], late[0]); 4-7, 12-15 to side 1
 	}
 	float tmin = 1e30f;
-	for (int r = 0; r < rv.count; r++) tmin = fminf(tmin, rv.times[r]);
+	for (int r = 0; r < count; r++) tmin = fminf(tmin, times[r]);
 	chunk = min(chunk, (int)tmin - 3);
 	chunk &= ~3;
 	KbFxPlan p;
 	p.chunk = chunk;
-	const bool resident = need[0] <= KB_RV3_LRCAP && need[1] <= KB_RV3_LRCAP && rv.dl.SIZE == KB_RV3_ESIZE && rv.dr.SIZE == KB_RV3_ESIZE;
+	const bool resident = need[0] <= KB_RV3_LRCAP && need[1] <= KB_RV3_LRCAP && esize_l == KB_RV3_ESIZE && esize_r == KB_RV3_ESIZE;
 	p.mode = chunk >= 8 ? (KB_PLAN_PARALLEL | (resident ? KB_PLAN_RESIDENT | (scan_ok ? KB_PLAN_SCAN_OK : 0) : 0)) : KB_PLAN_SEQUENTIAL;
 	p.gain = p.delay = p.dry = 0.f;
-	plan[inst] = p;
+	return p;
+}
+// (stand-alone form: used when the kernels below are not launched, and by tests of the plan itself)
+__global__ void kb_reverb_plan3_kernel(const KbReverb* __restrict__ states, KbFxPlan* __restrict__ plan, int instances) {
+	const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+	if (inst >= instances) return;
+	KbReverb& rv = const_cast<KbReverb&>(states[inst]);
+	KbRv3LinePlan lines[16];
+	for (int line = 0; line < 16; line++) lines[line] = kb_rv3_plan_line(kb_rv_line(rv, line));
+	plan[inst] = kb_rv3_plan_combine(lines, rv.times, rv.count, rv.dl.SIZE, rv.dr.SIZE);
 }
 
 // Biquad::Filter::process (klang.h:5605-5612) over pre-multiplied operands, strictly in order, by ONE thread: per tick
 //   y = b0 x + z0;  z0' = b1 x - a1 y + z1;  z1' = b2 x - a2 y        with q = (b0 x, b1 x, b2 x)
+// Two register sets of 8 ticks used alternately (no copies): while one set is consumed — 8 x 4 dependent operations — the other is loaded, so no
+// shared-memory latency sits on the recurrence.  Rows are padded: reads up to 16 ticks past `ticks` stay inside the row's allocation and are unused.
+#define KB_RV3_TICK(P, O) { O = P.x + z0; z0 = (P.y - a1 * O) + z1; z1 = P.z - a2 * O; }
 KB_D void kb_rv3_filter_row(const float4* __restrict__ q, float* __restrict__ yr, int ticks, float a1, float a2, float& z0, float& z1) {
 	float4* y4 = reinterpret_cast<float4*>(yr);
+	float4 A0 = q[0], A1 = q[1], A2 = q[2], A3 = q[3], A4 = q[4], A5 = q[5], A6 = q[6], A7 = q[7];
+	float4 B0, B1, B2, B3, B4, B5, B6, B7;
 	int f = 0;
-	float4 p0 = q[0], p1 = q[1], p2 = q[2], p3 = q[3];
-	for (; f + 4 <= ticks; f += 4) {
-		float4 n0 = p0, n1 = p1, n2 = p2, n3 = p3;
-		if (f + 8 <= ticks) { n0 = q[f + 4]; n1 = q[f + 5]; n2 = q[f + 6]; n3 = q[f + 7]; }
+	for (; f + 16 <= ticks; f += 16) {
 		float4 o;
-		o.x = p0.x + z0; z0 = (p0.y - a1 * o.x) + z1; z1 = p0.z - a2 * o.x;
-		o.y = p1.x + z0; z0 = (p1.y - a1 * o.y) + z1; z1 = p1.z - a2 * o.y;
-		o.z = p2.x + z0; z0 = (p2.y - a1 * o.z) + z1; z1 = p2.z - a2 * o.z;
-		o.w = p3.x + z0; z0 = (p3.y - a1 * o.w) + z1; z1 = p3.z - a2 * o.w;
-		y4[f >> 2] = o;
-		p0 = n0; p1 = n1; p2 = n2; p3 = n3;
+		B0 = q[f + 8]; B1 = q[f + 9]; B2 = q[f + 10]; B3 = q[f + 11]; B4 = q[f + 12]; B5 = q[f + 13]; B6 = q[f + 14]; B7 = q[f + 15];
+		KB_RV3_TICK(A0, o.x) KB_RV3_TICK(A1, o.y) KB_RV3_TICK(A2, o.z) KB_RV3_TICK(A3, o.w) y4[(f >> 2)] = o;
+		KB_RV3_TICK(A4, o.x) KB_RV3_TICK(A5, o.y) KB_RV3_TICK(A6, o.z) KB_RV3_TICK(A7, o.w) y4[(f >> 2) + 1] = o;
+		A0 = q[f + 16]; A1 = q[f + 17]; A2 = q[f + 18]; A3 = q[f + 19]; A4 = q[f + 20]; A5 = q[f + 21]; A6 = q[f + 22]; A7 = q[f + 23];
+		KB_RV3_TICK(B0, o.x) KB_RV3_TICK(B1, o.y) KB_RV3_TICK(B2, o.z) KB_RV3_TICK(B3, o.w) y4[(f >> 2) + 2] = o;
+		KB_RV3_TICK(B4, o.x) KB_RV3_TICK(B5, o.y) KB_RV3_TICK(B6, o.z) KB_RV3_TICK(B7, o.w) y4[(f >> 2) + 3] = o;
+	}
+	if (f + 8 <= ticks) {                                            // (set A holds ticks f .. f+7)
+		float4 o;
+		KB_RV3_TICK(A0, o.x) KB_RV3_TICK(A1, o.y) KB_RV3_TICK(A2, o.z) KB_RV3_TICK(A3, o.w) y4[(f >> 2)] = o;
+		KB_RV3_TICK(A4, o.x) KB_RV3_TICK(A5, o.y) KB_RV3_TICK(A6, o.z) KB_RV3_TICK(A7, o.w) y4[(f >> 2) + 1] = o;
+		f += 8;
 	}
 	for (; f < ticks; f++) {
 		const float4 p = q[f];
-		const float y = p.x + z0;
-		z0 = (p.y - a1 * y) + z1;
-		z1 = p.z - a2 * y;
+		float y;
+		KB_RV3_TICK(p, y)
 		yr[f] = y;
 	}
 }
@@ -187,40 +218,65 @@ KB_D void kb_rv3_scan_chunk(const KbRv3ScanCoef& c, const float* __restrict__ ri
 	z0 = __shfl_sync(0xffffffffu, s0, last); z1 = __shfl_sync(0xffffffffu, s1, last);
 }
 
-// role of a warp.  Exact mode (16 warps): the filter warp F is ALONE on SM sub-partition 0 (warps 4, 8, 12 exit at once).
-// Tolerance mode (20 warps): the early cascade E — now the longest serial chain — is alone on sub-partition 1 (warps 5, 9, 13, 17 exit).
+// role of a warp.  The warp scheduler of an SM sub-partition (warp id mod 4) favours HIGHER warp ids, so a serial role whose latency bounds the
+// kernel is either alone on its sub-partition or holds the highest id there.
+// Exact mode (20 warps): sub-partition 0 holds only the two serial chains — the filter warp F (highest id) and the early cascade E; warps 4, 8, 12
+//   exit at once.  The parallel roles are spread evenly over sub-partitions 1-3, the roles of the F -> W -> P -> F loop (W, P) above the taps (T).
+// Tolerance mode (24 warps): E — now the longest serial chain — is alone on sub-partition 1; the 8 scan warps S hold the highest ids of the others.
 enum { KB_RV3_IDLE = 0, KB_RV3_F, KB_RV3_E, KB_RV3_M, KB_RV3_P, KB_RV3_T, KB_RV3_W, KB_RV3_S };
 template <int MODE> KB_D void kb_rv3_role(int warp, int& role, int& slot) {
 	if (MODE == 0) {
-		//                       0         1         2         3         4            5         6         7
-		const int r[16] = { KB_RV3_F, KB_RV3_E, KB_RV3_M, KB_RV3_P, KB_RV3_IDLE, KB_RV3_T, KB_RV3_P, KB_RV3_P,
-		                    KB_RV3_IDLE, KB_RV3_T, KB_RV3_W, KB_RV3_W, KB_RV3_IDLE, KB_RV3_T, KB_RV3_W, KB_RV3_IDLE };
-		const int q[16] = { 0, 0, 0, 0, 0, 0, 1, 2,  0, 1, 0, 1, 0, 2, 2, 0 };       // index of the warp inside its role
-		role = r[warp & 15]; slot = q[warp & 15];
-	} else {
-		const int r[20] = { KB_RV3_S, KB_RV3_E, KB_RV3_M, KB_RV3_S, KB_RV3_S, KB_RV3_IDLE, KB_RV3_S, KB_RV3_S,
-		                    KB_RV3_S, KB_RV3_IDLE, KB_RV3_S, KB_RV3_S, KB_RV3_T, KB_RV3_IDLE, KB_RV3_T, KB_RV3_T,
-		                    KB_RV3_W, KB_RV3_IDLE, KB_RV3_W, KB_RV3_W };
-		const int q[20] = { 0, 0, 0, 1, 2, 0, 3, 4,  5, 0, 6, 7, 0, 0, 1, 2,  0, 0, 1, 2 };
+		//                       0            1            2         3            (sub-partition = column)
+		const int r[20] = { KB_RV3_E,    KB_RV3_IDLE, KB_RV3_M, KB_RV3_IDLE,
+		                    KB_RV3_IDLE, KB_RV3_T,    KB_RV3_T, KB_RV3_T,
+		                    KB_RV3_IDLE, KB_RV3_P,    KB_RV3_P, KB_RV3_P,
+		                    KB_RV3_IDLE, KB_RV3_W,    KB_RV3_W, KB_RV3_W,
+		                    KB_RV3_F,    KB_RV3_W,    KB_RV3_W, KB_RV3_IDLE };
+		const int q[20] = { 0, 0, 0, 0,  0, 0, 1, 2,  0, 0, 1, 2,  0, 0, 1, 2,  0, 3, 4, 0 };       // index of the warp inside its role
 		role = r[warp % 20]; slot = q[warp % 20];
+	} else {
+		const int r[24] = { KB_RV3_T, KB_RV3_IDLE, KB_RV3_M, KB_RV3_T,
+		                    KB_RV3_W, KB_RV3_IDLE, KB_RV3_T, KB_RV3_W,
+		                    KB_RV3_W, KB_RV3_IDLE, KB_RV3_W, KB_RV3_W,
+		                    KB_RV3_S, KB_RV3_IDLE, KB_RV3_S, KB_RV3_S,
+		                    KB_RV3_S, KB_RV3_IDLE, KB_RV3_S, KB_RV3_S,
+		                    KB_RV3_S, KB_RV3_E,    KB_RV3_S, KB_RV3_IDLE };
+		const int q[24] = { 0, 0, 0, 2,  0, 0, 1, 2,  3, 0, 1, 4,  0, 0, 3, 6,  1, 0, 4, 7,  2, 0, 5, 0 };
+		role = r[warp % 24]; slot = q[warp % 24];
 	}
 }
 
+// Measurement aid (KB_RV3_TRACE=<file>, tools/rv3_trace.py): CTA 0 records clock64() when each role starts (after its waits) and ends the work of
+// each chunk: trace[((role * KB_RV3_TRACE_CHUNKS + chunk) * 2 + phase)].  nullptr in normal runs.
+#define KB_RV3_TRACE_CHUNKS 64
+#define KB_RV3_TRACE_ROLES 16
+#define KB_RV3_TR(role_, k_, phase_) do { if (trace && blockIdx.x == 0 && (k_) < KB_RV3_TRACE_CHUNKS) trace[(((role_) * KB_RV3_TRACE_CHUNKS + (k_)) * 2 + (phase_))] = clock64(); } while (0)
 // skip_scan_ok (exact kernel only): this launch leaves the instances the scan admits to the tolerance kernel launched beside it
 template <int MODE>
-__global__ void __launch_bounds__(MODE == 0 ? KB_RV3_NT : KB_RV3_NT_TOL) kb_reverb3_kernel(const KbFxHdr* __restrict__ hdrs, KbReverb* __restrict__ states, const KbFxPlan* __restrict__ plan,
-                                                                                           float* __restrict__ rings, float* __restrict__ io, int n, int stride, int skip_scan_ok) {
+__global__ void __launch_bounds__(MODE == 0 ? KB_RV3_NT : KB_RV3_NT_TOL) kb_reverb3_kernel(const KbFxHdr* __restrict__ hdrs, KbReverb* __restrict__ states, KbFxPlan* __restrict__ plan,
+                                                                                           float* __restrict__ rings, float* __restrict__ io, int n, int stride, int skip_scan_ok, long long* __restrict__ trace) {
 	extern __shared__ __align__(128) unsigned char kb_rv3_smem_raw[];
 	KbRv3Smem& S = *reinterpret_cast<KbRv3Smem*>(kb_rv3_smem_raw);
 	const int inst = blockIdx.x >> 1, side = blockIdx.x & 1;
-	const KbFxPlan pl = plan[inst];
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	KbReverb& rv = states[inst];
+	// the plan of the instance, made here (no plan launch): 16 threads read one line each, thread 0 combines.  It depends only on quantities a
+	// block leaves unchanged (read-to-write distances, filter coefficients, tap times), so both CTAs of an instance — and the kernels launched
+	// after this one, which read plan[inst] — agree even when one side has already finished.
+	if (tid < KB_RV_MAXREFL) { S.times[tid] = rv.times[tid]; S.gg[tid] = side ? rv.gr[tid] : rv.gl[tid]; }
+	if (tid >= 32 && tid < 48) S.pline[tid - 32] = kb_rv3_plan_line(kb_rv_line(rv, tid - 32));
+	__syncthreads();
+	if (tid == 0) {
+		S.plan = kb_rv3_plan_combine(S.pline, S.times, rv.count, rv.dl.SIZE, rv.dr.SIZE);
+		if (side == 0) plan[inst] = S.plan;
+	}
+	__syncthreads();
+	const KbFxPlan pl = S.plan;
 	if (!(pl.mode & KB_PLAN_PARALLEL) || !(pl.mode & KB_PLAN_RESIDENT)) return;
 	if (MODE == 1 && !(pl.mode & KB_PLAN_SCAN_OK)) return;          // (the exact kernel launched beside this one takes those)
 	if (MODE == 0 && (pl.mode & KB_PLAN_SCAN_OK) && skip_scan_ok) return;
-	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	int role, rslot;
 	kb_rv3_role<MODE>(warp, role, rslot);
-	KbReverb& rv = states[inst];
 	const KbControl* c = hdrs[inst].controls;
 	float* X = io + ((size_t)inst * 2 + side) * stride;
 	const int Lc = pl.chunk, K = (n + Lc - 1) / Lc;
@@ -230,7 +286,6 @@ __global__ void __launch_bounds__(MODE == 0 ? KB_RV3_NT : KB_RV3_NT_TOL) kb_reve
 	auto chunk_len = [&](int k) { return min(Lc, n - k * Lc); };
 
 	// ---- prologue: per-line geometry and coefficients, mbarriers, counters
-	if (tid < KB_RV_MAXREFL) { S.times[tid] = rv.times[tid]; S.gg[tid] = side ? rv.gr[tid] : rv.gl[tid]; }
 	if (tid < 8) {
 		const KbRvFDelay& d = kb_rv_side_line(rv, side, tid);
 		S.carry[0][tid] = d.in; S.carry[1][tid] = d.in;
@@ -285,7 +340,7 @@ __global__ void __launch_bounds__(MODE == 0 ? KB_RV3_NT : KB_RV3_NT_TOL) kb_reve
 		};
 		for (int k = 0; k < KB_RV3_DI && k < K; k++) issue_xin(k);
 		for (int k = KB_RV3_DI; k < K; k++) {
-			kb_wait_ge(&S.w_done, k - KB_RV3_DI + 1);                // W (the last reader of an io chunk) is done with chunk k - DI: its slot is free
+			kb_wait_ge(&S.w_done, k - KB_RV3_DI + 2);                // W reads an io chunk BEHIND its signal: chunk k - DI is done with once chunk k - DI + 1 is signalled
 			issue_xin(k);
 		}
 		return;
@@ -302,12 +357,14 @@ __global__ void __launch_bounds__(MODE == 0 ? KB_RV3_NT : KB_RV3_NT_TOL) kb_reve
 			if (s < K) kb_mbar_wait(&S.bar_xin[s % KB_RV3_DI], (unsigned)(s / KB_RV3_DI) & 1u);
 			if (s >= 1) kb_wait_ge(&S.t_done, s - KB_RV3_DE);        // xf slot (s - 1) % DE was last read by T(s - 1 - DE)
 			const int k = s - lane;
+			if (lane == 0) KB_RV3_TR(KB_RV3_E, s, 0);
 			if (lane < 2 && k >= 0 && k < K) {
 				const float* xi = lane == 0 ? S.xin[k % KB_RV3_DI] : S.ylp[k & 1];
 				float* xo = lane == 0 ? S.ylp[k & 1] : S.xf[k % KB_RV3_DE];
 				kb_rv2_filter_row(xi, xo, chunk_len(k), b0, b1, b2, a1, a2, z0, z1);
 			}
 			__syncwarp();
+			if (lane == 0) KB_RV3_TR(KB_RV3_E, s, 1);
 			if (lane == 0) kb_signal(&S.e_done, s + 1);
 		}
 		if (lane == 0) { rv.lpf[side].z0 = z0; rv.lpf[side].z1 = z1; }
@@ -323,8 +380,9 @@ __global__ void __launch_bounds__(MODE == 0 ? KB_RV3_NT : KB_RV3_NT_TOL) kb_reve
 		int ebase = epos0;
 		for (int k = 0; k < K; k++) {
 			const int L = chunk_len(k);
-			kb_wait_ge(&S.e_done, k + 2);                            // xf(k) complete
-			kb_wait_ge(&S.w_done, k - KB_RV3_DR + 1);                // r1 slot k % DR was read by W(k - DR)
+			if (rslot == 0) { kb_wait_ge(&S.e_done, k + 2); kb_wait_ge(&S.w_done, k - KB_RV3_DR + 1); }    // xf(k) complete; r1 slot k % DR was read by W(k - DR)
+			kb_bar_group(2, 96);
+			if (tt == 0) KB_RV3_TR(KB_RV3_T, k, 0);
 			if (tt < L) {
 				int idx = ebase + tt; if (idx >= KB_RV3_ESIZE) idx -= KB_RV3_ESIZE;
 				const float v = S.xf[k % KB_RV3_DE][tt];
@@ -333,22 +391,30 @@ __global__ void __launch_bounds__(MODE == 0 ? KB_RV3_NT : KB_RV3_NT_TOL) kb_reve
 				int pos = idx + 1; if (pos >= KB_RV3_ESIZE) pos -= KB_RV3_ESIZE;      // position after this frame's write
 				const float posf = (float)(pos - 1);
 				float acc = 0.f;
-				for (int d0 = 0; d0 < count; d0 += 4) {
-					float va[4], vb[4], fr[4];
+				// batches of 5 taps, branch-free: a tap index past `count` is clamped for the loads and only its accumulation is predicated off, so the
+				// address chains (float subtract, truncation, two dependent shared-memory gathers) of a batch overlap
+				#pragma unroll
+				for (int d0 = 0; d0 < KB_RV_MAXREFL; d0 += 5) {
+					float va[5], vb[5], fr[5], gn[5];
 					#pragma unroll
-					for (int j = 0; j < 4; j++) if (d0 + j < count) {
-						float read = posf - S.times[d0 + j]; if (read < 0.f) read += KB_RV3_ESIZE;      // Stereo::Delay::tap(float)  klang.h:4668-4681
+					for (int j = 0; j < 5; j++) {
+						const int d = min(d0 + j, count - 1);
+						float read = posf - S.times[d]; if (read < 0.f) read += KB_RV3_ESIZE;      // Stereo::Delay::tap(float)  klang.h:4668-4681
 						const float fl = floorf(read); fr[j] = read - fl;
 						const int ii = (int)read, jj = (ii == KB_RV3_ESIZE - 1) ? 0 : ii + 1;
-						va[j] = S.er[ii]; vb[j] = S.er[jj];
+						va[j] = S.er[ii]; vb[j] = S.er[jj]; gn[j] = S.gg[d];
 					}
 					#pragma unroll
-					for (int j = 0; j < 4; j++) if (d0 + j < count) acc += (va[j] * (1.f - fr[j]) + vb[j] * fr[j]) * S.gg[d0 + j];   // out += delay(times[d]) * gains[d]  Reverb.k:89-90
+					for (int j = 0; j < 5; j++) {
+						const float term = (va[j] * (1.f - fr[j]) + vb[j] * fr[j]) * gn[j];          // out += delay(times[d]) * gains[d]  Reverb.k:89-90
+						if (d0 + j < count) acc += term;
+					}
 				}
 				S.r1[k % KB_RV3_DR][tt] = acc;
 			}
 			ebase += L; if (ebase >= KB_RV3_ESIZE) ebase -= KB_RV3_ESIZE;
 			kb_bar_group(2, 96);
+			if (tt == 0) KB_RV3_TR(KB_RV3_T, k, 1);
 			if (tt == 0) kb_signal(&S.t_done, k + 1);
 		}
 		if (tt == 0) ed.position = (int)(((long long)epos0 + n) % KB_RV3_ESIZE);
@@ -357,6 +423,7 @@ __global__ void __launch_bounds__(MODE == 0 ? KB_RV3_NT : KB_RV3_NT_TOL) kb_reve
 
 	if (role == KB_RV3_P) {
 		// ================================================================ P (exact mode): ring windows -> Delay::process interpolation -> pre-multiplied operands
+		// thread pt owns ticks pt and pt + 96 of every line: all 32 gathers of a chunk are issued before the first of them is consumed
 		const int pt = rslot * 32 + lane;
 		kb_mbar_wait(&S.bar_res, 0u);
 		int rb[8];                                                   // index of the read head's sample in each line's shared-memory ring
@@ -364,22 +431,33 @@ __global__ void __launch_bounds__(MODE == 0 ? KB_RV3_NT : KB_RV3_NT_TOL) kb_reve
 		for (int l = 0; l < 8; l++) rb[l] = S.lro[l];
 		for (int k = 0; k < K; k++) {
 			const int ticks = 2 * chunk_len(k), sl = k & 1;
-			kb_wait_ge(&S.w_done, k - 1);                            // chunks 0 .. k-2 written: the windows of chunk k are complete, xq slot k & 1 is free
+			kb_wait_ge_group(&S.w_done, k - 1, rslot == 0, 1, 96);   // chunks 0 .. k-2 written: the windows of chunk k are complete, xq slot k & 1 is free
+			if (pt == 0) KB_RV3_TR(KB_RV3_P, k, 0);
+			const int tk1 = pt + 96;
+			const bool has1 = tk1 < ticks;
+			float xa[8][2], xb[8][2];
 			#pragma unroll
 			for (int l = 0; l < 8; l++) {
 				const float* ring = &S.lr[S.lbase[l]];
 				const int cap = S.lcap[l];
-				const float fr = S.frac[l], b0 = S.b0[l], b1 = S.b1[l], b2 = S.b2[l];
-				for (int tk = pt; tk < ticks; tk += 96) {
-					int i = rb[l] + tk; if (i >= cap) i -= cap;
-					int j = i + 1; if (j >= cap) j -= cap;
-					const float xa = ring[i], xb = ring[j];
-					const float x = xa + fr * (xb - xa);                 // Delay::process  klang.h:3461-3473
-					S.xq[sl][l][tk] = make_float4(b0 * x, b1 * x, b2 * x, 0.f);
-				}
+				int i = rb[l] + pt; if (i >= cap) i -= cap;
+				int j = i + 1; if (j >= cap) j -= cap;
+				xa[l][0] = ring[i]; xb[l][0] = ring[j];
+				i = rb[l] + (has1 ? tk1 : pt); if (i >= cap) i -= cap;
+				j = i + 1; if (j >= cap) j -= cap;
+				xa[l][1] = ring[i]; xb[l][1] = ring[j];
 				rb[l] += ticks; if (rb[l] >= cap) rb[l] -= cap;
 			}
+			#pragma unroll
+			for (int l = 0; l < 8; l++) {
+				const float fr = S.frac[l], b0 = S.b0[l], b1 = S.b1[l], b2 = S.b2[l];
+				const float x0 = xa[l][0] + fr * (xb[l][0] - xa[l][0]);          // Delay::process  klang.h:3461-3473
+				const float x1 = xa[l][1] + fr * (xb[l][1] - xa[l][1]);
+				if (pt < ticks) S.xq[sl][l][pt] = make_float4(b0 * x0, b1 * x0, b2 * x0, 0.f);
+				if (has1) S.xq[sl][l][tk1] = make_float4(b0 * x1, b1 * x1, b2 * x1, 0.f);
+			}
 			kb_bar_group(1, 96);
+			if (pt == 0) KB_RV3_TR(KB_RV3_P, k, 1);
 			if (pt == 0) kb_signal(&S.p_done, k + 1);
 		}
 		return;
@@ -391,8 +469,10 @@ __global__ void __launch_bounds__(MODE == 0 ? KB_RV3_NT : KB_RV3_NT_TOL) kb_reve
 		if (lane < 8) { const KbBiquad& f = kb_rv_side_line(rv, side, lane).filter; z0 = f.z0; z1 = f.z1; a1 = f.a1; a2 = f.a2; }
 		for (int k = 0; k < K; k++) {
 			kb_wait_ge(&S.p_done, k + 1);
+			if (lane == 0) KB_RV3_TR(KB_RV3_F, k, 0);
 			if (lane < 8) kb_rv3_filter_row(S.xq[k & 1][lane], S.y[k & 1][lane], 2 * chunk_len(k), a1, a2, z0, z1);
 			__syncwarp();
+			if (lane == 0) KB_RV3_TR(KB_RV3_F, k, 1);
 			if (lane == 0) kb_signal(&S.f_done, k + 1);
 		}
 		if (lane < 8) { KbBiquad& f = kb_rv_side_line(rv, side, lane).filter; f.z0 = z0; f.z1 = z1; }
@@ -412,83 +492,112 @@ __global__ void __launch_bounds__(MODE == 0 ? KB_RV3_NT : KB_RV3_NT_TOL) kb_reve
 		kb_mbar_wait(&S.bar_res, 0u);
 		for (int k = 0; k < K; k++) {
 			const int sl = k & 1, ticks = 2 * chunk_len(k);
-			kb_wait_ge(&S.w_done, k - 1);                            // the window of chunk k is complete, y slot k & 1 is free
+			kb_wait_ge_group(&S.w_done, k - 1, l == 0, 4, 256);      // the window of chunk k is complete, y slot k & 1 is free
+			if (lane == 0) KB_RV3_TR(8 + l, k, 0);
 			kb_rv3_scan_chunk(sc, ring, cap, rb, fr, ticks, S.y[sl][l], z0, z1, lane);
 			rb += ticks; if (rb >= cap) rb -= cap;
 			__syncwarp();
-			if (lane == 0) { __threadfence_block(); atomicAdd(&S.f_cnt[sl], 1); }       // chunk k is complete when its parity's count reaches 8 (k / 2 + 1)
+			if (lane == 0) KB_RV3_TR(8 + l, k, 1);
+			if (lane == 0) asm volatile("red.release.cta.shared.add.s32 [%0], 1;" :: "r"(kb_smem_u32(&S.f_cnt[sl])) : "memory");   // chunk k is complete when its parity's count reaches 8 (k / 2 + 1)
 		}
 		if (lane == 0) { KbBiquad& f = kb_rv_side_line(rv, side, l).filter; f.z0 = z0; f.z1 = z1; }
 		return;
 	}
 
-	// ==================================================================== W: FDN matrix, ring writes, mid -> late, output mix (Reverb.k:152-169, 212-231, 272), thread = frame
+	// ==================================================================== W: FDN matrix, ring writes, mid -> late, output mix (Reverb.k:152-169, 212-231, 272)
+	// thread = (frame t, stage): stage 0 = mid, 1 = late (5 warps: 2 x 80 threads).  Both stages of a frame are independent once the filter outputs
+	// are known: late's input r2 is the in-order sum of mid's second-tick outputs, which the stage-1 thread forms itself (same expression, same bits).
+	// The shared-memory ring writes — all that the next windows wait for — come first and are signalled at once; the write-through to the global
+	// rings and the output mix follow behind the signal.
 	{
-		const int t = rslot * 32 + lane;
+		const int wt = rslot * 32 + lane;
+		const int stage = wt >= KB_RV3_LMAX ? 1 : 0, t = wt - stage * KB_RV3_LMAX, base = stage * 4;
 		const float dry = c[0].value, wet = side == 0 ? c[4].value : 0.f;        // Reverb.k:272 (Q7): the right wet gain is the literal 0
 		const float cE = c[1].value, cM = c[2].value, cL = c[3].value;
 		const float M[4][4] = { { 0, 1, 1, -1 }, { -1, 0, -1, 1 }, { -1, 1, 0, -1 }, { 1, -1, 1, 0 } };      // Reverb.k:158-161
-		int wp[8], ws[8];                                            // write head of each line: in its global ring, in its shared-memory ring
+		int wp[4], ws[4], size[4], cap[4];                           // the four lines of this thread's stage: write head in the global / shared-memory ring, sizes
+		float* ring[4]; float* sring[4]; float gain[4], gmid[4];
 		#pragma unroll
-		for (int l = 0; l < 8; l++) { wp[l] = S.wpos0[l]; ws[l] = S.lwo[l]; if (ws[l] >= S.lcap[l]) ws[l] -= S.lcap[l]; }
+		for (int q = 0; q < 4; q++) {
+			const int l = base + q;
+			wp[q] = S.wpos0[l]; size[q] = S.lsize[l]; cap[q] = S.lcap[l];
+			ws[q] = S.lwo[l]; if (ws[q] >= cap[q]) ws[q] -= cap[q];
+			ring[q] = rings + S.lring[l]; sring[q] = &S.lr[S.lbase[l]];
+			gain[q] = S.gain[l]; gmid[q] = S.gain[q];
+		}
 		kb_mbar_wait(&S.bar_res, 0u);                                // (the resident spans must have landed before this role writes behind them)
 		int cpar = 0;
 		for (int k = 0; k < K; k++, cpar ^= 1) {
 			const int L = chunk_len(k), sl = k & 1;
-			if (MODE == 1) kb_wait_ge(&S.f_cnt[sl], 8 * ((k >> 1) + 1)); else kb_wait_ge(&S.f_done, k + 1);
-			kb_wait_ge(&S.t_done, k + 1);
-			if (t < L) {
-				const float r1 = S.r1[k % KB_RV3_DR][t];
-				float in = r1, r2 = 0.f, r3 = 0.f;
+			if (rslot == 0) {
+				if (MODE == 1) kb_wait_ge(&S.f_cnt[sl], 8 * ((k >> 1) + 1)); else kb_wait_ge(&S.f_done, k + 1);
+				kb_wait_ge(&S.t_done, k + 1);
+			}
+			kb_bar_group(3, 160);
+			if (wt == 0) KB_RV3_TR(KB_RV3_W, k, 0);
+			float fb[4], r1 = 0.f, r2 = 0.f, sum = 0.f, cv[4];
+			int w0[4];
+			const bool on = t < L;
+			if (on) {
+				r1 = S.r1[k % KB_RV3_DR][t];
+				float dv[4], sv[4];
 				#pragma unroll
-				for (int stage = 0; stage < 2; stage++) {
-					const int base = stage * 4;
-					float dv[4], sv[4];
-					#pragma unroll
-					for (int j = 0; j < 4; j++) {
-						const float2 yy = *reinterpret_cast<const float2*>(&S.y[sl][base + j][2 * t]);
-						dv[j] = yy.x * S.gain[base + j];                         // FilteredDelay::process  Reverb.k:130-132
-						sv[j] = yy.y * S.gain[base + j];
-					}
-					float sum = sv[0];
-					sum = sum + sv[1];
-					sum = sum + sv[2];
-					sum = sum + sv[3];
-					#pragma unroll
-					for (int q = 0; q < 4; q++) {
-						// feedback * delays + in, row q with its literal 0 / +-1 products (Reverb.k:158-163, klang.h:1446-1470)
-						const float fb = (M[q][0] * dv[0] + M[q][1] * dv[1] + M[q][2] * dv[2] + M[q][3] * dv[3]) + in;
-						const int size = S.lsize[base + q], cap = S.lcap[base + q];
-						float* ring = rings + S.lring[base + q];
-						float* sring = &S.lr[S.lbase[base + q]];
-						int w0 = wp[base + q] + 2 * t; if (w0 >= size) w0 -= size;
-						int s0 = ws[base + q] + 2 * t; if (s0 >= cap) s0 -= cap;
-						int wa = w0 + 1; if (wa >= size) wa -= size;
-						int sa = s0 + 1; if (sa >= cap) sa -= cap;
-						ring[wa] = fb; sring[sa] = fb;                           // second tick of this frame writes fb
-						if (t + 1 < L) {                                         // = first tick of the next frame
-							int wb = w0 + 2; if (wb >= size) wb -= size;
-							int sb = s0 + 2; if (sb >= cap) sb -= cap;
-							ring[wb] = fb; sring[sb] = fb;
-						} else S.carry[cpar ^ 1][base + q] = fb;
-						if (t == 0) { const float cv = S.carry[cpar][base + q]; ring[w0] = cv; sring[s0] = cv; }
-					}
-					if (stage == 0) { r2 = sum; in = sum; } else r3 = sum;
+				for (int j = 0; j < 4; j++) {
+					const float2 yy = *reinterpret_cast<const float2*>(&S.y[sl][base + j][2 * t]);
+					dv[j] = yy.x * gain[j];                                      // FilteredDelay::process  Reverb.k:130-132
+					sv[j] = yy.y * gain[j];
 				}
-				const float refl = (r1 * cE + r2 * cM) + r3 * cL;
-				X[(size_t)k * Lc + t] = S.xin[k % KB_RV3_DI][t] * dry + refl * wet;      // Reverb.k:272
+				sum = sv[0];
+				sum = sum + sv[1];
+				sum = sum + sv[2];
+				sum = sum + sv[3];
+				float in = r1;
+				if (stage == 1) {                                            // late's input = mid's output of this frame
+					r2 = S.y[sl][0][2 * t + 1] * gmid[0];
+					r2 = r2 + S.y[sl][1][2 * t + 1] * gmid[1];
+					r2 = r2 + S.y[sl][2][2 * t + 1] * gmid[2];
+					r2 = r2 + S.y[sl][3][2 * t + 1] * gmid[3];
+					in = r2;
+				}
+				#pragma unroll
+				for (int q = 0; q < 4; q++) {
+					// feedback * delays + in, row q with its literal 0 / +-1 products (Reverb.k:158-163, klang.h:1446-1470)
+					fb[q] = (M[q][0] * dv[0] + M[q][1] * dv[1] + M[q][2] * dv[2] + M[q][3] * dv[3]) + in;
+					int s0 = ws[q] + 2 * t; if (s0 >= cap[q]) s0 -= cap[q];
+					int sa = s0 + 1; if (sa >= cap[q]) sa -= cap[q];
+					sring[q][sa] = fb[q];                                        // second tick of this frame writes fb
+					if (t + 1 < L) { int sb = s0 + 2; if (sb >= cap[q]) sb -= cap[q]; sring[q][sb] = fb[q]; }   // = first tick of the next frame
+					else S.carry[cpar ^ 1][base + q] = fb[q];
+					if (t == 0) { cv[q] = S.carry[cpar][base + q]; sring[q][s0] = cv[q]; }
+				}
+			}
+			kb_bar_group(3, 160);
+			if (wt == 0) { KB_RV3_TR(KB_RV3_W, k, 1); kb_signal(&S.w_done, k + 1); }
+			// ---- behind the signal: write-through to the global rings (read again only by a later launch) and the output
+			if (on) {
+				#pragma unroll
+				for (int q = 0; q < 4; q++) {
+					w0[q] = wp[q] + 2 * t; if (w0[q] >= size[q]) w0[q] -= size[q];
+					int wa = w0[q] + 1; if (wa >= size[q]) wa -= size[q];
+					ring[q][wa] = fb[q];
+					if (t + 1 < L) { int wb = w0[q] + 2; if (wb >= size[q]) wb -= size[q]; ring[q][wb] = fb[q]; }
+					if (t == 0) ring[q][w0[q]] = cv[q];
+				}
+				if (stage == 1) {
+					const float refl = (r1 * cE + r2 * cM) + sum * cL;
+					X[(size_t)k * Lc + t] = S.xin[k % KB_RV3_DI][t] * dry + refl * wet;      // Reverb.k:272
+				}
 			}
 			#pragma unroll
-			for (int l = 0; l < 8; l++) {
-				wp[l] += 2 * L; if (wp[l] >= S.lsize[l]) wp[l] -= S.lsize[l];
-				ws[l] += 2 * L; if (ws[l] >= S.lcap[l]) ws[l] -= S.lcap[l];
+			for (int q = 0; q < 4; q++) {
+				wp[q] += 2 * L; if (wp[q] >= size[q]) wp[q] -= size[q];
+				ws[q] += 2 * L; if (ws[q] >= cap[q]) ws[q] -= cap[q];
 			}
-			kb_bar_group(3, 96);
-			if (t == 0) kb_signal(&S.w_done, k + 1);
 		}
-		if (t < 8) {
-			KbRvFDelay& d = kb_rv_side_line(rv, side, t);
-			d.in = S.carry[cpar][t];
+		kb_bar_group(3, 160);
+		if (wt < 8) {
+			KbRvFDelay& d = kb_rv_side_line(rv, side, wt);
+			d.in = S.carry[cpar][wt];
 			d.delay.position = (int)(((long long)d.delay.position + 2LL * n) % d.delay.SIZE);
 			d.delay.last_position = (int)(((long long)d.delay.last_position + 2LL * n) % d.delay.SIZE);
 		}

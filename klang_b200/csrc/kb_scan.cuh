@@ -35,12 +35,18 @@ KB_HD float kb_fma(float a, float b, float c) {
 	return fmaf(a, b, c);
 #endif
 }
-// `cnt` ticks of one lane from state (z0, z1); y (if not null) receives the outputs
+// `cnt` <= KB_RV3_SCAN_P ticks of one lane from state (z0, z1); y (if not null) receives the outputs.  Fully unrolled with a predicate per tick, so x
+// and y stay in registers.
 KB_HD void kb_rv3_scan_run(const KbRv3ScanCoef& c, const float* x, int cnt, float& z0, float& z1, float* y) {
-	for (int j = 0; j < cnt; j++) {
-		const float o = kb_fma(c.b0, x[j], z0);
-		z0 = kb_fma(c.b1, x[j], kb_fma(-c.a1, o, z1));
-		z1 = kb_fma(c.b2, x[j], -c.a2 * o);
-		if (y) y[j] = o;
+#ifdef __CUDA_ARCH__
+	#pragma unroll
+#endif
+	for (int j = 0; j < KB_RV3_SCAN_P; j++) {
+		if (j < cnt) {
+			const float o = kb_fma(c.b0, x[j], z0);
+			z0 = kb_fma(c.b1, x[j], kb_fma(-c.a1, o, z1));
+			z1 = kb_fma(c.b2, x[j], -c.a2 * o);
+			if (y) y[j] = o;
+		}
 	}
 }
