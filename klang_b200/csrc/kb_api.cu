@@ -72,6 +72,7 @@ struct kb_fx_bank : kb_bank_base {
 	KbFxHdr* d_hdr = nullptr; unsigned char* d_state = nullptr; float* d_rings = nullptr; KbFxPlan* d_plan = nullptr; void* d_sync = nullptr; int epoch = 0; std::vector<KbFxPlan> plan_cache;
 	bool device_writes_controls = false;
 	unsigned last_flags = 0; int last_schedule = 0;             // flags / Reverb.k schedule of the last process() call
+	bool rv_all_resident = false;                               // Reverb.k: every instance runs on kb_reverb3_kernel (no fallback launches needed)
 	template <class T> T& st(int i) { return *reinterpret_cast<T*>(state.data() + (size_t)i * state_bytes); }
 };
 
@@ -277,6 +278,16 @@ static int fx_prepare(kb_fx_bank* b) {
 			int rc = fx_fetch(b); if (rc) return rc;
 			for (int i = 0; i < b->instances; i++) kb_reverb_prepare(b->fs, b->hdr[i], b->st<KbReverb>(i));
 			b->dirty = true;
+			// the schedule of an instance depends only on what prepare() sets (read-to-write distances, damping coefficients, tap times): evaluate
+			// the kernel's own plan on the mirror, so the fallback kernels are launched only for banks that need them
+			b->rv_all_resident = true;
+			for (int i = 0; i < b->instances; i++) {
+				const KbReverb& rv = b->st<KbReverb>(i);
+				KbRv3LinePlan lines[16];
+				for (int line = 0; line < 16; line++) lines[line] = kb_rv3_plan_line((line < 8 ? rv.mid[line >> 2] : rv.late[(line - 8) >> 2]).d[line & 3]);
+				const KbFxPlan p = kb_rv3_plan_combine(lines, rv.times, rv.count, rv.dl.SIZE, rv.dr.SIZE);
+				if (!(p.mode & KB_PLAN_PARALLEL) || !(p.mode & KB_PLAN_RESIDENT)) b->rv_all_resident = false;
+			}
 		}
 	} else if (b->graph == KB_FX_RM || b->graph == KB_FX_TREMOLO) {
 		// `lfo(rate)` = Fast::Sine::set(rate), a no-op while the rate equals the cached frequency (RM.k:21, Tremolo.k:26, klang.h:5143-5147, Q3).
@@ -426,8 +437,10 @@ extern "C" int kb_fx_bank_process(kb_fx_bank* b, float* io, int n, unsigned flag
 						}
 					}
 					// instances whose live delay spans do not fit in shared memory (fs = 192 kHz) keep the round-1 pipeline (its CTAs exit at once otherwise)
-					kb_reverb_pipe_kernel<<<b->instances * 2, KB_RV2_NT, sizeof(KbRv2Smem), b->stream>>>(b->d_hdr, st, b->d_plan, b->d_rings, d + o, len, n);
-					b->launches++;
+					if (!b->rv_all_resident) {
+						kb_reverb_pipe_kernel<<<b->instances * 2, KB_RV2_NT, sizeof(KbRv2Smem), b->stream>>>(b->d_hdr, st, b->d_plan, b->d_rings, d + o, len, n);
+						b->launches++;
+					}
 				} else if (rv_schedule == 1) {
 					kb_reverb_plan_kernel<<<ib, 32, 0, b->stream>>>(st, b->d_plan, b->instances);
 					kb_reverb_par_kernel<<<b->instances * 2, 256, sizeof(KbRvSmem), b->stream>>>(b->d_hdr, st, b->d_plan, b->d_rings, d + o, len, n);
@@ -437,8 +450,10 @@ extern "C" int kb_fx_bank_process(kb_fx_bank* b, float* io, int n, unsigned flag
 				}
 				b->launches += 2;
 			}
-			kb_fx_seq_kernel<KB_FX_REVERB, KbReverb><<<ib, 32, 0, b->stream>>>(b->d_hdr, st, b->d_rings, d + o, len, n, 2, b->instances, b->fs, seq_only ? nullptr : b->d_plan);
-			if (o + sub < n) b->launches++;
+			if (seq_only || rv_schedule != 3 || !b->rv_all_resident) {
+				kb_fx_seq_kernel<KB_FX_REVERB, KbReverb><<<ib, 32, 0, b->stream>>>(b->d_hdr, st, b->d_rings, d + o, len, n, 2, b->instances, b->fs, seq_only ? nullptr : b->d_plan);
+				if (o + sub < n) b->launches++;
+			} else b->launches--;                         // (the common accounting below counts one launch for the sequential kernel)
 		}
 		break; }
 	case KB_FX_DELAY_PINGPONG: {

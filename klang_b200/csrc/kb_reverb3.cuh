@@ -39,7 +39,7 @@
 #define KB_RV3_NT 640                         // threads, exact mode (20 warps)
 #define KB_RV3_NT_TOL 768                     // threads, tolerance mode (24 warps)
 
-struct KbRv3LinePlan { int lag, cap, scan_ok; };
+struct KbRv3LinePlan { int lag, cap, scan_ok, rpos; };
 struct KbRv3Smem {
 	float er[KB_RV3_ESIZE];                   // the early ring of this side, resident for the launch
 	float lr[KB_RV3_LRCAP];                   // the live spans of the 8 feedback lines: line l = a ring of lcap[l] floats at lbase[l]
@@ -108,25 +108,26 @@ enum { KB_PLAN_SCAN_OK = 2, KB_PLAN_RESIDENT = 4 };
 // shared-memory ring of one line: holds the global ring indices a0 = (read head & ~3) .. write head + one chunk, i.e. lag + 2 LMAX + slack floats
 KB_HD int kb_rv3_line_cap(int lag) { return (lag + 2 * KB_RV3_LMAX + 8 + 3) & ~3; }
 // one line's contribution (any thread), and the combination (one thread)
-KB_D KbRv3LinePlan kb_rv3_plan_line(const KbRvFDelay& fd) {
+KB_HD KbRv3LinePlan kb_rv3_plan_line(const KbRvFDelay& fd) {
 	const KbDelay& d = fd.delay;
 	KbRv3LinePlan r;
 	r.lag = d.position - d.last_position; if (r.lag <= 0) r.lag += d.SIZE;      // write head minus read head, in ring samples
 	r.cap = kb_rv3_line_cap(r.lag);
 	r.scan_ok = kb_rv3_scan_admissible(fd.filter) ? 1 : 0;
+	r.rpos = d.last_position;
 	return r;
 }
-KB_D KbFxPlan kb_rv3_plan_combine(const KbRv3LinePlan* lines, const float* times, int count, int esize_l, int esize_r) {
+KB_HD KbFxPlan kb_rv3_plan_combine(const KbRv3LinePlan* lines, const float* times, int count, int esize_l, int esize_r) {
 	int chunk = KB_RV3_LMAX, need[2] = { 0, 0 };
 	bool scan_ok = true;
 	for (int line = 0; line < 16; line++) {
-		chunk = min(chunk, (lines[line].lag - 2) / 4);                          // two ticks per frame, window of chunk k closed by chunk k-2
+		chunk = chunk < (lines[line].lag - 2) / 4 ? chunk : (lines[line].lag - 2) / 4;   // two ticks per frame, window of chunk k closed by chunk k-2
 		scan_ok = scan_ok && lines[line].scan_ok;
 		need[(line >> 2) & 1] += lines[line].cap;                               // lines 0-3, 8-11 belong to side 0 (mid[0], late[0]); 4-7, 12-15 to side 1
 	}
 	float tmin = 1e30f;
 	for (int r = 0; r < count; r++) tmin = fminf(tmin, times[r]);
-	chunk = min(chunk, (int)tmin - 3);
+	chunk = chunk < (int)tmin - 3 ? chunk : (int)tmin - 3;
 	chunk &= ~3;
 	KbFxPlan p;
 	p.chunk = chunk;
@@ -298,13 +299,11 @@ __global__ void __launch_bounds__(MODE == 0 ? KB_RV3_NT : KB_RV3_NT_TOL) kb_reve
 		// the shared-memory rings: line l holds the global ring indices from a0 = read head & ~3 on; offset o (from a0) lives at lbase + o mod lcap
 		int base = 0;
 		for (int l = 0; l < 8; l++) {
-			const KbDelay& d = kb_rv_side_line(rv, side, l).delay;
-			int lag = d.position - d.last_position; if (lag <= 0) lag += d.SIZE;
-			const int a0 = d.last_position & ~3;
-			S.lbase[l] = base; S.lcap[l] = kb_rv3_line_cap(lag);
-			S.lro[l] = d.last_position - a0;                                    // 0 .. 3
-			S.lwo[l] = S.lro[l] + lag;
-			base += S.lcap[l];
+			const KbRv3LinePlan& lp = S.pline[(l < 4 ? 0 : 8) + side * 4 + (l & 3)];   // line l of this side in kb_rv_line order
+			S.lbase[l] = base; S.lcap[l] = lp.cap;
+			S.lro[l] = lp.rpos & 3;                                             // read head relative to a0 = read head & ~3
+			S.lwo[l] = S.lro[l] + lp.lag;
+			base += lp.cap;
 		}
 		kb_mbar_init(&S.bar_res, 1);
 		for (int i = 0; i < KB_RV3_DI; i++) kb_mbar_init(&S.bar_xin[i], 1);
