@@ -64,6 +64,23 @@ struct kb_bank_base {
 	void prof_free() { for (auto& e : prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); } prof_events.clear(); prof_used = 0; }
 };
 
+// multi-GPU mix-down state (the entry points are further down: "multi-GPU mix-down")
+struct kb_mixdown {
+	int device = 0, world = 1, rank = 0, max_floats = 0;
+	unsigned step = 0;                  // steps acquired so far on this rank
+	unsigned collected = 0;             // rank 0: the last step whose slots have been summed
+	unsigned char* arena = nullptr;     // rank 0: own allocation; others: the IPC mapping
+	unsigned* d_tickets = nullptr;      // local device memory: two CTA tickets of the fused step kernel (publish, collect)
+	cudaEvent_t ev_done = nullptr;      // recorded behind the last fused step kernel (which may run on a bank's side stream)
+	bool step_pending = false;
+	bool mapped = false;
+	size_t slot_bytes() const { return (size_t)max_floats * sizeof(float); }
+	float* slot(unsigned step_, int r) const { return (float*)(arena + ((size_t)(step_ & 1u) * world + r) * slot_bytes()); }
+	volatile unsigned* flags() const { return (volatile unsigned*)(arena + 2 * (size_t)world * slot_bytes()); }
+	volatile unsigned* consumed() const { return flags() + world; }
+	size_t arena_bytes() const { return 2 * (size_t)world * slot_bytes() + sizeof(unsigned) * ((size_t)world + 1); }
+};
+
 // =============================================================================================== effects
 struct kb_fx_bank : kb_bank_base {
 	int graph = 0, instances = 0, channels = 0, ncontrols = 0;
@@ -544,6 +561,8 @@ struct kb_synth_bank : kb_bank_base {
 	std::vector<KbSynthBlock> blk; bool blk_dirty = true;
 	KbVoiceHdr* d_hdr = nullptr; unsigned char* d_vstate = nullptr; KbSynthBlock* d_blk = nullptr;
 	float *d_scratch = nullptr, *d_out = nullptr, *d_adsr = nullptr, *d_mix = nullptr;
+	// kb_synth_bank_process_mixdown: the exchange kernel of block k runs on a side stream beside the voice kernels of block k + 1
+	cudaStream_t mix_stream = nullptr; cudaEvent_t ev_mix_in = nullptr; kb_mixdown* last_mixdown = nullptr;
 	int total() const { return instances * voices; }
 	template <class T> T& vs(int v) { return *reinterpret_cast<T*>(vstate + (size_t)v * voice_bytes); }
 	KbControl* ctl(int inst) { return controls.data() + (size_t)inst * KB_MAX_CONTROLS; }
@@ -731,6 +750,8 @@ extern "C" void kb_synth_bank_destroy(kb_synth_bank* b) {
 	cudaFreeHost(b->hdr); cudaFreeHost(b->vstate); cudaFreeHost(b->staging);
 	cudaFree(b->d_staging);
 	cudaFree(b->d_hdr); cudaFree(b->d_vstate); cudaFree(b->d_blk); cudaFree(b->d_scratch); cudaFree(b->d_out); cudaFree(b->d_adsr); cudaFree(b->d_mix);
+	if (b->mix_stream) { cudaStreamSynchronize(b->mix_stream); cudaStreamDestroy(b->mix_stream); }
+	if (b->ev_mix_in) cudaEventDestroy(b->ev_mix_in);
 	if (b->own_stream) cudaStreamDestroy(b->own_stream);
 	delete b;
 }
@@ -743,7 +764,12 @@ extern "C" long long kb_synth_bank_state_bytes(const kb_synth_bank* b) { return 
 extern "C" int kb_synth_bank_transfer_bytes(const kb_synth_bank* b, long long* h2d, long long* d2h) { if (!b) return kb_fail(KB_EINVAL, "null bank"); if (h2d) *h2d = b->h2d_bytes; if (d2h) *d2h = b->d2h_bytes; return KB_OK; }
 extern "C" int kb_synth_bank_profile(kb_synth_bank* b, int enable) { if (!b) return kb_fail(KB_EINVAL, "null bank"); cudaSetDevice(b->device); cudaStreamSynchronize(b->stream); b->profiling = enable != 0; b->prof_used = 0; return KB_OK; }
 extern "C" int kb_synth_bank_profile_read(kb_synth_bank* b, double* ms, long long* count) { if (!b) return kb_fail(KB_EINVAL, "null bank"); cudaSetDevice(b->device); return b->prof_read(ms, count); }
-extern "C" int kb_synth_bank_sync(kb_synth_bank* b) { if (!b) return kb_fail(KB_EINVAL, "null bank"); KB_CUDA(cudaSetDevice(b->device)); KB_CUDA(cudaStreamSynchronize(b->stream)); return KB_OK; }
+extern "C" int kb_synth_bank_sync(kb_synth_bank* b) {
+	if (!b) return kb_fail(KB_EINVAL, "null bank");
+	KB_CUDA(cudaSetDevice(b->device)); KB_CUDA(cudaStreamSynchronize(b->stream));
+	if (b->mix_stream) KB_CUDA(cudaStreamSynchronize(b->mix_stream));
+	return KB_OK;
+}
 extern "C" int kb_synth_bank_set_stream(kb_synth_bank* b, void* s) {
 	if (!b) return kb_fail(KB_EINVAL, "null bank");
 	KB_CUDA(cudaStreamSynchronize(b->stream));
@@ -876,7 +902,6 @@ extern "C" int kb_synth_bank_events(kb_synth_bank* b, int count, const kb_note_e
 	return KB_OK;
 }
 
-struct kb_mixdown;
 static int mixdown_step(kb_mixdown* m, const float* src, int rows, size_t row_stride, int count, float* out_prev, cudaStream_t stream);
 static int sy_process(kb_synth_bank* b, float* out, int n, unsigned flags, kb_mixdown* mixdown, float* out_prev);
 extern "C" int kb_synth_bank_process(kb_synth_bank* b, float* out, int n, unsigned flags) {
@@ -896,6 +921,13 @@ static int sy_process(kb_synth_bank* b, float* out, int n, unsigned flags, kb_mi
 	const bool per_voice = flags & KB_PER_VOICE, dev = flags & KB_DEVICE_PTR, bank_mix = (flags & KB_BANK_MIX) && !per_voice;
 	const size_t out_floats = per_voice ? (size_t)total * C * n : bank_mix ? (size_t)C * n : (size_t)b->instances * C * n;
 	cudaStream_t st = b->stream;
+	// the exchange kernel of the previous block (side stream) reads d_out: the kernels that rewrite d_out wait for it (kb_mix_kernel, which is
+	// queued behind this block's voice kernel; SynTHX's render kernel writes d_out itself, so it waits at once)
+	auto wait_prev_exchange = [&]() -> int {
+		if (b->last_mixdown && b->last_mixdown->step_pending) KB_CUDA(cudaStreamWaitEvent(st, b->last_mixdown->ev_done, 0));
+		return KB_OK;
+	};
+	if (b->graph == KB_SY_SYNTHX || per_voice) { rc = wait_prev_exchange(); if (rc) return rc; }
 	float* d_voice_dst = (per_voice && dev) ? out : b->d_scratch;
 	float* d_inst_dst = (!per_voice && !bank_mix && dev) ? out : b->d_out;
 	if (b->graph == KB_SY_SYNTHX) {
@@ -1000,6 +1032,7 @@ static int sy_process(kb_synth_bank* b, float* out, int n, unsigned flags, kb_mi
 		b->launches++;
 		if (!per_voice) {
 			dim3 grid((n + 255) / 256, b->instances);
+			rc = wait_prev_exchange(); if (rc) return rc;
 			kb_mix_kernel<<<grid, 256, 0, st>>>(b->d_scratch, b->d_hdr, d_inst_dst, n, b->voices, (flags & KB_MIX_SUM) ? 1 : 0);
 			b->launches++;
 		}
@@ -1007,7 +1040,11 @@ static int sy_process(kb_synth_bank* b, float* out, int n, unsigned flags, kb_mi
 	float* d_result = per_voice ? d_voice_dst : d_inst_dst;
 	if (bank_mix && mixdown) {
 		// the bank mix goes straight into rank 0's arena (kb_mixdown_step_kernel); nothing is returned through `out`
-		rc = mixdown_step(mixdown, b->d_out, b->instances, (size_t)C * n, C * n, out_prev, st); if (rc) return rc;
+		if (!b->mix_stream) { KB_CUDA(cudaStreamCreateWithFlags(&b->mix_stream, cudaStreamNonBlocking)); KB_CUDA(cudaEventCreateWithFlags(&b->ev_mix_in, cudaEventDisableTiming)); }
+		KB_CUDA(cudaEventRecord(b->ev_mix_in, st));
+		KB_CUDA(cudaStreamWaitEvent(b->mix_stream, b->ev_mix_in, 0));
+		rc = mixdown_step(mixdown, b->d_out, b->instances, (size_t)C * n, C * n, out_prev, b->mix_stream); if (rc) return rc;
+		b->last_mixdown = mixdown;
 		b->launches++;
 		b->host_stale = true; b->hdr_stale = true; b->vstate_stale = true;
 		return KB_OK;
@@ -1031,19 +1068,6 @@ static int sy_process(kb_synth_bank* b, float* out, int n, unsigned flags, kb_mi
 // (include/klang_b200.h: kb_mixdown_*)  Arena on rank 0: float slots[2][world][max_floats]; then unsigned flags[world] (the
 // last step each rank has published) and unsigned consumed (the last step rank 0 has summed).  All waits are device-side
 // spins on system-scope volatile words, reached over NVLink by the peers.
-struct kb_mixdown {
-	int device = 0, world = 1, rank = 0, max_floats = 0;
-	unsigned step = 0;                  // steps acquired so far on this rank
-	unsigned collected = 0;             // rank 0: the last step whose slots have been summed
-	unsigned char* arena = nullptr;     // rank 0: own allocation; others: the IPC mapping
-	unsigned* d_tickets = nullptr;      // local device memory: two CTA tickets of the fused step kernel (publish, collect)
-	bool mapped = false;
-	size_t slot_bytes() const { return (size_t)max_floats * sizeof(float); }
-	float* slot(unsigned step_, int r) const { return (float*)(arena + ((size_t)(step_ & 1u) * world + r) * slot_bytes()); }
-	volatile unsigned* flags() const { return (volatile unsigned*)(arena + 2 * (size_t)world * slot_bytes()); }
-	volatile unsigned* consumed() const { return flags() + world; }
-	size_t arena_bytes() const { return 2 * (size_t)world * slot_bytes() + sizeof(unsigned) * ((size_t)world + 1); }
-};
 __global__ void kb_mixdown_wait_free_kernel(volatile unsigned* consumed, unsigned need) {
 	while ((int)(*consumed - need) < 0) __nanosleep(200);
 }
@@ -1086,6 +1110,7 @@ extern "C" void kb_mixdown_destroy(kb_mixdown* m) {
 	cudaDeviceSynchronize();
 	if (m->arena) { if (m->mapped) cudaIpcCloseMemHandle(m->arena); else cudaFree(m->arena); }
 	cudaFree(m->d_tickets);
+	if (m->ev_done) cudaEventDestroy(m->ev_done);
 	delete m;
 }
 extern "C" int kb_mixdown_export(kb_mixdown* m, void* handle) {
@@ -1130,6 +1155,8 @@ extern "C" int kb_mixdown_put(kb_mixdown* m, const float* src, int count, void* 
 extern "C" int kb_mixdown_collect(kb_mixdown* m, float* dst, int count, void* stream) {
 	if (!m || !dst || m->rank != 0 || count < 0 || count > m->max_floats || m->step == 0) return kb_fail(KB_EINVAL, "kb_mixdown_collect: bad argument (rank 0 only, count <= max_floats)");
 	KB_CUDA(cudaSetDevice(m->device));
+	// (a fused step may still be running on another stream and writes the caller's out_prev buffer: order this collect behind it)
+	if (m->step_pending) { KB_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, m->ev_done, 0)); m->step_pending = false; }
 	kb_mixdown_collect_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(m->slot(m->step, 0), (size_t)m->max_floats, m->flags(), m->consumed(), m->step, m->world, dst, count);
 	m->collected = m->step;
 	KB_CUDA(cudaGetLastError());
@@ -1185,6 +1212,9 @@ static int mixdown_step(kb_mixdown* m, const float* src, int rows, size_t row_st
 	                                                                                          step, m->rank, m->world, m->slot(step - 1, 0), (size_t)m->max_floats, out_prev, do_prev);
 	if (do_prev) m->collected = step - 1;
 	KB_CUDA(cudaGetLastError());
+	if (!m->ev_done) KB_CUDA(cudaEventCreateWithFlags(&m->ev_done, cudaEventDisableTiming));
+	KB_CUDA(cudaEventRecord(m->ev_done, stream));
+	m->step_pending = true;
 	return KB_OK;
 }
 extern "C" int kb_synth_bank_process_mixdown(kb_synth_bank* b, kb_mixdown* m, float* out_prev, int n, unsigned flags) {
