@@ -419,6 +419,17 @@ namespace b200 {
 
 template <class PLUGIN> struct graph_of;      // specialised by KLANG_B200_EFFECT / KLANG_B200_SYNTH
 
+// The device runs a hand-written restatement of ONE reference program per graph id; this header only type-checks a `.k` body, it does not
+// evaluate it.  So a program is bound to an id only when the hash of the `.k` source that was actually compiled (tools/k_hash.py, passed
+// by the build: tools/build_k_host.py) equals the hash of the program the id restates (kb_graph_source_hash): an edited body, or another
+// plugin with the same controls table, is refused instead of silently running the old DSP.
+inline void check_source(bool synth, int graph, unsigned long long compiled_hash) {
+	const unsigned long long want = kb_graph_source_hash(synth ? 1 : 0, graph);
+	if (want == 0ULL || compiled_hash != want)
+		throw std::logic_error(std::string("the .k program compiled here is not the program graph ") + std::to_string(graph) + " restates (" + kb_graph_source_path(synth ? 1 : 0, graph) +
+		                       "): source hash mismatch — the device would run different DSP than the program describes; refusing to bind");
+}
+
 struct Error : std::runtime_error { explicit Error(const std::string& what) : std::runtime_error(what + ": " + kb_last_error()) {} };
 
 // Owns one PLUGIN object (for its controls / presets, as the reference host does) and the bank that evaluates it.
@@ -429,7 +440,7 @@ template <class PLUGIN> class EffectHost {
 public:
 	PLUGIN plugin;
 	EffectHost(float sample_rate, int max_block, int instances = 1, int device = 0)
-		: bank_(kb_fx_bank_create(graph_of<PLUGIN>::id, instances, sample_rate, max_block, device)) {
+		: bank_((check_source(false, graph_of<PLUGIN>::id, graph_of<PLUGIN>::source_hash), kb_fx_bank_create(graph_of<PLUGIN>::id, instances, sample_rate, max_block, device))) {
 		if (!bank_) throw Error("kb_fx_bank_create");
 		const int n = kb_fx_bank_num_controls(bank_);
 		if (n != plugin.controls.size()) throw std::logic_error("controls table of the .k program does not match the bound graph");
@@ -467,7 +478,7 @@ template <class PLUGIN> class SynthHost {
 public:
 	PLUGIN plugin;
 	SynthHost(float sample_rate, int max_block, int instances = 1, int device = 0)
-		: bank_(kb_synth_bank_create(graph_of<PLUGIN>::id, instances, plugin.notes.size() > 0 ? plugin.notes.size() : 32, sample_rate, max_block, device)) {
+		: bank_((check_source(true, graph_of<PLUGIN>::id, graph_of<PLUGIN>::source_hash), kb_synth_bank_create(graph_of<PLUGIN>::id, instances, plugin.notes.size() > 0 ? plugin.notes.size() : 32, sample_rate, max_block, device))) {
 		if (!bank_) throw Error("kb_synth_bank_create");
 		const int n = kb_synth_bank_num_controls(bank_);
 		if (n != plugin.controls.size()) throw std::logic_error("controls table of the .k program does not match the bound graph");
@@ -505,7 +516,8 @@ private:
 }  // namespace b200
 }  // namespace klang
 
-#define KLANG_B200_EFFECT(PLUGIN, GRAPH) namespace klang { namespace b200 { template <> struct graph_of<PLUGIN> { static constexpr int id = GRAPH; }; } }
-#define KLANG_B200_SYNTH(PLUGIN, GRAPH) namespace klang { namespace b200 { template <> struct graph_of<PLUGIN> { static constexpr int id = GRAPH; }; } }
+// SOURCE_HASH = the hash of the `.k` file PLUGIN was compiled from (python tools/k_hash.py file.k prints the #define)
+#define KLANG_B200_EFFECT(PLUGIN, GRAPH, SOURCE_HASH) namespace klang { namespace b200 { template <> struct graph_of<PLUGIN> { static constexpr int id = GRAPH; static constexpr unsigned long long source_hash = SOURCE_HASH; }; } }
+#define KLANG_B200_SYNTH(PLUGIN, GRAPH, SOURCE_HASH) namespace klang { namespace b200 { template <> struct graph_of<PLUGIN> { static constexpr int id = GRAPH; static constexpr unsigned long long source_hash = SOURCE_HASH; }; } }
 
 using namespace klang;

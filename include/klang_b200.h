@@ -90,6 +90,11 @@ int kb_device_count(void);                          /* 0 when no CUDA device / d
 const char* kb_last_error(void);                    /* thread-local, never NULL */
 void kb_srand(unsigned seed);                       /* klang::random(seed) = srand()            klang.h:240 */
 float kb_pitch_to_frequency(float pitch);           /* Pitch::operator-> Frequency              klang.h:1568-1571 */
+/* The klang program a graph id restates: path under the reference tree and the hash of its source (comments removed, white space collapsed,
+ * FNV-1a 64 — tools/k_hash.py).  A host that compiled a `.k` file binds it to the id only if the hashes agree (include/compat/klang.h):
+ * an edited program must never silently run the unedited DSP.  synth = 0: KB_FX_* ids, 1: KB_SY_* ids; hash 0 = no single program. */
+unsigned long long kb_graph_source_hash(int synth, int graph);
+const char* kb_graph_source_path(int synth, int graph);
 
 /* ------------------------------------------------------------------------------------ effect banks */
 /* `instances` objects of the Effect / Stereo::Effect subclass `graph`, constructed with klang::fs = fs

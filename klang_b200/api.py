@@ -22,6 +22,7 @@ _fp, _ip = C.POINTER(C.c_float), C.POINTER(C.c_int)
 SYMBOLS = [
     ("kb_version", _i, []), ("kb_device_count", _i, []), ("kb_last_error", C.c_char_p, []),
     ("kb_srand", None, [_u]), ("kb_pitch_to_frequency", _f, [_f]),
+    ("kb_graph_source_hash", C.c_ulonglong, [_i, _i]), ("kb_graph_source_path", C.c_char_p, [_i, _i]),
     ("kb_fx_bank_create", _vp, [_i, _i, _f, _i, _i]), ("kb_fx_bank_destroy", None, [_vp]),
     ("kb_fx_bank_channels", _i, [_vp]), ("kb_fx_bank_instances", _i, [_vp]), ("kb_fx_bank_num_controls", _i, [_vp]),
     ("kb_fx_bank_set_control", _i, [_vp, _i, _i, _f]), ("kb_fx_bank_get_control", _i, [_vp, _i, _i, _fp]),

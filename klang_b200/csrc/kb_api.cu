@@ -19,6 +19,7 @@
 #include "kb_tiled.cuh"
 #include "kb_reverb3.cuh"
 #include "kb_pingpong3.cuh"
+#include "kb_k_hashes.h"
 
 static thread_local std::string g_err = "";
 static int kb_fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -33,6 +34,15 @@ extern "C" const char* kb_last_error(void) { return g_err.c_str(); }
 extern "C" int kb_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
 extern "C" void kb_srand(unsigned seed) { srand(seed); }
 extern "C" float kb_pitch_to_frequency(float pitch) { return kb_pitch_to_frequency_host(pitch); }
+// which klang program a graph id restates (kb_k_hashes.h): a host binds its compiled `.k` to an id only when the source hashes agree
+extern "C" unsigned long long kb_graph_source_hash(int synth, int graph) {
+	if (graph < 0 || graph >= (synth ? KB_SY_COUNT : KB_FX_COUNT)) return 0ULL;
+	return (synth ? kb_k_synth_sources : kb_k_fx_sources)[graph].hash;
+}
+extern "C" const char* kb_graph_source_path(int synth, int graph) {
+	if (graph < 0 || graph >= (synth ? KB_SY_COUNT : KB_FX_COUNT)) return "";
+	return (synth ? kb_k_synth_sources : kb_k_fx_sources)[graph].path;
+}
 
 template <class T> static cudaError_t dev_alloc(T** p, size_t count) { return cudaMalloc((void**)p, count * sizeof(T) > 0 ? count * sizeof(T) : 1); }
 

@@ -92,3 +92,34 @@ def run_k_program_on_device(prog, tmp_path):
 @pytest.mark.parametrize("prog", PROGRAMS)
 def test_reference_k_programs_run_on_the_device_bit_exact(prog, tmp_path):
     run_k_program_on_device(prog, tmp_path)
+
+
+@pytest.mark.skipif(not HAVE_REFERENCE, reason="reference examples not present")
+def test_edited_k_program_is_refused_not_silently_bound(tmp_path):
+    """ADVICE r1 / VERDICT r1: include/compat/klang.h type-checks a `.k` body but the device runs the hand-written graph the plugin type is
+    bound to.  A one-token edit of Gain.k (`in * gain` -> `in * gain * 0.5`) must therefore be REFUSED at bind time — the hash of the source
+    that was compiled no longer matches the program graph KB_FX_GAIN restates (kb_graph_source_hash) — while the unedited program binds
+    (and then, on a box without a GPU, fails for lack of a device, never computing anything on the host)."""
+    import klang_b200 as kb
+    from klang_b200 import build
+    build.build(verbose=False)
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import build_k_host
+    import k_hash
+    src = open("/root/reference/examples/Gain/Gain.k").read()
+    assert "in * gain >> out;" in src
+    overlay = tmp_path / "overlay"
+    (overlay / "Gain").mkdir(parents=True)
+    (overlay / "Gain" / "Gain.k").write_text(src.replace("in * gain >> out;", "in * gain * 0.5 >> out;"))
+    # comments and white space do not change the hash, a token does
+    (tmp_path / "ws.k").write_text(src.replace("in * gain >> out;", "in  *  gain >> out;   // same program"))
+    assert k_hash.k_hash(str(tmp_path / "ws.k")) == k_hash.k_hash("/root/reference/examples/Gain/Gain.k") == kb.lib().kb_graph_source_hash(0, kb.FX_GAIN)
+    assert k_hash.k_hash(str(overlay / "Gain" / "Gain.k")) != kb.lib().kb_graph_source_hash(0, kb.FX_GAIN)
+    exe = build_k_host.build(verbose=False, overlay=str(overlay), out=str(tmp_path / "bin" / "k_host_edited"))
+    out = subprocess.run([exe, "gain", "48000", "64", "1", str(tmp_path / "o.f32")], capture_output=True, text=True)
+    assert out.returncode == 5 and "source hash mismatch" in out.stderr and "examples/Gain/Gain.k" in out.stderr, (out.returncode, out.stderr)
+    # every other program of the same binary still binds (and stops at the missing device off the GPU box)
+    out = subprocess.run([exe, "pan", "48000", "64", "1", str(tmp_path / "o.f32")], capture_output=True, text=True)
+    assert out.returncode == (3 if kb.device_count() == 0 else 0), out.stderr
+    # the library names the program every bound id restates
+    assert kb.lib().kb_graph_source_path(1, kb.SY_TB303) == b"examples/TB303.k" and kb.lib().kb_graph_source_hash(1, kb.SY_SUBTRACTIVE) == 0
