@@ -1,0 +1,117 @@
+"""Tier B, first step: `.k` Effect programs evaluated on the device from their OWN process() body (klang_b200/kcc.py,
+klang_b200/csrc/kb_kdev.cuh, include/klang_b200_user.h).
+
+  * CPU: the reference's elementwise examples and a stateful one translate and compile for sm_100a with nvcc, export the user ABI, and refuse
+    to create a bank without a CUDA device; programs outside the supported subset fail loudly at translation / compile time.
+  * GPU (-m gpu): every translated program is bit-identical to the reference running the same `.k` (oracle.ref), control changes included —
+    and an EDITED program (Gain.k with `in * gain * 0.5`) computes what the edited text says, which no hand-bound graph id can."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import cases
+import oracle
+from klang_b200 import kcc
+
+REF = "/root/reference/examples"
+HAVE_REFERENCE = os.path.isfile(os.path.join(REF, "Gain", "Gain.k"))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "tests", "_k_bin", "kcc")          # git-ignored build output: travels to the GPU box with the snapshot
+PROGRAMS = {"gain": ("Gain/Gain.k", oracle.FX_GAIN), "pan": ("Gain/Pan.k", oracle.FX_PAN), "clipping": ("Distortion/Clipping.k", oracle.FX_CLIPPING),
+            "functions": ("Distortion/Functions.k", oracle.FX_FUNCTIONS), "mute": ("Distortion/Mute.k", oracle.FX_MUTE), "iir": ("Filtering/IIR.k", oracle.FX_IIR)}
+EDITED = "gain_edited"
+
+
+def so_path(name):
+    return os.path.join(BIN, f"lib{name}_k.so")
+
+
+def build_all():
+    """(run where /root/reference exists: here, by the CPU test below and by __graft_entry__.build())"""
+    os.makedirs(BIN, exist_ok=True)
+    for name, (rel, _) in PROGRAMS.items():
+        kcc.compile_k(os.path.join(REF, rel), so_path(name))
+    src = open(os.path.join(REF, "Gain", "Gain.k")).read().replace("in * gain >> out;", "in * gain * 0.5 >> out;")
+    edited = os.path.join(BIN, "gain_edited.k")
+    with open(edited, "w") as f:
+        f.write(src)
+    kcc.compile_k(edited, so_path(EDITED))
+
+
+@pytest.mark.skipif(not HAVE_REFERENCE, reason="reference examples not present")
+def test_k_programs_translate_and_compile_for_the_device(tmp_path):
+    build_all()
+    for name in list(PROGRAMS) + [EDITED]:
+        L = C.CDLL(so_path(name))
+        for sym in ("kb_user_name", "kb_user_channels", "kb_user_num_controls", "kb_user_stateless", "kb_user_last_error", "kb_user_fx_create",
+                    "kb_user_fx_destroy", "kb_user_fx_set_control", "kb_user_fx_get_control", "kb_user_fx_process"):
+            assert hasattr(L, sym), f"{name}: {sym} not exported"
+        L.kb_user_name.restype = C.c_char_p
+        assert L.kb_user_num_controls() == 1
+        assert L.kb_user_channels() == (2 if name == "pan" else 1)
+        assert L.kb_user_stateless() == (0 if name == "iir" else 1)           # IIR.k carries `signal last`: lane per instance, frame by frame
+    # the translated text is the user's: only the function definitions gained a qualifier
+    src, plugin, ch = kcc.translate(open(os.path.join(REF, "Distortion", "Functions.k")).read(), "Functions.k")
+    assert plugin == "Functions" and ch == 1
+    assert "KB_KD float hardclip(float x){" in src and "KB_KD void process() {" in src and "hardclip(in * gain) >> out;" in src
+    assert "KB_KD Functions()" not in src                                        # constructors stay host code
+    # outside the subset: a synth program is refused at translation, an effect that uses primitives this header lacks fails in nvcc — loudly
+    with pytest.raises(kcc.KccError):
+        kcc.translate(open(os.path.join(REF, "SuperSaw.k")).read(), "SuperSaw.k")
+    with pytest.raises(kcc.KccError):
+        kcc.compile_k(os.path.join(REF, "Delay", "Echo.k"), str(tmp_path / "libecho_k.so"))
+    import klang_b200 as kb
+    if kb.device_count() == 0:
+        with pytest.raises(kcc.KccError, match="no such CUDA device"):
+            kcc.UserFx(so_path("gain"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(PROGRAMS))
+def test_translated_k_program_matches_the_reference_on_the_device(name):
+    """The program's own process() body on the B200 against the reference running the same .k: 3 instances with different inputs, four blocks
+    with a control change before each, bit-exact."""
+    rel, graph = PROGRAMS[name]
+    assert os.path.isfile(so_path(name)), "tests/_k_bin/kcc is built where /root/reference exists and travels with the snapshot"
+    chk = oracle.ref if oracle.ref.available() else oracle.port
+    fs, n, inst, blocks = 48000, 2048, 3, 4
+    chk.set_fs(fs)
+    fx = kcc.UserFx(so_path(name), inst, fs, n)
+    assert fx.stateless == (name != "iir")
+    refs = [chk.Fx(graph) for _ in range(inst)]
+    ch = fx.channels
+    lo, hi = {"clipping": (1.0, 11.0), "functions": (1.0, 25.0)}.get(name, (0.0, 1.0))
+    for b in range(blocks):
+        x = np.stack([cases.fx_input(ch, n, seed=900 + 7 * b + i) for i in range(inst)]) * np.float32(4.0 if name in ("clipping", "functions") else 1.0)
+        for i in range(inst):
+            v = lo + (hi - lo) * ((3 * b + 5 * i + 1) % 11) / 10.0
+            fx.set_control(0, v, i)
+            refs[i].set_control(0, v)
+            assert fx.get_control(0, i) == refs[i].get_control(0)
+        want = np.stack([np.atleast_2d(refs[i].process(x[i, 0] if ch == 1 else x[i])) for i in range(inst)])
+        got = np.ascontiguousarray(x)
+        fx.process_inplace(got)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"{name}: block {b} differs from the reference"
+        assert np.abs(want).max() > 0 or name == "mute"
+    fx.close()
+    for r in refs:
+        r.close()
+
+
+@pytest.mark.gpu
+def test_edited_k_program_runs_what_the_edited_text_says():
+    """Gain.k with `in * gain * 0.5 >> out;`: the hand-bound graph KB_FX_GAIN refuses this source (tests/test_k_programs.py); the translated
+    program evaluates it — (x * gain) * 0.5 in fp32, exactly."""
+    fs, n = 48000, 4096
+    fx = kcc.UserFx(so_path(EDITED), 2, fs, n)
+    x = np.stack([cases.fx_input(1, n, seed=950 + i) for i in range(2)])
+    fx.set_control(0, 0.8, 0)
+    fx.set_control(0, 0.3, 1)
+    got = np.ascontiguousarray(x)
+    fx.process_inplace(got)
+    for i, g in enumerate((np.float32(0.8), np.float32(0.3))):
+        want = (x[i] * g) * np.float32(0.5)
+        assert np.array_equal(got[i].view(np.uint32), want.view(np.uint32))
+    fx.close()
