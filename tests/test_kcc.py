@@ -91,7 +91,7 @@ def test_translated_k_program_matches_the_reference_on_the_device(name):
             refs[i].set_control(0, v)
             assert fx.get_control(0, i) == refs[i].get_control(0)
         want = np.stack([np.atleast_2d(refs[i].process(x[i, 0] if ch == 1 else x[i])) for i in range(inst)])
-        got = np.ascontiguousarray(x)
+        got = x.copy()
         fx.process_inplace(got)
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"{name}: block {b} differs from the reference"
         assert np.abs(want).max() > 0 or name == "mute"
@@ -109,7 +109,7 @@ def test_edited_k_program_runs_what_the_edited_text_says():
     x = np.stack([cases.fx_input(1, n, seed=950 + i) for i in range(2)])
     fx.set_control(0, 0.8, 0)
     fx.set_control(0, 0.3, 1)
-    got = np.ascontiguousarray(x)
+    got = x.copy()
     fx.process_inplace(got)
     for i, g in enumerate((np.float32(0.8), np.float32(0.3))):
         want = (x[i] * g) * np.float32(0.5)
