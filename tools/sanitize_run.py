@@ -27,6 +27,13 @@ for graph, n, blocks in ((kb.FX_GAIN, 1001, 2), (kb.FX_PINGPONG, 2048, 24), (kb.
     x = (np.random.default_rng(1).random((3, fx.channels, n), dtype=np.float32) - 0.5)
     for k in range(blocks):
         fx.process_inplace(x.copy())
+    if graph == kb.FX_REVERB:                          # the tolerance schedule (parallel-scan line filters) and a ragged block (round-1 pipeline)
+        for c, v in ((0, 0.3), (2, 0.4), (3, 0.5)):
+            fx.set_control(c, v)
+        fx.process_inplace(x.copy(), flags=kb.FX_TOLERANCE)
+        fx.process_inplace(x.copy(), flags=kb.FX_TOLERANCE)
+        print(graph, "tolerance instances", fx.tolerance_instances())
+        fx.process_inplace(x[:, :, :333].copy())
     print(graph, "parallel instances", fx.parallel_instances())
     fx.close()
 # the mix-down protocol on one rank (put / acquire + publish / collect over more steps than slot parities)
@@ -41,5 +48,11 @@ for k in range(5):
     L.kb_mixdown_collect(h, dst.data_ptr(), 512, ts.cuda_stream)
 torch.cuda.synchronize()
 assert torch.equal(src, dst)
+prev = torch.zeros(512, device="cuda")
+for k in range(5):                                      # the fused step: store + flag + rank 0 sums the previous step
+    L.kb_mixdown_step(h, src.data_ptr(), 512, prev.data_ptr(), ts.cuda_stream)
+L.kb_mixdown_collect(h, dst.data_ptr(), 512, ts.cuda_stream)
+torch.cuda.synchronize()
+assert torch.equal(src, dst) and torch.equal(src, prev)
 L.kb_mixdown_destroy(h)
 print("sanitize run done")
