@@ -731,7 +731,7 @@ def extras(kb, torch, dev, stream, flush_l2, hbm_peak, peak_src, device_index, w
                 pre()
             fn()
         torch.cuda.synchronize()
-        tot = 0.0
+        evs = []
         for _ in range(steps):
             if pre:
                 pre()
@@ -740,9 +740,11 @@ def extras(kb, torch, dev, stream, flush_l2, hbm_peak, peak_src, device_index, w
             a.record(stream)
             fn()
             b.record(stream)
-            torch.cuda.synchronize()
-            tot += a.elapsed_time(b)
-        return tot / steps
+            evs.append((a, b))
+        # (no host join between steps: while the GPU writes the 256 MiB flush the host has already queued the step behind it, so the event
+        # interval is the device time of the call's kernels, not the host's launch latency on an idle stream)
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs) / steps
 
     def roof(gbs):
         return {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "peak_source": peak_src}
