@@ -579,6 +579,15 @@ def main():
                 if isinstance(w, dict) and "roofline" in w:
                     roofline[name + "_frac"] = w["roofline"]["frac"]
                     roofline[name + "_ms"] = w["ms_per_step"]
+            try:
+                with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                    tj = json.load(f)
+                roofline["c4_reverb_traffic"] = tj.get("kb_reverb3_kernel<0>")
+                roofline["c4_reverb_tolerance_traffic"] = tj.get("kb_reverb3_kernel<1>")
+                roofline["c4_pingpong_traffic"] = tj.get("kb_pingpong3_kernel")
+                roofline["c4_reverb_algorithmic_bytes"] = 64 * 4096 * 664
+            except Exception:
+                pass
             roofline["c4_note"] = ("C4 = 64 stereo instances x 4096-frame blocks, distinct input per step, L2 flushed before every timed step; frac = algorithmic bytes per frame "
                                    "(SURVEY 8d: Reverb.k 664, PingPong.k 48, Delay/PingPong.k 40, Delay/Reverb.k 88) x frames / time / measured copy peak; "
                                    "*_tolerance = the 1e-5-tolerance schedule (KB_FX_TOLERANCE), everything else bit-exact")
