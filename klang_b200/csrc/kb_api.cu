@@ -1011,11 +1011,16 @@ static int sy_process(kb_synth_bank* b, float* out, int n, unsigned flags, kb_mi
 				// KB_TILE_LAYOUT (A/B measurement, same results): 2 = default for 800..1599 voices, the filter warp alone on its SM
 				// sub-partition and both envelopes in one warp (kb_tiled.cuh); 0 = serial roles spread over the sub-partitions
 				static const int layout = getenv("KB_TILE_LAYOUT") ? atoi(getenv("KB_TILE_LAYOUT")) : 2;
+				// KB_C2_TRACE=<file> (measurement aid): per-role clock64() stamps of CTA 0 for every tick of the last launch
+				static const char* c2_trace_path = getenv("KB_C2_TRACE");
+				static long long* c2_trace = nullptr;
+				if (c2_trace_path && !c2_trace) { KB_CUDA(cudaMalloc(&c2_trace, 4 * 64 * 2 * sizeof(long long))); }
+				if (c2_trace) KB_CUDA(cudaMemsetAsync(c2_trace, 0, 4 * 64 * 2 * sizeof(long long), st));
 #define KB_LAUNCH_SUB(GG, NT, LAY)                                                                                                    \
 	do {                                                                                                                             \
 		static bool attr_set = false;                                                                                                \
 		if (!attr_set) { cudaFuncSetAttribute(kb_sub_tiled_kernel<GG, NT, LAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KbSubSmem<GG>)); attr_set = true; } \
-		kb_sub_tiled_kernel<GG, NT, LAY><<<(total + GG - 1) / GG, NT, sizeof(KbSubSmem<GG>), st>>>(vs, b->d_hdr, d_voice_dst, n, total, b->fs); \
+		kb_sub_tiled_kernel<GG, NT, LAY><<<(total + GG - 1) / GG, NT, sizeof(KbSubSmem<GG>), st>>>(vs, b->d_hdr, d_voice_dst, n, total, b->fs, c2_trace); \
 	} while (0)
 				if (g >= 16) KB_LAUNCH_SUB(16, 1024, 0);
 				else if (g >= 7 && layout == 2) KB_LAUNCH_SUB(8, 768, 2);
@@ -1023,6 +1028,15 @@ static int sy_process(kb_synth_bank* b, float* out, int n, unsigned flags, kb_mi
 				else if (g == 7) KB_LAUNCH_SUB(7, 544, 0);               // 448 worker threads cover a 7 x 128 tile in exactly two rounds
 				else KB_LAUNCH_SUB(4, 320, 0);
 #undef KB_LAUNCH_SUB
+				if (c2_trace) {
+					std::vector<long long> tr(4 * 64 * 2);
+					KB_CUDA(cudaMemcpyAsync(tr.data(), c2_trace, tr.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
+					KB_CUDA(cudaStreamSynchronize(st));
+					if (FILE* f = fopen(c2_trace_path, "w")) {
+						for (int r = 0; r < 4; r++) for (int k = 0; k < 64; k++) if (tr[(r * 64 + k) * 2] || tr[(r * 64 + k) * 2 + 1]) fprintf(f, "%d %d %lld %lld\n", r, k, tr[(r * 64 + k) * 2], tr[(r * 64 + k) * 2 + 1]);
+						fclose(f);
+					}
+				}
 			} else if (b->graph == KB_SY_SUPERSAW) {
 				KbSsawVoice* vs = (KbSsawVoice*)b->d_vstate;
 				if (g >= 8) KB_LAUNCH_TILED(kb_ssaw_tiled_kernel, KbSsawSmem, 8, 1024, vs, b->d_hdr, d_voice_dst, n, total, b->fs);

@@ -14,6 +14,7 @@
 // sequential kernel: a plan kernel classifies every instance on the device before each launch, no host round trip.
 #pragma once
 #include "kb_graphs.cuh"
+#include "kb_sync.cuh"
 
 enum { KB_PLAN_SEQUENTIAL = 0, KB_PLAN_PARALLEL = 1 };
 struct KbFxPlan { int mode; int chunk; float gain, delay, dry; };
@@ -542,7 +543,6 @@ KB_D void kb_rv2_filter_row(const float* xr, float* yr, int ticks, float b0, flo
 		yr[f] = y;
 	}
 }
-KB_D void kb_bar_group(int id, int threads) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(threads) : "memory"); }
 
 __global__ void __launch_bounds__(KB_RV2_NT) kb_reverb_pipe_kernel(const KbFxHdr* __restrict__ hdrs, KbReverb* __restrict__ states, const KbFxPlan* __restrict__ plan,
                                                                    float* __restrict__ rings, float* __restrict__ io, int n, int stride) {

@@ -26,6 +26,7 @@
 #pragma once
 #include "kb_fx_parallel.cuh"
 #include "kb_scan.cuh"
+#include "kb_sync.cuh"
 
 #define KB_RV3_LMAX 80                        // frames per chunk (a multiple of 4: io chunks are 16-byte bulk copies)
 #define KB_RV3_XROW 161                       // float4 per operand row (odd: the 8 lanes of the filter warp hit distinct banks)
@@ -60,26 +61,6 @@ struct KbRv3Smem {
 	KbRv3LinePlan pline[16]; KbFxPlan plan;                         // the plan of this instance, made by the CTA itself
 };
 
-// ---- hand-over primitives: a progress counter in shared memory, written with st.release.cta by ONE thread of the producing role (after the
-// role's own barrier, which orders the other threads' writes before it) and polled with ld.acquire.cta.  No sequentially-consistent fence
-// (__threadfence_block() is MEMBAR.SC.CTA, which also waits for the thread's outstanding global stores: ~1000 cycles per hand-over here).
-KB_D int kb_ld_acquire(const int* p) {
-	int v;
-	asm volatile("ld.acquire.cta.shared.b32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
-	return v;
-}
-KB_D void kb_wait_ge(const int* counter, int target) {
-	while (kb_ld_acquire(counter) < target) __nanosleep(48);
-}
-KB_D void kb_signal(int* counter, int value) {
-	asm volatile("st.release.cta.shared.b32 [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(counter)), "r"(value) : "memory");
-}
-KB_D void kb_bar_group(int id, int threads);
-// a multi-warp role waits: its first warp polls, the others sleep at the role's named barrier (no issue slots, no shared-memory polling)
-KB_D void kb_wait_ge_group(const int* counter, int target, bool first_warp, int bar_id, int threads) {
-	if (first_warp) kb_wait_ge(counter, target);
-	asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "r"(threads) : "memory");
-}
 KB_D unsigned kb_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 KB_D void kb_mbar_init(unsigned long long* bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(kb_smem_u32(bar)), "r"(count) : "memory"); }
 KB_D void kb_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {

@@ -87,7 +87,7 @@ template <int LAYOUT, int NT> KB_D int kb_tile_worker_tid(int warp, int lane) {
 template <int LAYOUT, int NT> constexpr int kb_tile_worker_threads_v = LAYOUT == 0 ? NT - 96 : (3 * (NT / 128) - 2) * 32;
 template <int G, int NT, int LAYOUT = 0>
 __global__ void __launch_bounds__(NT, 1) kb_sub_tiled_kernel(KbSubVoice* __restrict__ voices, KbVoiceHdr* __restrict__ hdr,
-                                                                        float* __restrict__ dst, int n, int total, KbFs fs) {
+                                                                        float* __restrict__ dst, int n, int total, KbFs fs, long long* __restrict__ trace = nullptr) {
 	constexpr int T = KB_TILE_T;
 	extern __shared__ __align__(16) unsigned char kb_smem[];
 	KbSubSmem<G>& S = *reinterpret_cast<KbSubSmem<G>*>(kb_smem);
@@ -116,7 +116,14 @@ __global__ void __launch_bounds__(NT, 1) kb_sub_tiled_kernel(KbSubVoice* __restr
 	const int wtid = kb_tile_worker_tid<LAYOUT, NT>(warp, lane);         // the B/D worker threads
 	constexpr int wthreads = kb_tile_worker_threads_v<LAYOUT, NT>;
 	static_assert(LAYOUT != 2 || NT % 128 == 0, "layout 2 needs whole rows of four warps");
+	// measurement aid (KB_C2_TRACE=<file>, tools/c2_trace.py): CTA 0 stamps clock64() at the start of every tick and when each role has finished its
+	// part of it: trace[(row * 64 + tick) * 2 + {0 start, 1 end}], rows 0 = A, 1 = C, 2 = a worker after B, 3 = the same worker after D
+	#define KB_C2_TR(row_, k_, ph_) do { if (trace && blockIdx.x == 0 && (k_) < 64) trace[(((row_) * 64 + (k_)) * 2 + (ph_))] = clock64(); } while (0)
+	const bool tr_a = (role == 0 || role == 1) && lane == 0, tr_c = role == 2 && lane == 0, tr_w = first_worker && lane == 0;
 	for (int k = 0; k < ntiles + 3; k++) {
+		if (tr_a) KB_C2_TR(0, k, 0);
+		if (tr_c) KB_C2_TR(1, k, 0);
+		if (tr_w) KB_C2_TR(2, k, 0);
 		if (role == 0 || role == 1) {                                    // ---- A, tile k
 			if ((is_env || is_adsr) && k < ntiles) {
 				const int steps = min(T, n - k * T);
@@ -189,6 +196,7 @@ __global__ void __launch_bounds__(NT, 1) kb_sub_tiled_kernel(KbSubVoice* __restr
 					}
 				}
 			}
+			if (tr_w) KB_C2_TR(2, k, 1);
 			if (d >= 0 && d < ntiles) {                                      // ---- D, tile k-3
 				const int steps = min(T, n - d * T);
 				for (int item = wtid; item < G * T; item += wthreads) {
@@ -198,8 +206,12 @@ __global__ void __launch_bounds__(NT, 1) kb_sub_tiled_kernel(KbSubVoice* __restr
 				}
 			}
 		}
+		if (tr_a) KB_C2_TR(0, k, 1);
+		if (tr_c) KB_C2_TR(1, k, 1);
+		if (tr_w) KB_C2_TR(3, k, 1);
 		__syncthreads();
 	}
+	#undef KB_C2_TR
 
 	// write the state back
 	if (is_env) { kb_envr_store(env, voices[v0 + role_voice].env); voices[v0 + role_voice].filter.f = env.out; voices[v0 + role_voice].filter.Q = 10.f; }

@@ -1,0 +1,18 @@
+"""Per-role timeline of kb_sub_tiled_kernel (measurement aid): KB_C2_TRACE=<file> makes the library dump clock64() stamps of CTA 0 for every tick
+(tile) of the last launch: row 0 = envelope warp A (start of tick, end of its work), 1 = filter warp C, 2 = a worker (start, end of B), 3 = the same
+worker's end of D.  Usage: KB_C2_TRACE=/tmp/t.txt python tools/c2_probe.py sub; python tools/c2_trace.py /tmp/t.txt"""
+import collections
+import statistics
+import sys
+
+rows = [tuple(int(x) for x in l.split()) for l in open(sys.argv[1]) if l.strip()]
+by = collections.defaultdict(dict)
+for r, k, a, b in rows:
+    by[r][k] = (a, b)
+ks = [k for k in sorted(by[0]) if 6 <= k <= 28 and k + 1 in by[0]]
+tick = statistics.median(by[0][k + 1][0] - by[0][k][0] for k in ks)
+print(f"tick (start to start) {tick:.0f} cycles")
+for r, name in ((0, "A envelopes"), (1, "C filter")):
+    print(f"{name:14s} busy {statistics.median(by[r][k][1] - by[r][k][0] for k in ks):8.0f}")
+print(f"{'workers B':14s} busy {statistics.median(by[2][k][1] - by[2][k][0] for k in ks):8.0f}")
+print(f"{'workers B+D':14s} busy {statistics.median(by[3][k][1] - by[2][k][0] for k in ks):8.0f}")
