@@ -573,6 +573,7 @@ struct kb_synth_bank : kb_bank_base {
 	float *d_scratch = nullptr, *d_out = nullptr, *d_adsr = nullptr, *d_mix = nullptr;
 	// kb_synth_bank_process_mixdown: the exchange kernel of block k runs on a side stream beside the voice kernels of block k + 1
 	cudaStream_t mix_stream = nullptr; cudaEvent_t ev_mix_in = nullptr; kb_mixdown* last_mixdown = nullptr;
+	KbStaged staged = {}; int staged_slot = -1;   // dirty-voice records the next voice kernel picks up itself (sy_upload with defer_scatter)
 	int total() const { return instances * voices; }
 	template <class T> T& vs(int v) { return *reinterpret_cast<T*>(vstate + (size_t)v * voice_bytes); }
 	KbControl* ctl(int inst) { return controls.data() + (size_t)inst * KB_MAX_CONTROLS; }
@@ -609,7 +610,8 @@ static int sy_fetch(kb_synth_bank* b, bool need_hdr = true, bool need_vstate = t
 	b->host_stale = b->hdr_stale || b->vstate_stale;
 	return KB_OK;
 }
-static int sy_upload(kb_synth_bank* b) {
+static int sy_upload(kb_synth_bank* b, bool defer_scatter = false) {
+	b->staged.records = nullptr; b->staged.count = 0; b->staged.voice_bytes = (int)b->voice_bytes;
 	if (b->dirty) {
 		const size_t rec = sizeof(KbVoiceHdr) + b->voice_bytes;
 		// a full copy is only legal while the whole mirror is current; otherwise only the re-written voices may travel
@@ -628,12 +630,20 @@ static int sy_upload(kb_synth_bank* b) {
 				memcpy(stage + rec_off + (size_t)k * rec, b->hdr + v, sizeof(KbVoiceHdr));
 				memcpy(stage + rec_off + (size_t)k * rec + sizeof(KbVoiceHdr), b->vstate + (size_t)v * b->voice_bytes, b->voice_bytes);
 			}
-			KB_CUDA(cudaMemcpyAsync(b->d_staging, stage, rec_off + (size_t)count * rec, cudaMemcpyHostToDevice, b->stream));
-			KB_CUDA(cudaEventRecord(b->stage_done[slot], b->stream));
+			if (defer_scatter && count <= KB_STAGED_MAX) {
+				// the voice kernel reads the records from this pinned slot itself (kb_tile_scatter); the slot is free again when that kernel has
+				// run: sy_process records stage_done[slot] behind it
+				b->staged.records = stage + rec_off; b->staged.count = count;
+				for (int k = 0; k < count; k++) b->staged.index[k] = stage_index[k];
+				b->staged_slot = slot;
+			} else {
+				KB_CUDA(cudaMemcpyAsync(b->d_staging, stage, rec_off + (size_t)count * rec, cudaMemcpyHostToDevice, b->stream));
+				KB_CUDA(cudaEventRecord(b->stage_done[slot], b->stream));
+				const int words = count * (int)(rec / 4);
+				kb_scatter_voices_kernel<<<std::min(148, (words + 255) / 256), 256, 0, b->stream>>>(b->d_staging + rec_off, (const int*)b->d_staging, count, (int)b->voice_bytes, b->d_hdr, b->d_vstate);
+				b->launches++;
+			}
 			b->stage_used[slot] = true;
-			const int words = count * (int)(rec / 4);
-			kb_scatter_voices_kernel<<<std::min(148, (words + 255) / 256), 256, 0, b->stream>>>(b->d_staging + rec_off, (const int*)b->d_staging, count, (int)b->voice_bytes, b->d_hdr, b->d_vstate);
-			b->launches++;
 			b->h2d_bytes += (long long)count * (long long)(rec + sizeof(int));
 		} else {
 			KB_CUDA(cudaMemcpyAsync(b->d_hdr, b->hdr, b->hdr_count * sizeof(KbVoiceHdr), cudaMemcpyHostToDevice, b->stream));
@@ -712,7 +722,7 @@ extern "C" kb_synth_bank* kb_synth_bank_create(int graph, int instances, int voi
 	b->hdr_count = total; b->vstate_bytes = (size_t)total * b->voice_bytes;
 	if (cudaSetDevice(device) != cudaSuccess || cudaHostAlloc((void**)&b->hdr, total * sizeof(KbVoiceHdr), cudaHostAllocDefault) != cudaSuccess ||
 	    cudaHostAlloc((void**)&b->vstate, b->vstate_bytes, cudaHostAllocDefault) != cudaSuccess ||
-	    cudaHostAlloc((void**)&b->staging, kb_synth_bank::KB_NSTAGE * ((size_t)(total + 1) * (sizeof(KbVoiceHdr) + b->voice_bytes + sizeof(int)) + 16), cudaHostAllocDefault) != cudaSuccess) {
+	    cudaHostAlloc((void**)&b->staging, kb_synth_bank::KB_NSTAGE * ((size_t)(total + 1) * (sizeof(KbVoiceHdr) + b->voice_bytes + sizeof(int)) + 16), cudaHostAllocMapped) != cudaSuccess) {
 		kb_fail(KB_ECUDA, std::string("kb_synth_bank_create: pinned host allocation: ") + cudaGetErrorString(cudaGetLastError()));
 		kb_synth_bank_destroy(b); return nullptr;
 	}
@@ -926,8 +936,17 @@ extern "C" int kb_synth_bank_step(kb_synth_bank* b, int count, const kb_note_eve
 static int sy_process(kb_synth_bank* b, float* out, int n, unsigned flags, kb_mixdown* mixdown, float* out_prev) {
 	if (n == 0) return KB_OK;
 	KB_CUDA(cudaSetDevice(b->device));
-	int rc = sy_upload(b); if (rc) return rc;
 	const int total = b->total(), C = b->channels;
+	// Subtractive / Filter.k, 800..1184 voices: the decoupled kernel (kb_sub_flow_kernel, layout 3), which also scatters the block's re-written
+	// voices itself.  KB_TILE_LAYOUT = 2 / 0 select the lock-step kernels, KB_TILE_G the voices per CTA (A/B measurement, same results)
+	static const int force_g = getenv("KB_TILE_G") ? atoi(getenv("KB_TILE_G")) : 0;
+	static const int layout = getenv("KB_TILE_LAYOUT") ? atoi(getenv("KB_TILE_LAYOUT")) : 3;
+	const bool sub = b->graph == KB_SY_SUBTRACTIVE || b->graph == KB_SY_FILTER_K;
+	int sub_g = total >= 1600 ? 16 : total > 7 * 148 ? 8 : total >= 800 ? 7 : 4;
+	if (force_g) sub_g = force_g;
+	const bool sub_flow = sub && !(flags & KB_LANE_PER_VOICE) && layout == 3 && (sub_g == 7 || sub_g == 8);
+	static const bool scatter_fused = !getenv("KB_SCATTER_FUSED") || atoi(getenv("KB_SCATTER_FUSED")) != 0;     // (A/B measurement)
+	int rc = sy_upload(b, sub_flow && scatter_fused); if (rc) return rc;
 	const bool per_voice = flags & KB_PER_VOICE, dev = flags & KB_DEVICE_PTR, bank_mix = (flags & KB_BANK_MIX) && !per_voice;
 	const size_t out_floats = per_voice ? (size_t)total * C * n : bank_mix ? (size_t)C * n : (size_t)b->instances * C * n;
 	cudaStream_t st = b->stream;
@@ -939,6 +958,7 @@ static int sy_process(kb_synth_bank* b, float* out, int n, unsigned flags, kb_mi
 	};
 	if (b->graph == KB_SY_SYNTHX || per_voice) { rc = wait_prev_exchange(); if (rc) return rc; }
 	float* d_voice_dst = (per_voice && dev) ? out : b->d_scratch;
+	float* d_result_fused = nullptr;                 // set when kb_mix_fused_kernel has also written the bank mix
 	float* d_inst_dst = (!per_voice && !bank_mix && dev) ? out : b->d_out;
 	if (b->graph == KB_SY_SYNTHX) {
 		const int pthreads = total * 132;
@@ -996,9 +1016,7 @@ static int sy_process(kb_synth_bank* b, float* out, int n, unsigned flags, kb_mi
 			}
 		} else {
 			// voices per CTA: as many as still leave >= ~100 CTAs (the serial stages cost the same for any G), KB_TILE_G overrides
-			static const int force_g = getenv("KB_TILE_G") ? atoi(getenv("KB_TILE_G")) : 0;
-			const bool sub = b->graph == KB_SY_SUBTRACTIVE || b->graph == KB_SY_FILTER_K;
-			int g = sub ? (total >= 1600 ? 16 : total >= 800 ? 8 : 4) : (b->graph == KB_SY_SUPERSAW ? (total >= 1024 ? 8 : 2) : (total >= 800 ? 8 : 4));
+			int g = sub ? sub_g : (b->graph == KB_SY_SUPERSAW ? (total >= 1024 ? 8 : 2) : (total >= 800 ? 8 : 4));
 			if (force_g) g = force_g;
 #define KB_LAUNCH_TILED(KERNEL, SMEM, GG, NT, ...)                                                                                   \
 	do {                                                                                                                             \
@@ -1010,30 +1028,43 @@ static int sy_process(kb_synth_bank* b, float* out, int n, unsigned flags, kb_mi
 				KbSubVoice* vs = (KbSubVoice*)b->d_vstate;
 				// KB_TILE_LAYOUT (A/B measurement, same results): 2 = default for 800..1599 voices, the filter warp alone on its SM
 				// sub-partition and both envelopes in one warp (kb_tiled.cuh); 0 = serial roles spread over the sub-partitions
-				static const int layout = getenv("KB_TILE_LAYOUT") ? atoi(getenv("KB_TILE_LAYOUT")) : 2;
 				// KB_C2_TRACE=<file> (measurement aid): per-role clock64() stamps of CTA 0 for every tick of the last launch
 				static const char* c2_trace_path = getenv("KB_C2_TRACE");
 				static long long* c2_trace = nullptr;
-				if (c2_trace_path && !c2_trace) { KB_CUDA(cudaMalloc(&c2_trace, 4 * 64 * 2 * sizeof(long long))); }
-				if (c2_trace) KB_CUDA(cudaMemsetAsync(c2_trace, 0, 4 * 64 * 2 * sizeof(long long), st));
+				if (c2_trace_path && !c2_trace) { KB_CUDA(cudaMalloc(&c2_trace, 8 * 64 * 2 * sizeof(long long))); }
+				if (c2_trace) KB_CUDA(cudaMemsetAsync(c2_trace, 0, 8 * 64 * 2 * sizeof(long long), st));
 #define KB_LAUNCH_SUB(GG, NT, LAY)                                                                                                    \
 	do {                                                                                                                             \
 		static bool attr_set = false;                                                                                                \
 		if (!attr_set) { cudaFuncSetAttribute(kb_sub_tiled_kernel<GG, NT, LAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KbSubSmem<GG>)); attr_set = true; } \
 		kb_sub_tiled_kernel<GG, NT, LAY><<<(total + GG - 1) / GG, NT, sizeof(KbSubSmem<GG>), st>>>(vs, b->d_hdr, d_voice_dst, n, total, b->fs, c2_trace); \
 	} while (0)
-				if (g >= 16) KB_LAUNCH_SUB(16, 1024, 0);
-				else if (g >= 7 && layout == 2) KB_LAUNCH_SUB(8, 768, 2);
+				// layout 3 (round 2): the same stages decoupled, kb_sub_flow_kernel; KB_TILE_G=7 -> 147 CTAs, KB_TILE_ASP0=1 -> envelope warp beside the filter warp
+				static const int asp0 = getenv("KB_TILE_ASP0") ? atoi(getenv("KB_TILE_ASP0")) : 1;
+#define KB_LAUNCH_FLOW(GG, ASP0)                                                                                                      \
+	do {                                                                                                                             \
+		static bool attr_set = false;                                                                                                \
+		if (!attr_set) { cudaFuncSetAttribute(kb_sub_flow_kernel<GG, ASP0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KbSubFlowSmem<GG>)); attr_set = true; } \
+		kb_sub_flow_kernel<GG, ASP0><<<(total + GG - 1) / GG, 768, sizeof(KbSubFlowSmem<GG>), st>>>(vs, b->d_hdr, d_voice_dst, n, total, b->fs, b->staged, c2_trace); \
+	} while (0)
+				if (sub_flow) {
+					if (g == 7) { if (asp0) KB_LAUNCH_FLOW(7, true); else KB_LAUNCH_FLOW(7, false); }
+					else { if (asp0) KB_LAUNCH_FLOW(8, true); else KB_LAUNCH_FLOW(8, false); }
+					if (b->staged.count > 0) { KB_CUDA(cudaEventRecord(b->stage_done[b->staged_slot], st)); b->staged.count = 0; }
+				}
+				else if (g >= 16) KB_LAUNCH_SUB(16, 1024, 0);
+				else if (g >= 7 && layout >= 2) KB_LAUNCH_SUB(8, 768, 2);
 				else if (g >= 8) KB_LAUNCH_SUB(8, 512, 0);
 				else if (g == 7) KB_LAUNCH_SUB(7, 544, 0);               // 448 worker threads cover a 7 x 128 tile in exactly two rounds
 				else KB_LAUNCH_SUB(4, 320, 0);
 #undef KB_LAUNCH_SUB
+#undef KB_LAUNCH_FLOW
 				if (c2_trace) {
-					std::vector<long long> tr(4 * 64 * 2);
+					std::vector<long long> tr(8 * 64 * 2);
 					KB_CUDA(cudaMemcpyAsync(tr.data(), c2_trace, tr.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
 					KB_CUDA(cudaStreamSynchronize(st));
 					if (FILE* f = fopen(c2_trace_path, "w")) {
-						for (int r = 0; r < 4; r++) for (int k = 0; k < 64; k++) if (tr[(r * 64 + k) * 2] || tr[(r * 64 + k) * 2 + 1]) fprintf(f, "%d %d %lld %lld\n", r, k, tr[(r * 64 + k) * 2], tr[(r * 64 + k) * 2 + 1]);
+						for (int r = 0; r < 8; r++) for (int k = 0; k < 64; k++) if (tr[(r * 64 + k) * 2] || tr[(r * 64 + k) * 2 + 1]) fprintf(f, "%d %d %lld %lld\n", r, k, tr[(r * 64 + k) * 2], tr[(r * 64 + k) * 2 + 1]);
 						fclose(f);
 					}
 				}
@@ -1055,9 +1086,22 @@ static int sy_process(kb_synth_bank* b, float* out, int n, unsigned flags, kb_mi
 		b->prof_end();
 		b->launches++;
 		if (!per_voice) {
-			dim3 grid((n + 255) / 256, b->instances);
 			rc = wait_prev_exchange(); if (rc) return rc;
-			kb_mix_kernel<<<grid, 256, 0, st>>>(b->d_scratch, b->d_hdr, d_inst_dst, n, b->voices, (flags & KB_MIX_SUM) ? 1 : 0);
+			// KB_MIX_FUSED=0 keeps the two-kernel mix (A/B measurement, same results)
+			static const bool mix_fused = !getenv("KB_MIX_FUSED") || atoi(getenv("KB_MIX_FUSED")) != 0;
+			if (mix_fused && C == 1 && (flags & KB_MIX_SUM)) {
+				// one launch for the voice sums of every instance and — on one GPU — the bank mix (kb_mix_fused_kernel)
+				static int smem_max = 0;
+				if (!smem_max) { KB_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, b->device)); KB_CUDA(cudaFuncSetAttribute(kb_mix_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max)); }
+				const size_t per_inst = (size_t)b->voices * KB_MIXF_TS * sizeof(float) + KB_MIXF_TS * sizeof(float) + (size_t)b->voices * sizeof(int);
+				const int group = (int)std::max<size_t>(1, std::min<size_t>((size_t)b->instances, (size_t)smem_max / per_inst));
+				const bool fuse_bank = bank_mix && !mixdown;
+				if (fuse_bank) d_result_fused = dev ? out : b->d_mix;
+				kb_mix_fused_kernel<<<(n + KB_MIXF_TS - 1) / KB_MIXF_TS, 1024, group * per_inst, st>>>(b->d_scratch, b->d_hdr, d_inst_dst, d_result_fused, n, b->voices, b->instances, group);
+			} else {
+				dim3 grid((n + 255) / 256, b->instances);
+				kb_mix_kernel<<<grid, 256, 0, st>>>(b->d_scratch, b->d_hdr, d_inst_dst, n, b->voices, (flags & KB_MIX_SUM) ? 1 : 0);
+			}
 			b->launches++;
 		}
 	}
@@ -1073,7 +1117,8 @@ static int sy_process(kb_synth_bank* b, float* out, int n, unsigned flags, kb_mi
 		b->host_stale = true; b->hdr_stale = true; b->vstate_stale = true;
 		return KB_OK;
 	}
-	if (bank_mix) {
+	if (bank_mix && d_result_fused) d_result = d_result_fused;
+	else if (bank_mix) {
 		d_result = dev ? out : b->d_mix;
 		kb_bank_mix_kernel<<<(C * n + 255) / 256, 256, 0, st>>>(b->d_out, d_result, C * n, b->instances);
 		b->launches++;

@@ -121,6 +121,51 @@ __global__ void __launch_bounds__(256) kb_mix_kernel(const float* __restrict__ s
 	out[(size_t)inst * n + t] = acc;
 }
 
+// The same voice sum for a whole bank in one launch (round 2; sum mode, one channel row per voice): CTA = 32 samples of every instance.  All
+// threads first pull the CTA's [instances][voices][32] slab of the per-voice streams from L2 with every load in flight at once (the loop of
+// kb_mix_kernel walks the 128 voices eight loads at a time: 16 dependent L2 round trips); then one warp per instance adds its voices in voice
+// order from shared memory (the reference's order, klang.h:4450-4456 / 4842-4848) and writes the instance output; warp 0 finally adds the
+// instance sums in instance order into the bank mix (kb_bank_mix_kernel's sum).  Instances are taken in groups that fit the shared memory.
+#define KB_MIXF_TS 32
+__global__ void __launch_bounds__(1024) kb_mix_fused_kernel(const float* __restrict__ scratch, const KbVoiceHdr* __restrict__ hdr, float* __restrict__ inst_out,
+                                                            float* __restrict__ bank_out, int n, int voices, int instances, int group) {
+	extern __shared__ __align__(16) unsigned char kb_mixf_smem[];
+	float* tile = reinterpret_cast<float*>(kb_mixf_smem);                   // [group][voices][32]
+	float* isum = tile + (size_t)group * voices * KB_MIXF_TS;               // [group][32]
+	int* s_act = reinterpret_cast<int*>(isum + (size_t)group * KB_MIXF_TS);  // [group][voices]
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+	const int t = blockIdx.x * KB_MIXF_TS + lane;
+	float bank = 0.f;
+	for (int i0 = 0; i0 < instances; i0 += group) {
+		const int gi = min(group, instances - i0), rows = gi * voices;
+		if (i0) __syncthreads();
+		for (int r = tid; r < rows; r += blockDim.x) s_act[r] = hdr[(size_t)i0 * voices + r].active;
+		__syncthreads();
+		for (int r0 = warp; r0 < rows; r0 += 16 * nwarps) {
+			float x[16];
+			#pragma unroll
+			for (int j = 0; j < 16; j++) {
+				const int r = r0 + j * nwarps;
+				x[j] = (r < rows && t < n && s_act[r < rows ? r : 0]) ? __ldcs(scratch + ((size_t)i0 * voices + r) * n + t) : 0.f;
+			}
+			#pragma unroll
+			for (int j = 0; j < 16; j++) { const int r = r0 + j * nwarps; if (r < rows) tile[(size_t)r * KB_MIXF_TS + lane] = x[j]; }
+		}
+		__syncthreads();
+		for (int i = warp; i < gi; i += nwarps) {
+			const float* tp = tile + (size_t)i * voices * KB_MIXF_TS + lane;
+			const int* ap = s_act + i * voices;
+			float acc = 0.f;
+			for (int v = 0; v < voices; v++) if (ap[v]) acc = acc + tp[(size_t)v * KB_MIXF_TS];   // summed in voice order; inactive voices are skipped like kb_mix_kernel
+			isum[i * KB_MIXF_TS + lane] = acc;
+			if (t < n) inst_out[(size_t)(i0 + i) * n + t] = acc;
+		}
+		__syncthreads();
+		if (warp == 0 && bank_out) for (int i = 0; i < gi; i++) bank += isum[i * KB_MIXF_TS + lane];
+	}
+	if (warp == 0 && bank_out && t < n) bank_out[t] = bank;
+}
+
 // event upload: dirty voices travel packed in one staging buffer [count][hdr | blob] and are scattered to their slots
 __global__ void kb_scatter_voices_kernel(const unsigned char* __restrict__ staging, const int* __restrict__ index, int count, int voice_bytes,
                                          KbVoiceHdr* __restrict__ hdr, unsigned char* __restrict__ vstate) {

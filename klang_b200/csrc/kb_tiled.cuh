@@ -17,6 +17,7 @@
 // buffers are double buffered (A->B, B->C, C->D).
 #pragma once
 #include "kb_graphs.cuh"
+#include "kb_sync.cuh"
 
 #define KB_TILE_T 128      // samples per tile
 // G = voices per CTA and NT = threads per CTA are template parameters: the serial stages cost the same for any G <= 32
@@ -229,6 +230,236 @@ __global__ void __launch_bounds__(NT, 1) kb_sub_tiled_kernel(KbSubVoice* __restr
 		kb_osm_advance(o, (uint32_t)n);
 		voices[v0 + lane].osc.offset = o.offset;
 		voices[v0 + lane].osc.state = o.state;
+	}
+}
+
+// The event upload folded into the voice kernel (round 2: no copy-engine operation and no scatter launch in front of the voice kernel — a
+// kernel queued behind a host-to-device copy starts several microseconds after it).  Voices re-written by the host since the last block wait
+// packed in PINNED HOST memory, [count][hdr | blob]; their voice indices travel in the kernel's parameters.  A CTA whose voices are listed
+// pulls their records over PCIe into shared memory (one round trip, and only for the CTAs concerned), LOADS those voices from there, and
+// copies the records to the voices' slots by fire-and-forget stores (the slot is next read by the following launch; this kernel's own state
+// write-back comes many barriers later).  The header's `active` word is written by the prologue, not by the copy.  More than KB_STAGED_MAX
+// re-written voices, and every other kernel, take the copy + kb_scatter_voices_kernel path.
+#define KB_STAGED_MAX 128
+struct KbStaged { const unsigned char* records; int count, voice_bytes; int index[KB_STAGED_MAX]; };
+template <int G, class VOICE> struct KbStagedSmem { int src[G]; unsigned rec[G][(sizeof(KbVoiceHdr) + sizeof(VOICE)) / 4]; };
+template <int G, class VOICE>
+KB_D void kb_tile_scatter(const KbStaged& sg, KbVoiceHdr* hdr, VOICE* voices, int v0, KbStagedSmem<G, VOICE>& m) {
+	if (threadIdx.x < G) m.src[threadIdx.x] = -1;
+	if (sg.count <= 0) return;                                           // (uniform over the grid)
+	__syncthreads();
+	for (int k = threadIdx.x; k < sg.count; k += blockDim.x) {
+		const int v = sg.index[k];
+		if (v >= v0 && v < v0 + G) m.src[v - v0] = k;                     // (a voice is listed once)
+	}
+	__syncthreads();
+	constexpr int rec_words = (int)(sizeof(KbVoiceHdr) + sizeof(VOICE)) / 4, hdr_words = (int)sizeof(KbVoiceHdr) / 4;
+	for (int i = threadIdx.x; i < G * rec_words; i += blockDim.x) {
+		const int g = i / rec_words, w = i % rec_words, k = m.src[g];
+		if (k >= 0) m.rec[g][w] = reinterpret_cast<const unsigned*>(sg.records)[(size_t)k * rec_words + w];
+	}
+	__syncthreads();
+	for (int i = threadIdx.x; i < G * rec_words; i += blockDim.x) {
+		const int g = i / rec_words, w = i % rec_words;
+		if (m.src[g] < 0 || w == (int)(offsetof(KbVoiceHdr, active) / 4)) continue;
+		if (w < hdr_words) reinterpret_cast<unsigned*>(hdr + v0 + g)[w] = m.rec[g][w];
+		else reinterpret_cast<unsigned*>(voices + v0 + g)[w - hdr_words] = m.rec[g][w];
+	}
+}
+template <int G, class VOICE>
+KB_D const KbVoiceHdr& kb_tile_hdr_src(const KbStagedSmem<G, VOICE>& m, const KbVoiceHdr* hdr, int v0, int i) {
+	return m.src[i] < 0 ? hdr[v0 + i] : *reinterpret_cast<const KbVoiceHdr*>(m.rec[i]);
+}
+template <int G, class VOICE>
+KB_D const VOICE& kb_tile_voice_src(const KbStagedSmem<G, VOICE>& m, const VOICE* voices, int v0, int i) {
+	return m.src[i] < 0 ? voices[v0 + i] : *reinterpret_cast<const VOICE*>(m.rec[i] + sizeof(KbVoiceHdr) / 4);
+}
+
+// ---- the same four stages WITHOUT the lock step (round 2): every role runs its own tile loop and meets the others through progress
+// counters in shared memory (kb_sync.cuh: st.release by one thread behind the role's own barrier, ld.acquire polling), over hand-over
+// buffers four tiles deep (A -> D: eight), so a role waits only when the role it depends on is really behind — the tick of the lock-step
+// kernel was max(A, B + D, C) PLUS the skew of one CTA-wide barrier per tile.  768 threads: warp 0 = C alone on SM sub-partition 0 (with
+// A_SP0 the envelope warp is warp 4, the only other warp there — two latency-bound chains interleave in the issue slots neither fills;
+// without it A is warp 1 and shares sub-partition 1 with worker warps), 2 * G worker warps on sub-partitions 1-3 = exactly two rounds
+// over a G x 128 tile (G = 7: 147 CTAs for 1024 voices, one per SM, and an eighth less B + D work per CTA than G = 8 on 128 CTAs).
+// Arithmetic and its order per voice are those of kb_sub_tiled_kernel: bit-identical output and state.
+template <int G> struct KbSubFlowSmem {
+	KbTileCommon<G> c;
+	KbTileRows4<G> coef[4];          // B -> C
+	KbTileRows<G> cut[4], amp[8];    // A -> B, A -> D
+	KbTileRowsA<G> out[4];           // C -> D
+	float4 lastc[G];
+	KbOsm osc[G];
+	int a_done, b_done, c_done, d_done;   // tiles finished by each stage
+	KbStagedSmem<G, KbSubVoice> sc;       // the staged upload of this CTA's voices (kb_tile_scatter)
+};
+template <int G, bool A_SP0>
+__global__ void __launch_bounds__(768, 1) kb_sub_flow_kernel(KbSubVoice* __restrict__ voices, KbVoiceHdr* __restrict__ hdr,
+                                                             float* __restrict__ dst, int n, int total, KbFs fs, const __grid_constant__ KbStaged staged, long long* __restrict__ trace = nullptr) {
+	constexpr int T = KB_TILE_T, W = 2 * G, wthreads = W * 32, LAG = 3;
+	static_assert(2 * G <= 32 && W <= 17, "both envelopes of the G voices in one warp; worker warps on three sub-partitions of six rows");
+	extern __shared__ __align__(16) unsigned char kb_smem[];
+	KbSubFlowSmem<G>& S = *reinterpret_cast<KbSubFlowSmem<G>*>(kb_smem);
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int v0 = blockIdx.x * G;
+	const long long t_entry = trace ? clock64() : 0;
+	if (tid == 0) { S.a_done = 0; S.b_done = 0; S.c_done = 0; S.d_done = 0; }
+	kb_tile_scatter(staged, hdr, voices, v0, S.sc);
+	if (tid < G) {                                                       // kb_tile_prologue with the staged headers
+		const int v = v0 + tid;
+		const int act = (v < total && kb_tile_hdr_src(S.sc, hdr, v0, tid).stage != KB_NOTE_OFF) ? 1 : 0;
+		S.c.active[tid] = act;
+		if (v < total) hdr[v].active = act;
+	}
+	__syncthreads();
+
+	const int sp = warp & 3, row = warp >> 2;
+	const bool is_c_warp = warp == 0, is_a_warp = A_SP0 ? warp == 4 : warp == 1;
+	const int widx = sp == 0 ? -1 : (A_SP0 ? row * 3 + (sp - 1) : row * 3 + (sp - 1) - 1);      // worker warps, spread evenly over sub-partitions 1-3
+	const bool worker = widx >= 0 && widx < W && !is_a_warp;
+	const int wtid = widx * 32 + lane;
+	const int a_sub = (is_a_warp && lane >= G) ? 1 : 0;
+	const int role_voice = lane - a_sub * G;
+	const bool role_ok = role_voice < G && S.c.active[role_voice < G ? role_voice : 0];
+	const bool is_env = is_a_warp && a_sub == 0 && role_ok, is_adsr = is_a_warp && a_sub == 1 && role_ok, is_flt = is_c_warp && role_ok;
+	const int slot = (is_adsr ? G : 0) + role_voice;
+	KbEnvR env;
+	float z0 = 0.f, z1 = 0.f;
+	if (is_env) kb_tile_load_env(S.c, slot, kb_tile_voice_src(S.sc, voices, v0, role_voice).env, env);
+	if (is_adsr) kb_tile_load_env(S.c, slot, kb_tile_voice_src(S.sc, voices, v0, role_voice).adsr, env);
+	if (is_flt) { const KbBiquad& b = kb_tile_voice_src(S.sc, voices, v0, role_voice).filter; z0 = b.z0; z1 = b.z1; }
+	if (worker && wtid < G && S.c.active[wtid]) S.osc[wtid] = kb_tile_voice_src(S.sc, voices, v0, wtid).osc;
+	__syncthreads();
+
+	const int ntiles = (n + T - 1) / T;
+	const long long t_loop = trace ? clock64() : 0;
+	#define KB_C2_TR(row_, k_, ph_) do { if (trace && blockIdx.x == 0 && (k_) < 64) trace[(((row_) * 64 + (k_)) * 2 + (ph_))] = clock64(); } while (0)
+	if (is_a_warp) {                                                     // ---- A: both envelopes of every voice, tile after tile
+		for (int k = 0; k < ntiles; k++) {
+			if (k >= 4) kb_wait_ge(&S.b_done, k - 3);                    // cut[k & 3] was tile k-4's
+			if (k >= 8) kb_wait_ge(&S.d_done, k - 7);                    // amp[k & 7] was tile k-8's
+			if (lane == 0) KB_C2_TR(0, k, 0);
+			if (is_env || is_adsr) {
+				const int steps = min(T, n - k * T);
+				float* rowp = is_env ? S.cut[k & 3].r[role_voice] : S.amp[k & 7].r[role_voice];
+				kb_envr_run(fs, env, S.c.px[slot], S.c.py[slot], rowp, steps);
+			}
+			__syncwarp();
+			if (lane == 0) { kb_signal(&S.a_done, k + 1); KB_C2_TR(0, k, 1); }
+		}
+	} else if (is_c_warp) {                                              // ---- C: the filter recurrence
+		for (int c = 0; c < ntiles; c++) {
+			kb_wait_ge(&S.b_done, c + 1);
+			if (c >= 4) kb_wait_ge(&S.d_done, c - 3);                    // out[c & 3] was tile c-4's
+			if (lane == 0) KB_C2_TR(1, c, 0);
+			if (is_flt) {
+				const int steps = min(T, n - c * T), v = role_voice;
+				const float4* pc = S.coef[c & 3].r[v];
+				float* po = S.out[c & 3].r[v];
+				auto group = [&](const float4 (&cf)[4], int t) {         // Filter::process, klang.h:5605-5612 (see kb_sub_tiled_kernel)
+					float y[4];
+					#pragma unroll
+					for (int j = 0; j < 4; j++) {
+						y[j] = cf[j].x + z0;
+						z0 = cf[j].y - cf[j].z * y[j] + z1;
+						z1 = cf[j].x - cf[j].w * y[j];
+					}
+					*reinterpret_cast<float4*>(po + t) = make_float4(y[0], y[1], y[2], y[3]);
+				};
+				float4 ca[4], cb[4];
+				#pragma unroll
+				for (int j = 0; j < 4; j++) ca[j] = pc[j];
+				int t = 0;
+				for (; t + 8 <= steps; t += 8) {
+					#pragma unroll
+					for (int j = 0; j < 4; j++) cb[j] = pc[t + 4 + j];
+					group(ca, t);
+					#pragma unroll
+					for (int j = 0; j < 4; j++) ca[j] = pc[t + 8 + j];
+					group(cb, t + 4);
+				}
+				for (; t < steps; t++) {
+					const float4 c1 = pc[t];
+					const float y = c1.x + z0;
+					z0 = c1.y - c1.z * y + z1;
+					z1 = c1.x - c1.w * y;
+					po[t] = y;
+				}
+			}
+			__syncwarp();
+			if (lane == 0) { kb_signal(&S.c_done, c + 1); KB_C2_TR(1, c, 1); }
+		}
+	} else if (worker) {                                                 // ---- B (tile j) then D (tile j - LAG), two rounds each
+		const bool first = widx == 0;
+		for (int j = 0; j < ntiles + LAG; j++) {
+			// one poll per iteration by the first worker warp, the others park at the role's barrier: B needs A's tile j and its coef buffer
+			// back from C (tile j-4), D needs C's tile j-LAG.  The barrier also closes the previous iteration's D for every worker.
+			if (first) {
+				if (j < ntiles) kb_wait_ge(&S.a_done, j + 1);
+				kb_wait_ge(&S.c_done, min(max(j - LAG + 1, 0), ntiles));
+			}
+			kb_bar_group(1, wthreads);
+			if (wtid == 0) { if (j - 1 - LAG >= 0) kb_signal(&S.d_done, j - LAG); KB_C2_TR(2, j, 0); }
+			if (j < ntiles) {
+				const int b = j, steps = min(T, n - b * T);
+				#pragma unroll
+				for (int r = 0; r < 2; r++) {
+					const int item = wtid + r * wthreads, v = item / T, t = item % T;
+					if (t < steps && S.c.active[v]) {
+						const float f = S.cut[b & 3].r[v][t];
+						const float w = f * fs.w;
+						float sin0, cos0;
+						kb_sincosf(w, sin0, cos0);
+						const float a = sin0 / (2.f * 10.f);
+						const float inv = kb_const_inv(1.f + a);
+						float4 cf;
+						cf.z = inv * (-2.f * cos0);
+						cf.w = inv * (1.f - a);
+						cf.x = inv * (1.f - cos0) * 0.5f;
+						cf.y = inv * (1.f - cos0);
+						if (b * T + t == n - 1) S.lastc[v] = cf;
+						const float in = kb_osm_at(S.osc[v], (uint32_t)(b * T + t));
+						cf.x = cf.x * in; cf.y = cf.y * in;
+						S.coef[b & 3].r[v][t] = cf;
+					}
+				}
+				kb_bar_group(2, wthreads);
+				if (wtid == 0) { kb_signal(&S.b_done, b + 1); KB_C2_TR(2, j, 1); }
+			}
+			const int d = j - LAG;
+			if (d >= 0 && d < ntiles) {
+				const int steps = min(T, n - d * T);
+				#pragma unroll
+				for (int r = 0; r < 2; r++) {
+					const int item = wtid + r * wthreads, v = item / T, t = item % T;
+					if (t < steps && v0 + v < total)                             // out *= adsr++   Filter.k:33
+						dst[(size_t)(v0 + v) * n + d * T + t] = S.c.active[v] ? S.out[d & 3].r[v][t] * S.amp[d & 7].r[v][t] : 0.f;
+				}
+			}
+			if (wtid == 0) KB_C2_TR(3, j, 1);
+		}
+	}
+	#undef KB_C2_TR
+	__syncthreads();
+	// rows 4-7 of the trace: per CTA (prologue, tile loop) cycles
+	if (trace && tid == 0 && blockIdx.x < 256) { const long long t1 = clock64(); trace[(4 * 64 + blockIdx.x) * 2] = t_loop - t_entry; trace[(4 * 64 + blockIdx.x) * 2 + 1] = t1 - t_loop; }
+
+	// write the state back
+	if (is_env) { kb_envr_store(env, voices[v0 + role_voice].env); voices[v0 + role_voice].filter.f = env.out; voices[v0 + role_voice].filter.Q = 10.f; }
+	if (is_adsr) {
+		kb_envr_store(env, voices[v0 + role_voice].adsr);
+		if (env.stage == KB_ENV_OFF) hdr[v0 + role_voice].stage = KB_NOTE_OFF;
+	}
+	if (is_flt) {
+		KbBiquad& b = voices[v0 + role_voice].filter;
+		const float4 lc = S.lastc[role_voice];
+		b.z0 = z0; b.z1 = z1; b.b0 = lc.x; b.b2 = lc.x; b.b1 = lc.y; b.a1 = lc.z; b.a2 = lc.w;
+	}
+	if (worker && wtid < G && S.c.active[wtid]) {
+		KbOsm o = S.osc[wtid];
+		kb_osm_advance(o, (uint32_t)n);
+		voices[v0 + wtid].osc.offset = o.offset;
+		voices[v0 + wtid].osc.state = o.state;
 	}
 }
 

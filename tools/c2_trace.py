@@ -16,3 +16,8 @@ for r, name in ((0, "A envelopes"), (1, "C filter")):
     print(f"{name:14s} busy {statistics.median(by[r][k][1] - by[r][k][0] for k in ks):8.0f}")
 print(f"{'workers B':14s} busy {statistics.median(by[2][k][1] - by[2][k][0] for k in ks):8.0f}")
 print(f"{'workers B+D':14s} busy {statistics.median(by[3][k][1] - by[2][k][0] for k in ks):8.0f}")
+
+cta = [(a, b) for r in (4, 5, 6, 7) for k, (a, b) in sorted(by.get(r, {}).items())]
+if cta:
+    pro = [a for a, b in cta]; loop = [b for a, b in cta]
+    print(f"per CTA ({len(cta)}): prologue median {statistics.median(pro):.0f} max {max(pro)}; tile loop median {statistics.median(loop):.0f} min {min(loop)} max {max(loop)} cycles")
