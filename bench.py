@@ -526,7 +526,7 @@ def main():
     traffic = None
     try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("kb_sub_tiled_kernel")
+            traffic = (lambda t: t.get("kb_sub_flow_kernel", t.get("kb_sub_tiled_kernel")))(json.load(f))
     except Exception:
         pass
     # What bounds this kernel: one fp32 recurrence per voice (the TDF-II biquad, klang.h:5605-5612) that parity forbids re-ordering:
@@ -536,7 +536,7 @@ def main():
     floor_cycles = 16.9
     kernel_vs = total * BLOCK / (k_ms_avg * 1e-3)
     floor_vs = total * sm_max * 1e6 / floor_cycles
-    roofline = {"bound": "latency", "kernel": "kb_sub_tiled_kernel", "achieved": kernel_vs, "peak": floor_vs, "unit": "voice-samples/s",
+    roofline = {"bound": "latency", "kernel": "kb_sub_flow_kernel", "achieved": kernel_vs, "peak": floor_vs, "unit": "voice-samples/s",
                 "frac": kernel_vs / floor_vs, "traffic": traffic,
                 "peak_source": f"serial-chain floor: {floor_cycles} cycles per sample of the TDF-II biquad recurrence (measured alone, profiles/r01_probes.txt) at the {sm_max:.0f} MHz of MEASURED_PEAKS.json, x {total} voices in flight",
                 "latency_frac": kernel_vs / floor_vs,
@@ -769,6 +769,7 @@ def extras(kb, torch, dev, stream, flush_l2, hbm_peak, peak_src, device_index, w
 
     streaming_line("c1_gain_1x4096", kb.FX_GAIN, 1, 4096)
     streaming_line("c1_gain_batched_64x1Mi", kb.FX_GAIN, 64, 1 << 20)
+    streaming_line("c1_gain_batched_256x1Mi", kb.FX_GAIN, 256, 1 << 20)      # 2 GiB of traffic per call: the size class the copy peak was measured on
     if with_cpu:
         res["c1_gain_1x4096"]["cpu_reference"] = cpu_extra("fx", oracle.FX_GAIN, 1, 4096, 2000)
 

@@ -127,6 +127,14 @@ long long kb_fx_bank_state_bytes(const kb_fx_bank* bank); /* bytes of instance s
 int kb_fx_bank_profile(kb_fx_bank* bank, int enable);
 int kb_fx_bank_profile_read(kb_fx_bank* bank, double* kernel_ms, long long* kernel_launches);
 
+/* Debug taps: `x >> debug` in a program's process() (klang.h:3132-3287 Debug / Debug::Buffer / Debug::Session; examples/PingPong.k:61,
+ * Gain/RM.k:22, Gain/Tremolo.k:27, Modulation/ModDelay.k:24).  In the reference the host opens a Debug::Session per block (clears the buffer),
+ * every `>> debug` adds into the current frame's sample, and Session::getAudio() hands the block's capture to the IDE.  Here: while enabled,
+ * each process() also leaves the capture of every instance on the device; debug_read copies the last block's capture, dst = [instances][n]
+ * (host memory, or device memory with KB_DEVICE_PTR), and returns 1 — or 0 if the bank's program has no tap / nothing new (Buffer::get). */
+int kb_fx_bank_debug_enable(kb_fx_bank* bank, int enable);
+int kb_fx_bank_debug_read(kb_fx_bank* bank, float* dst, int n, unsigned flags);
+
 /* ------------------------------------------------------------------------------------- synth bank */
 /* `instances` Synth objects of `graph`, each with `voices` notes (notes.add<MyNote>(voices), <= 128, klang.h:4311). */
 kb_synth_bank* kb_synth_bank_create(int graph, int instances, int voices, float fs, int max_block, int device);

@@ -29,6 +29,7 @@ SYMBOLS = [
     ("kb_fx_bank_process", _i, [_vp, _vp, _i, _u]), ("kb_fx_bank_sync", _i, [_vp]), ("kb_fx_bank_set_stream", _i, [_vp, _vp]),
     ("kb_fx_bank_bytes_per_frame", _d, [_vp]), ("kb_fx_bank_launches", _ll, [_vp]), ("kb_fx_bank_state_bytes", _ll, [_vp]), ("kb_fx_bank_parallel_instances", _i, [_vp]), ("kb_fx_bank_tolerance_instances", _i, [_vp]),
     ("kb_fx_bank_profile", _i, [_vp, _i]), ("kb_fx_bank_profile_read", _i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
+    ("kb_fx_bank_debug_enable", _i, [_vp, _i]), ("kb_fx_bank_debug_read", _i, [_vp, _vp, _i, _u]),
     ("kb_synth_bank_create", _vp, [_i, _i, _i, _f, _i, _i]), ("kb_synth_bank_destroy", None, [_vp]),
     ("kb_synth_bank_channels", _i, [_vp]), ("kb_synth_bank_instances", _i, [_vp]), ("kb_synth_bank_voices", _i, [_vp]),
     ("kb_synth_bank_num_controls", _i, [_vp]),
@@ -142,6 +143,18 @@ class FxBank:
         v = C.c_float()
         _check(lib().kb_fx_bank_get_control(self.h, instance, idx, C.byref(v)), "kb_fx_bank_get_control")
         return float(v.value)
+
+    def debug_enable(self, on=True):
+        """`>> debug` capture (klang.h:3132-3287): while on, every process() also records the block's debug tap of every instance."""
+        _check(lib().kb_fx_bank_debug_enable(self.h, 1 if on else 0), "kb_fx_bank_debug_enable")
+
+    def debug_read(self, n):
+        """The last block's capture, float32 [instances, n], or None if the program taps nothing (Debug::Buffer::get)."""
+        out = np.zeros((self.instances, n), np.float32)
+        rc = lib().kb_fx_bank_debug_read(self.h, out.ctypes.data, n, 0)
+        if rc < 0:
+            _check(rc, "kb_fx_bank_debug_read")
+        return out if rc == 1 else None
 
     def process_inplace(self, io, n=None, flags=0):
         """io: float32 [instances, channels, n], numpy (host) or torch CUDA tensor (asynchronous)."""
@@ -313,6 +326,7 @@ class SynthBank:
 class _Fx:
     def __init__(self, eng, graph):
         self.bank = FxBank(graph, 1, eng.fs, eng.max_block, eng.device)
+        self.bank.debug_enable(True)
         self.channels, self.num_controls = self.bank.channels, self.bank.num_controls
 
     def close(self):
@@ -328,7 +342,13 @@ class _Fx:
         """x: float32 [channels, n] ([n] for mono effects). Returns a processed copy (the reference works in place)."""
         y = np.array(x, np.float32, copy=True, order="C")
         self.bank.process_inplace(y.reshape(1, self.channels, -1))
+        self._last_n = y.shape[-1]
         return y
+
+    def debug(self):
+        """The `>> debug` capture of the last block, float32 [n], or None (same call as oracle.bindings.Fx.debug)."""
+        d = self.bank.debug_read(self._last_n)
+        return None if d is None else d[0]
 
 
 class _Synth:

@@ -100,6 +100,7 @@ struct kb_fx_bank : kb_bank_base {
 	bool device_writes_controls = false;
 	unsigned last_flags = 0; int last_schedule = 0;             // flags / Reverb.k schedule of the last process() call
 	bool rv_all_resident = false;                               // Reverb.k: every instance runs on kb_reverb3_kernel (no fallback launches needed)
+	float* d_debug = nullptr; bool debug_on = false; int debug_n = -1;   // `>> debug` capture of the last block, [instances][max_block] (kb_fx_bank_debug_*)
 	template <class T> T& st(int i) { return *reinterpret_cast<T*>(state.data() + (size_t)i * state_bytes); }
 };
 
@@ -205,7 +206,7 @@ extern "C" void kb_fx_bank_destroy(kb_fx_bank* b) {
 	if (!b) return;
 	cudaSetDevice(b->device);
 	if (b->stream) cudaStreamSynchronize(b->stream);
-	cudaFree(b->d_hdr); cudaFree(b->d_state); cudaFree(b->d_rings); cudaFree(b->d_io); cudaFree(b->d_old); cudaFree(b->d_plan); cudaFree(b->d_sync);
+	cudaFree(b->d_hdr); cudaFree(b->d_state); cudaFree(b->d_rings); cudaFree(b->d_io); cudaFree(b->d_old); cudaFree(b->d_plan); cudaFree(b->d_sync); cudaFree(b->d_debug);
 	b->prof_free();
 	if (b->own_stream) cudaStreamDestroy(b->own_stream);
 	delete b;
@@ -339,6 +340,36 @@ static int fx_prepare(kb_fx_bank* b) {
 	return KB_OK;
 }
 
+// Debug taps (include/klang_b200.h).  While enabled, every process() also leaves the block's `>> debug` capture on the device.
+extern "C" int kb_fx_bank_debug_enable(kb_fx_bank* b, int enable) {
+	if (!b) return kb_fail(KB_EINVAL, "kb_fx_bank_debug_enable: null bank");
+	KB_CUDA(cudaSetDevice(b->device));
+	if (enable && !b->d_debug) KB_CUDA(cudaMalloc(&b->d_debug, (size_t)b->instances * b->max_block * sizeof(float)));
+	b->debug_on = enable != 0; b->debug_n = -1;
+	return KB_OK;
+}
+extern "C" int kb_fx_bank_debug_read(kb_fx_bank* b, float* dst, int n, unsigned flags) {
+	if (!b || !dst || n < 0) return kb_fail(KB_EINVAL, "kb_fx_bank_debug_read: bad argument");
+	if (!b->debug_on) return kb_fail(KB_EINVAL, "kb_fx_bank_debug_read: debug capture is not enabled (kb_fx_bank_debug_enable)");
+	if (b->debug_n < 0) return 0;                              // the program has no tap, or no block since the last read (Buffer::get, klang.h:3164-3172)
+	if (n != b->debug_n) return kb_fail(KB_EINVAL, "kb_fx_bank_debug_read: n differs from the last block's length");
+	KB_CUDA(cudaSetDevice(b->device));
+	KB_CUDA(cudaMemcpy2DAsync(dst, (size_t)n * sizeof(float), b->d_debug, (size_t)b->max_block * sizeof(float), (size_t)n * sizeof(float), b->instances,
+	                          (flags & KB_DEVICE_PTR) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, b->stream));
+	if (!(flags & KB_DEVICE_PTR)) KB_CUDA(cudaStreamSynchronize(b->stream));
+	b->debug_n = -1;
+	return 1;
+}
+
+// CTAs per row of a streaming kernel (256 threads, 4 x 16 bytes in flight per thread): one trip per thread — many short CTAs that the hardware
+// scheduler balances, like a library copy.  A grid of long-running CTAs that is a few CTAs larger than one wave leaves those few running alone,
+// latency-bound, behind the wave.  KB_STREAM_WAVE=1 (A/B measurement): at most one wave of 148 SMs x 8 resident CTAs, grid-stride loops.
+static unsigned kb_stream_grid_x(int n, int rows, int vectors_per_trip = 4) {
+	static const bool one_wave = getenv("KB_STREAM_WAVE") && atoi(getenv("KB_STREAM_WAVE")) != 0;
+	const int cover = (n / (4 * vectors_per_trip) + 255) / 256;
+	const int wave = (148 * 8) / std::max(1, std::min(rows, 148 * 8));
+	return (unsigned)std::max(1, one_wave ? std::min(cover, wave) : cover);
+}
 extern "C" int kb_fx_bank_process(kb_fx_bank* b, float* io, int n, unsigned flags) {
 	if (!b || !io || n < 0 || n > b->max_block) return kb_fail(KB_EINVAL, "kb_fx_bank_process: bad argument (n > max_block?)");
 	if (n == 0) return KB_OK;
@@ -348,20 +379,36 @@ extern "C" int kb_fx_bank_process(kb_fx_bank* b, float* io, int n, unsigned flag
 	const size_t floats = (size_t)b->instances * b->channels * n;
 	float* d = io;
 	if (!(flags & KB_DEVICE_PTR)) { d = b->d_io; KB_CUDA(cudaMemcpyAsync(d, io, floats * sizeof(float), cudaMemcpyHostToDevice, b->stream)); }
+	const int ib = (b->instances + 31) / 32;
+	b->debug_n = -1;
+	if (b->debug_on) {                                         // the block's `>> debug` capture, from the state the block starts with (kb_kernels.cuh)
+		if (b->graph == KB_FX_PINGPONG || b->graph == KB_FX_MODDELAY) {
+			kb_debug_tap_kernel<<<ib, 32, 0, b->stream>>>(b->graph, b->d_hdr, b->d_state, b->state_bytes, b->d_debug, n, b->max_block, b->instances, b->fs);
+			b->debug_n = n; b->launches++;
+		} else if (b->graph == KB_FX_RM || b->graph == KB_FX_TREMOLO) {
+			dim3 grid((unsigned)std::max(1, std::min((n + 255) / 256, 64)), b->instances);
+			kb_debug_tap_lfo_kernel<<<grid, 256, 0, b->stream>>>(b->graph, b->d_hdr, (const KbLfoFx*)b->d_state, b->d_debug, n, b->max_block);
+			b->debug_n = n; b->launches++;
+		}
+	}
 	b->prof_begin();
 	b->last_flags = flags;
-	const int ib = (b->instances + 31) / 32;
 	const bool seq_only = flags & KB_FX_SEQUENTIAL;
 	switch (b->graph) {
 	case KB_FX_GAIN: {
-		dim3 grid((unsigned)std::max(1, std::min((n / 4 + 255) / 256, 148 * 8 / std::min(b->instances, 148 * 8) + 1)), b->instances);
+		dim3 grid(kb_stream_grid_x(n, b->instances), b->instances);
 		kb_gain_kernel<<<grid, 256, 0, b->stream>>>(b->d_hdr, d, n);
 		break; }
 	case KB_FX_PAN: case KB_FX_RM: case KB_FX_TREMOLO: case KB_FX_CLIPPING: case KB_FX_FUNCTIONS: case KB_FX_MUTE: {
 		const int rows = b->instances * b->channels;
 		const bool lfo = b->graph == KB_FX_RM || b->graph == KB_FX_TREMOLO;
-		dim3 grid((unsigned)std::max(1, std::min((n / 4 + 255) / 256, 148 * 8 / std::min(rows, 148 * 8) + 1)), rows);
-		kb_elementwise_kernel<<<grid, 256, 0, b->stream>>>(b->graph, b->channels, b->d_hdr, lfo ? (const KbLfoFx*)b->d_state : nullptr, d, n, n);
+		dim3 grid(kb_stream_grid_x(n, rows), rows);
+		const KbLfoFx* lfos = lfo ? (const KbLfoFx*)b->d_state : nullptr;
+		switch (b->graph) {
+#define KB_EW(G) case G: kb_elementwise_kernel<G><<<grid, 256, 0, b->stream>>>(b->channels, b->d_hdr, lfos, d, n, n); break
+		KB_EW(KB_FX_PAN); KB_EW(KB_FX_RM); KB_EW(KB_FX_TREMOLO); KB_EW(KB_FX_CLIPPING); KB_EW(KB_FX_FUNCTIONS); KB_EW(KB_FX_MUTE);
+#undef KB_EW
+		}
 		if (lfo) { kb_lfo_advance_kernel<<<ib, 32, 0, b->stream>>>((KbLfoFx*)b->d_state, b->instances, n); b->launches++; }
 		break; }
 	case KB_FX_ECHO: {
@@ -369,7 +416,7 @@ extern "C" int kb_fx_bank_process(kb_fx_bank* b, float* io, int n, unsigned flag
 		for (int i = 0; i < b->instances && echo_par; i++) echo_par = kb_echo_parallel_ok(b->fs, n, b->hdr[i].controls[0].value);
 		if (echo_par) {                                        // time-parallel: write sweep, read sweep, position advance (kb_graphs.cuh)
 			KbOneDelayFx* st = (KbOneDelayFx*)b->d_state;
-			dim3 grid((unsigned)std::max(1, std::min((n + 255) / 256, 148 * 8 / std::min(b->instances, 148 * 8) + 1)), b->instances);
+			dim3 grid(kb_stream_grid_x(n, b->instances, 1), b->instances);      // (one frame per thread and trip, four trips: n / 4 threads per row)
 			kb_echo_write_kernel<<<grid, 256, 0, b->stream>>>(st, b->d_rings, d, n, n);
 			kb_echo_read_kernel<<<grid, 256, 0, b->stream>>>(b->d_hdr, st, b->d_rings, d, n, n, b->fs);
 			kb_onedelay_advance_kernel<<<ib, 32, 0, b->stream>>>(st, b->instances, n);
@@ -384,10 +431,11 @@ extern "C" int kb_fx_bank_process(kb_fx_bank* b, float* io, int n, unsigned flag
 	case KB_FX_FLANGER: case KB_FX_MOD_CHORUS: case KB_FX_MODDELAY:
 		if (!seq_only && n < 192000) {                         // time-parallel: write sweep with stash, read sweep (kb_modline_*, kb_graphs.cuh)
 			KbModDelayFx* st = (KbModDelayFx*)b->d_state;
-			dim3 grid((unsigned)std::max(1, std::min((n + 255) / 256, 148 * 8 / std::min(b->instances, 148 * 8) + 1)), b->instances);
+			dim3 grid(kb_stream_grid_x(n, b->instances, 1), b->instances);
 			float* depth = b->graph == KB_FX_MODDELAY ? b->d_old + (size_t)b->instances * b->max_block : nullptr;   // ModDelay.k: serial smoother pre-pass
 			kb_modline_begin_kernel<<<ib, 32, 0, b->stream>>>(b->graph, b->d_hdr, st, b->instances, b->fs, depth, n, n);
 			kb_modline_write_kernel<<<grid, 256, 0, b->stream>>>(st, b->d_rings, b->d_old, d, n, n);
+			grid.x = kb_stream_grid_x(2 * n, b->instances, 1);                  // (two trips per thread)
 			kb_modline_read_kernel<<<grid, 256, 0, b->stream>>>(b->graph, b->d_hdr, st, b->d_rings, b->d_old, depth, d, n, n, b->fs);
 			kb_modline_end_kernel<<<ib, 32, 0, b->stream>>>(b->graph, st, b->instances, n);
 			b->launches += 3;

@@ -334,40 +334,63 @@ __global__ void kb_sx_advance_kernel(KbSxVoice* __restrict__ voices, const KbVoi
 }
 
 // ================================================================================================ effects
-// Gain.k: no state, one multiply per sample: a pure streaming kernel, 16-byte vector loads/stores.
-__global__ void kb_gain_kernel(const KbFxHdr* __restrict__ hdr, float* __restrict__ io, int n) {
-	const int inst = blockIdx.y;
-	const float gain = hdr[inst].controls[0].value;
-	float* p = io + (size_t)inst * n;
+// Streaming rows in place, 16-byte vectors, FOUR loads in flight per thread before the first store (round 2: with one vector in flight per
+// thread and a grid of one wave plus a few CTAs — the few ran alone, latency-bound, after the wave — Gain.k reached 0.74 of the copy peak).
+// The launch covers a row with one trip per thread (kb_stream_grid_x in kb_api.cu): many short CTAs, no tail.  `f(x, t)` maps sample t of the row.
+template <int U = 4, class F>
+KB_D void kb_stream_row(float* __restrict__ p, int n, F f) {
 	const int n4 = ((reinterpret_cast<uintptr_t>(p) & 15) == 0) ? (n >> 2) : 0;
 	float4* p4 = reinterpret_cast<float4*>(p);
-	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
-		float4 x = p4[i];
-		x.x = x.x * gain; x.y = x.y * gain; x.z = x.z * gain; x.w = x.w * gain;
-		p4[i] = x;
+	const int stride = gridDim.x * blockDim.x;
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	auto map4 = [&](float4 x, int i4) { const uint32_t t = (uint32_t)i4 << 2; x.x = f(x.x, t); x.y = f(x.y, t + 1); x.z = f(x.z, t + 2); x.w = f(x.w, t + 3); return x; };
+	if (U == 4) {
+		for (; i + 3 * stride < n4; i += 4 * stride) {
+			float4 x0 = __ldcs(p4 + i), x1 = __ldcs(p4 + i + stride), x2 = __ldcs(p4 + i + 2 * stride), x3 = __ldcs(p4 + i + 3 * stride);
+			__stcs(p4 + i, map4(x0, i)); __stcs(p4 + i + stride, map4(x1, i + stride));
+			__stcs(p4 + i + 2 * stride, map4(x2, i + 2 * stride)); __stcs(p4 + i + 3 * stride, map4(x3, i + 3 * stride));
+		}
 	}
-	for (int i = (n4 << 2) + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = p[i] * gain;
+	#pragma unroll 1
+	for (; i < n4; i += stride) __stcs(p4 + i, map4(__ldcs(p4 + i), i));
+	#pragma unroll 1
+	for (int j = (n4 << 2) + blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) p[j] = f(p[j], (uint32_t)j);
+}
+// Sweeps whose body gathers from a delay ring: ONE frame per thread and trip, so that the lanes of a warp tap consecutive ring slots (with
+// four consecutive frames per thread every tap instruction of a warp touches four times as many lines: measured slower for Flanger.k),
+// U independent trips in flight.  STORE = false: `f(x, t)` only consumes sample t.
+template <int U, bool STORE, class F>
+KB_D void kb_sweep_row(float* __restrict__ p, int n, F f) {
+	const int stride = gridDim.x * blockDim.x;
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	for (; i + (U - 1) * stride < n; i += U * stride) {
+		float x[U];
+		#pragma unroll
+		for (int u = 0; u < U; u++) x[u] = p[i + u * stride];
+		#pragma unroll
+		for (int u = 0; u < U; u++) { const float y = f(x[u], (uint32_t)(i + u * stride)); if (STORE) p[i + u * stride] = y; }
+	}
+	#pragma unroll 1
+	for (; i < n; i += stride) { const float y = f(p[i], (uint32_t)i); if (STORE) p[i] = y; }
+}
+// Gain.k: no state, one multiply per sample.
+__global__ void __launch_bounds__(256) kb_gain_kernel(const KbFxHdr* __restrict__ hdr, float* __restrict__ io, int n) {
+	const int inst = blockIdx.y;
+	const float gain = hdr[inst].controls[0].value;
+	kb_stream_row(io + (size_t)inst * n, n, [gain](float x, uint32_t) { return x * gain; });
 }
 
-// Pan.k / RM.k / Tremolo.k / Clipping.k: elementwise streaming kernel over planar rows [instance][channel][n], 16-byte vector loads and
-// stores like kb_gain_kernel; blockIdx.y = instance * channels + channel.  The LFO phase of sample t is closed-form (kb_ew_sample).
-__global__ void kb_elementwise_kernel(int graph, int channels, const KbFxHdr* __restrict__ hdr, const KbLfoFx* __restrict__ lfos,
+// Pan.k / RM.k / Tremolo.k / Clipping.k: elementwise streaming kernel over planar rows [instance][channel][n]; blockIdx.y = instance * channels +
+// channel.  The LFO phase of sample t is closed-form (kb_ew_sample).
+template <int GRAPH>
+__global__ void __launch_bounds__(256) kb_elementwise_kernel(int channels, const KbFxHdr* __restrict__ hdr, const KbLfoFx* __restrict__ lfos,
                                       float* __restrict__ io, int n, int stride) {
+	constexpr int graph = GRAPH;                                           // (a compile-time graph: no per-sample dispatch in kb_ew_sample)
 	const int inst = blockIdx.y / channels, ch = blockIdx.y % channels;
 	const float c0 = hdr[inst].controls[0].value, c1 = hdr[inst].controls[1].value;
 	KbFastSine lfo = { 0.f, 0, 0u, 0u };
 	if (lfos) lfo = lfos[inst].lfo;
-	float* p = io + ((size_t)inst * channels + ch) * stride;
-	const int n4 = ((reinterpret_cast<uintptr_t>(p) & 15) == 0) ? (n >> 2) : 0;
-	float4* p4 = reinterpret_cast<float4*>(p);
-	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
-		float4 x = p4[i];
-		const uint32_t t = (uint32_t)i << 2;
-		x.x = kb_ew_sample(graph, c0, c1, lfo, ch, t, x.x); x.y = kb_ew_sample(graph, c0, c1, lfo, ch, t + 1, x.y);
-		x.z = kb_ew_sample(graph, c0, c1, lfo, ch, t + 2, x.z); x.w = kb_ew_sample(graph, c0, c1, lfo, ch, t + 3, x.w);
-		p4[i] = x;
-	}
-	for (int i = (n4 << 2) + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = kb_ew_sample(graph, c0, c1, lfo, ch, (uint32_t)i, p[i]);
+	kb_stream_row(io + ((size_t)inst * channels + ch) * stride, n, [=](float x, uint32_t t) { return kb_ew_sample(graph, c0, c1, lfo, ch, t, x); });
 }
 // after the block: the n ticks the LFO made (Fast::Sine::process, klang.h:5164-5170)
 __global__ void kb_lfo_advance_kernel(KbLfoFx* __restrict__ lfos, int instances, int n) {
@@ -379,14 +402,14 @@ __global__ void kb_lfo_advance_kernel(KbLfoFx* __restrict__ lfos, int instances,
 __global__ void kb_echo_write_kernel(const KbOneDelayFx* __restrict__ st, float* __restrict__ rings, const float* __restrict__ io, int n, int stride) {
 	const KbOneDelayFx s = st[blockIdx.y];
 	const float* p = io + (size_t)blockIdx.y * stride;
-	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) kb_echo_write_at(s, rings, t, p[t]);
+	kb_sweep_row<4, false>(const_cast<float*>(p), n, [&](float x, uint32_t t) { kb_echo_write_at(s, rings, (int)t, x); return 0.f; });
 }
 __global__ void kb_echo_read_kernel(const KbFxHdr* __restrict__ hdr, const KbOneDelayFx* __restrict__ st, const float* __restrict__ rings,
                                     float* __restrict__ io, int n, int stride, KbFs fs) {
 	const KbOneDelayFx s = st[blockIdx.y];
 	const KbFxHdr& h = hdr[blockIdx.y];
 	float* p = io + (size_t)blockIdx.y * stride;
-	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) p[t] = kb_echo_read_at(fs, h, s, rings, t, p[t]);
+	kb_sweep_row<4, true>(p, n, [&](float x, uint32_t t) { return kb_echo_read_at(fs, h, s, rings, (int)t, x); });
 }
 // Flanger.k / Modulation/Chorus.k, time-parallel (kb_modline_*): LFO settings of the block's first frame, write sweep with stash, read sweep,
 // LFO / position advance.  blockIdx.y = instance; `old` is [instances][stride] scratch.
@@ -398,7 +421,7 @@ __global__ void kb_modline_write_kernel(const KbModDelayFx* __restrict__ st, flo
 	const KbDelay d = st[blockIdx.y].delay;
 	const float* p = io + (size_t)blockIdx.y * stride;
 	float* o = old + (size_t)blockIdx.y * stride;
-	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) kb_modline_write_at(d, rings, o, t, p[t]);
+	kb_sweep_row<4, false>(const_cast<float*>(p), n, [&](float x, uint32_t t) { kb_modline_write_at(d, rings, o, (int)t, x); return 0.f; });
 }
 __global__ void kb_modline_read_kernel(int graph, const KbFxHdr* __restrict__ hdr, const KbModDelayFx* __restrict__ st, const float* __restrict__ rings,
                                        const float* __restrict__ old, const float* __restrict__ depth, float* __restrict__ io, int n, int stride, KbFs fs) {
@@ -410,7 +433,7 @@ __global__ void kb_modline_read_kernel(int graph, const KbFxHdr* __restrict__ hd
 	float* p = io + (size_t)blockIdx.y * stride;
 	const float* o = old + (size_t)blockIdx.y * stride;
 	const float* dr = depth ? depth + (size_t)blockIdx.y * stride : nullptr;
-	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) p[t] = kb_modline_read_at(graph, fs, h, s, rings, o, dr, n, t, p[t]);
+	kb_sweep_row<2, true>(p, n, [&](float x, uint32_t t) { return kb_modline_read_at(graph, fs, h, s, rings, o, dr, n, (int)t, x); });
 }
 __global__ void kb_modline_end_kernel(int graph, KbModDelayFx* __restrict__ st, int instances, int n) {
 	const int inst = blockIdx.x * blockDim.x + threadIdx.x;
@@ -467,6 +490,43 @@ __global__ void kb_fx_seq_kernel(KbFxHdr* __restrict__ hdrs, STATE* __restrict__
 	}
 	hdrs[inst] = h;
 	states[inst] = s;
+}
+
+// ================================================================================================ debug taps
+// `x >> debug` (klang.h:3132-3287): Debug::input ADDS x into the sample of the current frame of Debug::buffer, which the host's Debug::Session
+// cleared before the block and the block drivers step once per frame (klang.h:4214, 4714) — so a block's capture is `0.f + x` per frame.
+// The four bound programs that tap a signal (PingPong.k:61, Gain/RM.k:22, Gain/Tremolo.k:27, Modulation/ModDelay.k:24) all tap a quantity of
+// the CONTROL half of the frame (smoothers and LFOs: no audio, no ring), so the capture is produced by a replay of that half on a copy of the
+// state, ahead of the block's kernels whatever schedule they run on.  Launched only while kb_fx_bank_debug_enable is on; dbg = [instances][stride].
+__global__ void kb_debug_tap_kernel(int graph, const KbFxHdr* __restrict__ hdrs, const unsigned char* __restrict__ states, size_t state_bytes,
+                                    float* __restrict__ dbg, int n, int stride, int instances, KbFs fs) {
+	const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+	if (inst >= instances) return;
+	KbFxHdr h = hdrs[inst];
+	float* row = dbg + (size_t)inst * stride;
+	if (graph == KB_FX_PINGPONG) {                                         // controls[1].smoothed >> debug   PingPong.k:61
+		KbPingPong p = *reinterpret_cast<const KbPingPong*>(states + inst * state_bytes);
+		for (int i = 0; i < n; i++) { float gain, delay, dry; kb_pingpong_control(fs, h, p, gain, delay, dry); row[i] = 0.f + h.controls[1].smoothed; }
+	} else if (graph == KB_FX_MODDELAY) {                                  // mod * 10.f >> debug             ModDelay.k:19-24
+		KbFastSine lfo = reinterpret_cast<const KbModDelayFx*>(states + inst * state_bytes)->lfo[0];
+		for (int i = 0; i < n; i++) {
+			const float sm = kb_control_smooth(h.controls[1]);
+			const float depth = (sm * sm * sm) / 10.f;
+			kb_fsine_set_f(fs, lfo, h.controls[0].value);
+			const float mod = kb_fsine_tick(lfo) * depth + depth;
+			row[i] = 0.f + mod * 10.f;
+		}
+	}
+}
+// RM.k / Tremolo.k: mod >> debug, the LFO in closed form like kb_ew_sample; blockIdx.y = instance
+__global__ void kb_debug_tap_lfo_kernel(int graph, const KbFxHdr* __restrict__ hdr, const KbLfoFx* __restrict__ lfos, float* __restrict__ dbg, int n, int stride) {
+	const KbFastSine lfo = lfos[blockIdx.y].lfo;
+	const float c1 = hdr[blockIdx.y].controls[1].value;
+	float* row = dbg + (size_t)blockIdx.y * stride;
+	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+		const float s = kb_fsine_value(lfo.position + (uint32_t)t * (uint32_t)lfo.increment + lfo.offset);
+		row[t] = 0.f + (graph == KB_FX_RM ? s : s * c1 + (1 - c1));
+	}
 }
 
 // ============================================================================================= primitives

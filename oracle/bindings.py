@@ -71,6 +71,7 @@ class Oracle:
         sig("fx_set_control", [vp, i, f32], None)
         sig("fx_get_control", [vp, i], f32)
         sig("fx_process", [vp, vp, vp, i])
+        sig("fx_debug", [vp, vp, i])
         sig("synth_create", [i, i], vp)
         sig("synth_destroy", [vp], None)
         sig("synth_channels", [vp])
@@ -218,7 +219,13 @@ class Fx:
             assert y.ndim == 2 and y.shape[0] == 2
             rc = self.o.fn("fx_process")(self.h, y[0].ctypes.data, y[1].ctypes.data, y.shape[1])
         assert rc == 0
+        self._last_n = y.shape[-1]
         return y
+
+    def debug(self):
+        """The `>> debug` capture of the last block (klang.h:3132-3287): float32 [n], or None if the block wrote none."""
+        d = np.zeros(self._last_n, np.float32)
+        return d if self.o.fn("fx_debug")(self.h, d.ctypes.data, self._last_n) else None
 
 
 class Synth:

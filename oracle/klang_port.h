@@ -46,6 +46,7 @@ int   kp_fx_num_controls(void* h);
 void  kp_fx_set_control(void* h, int idx, float v);
 float kp_fx_get_control(void* h, int idx);
 int   kp_fx_process(void* h, float* l, float* r, int n);
+int   kp_fx_debug(void* h, float* dst, int n);   /* the block's `>> debug` capture (klang.h:3132-3287); 1 if written */
 
 /* ------------------------------------------------------------------- synths */
 void* kp_synth_create(int graph, int nvoices);

@@ -479,6 +479,17 @@ int ref_fx_process(void* h, float* l, float* r, int n) {
 	return 0;
 }
 
+// The debug tap of the last block (`x >> debug`: Debug::input adds into Debug::buffer, klang.h:3132-3287; the block drivers step it,
+// klang.h:4214 / 4300 / 4714; the host's Debug::Session clears it before the block, klang.h:3223-3245).  Returns 1 and copies n samples if
+// the block wrote to it (Buffer::get, klang.h:3164-3172), else 0.
+int ref_fx_debug(void* h, float* dst, int n) {
+	(void)h;
+	const float* p = Debug::buffer.get();
+	if (!p) return 0;
+	memcpy(dst, p, (size_t)n * sizeof(float));
+	return 1;
+}
+
 // ----------------------------------------------------------------------- synths
 enum { SY_SUBTRACTIVE = 0, SY_SUPERSAW = 1, SY_TB303 = 2, SY_SYNTHX = 3, SY_FILTER_K = 4, SY_FM = 5, SY_BREAKPOINT = 6, SY_RAMP = 7, SY_RELEASE = 8, SY_ADDITIVE_SAW = 9, SY_ADDITIVE_SQUARE = 10, SY_AM = 11, SY_MOD_FM = 12, SY_MOD_FM2 = 13, SY_ADDITIVE_NYQUIST = 14 };
 

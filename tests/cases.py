@@ -236,7 +236,12 @@ FX_SCRIPTS_LATE = {
 }
 
 
-def run_fx_script(eng, name, fs, seed=1):
+# scripts whose program taps a signal with `>> debug` (PingPong.k:61, RM.k:22, Tremolo.k:27, ModDelay.k:24): the capture of every block is a case too
+FX_DEBUG_TAPS = ("pingpong_default", "pingpong_short", "rm", "rm_at_cached_rate", "tremolo", "moddelay")
+
+
+def run_fx_script(eng, name, fs, seed=1, debug=False):
+    """debug=True returns (output, the concatenated `>> debug` captures of the blocks); a block without a capture raises."""
     graph, total, block, events, burst = (FX_SCRIPTS.get(name) or FX_SCRIPTS_LATE[name])
     eng.set_fs(fs)
     eng.srand(1)
@@ -244,14 +249,18 @@ def run_fx_script(eng, name, fs, seed=1):
     x = fx_input(fx.channels, total, seed, burst)
     if fx.channels == 1:
         x = x[0]
-    ys = []
+    ys, ds = [], []
     for b in range(total // block):
         for (bi, c, v) in events:
             if bi == b:
                 fx.set_control(c, v)
         ys.append(fx.process(x[..., b * block:(b + 1) * block]))
+        if debug:
+            d = fx.debug()
+            assert d is not None and d.shape == (block,), f"{name}: block {b} left no debug capture"
+            ds.append(d)
     fx.close()
-    return np.concatenate(ys, axis=-1)
+    return (np.concatenate(ys, axis=-1), np.concatenate(ds)) if debug else np.concatenate(ys, axis=-1)
 
 
 # --------------------------------------------------------------------------------- synths
@@ -341,7 +350,10 @@ def run_synth_noteon_script(eng, graph, fs, nvoices=32, notes=40, blocks=4, n=25
 def all_graph_cases(eng, fs):
     out = {}
     for name in list(FX_SCRIPTS) + list(FX_SCRIPTS_LATE):
-        out[f"fx/{name}"] = run_fx_script(eng, name, fs)
+        if name in FX_DEBUG_TAPS:
+            out[f"fx/{name}"], out[f"fx/{name}/debug"] = run_fx_script(eng, name, fs, debug=True)
+        else:
+            out[f"fx/{name}"] = run_fx_script(eng, name, fs)
     for name in list(SYNTH_SCRIPTS) + list(SYNTH_SCRIPTS_LATE):
         r = run_synth_script(eng, name, fs, per_voice=True)
         out[f"synth/{name}/voices"] = r["out"]

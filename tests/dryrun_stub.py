@@ -107,6 +107,15 @@ class FxBank:
     def parallel_instances(self):
         return self.instances
 
+    def debug_enable(self, on=True):
+        self.dbg = on
+
+    def debug_read(self, n):
+        if not getattr(self, "dbg", False):
+            raise real.KlangB200Error("debug capture is not enabled")
+        d = [f.debug() for f in self.f]
+        return None if d[0] is None else np.stack(d)
+
     def close(self):
         for f in self.f:
             f.close()

@@ -335,3 +335,55 @@ def test_modulated_line_time_parallel_schedule_equals_sequential_schedule(graph)
         outs.append(np.concatenate(res, axis=-1))
     _exact(np.ascontiguousarray(outs[1]), np.ascontiguousarray(outs[0]), f"graph {graph} schedules")
     assert np.abs(outs[0]).max() > 0.4
+
+
+# ------------------------------------------------------------------------------------------ debug taps
+@pytest.mark.parametrize("graph,ctl,flags", [
+    (kb.FX_PINGPONG, {1: 0.02, 5: 0.02, 2: 0.4, 3: 0.579}, 0), (kb.FX_PINGPONG, {1: 0.02, 5: 0.02, 2: 0.4, 3: 0.579}, kb.FX_SEQUENTIAL),
+    (kb.FX_RM, {0: 440.0}, 0), (kb.FX_TREMOLO, {0: 7.0, 1: 0.3}, 0), (kb.FX_MODDELAY, {0: 3.0, 1: 0.8}, 0), (kb.FX_MODDELAY, {0: 3.0, 1: 0.8}, kb.FX_SEQUENTIAL)])
+def test_debug_taps_of_a_bank_match_the_reference(graph, ctl, flags):
+    """`x >> debug` (klang.h:3132-3287; PingPong.k:61, RM.k:22, Tremolo.k:27, ModDelay.k:24): 6 instances with different control settings,
+    5 blocks of 1000 frames; the capture of every block and instance equals the reference's Debug::buffer bit for bit, on either schedule,
+    and the audio is what it is without the capture."""
+    fs, n, inst, blocks = 48000, 1000, 6, 5
+    chk = oracle.ref if oracle.ref.available() else oracle.port
+    chk.set_fs(fs)
+    bank = kb.FxBank(graph, inst, fs, n)
+    bank.debug_enable(True)
+    plain = kb.FxBank(graph, inst, fs, n)
+    refs = [chk.Fx(graph) for _ in range(inst)]
+    for i in range(inst):
+        for c, v in ctl.items():
+            vi = v * (1.0 + 0.1 * i)
+            bank.set_control(c, vi, i); plain.set_control(c, vi, i); refs[i].set_control(c, vi)
+    ch = bank.channels
+    for b in range(blocks):
+        x = np.stack([cases.fx_input(ch, n, seed=900 + 7 * i + b) for i in range(inst)])
+        io, io2 = x.copy(), x.copy()
+        bank.process_inplace(io, flags=flags)
+        plain.process_inplace(io2, flags=flags)
+        got = bank.debug_read(n)
+        assert got is not None and got.shape == (inst, n)
+        assert bank.debug_read(n) is None                                  # Buffer::get hands a capture out once
+        for i in range(inst):
+            want = refs[i].process(x[i][0] if ch == 1 else x[i])
+            _exact(io[i].reshape(want.shape), want, f"audio, instance {i} block {b}")
+            wd = refs[i].debug()
+            assert wd is not None
+            _exact(got[i], wd, f"debug tap, instance {i} block {b}")
+        _exact(io, io2, f"block {b}: capture on / off")
+    for r in refs:
+        r.close()
+    bank.close(); plain.close()
+
+
+def test_a_program_without_a_tap_leaves_no_capture():
+    bank = kb.FxBank(kb.FX_GAIN, 2, 48000.0, 256)
+    bank.debug_enable(True)
+    io = np.ones((2, 1, 256), np.float32)
+    bank.process_inplace(io)
+    assert bank.debug_read(256) is None
+    bank.debug_enable(False)
+    with pytest.raises(kb.KlangB200Error):
+        bank.debug_read(256)
+    bank.close()
