@@ -127,6 +127,13 @@ long long kb_fx_bank_state_bytes(const kb_fx_bank* bank); /* bytes of instance s
 int kb_fx_bank_profile(kb_fx_bank* bank, int enable);
 int kb_fx_bank_profile_read(kb_fx_bank* bank, double* kernel_ms, long long* kernel_launches);
 
+/* Factory presets of the bound programs (Plugin::presets, klang.h:1940-1981, 4195-4200; e.g. examples/PingPong.k:23-32).
+ * kb_graph_preset returns the number of values of preset `index` of the program behind `graph` (is_synth selects KB_SY_* / KB_FX_*) and copies
+ * its name and values.  load_preset is what a host does with one: every value through Control::set (klang.h:1725-1728), then onPreset. */
+int kb_graph_num_presets(int is_synth, int graph);
+int kb_graph_preset(int is_synth, int graph, int index, char* name, int name_max, float* values, int max_values);
+int kb_fx_bank_load_preset(kb_fx_bank* bank, int instance, int index);
+
 /* Debug taps: `x >> debug` in a program's process() (klang.h:3132-3287 Debug / Debug::Buffer / Debug::Session; examples/PingPong.k:61,
  * Gain/RM.k:22, Gain/Tremolo.k:27, Modulation/ModDelay.k:24).  In the reference the host opens a Debug::Session per block (clears the buffer),
  * every `>> debug` adds into the current frame's sample, and Session::getAudio() hands the block's capture to the IDE.  Here: while enabled,
@@ -154,6 +161,13 @@ int kb_synth_bank_note_off(kb_synth_bank* bank, int instance, int pitch, float v
  * 0x80 or 0x90 with velocity 0 = noteOff, anything else = onMIDI() (a no-op for the bound graphs).  Returns 0 or a negative
  * error.                                                                 templates/juce/synth/Source/klang.h:3921-3929 */
 int kb_synth_bank_midi(kb_synth_bank* bank, int instance, int status, int byte1, int byte2);
+/* Synth::onControl(index, value) / Synth::onPreset(index): the synth's control() / preset() hook, then the hook of every note that is not Off
+ * (klang.h:4399-4404, 4415-4420; Stereo::Synth 4789-4810).  No bound program overrides these hooks, so the audio is unaffected; the calls return
+ * how many notes the reference would notify (stages as the device has evolved them).  load_preset = the preset's values through Control::set, then
+ * onPreset.  (Synth::onMIDI, klang.h:4407-4412, calls itself and cannot return in the reference; raw MIDI enters through kb_synth_bank_midi.) */
+int kb_synth_bank_on_control(kb_synth_bank* bank, int instance, int idx, float value);
+int kb_synth_bank_on_preset(kb_synth_bank* bank, int instance, int index);
+int kb_synth_bank_load_preset(kb_synth_bank* bank, int instance, int index);
 /* NoteBase::start / release / stage of one voice                                          klang.h:4257-4284 */
 int kb_synth_bank_voice_start(kb_synth_bank* bank, int instance, int voice, float pitch, float velocity);
 int kb_synth_bank_voice_release(kb_synth_bank* bank, int instance, int voice, float velocity);

@@ -29,6 +29,9 @@ SYMBOLS = [
     ("kb_fx_bank_process", _i, [_vp, _vp, _i, _u]), ("kb_fx_bank_sync", _i, [_vp]), ("kb_fx_bank_set_stream", _i, [_vp, _vp]),
     ("kb_fx_bank_bytes_per_frame", _d, [_vp]), ("kb_fx_bank_launches", _ll, [_vp]), ("kb_fx_bank_state_bytes", _ll, [_vp]), ("kb_fx_bank_parallel_instances", _i, [_vp]), ("kb_fx_bank_tolerance_instances", _i, [_vp]),
     ("kb_fx_bank_profile", _i, [_vp, _i]), ("kb_fx_bank_profile_read", _i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
+    ("kb_graph_num_presets", _i, [_i, _i]), ("kb_graph_preset", _i, [_i, _i, _i, C.c_char_p, _i, _vp, _i]),
+    ("kb_fx_bank_load_preset", _i, [_vp, _i, _i]), ("kb_synth_bank_load_preset", _i, [_vp, _i, _i]),
+    ("kb_synth_bank_on_control", _i, [_vp, _i, _i, _f]), ("kb_synth_bank_on_preset", _i, [_vp, _i, _i]),
     ("kb_fx_bank_debug_enable", _i, [_vp, _i]), ("kb_fx_bank_debug_read", _i, [_vp, _vp, _i, _u]),
     ("kb_synth_bank_create", _vp, [_i, _i, _i, _f, _i, _i]), ("kb_synth_bank_destroy", None, [_vp]),
     ("kb_synth_bank_channels", _i, [_vp]), ("kb_synth_bank_instances", _i, [_vp]), ("kb_synth_bank_voices", _i, [_vp]),
@@ -117,6 +120,16 @@ def _ptr(x, numel=None, what="buffer", device=None):
     return x.data_ptr(), bool(x.is_cuda)
 
 
+def presets(is_synth, graph):
+    """Factory presets of the program behind a graph id: [(name, [values])] (Plugin::presets, klang.h:1940-1981)."""
+    out = []
+    for p in range(lib().kb_graph_num_presets(1 if is_synth else 0, graph)):
+        name, vals = C.create_string_buffer(40), (C.c_float * 16)()
+        k = lib().kb_graph_preset(1 if is_synth else 0, graph, p, name, 40, vals, 16)
+        out.append((name.value.decode(), [float(vals[i]) for i in range(k)]))
+    return out
+
+
 class FxBank:
     """`instances` objects of one klang Effect evaluated together (Effect::process(buffer), klang.h:4208-4216)."""
 
@@ -143,6 +156,10 @@ class FxBank:
         v = C.c_float()
         _check(lib().kb_fx_bank_get_control(self.h, instance, idx, C.byref(v)), "kb_fx_bank_get_control")
         return float(v.value)
+
+    def load_preset(self, index, instance=None):
+        for i in (range(self.instances) if instance is None else [instance]):
+            _check(lib().kb_fx_bank_load_preset(self.h, i, index), "kb_fx_bank_load_preset")
 
     def debug_enable(self, on=True):
         """`>> debug` capture (klang.h:3132-3287): while on, every process() also records the block's debug tap of every instance."""
@@ -237,6 +254,20 @@ class SynthBank:
     def midi(self, status, byte1, byte2, instance=0):
         """Synth::input(status, byte1, byte2) (templates/juce/synth/Source/klang.h:3921-3929)."""
         _check(lib().kb_synth_bank_midi(self.h, instance, int(status), int(byte1), int(byte2)), "kb_synth_bank_midi")
+
+    def on_control(self, idx, value, instance=0):
+        """Synth::onControl (klang.h:4399-4404): returns the number of notes (stage != Off) the reference notifies."""
+        rc = lib().kb_synth_bank_on_control(self.h, instance, int(idx), float(value))
+        if rc < 0:
+            _check(rc, "kb_synth_bank_on_control")
+        return rc
+
+    def load_preset(self, index, instance=0):
+        """The preset's values through Control::set, then Synth::onPreset (klang.h:4415-4420); returns the notes notified."""
+        rc = lib().kb_synth_bank_load_preset(self.h, instance, int(index))
+        if rc < 0:
+            _check(rc, "kb_synth_bank_load_preset")
+        return rc
 
     def voice_start(self, voice, pitch, velocity, instance=0):
         _check(lib().kb_synth_bank_voice_start(self.h, instance, voice, float(pitch), float(velocity)), "kb_synth_bank_voice_start")

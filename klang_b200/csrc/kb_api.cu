@@ -20,6 +20,7 @@
 #include "kb_reverb3.cuh"
 #include "kb_pingpong3.cuh"
 #include "kb_k_hashes.h"
+#include "kb_presets.h"
 
 static thread_local std::string g_err = "";
 static int kb_fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -267,6 +268,23 @@ extern "C" int kb_fx_bank_get_control(kb_fx_bank* b, int inst, int idx, float* v
 	if (!b || !v || inst < 0 || inst >= b->instances || idx < 0 || idx >= b->ncontrols) return kb_fail(KB_EINVAL, "kb_fx_bank_get_control: bad argument");
 	if (b->device_writes_controls) { int rc = fx_fetch(b); if (rc) return rc; }
 	*v = b->hdr[inst].controls[idx].value;
+	return KB_OK;
+}
+// Factory presets (kb_presets.h) -------------------------------------------------------------------------------------------------
+extern "C" int kb_graph_num_presets(int is_synth, int graph) { return kb_preset_count(is_synth ? 1 : 0, graph); }
+extern "C" int kb_graph_preset(int is_synth, int graph, int index, char* name, int name_max, float* values, int max_values) {
+	const KbPreset* p = kb_preset_find(is_synth ? 1 : 0, graph, index);
+	if (!p || index < 0) return kb_fail(KB_EINVAL, "kb_graph_preset: no such preset");
+	if (name && name_max > 0) { strncpy(name, p->name, (size_t)name_max - 1); name[name_max - 1] = 0; }
+	for (int c = 0; values && c < p->count && c < max_values; c++) values[c] = p->values[c];
+	return p->count;
+}
+// the host's preset load: every value through Control::set (klang.h:1725-1728), then onPreset (klang.h:4190 — no bound program overrides preset())
+extern "C" int kb_fx_bank_load_preset(kb_fx_bank* b, int inst, int index) {
+	if (!b || inst < 0 || inst >= b->instances) return kb_fail(KB_EINVAL, "kb_fx_bank_load_preset: bad argument");
+	const KbPreset* p = index >= 0 ? kb_preset_find(0, b->graph, index) : nullptr;
+	if (!p) return kb_fail(KB_EINVAL, "kb_fx_bank_load_preset: the bank's program has no such preset");
+	for (int c = 0; c < p->count && c < b->ncontrols; c++) { int rc = kb_fx_bank_set_control(b, inst, c, p->values[c]); if (rc) return rc; }
 	return KB_OK;
 }
 extern "C" double kb_fx_bank_bytes_per_frame(kb_fx_bank* b) {
@@ -854,6 +872,33 @@ extern "C" int kb_synth_bank_get_control(kb_synth_bank* b, int inst, int idx, fl
 	if (!b || !v || inst < 0 || inst >= b->instances || idx < 0 || idx >= b->ncontrols) return kb_fail(KB_EINVAL, "kb_synth_bank_get_control: bad argument");
 	*v = b->ctl(inst)[idx].value;
 	return KB_OK;
+}
+
+// Synth::onControl / onPreset (klang.h:4399-4404, 4415-4420; stereo 4789-4794, 4805-4810): the synth's own control() / preset() hook, then the
+// hook of every note whose stage is not Off.  No bound program overrides either hook (their process() reads controls[] directly), so the call
+// has no effect on the audio; what is observable — and returned — is how many notes the reference would notify, which needs the stages the
+// DEVICE has evolved (a note that finished inside a block is Off), fetched here when stale.
+static int sy_notified(kb_synth_bank* b, int inst) {
+	int rc = sy_fetch(b, true, false); if (rc) return rc;
+	int n = 0;
+	for (int v = 0; v < b->voices; v++) n += b->hdr[(size_t)inst * b->voices + v].stage != KB_NOTE_OFF;
+	return n;
+}
+extern "C" int kb_synth_bank_on_control(kb_synth_bank* b, int inst, int idx, float value) {
+	(void)value;
+	if (!b || inst < 0 || inst >= b->instances || idx < 0) return kb_fail(KB_EINVAL, "kb_synth_bank_on_control: bad argument");
+	return sy_notified(b, inst);
+}
+extern "C" int kb_synth_bank_on_preset(kb_synth_bank* b, int inst, int index) {
+	if (!b || inst < 0 || inst >= b->instances || index < 0) return kb_fail(KB_EINVAL, "kb_synth_bank_on_preset: bad argument");
+	return sy_notified(b, inst);
+}
+extern "C" int kb_synth_bank_load_preset(kb_synth_bank* b, int inst, int index) {
+	if (!b || inst < 0 || inst >= b->instances) return kb_fail(KB_EINVAL, "kb_synth_bank_load_preset: bad argument");
+	const KbPreset* p = index >= 0 ? kb_preset_find(1, b->graph, index) : nullptr;
+	if (!p) return kb_fail(KB_EINVAL, "kb_synth_bank_load_preset: the bank's program has no such preset");
+	for (int c = 0; c < p->count && c < b->ncontrols; c++) { int rc = kb_synth_bank_set_control(b, inst, c, p->values[c]); if (rc) return rc; }
+	return kb_synth_bank_on_preset(b, inst, index);
 }
 
 // NoteBase::start: stage = Onset; on(pitch, velocity); stage = Sustain           klang.h:4257-4263

@@ -72,6 +72,13 @@ class Oracle:
         sig("fx_get_control", [vp, i], f32)
         sig("fx_process", [vp, vp, vp, i])
         sig("fx_debug", [vp, vp, i])
+        sig("fx_num_presets", [vp])
+        sig("fx_preset", [vp, i, C.c_char_p, i, vp, i])
+        sig("fx_load_preset", [vp, i])
+        sig("synth_num_presets", [vp])
+        sig("synth_preset", [vp, i, C.c_char_p, i, vp, i])
+        sig("synth_load_preset", [vp, i])
+        sig("synth_on_control", [vp, i, f32])
         sig("synth_create", [i, i], vp)
         sig("synth_destroy", [vp], None)
         sig("synth_channels", [vp])
@@ -184,6 +191,15 @@ class Oracle:
         return Synth(self, graph, nvoices)
 
 
+def _presets(o, kind, h):
+    out = []
+    for p in range(o.fn(kind + "_num_presets")(h)):
+        name, vals = C.create_string_buffer(40), (C.c_float * 16)()
+        k = o.fn(kind + "_preset")(h, p, name, 40, C.addressof(vals), 16)
+        out.append((name.value.decode(), [float(vals[i]) for i in range(k)]))
+    return out
+
+
 class Fx:
     """One oracle Effect instance (Effect::process(buffer), klang.h:4208-4216 / 4708-4716)."""
 
@@ -222,6 +238,13 @@ class Fx:
         self._last_n = y.shape[-1]
         return y
 
+    def presets(self):
+        """Plugin::presets (klang.h:1940-1981): [(name, [values])]."""
+        return _presets(self.o, "fx", self.h)
+
+    def load_preset(self, index):
+        assert self.o.fn("fx_load_preset")(self.h, index) == 0
+
     def debug(self):
         """The `>> debug` capture of the last block (klang.h:3132-3287): float32 [n], or None if the block wrote none."""
         d = np.zeros(self._last_n, np.float32)
@@ -247,6 +270,16 @@ class Synth:
 
     def __del__(self):
         self.close()
+
+    def presets(self):
+        return _presets(self.o, "synth", self.h)
+
+    def load_preset(self, index):
+        assert self.o.fn("synth_load_preset")(self.h, index) == 0
+
+    def on_control(self, idx, value):
+        """Synth::onControl (klang.h:4399-4404); returns how many notes (stage != Off) were notified."""
+        return int(self.o.fn("synth_on_control")(self.h, idx, float(value)))
 
     def set_control(self, idx, v):
         self.o.fn("synth_set_control")(self.h, idx, float(v))

@@ -48,6 +48,10 @@ float kp_fx_get_control(void* h, int idx);
 int   kp_fx_process(void* h, float* l, float* r, int n);
 int   kp_fx_debug(void* h, float* dst, int n);   /* the block's `>> debug` capture (klang.h:3132-3287); 1 if written */
 
+int   kp_fx_num_presets(void* h);           /* Plugin::presets  klang.h:1940-1981, 4195-4200 */
+int   kp_fx_preset(void* h, int p, char* name, int name_max, float* values, int max);
+int   kp_fx_load_preset(void* h, int p);    /* values through Control::set, then onPreset  klang.h:4190 */
+
 /* ------------------------------------------------------------------- synths */
 void* kp_synth_create(int graph, int nvoices);
 void  kp_synth_destroy(void* h);
@@ -61,6 +65,10 @@ void  kp_synth_note_off(void* h, int pitch, float velocity);
 void  kp_synth_voice_start(void* h, int voice, float pitch, float velocity);
 void  kp_synth_voice_release(void* h, int voice, float velocity);
 int   kp_synth_voice_stage(void* h, int voice);
+int   kp_synth_num_presets(void* h);
+int   kp_synth_preset(void* h, int p, char* name, int name_max, float* values, int max);
+int   kp_synth_load_preset(void* h, int p);
+int   kp_synth_on_control(void* h, int idx, float value);   /* Synth::onControl  klang.h:4399-4404; returns the notes notified */
 int   kp_synth_process(void* h, float* l, float* r, int n);
 int   kp_synth_process_voices(void* h, float* out, int n, int* active);
 

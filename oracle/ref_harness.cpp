@@ -490,6 +490,28 @@ int ref_fx_debug(void* h, float* dst, int n) {
 	return 1;
 }
 
+// Factory presets (Plugin::presets, klang.h:1940-1981, 4195-4200) and the host's preset load: every value goes through Control::set like a
+// host parameter (klang.h:1725-1728, 4444-4447), then Controller::onPreset (klang.h:4190, 4415-4420).
+static int preset_get(klang::Plugin* pl, int p, char* name, int name_max, float* values, int max) {
+	if (p < 0 || p >= (int)pl->presets.count) return -1;
+	const klang::Preset& pr = pl->presets[p];
+	if (name && name_max > 0) { strncpy(name, pr.name.c_str(), name_max - 1); name[name_max - 1] = 0; }
+	const int nv = (int)pr.values.count;
+	for (int c = 0; c < nv && c < max; c++) values[c] = pr.values[c];
+	return nv;
+}
+static int preset_load(klang::Plugin* pl, int p) {
+	if (p < 0 || p >= (int)pl->presets.count) return -1;
+	const klang::Preset& pr = pl->presets[p];
+	for (int c = 0; c < (int)pr.values.count && c < (int)pl->controls.size(); c++) pl->controls[c].set(pr.values[c]);
+	pl->onPreset(p);
+	return 0;
+}
+static klang::Plugin* fx_plugin(void* h) { RefFx* fx = (RefFx*)h; return fx->mono ? static_cast<klang::Plugin*>(fx->mono) : static_cast<klang::Plugin*>(fx->stereo); }
+int ref_fx_num_presets(void* h) { return (int)fx_plugin(h)->presets.count; }
+int ref_fx_preset(void* h, int p, char* name, int name_max, float* values, int max) { return preset_get(fx_plugin(h), p, name, name_max, values, max); }
+int ref_fx_load_preset(void* h, int p) { return preset_load(fx_plugin(h), p); }
+
 // ----------------------------------------------------------------------- synths
 enum { SY_SUBTRACTIVE = 0, SY_SUPERSAW = 1, SY_TB303 = 2, SY_SYNTHX = 3, SY_FILTER_K = 4, SY_FM = 5, SY_BREAKPOINT = 6, SY_RAMP = 7, SY_RELEASE = 8, SY_ADDITIVE_SAW = 9, SY_ADDITIVE_SQUARE = 10, SY_AM = 11, SY_MOD_FM = 12, SY_MOD_FM2 = 13, SY_ADDITIVE_NYQUIST = 14 };
 
@@ -544,6 +566,19 @@ void ref_synth_destroy(void* h) {
 	delete s->mono;
 	delete s->stereo;
 	delete s;
+}
+
+static klang::Plugin* synth_plugin(void* h) { RefSynth* s = (RefSynth*)h; return s->mono ? static_cast<klang::Plugin*>(s->mono) : static_cast<klang::Plugin*>(s->stereo); }
+int ref_synth_num_presets(void* h) { return (int)synth_plugin(h)->presets.count; }
+int ref_synth_preset(void* h, int p, char* name, int name_max, float* values, int max) { return preset_get(synth_plugin(h), p, name, name_max, values, max); }
+int ref_synth_load_preset(void* h, int p) { return preset_load(synth_plugin(h), p); }
+// Synth::onControl (klang.h:4399-4404 / 4789-4794): the synth's control() hook, then every note that is not Off.  Returns how many notes that is.
+int ref_synth_on_control(void* h, int idx, float value) {
+	RefSynth* s = (RefSynth*)h;
+	int notified = 0;
+	if (s->mono) { s->mono->onControl(idx, value); for (unsigned i = 0; i < s->mono->notes.count; i++) notified += s->mono->notes[i]->stage != klang::Synth::Note::Off; }
+	else { s->stereo->onControl(idx, value); for (unsigned i = 0; i < s->stereo->notes.count; i++) notified += s->stereo->notes[i]->stage != klang::Stereo::Synth::Note::Off; }
+	return notified;
 }
 
 int ref_synth_channels(void* h) { return ((RefSynth*)h)->stereo ? 2 : 1; }

@@ -19,6 +19,7 @@ for name in dir(real):
     if name.isupper():
         setattr(stub, name, getattr(real, name))
 stub.device_count = lambda: 1
+stub.presets = real.presets
 
 
 class Engine:
@@ -57,6 +58,13 @@ class SynthBank:
 
     def note_off(self, pitch, vel=0.0, instance=0):
         self.s[instance].note_off(pitch, vel)
+
+    def on_control(self, idx, value, instance=0):
+        return self.s[instance].on_control(idx, value)
+
+    def load_preset(self, index, instance=0):
+        self.s[instance].load_preset(index)
+        return self.s[instance].on_control(0, 0.0)
 
     def midi(self, st, b1, b2, instance=0):
         if st == 0x90 and b2 > 0:
@@ -106,6 +114,13 @@ class FxBank:
 
     def parallel_instances(self):
         return self.instances
+
+    def load_preset(self, index, instance=None):
+        for i in (range(self.instances) if instance is None else [instance]):
+            self.f[i].load_preset(index)
+
+    def get_control(self, idx, instance=0):
+        return self.f[instance].get_control(idx)
 
     def debug_enable(self, on=True):
         self.dbg = on

@@ -29,6 +29,26 @@ def main():
         path = os.path.join(HERE, "golden", f"klang_ref_fs{fs}.npz")
         np.savez_compressed(path, **out)
         print(path, len(out), "arrays", os.path.getsize(path) // 1024, "KiB")
+    import json
+    path = os.path.join(HERE, "golden", "presets.json")
+    with open(path, "w") as f:
+        json.dump(preset_tables(oracle.ref), f, indent=1)
+    print(path)
+
+
+def preset_tables(eng):
+    """Plugin::presets of every bound program (klang.h:1940-1981): {"fx/<name>" | "synth/<name>": [[preset name, [values]], ...]}."""
+    eng.set_fs(48000)
+    out = {}
+    for g, nm in cases.FX_NAMES.items():
+        fx = eng.Fx(g)
+        out[f"fx/{nm}"] = [[n, v] for n, v in fx.presets()]
+        fx.close()
+    for g, nm in cases.SY_NAMES.items():
+        sy = eng.Synth(g, 4)
+        out[f"synth/{nm}"] = [[n, v] for n, v in sy.presets()]
+        sy.close()
+    return out
 
 
 if __name__ == "__main__":

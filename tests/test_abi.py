@@ -102,3 +102,26 @@ int main() {
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert ("no device" in out.stdout) == (kb.device_count() == 0)
+
+
+def test_preset_tables_match_the_reference_fixture(library):
+    """kb_graph_num_presets / kb_graph_preset (klang_b200/csrc/kb_presets.h) against tests/golden/presets.json, the tables of the compiled
+    reference (Plugin::presets, klang.h:1940-1981): same presets, same names, same float32 values for every bound program."""
+    import json
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cases
+    with open(os.path.join(ROOT, "tests", "golden", "presets.json")) as f:
+        want = json.load(f)
+    seen = 0
+    for is_synth, names in ((0, cases.FX_NAMES), (1, cases.SY_NAMES)):
+        for g, nm in names.items():
+            got = kb.presets(is_synth, g)
+            w = want[("synth/" if is_synth else "fx/") + nm]
+            assert [n for n, _ in got] == [n for n, _ in w], nm
+            for (_, gv), (_, wv) in zip(got, w):
+                assert np.array_equal(np.array(gv, np.float32).view(np.uint32), np.array(wv, np.float32).view(np.uint32)), nm
+            seen += len(got)
+    assert seen == 17
+    assert library.kb_graph_preset(0, 0, 0, None, 0, None, 0) < 0            # Gain.k has none

@@ -73,3 +73,48 @@ def test_mono_synth_overwrites_and_stereo_accumulates(golden):
     g = golden[48000]
     voices, mix = g["synth/subtractive/voices"], g["synth/subtractive/mix"]
     assert np.array_equal(mix[0, :512], voices[-1, 0, :512])
+
+
+def _preset_fixture():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "presets.json")) as f:
+        return json.load(f)
+
+
+def _assert_presets(eng):
+    import gen_golden
+    got, want = gen_golden.preset_tables(eng), _preset_fixture()
+    assert set(got) == set(want)
+    for k in want:
+        assert [n for n, _ in got[k]] == [n for n, _ in want[k]], k
+        for (_, gv), (_, wv) in zip(got[k], want[k]):
+            assert np.array_equal(np.array(gv, np.float32).view(np.uint32), np.array(wv, np.float32).view(np.uint32)), k
+
+
+def test_port_presets_match_the_reference_fixture():
+    """Plugin::presets (klang.h:1940-1981) of every bound program, names and values, against tests/golden/presets.json (written by
+    tests/gen_golden.py from the compiled reference)."""
+    _assert_presets(oracle.port)
+
+
+@pytest.mark.skipif(not oracle.ref.available(), reason="compiled reference not present")
+def test_reference_reproduces_the_preset_fixture():
+    _assert_presets(oracle.ref)
+
+
+def test_on_control_fan_out_counts_the_notes_that_are_not_off():
+    """Synth::onControl (klang.h:4399-4404) reaches every note whose stage is not Off: port against the compiled reference when present."""
+    for eng in ([oracle.port, oracle.ref] if oracle.ref.available() else [oracle.port]):
+        eng.set_fs(48000)
+        eng.srand(1)
+        sy = eng.Synth(cases.SY_SUBTRACTIVE, 16)
+        sy.set_control(3, 0.01)
+        assert sy.on_control(0, 0.5) == 0
+        for v in range(5):
+            sy.voice_start(v, 50 + v, 0.8)
+        assert sy.on_control(0, 0.5) == 5
+        sy.voice_release(1, 0.0); sy.voice_release(3, 0.0)
+        sy.process(4096)                                   # the two released notes finish inside the block and stop()
+        assert sy.on_control(1, 0.2) == 3
+        sy.close()

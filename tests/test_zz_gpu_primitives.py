@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 def _exact(got, want, name):
     assert got.shape == want.shape, name
     same = got.view(np.uint32) == want.view(np.uint32)
-    assert same.all(), f"{name}: first mismatch at {int(np.argmin(same))}: got {got[np.argmin(same)]!r} want {want[np.argmin(same)]!r}"
+    assert same.all(), f"{name}: first mismatch at {int(np.argmin(same))}: got {got.reshape(-1)[np.argmin(same)]!r} want {want.reshape(-1)[np.argmin(same)]!r}"
 
 
 @pytest.mark.parametrize("fs", [44100, 48000])
@@ -387,3 +387,66 @@ def test_a_program_without_a_tap_leaves_no_capture():
     with pytest.raises(kb.KlangB200Error):
         bank.debug_read(256)
     bank.close()
+
+
+# ------------------------------------------------------------------- presets and onControl
+@pytest.mark.parametrize("graph,index", [(kb.FX_PINGPONG, 0), (kb.FX_PINGPONG, 5), (kb.FX_REVERB, 0)])
+def test_an_effect_preset_loads_like_in_the_reference(graph, index):
+    """Plugin::presets (klang.h:1940-1981): the preset goes in through Control::set and the next blocks are the reference's, bit for bit
+    (Reverb.k 'Large Hall' changes every delay time: prepare() runs its controls.changed() branch on the device mirror)."""
+    fs, n = 48000, 1024
+    chk = oracle.ref if oracle.ref.available() else oracle.port
+    chk.set_fs(fs); chk.srand(1); kb.Engine().srand(1)
+    ref = chk.Fx(graph)
+    bank = kb.FxBank(graph, 2, fs, n)
+    x = cases.fx_input(2, 4 * n, seed=31)
+    for b in range(4):
+        if b == 1:
+            ref.load_preset(index)
+            bank.load_preset(index, instance=1)                            # instance 0 keeps its defaults
+        blk = np.stack([x[:, b * n:(b + 1) * n]] * 2).copy()
+        bank.process_inplace(blk)
+        want = ref.process(x[:, b * n:(b + 1) * n])
+        _exact(blk[1], want, f"block {b}")
+        if b >= 1:
+            assert not np.array_equal(blk[0], blk[1])
+    for c, v in enumerate(kb.presets(0, graph)[index][1]):
+        if graph != kb.FX_PINGPONG or c not in (1,):                       # PingPong.k rewrites controls[1] every sample
+            assert abs(bank.get_control(c, 1) - ref.get_control(c)) == 0, c
+    ref.close(); bank.close()
+
+
+def test_synth_preset_and_on_control_fan_out():
+    """SuperSaw.k preset 'Synth Pad' (attack 1.0, detune, mix) loaded before the notes start; Synth::onControl / onPreset (klang.h:4399-4420)
+    reach the notes that are not Off — stages as the DEVICE left them.  (SuperSaw.k:17 draws libc rand() in on(): the reference runs first,
+    then the product from the same seed.)"""
+    fs, n = 48000, 512
+    chk = oracle.ref if oracle.ref.available() else oracle.port
+
+    def script(sy, process, srand):
+        srand(7)
+        outs, counts = [], []
+        counts.append(sy.load_preset(2))
+        for v in range(6):
+            sy.voice_start(v, 48 + 3 * v, 0.7)
+        counts.append(sy.on_control(0, 0.3))
+        for b in range(3):
+            outs.append(process())
+        sy.load_preset(0)                                                  # 'Pluck': short release
+        for v in (0, 2, 4):
+            sy.voice_release(v, 0.0)
+        for b in range(50):                                                # (the release lasts 0.5 s + 5 ms: the three notes stop() inside these blocks)
+            outs.append(process())
+        counts.append(sy.on_control(1, 0.5))
+        return np.concatenate(outs, axis=-1), counts
+
+    chk.set_fs(fs)
+    ref = chk.Synth(kb.SY_SUPERSAW, 16)
+    want, wc = script(ref, lambda: np.atleast_2d(ref.process(n)), chk.srand)
+    ref.close()
+    bank = kb.SynthBank(kb.SY_SUPERSAW, 1, 16, fs, n)
+    got, gc = script(bank, lambda: bank.process_block(n)[0], kb.Engine().srand)
+    bank.close()
+    _exact(got, want, "SuperSaw.k with presets")
+    assert gc[1:] == wc[1:] and wc[1] == 6 and wc[2] < 6, (gc, wc)
+    assert gc[0] == 0
