@@ -237,6 +237,12 @@ int kb_synth_bank_process_mixdown(kb_synth_bank* bank, kb_mixdown* m, float* out
  * (klang.h:4947-4951, 5357-5366): the n ticks are the next n draws of the PROCESS's libc rand() stream, produced on the device,
  * and the call leaves libc's rand() advanced by n draws exactly as the reference's loop would. */
 int kb_prim_osc(int kind, int nargs, float f, float phase, float duty, float fs, int n, float* out);
+/* File::WAV (klang.h:5951-6085: load + operator>> into a variable::buffer) over a file image in host memory — host code in the reference as
+ * well; returns the number of decoded samples (data->size / BlockAlign), copies at most max_samples, info = { NumChannels, SampleRate,
+ * BitsPerSample }.  klang::Sample (klang.h:3679-3720: set(f) [nargs 1] or set(f, phase) [nargs 2], then n ticks) played on the device from a
+ * table in host memory, e.g. the decoded file. */
+int kb_wav_decode(const void* image, long long nbytes, float* out, int max_samples, int* info);
+int kb_prim_sample(const float* table, int size, int nargs, float f, float phase, int n, float* out);
 /* One Delay<1000> (klang.h:3381-3512), sample by sample: write in[s]; out_i = tap(int di[s]); out_f = tap(float df[s]);
  * out_l = lagrange(df[s]) (klang.h:3429-3458); set(set_at[s]) when set_at[s] >= 0; out_p = process() once set() has placed a read
  * head, else 0.  Delays must lie inside the line (0 <= di < 1000, 0 <= df < 999). */

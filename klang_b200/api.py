@@ -57,6 +57,7 @@ SYMBOLS = [
     ("kb_prim_adsr", _i, [_f, _f, _f, _f, _f, _i, _i, _vp, _vp]),
     ("kb_prim_math", _i, [_i, _i, _vp, _vp]),
     ("kb_prim_delay", _i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    ("kb_wav_decode", _i, [_vp, _ll, _vp, _i, _vp]), ("kb_prim_sample", _i, [_vp, _i, _i, _f, _f, _i, _vp]),
     ("kb_prim_wavetable", _i, [_i, _f, _vp]), ("kb_prim_stereo_delay", _i, [_i, _vp, _vp, _vp, _vp, _vp]),
     ("kb_prim_control_smooth", _i, [_f, _f, _f, _i, _vp, _vp]), ("kb_prim_envelope_at", _i, [_i, _vp, _i, _vp, _vp]),
 ]
@@ -128,6 +129,18 @@ def presets(is_synth, graph):
         k = lib().kb_graph_preset(1 if is_synth else 0, graph, p, name, 40, vals, 16)
         out.append((name.value.decode(), [float(vals[i]) for i in range(k)]))
     return out
+
+
+def wav_decode(image):
+    """File::WAV::load + operator>> (klang.h:5997-6085) over a file image: (float32 samples, (channels, samplerate, bits)).  Host code."""
+    buf = (C.c_ubyte * len(image)).from_buffer_copy(image)
+    info = (C.c_int * 3)()
+    n = lib().kb_wav_decode(C.addressof(buf), len(image), None, 0, info)
+    if n < 0:
+        _check(n, "kb_wav_decode")
+    out = np.zeros(n, np.float32)
+    _check(min(0, lib().kb_wav_decode(C.addressof(buf), len(image), out.ctypes.data, n, info)), "kb_wav_decode")
+    return out, tuple(info)
 
 
 class FxBank:
@@ -466,6 +479,17 @@ class Engine:
         """Delay<1000>::lagrange(df[s]) after writing x[s] (klang.h:3429-3458)."""
         n = len(x)
         return self._delay_kat(x, np.zeros(n, np.int32), df, np.full(n, -1.0, np.float32))[3]
+
+    def sample(self, table, n, f, phase=None):
+        """klang::Sample over `table` (klang.h:3679-3720): set(f) or set(f, phase), then n ticks on the device."""
+        table = np.ascontiguousarray(table, np.float32)
+        out = np.zeros(n, np.float32)
+        _check(lib().kb_prim_sample(table.ctypes.data, len(table), 1 if phase is None else 2, float(f), float(phase or 0.0), n, out.ctypes.data), "kb_prim_sample")
+        return out
+
+    def wav_decode(self, image):
+        """File::WAV (klang.h:5951-6085) over a file image (bytes): (float32 samples, (channels, samplerate, bits))."""
+        return wav_decode(image)
 
     def wavetable(self, kind):
         """Wavetables::Sine / Saw (kinds 10 / 11): the 2048-entry table as the device reads it."""

@@ -1480,6 +1480,56 @@ extern "C" int kb_prim_osc(int kind, int nargs, float f, float phase, float duty
 	cudaMemcpy(out, dout.p, sizeof(float) * n, cudaMemcpyDeviceToHost);
 	return KB_OK;
 }
+// klang::Sample on the device over a caller's table (host memory; typically what kb_wav_decode produced)
+extern "C" int kb_prim_sample(const float* table, int size, int nargs, float f, float phase, int n, float* out) {
+	(void)f;                                                   // (Sample::set keeps the frequency but plays at one sample per tick, klang.h:3697-3700)
+	if (kb_device_count() < 1) return kb_fail(KB_ENODEV, "no CUDA device");
+	if (!table || !out || size < 1 || n < 0 || nargs < 1 || nargs > 2) return kb_fail(KB_EINVAL, "kb_prim_sample: bad argument");
+	if (nargs == 2 && !(phase >= 0.f && phase * (float)44100 + 1.f <= (float)size)) return kb_fail(KB_EINVAL, "kb_prim_sample: the start phase lies outside the table");
+	if (n == 0) return KB_OK;
+	std::vector<float> padded((size_t)size + 2, 0.f);
+	memcpy(padded.data(), table, sizeof(float) * (size_t)size);
+	DevBuf dtab(sizeof(float) * padded.size(), padded.data()), dout(sizeof(float) * n);
+	kb_prim_sample_kernel<<<1, 32>>>(dtab.as<float>(), size, nargs, phase, n, dout.as<float>());
+	int rc = prim_finish("kb_prim_sample"); if (rc) return rc;
+	cudaMemcpy(out, dout.p, sizeof(float) * n, cudaMemcpyDeviceToHost);
+	return KB_OK;
+}
+// File::WAV::load + operator>> (klang.h:5997-6085) — host code in the reference too: the decoded floats are what a Sample (or any table) is fed.
+// RIFF/WAVE header, chunk walk with the sizes as written (no pad byte), data->size / BlockAlign samples from CONSECUTIVE elements (a stereo file
+// yields its first half, interleaved — as there): 8-bit unsigned (x - 128) / 255, 16- and 32-bit signed x / 2^15, x / 2^31, 32-bit float as is;
+// any other encoding leaves zeros.  Returns the sample count (copies min(count, max_samples)); info = { NumChannels, SampleRate, BitsPerSample }.
+extern "C" int kb_wav_decode(const void* image, long long nbytes, float* out, int max_samples, int* info) {
+	const unsigned char* bytes = (const unsigned char*)image;
+	if (!bytes || (!out && max_samples > 0) || max_samples < 0) return kb_fail(KB_EINVAL, "kb_wav_decode: bad argument");
+	if (nbytes < 12 || memcmp(bytes, "RIFF", 4) || memcmp(bytes + 8, "WAVE", 4)) return kb_fail(KB_EINVAL, "kb_wav_decode: not a RIFF/WAVE image");
+	long long at = 12, fmt = -1, data = -1;
+	while (at + 8 <= nbytes) {
+		uint32_t size; memcpy(&size, bytes + at + 4, 4);
+		if (!memcmp(bytes + at, "fmt ", 4)) fmt = at;
+		else if (!memcmp(bytes + at, "data", 4)) { if (at + (long long)size > nbytes) return kb_fail(KB_EINVAL, "kb_wav_decode: corrupt data chunk"); data = at; }
+		at += 8 + (long long)size;
+	}
+	if (fmt < 0 || data < 0 || fmt + 24 > nbytes) return kb_fail(KB_EINVAL, "kb_wav_decode: fmt or data chunk missing");
+	uint16_t af, ch, align, bits; uint32_t rate, dsize;
+	memcpy(&af, bytes + fmt + 8, 2); memcpy(&ch, bytes + fmt + 10, 2); memcpy(&rate, bytes + fmt + 12, 4);
+	memcpy(&align, bytes + fmt + 20, 2); memcpy(&bits, bytes + fmt + 22, 2); memcpy(&dsize, bytes + data + 4, 4);
+	if (!align) return kb_fail(KB_EINVAL, "kb_wav_decode: BlockAlign is zero");
+	const long long count = dsize / align;
+	if (count > 0x7fffffff) return kb_fail(KB_EINVAL, "kb_wav_decode: too long");
+	if (info) { info[0] = ch; info[1] = (int)rate; info[2] = bits; }
+	const bool pcm = af == 1 && (bits == 8 || bits == 16 || bits == 32), flt = af == 3 && bits == 32;
+	if ((pcm || flt) && data + 8 + count * (bits / 8) > nbytes) return kb_fail(KB_EINVAL, "kb_wav_decode: data chunk shorter than its size");   // (the reference would read past the image)
+	const unsigned char* d = bytes + data + 8;
+	for (long long i = 0; i < count && i < max_samples; i++) {
+		if (pcm && bits == 8) out[i] = ((float)d[i] - 128u) * (1.f / 255);
+		else if (pcm && bits == 16) { int16_t v; memcpy(&v, d + 2 * i, 2); out[i] = (float)v * (1.f / 32768u); }
+		else if (pcm) { int32_t v; memcpy(&v, d + 4 * i, 4); out[i] = (float)v * (1.f / 2147483648u); }
+		else if (flt) memcpy(out + i, d + 4 * i, 4);
+		else out[i] = 0.f;
+	}
+	return (int)count;
+}
 extern "C" int kb_prim_delay(int n, const float* in, const int* di, const float* df, const float* set_at,
                              float* out_i, float* out_f, float* out_p, float* out_l) {
 	if (kb_device_count() < 1) return kb_fail(KB_ENODEV, "no CUDA device");

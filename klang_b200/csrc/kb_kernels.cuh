@@ -581,6 +581,20 @@ __global__ void kb_prim_osc_kernel(int kind, int nargs, float f, float phase, fl
 		}
 	}
 }
+// klang::Sample (klang.h:3679-3720) over a table in device memory (size + 1 floats: the reference reads samples[size] when the position reaches
+// `size` exactly — Phase::operator+= wraps on `>`, klang.h:1527-1534 — the extra slot holds 0): set(f) -> increment 1; set(f, phase) ->
+// position = phase * 44100 first; per tick the position advances and the table is read with buffer::operator[](float) (klang.h:2070-2078).
+__global__ void kb_prim_sample_kernel(const float* __restrict__ table, int size, int nargs, float phase, int n, float* __restrict__ out) {
+	if (threadIdx.x || blockIdx.x) return;
+	float position = nargs >= 2 ? phase * (float)44100 : 0.f;
+	const float increment = 1.f, offset = 0.f;
+	for (int s = 0; s < n; s++) {
+		if (!(increment >= (float)size)) { position += increment; if (position > (float)size) position -= (float)size; }
+		const float off = position + offset, fl = floorf(off), frac = off - fl;
+		const int i = (int)off, j = (i == size - 1) ? 0 : i + 1;
+		out[s] = table[i] * (1.f - frac) + table[j] * frac;
+	}
+}
 // kinds (tests/cases.py): 0 Biquad::LPF 1 Biquad::HPF 2 OnePole::LPF 3 OnePole::HPF 4 Biquad::BPF 5 Biquad::BRF 6 Biquad::APF
 // 7 Butterworth::LPF<1> 8 Butterworth::LPF<2> 9 DCF 10 IIR<1> 11 IIR<2>; one-pole coefficients (expf / tanf) come from the host
 // 12 Modifiers::Modal, 13 / 14 Envelope::Follower peak / rms, 15 / 16 Follower::Window<64> mean / rms: coefficients hc from the host

@@ -64,6 +64,7 @@ class Oracle:
         sig("stereo_delay1000", [i, _f32p, _f32p, _f32p, _f32p, _f32p])
         sig("delay1000_lagrange", [i, _f32p, _f32p, _f32p])
         sig("control_smooth", [f32, f32, f32, i, _f32p, _f32p])
+        sig("sample", [_f32p, i, i, f32, f32, i, _f32p])
         sig("fx_create", [i], vp)
         sig("fx_destroy", [vp], None)
         sig("fx_channels", [vp])
@@ -113,6 +114,39 @@ class Oracle:
         rc = self.fn("osc")(kind, nargs, float(f), float(phase or 0.0), float(duty or 0.0), n, out)
         assert rc == 0
         return out
+
+    def sample(self, table, n, f, phase=None):
+        """klang::Sample over `table` (klang.h:3679-3720): set(f) or set(f, phase), then n ticks."""
+        table = np.ascontiguousarray(table, np.float32)
+        out = np.zeros(n, np.float32)
+        assert self.fn("sample")(table, len(table), 1 if phase is None else 2, float(f), float(phase or 0.0), n, out) == 0
+        return out
+
+    def wav_decode(self, image):
+        """File::WAV (klang.h:5951-6085): (float32 samples, (channels, samplerate, bits)).  The compiled reference loads a file
+        (WAV::load(path); its load(Memory&) overload assigns a pointer to a Memory and cannot work), the port reads the image."""
+        info = (C.c_int * 3)()
+        f = getattr(self.lib(), self.prefix + "wav_decode")
+        f.restype = C.c_int
+        if self.prefix == "ref_":
+            import tempfile
+            with tempfile.NamedTemporaryFile(suffix=".wav") as t:
+                t.write(image)
+                t.flush()
+                f.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_void_p]
+                n = f(t.name.encode(), None, 0, info)
+                if n < 0:
+                    raise ValueError(f"File::WAV refused the image ({n})")
+                out = np.zeros(n, np.float32)
+                f(t.name.encode(), out.ctypes.data, n, info)
+        else:
+            f.argtypes = [C.c_char_p, C.c_longlong, C.c_void_p, C.c_int, C.c_void_p]
+            n = f(image, len(image), None, 0, info)
+            if n < 0:
+                raise ValueError(f"File::WAV refused the image ({n})")
+            out = np.zeros(n, np.float32)
+            f(image, len(image), out.ctypes.data, n, info)
+        return out, tuple(info)
 
     def wavetable(self, kind):
         t = np.zeros(2048, np.float32)

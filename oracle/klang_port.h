@@ -38,6 +38,9 @@ int kp_delay1000(int n, const float* in, const int* di, const float* df, const f
 int kp_stereo_delay1000(int n, const float* inl, const float* inr, const float* df, float* outl, float* outr);
 int kp_control_smooth(float lo, float hi, float initial, int n, const float* values, float* out);
 
+int kp_sample(const float* table, int size, int nargs, float f, float phase, int n, float* out);       /* klang::Sample  klang.h:3679-3720 */
+int kp_wav_decode(const unsigned char* bytes, long long nbytes, float* out, int max, int* info);     /* File::WAV      klang.h:5997-6085 */
+
 /* ------------------------------------------------------------------ effects */
 void* kp_fx_create(int graph);
 void  kp_fx_destroy(void* h);

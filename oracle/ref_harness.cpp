@@ -234,6 +234,28 @@ int ref_osc(int kind, int nargs, float f, float phase, float duty, int n, float*
 	return 0;
 }
 
+// klang::Sample (klang.h:3679-3720) attached to a caller's table: set(f) / set(f, phase) then n ticks.  (Phase::operator+= wraps on
+// `position > size`, klang.h:1527-1534, so a run that reaches position == size reads samples[size]: callers stop before that.)
+int ref_sample(const float* table, int size, int nargs, float f, float phase, int n, float* out) {
+	klang::buffer buf(const_cast<float*>(table), size);
+	klang::Sample smp;
+	smp = buf;
+	if (nargs == 1) smp(klang::param(f)); else smp(klang::param(f), klang::param(phase));
+	for (int s = 0; s < n; s++) { klang::signal y = smp; out[s] = y; }
+	return 0;
+}
+// File::WAV (klang.h:5951-6085): load(path) walks the RIFF chunks, operator>> decodes data->size / BlockAlign samples (8-bit unsigned, 16 / 32-bit
+// signed PCM, 32-bit float) into a variable::buffer.  info = { NumChannels, SampleRate, BitsPerSample }.  Returns the number of samples decoded.
+int ref_wav_decode(const char* path, float* out, int max, int* info) {
+	klang::File::WAV wav;
+	if (!wav.load(path)) return -1;
+	klang::variable::buffer buf;
+	if (!(wav >> buf)) return -2;
+	if (info) { info[0] = wav.format->NumChannels; info[1] = (int)wav.format->SampleRate; info[2] = wav.format->BitsPerSample; }
+	for (int i = 0; i < buf.size && i < max; i++) out[i] = buf.data()[i];
+	return buf.size;
+}
+
 // Wavetable contents (2048 floats) as the reference builds them (klang.h:3645-3650, 5372-5379).
 int ref_wavetable(int kind, float* table) {
 	using namespace klang::Generators;

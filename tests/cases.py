@@ -82,6 +82,51 @@ def noise_cases(eng):
 
 
 
+def wav_image(fmt, channels, bits, payload, rate=44100, extra=b""):
+    """A RIFF/WAVE file image: fmt chunk (16 bytes), optional extra chunks, data chunk."""
+    import struct
+    block = channels * bits // 8
+    f = struct.pack("<4sIHHIIHH", b"fmt ", 16, fmt, channels, rate, rate * block, block, bits)
+    body = b"WAVE" + f + extra + struct.pack("<4sI", b"data", len(payload)) + payload
+    return struct.pack("<4sI", b"RIFF", len(body)) + body
+
+
+def wav_images():
+    """name -> file image: the four encodings File::WAV decodes (klang.h:6063-6083), a chunk to skip, a stereo file, an encoding it leaves as zeros."""
+    import struct
+    i = np.arange(1500, dtype=np.int64)
+    s16 = ((i * 7919) % 65536 - 32768).astype(np.int16)
+    s16[:4] = [-32768, 32767, 0, -1]
+    u8 = ((i * 37) % 256).astype(np.uint8)
+    s32 = ((i * 2654435761) % (1 << 32) - (1 << 31)).astype(np.int32)
+    s32[:3] = [-(1 << 31), (1 << 31) - 1, 1]
+    f32 = noise(1500, seed=77)
+    return {
+        "pcm16": wav_image(1, 1, 16, s16.tobytes()),
+        "pcm8": wav_image(1, 1, 8, u8.tobytes(), rate=22050),
+        "pcm32": wav_image(1, 1, 32, s32.tobytes(), rate=48000),
+        "float32": wav_image(3, 1, 32, f32.tobytes(), rate=96000),
+        "pcm16_list_chunk": wav_image(1, 1, 16, s16.tobytes(), extra=struct.pack("<4sI", b"LIST", 6) + b"abcdef"),
+        "pcm16_stereo": wav_image(1, 2, 16, s16.tobytes()),                  # BlockAlign 4: the first half of the interleaved data
+        "pcm24_unsupported": wav_image(1, 1, 24, bytes(300)),                # decoded as zeros (no 24-bit branch)
+    }
+
+
+def sample_wav_cases(eng):
+    """File::WAV decode (klang.h:5951-6085) and klang::Sample playback (klang.h:3679-3720) of the decoded table: from the start, and from a
+    fractional phase (interpolated reads).  Runs stop before the position reaches the table size (the reference reads samples[size] there)."""
+    out = {}
+    for name, image in wav_images().items():
+        y, info = eng.wav_decode(image)
+        out[f"wav/{name}"] = y
+        out[f"wav/{name}/info"] = np.array(info, np.int32)
+    table = out["wav/float32"]
+    out["sample/from_start"] = eng.sample(table, 1400, 440.0)
+    out["sample/from_phase"] = eng.sample(table, 1000, 220.0, 0.0101)         # position 445.41: every read interpolates
+    out["sample/pcm16_table"] = eng.sample(out["wav/pcm16"], 700, 1000.0, 0.005)
+    return out
+
+
 def primitive_cases(eng, fs):
     """dict name -> float32/int32 array for every primitive on the hot path."""
     eng.set_fs(fs)
@@ -102,6 +147,7 @@ def primitive_cases(eng, fs):
     out["wavetable/sine"] = eng.wavetable(OSC_WT_SINE)
     out["wavetable/saw"] = eng.wavetable(OSC_WT_SAW)
     out.update(noise_cases(eng))
+    out.update(sample_wav_cases(eng))
 
     x = noise(512, seed=7)
     imp = np.zeros(64, np.float32)

@@ -20,6 +20,7 @@ for name in dir(real):
         setattr(stub, name, getattr(real, name))
 stub.device_count = lambda: 1
 stub.presets = real.presets
+stub.wav_decode = lambda image: oracle.port.wav_decode(image)
 
 
 class Engine:

@@ -125,3 +125,24 @@ def test_preset_tables_match_the_reference_fixture(library):
             seen += len(got)
     assert seen == 17
     assert library.kb_graph_preset(0, 0, 0, None, 0, None, 0) < 0            # Gain.k has none
+
+
+def test_wav_decode_matches_the_reference_golden(library):
+    """kb_wav_decode is host code (as File::WAV is in the reference, klang.h:5951-6085), so it is checked here, on the CPU, against the golden
+    vectors the compiled reference decoded from the same file images — every encoding, bit for bit — plus the images it must refuse."""
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cases
+    g = np.load(os.path.join(ROOT, "tests", "golden", "klang_ref_fs48000.npz"))
+    images = cases.wav_images()
+    assert len(images) == 7
+    for name, image in images.items():
+        y, info = kb.wav_decode(image)
+        assert y.shape == g[f"wav/{name}"].shape, name
+        assert np.array_equal(y.view(np.uint32), g[f"wav/{name}"].view(np.uint32)), name
+        assert list(info) == list(g[f"wav/{name}/info"]), name
+    good = images["pcm16"]
+    for bad in (good[:8], b"RIFX" + good[4:], good[:12], good[:-100], good[:36]):
+        with pytest.raises(kb.KlangB200Error):
+            kb.wav_decode(bad)
