@@ -16,33 +16,84 @@
 #include <cuda_runtime.h>
 #include <initializer_list>
 #include <string>
+#include <type_traits>
+#include <utility>
 #include <vector>
 #include <string.h>
 
-#include "kb_math.cuh"
+#include "kb_prims.cuh"
 
 #define KB_KD __host__ __device__ __forceinline__
 
+// klang::fs (klang.h:1593-1604) as translated programs see it: kcc rewrites the identifier `fs` to kb_fs(), which reads the bank's sample
+// rate from constant memory on the device and from a global on the host (constructors, prepare()).
+__constant__ KbFs kb_kd_fs_dev;
+static KbFs kb_kd_fs_host = { 44100.f, 44100, 1.f / 44100.f, 2.0f * KB_PI_F * (1.f / 44100.f), 22050.f };
+
 namespace klang {
 
-struct signal {
-	float value;
-	KB_KD signal(float v = 0.f) : value(v) {}
-	KB_KD operator float() const { return value; }
-	KB_KD signal& operator=(float v) { value = v; return *this; }
-	KB_KD signal& operator+=(float v) { value += v; return *this; }
-	KB_KD signal& operator-=(float v) { value -= v; return *this; }
-	KB_KD signal& operator*=(float v) { value *= v; return *this; }
-	KB_KD signal& operator/=(float v) { value /= v; return *this; }
-	KB_KD signal& operator>>(signal& dst) const { dst.value = value; return dst; }          // `a >> out`            klang.h:2211-2215, 4869-4890
+struct SampleRate {                                                                            // klang.h:1593-1604
+	float f; int i; float inv, w, nyquist; KbFs k;
+	KB_KD SampleRate(const KbFs& s) : f(s.f), i(s.i), inv(s.inv), w(s.w), nyquist(s.nyquist), k(s) {}
+	KB_KD operator float() const { return f; }
 };
-typedef signal param;                                                                         // klang.h:1168-1199 (a signal that is passed by value)
-KB_KD signal& operator>>(float v, signal& dst) { dst.value = v; return dst; }               // `in * gain >> out`: the expression's value lands in out
+KB_KD SampleRate kb_fs() {
+#ifdef __CUDA_ARCH__
+	return SampleRate(kb_kd_fs_dev);
+#else
+	return SampleRate(kb_kd_fs_host);
+#endif
+}
+
+struct signal {                                                                               // klang.h:1062-1166: the operator set as written there,
+	float value;                                                                              // so that every expression has the reference's types
+	KB_KD signal(float v = 0.f) : value(v) {}
+	KB_KD signal(double v) : value((float)v) {}
+	KB_KD signal(int v) : value((float)v) {}
+	KB_KD const signal& operator<<(const signal& input) { value = input.value; return *this; }   // feedback operator   klang.h:1079-1083
+	KB_KD signal& operator>>(signal& dst) const { dst.value = value; return dst; }               // `a >> out`          klang.h:1085-1089
+	KB_KD signal& operator+=(const signal& x) { value += x.value; return *this; }
+	KB_KD signal& operator-=(const signal& x) { value -= x.value; return *this; }
+	KB_KD signal& operator*=(const signal& x) { value *= x.value; return *this; }
+	KB_KD signal& operator/=(const signal& x) { value /= x.value; return *this; }
+	KB_KD signal& operator+=(float x) { value += x; return *this; }
+	KB_KD signal& operator-=(float x) { value -= x; return *this; }
+	KB_KD signal& operator*=(float x) { value *= x; return *this; }
+	KB_KD signal& operator/=(float x) { value /= x; return *this; }
+	KB_KD signal& operator+=(double x) { value += (float)x; return *this; }
+	KB_KD signal& operator-=(double x) { value -= (float)x; return *this; }
+	KB_KD signal& operator*=(double x) { value *= (float)x; return *this; }
+	KB_KD signal& operator/=(double x) { value /= (float)x; return *this; }
+	KB_KD signal& operator+=(int x) { value += (float)x; return *this; }
+	KB_KD signal& operator-=(int x) { value -= (float)x; return *this; }
+	KB_KD signal& operator*=(int x) { value *= (float)x; return *this; }
+	KB_KD signal& operator/=(int x) { value /= (float)x; return *this; }
+	KB_KD signal operator+(float x) const { return value + x; }
+	KB_KD signal operator-(float x) const { return value - x; }
+	KB_KD signal operator*(float x) const { return value * x; }
+	KB_KD signal operator/(float x) const { return value / x; }
+	KB_KD signal operator+(double x) const { return value + (float)x; }
+	KB_KD signal operator-(double x) const { return value - (float)x; }
+	KB_KD signal operator*(double x) const { return value * (float)x; }
+	KB_KD signal operator/(double x) const { return value / (float)x; }
+	KB_KD signal operator+(int x) const { return value + (float)x; }
+	KB_KD signal operator-(int x) const { return value - (float)x; }
+	KB_KD signal operator*(int x) const { return value * (float)x; }
+	KB_KD signal operator/(int x) const { return value / (float)x; }
+	KB_KD operator const float() const { return value; }
+	KB_KD operator float&() { return value; }
+};
+typedef signal param;                                                                         // klang.h:1357-1371 (a signal that is passed by value)
+KB_KD signal& operator>>(float v, signal& dst) { dst.value = v; return dst; }               // `in * gain >> out`   klang.h:1196-1199
 
 struct Control {                                                                              // klang.h:1655-1755 (UI fields reduced to the name)
 	const char* name; int type; float min, max, initial; signal value, smoothed;
 	KB_KD operator float() const { return value.value; }
 	KB_KD operator signal() const { return value; }
+	KB_KD signal operator+(float x) const { return value.value + x; }                        // (Control derives from signal in the reference: its
+	KB_KD signal operator-(float x) const { return value.value - x; }                        //  arithmetic is signal's)
+	KB_KD signal operator*(float x) const { return value.value * x; }
+	KB_KD signal operator/(float x) const { return value.value / x; }
 	KB_KD float smooth() { smoothed = smoothed.value * 0.999f + (1.f - 0.999f) * value.value; return smoothed; }   // klang.h:1715-1716
 	KB_KD Control& set(float x) { value = x < min ? min : (max < x ? max : x); return *this; }                      // std::clamp   klang.h:1725-1728
 };
@@ -67,6 +118,124 @@ inline Graph graph(double = 0, double = 0, double = 0, double = 0) { return Grap
 template <class F> inline void operator>>(F, Graph&&) { }
 template <class F> inline void operator>>(F, Graph&) { }
 
+// ------------------------------------------------------------------------------------------------ the dataflow protocol (klang.h:2181-2329, 4869-4890)
+// Generic::Output / Generator / Input / Modifier with the reference's rules: reading an object's output (conversion to signal, arithmetic,
+// `obj >> dst`) TICKS its process(); feeding an object (`src >> obj`, `obj << src`) stores the value in `in` and runs its input() hook; `obj(args)`
+// calls set(args) and yields the object.  The reference dispatches through virtual functions; objects that travel to the device as bytes cannot
+// carry a host vptr, so the dispatch here is static (CRTP over the concrete type), which is the same call for every concrete object.
+struct kb_output_tag {};
+struct kb_input_tag {};
+template <class D> struct OutputT : kb_output_tag {
+	signal out;
+	KB_KD D& kb_self() { return *static_cast<D*>(this); }
+	KB_KD operator signal() { kb_self().process(); return out; }                              // processed output        klang.h:2214
+	KB_KD operator signal() const { return out; }                                             // last output             klang.h:2215
+	KB_KD void reset() { out = 0.f; }
+};
+template <class S> KB_KD signal kb_read(S& s) { signal v = s; return v; }                     // (an Output lvalue ticks; a value is copied)
+template <class S> KB_KD signal kb_read(const S& s) { signal v = s; return v; }
+template <class D> struct GeneratorT : OutputT<D> {
+	template <class... P> KB_KD D& operator()(P... p) { this->kb_self().set(p...); return this->kb_self(); }   // klang.h:2251-2254
+};
+template <class D> struct ModifierT : kb_input_tag, OutputT<D> {
+	signal in;
+	KB_KD void input() {}                                                                     // pre-processing hook     klang.h:2199-2200
+	KB_KD void input(const signal& source) { in = source; this->kb_self().input(); }           //                         klang.h:2195
+	KB_KD void operator<<(const signal& source) { in = source; this->kb_self().input(); }      // feedback input          klang.h:2194
+	KB_KD void process() { this->out = in; }                                                  // pass-through            klang.h:2296
+	template <class... P> KB_KD D& operator()(P... p) { this->kb_self().set(p...); return this->kb_self(); }   // klang.h:2299-2302
+};
+// `source >> destination` (klang.h:4869-4890): an Input receives it through input(); a signal is assigned the (processed) value
+template <class S, class D, typename std::enable_if<std::is_base_of<kb_input_tag, D>::value, int>::type = 0>
+KB_KD D& operator>>(S&& source, D& destination) { destination.input(kb_read(source)); return destination; }
+template <class S, typename std::enable_if<std::is_base_of<kb_output_tag, typename std::remove_reference<S>::type>::value, int>::type = 0>
+KB_KD signal& operator>>(S&& source, signal& destination) { destination = kb_read(source); return destination; }
+// arithmetic on an Output ticks it once (klang.h:2218-2244); the other operand arrives as float like there
+#define KB_KD_OUT_OP(OP)                                                                                                                   \
+	template <class D> KB_KD signal operator OP(OutputT<D>& o, float x) { return kb_read(static_cast<D&>(o)) OP x; }                        \
+	template <class D> KB_KD signal operator OP(float x, OutputT<D>& o) { return signal(x) OP (float)kb_read(static_cast<D&>(o)); }          \
+	template <class D, class E> KB_KD signal operator OP(OutputT<D>& o, OutputT<E>& p) { const signal a = kb_read(static_cast<D&>(o)); return a OP (float)kb_read(static_cast<E&>(p)); }
+KB_KD_OUT_OP(+) KB_KD_OUT_OP(-) KB_KD_OUT_OP(*) KB_KD_OUT_OP(/)
+#undef KB_KD_OUT_OP
+
+// `x >> debug` (klang.h:3132-3287): kcc rewrites the sink to a temporary of this type; the source is still evaluated (an Output ticks)
+struct Debug { };
+template <class S> KB_KD void operator>>(S&& source, Debug&&) { (void)kb_read(source); }
+
+// ------------------------------------------------------------------------------------------------ primitives with state (klang.h regions cited per class)
+// Thin klang-shaped classes over the POD state and the __host__ __device__ functions of kb_prims.cuh — the functions the hand-written graphs
+// are made of, so a translated program and the bound graph of the same `.k` file execute the same arithmetic.
+namespace Generators { namespace Fast {
+	struct Sine : GeneratorT<Sine> {                                                          // Fast::Sine   klang.h:5135-5172
+		KbFastSine o;
+		Sine() { kb_fsine_init(o); }
+		KB_KD void set(param f) { kb_fsine_set_f(kb_fs().k, o, f); }
+		KB_KD void set(param f, param phase) { kb_fsine_set_fp(kb_fs().k, o, f, phase); }
+		KB_KD void process() { out = kb_fsine_tick(o); }
+	};
+	template <int WAVEFORM, int DUTY_PERCENT> struct OsmT : GeneratorT<OsmT<WAVEFORM, DUTY_PERCENT>> {   // Fast::Saw / Triangle / Square / Pulse   klang.h:5175-5354
+		KbOsm o;
+		OsmT() { kb_osm_construct(o, WAVEFORM, DUTY_PERCENT / 100.f); }
+		KB_KD void set(param f) { kb_osm_set_f(kb_fs().k, o, f); }
+		KB_KD void set(param f, param phase) { kb_osm_set_fp(kb_fs().k, o, f, phase); }
+		KB_KD void set(param f, param phase, param duty) { kb_osm_set_fpd(kb_fs().k, o, f, phase, duty); }
+		KB_KD void process() { this->out = kb_osm_tick(o); }
+	};
+	typedef OsmT<0, 0> Saw; typedef OsmT<0, 100> Triangle; typedef OsmT<1, 100> Square; typedef OsmT<1, 50> Pulse;
+} }
+namespace Filters { namespace Biquad {
+	template <int TYPE> struct FilterT : ModifierT<FilterT<TYPE>> {                           // Biquad::Filter + LPF / HPF   klang.h:5550-5687
+		KbBiquad b;
+		FilterT() { kb_biquad_construct(b, TYPE); }
+		KB_KD void reset() { kb_biquad_reset(b); }
+		KB_KD void set(param f) { kb_biquad_set_f(kb_fs().k, b, f); }
+		KB_KD void set(param f, param Q) { kb_biquad_set(kb_fs().k, b, f, Q); }
+		KB_KD void process() { this->out = kb_biquad_tick(b, this->in); }
+	};
+	typedef FilterT<KB_BQ_LPF> LPF; typedef FilterT<KB_BQ_HPF> HPF;
+} }
+template <int SIZE> struct Delay : ModifierT<Delay<SIZE>> {                                   // Delay<SIZE>   klang.h:3377-3500
+	using ModifierT<Delay<SIZE>>::input;
+	float ring[SIZE + 1];                                                                     // buffer of SIZE + 1 floats like klang::buffer
+	int position; int last_position; float last_fraction; float time;
+	Delay() { clear(); time = 1.f; last_position = 0; last_fraction = 0.f; }
+	KB_KD void clear() { for (int i = 0; i <= SIZE; i++) ring[i] = 0.f; position = 0; }
+	KB_KD void input() {                                                                      // Delay::input    klang.h:3396-3403
+		ring[position] = this->in;
+		position++;
+		if (position == SIZE) position = 0;
+	}
+	KB_KD signal tap(int delay) const {                                                       // klang.h:3405-3410
+		int read = (position - 1) - delay;
+		if (read < 0) read += SIZE;
+		return ring[read];
+	}
+	KB_KD signal tap(float delay) const {                                                     // klang.h:3412-3427
+		float read = (float)(position - 1) - delay;
+		if (read < 0.f) read += SIZE;
+		const int i = (int)read;
+		const float fraction = read - i;
+		const int j = (i + 1) % SIZE;
+		return ring[i] + fraction * (ring[j] - ring[i]);
+	}
+	KB_KD void set(param samples) {                                                           // Delay::set      klang.h:3480-3489
+		time = samples < SIZE ? (float)samples : SIZE;
+		float read = (float)(position - 1) - time;
+		if (read < 0.f) read += SIZE;
+		last_position = (int)read;
+		last_fraction = read - last_position;
+	}
+	KB_KD void process() {                                                                    // Delay::process  klang.h:3461-3473
+		const int i = last_position, j = (i + 1) % SIZE;
+		this->out = ring[i] + last_fraction * (ring[j] - ring[i]);
+		last_position = (last_position + 1) % SIZE;
+	}
+	KB_KD signal operator()(int delay) const { return tap(delay); }                           // klang.h:3603-3621
+	KB_KD signal operator()(float delay) const { return tap(delay); }
+	KB_KD signal operator()(double delay) const { return tap((float)delay); }
+	KB_KD signal operator()(const signal& delay) const { return tap(delay.value); }
+};
+
 struct Effect {                                                                               // klang.h:4203-4217
 	signal in, out;
 	Controls controls;
@@ -85,8 +254,8 @@ namespace Stereo {
 	};
 }
 namespace stereo = Stereo;
-namespace optimised { }
-namespace basic { }
+namespace optimised { using namespace Generators::Fast; using namespace Filters::Biquad; }   // klang.h:6145-6152
+namespace basic { using namespace Filters::Biquad; }
 namespace minimal { }
 
 // libm as the reference's translation unit sees it (float overloads); the device halves restate the host's functions bit for bit
@@ -126,18 +295,23 @@ template <class FX> __global__ void kb_user_stream_kernel(const FX* __restrict__
 template <class FX> __global__ void kb_user_seq_kernel(FX* __restrict__ objs, float* __restrict__ io, int n, int stride, int instances) {
 	const int inst = blockIdx.x * blockDim.x + threadIdx.x;
 	if (inst >= instances) return;
-	FX fx = objs[inst];
 	float* l = io + (size_t)inst * FX::kb_channels * stride;
 	float* r = l + stride;
-	for (int t = 0; t < n; t++) kb_user_frame(fx, l + t, r + t);
-	objs[inst] = fx;
+	if constexpr (sizeof(FX) <= 4096) {                                  // small state: a private copy the compiler can keep in registers
+		FX fx = objs[inst];
+		for (int t = 0; t < n; t++) kb_user_frame(fx, l + t, r + t);
+		objs[inst] = fx;
+	} else {                                                             // objects that hold delay lines stay where they are, in HBM
+		FX& fx = objs[inst];
+		for (int t = 0; t < n; t++) kb_user_frame(fx, l + t, r + t);
+	}
 }
 
 // ------------------------------------------------------------------------------------------------------------- the program's C ABI
 struct kb_user_fx_base { virtual ~kb_user_fx_base() {} };
 static thread_local std::string kb_user_err;
 template <class FX> struct kb_user_bank : kb_user_fx_base {
-	int instances = 0, max_block = 0, device = 0;
+	int instances = 0, max_block = 0, device = 0; KbFs fs;
 	std::vector<FX> host;
 	FX* d_objs = nullptr; float* d_io = nullptr;
 	cudaStream_t stream = nullptr;
@@ -153,11 +327,17 @@ template <class FX> struct kb_user_bank : kb_user_fx_base {
 		if (n < 0 || n > max_block || !io) { kb_user_err = "kb_user_fx_process: bad argument (n > max_block?)"; return -1; }
 		if (n == 0) return 0;
 		cudaSetDevice(device);
-		// Effect::process(buffer) calls prepare() once per block (klang.h:4209): event-rate code, on the host mirror
-		if (fetch()) { kb_user_err = "kb_user_fx_process: state fetch failed"; return -2; }
-		for (FX& fx : host) fx.prepare();
-		if (cudaMemcpyAsync(d_objs, host.data(), sizeof(FX) * instances, cudaMemcpyHostToDevice, stream) != cudaSuccess) { kb_user_err = "kb_user_fx_process: upload failed"; return -2; }
-		cudaStreamSynchronize(stream);                                   // (the mirror is pageable and may change before the copy engine has read it)
+		// Effect::process(buffer) calls prepare() once per block (klang.h:4209): event-rate code, on the host mirror — a round trip of the objects
+		// that programs WITHOUT a prepare() of their own are spared (their objects travel only when a control was set)
+		constexpr bool has_prepare = !std::is_same<decltype(&FX::prepare), void (FX::kb_base::*)()>::value;
+		if (has_prepare || dirty) {
+			if (fetch()) { kb_user_err = "kb_user_fx_process: state fetch failed"; return -2; }
+			kb_kd_fs_host = fs;
+			for (FX& fx : host) fx.prepare();
+			if (cudaMemcpyAsync(d_objs, host.data(), sizeof(FX) * instances, cudaMemcpyHostToDevice, stream) != cudaSuccess) { kb_user_err = "kb_user_fx_process: upload failed"; return -2; }
+			cudaStreamSynchronize(stream);                               // (the mirror is pageable and may change before the copy engine has read it)
+			dirty = false;
+		}
 		const size_t floats = (size_t)instances * FX::kb_channels * n;
 		float* d = io;
 		if (!(flags & 1u)) { d = d_io; if (cudaMemcpyAsync(d, io, floats * 4, cudaMemcpyHostToDevice, stream) != cudaSuccess) { kb_user_err = "kb_user_fx_process: H2D failed"; return -2; } }
@@ -182,16 +362,18 @@ template <class FX> struct kb_user_bank : kb_user_fx_base {
 	extern "C" int kb_user_channels(void) { return FX::kb_channels; }                                                                        \
 	extern "C" int kb_user_stateless(void) { return kb_user_traits<FX>::stateless ? 1 : 0; }                                                  \
 	extern "C" const char* kb_user_last_error(void) { return kb_user_err.c_str(); }                                                           \
-	extern "C" int kb_user_num_controls(void) { FX fx; return fx.controls.size(); }                                                           \
+	extern "C" int kb_user_num_controls(void) { std::vector<FX> one(1); return one[0].controls.size(); }                                                        \
 	extern "C" void* kb_user_fx_create(int instances, float fs, int max_block, int device) {                                                  \
-		(void)fs;                                                                                                                             \
+		if (!(fs > 0.f)) { kb_user_err = "kb_user_fx_create: bad sample rate"; return nullptr; }                                              \
 		int ndev = 0;                                                                                                                         \
 		if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { cudaGetLastError(); kb_user_err = "kb_user_fx_create: no such CUDA device (there is no CPU path)"; return nullptr; } \
 		if (instances < 1 || instances > 32767 || max_block < 1) { kb_user_err = "kb_user_fx_create: bad argument"; return nullptr; }          \
 		kb_user_bank<FX>* b = new kb_user_bank<FX>();                                                                                         \
-		b->instances = instances; b->max_block = max_block; b->device = device;                                                               \
+		b->instances = instances; b->max_block = max_block; b->device = device; b->fs = kb_make_fs(fs);                                        \
+		kb_kd_fs_host = b->fs;                                            /* constructors see klang::fs */                                     \
 		b->host.resize(instances);                                                                                                            \
 		bool ok = cudaSetDevice(device) == cudaSuccess && cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) == cudaSuccess &&       \
+		          cudaMemcpyToSymbol(kb_kd_fs_dev, &b->fs, sizeof(KbFs)) == cudaSuccess &&                                                     \
 		          cudaMalloc(&b->d_objs, sizeof(FX) * instances) == cudaSuccess &&                                                            \
 		          cudaMalloc(&b->d_io, sizeof(float) * (size_t)instances * FX::kb_channels * max_block) == cudaSuccess;                        \
 		if (!ok) { kb_user_err = "kb_user_fx_create: CUDA allocation failed"; delete b; return nullptr; }                                      \
@@ -202,7 +384,7 @@ template <class FX> struct kb_user_bank : kb_user_fx_base {
 		kb_user_bank<FX>* b = static_cast<kb_user_bank<FX>*>(p);                                                                              \
 		if (!b || inst < 0 || inst >= b->instances || idx < 0 || idx >= b->host[0].controls.size()) { kb_user_err = "kb_user_fx_set_control: bad argument"; return -1; } \
 		if (b->fetch()) return -2;                                                                                                            \
-		b->host[inst].controls[idx].set(v);                                                                                                   \
+		b->host[inst].controls[idx].set(v); b->dirty = true;                                                                                  \
 		return 0;                                                                                                                             \
 	}                                                                                                                                         \
 	extern "C" int kb_user_fx_get_control(void* p, int inst, int idx, float* v) {                                                             \
