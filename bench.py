@@ -419,6 +419,7 @@ def main():
 
     host_bufs = [out_host, torch.empty_like(out_host).pin_memory()]
     host_done = [torch.cuda.Event(), torch.cuda.Event()]
+    copy_stream = torch.cuda.Stream(device=dev)
     e2e_k = [0]
 
     def step_e2e():
@@ -432,12 +433,36 @@ def main():
             bank.step_into(next_events(), host_bufs[i].numpy(), BLOCK, flags | kb.ASYNC_HOST)
             host_done[i].record(stream)
             e2e_k[0] += 1
+        elif mixdown is not None:
+            # fused peer mix-down: the exchange kernel of block k delivers the rank-order sum of block k-1 into a device buffer on rank 0; a copy
+            # stream of its own waits for that kernel and reads the buffer back into pinned memory (two device and two host buffers, each joined
+            # before reuse, the last block by drain_e2e() inside the timed region).  Every block's reduced mix crosses PCIe.
+            k = e2e_k[0]
+            i = k & 1
+            if rank == 0 and k >= 2:
+                host_done[i].synchronize()
+            bank.events(next_events())
+            bank.process_mixdown(mixdown, mix_bufs[i] if rank == 0 else None, BLOCK, kb.MIX_SUM)
+            if rank == 0 and k >= 1:
+                mixdown.stream_wait(copy_stream.cuda_stream)
+                with torch.cuda.stream(copy_stream):
+                    host_bufs[i].copy_(mix_bufs[i], non_blocking=True)
+                    host_done[i].record(copy_stream)
+            e2e_k[0] += 1
         else:
             step_device()
-            drain()                                              # e2e: every block's reduced mix is read back before the next block
+            drain()                                              # NCCL transport: every block's reduced mix is joined and read back
             if rank == 0:
-                out_host.copy_(pipe["last"] if mixdown is None else out_dev, non_blocking=True)
+                out_host.copy_(pipe["last"], non_blocking=True)
             torch.cuda.synchronize()
+
+    def drain_e2e():
+        """the last block's sum (fused transport) and every copy still in flight"""
+        if dist is not None and mixdown is not None:
+            drain()
+            if rank == 0:
+                out_host.copy_(out_dev, non_blocking=True)
+        torch.cuda.synchronize()
 
     def timed(step_fn, steps, warmup, clocks=None):
         for _ in range(warmup):
@@ -481,13 +506,17 @@ def main():
     value = world * total * BLOCK / (ms_per_step * 1e-3)
 
     # ---- e2e through host buffers (host wall clock is part of it: events run on the host)
+    drain()
     for _ in range(2):
         step_e2e()
+    drain_e2e()
+    e2e_k[0] = 0
     barrier()
     h2d0, d2h0 = bank.transfer_bytes()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step_e2e()
+    drain_e2e()
     barrier()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -500,7 +529,7 @@ def main():
            "h2d_bytes_per_step": int((h2d1 - h2d0) / args.steps), "d2h_bytes_per_step": int((d2h1 - d2h0) / args.steps + out_bytes),
            "note": "per step: the host applies 64 note events on its state mirror (packed dirty-voice upload H2D), kernels, output D2H "
                    "into pinned memory (N=1: KB_ASYNC_HOST, two host buffers, block k+1's events are prepared while block k renders; "
-                   "every buffer is joined before reuse and at the end of the timed region; N>1: the reduced mix is joined and read back every block); "
+                   "every buffer is joined before reuse and at the end of the timed region; N>1, fused peer mix-down: the same with the reduced mix of block k-1 read back by a copy stream while block k renders; N>1 over NCCL: joined and read back every block); "
                    "bytes counted by the library"}
 
     # ---- dominant kernel, CUDA events inside the library

@@ -227,6 +227,8 @@ int kb_mixdown_collect(kb_mixdown* m, float* dst, int count, void* cuda_stream);
  * PREVIOUS step in rank order into out_prev (device memory, rank 0 only; ignored elsewhere).  The exchange of block k thus runs beside the
  * kernels of block k + 1; kb_mixdown_collect() after the last block returns the last sum.  Do not mix with acquire / publish in one step. */
 int kb_mixdown_step(kb_mixdown* m, const float* src, int count, float* out_prev, void* cuda_stream);
+/* queue on `stream` a wait for the exchange kernel of the last fused step (a consumer of out_prev on a stream of its own) */
+int kb_mixdown_stream_wait(kb_mixdown* mix, void* stream);
 /* kb_synth_bank_process(KB_BANK_MIX) whose bank-mix kernel IS that fused step: the in-order sum of the bank's instances goes straight into
  * rank 0's arena over NVLink (Synth voices / instances shard across GPUs; this is the path's only exchange). */
 int kb_synth_bank_process_mixdown(kb_synth_bank* bank, kb_mixdown* m, float* out_prev, int n, unsigned flags);

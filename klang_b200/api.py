@@ -49,7 +49,7 @@ SYMBOLS = [
     ("kb_mixdown_export", _i, [_vp, _vp]), ("kb_mixdown_import", _i, [_vp, _vp]),
     ("kb_mixdown_acquire", _vp, [_vp, _vp]), ("kb_mixdown_publish", _i, [_vp, _vp]), ("kb_mixdown_put", _i, [_vp, _vp, _i, _vp]),
     ("kb_mixdown_collect", _i, [_vp, _vp, _i, _vp]),
-    ("kb_mixdown_step", _i, [_vp, _vp, _i, _vp, _vp]), ("kb_synth_bank_process_mixdown", _i, [_vp, _vp, _vp, _i, _u]),
+    ("kb_mixdown_step", _i, [_vp, _vp, _i, _vp, _vp]), ("kb_mixdown_stream_wait", _i, [_vp, _vp]), ("kb_synth_bank_process_mixdown", _i, [_vp, _vp, _vp, _i, _u]),
     ("kb_synth_bank_step", _i, [_vp, _i, _vp, _vp, _i, _u]),
     ("kb_prim_osc", _i, [_i, _i, _f, _f, _f, _f, _i, _vp]),
     ("kb_prim_filter", _i, [_i, _i, _vp, _vp, _f, _i, _vp, _vp, _vp]),

@@ -1386,6 +1386,14 @@ extern "C" int kb_synth_bank_process_mixdown(kb_synth_bank* b, kb_mixdown* m, fl
 	if (m->device != b->device) return kb_fail(KB_EINVAL, "kb_synth_bank_process_mixdown: bank and mix-down live on different devices");
 	return sy_process(b, (float*)b->d_mix, n, flags | KB_BANK_MIX | KB_DEVICE_PTR, m, out_prev);
 }
+// make `stream` wait for the exchange kernel of the last fused step (it runs on the bank's side stream): what a consumer of `out_prev` queues
+// before it reads the buffer, without tying the bank's own stream to the exchange
+extern "C" int kb_mixdown_stream_wait(kb_mixdown* m, void* stream) {
+	if (!m) return kb_fail(KB_EINVAL, "kb_mixdown_stream_wait: null mix-down");
+	KB_CUDA(cudaSetDevice(m->device));
+	if (m->step_pending && m->ev_done) KB_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, m->ev_done, 0));
+	return KB_OK;
+}
 extern "C" int kb_mixdown_step(kb_mixdown* m, const float* src, int count, float* out_prev, void* stream) {
 	if (!m || !m->arena || !src || count < 1 || count > m->max_floats) return kb_fail(KB_EINVAL, "kb_mixdown_step: bad argument (arena mapped? count <= max_floats?)");
 	if (m->rank == 0 && m->step > m->collected + 1) return kb_fail(KB_EINVAL, "kb_mixdown_step: rank 0 must pass out_prev on every step (or collect) so the slots are consumed");

@@ -80,6 +80,10 @@ class PeerMixdown:
         PREVIOUS step's slots into `out_prev`."""
         self._api._check(self._api.lib().kb_mixdown_step(self.h, src.data_ptr(), int(count), out_prev.data_ptr() if out_prev is not None else 0, cuda_stream), "kb_mixdown_step")
 
+    def stream_wait(self, cuda_stream):
+        """`cuda_stream` waits for the exchange kernel of the last fused step (before it reads that step's out_prev)."""
+        self._api._check(self._api.lib().kb_mixdown_stream_wait(self.h, cuda_stream), "kb_mixdown_stream_wait")
+
     def collect(self, dst, count, cuda_stream):
         self._api._check(self._api.lib().kb_mixdown_collect(self.h, dst.data_ptr(), int(count), cuda_stream), "kb_mixdown_collect")
 
