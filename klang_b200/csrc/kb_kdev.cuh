@@ -32,6 +32,8 @@ static KbFs kb_kd_fs_host = { 44100.f, 44100, 1.f / 44100.f, 2.0f * KB_PI_F * (1
 
 namespace klang {
 
+typedef void event;                                                                            // klang.h:242-243
+
 struct SampleRate {                                                                            // klang.h:1593-1604
 	float f; int i; float inv, w, nyquist; KbFs k;
 	KB_KD SampleRate(const KbFs& s) : f(s.f), i(s.i), inv(s.inv), w(s.w), nyquist(s.nyquist), k(s) {}
@@ -80,7 +82,7 @@ struct signal {                                                                 
 	KB_KD signal operator-(int x) const { return value - (float)x; }
 	KB_KD signal operator*(int x) const { return value * (float)x; }
 	KB_KD signal operator/(int x) const { return value / (float)x; }
-	KB_KD operator const float() const { return value; }
+	KB_KD operator float() const { return value; }
 	KB_KD operator float&() { return value; }
 };
 typedef signal param;                                                                         // klang.h:1357-1371 (a signal that is passed by value)
@@ -166,12 +168,12 @@ template <class S> KB_KD void operator>>(S&& source, Debug&&) { (void)kb_read(so
 // Thin klang-shaped classes over the POD state and the __host__ __device__ functions of kb_prims.cuh — the functions the hand-written graphs
 // are made of, so a translated program and the bound graph of the same `.k` file execute the same arithmetic.
 namespace Generators { namespace Fast {
-	struct Sine : GeneratorT<Sine> {                                                          // Fast::Sine   klang.h:5135-5172
-		KbFastSine o;
-		Sine() { kb_fsine_init(o); }
-		KB_KD void set(param f) { kb_fsine_set_f(kb_fs().k, o, f); }
-		KB_KD void set(param f, param phase) { kb_fsine_set_fp(kb_fs().k, o, f, phase); }
-		KB_KD void process() { out = kb_fsine_tick(o); }
+	struct Sine : GeneratorT<Sine>, KbFastSine {                                              // Fast::Sine   klang.h:5135-5172 (`frequency` is a public member there too)
+		Sine() { kb_fsine_init(*this); }
+		KB_KD void reset() { position = 0u; offset = 0u; }                                    // klang.h:5136-5140 (set(frequency, 0) finds the frequency unchanged)
+		KB_KD void set(param f) { kb_fsine_set_f(kb_fs().k, *this, f); }
+		KB_KD void set(param f, param phase) { kb_fsine_set_fp(kb_fs().k, *this, f, phase); }
+		KB_KD void process() { out = kb_fsine_tick(*this); }
 	};
 	template <int WAVEFORM, int DUTY_PERCENT> struct OsmT : GeneratorT<OsmT<WAVEFORM, DUTY_PERCENT>> {   // Fast::Saw / Triangle / Square / Pulse   klang.h:5175-5354
 		KbOsm o;
@@ -236,18 +238,122 @@ template <int SIZE> struct Delay : ModifierT<Delay<SIZE>> {                     
 	KB_KD signal operator()(const signal& delay) const { return tap(delay.value); }
 };
 
+template <class D> struct OscillatorT : GeneratorT<D> { };                                    // a program's own `struct X : Oscillator` (kcc names the concrete type)
+
+struct Envelope : GeneratorT<Envelope> {                                                      // Envelope   klang.h:3722-4060 over KbEnv (kb_prims.cuh)
+	KbEnv e;
+	struct Point { float x, y; template <class A, class B> KB_KD Point(A x_, B y_) : x((float)x_), y((float)y_) {} };   // klang.h:3835-3850
+	enum Stage { Sustain = KB_ENV_SUSTAIN, Release = KB_ENV_RELEASE, Off = KB_ENV_OFF };
+	Envelope() { kb_env_construct(kb_fs().k, e); }
+	KB_KD Envelope& operator=(std::initializer_list<Point> points) {                          // klang.h:3884-3896
+		float xy[2 * KB_ENV_MAXPTS]; int n = 0;
+		for (const Point& p : points) if (n < KB_ENV_MAXPTS) { xy[2 * n] = p.x; xy[2 * n + 1] = p.y; n++; }
+		kb_env_set_points(kb_fs().k, e, n, xy);
+		return *this;
+	}
+	KB_KD void setLoop(int start, int end) { kb_env_set_loop(e, start, end); }                // klang.h:3923-3926
+	KB_KD void release(float time = 0.f, float level = 0.f) { kb_env_release(kb_fs().k, e, time, level); }   // klang.h:3961-3966
+	KB_KD bool finished() const { return e.stage == KB_ENV_OFF; }
+	KB_KD bool operator==(Stage st) const { return e.stage == (int)st; }
+	KB_KD bool operator!=(Stage st) const { return e.stage != (int)st; }
+	KB_KD void process() { out = kb_env_tick(kb_fs().k, e); }                                 // klang.h:4018-4051
+	KB_KD signal& operator++(int) { process(); return out; }                                  // klang.h:4013-4016
+};
+struct ADSR : Envelope {                                                                      // ADSR   klang.h:4063-4138
+	ADSR() { kb_adsr_construct(kb_fs().k, e); }
+	KB_KD void set(param A, param D, param S, param R) { kb_adsr_set(kb_fs().k, e, A, D, S, R); }
+	KB_KD ADSR& operator()(param A, param D, param S, param R) { set(A, D, S, R); return *this; }
+	KB_KD void release() { kb_adsr_release(kb_fs().k, e); }
+	using Envelope::release;
+};
+
+// host-only pieces of Note::on(): libc rand() and the host libm, exactly where the reference calls them (a device call would be a bug: trap)
+template <class T> KB_KD T random(const T min, const T max) {                                 // klang.h:236-237
+#ifdef __CUDA_ARCH__
+	__trap(); return min;
+#else
+	return rand() * ((max - min) / (T)RAND_MAX) + min;
+#endif
+}
+KB_KD float power(float base, float e) {                                                      // klang.h:187-218, as Pitch -> Frequency uses it
+#ifdef __CUDA_ARCH__
+	__trap(); return base * e;
+#else
+	if (base == 10.f) return (float)::expf(e * (float)2.3025850929940456840179914546843642076011014886287729760333279009);
+	else if (e == 0.f) return 1.f;
+	else if (e == 1.f) return base;
+	else if (e == 2.f) return base * base;
+	else if (e == 3.f) return base * base * base;
+	return ::powf(base, e);
+#endif
+}
+struct Amplitude : signal { using signal::signal; KB_KD Amplitude(const signal& s) : signal(s) {} };
+typedef Amplitude Velocity;
+struct Pitch : signal {                                                                       // klang.h:1551-1578 (Frequency: a member here, a thread-local there)
+	using signal::signal;
+	signal Frequency;
+	KB_KD Pitch(const signal& s) : signal(s) {}
+	KB_KD const Pitch* operator->() { Frequency = 440.f * power(2.f, (value - 69.f) / 12.f); return this; }
+	template <class T> KB_KD Pitch operator+(T in) const { return Pitch(value + in); }
+	template <class T> KB_KD Pitch operator-(T in) const { return Pitch(value - in); }
+	template <class T> KB_KD Pitch operator*(T in) const { return Pitch(value * in); }
+	template <class T> KB_KD Pitch operator/(T in) const { return Pitch(value / in); }
+};
+
+struct Preset { const char* name; float values[16]; int count;                                // klang.h:1940-1981
+	Preset() : name(nullptr), count(0) { memset(values, 0, sizeof(values)); }
+	Preset(const char* n, std::initializer_list<double> v) : name(n), count(0) { memset(values, 0, sizeof(values)); for (double x : v) if (count < 16) values[count++] = (float)x; } };
+struct Presets { Preset items[16]; int count; Presets() : count(0) {}
+	Presets& operator=(std::initializer_list<Preset> list) { count = 0; for (const Preset& p : list) if (count < 16) items[count++] = p; return *this; } };
+
 struct Effect {                                                                               // klang.h:4203-4217
 	signal in, out;
 	Controls controls;
+	Presets presets;
 	typedef Effect kb_base;
 	enum { kb_channels = 1 };
 	void prepare() { }
+};
+
+// ---- Note / Synth (klang.h:4220-4304, 4376-4467): the note object carries the program's members and travels as bytes; on() / off() run on the
+// host mirror (NoteBase::start / release), process() per sample on the device, one lane per voice.
+struct NoteControls {                                                                         // NoteBase::Controls: a view of the synth's table   klang.h:4224-4234
+	Controls* kb_table;
+	KB_KD Control& operator[](int i) { return (*kb_table)[i]; }
+	KB_KD const Control& operator[](int i) const { return (*kb_table)[i]; }
+	KB_KD unsigned int size() const { return kb_table ? (unsigned)kb_table->size() : 0u; }
+};
+struct Note {
+	signal out;
+	Pitch pitch; Velocity velocity;
+	NoteControls controls;
+	void* kb_synth;
+	enum Stage { Onset, Sustain, Release, Off };
+	int stage;
+	Note() : kb_synth(nullptr), stage(Off) { controls.kb_table = nullptr; }
+	KB_KD void on(Pitch, Velocity) { }                                                        // klang.h:4237-4238 (defaults a program may replace)
+	KB_KD void off(Velocity = 0) { stage = Off; }
+	KB_KD void prepare() { }
+	KB_KD bool stop(Velocity = 0) { stage = Off; return true; }                               // klang.h:4277-4280
+	KB_KD bool finished() const { return stage == Off; }
+	template <class S = void> KB_KD S* getSynth() { return static_cast<S*>(kb_synth); }
+};
+struct NotesDecl { int count; NotesDecl() : count(0) {} template <class N> void add(int n) { count += n; } };   // Notes::add<NOTE>(n)   klang.h:4325-4331
+struct Synth {                                                                                // klang.h:4376-4467 (post-processing: Effect::process over the mix)
+	signal in, out;
+	Controls controls;
+	Presets presets;
+	NotesDecl notes;
+	typedef Synth kb_base;
+	void prepare() { }
+	KB_KD void process() { out = in; }
 };
 namespace Stereo {
 	struct signal { klang::signal l, r; KB_KD signal(float a = 0.f, float b = 0.f) : l(a), r(b) {} };
 	struct Effect {                                                                           // klang.h:4703-4716
 		Stereo::signal in, out;
 		Controls controls;
+		Presets presets;
 		typedef Stereo::Effect kb_base;
 		enum { kb_channels = 2 };
 		void prepare() { }
@@ -359,6 +465,7 @@ template <class FX> struct kb_user_bank : kb_user_fx_base {
 
 #define KB_USER_EXPORT(FX, NAME)                                                                                                             \
 	extern "C" const char* kb_user_name(void) { return NAME; }                                                                               \
+	extern "C" int kb_user_kind(void) { return 0; }                                                                                          \
 	extern "C" int kb_user_channels(void) { return FX::kb_channels; }                                                                        \
 	extern "C" int kb_user_stateless(void) { return kb_user_traits<FX>::stateless ? 1 : 0; }                                                  \
 	extern "C" const char* kb_user_last_error(void) { return kb_user_err.c_str(); }                                                           \
@@ -398,4 +505,207 @@ template <class FX> struct kb_user_bank : kb_user_fx_base {
 		kb_user_bank<FX>* b = static_cast<kb_user_bank<FX>*>(p);                                                                              \
 		if (!b) { kb_user_err = "kb_user_fx_process: null bank"; return -1; }                                                                  \
 		return b->process(io, n, flags);                                                                                                      \
+	}
+
+// ============================================================================================================= translated synths
+// Lane = voice: Note::process(buffer) (klang.h:4295-4303) — prepare(), then process() per sample into the voice's stream — for every note
+// that was not Off when the block began.  Objects that hold delay lines stay in HBM, small ones are copied to the lane.
+template <class NOTE> __global__ void kb_user_note_kernel(NOTE* __restrict__ notes, klang::Controls* __restrict__ controls, int* __restrict__ active,
+                                                          float* __restrict__ streams, int n, int voices, int total) {
+	const int v = blockIdx.x * blockDim.x + threadIdx.x;
+	if (v >= total) return;
+	float* o = streams + (size_t)v * n;
+	const int act = notes[v].stage != klang::Note::Off;
+	active[v] = act;
+	if (!act) { for (int t = 0; t < n; t++) o[t] = 0.f; return; }
+	auto run = [&](NOTE& nt) {
+		nt.controls.kb_table = controls + v / voices;
+		nt.prepare();
+		for (int t = 0; t < n; t++) { nt.process(); o[t] = nt.out; }
+	};
+	if constexpr (sizeof(NOTE) <= 4096) { NOTE nt = notes[v]; run(nt); notes[v] = nt; } else run(notes[v]);
+}
+// Synth::process voice loop for a mono synth (klang.h:4450-4456): every active note ASSIGNS the block, so it holds the last active note's
+// stream; thread = (instance, sample)
+__global__ void kb_user_mono_mix_kernel(const float* __restrict__ streams, const int* __restrict__ active, float* __restrict__ out, int n, int voices) {
+	const int inst = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n) return;
+	int last = -1;
+	for (int v = voices - 1; v >= 0 && last < 0; v--) if (active[inst * voices + v]) last = v;
+	out[(size_t)inst * n + t] = last >= 0 ? streams[((size_t)inst * voices + last) * n + t] : 0.f;
+}
+// the synth's own process() over the mix (Effect::process(buffer), klang.h:4208-4216, called at klang.h:4459): lane = instance
+template <class SYN> __global__ void kb_user_post_kernel(SYN* __restrict__ syns, float* __restrict__ out, int n, int instances) {
+	const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+	if (inst >= instances) return;
+	SYN& syn = syns[inst];
+	float* o = out + (size_t)inst * n;
+	for (int t = 0; t < n; t++) { syn.in = o[t]; syn.process(); o[t] = syn.out; }
+}
+
+template <class SYN, class NOTE> struct kb_user_synth_bank : kb_user_fx_base {
+	int instances = 0, voices = 0, max_block = 0, device = 0; KbFs fs;
+	std::vector<SYN> syn; std::vector<NOTE> notes;                       // host mirrors: the plugin objects (controls) and every note
+	std::vector<unsigned> noteOns, noteStart;                            // Notes::noteOns / noteStart   klang.h:4333-4334
+	std::vector<unsigned char> dirty_note; bool notes_stale = false, ctl_dirty = true, syn_dirty = true;
+	SYN* d_syn = nullptr; NOTE* d_notes = nullptr; klang::Controls* d_ctl = nullptr; int* d_active = nullptr;
+	float *d_streams = nullptr, *d_out = nullptr;
+	cudaStream_t stream = nullptr;
+	static constexpr bool has_post = !std::is_same<decltype(&SYN::process), void (klang::Synth::*)()>::value;
+	int total() const { return instances * voices; }
+	NOTE& note(int inst, int v) { return notes[(size_t)inst * voices + v]; }
+	int fetch() {                                                        // the device has evolved the notes: events need their current state
+		if (!notes_stale) return 0;
+		if (cudaMemcpyAsync(notes.data(), d_notes, sizeof(NOTE) * total(), cudaMemcpyDeviceToHost, stream) != cudaSuccess || cudaStreamSynchronize(stream) != cudaSuccess) return -2;
+		notes_stale = false;
+		return 0;
+	}
+	void bind(int inst, int v) { NOTE& nt = note(inst, v); nt.controls.kb_table = &syn[inst].controls; nt.kb_synth = &syn[inst]; kb_kd_fs_host = fs; }
+	// NoteBase::start / release (klang.h:4257-4275) on the host mirror
+	int start(int inst, int v, float pitch, float velocity) {
+		if (fetch()) return -2;
+		bind(inst, v);
+		NOTE& nt = note(inst, v);
+		nt.stage = klang::Note::Onset; nt.pitch = klang::Pitch(pitch); nt.velocity = klang::Velocity(velocity);
+		nt.on(nt.pitch, nt.velocity);
+		nt.stage = klang::Note::Sustain;
+		dirty_note[(size_t)inst * voices + v] = 1;
+		return 0;
+	}
+	int release(int inst, int v, float velocity) {
+		if (fetch()) return -2;
+		NOTE& nt = note(inst, v);
+		if (nt.stage == klang::Note::Off) return 0;
+		if (nt.stage != klang::Note::Release) { bind(inst, v); nt.stage = klang::Note::Release; nt.off(klang::Velocity(velocity)); dirty_note[(size_t)inst * voices + v] = 1; }
+		return 0;
+	}
+	int assign(int inst) {                                               // Notes::assign   klang.h:4336-4372
+		unsigned* ns = noteStart.data() + (size_t)inst * voices;
+		for (int i = 0; i < voices; i++) if (note(inst, i).stage == klang::Note::Off) { ns[i] = noteOns[inst]++; return i; }
+		int oldest = -1; unsigned oldest_start = 0;
+		for (int i = 0; i < voices; i++) if (note(inst, i).stage == klang::Note::Release && (oldest == -1 || ns[i] < oldest_start)) { oldest = i; oldest_start = ns[i]; }
+		if (oldest != -1) { ns[oldest] = noteOns[inst]++; return oldest; }
+		for (int i = 0; i < voices; i++) if (oldest == -1 || ns[i] < oldest_start) { oldest = i; oldest_start = ns[i]; }
+		ns[oldest] = noteOns[inst]++;
+		return oldest;
+	}
+	int process(float* out, int n, unsigned flags) {
+		if (n < 0 || n > max_block || !out) { kb_user_err = "kb_user_synth_process: bad argument (n > max_block?)"; return -1; }
+		if (n == 0) return 0;
+		cudaSetDevice(device);
+		const bool dev = flags & 1u, per_voice = flags & 2u;
+		bool ok = true;
+		for (int k = 0; k < total() && ok; k++) if (dirty_note[k]) { ok = cudaMemcpyAsync(d_notes + k, &notes[k], sizeof(NOTE), cudaMemcpyHostToDevice, stream) == cudaSuccess; dirty_note[k] = 0; }
+		if (ctl_dirty) {
+			std::vector<klang::Controls> c(instances);
+			for (int i = 0; i < instances; i++) c[i] = syn[i].controls;
+			ok = ok && cudaMemcpyAsync(d_ctl, c.data(), sizeof(klang::Controls) * instances, cudaMemcpyHostToDevice, stream) == cudaSuccess;
+			ok = ok && cudaStreamSynchronize(stream) == cudaSuccess;
+			ctl_dirty = false;
+		}
+		if (has_post && syn_dirty) {
+			// (the synth object's controls are refreshed; its other members are the post-processing state the device evolves)
+			for (int i = 0; i < instances && ok; i++) ok = cudaMemcpyAsync(&d_syn[i].controls, &syn[i].controls, sizeof(klang::Controls), cudaMemcpyHostToDevice, stream) == cudaSuccess;
+			syn_dirty = false;
+		}
+		if (!ok || cudaStreamSynchronize(stream) != cudaSuccess) { kb_user_err = "kb_user_synth_process: upload failed"; return -2; }
+		float* d_streams_dst = (per_voice && dev) ? out : d_streams;
+		kb_user_note_kernel<NOTE><<<(total() + 31) / 32, 32, 0, stream>>>(d_notes, d_ctl, d_active, d_streams_dst, n, voices, total());
+		notes_stale = true;
+		float* d_result = d_streams_dst;
+		size_t floats = (size_t)total() * n;
+		if (!per_voice) {
+			d_result = dev ? out : d_out;
+			floats = (size_t)instances * n;
+			dim3 grid((n + 255) / 256, instances);
+			kb_user_mono_mix_kernel<<<grid, 256, 0, stream>>>(d_streams, d_active, d_result, n, voices);
+			if constexpr (has_post) kb_user_post_kernel<SYN><<<(instances + 31) / 32, 32, 0, stream>>>(d_syn, d_result, n, instances);
+		}
+		if (cudaGetLastError() != cudaSuccess) { kb_user_err = "kb_user_synth_process: launch failed"; return -2; }
+		if (!dev && (cudaMemcpyAsync(out, d_result, floats * 4, cudaMemcpyDeviceToHost, stream) != cudaSuccess || cudaStreamSynchronize(stream) != cudaSuccess)) { kb_user_err = "kb_user_synth_process: D2H failed"; return -2; }
+		return 0;
+	}
+	~kb_user_synth_bank() { cudaSetDevice(device); if (stream) cudaStreamSynchronize(stream); cudaFree(d_syn); cudaFree(d_notes); cudaFree(d_ctl); cudaFree(d_active); cudaFree(d_streams); cudaFree(d_out); if (stream) cudaStreamDestroy(stream); }
+};
+
+#define KB_USER_EXPORT_SYNTH(SYN, NOTE, NAME)                                                                                                \
+	typedef kb_user_synth_bank<SYN, NOTE> kb_user_sbank;                                                                                     \
+	extern "C" const char* kb_user_name(void) { return NAME; }                                                                               \
+	extern "C" int kb_user_kind(void) { return 1; }                                                                                          \
+	extern "C" int kb_user_channels(void) { return 1; }                                                                                      \
+	extern "C" const char* kb_user_last_error(void) { return kb_user_err.c_str(); }                                                           \
+	extern "C" int kb_user_num_controls(void) { std::vector<SYN> one(1); return one[0].controls.size(); }                                      \
+	extern "C" int kb_user_synth_voices(void) { std::vector<SYN> one(1); return one[0].notes.count; }                                          \
+	extern "C" void* kb_user_synth_create(int instances, float fs, int max_block, int device) {                                               \
+		int ndev = 0;                                                                                                                         \
+		if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { cudaGetLastError(); kb_user_err = "kb_user_synth_create: no such CUDA device (there is no CPU path)"; return nullptr; } \
+		if (instances < 1 || instances > 4096 || max_block < 1 || !(fs > 0.f)) { kb_user_err = "kb_user_synth_create: bad argument"; return nullptr; } \
+		kb_user_sbank* b = new kb_user_sbank();                                                                                               \
+		b->instances = instances; b->max_block = max_block; b->device = device; b->fs = kb_make_fs(fs);                                        \
+		kb_kd_fs_host = b->fs;                                                                                                                \
+		b->syn.resize(instances);                                                                                                             \
+		b->voices = b->syn[0].notes.count;                                                                                                    \
+		if (b->voices < 1 || b->voices > 128) { kb_user_err = "kb_user_synth_create: the program adds no notes (or more than 128)"; delete b; return nullptr; } \
+		b->notes.resize((size_t)instances * b->voices);                                                                                       \
+		b->noteOns.assign(instances, 0u); b->noteStart.assign((size_t)instances * b->voices, 0u); b->dirty_note.assign((size_t)instances * b->voices, 1); \
+		bool ok = cudaSetDevice(device) == cudaSuccess && cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) == cudaSuccess &&       \
+		          cudaMemcpyToSymbol(kb_kd_fs_dev, &b->fs, sizeof(KbFs)) == cudaSuccess &&                                                     \
+		          cudaMalloc(&b->d_syn, sizeof(SYN) * instances) == cudaSuccess && cudaMalloc(&b->d_notes, sizeof(NOTE) * b->notes.size()) == cudaSuccess && \
+		          cudaMalloc(&b->d_ctl, sizeof(klang::Controls) * instances) == cudaSuccess && cudaMalloc(&b->d_active, sizeof(int) * b->notes.size()) == cudaSuccess && \
+		          cudaMalloc(&b->d_streams, sizeof(float) * b->notes.size() * max_block) == cudaSuccess &&                                     \
+		          cudaMalloc(&b->d_out, sizeof(float) * (size_t)instances * max_block) == cudaSuccess &&                                       \
+		          cudaMemcpy(b->d_syn, b->syn.data(), sizeof(SYN) * instances, cudaMemcpyHostToDevice) == cudaSuccess;                         \
+		if (!ok) { kb_user_err = "kb_user_synth_create: CUDA allocation failed"; delete b; return nullptr; }                                   \
+		return b;                                                                                                                             \
+	}                                                                                                                                         \
+	extern "C" void kb_user_synth_destroy(void* p) { delete static_cast<kb_user_sbank*>(p); }                                                  \
+	extern "C" int kb_user_synth_set_control(void* p, int inst, int idx, float v) {                                                           \
+		kb_user_sbank* b = static_cast<kb_user_sbank*>(p);                                                                                    \
+		if (!b || inst < 0 || inst >= b->instances || idx < 0 || idx >= b->syn[0].controls.size()) { kb_user_err = "kb_user_synth_set_control: bad argument"; return -1; } \
+		b->syn[inst].controls[idx].set(v); b->ctl_dirty = true; b->syn_dirty = true;                                                          \
+		return 0;                                                                                                                             \
+	}                                                                                                                                         \
+	extern "C" int kb_user_synth_get_control(void* p, int inst, int idx, float* v) {                                                          \
+		kb_user_sbank* b = static_cast<kb_user_sbank*>(p);                                                                                    \
+		if (!b || !v || inst < 0 || inst >= b->instances || idx < 0 || idx >= b->syn[0].controls.size()) { kb_user_err = "kb_user_synth_get_control: bad argument"; return -1; } \
+		*v = b->syn[inst].controls[idx].value;                                                                                                \
+		return 0;                                                                                                                             \
+	}                                                                                                                                         \
+	extern "C" int kb_user_synth_voice_start(void* p, int inst, int voice, float pitch, float velocity) {                                     \
+		kb_user_sbank* b = static_cast<kb_user_sbank*>(p);                                                                                    \
+		if (!b || inst < 0 || inst >= b->instances || voice < 0 || voice >= b->voices) { kb_user_err = "kb_user_synth_voice_start: bad argument"; return -1; } \
+		return b->start(inst, voice, pitch, velocity);                                                                                        \
+	}                                                                                                                                         \
+	extern "C" int kb_user_synth_voice_release(void* p, int inst, int voice, float velocity) {                                                \
+		kb_user_sbank* b = static_cast<kb_user_sbank*>(p);                                                                                    \
+		if (!b || inst < 0 || inst >= b->instances || voice < 0 || voice >= b->voices) { kb_user_err = "kb_user_synth_voice_release: bad argument"; return -1; } \
+		return b->release(inst, voice, velocity);                                                                                             \
+	}                                                                                                                                         \
+	extern "C" int kb_user_synth_voice_stage(void* p, int inst, int voice) {                                                                  \
+		kb_user_sbank* b = static_cast<kb_user_sbank*>(p);                                                                                    \
+		if (!b || inst < 0 || inst >= b->instances || voice < 0 || voice >= b->voices) { kb_user_err = "kb_user_synth_voice_stage: bad argument"; return -1; } \
+		if (b->fetch()) return -2;                                                                                                            \
+		return b->note(inst, voice).stage;                                                                                                    \
+	}                                                                                                                                         \
+	/* Synth::noteOn / noteOff   klang.h:4423-4434 */                                                                                          \
+	extern "C" int kb_user_synth_note_on(void* p, int inst, int pitch, float velocity) {                                                      \
+		kb_user_sbank* b = static_cast<kb_user_sbank*>(p);                                                                                    \
+		if (!b || inst < 0 || inst >= b->instances) { kb_user_err = "kb_user_synth_note_on: bad argument"; return -1; }                        \
+		if (b->fetch()) return -2;                                                                                                            \
+		const int v = b->assign(inst);                                                                                                        \
+		const int rc = b->start(inst, v, (float)pitch, velocity);                                                                             \
+		return rc ? rc : v;                                                                                                                   \
+	}                                                                                                                                         \
+	extern "C" int kb_user_synth_note_off(void* p, int inst, int pitch, float velocity) {                                                     \
+		kb_user_sbank* b = static_cast<kb_user_sbank*>(p);                                                                                    \
+		if (!b || inst < 0 || inst >= b->instances) { kb_user_err = "kb_user_synth_note_off: bad argument"; return -1; }                       \
+		if (b->fetch()) return -2;                                                                                                            \
+		for (int v = 0; v < b->voices; v++)                                                                                                   \
+			if (b->note(inst, v).pitch == pitch && b->note(inst, v).stage == klang::Note::Sustain) { const int rc = b->release(inst, v, velocity); if (rc) return rc; } \
+		return 0;                                                                                                                             \
+	}                                                                                                                                         \
+	extern "C" int kb_user_synth_process(void* p, float* out, int n, unsigned flags) {                                                        \
+		kb_user_sbank* b = static_cast<kb_user_sbank*>(p);                                                                                    \
+		if (!b) { kb_user_err = "kb_user_synth_process: null bank"; return -1; }                                                               \
+		return b->process(out, n, flags);                                                                                                     \
 	}

@@ -38,6 +38,11 @@ SCHEDULES = {
     "mod_chorus": lambda b, i: {},
 }
 EDITED = "gain_edited"
+# third step: mono Synth programs — the note's on() / off() on the host mirror, its process() per sample on the device (lane = voice)
+SYNTHS = {"filter_k": ("Subtractive/Filter.k", "filter_k"), "breakpoint": ("Subtractive/Breakpoint.k", "breakpoint"), "ramp": ("Subtractive/Ramp.k", "ramp"),
+          "release": ("Subtractive/Release.k", "release"), "release_slow_attack": ("Subtractive/Release.k", "release"), "supersaw": ("SuperSaw.k", "supersaw"),
+          "supersaw_wide": ("SuperSaw.k", "supersaw"), "am": ("Modulation/AM.k", "am"), "mod_fm": ("Modulation/FM.k", "mod_fm"), "mod_fm2": ("Modulation/FM2.k", "mod_fm2"),
+          "additive_saw": ("Additive/Saw.k", "additive_saw"), "additive_square": ("Additive/Square.k", "additive_square"), "additive_nyquist": ("Additive/Nyquist.k", "additive_nyquist")}
 
 
 def so_path(name):
@@ -49,6 +54,8 @@ def build_all():
     os.makedirs(BIN, exist_ok=True)
     for name, (rel, _) in PROGRAMS.items():
         kcc.compile_k(os.path.join(REF, rel), so_path(name))
+    for rel, lib in set(SYNTHS.values()):
+        kcc.compile_k(os.path.join(REF, rel), so_path("synth_" + lib))
     src = open(os.path.join(REF, "Gain", "Gain.k")).read().replace("in * gain >> out;", "in * gain * 0.5 >> out;")
     edited = os.path.join(BIN, "gain_edited.k")
     with open(edited, "w") as f:
@@ -75,7 +82,12 @@ def test_k_programs_translate_and_compile_for_the_device(tmp_path):
     assert "KB_KD Functions()" not in src                                        # constructors stay host code
     # outside the subset: a synth program is refused at translation, an effect that uses primitives this header lacks fails in nvcc — loudly
     with pytest.raises(kcc.KccError):
-        kcc.translate(open(os.path.join(REF, "SuperSaw.k")).read(), "SuperSaw.k")
+        kcc.translate(open(os.path.join(REF, "SynTHX.k")).read(), "SynTHX.k")          # a Stereo::Synth
+    src, plugin, _ = kcc.translate(open(os.path.join(REF, "Additive", "Square.k")).read(), "Square.k")
+    assert plugin == "Square" and "struct Additive : OscillatorT<Additive>" in src and 'KB_USER_EXPORT_SYNTH(kb_user::Square, kb_user::Square::SquareNote, "Square")' in src
+    for rel, lib in set(SYNTHS.values()):
+        L = C.CDLL(so_path("synth_" + lib))
+        assert L.kb_user_kind() == 1 and L.kb_user_synth_voices() == 32
     with pytest.raises(kcc.KccError):
         kcc.compile_k(os.path.join(REF, "Filtering", "Objects.k"), str(tmp_path / "libobjects_k.so"))     # (Noise: the device rand() stream is not wired to translated programs yet)
     # klang::fs and the debug sink are host objects in the reference: the translation routes them through kb_fs() / a sink value
@@ -137,3 +149,66 @@ def test_edited_k_program_runs_what_the_edited_text_says():
         want = (x[i] * g) * np.float32(0.5)
         assert np.array_equal(got[i].view(np.uint32), want.view(np.uint32))
     fx.close()
+
+
+class _UserSynthEngine:
+    """tests/cases.py drives an `engine`: this one hands out translated synths (one .so per program)."""
+
+    def __init__(self, lib):
+        self.lib, self.fs = lib, 44100.0
+
+    def set_fs(self, fs):
+        self.fs = float(fs)
+
+    def srand(self, seed):
+        import klang_b200 as kb
+        kb.lib().kb_srand(seed)                            # libc srand(): on() draws the process's rand() stream on the host
+
+    def Synth(self, graph, nvoices):
+        eng = self
+
+        class S:
+            def __init__(self):
+                self.u = kcc.UserSynth(so_path("synth_" + eng.lib), 1, eng.fs, 16384)
+                assert self.u.voices == nvoices
+
+            def set_control(self, c, v):
+                self.u.set_control(c, v)
+
+            def voice_start(self, v, p, vel):
+                self.u.voice_start(v, p, vel)
+
+            def voice_release(self, v, vel=0.0):
+                self.u.voice_release(v, vel)
+
+            def voice_stage(self, v):
+                return self.u.voice_stage(v)
+
+            def process_voices(self, n):
+                o = self.u.process_block(n, per_voice=True)
+                return o.reshape(nvoices, 1, n), None
+
+            def process(self, n):
+                return self.u.process_block(n)[0]
+
+            def close(self):
+                self.u.close()
+
+        return S()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fs", [44100, 48000])
+@pytest.mark.parametrize("name", list(SYNTHS))
+def test_translated_synth_matches_the_reference_golden(golden, name, fs):
+    """The scripts of tests/cases.py (voices started, controls changed, voices released over several blocks) run on the TRANSLATED program:
+    per-voice streams, note stages and the Synth::process mix are the golden vectors of the compiled reference, bit for bit."""
+    rel, lib = SYNTHS[name]
+    assert os.path.isfile(so_path("synth_" + lib)), "tests/_k_bin/kcc is built where /root/reference exists and travels with the snapshot"
+    eng = _UserSynthEngine(lib)
+    r = cases.run_synth_script(eng, name, fs, per_voice=True)
+    g = golden[fs]
+    assert np.array_equal(r["out"].view(np.uint32), g[f"synth/{name}/voices"].view(np.uint32)), f"{name}: per-voice streams differ from the reference"
+    assert np.array_equal(r["stages"], g[f"synth/{name}/stages"])
+    r = cases.run_synth_script(eng, name, fs, per_voice=False)
+    assert np.array_equal(np.atleast_2d(r["out"]).view(np.uint32), np.atleast_2d(g[f"synth/{name}/mix"]).view(np.uint32)), f"{name}: Synth::process output differs"
