@@ -19,6 +19,7 @@
 #include <type_traits>
 #include <utility>
 #include <vector>
+#include <algorithm>
 #include <string.h>
 
 #include "kb_prims.cuh"
@@ -33,6 +34,16 @@ static KbFs kb_kd_fs_host = { 44100.f, 44100, 1.f / 44100.f, 2.0f * KB_PI_F * (1
 namespace klang {
 
 typedef void event;                                                                            // klang.h:242-243
+struct constant {                                                                              // klang.h:93-113: a double, its float and the float of its inverse
+	double d; float f; float inv;
+	KB_KD constexpr constant(double value) : d(value), f((float)value), inv((float)(1.0 / value)) {}
+	KB_KD constexpr operator float() const { return f; }
+	KB_KD constexpr float operator^(float x) const { return f; }
+};
+#define KB_KD_CONST static constexpr constant
+KB_KD_CONST pi = { 3.1415926535897932384626433832795 };                                        // klang.h:227-233
+KB_KD_CONST ln2 = { 0.6931471805599453094172321214581 };
+KB_KD_CONST root2 = { 1.4142135623730950488016887242097 };
 
 struct SampleRate {                                                                            // klang.h:1593-1604
 	float f; int i; float inv, w, nyquist; KbFs k;
@@ -105,10 +116,19 @@ inline Control Slider(const char* name, float min = 0.f, float max = 1.f, float 
 inline Control Toggle(const char* name, bool initial = false) { return { name, KB_KD_TOGGLE, 0.f, 1.f, initial ? 1.f : 0.f, initial ? 1.f : 0.f, 0.f }; }
 inline Control Button(const char* name) { return { name, KB_KD_BUTTON, 0.f, 1.f, 0.f, 0.f, 0.f }; }
 
+struct ControlGroup {                                                                         // a control, or `{ "Caption", Dial(...), Dial(...) }`: a captioned group whose
+	Control items[8]; int count;                                                              // members join the table in order   klang.h:1835-1891
+	ControlGroup(const Control& c) : count(1) { items[0] = c; }
+	template <class... C> ControlGroup(const char*, C... members) : count(0) { const Control all[] = { members... }; for (const Control& c : all) if (count < 8) items[count++] = c; }
+};
 struct Controls {                                                                             // klang.h:1893-1925 (Array<Control, 128> reduced to 16)
 	Control items[16]; int count;
 	Controls() : count(0) { memset(items, 0, sizeof(items)); }
-	Controls& operator=(std::initializer_list<Control> list) { count = 0; for (const Control& c : list) if (count < 16) items[count++] = c; return *this; }
+	Controls& operator=(std::initializer_list<ControlGroup> list) {
+		count = 0;
+		for (const ControlGroup& g : list) for (int k = 0; k < g.count; k++) if (count < 16) items[count++] = g.items[k];
+		return *this;
+	}
 	KB_KD Control& operator[](int i) { return items[i]; }
 	KB_KD const Control& operator[](int i) const { return items[i]; }
 	KB_KD int size() const { return count; }
@@ -185,6 +205,36 @@ namespace Generators { namespace Fast {
 	};
 	typedef OsmT<0, 0> Saw; typedef OsmT<0, 100> Triangle; typedef OsmT<1, 100> Square; typedef OsmT<1, 50> Pulse;
 } }
+// Noise (klang.h:4947-4951 Basic, 5357-5366 Fast): one libc rand() per tick from the PROCESS-WIDE stream.  The device continues that stream
+// (kb_rand.h: glibc's TYPE_3 generator, jump-ahead, hand-over of the live libc state): before a block the host gives every Noise object the
+// generator positioned where the reference's draws for that object begin — objects in the reference's processing order (instance by instance,
+// inside a synth note by note over the notes that are not Off), each ticking once per sample — and afterwards advances libc by the draws the
+// block consumed.  The objects are found through the registry their constructors fill while the bank builds its host mirror.  Programs with
+// several Noise objects per plugin / note interleave their draws sample by sample in declaration order (`skip` draws between two ticks).
+struct kb_noise_state { KbRand g; unsigned skip, draws; };
+static thread_local std::vector<void*> kb_noise_registry;
+template <bool FAST> struct NoiseT : GeneratorT<NoiseT<FAST>> {
+	kb_noise_state kb;
+	NoiseT() { memset(&kb, 0, sizeof(kb)); kb_noise_registry.push_back(&kb); }
+	KB_KD NoiseT(const NoiseT& o) : kb(o.kb) { this->out = o.out; }       // (copies — a vector growing, a lane's private copy — are not new objects)
+	KB_KD void process() {
+		const uint32_t r = kb_rand_next(kb.g);
+		for (unsigned k = 0; k < kb.skip; k++) kb_rand_next(kb.g);
+		kb.draws++;
+		this->out = FAST ? kb_noise_fast(r) : kb_noise_basic(r);
+	}
+};
+namespace Generators { namespace Fast { typedef NoiseT<true> Noise; } namespace Basic { typedef NoiseT<false> Noise; } }
+
+namespace Filters {
+	template <int ORDER = 1> struct IIR;
+	template <> struct IIR<1> : ModifierT<IIR<1>> {                                           // optimised first-order IIR   klang.h:5433-5447
+		float a, b;
+		IIR() : a(1.f), b(0.f) {}
+		KB_KD void set(param coeff) { a = coeff; b = 1.f - a; }
+		KB_KD void process() { out = in * a + out * b; }
+	};
+}
 namespace Filters { namespace Biquad {
 	template <int TYPE> struct FilterT : ModifierT<FilterT<TYPE>> {                           // Biquad::Filter + LPF / HPF   klang.h:5550-5687
 		KbBiquad b;
@@ -194,7 +244,7 @@ namespace Filters { namespace Biquad {
 		KB_KD void set(param f, param Q) { kb_biquad_set(kb_fs().k, b, f, Q); }
 		KB_KD void process() { this->out = kb_biquad_tick(b, this->in); }
 	};
-	typedef FilterT<KB_BQ_LPF> LPF; typedef FilterT<KB_BQ_HPF> HPF;
+	typedef FilterT<KB_BQ_LPF> LPF; typedef FilterT<KB_BQ_HPF> HPF; typedef FilterT<KB_BQ_BPF> BPF; typedef FilterT<KB_BQ_BRF> BRF;
 } }
 template <int SIZE> struct Delay : ModifierT<Delay<SIZE>> {                                   // Delay<SIZE>   klang.h:3377-3500
 	using ModifierT<Delay<SIZE>>::input;
@@ -360,8 +410,8 @@ namespace Stereo {
 	};
 }
 namespace stereo = Stereo;
-namespace optimised { using namespace Generators::Fast; using namespace Filters::Biquad; }   // klang.h:6145-6152
-namespace basic { using namespace Filters::Biquad; }
+namespace optimised { using namespace Generators::Fast; using namespace Filters; using namespace Filters::Biquad; }   // klang.h:6145-6152
+namespace basic { using namespace Generators::Basic; using namespace Filters; using namespace Filters::Biquad; }
 namespace minimal { }
 
 // libm as the reference's translation unit sees it (float overloads); the device halves restate the host's functions bit for bit
@@ -429,6 +479,29 @@ template <class FX> struct kb_user_bank : kb_user_fx_base {
 		host_stale = false;
 		return 0;
 	}
+	std::vector<size_t> noise_off;                                       // byte offsets of the Noise states inside the host mirror, in address order
+	void find_noise() {
+		const char* lo = reinterpret_cast<const char*>(host.data()); const char* hi = lo + sizeof(FX) * host.size();
+		for (void* p : klang::kb_noise_registry) if ((const char*)p >= lo && (const char*)p < hi) noise_off.push_back((size_t)((const char*)p - lo));
+		std::sort(noise_off.begin(), noise_off.end());
+		klang::kb_noise_registry.clear();
+	}
+	// Noise: hand every object the libc stream at the position of its first draw of this block (instance by instance; inside an instance the
+	// objects tick once per sample in declaration order), then advance libc by what the block consumes
+	int place_noise(int n) {
+		if (noise_off.empty()) return 0;
+		const size_t per = noise_off.size() / (size_t)instances;
+		KbRand base;
+		if (!kb_rand_capture(base)) { kb_user_err = "libc rand() is not running its default (TYPE_3) generator"; return -1; }
+		for (size_t k = 0; k < noise_off.size(); k++) {
+			klang::kb_noise_state st; st.g = base; st.skip = (unsigned)per - 1u; st.draws = 0u;
+			kb_rand_jump(st.g, (unsigned long long)(k / per) * (unsigned long long)n * per + (k % per));
+			if (cudaMemcpyAsync(reinterpret_cast<char*>(d_objs) + noise_off[k], &st, sizeof(st), cudaMemcpyHostToDevice, stream) != cudaSuccess) return -2;
+		}
+		if (cudaStreamSynchronize(stream) != cudaSuccess) return -2;
+		kb_rand_jump(base, (unsigned long long)instances * (unsigned long long)n * per);
+		return kb_rand_commit(base) ? 0 : -1;
+	}
 	int process(float* io, int n, unsigned flags) {
 		if (n < 0 || n > max_block || !io) { kb_user_err = "kb_user_fx_process: bad argument (n > max_block?)"; return -1; }
 		if (n == 0) return 0;
@@ -444,6 +517,7 @@ template <class FX> struct kb_user_bank : kb_user_fx_base {
 			cudaStreamSynchronize(stream);                               // (the mirror is pageable and may change before the copy engine has read it)
 			dirty = false;
 		}
+		if (int rc = place_noise(n)) { if (kb_user_err.empty()) kb_user_err = "kb_user_fx_process: noise placement failed"; return rc; }
 		const size_t floats = (size_t)instances * FX::kb_channels * n;
 		float* d = io;
 		if (!(flags & 1u)) { d = d_io; if (cudaMemcpyAsync(d, io, floats * 4, cudaMemcpyHostToDevice, stream) != cudaSuccess) { kb_user_err = "kb_user_fx_process: H2D failed"; return -2; } }
@@ -478,7 +552,9 @@ template <class FX> struct kb_user_bank : kb_user_fx_base {
 		kb_user_bank<FX>* b = new kb_user_bank<FX>();                                                                                         \
 		b->instances = instances; b->max_block = max_block; b->device = device; b->fs = kb_make_fs(fs);                                        \
 		kb_kd_fs_host = b->fs;                                            /* constructors see klang::fs */                                     \
+		klang::kb_noise_registry.clear();                                                                                                     \
 		b->host.resize(instances);                                                                                                            \
+		b->find_noise();                                                                                                                      \
 		bool ok = cudaSetDevice(device) == cudaSuccess && cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) == cudaSuccess &&       \
 		          cudaMemcpyToSymbol(kb_kd_fs_dev, &b->fs, sizeof(KbFs)) == cudaSuccess &&                                                     \
 		          cudaMalloc(&b->d_objs, sizeof(FX) * instances) == cudaSuccess &&                                                            \
@@ -589,6 +665,40 @@ template <class SYN, class NOTE> struct kb_user_synth_bank : kb_user_fx_base {
 		ns[oldest] = noteOns[inst]++;
 		return oldest;
 	}
+	std::vector<size_t> noise_off;                                       // Noise states inside the notes, in address order (note-major)
+	void find_noise() {
+		const char* lo = reinterpret_cast<const char*>(notes.data()); const char* hi = lo + sizeof(NOTE) * notes.size();
+		for (void* p : klang::kb_noise_registry) if ((const char*)p >= lo && (const char*)p < hi) noise_off.push_back((size_t)((const char*)p - lo));
+		std::sort(noise_off.begin(), noise_off.end());
+		klang::kb_noise_registry.clear();
+	}
+	// Synth::process renders note after note (klang.h:4450-4456): the notes that are not Off draw n values each, in note order, instance by instance
+	int place_noise(int n) {
+		if (noise_off.empty()) return 0;
+		const size_t per = noise_off.size() / notes.size();
+		if (notes_stale) {                                               // only the stages are needed: 4 bytes per note
+			std::vector<int> st(notes.size());
+			const size_t stage_off = (size_t)(reinterpret_cast<const char*>(&static_cast<const klang::Note&>(notes[0]).stage) - reinterpret_cast<const char*>(&notes[0]));
+			if (cudaMemcpy2DAsync(st.data(), sizeof(int), reinterpret_cast<const char*>(d_notes) + stage_off, sizeof(NOTE), sizeof(int), notes.size(), cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
+			    cudaStreamSynchronize(stream) != cudaSuccess) return -2;
+			for (size_t k = 0; k < notes.size(); k++) if (!dirty_note[k]) notes[k].stage = st[k];
+		}
+		KbRand base;
+		if (!kb_rand_capture(base)) { kb_user_err = "libc rand() is not running its default (TYPE_3) generator"; return -1; }
+		unsigned long long at = 0;
+		for (size_t v = 0; v < notes.size(); v++) {
+			if (notes[v].stage == klang::Note::Off) continue;
+			for (size_t j = 0; j < per; j++) {
+				klang::kb_noise_state st; st.g = base; st.skip = (unsigned)per - 1u; st.draws = 0u;
+				kb_rand_jump(st.g, at + j);
+				if (cudaMemcpyAsync(reinterpret_cast<char*>(d_notes) + noise_off[v * per + j], &st, sizeof(st), cudaMemcpyHostToDevice, stream) != cudaSuccess) return -2;
+			}
+			at += (unsigned long long)n * per;
+		}
+		if (cudaStreamSynchronize(stream) != cudaSuccess) return -2;
+		kb_rand_jump(base, at);
+		return kb_rand_commit(base) ? 0 : -1;
+	}
 	int process(float* out, int n, unsigned flags) {
 		if (n < 0 || n > max_block || !out) { kb_user_err = "kb_user_synth_process: bad argument (n > max_block?)"; return -1; }
 		if (n == 0) return 0;
@@ -609,6 +719,7 @@ template <class SYN, class NOTE> struct kb_user_synth_bank : kb_user_fx_base {
 			syn_dirty = false;
 		}
 		if (!ok || cudaStreamSynchronize(stream) != cudaSuccess) { kb_user_err = "kb_user_synth_process: upload failed"; return -2; }
+		if (int rc = place_noise(n)) { if (kb_user_err.empty()) kb_user_err = "kb_user_synth_process: noise placement failed"; return rc; }
 		float* d_streams_dst = (per_voice && dev) ? out : d_streams;
 		kb_user_note_kernel<NOTE><<<(total() + 31) / 32, 32, 0, stream>>>(d_notes, d_ctl, d_active, d_streams_dst, n, voices, total());
 		notes_stale = true;
@@ -646,7 +757,9 @@ template <class SYN, class NOTE> struct kb_user_synth_bank : kb_user_fx_base {
 		b->syn.resize(instances);                                                                                                             \
 		b->voices = b->syn[0].notes.count;                                                                                                    \
 		if (b->voices < 1 || b->voices > 128) { kb_user_err = "kb_user_synth_create: the program adds no notes (or more than 128)"; delete b; return nullptr; } \
+		klang::kb_noise_registry.clear();                                                                                                     \
 		b->notes.resize((size_t)instances * b->voices);                                                                                       \
+		b->find_noise();                                                                                                                      \
 		b->noteOns.assign(instances, 0u); b->noteStart.assign((size_t)instances * b->voices, 0u); b->dirty_note.assign((size_t)instances * b->voices, 1); \
 		bool ok = cudaSetDevice(device) == cudaSuccess && cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) == cudaSuccess &&       \
 		          cudaMemcpyToSymbol(kb_kd_fs_dev, &b->fs, sizeof(KbFs)) == cudaSuccess &&                                                     \

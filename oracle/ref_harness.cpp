@@ -124,6 +124,16 @@ namespace k_delay_pingpong {
 namespace k_delay_reverb {
 #include "Delay/Reverb.k"
 }
+// programs the product has NO hand-written graph for: it runs them from their own source (klang_b200/kcc.py); ids from 100
+namespace k_objects {
+#include "Filtering/Objects.k"
+}
+namespace k_bands {
+#include "Filtering/Bands.k"
+}
+namespace k_eq {
+#include "Filtering/EQ.k"
+}
 
 // ---------------------------------------------------------------------------
 // Canonical C2 graph: examples/Subtractive/Filter.k's note with
@@ -467,6 +477,9 @@ void* ref_fx_create(int graph) {
 	case FX_FLANGER:  { auto* e = new k_flanger::Flanger();   fx->mono = e;   fx->controls = &e->controls; } break;
 	case FX_MODDELAY: { auto* e = new k_moddelay::ModDelay(); fx->mono = e;   fx->controls = &e->controls; } break;
 	case FX_MOD_CHORUS: { auto* e = new k_mod_chorus::Chorus(); fx->mono = e; fx->controls = &e->controls; } break;
+	case 100: { auto* e = new k_objects::Objects(); fx->mono = e; fx->controls = &e->controls; } break;     // Filtering/Objects.k (Noise >> LPF)
+	case 101: { auto* e = new k_bands::Bands();     fx->mono = e; fx->controls = &e->controls; } break;     // Filtering/Bands.k (two BPF, grouped controls)
+	case 102: { auto* e = new k_eq::EQ();           fx->mono = e; fx->controls = &e->controls; } break;     // Filtering/EQ.k (LPF / HPF set in prepare())
 	default: delete fx; return nullptr;
 	}
 	return fx;

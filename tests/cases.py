@@ -286,9 +286,22 @@ FX_SCRIPTS_LATE = {
 FX_DEBUG_TAPS = ("pingpong_default", "pingpong_short", "rm", "rm_at_cached_rate", "tremolo", "moddelay")
 
 
+# Programs the product has no hand-written graph for and runs from their own source (klang_b200/kcc.py): reference-only effect ids from 100
+# (oracle/ref_harness.cpp); their golden vectors live in tests/golden/klang_ref_translated_fs*.npz.
+#   name: (reference id, path under examples/, total frames, block, [(block_index, control, value)], burst)
+TRANSLATED_FX_SCRIPTS = {
+    "k_objects": (100, "Filtering/Objects.k", 4096, 1024, [(2, 0, 300.0), (2, 1, 4.0)], None),          # Noise >> LPF: one libc rand() per sample
+    "k_bands": (101, "Filtering/Bands.k", 4096, 1024, [(1, 0, 250.0), (1, 3, 5.0), (3, 2, 900.0)], None),
+    "k_eq": (102, "Filtering/EQ.k", 4096, 1024, [(1, 0, 0.9), (2, 1, 0.1), (3, 2, 1.0)], None),
+}
+
+
 def run_fx_script(eng, name, fs, seed=1, debug=False):
     """debug=True returns (output, the concatenated `>> debug` captures of the blocks); a block without a capture raises."""
-    graph, total, block, events, burst = (FX_SCRIPTS.get(name) or FX_SCRIPTS_LATE[name])
+    if name in TRANSLATED_FX_SCRIPTS:
+        graph, _, total, block, events, burst = TRANSLATED_FX_SCRIPTS[name]
+    else:
+        graph, total, block, events, burst = (FX_SCRIPTS.get(name) or FX_SCRIPTS_LATE[name])
     eng.set_fs(fs)
     eng.srand(1)
     fx = eng.Fx(graph)
@@ -411,3 +424,8 @@ def all_graph_cases(eng, fs):
         out[f"synth/{SY_NAMES[graph]}/noteon_mix"] = r["out"]
         out[f"synth/{SY_NAMES[graph]}/noteon_assigned"] = r["assigned"]
     return out
+
+
+def translated_cases(eng, fs):
+    """The scripts of TRANSLATED_FX_SCRIPTS (reference side: eng = oracle.ref; product side: an engine that hands out translated programs)."""
+    return {f"fx/{name}": run_fx_script(eng, name, fs) for name in TRANSLATED_FX_SCRIPTS}

@@ -29,6 +29,11 @@ def main():
         path = os.path.join(HERE, "golden", f"klang_ref_fs{fs}.npz")
         np.savez_compressed(path, **out)
         print(path, len(out), "arrays", os.path.getsize(path) // 1024, "KiB")
+    for fs in (44100, 48000):
+        path = os.path.join(HERE, "golden", f"klang_ref_translated_fs{fs}.npz")
+        out = cases.translated_cases(oracle.ref, fs)
+        np.savez_compressed(path, **out)
+        print(path, len(out), "arrays", os.path.getsize(path) // 1024, "KiB")
     import json
     path = os.path.join(HERE, "golden", "presets.json")
     with open(path, "w") as f:

@@ -24,7 +24,8 @@ PROGRAMS = {"gain": ("Gain/Gain.k", oracle.FX_GAIN), "pan": ("Gain/Pan.k", oracl
             # second step: programs whose members are klang objects with state — oscillators, a biquad, a delay line (kb_kdev.cuh)
             "rm": ("Gain/RM.k", oracle.FX_RM), "tremolo": ("Gain/Tremolo.k", oracle.FX_TREMOLO), "wahwah": ("Filtering/WahWah.k", oracle.FX_WAHWAH),
             "echo": ("Delay/Echo.k", oracle.FX_ECHO), "feedback": ("Delay/Feedback.k", oracle.FX_FEEDBACK), "flanger": ("Modulation/Flanger.k", oracle.FX_FLANGER),
-            "moddelay": ("Modulation/ModDelay.k", oracle.FX_MODDELAY), "mod_chorus": ("Modulation/Chorus.k", oracle.FX_MOD_CHORUS)}
+            "moddelay": ("Modulation/ModDelay.k", oracle.FX_MODDELAY), "mod_chorus": ("Modulation/Chorus.k", oracle.FX_MOD_CHORUS),
+            "delay_reverb": ("Delay/Reverb.k", oracle.FX_DELAY_REVERB)}
 STATELESS = ("gain", "pan", "clipping", "functions", "mute")
 # control values per (block b, instance i) for the programs of the second step: {control: value}
 SCHEDULES = {
@@ -36,6 +37,7 @@ SCHEDULES = {
     "flanger": lambda b, i: {0: 0.2 + 0.3 * i + 0.1 * b, 1: 0.5 + 1.5 * i},
     "moddelay": lambda b, i: {0: 2.0 + 3.0 * i, 1: 0.2 + 0.25 * ((b + i) % 3)},
     "mod_chorus": lambda b, i: {},
+    "delay_reverb": lambda b, i: {0: 0.2 + 0.3 * i, 1: 0.02 + 0.03 * i + 0.01 * b},
 }
 EDITED = "gain_edited"
 # third step: mono Synth programs — the note's on() / off() on the host mirror, its process() per sample on the device (lane = voice)
@@ -56,6 +58,8 @@ def build_all():
         kcc.compile_k(os.path.join(REF, rel), so_path(name))
     for rel, lib in set(SYNTHS.values()):
         kcc.compile_k(os.path.join(REF, rel), so_path("synth_" + lib))
+    for name, spec in cases.TRANSLATED_FX_SCRIPTS.items():
+        kcc.compile_k(os.path.join(REF, spec[1]), so_path(name))
     src = open(os.path.join(REF, "Gain", "Gain.k")).read().replace("in * gain >> out;", "in * gain * 0.5 >> out;")
     edited = os.path.join(BIN, "gain_edited.k")
     with open(edited, "w") as f:
@@ -72,7 +76,7 @@ def test_k_programs_translate_and_compile_for_the_device(tmp_path):
                     "kb_user_fx_destroy", "kb_user_fx_set_control", "kb_user_fx_get_control", "kb_user_fx_process"):
             assert hasattr(L, sym), f"{name}: {sym} not exported"
         L.kb_user_name.restype = C.c_char_p
-        assert L.kb_user_num_controls() == (3 if name == "wahwah" else 1 if name in STATELESS + ("iir", EDITED) else 2)
+        assert L.kb_user_num_controls() == {"wahwah": 3, "delay_reverb": 3}.get(name, 1 if name in STATELESS + ("iir", EDITED) else 2), name
         assert L.kb_user_channels() == (2 if name == "pan" else 1)
         assert L.kb_user_stateless() == (1 if name in STATELESS + (EDITED,) else 0)   # data members (IIR.k's `signal last`, an LFO, a delay line): lane per instance
     # the translated text is the user's: only the function definitions gained a qualifier
@@ -212,3 +216,75 @@ def test_translated_synth_matches_the_reference_golden(golden, name, fs):
     assert np.array_equal(r["stages"], g[f"synth/{name}/stages"])
     r = cases.run_synth_script(eng, name, fs, per_voice=False)
     assert np.array_equal(np.atleast_2d(r["out"]).view(np.uint32), np.atleast_2d(g[f"synth/{name}/mix"]).view(np.uint32)), f"{name}: Synth::process output differs"
+
+
+class _UserFxEngine:
+    """tests/cases.py drives an `engine`: this one hands out the translated program behind a reference-only effect id."""
+
+    def __init__(self):
+        self.fs = 44100.0
+
+    def set_fs(self, fs):
+        self.fs = float(fs)
+
+    def srand(self, seed):
+        import klang_b200 as kb
+        kb.lib().kb_srand(seed)
+
+    def Fx(self, graph):
+        name = next(k for k, v in cases.TRANSLATED_FX_SCRIPTS.items() if v[0] == graph)
+        u = kcc.UserFx(so_path(name), 1, self.fs, 16384)
+
+        class F:
+            channels, num_controls = u.channels, u.num_controls
+
+            def set_control(self, c, v):
+                u.set_control(c, v)
+
+            def process(self, x):
+                y = np.array(x, np.float32, copy=True, order="C")
+                u.process_inplace(y.reshape(1, u.channels, -1))
+                return y
+
+            def close(self):
+                u.close()
+
+        return F()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fs", [44100, 48000])
+def test_programs_without_a_bound_graph_match_the_reference(fs):
+    """Filtering/Objects.k (Noise >> LPF: the device continues the process's libc rand() stream), Filtering/Bands.k (two BPF, grouped controls),
+    Filtering/EQ.k (LPF / HPF set in prepare()): no KB_FX_* id exists for them — the product runs their own text — and every block is the compiled
+    reference's (tests/golden/klang_ref_translated_fs*.npz, written by tests/gen_golden.py; live against oracle.ref where it is present)."""
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", f"klang_ref_translated_fs{fs}.npz")))
+    got = cases.translated_cases(_UserFxEngine(), fs)
+    assert set(got) == set(g) and len(g) == 3
+    for k in g:
+        assert np.array_equal(got[k].view(np.uint32), g[k].view(np.uint32)), f"{k}: differs from the reference"
+        assert np.abs(g[k]).max() > 0
+    if oracle.ref.available():
+        live = cases.translated_cases(oracle.ref, fs)
+        for k in g:
+            assert np.array_equal(live[k].view(np.uint32), g[k].view(np.uint32)), k
+
+
+@pytest.mark.gpu
+def test_noise_program_hands_the_rand_stream_back_to_the_host():
+    """Objects.k draws one rand() per sample on the device; afterwards libc continues where the reference's would: a host draw after two blocks
+    equals the draw after srand(5) + 2 x 1000 rand() calls."""
+    import ctypes
+    import klang_b200 as kb
+    libc = ctypes.CDLL(None)
+    kb.lib().kb_srand(5)
+    for _ in range(2000):
+        libc.rand()
+    want = libc.rand()
+    kb.lib().kb_srand(5)
+    u = kcc.UserFx(so_path("k_objects"), 1, 48000.0, 1000)
+    io = np.zeros((1, 1, 1000), np.float32)
+    u.process_inplace(io)
+    u.process_inplace(io)
+    assert libc.rand() == want
+    u.close()
