@@ -52,19 +52,19 @@ def so_path(name):
 
 
 def build_all():
-    """(run where /root/reference exists: here, by the CPU test below and by __graft_entry__.build())"""
+    """(run where /root/reference exists: here, by the CPU test below and by __graft_entry__.build()); the nvcc runs go in parallel"""
+    from concurrent.futures import ThreadPoolExecutor
     os.makedirs(BIN, exist_ok=True)
-    for name, (rel, _) in PROGRAMS.items():
-        kcc.compile_k(os.path.join(REF, rel), so_path(name))
-    for rel, lib in set(SYNTHS.values()):
-        kcc.compile_k(os.path.join(REF, rel), so_path("synth_" + lib))
-    for name, spec in cases.TRANSLATED_FX_SCRIPTS.items():
-        kcc.compile_k(os.path.join(REF, spec[1]), so_path(name))
+    jobs = [(os.path.join(REF, rel), so_path(name)) for name, (rel, _) in PROGRAMS.items()]
+    jobs += [(os.path.join(REF, rel), so_path("synth_" + lib)) for rel, lib in sorted(set(SYNTHS.values()))]
+    jobs += [(os.path.join(REF, spec[1]), so_path(name)) for name, spec in cases.TRANSLATED_FX_SCRIPTS.items()]
     src = open(os.path.join(REF, "Gain", "Gain.k")).read().replace("in * gain >> out;", "in * gain * 0.5 >> out;")
     edited = os.path.join(BIN, "gain_edited.k")
     with open(edited, "w") as f:
         f.write(src)
-    kcc.compile_k(edited, so_path(EDITED))
+    jobs.append((edited, so_path(EDITED)))
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+        list(pool.map(lambda j: kcc.compile_k(*j), jobs))
 
 
 @pytest.mark.skipif(not HAVE_REFERENCE, reason="reference examples not present")
