@@ -41,6 +41,13 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:kb_s
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:kb_reverb3 -s 3 -c 1 -o $OUT/prof_reverb3 -f python tools/fx_probe.py reverb 4096 --allbus > $OUT/ncu_rv.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:kb_reverb3 -s 6 -c 1 -o $OUT/prof_reverb3_tol -f python tools/fx_probe.py reverb 4096 --tol --allbus > $OUT/ncu_rvt.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:kb_pingpong3 -s 12 -c 1 -o $OUT/prof_pingpong3 -f python tools/fx_probe.py pingpong 4096 > $OUT/ncu_pp.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:kb_mix_fused -s 3 -c 1 -o $OUT/prof_mix_fused -f python bench.py --steps 2 --warmup 3 --no-extras --no-cpu > $OUT/ncu_mix.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:kb_gain_kernel -s 2 -c 1 -o $OUT/prof_gain -f python tools/stream_probe.py > $OUT/ncu_gain.log 2>&1
+echo "== stream probe, C2 variants, C2 trace"
+timeout 300 python tools/stream_probe.py 2>&1 | tee $OUT/stream_probe.txt
+timeout 300 python tools/stream_probe.py 4 2>&1 | tee $OUT/stream_probe_x4.txt
+timeout 600 bash tools/bench_ab.sh 2>&1 | tee $OUT/c2_step_ab.txt
+KB_C2_TRACE=$OUT/c2_trace.txt timeout 300 python bench.py --steps 5 --warmup 3 --no-extras --no-cpu > /dev/null 2>&1; python tools/c2_trace.py $OUT/c2_trace.txt | tee $OUT/c2_trace_summary.txt
 echo "== sanitizer"
 timeout 900 compute-sanitizer --tool memcheck python tools/sanitize_run.py > $OUT/compute_sanitizer_memcheck.log 2>&1; tail -3 $OUT/compute_sanitizer_memcheck.log
 timeout 900 compute-sanitizer --tool racecheck python tools/sanitize_run.py > $OUT/compute_sanitizer_racecheck.log 2>&1; tail -3 $OUT/compute_sanitizer_racecheck.log

@@ -55,4 +55,39 @@ L.kb_mixdown_collect(h, dst.data_ptr(), 512, ts.cuda_stream)
 torch.cuda.synchronize()
 assert torch.equal(src, dst) and torch.equal(src, prev)
 L.kb_mixdown_destroy(h)
+# round 2, second half: the decoupled C2 kernel with the staged voice upload (8 x 100 = 800 voices -> kb_sub_flow_kernel<7>) and re-triggers in every
+# block, the fused voice-sum / bank-mix launch, debug taps, klang::Sample, and translated programs (an effect with a delay line, a synth, noise)
+b = kb.SynthBank(kb.SY_SUBTRACTIVE, 8, 100, fs, 260)
+for g in range(800):
+    b.voice_start(g % 100, 40 + g % 30, 0.7, g // 100)
+for k in range(4):
+    for g in range(k, 800, 17):
+        b.voice_start(g % 100, 45 + g % 20, 0.6, g // 100)
+    b.process_block(260 if k != 2 else 131, kb.BANK_MIX | kb.MIX_SUM)
+b.close()
+for graph in (kb.FX_PINGPONG, kb.FX_RM, kb.FX_MODDELAY):
+    fx = kb.FxBank(graph, 3, fs, 500)
+    fx.debug_enable(True)
+    fx.process_inplace(np.zeros((3, fx.channels, 500), np.float32))
+    assert fx.debug_read(500) is not None
+    fx.close()
+kb.Engine().sample(np.linspace(-1, 1, 300, dtype=np.float32), 250, 440.0, 0.001)
+from klang_b200 import kcc
+kdir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "_k_bin", "kcc")
+if os.path.isfile(os.path.join(kdir, "libecho_k.so")):
+    u = kcc.UserFx(os.path.join(kdir, "libecho_k.so"), 2, fs, 400)
+    u.set_control(0, 0.002)
+    for k in range(3):
+        u.process_inplace(np.ones((2, 1, 400), np.float32))
+    u.close()
+    u = kcc.UserFx(os.path.join(kdir, "libk_objects_k.so"), 2, fs, 400)
+    u.process_inplace(np.zeros((2, 1, 400), np.float32))
+    u.close()
+    sy = kcc.UserSynth(os.path.join(kdir, "libsynth_supersaw_k.so"), 2, fs, 300)
+    for v in range(5):
+        sy.note_on(50 + v, 0.7, v % 2)
+    sy.process_block(300)
+    sy.note_off(50, 0.0, 0)
+    sy.process_block(300, per_voice=True)
+    sy.close()
 print("sanitize run done")
