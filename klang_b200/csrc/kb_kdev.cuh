@@ -40,10 +40,11 @@ struct constant {                                                               
 	KB_KD constexpr operator float() const { return f; }
 	KB_KD constexpr float operator^(float x) const { return f; }
 };
-#define KB_KD_CONST static constexpr constant
-KB_KD_CONST pi = { 3.1415926535897932384626433832795 };                                        // klang.h:227-233
-KB_KD_CONST ln2 = { 0.6931471805599453094172321214581 };
-KB_KD_CONST root2 = { 1.4142135623730950488016887242097 };
+// pi, ln2, root2 (klang.h:227-233) are namespace-scope objects there; device code cannot name a host object, so kcc rewrites the identifiers
+// to these functions (the controls tables of the constructors — host code — use them as well)
+KB_KD constexpr constant kb_pi() { return constant(3.1415926535897932384626433832795); }
+KB_KD constexpr constant kb_ln2() { return constant(0.6931471805599453094172321214581); }
+KB_KD constexpr constant kb_root2() { return constant(1.4142135623730950488016887242097); }
 
 struct SampleRate {                                                                            // klang.h:1593-1604
 	float f; int i; float inv, w, nyquist; KbFs k;
@@ -63,6 +64,7 @@ struct signal {                                                                 
 	KB_KD signal(float v = 0.f) : value(v) {}
 	KB_KD signal(double v) : value((float)v) {}
 	KB_KD signal(int v) : value((float)v) {}
+	KB_KD signal(const constant& c) : value(c.f) {}                                          // klang.h:1067
 	KB_KD const signal& operator<<(const signal& input) { value = input.value; return *this; }   // feedback operator   klang.h:1079-1083
 	KB_KD signal& operator>>(signal& dst) const { dst.value = value; return dst; }               // `a >> out`          klang.h:1085-1089
 	KB_KD signal& operator+=(const signal& x) { value += x.value; return *this; }
@@ -204,6 +206,17 @@ namespace Generators { namespace Fast {
 		KB_KD void process() { this->out = kb_osm_tick(o); }
 	};
 	typedef OsmT<0, 0> Saw; typedef OsmT<0, 100> Triangle; typedef OsmT<1, 100> Square; typedef OsmT<1, 50> Pulse;
+}
+namespace Basic {                                                                             // Generators::Basic   klang.h:4897-4944 (float phase, libm sine)
+	template <int SHAPE> struct OscT : GeneratorT<OscT<SHAPE>>, KbBasicOsc {
+		OscT() { kb_bosc_init(*this); }
+		KB_KD void reset() { position = 0.f; }                                                // Oscillator::reset   klang.h:2859
+		KB_KD void set(param f) { kb_bosc_set_f(kb_fs().k, *this, f); }
+		KB_KD void set(param f, param phase) { kb_bosc_set_fp(kb_fs().k, *this, f, phase); }
+		KB_KD void set(param f, param phase, param duty_) { kb_bosc_set_fp(kb_fs().k, *this, f, phase); duty = duty_; }   // Pulse   klang.h:4935-4938
+		KB_KD void process() { this->out = SHAPE == 0 ? kb_bosc_sine_tick(*this) : kb_bosc_shape_tick(*this, SHAPE); }
+	};
+	typedef OscT<0> Sine; typedef OscT<KB_BOSC_SAW> Saw; typedef OscT<KB_BOSC_TRIANGLE> Triangle; typedef OscT<KB_BOSC_SQUARE> Square; typedef OscT<KB_BOSC_PULSE> Pulse;
 } }
 // Noise (klang.h:4947-4951 Basic, 5357-5366 Fast): one libc rand() per tick from the PROCESS-WIDE stream.  The device continues that stream
 // (kb_rand.h: glibc's TYPE_3 generator, jump-ahead, hand-over of the live libc state): before a block the host gives every Noise object the
@@ -399,7 +412,36 @@ struct Synth {                                                                  
 	KB_KD void process() { out = in; }
 };
 namespace Stereo {
-	struct signal { klang::signal l, r; KB_KD signal(float a = 0.f, float b = 0.f) : l(a), r(b) {} };
+	struct signal {                                                                           // Stereo::signal (frame)   klang.h:4484-4560: channel-wise arithmetic
+		klang::signal l, r;
+		KB_KD signal(float a = 0.f, float b = 0.f) : l(a), r(b) {}
+		KB_KD signal operator+(const signal& x) const { return signal(l.value + x.l.value, r.value + x.r.value); }
+		KB_KD signal operator-(const signal& x) const { return signal(l.value - x.l.value, r.value - x.r.value); }
+		KB_KD signal operator*(const signal& x) const { return signal(l.value * x.l.value, r.value * x.r.value); }
+		KB_KD signal operator/(const signal& x) const { return signal(l.value / x.l.value, r.value / x.r.value); }
+		KB_KD signal operator+(float x) const { return signal(l.value + x, r.value + x); }
+		KB_KD signal operator-(float x) const { return signal(l.value - x, r.value - x); }
+		KB_KD signal operator*(float x) const { return signal(l.value * x, r.value * x); }
+		KB_KD signal operator/(float x) const { return signal(l.value / x, r.value / x); }
+	};
+	template <int SIZE> struct Delay : kb_input_tag {                                         // Stereo::Delay = Bank<klang::Delay<SIZE>, 2>   klang.h:4645-4699
+		klang::Delay<SIZE> items[2];
+		Stereo::signal in, out;
+		KB_KD void clear() { items[0].clear(); items[1].clear(); }
+		KB_KD void input(const Stereo::signal& source) { in = source; items[0].input(source.l); items[1].input(source.r); }   // Bank::input   klang.h:2917-2920
+		KB_KD void operator<<(const Stereo::signal& source) { input(source); }
+		KB_KD Stereo::signal tap(float delay) const {                                         // both channels at the LEFT line's position   klang.h:4668-4681
+			float read = (float)(items[0].position - 1) - delay;
+			if (read < 0.f) read += SIZE;
+			const float f = floorf(read);
+			delay = read - f;
+			const int i = (int)read, j = (i == (SIZE - 1)) ? 0 : (i + 1);
+			return Stereo::signal(items[0].ring[i] * (1.f - delay) + items[0].ring[j] * delay, items[1].ring[i] * (1.f - delay) + items[1].ring[j] * delay);
+		}
+		KB_KD Stereo::signal operator()(const Stereo::signal& delay) const { return Stereo::signal(items[0].tap(delay.l.value), items[1].tap(delay.r.value)); }   // klang.h:4687-4696
+		KB_KD Stereo::signal operator()(float delay) const { return tap(delay); }
+	};
+	template <class S> KB_KD Stereo::signal kb_read(const S& s) { return s; }
 	struct Effect {                                                                           // klang.h:4703-4716
 		Stereo::signal in, out;
 		Controls controls;

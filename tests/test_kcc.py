@@ -25,7 +25,9 @@ PROGRAMS = {"gain": ("Gain/Gain.k", oracle.FX_GAIN), "pan": ("Gain/Pan.k", oracl
             "rm": ("Gain/RM.k", oracle.FX_RM), "tremolo": ("Gain/Tremolo.k", oracle.FX_TREMOLO), "wahwah": ("Filtering/WahWah.k", oracle.FX_WAHWAH),
             "echo": ("Delay/Echo.k", oracle.FX_ECHO), "feedback": ("Delay/Feedback.k", oracle.FX_FEEDBACK), "flanger": ("Modulation/Flanger.k", oracle.FX_FLANGER),
             "moddelay": ("Modulation/ModDelay.k", oracle.FX_MODDELAY), "mod_chorus": ("Modulation/Chorus.k", oracle.FX_MOD_CHORUS),
-            "delay_reverb": ("Delay/Reverb.k", oracle.FX_DELAY_REVERB)}
+            "delay_reverb": ("Delay/Reverb.k", oracle.FX_DELAY_REVERB),
+            # a BASELINE C4 program from its own text: Stereo::Effect, two Delay<192000>, a libm Sine LFO, two DC blockers, a control it rewrites per sample
+            "pingpong": ("PingPong.k", oracle.FX_PINGPONG), "delay_pingpong": ("Delay/PingPong.k", oracle.FX_DELAY_PINGPONG)}
 STATELESS = ("gain", "pan", "clipping", "functions", "mute")
 # control values per (block b, instance i) for the programs of the second step: {control: value}
 SCHEDULES = {
@@ -38,6 +40,8 @@ SCHEDULES = {
     "moddelay": lambda b, i: {0: 2.0 + 3.0 * i, 1: 0.2 + 0.25 * ((b + i) % 3)},
     "mod_chorus": lambda b, i: {},
     "delay_reverb": lambda b, i: {0: 0.2 + 0.3 * i, 1: 0.02 + 0.03 * i + 0.01 * b},
+    "delay_pingpong": lambda b, i: {0: 0.01 + 0.004 * i, 1: 0.03 + 0.01 * b, 2: 0.02, 3: 0.6 - 0.1 * i},
+    "pingpong": lambda b, i: ({0: 0.9 - 0.1 * i, 1: 0.02 + 0.01 * i, 5: 0.02 + 0.01 * i, 4: 0.3} if b == 0 else {2: 0.4, 3: 0.579} if b == 2 else {}),
 }
 EDITED = "gain_edited"
 # third step: mono Synth programs — the note's on() / off() on the host mirror, its process() per sample on the device (lane = voice)
@@ -76,8 +80,8 @@ def test_k_programs_translate_and_compile_for_the_device(tmp_path):
                     "kb_user_fx_destroy", "kb_user_fx_set_control", "kb_user_fx_get_control", "kb_user_fx_process"):
             assert hasattr(L, sym), f"{name}: {sym} not exported"
         L.kb_user_name.restype = C.c_char_p
-        assert L.kb_user_num_controls() == {"wahwah": 3, "delay_reverb": 3}.get(name, 1 if name in STATELESS + ("iir", EDITED) else 2), name
-        assert L.kb_user_channels() == (2 if name == "pan" else 1)
+        assert L.kb_user_num_controls() == {"wahwah": 3, "delay_reverb": 3, "pingpong": 6, "delay_pingpong": 4}.get(name, 1 if name in STATELESS + ("iir", EDITED) else 2), name
+        assert L.kb_user_channels() == (2 if name in ("pan", "pingpong", "delay_pingpong") else 1)
         assert L.kb_user_stateless() == (1 if name in STATELESS + (EDITED,) else 0)   # data members (IIR.k's `signal last`, an LFO, a delay line): lane per instance
     # the translated text is the user's: only the function definitions gained a qualifier
     src, plugin, ch = kcc.translate(open(os.path.join(REF, "Distortion", "Functions.k")).read(), "Functions.k")
