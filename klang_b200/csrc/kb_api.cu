@@ -1030,14 +1030,15 @@ static int sy_process(kb_synth_bank* b, float* out, int n, unsigned flags, kb_mi
 	if (n == 0) return KB_OK;
 	KB_CUDA(cudaSetDevice(b->device));
 	const int total = b->total(), C = b->channels;
-	// Subtractive / Filter.k, 800..1184 voices: the decoupled kernel (kb_sub_flow_kernel, layout 3), which also scatters the block's re-written
-	// voices itself.  KB_TILE_LAYOUT = 2 / 0 select the lock-step kernels, KB_TILE_G the voices per CTA (A/B measurement, same results)
+	// Subtractive / Filter.k, 800..1184 voices: the decoupled kernel with mbarrier hand-over (kb_sub_mbar_kernel, layout 4), which also scatters
+	// the block's re-written voices itself.  KB_TILE_LAYOUT = 3 selects the polled-counter form (kb_sub_flow_kernel), 2 / 0 the lock-step
+	// kernels, KB_TILE_G the voices per CTA (A/B measurement, same results)
 	static const int force_g = getenv("KB_TILE_G") ? atoi(getenv("KB_TILE_G")) : 0;
-	static const int layout = getenv("KB_TILE_LAYOUT") ? atoi(getenv("KB_TILE_LAYOUT")) : 3;
+	static const int layout = getenv("KB_TILE_LAYOUT") ? atoi(getenv("KB_TILE_LAYOUT")) : 4;
 	const bool sub = b->graph == KB_SY_SUBTRACTIVE || b->graph == KB_SY_FILTER_K;
 	int sub_g = total >= 1600 ? 16 : total > 7 * 148 ? 8 : total >= 800 ? 7 : 4;
 	if (force_g) sub_g = force_g;
-	const bool sub_flow = sub && !(flags & KB_LANE_PER_VOICE) && layout == 3 && (sub_g == 7 || sub_g == 8);
+	const bool sub_flow = sub && !(flags & KB_LANE_PER_VOICE) && layout >= 3 && (sub_g == 7 || sub_g == 8);
 	static const bool scatter_fused = !getenv("KB_SCATTER_FUSED") || atoi(getenv("KB_SCATTER_FUSED")) != 0;     // (A/B measurement)
 	int rc = sy_upload(b, sub_flow && scatter_fused); if (rc) return rc;
 	const bool per_voice = flags & KB_PER_VOICE, dev = flags & KB_DEVICE_PTR, bank_mix = (flags & KB_BANK_MIX) && !per_voice;
@@ -1124,8 +1125,8 @@ static int sy_process(kb_synth_bank* b, float* out, int n, unsigned flags, kb_mi
 				// KB_C2_TRACE=<file> (measurement aid): per-role clock64() stamps of CTA 0 for every tick of the last launch
 				static const char* c2_trace_path = getenv("KB_C2_TRACE");
 				static long long* c2_trace = nullptr;
-				if (c2_trace_path && !c2_trace) { KB_CUDA(cudaMalloc(&c2_trace, 8 * 64 * 2 * sizeof(long long))); }
-				if (c2_trace) KB_CUDA(cudaMemsetAsync(c2_trace, 0, 8 * 64 * 2 * sizeof(long long), st));
+				if (c2_trace_path && !c2_trace) { KB_CUDA(cudaMalloc(&c2_trace, 12 * 64 * 2 * sizeof(long long))); }
+				if (c2_trace) KB_CUDA(cudaMemsetAsync(c2_trace, 0, 12 * 64 * 2 * sizeof(long long), st));
 #define KB_LAUNCH_SUB(GG, NT, LAY)                                                                                                    \
 	do {                                                                                                                             \
 		static bool attr_set = false;                                                                                                \
@@ -1133,14 +1134,25 @@ static int sy_process(kb_synth_bank* b, float* out, int n, unsigned flags, kb_mi
 		kb_sub_tiled_kernel<GG, NT, LAY><<<(total + GG - 1) / GG, NT, sizeof(KbSubSmem<GG>), st>>>(vs, b->d_hdr, d_voice_dst, n, total, b->fs, c2_trace); \
 	} while (0)
 				// layout 3 (round 2): the same stages decoupled, kb_sub_flow_kernel; KB_TILE_G=7 -> 147 CTAs, KB_TILE_ASP0=1 -> envelope warp beside the filter warp
+				static const int c2_variant = getenv("KB_C2_VARIANT") ? atoi(getenv("KB_C2_VARIANT")) : 0;
 				static const int asp0 = getenv("KB_TILE_ASP0") ? atoi(getenv("KB_TILE_ASP0")) : 1;
 #define KB_LAUNCH_FLOW(GG, ASP0)                                                                                                      \
 	do {                                                                                                                             \
 		static bool attr_set = false;                                                                                                \
 		if (!attr_set) { cudaFuncSetAttribute(kb_sub_flow_kernel<GG, ASP0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KbSubFlowSmem<GG>)); attr_set = true; } \
-		kb_sub_flow_kernel<GG, ASP0><<<(total + GG - 1) / GG, 768, sizeof(KbSubFlowSmem<GG>), st>>>(vs, b->d_hdr, d_voice_dst, n, total, b->fs, b->staged, c2_trace); \
+		kb_sub_flow_kernel<GG, ASP0><<<(total + GG - 1) / GG, 768, sizeof(KbSubFlowSmem<GG>), st>>>(vs, b->d_hdr, d_voice_dst, n, total, b->fs, b->staged, c2_trace, c2_variant); \
 	} while (0)
-				if (sub_flow) {
+#define KB_LAUNCH_MBAR(GG)                                                                                                            \
+	do {                                                                                                                             \
+		static bool attr_set = false;                                                                                                \
+		if (!attr_set) { cudaFuncSetAttribute(kb_sub_mbar_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KbSubMbarSmem<GG>)); attr_set = true; } \
+		kb_sub_mbar_kernel<GG><<<(total + GG - 1) / GG, 768, sizeof(KbSubMbarSmem<GG>), st>>>(vs, b->d_hdr, d_voice_dst, n, total, b->fs, b->staged, c2_trace, c2_variant); \
+	} while (0)
+				if (sub_flow && layout >= 4) {
+					if (g == 7) KB_LAUNCH_MBAR(7); else KB_LAUNCH_MBAR(8);
+					if (b->staged.count > 0) { KB_CUDA(cudaEventRecord(b->stage_done[b->staged_slot], st)); b->staged.count = 0; }
+				}
+				else if (sub_flow) {
 					if (g == 7) { if (asp0) KB_LAUNCH_FLOW(7, true); else KB_LAUNCH_FLOW(7, false); }
 					else { if (asp0) KB_LAUNCH_FLOW(8, true); else KB_LAUNCH_FLOW(8, false); }
 					if (b->staged.count > 0) { KB_CUDA(cudaEventRecord(b->stage_done[b->staged_slot], st)); b->staged.count = 0; }
@@ -1152,12 +1164,13 @@ static int sy_process(kb_synth_bank* b, float* out, int n, unsigned flags, kb_mi
 				else KB_LAUNCH_SUB(4, 320, 0);
 #undef KB_LAUNCH_SUB
 #undef KB_LAUNCH_FLOW
+#undef KB_LAUNCH_MBAR
 				if (c2_trace) {
-					std::vector<long long> tr(8 * 64 * 2);
+					std::vector<long long> tr(12 * 64 * 2);
 					KB_CUDA(cudaMemcpyAsync(tr.data(), c2_trace, tr.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
 					KB_CUDA(cudaStreamSynchronize(st));
 					if (FILE* f = fopen(c2_trace_path, "w")) {
-						for (int r = 0; r < 8; r++) for (int k = 0; k < 64; k++) if (tr[(r * 64 + k) * 2] || tr[(r * 64 + k) * 2 + 1]) fprintf(f, "%d %d %lld %lld\n", r, k, tr[(r * 64 + k) * 2], tr[(r * 64 + k) * 2 + 1]);
+						for (int r = 0; r < 12; r++) for (int k = 0; k < 64; k++) if (tr[(r * 64 + k) * 2] || tr[(r * 64 + k) * 2 + 1]) fprintf(f, "%d %d %lld %lld\n", r, k, tr[(r * 64 + k) * 2], tr[(r * 64 + k) * 2 + 1]);
 						fclose(f);
 					}
 				}

@@ -514,6 +514,104 @@ KB_HD void kb_envr_run(const KbFs& fs, KbEnvR& e, const float* px, const float* 
 		row[t++] = kb_envr_tick(fs, e, px, py);
 	}
 }
+// ---- the same run in UNIFORM GROUPS of 16 ticks (round 2, kb_sub_flow_kernel).  kb_envr_run leaves its fast loop through ever smaller
+// groups and single ticks at a mode change, which costs the lane that changes ~5000 cycles while the other lanes of the warp wait
+// (measured: profiles/r02_c2_trace.txt, ticks 3 / 11 / 29).  Here every lane walks the same loop: per group a lane either takes the 16
+// branch-free steps of its steady mode or — when it is in no steady mode, or the group's last value crosses the mode's bound — 16
+// generic ticks, after which its mode constants are re-derived; the warp reconverges after every group, so a mode change costs one
+// group of generic ticks.  The values are those of kb_envr_tick bit for bit (same argument as kb_envr_run: r and time move one way,
+// so "the value after the group has not crossed / arrived" implies no tick of the group changed mode).
+struct KbEnvMode { float srate, tinc, r_hi, r_lo, t_hi; bool fast; };
+KB_HD KbEnvMode kb_envr_mode(const KbEnvR& e, const float* px, const float* py) {
+	const bool act = e.r_active != 0, sus = e.stage == KB_ENV_SUSTAIN;
+	const bool at_loop_end = e.loop_start != -1 && e.loop_end != -1 && (e.point + 1) >= e.loop_end;
+	const bool is_ramp = act && e.stage != KB_ENV_OFF && e.r_rate > 0.f && e.r_rate <= 3.0e38f;
+	const bool is_off = !act && e.stage == KB_ENV_OFF;
+	const bool is_wait = !act && sus && !at_loop_end && (e.point + 1) < e.npoints;
+	bool is_hold = false;
+	if (!act && sus && at_loop_end && e.loop_start == e.loop_end && e.point == e.loop_start) {
+		const uint32_t lvl = kb_fbits(py[e.loop_start]);
+		is_hold = lvl == kb_fbits(e.r_out) && lvl == kb_fbits(e.r_target);
+	}
+	const bool up = e.r_target > e.r_out;
+	const float inf = kb_bits(0x7f800000u);
+	KbEnvMode m;
+	m.fast = is_ramp || is_off || is_wait || is_hold;
+	m.srate = is_ramp ? (up ? e.r_rate : -e.r_rate) : -0.f;
+	m.tinc = sus ? e.timeInc : -0.f;
+	m.r_hi = (is_ramp && up) ? e.r_target : inf;
+	m.r_lo = (is_ramp && !up) ? e.r_target : -inf;
+	m.t_hi = is_wait ? px[e.point + 1] : inf;
+	return m;
+}
+// ALIGNED16: `row` is 16-byte aligned (the groups are then stored as four 128-bit words on the device)
+template <bool ALIGNED16>
+KB_HD void kb_envr_run16(const KbFs& fs, KbEnvR& e, const float* px, const float* py, float* row, int steps) {
+	int t = 0;
+	KbEnvMode m = kb_envr_mode(e, px, py);
+	for (; t + 16 <= steps; t += 16) {
+		bool done = false;
+		if (m.fast) {
+			float rr[17], tt = e.time;
+			rr[0] = e.r_out;
+			#pragma unroll
+			for (int j = 0; j < 16; j++) { rr[j + 1] = rr[j] + m.srate; tt = tt + m.tinc; }
+			if ((rr[16] < m.r_hi) & (rr[16] > m.r_lo) & (tt < m.t_hi)) {
+#ifdef __CUDA_ARCH__
+				if (ALIGNED16) {
+					#pragma unroll
+					for (int q = 0; q < 4; q++) *reinterpret_cast<float4*>(row + t + 4 * q) = make_float4(rr[4 * q], rr[4 * q + 1], rr[4 * q + 2], rr[4 * q + 3]);
+				} else
+#endif
+				{
+					#pragma unroll
+					for (int j = 0; j < 16; j++) row[t + j] = rr[j];
+				}
+				e.out = rr[15]; e.r_out = rr[16]; e.time = tt;
+				done = true;
+			}
+		}
+		if (!done) {
+			for (int j = 0; j < 16; j++) row[t + j] = kb_envr_tick(fs, e, px, py);
+			m = kb_envr_mode(e, px, py);
+		}
+	}
+	for (; t < steps; t++) row[t] = kb_envr_tick(fs, e, px, py);
+}
+// ---- a whole tile at once.  Even the uniform groups pay ~10 cycles per tick, most of it the exit test and its branch after every group
+// (tools/micro/env_floor.cu: the two FADD chains and the stores alone cost 6.4).  r and time move one way, so ONE test after the tile's
+// last tick decides for all of them: a lane in a steady mode runs the tile's ticks straight through, storing as it goes, and keeps the
+// result if the value after the last tick has not crossed the mode's bound; otherwise — a few tiles per note — the tile is done again
+// from the untouched state by kb_envr_run16, whose generic ticks overwrite the row.  `steps` must be a multiple of 16 for the straight
+// run (else kb_envr_run16 does the tile).  Bit-identical to kb_envr_tick.
+template <bool ALIGNED16>
+KB_HD void kb_envr_run_tile(const KbFs& fs, KbEnvR& e, const float* px, const float* py, float* row, int steps) {
+	if (steps > 0 && (steps & 15) == 0) {
+		const KbEnvMode m = kb_envr_mode(e, px, py);
+		if (m.fast) {
+			float r = e.r_out, tt = e.time, last = e.out;
+			for (int t = 0; t < steps; t += 16) {
+				float rr[17];
+				rr[0] = r;
+				#pragma unroll
+				for (int j = 0; j < 16; j++) { rr[j + 1] = rr[j] + m.srate; tt = tt + m.tinc; }
+#ifdef __CUDA_ARCH__
+				if (ALIGNED16) {
+					#pragma unroll
+					for (int q = 0; q < 4; q++) *reinterpret_cast<float4*>(row + t + 4 * q) = make_float4(rr[4 * q], rr[4 * q + 1], rr[4 * q + 2], rr[4 * q + 3]);
+				} else
+#endif
+				{
+					#pragma unroll
+					for (int j = 0; j < 16; j++) row[t + j] = rr[j];
+				}
+				last = rr[15]; r = rr[16];
+			}
+			if ((r < m.r_hi) & (r > m.r_lo) & (tt < m.t_hi)) { e.out = last; e.r_out = r; e.time = tt; return; }
+		}
+	}
+	kb_envr_run16<ALIGNED16>(fs, e, px, py, row, steps);
+}
 // Envelope::at                                                              klang.h:3929-3942
 KB_HD float kb_env_at(const float* px, const float* py, int npoints, float time) {
 	if (npoints == 0) return 0;

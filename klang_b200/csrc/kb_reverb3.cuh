@@ -61,21 +61,6 @@ struct KbRv3Smem {
 	KbRv3LinePlan pline[16]; KbFxPlan plan;                         // the plan of this instance, made by the CTA itself
 };
 
-KB_D unsigned kb_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-KB_D void kb_mbar_init(unsigned long long* bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(kb_smem_u32(bar)), "r"(count) : "memory"); }
-KB_D void kb_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(kb_smem_u32(bar)), "r"(bytes) : "memory");
-}
-KB_D void kb_mbar_wait(unsigned long long* bar, unsigned parity) {
-	asm volatile(
-		"{\n\t.reg .pred p;\n\t"
-		"KB_MBAR_WAIT_%=:\n\t"
-		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-		"@p bra KB_MBAR_DONE_%=;\n\t"
-		"bra KB_MBAR_WAIT_%=;\n\t"
-		"KB_MBAR_DONE_%=:\n\t}"
-		:: "r"(kb_smem_u32(bar)), "r"(parity) : "memory");
-}
 // 1-D bulk copy global -> shared, completing `bytes` on the mbarrier.  Addresses and size are multiples of 16 bytes.
 KB_D void kb_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

@@ -286,7 +286,7 @@ KB_D const VOICE& kb_tile_voice_src(const KbStagedSmem<G, VOICE>& m, const VOICE
 template <int G> struct KbSubFlowSmem {
 	KbTileCommon<G> c;
 	KbTileRows4<G> coef[4];          // B -> C
-	KbTileRows<G> cut[4], amp[8];    // A -> B, A -> D
+	KbTileRowsA<G> cut[4], amp[8];   // A -> B, A -> D (16-byte aligned rows: the envelope warp stores 128-bit words)
 	KbTileRowsA<G> out[4];           // C -> D
 	float4 lastc[G];
 	KbOsm osc[G];
@@ -295,7 +295,8 @@ template <int G> struct KbSubFlowSmem {
 };
 template <int G, bool A_SP0>
 __global__ void __launch_bounds__(768, 1) kb_sub_flow_kernel(KbSubVoice* __restrict__ voices, KbVoiceHdr* __restrict__ hdr,
-                                                             float* __restrict__ dst, int n, int total, KbFs fs, const __grid_constant__ KbStaged staged, long long* __restrict__ trace = nullptr) {
+                                                             float* __restrict__ dst, int n, int total, KbFs fs, const __grid_constant__ KbStaged staged, long long* __restrict__ trace = nullptr, int variant = 0) {
+	const bool sig_relaxed = (variant & 1) != 0;
 	constexpr int T = KB_TILE_T, W = 2 * G, wthreads = W * 32, LAG = 3;
 	static_assert(2 * G <= 32 && W <= 17, "both envelopes of the G voices in one warp; worker warps on three sub-partitions of six rows");
 	extern __shared__ __align__(16) unsigned char kb_smem[];
@@ -342,10 +343,12 @@ __global__ void __launch_bounds__(768, 1) kb_sub_flow_kernel(KbSubVoice* __restr
 			if (is_env || is_adsr) {
 				const int steps = min(T, n - k * T);
 				float* rowp = is_env ? S.cut[k & 3].r[role_voice] : S.amp[k & 7].r[role_voice];
-				kb_envr_run(fs, env, S.c.px[slot], S.c.py[slot], rowp, steps);
+				if (variant & 32) kb_envr_run(fs, env, S.c.px[slot], S.c.py[slot], rowp, steps);
+				else kb_envr_run16<true>(fs, env, S.c.px[slot], S.c.py[slot], rowp, steps);
 			}
+			if (lane == 0) KB_C2_TR(8, k, 0);
 			__syncwarp();
-			if (lane == 0) { kb_signal(&S.a_done, k + 1); KB_C2_TR(0, k, 1); }
+			if (lane == 0) { KB_C2_TR(8, k, 1); kb_signal_v(sig_relaxed, &S.a_done, k + 1); KB_C2_TR(0, k, 1); }
 		}
 	} else if (is_c_warp) {                                              // ---- C: the filter recurrence
 		for (int c = 0; c < ntiles; c++) {
@@ -387,19 +390,20 @@ __global__ void __launch_bounds__(768, 1) kb_sub_flow_kernel(KbSubVoice* __restr
 				}
 			}
 			__syncwarp();
-			if (lane == 0) { kb_signal(&S.c_done, c + 1); KB_C2_TR(1, c, 1); }
+			if (lane == 0) { kb_signal_v(sig_relaxed, &S.c_done, c + 1); KB_C2_TR(1, c, 1); }
 		}
 	} else if (worker) {                                                 // ---- B (tile j) then D (tile j - LAG), two rounds each
 		const bool first = widx == 0;
 		for (int j = 0; j < ntiles + LAG; j++) {
 			// one poll per iteration by the first worker warp, the others park at the role's barrier: B needs A's tile j and its coef buffer
 			// back from C (tile j-4), D needs C's tile j-LAG.  The barrier also closes the previous iteration's D for every worker.
+			if (wtid == 0) KB_C2_TR(9, j, 0);
 			if (first) {
 				if (j < ntiles) kb_wait_ge(&S.a_done, j + 1);
 				kb_wait_ge(&S.c_done, min(max(j - LAG + 1, 0), ntiles));
 			}
 			kb_bar_group(1, wthreads);
-			if (wtid == 0) { if (j - 1 - LAG >= 0) kb_signal(&S.d_done, j - LAG); KB_C2_TR(2, j, 0); }
+			if (wtid == 0) { if (j - 1 - LAG >= 0) kb_signal_v(sig_relaxed, &S.d_done, j - LAG); KB_C2_TR(2, j, 0); }
 			if (j < ntiles) {
 				const int b = j, steps = min(T, n - b * T);
 				#pragma unroll
@@ -423,8 +427,9 @@ __global__ void __launch_bounds__(768, 1) kb_sub_flow_kernel(KbSubVoice* __restr
 						S.coef[b & 3].r[v][t] = cf;
 					}
 				}
+				if (wtid == 0) KB_C2_TR(9, j, 1);
 				kb_bar_group(2, wthreads);
-				if (wtid == 0) { kb_signal(&S.b_done, b + 1); KB_C2_TR(2, j, 1); }
+				if (wtid == 0) { kb_signal_v(sig_relaxed, &S.b_done, b + 1); KB_C2_TR(2, j, 1); }
 			}
 			const int d = j - LAG;
 			if (d >= 0 && d < ntiles) {
@@ -442,6 +447,243 @@ __global__ void __launch_bounds__(768, 1) kb_sub_flow_kernel(KbSubVoice* __restr
 	#undef KB_C2_TR
 	__syncthreads();
 	// rows 4-7 of the trace: per CTA (prologue, tile loop) cycles
+	if (trace && tid == 0 && blockIdx.x < 256) { const long long t1 = clock64(); trace[(4 * 64 + blockIdx.x) * 2] = t_loop - t_entry; trace[(4 * 64 + blockIdx.x) * 2 + 1] = t1 - t_loop; }
+
+	// write the state back
+	if (is_env) { kb_envr_store(env, voices[v0 + role_voice].env); voices[v0 + role_voice].filter.f = env.out; voices[v0 + role_voice].filter.Q = 10.f; }
+	if (is_adsr) {
+		kb_envr_store(env, voices[v0 + role_voice].adsr);
+		if (env.stage == KB_ENV_OFF) hdr[v0 + role_voice].stage = KB_NOTE_OFF;
+	}
+	if (is_flt) {
+		KbBiquad& b = voices[v0 + role_voice].filter;
+		const float4 lc = S.lastc[role_voice];
+		b.z0 = z0; b.z1 = z1; b.b0 = lc.x; b.b2 = lc.x; b.b1 = lc.y; b.a1 = lc.z; b.a2 = lc.w;
+	}
+	if (worker && wtid < G && S.c.active[wtid]) {
+		KbOsm o = S.osc[wtid];
+		kb_osm_advance(o, (uint32_t)n);
+		voices[v0 + wtid].osc.offset = o.offset;
+		voices[v0 + wtid].osc.state = o.state;
+	}
+}
+
+// ---- the decoupled stages handed over through MBARRIERS (round 2, second step; SASS SYNCS).  kb_sub_flow_kernel's progress counters are
+// polled (ld.acquire + nanosleep) and its 14 worker warps meet at two named barriers per tile: ~500 of the workers' ~3150 cycles per tile
+// and ~300 of the filter warp's were hand-over (clock64 stamps, profiles/r02_c2_trace.txt).  Here every buffer slot has a `full` and an
+// `empty` mbarrier: a producing WARP arrives once behind its __syncwarp(), a consumer parks in mbarrier.try_wait — no polling, and no
+// barrier among the worker warps at all: each takes its own 32 items of a tile as soon as that tile's inputs are there.
+// One mbarrier ring per ROLE says "this role has finished tile n" (slot n & 3, the n-th use of a slot waits for parity (n >> 2) & 1):
+//   a_done (1 arrival: the envelope warp)    b_done (W arrivals: every worker warp after its B items)    c_done (1: the filter warp)
+// A worker warp's iteration j is: wait c_done(j-4) -> D(j-4) -> wait a_done(j) -> B(j) -> arrive b_done(j).  D before B, so that b_done(j)
+// also says "this warp has finished D(j-4)" and no barrier for D is needed:
+//   A(k) waits b_done(k-4): cut[k & 3] was read by B(k-4), amp[k & 7] by D(k-8) (before B(k-4) in every warp's order)
+//   C(c) waits b_done(c):   coef[c & 3] is written, and out[c & 3] was read by D(c-4)
+//   B(j) needs a_done(j) and coef[j & 3] back from C(j-4); D(d) needs C(d) and A(d) (A(d) was waited for by the same warp's B(d))
+// No barrier can complete twice before a waiter has looked: the next completion of a slot needs the role that waits on it to have moved on.
+// The envelope warp runs kb_envr_run_tile (one exit test per tile, 128-bit stores); the filter warp's loop is unrolled to 32 samples per
+// branch.  Arithmetic and order per voice unchanged: bit-identical.
+template <int G> struct KbSubMbarSmem {
+	KbTileCommon<G> c;
+	KbTileRows4<G> coef[4];
+	KbTileRowsA<G> cut[4], amp[8];
+	KbTileRowsA<G> out[4];
+	float4 lastc[G];
+	KbOsm osc[G];
+	unsigned long long a_done[4], b_done[4], c_done[4];
+	KbStagedSmem<G, KbSubVoice> sc;
+};
+template <int G>
+__global__ void __launch_bounds__(768, 1) kb_sub_mbar_kernel(KbSubVoice* __restrict__ voices, KbVoiceHdr* __restrict__ hdr,
+                                                             float* __restrict__ dst, int n, int total, KbFs fs, const __grid_constant__ KbStaged staged, long long* __restrict__ trace = nullptr, int variant = 0) {
+	constexpr int T = KB_TILE_T, W = 2 * G, wthreads = W * 32, LAG = 4;
+	static_assert(2 * G <= 32 && W <= 17, "both envelopes of the G voices in one warp; worker warps on three sub-partitions of six rows");
+	extern __shared__ __align__(16) unsigned char kb_smem[];
+	KbSubMbarSmem<G>& S = *reinterpret_cast<KbSubMbarSmem<G>*>(kb_smem);
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int v0 = blockIdx.x * G;
+	const long long t_entry = trace ? clock64() : 0;
+	if (tid == 0) {
+		for (int i = 0; i < 4; i++) { kb_mbar_init(&S.a_done[i], 1); kb_mbar_init(&S.b_done[i], W); kb_mbar_init(&S.c_done[i], 1); }
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	kb_tile_scatter(staged, hdr, voices, v0, S.sc);
+	if (tid < G) {                                                       // kb_tile_prologue with the staged headers
+		const int v = v0 + tid;
+		const int act = (v < total && kb_tile_hdr_src(S.sc, hdr, v0, tid).stage != KB_NOTE_OFF) ? 1 : 0;
+		S.c.active[tid] = act;
+		if (v < total) hdr[v].active = act;
+	}
+	__syncthreads();
+
+	// warp roles.  Sub-partition = warp & 3; the arbiter of a sub-partition prefers the HIGHER warp id.  Default: C = warp 20 and A = warp 4 on
+	// sub-partition 0 (the filter chain wins the issue slot whenever it is ready, the envelopes fill the gaps), workers on sub-partitions 1-3.
+	// variant bits 8-12 / 16-20 (measurement aid): C's / A's warp + 1
+	const int sp = warp & 3, row = warp >> 2;
+	const int c_warp = ((variant >> 8) & 31) ? ((variant >> 8) & 31) - 1 : 20, a_warp = ((variant >> 16) & 31) ? ((variant >> 16) & 31) - 1 : 4;
+	const bool is_c_warp = warp == c_warp, is_a_warp = warp == a_warp;
+	int widx = sp == 0 ? -1 : row * 3 + (sp - 1);                        // worker warps, spread evenly over sub-partitions 1-3
+	if ((a_warp & 3) != 0) { const int aw = (a_warp >> 2) * 3 + ((a_warp & 3) - 1); if (widx == aw) widx = -1; else if (widx > aw) widx--; }
+	if ((c_warp & 3) != 0) { const int cw = (c_warp >> 2) * 3 + ((c_warp & 3) - 1) - (((a_warp & 3) != 0 && a_warp < c_warp) ? 1 : 0); if (!is_a_warp) { if (widx == cw) widx = -1; else if (widx > cw) widx--; } }
+	const bool worker = widx >= 0 && widx < W && !is_a_warp && !is_c_warp;
+	const int wtid = widx * 32 + lane;
+	const int a_sub = (is_a_warp && lane >= G) ? 1 : 0;
+	const int role_voice = lane - a_sub * G;
+	const bool role_ok = role_voice < G && S.c.active[role_voice < G ? role_voice : 0];
+	const bool is_env = is_a_warp && a_sub == 0 && role_ok, is_adsr = is_a_warp && a_sub == 1 && role_ok, is_flt = is_c_warp && role_ok;
+	const int slot = (is_adsr ? G : 0) + role_voice;
+	KbEnvR env;
+	float z0 = 0.f, z1 = 0.f;
+	if (is_env) kb_tile_load_env(S.c, slot, kb_tile_voice_src(S.sc, voices, v0, role_voice).env, env);
+	if (is_adsr) kb_tile_load_env(S.c, slot, kb_tile_voice_src(S.sc, voices, v0, role_voice).adsr, env);
+	if (is_flt) { const KbBiquad& b = kb_tile_voice_src(S.sc, voices, v0, role_voice).filter; z0 = b.z0; z1 = b.z1; }
+	if (worker && wtid < G && S.c.active[wtid]) S.osc[wtid] = kb_tile_voice_src(S.sc, voices, v0, wtid).osc;
+	__syncthreads();
+
+	const int ntiles = (n + T - 1) / T;
+	const long long t_loop = trace ? clock64() : 0;
+	#define KB_C2_TR(row_, k_, ph_) do { if (trace && blockIdx.x == 0 && (k_) < 64) trace[(((row_) * 64 + (k_)) * 2 + (ph_))] = clock64(); } while (0)
+	if (is_a_warp) {                                                     // ---- A: both envelopes of every voice, tile after tile
+		for (int k = 0; k < ntiles; k++) {
+			if (k >= 4) kb_mbar_wait(&S.b_done[k & 3], ((k >> 2) - 1) & 1);
+			if (lane == 0) KB_C2_TR(0, k, 0);
+			if (is_env || is_adsr) {
+				const int steps = min(T, n - k * T);
+				float* rowp = is_env ? S.cut[k & 3].r[role_voice] : S.amp[k & 7].r[role_voice];
+				if (variant & 64) kb_envr_run16<true>(fs, env, S.c.px[slot], S.c.py[slot], rowp, steps);
+				else kb_envr_run_tile<true>(fs, env, S.c.px[slot], S.c.py[slot], rowp, steps);
+			}
+			if (lane == 0) KB_C2_TR(8, k, 0);
+			__syncwarp();
+			if (lane == 0) { kb_mbar_arrive(&S.a_done[k & 3]); KB_C2_TR(0, k, 1); }
+		}
+	} else if (is_c_warp) {                                              // ---- C: the filter recurrence
+		// The chain runs on across tile boundaries: two groups before a tile ends the lane looks (without blocking) whether the next
+		// tile's coefficients are there and, if so, loads the next tile's first group before the last group of this one — arriving and
+		// waiting between two tiles cost ~300 of ~2950 cycles per tile.  A lane that did not see them waits as before.
+		float4 ca[4], cb[4];
+		bool have_next = false;
+		for (int c = 0; c < ntiles; c++) {
+			if (!have_next) kb_mbar_wait(&S.b_done[c & 3], (c >> 2) & 1);
+			if (lane == 0) KB_C2_TR(1, c, 0);
+			if (is_flt) {
+				const int steps = min(T, n - c * T), v = role_voice;
+				const float4* pc = S.coef[c & 3].r[v];
+				float* po = S.out[c & 3].r[v];
+				auto group = [&](const float4 (&cf)[4], int t) {         // Filter::process, klang.h:5605-5612 (see kb_sub_tiled_kernel)
+					float y[4];
+					#pragma unroll
+					for (int j = 0; j < 4; j++) {
+						y[j] = cf[j].x + z0;
+						z0 = cf[j].y - cf[j].z * y[j] + z1;
+						z1 = cf[j].x - cf[j].w * y[j];
+					}
+					*reinterpret_cast<float4*>(po + t) = make_float4(y[0], y[1], y[2], y[3]);
+				};
+				if (!have_next) {
+					#pragma unroll
+					for (int j = 0; j < 4; j++) ca[j] = pc[j];
+				}
+				have_next = false;
+				int t = 0;
+				if (steps == T) {
+					#pragma unroll 7
+					for (; t < T - 16; t += 8) {
+						#pragma unroll
+						for (int j = 0; j < 4; j++) cb[j] = pc[t + 4 + j];
+						group(ca, t);
+						#pragma unroll
+						for (int j = 0; j < 4; j++) ca[j] = pc[t + 8 + j];
+						group(cb, t + 4);
+					}
+					const bool more = c + 1 < ntiles;
+					#pragma unroll
+					for (int j = 0; j < 4; j++) cb[j] = pc[T - 12 + j];
+					const bool ready = more && kb_mbar_test(&S.b_done[(c + 1) & 3], ((c + 1) >> 2) & 1);
+					group(ca, T - 16);
+					#pragma unroll
+					for (int j = 0; j < 4; j++) ca[j] = pc[T - 8 + j];
+					group(cb, T - 12);
+					#pragma unroll
+					for (int j = 0; j < 4; j++) cb[j] = pc[T - 4 + j];
+					group(ca, T - 8);
+					if (ready) {
+						const float4* pn = S.coef[(c + 1) & 3].r[v];
+						#pragma unroll
+						for (int j = 0; j < 4; j++) ca[j] = pn[j];
+						have_next = true;
+					}
+					group(cb, T - 4);
+				} else {
+					for (; t + 8 <= steps; t += 8) {
+						#pragma unroll
+						for (int j = 0; j < 4; j++) cb[j] = pc[t + 4 + j];
+						group(ca, t);
+						#pragma unroll
+						for (int j = 0; j < 4; j++) ca[j] = pc[t + 8 + j];
+						group(cb, t + 4);
+					}
+					for (; t < steps; t++) {
+						const float4 c1 = pc[t];
+						const float y = c1.x + z0;
+						z0 = c1.y - c1.z * y + z1;
+						z1 = c1.x - c1.w * y;
+						po[t] = y;
+					}
+				}
+			}
+			__syncwarp();
+			if (lane == 0) { kb_mbar_arrive(&S.c_done[c & 3]); KB_C2_TR(1, c, 1); }
+		}
+	} else if (worker) {                                                 // ---- D (tile j - LAG) then B (tile j), two rounds each, warp by warp
+		for (int j = 0; j < ntiles + LAG; j++) {
+			if (wtid == 0) KB_C2_TR(9, j, 0);
+			const int d = j - LAG;
+			if (d >= 0) {
+				const int steps = min(T, n - d * T);
+				kb_mbar_wait(&S.c_done[d & 3], (d >> 2) & 1);
+				if (wtid == 0) KB_C2_TR(9, j, 1);
+				#pragma unroll
+				for (int r = 0; r < 2; r++) {
+					const int item = wtid + r * wthreads, v = item / T, t = item % T;
+					if (t < steps && v0 + v < total)                             // out *= adsr++   Filter.k:33
+						dst[(size_t)(v0 + v) * n + d * T + t] = S.c.active[v] ? S.out[d & 3].r[v][t] * S.amp[d & 7].r[v][t] : 0.f;
+				}
+			}
+			if (wtid == 0) KB_C2_TR(3, j, 1);
+			if (j < ntiles) {
+				const int b = j, steps = min(T, n - b * T);
+				kb_mbar_wait(&S.a_done[b & 3], (b >> 2) & 1);
+				if (wtid == 0) KB_C2_TR(2, j, 0);
+				#pragma unroll
+				for (int r = 0; r < 2; r++) {
+					const int item = wtid + r * wthreads, v = item / T, t = item % T;
+					if (t < steps && S.c.active[v]) {
+						const float f = S.cut[b & 3].r[v][t];
+						const float w = f * fs.w;
+						float sin0, cos0;
+						kb_sincosf(w, sin0, cos0);
+						const float a = sin0 / (2.f * 10.f);
+						const float inv = kb_const_inv(1.f + a);
+						float4 cf;
+						cf.z = inv * (-2.f * cos0);
+						cf.w = inv * (1.f - a);
+						cf.x = inv * (1.f - cos0) * 0.5f;
+						cf.y = inv * (1.f - cos0);
+						if (b * T + t == n - 1) S.lastc[v] = cf;
+						const float in = kb_osm_at(S.osc[v], (uint32_t)(b * T + t));
+						cf.x = cf.x * in; cf.y = cf.y * in;
+						S.coef[b & 3].r[v][t] = cf;
+					}
+				}
+				__syncwarp();
+				if (lane == 0) kb_mbar_arrive(&S.b_done[b & 3]);
+				if (wtid == 0) KB_C2_TR(2, j, 1);
+			}
+		}
+	}
+	#undef KB_C2_TR
+	__syncthreads();
 	if (trace && tid == 0 && blockIdx.x < 256) { const long long t1 = clock64(); trace[(4 * 64 + blockIdx.x) * 2] = t_loop - t_entry; trace[(4 * 64 + blockIdx.x) * 2 + 1] = t1 - t_loop; }
 
 	// write the state back
@@ -497,7 +739,7 @@ __global__ void __launch_bounds__(NT, 1) kb_ssaw_tiled_kernel(KbSsawVoice* __res
 		if (warp == 0) {                                                     // ---- A, tile k
 			if (is_env && k < ntiles) {
 				const int steps = min(T, n - k * T);
-				kb_envr_run(fs, env, S.c.px[lane], S.c.py[lane], S.amp[k & 3].r[lane], steps);
+				kb_envr_run_tile<false>(fs, env, S.c.px[lane], S.c.py[lane], S.amp[k & 3].r[lane], steps);
 			}
 		} else {
 			const int b = k - 1, d = k - 2;
@@ -591,7 +833,7 @@ __global__ void __launch_bounds__(NT, 1) kb_fm_tiled_kernel(KbFmVoice* __restric
 		if (warp == 0) {                                                     // ---- A, tile k
 			if (is_env && k < ntiles) {
 				const int steps = min(T, n - k * T);
-				kb_envr_run(fs, env, esrc->px, esrc->py, S.env[k & 1][ee].r[ev], steps);
+				kb_envr_run_tile<false>(fs, env, esrc->px, esrc->py, S.env[k & 1][ee].r[ev], steps);
 			}
 		} else {
 			const int d = k - 1;
@@ -674,7 +916,7 @@ __global__ void __launch_bounds__(NT, 1) kb_esine_tiled_kernel(VOICE* __restrict
 		if (warp == 0) {                                                     // ---- A, tile k
 			if (is_env && k < ntiles) {
 				const int steps = min(T, n - k * T);
-				kb_envr_run(fs, env, esrc->px, esrc->py, S.env[k & 1].r[lane], steps);
+				kb_envr_run_tile<false>(fs, env, esrc->px, esrc->py, S.env[k & 1].r[lane], steps);
 			}
 		} else {
 			const int d = k - 1;
@@ -756,7 +998,7 @@ __global__ void __launch_bounds__(NT, 1) kb_tb_tiled_kernel(KbTbVoice* __restric
 			if ((is_env || is_adsr) && k < ntiles) {
 				const int steps = min(T, n - k * T);
 				float* row = is_env ? S.e[k & 1].r[role_voice] : S.amp[k & 3].r[role_voice];
-				kb_envr_run(fs, env, S.c.px[slot], S.c.py[slot], row, steps);
+				kb_envr_run_tile<false>(fs, env, S.c.px[slot], S.c.py[slot], row, steps);
 			}
 		} else if (role == 2) {                                          // ---- C, tile k-2
 			const int c = k - 2;

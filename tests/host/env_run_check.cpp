@@ -25,7 +25,7 @@ int main() {
 			kb_env_set_points(fs, a, np, xy);
 			if (rnd() % 3 == 0) { int s = rnd() % np, t = s + rnd() % (np - s); kb_env_set_loop(a, s, t); }
 		}
-		KbEnv b = a;
+		KbEnv b = a; const KbEnv b0 = a;
 		const int n = 200 + rnd() % 3000, release_at = (rnd() % 2) ? (int)(rnd() % n) : -1;
 		const float rel_time = frand(0, 0.01f), rel_level = frand(0, 1);
 		static float ref[4096], got[4096];
@@ -42,6 +42,24 @@ int main() {
 			kb_envr_run(fs, r, b.px, b.py, got + s, len);
 			kb_envr_store(r, b);
 			s += len;
+		}
+		for (int form = 0; form < 2; form++) {	// the uniform-group form (kb_envr_run16) and the whole-tile form (kb_envr_run_tile), in tiles of at most 128 ticks
+			KbEnv c = b0; static float got16[4096];
+			for (int s = 0; s < n;) {
+				int len = (trial & 4) ? 128 : (trial & 8) ? 16 * (1 + rnd() % 8) : 1 + rnd() % 200;
+				if (len > n - s) len = n - s;
+				if (release_at > s && release_at < s + len) len = release_at - s;
+				if (s == release_at) { if (trial % 3 == 0) kb_adsr_release(fs, c); else kb_env_release(fs, c, rel_time, rel_level); }
+				KbEnvR r; kb_envr_load(r, c);
+				if (form) kb_envr_run_tile<false>(fs, r, c.px, c.py, got16 + s, len); else kb_envr_run16<false>(fs, r, c.px, c.py, got16 + s, len);
+				kb_envr_store(r, c);
+				s += len;
+			}
+			for (int i = 0; i < n; i++) { checked++; if (bits(ref[i]) != bits(got16[i])) { if (bad < 5) printf("env16 trial %d i %d: %a vs %a\n", trial, i, ref[i], got16[i]); bad++; } }
+			if (bits(a.time) != bits(c.time) || a.stage != c.stage || a.point != c.point || bits(a.r_out) != bits(c.r_out) || a.r_active != c.r_active || bits(a.out) != bits(c.out)) {
+				if (bad < 5) printf("env16 trial %d final state differs\n", trial);
+				bad++;
+			}
 		}
 		for (int i = 0; i < n; i++) { checked++; if (bits(ref[i]) != bits(got[i])) { if (bad < 5) printf("env trial %d i %d: %a vs %a\n", trial, i, ref[i], got[i]); bad++; } }
 		if (bits(a.time) != bits(b.time) || a.stage != b.stage || a.point != b.point || bits(a.r_out) != bits(b.r_out) || a.r_active != b.r_active || bits(a.out) != bits(b.out)) {

@@ -5,8 +5,9 @@ import os, subprocess, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 
-VARIANTS = [("layout2 G8", dict(KB_TILE_LAYOUT="2")), ("flow G8", dict(KB_TILE_LAYOUT="3", KB_TILE_G="8")), ("flow G8 A@sp0", dict(KB_TILE_LAYOUT="3", KB_TILE_G="8", KB_TILE_ASP0="1")),
-            ("flow G7", dict(KB_TILE_LAYOUT="3", KB_TILE_G="7")), ("flow G7 A@sp0", dict(KB_TILE_LAYOUT="3", KB_TILE_G="7", KB_TILE_ASP0="1"))]
+VARIANTS = [("layout2 G8", dict(KB_TILE_LAYOUT="2")), ("flow G8", dict(KB_TILE_LAYOUT="3", KB_TILE_G="8")),
+            ("flow G7", dict(KB_TILE_LAYOUT="3", KB_TILE_G="7")), ("flow G7 envr_run", dict(KB_TILE_LAYOUT="3", KB_TILE_G="7", KB_C2_VARIANT="32")),
+            ("mbar G7", dict(KB_TILE_LAYOUT="4", KB_TILE_G="7")), ("mbar G8", dict(KB_TILE_LAYOUT="4", KB_TILE_G="8"))]
 
 def child(path):
     import torch
@@ -37,7 +38,7 @@ else:
     ref = None
     for i, (name, env) in enumerate(VARIANTS):
         p = f"/tmp/c2ab_{i}.npy"
-        r = subprocess.run([sys.executable, __file__, "child", p], env={**os.environ, **env}, capture_output=True, text=True, timeout=300)
+        r = subprocess.run([sys.executable, __file__, "child", p], env={**os.environ, **env}, capture_output=True, text=True, timeout=120)
         if r.returncode != 0:
             print(name, "FAILED", r.stderr[-800:]); continue
         x = np.load(p)

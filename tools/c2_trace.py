@@ -21,3 +21,11 @@ cta = [(a, b) for r in (4, 5, 6, 7) for k, (a, b) in sorted(by.get(r, {}).items(
 if cta:
     pro = [a for a, b in cta]; loop = [b for a, b in cta]
     print(f"per CTA ({len(cta)}): prologue median {statistics.median(pro):.0f} max {max(pro)}; tile loop median {statistics.median(loop):.0f} min {min(loop)} max {max(loop)} cycles")
+
+if "--raw" in sys.argv:
+    # every tick of CTA 0: start / end of each role relative to A's first stamp
+    t0 = min(a for r in (0, 1, 2) for a, b in by[r].values() if a)
+    print("tick |  A start   run-end  signalled |  C start    C end |  W iter-top  B start  B computed  B signalled   D end")
+    for k in range(0, 40):
+        g = lambda r, ph: (by[r][k][ph] - t0) if k in by[r] and by[r][k][ph] else -1
+        print(f"{k:4d} | {g(0,0):8d} {g(8,0):9d} {g(0,1):10d} | {g(1,0):8d} {g(1,1):8d} | {g(9,0):10d} {g(2,0):8d} {g(9,1):11d} {g(2,1):12d} {g(3,1):7d}")
