@@ -1203,7 +1203,15 @@ static int sy_process(kb_synth_bank* b, float* out, int n, unsigned flags, kb_mi
 				const int group = (int)std::max<size_t>(1, std::min<size_t>((size_t)b->instances, (size_t)smem_max / per_inst));
 				const bool fuse_bank = bank_mix && !mixdown;
 				if (fuse_bank) d_result_fused = dev ? out : b->d_mix;
-				kb_mix_fused_kernel<<<(n + KB_MIXF_TS - 1) / KB_MIXF_TS, 1024, group * per_inst, st>>>(b->d_scratch, b->d_hdr, d_inst_dst, d_result_fused, n, b->voices, b->instances, group);
+				// programmatic dependent launch behind the voice kernel (KB_PDL=0: a plain launch; same results): the launch latency of this
+				// kernel overlaps the voice kernel's tail
+				static const bool pdl = !getenv("KB_PDL") || atoi(getenv("KB_PDL")) != 0;
+				cudaLaunchConfig_t cfg = {};
+				cfg.gridDim = dim3((unsigned)((n + KB_MIXF_TS - 1) / KB_MIXF_TS)); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = group * per_inst; cfg.stream = st;
+				cudaLaunchAttribute attr[1];
+				attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
+				cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+				KB_CUDA(cudaLaunchKernelEx(&cfg, kb_mix_fused_kernel, (const float*)b->d_scratch, (const KbVoiceHdr*)b->d_hdr, d_inst_dst, d_result_fused, n, b->voices, b->instances, group));
 			} else {
 				dim3 grid((n + 255) / 256, b->instances);
 				kb_mix_kernel<<<grid, 256, 0, st>>>(b->d_scratch, b->d_hdr, d_inst_dst, n, b->voices, (flags & KB_MIX_SUM) ? 1 : 0);

@@ -136,6 +136,9 @@ __global__ void __launch_bounds__(1024) kb_mix_fused_kernel(const float* __restr
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
 	const int t = blockIdx.x * KB_MIXF_TS + lane;
 	float bank = 0.f;
+	// launched as the programmatic dependent of the voice kernel (kb_api.cu): this CTA may already be resident while the last voice CTAs
+	// run; everything the voice kernel wrote is visible once the wait returns (a plain launch passes straight through)
+	asm volatile("griddepcontrol.wait;" ::: "memory");
 	for (int i0 = 0; i0 < instances; i0 += group) {
 		const int gi = min(group, instances - i0), rows = gi * voices;
 		if (i0) __syncthreads();

@@ -503,6 +503,7 @@ __global__ void __launch_bounds__(768, 1) kb_sub_mbar_kernel(KbSubVoice* __restr
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int v0 = blockIdx.x * G;
 	const long long t_entry = trace ? clock64() : 0;
+	asm volatile("griddepcontrol.launch_dependents;");                   // the mix kernel's CTAs may take the SMs as this grid's CTAs leave (they wait for the whole grid)
 	if (tid == 0) {
 		for (int i = 0; i < 4; i++) { kb_mbar_init(&S.a_done[i], 1); kb_mbar_init(&S.b_done[i], W); kb_mbar_init(&S.c_done[i], 1); }
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
