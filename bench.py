@@ -555,7 +555,7 @@ def main():
     traffic = None
     try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = (lambda t: t.get("kb_sub_flow_kernel", t.get("kb_sub_tiled_kernel")))(json.load(f))
+            traffic = (lambda t: t.get("kb_sub_mbar_kernel", t.get("kb_sub_flow_kernel", t.get("kb_sub_tiled_kernel"))))(json.load(f))
     except Exception:
         pass
     # What bounds this kernel: one fp32 recurrence per voice (the TDF-II biquad, klang.h:5605-5612) that parity forbids re-ordering:
@@ -565,7 +565,7 @@ def main():
     floor_cycles = 16.9
     kernel_vs = total * BLOCK / (k_ms_avg * 1e-3)
     floor_vs = total * sm_max * 1e6 / floor_cycles
-    roofline = {"bound": "latency", "kernel": "kb_sub_flow_kernel", "achieved": kernel_vs, "peak": floor_vs, "unit": "voice-samples/s",
+    roofline = {"bound": "latency", "kernel": "kb_sub_mbar_kernel", "achieved": kernel_vs, "peak": floor_vs, "unit": "voice-samples/s",
                 "frac": kernel_vs / floor_vs, "traffic": traffic,
                 "peak_source": f"serial-chain floor: {floor_cycles} cycles per sample of the TDF-II biquad recurrence (measured alone, profiles/r01_probes.txt) at the {sm_max:.0f} MHz of MEASURED_PEAKS.json, x {total} voices in flight",
                 "latency_frac": kernel_vs / floor_vs,

@@ -46,6 +46,11 @@ KB_KD constexpr constant kb_pi() { return constant(3.141592653589793238462643383
 KB_KD constexpr constant kb_ln2() { return constant(0.6931471805599453094172321214581); }
 KB_KD constexpr constant kb_root2() { return constant(1.4142135623730950488016887242097); }
 
+// klang.h:221-224: the first argument's type is the result's — `max(1000, f0 * 1.5)` is an int.  kcc rewrites the program's unqualified
+// min( / max( to these (the CUDA headers' own overloads of ::min / ::max would make the call ambiguous)
+template <class A, class B> KB_KD A kb_min(A a, B b) { return a < b ? a : (A)b; }
+template <class A, class B> KB_KD A kb_max(A a, B b) { return a > b ? a : (A)b; }
+
 struct SampleRate {                                                                            // klang.h:1593-1604
 	float f; int i; float inv, w, nyquist; KbFs k;
 	KB_KD SampleRate(const KbFs& s) : f(s.f), i(s.i), inv(s.inv), w(s.w), nyquist(s.nyquist), k(s) {}
@@ -112,10 +117,13 @@ struct Control {                                                                
 	KB_KD float smooth() { smoothed = smoothed.value * 0.999f + (1.f - 0.999f) * value.value; return smoothed; }   // klang.h:1715-1716
 	KB_KD Control& set(float x) { value = x < min ? min : (max < x ? max : x); return *this; }                      // std::clamp   klang.h:1725-1728
 };
-enum { KB_KD_ROTARY = 1, KB_KD_BUTTON, KB_KD_TOGGLE, KB_KD_SLIDER };
+enum { KB_KD_ROTARY = 1, KB_KD_BUTTON, KB_KD_TOGGLE, KB_KD_SLIDER, KB_KD_MENU };
 inline Control Dial(const char* name, float min = 0.f, float max = 1.f, float initial = 0.f) { return { name, KB_KD_ROTARY, min, max, initial, initial, 0.f }; }
 inline Control Slider(const char* name, float min = 0.f, float max = 1.f, float initial = 0.f) { return { name, KB_KD_SLIDER, min, max, initial, initial, 0.f }; }
 inline Control Toggle(const char* name, bool initial = false) { return { name, KB_KD_TOGGLE, 0.f, 1.f, initial ? 1.f : 0.f, initial ? 1.f : 0.f, 0.f }; }
+template <class... Options> inline Control Menu(const char* name, const Options*...) {           // klang.h:1816-1825: value = index of the option, 0 .. count - 1
+	return { name, KB_KD_MENU, 0.f, (float)sizeof...(Options) - 1.f, 0.f, 0.f, 0.f };
+}
 inline Control Button(const char* name) { return { name, KB_KD_BUTTON, 0.f, 1.f, 0.f, 0.f, 0.f }; }
 
 struct ControlGroup {                                                                         // a control, or `{ "Caption", Dial(...), Dial(...) }`: a captioned group whose
@@ -423,6 +431,8 @@ namespace Stereo {
 		KB_KD signal operator-(float x) const { return signal(l.value - x, r.value - x); }
 		KB_KD signal operator*(float x) const { return signal(l.value * x, r.value * x); }
 		KB_KD signal operator/(float x) const { return signal(l.value / x, r.value / x); }
+		KB_KD klang::signal& operator[](int index) { return index ? r : l; }                   // signals<2>::operator[]   klang.h:1218-1220
+		KB_KD const klang::signal& operator[](int index) const { return index ? r : l; }
 	};
 	template <int SIZE> struct Delay : kb_input_tag {                                         // Stereo::Delay = Bank<klang::Delay<SIZE>, 2>   klang.h:4645-4699
 		klang::Delay<SIZE> items[2];

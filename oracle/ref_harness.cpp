@@ -134,6 +134,15 @@ namespace k_bands {
 namespace k_eq {
 #include "Filtering/EQ.k"
 }
+namespace k_patterns {
+#include "Delay/Patterns.k"
+}
+namespace k_reverb2 {
+#include "Delay/Reverb2.k"
+}
+namespace k_expression {
+#include "Subtractive/Expression.k"
+}
 
 // ---------------------------------------------------------------------------
 // Canonical C2 graph: examples/Subtractive/Filter.k's note with
@@ -480,6 +489,8 @@ void* ref_fx_create(int graph) {
 	case 100: { auto* e = new k_objects::Objects(); fx->mono = e; fx->controls = &e->controls; } break;     // Filtering/Objects.k (Noise >> LPF)
 	case 101: { auto* e = new k_bands::Bands();     fx->mono = e; fx->controls = &e->controls; } break;     // Filtering/Bands.k (two BPF, grouped controls)
 	case 102: { auto* e = new k_eq::EQ();           fx->mono = e; fx->controls = &e->controls; } break;     // Filtering/EQ.k (LPF / HPF set in prepare())
+	case 103: { auto* e = new k_patterns::Patterns(); fx->mono = e; fx->controls = &e->controls; } break;   // Delay/Patterns.k (a Menu control selects the tap pattern)
+	case 104: { auto* e = new k_reverb2::Reverb2();  fx->stereo = e; fx->controls = &e->controls; } break;  // Delay/Reverb2.k (four Delay<192000>, two LPF, in[c] / out.l)
 	default: delete fx; return nullptr;
 	}
 	return fx;
@@ -589,6 +600,8 @@ void* ref_synth_create(int graph, int nvoices) {
 	case SY_AM:      { auto* p = make_synth<k_am::AM, k_am::AM::AMNote>(nvoices); s->mono = p; s->controls = &p->controls; } break;
 	case SY_MOD_FM:  { auto* p = make_synth<k_mod_fm::FM, k_mod_fm::FM::FMNote>(nvoices); s->mono = p; s->controls = &p->controls; } break;
 	case SY_MOD_FM2: { auto* p = make_synth<k_mod_fm2::FM2, k_mod_fm2::FM2::FM2Note>(nvoices); s->mono = p; s->controls = &p->controls; } break;
+	// programs the product has NO hand-written graph for (run from their own source, klang_b200/kcc.py): ids from 100
+	case 100: { auto* p = make_synth<k_expression::Expression, k_expression::Expression::ExpressionNote>(nvoices); s->mono = p; s->controls = &p->controls; } break;   // Subtractive/Expression.k
 	default: delete s; return nullptr;
 	}
 	s->nvoices = s->mono ? (int)s->mono->notes.count : (int)s->stereo->notes.count;

@@ -293,6 +293,14 @@ TRANSLATED_FX_SCRIPTS = {
     "k_objects": (100, "Filtering/Objects.k", 4096, 1024, [(2, 0, 300.0), (2, 1, 4.0)], None),          # Noise >> LPF: one libc rand() per sample
     "k_bands": (101, "Filtering/Bands.k", 4096, 1024, [(1, 0, 250.0), (1, 3, 5.0), (3, 2, 900.0)], None),
     "k_eq": (102, "Filtering/EQ.k", 4096, 1024, [(1, 0, 0.9), (2, 1, 0.1), (3, 2, 1.0)], None),
+    "k_patterns": (103, "Delay/Patterns.k", 131072, 16384, [(3, 0, 1.0), (6, 0, 2.0)], 3000),              # a Menu control picks one of three tap patterns (taps up to 1.5 s)
+    "k_reverb2": (104, "Delay/Reverb2.k", 16384, 4096, [(1, 0, 0.45), (2, 1, 0.05), (2, 2, 4000.0)], None),  # Stereo::Effect: in[c], out.l >> feedback[0]
+}
+
+# The same for synths: reference-only synth ids from 100.
+#   name: (reference id, path under examples/, nvoices, started voices, blocks, block size, release block base, [(block, control, value)])
+TRANSLATED_SYNTH_SCRIPTS = {
+    "k_expression": (100, "Subtractive/Expression.k", 32, 8, 10, 4096, 4, []),   # three Saws with an enveloped vibrato LFO, LPF; on() draws random() four times per note
 }
 
 
@@ -362,7 +370,10 @@ def run_synth_script(eng, name, fs, per_voice=True):
 
     Returns dict with 'voices' [blocks][V, C, n] concatenated over time (per-voice streams, each voice
     rendered alone — SURVEY Q6) or 'mix' (the Synth::process block output), plus 'stages'."""
-    graph, nvoices, started, blocks, n, rel0, events = (SYNTH_SCRIPTS.get(name) or SYNTH_SCRIPTS_LATE[name])
+    if name in TRANSLATED_SYNTH_SCRIPTS:
+        graph, _, nvoices, started, blocks, n, rel0, events = TRANSLATED_SYNTH_SCRIPTS[name]
+    else:
+        graph, nvoices, started, blocks, n, rel0, events = (SYNTH_SCRIPTS.get(name) or SYNTH_SCRIPTS_LATE[name])
     eng.set_fs(fs)
     eng.srand(1)
     sy = eng.Synth(graph, nvoices)
@@ -429,3 +440,11 @@ def all_graph_cases(eng, fs):
 def translated_cases(eng, fs):
     """The scripts of TRANSLATED_FX_SCRIPTS (reference side: eng = oracle.ref; product side: an engine that hands out translated programs)."""
     return {f"fx/{name}": run_fx_script(eng, name, fs) for name in TRANSLATED_FX_SCRIPTS}
+
+
+def translated_synth_cases(eng, name, fs):
+    """One script of TRANSLATED_SYNTH_SCRIPTS: per-voice streams, note stages and the Synth::process mix."""
+    r = run_synth_script(eng, name, fs, per_voice=True)
+    out = {f"synth/{name}/voices": r["out"], f"synth/{name}/stages": r["stages"]}
+    out[f"synth/{name}/mix"] = run_synth_script(eng, name, fs, per_voice=False)["out"]
+    return out

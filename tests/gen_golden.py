@@ -32,6 +32,8 @@ def main():
     for fs in (44100, 48000):
         path = os.path.join(HERE, "golden", f"klang_ref_translated_fs{fs}.npz")
         out = cases.translated_cases(oracle.ref, fs)
+        for name in cases.TRANSLATED_SYNTH_SCRIPTS:
+            out.update(cases.translated_synth_cases(oracle.ref, name, fs))
         np.savez_compressed(path, **out)
         print(path, len(out), "arrays", os.path.getsize(path) // 1024, "KiB")
     import json

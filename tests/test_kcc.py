@@ -62,6 +62,7 @@ def build_all():
     jobs = [(os.path.join(REF, rel), so_path(name)) for name, (rel, _) in PROGRAMS.items()]
     jobs += [(os.path.join(REF, rel), so_path("synth_" + lib)) for rel, lib in sorted(set(SYNTHS.values()))]
     jobs += [(os.path.join(REF, spec[1]), so_path(name)) for name, spec in cases.TRANSLATED_FX_SCRIPTS.items()]
+    jobs += [(os.path.join(REF, spec[1]), so_path("synth_" + name)) for name, spec in cases.TRANSLATED_SYNTH_SCRIPTS.items()]
     src = open(os.path.join(REF, "Gain", "Gain.k")).read().replace("in * gain >> out;", "in * gain * 0.5 >> out;")
     edited = os.path.join(BIN, "gain_edited.k")
     with open(edited, "w") as f:
@@ -262,9 +263,9 @@ def test_programs_without_a_bound_graph_match_the_reference(fs):
     """Filtering/Objects.k (Noise >> LPF: the device continues the process's libc rand() stream), Filtering/Bands.k (two BPF, grouped controls),
     Filtering/EQ.k (LPF / HPF set in prepare()): no KB_FX_* id exists for them — the product runs their own text — and every block is the compiled
     reference's (tests/golden/klang_ref_translated_fs*.npz, written by tests/gen_golden.py; live against oracle.ref where it is present)."""
-    g = dict(np.load(os.path.join(ROOT, "tests", "golden", f"klang_ref_translated_fs{fs}.npz")))
+    g = {k: v for k, v in np.load(os.path.join(ROOT, "tests", "golden", f"klang_ref_translated_fs{fs}.npz")).items() if k.startswith("fx/")}
     got = cases.translated_cases(_UserFxEngine(), fs)
-    assert set(got) == set(g) and len(g) == 3
+    assert set(got) == set(g) and len(g) == len(cases.TRANSLATED_FX_SCRIPTS) == 5
     for k in g:
         assert np.array_equal(got[k].view(np.uint32), g[k].view(np.uint32)), f"{k}: differs from the reference"
         assert np.abs(g[k]).max() > 0
@@ -272,6 +273,25 @@ def test_programs_without_a_bound_graph_match_the_reference(fs):
         live = cases.translated_cases(oracle.ref, fs)
         for k in g:
             assert np.array_equal(live[k].view(np.uint32), g[k].view(np.uint32)), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fs", [44100, 48000])
+@pytest.mark.parametrize("name", list(cases.TRANSLATED_SYNTH_SCRIPTS))
+def test_synth_programs_without_a_bound_graph_match_the_reference(name, fs):
+    """Subtractive/Expression.k (three Saws under an enveloped vibrato LFO into an LPF; on() draws random() on the host mirror): no KB_SY_* id
+    exists — the product runs the program's own text — and per-voice streams, note stages and the Synth::process mix are the compiled
+    reference's (reference-only synth id, tests/golden/klang_ref_translated_fs*.npz; live against oracle.ref where it is present)."""
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", f"klang_ref_translated_fs{fs}.npz")))
+    got = cases.translated_synth_cases(_UserSynthEngine(name), name, fs)
+    for k, v in got.items():
+        a, b = np.atleast_2d(v), np.atleast_2d(g[k])
+        assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32)), f"{k}: differs from the reference"
+    assert np.abs(g[f"synth/{name}/mix"]).max() > 0
+    if oracle.ref.available():
+        live = cases.translated_synth_cases(oracle.ref, name, fs)
+        for k in got:
+            assert np.array_equal(np.atleast_2d(live[k]).view(np.uint32), np.atleast_2d(g[k]).view(np.uint32)), k
 
 
 @pytest.mark.gpu

@@ -37,7 +37,7 @@ KB_RV3_TRACE=$OUT/trace_tol.txt timeout 100 python tools/fx_probe.py reverb 4096
 echo "== ncu launches"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $OUT/launches.csv python bench.py --steps 3 --warmup 3 --no-cpu > $OUT/ncu_launch_run.log 2>&1
 echo "== ncu full"
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:kb_sub_flow -s 3 -c 1 -o $OUT/prof_sub -f python bench.py --steps 2 --warmup 3 --no-extras --no-cpu > $OUT/ncu_sub.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:kb_sub_mbar -s 3 -c 1 -o $OUT/prof_sub -f python bench.py --steps 2 --warmup 3 --no-extras --no-cpu > $OUT/ncu_sub.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:kb_reverb3 -s 3 -c 1 -o $OUT/prof_reverb3 -f python tools/fx_probe.py reverb 4096 --allbus > $OUT/ncu_rv.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:kb_reverb3 -s 6 -c 1 -o $OUT/prof_reverb3_tol -f python tools/fx_probe.py reverb 4096 --tol --allbus > $OUT/ncu_rvt.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:kb_pingpong3 -s 12 -c 1 -o $OUT/prof_pingpong3 -f python tools/fx_probe.py pingpong 4096 > $OUT/ncu_pp.log 2>&1

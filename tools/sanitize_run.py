@@ -55,7 +55,7 @@ L.kb_mixdown_collect(h, dst.data_ptr(), 512, ts.cuda_stream)
 torch.cuda.synchronize()
 assert torch.equal(src, dst) and torch.equal(src, prev)
 L.kb_mixdown_destroy(h)
-# round 2, second half: the decoupled C2 kernel with the staged voice upload (8 x 100 = 800 voices -> kb_sub_flow_kernel<7>) and re-triggers in every
+# round 2, second half: the decoupled C2 kernel with the staged voice upload (8 x 100 = 800 voices -> kb_sub_mbar_kernel<7>) and re-triggers in every
 # block, the fused voice-sum / bank-mix launch, debug taps, klang::Sample, and translated programs (an effect with a delay line, a synth, noise)
 b = kb.SynthBank(kb.SY_SUBTRACTIVE, 8, 100, fs, 260)
 for g in range(800):
