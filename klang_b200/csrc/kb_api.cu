@@ -1015,6 +1015,13 @@ extern "C" int kb_synth_bank_events(kb_synth_bank* b, int count, const kb_note_e
 	return KB_OK;
 }
 
+// is `p` page-locked host memory the device can address through the same pointer (cudaHostAlloc / cudaHostRegister under unified addressing)?
+// Asked on every call: an address can be freed and come back as pageable memory.
+static bool kb_host_ptr_mapped(const void* p) {
+	cudaPointerAttributes a;
+	if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+	return a.type == cudaMemoryTypeHost && a.devicePointer == p;
+}
 static int mixdown_step(kb_mixdown* m, const float* src, int rows, size_t row_stride, int count, float* out_prev, cudaStream_t stream);
 static int sy_process(kb_synth_bank* b, float* out, int n, unsigned flags, kb_mixdown* mixdown, float* out_prev);
 extern "C" int kb_synth_bank_process(kb_synth_bank* b, float* out, int n, unsigned flags) {
@@ -1202,7 +1209,10 @@ static int sy_process(kb_synth_bank* b, float* out, int n, unsigned flags, kb_mi
 				const size_t per_inst = (size_t)b->voices * KB_MIXF_TS * sizeof(float) + KB_MIXF_TS * sizeof(float) + (size_t)b->voices * sizeof(int);
 				const int group = (int)std::max<size_t>(1, std::min<size_t>((size_t)b->instances, (size_t)smem_max / per_inst));
 				const bool fuse_bank = bank_mix && !mixdown;
-				if (fuse_bank) d_result_fused = dev ? out : b->d_mix;
+				// a page-locked, device-mapped host buffer takes the mix straight from the kernel's stores (16 KiB per block over PCIe inside the
+				// kernel): no copy-engine operation queued behind the kernels (KB_ZERO_COPY_OUT=0: copy as before; same bytes)
+				static const bool zero_copy = !getenv("KB_ZERO_COPY_OUT") || atoi(getenv("KB_ZERO_COPY_OUT")) != 0;
+				if (fuse_bank) d_result_fused = dev ? out : (zero_copy && kb_host_ptr_mapped(out) ? out : b->d_mix);
 				// programmatic dependent launch behind the voice kernel (KB_PDL=0: a plain launch; same results): the launch latency of this
 				// kernel overlaps the voice kernel's tail
 				static const bool pdl = !getenv("KB_PDL") || atoi(getenv("KB_PDL")) != 0;
@@ -1240,7 +1250,7 @@ static int sy_process(kb_synth_bank* b, float* out, int n, unsigned flags, kb_mi
 	KB_CUDA(cudaGetLastError());
 	b->host_stale = true; b->hdr_stale = true; b->vstate_stale = true;
 	if (!dev) {
-		KB_CUDA(cudaMemcpyAsync(out, d_result, out_floats * sizeof(float), cudaMemcpyDeviceToHost, st));
+		if (d_result != out) KB_CUDA(cudaMemcpyAsync(out, d_result, out_floats * sizeof(float), cudaMemcpyDeviceToHost, st));
 		if (!(flags & KB_ASYNC_HOST)) KB_CUDA(cudaStreamSynchronize(st));
 		b->d2h_bytes += (long long)(out_floats * sizeof(float));
 	}
