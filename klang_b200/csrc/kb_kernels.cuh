@@ -159,6 +159,7 @@ __global__ void __launch_bounds__(1024) kb_mix_fused_kernel(const float* __restr
 			const float* tp = tile + (size_t)i * voices * KB_MIXF_TS + lane;
 			const int* ap = s_act + i * voices;
 			float acc = 0.f;
+			#pragma unroll 16                                                   // (operands of 16 voices in flight; the adds stay in voice order)
 			for (int v = 0; v < voices; v++) if (ap[v]) acc = acc + tp[(size_t)v * KB_MIXF_TS];   // summed in voice order; inactive voices are skipped like kb_mix_kernel
 			isum[i * KB_MIXF_TS + lane] = acc;
 			if (t < n) inst_out[(size_t)(i0 + i) * n + t] = acc;

@@ -275,6 +275,36 @@ KB_D const VOICE& kb_tile_voice_src(const KbStagedSmem<G, VOICE>& m, const VOICE
 	return m.src[i] < 0 ? voices[v0 + i] : *reinterpret_cast<const VOICE*>(m.rec[i] + sizeof(KbVoiceHdr) / 4);
 }
 
+// One round trip instead of three (kb_sub_mbar_kernel): every record of the CTA's voices — header and state, from the pinned staging slot for a
+// re-written voice, else from its slot in HBM — is requested in ONE cooperative pass into shared memory (the PCIe read and the HBM reads overlap);
+// all later prologue reads (note stage, envelopes, filter, oscillator) come from there.  The staged records are written through to their slots as
+// in kb_tile_scatter.  `m.src[g]` ends >= 0 for every voice that exists, so kb_tile_hdr_src / kb_tile_voice_src always pick the shared copy.
+template <int G, class VOICE>
+KB_D void kb_tile_gather(const KbStaged& sg, KbVoiceHdr* hdr, VOICE* voices, int v0, int total, KbStagedSmem<G, VOICE>& m, int* from_host) {
+	if (threadIdx.x < G) { m.src[threadIdx.x] = -1; from_host[threadIdx.x] = 0; }
+	__syncthreads();
+	for (int k = threadIdx.x; k < sg.count; k += blockDim.x) {
+		const int v = sg.index[k];
+		if (v >= v0 && v < v0 + G) { m.src[v - v0] = k; from_host[v - v0] = 1; }
+	}
+	__syncthreads();
+	constexpr int rec_words = (int)(sizeof(KbVoiceHdr) + sizeof(VOICE)) / 4, hdr_words = (int)sizeof(KbVoiceHdr) / 4;
+	for (int i = threadIdx.x; i < G * rec_words; i += blockDim.x) {
+		const int g = i / rec_words, w = i % rec_words, k = m.src[g];
+		if (v0 + g >= total) continue;
+		if (k >= 0) m.rec[g][w] = reinterpret_cast<const unsigned*>(sg.records)[(size_t)k * rec_words + w];
+		else m.rec[g][w] = w < hdr_words ? reinterpret_cast<const unsigned*>(hdr + v0 + g)[w] : reinterpret_cast<const unsigned*>(voices + v0 + g)[w - hdr_words];
+	}
+	__syncthreads();
+	for (int i = threadIdx.x; i < G * rec_words; i += blockDim.x) {
+		const int g = i / rec_words, w = i % rec_words;
+		if (!from_host[g] || w == (int)(offsetof(KbVoiceHdr, active) / 4)) continue;
+		if (w < hdr_words) reinterpret_cast<unsigned*>(hdr + v0 + g)[w] = m.rec[g][w];
+		else reinterpret_cast<unsigned*>(voices + v0 + g)[w - hdr_words] = m.rec[g][w];
+	}
+	if (threadIdx.x < G) m.src[threadIdx.x] = (v0 + (int)threadIdx.x < total) ? 0 : -1;   // (src is read again only behind the caller's next barrier)
+}
+
 // ---- the same four stages WITHOUT the lock step (round 2): every role runs its own tile loop and meets the others through progress
 // counters in shared memory (kb_sync.cuh: st.release by one thread behind the role's own barrier, ld.acquire polling), over hand-over
 // buffers four tiles deep (A -> D: eight), so a role waits only when the role it depends on is really behind — the tick of the lock-step
@@ -491,6 +521,7 @@ template <int G> struct KbSubMbarSmem {
 	float4 lastc[G];
 	KbOsm osc[G];
 	unsigned long long a_done[4], b_done[4], c_done[4];
+	int from_host[G];
 	KbStagedSmem<G, KbSubVoice> sc;
 };
 template <int G>
@@ -508,8 +539,9 @@ __global__ void __launch_bounds__(768, 1) kb_sub_mbar_kernel(KbSubVoice* __restr
 		for (int i = 0; i < 4; i++) { kb_mbar_init(&S.a_done[i], 1); kb_mbar_init(&S.b_done[i], W); kb_mbar_init(&S.c_done[i], 1); }
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
-	kb_tile_scatter(staged, hdr, voices, v0, S.sc);
-	if (tid < G) {                                                       // kb_tile_prologue with the staged headers
+	kb_tile_gather(staged, hdr, voices, v0, total, S.sc, S.from_host);
+	__syncthreads();
+	if (tid < G) {                                                       // kb_tile_prologue from the gathered headers
 		const int v = v0 + tid;
 		const int act = (v < total && kb_tile_hdr_src(S.sc, hdr, v0, tid).stage != KB_NOTE_OFF) ? 1 : 0;
 		S.c.active[tid] = act;
