@@ -1149,14 +1149,15 @@ static int sy_process(kb_synth_bank* b, float* out, int n, unsigned flags, kb_mi
 		if (!attr_set) { cudaFuncSetAttribute(kb_sub_flow_kernel<GG, ASP0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KbSubFlowSmem<GG>)); attr_set = true; } \
 		kb_sub_flow_kernel<GG, ASP0><<<(total + GG - 1) / GG, 768, sizeof(KbSubFlowSmem<GG>), st>>>(vs, b->d_hdr, d_voice_dst, n, total, b->fs, b->staged, c2_trace, c2_variant); \
 	} while (0)
-#define KB_LAUNCH_MBAR(GG)                                                                                                            \
+#define KB_LAUNCH_MBAR(GG, CHK)                                                                                                       \
 	do {                                                                                                                             \
 		static bool attr_set = false;                                                                                                \
-		if (!attr_set) { cudaFuncSetAttribute(kb_sub_mbar_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KbSubMbarSmem<GG>)); attr_set = true; } \
-		kb_sub_mbar_kernel<GG><<<(total + GG - 1) / GG, 768, sizeof(KbSubMbarSmem<GG>), st>>>(vs, b->d_hdr, d_voice_dst, n, total, b->fs, b->staged, c2_trace, c2_variant); \
+		if (!attr_set) { cudaFuncSetAttribute(kb_sub_mbar_kernel<GG, CHK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KbSubMbarSmem<GG>)); attr_set = true; } \
+		kb_sub_mbar_kernel<GG, CHK><<<(total + GG - 1) / GG, 768, sizeof(KbSubMbarSmem<GG>), st>>>(vs, b->d_hdr, d_voice_dst, n, total, b->fs, b->staged, c2_trace, c2_variant); \
 	} while (0)
 				if (sub_flow && layout >= 4) {
-					if (g == 7) KB_LAUNCH_MBAR(7); else KB_LAUNCH_MBAR(8);
+					if (c2_variant & 128) { if (g == 7) KB_LAUNCH_MBAR(7, true); else KB_LAUNCH_MBAR(8, true); }     // the self-checking instantiation
+					else if (g == 7) KB_LAUNCH_MBAR(7, false); else KB_LAUNCH_MBAR(8, false);
 					if (b->staged.count > 0) { KB_CUDA(cudaEventRecord(b->stage_done[b->staged_slot], st)); b->staged.count = 0; }
 				}
 				else if (sub_flow) {

@@ -522,9 +522,14 @@ template <int G> struct KbSubMbarSmem {
 	KbOsm osc[G];
 	unsigned long long a_done[4], b_done[4], c_done[4];
 	int from_host[G];
+	int protocol_error;                   // CHECK instantiation: a stamp did not match (the block's output is poisoned from then on)
 	KbStagedSmem<G, KbSubVoice> sc;
 };
-template <int G>
+// CHECK (KB_C2_VARIANT bit 7, a second instantiation; tests/test_gpu_schedules.py): the hand-over protocol checks itself.  Every producer stamps
+// the pad element of each row it is about to write with the tile number BEFORE the data; every consumer compares the stamp with the tile it
+// expects before AND after it has read the row — a buffer handed over early, or overwritten while it is still being read, poisons the block's
+// output with NaNs (compute-sanitizer's racecheck does not model mbarrier ordering expressed in inline PTX: it reports every buffer of the ring).
+template <int G, bool CHECK = false>
 __global__ void __launch_bounds__(768, 1) kb_sub_mbar_kernel(KbSubVoice* __restrict__ voices, KbVoiceHdr* __restrict__ hdr,
                                                              float* __restrict__ dst, int n, int total, KbFs fs, const __grid_constant__ KbStaged staged, long long* __restrict__ trace = nullptr, int variant = 0) {
 	constexpr int T = KB_TILE_T, W = 2 * G, wthreads = W * 32, LAG = 4;
@@ -536,6 +541,7 @@ __global__ void __launch_bounds__(768, 1) kb_sub_mbar_kernel(KbSubVoice* __restr
 	const long long t_entry = trace ? clock64() : 0;
 	asm volatile("griddepcontrol.launch_dependents;");                   // the mix kernel's CTAs may take the SMs as this grid's CTAs leave (they wait for the whole grid)
 	if (tid == 0) {
+		S.protocol_error = 0;
 		for (int i = 0; i < 4; i++) { kb_mbar_init(&S.a_done[i], 1); kb_mbar_init(&S.b_done[i], W); kb_mbar_init(&S.c_done[i], 1); }
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
@@ -583,6 +589,7 @@ __global__ void __launch_bounds__(768, 1) kb_sub_mbar_kernel(KbSubVoice* __restr
 			if (is_env || is_adsr) {
 				const int steps = min(T, n - k * T);
 				float* rowp = is_env ? S.cut[k & 3].r[role_voice] : S.amp[k & 7].r[role_voice];
+				if (CHECK) { rowp[T] = (float)k; __threadfence_block(); }
 				if (variant & 64) kb_envr_run16<true>(fs, env, S.c.px[slot], S.c.py[slot], rowp, steps);
 				else kb_envr_run_tile<true>(fs, env, S.c.px[slot], S.c.py[slot], rowp, steps);
 			}
@@ -595,7 +602,7 @@ __global__ void __launch_bounds__(768, 1) kb_sub_mbar_kernel(KbSubVoice* __restr
 		// tile's coefficients are there and, if so, loads the next tile's first group before the last group of this one — arriving and
 		// waiting between two tiles cost ~300 of ~2950 cycles per tile.  A lane that did not see them waits as before.
 		float4 ca[4], cb[4];
-		bool have_next = false;
+		bool have_next = false, bad = false;
 		for (int c = 0; c < ntiles; c++) {
 			if (!have_next) kb_mbar_wait(&S.b_done[c & 3], (c >> 2) & 1);
 			if (lane == 0) KB_C2_TR(1, c, 0);
@@ -603,6 +610,7 @@ __global__ void __launch_bounds__(768, 1) kb_sub_mbar_kernel(KbSubVoice* __restr
 				const int steps = min(T, n - c * T), v = role_voice;
 				const float4* pc = S.coef[c & 3].r[v];
 				float* po = S.out[c & 3].r[v];
+				if (CHECK) { if (pc[T].x != (float)c) bad = true; po[T] = (float)c; __threadfence_block(); }
 				auto group = [&](const float4 (&cf)[4], int t) {         // Filter::process, klang.h:5605-5612 (see kb_sub_tiled_kernel)
 					float y[4];
 					#pragma unroll
@@ -665,6 +673,8 @@ __global__ void __launch_bounds__(768, 1) kb_sub_mbar_kernel(KbSubVoice* __restr
 					}
 				}
 			}
+			if (CHECK && is_flt && S.coef[c & 3].r[role_voice][T].x != (float)c) bad = true;
+			if (CHECK && bad) S.protocol_error = 1;
 			__syncwarp();
 			if (lane == 0) { kb_mbar_arrive(&S.c_done[c & 3]); KB_C2_TR(1, c, 1); }
 		}
@@ -679,8 +689,14 @@ __global__ void __launch_bounds__(768, 1) kb_sub_mbar_kernel(KbSubVoice* __restr
 				#pragma unroll
 				for (int r = 0; r < 2; r++) {
 					const int item = wtid + r * wthreads, v = item / T, t = item % T;
-					if (t < steps && v0 + v < total)                             // out *= adsr++   Filter.k:33
-						dst[(size_t)(v0 + v) * n + d * T + t] = S.c.active[v] ? S.out[d & 3].r[v][t] * S.amp[d & 7].r[v][t] : 0.f;
+					if (t < steps && v0 + v < total) {                           // out *= adsr++   Filter.k:33
+						bool bad = false;
+						if (CHECK && S.c.active[v]) bad = S.out[d & 3].r[v][T] != (float)d || S.amp[d & 7].r[v][T] != (float)d;
+						float y = S.c.active[v] ? S.out[d & 3].r[v][t] * S.amp[d & 7].r[v][t] : 0.f;
+						if (CHECK && S.c.active[v]) { __threadfence_block(); bad = bad || S.out[d & 3].r[v][T] != (float)d || S.amp[d & 7].r[v][T] != (float)d || S.protocol_error; }
+						if (CHECK && bad) { y = __int_as_float(0x7fc00000); S.protocol_error = 1; }
+						dst[(size_t)(v0 + v) * n + d * T + t] = y;
+					}
 				}
 			}
 			if (wtid == 0) KB_C2_TR(3, j, 1);
@@ -692,6 +708,7 @@ __global__ void __launch_bounds__(768, 1) kb_sub_mbar_kernel(KbSubVoice* __restr
 				for (int r = 0; r < 2; r++) {
 					const int item = wtid + r * wthreads, v = item / T, t = item % T;
 					if (t < steps && S.c.active[v]) {
+						if (CHECK) { if (S.cut[b & 3].r[v][T] != (float)b) S.protocol_error = 1; if ((t & 31) == 0) { S.coef[b & 3].r[v][T].x = (float)b; } __threadfence_block(); }
 						const float f = S.cut[b & 3].r[v][t];
 						const float w = f * fs.w;
 						float sin0, cos0;
@@ -707,6 +724,7 @@ __global__ void __launch_bounds__(768, 1) kb_sub_mbar_kernel(KbSubVoice* __restr
 						const float in = kb_osm_at(S.osc[v], (uint32_t)(b * T + t));
 						cf.x = cf.x * in; cf.y = cf.y * in;
 						S.coef[b & 3].r[v][t] = cf;
+						if (CHECK && S.cut[b & 3].r[v][T] != (float)b) S.protocol_error = 1;
 					}
 				}
 				__syncwarp();
