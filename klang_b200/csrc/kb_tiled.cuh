@@ -679,6 +679,7 @@ __global__ void __launch_bounds__(768, 1) kb_sub_mbar_kernel(KbSubVoice* __restr
 			if (lane == 0) { kb_mbar_arrive(&S.c_done[c & 3]); KB_C2_TR(1, c, 1); }
 		}
 	} else if (worker) {                                                 // ---- D (tile j - LAG) then B (tile j), two rounds each, warp by warp
+		const bool pairs_ok = (n & 1) == 0 && (reinterpret_cast<size_t>(dst) & 7) == 0;
 		for (int j = 0; j < ntiles + LAG; j++) {
 			if (wtid == 0) KB_C2_TR(9, j, 0);
 			const int d = j - LAG;
@@ -686,6 +687,19 @@ __global__ void __launch_bounds__(768, 1) kb_sub_mbar_kernel(KbSubVoice* __restr
 				const int steps = min(T, n - d * T);
 				kb_mbar_wait(&S.c_done[d & 3], (d >> 2) & 1);
 				if (wtid == 0) KB_C2_TR(9, j, 1);
+				if (!CHECK && steps == T && pairs_ok) {                          // a full tile: two samples per thread, 64-bit loads and stores
+					for (int item = wtid; item < G * (T / 2); item += wthreads) {
+						const int v = item / (T / 2), t = (item % (T / 2)) * 2;
+						if (v0 + v < total) {
+							float2 y = make_float2(0.f, 0.f);
+							if (S.c.active[v]) {
+								const float2 o = *reinterpret_cast<const float2*>(&S.out[d & 3].r[v][t]), a = *reinterpret_cast<const float2*>(&S.amp[d & 7].r[v][t]);
+								y = make_float2(o.x * a.x, o.y * a.y);                   // out *= adsr++   Filter.k:33
+							}
+							*reinterpret_cast<float2*>(dst + (size_t)(v0 + v) * n + d * T + t) = y;
+						}
+					}
+				} else
 				#pragma unroll
 				for (int r = 0; r < 2; r++) {
 					const int item = wtid + r * wthreads, v = item / T, t = item % T;

@@ -47,7 +47,9 @@ echo "== stream probe, C2 variants, C2 trace"
 timeout 300 python tools/stream_probe.py 2>&1 | tee $OUT/stream_probe.txt
 timeout 300 python tools/stream_probe.py 4 2>&1 | tee $OUT/stream_probe_x4.txt
 timeout 600 bash tools/bench_ab.sh 2>&1 | tee $OUT/c2_step_ab.txt
-KB_C2_TRACE=$OUT/c2_trace.txt timeout 300 python bench.py --steps 5 --warmup 3 --no-extras --no-cpu > /dev/null 2>&1; python tools/c2_trace.py $OUT/c2_trace.txt | tee $OUT/c2_trace_summary.txt
+KB_C2_TRACE=$OUT/c2_trace.txt timeout 300 python bench.py --steps 5 --warmup 3 --no-extras --no-cpu > /dev/null 2>&1; python tools/c2_trace.py $OUT/c2_trace.txt --raw | tee $OUT/c2_trace_summary.txt | head -8
+timeout 120 tools/micro/env_floor > $OUT/env_floor.txt 2>&1
+timeout 600 python tools/c2_ab.py 2>&1 | tee $OUT/c2_ab.txt
 echo "== sanitizer"
 timeout 900 compute-sanitizer --tool memcheck python tools/sanitize_run.py > $OUT/compute_sanitizer_memcheck.log 2>&1; tail -3 $OUT/compute_sanitizer_memcheck.log
 timeout 900 compute-sanitizer --tool racecheck python tools/sanitize_run.py > $OUT/compute_sanitizer_racecheck.log 2>&1; tail -3 $OUT/compute_sanitizer_racecheck.log
