@@ -438,20 +438,18 @@ def main():
             host_done[i].record(stream)
             e2e_k[0] += 1
         elif mixdown is not None:
-            # fused peer mix-down: the exchange kernel of block k delivers the rank-order sum of block k-1 into a device buffer on rank 0; a copy
-            # stream of its own waits for that kernel and reads the buffer back into pinned memory (two device and two host buffers, each joined
+            # fused peer mix-down: the exchange kernel of block k delivers the rank-order sum of block k-1 straight into pinned host memory on rank 0
+            # (device-mapped: 16 KiB of stores over PCIe inside the kernel; two host buffers, each joined through an event behind that kernel
             # before reuse, the last block by drain_e2e() inside the timed region).  Every block's reduced mix crosses PCIe.
             k = e2e_k[0]
             i = k & 1
             if rank == 0 and k >= 2:
                 host_done[i].synchronize()
             bank.events(next_events())
-            bank.process_mixdown(mixdown, mix_bufs[i] if rank == 0 else None, BLOCK, kb.MIX_SUM)
+            bank.process_mixdown(mixdown, host_bufs[i] if rank == 0 else None, BLOCK, kb.MIX_SUM)     # (pinned: the exchange kernel stores the sum over PCIe)
             if rank == 0 and k >= 1:
                 mixdown.stream_wait(copy_stream.cuda_stream)
-                with torch.cuda.stream(copy_stream):
-                    host_bufs[i].copy_(mix_bufs[i], non_blocking=True)
-                    host_done[i].record(copy_stream)
+                host_done[i].record(copy_stream)
             e2e_k[0] += 1
         else:
             step_device()
@@ -535,7 +533,7 @@ def main():
            "h2d_bytes_per_step": int((h2d1 - h2d0) / args.steps), "d2h_bytes_per_step": int((d2h1 - d2h0) / args.steps + out_bytes),
            "note": "per step: the host applies 64 note events on its state mirror (packed dirty-voice upload H2D), kernels, output D2H "
                    "into pinned memory (N=1: KB_ASYNC_HOST, two host buffers, block k+1's events are prepared while block k renders; "
-                   "every buffer is joined before reuse and at the end of the timed region; N>1, fused peer mix-down: the same with the reduced mix of block k-1 read back by a copy stream while block k renders; N>1 over NCCL: joined and read back every block); "
+                   "every buffer is joined before reuse and at the end of the timed region; N>1, fused peer mix-down: the same with the reduced mix of block k-1 stored into pinned host memory by the exchange kernel while block k renders; N>1 over NCCL: joined and read back every block); "
                    "bytes counted by the library"}
 
     # ---- dominant kernel, CUDA events inside the library

@@ -320,12 +320,13 @@ class SynthBank:
 
     def process_mixdown(self, mixdown, out_prev, n, flags=0):
         """process(KB_BANK_MIX) whose bank-mix kernel stores into rank 0's arena (sharding.PeerMixdown); on rank 0 `out_prev` (a torch CUDA
-        tensor [channels, n]) receives the rank-order sum of the PREVIOUS block."""
+        tensor [channels, n], or a pinned host tensor the kernel writes over PCIe) receives the rank-order sum of the PREVIOUS block."""
         p = 0
         if out_prev is not None:
             p, dev = _ptr(out_prev, self.channels * n, "kb_synth_bank_process_mixdown out_prev", self.device)
-            if not dev:
-                raise KlangB200Error("kb_synth_bank_process_mixdown: out_prev must be device memory")
+            # device memory, or page-locked host memory (device-mapped under unified addressing: the exchange kernel stores the sum into it)
+            if not dev and not (hasattr(out_prev, "is_pinned") and out_prev.is_pinned()):
+                raise KlangB200Error("kb_synth_bank_process_mixdown: out_prev must be device memory or a page-locked (pinned) torch tensor")
         _check(lib().kb_synth_bank_process_mixdown(self.h, mixdown.h, p, n, flags), "kb_synth_bank_process_mixdown")
 
     def process_into_device_ptr(self, ptr, n, flags=0):

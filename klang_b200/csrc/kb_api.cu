@@ -639,6 +639,9 @@ struct kb_synth_bank : kb_bank_base {
 	float *d_scratch = nullptr, *d_out = nullptr, *d_adsr = nullptr, *d_mix = nullptr;
 	// kb_synth_bank_process_mixdown: the exchange kernel of block k runs on a side stream beside the voice kernels of block k + 1
 	cudaStream_t mix_stream = nullptr; cudaEvent_t ev_mix_in = nullptr; kb_mixdown* last_mixdown = nullptr;
+	// fused mix-down: the per-instance sums are double-buffered (block k's exchange kernel, on the side stream, reads buffer k & 1 while block
+	// k + 1's mix kernel writes the other one), so no event wait sits between a block's voice kernel and its mix kernel
+	float* d_out_alt = nullptr; cudaEvent_t ev_exch[2] = { nullptr, nullptr }; unsigned exch_count = 0;
 	KbStaged staged = {}; int staged_slot = -1;   // dirty-voice records the next voice kernel picks up itself (sy_upload with defer_scatter)
 	int total() const { return instances * voices; }
 	template <class T> T& vs(int v) { return *reinterpret_cast<T*>(vstate + (size_t)v * voice_bytes); }
@@ -838,6 +841,8 @@ extern "C" void kb_synth_bank_destroy(kb_synth_bank* b) {
 	cudaFree(b->d_hdr); cudaFree(b->d_vstate); cudaFree(b->d_blk); cudaFree(b->d_scratch); cudaFree(b->d_out); cudaFree(b->d_adsr); cudaFree(b->d_mix);
 	if (b->mix_stream) { cudaStreamSynchronize(b->mix_stream); cudaStreamDestroy(b->mix_stream); }
 	if (b->ev_mix_in) cudaEventDestroy(b->ev_mix_in);
+	for (int k = 0; k < 2; k++) if (b->ev_exch[k]) cudaEventDestroy(b->ev_exch[k]);
+	cudaFree(b->d_out_alt);
 	if (b->own_stream) cudaStreamDestroy(b->own_stream);
 	delete b;
 }
@@ -1061,6 +1066,19 @@ static int sy_process(kb_synth_bank* b, float* out, int n, unsigned flags, kb_mi
 	float* d_voice_dst = (per_voice && dev) ? out : b->d_scratch;
 	float* d_result_fused = nullptr;                 // set when kb_mix_fused_kernel has also written the bank mix
 	float* d_inst_dst = (!per_voice && !bank_mix && dev) ? out : b->d_out;
+	const bool exch_db = bank_mix && mixdown && b->graph != KB_SY_SYNTHX;
+	int exch_parity = 0;
+	if (exch_db) {
+		if (!b->d_out_alt) {
+			KB_CUDA(cudaMalloc(&b->d_out_alt, (size_t)b->instances * b->channels * b->max_block * sizeof(float)));
+			for (int k = 0; k < 2; k++) KB_CUDA(cudaEventCreateWithFlags(&b->ev_exch[k], cudaEventDisableTiming));
+		}
+		exch_parity = (int)(b->exch_count & 1);
+		d_inst_dst = exch_parity ? b->d_out_alt : b->d_out;
+		// the exchange kernel of block k - 2 read this buffer: waited for HERE, before the voice kernel (it finished a block ago), so that the
+		// mix kernel stays the voice kernel's programmatic dependent.  A plain process() in between wrote d_out behind wait_prev_exchange().
+		if (b->exch_count >= 2) KB_CUDA(cudaStreamWaitEvent(st, b->ev_exch[exch_parity], 0));
+	}
 	if (b->graph == KB_SY_SYNTHX) {
 		const int pthreads = total * 132;
 		kb_sx_prepare_kernel<<<(pthreads + 127) / 128, 128, 0, st>>>((KbSxVoice*)b->d_vstate, b->d_hdr, b->d_blk, b->voices, total, b->fs);
@@ -1200,7 +1218,7 @@ static int sy_process(kb_synth_bank* b, float* out, int n, unsigned flags, kb_mi
 		b->prof_end();
 		b->launches++;
 		if (!per_voice) {
-			rc = wait_prev_exchange(); if (rc) return rc;
+			if (!exch_db) { rc = wait_prev_exchange(); if (rc) return rc; }
 			// KB_MIX_FUSED=0 keeps the two-kernel mix (A/B measurement, same results)
 			static const bool mix_fused = !getenv("KB_MIX_FUSED") || atoi(getenv("KB_MIX_FUSED")) != 0;
 			if (mix_fused && C == 1 && (flags & KB_MIX_SUM)) {
@@ -1236,7 +1254,8 @@ static int sy_process(kb_synth_bank* b, float* out, int n, unsigned flags, kb_mi
 		if (!b->mix_stream) { KB_CUDA(cudaStreamCreateWithFlags(&b->mix_stream, cudaStreamNonBlocking)); KB_CUDA(cudaEventCreateWithFlags(&b->ev_mix_in, cudaEventDisableTiming)); }
 		KB_CUDA(cudaEventRecord(b->ev_mix_in, st));
 		KB_CUDA(cudaStreamWaitEvent(b->mix_stream, b->ev_mix_in, 0));
-		rc = mixdown_step(mixdown, b->d_out, b->instances, (size_t)C * n, C * n, out_prev, b->mix_stream); if (rc) return rc;
+		rc = mixdown_step(mixdown, d_inst_dst, b->instances, (size_t)C * n, C * n, out_prev, b->mix_stream); if (rc) return rc;
+		if (exch_db) { KB_CUDA(cudaEventRecord(b->ev_exch[exch_parity], b->mix_stream)); b->exch_count++; }
 		b->last_mixdown = mixdown;
 		b->launches++;
 		b->host_stale = true; b->hdr_stale = true; b->vstate_stale = true;
