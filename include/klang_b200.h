@@ -79,7 +79,9 @@ extern "C" {
 #define KB_BANK_MIX 8u            /* synth: additionally sum all instances, out = [channels][n] (the multi-GPU mix-down input) */
 #define KB_ASYNC_HOST 64u         /* host-pointer call: return once the work and the device-to-host copy are queued on the bank stream;
                                      `io` / `out` must be page-locked and is valid after kb_*_bank_sync (or an event the caller
-                                     records on its stream).  Lets a host prepare block k+1's events while block k renders. */
+                                     records on its stream).  Lets a host prepare block k+1's events while block k renders.
+                                     (A page-locked, device-mapped `out` of a synth bank's KB_BANK_MIX | KB_MIX_SUM call is written by the mix
+                                     kernel itself — no copy is queued — with or without this flag; the bytes and their validity are the same.) */
 
 typedef struct kb_fx_bank kb_fx_bank;
 typedef struct kb_synth_bank kb_synth_bank;
@@ -224,7 +226,7 @@ int kb_mixdown_put(kb_mixdown* m, const float* src, int count, void* cuda_stream
 int kb_mixdown_collect(kb_mixdown* m, float* dst, int count, void* cuda_stream);
 /* The fused form — ONE kernel per block and rank, no acquire / publish / collect launches: the kernel waits for the slot of the step to be
  * free, stores `count` floats of `src` (device memory) into it, raises the rank's flag, and on rank 0 additionally sums the slots of the
- * PREVIOUS step in rank order into out_prev (device memory, rank 0 only; ignored elsewhere).  The exchange of block k thus runs beside the
+ * PREVIOUS step in rank order into out_prev (device memory, or page-locked device-mapped host memory; rank 0 only; ignored elsewhere).  The exchange of block k thus runs beside the
  * kernels of block k + 1; kb_mixdown_collect() after the last block returns the last sum.  Do not mix with acquire / publish in one step. */
 int kb_mixdown_step(kb_mixdown* m, const float* src, int count, float* out_prev, void* cuda_stream);
 /* queue on `stream` a wait for the exchange kernel of the last fused step (a consumer of out_prev on a stream of its own) */
