@@ -271,7 +271,7 @@ int kb_prim_stereo_delay(int n, const float* inl, const float* inr, const float*
 int kb_prim_control_smooth(float lo, float hi, float initial, int n, const float* values, float* out);
 /* Envelope::at(t[s]) on the breakpoints xy = {x0, y0, x1, y1, ...}                              klang.h:3929-3942 */
 int kb_prim_envelope_at(int npts, const float* xy, int n, const float* t, float* out);
-/* libm agreement probe: out[i] = device sinf / cosf / tanhf of x[i] (fn 0 / 1 / 2) */
+/* libm agreement probe: out[i] = device sinf / cosf / tanhf / expf of x[i] (fn 0 / 1 / 2 / 3) */
 int kb_prim_math(int fn, int n, const float* x, float* out);
 
 #ifdef __cplusplus

@@ -547,5 +547,5 @@ class Engine:
     def math(self, fn, x):
         x = np.ascontiguousarray(x, np.float32)
         out = np.zeros_like(x)
-        _check(lib().kb_prim_math({"sinf": 0, "cosf": 1, "tanhf": 2}[fn], len(x), x.ctypes.data, out.ctypes.data), "kb_prim_math")
+        _check(lib().kb_prim_math({"sinf": 0, "cosf": 1, "tanhf": 2, "expf": 3}[fn], len(x), x.ctypes.data, out.ctypes.data), "kb_prim_math")
         return out

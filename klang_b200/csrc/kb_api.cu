@@ -1664,7 +1664,7 @@ extern "C" int kb_prim_adsr(float A, float D, float S, float R, float fs, int n,
 }
 extern "C" int kb_prim_math(int fn, int n, const float* x, float* out) {
 	if (kb_device_count() < 1) return kb_fail(KB_ENODEV, "no CUDA device");
-	if (fn < 0 || fn > 2 || !x || !out || n < 0) return kb_fail(KB_EINVAL, "kb_prim_math: bad argument");
+	if (fn < 0 || fn > 3 || !x || !out || n < 0) return kb_fail(KB_EINVAL, "kb_prim_math: bad argument");
 	DevBuf dx(sizeof(float) * n, x), dout(sizeof(float) * n);
 	kb_prim_math_kernel<<<148, 256>>>(fn, n, dx.as<float>(), dout.as<float>());
 	int rc = prim_finish("kb_prim_math"); if (rc) return rc;

@@ -66,9 +66,9 @@ KB_KD SampleRate kb_fs() {
 
 struct signal {                                                                               // klang.h:1062-1166: the operator set as written there,
 	float value;                                                                              // so that every expression has the reference's types
-	KB_KD signal(float v = 0.f) : value(v) {}
-	KB_KD signal(double v) : value((float)v) {}
-	KB_KD signal(int v) : value((float)v) {}
+	KB_KD constexpr signal(float v = 0.f) : value(v) {}                                      // (constexpr: a program's namespace-scope constants
+	KB_KD constexpr signal(double v) : value((float)v) {}                                    //  are also emitted as __device__ objects, which need
+	KB_KD constexpr signal(int v) : value((float)v) {}                                       //  constant initialisation)
 	KB_KD signal(const constant& c) : value(c.f) {}                                          // klang.h:1067
 	KB_KD const signal& operator<<(const signal& input) { value = input.value; return *this; }   // feedback operator   klang.h:1079-1083
 	KB_KD signal& operator>>(signal& dst) const { dst.value = value; return dst; }               // `a >> out`          klang.h:1085-1089
@@ -256,6 +256,16 @@ namespace Filters {
 		KB_KD void process() { out = in * a + out * b; }
 	};
 }
+namespace Filters { namespace OnePole {
+	template <int TYPE> struct FilterT : ModifierT<FilterT<TYPE>> {                           // OnePole::Filter + LPF / HPF   klang.h:5470-5545
+		KbOnePole p;
+		FilterT() { kb_onepole_construct(p, TYPE); }
+		KB_KD void reset() { kb_onepole_reset(p); }
+		KB_KD void set(param f) { kb_onepole_set(kb_fs().k, p, f); }
+		KB_KD void process() { p.out = this->out; this->out = kb_onepole_tick(p, this->in); }
+	};
+	typedef FilterT<KB_OP_LPF> LPF; typedef FilterT<KB_OP_HPF> HPF;
+} }
 namespace Filters { namespace Biquad {
 	template <int TYPE> struct FilterT : ModifierT<FilterT<TYPE>> {                           // Biquad::Filter + LPF / HPF   klang.h:5550-5687
 		KbBiquad b;
@@ -348,6 +358,12 @@ template <class T> KB_KD T random(const T min, const T max) {                   
 }
 KB_KD float power(float base, float e) {                                                      // klang.h:187-218, as Pitch -> Frequency uses it
 #ifdef __CUDA_ARCH__
+	// base 10 goes through expf in the reference (klang.h:206) and expf is restated for the device (kb_expf); a general powf is not
+	if (base == 10.f) return kb_expf(e * (float)2.3025850929940456840179914546843642076011014886287729760333279009);
+	else if (e == 0.f) return 1.f;
+	else if (e == 1.f) return base;
+	else if (e == 2.f) return base * base;
+	else if (e == 3.f) return base * base * base;
 	__trap(); return base * e;
 #else
 	if (base == 10.f) return (float)::expf(e * (float)2.3025850929940456840179914546843642076011014886287729760333279009);
@@ -360,6 +376,12 @@ KB_KD float power(float base, float e) {                                        
 }
 struct Amplitude : signal { using signal::signal; KB_KD Amplitude(const signal& s) : signal(s) {} };
 typedef Amplitude Velocity;
+struct dB : signal {                                                                          // klang.h:1609-1621: `x -> Amplitude` (a thread-local there; here
+	using signal::signal;                                                                     //  operator-> hands out a value that carries it, so a const dB works)
+	struct Conversion { signal Amplitude; KB_KD const Conversion* operator->() const { return this; } };
+	KB_KD constexpr dB(const signal& s) : signal(s) {}
+	KB_KD Conversion operator->() const { Conversion c; c.Amplitude = power(10.f, value * 0.05f); return c; }
+};
 struct Pitch : signal {                                                                       // klang.h:1551-1578 (Frequency: a member here, a thread-local there)
 	using signal::signal;
 	signal Frequency;
@@ -474,6 +496,15 @@ KB_KD float tanh(float x) {
 	return ::tanhf(x);
 #endif
 }
+KB_KD float exp(float x) {                                                                    // (`exp(float)` binds to expf)
+#ifdef __CUDA_ARCH__
+	return kb_expf(x);
+#else
+	return ::expf(x);
+#endif
+}
+KB_KD float kb_tanh(float x) { return tanh(x); }                                              // kcc rewrites a program's unqualified tanh( / exp( to these:
+KB_KD float kb_exp(float x) { return exp(x); }                                                //  with a plain float argument ::tanh(float) of <cmath> would tie
 KB_KD float abs(float x) { return ::fabsf(x); }
 KB_KD float sqr(float x) { return x * x; }
 KB_KD float cube(float x) { return x * x * x; }
@@ -651,7 +682,7 @@ template <class NOTE> __global__ void kb_user_note_kernel(NOTE* __restrict__ not
 		nt.prepare();
 		for (int t = 0; t < n; t++) { nt.process(); o[t] = nt.out; }
 	};
-	if constexpr (sizeof(NOTE) <= 4096) { NOTE nt = notes[v]; run(nt); notes[v] = nt; } else run(notes[v]);
+	if constexpr (sizeof(NOTE) <= 4096) { NOTE nt = notes[v]; run(nt); memcpy((void*)&notes[v], (const void*)&nt, sizeof(NOTE)); } else run(notes[v]);   // (bytes: a note with a const member has no operator=)
 }
 // Synth::process voice loop for a mono synth (klang.h:4450-4456): every active note ASSIGNS the block, so it holds the last active note's
 // stream; thread = (instance, sample)

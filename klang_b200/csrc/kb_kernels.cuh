@@ -692,7 +692,7 @@ __global__ void kb_prim_env_kernel(KbEnv e, KbFs fs, int n, int release_at, floa
 }
 __global__ void kb_prim_math_kernel(int fn, int n, const float* x, float* out) {
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-		out[i] = fn == 0 ? kb_sinf(x[i]) : fn == 1 ? kb_cosf(x[i]) : kb_tanhf(x[i]);
+		out[i] = fn == 0 ? kb_sinf(x[i]) : fn == 1 ? kb_cosf(x[i]) : fn == 2 ? kb_tanhf(x[i]) : kb_expf(x[i]);
 }
 
 // Stereo::Delay<1000> (klang.h:4647-4700), sample by sample: `x >> delay` writes both lines at the same position (Bank<Delay,2>,

@@ -93,6 +93,73 @@ KB_D void kb_sincosf(float y, float& sn, float& cs) {
 KB_D float kb_sinf(float y) { return kb_sincosf_impl(y, 0); }
 KB_D float kb_cosf(float y) { return kb_sincosf_impl(y, 1); }
 
+// expf (TB303.k's Filter::set evaluates `exp()` per sample; OnePole::set does when a program sets it per sample): glibc 2.39's expf
+// (sysdeps/ieee754/flt-32/e_expf.c — the ARM optimized-routines algorithm: x*N/ln2 = k + r, 2^(k/N) from a 32-entry table, a cubic in r, all in
+// double) restated operation by operation.  The table is 2^(i/32) with the exponent pre-subtracted (bits(2^(i/32)) - (i << 47)), regenerated from
+// exact integer arithmetic.  glibc's FMA build (e_expf-fma.c, selected on every x86-64 host with FMA + AVX2) contracts four sites — `r = z - kd`
+// with z = InvLn2N * x, and the three polynomial steps; with exactly these the restatement is bit-identical to the build host's libm for ALL
+// 2^32 floats (without the first one, two inputs differ by an ulp).  KB_LIBM_NO_FMA for a host without FMA.
+__device__ __constant__ unsigned long long kb_exp2f_tab[32] = {
+0x3ff0000000000000ull,
+0x3fefd9b0d3158574ull,
+0x3fefb5586cf9890full,
+0x3fef9301d0125b51ull,
+0x3fef72b83c7d517bull,
+0x3fef54873168b9aaull,
+0x3fef387a6e756238ull,
+0x3fef1e9df51fdee1ull,
+0x3fef06fe0a31b715ull,
+0x3feef1a7373aa9cbull,
+0x3feedea64c123422ull,
+0x3feece086061892dull,
+0x3feebfdad5362a27ull,
+0x3feeb42b569d4f82ull,
+0x3feeab07dd485429ull,
+0x3feea47eb03a5585ull,
+0x3feea09e667f3bcdull,
+0x3fee9f75e8ec5f74ull,
+0x3feea11473eb0187ull,
+0x3feea589994cce13ull,
+0x3feeace5422aa0dbull,
+0x3feeb737b0cdc5e5ull,
+0x3feec49182a3f090ull,
+0x3feed503b23e255dull,
+0x3feee89f995ad3adull,
+0x3feeff76f2fb5e47ull,
+0x3fef199bdd85529cull,
+0x3fef3720dcef9069ull,
+0x3fef5818dcfba487ull,
+0x3fef7c97337b9b5full,
+0x3fefa4afa2a490daull,
+0x3fefd0765b6e4540ull
+};
+KB_D float kb_expf(float x) {
+	const double InvLn2N = 0x1.71547652b82fep+0 * 32, SHIFT = 0x1.8p+52;
+	const double C0 = 0x1.c6af84b912394p-5 / 32 / 32 / 32, C1 = 0x1.ebfce50fac4f3p-3 / 32 / 32, C2 = 0x1.62e42ff0c52d6p-1 / 32;
+	const double xd = (double)x;
+	const uint32_t abstop = kb_abstop12(x);
+	if (abstop >= 0x42b /* abstop12(88.0f) */) {
+		if (__float_as_uint(x) == 0xff800000u) return 0.0f;               // -inf
+		if (abstop >= 0x7f8) return x + x;                                // +inf, nan
+		if (x > 0x1.62e42ep6f) return __uint_as_float(0x7f800000u);       // overflow
+		if (x < -0x1.9fe368p6f) return 0.0f;                              // underflow
+	}
+	const double z = InvLn2N * xd;
+	double kd = z + SHIFT;
+	const unsigned long long ki = (unsigned long long)__double_as_longlong(kd);
+	kd -= SHIFT;
+	const double r = KB_MADD(InvLn2N, xd, -kd);
+	unsigned long long t = kb_exp2f_tab[ki % 32];
+	t += ki << (52 - 5);
+	const double s = __longlong_as_double((long long)t);
+	const double p = KB_MADD(C0, r, C1);
+	const double r2 = r * r;
+	double y = KB_MADD(C2, r, 1.0);
+	y = KB_MADD(p, r2, y);
+	y = y * s;
+	return (float)y;
+}
+
 // tanhf (TB303 soft clip, SynTHX post-fx): glibc 2.39 still ships the FDLIBM float routines
 // (sysdeps/ieee754/flt-32/s_tanhf.c on top of s_expm1f.c, no FMA variant), restated here operation by operation in
 // fp32; bit-identical to the host libm for every finite float (exhaustive check on the build host).

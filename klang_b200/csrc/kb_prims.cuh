@@ -281,7 +281,8 @@ enum { KB_OP_LPF = 0, KB_OP_HPF, KB_OP_BW1 };
 KB_HD void kb_onepole_construct(KbOnePole& p, int type) { memset(&p, 0, sizeof(p)); p.type = type; p.b0 = 1.f; }
 KB_HD void kb_onepole_reset(KbOnePole& p) { p.a1 = 0; p.b0 = 1; p.b1 = 0; p.f = 0; p.z = 0; }   // klang.h:5482-5488
 // OnePole::LPF::init / HPF::init — control-rate only (expf from the host libm)    klang.h:5508-5512, 5535-5541
-inline void kb_onepole_set(const KbFs& fs, KbOnePole& p, float f) {
+// (on the device — translated programs that set the filter per sample — expf is kb_expf, the restatement of the host's; tanf has none)
+KB_HD void kb_onepole_set(const KbFs& fs, KbOnePole& p, float f) {
 	if (p.f != f) {
 		p.f = f;
 		if (p.type == KB_OP_BW1) {                                             // Butterworth::LPF<1>::init  klang.h:5786-5793
@@ -290,7 +291,11 @@ inline void kb_onepole_set(const KbFs& fs, KbOnePole& p, float f) {
 			p.b0 = inv; p.a1 = (1.f - c) * inv;
 			return;
 		}
+#ifdef __CUDA_ARCH__
+		const float e = kb_expf(-f * fs.w);
+#else
 		const float e = ::expf(-f * fs.w);
+#endif
 		if (p.type == KB_OP_LPF) { p.b0 = 1 - e; p.a1 = e; }
 		else { p.b0 = 0.5f * (1.f + e); p.b1 = -p.b0; p.a1 = e; }
 	}

@@ -43,14 +43,25 @@ def translate(text, source_name="program.k"):
     else:
         raise KccError(f"{source_name}: no struct derived from Effect / Stereo::Effect / Synth (Stereo::Synth programs are not translated yet)")
     out = []
-    for line in text.splitlines():
+    depth = 0
+    for lineno, line in enumerate(text.splitlines(), 1):
         code, sep, comment = line.partition("//")
+        # a namespace-scope constant (`const float FREQ[6] = { ... };`) is a host object: device code gets a __device__ twin and the name picks
+        # the one of the side it is compiled for
+        gm = re.match(r"^\s*(?:static\s+)?const\s+([A-Za-z_][\w:]*)\s+([A-Za-z_]\w*)\s*((?:\[[^\]]*\])*)\s*=\s*(.+);\s*$", code) if depth == 0 else None
+        depth += code.count("{") - code.count("}")
+        if gm:
+            ty, name, dims, init = gm.groups()
+            out.append(f"const {ty} {name}_kbh{dims} = {init}; __device__ const {ty} {name}_kbd{dims} = {init};{sep}{comment}")
+            out.append(f"#ifdef __CUDA_ARCH__\n#define {name} {name}_kbd\n#else\n#define {name} {name}_kbh\n#endif\n#line {lineno + 1}")
+            continue
         # klang::fs is a host global and `debug` a host object: device code reads the bank's rate through kb_fs() and taps into a sink value
         code = re.sub(r"\bklang::fs\b", "kb_fs()", code)
         code = re.sub(r"(?<![\w.>:])fs\b(?!\s*[\(:])", "kb_fs()", code)
         code = re.sub(r">>\s*debug\b", ">> klang::Debug()", code)
         code = re.sub(r"(?<![\w.>:])(pi|ln2|root2)\b(?!\s*[\(:])", r"kb_\1()", code)
         code = re.sub(r"(?<![\w.>:])(min|max)\s*\(", r"kb_\1(", code)          # klang's own min / max (klang.h:221-224), not ::min / ::max
+        code = re.sub(r"(?<![\w.>:])(tanh|exp)\s*\(", r"kb_\1(", code)         # the float overloads that restate the host's libm on the device
         line = code + sep + comment
         if re.match(r"\s*#\s*include\s*<klang\.h>", line):
             out.append("// (klang.h -> klang_b200/csrc/kb_kdev.cuh)")
@@ -63,7 +74,7 @@ def translate(text, source_name="program.k"):
         fm = re.match(r"^(\s*)((?:static\s+|inline\s+|constexpr\s+)*)([A-Za-z_][\w:<>,\*&\s]*?[\w>\*&])\s+([A-Za-z_]\w*)\s*\(([^;{}]*)\)\s*(const\s*)?\{?\s*$", line)
         if fm and fm.group(4) not in _KEYWORDS and fm.group(3).split()[-1] not in _KEYWORDS | {"struct", "class", "namespace", "using", "typedef"} \
                 and "=" not in fm.group(3):
-            line = f"{fm.group(1)}KB_KD {line.lstrip()}"
+            line = f"{fm.group(1)}KB_KD {re.sub(r'^((?:static\s+|constexpr\s+)*)inline\s+', r'\1', line.lstrip())}"   # (KB_KD carries the inline)
         out.append(line)
     body = "\n".join(out)
     src = (f'// GENERATED by klang_b200/kcc.py from {source_name}: the program text below is the user\'s, with its functions marked __host__ __device__\n'

@@ -143,6 +143,9 @@ namespace k_reverb2 {
 namespace k_expression {
 #include "Subtractive/Expression.k"
 }
+namespace k_resynthesis {
+#include "Additive/Resynthesis.k"
+}
 
 // ---------------------------------------------------------------------------
 // Canonical C2 graph: examples/Subtractive/Filter.k's note with
@@ -602,6 +605,7 @@ void* ref_synth_create(int graph, int nvoices) {
 	case SY_MOD_FM2: { auto* p = make_synth<k_mod_fm2::FM2, k_mod_fm2::FM2::FM2Note>(nvoices); s->mono = p; s->controls = &p->controls; } break;
 	// programs the product has NO hand-written graph for (run from their own source, klang_b200/kcc.py): ids from 100
 	case 100: { auto* p = make_synth<k_expression::Expression, k_expression::Expression::ExpressionNote>(nvoices); s->mono = p; s->controls = &p->controls; } break;   // Subtractive/Expression.k
+	case 101: { auto* p = make_synth<k_resynthesis::Resynthesis, k_resynthesis::Resynthesis::ResynthesisNote>(nvoices); s->mono = p; s->controls = &p->controls; } break;   // Additive/Resynthesis.k
 	default: delete s; return nullptr;
 	}
 	s->nvoices = s->mono ? (int)s->mono->notes.count : (int)s->stereo->notes.count;

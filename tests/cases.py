@@ -301,6 +301,8 @@ TRANSLATED_FX_SCRIPTS = {
 #   name: (reference id, path under examples/, nvoices, started voices, blocks, block size, release block base, [(block, control, value)])
 TRANSLATED_SYNTH_SCRIPTS = {
     "k_expression": (100, "Subtractive/Expression.k", 32, 8, 10, 4096, 4, []),   # three Saws with an enveloped vibrato LFO, LPF; on() draws random() four times per note
+    # six Sine partials of the program's own Oscillator, each scaled by `GAIN[o] -> Amplitude` (dB -> expf) per sample; namespace-scope constants
+    "k_resynthesis": (101, "Additive/Resynthesis.k", 32, 8, 6, 2048, 2, []),
 }
 
 

@@ -82,6 +82,18 @@ def test_device_tanhf_matches_host_libm(eng):
     assert_parity(eng.math("tanhf", x), want, "device tanhf", exact=True)
 
 
+def test_device_expf_matches_host_libm(eng):
+    """kb_expf restates glibc's expf (double-precision table + cubic, FMA build): bit-identical to the box's libm — exhaustively so on the build
+    host (all 2^32 floats); here a million arguments over the ranges programs use and the special cases."""
+    libm = C.CDLL("libm.so.6")
+    libm.expf.restype, libm.expf.argtypes = C.c_float, [C.c_float]
+    x = np.concatenate([cases.noise(400000, seed=21, lo=-4.0, hi=0.5), cases.noise(300000, seed=22, lo=-104.0, hi=89.0), cases.noise(200000, seed=23, lo=-0.05, hi=0.05),
+                        np.float32(2.0) ** np.arange(-60, 8, dtype=np.float32), -(np.float32(2.0) ** np.arange(-60, 8, dtype=np.float32)),
+                        np.array([0.0, -0.0, 88.0, 88.72, 88.73, -103.9, -104.0, float.fromhex('0x1.04845ep+5'), float.fromhex('-0x1.f8cbb2p+5'), np.inf, -np.inf], np.float32)]).astype(np.float32)
+    want = np.array([libm.expf(float(v)) for v in x], np.float32)
+    assert_parity(eng.math("expf", x), want, "device expf", exact=True)
+
+
 # ------------------------------------------------------------------------------------------ primitives
 PRIM_EXACT = ("osc/fast_", "osc/basic_sine", "osc/wt_", "filter/biquad_lpf", "filter/biquad_hpf",
               "filter/onepole_lpf/impulse", "filter/onepole_lpf/coeffs", "filter/onepole_hpf/impulse", "filter/onepole_hpf/coeffs",

@@ -48,6 +48,8 @@ EDITED = "gain_edited"
 SYNTHS = {"filter_k": ("Subtractive/Filter.k", "filter_k"), "breakpoint": ("Subtractive/Breakpoint.k", "breakpoint"), "ramp": ("Subtractive/Ramp.k", "ramp"),
           "release": ("Subtractive/Release.k", "release"), "release_slow_attack": ("Subtractive/Release.k", "release"), "supersaw": ("SuperSaw.k", "supersaw"),
           "supersaw_wide": ("SuperSaw.k", "supersaw"), "am": ("Modulation/AM.k", "am"), "mod_fm": ("Modulation/FM.k", "mod_fm"), "mod_fm2": ("Modulation/FM2.k", "mod_fm2"),
+          # TB303.k from its own text: the ladder filter's set() evaluates exp() on the device every sample (kb_expf), OnePole::HPF, tanh
+          "tb303": ("TB303.k", "tb303"), "tb303_square": ("TB303.k", "tb303"),
           "additive_saw": ("Additive/Saw.k", "additive_saw"), "additive_square": ("Additive/Square.k", "additive_square"), "additive_nyquist": ("Additive/Nyquist.k", "additive_nyquist")}
 
 
