@@ -1385,12 +1385,25 @@ extern "C" int kb_mixdown_collect(kb_mixdown* m, float* dst, int count, void* st
 //   (c) the last CTA to finish raises the rank's flag behind a system-scope fence;
 //   (d) on rank 0 the same kernel then sums the slots of the PREVIOUS step in rank order into out_prev and marks that step consumed:
 //       the exchange of block k overlaps the voice kernels of block k + 1, and a late rank never stalls the others' current block.
-__global__ void __launch_bounds__(256) kb_mixdown_step_kernel(const float* __restrict__ src, int rows, size_t row_stride, int count, float* __restrict__ slot,
+__global__ void __launch_bounds__(256, 8) kb_mixdown_step_kernel(const float* __restrict__ src, int rows, size_t row_stride, int count, float* __restrict__ slot,
                                                               volatile unsigned* flags, volatile unsigned* consumed, unsigned* tickets, unsigned step, int rank, int world,
                                                               const float* prev_slots, size_t slot_floats, float* __restrict__ out_prev, int do_prev) {
 	__shared__ bool s_last;
 	if (threadIdx.x == 0 && step > 2) while ((int)(*consumed - (step - 2)) < 0) __nanosleep(200);
 	__syncthreads();
+	// (128-bit accesses with the rows' loads in flight together where the layout allows: one small CTA moves the whole mix)
+	const bool vec = (count & 3) == 0 && (row_stride & 3) == 0 && ((reinterpret_cast<size_t>(src) | reinterpret_cast<size_t>(slot)) & 15) == 0;
+	if (vec) {
+		const float4* s4 = reinterpret_cast<const float4*>(src);
+		float4* d4 = reinterpret_cast<float4*>(slot);
+		const size_t rs4 = row_stride / 4;
+		for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count / 4; i += gridDim.x * blockDim.x) {
+			float4 acc = s4[i];
+			#pragma unroll 4
+			for (int k = 1; k < rows; k++) { const float4 v = s4[(size_t)k * rs4 + i]; acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }   // row order kept per sample
+			d4[i] = acc;
+		}
+	} else
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
 		float acc = src[i];
 		for (int k = 1; k < rows; k++) acc += src[(size_t)k * row_stride + i];
@@ -1406,6 +1419,17 @@ __global__ void __launch_bounds__(256) kb_mixdown_step_kernel(const float* __res
 	for (int r = threadIdx.x; r < world; r += blockDim.x) while ((int)(flags[r] - (step - 1)) < 0) __nanosleep(100);
 	__syncthreads();
 	__threadfence_system();
+	const bool vec_prev = (count & 3) == 0 && (slot_floats & 3) == 0 && ((reinterpret_cast<size_t>(prev_slots) | reinterpret_cast<size_t>(out_prev)) & 15) == 0;
+	if (vec_prev) {
+		const float4* p4 = reinterpret_cast<const float4*>(prev_slots);
+		const size_t sf4 = slot_floats / 4;
+		for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count / 4; i += gridDim.x * blockDim.x) {
+			float4 acc = __ldcv(p4 + i);                                   // (peer-written memory: never from a stale cache line)
+			#pragma unroll 4
+			for (int r = 1; r < world; r++) { const float4 v = __ldcv(p4 + (size_t)r * sf4 + i); acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }   // rank order
+			reinterpret_cast<float4*>(out_prev)[i] = acc;
+		}
+	} else
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
 		float acc = __ldcv(prev_slots + i);                                // (peer-written memory: never from a stale cache line)
 		for (int r = 1; r < world; r++) acc += __ldcv(prev_slots + (size_t)r * slot_floats + i);
@@ -1421,7 +1445,12 @@ static int mixdown_step(kb_mixdown* m, const float* src, int rows, size_t row_st
 	if (!m->d_tickets) { KB_CUDA(cudaMalloc(&m->d_tickets, 2 * sizeof(unsigned))); KB_CUDA(cudaMemset(m->d_tickets, 0, 2 * sizeof(unsigned))); }
 	const unsigned step = ++m->step;
 	const int do_prev = (m->rank == 0 && step > 1 && m->collected < step - 1 && out_prev) ? 1 : 0;
-	kb_mixdown_step_kernel<<<std::max(1, std::min(32, (count + 255) / 256)), 256, 0, stream>>>(src, rows, row_stride, count, m->slot(step, m->rank), m->flags(), m->consumed(), m->d_tickets,
+	// ONE CTA of 128 threads and at most 32 registers by default (KB_MIXDOWN_CTAS / KB_MIXDOWN_THREADS: A/B).  The exchange kernel runs beside
+	// the next block's voice kernel, whose CTAs take 61440 of an SM's 65536 registers: this CTA fits into the 4096 that are left on ANY SM, so it
+	// never keeps a voice CTA out while it waits for the peers' flags (32 CTAs of 256 threads did, on 32 SMs: +10 us per block at N > 1)
+	static const int exch_ctas = getenv("KB_MIXDOWN_CTAS") ? std::max(1, atoi(getenv("KB_MIXDOWN_CTAS"))) : 1;
+	static const int exch_threads = getenv("KB_MIXDOWN_THREADS") ? std::min(256, std::max(32, atoi(getenv("KB_MIXDOWN_THREADS")))) : 128;
+	kb_mixdown_step_kernel<<<std::max(1, std::min(exch_ctas, (count + 255) / 256)), exch_threads, 0, stream>>>(src, rows, row_stride, count, m->slot(step, m->rank), m->flags(), m->consumed(), m->d_tickets,
 	                                                                                          step, m->rank, m->world, m->slot(step - 1, 0), (size_t)m->max_floats, out_prev, do_prev);
 	if (do_prev) m->collected = step - 1;
 	KB_CUDA(cudaGetLastError());
