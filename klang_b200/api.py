@@ -235,6 +235,7 @@ class SynthBank:
 
     def __init__(self, graph, instances=1, voices=32, fs=44100.0, max_block=16384, device=0):
         self.h = lib().kb_synth_bank_create(graph, instances, voices, float(fs), max_block, device)
+        self._pinned_seen = set()          # pinned host buffers already accepted as `out_prev` (process_mixdown)
         if not self.h:
             raise KlangB200Error("kb_synth_bank_create: " + lib().kb_last_error().decode())
         self.graph, self.instances, self.max_block, self.device = graph, instances, max_block, device
@@ -325,8 +326,10 @@ class SynthBank:
         if out_prev is not None:
             p, dev = _ptr(out_prev, self.channels * n, "kb_synth_bank_process_mixdown out_prev", self.device)
             # device memory, or page-locked host memory (device-mapped under unified addressing: the exchange kernel stores the sum into it)
-            if not dev and not (hasattr(out_prev, "is_pinned") and out_prev.is_pinned()):
-                raise KlangB200Error("kb_synth_bank_process_mixdown: out_prev must be device memory or a page-locked (pinned) torch tensor")
+            if not dev and p not in self._pinned_seen:           # (is_pinned() asks the driver: ~10 us — once per buffer, not once per block)
+                if not (hasattr(out_prev, "is_pinned") and out_prev.is_pinned()):
+                    raise KlangB200Error("kb_synth_bank_process_mixdown: out_prev must be device memory or a page-locked (pinned) torch tensor")
+                self._pinned_seen.add(p)
         _check(lib().kb_synth_bank_process_mixdown(self.h, mixdown.h, p, n, flags), "kb_synth_bank_process_mixdown")
 
     def process_into_device_ptr(self, ptr, n, flags=0):
