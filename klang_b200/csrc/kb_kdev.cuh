@@ -340,6 +340,29 @@ struct Envelope : GeneratorT<Envelope> {                                        
 	KB_KD void process() { out = kb_env_tick(kb_fs().k, e); }                                 // klang.h:4018-4051
 	KB_KD signal& operator++(int) { process(); return out; }                                  // klang.h:4013-4016
 };
+// FM operator (klang.h:4139-4180): an oscillator whose phase offset is its input, scaled by its own envelope and an amplitude.  The reference
+// derives from the oscillator and overrides process() virtually; here the operator re-derives the dataflow base with its own type (static
+// dispatch) and carries Fast::Sine's state — the only oscillator the examples put in an Operator.  Restates kb_fm_op_tick (kb_graphs.cuh).
+template <class OSCILLATOR> struct Operator;
+template <> struct Operator<Generators::Fast::Sine> : GeneratorT<Operator<Generators::Fast::Sine>>, KbFastSine, kb_input_tag {
+	Envelope env;
+	signal amp, in;
+	Operator() : amp(1.f) { kb_fsine_init(*this); }
+	KB_KD void reset() { position = 0u; offset = 0u; }
+	KB_KD void set(param f) { kb_fsine_set_f(kb_fs().k, *this, f); }
+	KB_KD void set(param f, param phase) { kb_fsine_set_fp(kb_fs().k, *this, f, phase); }
+	KB_KD void input(const signal& source) { in = source; }                                   // Input::input (no hook)
+	KB_KD void operator<<(const signal& source) { in = source; }
+	KB_KD Operator& operator=(std::initializer_list<Envelope::Point> points) { env = points; return *this; }   // klang.h:4149-4152
+	KB_KD Operator& operator*(signal a) { amp = a; return *this; }                            // klang.h:4159-4162 (hides the Output arithmetic, as there)
+	KB_KD void process() {                                                                    // klang.h:4164-4168: set(+in) = Sine::set(relative), process, out *= env++ * amp
+		offset = kb_phase_from_radians(in.value * KB_TWO_PI_F);
+		this->out = kb_fsine_tick(*this);
+		this->out *= (float)(env++) * amp.value;
+	}
+	KB_KD Operator& operator>>(Operator& carrier) { carrier << kb_read(*this); return carrier; }   // klang.h:4170-4173: `carrier << *this` ticks this operator
+};
+
 struct ADSR : Envelope {                                                                      // ADSR   klang.h:4063-4138
 	ADSR() { kb_adsr_construct(kb_fs().k, e); }
 	KB_KD void set(param A, param D, param S, param R) { kb_adsr_set(kb_fs().k, e, A, D, S, R); }

@@ -146,6 +146,9 @@ namespace k_expression {
 namespace k_resynthesis {
 #include "Additive/Resynthesis.k"
 }
+namespace k_operators {
+#include "Modulation/Operators.k"
+}
 
 // ---------------------------------------------------------------------------
 // Canonical C2 graph: examples/Subtractive/Filter.k's note with
@@ -606,6 +609,7 @@ void* ref_synth_create(int graph, int nvoices) {
 	// programs the product has NO hand-written graph for (run from their own source, klang_b200/kcc.py): ids from 100
 	case 100: { auto* p = make_synth<k_expression::Expression, k_expression::Expression::ExpressionNote>(nvoices); s->mono = p; s->controls = &p->controls; } break;   // Subtractive/Expression.k
 	case 101: { auto* p = make_synth<k_resynthesis::Resynthesis, k_resynthesis::Resynthesis::ResynthesisNote>(nvoices); s->mono = p; s->controls = &p->controls; } break;   // Additive/Resynthesis.k
+	case 102: { auto* p = make_synth<k_operators::Operators, k_operators::Operators::OperatorsNote>(nvoices); s->mono = p; s->controls = &p->controls; } break;   // Modulation/Operators.k
 	default: delete s; return nullptr;
 	}
 	s->nvoices = s->mono ? (int)s->mono->notes.count : (int)s->stereo->notes.count;

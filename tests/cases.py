@@ -303,6 +303,8 @@ TRANSLATED_SYNTH_SCRIPTS = {
     "k_expression": (100, "Subtractive/Expression.k", 32, 8, 10, 4096, 4, []),   # three Saws with an enveloped vibrato LFO, LPF; on() draws random() four times per note
     # six Sine partials of the program's own Oscillator, each scaled by `GAIN[o] -> Amplitude` (dB -> expf) per sample; namespace-scope constants
     "k_resynthesis": (101, "Additive/Resynthesis.k", 32, 8, 6, 2048, 2, []),
+    # three Operator<Sine> in series (`(op1 * c1) >> (op2 * c3) >> op3) * adsr >> dcfilter`: the ADSR becomes op3's amplitude), Biquad HPF; controls read in on()
+    "k_operators": (102, "Modulation/Operators.k", 32, 8, 6, 2048, 2, [(0, 0, 1.0), (0, 1, 0.5), (0, 2, 1.0), (0, 3, 4.296), (0, 4, 2.0), (3, 1, 2.5)]),
 }
 
 
