@@ -145,8 +145,30 @@ struct Controls {                                                               
 };
 
 // UI-only objects of the constructors (`hardclip >> graph(-2,2,-2,2)`, klang.h:2536-2840): accepted, ignored
-struct Graph { };
+struct Graph { void clear() { } template <class T> void add(T) { } };                        // (`graph.clear()` / `graph.add(y)` in a note's on(): kcc routes `graph.` to kb_graph().)
 inline Graph graph(double = 0, double = 0, double = 0, double = 0) { return Graph(); }
+inline Graph kb_graph() { return Graph(); }
+
+// Lookup tables filled at start-up from a function (klang.h:3303-3400): host objects — the examples read them in constructors and on() only.
+template <class TYPE> struct Result {                                                         // klang.h:3306-3328
+	TYPE* y; int i; TYPE sum;
+	Result(TYPE* array, int index) : y(&array[index]), i(index), sum(0) { }
+	TYPE& operator[](int index) { return *(y + index); }
+	operator TYPE() const { return *y; }
+	Result& operator=(const TYPE& in) { *y = in; return *this; }
+	TYPE& operator++(int) { i++; return *++y; }
+};
+#define FUNCTION(type) (void(*)(type, klang::Result<type>&))[](type x, klang::Result<type>& y)
+template <class TYPE, int SIZE> struct Table {                                                // klang.h:3330-3400 (Array<TYPE, SIZE> reduced to its items)
+	TYPE items[SIZE]; int count;
+	Table(TYPE (*function)(TYPE)) : count(0) { for (int x = 0; x < SIZE; x++) items[count++] = function((TYPE)x); }
+	Table(void (*function)(TYPE, Result<TYPE>&)) : count(SIZE) {
+		Result<TYPE> y(items, 0);
+		for (int x = 0; x < SIZE; x++) { function((TYPE)x, y); y.sum += items[x]; y++; }
+	}
+	Table(std::initializer_list<TYPE> values) : count(0) { for (TYPE v : values) if (count < SIZE) items[count++] = v; }
+	TYPE operator[](int index) const { return items[index]; }
+};
 template <class F> inline void operator>>(F, Graph&&) { }
 template <class F> inline void operator>>(F, Graph&) { }
 
@@ -399,6 +421,7 @@ KB_KD float power(float base, float e) {                                        
 }
 struct Amplitude : signal { using signal::signal; KB_KD Amplitude(const signal& s) : signal(s) {} };
 typedef Amplitude Velocity;
+struct Frequency : signal { using signal::signal; KB_KD constexpr Frequency(const signal& s) : signal(s) {} };   // klang.h:1580-1590 (a param with a unit)
 struct dB : signal {                                                                          // klang.h:1609-1621: `x -> Amplitude` (a thread-local there; here
 	using signal::signal;                                                                     //  operator-> hands out a value that carries it, so a const dB works)
 	struct Conversion { signal Amplitude; KB_KD const Conversion* operator->() const { return this; } };

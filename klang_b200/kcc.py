@@ -59,6 +59,7 @@ def translate(text, source_name="program.k"):
         code = re.sub(r"\bklang::fs\b", "kb_fs()", code)
         code = re.sub(r"(?<![\w.>:])fs\b(?!\s*[\(:])", "kb_fs()", code)
         code = re.sub(r">>\s*debug\b", ">> klang::Debug()", code)
+        code = re.sub(r"(?<![\w.>:])graph\s*\.", "kb_graph().", code)             # `graph.clear()` / `graph.add(y)`: the UI plot, a host object there
         code = re.sub(r"(?<![\w.>:])(pi|ln2|root2)\b(?!\s*[\(:])", r"kb_\1()", code)
         code = re.sub(r"(?<![\w.>:])(min|max)\s*\(", r"kb_\1(", code)          # klang's own min / max (klang.h:221-224), not ::min / ::max
         code = re.sub(r"(?<![\w.>:])(tanh|exp)\s*\(", r"kb_\1(", code)         # the float overloads that restate the host's libm on the device
@@ -72,6 +73,9 @@ def translate(text, source_name="program.k"):
         line = re.sub(r"\)\s*override\b", ")", line)
         # a function definition: [qualifiers] type name(args) [const] {     — not a control statement, not a constructor (no return type)
         fm = re.match(r"^(\s*)((?:static\s+|inline\s+|constexpr\s+)*)([A-Za-z_][\w:<>,\*&\s]*?[\w>\*&])\s+([A-Za-z_]\w*)\s*\(([^;{}]*)\)\s*(const\s*)?\{?\s*$", line)
+        # a note's on() / off() run on the host mirror only (kb_kdev.cuh): they stay host functions, so they may read host tables (FM.k)
+        if fm and fm.group(3).strip() == "event" and fm.group(4) in ("on", "off"):
+            fm = None
         if fm and fm.group(4) not in _KEYWORDS and fm.group(3).split()[-1] not in _KEYWORDS | {"struct", "class", "namespace", "using", "typedef"} \
                 and "=" not in fm.group(3):
             line = f"{fm.group(1)}KB_KD {re.sub(r'^((?:static\s+|constexpr\s+)*)inline\s+', r'\1', line.lstrip())}"   # (KB_KD carries the inline)

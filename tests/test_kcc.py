@@ -50,6 +50,8 @@ SYNTHS = {"filter_k": ("Subtractive/Filter.k", "filter_k"), "breakpoint": ("Subt
           "supersaw_wide": ("SuperSaw.k", "supersaw"), "am": ("Modulation/AM.k", "am"), "mod_fm": ("Modulation/FM.k", "mod_fm"), "mod_fm2": ("Modulation/FM2.k", "mod_fm2"),
           # TB303.k from its own text: the ladder filter's set() evaluates exp() on the device every sample (kb_expf), OnePole::HPF, tanh
           "tb303": ("TB303.k", "tb303"), "tb303_square": ("TB303.k", "tb303"),
+          # FM.k from its own text: three Operator<Sine> in series; its start-up lookup tables (Table / FUNCTION) and graph plot stay on the host
+          "fm": ("FM.k", "fm"), "fm_deep": ("FM.k", "fm"),
           "additive_saw": ("Additive/Saw.k", "additive_saw"), "additive_square": ("Additive/Square.k", "additive_square"), "additive_nyquist": ("Additive/Nyquist.k", "additive_nyquist")}
 
 
