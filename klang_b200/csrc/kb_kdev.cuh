@@ -34,6 +34,13 @@ static KbFs kb_kd_fs_host = { 44100.f, 44100, 1.f / 44100.f, 2.0f * KB_PI_F * (1
 namespace klang {
 
 typedef void event;                                                                            // klang.h:242-243
+KB_KD float kb_kd_expf(float x) {                                                             // expf as the reference's translation unit sees it: the host's, restated on the device
+#ifdef __CUDA_ARCH__
+	return kb_expf(x);
+#else
+	return ::expf(x);
+#endif
+}
 struct constant {                                                                              // klang.h:93-113: a double, its float and the float of its inverse
 	double d; float f; float inv;
 	KB_KD constexpr constant(double value) : d(value), f((float)value), inv((float)(1.0 / value)) {}
@@ -117,7 +124,7 @@ struct Control {                                                                
 	KB_KD float smooth() { smoothed = smoothed.value * 0.999f + (1.f - 0.999f) * value.value; return smoothed; }   // klang.h:1715-1716
 	KB_KD Control& set(float x) { value = x < min ? min : (max < x ? max : x); return *this; }                      // std::clamp   klang.h:1725-1728
 };
-enum { KB_KD_ROTARY = 1, KB_KD_BUTTON, KB_KD_TOGGLE, KB_KD_SLIDER, KB_KD_MENU };
+enum { KB_KD_ROTARY = 1, KB_KD_BUTTON, KB_KD_TOGGLE, KB_KD_SLIDER, KB_KD_MENU, KB_KD_METER };
 inline Control Dial(const char* name, float min = 0.f, float max = 1.f, float initial = 0.f) { return { name, KB_KD_ROTARY, min, max, initial, initial, 0.f }; }
 inline Control Slider(const char* name, float min = 0.f, float max = 1.f, float initial = 0.f) { return { name, KB_KD_SLIDER, min, max, initial, initial, 0.f }; }
 inline Control Toggle(const char* name, bool initial = false) { return { name, KB_KD_TOGGLE, 0.f, 1.f, initial ? 1.f : 0.f, initial ? 1.f : 0.f, 0.f }; }
@@ -125,6 +132,24 @@ template <class... Options> inline Control Menu(const char* name, const Options*
 	return { name, KB_KD_MENU, 0.f, (float)sizeof...(Options) - 1.f, 0.f, 0.f, 0.f };
 }
 inline Control Button(const char* name) { return { name, KB_KD_BUTTON, 0.f, 1.f, 0.f, 0.f, 0.f }; }
+inline Control Meter(const char* name, float min = 0.f, float max = 1.f, float initial = 0.f) { return { name, KB_KD_METER, min, max, initial, initial, 0.f }; }   // klang.h:1838-1841
+enum Mode { Peak, RMS, Mean };                                                                // klang.h:88
+// A member that stands for one of the plugin's controls (klang.h:1775-1790).  The reference keeps a Control*; an object that travels to the
+// device as bytes cannot, so the link is the distance from this member to the control — both live inside the plugin object and move together.
+struct ControlMap {
+	long long rel;
+	KB_KD ControlMap() : rel(0) {}
+	KB_KD ControlMap(Control& c) : rel((const char*)&c - (const char*)this) {}
+	KB_KD ControlMap(const ControlMap& o) : rel(o.rel ? (const char*)&o + o.rel - (const char*)this : 0) {}
+	KB_KD ControlMap& operator=(const ControlMap& o) { rel = o.rel ? (const char*)&o + o.rel - (const char*)this : 0; return *this; }
+	KB_KD ControlMap& operator=(Control& c) { rel = (const char*)&c - (const char*)this; return *this; }
+	KB_KD Control& control() const { return *(Control*)((char*)this + rel); }
+	KB_KD operator signal&() { return control().value; }
+	KB_KD operator float() const { return control().value.value; }
+	KB_KD signal smooth() { return control().smooth(); }
+};
+KB_KD signal& operator>>(float v, ControlMap& m) { m.control().value = v; return m.control().value; }   // `gain(level) >> meter`
+KB_KD signal& operator>>(float v, Control& c) { c.value = v; return c.value; }
 
 struct ControlGroup {                                                                         // a control, or `{ "Caption", Dial(...), Dial(...) }`: a captioned group whose
 	Control items[8]; int count;                                                              // members join the table in order   klang.h:1835-1891
@@ -214,7 +239,10 @@ KB_KD_OUT_OP(+) KB_KD_OUT_OP(-) KB_KD_OUT_OP(*) KB_KD_OUT_OP(/)
 
 // `x >> debug` (klang.h:3132-3287): kcc rewrites the sink to a temporary of this type; the source is still evaluated (an Output ticks)
 struct Debug { };
-template <class S> KB_KD void operator>>(S&& source, Debug&&) { (void)kb_read(source); }
+template <class S> KB_KD signal operator>>(S&& source, Debug&&) { return kb_read(source); }     // (`(in >> debug) >> follower`: the tapped value flows on)
+// an Output into a control (`follower >> controls[0]`: a meter): ticks the source   klang.h:2209-2210
+template <class S, typename std::enable_if<std::is_base_of<kb_output_tag, typename std::remove_reference<S>::type>::value, int>::type = 0>
+KB_KD signal& operator>>(S&& source, Control& destination) { destination.value = kb_read(source); return destination.value; }
 
 // ------------------------------------------------------------------------------------------------ primitives with state (klang.h regions cited per class)
 // Thin klang-shaped classes over the POD state and the __host__ __device__ functions of kb_prims.cuh — the functions the hand-written graphs
@@ -347,6 +375,7 @@ struct Envelope : GeneratorT<Envelope> {                                        
 	KbEnv e;
 	struct Point { float x, y; template <class A, class B> KB_KD Point(A x_, B y_) : x((float)x_), y((float)y_) {} };   // klang.h:3835-3850
 	enum Stage { Sustain = KB_ENV_SUSTAIN, Release = KB_ENV_RELEASE, Off = KB_ENV_OFF };
+	struct Follower;                                                                          // klang.h:5861-5900 (defined below)
 	Envelope() { kb_env_construct(kb_fs().k, e); }
 	KB_KD Envelope& operator=(std::initializer_list<Point> points) {                          // klang.h:3884-3896
 		float xy[2 * KB_ENV_MAXPTS]; int n = 0;
@@ -393,6 +422,29 @@ struct ADSR : Envelope {                                                        
 	using Envelope::release;
 };
 
+// Envelope follower (klang.h:5861-5900): |in| or in^2 through an attack / release one-pole, rms takes the root.  The reference selects peak() /
+// rms() through a member-function pointer — a host address; here the mode is a flag.  expf is the host's on the host and its restatement on the
+// device (kb_math.cuh), sqrt / abs bind to sqrtf / fabsf.
+struct Envelope::Follower : ModifierT<Envelope::Follower> {
+	signal attack, release, A, R, ar;                                                         // AR: attack = release = 0, A = R = 1, its own out
+	int rms_mode;
+	Follower() : attack(0.f), release(0.f), A(1.f), R(1.f), ar(0.f), rms_mode(1) { set(0.01f, 0.1f); }
+	KB_KD void set(param attack_, param release_) {                                           // AR::set   klang.h:5871-5878
+		if (attack.value != attack_.value || release.value != release_.value) {
+			attack = attack_; release = release_;
+			A = 1.f - (attack_.value == 0.f ? 0.f : kb_kd_expf(-1.0f / (kb_fs().f * attack_.value)));
+			R = 1.f - (release_.value == 0.f ? 0.f : kb_kd_expf(-1.0f / (kb_fs().f * release_.value)));
+		}
+	}
+	KB_KD Follower& operator=(Mode mode) { rms_mode = mode == RMS ? 1 : 0; return *this; }
+	KB_KD void process() {                                                                    // peak(): abs(in) >> ar >> out;  rms(): (in * in) >> ar >> sqrt >> out
+		const float x = rms_mode ? in.value * in.value : ::fabsf(in.value);
+		const float smoothing = x > ar.value ? A.value : R.value;                             // AR::process   klang.h:5880-5883
+		ar = ar.value + smoothing * (x - ar.value);
+		out = rms_mode ? ::sqrtf(ar.value) : ar.value;
+	}
+};
+
 // host-only pieces of Note::on(): libc rand() and the host libm, exactly where the reference calls them (a device call would be a bug: trap)
 template <class T> KB_KD T random(const T min, const T max) {                                 // klang.h:236-237
 #ifdef __CUDA_ARCH__
@@ -426,6 +478,7 @@ struct dB : signal {                                                            
 	using signal::signal;                                                                     //  operator-> hands out a value that carries it, so a const dB works)
 	struct Conversion { signal Amplitude; KB_KD const Conversion* operator->() const { return this; } };
 	KB_KD constexpr dB(const signal& s) : signal(s) {}
+	KB_KD dB(const Control& c) : signal(c.value) {}
 	KB_KD Conversion operator->() const { Conversion c; c.Amplitude = power(10.f, value * 0.05f); return c; }
 };
 struct Pitch : signal {                                                                       // klang.h:1551-1578 (Frequency: a member here, a thread-local there)
@@ -550,7 +603,9 @@ KB_KD float exp(float x) {                                                      
 #endif
 }
 KB_KD float kb_tanh(float x) { return tanh(x); }                                              // kcc rewrites a program's unqualified tanh( / exp( to these:
-KB_KD float kb_exp(float x) { return exp(x); }                                                //  with a plain float argument ::tanh(float) of <cmath> would tie
+KB_KD float kb_exp(float x) { return exp(x); }
+KB_KD float kb_abs(float x) { return ::fabsf(x); }                                             // (abs binds to fabsf for a float)
+KB_KD int kb_abs(int x) { return x < 0 ? -x : x; }                                                //  with a plain float argument ::tanh(float) of <cmath> would tie
 KB_KD float abs(float x) { return ::fabsf(x); }
 KB_KD float sqr(float x) { return x * x; }
 KB_KD float cube(float x) { return x * x * x; }

@@ -62,7 +62,7 @@ def translate(text, source_name="program.k"):
         code = re.sub(r"(?<![\w.>:])graph\s*\.", "kb_graph().", code)             # `graph.clear()` / `graph.add(y)`: the UI plot, a host object there
         code = re.sub(r"(?<![\w.>:])(pi|ln2|root2)\b(?!\s*[\(:])", r"kb_\1()", code)
         code = re.sub(r"(?<![\w.>:])(min|max)\s*\(", r"kb_\1(", code)          # klang's own min / max (klang.h:221-224), not ::min / ::max
-        code = re.sub(r"(?<![\w.>:])(tanh|exp)\s*\(", r"kb_\1(", code)         # the float overloads that restate the host's libm on the device
+        code = re.sub(r"(?<![\w.>:])(tanh|exp|abs)\s*\(", r"kb_\1(", code)         # the float overloads that restate the host's libm on the device
         line = code + sep + comment
         if re.match(r"\s*#\s*include\s*<klang\.h>", line):
             out.append("// (klang.h -> klang_b200/csrc/kb_kdev.cuh)")
