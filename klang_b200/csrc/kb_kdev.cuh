@@ -237,6 +237,24 @@ KB_KD signal& operator>>(S&& source, signal& destination) { destination = kb_rea
 KB_KD_OUT_OP(+) KB_KD_OUT_OP(-) KB_KD_OUT_OP(*) KB_KD_OUT_OP(/)
 #undef KB_KD_OUT_OP
 
+// Function<Args...> (klang.h:2331-2510, 2929-2941): a Modifier that applies a C function to its input and up to two stored arguments.  The
+// reference holds the function in a std::function — a host address; kcc reads the function's name from the constructor's initialiser
+// (`Shaping() : f(softclip)`) and names it in the member's TYPE (FN::call), so the call is static.  `f(args)` with one argument fewer than the
+// function takes stores them and leaves x to the input (`in >> f(distort) >> out`); with all of them it also sets x.
+template <class FN, int ARGS> struct FunctionT : ModifierT<FunctionT<FN, ARGS>> {
+	float a[3];
+	FunctionT() { a[0] = a[1] = a[2] = 0.f; }
+	KB_KD float evaluate() const {
+		if constexpr (ARGS == 1) return FN::call(this->in.value);
+		else if constexpr (ARGS == 2) return FN::call(this->in.value, a[0]);
+		else return FN::call(this->in.value, a[0], a[1]);
+	}
+	KB_KD void process() { this->out = evaluate(); }
+	KB_KD FunctionT& operator()(float x0) { if (ARGS == 1) this->in = x0; else a[0] = x0; return *this; }
+	KB_KD FunctionT& operator()(float x0, float x1) { if (ARGS == 2) { this->in = x0; a[0] = x1; } else { a[0] = x0; a[1] = x1; } return *this; }
+	KB_KD FunctionT& operator()(float x0, float x1, float x2) { this->in = x0; a[0] = x1; a[1] = x2; return *this; }
+};
+
 // `x >> debug` (klang.h:3132-3287): kcc rewrites the sink to a temporary of this type; the source is still evaluated (an Output ticks)
 struct Debug { };
 template <class S> KB_KD signal operator>>(S&& source, Debug&&) { return kb_read(source); }     // (`(in >> debug) >> follower`: the tapped value flows on)

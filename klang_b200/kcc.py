@@ -42,6 +42,19 @@ def translate(text, source_name="program.k"):
         plugin, channels = m.group(1), 2 if "::" in m.group(2) else 1
     else:
         raise KccError(f"{source_name}: no struct derived from Effect / Stereo::Effect / Synth (Stereo::Synth programs are not translated yet)")
+    # Function<Args...> members hold a std::function in the reference (a host address).  The function each one is constructed with is read
+    # from the constructor's initialiser list and named in the member's type: `Function<float, float> f;` + `Shaping() : f(softclip)`
+    # become `klang::FunctionT<kb_fn_f, 2> f;` + `Shaping() : f()`, with `struct kb_fn_f { call(...) -> softclip(...) }` in front of the plugin.
+    functors = []
+    for fmem in re.finditer(r"\bFunction\s*<([^<>;]*)>\s+(\w+)\s*;", text):
+        nargs, member = len([a for a in fmem.group(1).split(",") if a.strip()]), fmem.group(2)
+        init = re.search(r"\)\s*:\s*(?:[^{;]*,\s*)?" + member + r"\s*\(\s*([A-Za-z_]\w*)\s*\)", text)
+        if not init:
+            raise KccError(f"{source_name}: Function member `{member}` is not constructed from a named function in a constructor initialiser")
+        functors.append((member, nargs, init.group(1), fmem.group(0), init.group(0)))
+    for member, nargs, fn, decl, init in functors:
+        text = text.replace(decl, f"klang::FunctionT<kb_fn_{member}, {nargs}> {member};")
+        text = text.replace(init, re.sub(r"\b" + member + r"\s*\(\s*" + fn + r"\s*\)$", f"{member}()", init))
     out = []
     depth = 0
     for lineno, line in enumerate(text.splitlines(), 1):
@@ -60,6 +73,14 @@ def translate(text, source_name="program.k"):
         code = re.sub(r"(?<![\w.>:])fs\b(?!\s*[\(:])", "kb_fs()", code)
         code = re.sub(r">>\s*debug\b", ">> klang::Debug()", code)
         code = re.sub(r"(?<![\w.>:])graph\s*\.", "kb_graph().", code)             # `graph.clear()` / `graph.add(y)`: the UI plot, a host object there
+        code = re.sub(r">>\s*graph\s*;", ">> kb_graph();", code)
+        if functors and re.match(r"\s*struct\s+" + re.escape(plugin) + r"\b", code):
+            args = ", ".join(f"float x{i}" for i in range(3))
+            for member, nargs, fn, _, _ in functors:
+                params = ", ".join(f"float x{i}" for i in range(nargs))
+                call = ", ".join(f"x{i}" for i in range(nargs))
+                out.append(f"struct kb_fn_{member} {{ KB_KD static float call({params}) {{ return {fn}({call}); }} }};")
+                out.append(f"#line {lineno}")
         code = re.sub(r"(?<![\w.>:])(pi|ln2|root2)\b(?!\s*[\(:])", r"kb_\1()", code)
         code = re.sub(r"(?<![\w.>:])(min|max)\s*\(", r"kb_\1(", code)          # klang's own min / max (klang.h:221-224), not ::min / ::max
         code = re.sub(r"(?<![\w.>:])(tanh|exp|abs)\s*\(", r"kb_\1(", code)         # the float overloads that restate the host's libm on the device

@@ -140,6 +140,9 @@ namespace k_patterns {
 namespace k_reverb2 {
 #include "Delay/Reverb2.k"
 }
+namespace k_shaping {
+#include "Distortion/Shaping.k"
+}
 namespace k_expression {
 #include "Subtractive/Expression.k"
 }
@@ -497,6 +500,7 @@ void* ref_fx_create(int graph) {
 	case 102: { auto* e = new k_eq::EQ();           fx->mono = e; fx->controls = &e->controls; } break;     // Filtering/EQ.k (LPF / HPF set in prepare())
 	case 103: { auto* e = new k_patterns::Patterns(); fx->mono = e; fx->controls = &e->controls; } break;   // Delay/Patterns.k (a Menu control selects the tap pattern)
 	case 104: { auto* e = new k_reverb2::Reverb2();  fx->stereo = e; fx->controls = &e->controls; } break;  // Delay/Reverb2.k (four Delay<192000>, two LPF, in[c] / out.l)
+	case 105: { auto* e = new k_shaping::Shaping();  fx->mono = e;   fx->controls = &e->controls; } break;  // Distortion/Shaping.k (Function<float, float> over softclip: tanh(c x) / tanh(c))
 	default: delete fx; return nullptr;
 	}
 	return fx;

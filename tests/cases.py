@@ -294,6 +294,7 @@ TRANSLATED_FX_SCRIPTS = {
     "k_bands": (101, "Filtering/Bands.k", 4096, 1024, [(1, 0, 250.0), (1, 3, 5.0), (3, 2, 900.0)], None),
     "k_eq": (102, "Filtering/EQ.k", 4096, 1024, [(1, 0, 0.9), (2, 1, 0.1), (3, 2, 1.0)], None),
     "k_patterns": (103, "Delay/Patterns.k", 131072, 16384, [(3, 0, 1.0), (6, 0, 2.0)], 3000),              # a Menu control picks one of three tap patterns (taps up to 1.5 s)
+    "k_shaping": (105, "Distortion/Shaping.k", 4096, 1024, [(1, 0, 2.5), (2, 0, 5.6), (3, 0, 0.4)], None),      # Function<float, float>: `in >> f(distort) >> out` = tanh(c x) / tanh(c)
     "k_reverb2": (104, "Delay/Reverb2.k", 16384, 4096, [(1, 0, 0.45), (2, 1, 0.05), (2, 2, 4000.0)], None),  # Stereo::Effect: in[c], out.l >> feedback[0]
 }
 

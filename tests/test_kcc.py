@@ -269,7 +269,7 @@ def test_programs_without_a_bound_graph_match_the_reference(fs):
     reference's (tests/golden/klang_ref_translated_fs*.npz, written by tests/gen_golden.py; live against oracle.ref where it is present)."""
     g = {k: v for k, v in np.load(os.path.join(ROOT, "tests", "golden", f"klang_ref_translated_fs{fs}.npz")).items() if k.startswith("fx/")}
     got = cases.translated_cases(_UserFxEngine(), fs)
-    assert set(got) == set(g) and len(g) == len(cases.TRANSLATED_FX_SCRIPTS) == 5
+    assert set(got) == set(g) and len(g) == len(cases.TRANSLATED_FX_SCRIPTS) == 6
     for k in g:
         assert np.array_equal(got[k].view(np.uint32), g[k].view(np.uint32)), f"{k}: differs from the reference"
         assert np.abs(g[k]).max() > 0
