@@ -144,6 +144,23 @@ __global__ void __launch_bounds__(1024) kb_mix_fused_kernel(const float* __restr
 		if (i0) __syncthreads();
 		for (int r = tid; r < rows; r += blockDim.x) s_act[r] = hdr[(size_t)i0 * voices + r].active;
 		__syncthreads();
+		// full 32-sample groups with 16-byte aligned rows: a warp pulls FOUR rows per instruction (8 lanes x 16 bytes per row) — a quarter of the
+		// load / store instructions of the lane = sample form below, which remains for ragged blocks
+		const int t0 = blockIdx.x * KB_MIXF_TS;
+		const bool vec = (n & 3) == 0 && t0 + KB_MIXF_TS <= n && (reinterpret_cast<size_t>(scratch) & 15) == 0;
+		if (vec) {
+			const int sub = lane >> 3, c4 = (lane & 7) * 4;
+			for (int g0 = warp; g0 * 4 < rows; g0 += 4 * nwarps) {
+				float4 x[4];
+				#pragma unroll
+				for (int j = 0; j < 4; j++) {
+					const int r = (g0 + j * nwarps) * 4 + sub;
+					x[j] = (r < rows && s_act[r < rows ? r : 0]) ? __ldcs(reinterpret_cast<const float4*>(scratch + ((size_t)i0 * voices + r) * n + t0 + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+				}
+				#pragma unroll
+				for (int j = 0; j < 4; j++) { const int r = (g0 + j * nwarps) * 4 + sub; if (r < rows) *reinterpret_cast<float4*>(&tile[(size_t)r * KB_MIXF_TS + c4]) = x[j]; }
+			}
+		} else
 		for (int r0 = warp; r0 < rows; r0 += 16 * nwarps) {
 			float x[16];
 			#pragma unroll
