@@ -270,6 +270,47 @@ def test_c2_bench_schedule_vs_oracle(eng, per_voice):
     bank.close()
 
 
+def test_c2_bank_mix_into_a_pinned_host_buffer_is_the_copied_result_bit_for_bit():
+    """bench.py's end-to-end step hands the library a page-locked, device-mapped output buffer: the mix kernel then stores the bank mix into it
+    directly instead of a device-to-host copy (kb_api.cu: kb_host_ptr_mapped).  Same bank, same events (the bench's re-trigger groups), once
+    into a pageable numpy array (the copy) and once into a pinned buffer, synchronous and KB_ASYNC_HOST: the same bits, block after block."""
+    import torch
+    fs, n, inst, voices, groups = 48000, 4096, 8, 128, 16
+    total = inst * voices
+    flags = kb.BANK_MIX | kb.MIX_SUM
+
+    def make():
+        kb.lib().kb_srand(1)
+        bank = kb.SynthBank(kb.SY_SUBTRACTIVE, inst, voices, fs, n)
+        for g in range(total):
+            bank.voice_start(g % voices, cases.voice_pitch(g), cases.voice_velocity(g), g // voices)
+        return bank
+
+    def events(grp):
+        ids = np.arange(grp, total, groups)
+        ev = np.zeros(len(ids), kb.EVENT_DTYPE)
+        ev["type"] = kb.EV_VOICE_START
+        ev["instance"], ev["key"] = ids // voices, ids % voices
+        ev["pitch"] = [cases.voice_pitch(int(g)) for g in ids]
+        ev["velocity"] = [cases.voice_velocity(int(g)) for g in ids]
+        return ev
+
+    a, b, c = make(), make(), make()
+    pinned = [torch.empty(a.out_shape(n, flags), dtype=torch.float32).pin_memory() for _ in range(3)]
+    for blk in range(5):
+        ev = events(blk % groups)
+        want = a.step_into(ev, np.empty(a.out_shape(n, flags), np.float32), n, flags)
+        got = b.step_into(ev, pinned[0].numpy(), n, flags)                          # synchronous call, pinned buffer
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"block {blk}: pinned (synchronous)"
+        buf = pinned[1 + (blk & 1)]
+        c.step_into(ev, buf.numpy(), n, flags | kb.ASYNC_HOST)
+        c.sync()
+        assert np.array_equal(buf.numpy().view(np.uint32), want.view(np.uint32)), f"block {blk}: pinned (KB_ASYNC_HOST)"
+        assert np.abs(want).max() > 0.01
+    for bank in (a, b, c):
+        bank.close()
+
+
 # ------------------------------------------------------------------------------------------ far-end ring wrap (ADVICE r1)
 def test_delay_pingpong_far_end_wrap_at_192k(eng):
     """Delay/PingPong.k at fs = 192 kHz with delay controls near 1.0: t = 191040 frames passes `t < SIZE`, but a launch longer than

@@ -99,6 +99,29 @@ def test_mixdown_fused_step_single_rank():
         assert torch.equal(got[blk + 1], want[blk]) and float(want[blk].abs().max()) > 1e-3, f"block {blk}"
     a.close(); b.close()
     L.kb_mixdown_destroy(h)
+    # the same with out_prev in page-locked host memory (the exchange kernel stores the sum over PCIe: bench.py's end-to-end leg at N > 1)
+    h = L.kb_mixdown_create(0, 1, 0, n)
+    a, b = _bank(0, 0, fs, n), _bank(0, 0, fs, n)
+    b.set_stream(stream)
+    want = torch.empty(6, 1, n, device="cuda")
+    host = [torch.zeros(1, n).pin_memory() for _ in range(7)]
+    for blk in range(6):
+        a.process_into(want[blk], n, kb.BANK_MIX | kb.MIX_SUM)
+        b.process_mixdown(_Mix(h), host[blk], n, kb.MIX_SUM)
+    last = torch.empty(1, n, device="cuda")
+    assert L.kb_mixdown_collect(h, last.data_ptr(), n, stream) == 0
+    a.sync()
+    torch.cuda.synchronize()
+    for blk in range(5):
+        assert torch.equal(host[blk + 1], want[blk].cpu()), f"pinned out_prev, block {blk}"
+    assert torch.equal(last, want[5])
+    a.close(); b.close()
+    L.kb_mixdown_destroy(h)
+
+
+class _Mix:                                                        # (process_mixdown reads `.h` of a sharding.PeerMixdown)
+    def __init__(self, h):
+        self.h = h
 
 
 def _worker(rank, world, port, n, fs, out_path):
