@@ -147,4 +147,4 @@ if __name__ == "__main__":
     # subprocess-based tests (k_host, probes) cannot be dry-run: deselect them
     # (the far-end and validation tests of test_gpu_baseline_shapes.py assert on the schedule the CUDA library picked / on its argument checks)
     sys.exit(pytest.main([os.path.join(HERE, "test_zz_gpu_primitives.py"), os.path.join(HERE, "test_gpu_baseline_shapes.py"), "-q", "-x", "-p", "no:cacheprovider",
-                          "-k", "not k_programs and not far_end and not validation and not tolerance_mode"]))
+                          "-k", "not k_programs and not far_end and not validation and not tolerance_mode and not pinned_host_buffer"]))
