@@ -627,6 +627,10 @@ struct kb_synth_bank : kb_bank_base {
 	cudaEvent_t stage_done[KB_NSTAGE] = {}; bool stage_used[KB_NSTAGE] = {}; int stage_next = 0;
 	size_t stage_bytes = 0;
 	unsigned char* d_staging = nullptr;
+	// the staged records also travel to a device slot by an asynchronous copy on a stream of its own, issued when the host has packed them (the
+	// GPU is still rendering the previous block), and the voice kernel gathers them from there: a CTA with a re-written voice no longer starts
+	// its tile loop a PCIe round trip (~2.5 us) after the others.  KB_STAGE_COPY=0: the kernel reads the pinned slot itself (A/B, same results)
+	unsigned char* d_stage_slots = nullptr; cudaStream_t stage_stream = nullptr; cudaEvent_t stage_copied[KB_NSTAGE] = {};
 	std::vector<unsigned char> voice_dirty; std::vector<int> dirty_list; bool all_dirty = true;
 	long long h2d_bytes = 0, d2h_bytes = 0;                                     // state traffic so far (for the e2e accounting)
 	bool hdr_stale = false, vstate_stale = false;                               // finer than host_stale: what the device has changed
@@ -703,6 +707,19 @@ static int sy_upload(kb_synth_bank* b, bool defer_scatter = false) {
 				// the voice kernel reads the records from this pinned slot itself (kb_tile_scatter); the slot is free again when that kernel has
 				// run: sy_process records stage_done[slot] behind it
 				b->staged.records = stage + rec_off; b->staged.count = count;
+				static const bool stage_copy = !getenv("KB_STAGE_COPY") || atoi(getenv("KB_STAGE_COPY")) != 0;
+				if (stage_copy) {
+					if (!b->d_stage_slots) {
+						KB_CUDA(cudaMalloc(&b->d_stage_slots, kb_synth_bank::KB_NSTAGE * b->stage_bytes));
+						KB_CUDA(cudaStreamCreateWithFlags(&b->stage_stream, cudaStreamNonBlocking));
+						for (int k = 0; k < kb_synth_bank::KB_NSTAGE; k++) KB_CUDA(cudaEventCreateWithFlags(&b->stage_copied[k], cudaEventDisableTiming));
+					}
+					unsigned char* dslot = b->d_stage_slots + (size_t)slot * b->stage_bytes;
+					KB_CUDA(cudaMemcpyAsync(dslot + rec_off, stage + rec_off, (size_t)count * rec, cudaMemcpyHostToDevice, b->stage_stream));
+					KB_CUDA(cudaEventRecord(b->stage_copied[slot], b->stage_stream));
+					KB_CUDA(cudaStreamWaitEvent(b->stream, b->stage_copied[slot], 0));
+					b->staged.records = dslot + rec_off;
+				}
 				for (int k = 0; k < count; k++) b->staged.index[k] = stage_index[k];
 				b->staged_slot = slot;
 			} else {
@@ -838,6 +855,9 @@ extern "C" void kb_synth_bank_destroy(kb_synth_bank* b) {
 	for (int k = 0; k < kb_synth_bank::KB_NSTAGE; k++) if (b->stage_done[k]) cudaEventDestroy(b->stage_done[k]);
 	cudaFreeHost(b->hdr); cudaFreeHost(b->vstate); cudaFreeHost(b->staging);
 	cudaFree(b->d_staging);
+	if (b->stage_stream) { cudaStreamSynchronize(b->stage_stream); cudaStreamDestroy(b->stage_stream); }
+	for (int k = 0; k < kb_synth_bank::KB_NSTAGE; k++) if (b->stage_copied[k]) cudaEventDestroy(b->stage_copied[k]);
+	cudaFree(b->d_stage_slots);
 	cudaFree(b->d_hdr); cudaFree(b->d_vstate); cudaFree(b->d_blk); cudaFree(b->d_scratch); cudaFree(b->d_out); cudaFree(b->d_adsr); cudaFree(b->d_mix);
 	if (b->mix_stream) { cudaStreamSynchronize(b->mix_stream); cudaStreamDestroy(b->mix_stream); }
 	if (b->ev_mix_in) cudaEventDestroy(b->ev_mix_in);

@@ -5,6 +5,7 @@ run KB_TILE_LAYOUT=2
 run KB_TILE_LAYOUT=3
 run KB_TILE_LAYOUT=4
 run "KB_TILE_LAYOUT=4 KB_PDL=0"
+run "KB_TILE_LAYOUT=4 KB_STAGE_COPY=0"
 run "KB_TILE_LAYOUT=4 KB_ZERO_COPY_OUT=0"
 run "KB_TILE_LAYOUT=4 KB_TILE_G=8"
 run "KB_TILE_LAYOUT=4 KB_C2_VARIANT=64"
