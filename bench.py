@@ -423,6 +423,8 @@ def main():
 
     host_bufs = [out_host, torch.empty_like(out_host).pin_memory()]
     host_done = [torch.cuda.Event(), torch.cuda.Event()]
+    assert all(hb.is_pinned() and hb.is_contiguous() and hb.dtype == torch.float32 for hb in host_bufs)
+    host_ptrs = [hb.data_ptr() for hb in host_bufs]
     copy_stream = torch.cuda.Stream(device=dev)
     e2e_k = [0]
 
@@ -444,12 +446,9 @@ def main():
             k = e2e_k[0]
             i = k & 1
             if rank == 0 and k >= 2:
-                host_done[i].synchronize()
-            bank.events(next_events())
-            bank.process_mixdown(mixdown, host_bufs[i] if rank == 0 else None, BLOCK, kb.MIX_SUM)     # (pinned: the exchange kernel stores the sum over PCIe)
-            if rank == 0 and k >= 1:
-                mixdown.stream_wait(copy_stream.cuda_stream)
-                host_done[i].record(copy_stream)
+                mixdown.host_wait(1)                                   # the exchange that wrote host_bufs[i] two blocks ago (one before the last) has finished
+            # one call per block: the events, the kernels, the exchange; pinned out_prev: the exchange kernel stores the sum over PCIe
+            bank.step_mixdown(next_events(), mixdown, host_ptrs[i] if rank == 0 else 0, BLOCK, kb.MIX_SUM)
             e2e_k[0] += 1
         else:
             step_device()

@@ -234,6 +234,10 @@ int kb_mixdown_stream_wait(kb_mixdown* mix, void* stream);
 /* kb_synth_bank_process(KB_BANK_MIX) whose bank-mix kernel IS that fused step: the in-order sum of the bank's instances goes straight into
  * rank 0's arena over NVLink (Synth voices / instances shard across GPUs; this is the path's only exchange). */
 int kb_synth_bank_process_mixdown(kb_synth_bank* bank, kb_mixdown* m, float* out_prev, int n, unsigned flags);
+/* kb_synth_bank_events + kb_synth_bank_process_mixdown in one call (what a host's audio callback does per block, klang.h:4399-4466 over a sharded bank) */
+int kb_synth_bank_step_mixdown(kb_synth_bank* bank, int count, const kb_note_event* events, kb_mixdown* m, float* out_prev, int n, unsigned flags);
+/* block the host until the exchange kernel of the fused step `back` steps before the last one (0 .. 3) has finished: its out_prev is then valid */
+int kb_mixdown_host_wait(kb_mixdown* mix, int back);
 
 /* ---------------------------------------------------------------------------- primitive operators */
 /* Single-object runs of the primitive operators ON THE DEVICE (one thread), for known-answer tests.

@@ -51,6 +51,7 @@ SYMBOLS = [
     ("kb_mixdown_collect", _i, [_vp, _vp, _i, _vp]),
     ("kb_mixdown_step", _i, [_vp, _vp, _i, _vp, _vp]), ("kb_mixdown_stream_wait", _i, [_vp, _vp]), ("kb_synth_bank_process_mixdown", _i, [_vp, _vp, _vp, _i, _u]),
     ("kb_synth_bank_step", _i, [_vp, _i, _vp, _vp, _i, _u]),
+    ("kb_synth_bank_step_mixdown", _i, [_vp, _i, _vp, _vp, _vp, _i, _u]), ("kb_mixdown_host_wait", _i, [_vp, _i]),
     ("kb_prim_osc", _i, [_i, _i, _f, _f, _f, _f, _i, _vp]),
     ("kb_prim_filter", _i, [_i, _i, _vp, _vp, _f, _i, _vp, _vp, _vp]),
     ("kb_prim_envelope", _i, [_i, _vp, _i, _i, _f, _i, _i, _f, _f, _vp, _vp]),
@@ -331,6 +332,12 @@ class SynthBank:
                     raise KlangB200Error("kb_synth_bank_process_mixdown: out_prev must be device memory or a page-locked (pinned) torch tensor")
                 self._pinned_seen.add(p)
         _check(lib().kb_synth_bank_process_mixdown(self.h, mixdown.h, p, n, flags), "kb_synth_bank_process_mixdown")
+
+    def step_mixdown(self, ev, mixdown, out_prev_ptr, n, flags=0):
+        """events(ev) then process_mixdown in ONE call into the library (kb_synth_bank_step_mixdown).  `out_prev_ptr`: 0 / None, or the raw address
+        of a buffer process_mixdown() has accepted before (device memory or pinned host memory) — a per-block host loop checks its buffers once."""
+        ev = np.ascontiguousarray(ev, EVENT_DTYPE)
+        _check(lib().kb_synth_bank_step_mixdown(self.h, len(ev), ev.ctypes.data, mixdown.h, out_prev_ptr or 0, n, flags), "kb_synth_bank_step_mixdown")
 
     def process_into_device_ptr(self, ptr, n, flags=0):
         """out = a raw device pointer (e.g. a peer-mapped slot of sharding.PeerMixdown); asynchronous on the bank stream."""

@@ -83,6 +83,7 @@ struct kb_mixdown {
 	unsigned char* arena = nullptr;     // rank 0: own allocation; others: the IPC mapping
 	unsigned* d_tickets = nullptr;      // local device memory: two CTA tickets of the fused step kernel (publish, collect)
 	cudaEvent_t ev_done = nullptr;      // recorded behind the last fused step kernel (which may run on a bank's side stream)
+	cudaEvent_t ev_ring[4] = { nullptr, nullptr, nullptr, nullptr };   // the same per step (step & 3): kb_mixdown_host_wait joins an older step
 	bool step_pending = false;
 	bool mapped = false;
 	size_t slot_bytes() const { return (size_t)max_floats * sizeof(float); }
@@ -1344,6 +1345,7 @@ extern "C" void kb_mixdown_destroy(kb_mixdown* m) {
 	if (m->arena) { if (m->mapped) cudaIpcCloseMemHandle(m->arena); else cudaFree(m->arena); }
 	cudaFree(m->d_tickets);
 	if (m->ev_done) cudaEventDestroy(m->ev_done);
+	for (int k = 0; k < 4; k++) if (m->ev_ring[k]) cudaEventDestroy(m->ev_ring[k]);
 	delete m;
 }
 extern "C" int kb_mixdown_export(kb_mixdown* m, void* handle) {
@@ -1476,7 +1478,18 @@ static int mixdown_step(kb_mixdown* m, const float* src, int rows, size_t row_st
 	KB_CUDA(cudaGetLastError());
 	if (!m->ev_done) KB_CUDA(cudaEventCreateWithFlags(&m->ev_done, cudaEventDisableTiming));
 	KB_CUDA(cudaEventRecord(m->ev_done, stream));
+	if (!m->ev_ring[step & 3]) KB_CUDA(cudaEventCreateWithFlags(&m->ev_ring[step & 3], cudaEventDisableTiming));
+	KB_CUDA(cudaEventRecord(m->ev_ring[step & 3], stream));
 	m->step_pending = true;
+	return KB_OK;
+}
+// the host waits until the exchange kernel of the fused step `back` steps before the last one has finished (back = 0 .. 3): what a host that
+// rotates its out_prev buffers does before it hands one out again, without joining the steps still in flight
+extern "C" int kb_mixdown_host_wait(kb_mixdown* m, int back) {
+	if (!m || back < 0 || back > 3) return kb_fail(KB_EINVAL, "kb_mixdown_host_wait: bad argument (back = 0 .. 3)");
+	if ((unsigned)back >= m->step) return KB_OK;                         // that step never ran
+	cudaEvent_t ev = m->ev_ring[(m->step - (unsigned)back) & 3];
+	if (ev) { KB_CUDA(cudaSetDevice(m->device)); KB_CUDA(cudaEventSynchronize(ev)); }
 	return KB_OK;
 }
 extern "C" int kb_synth_bank_process_mixdown(kb_synth_bank* b, kb_mixdown* m, float* out_prev, int n, unsigned flags) {
@@ -1485,6 +1498,11 @@ extern "C" int kb_synth_bank_process_mixdown(kb_synth_bank* b, kb_mixdown* m, fl
 	if (m->rank == 0 && m->step > m->collected + 1) return kb_fail(KB_EINVAL, "kb_synth_bank_process_mixdown: rank 0 must pass out_prev on every step (or collect) so the slots are consumed");
 	if (m->device != b->device) return kb_fail(KB_EINVAL, "kb_synth_bank_process_mixdown: bank and mix-down live on different devices");
 	return sy_process(b, (float*)b->d_mix, n, flags | KB_BANK_MIX | KB_DEVICE_PTR, m, out_prev);
+}
+// the block's events, then kb_synth_bank_process_mixdown: one call per block for a host that drives a sharded bank
+extern "C" int kb_synth_bank_step_mixdown(kb_synth_bank* b, int count, const kb_note_event* events, kb_mixdown* m, float* out_prev, int n, unsigned flags) {
+	int rc = kb_synth_bank_events(b, count, events); if (rc) return rc;
+	return kb_synth_bank_process_mixdown(b, m, out_prev, n, flags);
 }
 // make `stream` wait for the exchange kernel of the last fused step (it runs on the bank's side stream): what a consumer of `out_prev` queues
 // before it reads the buffer, without tying the bank's own stream to the exchange

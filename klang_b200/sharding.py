@@ -84,6 +84,10 @@ class PeerMixdown:
         """`cuda_stream` waits for the exchange kernel of the last fused step (before it reads that step's out_prev)."""
         self._api._check(self._api.lib().kb_mixdown_stream_wait(self.h, cuda_stream), "kb_mixdown_stream_wait")
 
+    def host_wait(self, back=0):
+        """the host blocks until the exchange kernel of the fused step `back` steps before the last one has finished (its out_prev is valid)"""
+        self._api._check(self._api.lib().kb_mixdown_host_wait(self.h, int(back)), "kb_mixdown_host_wait")
+
     def collect(self, dst, count, cuda_stream):
         self._api._check(self._api.lib().kb_mixdown_collect(self.h, dst.data_ptr(), int(count), cuda_stream), "kb_mixdown_collect")
 
