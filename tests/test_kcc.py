@@ -103,6 +103,19 @@ def test_k_programs_translate_and_compile_for_the_device(tmp_path):
         assert L.kb_user_kind() == 1 and L.kb_user_synth_voices() == 32
     with pytest.raises(kcc.KccError):
         kcc.compile_k(os.path.join(REF, "Vocoder.k"), str(tmp_path / "libvocoder_k.so"))            # (controls.add / 27 controls / Function<> locals are not in the device header)
+    # the rewrites of the later steps, on the text: a Function<> member names the function it is constructed with in its type; a namespace-scope
+    # constant gets a __device__ twin; a note's on() / off() stay host functions; klang's own min / max and the float libm overloads are named
+    src, _, _ = kcc.translate(open(os.path.join(REF, "Distortion", "Shaping.k")).read(), "Shaping.k")
+    assert "klang::FunctionT<kb_fn_f, 2> f;" in src and "struct kb_fn_f { KB_KD static float call(float x0, float x1) { return softclip(x0, x1); } };" in src
+    assert "Shaping() : f() {" in src and "return kb_tanh(c * x) / kb_tanh(c);" in src and ">> kb_graph();" in src
+    src, _, _ = kcc.translate(open(os.path.join(REF, "Additive", "Resynthesis.k")).read(), "Resynthesis.k")
+    assert "__device__ const float FREQ_kbd[6]" in src and "#define FREQ FREQ_kbd" in src and "#define GAIN GAIN_kbh" in src
+    src, _, _ = kcc.translate(open(os.path.join(REF, "FM.k")).read(), "FM.k")
+    assert "KB_KD event on(" not in src and "\t\tevent on(Pitch p, Velocity v) {" in src and "kb_graph().clear();" in src and "KB_KD void process() {" in src
+    src, _, _ = kcc.translate(open(os.path.join(REF, "Subtractive", "Expression.k")).read(), "Expression.k")
+    assert "kb_max(1000,f0 * 1.5)" in src
+    src, _, _ = kcc.translate(open(os.path.join(REF, "TB303.k")).read(), "TB303.k")
+    assert "KB_KD static float shape(float x) {" in src and "kb_exp(-0.03f*resonance)" in src           # (`static inline`: KB_KD carries the inline)
     # klang::fs and the debug sink are host objects in the reference: the translation routes them through kb_fs() / a sink value
     src, _, _ = kcc.translate(open(os.path.join(REF, "Gain", "Tremolo.k")).read(), "Tremolo.k")
     assert "mod >> klang::Debug();" in src
