@@ -500,9 +500,9 @@ __global__ void __launch_bounds__(768, 1) kb_sub_flow_kernel(KbSubVoice* __restr
 
 // ---- the decoupled stages handed over through MBARRIERS (round 2, second step; SASS SYNCS).  kb_sub_flow_kernel's progress counters are
 // polled (ld.acquire + nanosleep) and its 14 worker warps meet at two named barriers per tile: ~500 of the workers' ~3150 cycles per tile
-// and ~300 of the filter warp's were hand-over (clock64 stamps, profiles/r02_c2_trace.txt).  Here every buffer slot has a `full` and an
-// `empty` mbarrier: a producing WARP arrives once behind its __syncwarp(), a consumer parks in mbarrier.try_wait — no polling, and no
-// barrier among the worker warps at all: each takes its own 32 items of a tile as soon as that tile's inputs are there.
+// and ~300 of the filter warp's were hand-over (clock64 stamps, profiles/r02_c2_mbar.txt).  Here a producing WARP arrives on an mbarrier
+// once behind its __syncwarp() and a consumer parks in mbarrier.try_wait — no polling, and no barrier among the worker warps at all: each
+// takes its own items of a tile as soon as that tile's inputs are there.
 // One mbarrier ring per ROLE says "this role has finished tile n" (slot n & 3, the n-th use of a slot waits for parity (n >> 2) & 1):
 //   a_done (1 arrival: the envelope warp)    b_done (W arrivals: every worker warp after its B items)    c_done (1: the filter warp)
 // A worker warp's iteration j is: wait c_done(j-4) -> D(j-4) -> wait a_done(j) -> B(j) -> arrive b_done(j).  D before B, so that b_done(j)
@@ -511,8 +511,10 @@ __global__ void __launch_bounds__(768, 1) kb_sub_flow_kernel(KbSubVoice* __restr
 //   C(c) waits b_done(c):   coef[c & 3] is written, and out[c & 3] was read by D(c-4)
 //   B(j) needs a_done(j) and coef[j & 3] back from C(j-4); D(d) needs C(d) and A(d) (A(d) was waited for by the same warp's B(d))
 // No barrier can complete twice before a waiter has looked: the next completion of a slot needs the role that waits on it to have moved on.
-// The envelope warp runs kb_envr_run_tile (one exit test per tile, 128-bit stores); the filter warp's loop is unrolled to 32 samples per
-// branch.  Arithmetic and order per voice unchanged: bit-identical.
+// The envelope warp runs kb_envr_run_tile (one exit test per tile, 128-bit stores); the filter warp's loop is unrolled to 56 samples per
+// branch and carries on across tile boundaries when the next tile's coefficients are already there (non-blocking look at b_done); the
+// prologue gathers every record of the CTA's voices in one round trip (kb_tile_gather); full tiles leave the D stage two samples per
+// thread.  Arithmetic and order per voice unchanged: bit-identical.
 template <int G> struct KbSubMbarSmem {
 	KbTileCommon<G> c;
 	KbTileRows4<G> coef[4];
